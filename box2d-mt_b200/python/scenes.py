@@ -1,0 +1,159 @@
+"""Headless restatements of the scenes named by BASELINE.json / SURVEY.md 8d, as flat Scene descriptions.
+
+The Testbed scene classes of the reference derive from a GL `Test` base and cannot be built headless, so the
+recipes are restated here (citing the scene file they follow).  All position arithmetic that the reference
+does in float32 is done in np.float32 here so that body placement is bit-identical.
+"""
+import numpy as np
+
+import b2cuda_types as T
+from b2scene import Scene, BODYDEF_DEFAULT, BODYDEF_BULLET, BODYDEF_ALLOW_SLEEP
+
+F = np.float32
+
+
+def hello_world():
+    """HelloWorld/HelloWorld.cpp:29-76: ground box 50x10 at (0,-10), dynamic 1x1 box at (0,4), friction 0.3."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, -10.0))
+    s.fixture(g, s.box(50.0, 10.0), density=0.0)
+    b = s.body(T.DYNAMIC_BODY, (0.0, 4.0))
+    s.fixture(b, s.box(1.0, 1.0), density=1.0, friction=0.3)
+    return s
+
+
+def _pyramid_rows(s, shape, x0, y0, count, density=5.0):
+    """Testbed/Tests/Pyramid.h:49-68: row i has count-i boxes, offsets (0.5625, 1.25) / (1.125, 0)."""
+    x = np.array([x0, y0], dtype=F)
+    dx = np.array([0.5625, 1.25], dtype=F)
+    dy = np.array([1.125, 0.0], dtype=F)
+    for i in range(count):
+        y = x.copy()
+        for _ in range(i, count):
+            b = s.body(T.DYNAMIC_BODY, (y[0], y[1]))
+            s.fixture(b, shape, density=density)
+            y = (y + dy).astype(F)
+        x = (x + dx).astype(F)
+
+
+def pyramid(count=20, continuous=True):
+    """Testbed/Tests/Pyramid.h:30-69 exactly: edge ground (-40,0)-(40,0), boxes 0.5 half-extent, density 5."""
+    flags = T.WORLD_DEFAULT if continuous else (T.WORLD_DEFAULT & ~T.WORLD_CONTINUOUS)
+    s = Scene(world_flags=flags)
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.edge((-40.0, 0.0), (40.0, 0.0)), density=0.0)
+    _pyramid_rows(s, s.box(0.5, 0.5), -7.0, 0.75, count)
+    return s
+
+
+def pyramids(pyramid_count=40, size=20, thick_polygon_ground=False, continuous=True):
+    """Testbed/Tests/SleepCollidePerf.h:35-83 (pyramids only; SURVEY.md Appendix B layout).
+
+    thick_polygon_ground replaces the edge ground by a static thick-shape box (config C4 of SURVEY.md 8d),
+    which removes the ground contacts from the TOI candidate set."""
+    flags = T.WORLD_DEFAULT if continuous else (T.WORLD_DEFAULT & ~T.WORLD_CONTINUOUS)
+    s = Scene(world_flags=flags)
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    half = float(F(20.0) * F(pyramid_count))
+    if thick_polygon_ground:
+        s.fixture(g, s.box(half + 20.0, 1.0, center=(0.0, -1.0), angle=0.0), density=0.0, thick=True)
+    else:
+        s.fixture(g, s.edge((-half, 0.0), (half, 0.0)), density=0.0)
+    spacing = F(1.125) * F(size)
+    x_init = F(F(F(-spacing * F(pyramid_count)) * F(0.5)) - F(7.0))
+    box = s.box(0.5, 0.5)
+    for _ in range(pyramid_count):
+        _pyramid_rows(s, box, x_init, 0.75, size)
+        x_init = F(x_init + spacing)
+    return s
+
+
+class _Rand:
+    """rand() & 32767 based RandomFloat of Testbed/Framework/Test.h:45-60, with a portable LCG behind it."""
+
+    def __init__(self, seed=0):
+        self.rng = np.random.RandomState(seed)
+
+    def uniform(self, lo, hi, n=None):
+        r = self.rng.randint(0, 32768, size=n).astype(F) / F(32767.0)
+        return (F(hi - lo) * r + F(lo)).astype(F)
+
+
+def add_pair(count=400, seed=0):
+    """Testbed/Tests/AddPair.h:26-60 scaled to `count` circles at constant density:
+    circles r=0.1 density 0.01 in [-6s,0]x[5-s,5+s], s = sqrt(count/400); zero gravity; bullet box 1.5
+    half-extent at (-40,5) with v=(150,0)."""
+    s = Scene(gravity=(0.0, 0.0))
+    scale = float(np.sqrt(count / 400.0))
+    rnd = _Rand(seed)
+    circle = s.circle(0.1)
+    xs = rnd.uniform(-6.0 * scale, 0.0, count)
+    ys = rnd.uniform(5.0 - scale, 5.0 + scale, count)
+    for i in range(count):
+        b = s.body(T.DYNAMIC_BODY, (xs[i], ys[i]))
+        s.fixture(b, circle, density=0.01)
+    b = s.body(T.DYNAMIC_BODY, (-40.0, 5.0), vel=(150.0, 0.0), flags=BODYDEF_DEFAULT | BODYDEF_BULLET)
+    s.fixture(b, s.box(1.5, 1.5), density=1.0)
+    return s
+
+
+def tumbler(count=800, seed=0, scale=None):
+    """Testbed/Tests/Tumbler.h:47-54 walls on a KINEMATIC body at (0,10) spinning at 0.05*pi rad/s
+    (the revolute-joint motor is replaced by a kinematic container), scaled so that `count`
+    boxes of half-extent 0.125 pre-placed on a jittered grid fit inside."""
+    s = Scene(world_flags=T.WORLD_DEFAULT & ~T.WORLD_ALLOW_SLEEP)
+    if scale is None:
+        scale = max(1.0, float(np.sqrt(count / 800.0)))
+    k = scale
+    c = s.body(T.KINEMATIC_BODY, (0.0, 10.0 * k), w=0.05 * np.pi, flags=BODYDEF_DEFAULT & ~BODYDEF_ALLOW_SLEEP)
+    s.fixture(c, s.box(0.5 * k, 10.0 * k, center=(10.0 * k, 0.0), angle=0.0), density=5.0, thick=True)
+    s.fixture(c, s.box(0.5 * k, 10.0 * k, center=(-10.0 * k, 0.0), angle=0.0), density=5.0, thick=True)
+    s.fixture(c, s.box(10.0 * k, 0.5 * k, center=(0.0, 10.0 * k), angle=0.0), density=5.0, thick=True)
+    s.fixture(c, s.box(10.0 * k, 0.5 * k, center=(0.0, -10.0 * k), angle=0.0), density=5.0, thick=True)
+    box = s.box(0.125, 0.125)
+    rnd = _Rand(seed)
+    n = int(np.ceil(np.sqrt(count)))
+    pitch = 0.3
+    jx = rnd.uniform(-0.02, 0.02, count)
+    jy = rnd.uniform(-0.02, 0.02, count)
+    for i in range(count):
+        gx, gy = i % n, i // n
+        x = (gx - 0.5 * (n - 1)) * pitch + jx[i]
+        y = 10.0 * k + (gy - 0.5 * (n - 1)) * pitch + jy[i]
+        b = s.body(T.DYNAMIC_BODY, (x, y))
+        s.fixture(b, box, density=1.0)
+    return s
+
+
+def _regular_polygon(sides, radius):
+    """Testbed/Tests/ManyBodies.h:277-291: regular polygon, vertex k at angle 2*pi*k/sides."""
+    ang = (2.0 * np.pi * np.arange(sides) / sides)
+    return [(float(F(radius * np.cos(a))), float(F(radius * np.sin(a)))) for a in ang]
+
+
+def pile(columns, rows, seed=0, pitch=0.56, radius=0.25, sleep=False, wall_height=None):
+    """mixed circle / regular 3-8-gon pile (circumradius 0.25, density 1) dropped from a jittered
+    grid into a static thick-shape container.  columns*rows bodies; 50% circles."""
+    flags = T.WORLD_DEFAULT if sleep else (T.WORLD_DEFAULT & ~T.WORLD_ALLOW_SLEEP)
+    s = Scene(world_flags=flags)
+    width = columns * pitch
+    height = rows * pitch if wall_height is None else wall_height
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.box(0.5 * width + 2.0, 1.0, center=(0.0, -1.0), angle=0.0), thick=True)
+    s.fixture(g, s.box(1.0, 0.5 * height + 2.0, center=(-0.5 * width - 1.0, 0.5 * height), angle=0.0), thick=True)
+    s.fixture(g, s.box(1.0, 0.5 * height + 2.0, center=(0.5 * width + 1.0, 0.5 * height), angle=0.0), thick=True)
+    shapes = [s.circle(radius)] + [s.polygon(_regular_polygon(k, radius)) for k in range(3, 9)]
+    rnd = _Rand(seed)
+    n = columns * rows
+    kind = rnd.rng.randint(0, 12, size=n)
+    jx = rnd.uniform(-0.02, 0.02, n)
+    jy = rnd.uniform(-0.02, 0.02, n)
+    ang = rnd.uniform(0.0, 2.0 * np.pi, n)
+    for i in range(n):
+        cx, cy = i % columns, i // columns
+        x = (cx + 0.5) * pitch - 0.5 * width + jx[i]
+        y = (cy + 0.5) * pitch + 0.05 + jy[i]
+        b = s.body(T.DYNAMIC_BODY, (x, y), angle=ang[i])
+        shape = shapes[0] if kind[i] >= 6 else shapes[1 + kind[i]]
+        s.fixture(b, shape, density=1.0)
+    return s

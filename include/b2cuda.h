@@ -1,0 +1,291 @@
+/*
+ * b2cuda.h -- C ABI of libb2cuda.so: the B200 (sm_100a) implementation of the
+ * Box2D-MT b2World::Step hot path.
+ *
+ * This is the drop-in boundary.  Everything above it is host
+ * C++ that keeps the reference API (b2World, b2Body, b2Fixture, b2ContactListener,
+ * b2TaskExecutor); everything below it is hand-written CUDA.  Only plain pointers
+ * and sizes cross it: no C++ types, no torch types.  The caller owns every host
+ * buffer, the library owns every device buffer.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * the reference tree, Box2D/...):
+ *
+ *   b2cuCreateWorld / b2cuDestroyWorld   b2World::b2World / ~b2World       Dynamics/b2World.cpp:444-520
+ *   b2cuSetWorldParams                   b2World::SetGravity, SetAllowSleeping, SetWarmStarting,
+ *                                        SetContinuousPhysics, SetAutoClearForces
+ *                                                                          Dynamics/b2World.h:133-228
+ *   b2cuSetBodies / b2cuGetBodies        b2Body state (m_xf, m_sweep, velocities, forces, mass, flags)
+ *                                                                          Dynamics/b2Body.h:471-508
+ *   b2cuSetShapes                        b2PolygonShape / b2CircleShape / b2EdgeShape geometry
+ *                                                                          Collision/Shapes/*.h
+ *   b2cuSetProxies / b2cuGetProxies      b2Fixture + b2FixtureProxy + tree-leaf fat AABB
+ *                                                                          Dynamics/b2Fixture.h:100-106, Collision/b2DynamicTree.h:36
+ *   b2cuSetContacts / b2cuGetContacts    b2Contact persistent state (m_flags, m_manifold, mixes, TOI)
+ *                                                                          Dynamics/Contacts/b2Contact.h:231-259
+ *   b2cuStep                             b2World::Step(dt, velocityIterations, positionIterations, executor)
+ *                                                                          Dynamics/b2World.cpp:1613-1710
+ *   b2cuGetEvents                        deferred BeginContact/EndContact buffers, sorted by proxy-id key
+ *                                                                          Dynamics/b2ContactManager.cpp:388-439
+ *   b2cuGetSolverOrder                   (new) the colour-ordered constraint list the coloured Gauss-Seidel
+ *                                        used this step; feeds the permuted-order oracle
+ *   b2cuGetToiCandidates                 TOI-eligible front partition of b2ContactManager::m_contacts
+ *                                                                          Dynamics/b2ContactManager.cpp:659-713, b2World.cpp:317-341
+ *   b2cuCollidePairs                     b2CollidePolygons / b2CollideCircles / b2CollidePolygonAndCircle /
+ *                                        b2CollideEdgeAndCircle / b2CollideEdgeAndPolygon, batched
+ *                                                                          Collision/b2Collide*.cpp
+ *
+ * All functions return B2CU_OK (0) or a negative b2cuStatus; b2cuGetLastError gives
+ * the message.  There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef B2CUDA_H
+#define B2CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2CU_API __attribute__((visibility("default")))
+
+typedef struct b2cuWorld b2cuWorld;
+
+typedef enum b2cuStatus
+{
+	B2CU_OK = 0,
+	B2CU_ERR_CUDA = -1,        /* a CUDA runtime call failed */
+	B2CU_ERR_CAPACITY = -2,    /* a device buffer overflowed its capacity (grow and retry) */
+	B2CU_ERR_ARGUMENT = -3,    /* bad argument */
+	B2CU_ERR_UNSUPPORTED = -4, /* feature outside the GPU path (joints, chains, sensors, custom filters) */
+	B2CU_ERR_NO_DEVICE = -5    /* no CUDA device: there is no CPU fallback */
+} b2cuStatus;
+
+/* ---- body ------------------------------------------------------------------ */
+
+/* b2BodyType, Dynamics/b2Body.h:36-46 */
+enum { B2CU_STATIC_BODY = 0, B2CU_KINEMATIC_BODY = 1, B2CU_DYNAMIC_BODY = 2 };
+
+/* b2cuBody.flags: bits 0-1 = body type, then the b2Body m_flags (Dynamics/b2Body.h:441-449) */
+enum
+{
+	B2CU_BODY_TYPE_MASK = 0x0003,
+	B2CU_BODY_ISLAND = 0x0004,
+	B2CU_BODY_AWAKE = 0x0008,
+	B2CU_BODY_AUTOSLEEP = 0x0010,
+	B2CU_BODY_BULLET = 0x0020,
+	B2CU_BODY_FIXED_ROTATION = 0x0040,
+	B2CU_BODY_ACTIVE = 0x0080
+};
+
+typedef struct b2cuBody
+{
+	float px, py, qs, qc;          /* m_xf: origin position, sin, cos */
+	float cx, cy, a;               /* m_sweep.c, m_sweep.a */
+	float c0x, c0y, a0, alpha0;    /* m_sweep.c0, a0, alpha0 */
+	float lcx, lcy;                /* m_sweep.localCenter */
+	float vx, vy, w;               /* m_linearVelocity, m_angularVelocity */
+	float fx, fy, torque;          /* m_force, m_torque */
+	float invMass, invI;
+	float linearDamping, angularDamping, gravityScale;
+	float sleepTime;
+	uint32_t flags;
+} b2cuBody;
+
+/* ---- shape geometry ---------------------------------------------------------- */
+
+/* b2Shape::Type, Collision/Shapes/b2Shape.h:48-55 (chain is outside the GPU path) */
+enum { B2CU_SHAPE_CIRCLE = 0, B2CU_SHAPE_EDGE = 1, B2CU_SHAPE_POLYGON = 2 };
+
+enum { B2CU_EDGE_HAS_VERTEX0 = 1, B2CU_EDGE_HAS_VERTEX3 = 2 };
+
+#define B2CU_MAX_POLYGON_VERTICES 8
+
+/* One geometry record, 160 bytes.
+ *   circle : v[0] = m_p
+ *   edge   : v[0] = m_vertex1, v[1] = m_vertex2, v[2] = m_vertex0, v[3] = m_vertex3, flags = hasVertex bits
+ *   polygon: v[i] = m_vertices[i], n[i] = m_normals[i], centroid = m_centroid, count = m_count          */
+typedef struct b2cuShape
+{
+	int32_t type;
+	int32_t count;
+	float radius;
+	uint32_t flags;
+	float v[B2CU_MAX_POLYGON_VERTICES][2];
+	float n[B2CU_MAX_POLYGON_VERTICES][2];
+	float centroid[2];
+	float pad[2];
+} b2cuShape;
+
+/* ---- proxy = fixture child ---------------------------------------------------- */
+
+enum
+{
+	B2CU_PROXY_SENSOR = 0x0001,
+	B2CU_PROXY_THICK = 0x0002,
+	B2CU_PROXY_MOVED = 0x0004   /* in the broad-phase move buffer (b2BroadPhase::BufferMove) */
+};
+
+typedef struct b2cuProxy
+{
+	float aabb[4];      /* b2FixtureProxy::aabb, swept tight AABB (lower.xy, upper.xy) */
+	float fat[4];       /* tree-leaf fat AABB */
+	int32_t body;       /* dense body index */
+	int32_t shape;      /* index into the geometry table */
+	float friction, restitution;
+	uint16_t categoryBits, maskBits;
+	int16_t groupIndex;
+	uint16_t flags;
+	int32_t fixture;    /* caller's fixture id (opaque to the device) */
+	int32_t child;      /* child index (always 0: chains are outside the GPU path) */
+} b2cuProxy;
+
+/* ---- contact ------------------------------------------------------------------ */
+
+/* b2Contact m_flags, Dynamics/Contacts/b2Contact.h:178-203 */
+enum
+{
+	B2CU_CONTACT_ISLAND = 0x0001,
+	B2CU_CONTACT_TOUCHING = 0x0002,
+	B2CU_CONTACT_ENABLED = 0x0004,
+	B2CU_CONTACT_FILTER = 0x0008,
+	B2CU_CONTACT_BULLET_HIT = 0x0010,
+	B2CU_CONTACT_TOI = 0x0020,
+	B2CU_CONTACT_TOI_CANDIDATE = 0x0040,
+	B2CU_CONTACT_INACTIVE = 0x0080
+};
+
+/* b2Manifold::Type, Collision/b2Collision.h:93-98 */
+enum { B2CU_MANIFOLD_CIRCLES = 0, B2CU_MANIFOLD_FACE_A = 1, B2CU_MANIFOLD_FACE_B = 2 };
+
+/* b2Manifold, 64 bytes (Collision/b2Collision.h:76-107) */
+typedef struct b2cuManifold
+{
+	float localNormal[2];
+	float localPoint[2];
+	struct
+	{
+		float localPoint[2];
+		float normalImpulse;
+		float tangentImpulse;
+	} points[2];
+	uint32_t id[2];        /* b2ContactID::key: indexA | indexB<<8 | typeA<<16 | typeB<<24 */
+	int32_t type;
+	int32_t pointCount;
+} b2cuManifold;
+
+typedef struct b2cuContact
+{
+	int32_t proxyA, proxyB;  /* fixture A / fixture B side, after the primary-type swap (b2Contact.cpp:82-93) */
+	uint32_t flags;
+	float friction, restitution, tangentSpeed;
+	int32_t toiCount;
+	float toi;
+	b2cuManifold manifold;
+} b2cuContact;
+
+/* ---- world -------------------------------------------------------------------- */
+
+enum
+{
+	B2CU_WORLD_ALLOW_SLEEP = 0x0001,
+	B2CU_WORLD_WARM_STARTING = 0x0002,
+	B2CU_WORLD_CONTINUOUS = 0x0004,
+	B2CU_WORLD_SUB_STEPPING = 0x0008,
+	B2CU_WORLD_CLEAR_FORCES = 0x0010
+};
+
+typedef struct b2cuWorldDef
+{
+	int32_t device;           /* CUDA device ordinal */
+	float gravity[2];
+	uint32_t flags;           /* B2CU_WORLD_* (b2World defaults: all but SUB_STEPPING, b2World.cpp:460-474) */
+	int32_t bodyCapacity;     /* initial capacities; buffers grow geometrically */
+	int32_t proxyCapacity;
+	int32_t shapeCapacity;
+	int32_t contactCapacity;
+} b2cuWorldDef;
+
+/* Per-step report.  The first 13 floats mirror b2Profile (Dynamics/b2TimeStep.h:25-40), in ms,
+ * measured with CUDA events on the step stream. */
+typedef struct b2cuStepInfo
+{
+	float step, collide, solve, solveTraversal, solveInit, solveVelocity, solvePosition;
+	float solveTOI, broadphase, broadphaseSyncFixtures, broadphaseFindContacts, locking, reserved;
+	int32_t bodyCount, proxyCount, contactCount;
+	int32_t touchingCount;     /* touching solid contacts after Collide */
+	int32_t constraintCount;   /* contacts handed to the solver (touching, enabled, in an awake island) */
+	int32_t colourCount;       /* colours used by the coloured Gauss-Seidel this step */
+	int32_t overflowCount;     /* constraints that found no colour and were solved serially */
+	int32_t islandBodyCount;   /* non-static bodies that were in an awake island */
+	int32_t awakeBodyCount;    /* non-static bodies awake at the end of the step */
+	int32_t moveCount;         /* proxies whose fat AABB moved */
+	int32_t newContactCount, destroyedContactCount;
+	int32_t beginCount, endCount;
+	int32_t toiCandidateCount;
+	int32_t kernelLaunches;    /* kernels launched by this step */
+} b2cuStepInfo;
+
+enum { B2CU_EVENT_BEGIN = 0, B2CU_EVENT_END = 1 };
+
+/* contact key = (min(proxyA,proxyB) << 32) | max(proxyA,proxyB): the b2ContactProxyIds ordering key
+ * (Dynamics/Contacts/b2Contact.h:65-77) over dense proxy ids assigned in fixture creation order. */
+typedef uint64_t b2cuContactKey;
+
+B2CU_API int b2cuGetDeviceCount(void);
+B2CU_API const char* b2cuVersion(void);
+
+B2CU_API int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out);
+B2CU_API void b2cuDestroyWorld(b2cuWorld* w);
+B2CU_API const char* b2cuGetLastError(const b2cuWorld* w);
+
+B2CU_API int b2cuSetWorldParams(b2cuWorld* w, const float gravity[2], uint32_t flags);
+/* m_inv_dt0 (b2World.h:340): previous step's 1/dt, scales warm-start impulses */
+B2CU_API int b2cuSetInvDt0(b2cuWorld* w, float invDt0);
+
+/* Resize the live element counts (new elements must then be filled with the Set calls). */
+B2CU_API int b2cuSetCounts(b2cuWorld* w, int32_t bodyCount, int32_t shapeCount, int32_t proxyCount);
+
+B2CU_API int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bodies);
+B2CU_API int b2cuGetBodies(b2cuWorld* w, int32_t first, int32_t count, b2cuBody* bodies);
+B2CU_API int b2cuSetShapes(b2cuWorld* w, int32_t first, int32_t count, const b2cuShape* shapes);
+B2CU_API int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* proxies);
+B2CU_API int b2cuGetProxies(b2cuWorld* w, int32_t first, int32_t count, b2cuProxy* proxies);
+
+/* Replace the whole contact set (teacher forcing, checkpoint restore).  Any order; sorted on device. */
+B2CU_API int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts);
+B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
+/* Contacts in key order. */
+B2CU_API int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32_t* count);
+
+B2CU_API int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positionIterations,
+                      b2cuStepInfo* info);
+
+/* Begin/End touch events of the last step as contact keys, sorted ascending (deferred-callback order). */
+B2CU_API int b2cuGetEvents(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* keys, int32_t* count);
+
+/* Solver order of the last step: keys[i] is the i-th constraint, colour[i] its colour (overflow = colourCount). */
+B2CU_API int b2cuGetSolverOrder(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* colour,
+                                int32_t* count);
+
+/* Island label (smallest body index of the island) per body after the last step; -1 = not in an island. */
+B2CU_API int b2cuGetIslandLabels(b2cuWorld* w, int32_t first, int32_t count, int32_t* labels);
+
+/* TOI-eligible contacts (candidate flag, active, enabled, toiCount <= b2_maxSubSteps), key order. */
+B2CU_API int b2cuGetToiCandidates(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* count);
+
+/* Batched stand-alone narrow phase: manifold i = collide(shapes[shapeA[i]], xfA[i], shapes[shapeB[i]], xfB[i]).
+ * xf = (p.x, p.y, sin, cos).  Shape A must be the primary type (polygon/edge before circle, edge before polygon). */
+B2CU_API int b2cuCollidePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
+                              const int32_t* shapeA, const float* xfA, const int32_t* shapeB, const float* xfB,
+                              b2cuManifold* manifolds);
+
+/* sin/cos used by every transform on the device (one correctly-rounded-in-practice fp32 sincos shared with the
+ * oracle so that fat-AABB decisions are reproducible); evaluated on the device. */
+B2CU_API int b2cuSinCos(int32_t device, int32_t count, const float* angles, float* sinOut, float* cosOut);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* B2CUDA_H */

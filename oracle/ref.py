@@ -1,0 +1,180 @@
+"""oracle/ref.py -- TEST INFRASTRUCTURE: ctypes wrapper over oracle/_ref/libb2ref.so (the compiled reference).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+sys.path.insert(0, os.path.join(_ROOT, "box2d-mt_b200", "python"))
+import b2cuda_types as T  # noqa: E402
+
+from b2scene import (BODY_DEF, SHAPE_DEF, FIXTURE_DEF, Scene, BODYDEF_ALLOW_SLEEP, BODYDEF_AWAKE,  # noqa: E402,F401
+                     BODYDEF_FIXED_ROTATION, BODYDEF_BULLET, BODYDEF_ACTIVE, BODYDEF_DEFAULT,
+                     KIND_CIRCLE, KIND_EDGE, KIND_POLYGON, KIND_BOX, KIND_RAW)
+
+_libs = {}
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def load(stock=False):
+    """Load (building first if the reference tree is present) the oracle library."""
+    if stock in _libs:
+        return _libs[stock]
+    sys.path.insert(0, _HERE)
+    import build_ref
+    build_ref.build()
+    lib = ctypes.CDLL(build_ref.lib_path(stock))
+    vp, i32, f32, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float, ctypes.c_uint32
+    lib.b2ref_create.restype = vp
+    lib.b2ref_create.argtypes = [f32, f32, u32, i32]
+    lib.b2ref_destroy.argtypes = [vp]
+    lib.b2ref_build.argtypes = [vp, i32, vp, i32, vp, i32, vp]
+    lib.b2ref_step.argtypes = [vp, f32, i32, i32]
+    lib.b2ref_step_ordered.argtypes = [vp, f32, i32, i32, i32, vp]
+    lib.b2ref_counts.argtypes = [vp, vp, vp, vp]
+    lib.b2ref_inv_dt0.restype = f32
+    lib.b2ref_inv_dt0.argtypes = [vp]
+    lib.b2ref_export_bodies.argtypes = [vp, vp]
+    lib.b2ref_export_shapes.argtypes = [vp, vp]
+    lib.b2ref_export_proxies.argtypes = [vp, vp, vp]
+    lib.b2ref_export_contacts.argtypes = [vp, i32, vp]
+    lib.b2ref_events.argtypes = [vp, i32, i32, vp]
+    lib.b2ref_toi_candidates.argtypes = [vp, i32, vp]
+    lib.b2ref_profile.argtypes = [vp, vp]
+    lib.b2ref_set_transform.argtypes = [vp, i32, f32, f32, f32]
+    lib.b2ref_set_velocity.argtypes = [vp, i32, f32, f32, f32]
+    lib.b2ref_apply_force.argtypes = [vp, i32, f32, f32, f32]
+    lib.b2ref_set_awake.argtypes = [vp, i32, i32]
+    lib.b2ref_hash.restype = u32
+    lib.b2ref_hash.argtypes = [vp]
+    lib.b2ref_collide.argtypes = [vp, vp, vp, vp, vp]
+    lib.b2ref_sincos.argtypes = [f32, vp, vp]
+    _libs[stock] = lib
+    return lib
+
+
+class RefWorld:
+    """A reference b2World built from a Scene (or raw def arrays)."""
+
+    def __init__(self, scene=None, threads=1, stock_libm=False, gravity=None, world_flags=None, arrays=None):
+        self.lib = load(stock_libm)
+        if scene is not None:
+            gravity = scene.gravity
+            world_flags = scene.world_flags
+            arrays = scene.arrays()
+        self.h = self.lib.b2ref_create(gravity[0], gravity[1], world_flags, threads)
+        b, s, f = arrays
+        b = np.ascontiguousarray(b, BODY_DEF)
+        s = np.ascontiguousarray(s, SHAPE_DEF)
+        f = np.ascontiguousarray(f, FIXTURE_DEF)
+        rc = self.lib.b2ref_build(self.h, len(b), _ptr(b), len(s), _ptr(s), len(f), _ptr(f))
+        if rc != 0:
+            raise RuntimeError("b2ref_build failed: %d" % rc)
+        self.gravity = gravity
+        self.world_flags = world_flags
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.b2ref_destroy(self.h)
+            self.h = None
+
+    def counts(self):
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self.lib.b2ref_counts(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return a.value, b.value, c.value
+
+    def step(self, dt=1.0 / 60.0, vel_iters=8, pos_iters=3):
+        self.lib.b2ref_step(self.h, dt, vel_iters, pos_iters)
+
+    def step_ordered(self, keys, dt=1.0 / 60.0, vel_iters=8, pos_iters=3):
+        keys = np.ascontiguousarray(keys, np.uint64)
+        return self.lib.b2ref_step_ordered(self.h, dt, vel_iters, pos_iters, len(keys), _ptr(keys))
+
+    def inv_dt0(self):
+        return self.lib.b2ref_inv_dt0(self.h)
+
+    def bodies(self):
+        out = np.zeros(self.counts()[0], T.BODY)
+        self.lib.b2ref_export_bodies(self.h, _ptr(out))
+        return out
+
+    def shapes(self):
+        out = np.zeros(self.counts()[1], T.SHAPE)
+        self.lib.b2ref_export_shapes(self.h, _ptr(out))
+        return out
+
+    def proxies(self, with_tree_ids=False):
+        n = self.counts()[1]
+        out = np.zeros(n, T.PROXY)
+        ids = np.zeros(n, np.int32)
+        self.lib.b2ref_export_proxies(self.h, _ptr(out), _ptr(ids))
+        return (out, ids) if with_tree_ids else out
+
+    def contacts(self):
+        n = self.counts()[2]
+        out = np.zeros(n, T.CONTACT)
+        m = self.lib.b2ref_export_contacts(self.h, n, _ptr(out))
+        assert m == n
+        return out
+
+    def events(self, kind):
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, np.uint64)
+            n = self.lib.b2ref_events(self.h, kind, cap, _ptr(out))
+            if n <= cap:
+                return out[:n]
+            cap = n
+
+    def toi_candidates(self):
+        cap = max(16, self.counts()[2])
+        out = np.zeros(cap, np.uint64)
+        n = self.lib.b2ref_toi_candidates(self.h, cap, _ptr(out))
+        return out[:n]
+
+    def profile(self):
+        out = np.zeros(13, np.float32)
+        self.lib.b2ref_profile(self.h, _ptr(out))
+        return out
+
+    def hash(self):
+        return self.lib.b2ref_hash(self.h)
+
+    def set_transform(self, body, x, y, angle):
+        self.lib.b2ref_set_transform(self.h, body, x, y, angle)
+
+    def set_velocity(self, body, vx, vy, w):
+        self.lib.b2ref_set_velocity(self.h, body, vx, vy, w)
+
+    def apply_force(self, body, fx, fy, torque):
+        self.lib.b2ref_apply_force(self.h, body, fx, fy, torque)
+
+    def set_awake(self, body, awake):
+        self.lib.b2ref_set_awake(self.h, body, int(awake))
+
+
+def collide(shape_a, xf_a, shape_b, xf_b, stock_libm=False):
+    """Reference manifold for two b2cuShape records and transforms (p.x, p.y, sin, cos)."""
+    lib = load(stock_libm)
+    sa = np.ascontiguousarray(shape_a, T.SHAPE)
+    sb = np.ascontiguousarray(shape_b, T.SHAPE)
+    xa = np.ascontiguousarray(xf_a, np.float32)
+    xb = np.ascontiguousarray(xf_b, np.float32)
+    out = np.zeros((), T.MANIFOLD)
+    lib.b2ref_collide(_ptr(sa), _ptr(xa), _ptr(sb), _ptr(xb), _ptr(out))
+    return out
+
+
+def sincos(x, stock_libm=False):
+    lib = load(stock_libm)
+    s, c = ctypes.c_float(), ctypes.c_float()
+    lib.b2ref_sincos(np.float32(x), ctypes.byref(s), ctypes.byref(c))
+    return np.float32(s.value), np.float32(c.value)

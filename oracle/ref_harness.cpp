@@ -1,0 +1,803 @@
+/*
+ * oracle/ref_harness.cpp -- TEST INFRASTRUCTURE (CPU oracle). Not part of the product path.
+ *
+ * Headless driver around the UNMODIFIED reference sources (compiled from /root/reference by
+ * oracle/build_ref.py; nothing from the reference is copied into this repository).  This file is
+ * compiled with -fno-access-control so that it can read the reference's private state (proxy ids,
+ * fat AABBs, contact flags) and call its private phase drivers, as SURVEY.md 8c describes.
+ *
+ * Two ways of stepping:
+ *   b2ref_step          -- the reference's own b2World::Step + b2ThreadPoolTaskExecutor.
+ *   b2ref_step_ordered  -- the same phase sequence (Box2D/Dynamics/b2World.cpp:1613-1710), but the island
+ *                          traversal of b2World::Solve (:1200-1371) is re-driven here so that every island's
+ *                          contact array can be put into a caller-supplied order before the reference's own
+ *                          b2Island::Solve runs on it.  Sequential Gauss-Seidel in colour order is what a
+ *                          coloured parallel Gauss-Seidel computes, so this is the oracle for the GPU solver.
+ *
+ * sinf/cosf/sincosf are defined here (in terms of oracle/b2o_math.c) and the library is linked with
+ * -Bsymbolic-functions, so every b2Rot::Set inside the reference uses the same sincos as the device.
+ */
+#include "ref_harness.h"
+#include "b2o_math.h"
+
+#include "Box2D/Box2D.h"
+#include "Box2D/Dynamics/b2Island.h"
+#include "Box2D/Dynamics/Contacts/b2ContactSolver.h"
+#include "Box2D/MT/b2ThreadPool.h"
+
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#ifndef B2REF_STOCK_LIBM
+extern "C" {
+float sinf(float x) noexcept
+{
+	float s, c;
+	b2o_sincosf(x, &s, &c);
+	return s;
+}
+float cosf(float x) noexcept
+{
+	float s, c;
+	b2o_sincosf(x, &s, &c);
+	return c;
+}
+void sincosf(float x, float* s, float* c) noexcept
+{
+	b2o_sincosf(x, s, c);
+}
+}
+#endif
+
+namespace
+{
+
+inline int32 FixtureIndex(const b2Fixture* f)
+{
+	return (int32)(intptr_t)f->GetUserData();
+}
+
+inline uint64_t MakeKey(int32 a, int32 b)
+{
+	uint32_t lo = (uint32_t)std::min(a, b), hi = (uint32_t)std::max(a, b);
+	return ((uint64_t)lo << 32) | hi;
+}
+
+inline uint64_t ContactKey(const b2Contact* c)
+{
+	return MakeKey(FixtureIndex(c->GetFixtureA()), FixtureIndex(c->GetFixtureB()));
+}
+
+class RecordingListener : public b2ContactListener
+{
+public:
+	bool BeginContactImmediate(b2Contact*, uint32) override { return true; }
+	bool EndContactImmediate(b2Contact*, uint32) override { return true; }
+	bool PreSolveImmediate(b2Contact*, const b2Manifold*, uint32) override { return false; }
+	bool PostSolveImmediate(b2Contact*, const b2ContactImpulse*, uint32) override { return false; }
+	void BeginContact(b2Contact* c) override { begins.push_back(ContactKey(c)); }
+	void EndContact(b2Contact* c) override { ends.push_back(ContactKey(c)); }
+
+	std::vector<uint64_t> begins, ends;
+};
+
+} // namespace
+
+struct b2refWorld
+{
+	b2World* world;
+	b2ThreadPoolTaskExecutor* executor;
+	RecordingListener listener;
+	std::vector<b2Body*> bodies;
+	std::vector<b2Fixture*> fixtures;
+};
+
+extern "C" {
+
+b2refWorld* b2ref_create(float gx, float gy, uint32_t worldFlags, int32_t threads)
+{
+	b2refWorld* w = new b2refWorld;
+	w->world = new b2World(b2Vec2(gx, gy));
+	w->world->SetAllowSleeping((worldFlags & B2CU_WORLD_ALLOW_SLEEP) != 0);
+	w->world->SetWarmStarting((worldFlags & B2CU_WORLD_WARM_STARTING) != 0);
+	w->world->SetContinuousPhysics((worldFlags & B2CU_WORLD_CONTINUOUS) != 0);
+	w->world->SetSubStepping((worldFlags & B2CU_WORLD_SUB_STEPPING) != 0);
+	w->world->SetAutoClearForces((worldFlags & B2CU_WORLD_CLEAR_FORCES) != 0);
+	w->world->SetContactListener(&w->listener);
+	b2ThreadPoolOptions options;
+	options.totalThreadCount = threads;
+	w->executor = new b2ThreadPoolTaskExecutor(options);
+	return w;
+}
+
+void b2ref_destroy(b2refWorld* w)
+{
+	if (w == nullptr)
+	{
+		return;
+	}
+	delete w->world;
+	delete w->executor;
+	delete w;
+}
+
+static void MakeShape(const b2refShapeDef& sd, b2CircleShape& circle, b2EdgeShape& edge, b2PolygonShape& poly,
+                      const b2Shape** out)
+{
+	switch (sd.kind)
+	{
+	case B2REF_SHAPE_CIRCLE:
+		circle.m_radius = sd.radius;
+		circle.m_p.Set(sd.v[0][0], sd.v[0][1]);
+		*out = &circle;
+		break;
+	case B2REF_SHAPE_EDGE:
+		edge.Set(b2Vec2(sd.v[0][0], sd.v[0][1]), b2Vec2(sd.v[1][0], sd.v[1][1]));
+		if (sd.flags & B2CU_EDGE_HAS_VERTEX0)
+		{
+			edge.m_vertex0.Set(sd.v[2][0], sd.v[2][1]);
+			edge.m_hasVertex0 = true;
+		}
+		if (sd.flags & B2CU_EDGE_HAS_VERTEX3)
+		{
+			edge.m_vertex3.Set(sd.v[3][0], sd.v[3][1]);
+			edge.m_hasVertex3 = true;
+		}
+		*out = &edge;
+		break;
+	case B2REF_SHAPE_POLYGON:
+	{
+		b2Vec2 vs[b2_maxPolygonVertices];
+		for (int32 i = 0; i < sd.count; ++i)
+		{
+			vs[i].Set(sd.v[i][0], sd.v[i][1]);
+		}
+		poly.Set(vs, sd.count);
+		*out = &poly;
+		break;
+	}
+	case B2REF_SHAPE_BOX:
+		if (sd.flags & 1)
+		{
+			poly.SetAsBox(sd.v[0][0], sd.v[0][1], b2Vec2(sd.v[1][0], sd.v[1][1]), sd.v[2][0]);
+		}
+		else
+		{
+			poly.SetAsBox(sd.v[0][0], sd.v[0][1]);
+		}
+		*out = &poly;
+		break;
+	default: /* B2REF_SHAPE_RAW */
+		poly.m_count = sd.count;
+		for (int32 i = 0; i < sd.count; ++i)
+		{
+			poly.m_vertices[i].Set(sd.v[i][0], sd.v[i][1]);
+			poly.m_normals[i].Set(sd.n[i][0], sd.n[i][1]);
+		}
+		poly.m_centroid.Set(sd.centroid[0], sd.centroid[1]);
+		poly.m_radius = sd.radius;
+		*out = &poly;
+		break;
+	}
+}
+
+int b2ref_build(b2refWorld* w, int32_t bodyCount, const b2refBodyDef* bodies, int32_t shapeCount,
+                const b2refShapeDef* shapes, int32_t fixtureCount, const b2refFixtureDef* fixtures)
+{
+	int32 f = 0;
+	for (int32 i = 0; i < bodyCount; ++i)
+	{
+		const b2refBodyDef& d = bodies[i];
+		b2BodyDef bd;
+		bd.type = (b2BodyType)d.type;
+		bd.position.Set(d.px, d.py);
+		bd.angle = d.angle;
+		bd.linearVelocity.Set(d.vx, d.vy);
+		bd.angularVelocity = d.w;
+		bd.linearDamping = d.linearDamping;
+		bd.angularDamping = d.angularDamping;
+		bd.gravityScale = d.gravityScale;
+		bd.allowSleep = (d.flags & B2REF_BODY_ALLOW_SLEEP) != 0;
+		bd.awake = (d.flags & B2REF_BODY_AWAKE) != 0;
+		bd.fixedRotation = (d.flags & B2REF_BODY_FIXED_ROTATION) != 0;
+		bd.bullet = (d.flags & B2REF_BODY_BULLET) != 0;
+		bd.active = (d.flags & B2REF_BODY_ACTIVE) != 0;
+		bd.userData = (void*)(intptr_t)w->bodies.size();
+		b2Body* body = w->world->CreateBody(&bd);
+		w->bodies.push_back(body);
+
+		while (f < fixtureCount && fixtures[f].body == i)
+		{
+			const b2refFixtureDef& fd = fixtures[f];
+			if (fd.shape < 0 || fd.shape >= shapeCount)
+			{
+				return -1;
+			}
+			b2CircleShape circle;
+			b2EdgeShape edge;
+			b2PolygonShape poly;
+			const b2Shape* shape = nullptr;
+			MakeShape(shapes[fd.shape], circle, edge, poly, &shape);
+
+			b2FixtureDef def;
+			def.shape = shape;
+			def.density = fd.density;
+			def.friction = fd.friction;
+			def.restitution = fd.restitution;
+			def.isSensor = (fd.flags & B2CU_PROXY_SENSOR) != 0;
+			def.thickShape = (fd.flags & B2CU_PROXY_THICK) != 0;
+			def.filter.categoryBits = fd.categoryBits;
+			def.filter.maskBits = fd.maskBits;
+			def.filter.groupIndex = fd.groupIndex;
+			def.userData = (void*)(intptr_t)w->fixtures.size();
+			b2Fixture* fixture = body->CreateFixture(&def);
+			w->fixtures.push_back(fixture);
+			++f;
+		}
+	}
+	return f == fixtureCount ? 0 : -2;
+}
+
+void b2ref_step(b2refWorld* w, float dt, int32_t velocityIterations, int32_t positionIterations)
+{
+	w->listener.begins.clear();
+	w->listener.ends.clear();
+	w->world->Step(dt, velocityIterations, positionIterations, *w->executor);
+}
+
+/* Island traversal + ordered solve.  Follows the semantics of b2World::Solve (b2World.cpp:1166-1431):
+ * seeds are awake, active, non-static bodies not yet in an island; the search crosses enabled, touching,
+ * non-sensor contacts; static bodies join an island but are not crossed and may join several islands. */
+static int SolveOrdered(b2refWorld* rw, const b2TimeStep& step, const std::unordered_map<uint64_t, int32>& rank)
+{
+	b2World* world = rw->world;
+	b2ContactManager& cm = world->m_contactManager;
+	b2ContactManagerPerThreadData& td = cm.m_perThreadData[0];
+	int unranked = 0;
+
+	world->SetMtLock(b2World::e_mtLocked | b2World::e_mtSolveLocked);
+
+	std::vector<b2Body*> islandBodies;
+	std::vector<b2Contact*> islandContacts;
+	std::vector<b2Body*> pending;
+	std::vector<b2Velocity> velocities;
+	std::vector<b2Position> positions;
+
+	for (uint32 s = 0; s < world->m_nonStaticBodies.size(); ++s)
+	{
+		b2Body* seed = world->m_nonStaticBodies[s];
+		if ((seed->m_flags & b2Body::e_islandFlag) || !seed->IsAwake() || !seed->IsActive())
+		{
+			continue;
+		}
+
+		islandBodies.clear();
+		islandContacts.clear();
+		pending.clear();
+		pending.push_back(seed);
+		seed->m_flags |= b2Body::e_islandFlag;
+
+		while (!pending.empty())
+		{
+			b2Body* b = pending.back();
+			pending.pop_back();
+			islandBodies.push_back(b);
+
+			if (b->GetType() == b2_staticBody)
+			{
+				continue;
+			}
+
+			b->m_flags |= b2Body::e_awakeFlag;
+
+			for (b2ContactEdge* ce = b->m_contactList; ce; ce = ce->next)
+			{
+				b2Contact* contact = ce->contact;
+				if (contact->m_flags & b2Contact::e_islandFlag)
+				{
+					continue;
+				}
+				contact->m_flags &= ~b2Contact::e_inactiveFlag;
+				if (!contact->IsEnabled() || !contact->IsTouching())
+				{
+					continue;
+				}
+				if (contact->m_fixtureA->m_isSensor || contact->m_fixtureB->m_isSensor)
+				{
+					continue;
+				}
+				islandContacts.push_back(contact);
+				contact->m_flags |= b2Contact::e_islandFlag;
+
+				b2Body* other = ce->other;
+				if (other->m_flags & b2Body::e_islandFlag)
+				{
+					continue;
+				}
+				pending.push_back(other);
+				other->m_flags |= b2Body::e_islandFlag;
+			}
+			/* joints: worlds with joints are outside the GPU path and are not built by this harness */
+		}
+
+		for (size_t j = 0; j < islandBodies.size(); ++j)
+		{
+			if (islandBodies[j]->GetType() == b2_staticBody)
+			{
+				islandBodies[j]->m_flags &= ~b2Body::e_islandFlag;
+			}
+		}
+
+		/* the one deliberate difference from b2World::Solve: the caller's contact order */
+		struct Ranked
+		{
+			int32 r;
+			uint64_t key;
+			b2Contact* c;
+		};
+		std::vector<Ranked> ranked(islandContacts.size());
+		for (size_t j = 0; j < islandContacts.size(); ++j)
+		{
+			uint64_t key = ContactKey(islandContacts[j]);
+			auto it = rank.find(key);
+			int32 r;
+			if (it == rank.end())
+			{
+				r = INT32_MAX;
+				++unranked;
+			}
+			else
+			{
+				r = it->second;
+			}
+			ranked[j] = {r, key, islandContacts[j]};
+		}
+		std::sort(ranked.begin(), ranked.end(), [](const Ranked& a, const Ranked& b) {
+			return a.r != b.r ? a.r < b.r : a.key < b.key;
+		});
+		for (size_t j = 0; j < ranked.size(); ++j)
+		{
+			islandContacts[j] = ranked[j].c;
+		}
+
+		velocities.resize(islandBodies.size());
+		positions.resize(islandBodies.size());
+		b2Island island((int32)islandBodies.size(), (int32)islandContacts.size(), 0, islandBodies.data(),
+		                islandContacts.data(), nullptr, velocities.data(), positions.data());
+		island.Solve(&td.m_profile, step, world->m_gravity, &world->m_stackAllocator, cm.m_contactListener, 0,
+		             world->m_allowSleep, td.m_postSolves);
+	}
+
+	world->SetMtLock(0);
+	return unranked;
+}
+
+int b2ref_step_ordered(b2refWorld* rw, float dt, int32_t velocityIterations, int32_t positionIterations,
+                       int32_t orderCount, const uint64_t* keys)
+{
+	rw->listener.begins.clear();
+	rw->listener.ends.clear();
+
+	std::unordered_map<uint64_t, int32> rank;
+	rank.reserve((size_t)orderCount * 2 + 1);
+	for (int32 i = 0; i < orderCount; ++i)
+	{
+		rank[keys[i]] = i;
+	}
+
+	b2World* world = rw->world;
+	b2TaskExecutor& executor = *rw->executor;
+
+	memset(&world->m_profile, 0, sizeof(world->m_profile));
+	memset(&world->m_contactManager.m_perThreadData[0].m_profile, 0, sizeof(b2Profile));
+
+	b2TaskGroup* group = executor.AcquireTaskGroup();
+
+	if (world->m_flags & b2World::e_newFixture)
+	{
+		world->FindNewContacts(executor, group);
+		world->m_flags &= ~b2World::e_newFixture;
+	}
+
+	world->m_flags |= b2World::e_locked;
+
+	world->Collide(executor, group);
+
+	b2TimeStep step;
+	step.dt = dt;
+	step.velocityIterations = velocityIterations;
+	step.positionIterations = positionIterations;
+	step.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
+	step.dtRatio = world->m_inv_dt0 * dt;
+	step.warmStarting = world->m_warmStarting;
+
+	int unranked = 0;
+	if (world->m_stepComplete && step.dt > 0.0f)
+	{
+		unranked = SolveOrdered(rw, step, rank);
+		world->m_contactManager.FinishSolve(executor, group, world->m_stackAllocator);
+		world->SynchronizeFixtures(executor, group);
+		world->FindNewContacts(executor, group);
+		world->ClearPostSolve(executor, group);
+	}
+
+	if (world->m_continuousPhysics && step.dt > 0.0f)
+	{
+		world->SolveTOI(executor, group, step);
+	}
+
+	if (step.dt > 0.0f)
+	{
+		world->m_inv_dt0 = step.inv_dt;
+	}
+
+	if (world->m_flags & b2World::e_clearForces)
+	{
+		world->ClearForces(executor, group);
+	}
+
+	world->m_flags &= ~b2World::e_locked;
+	executor.ReleaseTaskGroup(group);
+	return unranked;
+}
+
+void b2ref_counts(b2refWorld* w, int32_t* bodyCount, int32_t* fixtureCount, int32_t* contactCount)
+{
+	*bodyCount = (int32_t)w->bodies.size();
+	*fixtureCount = (int32_t)w->fixtures.size();
+	*contactCount = w->world->GetContactCount();
+}
+
+float b2ref_inv_dt0(b2refWorld* w)
+{
+	return w->world->m_inv_dt0;
+}
+
+void b2ref_export_bodies(b2refWorld* w, b2cuBody* out)
+{
+	for (size_t i = 0; i < w->bodies.size(); ++i)
+	{
+		const b2Body* b = w->bodies[i];
+		b2cuBody& o = out[i];
+		o.px = b->m_xf.p.x;
+		o.py = b->m_xf.p.y;
+		o.qs = b->m_xf.q.s;
+		o.qc = b->m_xf.q.c;
+		o.cx = b->m_sweep.c.x;
+		o.cy = b->m_sweep.c.y;
+		o.a = b->m_sweep.a;
+		o.c0x = b->m_sweep.c0.x;
+		o.c0y = b->m_sweep.c0.y;
+		o.a0 = b->m_sweep.a0;
+		o.alpha0 = b->m_sweep.alpha0;
+		o.lcx = b->m_sweep.localCenter.x;
+		o.lcy = b->m_sweep.localCenter.y;
+		o.vx = b->m_linearVelocity.x;
+		o.vy = b->m_linearVelocity.y;
+		o.w = b->m_angularVelocity;
+		o.fx = b->m_force.x;
+		o.fy = b->m_force.y;
+		o.torque = b->m_torque;
+		o.invMass = b->m_invMass;
+		o.invI = b->m_invI;
+		o.linearDamping = b->m_linearDamping;
+		o.angularDamping = b->m_angularDamping;
+		o.gravityScale = b->m_gravityScale;
+		o.sleepTime = b->m_sleepTime;
+		o.flags = (uint32_t)b->m_type | ((uint32_t)b->m_flags << 2);
+	}
+}
+
+static void ExportShape(const b2Shape* shape, b2cuShape* o)
+{
+	memset(o, 0, sizeof(*o));
+	o->radius = shape->m_radius;
+	switch (shape->GetType())
+	{
+	case b2Shape::e_circle:
+	{
+		const b2CircleShape* s = (const b2CircleShape*)shape;
+		o->type = B2CU_SHAPE_CIRCLE;
+		o->count = 1;
+		o->v[0][0] = s->m_p.x;
+		o->v[0][1] = s->m_p.y;
+		break;
+	}
+	case b2Shape::e_edge:
+	{
+		const b2EdgeShape* s = (const b2EdgeShape*)shape;
+		o->type = B2CU_SHAPE_EDGE;
+		o->count = 2;
+		o->v[0][0] = s->m_vertex1.x;
+		o->v[0][1] = s->m_vertex1.y;
+		o->v[1][0] = s->m_vertex2.x;
+		o->v[1][1] = s->m_vertex2.y;
+		o->v[2][0] = s->m_vertex0.x;
+		o->v[2][1] = s->m_vertex0.y;
+		o->v[3][0] = s->m_vertex3.x;
+		o->v[3][1] = s->m_vertex3.y;
+		o->flags = (s->m_hasVertex0 ? B2CU_EDGE_HAS_VERTEX0 : 0) | (s->m_hasVertex3 ? B2CU_EDGE_HAS_VERTEX3 : 0);
+		break;
+	}
+	case b2Shape::e_polygon:
+	{
+		const b2PolygonShape* s = (const b2PolygonShape*)shape;
+		o->type = B2CU_SHAPE_POLYGON;
+		o->count = s->m_count;
+		for (int32 i = 0; i < s->m_count; ++i)
+		{
+			o->v[i][0] = s->m_vertices[i].x;
+			o->v[i][1] = s->m_vertices[i].y;
+			o->n[i][0] = s->m_normals[i].x;
+			o->n[i][1] = s->m_normals[i].y;
+		}
+		o->centroid[0] = s->m_centroid.x;
+		o->centroid[1] = s->m_centroid.y;
+		break;
+	}
+	default:
+		o->type = -1;
+		break;
+	}
+}
+
+void b2ref_export_shapes(b2refWorld* w, b2cuShape* out)
+{
+	for (size_t i = 0; i < w->fixtures.size(); ++i)
+	{
+		ExportShape(w->fixtures[i]->GetShape(), out + i);
+	}
+}
+
+void b2ref_export_proxies(b2refWorld* w, b2cuProxy* out, int32_t* treeProxyIds)
+{
+	const b2BroadPhase& bp = w->world->m_contactManager.m_broadPhase;
+
+	std::vector<uint8_t> moved(bp.m_tree.m_nodeCapacity, 0);
+	for (uint32 i = 0; i < bp.m_moveBuffer.size(); ++i)
+	{
+		int32 id = bp.m_moveBuffer[i];
+		if (id != b2BroadPhase::e_nullProxy)
+		{
+			moved[id] = 1;
+		}
+	}
+
+	for (size_t i = 0; i < w->fixtures.size(); ++i)
+	{
+		const b2Fixture* f = w->fixtures[i];
+		b2cuProxy& o = out[i];
+		memset(&o, 0, sizeof(o));
+		o.body = (int32_t)(intptr_t)f->GetBody()->GetUserData();
+		o.shape = (int32_t)i;
+		o.friction = f->m_friction;
+		o.restitution = f->m_restitution;
+		o.categoryBits = f->m_filter.categoryBits;
+		o.maskBits = f->m_filter.maskBits;
+		o.groupIndex = f->m_filter.groupIndex;
+		o.flags = (uint16_t)((f->m_isSensor ? B2CU_PROXY_SENSOR : 0) | (f->IsThickShape() ? B2CU_PROXY_THICK : 0));
+		o.fixture = (int32_t)i;
+		o.child = 0;
+		int32 treeId = -1;
+		if (f->m_proxyCount > 0)
+		{
+			const b2FixtureProxy& p = f->m_proxies[0];
+			treeId = p.proxyId;
+			o.aabb[0] = p.aabb.lowerBound.x;
+			o.aabb[1] = p.aabb.lowerBound.y;
+			o.aabb[2] = p.aabb.upperBound.x;
+			o.aabb[3] = p.aabb.upperBound.y;
+			const b2AABB& fat = bp.GetFatAABB(p.proxyId);
+			o.fat[0] = fat.lowerBound.x;
+			o.fat[1] = fat.lowerBound.y;
+			o.fat[2] = fat.upperBound.x;
+			o.fat[3] = fat.upperBound.y;
+			if (moved[p.proxyId])
+			{
+				o.flags |= B2CU_PROXY_MOVED;
+			}
+		}
+		if (treeProxyIds)
+		{
+			treeProxyIds[i] = treeId;
+		}
+	}
+}
+
+static void ExportManifold(const b2Manifold& m, b2cuManifold* o)
+{
+	o->localNormal[0] = m.localNormal.x;
+	o->localNormal[1] = m.localNormal.y;
+	o->localPoint[0] = m.localPoint.x;
+	o->localPoint[1] = m.localPoint.y;
+	for (int32 i = 0; i < 2; ++i)
+	{
+		o->points[i].localPoint[0] = m.points[i].localPoint.x;
+		o->points[i].localPoint[1] = m.points[i].localPoint.y;
+		o->points[i].normalImpulse = m.points[i].normalImpulse;
+		o->points[i].tangentImpulse = m.points[i].tangentImpulse;
+		o->id[i] = m.points[i].id.key;
+	}
+	o->type = (int32_t)m.type;
+	o->pointCount = m.pointCount;
+}
+
+int b2ref_export_contacts(b2refWorld* w, int32_t capacity, b2cuContact* out)
+{
+	std::vector<std::pair<uint64_t, const b2Contact*>> sorted;
+	for (const b2Contact* c = w->world->GetContactList(); c; c = c->GetNext())
+	{
+		sorted.push_back(std::make_pair(ContactKey(c), c));
+	}
+	std::sort(sorted.begin(), sorted.end());
+	int32_t n = (int32_t)sorted.size();
+	for (int32_t i = 0; i < n && i < capacity; ++i)
+	{
+		const b2Contact* c = sorted[i].second;
+		b2cuContact& o = out[i];
+		memset(&o, 0, sizeof(o));
+		o.proxyA = FixtureIndex(c->GetFixtureA());
+		o.proxyB = FixtureIndex(c->GetFixtureB());
+		o.flags = c->m_flags;
+		o.friction = c->m_friction;
+		o.restitution = c->m_restitution;
+		o.tangentSpeed = c->m_tangentSpeed;
+		o.toiCount = c->m_toiCount;
+		o.toi = c->m_toi;
+		ExportManifold(c->m_manifold, &o.manifold);
+	}
+	return n;
+}
+
+int b2ref_events(b2refWorld* w, int32_t kind, int32_t capacity, uint64_t* keys)
+{
+	const std::vector<uint64_t>& v = kind == B2CU_EVENT_BEGIN ? w->listener.begins : w->listener.ends;
+	int32_t n = (int32_t)v.size();
+	for (int32_t i = 0; i < n && i < capacity; ++i)
+	{
+		keys[i] = v[i];
+	}
+	return n;
+}
+
+int b2ref_toi_candidates(b2refWorld* w, int32_t capacity, uint64_t* keys)
+{
+	b2ContactManager& cm = w->world->m_contactManager;
+	std::vector<uint64_t> v;
+	for (uint32 i = 0; i < cm.m_toiCount; ++i)
+	{
+		v.push_back(ContactKey(cm.m_contacts[i]));
+	}
+	std::sort(v.begin(), v.end());
+	for (size_t i = 0; i < v.size() && (int32_t)i < capacity; ++i)
+	{
+		keys[i] = v[i];
+	}
+	return (int)v.size();
+}
+
+void b2ref_profile(b2refWorld* w, float* out13)
+{
+	const b2Profile& p = w->world->GetProfile();
+	memcpy(out13, &p, 13 * sizeof(float));
+}
+
+void b2ref_set_transform(b2refWorld* w, int32_t body, float x, float y, float angle)
+{
+	w->bodies[body]->SetTransform(b2Vec2(x, y), angle);
+}
+
+void b2ref_set_velocity(b2refWorld* w, int32_t body, float vx, float vy, float angw)
+{
+	w->bodies[body]->SetLinearVelocity(b2Vec2(vx, vy));
+	w->bodies[body]->SetAngularVelocity(angw);
+}
+
+void b2ref_apply_force(b2refWorld* w, int32_t body, float fx, float fy, float torque)
+{
+	w->bodies[body]->ApplyForceToCenter(b2Vec2(fx, fy), true);
+	w->bodies[body]->ApplyTorque(torque, true);
+}
+
+void b2ref_set_awake(b2refWorld* w, int32_t body, int32_t awake)
+{
+	w->bodies[body]->SetAwake(awake != 0);
+}
+
+uint32_t b2ref_hash(b2refWorld* w)
+{
+	uint32_t h = 2166136261u;
+	for (const b2Body* b = w->world->GetBodyList(); b; b = b->GetNext())
+	{
+		float v[3] = {b->GetPosition().x, b->GetPosition().y, b->GetAngle()};
+		const unsigned char* p = (const unsigned char*)v;
+		for (size_t i = 0; i < sizeof(v); ++i)
+		{
+			h ^= p[i];
+			h *= 16777619u;
+		}
+	}
+	return h;
+}
+
+static void ImportShape(const b2cuShape* s, b2CircleShape& circle, b2EdgeShape& edge, b2PolygonShape& poly)
+{
+	switch (s->type)
+	{
+	case B2CU_SHAPE_CIRCLE:
+		circle.m_radius = s->radius;
+		circle.m_p.Set(s->v[0][0], s->v[0][1]);
+		break;
+	case B2CU_SHAPE_EDGE:
+		edge.m_radius = s->radius;
+		edge.m_vertex1.Set(s->v[0][0], s->v[0][1]);
+		edge.m_vertex2.Set(s->v[1][0], s->v[1][1]);
+		edge.m_vertex0.Set(s->v[2][0], s->v[2][1]);
+		edge.m_vertex3.Set(s->v[3][0], s->v[3][1]);
+		edge.m_hasVertex0 = (s->flags & B2CU_EDGE_HAS_VERTEX0) != 0;
+		edge.m_hasVertex3 = (s->flags & B2CU_EDGE_HAS_VERTEX3) != 0;
+		break;
+	default:
+		poly.m_radius = s->radius;
+		poly.m_count = s->count;
+		for (int32 i = 0; i < s->count; ++i)
+		{
+			poly.m_vertices[i].Set(s->v[i][0], s->v[i][1]);
+			poly.m_normals[i].Set(s->n[i][0], s->n[i][1]);
+		}
+		poly.m_centroid.Set(s->centroid[0], s->centroid[1]);
+		break;
+	}
+}
+
+void b2ref_collide(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
+                   b2cuManifold* out)
+{
+	b2CircleShape circleA, circleB;
+	b2EdgeShape edgeA, edgeB;
+	b2PolygonShape polyA, polyB;
+	ImportShape(shapeA, circleA, edgeA, polyA);
+	ImportShape(shapeB, circleB, edgeB, polyB);
+	b2Transform tA, tB;
+	tA.p.Set(xfA[0], xfA[1]);
+	tA.q.s = xfA[2];
+	tA.q.c = xfA[3];
+	tB.p.Set(xfB[0], xfB[1]);
+	tB.q.s = xfB[2];
+	tB.q.c = xfB[3];
+
+	b2Manifold m;
+	memset(&m, 0, sizeof(m));
+	if (shapeA->type == B2CU_SHAPE_POLYGON && shapeB->type == B2CU_SHAPE_POLYGON)
+	{
+		b2CollidePolygons(&m, &polyA, tA, &polyB, tB);
+	}
+	else if (shapeA->type == B2CU_SHAPE_POLYGON && shapeB->type == B2CU_SHAPE_CIRCLE)
+	{
+		b2CollidePolygonAndCircle(&m, &polyA, tA, &circleB, tB);
+	}
+	else if (shapeA->type == B2CU_SHAPE_CIRCLE && shapeB->type == B2CU_SHAPE_CIRCLE)
+	{
+		b2CollideCircles(&m, &circleA, tA, &circleB, tB);
+	}
+	else if (shapeA->type == B2CU_SHAPE_EDGE && shapeB->type == B2CU_SHAPE_CIRCLE)
+	{
+		b2CollideEdgeAndCircle(&m, &edgeA, tA, &circleB, tB);
+	}
+	else if (shapeA->type == B2CU_SHAPE_EDGE && shapeB->type == B2CU_SHAPE_POLYGON)
+	{
+		b2CollideEdgeAndPolygon(&m, &edgeA, tA, &polyB, tB);
+	}
+	ExportManifold(m, out);
+}
+
+void b2ref_sincos(float x, float* s, float* c)
+{
+	b2Rot r(x);
+	*s = r.s;
+	*c = r.c;
+}
+
+} // extern "C"
