@@ -1,0 +1,43 @@
+#!/usr/bin/env python3
+"""Build libb2cuda.so (the sm_100a device library behind include/b2cuda.h) in-tree with nvcc.
+
+    python box2d-mt_b200/build.py [--force] [--verbose]
+
+-fmad=false: the parity contract needs every fp32 result to equal what the reference's x86-64 build
+computes (no fused multiply-add there); -prec-div / -prec-sqrt keep IEEE division and sqrt.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libb2cuda.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-O3", "-std=c++17", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "--shared", "-cudart", "shared",
+]
+SOURCES = ["prims.cu", "world.cu"]
+
+
+def lib_path():
+    return OUT
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b2cuda.h")]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
+        return OUT
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", OUT]
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

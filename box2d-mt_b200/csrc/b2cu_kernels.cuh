@@ -1,0 +1,1503 @@
+// b2cu_kernels.cuh -- the phase kernels of b2cuStep.  One work item per thread, grid-stride, SoA float4 traffic.
+// Included only by world.cu.  Each kernel names the reference code it replaces.
+#pragma once
+
+#include "b2cu_collide.cuh"
+#include "b2cu_world.cuh"
+
+namespace b2cu
+{
+
+#define B2CU_GRID_STRIDE(i, n) \
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += gridDim.x * blockDim.x)
+
+#define B2CU_EV_BEGIN 1
+#define B2CU_EV_END 2
+#define B2CU_EV_DESTROY 4
+#define B2CU_EV_DESTROY_TOUCHING 8
+
+__device__ __forceinline__ bool IsStatic(uint32_t bf) { return (bf & B2CU_BODY_TYPE_MASK) == B2CU_STATIC_BODY; }
+__device__ __forceinline__ bool IsDynamic(uint32_t bf) { return (bf & B2CU_BODY_TYPE_MASK) == B2CU_DYNAMIC_BODY; }
+__device__ __forceinline__ bool IsAwakeNonStatic(uint32_t bf) { return (bf & B2CU_BODY_AWAKE) && !IsStatic(bf); }
+
+// ordered-int encoding of a float so that signed integer min == float min
+__device__ __forceinline__ int FloatToOrdered(float f)
+{
+	int i = __float_as_int(f);
+	return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float OrderedToFloat(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+// b2TestOverlap(b2AABB, b2AABB), Box2D/Collision/b2Collision.h:273-286
+__device__ __forceinline__ bool AabbOverlap(float4 a, float4 b)
+{
+	float d1x = b.x - a.z, d1y = b.y - a.w;
+	float d2x = a.x - b.z, d2y = a.y - b.w;
+	if (d1x > 0.0f || d1y > 0.0f) return false;
+	if (d2x > 0.0f || d2y > 0.0f) return false;
+	return true;
+}
+
+// b2ContactFilter::ShouldCollide, Box2D/Dynamics/b2WorldCallbacks.cpp:24-38
+__device__ __forceinline__ bool DefaultFilter(uint32_t filterA, uint32_t groupA, uint32_t filterB, uint32_t groupB)
+{
+	int16_t gA = (int16_t)(groupA & 0xFFFFu), gB = (int16_t)(groupB & 0xFFFFu);
+	if (gA == gB && gA != 0)
+	{
+		return gA > 0;
+	}
+	uint32_t catA = filterA & 0xFFFFu, maskA = filterA >> 16;
+	uint32_t catB = filterB & 0xFFFFu, maskB = filterB >> 16;
+	return (maskA & catB) != 0 && (catA & maskB) != 0;
+}
+
+__device__ __forceinline__ int LowerBound64(const uint64_t* __restrict__ keys, int n, uint64_t key)
+{
+	int lo = 0, hi = n;
+	while (lo < hi)
+	{
+		int mid = (lo + hi) >> 1;
+		if (keys[mid] < key) lo = mid + 1;
+		else hi = mid;
+	}
+	return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Collide: b2ContactManager::Collide (Box2D/Dynamics/b2ContactManager.cpp:177-230) fused with
+// b2Contact::UpdateImpl (Box2D/Dynamics/Contacts/b2Contact.cpp:173-298).  One thread per contact.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contactCount)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		int2 pr = d.c.proxies[i];
+		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		uint32_t fbA = d.bflags[bA], fbB = d.bflags[bB];
+		uint32_t flags = d.c.flags[i];
+		uint32_t gA = d.pgroup[pr.x], gB = d.pgroup[pr.y];
+		uint4 m3 = d.c.m3[i];
+		bool destroy = false;
+
+		if (flags & B2CU_CONTACT_FILTER)
+		{
+			bool should = IsDynamic(fbA) || IsDynamic(fbB);
+			if (should)
+			{
+				should = DefaultFilter(d.pfilter[pr.x], gA, d.pfilter[pr.y], gB);
+			}
+			if (!should)
+			{
+				destroy = true;
+			}
+			else
+			{
+				flags &= ~B2CU_CONTACT_FILTER;
+			}
+		}
+
+		if (!destroy)
+		{
+			bool active = IsAwakeNonStatic(fbA) || IsAwakeNonStatic(fbB);
+			if (!active)
+			{
+				d.c.flags[i] = flags | B2CU_CONTACT_INACTIVE;
+				d.cEvent[i] = 0;
+				continue;
+			}
+			flags &= ~B2CU_CONTACT_INACTIVE;
+			if (!AabbOverlap(d.fat[pr.x], d.fat[pr.y]))
+			{
+				destroy = true;
+			}
+		}
+
+		if (destroy)
+		{
+			int ev = B2CU_EV_DESTROY;
+			if (flags & B2CU_CONTACT_TOUCHING) ev |= B2CU_EV_DESTROY_TOUCHING;
+			// b2Contact::Destroy wakes both bodies if the manifold had points (b2Contact.cpp:107-113)
+			if ((int)m3.w > 0)
+			{
+				d.wake[bA] = 1;
+				d.wake[bB] = 1;
+			}
+			d.c.flags[i] = flags;
+			d.cEvent[i] = ev;
+			continue;
+		}
+
+		// ---- b2Contact::Update ----
+		float4 o1 = d.c.m1[i], o2 = d.c.m2[i];
+		int oldCount = (int)m3.w;
+		flags |= B2CU_CONTACT_ENABLED;
+		bool wasTouching = (flags & B2CU_CONTACT_TOUCHING) != 0;
+
+		Manifold m;
+		float4 o0 = d.c.m0[i];
+		m.localNormal = V(o0.x, o0.y);
+		m.localPoint = V(o0.z, o0.w);
+		m.lp[0] = V(o1.x, o1.y);
+		m.lp[1] = V(o2.x, o2.y);
+		m.id[0] = m3.x;
+		m.id[1] = m3.y;
+		m.type = (int)m3.z;
+		m.pointCount = 0;
+
+		Xf xfA = MakeXf(d.xf[bA]);
+		Xf xfB = MakeXf(d.xf[bB]);
+		Evaluate(&m, d.shapes + d.pshape[pr.x], xfA, d.shapes + d.pshape[pr.y], xfB);
+		bool touching = m.pointCount > 0;
+
+		// warm-start transfer by feature id
+		for (int k = 0; k < m.pointCount; ++k)
+		{
+			float ni = 0.0f, ti = 0.0f;
+			uint32_t id2 = m.id[k];
+			if (oldCount > 0 && m3.x == id2)
+			{
+				ni = o1.z;
+				ti = o1.w;
+			}
+			else if (oldCount > 1 && m3.y == id2)
+			{
+				ni = o2.z;
+				ti = o2.w;
+			}
+			m.ni[k] = ni;
+			m.ti[k] = ti;
+		}
+		for (int k = m.pointCount; k < 2; ++k)
+		{
+			// points beyond pointCount keep their previous impulses, as the untouched b2ManifoldPoint would
+			m.ni[k] = k == 0 ? o1.z : o2.z;
+			m.ti[k] = k == 0 ? o1.w : o2.w;
+		}
+
+		int ev = 0;
+		if (touching != wasTouching)
+		{
+			// b2ContactManager::ConsumeAwakes wakes m_nodeB.other (= fixture A's body) only (:472-486)
+			d.wake[bA] = 1;
+			ev = touching ? B2CU_EV_BEGIN : B2CU_EV_END;
+		}
+		if (touching) flags |= B2CU_CONTACT_TOUCHING;
+		else flags &= ~B2CU_CONTACT_TOUCHING;
+
+		d.c.flags[i] = flags;
+		d.c.m0[i] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
+		d.c.m1[i] = make_float4(m.lp[0].x, m.lp[0].y, m.ni[0], m.ti[0]);
+		d.c.m2[i] = make_float4(m.lp[1].x, m.lp[1].y, m.ni[1], m.ti[1]);
+		d.c.m3[i] = make_uint4(m.id[0], m.id[1], (uint32_t)m.type, (uint32_t)m.pointCount);
+		d.cEvent[i] = ev;
+	}
+}
+
+// b2Body::SetAwake(true) for every body flagged by Collide / contact creation / contact destruction
+// (Box2D/Dynamics/b2Body.h:690-718: sets e_awakeFlag and resets m_sleepTime).
+__global__ void ApplyWakeKernel(DeviceArrays d, int bodyCount)
+{
+	B2CU_GRID_STRIDE(b, bodyCount)
+	{
+		if (d.wake[b])
+		{
+			d.wake[b] = 0;
+			d.bflags[b] |= B2CU_BODY_AWAKE;
+			d.force[b].w = 0.0f;
+		}
+	}
+}
+
+// out[offset + j] = key[list[j]] for j < *count
+__global__ void GatherKeysKernel(const uint64_t* __restrict__ key, const int* __restrict__ list,
+                                 const int* __restrict__ count, const int* __restrict__ offset,
+                                 uint64_t* __restrict__ out, int capacity)
+{
+	int n = *count;
+	int off = offset ? *offset : 0;
+	B2CU_GRID_STRIDE(j, n)
+	{
+		if (off + j < capacity) out[off + j] = key[list[j]];
+	}
+}
+
+__global__ void CountMaskKernel(const uint32_t* __restrict__ flags, uint32_t mask, int n, int* counter)
+{
+	int local = 0;
+	B2CU_GRID_STRIDE(i, n)
+	{
+		if (flags[i] & mask) ++local;
+	}
+	for (int dlt = 16; dlt > 0; dlt >>= 1) local += __shfl_down_sync(0xffffffffu, local, dlt);
+	if ((threadIdx.x & 31) == 0 && local) atomicAdd(counter, local);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Islands: parallel union-find replaces the serial DFS of b2World::Solve (Box2D/Dynamics/b2World.cpp:1200-1371).
+// Non-static bodies joined by a touching, enabled, solid contact share an island; static bodies never merge
+// islands (:1236-1241).  The island label is the smallest body id of the island, whatever the thread order.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void SolveInitBodiesKernel(DeviceArrays d, int bodyCount, int positionIterations)
+{
+	B2CU_GRID_STRIDE(b, bodyCount)
+	{
+		d.island[b] = b;
+		d.islandAwake[b] = 0;
+		d.islandMinSleep[b] = 0x7F7FFFFF;
+		d.colourMask[b] = 0u;
+		d.colourClaim[b] = 0ull;
+		for (int k = 0; k < positionIterations; ++k)
+		{
+			d.islandMinSep[k * bodyCount + b] = 0x7F7FFFFF;
+		}
+	}
+}
+
+__device__ __forceinline__ int UfFind(int* parent, int x)
+{
+	int p = parent[x];
+	while (p != x)
+	{
+		int gp = parent[p];
+		if (gp != p) parent[x] = gp; // path halving; benign race (only ever points further up)
+		x = p;
+		p = gp;
+	}
+	return x;
+}
+
+__device__ __forceinline__ void UfUnion(int* parent, int a, int b)
+{
+	while (true)
+	{
+		a = UfFind(parent, a);
+		b = UfFind(parent, b);
+		if (a == b) return;
+		if (a < b)
+		{
+			int t = a;
+			a = b;
+			b = t;
+		}
+		// hook the larger root under the smaller one
+		int old = atomicCAS(&parent[a], a, b);
+		if (old == a) return;
+	}
+}
+
+__device__ __forceinline__ bool IsSolidTouching(const DeviceArrays& d, int i)
+{
+	uint32_t f = d.c.flags[i];
+	if ((f & (B2CU_CONTACT_TOUCHING | B2CU_CONTACT_ENABLED)) != (B2CU_CONTACT_TOUCHING | B2CU_CONTACT_ENABLED)) return false;
+	if (d.cEvent[i] & B2CU_EV_DESTROY) return false;
+	return true;
+}
+
+__global__ void IslandUnionKernel(DeviceArrays d, int contactCount)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		if (!IsSolidTouching(d, i)) continue;
+		int2 pr = d.c.proxies[i];
+		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		if (IsStatic(d.bflags[bA]) || IsStatic(d.bflags[bB])) continue;
+		UfUnion(d.island, bA, bB);
+	}
+}
+
+__global__ void IslandFlattenKernel(DeviceArrays d, int bodyCount)
+{
+	B2CU_GRID_STRIDE(b, bodyCount)
+	{
+		int r = UfFind(d.island, b);
+		uint32_t bf = d.bflags[b];
+		// seeds: awake, active, non-static (b2World.cpp:1207-1219)
+		if (IsAwakeNonStatic(bf) && (bf & B2CU_BODY_ACTIVE)) d.islandAwake[r] = 1;
+	}
+}
+
+__global__ void IslandMarkKernel(DeviceArrays d, int bodyCount)
+{
+	int local = 0;
+	B2CU_GRID_STRIDE(b, bodyCount)
+	{
+		int r = UfFind(d.island, b);
+		d.island[b] = r;
+		uint32_t bf = d.bflags[b];
+		if (!IsStatic(bf) && d.islandAwake[r])
+		{
+			// the traversal wakes every body it reaches without resetting its sleep timer (:1243-1244)
+			d.bflags[b] = bf | B2CU_BODY_ISLAND | B2CU_BODY_AWAKE;
+			++local;
+		}
+	}
+	for (int dlt = 16; dlt > 0; dlt >>= 1) local += __shfl_down_sync(0xffffffffu, local, dlt);
+	if ((threadIdx.x & 31) == 0 && local) atomicAdd(&d.counters[CNT_ISLAND_BODIES], local);
+}
+
+// which contacts go to the solver: touching, enabled, solid, attached to a body of an awake island
+__global__ void SelectConstraintsKernel(DeviceArrays d, int contactCount)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		int sel = 0;
+		if (IsSolidTouching(d, i))
+		{
+			int2 pr = d.c.proxies[i];
+			uint32_t fA = d.bflags[d.pbody[pr.x]], fB = d.bflags[d.pbody[pr.y]];
+			if ((!IsStatic(fA) && (fA & B2CU_BODY_ISLAND)) || (!IsStatic(fB) && (fB & B2CU_BODY_ISLAND))) sel = 1;
+		}
+		d.cSelect[i] = sel;
+		if (!sel) d.c.colour[i] = B2CU_COLOUR_NONE;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Graph colouring of the constraint graph (bodies = vertices, constraints = edges; only dynamic bodies
+// constrain a colour).  New in this design: it is what lets b2ContactSolver's sequential Gauss-Seidel
+// (Box2D/Dynamics/Contacts/b2ContactSolver.cpp:293-603) run one colour at a time in parallel.  Colours persist
+// across steps, so only new constraints are coloured.  Deterministic: ties are broken by contact index.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void ColourPrepareKernel(DeviceArrays d, const int* __restrict__ list, int* uncoloured)
+{
+	int n = d.counters[CNT_CONSTRAINT];
+	B2CU_GRID_STRIDE(j, n)
+	{
+		int i = list[j];
+		int c = d.c.colour[i];
+		int2 pr = d.c.proxies[i];
+		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		if (c >= 0 && c < B2CU_MAX_COLOURS)
+		{
+			if (IsDynamic(d.bflags[bA])) atomicOr(&d.colourMask[bA], 1u << c);
+			if (IsDynamic(d.bflags[bB])) atomicOr(&d.colourMask[bB], 1u << c);
+		}
+		else
+		{
+			d.c.colour[i] = B2CU_COLOUR_NONE;
+			int slot = atomicAdd(&d.counters[CNT_UNCOLOURED], 1);
+			uncoloured[slot] = i;
+		}
+	}
+}
+
+__device__ __forceinline__ uint32_t ColourFreeMask(const DeviceArrays& d, int bA, int bB, bool dynA, bool dynB)
+{
+	uint32_t used = 0u;
+	if (dynA) used |= d.colourMask[bA];
+	if (dynB) used |= d.colourMask[bB];
+	return ~used;
+}
+
+__global__ void ColourProposeKernel(DeviceArrays d, const int* __restrict__ list, int counterIndex, uint32_t round)
+{
+	int n = d.counters[counterIndex];
+	B2CU_GRID_STRIDE(j, n)
+	{
+		int i = list[j];
+		int2 pr = d.c.proxies[i];
+		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		bool dynA = IsDynamic(d.bflags[bA]), dynB = IsDynamic(d.bflags[bB]);
+		uint32_t freeMask = ColourFreeMask(d, bA, bB, dynA, dynB);
+		if (freeMask == 0u)
+		{
+			d.c.colour[i] = B2CU_COLOUR_OVERFLOW;
+			continue;
+		}
+		unsigned long long claim = ((unsigned long long)round << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+		if (dynA) atomicMax(&d.colourClaim[bA], claim);
+		if (dynB) atomicMax(&d.colourClaim[bB], claim);
+	}
+}
+
+__global__ void ColourCommitKernel(DeviceArrays d, const int* __restrict__ list, int counterIndex, int* next,
+                                   int nextCounterIndex, uint32_t round)
+{
+	int n = d.counters[counterIndex];
+	B2CU_GRID_STRIDE(j, n)
+	{
+		int i = list[j];
+		if (d.c.colour[i] == B2CU_COLOUR_OVERFLOW) continue;
+		int2 pr = d.c.proxies[i];
+		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		bool dynA = IsDynamic(d.bflags[bA]), dynB = IsDynamic(d.bflags[bB]);
+		unsigned long long claim = ((unsigned long long)round << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+		bool win = (!dynA || d.colourClaim[bA] == claim) && (!dynB || d.colourClaim[bB] == claim);
+		if (win)
+		{
+			uint32_t freeMask = ColourFreeMask(d, bA, bB, dynA, dynB);
+			int c = __ffs((int)freeMask) - 1;
+			d.c.colour[i] = c;
+			// this constraint is the only winner on each of its dynamic bodies this round
+			if (dynA) d.colourMask[bA] |= 1u << c;
+			if (dynB) d.colourMask[bB] |= 1u << c;
+		}
+		else
+		{
+			int slot = atomicAdd(&d.counters[nextCounterIndex], 1);
+			next[slot] = i;
+		}
+	}
+}
+
+__global__ void ColourKeysKernel(DeviceArrays d, const int* __restrict__ list)
+{
+	int n = d.counters[CNT_CONSTRAINT];
+	B2CU_GRID_STRIDE(j, n)
+	{
+		int i = list[j];
+		d.orderKeys[j] = ((uint64_t)(uint32_t)d.c.colour[i] << 32) | (uint32_t)i;
+	}
+}
+
+// colourCount[c] = first position of colour c in the sorted order (or -1)
+__global__ void ColourStartsKernel(DeviceArrays d)
+{
+	int n = d.counters[CNT_CONSTRAINT];
+	B2CU_GRID_STRIDE(j, n)
+	{
+		int c = (int)(d.orderKeys[j] >> 32);
+		if (j == 0 || (int)(d.orderKeys[j - 1] >> 32) != c) d.colourCount[c] = j;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// b2Island::Solve, body part 1 (Box2D/Dynamics/b2Island.cpp:192-230): integrate velocities, damping, store
+// c0/a0.  Streaming kernel over bodies.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void IntegrateVelocitiesKernel(DeviceArrays d, int bodyCount, float h, float2 gravity)
+{
+	B2CU_GRID_STRIDE(b, bodyCount)
+	{
+		uint32_t bf = d.bflags[b];
+		if (IsStatic(bf) || !(bf & B2CU_BODY_ISLAND)) continue;
+
+		float4 p = d.pos[b];
+		float4 p0 = d.pos0[b];
+		p0.x = p.x;
+		p0.y = p.y;
+		p0.z = p.z;
+		d.pos0[b] = p0;
+
+		if (IsDynamic(bf))
+		{
+			float4 v = d.vel[b];
+			float4 ms = d.mass[b];
+			float4 f = d.force[b];
+			float4 dm = d.damp[b];
+			Vec2 lin = V(v.x, v.y);
+			float w = v.z;
+			Vec2 acc = dm.z * V(gravity.x, gravity.y) + ms.x * V(f.x, f.y);
+			lin = lin + h * acc;
+			w = w + h * ms.y * f.z;
+			float ld = 1.0f / (1.0f + h * dm.x);
+			float ad = 1.0f / (1.0f + h * dm.y);
+			lin = V(lin.x * ld, lin.y * ld);
+			w = w * ad;
+			d.vel[b] = make_float4(lin.x, lin.y, w, v.w);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// b2ContactSolver constructor + InitializeVelocityConstraints (b2ContactSolver.cpp:47-251) with
+// b2WorldManifold::Initialize (Box2D/Collision/b2Collision.cpp:22-86).  One thread per constraint, written
+// straight into the colour-sorted SoA.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) InitConstraintsKernel(DeviceArrays d, float dtRatio, int warmStarting)
+{
+	int n = d.counters[CNT_CONSTRAINT];
+	B2CU_GRID_STRIDE(k, n)
+	{
+		int i = (int)(uint32_t)(d.orderKeys[k] & 0xFFFFFFFFull);
+		int2 pr = d.c.proxies[i];
+		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		float radiusA = d.shapes[d.pshape[pr.x]].radius;
+		float radiusB = d.shapes[d.pshape[pr.y]].radius;
+
+		float4 m0 = d.c.m0[i], m1 = d.c.m1[i], m2 = d.c.m2[i];
+		uint4 m3 = d.c.m3[i];
+		float4 mix = d.c.mix[i];
+		int type = (int)m3.z;
+		int pointCount = (int)m3.w;
+
+		float4 msA = d.mass[bA], msB = d.mass[bB];
+		float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
+		float4 pA = d.pos[bA], pB = d.pos[bB];
+		float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+		Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+		float aA = pA.z, aB = pB.z;
+		Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+		float wA = vA4.z, wB = vB4.z;
+		Vec2 localCenterA = V(msA.z, msA.w), localCenterB = V(msB.z, msB.w);
+
+		Xf xfA, xfB;
+		xfA.q = SinCos(aA);
+		xfB.q = SinCos(aB);
+		xfA.p = cA - Mul(xfA.q, localCenterA);
+		xfB.p = cB - Mul(xfB.q, localCenterB);
+
+		Vec2 localNormal = V(m0.x, m0.y), localPoint = V(m0.z, m0.w);
+		Vec2 lp[2] = {V(m1.x, m1.y), V(m2.x, m2.y)};
+
+		// b2WorldManifold::Initialize
+		Vec2 normal = V(1.0f, 0.0f);
+		Vec2 wp[2] = {V(0.0f, 0.0f), V(0.0f, 0.0f)};
+		if (type == B2CU_MANIFOLD_CIRCLES)
+		{
+			Vec2 pointA = Mul(xfA, localPoint);
+			Vec2 pointB = Mul(xfB, lp[0]);
+			if (DistanceSquared(pointA, pointB) > B2CU_EPSILON * B2CU_EPSILON)
+			{
+				normal = Normalized(pointB - pointA);
+			}
+			Vec2 ccA = pointA + radiusA * normal;
+			Vec2 ccB = pointB - radiusB * normal;
+			wp[0] = 0.5f * (ccA + ccB);
+		}
+		else if (type == B2CU_MANIFOLD_FACE_A)
+		{
+			normal = Mul(xfA.q, localNormal);
+			Vec2 planePoint = Mul(xfA, localPoint);
+			for (int j = 0; j < pointCount; ++j)
+			{
+				Vec2 clipPoint = Mul(xfB, lp[j]);
+				Vec2 ccA = clipPoint + (radiusA - Dot(clipPoint - planePoint, normal)) * normal;
+				Vec2 ccB = clipPoint - radiusB * normal;
+				wp[j] = 0.5f * (ccA + ccB);
+			}
+		}
+		else
+		{
+			normal = Mul(xfB.q, localNormal);
+			Vec2 planePoint = Mul(xfB, localPoint);
+			for (int j = 0; j < pointCount; ++j)
+			{
+				Vec2 clipPoint = Mul(xfA, lp[j]);
+				Vec2 ccB = clipPoint + (radiusB - Dot(clipPoint - planePoint, normal)) * normal;
+				Vec2 ccA = clipPoint - radiusA * normal;
+				wp[j] = 0.5f * (ccA + ccB);
+			}
+			normal = -normal;
+		}
+
+		float friction = mix.x, restitution = mix.y, tangentSpeed = mix.z;
+
+		float4 pa[2], pb[2];
+		float imp[4];
+		float oldImp[4] = {m1.z, m1.w, m2.z, m2.w};
+		Vec2 rAs[2], rBs[2];
+		for (int j = 0; j < 2; ++j)
+		{
+			pa[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			pb[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			imp[2 * j] = 0.0f;
+			imp[2 * j + 1] = 0.0f;
+			rAs[j] = V(0.0f, 0.0f);
+			rBs[j] = V(0.0f, 0.0f);
+		}
+		for (int j = 0; j < pointCount; ++j)
+		{
+			if (warmStarting)
+			{
+				imp[2 * j] = dtRatio * oldImp[2 * j];
+				imp[2 * j + 1] = dtRatio * oldImp[2 * j + 1];
+			}
+			Vec2 rA = wp[j] - cA;
+			Vec2 rB = wp[j] - cB;
+			rAs[j] = rA;
+			rBs[j] = rB;
+
+			float rnA = Cross(rA, normal);
+			float rnB = Cross(rB, normal);
+			float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+			float normalMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+
+			Vec2 tangent = CrossVS(normal, 1.0f);
+			float rtA = Cross(rA, tangent);
+			float rtB = Cross(rB, tangent);
+			float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+			float tangentMass = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+
+			float velocityBias = 0.0f;
+			float vRel = Dot(normal, vB + CrossSV(wB, rB) - vA - CrossSV(wA, rA));
+			if (vRel < -B2CU_VELOCITY_THRESHOLD)
+			{
+				velocityBias = -restitution * vRel;
+			}
+			pa[j] = make_float4(rA.x, rA.y, rB.x, rB.y);
+			pb[j] = make_float4(normalMass, tangentMass, velocityBias, 0.0f);
+		}
+
+		int solvePoints = pointCount;
+		float4 K = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		float4 NM = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		if (pointCount == 2)
+		{
+			float rn1A = Cross(rAs[0], normal);
+			float rn1B = Cross(rBs[0], normal);
+			float rn2A = Cross(rAs[1], normal);
+			float rn2B = Cross(rBs[1], normal);
+
+			float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+			float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+			float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+
+			const float k_maxConditionNumber = 1000.0f;
+			if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12))
+			{
+				K = make_float4(k11, k12, k22, 0.0f);
+				// b2Mat22::GetInverse (b2Math.h:205-216) of [[k11 k12][k12 k22]]
+				float a = k11, b = k12, c = k12, dd = k22;
+				float det = a * dd - b * c;
+				if (det != 0.0f)
+				{
+					det = 1.0f / det;
+				}
+				NM = make_float4(det * dd, -det * b, -det * c, det * a); // ex.x, ey.x, ex.y, ey.y
+			}
+			else
+			{
+				solvePoints = 1;
+			}
+		}
+
+		uint32_t bfA = d.bflags[bA];
+		int root = d.island[IsStatic(bfA) ? bB : bA];
+
+		d.solverKeys[k] = d.c.key[i];
+		d.sBody[k] = make_int4(bA, bB, i, solvePoints | (pointCount << 8));
+		d.sMass[k] = make_float4(mA, iA, mB, iB);
+		d.sNormal[k] = make_float4(normal.x, normal.y, friction, tangentSpeed);
+		d.sP0a[k] = pa[0];
+		d.sP0b[k] = pb[0];
+		d.sP1a[k] = pa[1];
+		d.sP1b[k] = pb[1];
+		d.sImp[k] = make_float4(imp[0], imp[1], imp[2], imp[3]);
+		d.sK[k] = K;
+		d.sNM[k] = NM;
+		d.sLocal[k] = m0;
+		d.sLocalP[k] = make_float4(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
+		d.sCenters[k] = make_float4(localCenterA.x, localCenterA.y, localCenterB.x, localCenterB.y);
+		d.sRadius[k] = make_float4(radiusA, radiusB, __int_as_float(type), __int_as_float(root));
+	}
+}
+
+// b2ContactSolver::WarmStart (b2ContactSolver.cpp:253-291), constraints [begin, begin+count) of one colour
+__device__ __forceinline__ void WarmStartOne(const DeviceArrays& d, int k)
+{
+	int4 sb = d.sBody[k];
+	float4 ms = d.sMass[k];
+	float4 nf = d.sNormal[k];
+	float4 imp = d.sImp[k];
+	int pointCount = sb.w & 0xFF;
+	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
+
+	float4 vA4 = d.vel[sb.x], vB4 = d.vel[sb.y];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	Vec2 normal = V(nf.x, nf.y);
+	Vec2 tangent = CrossVS(normal, 1.0f);
+
+	for (int j = 0; j < pointCount; ++j)
+	{
+		float4 r = j == 0 ? d.sP0a[k] : d.sP1a[k];
+		float ni = j == 0 ? imp.x : imp.z;
+		float ti = j == 0 ? imp.y : imp.w;
+		Vec2 rA = V(r.x, r.y), rB = V(r.z, r.w);
+		Vec2 P = ni * normal + ti * tangent;
+		wA -= iA * Cross(rA, P);
+		vA = vA - mA * P;
+		wB += iB * Cross(rB, P);
+		vB = vB + mB * P;
+	}
+	if (mA != 0.0f || iA != 0.0f) d.vel[sb.x] = make_float4(vA.x, vA.y, wA, vA4.w);
+	if (mB != 0.0f || iB != 0.0f) d.vel[sb.y] = make_float4(vB.x, vB.y, wB, vB4.w);
+}
+
+__global__ void __launch_bounds__(256) WarmStartKernel(DeviceArrays d, int begin, int count)
+{
+	B2CU_GRID_STRIDE(t, count) { WarmStartOne(d, begin + t); }
+}
+
+// b2ContactSolver::SolveVelocityConstraints (b2ContactSolver.cpp:293-603) for one constraint
+__device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k)
+{
+	int4 sb = d.sBody[k];
+	float4 ms = d.sMass[k];
+	float4 nf = d.sNormal[k];
+	float4 imp = d.sImp[k];
+	float4 p0a = d.sP0a[k], p0b = d.sP0b[k];
+	int pointCount = sb.w & 0xFF;
+	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
+
+	float4 vA4 = d.vel[sb.x], vB4 = d.vel[sb.y];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	Vec2 normal = V(nf.x, nf.y);
+	Vec2 tangent = CrossVS(normal, 1.0f);
+	float friction = nf.z, tangentSpeed = nf.w;
+
+	float4 p1a = make_float4(0.f, 0.f, 0.f, 0.f), p1b = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (pointCount == 2)
+	{
+		p1a = d.sP1a[k];
+		p1b = d.sP1b[k];
+	}
+
+	// tangent constraints first
+	for (int j = 0; j < pointCount; ++j)
+	{
+		float4 r = j == 0 ? p0a : p1a;
+		float4 q = j == 0 ? p0b : p1b;
+		Vec2 rA = V(r.x, r.y), rB = V(r.z, r.w);
+		float normalImpulse = j == 0 ? imp.x : imp.z;
+		float tangentImpulse = j == 0 ? imp.y : imp.w;
+
+		Vec2 dv = vB + CrossSV(wB, rB) - vA - CrossSV(wA, rA);
+		float vt = Dot(dv, tangent) - tangentSpeed;
+		float lambda = q.y * (-vt);
+
+		float maxFriction = friction * normalImpulse;
+		float newImpulse = Clamp(tangentImpulse + lambda, -maxFriction, maxFriction);
+		lambda = newImpulse - tangentImpulse;
+		if (j == 0) imp.y = newImpulse;
+		else imp.w = newImpulse;
+
+		Vec2 P = lambda * tangent;
+		vA = vA - mA * P;
+		wA -= iA * Cross(rA, P);
+		vB = vB + mB * P;
+		wB += iB * Cross(rB, P);
+	}
+
+	if (pointCount == 1)
+	{
+		Vec2 rA = V(p0a.x, p0a.y), rB = V(p0a.z, p0a.w);
+		Vec2 dv = vB + CrossSV(wB, rB) - vA - CrossSV(wA, rA);
+		float vn = Dot(dv, normal);
+		float lambda = -p0b.x * (vn - p0b.z);
+
+		float newImpulse = Max(imp.x + lambda, 0.0f);
+		lambda = newImpulse - imp.x;
+		imp.x = newImpulse;
+
+		Vec2 P = lambda * normal;
+		vA = vA - mA * P;
+		wA -= iA * Cross(rA, P);
+		vB = vB + mB * P;
+		wB += iB * Cross(rB, P);
+	}
+	else
+	{
+		// block solver, total enumeration of the 2x2 LCP (b2ContactSolver.cpp:375-596)
+		float4 Kq = d.sK[k];
+		float4 NM = d.sNM[k];
+		Vec2 rA1 = V(p0a.x, p0a.y), rB1 = V(p0a.z, p0a.w);
+		Vec2 rA2 = V(p1a.x, p1a.y), rB2 = V(p1a.z, p1a.w);
+
+		Vec2 a = V(imp.x, imp.z);
+
+		Vec2 dv1 = vB + CrossSV(wB, rB1) - vA - CrossSV(wA, rA1);
+		Vec2 dv2 = vB + CrossSV(wB, rB2) - vA - CrossSV(wA, rA2);
+		float vn1 = Dot(dv1, normal);
+		float vn2 = Dot(dv2, normal);
+
+		Vec2 b;
+		b.x = vn1 - p0b.z;
+		b.y = vn2 - p1b.z;
+		// b -= K * a, K = [ex=(k11,k12), ey=(k12,k22)]
+		b.x -= Kq.x * a.x + Kq.y * a.y;
+		b.y -= Kq.y * a.x + Kq.z * a.y;
+
+		Vec2 x;
+		bool found = false;
+		// case 1: x = -normalMass * b
+		x.x = -(NM.x * b.x + NM.y * b.y);
+		x.y = -(NM.z * b.x + NM.w * b.y);
+		if (x.x >= 0.0f && x.y >= 0.0f)
+		{
+			found = true;
+		}
+		if (!found)
+		{
+			// case 2: vn1 = 0, x2 = 0
+			x.x = -p0b.x * b.x;
+			x.y = 0.0f;
+			vn2 = Kq.y * x.x + b.y;
+			if (x.x >= 0.0f && vn2 >= 0.0f) found = true;
+		}
+		if (!found)
+		{
+			// case 3: vn2 = 0, x1 = 0
+			x.x = 0.0f;
+			x.y = -p1b.x * b.y;
+			vn1 = Kq.y * x.y + b.x;
+			if (x.y >= 0.0f && vn1 >= 0.0f) found = true;
+		}
+		if (!found)
+		{
+			// case 4: x1 = 0, x2 = 0
+			x.x = 0.0f;
+			x.y = 0.0f;
+			vn1 = b.x;
+			vn2 = b.y;
+			if (vn1 >= 0.0f && vn2 >= 0.0f) found = true;
+		}
+		if (found)
+		{
+			Vec2 dd = x - a;
+			Vec2 P1 = dd.x * normal;
+			Vec2 P2 = dd.y * normal;
+			vA = vA - mA * (P1 + P2);
+			wA -= iA * (Cross(rA1, P1) + Cross(rA2, P2));
+			vB = vB + mB * (P1 + P2);
+			wB += iB * (Cross(rB1, P1) + Cross(rB2, P2));
+			imp.x = x.x;
+			imp.z = x.y;
+		}
+		// no solution: give up, as the reference does (:593-594)
+	}
+
+	d.sImp[k] = imp;
+	if (mA != 0.0f || iA != 0.0f) d.vel[sb.x] = make_float4(vA.x, vA.y, wA, vA4.w);
+	if (mB != 0.0f || iB != 0.0f) d.vel[sb.y] = make_float4(vB.x, vB.y, wB, vB4.w);
+}
+
+__global__ void __launch_bounds__(256) SolveVelocityKernel(DeviceArrays d, int begin, int count)
+{
+	B2CU_GRID_STRIDE(t, count) { SolveVelocityOne(d, begin + t); }
+}
+
+// b2ContactSolver::StoreImpulses (b2ContactSolver.cpp:605-618)
+__global__ void StoreImpulsesKernel(DeviceArrays d)
+{
+	int n = d.counters[CNT_CONSTRAINT];
+	B2CU_GRID_STRIDE(k, n)
+	{
+		int4 sb = d.sBody[k];
+		float4 imp = d.sImp[k];
+		int i = sb.z;
+		int pointCount = sb.w & 0xFF;
+		float4 m1 = d.c.m1[i];
+		m1.z = imp.x;
+		m1.w = imp.y;
+		d.c.m1[i] = m1;
+		if (pointCount == 2)
+		{
+			float4 m2 = d.c.m2[i];
+			m2.z = imp.z;
+			m2.w = imp.w;
+			d.c.m2[i] = m2;
+		}
+	}
+}
+
+// b2Island::Solve, body part 2 (b2Island.cpp:283-313): clamp and integrate positions
+__global__ void IntegratePositionsKernel(DeviceArrays d, int bodyCount, float h)
+{
+	B2CU_GRID_STRIDE(b, bodyCount)
+	{
+		uint32_t bf = d.bflags[b];
+		if (IsStatic(bf) || !(bf & B2CU_BODY_ISLAND)) continue;
+		float4 p = d.pos[b];
+		float4 v4 = d.vel[b];
+		Vec2 c = V(p.x, p.y);
+		float a = p.z;
+		Vec2 v = V(v4.x, v4.y);
+		float w = v4.z;
+
+		Vec2 translation = h * v;
+		if (Dot(translation, translation) > B2CU_MAX_TRANSLATION_SQUARED)
+		{
+			float ratio = B2CU_MAX_TRANSLATION / Length(translation);
+			v = V(v.x * ratio, v.y * ratio);
+		}
+		float rotation = h * w;
+		if (rotation * rotation > B2CU_MAX_ROTATION_SQUARED)
+		{
+			float ratio = B2CU_MAX_ROTATION / Abs(rotation);
+			w *= ratio;
+		}
+		c = c + h * v;
+		a += h * w;
+
+		d.pos[b] = make_float4(c.x, c.y, a, p.w);
+		d.vel[b] = make_float4(v.x, v.y, w, v4.w);
+	}
+}
+
+// b2ContactSolver::SolvePositionConstraints (b2ContactSolver.cpp:676-752) for one constraint.
+// Returns the smallest separation seen; islands stop iterating once theirs is >= -3*linearSlop
+// (b2Island.cpp:318-335), which is tracked per island root in islandMinSep[iteration][root].
+__device__ __forceinline__ float SolvePositionOne(const DeviceArrays& d, int k)
+{
+	int4 sb = d.sBody[k];
+	float4 ms = d.sMass[k];
+	float4 loc = d.sLocal[k];
+	float4 lps = d.sLocalP[k];
+	float4 cen = d.sCenters[k];
+	float4 rad = d.sRadius[k];
+	int pointCount = sb.w >> 8;
+	int type = __float_as_int(rad.z);
+	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
+	Vec2 localCenterA = V(cen.x, cen.y), localCenterB = V(cen.z, cen.w);
+	Vec2 localNormal = V(loc.x, loc.y), localPoint = V(loc.z, loc.w);
+
+	float4 pA4 = d.pos[sb.x], pB4 = d.pos[sb.y];
+	Vec2 cA = V(pA4.x, pA4.y), cB = V(pB4.x, pB4.y);
+	float aA = pA4.z, aB = pB4.z;
+	float minSeparation = B2CU_MAX_FLOAT;
+
+	for (int j = 0; j < pointCount; ++j)
+	{
+		Xf xfA, xfB;
+		xfA.q = SinCos(aA);
+		xfB.q = SinCos(aB);
+		xfA.p = cA - Mul(xfA.q, localCenterA);
+		xfB.p = cB - Mul(xfB.q, localCenterB);
+
+		Vec2 normal, point;
+		float separation;
+		Vec2 lpj = j == 0 ? V(lps.x, lps.y) : V(lps.z, lps.w);
+		if (type == B2CU_MANIFOLD_CIRCLES)
+		{
+			Vec2 pointA = Mul(xfA, localPoint);
+			Vec2 pointB = Mul(xfB, V(lps.x, lps.y));
+			normal = Normalized(pointB - pointA);
+			point = 0.5f * (pointA + pointB);
+			separation = Dot(pointB - pointA, normal) - rad.x - rad.y;
+		}
+		else if (type == B2CU_MANIFOLD_FACE_A)
+		{
+			normal = Mul(xfA.q, localNormal);
+			Vec2 planePoint = Mul(xfA, localPoint);
+			Vec2 clipPoint = Mul(xfB, lpj);
+			separation = Dot(clipPoint - planePoint, normal) - rad.x - rad.y;
+			point = clipPoint;
+		}
+		else
+		{
+			normal = Mul(xfB.q, localNormal);
+			Vec2 planePoint = Mul(xfB, localPoint);
+			Vec2 clipPoint = Mul(xfA, lpj);
+			separation = Dot(clipPoint - planePoint, normal) - rad.x - rad.y;
+			point = clipPoint;
+			normal = -normal;
+		}
+
+		Vec2 rA = point - cA;
+		Vec2 rB = point - cB;
+
+		minSeparation = Min(minSeparation, separation);
+
+		float C = Clamp(B2CU_BAUMGARTE * (separation + B2CU_LINEAR_SLOP), -B2CU_MAX_LINEAR_CORRECTION, 0.0f);
+
+		float rnA = Cross(rA, normal);
+		float rnB = Cross(rB, normal);
+		float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+		float impulse = K > 0.0f ? -C / K : 0.0f;
+
+		Vec2 P = impulse * normal;
+		cA = cA - mA * P;
+		aA -= iA * Cross(rA, P);
+		cB = cB + mB * P;
+		aB += iB * Cross(rB, P);
+	}
+
+	if (mA != 0.0f || iA != 0.0f) d.pos[sb.x] = make_float4(cA.x, cA.y, aA, pA4.w);
+	if (mB != 0.0f || iB != 0.0f) d.pos[sb.y] = make_float4(cB.x, cB.y, aB, pB4.w);
+	return minSeparation;
+}
+
+__device__ __forceinline__ bool IslandDone(const DeviceArrays& d, int iteration, int root, int bodyCount)
+{
+	if (iteration == 0) return false;
+	float prev = OrderedToFloat(d.islandMinSep[(iteration - 1) * bodyCount + root]);
+	return prev >= -3.0f * B2CU_LINEAR_SLOP;
+}
+
+__global__ void __launch_bounds__(256) SolvePositionKernel(DeviceArrays d, int begin, int count, int iteration,
+                                                           int bodyCount)
+{
+	B2CU_GRID_STRIDE(t, count)
+	{
+		int k = begin + t;
+		int root = __float_as_int(d.sRadius[k].w);
+		if (IslandDone(d, iteration, root, bodyCount)) continue;
+		float minSep = SolvePositionOne(d, k);
+		atomicMin(&d.islandMinSep[iteration * bodyCount + root], FloatToOrdered(minSep));
+	}
+}
+
+// overflow constraints (no free colour): solved one after the other by a single thread, in key order
+__global__ void OverflowWarmStartKernel(DeviceArrays d, int begin, int count)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		for (int t = 0; t < count; ++t) WarmStartOne(d, begin + t);
+}
+__global__ void OverflowSolveVelocityKernel(DeviceArrays d, int begin, int count)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		for (int t = 0; t < count; ++t) SolveVelocityOne(d, begin + t);
+}
+__global__ void OverflowSolvePositionKernel(DeviceArrays d, int begin, int count, int iteration, int bodyCount)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		for (int t = 0; t < count; ++t)
+		{
+			int k = begin + t;
+			int root = __float_as_int(d.sRadius[k].w);
+			if (IslandDone(d, iteration, root, bodyCount)) continue;
+			float minSep = SolvePositionOne(d, k);
+			atomicMin(&d.islandMinSep[iteration * bodyCount + root], FloatToOrdered(minSep));
+		}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// b2Island::Solve, body part 3 (b2Island.cpp:338-395): copy back, SynchronizeTransform, sleep bookkeeping.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void FinalizeBodiesKernel(DeviceArrays d, int bodyCount, float h, int allowSleep)
+{
+	B2CU_GRID_STRIDE(b, bodyCount)
+	{
+		uint32_t bf = d.bflags[b];
+		if (IsStatic(bf) || !(bf & B2CU_BODY_ISLAND)) continue;
+		float4 p = d.pos[b];
+		float4 ms = d.mass[b];
+		Rot q = SinCos(p.z);
+		Vec2 o = V(p.x, p.y) - Mul(q, V(ms.z, ms.w));
+		d.xf[b] = make_float4(o.x, o.y, q.s, q.c);
+
+		if (allowSleep)
+		{
+			float4 v = d.vel[b];
+			float4 f = d.force[b];
+			const float linTolSqr = B2CU_LINEAR_SLEEP_TOLERANCE * B2CU_LINEAR_SLEEP_TOLERANCE;
+			const float angTolSqr = B2CU_ANGULAR_SLEEP_TOLERANCE * B2CU_ANGULAR_SLEEP_TOLERANCE;
+			float sleepTime;
+			if ((bf & B2CU_BODY_AUTOSLEEP) == 0 || v.z * v.z > angTolSqr || Dot(V(v.x, v.y), V(v.x, v.y)) > linTolSqr)
+			{
+				sleepTime = 0.0f;
+			}
+			else
+			{
+				sleepTime = f.w + h;
+			}
+			f.w = sleepTime;
+			d.force[b] = f;
+			atomicMin(&d.islandMinSleep[d.island[b]], __float_as_int(sleepTime));
+		}
+	}
+}
+
+__global__ void SleepIslandsKernel(DeviceArrays d, int bodyCount, int positionIterations)
+{
+	B2CU_GRID_STRIDE(b, bodyCount)
+	{
+		uint32_t bf = d.bflags[b];
+		if (IsStatic(bf) || !(bf & B2CU_BODY_ISLAND)) continue;
+		int root = d.island[b];
+		float minSleepTime = __int_as_float(d.islandMinSleep[root]);
+		bool positionSolved = positionIterations > 0 && IslandDone(d, positionIterations, root, bodyCount);
+		if (minSleepTime >= B2CU_TIME_TO_SLEEP && positionSolved)
+		{
+			// b2Body::SetAwake(false), Box2D/Dynamics/b2Body.h:702-711
+			d.bflags[b] = bf & ~B2CU_BODY_AWAKE;
+			float4 v = d.vel[b];
+			d.vel[b] = make_float4(0.0f, 0.0f, 0.0f, v.w);
+			d.force[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SynchronizeFixtures + MoveProxy: b2ContactManager::SynchronizeFixtures (b2ContactManager.cpp:315-364),
+// shape ComputeAABB (b2PolygonShape.cpp:340-357, b2CircleShape.cpp:83-90, b2EdgeShape.cpp:116-129) and the
+// fat-AABB rule of b2DynamicTree::MoveProxy (Box2D/Collision/b2DynamicTree.cpp:130-174).  One thread per proxy.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ComputeAABB(const b2cuShape* __restrict__ s, const Xf& xf)
+{
+	int type = s->type;
+	float r = s->radius;
+	if (type == B2CU_SHAPE_CIRCLE)
+	{
+		Vec2 p = xf.p + Mul(xf.q, ShapeV(s, 0));
+		return make_float4(p.x - r, p.y - r, p.x + r, p.y + r);
+	}
+	if (type == B2CU_SHAPE_EDGE)
+	{
+		Vec2 v1 = Mul(xf, ShapeV(s, 0));
+		Vec2 v2 = Mul(xf, ShapeV(s, 1));
+		Vec2 lower = V(Min(v1.x, v2.x), Min(v1.y, v2.y));
+		Vec2 upper = V(Max(v1.x, v2.x), Max(v1.y, v2.y));
+		return make_float4(lower.x - r, lower.y - r, upper.x + r, upper.y + r);
+	}
+	Vec2 lower = Mul(xf, ShapeV(s, 0));
+	Vec2 upper = lower;
+	int count = s->count;
+	for (int i = 1; i < count; ++i)
+	{
+		Vec2 v = Mul(xf, ShapeV(s, i));
+		lower = V(Min(lower.x, v.x), Min(lower.y, v.y));
+		upper = V(Max(upper.x, v.x), Max(upper.y, v.y));
+	}
+	return make_float4(lower.x - r, lower.y - r, upper.x + r, upper.y + r);
+}
+
+__global__ void __launch_bounds__(256) SyncProxiesKernel(DeviceArrays d, int proxyCount)
+{
+	B2CU_GRID_STRIDE(p, proxyCount)
+	{
+		int b = d.pbody[p];
+		uint32_t bf = d.bflags[b];
+		if (IsStatic(bf) || !(bf & B2CU_BODY_ISLAND)) continue;
+
+		float4 p0 = d.pos0[b];
+		float4 ms = d.mass[b];
+		Xf xf1;
+		xf1.q = SinCos(p0.z);
+		xf1.p = V(p0.x, p0.y) - Mul(xf1.q, V(ms.z, ms.w));
+		Xf xf2 = MakeXf(d.xf[b]);
+
+		const b2cuShape* s = d.shapes + d.pshape[p];
+		float4 a1 = ComputeAABB(s, xf1);
+		float4 a2 = ComputeAABB(s, xf2);
+		float4 ab = make_float4(Min(a1.x, a2.x), Min(a1.y, a2.y), Max(a1.z, a2.z), Max(a1.w, a2.w));
+		d.aabb[p] = ab;
+
+		float4 fat = d.fat[p];
+		bool contains = fat.x <= ab.x && fat.y <= ab.y && ab.z <= fat.z && ab.w <= fat.w;
+		if (!contains)
+		{
+			Vec2 disp = xf2.p - xf1.p;
+			float4 nb = make_float4(ab.x - B2CU_AABB_EXTENSION, ab.y - B2CU_AABB_EXTENSION, ab.z + B2CU_AABB_EXTENSION,
+			                        ab.w + B2CU_AABB_EXTENSION);
+			Vec2 dd = B2CU_AABB_MULTIPLIER * disp;
+			if (dd.x < 0.0f) nb.x += dd.x;
+			else nb.z += dd.x;
+			if (dd.y < 0.0f) nb.y += dd.y;
+			else nb.w += dd.y;
+			d.fat[p] = nb;
+			d.pgroup[p] |= ((uint32_t)B2CU_PROXY_MOVED << 16);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Broad-phase pair finding.  Replaces b2BroadPhase::UpdatePairs + b2DynamicTree::Query (Box2D/Collision/
+// b2BroadPhase.h:211-267, b2DynamicTree.h:168-201) and b2ContactManager::AddPair (b2ContactManager.cpp:237-312).
+// A hashed uniform grid over the fat AABBs is rebuilt each step (small proxies are registered in the cell of
+// their lower corner; proxies larger than a cell go to a short list tested exhaustively).  For every moved
+// proxy all proxies whose fat AABB overlaps are found exactly, so the pair SET equals the tree's.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int CellCoord(float x, float invCell) { return (int)floorf(x * invCell); }
+__device__ __forceinline__ uint32_t CellHash(int ix, int iy, uint32_t mask)
+{
+	return (((uint32_t)ix * 0x9E3779B1u) ^ ((uint32_t)iy * 0x85EBCA77u)) & mask;
+}
+__device__ __forceinline__ bool IsLargeProxy(float4 fat, float cellSize)
+{
+	// strictly smaller than a cell, with margin for the rounding of the cell coordinates
+	float lim = cellSize * 0.984375f;
+	return !((fat.z - fat.x) <= lim && (fat.w - fat.y) <= lim);
+}
+
+__global__ void GridCountKernel(DeviceArrays d, int proxyCount, float cellSize, float invCell, uint32_t gridMask)
+{
+	B2CU_GRID_STRIDE(p, proxyCount)
+	{
+		float4 fat = d.fat[p];
+		bool moved = ((d.pgroup[p] >> 16) & B2CU_PROXY_MOVED) != 0;
+		if (IsLargeProxy(fat, cellSize))
+		{
+			d.cellOfProxy[p] = -1;
+			d.largeList[atomicAdd(&d.counters[CNT_LARGE], 1)] = p;
+			if (moved) d.largeMovedList[atomicAdd(&d.counters[CNT_LARGE_MOVED], 1)] = p;
+		}
+		else
+		{
+			uint32_t h = CellHash(CellCoord(fat.x, invCell), CellCoord(fat.y, invCell), gridMask);
+			d.cellOfProxy[p] = (int)h;
+			atomicAdd(&d.cellCount[h], 1);
+			if (moved) d.movedList[atomicAdd(&d.counters[CNT_MOVED], 1)] = p;
+		}
+	}
+}
+
+__global__ void GridFillKernel(DeviceArrays d, int proxyCount)
+{
+	B2CU_GRID_STRIDE(p, proxyCount)
+	{
+		int h = d.cellOfProxy[p];
+		if (h < 0) continue;
+		int slot = d.cellStart[h] + atomicAdd(&d.cellCount[h], 1);
+		d.cellItems[slot] = p;
+	}
+}
+
+// b2ContactManager::AddPair: same body, existing contact, b2Body::ShouldCollide, default b2ContactFilter,
+// and the contact-class table (no edge-edge contact, b2Contact.cpp:44-50)
+__device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, int contactCount, int pairCapacity)
+{
+	int a = q < p ? q : p, b = q < p ? p : q;
+	int bodyA = d.pbody[a], bodyB = d.pbody[b];
+	if (bodyA == bodyB) return;
+	uint64_t key = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
+	int idx = LowerBound64(d.c.key, contactCount, key);
+	if (idx < contactCount && d.c.key[idx] == key && !(d.cEvent[idx] & B2CU_EV_DESTROY)) return;
+	if (!IsDynamic(d.bflags[bodyA]) && !IsDynamic(d.bflags[bodyB])) return;
+	if (!DefaultFilter(d.pfilter[a], d.pgroup[a], d.pfilter[b], d.pgroup[b])) return;
+	if (d.shapes[d.pshape[a]].type == B2CU_SHAPE_EDGE && d.shapes[d.pshape[b]].type == B2CU_SHAPE_EDGE) return;
+	int slot = atomicAdd(&d.counters[CNT_NEW_PAIRS], 1);
+	if (slot < pairCapacity) d.newKeys[slot] = key;
+	else d.counters[CNT_ERROR] = 1;
+}
+
+__device__ __forceinline__ bool IsMovedProxy(const DeviceArrays& d, int p)
+{
+	return ((d.pgroup[p] >> 16) & B2CU_PROXY_MOVED) != 0;
+}
+
+// one thread per moved small proxy
+__global__ void __launch_bounds__(128) QuerySmallKernel(DeviceArrays d, float invCell, uint32_t gridMask,
+                                                        int contactCount, int pairCapacity)
+{
+	int n = d.counters[CNT_MOVED];
+	int nLarge = d.counters[CNT_LARGE];
+	B2CU_GRID_STRIDE(t, n)
+	{
+		int q = d.movedList[t];
+		float4 fq = d.fat[q];
+		int x0 = CellCoord(fq.x, invCell) - 1, x1 = CellCoord(fq.z, invCell);
+		int y0 = CellCoord(fq.y, invCell) - 1, y1 = CellCoord(fq.w, invCell);
+		for (int cy = y0; cy <= y1; ++cy)
+		{
+			for (int cx = x0; cx <= x1; ++cx)
+			{
+				uint32_t h = CellHash(cx, cy, gridMask);
+				int start = d.cellStart[h];
+				int end = start + d.cellCount[h];
+				for (int s = start; s < end; ++s)
+				{
+					int p = d.cellItems[s];
+					if (p == q) continue;
+					float4 fp = d.fat[p];
+					// a bucket can hold several cells: take p only when it is registered in THIS cell
+					if (CellCoord(fp.x, invCell) != cx || CellCoord(fp.y, invCell) != cy) continue;
+					if (!AabbOverlap(fq, fp)) continue;
+					// both moved: the pair is reported by the query of the smaller proxy id
+					if (IsMovedProxy(d, p) && p < q) continue;
+					TryAddPair(d, q, p, contactCount, pairCapacity);
+				}
+			}
+		}
+		for (int s = 0; s < nLarge; ++s)
+		{
+			int p = d.largeList[s];
+			if (!AabbOverlap(fq, d.fat[p])) continue;
+			if (IsMovedProxy(d, p) && p < q) continue;
+			TryAddPair(d, q, p, contactCount, pairCapacity);
+		}
+	}
+}
+
+// moved large proxies: every proxy tests itself against the (short) list of moved large proxies
+__global__ void QueryLargeKernel(DeviceArrays d, int proxyCount, int contactCount, int pairCapacity)
+{
+	int nLargeMoved = d.counters[CNT_LARGE_MOVED];
+	if (nLargeMoved == 0) return;
+	B2CU_GRID_STRIDE(p, proxyCount)
+	{
+		float4 fp = d.fat[p];
+		bool pMoved = IsMovedProxy(d, p);
+		for (int s = 0; s < nLargeMoved; ++s)
+		{
+			int q = d.largeMovedList[s];
+			if (q == p) continue;
+			if (!AabbOverlap(d.fat[q], fp)) continue;
+			if (pMoved && p < q) continue;
+			TryAddPair(d, q, p, contactCount, pairCapacity);
+		}
+	}
+}
+
+__global__ void ClearMovedKernel(DeviceArrays d, int proxyCount)
+{
+	B2CU_GRID_STRIDE(p, proxyCount) { d.pgroup[p] &= ~((uint32_t)B2CU_PROXY_MOVED << 16); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Contact set rebuild: drops contacts destroyed by Collide and merges the new (sorted) pairs, keeping the set
+// in key order.  Replaces FinishFindNewContacts / OnContactCreate / b2Contact::Create / Destroy bookkeeping
+// (b2ContactManager.cpp:120-172, 366-386, 507-564; b2Contact.cpp:72-157).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void KeepFlagsKernel(DeviceArrays d, int contactCount, int* keep)
+{
+	B2CU_GRID_STRIDE(i, contactCount) { keep[i] = (d.cEvent[i] & B2CU_EV_DESTROY) ? 0 : 1; }
+}
+
+__global__ void RebuildExistingKernel(DeviceArrays d, int contactCount, const int* __restrict__ keepRank, int newCount)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		if (d.cEvent[i] & B2CU_EV_DESTROY) continue;
+		uint64_t key = d.c.key[i];
+		int dest = keepRank[i] + LowerBound64(d.newKeys, newCount, key);
+		d.cAlt.key[dest] = key;
+		d.cAlt.proxies[dest] = d.c.proxies[i];
+		d.cAlt.flags[dest] = d.c.flags[i];
+		d.cAlt.m0[dest] = d.c.m0[i];
+		d.cAlt.m1[dest] = d.c.m1[i];
+		d.cAlt.m2[dest] = d.c.m2[i];
+		d.cAlt.m3[dest] = d.c.m3[i];
+		d.cAlt.mix[dest] = d.c.mix[i];
+		d.cAlt.toiCount[dest] = d.c.toiCount[i];
+		d.cAlt.colour[dest] = d.c.colour[i];
+	}
+}
+
+__global__ void RebuildNewKernel(DeviceArrays d, int contactCount, const int* __restrict__ keepRank, int newCount)
+{
+	B2CU_GRID_STRIDE(j, newCount)
+	{
+		uint64_t key = d.newKeys[j];
+		int lb = LowerBound64(d.c.key, contactCount, key);
+		int keptBefore = lb < contactCount ? keepRank[lb] : d.counters[CNT_KEEP];
+		int dest = j + keptBefore;
+
+		int a = (int)(key >> 32), b = (int)(key & 0xFFFFFFFFull);
+		int typeA = d.shapes[d.pshape[a]].type, typeB = d.shapes[d.pshape[b]].type;
+		int pA = a, pB = b;
+		if (NeedsSwap(typeA, typeB))
+		{
+			pA = b;
+			pB = a;
+		}
+		int bodyA = d.pbody[pA], bodyB = d.pbody[pB];
+		uint32_t fbA = d.bflags[bodyA], fbB = d.bflags[bodyB];
+		uint32_t flA = d.pgroup[pA] >> 16, flB = d.pgroup[pB] >> 16;
+		bool sensor = ((flA | flB) & B2CU_PROXY_SENSOR) != 0;
+
+		uint32_t flags = B2CU_CONTACT_ENABLED;
+		// b2Contact::IsToiCandidate, b2Contact.cpp:300-324
+		if (!sensor)
+		{
+			if ((fbA | fbB) & B2CU_BODY_BULLET)
+			{
+				flags |= B2CU_CONTACT_TOI_CANDIDATE;
+			}
+			else
+			{
+				bool includesNonDynamic = !IsDynamic(fbA) || !IsDynamic(fbB);
+				bool neitherThick = ((flA | flB) & B2CU_PROXY_THICK) == 0;
+				if (includesNonDynamic && neitherThick) flags |= B2CU_CONTACT_TOI_CANDIDATE;
+			}
+			// OnContactCreate wakes both bodies (b2ContactManager.cpp:524-529)
+			d.wake[bodyA] = 1;
+			d.wake[bodyB] = 1;
+		}
+
+		float2 matA = d.pmat[pA], matB = d.pmat[pB];
+		float friction = sqrtf(matA.x * matB.x);                  // b2MixFriction, b2Contact.h:40-43
+		float restitution = matA.y > matB.y ? matA.y : matB.y;      // b2MixRestitution, b2Contact.h:47-50
+
+		d.cAlt.key[dest] = key;
+		d.cAlt.proxies[dest] = make_int2(pA, pB);
+		d.cAlt.flags[dest] = flags;
+		d.cAlt.m0[dest] = make_float4(0.f, 0.f, 0.f, 0.f);
+		d.cAlt.m1[dest] = make_float4(0.f, 0.f, 0.f, 0.f);
+		d.cAlt.m2[dest] = make_float4(0.f, 0.f, 0.f, 0.f);
+		d.cAlt.m3[dest] = make_uint4(0u, 0u, 0u, 0u);
+		d.cAlt.mix[dest] = make_float4(friction, restitution, 0.0f, 1.0f);
+		d.cAlt.toiCount[dest] = 0;
+		d.cAlt.colour[dest] = B2CU_COLOUR_NONE;
+	}
+}
+
+// TOI eligibility (b2World.cpp:317-341 filters + b2Contact::IsMinToiCandidate, b2Contact.h:404-419)
+__global__ void ToiFlagsKernel(DeviceArrays d, int contactCount, int* flagsOut)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		uint32_t f = d.c.flags[i];
+		int ok = 0;
+		if ((f & B2CU_CONTACT_TOI_CANDIDATE) && (f & B2CU_CONTACT_ENABLED) && d.c.toiCount[i] <= B2CU_MAX_SUB_STEPS)
+		{
+			int2 pr = d.c.proxies[i];
+			uint32_t fA = d.bflags[d.pbody[pr.x]], fB = d.bflags[d.pbody[pr.y]];
+			if (IsAwakeNonStatic(fA) || IsAwakeNonStatic(fB)) ok = 1;
+		}
+		flagsOut[i] = ok;
+	}
+}
+
+// end of step: clear island flags (b2World::ClearPostSolve, b2World.cpp:1433-1465), clear forces
+// (b2World::ClearForces :1506-1523), count awake bodies
+__global__ void EndStepBodiesKernel(DeviceArrays d, int bodyCount, int clearForces)
+{
+	int local = 0;
+	B2CU_GRID_STRIDE(b, bodyCount)
+	{
+		uint32_t bf = d.bflags[b];
+		if (bf & B2CU_BODY_ISLAND) d.bflags[b] = bf & ~B2CU_BODY_ISLAND;
+		if (clearForces && !IsStatic(bf))
+		{
+			float4 f = d.force[b];
+			f.x = 0.0f;
+			f.y = 0.0f;
+			f.z = 0.0f;
+			d.force[b] = f;
+		}
+		if (IsAwakeNonStatic(bf)) ++local;
+	}
+	for (int dlt = 16; dlt > 0; dlt >>= 1) local += __shfl_down_sync(0xffffffffu, local, dlt);
+	if ((threadIdx.x & 31) == 0 && local) atomicAdd(&d.counters[CNT_AWAKE_BODIES], local);
+}
+
+// stand-alone batched narrow phase (b2cuCollidePairs)
+__global__ void CollidePairsKernel(const b2cuShape* __restrict__ shapes, int pairCount, const int* __restrict__ shapeA,
+                                   const float4* __restrict__ xfA, const int* __restrict__ shapeB,
+                                   const float4* __restrict__ xfB, b2cuManifold* __restrict__ out)
+{
+	B2CU_GRID_STRIDE(i, pairCount)
+	{
+		Manifold m;
+		m.localNormal = V(0.f, 0.f);
+		m.localPoint = V(0.f, 0.f);
+		m.lp[0] = m.lp[1] = V(0.f, 0.f);
+		m.ni[0] = m.ni[1] = m.ti[0] = m.ti[1] = 0.0f;
+		m.id[0] = m.id[1] = 0u;
+		m.type = 0;
+		m.pointCount = 0;
+		Evaluate(&m, shapes + shapeA[i], MakeXf(xfA[i]), shapes + shapeB[i], MakeXf(xfB[i]));
+		b2cuManifold o;
+		o.localNormal[0] = m.localNormal.x;
+		o.localNormal[1] = m.localNormal.y;
+		o.localPoint[0] = m.localPoint.x;
+		o.localPoint[1] = m.localPoint.y;
+		for (int k = 0; k < 2; ++k)
+		{
+			o.points[k].localPoint[0] = m.lp[k].x;
+			o.points[k].localPoint[1] = m.lp[k].y;
+			o.points[k].normalImpulse = 0.0f;
+			o.points[k].tangentImpulse = 0.0f;
+			o.id[k] = m.id[k];
+		}
+		o.type = m.type;
+		o.pointCount = m.pointCount;
+		out[i] = o;
+	}
+}
+
+__global__ void SinCosKernel(int n, const float* __restrict__ x, float* __restrict__ s, float* __restrict__ c)
+{
+	B2CU_GRID_STRIDE(i, n)
+	{
+		Rot q = SinCos(x[i]);
+		s[i] = q.s;
+		c[i] = q.c;
+	}
+}
+
+} // namespace b2cu

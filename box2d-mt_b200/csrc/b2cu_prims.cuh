@@ -1,0 +1,42 @@
+// b2cu_prims.cuh -- data-parallel primitives used by every phase: exclusive scan, stable stream compaction,
+// LSD radix sort of 64-bit keys.  They replace the reference's per-thread buffers + b2ThreadDataSorter
+// (Box2D/MT/b2ThreadDataSorter.h:262-380): every list the step produces (events, new pairs, constraints) is
+// emitted in a deterministic total order.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2cu
+{
+
+struct PrimScratch
+{
+	int* scanLevel1 = nullptr; // tile sums, capacity/1024 + 1
+	int* scanLevel2 = nullptr; // capacity/1M + 1
+	int* radixHist = nullptr;  // 256 * numBlocks
+	uint64_t* radixAlt = nullptr;
+	int* compactPos = nullptr; // capacity
+	int capacity = 0;
+	int radixBlocks = 0;
+};
+
+// number of kernels launched by the primitives since the last reset (for b2cuStepInfo.kernelLaunches)
+extern int g_primLaunches;
+
+cudaError_t PrimScratchAlloc(PrimScratch* s, int capacity);
+void PrimScratchFree(PrimScratch* s);
+
+// out[i] = sum(in[0..i)), in and out may alias; *total (device) = sum of all, if total != nullptr
+void ExclusiveScan(PrimScratch* s, const int* in, int* out, int n, int* total, cudaStream_t stream);
+
+// outIdx = ascending indices i with flags[i] != 0; *outCount (device) = how many
+void CompactFlags(PrimScratch* s, const int* flags, int n, int* outIdx, int* outCount, cudaStream_t stream);
+// same with a bit mask test: (flags[i] & mask) != 0
+void CompactMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int n, int* outIdx, int* outCount,
+                 cudaStream_t stream);
+
+// stable ascending sort on bits [beginBit, endBit) of the keys; result ends up in `keys`
+void RadixSort64(PrimScratch* s, uint64_t* keys, int n, int beginBit, int endBit, cudaStream_t stream);
+
+} // namespace b2cu

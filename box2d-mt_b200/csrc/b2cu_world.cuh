@@ -1,0 +1,170 @@
+// b2cu_world.cuh -- device-resident world state (struct-of-arrays) shared by the phase kernels.
+//
+// Layout follows SURVEY.md 7.2: everything a phase streams is a float4/uint4 array indexed by a dense id, so
+// that a warp's loads are 512-byte coalesced transactions; body arrays (16 B x N_b each) stay L2-resident
+// while constraint data streams from HBM.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2cuda.h"
+#include "b2cu_prims.cuh"
+
+namespace b2cu
+{
+
+#define B2CU_MAX_COLOURS 32
+#define B2CU_COLOUR_NONE (-1)
+#define B2CU_COLOUR_OVERFLOW B2CU_MAX_COLOURS
+
+// device-side counters, one int each (index into DeviceArrays::counters)
+enum Counter
+{
+	CNT_BEGIN = 0,        // begin-touch events
+	CNT_END,              // end-touch events from Update
+	CNT_DESTROY,          // contacts destroyed in Collide
+	CNT_DESTROY_END,      // of those, touching ones (EndContact from Destroy)
+	CNT_TOUCHING,         // touching contacts after Collide
+	CNT_CONSTRAINT,       // contacts handed to the solver
+	CNT_UNCOLOURED,       // constraints still without a colour (ping)
+	CNT_UNCOLOURED_NEXT,  // (pong)
+	CNT_OVERFLOW,         // constraints with no free colour
+	CNT_MOVED,            // proxies in the move buffer
+	CNT_LARGE,            // proxies too large for the grid
+	CNT_LARGE_MOVED,
+	CNT_NEW_PAIRS,        // new contacts found by the broad-phase
+	CNT_KEEP,             // contacts surviving Collide
+	CNT_ISLAND_BODIES,
+	CNT_AWAKE_BODIES,
+	CNT_TOI,
+	CNT_ERROR,            // != 0: a buffer overflowed
+	CNT_SCRATCH,
+	CNT_COUNT
+};
+
+struct ContactSet
+{
+	uint64_t* key;      // (min proxy << 32) | max proxy, ascending
+	int2* proxies;      // (fixture A side, fixture B side) after the primary-type swap
+	uint32_t* flags;    // B2CU_CONTACT_*
+	float4* m0;         // localNormal.xy, localPoint.xy
+	float4* m1;         // point0: localPoint.xy, normalImpulse, tangentImpulse
+	float4* m2;         // point1
+	uint4* m3;          // id0, id1, type, pointCount
+	float4* mix;        // friction, restitution, tangentSpeed, toi
+	int* toiCount;
+	int* colour;        // colour kept from the previous step (B2CU_COLOUR_NONE if it was not a constraint)
+};
+
+struct DeviceArrays
+{
+	// ---- bodies (index = dense body id, creation order) ----
+	float4* xf;      // p.x, p.y, sin, cos
+	float4* pos;     // c.x, c.y, a, -
+	float4* pos0;    // c0.x, c0.y, a0, alpha0
+	float4* vel;     // v.x, v.y, w, -
+	float4* mass;    // invMass, invI, localCenter.x, localCenter.y
+	float4* force;   // f.x, f.y, torque, sleepTime
+	float4* damp;    // linearDamping, angularDamping, gravityScale, -
+	uint32_t* bflags;
+	int* wake;            // wake request flags written by Collide / contact creation
+	int* island;          // union-find parent, then island label (root = smallest body id)
+	int* islandAwake;     // per root: any awake member
+	int* islandMinSleep;  // per root: min sleepTime (float bits, non-negative)
+	int* islandMinSep;    // [positionIterations][root]: min separation of the iteration (ordered-int float)
+	uint32_t* colourMask; // per body: colours used by its constraints
+	unsigned long long* colourClaim; // per body: (round << 32) | (~contact index), max wins
+
+	// ---- shape geometry table ----
+	b2cuShape* shapes;
+
+	// ---- proxies (index = dense proxy id, fixture creation order) ----
+	float4* fat;
+	float4* aabb;
+	int* pbody;
+	int* pshape;
+	uint32_t* pfilter;  // categoryBits | maskBits << 16
+	uint32_t* pgroup;   // (uint16)groupIndex | flags << 16
+	float2* pmat;       // friction, restitution
+	int* pfixture;      // caller's fixture id
+
+	// ---- contacts ----
+	ContactSet c;       // live set
+	ContactSet cAlt;    // rebuild target
+	int* cEvent;        // per contact: bit0 begin, bit1 end, bit2 destroyed, bit3 destroyed while touching
+	int* cSelect;       // per contact: 1 = solver constraint this step
+
+	// ---- per-step lists ----
+	int* listA;             // scratch index lists, contact capacity each
+	int* listB;
+	uint64_t* beginKeys;
+	uint64_t* endKeys;
+	uint64_t* newKeys;      // new pair keys (unsorted, then sorted)
+	uint64_t* orderKeys;    // colour << 32 | contact index, sorted = solver order
+	uint64_t* solverKeys;   // contact key of the k-th constraint of the solver order (for b2cuGetSolverOrder)
+	int* listC;
+	int* movedList;         // proxy capacity
+	int* largeList;
+	int* largeMovedList;
+	int* colourCount;       // [B2CU_MAX_COLOURS + 1]
+	uint64_t* toiKeys;
+
+	// ---- broad-phase grid ----
+	int* cellCount;   // hash table, size gridSize (+1)
+	int* cellStart;
+	int* cellItems;   // proxy capacity
+	int* cellOfProxy; // proxy capacity (hash bucket or -1 for large)
+
+	// ---- solver constraints (index = position in solver order) ----
+	int4* sBody;      // bodyA, bodyB, contact index, pointCount (after block-solver demotion) | original << 8
+	float4* sMass;    // mA, iA, mB, iB
+	float4* sNormal;  // normal.xy, friction, tangentSpeed
+	float4* sP0a;     // rA.xy, rB.xy
+	float4* sP0b;     // normalMass, tangentMass, velocityBias, -
+	float4* sP1a;
+	float4* sP1b;
+	float4* sImp;     // normalImpulse0, tangentImpulse0, normalImpulse1, tangentImpulse1
+	float4* sK;       // k11, k12, k22, -
+	float4* sNM;      // normalMass matrix: ex.x, ey.x, ex.y, ey.y
+	float4* sLocal;   // localNormal.xy, localPoint.xy
+	float4* sLocalP;  // localPoints[0].xy, localPoints[1].xy
+	float4* sCenters; // localCenterA.xy, localCenterB.xy
+	float4* sRadius;  // radiusA, radiusB, manifold type (int bits), island root of the constraint (int bits)
+
+	int* counters;    // CNT_COUNT ints
+};
+
+struct WorldParams
+{
+	float2 gravity;
+	uint32_t flags;
+	float invDt0;
+};
+
+} // namespace b2cu
+
+struct b2cuWorld
+{
+	int device;
+	cudaStream_t stream;
+	b2cu::WorldParams params;
+	b2cu::DeviceArrays d;
+	b2cu::PrimScratch prims;
+
+	int bodyCapacity, proxyCapacity, shapeCapacity, contactCapacity;
+	int bodyCount, proxyCount, shapeCount, contactCount;
+	int gridSize;        // hash table size (power of two)
+	float cellSize;
+	bool newProxies;     // e_newFixture: run FindNewContacts at the start of the next step
+	int positionIterationsCapacity;
+
+	// last step
+	int beginCount, endCount, constraintCount, colourCount, overflowCount, toiCount;
+	int colourCounts[B2CU_MAX_COLOURS + 1];
+
+	int* hostCounters;   // pinned, CNT_COUNT + colour counts
+	cudaEvent_t ev[10];
+	int launches;
+	char lastError[512];
+};

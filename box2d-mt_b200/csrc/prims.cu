@@ -1,0 +1,308 @@
+// prims.cu -- exclusive scan, stable compaction, LSD radix sort (see b2cu_prims.cuh).
+#include "b2cu_prims.cuh"
+
+namespace b2cu
+{
+
+int g_primLaunches = 0;
+
+static const int SCAN_BLOCK = 256;
+static const int SCAN_ITEMS = 4;
+static const int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+static const int RADIX_BLOCK = 256;
+static const int RADIX_ITEMS = 8;
+static const int RADIX_TILE = RADIX_BLOCK * RADIX_ITEMS;
+
+struct IntLoader
+{
+	const int* p;
+	__device__ __forceinline__ int operator()(int i) const { return p[i]; }
+};
+struct NonZeroLoader
+{
+	const int* p;
+	__device__ __forceinline__ int operator()(int i) const { return p[i] != 0 ? 1 : 0; }
+};
+struct MaskLoader
+{
+	const uint32_t* p;
+	uint32_t mask;
+	__device__ __forceinline__ int operator()(int i) const { return (p[i] & mask) != 0 ? 1 : 0; }
+};
+
+template <typename Loader>
+__global__ void __launch_bounds__(SCAN_BLOCK) ScanTilesKernel(Loader load, int* __restrict__ out,
+                                                              int* __restrict__ tileSums, int n, int* total)
+{
+	__shared__ int warpSums[SCAN_BLOCK / 32];
+	const int tile = blockIdx.x;
+	const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+
+	int v[SCAN_ITEMS];
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k)
+	{
+		v[k] = (base + k < n) ? load(base + k) : 0;
+	}
+	int tsum = 0;
+	int pre[SCAN_ITEMS];
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k)
+	{
+		pre[k] = tsum;
+		tsum += v[k];
+	}
+
+	int inc = tsum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		int t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d) inc += t;
+	}
+	if (lane == 31) warpSums[warp] = inc;
+	__syncthreads();
+	if (warp == 0)
+	{
+		int w = lane < SCAN_BLOCK / 32 ? warpSums[lane] : 0;
+		int winc = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			int t = __shfl_up_sync(0xffffffffu, winc, d);
+			if (lane >= d) winc += t;
+		}
+		if (lane < SCAN_BLOCK / 32) warpSums[lane] = winc - w; // exclusive warp offsets
+		if (lane == SCAN_BLOCK / 32 - 1)
+		{
+			if (tileSums) tileSums[tile] = winc;
+			if (total && gridDim.x == 1) *total = winc;
+		}
+	}
+	__syncthreads();
+	const int threadOffset = (inc - tsum) + warpSums[warp];
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k)
+	{
+		if (base + k < n) out[base + k] = threadOffset + pre[k];
+	}
+}
+
+__global__ void AddTileOffsetsKernel(int* __restrict__ out, const int* __restrict__ tileOffsets, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+	{
+		out[i] += tileOffsets[i / SCAN_TILE];
+	}
+}
+
+__global__ void SetIntKernel(int* p, int v) { *p = v; }
+
+cudaError_t PrimScratchAlloc(PrimScratch* s, int capacity)
+{
+	PrimScratchFree(s);
+	if (capacity < 1024) capacity = 1024;
+	s->capacity = capacity;
+	s->radixBlocks = (capacity + RADIX_TILE - 1) / RADIX_TILE;
+	int histSize = 256 * s->radixBlocks;
+	int scanCap = capacity > histSize ? capacity : histSize;
+	cudaError_t e;
+	if ((e = cudaMalloc(&s->scanLevel1, sizeof(int) * (scanCap / SCAN_TILE + 2))) != cudaSuccess) return e;
+	if ((e = cudaMalloc(&s->scanLevel2, sizeof(int) * (scanCap / SCAN_TILE / SCAN_TILE + 2))) != cudaSuccess) return e;
+	if ((e = cudaMalloc(&s->radixHist, sizeof(int) * histSize)) != cudaSuccess) return e;
+	if ((e = cudaMalloc(&s->radixAlt, sizeof(uint64_t) * capacity)) != cudaSuccess) return e;
+	if ((e = cudaMalloc(&s->compactPos, sizeof(int) * capacity)) != cudaSuccess) return e;
+	return cudaSuccess;
+}
+
+void PrimScratchFree(PrimScratch* s)
+{
+	cudaFree(s->scanLevel1);
+	cudaFree(s->scanLevel2);
+	cudaFree(s->radixHist);
+	cudaFree(s->radixAlt);
+	cudaFree(s->compactPos);
+	*s = PrimScratch();
+}
+
+template <typename Loader>
+static void ScanImpl(PrimScratch* s, Loader load, int* out, int n, int* total, cudaStream_t stream)
+{
+	if (n <= 0)
+	{
+		if (total)
+		{
+			SetIntKernel<<<1, 1, 0, stream>>>(total, 0);
+			++g_primLaunches;
+		}
+		return;
+	}
+	int tiles1 = (n + SCAN_TILE - 1) / SCAN_TILE;
+	ScanTilesKernel<<<tiles1, SCAN_BLOCK, 0, stream>>>(load, out, s->scanLevel1, n, total);
+	++g_primLaunches;
+	if (tiles1 > 1)
+	{
+		int tiles2 = (tiles1 + SCAN_TILE - 1) / SCAN_TILE;
+		IntLoader l1{s->scanLevel1};
+		ScanTilesKernel<<<tiles2, SCAN_BLOCK, 0, stream>>>(l1, s->scanLevel1, s->scanLevel2, tiles1, total);
+		++g_primLaunches;
+		if (tiles2 > 1)
+		{
+			// third level: tiles2 <= 1024 for n < 2^30
+			IntLoader l2{s->scanLevel2};
+			ScanTilesKernel<<<1, SCAN_BLOCK, 0, stream>>>(l2, s->scanLevel2, (int*)nullptr, tiles2, total);
+			AddTileOffsetsKernel<<<(tiles1 + 255) / 256, 256, 0, stream>>>(s->scanLevel1, s->scanLevel2, tiles1);
+			g_primLaunches += 2;
+		}
+		AddTileOffsetsKernel<<<(n + 255) / 256, 256, 0, stream>>>(out, s->scanLevel1, n);
+		++g_primLaunches;
+	}
+}
+
+void ExclusiveScan(PrimScratch* s, const int* in, int* out, int n, int* total, cudaStream_t stream)
+{
+	IntLoader l{in};
+	ScanImpl(s, l, out, n, total, stream);
+}
+
+template <typename Loader>
+__global__ void CompactScatterKernel(Loader load, const int* __restrict__ pos, int n, int* __restrict__ outIdx)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && load(i))
+	{
+		outIdx[pos[i]] = i;
+	}
+}
+
+void CompactFlags(PrimScratch* s, const int* flags, int n, int* outIdx, int* outCount, cudaStream_t stream)
+{
+	NonZeroLoader l{flags};
+	ScanImpl(s, l, s->compactPos, n, outCount, stream);
+	if (n > 0)
+	{
+		CompactScatterKernel<<<(n + 255) / 256, 256, 0, stream>>>(l, s->compactPos, n, outIdx);
+		++g_primLaunches;
+	}
+}
+
+void CompactMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int n, int* outIdx, int* outCount,
+                 cudaStream_t stream)
+{
+	MaskLoader l{flags, mask};
+	ScanImpl(s, l, s->compactPos, n, outCount, stream);
+	if (n > 0)
+	{
+		CompactScatterKernel<<<(n + 255) / 256, 256, 0, stream>>>(l, s->compactPos, n, outIdx);
+		++g_primLaunches;
+	}
+}
+
+// ---- radix sort -----------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(RADIX_BLOCK) RadixHistogramKernel(const uint64_t* __restrict__ keys, int n, int shift,
+                                                                    int* __restrict__ hist, int numBlocks)
+{
+	__shared__ int sh[256];
+	sh[threadIdx.x] = 0;
+	__syncthreads();
+	const int base = blockIdx.x * RADIX_TILE;
+#pragma unroll
+	for (int r = 0; r < RADIX_ITEMS; ++r)
+	{
+		int i = base + r * RADIX_BLOCK + threadIdx.x;
+		if (i < n)
+		{
+			int d = (int)((keys[i] >> shift) & 0xFFull);
+			atomicAdd(&sh[d], 1);
+		}
+	}
+	__syncthreads();
+	hist[threadIdx.x * numBlocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RADIX_BLOCK) RadixScatterKernel(const uint64_t* __restrict__ keys,
+                                                                  uint64_t* __restrict__ out, int n, int shift,
+                                                                  const int* __restrict__ offsets, int numBlocks)
+{
+	__shared__ int warpCount[RADIX_BLOCK / 32][256];
+	__shared__ int running[256];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const unsigned ltMask = (1u << lane) - 1u;
+
+	running[threadIdx.x] = offsets[threadIdx.x * numBlocks + blockIdx.x];
+	const int base = blockIdx.x * RADIX_TILE;
+
+	for (int r = 0; r < RADIX_ITEMS; ++r)
+	{
+		for (int w = 0; w < RADIX_BLOCK / 32; ++w)
+		{
+			warpCount[w][threadIdx.x] = 0;
+		}
+		__syncthreads();
+
+		int i = base + r * RADIX_BLOCK + threadIdx.x;
+		bool valid = i < n;
+		uint64_t key = valid ? keys[i] : 0ull;
+		unsigned d = valid ? (unsigned)((key >> shift) & 0xFFull) : 0xFFFFFFFFu;
+		unsigned peers = __match_any_sync(0xffffffffu, d);
+		int rankInWarp = __popc(peers & ltMask);
+		if (valid && rankInWarp == 0)
+		{
+			warpCount[warp][d] = __popc(peers);
+		}
+		__syncthreads();
+
+		if (valid)
+		{
+			int pos = running[d] + rankInWarp;
+			for (int w = 0; w < warp; ++w)
+			{
+				pos += warpCount[w][d];
+			}
+			out[pos] = key;
+		}
+		__syncthreads();
+
+		int add = 0;
+		for (int w = 0; w < RADIX_BLOCK / 32; ++w)
+		{
+			add += warpCount[w][threadIdx.x];
+		}
+		running[threadIdx.x] += add;
+		__syncthreads();
+	}
+}
+
+void RadixSort64(PrimScratch* s, uint64_t* keys, int n, int beginBit, int endBit, cudaStream_t stream)
+{
+	if (n <= 1)
+	{
+		return;
+	}
+	int numBlocks = (n + RADIX_TILE - 1) / RADIX_TILE;
+	uint64_t* src = keys;
+	uint64_t* dst = s->radixAlt;
+	for (int shift = beginBit; shift < endBit; shift += 8)
+	{
+		RadixHistogramKernel<<<numBlocks, RADIX_BLOCK, 0, stream>>>(src, n, shift, s->radixHist, numBlocks);
+		++g_primLaunches;
+		ExclusiveScan(s, s->radixHist, s->radixHist, 256 * numBlocks, nullptr, stream);
+		RadixScatterKernel<<<numBlocks, RADIX_BLOCK, 0, stream>>>(src, dst, n, shift, s->radixHist, numBlocks);
+		++g_primLaunches;
+		uint64_t* t = src;
+		src = dst;
+		dst = t;
+	}
+	if (src != keys)
+	{
+		cudaMemcpyAsync(keys, src, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, stream);
+	}
+}
+
+} // namespace b2cu

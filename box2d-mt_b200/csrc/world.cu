@@ -1,0 +1,1150 @@
+// world.cu -- C ABI of libb2cuda.so (include/b2cuda.h) and the step driver.
+//
+// b2cuStep replaces b2World::Step (Box2D/Dynamics/b2World.cpp:1613-1710) and keeps its phase order:
+//   [FindNewContacts if new fixtures] -> Collide -> Solve (islands, solver, SynchronizeFixtures,
+//   FindNewContacts) -> TOI candidate compaction -> ClearForces.
+#include "b2cu_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+using namespace b2cu;
+
+namespace
+{
+
+const int kBlock = 256;
+int g_smCount = 148;
+
+inline int GridFor(int n, int block = kBlock)
+{
+	int blocks = (n + block - 1) / block;
+	int cap = g_smCount * 8;
+	if (blocks > cap) blocks = cap;
+	if (blocks < 1) blocks = 1;
+	return blocks;
+}
+
+int SetError(b2cuWorld* w, int code, const char* fmt, ...)
+{
+	if (w)
+	{
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(w->lastError, sizeof(w->lastError), fmt, ap);
+		va_end(ap);
+	}
+	return code;
+}
+
+#define CUDA_TRY(w, expr)                                                                                   \
+	do                                                                                                      \
+	{                                                                                                       \
+		cudaError_t _e = (expr);                                                                            \
+		if (_e != cudaSuccess)                                                                              \
+			return SetError(w, B2CU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+			                __LINE__);                                                                      \
+	} while (0)
+
+#define LAUNCH(w, kernel, grid, block, ...)                 \
+	do                                                      \
+	{                                                       \
+		kernel<<<grid, block, 0, (w)->stream>>>(__VA_ARGS__); \
+		++(w)->launches;                                    \
+	} while (0)
+
+enum CapKind
+{
+	CAP_BODY,
+	CAP_PROXY,
+	CAP_SHAPE,
+	CAP_CONTACT,
+	CAP_GRID,
+	CAP_FIXED
+};
+
+struct ArrayDesc
+{
+	void** ptr;
+	size_t elemSize;
+	CapKind kind;
+	size_t fixedCount;
+};
+
+template <typename T>
+ArrayDesc Desc(T** p, CapKind kind, size_t fixedCount = 0)
+{
+	ArrayDesc a;
+	a.ptr = reinterpret_cast<void**>(p);
+	a.elemSize = sizeof(T);
+	a.kind = kind;
+	a.fixedCount = fixedCount;
+	return a;
+}
+
+void ContactSetDescs(ContactSet* c, std::vector<ArrayDesc>& v)
+{
+	v.push_back(Desc(&c->key, CAP_CONTACT));
+	v.push_back(Desc(&c->proxies, CAP_CONTACT));
+	v.push_back(Desc(&c->flags, CAP_CONTACT));
+	v.push_back(Desc(&c->m0, CAP_CONTACT));
+	v.push_back(Desc(&c->m1, CAP_CONTACT));
+	v.push_back(Desc(&c->m2, CAP_CONTACT));
+	v.push_back(Desc(&c->m3, CAP_CONTACT));
+	v.push_back(Desc(&c->mix, CAP_CONTACT));
+	v.push_back(Desc(&c->toiCount, CAP_CONTACT));
+	v.push_back(Desc(&c->colour, CAP_CONTACT));
+}
+
+std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
+{
+	DeviceArrays* d = &w->d;
+	std::vector<ArrayDesc> v;
+	v.push_back(Desc(&d->xf, CAP_BODY));
+	v.push_back(Desc(&d->pos, CAP_BODY));
+	v.push_back(Desc(&d->pos0, CAP_BODY));
+	v.push_back(Desc(&d->vel, CAP_BODY));
+	v.push_back(Desc(&d->mass, CAP_BODY));
+	v.push_back(Desc(&d->force, CAP_BODY));
+	v.push_back(Desc(&d->damp, CAP_BODY));
+	v.push_back(Desc(&d->bflags, CAP_BODY));
+	v.push_back(Desc(&d->wake, CAP_BODY));
+	v.push_back(Desc(&d->island, CAP_BODY));
+	v.push_back(Desc(&d->islandAwake, CAP_BODY));
+	v.push_back(Desc(&d->islandMinSleep, CAP_BODY));
+	v.push_back(Desc(&d->colourMask, CAP_BODY));
+	v.push_back(Desc(&d->colourClaim, CAP_BODY));
+	v.push_back(Desc(&d->shapes, CAP_SHAPE));
+	v.push_back(Desc(&d->fat, CAP_PROXY));
+	v.push_back(Desc(&d->aabb, CAP_PROXY));
+	v.push_back(Desc(&d->pbody, CAP_PROXY));
+	v.push_back(Desc(&d->pshape, CAP_PROXY));
+	v.push_back(Desc(&d->pfilter, CAP_PROXY));
+	v.push_back(Desc(&d->pgroup, CAP_PROXY));
+	v.push_back(Desc(&d->pmat, CAP_PROXY));
+	v.push_back(Desc(&d->pfixture, CAP_PROXY));
+	ContactSetDescs(&d->c, v);
+	ContactSetDescs(&d->cAlt, v);
+	v.push_back(Desc(&d->cEvent, CAP_CONTACT));
+	v.push_back(Desc(&d->cSelect, CAP_CONTACT));
+	v.push_back(Desc(&d->listA, CAP_CONTACT));
+	v.push_back(Desc(&d->listB, CAP_CONTACT));
+	v.push_back(Desc(&d->beginKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->endKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->newKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->orderKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->solverKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->listC, CAP_CONTACT));
+	v.push_back(Desc(&d->toiKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->movedList, CAP_PROXY));
+	v.push_back(Desc(&d->largeList, CAP_PROXY));
+	v.push_back(Desc(&d->largeMovedList, CAP_PROXY));
+	v.push_back(Desc(&d->colourCount, CAP_FIXED, B2CU_MAX_COLOURS + 2));
+	v.push_back(Desc(&d->cellCount, CAP_GRID));
+	v.push_back(Desc(&d->cellStart, CAP_GRID));
+	v.push_back(Desc(&d->cellItems, CAP_PROXY));
+	v.push_back(Desc(&d->cellOfProxy, CAP_PROXY));
+	v.push_back(Desc(&d->sBody, CAP_CONTACT));
+	v.push_back(Desc(&d->sMass, CAP_CONTACT));
+	v.push_back(Desc(&d->sNormal, CAP_CONTACT));
+	v.push_back(Desc(&d->sP0a, CAP_CONTACT));
+	v.push_back(Desc(&d->sP0b, CAP_CONTACT));
+	v.push_back(Desc(&d->sP1a, CAP_CONTACT));
+	v.push_back(Desc(&d->sP1b, CAP_CONTACT));
+	v.push_back(Desc(&d->sImp, CAP_CONTACT));
+	v.push_back(Desc(&d->sK, CAP_CONTACT));
+	v.push_back(Desc(&d->sNM, CAP_CONTACT));
+	v.push_back(Desc(&d->sLocal, CAP_CONTACT));
+	v.push_back(Desc(&d->sLocalP, CAP_CONTACT));
+	v.push_back(Desc(&d->sCenters, CAP_CONTACT));
+	v.push_back(Desc(&d->sRadius, CAP_CONTACT));
+	v.push_back(Desc(&d->counters, CAP_FIXED, CNT_COUNT));
+	return v;
+}
+
+size_t CapOf(const b2cuWorld* w, const ArrayDesc& a)
+{
+	switch (a.kind)
+	{
+	case CAP_BODY: return (size_t)w->bodyCapacity;
+	case CAP_PROXY: return (size_t)w->proxyCapacity;
+	case CAP_SHAPE: return (size_t)w->shapeCapacity;
+	case CAP_CONTACT: return (size_t)w->contactCapacity;
+	case CAP_GRID: return (size_t)w->gridSize + 1;
+	default: return a.fixedCount;
+	}
+}
+
+int NextPow2(int x)
+{
+	int p = 1;
+	while (p < x) p <<= 1;
+	return p;
+}
+
+// (Re)allocate every array of the given kind for new capacities, preserving contents.
+int Reserve(b2cuWorld* w, int bodyCap, int proxyCap, int shapeCap, int contactCap)
+{
+	b2cuWorld old = *w;
+	bool first = w->d.counters == nullptr;
+	w->bodyCapacity = std::max(bodyCap, w->bodyCapacity);
+	w->proxyCapacity = std::max(proxyCap, w->proxyCapacity);
+	w->shapeCapacity = std::max(shapeCap, w->shapeCapacity);
+	w->contactCapacity = std::max(contactCap, w->contactCapacity);
+	w->gridSize = NextPow2(std::max(1024, 2 * w->proxyCapacity));
+
+	std::vector<ArrayDesc> arrays = AllArrays(w);
+	for (size_t k = 0; k < arrays.size(); ++k)
+	{
+		ArrayDesc& a = arrays[k];
+		size_t newCap = CapOf(w, a);
+		size_t oldCap = first ? 0 : CapOf(&old, a);
+		if (!first && newCap == oldCap) continue;
+		void* fresh = nullptr;
+		CUDA_TRY(w, cudaMalloc(&fresh, newCap * a.elemSize));
+		CUDA_TRY(w, cudaMemsetAsync(fresh, 0, newCap * a.elemSize, w->stream));
+		if (!first && *a.ptr && oldCap > 0)
+		{
+			CUDA_TRY(w, cudaMemcpyAsync(fresh, *a.ptr, std::min(oldCap, newCap) * a.elemSize, cudaMemcpyDeviceToDevice,
+			                            w->stream));
+			CUDA_TRY(w, cudaStreamSynchronize(w->stream));
+			cudaFree(*a.ptr);
+		}
+		*a.ptr = fresh;
+	}
+
+	// islandMinSep: [positionIterationsCapacity][bodyCapacity]
+	if (first || old.bodyCapacity != w->bodyCapacity)
+	{
+		cudaFree(w->d.islandMinSep);
+		CUDA_TRY(w, cudaMalloc(&w->d.islandMinSep,
+		                       sizeof(int) * (size_t)w->positionIterationsCapacity * (size_t)w->bodyCapacity));
+	}
+	int primCap = std::max(std::max(w->contactCapacity, w->gridSize + 1), std::max(w->bodyCapacity, w->proxyCapacity));
+	if (first || primCap > w->prims.capacity)
+	{
+		CUDA_TRY(w, PrimScratchAlloc(&w->prims, primCap));
+	}
+	return B2CU_OK;
+}
+
+int SyncCheck(b2cuWorld* w)
+{
+	CUDA_TRY(w, cudaStreamSynchronize(w->stream));
+	CUDA_TRY(w, cudaGetLastError());
+	return B2CU_OK;
+}
+
+// read all device counters (+ colour starts) into pinned host memory
+int ReadCounters(b2cuWorld* w)
+{
+	CUDA_TRY(w, cudaMemcpyAsync(w->hostCounters, w->d.counters, sizeof(int) * CNT_COUNT, cudaMemcpyDeviceToHost,
+	                            w->stream));
+	CUDA_TRY(w, cudaMemcpyAsync(w->hostCounters + CNT_COUNT, w->d.colourCount, sizeof(int) * (B2CU_MAX_COLOURS + 2),
+	                            cudaMemcpyDeviceToHost, w->stream));
+	return SyncCheck(w);
+}
+
+int ZeroCounter(b2cuWorld* w, int index)
+{
+	CUDA_TRY(w, cudaMemsetAsync(w->d.counters + index, 0, sizeof(int), w->stream));
+	return B2CU_OK;
+}
+
+float ChooseCellSize(const std::vector<float>& extents)
+{
+	if (extents.empty()) return 1.0f;
+	std::vector<float> e(extents);
+	size_t mid = e.size() / 2;
+	std::nth_element(e.begin(), e.begin() + mid, e.end());
+	float m = e[mid];
+	if (!(m > 1e-3f)) m = 1e-3f;
+	return 2.0f * m;
+}
+
+// ---- broad-phase pair finding + contact set rebuild ------------------------------------------------------
+
+// Finds new pairs for the proxies flagged MOVED, then rebuilds the contact set (drop destroyed, merge new).
+int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut, int* movedOut)
+{
+	DeviceArrays& d = w->d;
+	const int np = w->proxyCount;
+	const int nc = w->contactCount;
+	int rc;
+
+	if ((rc = ZeroCounter(w, CNT_MOVED))) return rc;
+	if ((rc = ZeroCounter(w, CNT_LARGE))) return rc;
+	if ((rc = ZeroCounter(w, CNT_LARGE_MOVED))) return rc;
+	if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
+	if ((rc = ZeroCounter(w, CNT_KEEP))) return rc;
+
+	if (np > 0)
+	{
+		const float cell = w->cellSize;
+		const float invCell = 1.0f / cell;
+		const uint32_t mask = (uint32_t)w->gridSize - 1u;
+		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
+		LAUNCH(w, GridCountKernel, GridFor(np), kBlock, d, np, cell, invCell, mask);
+		ExclusiveScan(&w->prims, d.cellCount, d.cellStart, w->gridSize, nullptr, w->stream);
+		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
+		LAUNCH(w, GridFillKernel, GridFor(np), kBlock, d, np);
+		LAUNCH(w, QuerySmallKernel, GridFor(np, 128), 128, d, invCell, mask, nc, w->contactCapacity);
+		LAUNCH(w, QueryLargeKernel, GridFor(np), kBlock, d, np, nc, w->contactCapacity);
+		LAUNCH(w, ClearMovedKernel, GridFor(np), kBlock, d, np);
+	}
+
+	// destroyed contacts -> keep flags and ranks
+	if (nc > 0)
+	{
+		LAUNCH(w, KeepFlagsKernel, GridFor(nc), kBlock, d, nc, d.cSelect);
+		ExclusiveScan(&w->prims, d.cSelect, d.listA, nc, d.counters + CNT_KEEP, w->stream);
+	}
+
+	if ((rc = ReadCounters(w))) return rc;
+	if (w->hostCounters[CNT_ERROR])
+	{
+		return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
+	}
+	const int newCount = w->hostCounters[CNT_NEW_PAIRS];
+	const int keepCount = nc > 0 ? w->hostCounters[CNT_KEEP] : 0;
+	const int moved = w->hostCounters[CNT_MOVED] + w->hostCounters[CNT_LARGE_MOVED];
+	*newCountOut = newCount;
+	*destroyedOut = nc - keepCount;
+	*movedOut = moved;
+
+	if (newCount == 0 && keepCount == nc)
+	{
+		return B2CU_OK; // contact set unchanged
+	}
+	if (keepCount + newCount > w->contactCapacity)
+	{
+		return SetError(w, B2CU_ERR_CAPACITY, "contact capacity %d exceeded (%d needed)", w->contactCapacity,
+		                keepCount + newCount);
+	}
+
+	if (newCount > 1)
+	{
+		int bits = 1;
+		while ((1 << bits) < std::max(2, np)) ++bits;
+		RadixSort64(&w->prims, d.newKeys, newCount, 0, bits, w->stream);
+		RadixSort64(&w->prims, d.newKeys, newCount, 32, 32 + bits, w->stream);
+	}
+	if (nc > 0)
+	{
+		LAUNCH(w, RebuildExistingKernel, GridFor(nc), kBlock, d, nc, d.listA, newCount);
+	}
+	if (newCount > 0)
+	{
+		LAUNCH(w, RebuildNewKernel, GridFor(newCount), kBlock, d, nc, d.listA, newCount);
+		LAUNCH(w, ApplyWakeKernel, GridFor(w->bodyCount), kBlock, d, w->bodyCount);
+	}
+	std::swap(d.c, d.cAlt);
+	w->contactCount = keepCount + newCount;
+	CUDA_TRY(w, cudaMemsetAsync(d.cEvent, 0, sizeof(int) * (size_t)w->contactCapacity, w->stream));
+	return B2CU_OK;
+}
+
+int CheckRange(b2cuWorld* w, int first, int count, int limit, const void* p)
+{
+	if (!w || !p || first < 0 || count < 0 || first + count > limit)
+		return SetError(w, B2CU_ERR_ARGUMENT, "range [%d,%d) outside [0,%d)", first, first + count, limit);
+	return B2CU_OK;
+}
+
+template <typename T>
+int Upload(b2cuWorld* w, T* dst, int first, const std::vector<T>& src)
+{
+	if (src.empty()) return B2CU_OK;
+	CUDA_TRY(w, cudaMemcpyAsync(dst + first, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, w->stream));
+	return B2CU_OK;
+}
+
+template <typename T>
+int Download(b2cuWorld* w, const T* src, int first, std::vector<T>& dst)
+{
+	if (dst.empty()) return B2CU_OK;
+	CUDA_TRY(w, cudaMemcpyAsync(dst.data(), src + first, sizeof(T) * dst.size(), cudaMemcpyDeviceToHost, w->stream));
+	return B2CU_OK;
+}
+
+} // namespace
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+
+extern "C" {
+
+int b2cuGetDeviceCount(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+const char* b2cuVersion(void) { return "b2cuda 0.1 (sm_100a)"; }
+
+int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
+{
+	if (!def || !out) return B2CU_ERR_ARGUMENT;
+	*out = nullptr;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return B2CU_ERR_NO_DEVICE;
+	if (def->device < 0 || def->device >= n) return B2CU_ERR_ARGUMENT;
+	if (cudaSetDevice(def->device) != cudaSuccess) return B2CU_ERR_CUDA;
+
+	b2cuWorld* w = new b2cuWorld();
+	memset(w, 0, sizeof(*w));
+	new (&w->prims) PrimScratch();
+	w->device = def->device;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, def->device) == cudaSuccess) g_smCount = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess)
+	{
+		delete w;
+		return B2CU_ERR_CUDA;
+	}
+	for (int i = 0; i < 10; ++i) cudaEventCreate(&w->ev[i]);
+	cudaMallocHost(&w->hostCounters, sizeof(int) * (CNT_COUNT + B2CU_MAX_COLOURS + 2));
+	w->params.gravity = make_float2(def->gravity[0], def->gravity[1]);
+	w->params.flags = def->flags;
+	w->params.invDt0 = 0.0f;
+	w->positionIterationsCapacity = 4;
+	w->cellSize = 1.0f;
+	int rc = Reserve(w, std::max(def->bodyCapacity, 64), std::max(def->proxyCapacity, 64),
+	                 std::max(def->shapeCapacity, 16), std::max(def->contactCapacity, 256));
+	if (rc != B2CU_OK)
+	{
+		fprintf(stderr, "b2cuCreateWorld: %s\n", w->lastError);
+		b2cuDestroyWorld(w);
+		return rc;
+	}
+	*out = w;
+	return B2CU_OK;
+}
+
+void b2cuDestroyWorld(b2cuWorld* w)
+{
+	if (!w) return;
+	cudaSetDevice(w->device);
+	cudaStreamSynchronize(w->stream);
+	std::vector<ArrayDesc> arrays = AllArrays(w);
+	for (size_t k = 0; k < arrays.size(); ++k) cudaFree(*arrays[k].ptr);
+	cudaFree(w->d.islandMinSep);
+	PrimScratchFree(&w->prims);
+	cudaFreeHost(w->hostCounters);
+	for (int i = 0; i < 10; ++i) cudaEventDestroy(w->ev[i]);
+	cudaStreamDestroy(w->stream);
+	delete w;
+}
+
+const char* b2cuGetLastError(const b2cuWorld* w) { return w ? w->lastError : "null world"; }
+
+int b2cuSetWorldParams(b2cuWorld* w, const float gravity[2], uint32_t flags)
+{
+	if (!w || !gravity) return B2CU_ERR_ARGUMENT;
+	w->params.gravity = make_float2(gravity[0], gravity[1]);
+	w->params.flags = flags;
+	return B2CU_OK;
+}
+
+int b2cuSetInvDt0(b2cuWorld* w, float invDt0)
+{
+	if (!w) return B2CU_ERR_ARGUMENT;
+	w->params.invDt0 = invDt0;
+	return B2CU_OK;
+}
+
+int b2cuSetCounts(b2cuWorld* w, int32_t bodyCount, int32_t shapeCount, int32_t proxyCount)
+{
+	if (!w || bodyCount < 0 || shapeCount < 0 || proxyCount < 0) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	if (bodyCount > w->bodyCapacity || shapeCount > w->shapeCapacity || proxyCount > w->proxyCapacity)
+	{
+		int bc = bodyCount > w->bodyCapacity ? std::max(bodyCount, 2 * w->bodyCapacity) : w->bodyCapacity;
+		int sc = shapeCount > w->shapeCapacity ? std::max(shapeCount, 2 * w->shapeCapacity) : w->shapeCapacity;
+		int pc = proxyCount > w->proxyCapacity ? std::max(proxyCount, 2 * w->proxyCapacity) : w->proxyCapacity;
+		int cc = std::max(w->contactCapacity, 8 * pc);
+		int rc = Reserve(w, bc, pc, sc, cc);
+		if (rc) return rc;
+	}
+	w->bodyCount = bodyCount;
+	w->shapeCount = shapeCount;
+	w->proxyCount = proxyCount;
+	return B2CU_OK;
+}
+
+int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bodies)
+{
+	int rc = CheckRange(w, first, count, w ? w->bodyCount : 0, bodies);
+	if (rc) return rc;
+	cudaSetDevice(w->device);
+	std::vector<float4> xf(count), pos(count), pos0(count), vel(count), mass(count), force(count), damp(count);
+	std::vector<uint32_t> flags(count);
+	for (int i = 0; i < count; ++i)
+	{
+		const b2cuBody& b = bodies[i];
+		xf[i] = make_float4(b.px, b.py, b.qs, b.qc);
+		pos[i] = make_float4(b.cx, b.cy, b.a, 0.0f);
+		pos0[i] = make_float4(b.c0x, b.c0y, b.a0, b.alpha0);
+		vel[i] = make_float4(b.vx, b.vy, b.w, 0.0f);
+		mass[i] = make_float4(b.invMass, b.invI, b.lcx, b.lcy);
+		force[i] = make_float4(b.fx, b.fy, b.torque, b.sleepTime);
+		damp[i] = make_float4(b.linearDamping, b.angularDamping, b.gravityScale, 0.0f);
+		flags[i] = b.flags;
+	}
+	DeviceArrays& d = w->d;
+	if ((rc = Upload(w, d.xf, first, xf)) || (rc = Upload(w, d.pos, first, pos)) || (rc = Upload(w, d.pos0, first, pos0)) ||
+	    (rc = Upload(w, d.vel, first, vel)) || (rc = Upload(w, d.mass, first, mass)) ||
+	    (rc = Upload(w, d.force, first, force)) || (rc = Upload(w, d.damp, first, damp)) ||
+	    (rc = Upload(w, d.bflags, first, flags)))
+		return rc;
+	return SyncCheck(w);
+}
+
+int b2cuGetBodies(b2cuWorld* w, int32_t first, int32_t count, b2cuBody* bodies)
+{
+	int rc = CheckRange(w, first, count, w ? w->bodyCount : 0, bodies);
+	if (rc) return rc;
+	cudaSetDevice(w->device);
+	std::vector<float4> xf(count), pos(count), pos0(count), vel(count), mass(count), force(count), damp(count);
+	std::vector<uint32_t> flags(count);
+	DeviceArrays& d = w->d;
+	if ((rc = Download(w, d.xf, first, xf)) || (rc = Download(w, d.pos, first, pos)) ||
+	    (rc = Download(w, d.pos0, first, pos0)) || (rc = Download(w, d.vel, first, vel)) ||
+	    (rc = Download(w, d.mass, first, mass)) || (rc = Download(w, d.force, first, force)) ||
+	    (rc = Download(w, d.damp, first, damp)) || (rc = Download(w, d.bflags, first, flags)))
+		return rc;
+	if ((rc = SyncCheck(w))) return rc;
+	for (int i = 0; i < count; ++i)
+	{
+		b2cuBody& b = bodies[i];
+		b.px = xf[i].x; b.py = xf[i].y; b.qs = xf[i].z; b.qc = xf[i].w;
+		b.cx = pos[i].x; b.cy = pos[i].y; b.a = pos[i].z;
+		b.c0x = pos0[i].x; b.c0y = pos0[i].y; b.a0 = pos0[i].z; b.alpha0 = pos0[i].w;
+		b.lcx = mass[i].z; b.lcy = mass[i].w;
+		b.vx = vel[i].x; b.vy = vel[i].y; b.w = vel[i].z;
+		b.fx = force[i].x; b.fy = force[i].y; b.torque = force[i].z;
+		b.invMass = mass[i].x; b.invI = mass[i].y;
+		b.linearDamping = damp[i].x; b.angularDamping = damp[i].y; b.gravityScale = damp[i].z;
+		b.sleepTime = force[i].w;
+		b.flags = flags[i];
+	}
+	return B2CU_OK;
+}
+
+int b2cuSetShapes(b2cuWorld* w, int32_t first, int32_t count, const b2cuShape* shapes)
+{
+	int rc = CheckRange(w, first, count, w ? w->shapeCount : 0, shapes);
+	if (rc) return rc;
+	cudaSetDevice(w->device);
+	for (int i = 0; i < count; ++i)
+	{
+		if (shapes[i].type < B2CU_SHAPE_CIRCLE || shapes[i].type > B2CU_SHAPE_POLYGON)
+			return SetError(w, B2CU_ERR_UNSUPPORTED, "shape %d: type %d is outside the GPU path (chains unsupported)",
+			                first + i, shapes[i].type);
+	}
+	if (count > 0)
+	{
+		CUDA_TRY(w, cudaMemcpyAsync(w->d.shapes + first, shapes, sizeof(b2cuShape) * count, cudaMemcpyHostToDevice,
+		                            w->stream));
+	}
+	return SyncCheck(w);
+}
+
+int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* proxies)
+{
+	int rc = CheckRange(w, first, count, w ? w->proxyCount : 0, proxies);
+	if (rc) return rc;
+	cudaSetDevice(w->device);
+	std::vector<float4> fat(count), aabb(count);
+	std::vector<int> body(count), shape(count), fixture(count);
+	std::vector<uint32_t> filter(count), group(count);
+	std::vector<float2> mat(count);
+	std::vector<float> extents;
+	extents.reserve(count);
+	bool anyMoved = false;
+	for (int i = 0; i < count; ++i)
+	{
+		const b2cuProxy& p = proxies[i];
+		if (p.flags & B2CU_PROXY_SENSOR)
+			return SetError(w, B2CU_ERR_UNSUPPORTED, "proxy %d: sensors are outside the GPU path", first + i);
+		if (p.body < 0 || p.body >= w->bodyCount || p.shape < 0 || p.shape >= w->shapeCount)
+			return SetError(w, B2CU_ERR_ARGUMENT, "proxy %d: body %d / shape %d out of range", first + i, p.body, p.shape);
+		fat[i] = make_float4(p.fat[0], p.fat[1], p.fat[2], p.fat[3]);
+		aabb[i] = make_float4(p.aabb[0], p.aabb[1], p.aabb[2], p.aabb[3]);
+		body[i] = p.body;
+		shape[i] = p.shape;
+		fixture[i] = p.fixture;
+		filter[i] = (uint32_t)p.categoryBits | ((uint32_t)p.maskBits << 16);
+		group[i] = (uint32_t)(uint16_t)p.groupIndex | ((uint32_t)p.flags << 16);
+		mat[i] = make_float2(p.friction, p.restitution);
+		extents.push_back(std::max(p.fat[2] - p.fat[0], p.fat[3] - p.fat[1]));
+		if (p.flags & B2CU_PROXY_MOVED) anyMoved = true;
+	}
+	DeviceArrays& d = w->d;
+	if ((rc = Upload(w, d.fat, first, fat)) || (rc = Upload(w, d.aabb, first, aabb)) ||
+	    (rc = Upload(w, d.pbody, first, body)) || (rc = Upload(w, d.pshape, first, shape)) ||
+	    (rc = Upload(w, d.pfixture, first, fixture)) || (rc = Upload(w, d.pfilter, first, filter)) ||
+	    (rc = Upload(w, d.pgroup, first, group)) || (rc = Upload(w, d.pmat, first, mat)))
+		return rc;
+	if (anyMoved) w->newProxies = true;
+	if (first == 0 && count > 0)
+	{
+		w->cellSize = ChooseCellSize(extents);
+	}
+	return SyncCheck(w);
+}
+
+int b2cuGetProxies(b2cuWorld* w, int32_t first, int32_t count, b2cuProxy* proxies)
+{
+	int rc = CheckRange(w, first, count, w ? w->proxyCount : 0, proxies);
+	if (rc) return rc;
+	cudaSetDevice(w->device);
+	std::vector<float4> fat(count), aabb(count);
+	std::vector<int> body(count), shape(count), fixture(count);
+	std::vector<uint32_t> filter(count), group(count);
+	std::vector<float2> mat(count);
+	DeviceArrays& d = w->d;
+	if ((rc = Download(w, d.fat, first, fat)) || (rc = Download(w, d.aabb, first, aabb)) ||
+	    (rc = Download(w, d.pbody, first, body)) || (rc = Download(w, d.pshape, first, shape)) ||
+	    (rc = Download(w, d.pfixture, first, fixture)) || (rc = Download(w, d.pfilter, first, filter)) ||
+	    (rc = Download(w, d.pgroup, first, group)) || (rc = Download(w, d.pmat, first, mat)))
+		return rc;
+	if ((rc = SyncCheck(w))) return rc;
+	for (int i = 0; i < count; ++i)
+	{
+		b2cuProxy& p = proxies[i];
+		p.aabb[0] = aabb[i].x; p.aabb[1] = aabb[i].y; p.aabb[2] = aabb[i].z; p.aabb[3] = aabb[i].w;
+		p.fat[0] = fat[i].x; p.fat[1] = fat[i].y; p.fat[2] = fat[i].z; p.fat[3] = fat[i].w;
+		p.body = body[i];
+		p.shape = shape[i];
+		p.friction = mat[i].x;
+		p.restitution = mat[i].y;
+		p.categoryBits = (uint16_t)(filter[i] & 0xFFFFu);
+		p.maskBits = (uint16_t)(filter[i] >> 16);
+		p.groupIndex = (int16_t)(group[i] & 0xFFFFu);
+		p.flags = (uint16_t)(group[i] >> 16);
+		p.fixture = fixture[i];
+		p.child = 0;
+	}
+	return B2CU_OK;
+}
+
+int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
+{
+	if (!w || count < 0 || (count > 0 && !contacts)) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	if (count > w->contactCapacity)
+	{
+		int rc = Reserve(w, w->bodyCapacity, w->proxyCapacity, w->shapeCapacity, std::max(count, 2 * w->contactCapacity));
+		if (rc) return rc;
+	}
+	std::vector<int> order(count);
+	std::vector<uint64_t> keys(count);
+	for (int i = 0; i < count; ++i)
+	{
+		order[i] = i;
+		const b2cuContact& c = contacts[i];
+		if (c.proxyA < 0 || c.proxyA >= w->proxyCount || c.proxyB < 0 || c.proxyB >= w->proxyCount || c.proxyA == c.proxyB)
+			return SetError(w, B2CU_ERR_ARGUMENT, "contact %d: proxies %d,%d out of range", i, c.proxyA, c.proxyB);
+		uint32_t lo = (uint32_t)std::min(c.proxyA, c.proxyB), hi = (uint32_t)std::max(c.proxyA, c.proxyB);
+		keys[i] = ((uint64_t)lo << 32) | hi;
+	}
+	std::sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+	std::vector<uint64_t> key(count);
+	std::vector<int2> proxies(count);
+	std::vector<uint32_t> flags(count);
+	std::vector<float4> m0(count), m1(count), m2(count), mix(count);
+	std::vector<uint4> m3(count);
+	std::vector<int> toiCount(count), colour(count, B2CU_COLOUR_NONE);
+	for (int j = 0; j < count; ++j)
+	{
+		const b2cuContact& c = contacts[order[j]];
+		const b2cuManifold& m = c.manifold;
+		key[j] = keys[order[j]];
+		if (j > 0 && key[j] == key[j - 1]) return SetError(w, B2CU_ERR_ARGUMENT, "duplicate contact key");
+		proxies[j] = make_int2(c.proxyA, c.proxyB);
+		flags[j] = c.flags & ~(uint32_t)B2CU_CONTACT_ISLAND;
+		m0[j] = make_float4(m.localNormal[0], m.localNormal[1], m.localPoint[0], m.localPoint[1]);
+		m1[j] = make_float4(m.points[0].localPoint[0], m.points[0].localPoint[1], m.points[0].normalImpulse,
+		                    m.points[0].tangentImpulse);
+		m2[j] = make_float4(m.points[1].localPoint[0], m.points[1].localPoint[1], m.points[1].normalImpulse,
+		                    m.points[1].tangentImpulse);
+		m3[j] = make_uint4(m.id[0], m.id[1], (uint32_t)m.type, (uint32_t)m.pointCount);
+		mix[j] = make_float4(c.friction, c.restitution, c.tangentSpeed, c.toi);
+		toiCount[j] = c.toiCount;
+	}
+	DeviceArrays& d = w->d;
+	int rc;
+	if ((rc = Upload(w, d.c.key, 0, key)) || (rc = Upload(w, d.c.proxies, 0, proxies)) ||
+	    (rc = Upload(w, d.c.flags, 0, flags)) || (rc = Upload(w, d.c.m0, 0, m0)) || (rc = Upload(w, d.c.m1, 0, m1)) ||
+	    (rc = Upload(w, d.c.m2, 0, m2)) || (rc = Upload(w, d.c.m3, 0, m3)) || (rc = Upload(w, d.c.mix, 0, mix)) ||
+	    (rc = Upload(w, d.c.toiCount, 0, toiCount)) || (rc = Upload(w, d.c.colour, 0, colour)))
+		return rc;
+	CUDA_TRY(w, cudaMemsetAsync(d.cEvent, 0, sizeof(int) * (size_t)w->contactCapacity, w->stream));
+	w->contactCount = count;
+	return SyncCheck(w);
+}
+
+int b2cuGetContactCount(b2cuWorld* w, int32_t* count)
+{
+	if (!w || !count) return B2CU_ERR_ARGUMENT;
+	*count = w->contactCount;
+	return B2CU_OK;
+}
+
+int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32_t* countOut)
+{
+	if (!w || capacity < 0 || (capacity > 0 && !contacts)) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	int count = std::min(capacity, w->contactCount);
+	if (countOut) *countOut = w->contactCount;
+	std::vector<int2> proxies(count);
+	std::vector<uint32_t> flags(count);
+	std::vector<float4> m0(count), m1(count), m2(count), mix(count);
+	std::vector<uint4> m3(count);
+	std::vector<int> toiCount(count);
+	std::vector<int> pbody(count > 0 ? w->proxyCount : 0);
+	std::vector<uint32_t> bflags(count > 0 ? w->bodyCount : 0);
+	DeviceArrays& d = w->d;
+	int rc;
+	if ((rc = Download(w, d.pbody, 0, pbody)) || (rc = Download(w, d.bflags, 0, bflags))) return rc;
+	if ((rc = Download(w, d.c.proxies, 0, proxies)) || (rc = Download(w, d.c.flags, 0, flags)) ||
+	    (rc = Download(w, d.c.m0, 0, m0)) || (rc = Download(w, d.c.m1, 0, m1)) || (rc = Download(w, d.c.m2, 0, m2)) ||
+	    (rc = Download(w, d.c.m3, 0, m3)) || (rc = Download(w, d.c.mix, 0, mix)) ||
+	    (rc = Download(w, d.c.toiCount, 0, toiCount)))
+		return rc;
+	if ((rc = SyncCheck(w))) return rc;
+	for (int j = 0; j < count; ++j)
+	{
+		b2cuContact& c = contacts[j];
+		c.proxyA = proxies[j].x;
+		c.proxyB = proxies[j].y;
+		// e_inactiveFlag is not stored on the device: it is a function of the bodies' awake state
+		// (b2ContactManager::IsContactActive, b2ContactManager.cpp:94-107)
+		{
+			uint32_t fA = bflags[pbody[proxies[j].x]], fB = bflags[pbody[proxies[j].y]];
+			bool activeA = (fA & B2CU_BODY_AWAKE) && (fA & B2CU_BODY_TYPE_MASK) != B2CU_STATIC_BODY;
+			bool activeB = (fB & B2CU_BODY_AWAKE) && (fB & B2CU_BODY_TYPE_MASK) != B2CU_STATIC_BODY;
+			uint32_t f = flags[j] & ~(uint32_t)B2CU_CONTACT_INACTIVE;
+			if (!activeA && !activeB) f |= B2CU_CONTACT_INACTIVE;
+			c.flags = f;
+		}
+		c.friction = mix[j].x;
+		c.restitution = mix[j].y;
+		c.tangentSpeed = mix[j].z;
+		c.toi = mix[j].w;
+		c.toiCount = toiCount[j];
+		b2cuManifold& m = c.manifold;
+		m.localNormal[0] = m0[j].x; m.localNormal[1] = m0[j].y;
+		m.localPoint[0] = m0[j].z; m.localPoint[1] = m0[j].w;
+		m.points[0].localPoint[0] = m1[j].x; m.points[0].localPoint[1] = m1[j].y;
+		m.points[0].normalImpulse = m1[j].z; m.points[0].tangentImpulse = m1[j].w;
+		m.points[1].localPoint[0] = m2[j].x; m.points[1].localPoint[1] = m2[j].y;
+		m.points[1].normalImpulse = m2[j].z; m.points[1].tangentImpulse = m2[j].w;
+		m.id[0] = m3[j].x; m.id[1] = m3[j].y;
+		m.type = (int32_t)m3[j].z;
+		m.pointCount = (int32_t)m3[j].w;
+	}
+	return B2CU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------------------------------------
+int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positionIterations, b2cuStepInfo* info)
+{
+	if (!w || velocityIterations < 0 || positionIterations < 0) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	DeviceArrays& d = w->d;
+	int rc;
+	w->launches = 0;
+	g_primLaunches = 0;
+	b2cuStepInfo out;
+	memset(&out, 0, sizeof(out));
+	const int nb = w->bodyCount;
+	const int np = w->proxyCount;
+
+	if (positionIterations > w->positionIterationsCapacity)
+	{
+		w->positionIterationsCapacity = positionIterations;
+		cudaFree(d.islandMinSep);
+		CUDA_TRY(w, cudaMalloc(&d.islandMinSep, sizeof(int) * (size_t)positionIterations * (size_t)w->bodyCapacity));
+	}
+
+	CUDA_TRY(w, cudaMemsetAsync(d.counters, 0, sizeof(int) * CNT_COUNT, w->stream));
+	cudaEventRecord(w->ev[0], w->stream);
+
+	int newContacts = 0, destroyed = 0, moved = 0;
+
+	// ---- new fixtures: find their contacts first (b2World.cpp:1628-1639) ----
+	if (w->newProxies)
+	{
+		int n0 = 0, d0 = 0, m0 = 0;
+		if ((rc = FindNewContactsAndRebuild(w, &n0, &d0, &m0))) return rc;
+		newContacts += n0;
+		moved += m0;
+		w->newProxies = false;
+	}
+	cudaEventRecord(w->ev[1], w->stream);
+
+	// ---- Collide (b2World.cpp:1120-1141) ----
+	int nc = w->contactCount;
+	w->beginCount = w->endCount = 0;
+	if (nc > 0)
+	{
+		LAUNCH(w, CollideKernel, GridFor(nc), kBlock, d, nc);
+		LAUNCH(w, ApplyWakeKernel, GridFor(nb), kBlock, d, nb);
+		// deferred Begin/End buffers in key order (FinishCollide, b2ContactManager.cpp:388-439); EndContact calls
+		// made by Destroy come after the sorted ends
+		CompactMask(&w->prims, (const uint32_t*)d.cEvent, B2CU_EV_BEGIN, nc, d.listA, d.counters + CNT_BEGIN, w->stream);
+		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_BEGIN, (const int*)nullptr,
+		       d.beginKeys, w->contactCapacity);
+		CompactMask(&w->prims, (const uint32_t*)d.cEvent, B2CU_EV_END, nc, d.listA, d.counters + CNT_END, w->stream);
+		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_END, (const int*)nullptr,
+		       d.endKeys, w->contactCapacity);
+		CompactMask(&w->prims, (const uint32_t*)d.cEvent, B2CU_EV_DESTROY_TOUCHING, nc, d.listA,
+		            d.counters + CNT_DESTROY_END, w->stream);
+		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_DESTROY_END,
+		       d.counters + CNT_END, d.endKeys, w->contactCapacity);
+		LAUNCH(w, CountMaskKernel, GridFor(nc), kBlock, d.c.flags, (uint32_t)B2CU_CONTACT_TOUCHING, nc,
+		       d.counters + CNT_TOUCHING);
+	}
+	cudaEventRecord(w->ev[2], w->stream);
+
+	const bool allowSleep = (w->params.flags & B2CU_WORLD_ALLOW_SLEEP) != 0;
+	const bool warmStarting = (w->params.flags & B2CU_WORLD_WARM_STARTING) != 0;
+	const float invDt = dt > 0.0f ? 1.0f / dt : 0.0f;
+	const float dtRatio = w->params.invDt0 * dt;
+
+	w->constraintCount = 0;
+	w->colourCount = 0;
+	w->overflowCount = 0;
+	for (int c = 0; c <= B2CU_MAX_COLOURS; ++c) w->colourCounts[c] = 0;
+
+	if (dt > 0.0f)
+	{
+		// ---- islands (serial DFS of b2World::Solve -> union-find) ----
+		LAUNCH(w, SolveInitBodiesKernel, GridFor(nb), kBlock, d, nb, positionIterations);
+		if (nc > 0) LAUNCH(w, IslandUnionKernel, GridFor(nc), kBlock, d, nc);
+		LAUNCH(w, IslandFlattenKernel, GridFor(nb), kBlock, d, nb);
+		LAUNCH(w, IslandMarkKernel, GridFor(nb), kBlock, d, nb);
+		cudaEventRecord(w->ev[3], w->stream);
+
+		// ---- constraint selection + colouring ----
+		int colourStart[B2CU_MAX_COLOURS + 2];
+		int nConstraints = 0;
+		if (nc > 0)
+		{
+			LAUNCH(w, SelectConstraintsKernel, GridFor(nc), kBlock, d, nc);
+			CompactFlags(&w->prims, d.cSelect, nc, d.listA, d.counters + CNT_CONSTRAINT, w->stream);
+			int* cur = d.listB;
+			int* next = d.listC;
+			LAUNCH(w, ColourPrepareKernel, GridFor(nc), kBlock, d, d.listA, cur);
+			if ((rc = ReadCounters(w))) return rc;
+			nConstraints = w->hostCounters[CNT_CONSTRAINT];
+			int remaining = w->hostCounters[CNT_UNCOLOURED];
+			int curCounter = CNT_UNCOLOURED, nextCounter = CNT_UNCOLOURED_NEXT;
+			uint32_t round = 1;
+			while (remaining > 0)
+			{
+				LAUNCH(w, ColourProposeKernel, GridFor(remaining), kBlock, d, cur, curCounter, round);
+				LAUNCH(w, ColourCommitKernel, GridFor(remaining), kBlock, d, cur, curCounter, next, nextCounter, round);
+				if ((rc = ZeroCounter(w, curCounter))) return rc;
+				CUDA_TRY(w, cudaMemcpyAsync(w->hostCounters + nextCounter, d.counters + nextCounter, sizeof(int),
+				                            cudaMemcpyDeviceToHost, w->stream));
+				if ((rc = SyncCheck(w))) return rc;
+				remaining = w->hostCounters[nextCounter];
+				std::swap(cur, next);
+				std::swap(curCounter, nextCounter);
+				++round;
+				if (round > 100000u) return SetError(w, B2CU_ERR_CUDA, "colouring did not converge");
+			}
+			if (nConstraints > 0)
+			{
+				CUDA_TRY(w, cudaMemsetAsync(d.colourCount, 0xFF, sizeof(int) * (B2CU_MAX_COLOURS + 2), w->stream));
+				LAUNCH(w, ColourKeysKernel, GridFor(nConstraints), kBlock, d, d.listA);
+				RadixSort64(&w->prims, d.orderKeys, nConstraints, 32, 40, w->stream);
+				LAUNCH(w, ColourStartsKernel, GridFor(nConstraints), kBlock, d);
+				if ((rc = ReadCounters(w))) return rc;
+				for (int c = 0; c <= B2CU_MAX_COLOURS; ++c) colourStart[c] = w->hostCounters[CNT_COUNT + c];
+				colourStart[B2CU_MAX_COLOURS + 1] = nConstraints;
+				// fill the gaps of absent colours from the right
+				int nextStart = nConstraints;
+				for (int c = B2CU_MAX_COLOURS; c >= 0; --c)
+				{
+					if (colourStart[c] < 0) colourStart[c] = nextStart;
+					else nextStart = colourStart[c];
+				}
+				for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
+				{
+					w->colourCounts[c] = colourStart[c + 1] - colourStart[c];
+					if (c < B2CU_MAX_COLOURS && w->colourCounts[c] > 0) w->colourCount = c + 1;
+				}
+				w->overflowCount = w->colourCounts[B2CU_MAX_COLOURS];
+			}
+		}
+		w->constraintCount = nConstraints;
+		cudaEventRecord(w->ev[4], w->stream);
+
+		// ---- b2Island::Solve ----
+		LAUNCH(w, IntegrateVelocitiesKernel, GridFor(nb), kBlock, d, nb, dt, w->params.gravity);
+		if (nConstraints > 0)
+		{
+			LAUNCH(w, InitConstraintsKernel, GridFor(nConstraints), kBlock, d, dtRatio, warmStarting ? 1 : 0);
+			if (warmStarting)
+			{
+				for (int c = 0; c < B2CU_MAX_COLOURS; ++c)
+				{
+					if (w->colourCounts[c] > 0)
+						LAUNCH(w, WarmStartKernel, GridFor(w->colourCounts[c]), kBlock, d, colourStart[c], w->colourCounts[c]);
+				}
+				if (w->overflowCount > 0)
+					LAUNCH(w, OverflowWarmStartKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->overflowCount);
+			}
+		}
+		cudaEventRecord(w->ev[5], w->stream);
+		if (nConstraints > 0)
+		{
+			for (int it = 0; it < velocityIterations; ++it)
+			{
+				for (int c = 0; c < B2CU_MAX_COLOURS; ++c)
+				{
+					if (w->colourCounts[c] > 0)
+						LAUNCH(w, SolveVelocityKernel, GridFor(w->colourCounts[c]), kBlock, d, colourStart[c],
+						       w->colourCounts[c]);
+				}
+				if (w->overflowCount > 0)
+					LAUNCH(w, OverflowSolveVelocityKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->overflowCount);
+			}
+			LAUNCH(w, StoreImpulsesKernel, GridFor(nConstraints), kBlock, d);
+		}
+		cudaEventRecord(w->ev[6], w->stream);
+		LAUNCH(w, IntegratePositionsKernel, GridFor(nb), kBlock, d, nb, dt);
+		if (nConstraints > 0)
+		{
+			for (int it = 0; it < positionIterations; ++it)
+			{
+				for (int c = 0; c < B2CU_MAX_COLOURS; ++c)
+				{
+					if (w->colourCounts[c] > 0)
+						LAUNCH(w, SolvePositionKernel, GridFor(w->colourCounts[c]), kBlock, d, colourStart[c],
+						       w->colourCounts[c], it, nb);
+				}
+				if (w->overflowCount > 0)
+					LAUNCH(w, OverflowSolvePositionKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->overflowCount, it, nb);
+			}
+		}
+		LAUNCH(w, FinalizeBodiesKernel, GridFor(nb), kBlock, d, nb, dt, allowSleep ? 1 : 0);
+		if (allowSleep) LAUNCH(w, SleepIslandsKernel, GridFor(nb), kBlock, d, nb, positionIterations);
+		cudaEventRecord(w->ev[7], w->stream);
+
+		// ---- SynchronizeFixtures + FindNewContacts (b2World.cpp:1410-1427) ----
+		if (np > 0) LAUNCH(w, SyncProxiesKernel, GridFor(np), kBlock, d, np);
+		int n1 = 0, d1 = 0, m1 = 0;
+		if ((rc = FindNewContactsAndRebuild(w, &n1, &d1, &m1))) return rc;
+		newContacts += n1;
+		destroyed += d1;
+		moved += m1;
+		w->params.invDt0 = invDt;
+	}
+	else
+	{
+		for (int k = 3; k < 8; ++k) cudaEventRecord(w->ev[k], w->stream);
+		int n1 = 0, d1 = 0, m1 = 0;
+		if ((rc = FindNewContactsAndRebuild(w, &n1, &d1, &m1))) return rc;
+		destroyed += d1;
+	}
+	cudaEvent_t evBroad = w->ev[8];
+	cudaEventRecord(evBroad, w->stream);
+
+	// ---- TOI eligibility compaction (b2World.cpp:283-352 filters; SolveTOI itself is host-driven) ----
+	w->toiCount = 0;
+	nc = w->contactCount;
+	if ((w->params.flags & B2CU_WORLD_CONTINUOUS) && dt > 0.0f && nc > 0)
+	{
+		LAUNCH(w, ToiFlagsKernel, GridFor(nc), kBlock, d, nc, d.cSelect);
+		CompactFlags(&w->prims, d.cSelect, nc, d.listA, d.counters + CNT_TOI, w->stream);
+		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_TOI, (const int*)nullptr,
+		       d.toiKeys, w->contactCapacity);
+	}
+
+	// ---- ClearPostSolve + ClearForces ----
+	LAUNCH(w, EndStepBodiesKernel, GridFor(nb), kBlock, d, nb, (w->params.flags & B2CU_WORLD_CLEAR_FORCES) ? 1 : 0);
+	cudaEvent_t evEnd = w->ev[9];
+	cudaEventRecord(evEnd, w->stream);
+
+	if ((rc = ReadCounters(w))) return rc;
+	w->beginCount = w->hostCounters[CNT_BEGIN];
+	w->endCount = w->hostCounters[CNT_END] + w->hostCounters[CNT_DESTROY_END];
+	w->toiCount = w->hostCounters[CNT_TOI];
+
+	float ms = 0.0f;
+	cudaEventElapsedTime(&ms, w->ev[0], evEnd); out.step = ms;
+	cudaEventElapsedTime(&ms, w->ev[1], w->ev[2]); out.collide = ms;
+	cudaEventElapsedTime(&ms, w->ev[2], w->ev[7]); out.solve = ms;
+	cudaEventElapsedTime(&ms, w->ev[2], w->ev[4]); out.solveTraversal = ms;
+	cudaEventElapsedTime(&ms, w->ev[4], w->ev[5]); out.solveInit = ms;
+	cudaEventElapsedTime(&ms, w->ev[5], w->ev[6]); out.solveVelocity = ms;
+	cudaEventElapsedTime(&ms, w->ev[6], w->ev[7]); out.solvePosition = ms;
+	cudaEventElapsedTime(&ms, w->ev[7], evBroad); out.broadphase = ms;
+	out.broadphaseFindContacts = ms;
+	cudaEventElapsedTime(&ms, evBroad, evEnd); out.solveTOI = ms;
+	cudaEventElapsedTime(&ms, w->ev[0], w->ev[1]); out.broadphase += ms;
+
+	out.bodyCount = nb;
+	out.proxyCount = np;
+	out.contactCount = w->contactCount;
+	out.touchingCount = w->hostCounters[CNT_TOUCHING];
+	out.constraintCount = w->constraintCount;
+	out.colourCount = w->colourCount;
+	out.overflowCount = w->overflowCount;
+	out.islandBodyCount = w->hostCounters[CNT_ISLAND_BODIES];
+	out.awakeBodyCount = w->hostCounters[CNT_AWAKE_BODIES];
+	out.moveCount = moved;
+	out.newContactCount = newContacts;
+	out.destroyedContactCount = destroyed;
+	out.beginCount = w->beginCount;
+	out.endCount = w->endCount;
+	out.toiCandidateCount = w->toiCount;
+	out.kernelLaunches = w->launches + g_primLaunches;
+	if (info) *info = out;
+	return B2CU_OK;
+}
+
+int b2cuGetEvents(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* keys, int32_t* count)
+{
+	if (!w || capacity < 0 || (capacity > 0 && !keys)) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	int n = kind == B2CU_EVENT_BEGIN ? w->beginCount : w->endCount;
+	if (count) *count = n;
+	int m = std::min(n, capacity);
+	if (m > 0)
+	{
+		CUDA_TRY(w, cudaMemcpyAsync(keys, kind == B2CU_EVENT_BEGIN ? w->d.beginKeys : w->d.endKeys, sizeof(uint64_t) * m,
+		                            cudaMemcpyDeviceToHost, w->stream));
+	}
+	return SyncCheck(w);
+}
+
+int b2cuGetSolverOrder(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* colour, int32_t* count)
+{
+	if (!w || capacity < 0) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	int n = w->constraintCount;
+	if (count) *count = n;
+	int m = std::min(n, capacity);
+	if (m <= 0) return B2CU_OK;
+	if (keys)
+	{
+		CUDA_TRY(w, cudaMemcpyAsync(keys, w->d.solverKeys, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, w->stream));
+	}
+	std::vector<uint64_t> order(m);
+	CUDA_TRY(w, cudaMemcpyAsync(order.data(), w->d.orderKeys, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, w->stream));
+	int rc = SyncCheck(w);
+	if (rc) return rc;
+	if (colour)
+	{
+		for (int k = 0; k < m; ++k) colour[k] = (int32_t)(order[k] >> 32);
+	}
+	return B2CU_OK;
+}
+
+int b2cuGetIslandLabels(b2cuWorld* w, int32_t first, int32_t count, int32_t* labels)
+{
+	int rc = CheckRange(w, first, count, w ? w->bodyCount : 0, labels);
+	if (rc) return rc;
+	cudaSetDevice(w->device);
+	if (count > 0)
+	{
+		CUDA_TRY(w, cudaMemcpyAsync(labels, w->d.island + first, sizeof(int) * count, cudaMemcpyDeviceToHost, w->stream));
+	}
+	return SyncCheck(w);
+}
+
+int b2cuGetToiCandidates(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* count)
+{
+	if (!w || capacity < 0 || (capacity > 0 && !keys)) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	int n = w->toiCount;
+	if (count) *count = n;
+	int m = std::min(n, capacity);
+	if (m > 0)
+	{
+		CUDA_TRY(w, cudaMemcpyAsync(keys, w->d.toiKeys, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, w->stream));
+	}
+	return SyncCheck(w);
+}
+
+int b2cuCollidePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
+                     const int32_t* shapeA, const float* xfA, const int32_t* shapeB, const float* xfB,
+                     b2cuManifold* manifolds)
+{
+	if (shapeCount <= 0 || pairCount < 0 || !shapes || !shapeA || !shapeB || !xfA || !xfB || !manifolds)
+		return B2CU_ERR_ARGUMENT;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return B2CU_ERR_NO_DEVICE;
+	if (cudaSetDevice(device) != cudaSuccess) return B2CU_ERR_CUDA;
+	if (pairCount == 0) return B2CU_OK;
+	b2cuShape* dShapes = nullptr;
+	int *dA = nullptr, *dB = nullptr;
+	float4 *dXa = nullptr, *dXb = nullptr;
+	b2cuManifold* dOut = nullptr;
+	cudaError_t e = cudaSuccess;
+	if (e == cudaSuccess) e = cudaMalloc(&dShapes, sizeof(b2cuShape) * shapeCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dA, sizeof(int) * pairCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dB, sizeof(int) * pairCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dXa, sizeof(float4) * pairCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dXb, sizeof(float4) * pairCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dOut, sizeof(b2cuManifold) * pairCount);
+	if (e == cudaSuccess) e = cudaMemcpy(dShapes, shapes, sizeof(b2cuShape) * shapeCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dA, shapeA, sizeof(int) * pairCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dB, shapeB, sizeof(int) * pairCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dXa, xfA, sizeof(float4) * pairCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dXb, xfB, sizeof(float4) * pairCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+	{
+		CollidePairsKernel<<<GridFor(pairCount), kBlock>>>(dShapes, pairCount, dA, dXa, dB, dXb, dOut);
+		e = cudaDeviceSynchronize();
+	}
+	if (e == cudaSuccess) e = cudaMemcpy(manifolds, dOut, sizeof(b2cuManifold) * pairCount, cudaMemcpyDeviceToHost);
+	cudaFree(dShapes);
+	cudaFree(dA);
+	cudaFree(dB);
+	cudaFree(dXa);
+	cudaFree(dXb);
+	cudaFree(dOut);
+	return e == cudaSuccess ? B2CU_OK : B2CU_ERR_CUDA;
+}
+
+int b2cuSinCos(int32_t device, int32_t count, const float* angles, float* sinOut, float* cosOut)
+{
+	if (count < 0 || !angles || !sinOut || !cosOut) return B2CU_ERR_ARGUMENT;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return B2CU_ERR_NO_DEVICE;
+	if (cudaSetDevice(device) != cudaSuccess) return B2CU_ERR_CUDA;
+	if (count == 0) return B2CU_OK;
+	float *dx = nullptr, *ds = nullptr, *dc = nullptr;
+	cudaError_t e = cudaMalloc(&dx, sizeof(float) * count);
+	if (e == cudaSuccess) e = cudaMalloc(&ds, sizeof(float) * count);
+	if (e == cudaSuccess) e = cudaMalloc(&dc, sizeof(float) * count);
+	if (e == cudaSuccess) e = cudaMemcpy(dx, angles, sizeof(float) * count, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+	{
+		SinCosKernel<<<GridFor(count), kBlock>>>(count, dx, ds, dc);
+		e = cudaDeviceSynchronize();
+	}
+	if (e == cudaSuccess) e = cudaMemcpy(sinOut, ds, sizeof(float) * count, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaMemcpy(cosOut, dc, sizeof(float) * count, cudaMemcpyDeviceToHost);
+	cudaFree(dx);
+	cudaFree(ds);
+	cudaFree(dc);
+	return e == cudaSuccess ? B2CU_OK : B2CU_ERR_CUDA;
+}
+
+} // extern "C"

@@ -18,7 +18,7 @@
  *   b2cuSetBodies / b2cuGetBodies        b2Body state (m_xf, m_sweep, velocities, forces, mass, flags)
  *                                                                          Dynamics/b2Body.h:471-508
  *   b2cuSetShapes                        b2PolygonShape / b2CircleShape / b2EdgeShape geometry
- *                                                                          Collision/Shapes/*.h
+ *                                                                          Collision/Shapes/b2{Polygon,Circle,Edge}Shape.h
  *   b2cuSetProxies / b2cuGetProxies      b2Fixture + b2FixtureProxy + tree-leaf fat AABB
  *                                                                          Dynamics/b2Fixture.h:100-106, Collision/b2DynamicTree.h:36
  *   b2cuSetContacts / b2cuGetContacts    b2Contact persistent state (m_flags, m_manifold, mixes, TOI)
@@ -33,7 +33,7 @@
  *                                                                          Dynamics/b2ContactManager.cpp:659-713, b2World.cpp:317-341
  *   b2cuCollidePairs                     b2CollidePolygons / b2CollideCircles / b2CollidePolygonAndCircle /
  *                                        b2CollideEdgeAndCircle / b2CollideEdgeAndPolygon, batched
- *                                                                          Collision/b2Collide*.cpp
+ *                                                                          Collision/b2CollidePolygon.cpp, b2CollideCircle.cpp, b2CollideEdge.cpp
  *
  * All functions return B2CU_OK (0) or a negative b2cuStatus; b2cuGetLastError gives
  * the message.  There is no CPU fallback anywhere behind this interface.

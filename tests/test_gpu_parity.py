@@ -1,0 +1,176 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle (the compiled reference).
+
+Bars (BASELINE.json north_star): broad-phase pair set, begin/end events, manifold point counts and feature ids
+bit-exact; manifold geometry and single-step body state within 1e-5 relative.  Because the device keeps the
+reference's fp32 operation order (no FMA, IEEE div/sqrt, one shared sincos), these tests assert the stronger
+property: bit-exact everywhere (tol = 0.0), single-step and free-running.
+"""
+import numpy as np
+import pytest
+
+import b2cuda_types as T
+import parity
+import ref
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+TOL = 0.0  # bit-exact; the contract would allow 1e-5 relative
+
+
+def test_sincos_bit_exact(gpu):
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.uniform(-10, 10, 20000), rng.uniform(-3000, 3000, 5000), rng.normal(0, 1e-3, 2000),
+                         [0.0, -0.0, np.pi, -np.pi / 2, 1e-20]]).astype(np.float32)
+    s, c = gpu.sincos(xs)
+    for i in range(0, len(xs), 7):
+        rs, rc = ref.sincos(xs[i])
+        assert s[i] == rs and c[i] == rc, (xs[i], s[i], rs, c[i], rc)
+    assert (s == np.sin(xs.astype(np.float64)).astype(np.float32)).all()
+    assert (c == np.cos(xs.astype(np.float64)).astype(np.float32)).all()
+
+
+def _shape_table():
+    """polygons (box, regular 3-8-gons, a skewed quad), circles, edges with and without ghost vertices"""
+    s = scenes.Scene()
+    g = s.body(T.STATIC_BODY, (0, 0))
+    ids = [s.box(0.5, 0.5), s.box(1.0, 0.25), s.box(0.3, 0.7, center=(0.2, -0.1), angle=0.4)]
+    ids += [s.polygon(scenes._regular_polygon(k, 0.5)) for k in range(3, 9)]
+    ids += [s.polygon([(-0.5, -0.2), (0.7, -0.4), (0.6, 0.5), (-0.3, 0.4)])]
+    ids += [s.circle(0.5), s.circle(0.2, p=(0.1, 0.05))]
+    ids += [s.edge((-1, 0), (1, 0)), s.edge((-1, 0), (1, 0.2), v0=(-2, 0.5), v3=(2, -0.3)),
+            s.edge((-1, 0), (1, 0), v0=(-2, -0.5)), s.edge((-1, 0), (1, 0), v3=(2, 0.6))]
+    for i in ids:
+        s.fixture(g, i)
+    w = ref.RefWorld(s)
+    return w.shapes()
+
+
+def test_collide_pairs_bit_exact(gpu):
+    shapes = _shape_table()
+    rng = np.random.default_rng(3)
+    types = shapes["type"]
+    n = 6000
+    a = rng.integers(0, len(shapes), n)
+    b = rng.integers(0, len(shapes), n)
+    # primary type order (b2Contact.cpp:44-50): polygon/edge before circle, edge before polygon; no edge-edge
+    rank = {T.SHAPE_EDGE: 0, T.SHAPE_POLYGON: 1, T.SHAPE_CIRCLE: 2}
+    keep = []
+    for i in range(n):
+        ta, tb = types[a[i]], types[b[i]]
+        if ta == T.SHAPE_EDGE and tb == T.SHAPE_EDGE:
+            continue
+        if rank[ta] > rank[tb]:
+            a[i], b[i] = b[i], a[i]
+        keep.append(i)
+    a, b = a[keep], b[keep]
+    n = len(a)
+    ang_a = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    ang_b = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    xa = np.zeros((n, 4), np.float32)
+    xb = np.zeros((n, 4), np.float32)
+    xa[:, :2] = rng.uniform(-0.3, 0.3, (n, 2))
+    xb[:, :2] = xa[:, :2] + rng.normal(0, 0.6, (n, 2))
+    xa[:, 2], xa[:, 3] = np.sin(ang_a.astype(np.float64)), np.cos(ang_a.astype(np.float64))
+    xb[:, 2], xb[:, 3] = np.sin(ang_b.astype(np.float64)), np.cos(ang_b.astype(np.float64))
+    # axis-aligned and exactly touching cases too
+    xa[:200, 2:] = (0, 1)
+    xb[:200, 2:] = (0, 1)
+    got = gpu.collide_pairs(shapes, a, xa, b, xb)
+    touching = 0
+    for i in range(n):
+        want = ref.collide(shapes[a[i]], xa[i], shapes[b[i]], xb[i])
+        assert got[i]["pointCount"] == want["pointCount"], i
+        pc = int(want["pointCount"])
+        if pc == 0:
+            continue
+        touching += 1
+        assert got[i]["type"] == want["type"], i
+        assert (got[i]["id"][:pc] == want["id"][:pc]).all(), i
+        parity.assert_floats_equal("localNormal", got[i]["localNormal"], want["localNormal"], TOL)
+        parity.assert_floats_equal("localPoint", got[i]["localPoint"], want["localPoint"], TOL)
+        parity.assert_floats_equal("points", got[i]["points"]["localPoint"][:pc], want["points"]["localPoint"][:pc], TOL)
+    assert touching > n // 10
+
+
+SCENES = {
+    "pyramid6": lambda: scenes.pyramid(6, continuous=False),
+    "pyramid20": lambda: scenes.pyramid(20, continuous=False),
+    "pile": lambda: scenes.pile(12, 10),
+    "pile_sleep": lambda: scenes.pile(8, 6, sleep=True),
+    "tumbler": lambda: scenes.tumbler(100),
+    "two_pyramids": lambda: scenes.pyramids(2, 6, thick_polygon_ground=True),
+}
+
+
+def _no_toi(scene):
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    return scene
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_single_step_teacher_forced(gpu, name):
+    """Single-step parity from identical state: before every step the oracle's bodies, fat AABBs
+    and contacts (manifolds, impulses) are injected into the device; after the step everything must be equal."""
+    scene = _no_toi(SCENES[name]())
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    infos = parity.lockstep(g, r, 60, teacher=True, tol=TOL)
+    assert max(i["constraintCount"] for i in infos) > 0
+
+
+@pytest.mark.parametrize("name,steps", [("pyramid6", 300), ("pyramid20", 240), ("pile", 300), ("pile_sleep", 400),
+                                        ("tumbler", 200), ("two_pyramids", 300)])
+def test_free_running_lockstep(gpu, name, steps):
+    """Multi-step parity: the device world runs freely; the oracle follows in the GPU's solver order.  Pair set,
+    events, manifolds, fat AABBs, body state and awake flags are compared after every step."""
+    scene = _no_toi(SCENES[name]())
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    infos = parity.lockstep(g, r, steps, tol=TOL)
+    assert sum(int(i["beginCount"]) for i in infos) > 0
+    if name == "pile_sleep":
+        # sleeping is exercised: every body asleep at the end, in both worlds
+        assert infos[-1]["awakeBodyCount"] == 0
+        assert not (r.bodies()["flags"][1:] & T.BODY_AWAKE).any()
+
+
+def test_add_pair_pair_set(gpu):
+    """BASELINE config 2 (Add Pair, scaled down): broad-phase stress with a fast bullet box; pair set bit-exact
+    every step.  Continuous physics is off on both sides (SolveTOI is host-driven and outside this test)."""
+    scene = _no_toi(scenes.add_pair(400))
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    infos = parity.lockstep(g, r, 90, tol=TOL)
+    assert max(int(i["contactCount"]) for i in infos) > 1000
+
+
+def test_deterministic_repeat(gpu):
+    """Two device worlds built from the same scene stay bit-identical (the reference's reproducibility claim,
+    README.md:161-173, restated for the GPU path)."""
+    scene = _no_toi(scenes.pile(16, 12))
+    r = ref.RefWorld(scene)
+    a = parity.gpu_world_from_ref(gpu, r)
+    b = parity.gpu_world_from_ref(gpu, r)
+    for _ in range(120):
+        a.step()
+        b.step()
+    ba, bb = a.get_bodies(), b.get_bodies()
+    assert ba.tobytes() == bb.tobytes()
+    assert a.get_contacts().tobytes() == b.get_contacts().tobytes()
+
+
+def test_invariants_long_run(gpu):
+    """1000-step invariants on a resting stack (Testbed/Tests/SleepCollideTest.h:104-110 rule: no body below the
+    ground; bounded penetration; the pyramid stays standing)."""
+    scene = _no_toi(scenes.pyramid(10, continuous=False))
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    y0 = g.get_bodies()["py"].copy()
+    for _ in range(1000):
+        g.step()
+    b = g.get_bodies()
+    assert (b["py"][1:] > 0.0).all()
+    assert np.abs(b["py"] - y0).max() < 0.1
+    m = g.get_contacts()["manifold"]
+    assert (m["pointCount"] <= 2).all()
