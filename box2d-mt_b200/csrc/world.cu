@@ -294,7 +294,6 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		LAUNCH(w, GridFillKernel, GridFor(np), kBlock, d, np);
 		LAUNCH(w, QuerySmallKernel, GridFor(np, 128), 128, d, invCell, mask, nc, w->contactCapacity);
 		LAUNCH(w, QueryLargeKernel, GridFor(np), kBlock, d, np, nc, w->contactCapacity);
-		LAUNCH(w, ClearMovedKernel, GridFor(np), kBlock, d, np);
 	}
 
 	// destroyed contacts -> keep flags and ranks
@@ -305,12 +304,27 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 	}
 
 	if ((rc = ReadCounters(w))) return rc;
-	if (w->hostCounters[CNT_ERROR])
+	int keepCount = nc > 0 ? w->hostCounters[CNT_KEEP] : 0;
+	if (w->hostCounters[CNT_ERROR] || keepCount + w->hostCounters[CNT_NEW_PAIRS] > w->contactCapacity)
 	{
-		return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
+		// the pair buffer (or the rebuilt set) would overflow: grow geometrically and repeat the queries; the
+		// pair counter kept counting past the capacity, so the size needed is known
+		int needed = keepCount + w->hostCounters[CNT_NEW_PAIRS];
+		int grown = std::max(needed + needed / 4, 2 * w->contactCapacity);
+		if ((rc = Reserve(w, w->bodyCapacity, w->proxyCapacity, w->shapeCapacity, grown))) return rc;
+		DeviceArrays& dd = w->d;
+		if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
+		if ((rc = ZeroCounter(w, CNT_ERROR))) return rc;
+		const float invCell = 1.0f / w->cellSize;
+		const uint32_t mask = (uint32_t)w->gridSize - 1u;
+		LAUNCH(w, QuerySmallKernel, GridFor(np, 128), 128, dd, invCell, mask, nc, w->contactCapacity);
+		LAUNCH(w, QueryLargeKernel, GridFor(np), kBlock, dd, np, nc, w->contactCapacity);
+		if ((rc = ReadCounters(w))) return rc;
+		if (w->hostCounters[CNT_ERROR])
+			return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
 	}
+	if (np > 0) LAUNCH(w, ClearMovedKernel, GridFor(np), kBlock, w->d, np);
 	const int newCount = w->hostCounters[CNT_NEW_PAIRS];
-	const int keepCount = nc > 0 ? w->hostCounters[CNT_KEEP] : 0;
 	const int moved = w->hostCounters[CNT_MOVED] + w->hostCounters[CNT_LARGE_MOVED];
 	*newCountOut = newCount;
 	*destroyedOut = nc - keepCount;
@@ -319,11 +333,6 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 	if (newCount == 0 && keepCount == nc)
 	{
 		return B2CU_OK; // contact set unchanged
-	}
-	if (keepCount + newCount > w->contactCapacity)
-	{
-		return SetError(w, B2CU_ERR_CAPACITY, "contact capacity %d exceeded (%d needed)", w->contactCapacity,
-		                keepCount + newCount);
 	}
 
 	if (newCount > 1)

@@ -31,10 +31,15 @@ class Scene:
     def __init__(self, gravity=(0.0, -10.0), world_flags=T.WORLD_DEFAULT):
         self.gravity = gravity
         self.world_flags = world_flags
-        self.bodies = []
         self.shapes = []
-        self.fixtures = []
         self._shape_cache = {}
+        self._body_chunks = []
+        self._fixture_chunks = []
+        self._pending_bodies = []
+        self._pending_fixtures = []
+        self.body_count = 0
+        self.fixture_count = 0
+        self._last_fixture_body = -1
 
     # -- shapes ------------------------------------------------------------------
     def _add_shape(self, rec):
@@ -98,12 +103,14 @@ class Scene:
         b["angularDamping"] = angular_damping
         b["gravityScale"] = gravity_scale
         b["flags"] = flags
-        self.bodies.append(b)
-        return len(self.bodies) - 1
+        self._pending_bodies.append(b)
+        self.body_count += 1
+        return self.body_count - 1
 
     def fixture(self, body, shape, density=0.0, friction=0.2, restitution=0.0, sensor=False, thick=False,
                 category=0x0001, mask=0xFFFF, group=0):
-        assert not self.fixtures or self.fixtures[-1]["body"] <= body, "fixtures must be added in body order"
+        assert self._last_fixture_body <= body, "fixtures must be added in body order"
+        self._last_fixture_body = body
         f = np.zeros((), FIXTURE_DEF)
         f["body"] = body
         f["shape"] = shape
@@ -114,11 +121,36 @@ class Scene:
         f["categoryBits"] = category
         f["maskBits"] = mask
         f["groupIndex"] = group
-        self.fixtures.append(f)
-        return len(self.fixtures) - 1
+        self._pending_fixtures.append(f)
+        self.fixture_count += 1
+        return self.fixture_count - 1
+
+    def _flush(self):
+        if self._pending_bodies:
+            self._body_chunks.append(np.array(self._pending_bodies, dtype=BODY_DEF))
+            self._pending_bodies = []
+        if self._pending_fixtures:
+            self._fixture_chunks.append(np.array(self._pending_fixtures, dtype=FIXTURE_DEF))
+            self._pending_fixtures = []
+
+    def add_bulk(self, bodies, fixtures):
+        """Append many bodies at once (vectorised scene builders).  `bodies` is a BODY_DEF array; `fixtures` a
+        FIXTURE_DEF array sorted by body, whose `body` field is relative to the first body of this batch."""
+        self._flush()
+        base = self.body_count
+        fx = np.array(fixtures, dtype=FIXTURE_DEF, copy=True)
+        fx["body"] += base
+        self._body_chunks.append(np.ascontiguousarray(bodies, dtype=BODY_DEF))
+        self._fixture_chunks.append(fx)
+        self.body_count += len(bodies)
+        self.fixture_count += len(fx)
+        if len(fx):
+            self._last_fixture_body = int(fx["body"][-1])
+        return base
 
     def arrays(self):
-        b = np.array(self.bodies, dtype=BODY_DEF) if self.bodies else np.zeros(0, BODY_DEF)
+        self._flush()
+        b = np.concatenate(self._body_chunks) if self._body_chunks else np.zeros(0, BODY_DEF)
+        f = np.concatenate(self._fixture_chunks) if self._fixture_chunks else np.zeros(0, FIXTURE_DEF)
         s = np.array(self.shapes, dtype=SHAPE_DEF) if self.shapes else np.zeros(0, SHAPE_DEF)
-        f = np.array(self.fixtures, dtype=FIXTURE_DEF) if self.fixtures else np.zeros(0, FIXTURE_DEF)
         return b, s, f

@@ -7,7 +7,7 @@ does in float32 is done in np.float32 here so that body placement is bit-identic
 import numpy as np
 
 import b2cuda_types as T
-from b2scene import Scene, BODYDEF_DEFAULT, BODYDEF_BULLET, BODYDEF_ALLOW_SLEEP
+from b2scene import Scene, BODY_DEF, FIXTURE_DEF, BODYDEF_DEFAULT, BODYDEF_BULLET, BODYDEF_ALLOW_SLEEP
 
 F = np.float32
 
@@ -142,18 +142,28 @@ def pile(columns, rows, seed=0, pitch=0.56, radius=0.25, sleep=False, wall_heigh
     s.fixture(g, s.box(0.5 * width + 2.0, 1.0, center=(0.0, -1.0), angle=0.0), thick=True)
     s.fixture(g, s.box(1.0, 0.5 * height + 2.0, center=(-0.5 * width - 1.0, 0.5 * height), angle=0.0), thick=True)
     s.fixture(g, s.box(1.0, 0.5 * height + 2.0, center=(0.5 * width + 1.0, 0.5 * height), angle=0.0), thick=True)
-    shapes = [s.circle(radius)] + [s.polygon(_regular_polygon(k, radius)) for k in range(3, 9)]
+    shapes = np.array([s.circle(radius)] + [s.polygon(_regular_polygon(k, radius)) for k in range(3, 9)])
     rnd = _Rand(seed)
     n = columns * rows
     kind = rnd.rng.randint(0, 12, size=n)
     jx = rnd.uniform(-0.02, 0.02, n)
     jy = rnd.uniform(-0.02, 0.02, n)
     ang = rnd.uniform(0.0, 2.0 * np.pi, n)
-    for i in range(n):
-        cx, cy = i % columns, i // columns
-        x = (cx + 0.5) * pitch - 0.5 * width + jx[i]
-        y = (cy + 0.5) * pitch + 0.05 + jy[i]
-        b = s.body(T.DYNAMIC_BODY, (x, y), angle=ang[i])
-        shape = shapes[0] if kind[i] >= 6 else shapes[1 + kind[i]]
-        s.fixture(b, shape, density=1.0)
+    idx = np.arange(n)
+    cx, cy = idx % columns, idx // columns
+    bodies = np.zeros(n, BODY_DEF)
+    bodies["type"] = T.DYNAMIC_BODY
+    bodies["px"] = ((cx + 0.5) * pitch - 0.5 * width + jx).astype(F)
+    bodies["py"] = ((cy + 0.5) * pitch + 0.05 + jy).astype(F)
+    bodies["angle"] = ang
+    bodies["gravityScale"] = 1.0
+    bodies["flags"] = BODYDEF_DEFAULT
+    fixtures = np.zeros(n, FIXTURE_DEF)
+    fixtures["body"] = idx
+    fixtures["shape"] = np.where(kind >= 6, shapes[0], shapes[1 + np.minimum(kind, 5)])
+    fixtures["density"] = 1.0
+    fixtures["friction"] = 0.2
+    fixtures["categoryBits"] = 0x0001
+    fixtures["maskBits"] = 0xFFFF
+    s.add_bulk(bodies, fixtures)
     return s
