@@ -28,6 +28,16 @@ __device__ __forceinline__ int FloatToOrdered(float f)
 }
 __device__ __forceinline__ float OrderedToFloat(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 
+// atomicMin(&base[root], value) with the lanes of a warp that share `root` combined first: a pile is one island,
+// so without this every constraint of a colour would hit the same address
+__device__ __forceinline__ void AtomicMinByRoot(int* base, int root, int value)
+{
+	unsigned active = __activemask();
+	unsigned peers = __match_any_sync(active, root);
+	int m = __reduce_min_sync(peers, value);
+	if ((int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicMin(&base[root], m);
+}
+
 // b2TestOverlap(b2AABB, b2AABB), Box2D/Collision/b2Collision.h:273-286
 __device__ __forceinline__ bool AabbOverlap(float4 a, float4 b)
 {
@@ -1026,7 +1036,7 @@ __global__ void __launch_bounds__(256) SolvePositionKernel(DeviceArrays d, int b
 		int root = __float_as_int(d.sRadius[k].w);
 		if (IslandDone(d, iteration, root, bodyCount)) continue;
 		float minSep = SolvePositionOne(d, k);
-		atomicMin(&d.islandMinSep[iteration * bodyCount + root], FloatToOrdered(minSep));
+		AtomicMinByRoot(d.islandMinSep + (size_t)iteration * bodyCount, root, FloatToOrdered(minSep));
 	}
 }
 
@@ -1086,7 +1096,7 @@ __global__ void FinalizeBodiesKernel(DeviceArrays d, int bodyCount, float h, int
 			}
 			f.w = sleepTime;
 			d.force[b] = f;
-			atomicMin(&d.islandMinSleep[d.island[b]], __float_as_int(sleepTime));
+			AtomicMinByRoot(d.islandMinSleep, d.island[b], __float_as_int(sleepTime));
 		}
 	}
 }
@@ -1187,41 +1197,80 @@ __global__ void __launch_bounds__(256) SyncProxiesKernel(DeviceArrays d, int pro
 // ---------------------------------------------------------------------------------------------------------
 // Broad-phase pair finding.  Replaces b2BroadPhase::UpdatePairs + b2DynamicTree::Query (Box2D/Collision/
 // b2BroadPhase.h:211-267, b2DynamicTree.h:168-201) and b2ContactManager::AddPair (b2ContactManager.cpp:237-312).
-// A hashed uniform grid over the fat AABBs is rebuilt each step (small proxies are registered in the cell of
-// their lower corner; proxies larger than a cell go to a short list tested exhaustively).  For every moved
-// proxy all proxies whose fat AABB overlaps are found exactly, so the pair SET equals the tree's.
+//
+// A hierarchical hashed grid over the fat AABBs is rebuilt every step.  Level k has square cells of size
+// S_k = S_0 * 2^k; a proxy lives on the finest level whose cell is larger than its fat AABB and is registered
+// once, in the cell of its lower corner, in one hash table shared by all levels.  A pair is always examined
+// from its finer-level member (or, on equal levels, from the moved one / the smaller id), which only has to
+// look at <= 3x3 cells per level.  Every overlap of fat AABBs involving a moved proxy is found exactly, so the
+// pair SET equals the dynamic tree's, whatever the tree shape would have been.
 // ---------------------------------------------------------------------------------------------------------
+#define B2CU_GRID_LEVELS 24
+
+struct GridParams
+{
+	float cell0;     // S_0
+	float invCell0;  // 1 / S_0 (S_k and 1/S_k are exact power-of-two multiples)
+	uint32_t mask;   // hash table size - 1
+};
+
 __device__ __forceinline__ int CellCoord(float x, float invCell) { return (int)floorf(x * invCell); }
-__device__ __forceinline__ uint32_t CellHash(int ix, int iy, uint32_t mask)
+__device__ __forceinline__ uint32_t CellHash(int level, int ix, int iy, uint32_t mask)
 {
-	return (((uint32_t)ix * 0x9E3779B1u) ^ ((uint32_t)iy * 0x85EBCA77u)) & mask;
+	return (((uint32_t)ix * 0x9E3779B1u) ^ ((uint32_t)iy * 0x85EBCA77u) ^ ((uint32_t)level * 0xC2B2AE3Du)) & mask;
 }
-__device__ __forceinline__ bool IsLargeProxy(float4 fat, float cellSize)
+// finest level whose cell holds the AABB with a 1/64 margin (the margin absorbs the rounding of the cell
+// coordinates, so that an overlapping proxy is never more than one cell below the query's lower cell)
+__device__ __forceinline__ int ProxyLevel(float4 fat, float cell0)
 {
-	// strictly smaller than a cell, with margin for the rounding of the cell coordinates
-	float lim = cellSize * 0.984375f;
-	return !((fat.z - fat.x) <= lim && (fat.w - fat.y) <= lim);
+	float ext = Max(fat.z - fat.x, fat.w - fat.y);
+	float lim = cell0 * 0.984375f;
+	int k = 0;
+	while (!(ext <= lim) && k < B2CU_GRID_LEVELS)
+	{
+		lim *= 2.0f;
+		++k;
+	}
+	return k; // == B2CU_GRID_LEVELS: larger than the coarsest cell ("huge")
+}
+__device__ __forceinline__ float LevelInvCell(float invCell0, int level) { return ldexpf(invCell0, -level); }
+
+__device__ __forceinline__ bool IsMovedProxy(const DeviceArrays& d, int p)
+{
+	return ((d.pgroup[p] >> 16) & B2CU_PROXY_MOVED) != 0;
 }
 
-__global__ void GridCountKernel(DeviceArrays d, int proxyCount, float cellSize, float invCell, uint32_t gridMask)
+// levelInfo[l] = proxies on level l, levelInfo[LEVELS+1+l] = moved proxies on level l (l == LEVELS: huge)
+__global__ void __launch_bounds__(256) GridCountKernel(DeviceArrays d, int proxyCount, GridParams g)
 {
+	__shared__ int sh[2 * (B2CU_GRID_LEVELS + 1)];
+	if (threadIdx.x < 2 * (B2CU_GRID_LEVELS + 1)) sh[threadIdx.x] = 0;
+	__syncthreads();
 	B2CU_GRID_STRIDE(p, proxyCount)
 	{
 		float4 fat = d.fat[p];
-		bool moved = ((d.pgroup[p] >> 16) & B2CU_PROXY_MOVED) != 0;
-		if (IsLargeProxy(fat, cellSize))
+		bool moved = IsMovedProxy(d, p);
+		int level = ProxyLevel(fat, g.cell0);
+		atomicAdd(&sh[level], 1);
+		if (moved) atomicAdd(&sh[B2CU_GRID_LEVELS + 1 + level], 1);
+		if (level == B2CU_GRID_LEVELS)
 		{
 			d.cellOfProxy[p] = -1;
 			d.largeList[atomicAdd(&d.counters[CNT_LARGE], 1)] = p;
-			if (moved) d.largeMovedList[atomicAdd(&d.counters[CNT_LARGE_MOVED], 1)] = p;
 		}
 		else
 		{
-			uint32_t h = CellHash(CellCoord(fat.x, invCell), CellCoord(fat.y, invCell), gridMask);
+			float inv = LevelInvCell(g.invCell0, level);
+			uint32_t h = CellHash(level, CellCoord(fat.x, inv), CellCoord(fat.y, inv), g.mask);
 			d.cellOfProxy[p] = (int)h;
 			atomicAdd(&d.cellCount[h], 1);
-			if (moved) d.movedList[atomicAdd(&d.counters[CNT_MOVED], 1)] = p;
 		}
+	}
+	__syncthreads();
+	if (threadIdx.x < 2 * (B2CU_GRID_LEVELS + 1) && sh[threadIdx.x])
+	{
+		atomicAdd(&d.levelInfo[threadIdx.x], sh[threadIdx.x]);
+		if (threadIdx.x > B2CU_GRID_LEVELS) atomicAdd(&d.counters[CNT_MOVED], sh[threadIdx.x]);
 	}
 }
 
@@ -1254,70 +1303,88 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 	else d.counters[CNT_ERROR] = 1;
 }
 
-__device__ __forceinline__ bool IsMovedProxy(const DeviceArrays& d, int p)
+// One thread per proxy p.  p examines
+//   its own level       if p moved:  every overlapping r, except a moved r with a smaller id (r reports that pair)
+//   each coarser level  every overlapping r such that p or r moved (r never looks down at p's level)
+//   the huge list       like a coarser level
+// so each pair with a moved member is examined exactly once.
+__global__ void __launch_bounds__(128) QueryPairsKernel(DeviceArrays d, int proxyCount, GridParams g, int contactCount,
+                                                        int pairCapacity)
 {
-	return ((d.pgroup[p] >> 16) & B2CU_PROXY_MOVED) != 0;
-}
-
-// one thread per moved small proxy
-__global__ void __launch_bounds__(128) QuerySmallKernel(DeviceArrays d, float invCell, uint32_t gridMask,
-                                                        int contactCount, int pairCapacity)
-{
-	int n = d.counters[CNT_MOVED];
-	int nLarge = d.counters[CNT_LARGE];
-	B2CU_GRID_STRIDE(t, n)
+	__shared__ int shCount[B2CU_GRID_LEVELS + 1];
+	__shared__ int shMoved[B2CU_GRID_LEVELS + 1];
+	if (threadIdx.x <= B2CU_GRID_LEVELS)
 	{
-		int q = d.movedList[t];
-		float4 fq = d.fat[q];
-		int x0 = CellCoord(fq.x, invCell) - 1, x1 = CellCoord(fq.z, invCell);
-		int y0 = CellCoord(fq.y, invCell) - 1, y1 = CellCoord(fq.w, invCell);
-		for (int cy = y0; cy <= y1; ++cy)
-		{
-			for (int cx = x0; cx <= x1; ++cx)
-			{
-				uint32_t h = CellHash(cx, cy, gridMask);
-				int start = d.cellStart[h];
-				int end = start + d.cellCount[h];
-				for (int s = start; s < end; ++s)
-				{
-					int p = d.cellItems[s];
-					if (p == q) continue;
-					float4 fp = d.fat[p];
-					// a bucket can hold several cells: take p only when it is registered in THIS cell
-					if (CellCoord(fp.x, invCell) != cx || CellCoord(fp.y, invCell) != cy) continue;
-					if (!AabbOverlap(fq, fp)) continue;
-					// both moved: the pair is reported by the query of the smaller proxy id
-					if (IsMovedProxy(d, p) && p < q) continue;
-					TryAddPair(d, q, p, contactCount, pairCapacity);
-				}
-			}
-		}
-		for (int s = 0; s < nLarge; ++s)
-		{
-			int p = d.largeList[s];
-			if (!AabbOverlap(fq, d.fat[p])) continue;
-			if (IsMovedProxy(d, p) && p < q) continue;
-			TryAddPair(d, q, p, contactCount, pairCapacity);
-		}
+		shCount[threadIdx.x] = d.levelInfo[threadIdx.x];
+		shMoved[threadIdx.x] = d.levelInfo[B2CU_GRID_LEVELS + 1 + threadIdx.x];
 	}
-}
+	__syncthreads();
+	const int nHuge = shCount[B2CU_GRID_LEVELS];
 
-// moved large proxies: every proxy tests itself against the (short) list of moved large proxies
-__global__ void QueryLargeKernel(DeviceArrays d, int proxyCount, int contactCount, int pairCapacity)
-{
-	int nLargeMoved = d.counters[CNT_LARGE_MOVED];
-	if (nLargeMoved == 0) return;
 	B2CU_GRID_STRIDE(p, proxyCount)
 	{
 		float4 fp = d.fat[p];
-		bool pMoved = IsMovedProxy(d, p);
-		for (int s = 0; s < nLargeMoved; ++s)
+		bool movedP = IsMovedProxy(d, p);
+		int levelP = ProxyLevel(fp, g.cell0);
+
+		for (int level = levelP; level < B2CU_GRID_LEVELS; ++level)
 		{
-			int q = d.largeMovedList[s];
-			if (q == p) continue;
-			if (!AabbOverlap(d.fat[q], fp)) continue;
-			if (pMoved && p < q) continue;
-			TryAddPair(d, q, p, contactCount, pairCapacity);
+			if (shCount[level] == 0) continue;
+			bool same = level == levelP;
+			if (!movedP && (same || shMoved[level] == 0)) continue;
+			float inv = LevelInvCell(g.invCell0, level);
+			int x0 = CellCoord(fp.x, inv) - 1, x1 = CellCoord(fp.z, inv);
+			int y0 = CellCoord(fp.y, inv) - 1, y1 = CellCoord(fp.w, inv);
+			for (int cy = y0; cy <= y1; ++cy)
+			{
+				for (int cx = x0; cx <= x1; ++cx)
+				{
+					uint32_t h = CellHash(level, cx, cy, g.mask);
+					int start = d.cellStart[h];
+					int end = start + d.cellCount[h];
+					for (int s = start; s < end; ++s)
+					{
+						int r = d.cellItems[s];
+						if (r == p) continue;
+						float4 fr = d.fat[r];
+						// a bucket can hold several cells and levels: take r only when it is registered in THIS cell
+						if (CellCoord(fr.x, inv) != cx || CellCoord(fr.y, inv) != cy) continue;
+						if (ProxyLevel(fr, g.cell0) != level) continue;
+						if (!AabbOverlap(fp, fr)) continue;
+						bool movedR = IsMovedProxy(d, r);
+						if (same)
+						{
+							if (movedR && r < p) continue;
+						}
+						else if (!movedP && !movedR)
+						{
+							continue;
+						}
+						TryAddPair(d, p, r, contactCount, pairCapacity);
+					}
+				}
+			}
+		}
+
+		if (nHuge > 0 && (movedP || shMoved[B2CU_GRID_LEVELS] > 0))
+		{
+			bool hugeP = levelP == B2CU_GRID_LEVELS;
+			for (int s = 0; s < nHuge; ++s)
+			{
+				int r = d.largeList[s];
+				if (r == p) continue;
+				if (!AabbOverlap(fp, d.fat[r])) continue;
+				bool movedR = IsMovedProxy(d, r);
+				if (hugeP)
+				{
+					if (!movedP || (movedR && r < p)) continue;
+				}
+				else if (!movedP && !movedR)
+				{
+					continue;
+				}
+				TryAddPair(d, p, r, contactCount, pairCapacity);
+			}
 		}
 	}
 }

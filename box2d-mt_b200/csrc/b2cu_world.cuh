@@ -105,8 +105,8 @@ struct DeviceArrays
 	uint64_t* solverKeys;   // contact key of the k-th constraint of the solver order (for b2cuGetSolverOrder)
 	int* listC;
 	int* movedList;         // proxy capacity
-	int* largeList;
-	int* largeMovedList;
+	int* largeList;         // proxies larger than the coarsest grid cell
+	int* levelInfo;         // per grid level: proxy count, then moved count
 	int* colourCount;       // [B2CU_MAX_COLOURS + 1]
 	uint64_t* toiKeys;
 

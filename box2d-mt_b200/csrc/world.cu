@@ -142,7 +142,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->toiKeys, CAP_CONTACT));
 	v.push_back(Desc(&d->movedList, CAP_PROXY));
 	v.push_back(Desc(&d->largeList, CAP_PROXY));
-	v.push_back(Desc(&d->largeMovedList, CAP_PROXY));
+	v.push_back(Desc(&d->levelInfo, CAP_FIXED, 64));
 	v.push_back(Desc(&d->colourCount, CAP_FIXED, B2CU_MAX_COLOURS + 2));
 	v.push_back(Desc(&d->cellCount, CAP_GRID));
 	v.push_back(Desc(&d->cellStart, CAP_GRID));
@@ -278,22 +278,22 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 
 	if ((rc = ZeroCounter(w, CNT_MOVED))) return rc;
 	if ((rc = ZeroCounter(w, CNT_LARGE))) return rc;
-	if ((rc = ZeroCounter(w, CNT_LARGE_MOVED))) return rc;
 	if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
 	if ((rc = ZeroCounter(w, CNT_KEEP))) return rc;
 
+	GridParams grid;
+	grid.cell0 = w->cellSize;
+	grid.invCell0 = 1.0f / w->cellSize;
+	grid.mask = (uint32_t)w->gridSize - 1u;
 	if (np > 0)
 	{
-		const float cell = w->cellSize;
-		const float invCell = 1.0f / cell;
-		const uint32_t mask = (uint32_t)w->gridSize - 1u;
 		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
-		LAUNCH(w, GridCountKernel, GridFor(np), kBlock, d, np, cell, invCell, mask);
+		CUDA_TRY(w, cudaMemsetAsync(d.levelInfo, 0, sizeof(int) * 64, w->stream));
+		LAUNCH(w, GridCountKernel, GridFor(np), kBlock, d, np, grid);
 		ExclusiveScan(&w->prims, d.cellCount, d.cellStart, w->gridSize, nullptr, w->stream);
 		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
 		LAUNCH(w, GridFillKernel, GridFor(np), kBlock, d, np);
-		LAUNCH(w, QuerySmallKernel, GridFor(np, 128), 128, d, invCell, mask, nc, w->contactCapacity);
-		LAUNCH(w, QueryLargeKernel, GridFor(np), kBlock, d, np, nc, w->contactCapacity);
+		LAUNCH(w, QueryPairsKernel, GridFor(np, 128), 128, d, np, grid, nc, w->contactCapacity);
 	}
 
 	// destroyed contacts -> keep flags and ranks
@@ -315,17 +315,14 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		DeviceArrays& dd = w->d;
 		if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
 		if ((rc = ZeroCounter(w, CNT_ERROR))) return rc;
-		const float invCell = 1.0f / w->cellSize;
-		const uint32_t mask = (uint32_t)w->gridSize - 1u;
-		LAUNCH(w, QuerySmallKernel, GridFor(np, 128), 128, dd, invCell, mask, nc, w->contactCapacity);
-		LAUNCH(w, QueryLargeKernel, GridFor(np), kBlock, dd, np, nc, w->contactCapacity);
+		LAUNCH(w, QueryPairsKernel, GridFor(np, 128), 128, dd, np, grid, nc, w->contactCapacity);
 		if ((rc = ReadCounters(w))) return rc;
 		if (w->hostCounters[CNT_ERROR])
 			return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
 	}
 	if (np > 0) LAUNCH(w, ClearMovedKernel, GridFor(np), kBlock, w->d, np);
 	const int newCount = w->hostCounters[CNT_NEW_PAIRS];
-	const int moved = w->hostCounters[CNT_MOVED] + w->hostCounters[CNT_LARGE_MOVED];
+	const int moved = w->hostCounters[CNT_MOVED];
 	*newCountOut = newCount;
 	*destroyedOut = nc - keepCount;
 	*movedOut = moved;
