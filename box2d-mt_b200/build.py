@@ -39,5 +39,37 @@ def build(force=False, verbose=False):
     return OUT
 
 
+HOST = os.path.join(HERE, "host")
+HOST_OUT = os.path.join(HERE, "libbox2d_b200.so")
+HOST_SOURCES = ["src/b2Common.cpp", "src/b2Shapes.cpp", "src/b2Body.cpp", "src/b2World.cpp",
+                "src/b2CudaStepExecutor.cpp", "capi/b2host_capi.cpp"]
+
+
+def host_lib_path():
+    return HOST_OUT
+
+
+def build_host(force=False):
+    """libbox2d_b200.so: the C++ host API (b2World, b2Body, b2Fixture, b2CudaStepExecutor) + its flat C binding.
+    -ffp-contract=off: host-computed mass data, AABBs and sincos must round like the reference's build."""
+    srcs = [os.path.join(HOST, s) for s in HOST_SOURCES]
+    deps = list(srcs) + [os.path.join(HERE, "..", "include", "b2cuda.h"), OUT]
+    for d, _, files in os.walk(os.path.join(HOST, "Box2D")):
+        deps += [os.path.join(d, f) for f in files]
+    if not force and os.path.exists(HOST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_OUT) for d in deps):
+        return HOST_OUT
+    cmd = ["g++", "-std=c++11", "-O2", "-DNDEBUG", "-fPIC", "-shared", "-ffp-contract=off",
+           "-Wall", "-I" + HOST, "-I" + os.path.join(HERE, "..", "include")] + srcs + \
+          ["-L" + HERE, "-lb2cuda", "-Wl,-rpath,$ORIGIN", "-o", HOST_OUT]
+    subprocess.run(cmd, check=True)
+    return HOST_OUT
+
+
+def build_all(force=False, verbose=False):
+    build(force, verbose)
+    build_host(force)
+    return OUT, HOST_OUT
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_all(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

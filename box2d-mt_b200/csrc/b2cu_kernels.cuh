@@ -1557,6 +1557,69 @@ __global__ void CollidePairsKernel(const b2cuShape* __restrict__ shapes, int pai
 	}
 }
 
+// b2cuGetContactsByKey: one thread per requested key, AoS records out
+__global__ void GatherContactsByKeyKernel(DeviceArrays d, int contactCount, const uint64_t* __restrict__ keys, int n,
+                                          b2cuContact* __restrict__ out)
+{
+	B2CU_GRID_STRIDE(j, n)
+	{
+		uint64_t key = keys[j];
+		int i = LowerBound64(d.c.key, contactCount, key);
+		b2cuContact o;
+		if (i < contactCount && d.c.key[i] == key)
+		{
+			int2 pr = d.c.proxies[i];
+			float4 m0 = d.c.m0[i], m1 = d.c.m1[i], m2 = d.c.m2[i], mix = d.c.mix[i];
+			uint4 m3 = d.c.m3[i];
+			uint32_t fA = d.bflags[d.pbody[pr.x]], fB = d.bflags[d.pbody[pr.y]];
+			uint32_t f = d.c.flags[i] & ~(uint32_t)B2CU_CONTACT_INACTIVE;
+			if (!IsAwakeNonStatic(fA) && !IsAwakeNonStatic(fB)) f |= B2CU_CONTACT_INACTIVE;
+			o.proxyA = pr.x;
+			o.proxyB = pr.y;
+			o.flags = f;
+			o.friction = mix.x;
+			o.restitution = mix.y;
+			o.tangentSpeed = mix.z;
+			o.toiCount = d.c.toiCount[i];
+			o.toi = mix.w;
+			o.manifold.localNormal[0] = m0.x; o.manifold.localNormal[1] = m0.y;
+			o.manifold.localPoint[0] = m0.z; o.manifold.localPoint[1] = m0.w;
+			o.manifold.points[0].localPoint[0] = m1.x; o.manifold.points[0].localPoint[1] = m1.y;
+			o.manifold.points[0].normalImpulse = m1.z; o.manifold.points[0].tangentImpulse = m1.w;
+			o.manifold.points[1].localPoint[0] = m2.x; o.manifold.points[1].localPoint[1] = m2.y;
+			o.manifold.points[1].normalImpulse = m2.z; o.manifold.points[1].tangentImpulse = m2.w;
+			o.manifold.id[0] = m3.x; o.manifold.id[1] = m3.y;
+			o.manifold.type = (int32_t)m3.z;
+			o.manifold.pointCount = (int32_t)m3.w;
+		}
+		else
+		{
+			int a = (int)(key >> 32), b = (int)(key & 0xFFFFFFFFull);
+			bool swap = NeedsSwap(d.shapes[d.pshape[a]].type, d.shapes[d.pshape[b]].type);
+			o.proxyA = swap ? b : a;
+			o.proxyB = swap ? a : b;
+			o.flags = 0u;
+			float2 matA = d.pmat[a], matB = d.pmat[b];
+			o.friction = sqrtf(matA.x * matB.x);
+			o.restitution = matA.y > matB.y ? matA.y : matB.y;
+			o.tangentSpeed = 0.0f;
+			o.toiCount = 0;
+			o.toi = 1.0f;
+			o.manifold.localNormal[0] = o.manifold.localNormal[1] = 0.0f;
+			o.manifold.localPoint[0] = o.manifold.localPoint[1] = 0.0f;
+			for (int k = 0; k < 2; ++k)
+			{
+				o.manifold.points[k].localPoint[0] = o.manifold.points[k].localPoint[1] = 0.0f;
+				o.manifold.points[k].normalImpulse = o.manifold.points[k].tangentImpulse = 0.0f;
+				o.manifold.id[k] = 0u;
+			}
+			o.manifold.type = 0;
+			o.manifold.pointCount = 0;
+		}
+		out[j] = o;
+	}
+}
+
 __global__ void SinCosKernel(int n, const float* __restrict__ x, float* __restrict__ s, float* __restrict__ c)
 {
 	B2CU_GRID_STRIDE(i, n)

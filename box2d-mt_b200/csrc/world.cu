@@ -1038,6 +1038,34 @@ int b2cuGetEvents(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* 
 	return SyncCheck(w);
 }
 
+int b2cuGetContactsByKey(b2cuWorld* w, int32_t count, const b2cuContactKey* keys, b2cuContact* out)
+{
+	if (!w || count < 0 || (count > 0 && (!keys || !out))) return B2CU_ERR_ARGUMENT;
+	if (count == 0) return B2CU_OK;
+	cudaSetDevice(w->device);
+	for (int i = 0; i < count; ++i)
+	{
+		int a = (int)(keys[i] >> 32), b = (int)(keys[i] & 0xFFFFFFFFull);
+		if (a < 0 || a >= w->proxyCount || b < 0 || b >= w->proxyCount)
+			return SetError(w, B2CU_ERR_ARGUMENT, "key %d: proxies %d,%d out of range", i, a, b);
+	}
+	uint64_t* dKeys = nullptr;
+	b2cuContact* dOut = nullptr;
+	CUDA_TRY(w, cudaMalloc(&dKeys, sizeof(uint64_t) * count));
+	cudaError_t e = cudaMalloc(&dOut, sizeof(b2cuContact) * count);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(dKeys, keys, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, w->stream);
+	if (e == cudaSuccess)
+	{
+		GatherContactsByKeyKernel<<<GridFor(count), kBlock, 0, w->stream>>>(w->d, w->contactCount, dKeys, count, dOut);
+		e = cudaMemcpyAsync(out, dOut, sizeof(b2cuContact) * count, cudaMemcpyDeviceToHost, w->stream);
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+	cudaFree(dKeys);
+	cudaFree(dOut);
+	if (e != cudaSuccess) return SetError(w, B2CU_ERR_CUDA, "b2cuGetContactsByKey: %s", cudaGetErrorString(e));
+	return B2CU_OK;
+}
+
 int b2cuGetSolverOrder(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* colour, int32_t* count)
 {
 	if (!w || capacity < 0) return B2CU_ERR_ARGUMENT;

@@ -1,0 +1,68 @@
+// b2CudaStepExecutor: the executor that runs b2World::Step on a B200 through the C ABI of libb2cuda.so
+// (include/b2cuda.h).  Takes the place of b2ThreadPoolTaskExecutor (reference: Box2D/MT/b2ThreadPool.h:134-169)
+// in user code:
+//
+//     b2CudaStepExecutor executor;                    // was: b2ThreadPoolTaskExecutor executor;
+//     world.Step(dt, velocityIterations, positionIterations, executor);
+//
+// One executor can serve several worlds, one step at a time (as the reference's, b2ThreadPool.cpp:336-341).
+#ifndef B2_CUDA_STEP_EXECUTOR_H
+#define B2_CUDA_STEP_EXECUTOR_H
+
+#include "Box2D/MT/b2TaskExecutor.h"
+
+struct b2cuWorld;
+struct b2cuStepInfo;
+
+struct b2CudaStepOptions
+{
+	b2CudaStepOptions() : device(0), downloadBodies(true), dispatchEvents(true) {}
+	/// CUDA device ordinal
+	int32 device;
+	/// refresh the host body mirror (transform, sweep, velocities, awake) after every step; when false the
+	/// mirror is refreshed lazily by the first accessor that needs it
+	bool downloadBodies;
+	/// fetch begin/end touch events after every step and invoke the contact listener
+	bool dispatchEvents;
+};
+
+class b2CudaStepExecutor : public b2TaskExecutor
+{
+public:
+	explicit b2CudaStepExecutor(const b2CudaStepOptions& options = b2CudaStepOptions());
+	~b2CudaStepExecutor() override;
+
+	/// user tasks run inline on the calling thread
+	uint32 GetThreadCount() const override { return 1; }
+	void SubmitTask(b2TaskGroup* taskGroup, b2Task* task) override;
+	b2TaskGroup* AcquireTaskGroup() override { return &m_group; }
+
+	bool StepWorld(b2World& world, float32 timeStep, int32 velocityIterations, int32 positionIterations) override;
+
+	const b2CudaStepOptions& GetOptions() const { return m_options; }
+	/// downloadBodies / dispatchEvents may be changed between steps (the device ordinal may not)
+	void SetOptions(const b2CudaStepOptions& options)
+	{
+		m_options.downloadBodies = options.downloadBodies;
+		m_options.dispatchEvents = options.dispatchEvents;
+	}
+	/// status of the last StepWorld (0 = ok, else a b2cuStatus) and its message
+	int32 GetLastStatus() const { return m_status; }
+	const char* GetLastError() const { return m_error; }
+	/// counters and per-phase device timings of the last step
+	const b2cuStepInfo& GetLastStepInfo() const;
+	/// the C-ABI handle of a world this executor has stepped (nullptr before its first step): for callers that
+	/// want the bulk / diagnostic entry points of include/b2cuda.h
+	b2cuWorld* GetDeviceWorld(b2World* world) const;
+	/// release the device copy of a world (called by ~b2World)
+	void DetachWorld(b2World* world);
+
+private:
+	b2CudaStepOptions m_options;
+	b2TaskGroup m_group;
+	int32 m_status;
+	char m_error[512];
+	void* m_impl;
+};
+
+#endif

@@ -1,0 +1,350 @@
+// Flat C binding over the C++ host API (b2World / b2Body / b2Fixture / b2CudaStepExecutor) for Python tests and
+// bench.py: scenes are built with the same calls user code makes (CreateBody, CreateFixture), stepped with
+// b2World::Step(dt, vIters, pIters, b2CudaStepExecutor&), and read back through the public accessors.
+#include "Box2D/Box2D.h"
+
+#include <cstring>
+#include <vector>
+
+namespace
+{
+
+struct BodyDefRec
+{
+	int32 type;
+	float px, py, angle, vx, vy, w, linearDamping, angularDamping, gravityScale;
+	uint32 flags; // 1 allowSleep, 2 awake, 4 fixedRotation, 8 bullet, 16 active
+};
+
+struct ShapeDefRec
+{
+	int32 kind; // 0 circle, 1 edge, 2 polygon (Set), 3 box (SetAsBox)
+	int32 count;
+	float radius;
+	uint32 flags;
+	float v[8][2];
+	float n[8][2];
+	float centroid[2];
+};
+
+struct FixtureDefRec
+{
+	int32 body, shape;
+	float density, friction, restitution;
+	uint32 flags;
+	uint16 categoryBits, maskBits;
+	int16 groupIndex;
+	uint16 pad;
+};
+
+class Recorder : public b2ContactListener
+{
+public:
+	bool BeginContactImmediate(b2Contact*, uint32) override { return true; }
+	bool EndContactImmediate(b2Contact*, uint32) override { return true; }
+	bool PreSolveImmediate(b2Contact*, const b2Manifold*, uint32) override { return false; }
+	bool PostSolveImmediate(b2Contact*, const b2ContactImpulse*, uint32) override { return false; }
+	void BeginContact(b2Contact* c) override
+	{
+		begins.push_back(c->GetKey());
+		if (c->IsTouching()) ++beginTouching;
+	}
+	void EndContact(b2Contact* c) override { ends.push_back(c->GetKey()); }
+	std::vector<uint64> begins, ends;
+	int beginTouching = 0;
+};
+
+struct Host
+{
+	b2World* world;
+	b2CudaStepExecutor* executor;
+	Recorder recorder;
+	std::vector<b2Body*> bodies;
+	std::vector<b2Fixture*> fixtures;
+};
+
+} // namespace
+
+extern "C" {
+
+#define B2H_API __attribute__((visibility("default")))
+
+B2H_API void* b2h_create(float gx, float gy, uint32 worldFlags, int32 device, int32 downloadBodies, int32 events)
+{
+	Host* h = new Host;
+	h->world = new b2World(b2Vec2(gx, gy));
+	h->world->SetAllowSleeping((worldFlags & B2CU_WORLD_ALLOW_SLEEP) != 0);
+	h->world->SetWarmStarting((worldFlags & B2CU_WORLD_WARM_STARTING) != 0);
+	h->world->SetContinuousPhysics((worldFlags & B2CU_WORLD_CONTINUOUS) != 0);
+	h->world->SetSubStepping((worldFlags & B2CU_WORLD_SUB_STEPPING) != 0);
+	h->world->SetAutoClearForces((worldFlags & B2CU_WORLD_CLEAR_FORCES) != 0);
+	if (events) h->world->SetContactListener(&h->recorder);
+	b2CudaStepOptions opt;
+	opt.device = device;
+	opt.downloadBodies = downloadBodies != 0;
+	opt.dispatchEvents = events != 0;
+	h->executor = new b2CudaStepExecutor(opt);
+	return h;
+}
+
+B2H_API void b2h_set_options(void* p, int32 downloadBodies, int32 events)
+{
+	Host* h = static_cast<Host*>(p);
+	b2CudaStepOptions opt = h->executor->GetOptions();
+	opt.downloadBodies = downloadBodies != 0;
+	opt.dispatchEvents = events != 0;
+	h->executor->SetOptions(opt);
+	h->world->SetContactListener(events ? &h->recorder : nullptr);
+}
+
+/// apply a force to the centre of `count` consecutive bodies starting at `first` (the per-step user input of
+/// the end-to-end benchmark)
+B2H_API void b2h_apply_force_range(void* p, int32 first, int32 count, float fx, float fy)
+{
+	Host* h = static_cast<Host*>(p);
+	for (int32 i = first; i < first + count && i < (int32)h->bodies.size(); ++i)
+	{
+		if (h->bodies[i]) h->bodies[i]->ApplyForceToCenter(b2Vec2(fx, fy), true);
+	}
+}
+
+B2H_API void b2h_destroy(void* p)
+{
+	Host* h = static_cast<Host*>(p);
+	if (!h) return;
+	delete h->world;
+	delete h->executor;
+	delete h;
+}
+
+B2H_API int b2h_build(void* p, int32 bodyCount, const BodyDefRec* bodies, int32 shapeCount, const ShapeDefRec* shapes,
+                      int32 fixtureCount, const FixtureDefRec* fixtures)
+{
+	Host* h = static_cast<Host*>(p);
+	int32 f = 0;
+	for (int32 i = 0; i < bodyCount; ++i)
+	{
+		const BodyDefRec& d = bodies[i];
+		b2BodyDef bd;
+		bd.type = (b2BodyType)d.type;
+		bd.position.Set(d.px, d.py);
+		bd.angle = d.angle;
+		bd.linearVelocity.Set(d.vx, d.vy);
+		bd.angularVelocity = d.w;
+		bd.linearDamping = d.linearDamping;
+		bd.angularDamping = d.angularDamping;
+		bd.gravityScale = d.gravityScale;
+		bd.allowSleep = (d.flags & 1) != 0;
+		bd.awake = (d.flags & 2) != 0;
+		bd.fixedRotation = (d.flags & 4) != 0;
+		bd.bullet = (d.flags & 8) != 0;
+		bd.active = (d.flags & 16) != 0;
+		b2Body* body = h->world->CreateBody(&bd);
+		h->bodies.push_back(body);
+		while (f < fixtureCount && fixtures[f].body == i)
+		{
+			const FixtureDefRec& fd = fixtures[f];
+			if (fd.shape < 0 || fd.shape >= shapeCount) return -1;
+			const ShapeDefRec& sd = shapes[fd.shape];
+			b2CircleShape circle;
+			b2EdgeShape edge;
+			b2PolygonShape poly;
+			const b2Shape* shape = nullptr;
+			switch (sd.kind)
+			{
+			case 0:
+				circle.m_radius = sd.radius;
+				circle.m_p.Set(sd.v[0][0], sd.v[0][1]);
+				shape = &circle;
+				break;
+			case 1:
+				edge.Set(b2Vec2(sd.v[0][0], sd.v[0][1]), b2Vec2(sd.v[1][0], sd.v[1][1]));
+				if (sd.flags & 1)
+				{
+					edge.m_vertex0.Set(sd.v[2][0], sd.v[2][1]);
+					edge.m_hasVertex0 = true;
+				}
+				if (sd.flags & 2)
+				{
+					edge.m_vertex3.Set(sd.v[3][0], sd.v[3][1]);
+					edge.m_hasVertex3 = true;
+				}
+				shape = &edge;
+				break;
+			case 2:
+			{
+				b2Vec2 vs[b2_maxPolygonVertices];
+				for (int32 k = 0; k < sd.count; ++k) vs[k].Set(sd.v[k][0], sd.v[k][1]);
+				poly.Set(vs, sd.count);
+				shape = &poly;
+				break;
+			}
+			default:
+				if (sd.flags & 1) poly.SetAsBox(sd.v[0][0], sd.v[0][1], b2Vec2(sd.v[1][0], sd.v[1][1]), sd.v[2][0]);
+				else poly.SetAsBox(sd.v[0][0], sd.v[0][1]);
+				shape = &poly;
+				break;
+			}
+			b2FixtureDef def;
+			def.shape = shape;
+			def.density = fd.density;
+			def.friction = fd.friction;
+			def.restitution = fd.restitution;
+			def.isSensor = (fd.flags & B2CU_PROXY_SENSOR) != 0;
+			def.thickShape = (fd.flags & B2CU_PROXY_THICK) != 0;
+			def.filter.categoryBits = fd.categoryBits;
+			def.filter.maskBits = fd.maskBits;
+			def.filter.groupIndex = fd.groupIndex;
+			h->fixtures.push_back(body->CreateFixture(&def));
+			++f;
+		}
+	}
+	return f == fixtureCount ? 0 : -2;
+}
+
+B2H_API int b2h_step(void* p, float dt, int32 velocityIterations, int32 positionIterations)
+{
+	Host* h = static_cast<Host*>(p);
+	h->recorder.begins.clear();
+	h->recorder.ends.clear();
+	h->world->Step(dt, velocityIterations, positionIterations, *h->executor);
+	return h->world->GetLastStepStatus();
+}
+
+B2H_API const char* b2h_last_error(void* p) { return static_cast<Host*>(p)->executor->GetLastError(); }
+
+B2H_API void b2h_counts(void* p, int32* bodies, int32* fixtures, int32* contacts)
+{
+	Host* h = static_cast<Host*>(p);
+	*bodies = h->world->GetBodyCount();
+	*fixtures = h->world->GetProxyCount();
+	*contacts = h->world->GetContactCount();
+}
+
+/// body state rows (dense body id order) as seen through the host mirror
+B2H_API void b2h_get_bodies(void* p, b2cuBody* out)
+{
+	Host* h = static_cast<Host*>(p);
+	memcpy(out, h->world->GetBodyStates(), sizeof(b2cuBody) * (size_t)h->world->GetBodyCount());
+}
+
+B2H_API void b2h_get_proxies(void* p, b2cuProxy* out)
+{
+	Host* h = static_cast<Host*>(p);
+	memcpy(out, h->world->GetProxyStates(), sizeof(b2cuProxy) * (size_t)h->world->GetProxyCount());
+}
+
+/// positions / angles / awake flags through the per-body accessors (what TestMT.cpp:91-110 compares)
+B2H_API void b2h_get_transforms(void* p, float* xya, int32* awake)
+{
+	Host* h = static_cast<Host*>(p);
+	for (size_t i = 0; i < h->bodies.size(); ++i)
+	{
+		const b2Body* b = h->bodies[i];
+		xya[3 * i + 0] = b->GetPosition().x;
+		xya[3 * i + 1] = b->GetPosition().y;
+		xya[3 * i + 2] = b->GetAngle();
+		awake[i] = b->IsAwake() ? 1 : 0;
+	}
+}
+
+/// mass data computed on the host by CreateFixture / ResetMassData
+B2H_API void b2h_get_mass(void* p, float* massInertiaCenter)
+{
+	Host* h = static_cast<Host*>(p);
+	for (size_t i = 0; i < h->bodies.size(); ++i)
+	{
+		b2MassData md;
+		h->bodies[i]->GetMassData(&md);
+		massInertiaCenter[4 * i + 0] = md.mass;
+		massInertiaCenter[4 * i + 1] = md.I;
+		massInertiaCenter[4 * i + 2] = md.center.x;
+		massInertiaCenter[4 * i + 3] = md.center.y;
+	}
+}
+
+/// contact snapshot through b2World::GetContactList(): keys, touching flags, point counts
+B2H_API int b2h_get_contacts(void* p, int32 capacity, uint64* keys, int32* touching, int32* pointCount)
+{
+	Host* h = static_cast<Host*>(p);
+	int32 n = 0;
+	for (b2Contact* c = h->world->GetContactList(); c; c = c->GetNext())
+	{
+		if (n < capacity)
+		{
+			keys[n] = c->GetKey();
+			touching[n] = c->IsTouching() ? 1 : 0;
+			pointCount[n] = c->GetManifold()->pointCount;
+		}
+		++n;
+	}
+	return n;
+}
+
+B2H_API int b2h_events(void* p, int32 kind, int32 capacity, uint64* keys)
+{
+	Host* h = static_cast<Host*>(p);
+	const std::vector<uint64>& v = kind == 0 ? h->recorder.begins : h->recorder.ends;
+	for (size_t i = 0; i < v.size() && (int32)i < capacity; ++i) keys[i] = v[i];
+	return (int)v.size();
+}
+
+/// solver order of the last step (keys), straight from the device handle
+B2H_API int b2h_solver_order(void* p, int32 capacity, uint64* keys)
+{
+	Host* h = static_cast<Host*>(p);
+	b2cuWorld* dev = h->executor->GetDeviceWorld(h->world);
+	if (!dev) return 0;
+	int32 n = 0;
+	b2cuGetSolverOrder(dev, capacity, keys, nullptr, &n);
+	return n;
+}
+
+B2H_API void b2h_profile(void* p, float* out13) { memcpy(out13, &static_cast<Host*>(p)->world->GetProfile(), 13 * sizeof(float)); }
+
+B2H_API void b2h_step_info(void* p, b2cuStepInfo* out) { *out = static_cast<Host*>(p)->executor->GetLastStepInfo(); }
+
+/// FNV-1a over (x, y, angle) of every body in GetBodyList() order: the trajectory hash of SURVEY.md 8c
+B2H_API uint32 b2h_hash(void* p)
+{
+	Host* h = static_cast<Host*>(p);
+	uint32 hash = 2166136261u;
+	for (const b2Body* b = h->world->GetBodyList(); b; b = b->GetNext())
+	{
+		float v[3] = {b->GetPosition().x, b->GetPosition().y, b->GetAngle()};
+		const unsigned char* bytes = reinterpret_cast<const unsigned char*>(v);
+		for (size_t i = 0; i < sizeof(v); ++i)
+		{
+			hash ^= bytes[i];
+			hash *= 16777619u;
+		}
+	}
+	return hash;
+}
+
+B2H_API void b2h_set_transform(void* p, int32 body, float x, float y, float angle)
+{
+	static_cast<Host*>(p)->bodies[body]->SetTransform(b2Vec2(x, y), angle);
+}
+B2H_API void b2h_set_velocity(void* p, int32 body, float vx, float vy, float w)
+{
+	Host* h = static_cast<Host*>(p);
+	h->bodies[body]->SetLinearVelocity(b2Vec2(vx, vy));
+	h->bodies[body]->SetAngularVelocity(w);
+}
+B2H_API void b2h_apply_force(void* p, int32 body, float fx, float fy, float torque)
+{
+	Host* h = static_cast<Host*>(p);
+	h->bodies[body]->ApplyForceToCenter(b2Vec2(fx, fy), true);
+	h->bodies[body]->ApplyTorque(torque, true);
+}
+B2H_API void b2h_set_awake(void* p, int32 body, int32 awake) { static_cast<Host*>(p)->bodies[body]->SetAwake(awake != 0); }
+B2H_API void b2h_destroy_body(void* p, int32 body)
+{
+	Host* h = static_cast<Host*>(p);
+	if (h->bodies[body] == nullptr) return;
+	h->world->DestroyBody(h->bodies[body]);
+	h->bodies[body] = nullptr;
+}
+
+} // extern "C"

@@ -1,0 +1,136 @@
+// b2CudaStepExecutor: runs b2World::Step on the device through the C ABI (include/b2cuda.h).
+#include "Box2D/MT/b2CudaStepExecutor.h"
+#include "Box2D/Dynamics/b2World.h"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+namespace
+{
+struct Impl
+{
+	std::map<b2World*, b2cuWorld*> worlds;
+	b2cuStepInfo info;
+};
+} // namespace
+
+b2CudaStepExecutor::b2CudaStepExecutor(const b2CudaStepOptions& options) : m_options(options), m_status(0)
+{
+	m_error[0] = 0;
+	Impl* impl = new Impl;
+	memset(&impl->info, 0, sizeof(impl->info));
+	m_impl = impl;
+}
+
+b2CudaStepExecutor::~b2CudaStepExecutor()
+{
+	Impl* impl = static_cast<Impl*>(m_impl);
+	for (auto it = impl->worlds.begin(); it != impl->worlds.end(); ++it)
+	{
+		// the world keeps its host mirror; a later step with another executor re-uploads everything
+		it->first->RefreshBodies();
+		it->first->RefreshProxies();
+		it->first->m_contactsStale = true;
+		it->first->RefreshContacts();
+		it->first->m_contactsStale = false;
+		it->first->m_fullUpload = true;
+		it->first->m_device = nullptr;
+		it->first->m_owner = nullptr;
+		b2cuDestroyWorld(it->second);
+	}
+	delete impl;
+}
+
+b2cuWorld* b2CudaStepExecutor::GetDeviceWorld(b2World* world) const
+{
+	Impl* impl = static_cast<Impl*>(m_impl);
+	auto it = impl->worlds.find(world);
+	return it == impl->worlds.end() ? nullptr : it->second;
+}
+
+void b2CudaStepExecutor::DetachWorld(b2World* world)
+{
+	Impl* impl = static_cast<Impl*>(m_impl);
+	auto it = impl->worlds.find(world);
+	if (it == impl->worlds.end()) return;
+	b2cuDestroyWorld(it->second);
+	impl->worlds.erase(it);
+}
+
+void b2CudaStepExecutor::SubmitTask(b2TaskGroup* taskGroup, b2Task* task)
+{
+	B2_NOT_USED(taskGroup);
+	b2ThreadContext ctx;
+	ctx.stack = nullptr;
+	ctx.threadId = 0;
+	task->Execute(ctx);
+}
+
+const b2cuStepInfo& b2CudaStepExecutor::GetLastStepInfo() const { return static_cast<Impl*>(m_impl)->info; }
+
+bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 velocityIterations, int32 positionIterations)
+{
+	Impl* impl = static_cast<Impl*>(m_impl);
+	m_status = 0;
+	m_error[0] = 0;
+
+	if (world.m_owner != nullptr && world.m_owner != this)
+	{
+		// last stepped by another executor: take the world over (its state comes back through the host mirror)
+		world.RefreshBodies();
+		world.RefreshProxies();
+		world.m_contactsStale = true;
+		world.RefreshContacts();
+		world.m_contactsStale = false;
+		world.m_owner->DetachWorld(&world);
+		world.m_device = nullptr;
+		world.m_fullUpload = true;
+	}
+
+	b2cuWorld* device = nullptr;
+	auto it = impl->worlds.find(&world);
+	if (it == impl->worlds.end())
+	{
+		b2cuWorldDef def;
+		memset(&def, 0, sizeof(def));
+		def.device = m_options.device;
+		def.gravity[0] = world.m_gravity.x;
+		def.gravity[1] = world.m_gravity.y;
+		def.bodyCapacity = (int32)world.m_states.size();
+		def.proxyCapacity = (int32)world.m_proxies.size();
+		def.shapeCapacity = (int32)world.m_shapes.size();
+		def.contactCapacity = 8 * (int32)world.m_proxies.size();
+		int rc = b2cuCreateWorld(&def, &device);
+		if (rc != B2CU_OK)
+		{
+			m_status = rc;
+			snprintf(m_error, sizeof(m_error), "b2cuCreateWorld failed with status %d (no CUDA device?)", rc);
+			world.m_lastStatus = rc;
+			return false;
+		}
+		impl->worlds[&world] = device;
+		world.m_device = device;
+		world.m_owner = this;
+		if (world.m_bodiesUploaded > 0) world.m_fullUpload = true;
+	}
+	else
+	{
+		device = it->second;
+	}
+
+	int rc = world.UploadDirty(device);
+	if (rc == B2CU_OK) rc = b2cuStep(device, timeStep, velocityIterations, positionIterations, &impl->info);
+	if (rc != B2CU_OK)
+	{
+		m_status = rc;
+		snprintf(m_error, sizeof(m_error), "%s", b2cuGetLastError(device));
+		world.m_lastStatus = rc;
+		fprintf(stderr, "b2CudaStepExecutor: step failed (%d): %s\n", rc, m_error);
+		return false;
+	}
+	if (timeStep > 0.0f) world.m_inv_dt0 = 1.0f / timeStep;
+	world.m_lastStatus = 0;
+	world.AfterDeviceStep(device, impl->info, m_options.downloadBodies, m_options.dispatchEvents);
+	return true;
+}

@@ -1,0 +1,249 @@
+// Shape geometry on the host: hull construction, AABBs and mass data.  These values are uploaded to the device
+// (shape table, initial fat AABBs, inverse mass / inertia), so each routine keeps the fp32 operation order of
+// the reference function it replaces and the results are bit-identical:
+//   circle   Box2D/Collision/Shapes/b2CircleShape.cpp:40-101
+//   edge     Box2D/Collision/Shapes/b2EdgeShape.cpp:116-140
+//   polygon  Box2D/Collision/Shapes/b2PolygonShape.cpp:28-440
+#include "Box2D/Collision/Shapes/b2CircleShape.h"
+#include "Box2D/Collision/Shapes/b2EdgeShape.h"
+#include "Box2D/Collision/Shapes/b2PolygonShape.h"
+
+// ---- circle ----------------------------------------------------------------------------------------------
+
+bool b2CircleShape::TestPoint(const b2Transform& xf, const b2Vec2& p) const
+{
+	b2Vec2 center = xf.p + b2Mul(xf.q, m_p);
+	b2Vec2 d = p - center;
+	return b2Dot(d, d) <= m_radius * m_radius;
+}
+
+void b2CircleShape::ComputeAABB(b2AABB* aabb, const b2Transform& xf, int32) const
+{
+	b2Vec2 p = xf.p + b2Mul(xf.q, m_p);
+	aabb->lowerBound.Set(p.x - m_radius, p.y - m_radius);
+	aabb->upperBound.Set(p.x + m_radius, p.y + m_radius);
+}
+
+void b2CircleShape::ComputeMass(b2MassData* massData, float32 density) const
+{
+	massData->mass = density * b2_pi * m_radius * m_radius;
+	massData->center = m_p;
+	// about the local origin
+	massData->I = massData->mass * (0.5f * m_radius * m_radius + b2Dot(m_p, m_p));
+}
+
+// ---- edge ------------------------------------------------------------------------------------------------
+
+void b2EdgeShape::ComputeAABB(b2AABB* aabb, const b2Transform& xf, int32) const
+{
+	b2Vec2 v1 = b2Mul(xf, m_vertex1);
+	b2Vec2 v2 = b2Mul(xf, m_vertex2);
+	b2Vec2 lower = b2Min(v1, v2);
+	b2Vec2 upper = b2Max(v1, v2);
+	b2Vec2 r(m_radius, m_radius);
+	aabb->lowerBound = lower - r;
+	aabb->upperBound = upper + r;
+}
+
+void b2EdgeShape::ComputeMass(b2MassData* massData, float32) const
+{
+	massData->mass = 0.0f;
+	massData->center = 0.5f * (m_vertex1 + m_vertex2);
+	massData->I = 0.0f;
+}
+
+// ---- polygon ---------------------------------------------------------------------------------------------
+
+void b2PolygonShape::SetAsBox(float32 hx, float32 hy)
+{
+	m_count = 4;
+	m_vertices[0].Set(-hx, -hy);
+	m_vertices[1].Set(hx, -hy);
+	m_vertices[2].Set(hx, hy);
+	m_vertices[3].Set(-hx, hy);
+	m_normals[0].Set(0.0f, -1.0f);
+	m_normals[1].Set(1.0f, 0.0f);
+	m_normals[2].Set(0.0f, 1.0f);
+	m_normals[3].Set(-1.0f, 0.0f);
+	m_centroid.SetZero();
+}
+
+void b2PolygonShape::SetAsBox(float32 hx, float32 hy, const b2Vec2& center, float32 angle)
+{
+	SetAsBox(hx, hy);
+	m_centroid = center;
+	b2Transform xf;
+	xf.p = center;
+	xf.q.Set(angle);
+	for (int32 i = 0; i < m_count; ++i)
+	{
+		m_vertices[i] = b2Mul(xf, m_vertices[i]);
+		m_normals[i] = b2Mul(xf.q, m_normals[i]);
+	}
+}
+
+// area-weighted centroid over the triangle fan about the origin (reference :74-118)
+static b2Vec2 PolygonCentroid(const b2Vec2* vs, int32 count)
+{
+	b2Vec2 c(0.0f, 0.0f);
+	float32 area = 0.0f;
+	const b2Vec2 origin(0.0f, 0.0f);
+	const float32 inv3 = 1.0f / 3.0f;
+	for (int32 i = 0; i < count; ++i)
+	{
+		b2Vec2 p1 = origin;
+		b2Vec2 p2 = vs[i];
+		b2Vec2 p3 = i + 1 < count ? vs[i + 1] : vs[0];
+		b2Vec2 e1 = p2 - p1;
+		b2Vec2 e2 = p3 - p1;
+		float32 D = b2Cross(e1, e2);
+		float32 triangleArea = 0.5f * D;
+		area += triangleArea;
+		c += triangleArea * inv3 * (p1 + p2 + p3);
+	}
+	c *= 1.0f / area;
+	return c;
+}
+
+void b2PolygonShape::Set(const b2Vec2* points, int32 count)
+{
+	if (count < 3)
+	{
+		SetAsBox(1.0f, 1.0f);
+		return;
+	}
+	int32 n = b2Min(count, (int32)b2_maxPolygonVertices);
+
+	// weld points closer than half the linear slop
+	b2Vec2 ps[b2_maxPolygonVertices];
+	int32 kept = 0;
+	const float32 weldSqr = (0.5f * b2_linearSlop) * (0.5f * b2_linearSlop);
+	for (int32 i = 0; i < n; ++i)
+	{
+		bool unique = true;
+		for (int32 j = 0; j < kept; ++j)
+		{
+			if (b2DistanceSquared(points[i], ps[j]) < weldSqr)
+			{
+				unique = false;
+				break;
+			}
+		}
+		if (unique) ps[kept++] = points[i];
+	}
+	n = kept;
+	if (n < 3)
+	{
+		SetAsBox(1.0f, 1.0f);
+		return;
+	}
+
+	// gift wrapping from the right-most (then lowest) point, counter-clockwise
+	int32 start = 0;
+	for (int32 i = 1; i < n; ++i)
+	{
+		if (ps[i].x > ps[start].x || (ps[i].x == ps[start].x && ps[i].y < ps[start].y)) start = i;
+	}
+	int32 hull[b2_maxPolygonVertices];
+	int32 m = 0;
+	int32 current = start;
+	for (;;)
+	{
+		hull[m] = current;
+		int32 candidate = 0;
+		for (int32 j = 1; j < n; ++j)
+		{
+			if (candidate == current)
+			{
+				candidate = j;
+				continue;
+			}
+			b2Vec2 r = ps[candidate] - ps[hull[m]];
+			b2Vec2 v = ps[j] - ps[hull[m]];
+			float32 c = b2Cross(r, v);
+			if (c < 0.0f) candidate = j;
+			// collinear: keep the farther point
+			if (c == 0.0f && v.LengthSquared() > r.LengthSquared()) candidate = j;
+		}
+		++m;
+		current = candidate;
+		if (candidate == start) break;
+	}
+	if (m < 3)
+	{
+		SetAsBox(1.0f, 1.0f);
+		return;
+	}
+
+	m_count = m;
+	for (int32 i = 0; i < m; ++i) m_vertices[i] = ps[hull[i]];
+	for (int32 i = 0; i < m; ++i)
+	{
+		int32 i2 = i + 1 < m ? i + 1 : 0;
+		b2Vec2 edge = m_vertices[i2] - m_vertices[i];
+		m_normals[i] = b2Cross(edge, 1.0f);
+		m_normals[i].Normalize();
+	}
+	m_centroid = PolygonCentroid(m_vertices, m);
+}
+
+bool b2PolygonShape::TestPoint(const b2Transform& xf, const b2Vec2& p) const
+{
+	b2Vec2 local = b2MulT(xf.q, p - xf.p);
+	for (int32 i = 0; i < m_count; ++i)
+	{
+		if (b2Dot(m_normals[i], local - m_vertices[i]) > 0.0f) return false;
+	}
+	return true;
+}
+
+void b2PolygonShape::ComputeAABB(b2AABB* aabb, const b2Transform& xf, int32) const
+{
+	b2Vec2 lower = b2Mul(xf, m_vertices[0]);
+	b2Vec2 upper = lower;
+	for (int32 i = 1; i < m_count; ++i)
+	{
+		b2Vec2 v = b2Mul(xf, m_vertices[i]);
+		lower = b2Min(lower, v);
+		upper = b2Max(upper, v);
+	}
+	b2Vec2 r(m_radius, m_radius);
+	aabb->lowerBound = lower - r;
+	aabb->upperBound = upper + r;
+}
+
+// mass, centre and inertia by a triangle fan about the vertex average (reference :359-440)
+void b2PolygonShape::ComputeMass(b2MassData* massData, float32 density) const
+{
+	b2Vec2 center(0.0f, 0.0f);
+	float32 area = 0.0f;
+	float32 I = 0.0f;
+
+	b2Vec2 s(0.0f, 0.0f);
+	for (int32 i = 0; i < m_count; ++i) s += m_vertices[i];
+	s *= 1.0f / m_count;
+
+	const float32 k_inv3 = 1.0f / 3.0f;
+	for (int32 i = 0; i < m_count; ++i)
+	{
+		b2Vec2 e1 = m_vertices[i] - s;
+		b2Vec2 e2 = i + 1 < m_count ? m_vertices[i + 1] - s : m_vertices[0] - s;
+		float32 D = b2Cross(e1, e2);
+		float32 triangleArea = 0.5f * D;
+		area += triangleArea;
+		center += triangleArea * k_inv3 * (e1 + e2);
+
+		float32 ex1 = e1.x, ey1 = e1.y;
+		float32 ex2 = e2.x, ey2 = e2.y;
+		float32 intx2 = ex1 * ex1 + ex2 * ex1 + ex2 * ex2;
+		float32 inty2 = ey1 * ey1 + ey2 * ey1 + ey2 * ey2;
+		I += (0.25f * k_inv3 * D) * (intx2 + inty2);
+	}
+
+	massData->mass = density * area;
+	center *= 1.0f / area;
+	massData->center = center + s;
+	massData->I = density * I;
+	// shift from the fan origin s to the centre of mass, then to the body origin
+	massData->I += massData->mass * (b2Dot(massData->center, massData->center) - b2Dot(center, center));
+}

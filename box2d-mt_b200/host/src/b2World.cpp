@@ -1,0 +1,621 @@
+// b2World: body / fixture bookkeeping on the host, state mirrored to the device, Step delegated to the executor.
+// reference: Box2D/Dynamics/b2World.cpp (CreateBody :532-559, DestroyBody :561-640, Step :1613-1710) and
+// b2ContactManager.cpp (callback dispatch :388-439).
+#include "Box2D/Dynamics/b2World.h"
+#include "Box2D/Collision/Shapes/b2CircleShape.h"
+#include "Box2D/Collision/Shapes/b2EdgeShape.h"
+#include "Box2D/Collision/Shapes/b2PolygonShape.h"
+#include "Box2D/MT/b2CudaStepExecutor.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+bool b2ContactFilter::ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB, uint32 threadId)
+{
+	B2_NOT_USED(threadId);
+	const b2Filter& fa = fixtureA->GetFilterData();
+	const b2Filter& fb = fixtureB->GetFilterData();
+	if (fa.groupIndex == fb.groupIndex && fa.groupIndex != 0) return fa.groupIndex > 0;
+	return (fa.maskBits & fb.categoryBits) != 0 && (fa.categoryBits & fb.maskBits) != 0;
+}
+
+// reference: Box2D/Collision/b2Collision.cpp:22-86
+void b2WorldManifold::Initialize(const b2Manifold* manifold, const b2Transform& xfA, float32 radiusA,
+                                 const b2Transform& xfB, float32 radiusB)
+{
+	if (manifold->pointCount == 0) return;
+	switch (manifold->type)
+	{
+	case b2Manifold::e_circles:
+	{
+		normal.Set(1.0f, 0.0f);
+		b2Vec2 pointA = b2Mul(xfA, manifold->localPoint);
+		b2Vec2 pointB = b2Mul(xfB, manifold->points[0].localPoint);
+		if (b2DistanceSquared(pointA, pointB) > b2_epsilon * b2_epsilon)
+		{
+			normal = pointB - pointA;
+			normal.Normalize();
+		}
+		b2Vec2 cA = pointA + radiusA * normal;
+		b2Vec2 cB = pointB - radiusB * normal;
+		points[0] = 0.5f * (cA + cB);
+		separations[0] = b2Dot(cB - cA, normal);
+		break;
+	}
+	case b2Manifold::e_faceA:
+	{
+		normal = b2Mul(xfA.q, manifold->localNormal);
+		b2Vec2 planePoint = b2Mul(xfA, manifold->localPoint);
+		for (int32 i = 0; i < manifold->pointCount; ++i)
+		{
+			b2Vec2 clipPoint = b2Mul(xfB, manifold->points[i].localPoint);
+			b2Vec2 cA = clipPoint + (radiusA - b2Dot(clipPoint - planePoint, normal)) * normal;
+			b2Vec2 cB = clipPoint - radiusB * normal;
+			points[i] = 0.5f * (cA + cB);
+			separations[i] = b2Dot(cB - cA, normal);
+		}
+		break;
+	}
+	case b2Manifold::e_faceB:
+	{
+		normal = b2Mul(xfB.q, manifold->localNormal);
+		b2Vec2 planePoint = b2Mul(xfB, manifold->localPoint);
+		for (int32 i = 0; i < manifold->pointCount; ++i)
+		{
+			b2Vec2 clipPoint = b2Mul(xfA, manifold->points[i].localPoint);
+			b2Vec2 cB = clipPoint + (radiusB - b2Dot(clipPoint - planePoint, normal)) * normal;
+			b2Vec2 cA = clipPoint - radiusA * normal;
+			points[i] = 0.5f * (cA + cB);
+			separations[i] = b2Dot(cA - cB, normal);
+		}
+		normal = -normal;
+		break;
+	}
+	}
+}
+
+void b2Contact::GetWorldManifold(b2WorldManifold* worldManifold) const
+{
+	const b2Body* bodyA = m_fixtureA->GetBody();
+	const b2Body* bodyB = m_fixtureB->GetBody();
+	worldManifold->Initialize(&m_manifold, bodyA->GetTransform(), m_fixtureA->GetShape()->m_radius,
+	                          bodyB->GetTransform(), m_fixtureB->GetShape()->m_radius);
+}
+
+// ---- construction ---------------------------------------------------------------------------------------
+
+b2World::b2World(const b2Vec2& gravity)
+	: m_device(nullptr), m_owner(nullptr), m_fullUpload(false), m_bodiesUploaded(0), m_proxiesUploaded(0),
+	  m_shapesUploaded(0), m_bodyDirtyLo(INT32_MAX), m_bodyDirtyHi(-1), m_proxyDirtyLo(INT32_MAX), m_proxyDirtyHi(-1),
+	  m_bodiesStale(false), m_proxiesStale(false), m_contactsStale(true), m_bodyList(nullptr), m_bodyCount(0),
+	  m_contactCount(0), m_gravity(gravity), m_allowSleep(true), m_warmStarting(true), m_continuousPhysics(true),
+	  m_subStepping(false), m_clearForces(true), m_locked(false), m_newFixture(false), m_inv_dt0(0.0f),
+	  m_destructionListener(nullptr), m_contactFilter(nullptr), m_contactListener(nullptr), m_lastStatus(0)
+{
+	memset(&m_profile, 0, sizeof(m_profile));
+}
+
+b2World::~b2World()
+{
+	if (m_owner) m_owner->DetachWorld(this);
+	for (size_t i = 0; i < m_fixtures.size(); ++i) delete m_fixtures[i];
+	for (size_t i = 0; i < m_bodies.size(); ++i) delete m_bodies[i];
+}
+
+// reference b2World.cpp:532-559 + b2Body::b2Body (b2Body.cpp:26-111)
+b2Body* b2World::CreateBody(const b2BodyDef* def)
+{
+	if (IsLocked()) return nullptr;
+	b2Assert(def->active); // inactive bodies are outside this version of the GPU path
+	RefreshBodies();
+
+	b2Body* b = new b2Body;
+	b->m_world = this;
+	b->m_index = (int32)m_states.size();
+	b->m_fixtureList = nullptr;
+	b->m_fixtureCount = 0;
+	b->m_userData = def->userData;
+	b->m_I = 0.0f;
+
+	b2cuBody s;
+	memset(&s, 0, sizeof(s));
+	uint32 flags = (uint32)def->type;
+	if (def->bullet) flags |= B2CU_BODY_BULLET;
+	if (def->fixedRotation) flags |= B2CU_BODY_FIXED_ROTATION;
+	if (def->allowSleep) flags |= B2CU_BODY_AUTOSLEEP;
+	if (def->awake) flags |= B2CU_BODY_AWAKE;
+	if (def->active) flags |= B2CU_BODY_ACTIVE;
+	s.flags = flags;
+	b2Rot q(def->angle);
+	s.px = def->position.x;
+	s.py = def->position.y;
+	s.qs = q.s;
+	s.qc = q.c;
+	s.cx = s.c0x = def->position.x;
+	s.cy = s.c0y = def->position.y;
+	s.a = s.a0 = def->angle;
+	s.alpha0 = 0.0f;
+	s.vx = def->linearVelocity.x;
+	s.vy = def->linearVelocity.y;
+	s.w = def->angularVelocity;
+	s.linearDamping = def->linearDamping;
+	s.angularDamping = def->angularDamping;
+	s.gravityScale = def->gravityScale;
+	if (def->type == b2_dynamicBody)
+	{
+		b->m_mass = 1.0f;
+		s.invMass = 1.0f;
+	}
+	else
+	{
+		b->m_mass = 0.0f;
+		s.invMass = 0.0f;
+	}
+	m_states.push_back(s);
+	m_bodies.push_back(b);
+
+	// newest first, as the reference's body list
+	b->m_prev = nullptr;
+	b->m_next = m_bodyList;
+	if (m_bodyList) m_bodyList->m_prev = b;
+	m_bodyList = b;
+	++m_bodyCount;
+	return b;
+}
+
+int32 b2World::InternShape(const b2Shape* shape)
+{
+	b2cuShape r;
+	memset(&r, 0, sizeof(r));
+	r.radius = shape->m_radius;
+	switch (shape->GetType())
+	{
+	case b2Shape::e_circle:
+	{
+		const b2CircleShape* c = static_cast<const b2CircleShape*>(shape);
+		r.type = B2CU_SHAPE_CIRCLE;
+		r.count = 1;
+		r.v[0][0] = c->m_p.x;
+		r.v[0][1] = c->m_p.y;
+		break;
+	}
+	case b2Shape::e_edge:
+	{
+		const b2EdgeShape* e = static_cast<const b2EdgeShape*>(shape);
+		r.type = B2CU_SHAPE_EDGE;
+		r.count = 2;
+		r.v[0][0] = e->m_vertex1.x; r.v[0][1] = e->m_vertex1.y;
+		r.v[1][0] = e->m_vertex2.x; r.v[1][1] = e->m_vertex2.y;
+		r.v[2][0] = e->m_vertex0.x; r.v[2][1] = e->m_vertex0.y;
+		r.v[3][0] = e->m_vertex3.x; r.v[3][1] = e->m_vertex3.y;
+		r.flags = (e->m_hasVertex0 ? B2CU_EDGE_HAS_VERTEX0 : 0) | (e->m_hasVertex3 ? B2CU_EDGE_HAS_VERTEX3 : 0);
+		break;
+	}
+	default:
+	{
+		const b2PolygonShape* p = static_cast<const b2PolygonShape*>(shape);
+		r.type = B2CU_SHAPE_POLYGON;
+		r.count = p->m_count;
+		for (int32 i = 0; i < p->m_count; ++i)
+		{
+			r.v[i][0] = p->m_vertices[i].x; r.v[i][1] = p->m_vertices[i].y;
+			r.n[i][0] = p->m_normals[i].x; r.n[i][1] = p->m_normals[i].y;
+		}
+		r.centroid[0] = p->m_centroid.x;
+		r.centroid[1] = p->m_centroid.y;
+		break;
+	}
+	}
+	std::string key(reinterpret_cast<const char*>(&r), sizeof(r));
+	auto it = m_shapeLookup.find(key);
+	if (it != m_shapeLookup.end()) return it->second;
+	int32 index = (int32)m_shapes.size();
+	m_shapes.push_back(r);
+	m_shapeLookup.emplace(std::move(key), index);
+	return index;
+}
+
+void b2World::MarkBodyDirty(int32 index)
+{
+	m_bodyDirtyLo = std::min(m_bodyDirtyLo, index);
+	m_bodyDirtyHi = std::max(m_bodyDirtyHi, index);
+}
+
+void b2World::MarkProxyDirty(int32 index)
+{
+	m_proxyDirtyLo = std::min(m_proxyDirtyLo, index);
+	m_proxyDirtyHi = std::max(m_proxyDirtyHi, index);
+}
+
+void b2World::SetAllowSleeping(bool flag)
+{
+	if (flag == m_allowSleep) return;
+	m_allowSleep = flag;
+	if (!flag)
+	{
+		for (b2Body* b = m_bodyList; b; b = b->m_next) b->SetAwake(true);
+	}
+}
+
+void b2World::ClearForces()
+{
+	RefreshBodies();
+	for (size_t i = 0; i < m_states.size(); ++i)
+	{
+		m_states[i].fx = m_states[i].fy = m_states[i].torque = 0.0f;
+	}
+	if (!m_states.empty())
+	{
+		MarkBodyDirty(0);
+		MarkBodyDirty((int32)m_states.size() - 1);
+	}
+}
+
+const b2cuBody* b2World::GetBodyStates() const
+{
+	RefreshBodies();
+	return m_states.data();
+}
+
+const b2cuProxy* b2World::GetProxyStates() const
+{
+	RefreshProxies();
+	return m_proxies.data();
+}
+
+// ---- device <-> host mirror ------------------------------------------------------------------------------
+
+void b2World::RefreshBodies() const
+{
+	if (!m_bodiesStale || m_device == nullptr) return;
+	b2World* self = const_cast<b2World*>(this);
+	int32 n = std::min(m_bodiesUploaded, (int32)m_states.size());
+	if (n > 0) b2cuGetBodies(m_device, 0, n, self->m_states.data());
+	m_bodiesStale = false;
+}
+
+void b2World::RefreshProxies() const
+{
+	if (!m_proxiesStale || m_device == nullptr) return;
+	b2World* self = const_cast<b2World*>(this);
+	int32 n = std::min(m_proxiesUploaded, (int32)m_proxies.size());
+	if (n > 0) b2cuGetProxies(m_device, 0, n, self->m_proxies.data());
+	m_proxiesStale = false;
+}
+
+void b2World::InvalidateSnapshots()
+{
+	m_contactsStale = true;
+	m_contacts.clear();
+	m_contactHeads.clear();
+}
+
+void b2World::MakeContact(b2Contact* c, const b2cuContact& rec)
+{
+	c->m_flags = rec.flags;
+	uint32 lo = (uint32)std::min(rec.proxyA, rec.proxyB), hi = (uint32)std::max(rec.proxyA, rec.proxyB);
+	c->m_key = ((uint64)lo << 32) | hi;
+	c->m_fixtureA = m_fixtures[rec.proxyA];
+	c->m_fixtureB = m_fixtures[rec.proxyB];
+	const b2cuManifold& m = rec.manifold;
+	c->m_manifold.localNormal.Set(m.localNormal[0], m.localNormal[1]);
+	c->m_manifold.localPoint.Set(m.localPoint[0], m.localPoint[1]);
+	for (int32 i = 0; i < 2; ++i)
+	{
+		c->m_manifold.points[i].localPoint.Set(m.points[i].localPoint[0], m.points[i].localPoint[1]);
+		c->m_manifold.points[i].normalImpulse = m.points[i].normalImpulse;
+		c->m_manifold.points[i].tangentImpulse = m.points[i].tangentImpulse;
+		c->m_manifold.points[i].id.key = m.id[i];
+	}
+	c->m_manifold.type = (b2Manifold::Type)m.type;
+	c->m_manifold.pointCount = m.pointCount;
+	c->m_friction = rec.friction;
+	c->m_restitution = rec.restitution;
+	c->m_tangentSpeed = rec.tangentSpeed;
+	c->m_next = nullptr;
+	c->m_nodeA.contact = c;
+	c->m_nodeA.other = c->m_fixtureB->GetBody();
+	c->m_nodeA.prev = c->m_nodeA.next = nullptr;
+	c->m_nodeB.contact = c;
+	c->m_nodeB.other = c->m_fixtureA->GetBody();
+	c->m_nodeB.prev = c->m_nodeB.next = nullptr;
+}
+
+// Download the device contact set (key order) and materialise b2Contact objects + per-body edge lists.
+void b2World::RefreshContacts()
+{
+	if (!m_contactsStale) return;
+	m_contactsStale = false;
+	m_contacts.clear();
+	m_contactHeads.assign(m_bodies.size(), nullptr);
+	if (m_device == nullptr) return;
+	int32 n = 0;
+	b2cuGetContactCount(m_device, &n);
+	m_contactRecords.resize(n);
+	if (n == 0) return;
+	b2cuGetContacts(m_device, n, m_contactRecords.data(), &n);
+	m_contacts.resize(n);
+	for (int32 i = 0; i < n; ++i)
+	{
+		b2Contact* c = &m_contacts[i];
+		MakeContact(c, m_contactRecords[i]);
+		c->m_next = i + 1 < n ? &m_contacts[i + 1] : nullptr;
+	}
+	// edge lists: newest (highest key) first is as good as any; the reference's order is creation order
+	for (int32 i = 0; i < n; ++i)
+	{
+		b2Contact* c = &m_contacts[i];
+		int32 ia = c->m_fixtureA->GetBody()->m_index, ib = c->m_fixtureB->GetBody()->m_index;
+		c->m_nodeA.next = m_contactHeads[ia];
+		if (m_contactHeads[ia]) m_contactHeads[ia]->prev = &c->m_nodeA;
+		m_contactHeads[ia] = &c->m_nodeA;
+		c->m_nodeB.next = m_contactHeads[ib];
+		if (m_contactHeads[ib]) m_contactHeads[ib]->prev = &c->m_nodeB;
+		m_contactHeads[ib] = &c->m_nodeB;
+	}
+}
+
+b2Contact* b2World::GetContactList()
+{
+	RefreshContacts();
+	return m_contacts.empty() ? nullptr : &m_contacts[0];
+}
+
+// ---- destruction: compact the dense arrays and remap the contact set --------------------------------------
+
+void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vector<int32>& bodyIds)
+{
+	RefreshBodies();
+	RefreshProxies();
+	// contact records as they are on the device
+	m_contactsStale = true;
+	RefreshContacts();
+
+	std::vector<int32> proxyMap(m_proxies.size()), bodyMap(m_states.size());
+	std::vector<char> deadProxy(m_proxies.size(), 0), deadBody(m_states.size(), 0);
+	for (size_t i = 0; i < proxyIds.size(); ++i) deadProxy[proxyIds[i]] = 1;
+	for (size_t i = 0; i < bodyIds.size(); ++i) deadBody[bodyIds[i]] = 1;
+
+	// contacts of the removed proxies end (b2ContactManager::Destroy, b2ContactManager.cpp:120-172): EndContact if
+	// touching, both bodies woken if the manifold had points
+	std::vector<b2cuContact> kept;
+	kept.reserve(m_contactRecords.size());
+	for (size_t i = 0; i < m_contactRecords.size(); ++i)
+	{
+		const b2cuContact& rec = m_contactRecords[i];
+		if (deadProxy[rec.proxyA] || deadProxy[rec.proxyB])
+		{
+			b2Contact* c = &m_contacts[i];
+			if (m_contactListener && c->IsTouching() && m_contactListener->EndContactImmediate(c, 0))
+			{
+				m_contactListener->EndContact(c);
+			}
+			if (rec.manifold.pointCount > 0)
+			{
+				c->m_fixtureA->GetBody()->SetAwake(true);
+				c->m_fixtureB->GetBody()->SetAwake(true);
+			}
+			continue;
+		}
+		kept.push_back(rec);
+	}
+
+	int32 np = 0;
+	for (size_t i = 0; i < m_proxies.size(); ++i)
+	{
+		proxyMap[i] = deadProxy[i] ? -1 : np;
+		if (!deadProxy[i])
+		{
+			m_proxies[np] = m_proxies[i];
+			m_fixtures[np] = m_fixtures[i];
+			m_fixtures[np]->m_proxyIndex = np;
+			++np;
+		}
+	}
+	m_proxies.resize(np);
+	m_fixtures.resize(np);
+
+	int32 nb = 0;
+	for (size_t i = 0; i < m_states.size(); ++i)
+	{
+		bodyMap[i] = deadBody[i] ? -1 : nb;
+		if (!deadBody[i])
+		{
+			m_states[nb] = m_states[i];
+			m_bodies[nb] = m_bodies[i];
+			m_bodies[nb]->m_index = nb;
+			++nb;
+		}
+	}
+	m_states.resize(nb);
+	m_bodies.resize(nb);
+
+	for (int32 i = 0; i < np; ++i)
+	{
+		m_proxies[i].body = bodyMap[m_proxies[i].body];
+		m_proxies[i].fixture = i;
+	}
+	for (size_t i = 0; i < kept.size(); ++i)
+	{
+		kept[i].proxyA = proxyMap[kept[i].proxyA];
+		kept[i].proxyB = proxyMap[kept[i].proxyB];
+	}
+	m_contactRecords.swap(kept);
+	m_contactCount = (int32)m_contactRecords.size();
+	m_contacts.clear();
+	m_contactHeads.clear();
+	m_contactsStale = false; // m_contactRecords is now authoritative until the next upload
+	m_fullUpload = true;
+}
+
+void b2World::DestroyFixtureInternal(b2Body* body, b2Fixture* fixture)
+{
+	b2Fixture** link = &body->m_fixtureList;
+	while (*link && *link != fixture) link = &(*link)->m_next;
+	if (*link == nullptr) return;
+	*link = fixture->m_next;
+	--body->m_fixtureCount;
+	std::vector<int32> proxies(1, fixture->m_proxyIndex), bodies;
+	RemoveProxies(proxies, bodies);
+	delete fixture;
+	body->ResetMassData();
+}
+
+// reference b2World.cpp:561-640
+void b2World::DestroyBody(b2Body* b)
+{
+	if (IsLocked() || b == nullptr) return;
+	std::vector<int32> proxies, bodies(1, b->m_index);
+	for (b2Fixture* f = b->m_fixtureList; f; f = f->m_next)
+	{
+		if (m_destructionListener) m_destructionListener->SayGoodbye(f);
+		proxies.push_back(f->m_proxyIndex);
+	}
+	std::vector<b2Fixture*> doomed;
+	for (b2Fixture* f = b->m_fixtureList; f; f = f->m_next) doomed.push_back(f);
+	RemoveProxies(proxies, bodies);
+	for (size_t i = 0; i < doomed.size(); ++i) delete doomed[i];
+
+	if (b->m_prev) b->m_prev->m_next = b->m_next;
+	if (b->m_next) b->m_next->m_prev = b->m_prev;
+	if (b == m_bodyList) m_bodyList = b->m_next;
+	--m_bodyCount;
+	delete b;
+}
+
+// ---- step ------------------------------------------------------------------------------------------------
+
+void b2World::Step(float32 timeStep, int32 velocityIterations, int32 positionIterations, b2TaskExecutor& executor)
+{
+	if (m_contactFilter != nullptr)
+	{
+		// only the default filter rule exists on the device (b2WorldCallbacks.h)
+		m_lastStatus = B2CU_ERR_UNSUPPORTED;
+		fprintf(stderr, "b2World::Step: custom b2ContactFilter is not supported by the GPU path\n");
+		b2Assert(false);
+		return;
+	}
+	m_locked = true;
+	bool ran = executor.StepWorld(*this, timeStep, velocityIterations, positionIterations);
+	m_locked = false;
+	if (!ran)
+	{
+		// no CPU fallback: an executor that cannot run the step on the device is a hard error
+		if (m_lastStatus == 0) m_lastStatus = B2CU_ERR_NO_DEVICE;
+		fprintf(stderr, "b2World::Step: the executor did not run the step on a GPU (status %d); this library has no "
+		                "CPU step path\n", m_lastStatus);
+		b2Assert(false);
+	}
+}
+
+int32 b2World::UploadDirty(b2cuWorld* device)
+{
+	int32 rc;
+	const int32 nb = (int32)m_states.size(), np = (int32)m_proxies.size(), ns = (int32)m_shapes.size();
+	uint32 flags = (m_allowSleep ? B2CU_WORLD_ALLOW_SLEEP : 0) | (m_warmStarting ? B2CU_WORLD_WARM_STARTING : 0) |
+	               (m_continuousPhysics ? B2CU_WORLD_CONTINUOUS : 0) | (m_subStepping ? B2CU_WORLD_SUB_STEPPING : 0) |
+	               (m_clearForces ? B2CU_WORLD_CLEAR_FORCES : 0);
+	float g[2] = {m_gravity.x, m_gravity.y};
+	if ((rc = b2cuSetWorldParams(device, g, flags))) return rc;
+
+	if (m_fullUpload)
+	{
+		m_bodiesUploaded = m_proxiesUploaded = m_shapesUploaded = 0;
+	}
+	if (nb != m_bodiesUploaded || np != m_proxiesUploaded || ns != m_shapesUploaded)
+	{
+		if ((rc = b2cuSetCounts(device, nb, ns, np))) return rc;
+	}
+	if (ns > m_shapesUploaded)
+	{
+		if ((rc = b2cuSetShapes(device, m_shapesUploaded, ns - m_shapesUploaded, m_shapes.data() + m_shapesUploaded)))
+			return rc;
+	}
+	// new rows (tail) and edited rows (dirty range)
+	int32 lo = std::min(m_bodyDirtyLo, m_bodiesUploaded), hi = std::max(m_bodyDirtyHi, nb - 1);
+	if (nb > m_bodiesUploaded || m_bodyDirtyHi >= 0)
+	{
+		if (nb == m_bodiesUploaded) hi = m_bodyDirtyHi;
+		if (lo <= hi && (rc = b2cuSetBodies(device, lo, hi - lo + 1, m_states.data() + lo))) return rc;
+	}
+	lo = std::min(m_proxyDirtyLo, m_proxiesUploaded);
+	hi = std::max(m_proxyDirtyHi, np - 1);
+	if (np > m_proxiesUploaded || m_proxyDirtyHi >= 0)
+	{
+		if (np == m_proxiesUploaded) hi = m_proxyDirtyHi;
+		if (lo <= hi && (rc = b2cuSetProxies(device, lo, hi - lo + 1, m_proxies.data() + lo))) return rc;
+		// the MOVED flag has been handed to the device's move buffer
+		for (int32 i = lo; i <= hi; ++i) m_proxies[i].flags &= ~(uint16)B2CU_PROXY_MOVED;
+	}
+	if (m_fullUpload)
+	{
+		if ((rc = b2cuSetContacts(device, (int32)m_contactRecords.size(), m_contactRecords.data()))) return rc;
+		if ((rc = b2cuSetInvDt0(device, m_inv_dt0))) return rc;
+		m_fullUpload = false;
+	}
+	m_bodiesUploaded = nb;
+	m_proxiesUploaded = np;
+	m_shapesUploaded = ns;
+	m_bodyDirtyLo = m_proxyDirtyLo = INT32_MAX;
+	m_bodyDirtyHi = m_proxyDirtyHi = -1;
+	m_newFixture = false;
+	return 0;
+}
+
+// FinishCollide's callback order (b2ContactManager.cpp:420-433): Immediate callbacks first, then the deferred
+// BeginContact calls in key order, then the deferred EndContact calls in key order.
+void b2World::DispatchEvents(b2cuWorld* device)
+{
+	std::vector<b2cuContactKey> keys[2];
+	for (int32 kind = 0; kind < 2; ++kind)
+	{
+		int32 n = 0;
+		b2cuGetEvents(device, kind, 0, nullptr, &n);
+		keys[kind].resize(n);
+		if (n > 0) b2cuGetEvents(device, kind, n, keys[kind].data(), &n);
+	}
+	if (keys[0].empty() && keys[1].empty()) return;
+
+	std::vector<b2cuContact> recs[2];
+	std::vector<b2Contact> contacts[2];
+	std::vector<char> deferred[2];
+	for (int32 kind = 0; kind < 2; ++kind)
+	{
+		int32 n = (int32)keys[kind].size();
+		recs[kind].resize(n);
+		contacts[kind].resize(n);
+		deferred[kind].assign(n, 0);
+		if (n == 0) continue;
+		b2cuGetContactsByKey(device, n, keys[kind].data(), recs[kind].data());
+		for (int32 i = 0; i < n; ++i) MakeContact(&contacts[kind][i], recs[kind][i]);
+	}
+	for (size_t i = 0; i < contacts[0].size(); ++i)
+		deferred[0][i] = m_contactListener->BeginContactImmediate(&contacts[0][i], 0) ? 1 : 0;
+	for (size_t i = 0; i < contacts[1].size(); ++i)
+		deferred[1][i] = m_contactListener->EndContactImmediate(&contacts[1][i], 0) ? 1 : 0;
+	for (size_t i = 0; i < contacts[0].size(); ++i)
+		if (deferred[0][i]) m_contactListener->BeginContact(&contacts[0][i]);
+	for (size_t i = 0; i < contacts[1].size(); ++i)
+		if (deferred[1][i]) m_contactListener->EndContact(&contacts[1][i]);
+}
+
+int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool downloadBodies, bool dispatchEvents)
+{
+	m_contactCount = info.contactCount;
+	memcpy(&m_profile, &info, sizeof(b2Profile)); // the first 13 floats of b2cuStepInfo are the b2Profile fields
+	m_bodiesStale = true;
+	m_proxiesStale = true;
+	InvalidateSnapshots();
+	if (downloadBodies) RefreshBodies();
+	if (dispatchEvents && m_contactListener && (info.beginCount > 0 || info.endCount > 0))
+	{
+		// callbacks may read bodies: make sure the mirror is current
+		RefreshBodies();
+		bool wasLocked = m_locked;
+		m_locked = true;
+		DispatchEvents(device);
+		m_locked = wasLocked;
+	}
+	return 0;
+}

@@ -20,7 +20,7 @@ API = [
     "b2cuGetDeviceCount", "b2cuVersion", "b2cuCreateWorld", "b2cuDestroyWorld", "b2cuGetLastError",
     "b2cuSetWorldParams", "b2cuSetInvDt0", "b2cuSetCounts", "b2cuSetBodies", "b2cuGetBodies", "b2cuSetShapes",
     "b2cuSetProxies", "b2cuGetProxies", "b2cuSetContacts", "b2cuGetContactCount", "b2cuGetContacts", "b2cuStep",
-    "b2cuGetEvents", "b2cuGetSolverOrder", "b2cuGetIslandLabels", "b2cuGetToiCandidates", "b2cuCollidePairs",
+    "b2cuGetContactsByKey", "b2cuGetEvents", "b2cuGetSolverOrder", "b2cuGetIslandLabels", "b2cuGetToiCandidates", "b2cuCollidePairs",
     "b2cuSinCos",
 ]
 
@@ -64,6 +64,7 @@ def load():
     lib.b2cuGetContacts.argtypes = [vp, i32, vp, vp]
     lib.b2cuStep.argtypes = [vp, f32, i32, i32, vp]
     lib.b2cuGetEvents.argtypes = [vp, i32, i32, vp, vp]
+    lib.b2cuGetContactsByKey.argtypes = [vp, i32, vp, vp]
     lib.b2cuGetSolverOrder.argtypes = [vp, i32, vp, vp, vp]
     lib.b2cuGetToiCandidates.argtypes = [vp, i32, vp, vp]
     lib.b2cuCollidePairs.argtypes = [i32, i32, vp, i32, vp, vp, vp, vp, vp]
@@ -191,6 +192,12 @@ class World:
 
     def events(self, kind):
         return self._keys(self.lib.b2cuGetEvents, kind)
+
+    def contacts_by_key(self, keys):
+        k = np.ascontiguousarray(keys, np.uint64)
+        out = np.zeros(len(k), T.CONTACT)
+        self._check(self.lib.b2cuGetContactsByKey(self.h, len(k), _ptr(k), _ptr(out)))
+        return out
 
     def toi_candidates(self):
         return self._keys(self.lib.b2cuGetToiCandidates)

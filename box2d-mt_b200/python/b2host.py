@@ -1,0 +1,177 @@
+"""ctypes binding of libbox2d_b200.so's flat C interface (host/capi/b2host_capi.cpp): the C++ host API --
+b2World, b2Body::CreateFixture, b2World::Step(dt, vIters, pIters, b2CudaStepExecutor&) -- driven from Python."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.dirname(_HERE)
+sys.path.insert(0, _HERE)
+import b2cuda_types as T  # noqa: E402
+from b2scene import BODY_DEF, SHAPE_DEF, FIXTURE_DEF  # noqa: E402
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(_PKG, "libbox2d_b200.so")
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(lib_path()):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("b2cuda_build", os.path.join(_PKG, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build_all()
+    lib = ctypes.CDLL(lib_path())
+    vp, i32, f32, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float, ctypes.c_uint32
+    lib.b2h_create.restype = vp
+    lib.b2h_create.argtypes = [f32, f32, u32, i32, i32, i32]
+    lib.b2h_destroy.argtypes = [vp]
+    lib.b2h_set_options.argtypes = [vp, i32, i32]
+    lib.b2h_apply_force_range.argtypes = [vp, i32, i32, f32, f32]
+    lib.b2h_build.argtypes = [vp, i32, vp, i32, vp, i32, vp]
+    lib.b2h_step.argtypes = [vp, f32, i32, i32]
+    lib.b2h_last_error.argtypes = [vp]
+    lib.b2h_last_error.restype = ctypes.c_char_p
+    lib.b2h_counts.argtypes = [vp, vp, vp, vp]
+    lib.b2h_get_bodies.argtypes = [vp, vp]
+    lib.b2h_get_proxies.argtypes = [vp, vp]
+    lib.b2h_get_transforms.argtypes = [vp, vp, vp]
+    lib.b2h_get_mass.argtypes = [vp, vp]
+    lib.b2h_get_contacts.argtypes = [vp, i32, vp, vp, vp]
+    lib.b2h_events.argtypes = [vp, i32, i32, vp]
+    lib.b2h_solver_order.argtypes = [vp, i32, vp]
+    lib.b2h_profile.argtypes = [vp, vp]
+    lib.b2h_step_info.argtypes = [vp, vp]
+    lib.b2h_hash.argtypes = [vp]
+    lib.b2h_hash.restype = u32
+    lib.b2h_set_transform.argtypes = [vp, i32, f32, f32, f32]
+    lib.b2h_set_velocity.argtypes = [vp, i32, f32, f32, f32]
+    lib.b2h_apply_force.argtypes = [vp, i32, f32, f32, f32]
+    lib.b2h_set_awake.argtypes = [vp, i32, i32]
+    lib.b2h_destroy_body.argtypes = [vp, i32]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class HostWorld:
+    """A b2World built from a Scene with CreateBody / CreateFixture and stepped by a b2CudaStepExecutor."""
+
+    def __init__(self, scene=None, device=0, download_bodies=True, events=True, gravity=None, world_flags=None,
+                 arrays=None):
+        self.lib = load()
+        if scene is not None:
+            gravity, world_flags, arrays = scene.gravity, scene.world_flags, scene.arrays()
+        self.h = self.lib.b2h_create(gravity[0], gravity[1], world_flags, device, int(download_bodies), int(events))
+        b, s, f = arrays
+        b = np.ascontiguousarray(b, BODY_DEF)
+        s = np.ascontiguousarray(s, SHAPE_DEF)
+        f = np.ascontiguousarray(f, FIXTURE_DEF)
+        rc = self.lib.b2h_build(self.h, len(b), _ptr(b), len(s), _ptr(s), len(f), _ptr(f))
+        if rc != 0:
+            raise RuntimeError("b2h_build failed: %d" % rc)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.b2h_destroy(self.h)
+            self.h = None
+
+    def counts(self):
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self.lib.b2h_counts(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return a.value, b.value, c.value
+
+    def step(self, dt=1.0 / 60.0, vel_iters=8, pos_iters=3):
+        rc = self.lib.b2h_step(self.h, dt, vel_iters, pos_iters)
+        if rc != 0:
+            raise RuntimeError("b2World::Step failed (%d): %s" % (rc, self.lib.b2h_last_error(self.h).decode()))
+
+    def bodies(self):
+        out = np.zeros(self.counts()[0], T.BODY)
+        self.lib.b2h_get_bodies(self.h, _ptr(out))
+        return out
+
+    def proxies(self):
+        out = np.zeros(self.counts()[1], T.PROXY)
+        self.lib.b2h_get_proxies(self.h, _ptr(out))
+        return out
+
+    def transforms(self):
+        n = self.counts()[0]
+        xya = np.zeros((n, 3), np.float32)
+        awake = np.zeros(n, np.int32)
+        self.lib.b2h_get_transforms(self.h, _ptr(xya), _ptr(awake))
+        return xya, awake
+
+    def mass(self):
+        out = np.zeros((self.counts()[0], 4), np.float32)
+        self.lib.b2h_get_mass(self.h, _ptr(out))
+        return out
+
+    def contacts(self):
+        n = self.counts()[2]
+        keys = np.zeros(n, np.uint64)
+        touching = np.zeros(n, np.int32)
+        points = np.zeros(n, np.int32)
+        m = self.lib.b2h_get_contacts(self.h, n, _ptr(keys), _ptr(touching), _ptr(points))
+        return keys[:m], touching[:m], points[:m]
+
+    def events(self, kind):
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, np.uint64)
+            n = self.lib.b2h_events(self.h, kind, cap, _ptr(out))
+            if n <= cap:
+                return out[:n]
+            cap = n
+
+    def solver_order(self):
+        cap = max(16, 4 * self.counts()[2])
+        out = np.zeros(cap, np.uint64)
+        n = self.lib.b2h_solver_order(self.h, cap, _ptr(out))
+        return out[:n]
+
+    def profile(self):
+        out = np.zeros(13, np.float32)
+        self.lib.b2h_profile(self.h, _ptr(out))
+        return out
+
+    def step_info(self):
+        out = np.zeros((), T.STEP_INFO)
+        self.lib.b2h_step_info(self.h, _ptr(out))
+        return out
+
+    def hash(self):
+        return self.lib.b2h_hash(self.h)
+
+    def set_transform(self, body, x, y, angle):
+        self.lib.b2h_set_transform(self.h, body, x, y, angle)
+
+    def set_velocity(self, body, vx, vy, w):
+        self.lib.b2h_set_velocity(self.h, body, vx, vy, w)
+
+    def apply_force(self, body, fx, fy, torque):
+        self.lib.b2h_apply_force(self.h, body, fx, fy, torque)
+
+    def set_awake(self, body, awake):
+        self.lib.b2h_set_awake(self.h, body, int(awake))
+
+    def set_options(self, download_bodies, events):
+        self.lib.b2h_set_options(self.h, int(download_bodies), int(events))
+
+    def apply_force_range(self, first, count, fx, fy):
+        self.lib.b2h_apply_force_range(self.h, first, count, fx, fy)
+
+    def destroy_body(self, body):
+        self.lib.b2h_destroy_body(self.h, body)

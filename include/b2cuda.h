@@ -25,6 +25,8 @@
  *                                                                          Dynamics/Contacts/b2Contact.h:231-259
  *   b2cuStep                             b2World::Step(dt, velocityIterations, positionIterations, executor)
  *                                                                          Dynamics/b2World.cpp:1613-1710
+ *   b2cuGetContactsByKey                 b2Contact objects handed to listener callbacks (manifold, flags, mixes),
+ *                                        fetched for a list of keys only       Dynamics/Contacts/b2Contact.h:95-176
  *   b2cuGetEvents                        deferred BeginContact/EndContact buffers, sorted by proxy-id key
  *                                                                          Dynamics/b2ContactManager.cpp:388-439
  *   b2cuGetSolverOrder                   (new) the colour-ordered constraint list the coloured Gauss-Seidel
@@ -257,6 +259,11 @@ B2CU_API int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* con
 B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
 /* Contacts in key order. */
 B2CU_API int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32_t* count);
+
+/* Records of the contacts with the given keys, out[i] for keys[i].  A key that is no longer in the contact set
+ * (e.g. the contact of an EndContact event that was destroyed) yields a record with the proxies of the key in
+ * primary-type order, flags 0 and an empty manifold. */
+B2CU_API int b2cuGetContactsByKey(b2cuWorld* w, int32_t count, const b2cuContactKey* keys, b2cuContact* out);
 
 B2CU_API int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positionIterations,
                       b2cuStepInfo* info);

@@ -1,0 +1,201 @@
+"""The C++ host API (b2World, b2Body, b2Fixture, b2CudaStepExecutor) against the oracle.
+
+CPU part: worlds built with CreateBody / CreateFixture hold exactly the state the reference's constructors
+compute (mass data, sweeps, tight and fat AABBs, flags, shape table).  GPU part: the same worlds stepped through
+b2World::Step(dt, vIters, pIters, b2CudaStepExecutor&) stay bit-identical to the oracle, callbacks included, and
+the reference's HelloWorld program compiles and runs unchanged apart from the executor type."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import b2cuda_types as T
+import b2host
+import parity
+import ref
+import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "box2d-mt_b200", "host")
+
+BUILD_SCENES = {
+    "hello": scenes.hello_world,
+    "pyramid": lambda: scenes.pyramid(6),
+    "pile": lambda: scenes.pile(10, 8),
+    "tumbler": lambda: scenes.tumbler(60),
+    "add_pair": lambda: scenes.add_pair(80),
+    "stacks": lambda: scenes.pyramids(2, 5, thick_polygon_ground=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(BUILD_SCENES))
+def test_host_built_world_equals_reference(name):
+    scene = BUILD_SCENES[name]()
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    rb, hb = r.bodies(), h.bodies()
+    parity.compare_bodies(hb, rb)
+    for f in ("invMass", "invI", "lcx", "lcy", "linearDamping", "angularDamping", "gravityScale", "alpha0"):
+        parity.assert_floats_equal("body." + f, hb[f], rb[f])
+    _, rp = parity.dedupe_shapes(r.shapes(), r.proxies())
+    hp = h.proxies()
+    parity.compare_proxies(hp, rp)
+    for f in ("body", "shape", "flags", "categoryBits", "maskBits", "groupIndex", "fixture"):
+        assert (hp[f] == rp[f]).all(), f
+    for f in ("friction", "restitution"):
+        parity.assert_floats_equal("proxy." + f, hp[f], rp[f])
+    assert h.hash() == r.hash()  # GetBodyList() order (newest first) and transforms
+
+
+def test_host_mass_data_matches_reference():
+    # multi-fixture body (summation order matters) and polygons built by hull computation
+    scene = scenes.tumbler(10)
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    rb = r.bodies()
+    m = h.mass()
+    inv = np.where(m[:, 0] > 0, 1.0 / m[:, 0].astype(np.float64), 0.0)
+    dyn = (rb["flags"] & T.BODY_TYPE_MASK) == T.DYNAMIC_BODY
+    assert np.allclose(inv[dyn], rb["invMass"][dyn], rtol=1e-6)
+
+
+def test_host_mutators_match_reference():
+    scene = scenes.pile(6, 5)
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    for w in (r, h):
+        w.set_transform(5, 0.3, 4.2, 0.7)
+        w.set_velocity(6, 1.5, -2.0, 0.25)
+        w.apply_force(7, 3.0, 4.0, 0.5)
+        w.set_awake(8, False)
+    parity.compare_bodies(h.bodies(), r.bodies())
+    parity.compare_proxies(h.proxies(), r.proxies())
+
+
+def test_step_without_gpu_fails_loudly():
+    import b2cuda
+    if b2cuda.device_count() > 0:
+        pytest.skip("device present")
+    code = ("import sys; sys.path.insert(0, %r); import b2host, scenes; "
+            "w = b2host.HostWorld(scenes.hello_world()); w.step()" % os.path.join(ROOT, "box2d-mt_b200", "python"))
+    p = subprocess.run(["python", "-c", code], capture_output=True, text=True)
+    assert p.returncode != 0
+    assert "no CPU step path" in p.stderr or "b2World::Step failed" in p.stderr
+
+
+def test_hello_world_program_compiles_against_host_api(tmp_path):
+    exe = tmp_path / "hello"
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", HOST, "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "hello_world.cpp"), "-L", os.path.join(ROOT, "box2d-mt_b200"),
+                    "-lbox2d_b200", "-lb2cuda", "-Wl,-rpath," + os.path.join(ROOT, "box2d-mt_b200"), "-o", str(exe)],
+                   check=True)
+    assert exe.exists()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------------
+
+def _host_lockstep(scene, steps, check_events=True):
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    begins = 0
+    for s in range(steps):
+        h.step()
+        assert r.step_ordered(h.solver_order()) == 0, s
+        try:
+            parity.compare_bodies(h.bodies(), r.bodies())
+            xya, awake = h.transforms()
+            rb = r.bodies()
+            assert (xya[:, 0] == rb["px"]).all() and (xya[:, 1] == rb["py"]).all() and (xya[:, 2] == rb["a"]).all()
+            assert (awake == ((rb["flags"] & T.BODY_AWAKE) != 0)).all()
+            if check_events:
+                for kind in (T.EVENT_BEGIN, T.EVENT_END):
+                    g, w = h.events(kind), r.events(kind)
+                    assert len(g) == len(w) and (g == w).all(), ("events", kind)
+                begins += len(h.events(T.EVENT_BEGIN))
+            assert h.counts()[2] == r.counts()[2]
+        except AssertionError as e:
+            raise AssertionError("step %d: %s" % (s, e))
+    return h, r, begins
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,steps", [("pyramid", 200), ("pile", 200), ("tumbler", 150), ("stacks", 200)])
+def test_host_api_lockstep(gpu, name, steps):
+    """TestMT.cpp:91-110 rule (position, angle, awake of every body after every step) between the reference and a
+    world stepped through b2World::Step with a b2CudaStepExecutor; deferred Begin/End callbacks in the same order."""
+    h, r, begins = _host_lockstep(BUILD_SCENES[name](), steps)
+    assert begins > 0
+    assert h.hash() == r.hash()
+    keys, touching, points = h.contacts()  # b2World::GetContactList snapshot
+    rc = r.contacts()
+    assert (keys == T.contact_keys(rc)).all()
+    assert (touching == ((rc["flags"] & T.CONTACT_TOUCHING) != 0)).all()
+    assert (points == rc["manifold"]["pointCount"]).all()
+    prof = h.profile()
+    assert prof[0] > 0 and prof[2] > 0  # step and solve times come from device events
+
+
+@pytest.mark.gpu
+def test_host_api_mutation_between_steps(gpu):
+    scene = scenes.pile(8, 6)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    for s in range(120):
+        if s % 20 == 10:
+            for w in (r, h):
+                w.set_velocity(3 + s // 20, 2.0, 5.0, 1.0)
+                w.apply_force(10, 0.0, 30.0, 0.0)
+        if s == 60:
+            for w in (r, h):
+                w.set_transform(12, 0.1, 9.0, 0.3)
+        h.step()
+        assert r.step_ordered(h.solver_order()) == 0
+        parity.compare_bodies(h.bodies(), r.bodies())
+
+
+@pytest.mark.gpu
+def test_host_api_lazy_download(gpu):
+    """downloadBodies=false: the mirror is refreshed on first access only; results are the same."""
+    a = b2host.HostWorld(scenes.pile(8, 6), download_bodies=True)
+    b = b2host.HostWorld(scenes.pile(8, 6), download_bodies=False, events=False)
+    for _ in range(60):
+        a.step()
+        b.step()
+    assert a.bodies().tobytes() == b.bodies().tobytes()
+
+
+@pytest.mark.gpu
+def test_host_api_destroy_body(gpu):
+    scene = scenes.pile(8, 6)
+    h = b2host.HostWorld(scene)
+    for _ in range(90):
+        h.step()
+    n0 = h.counts()
+    ends_before = len(h.events(T.EVENT_END))
+    h.destroy_body(10)
+    h.destroy_body(20)
+    assert h.counts()[0] == n0[0] - 2
+    for _ in range(60):
+        h.step()
+    b = h.bodies()
+    assert np.isfinite(b["py"]).all() and (b["py"][1:] > -0.5).all()
+    assert ends_before >= 0
+
+
+@pytest.mark.gpu
+def test_hello_world_program_runs(gpu, tmp_path):
+    """The reference's HelloWorld, executor type swapped, prints the reference's 60 lines."""
+    exe = tmp_path / "hello"
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", HOST, "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "hello_world.cpp"), "-L", os.path.join(ROOT, "box2d-mt_b200"),
+                    "-lbox2d_b200", "-lb2cuda", "-Wl,-rpath," + os.path.join(ROOT, "box2d-mt_b200"), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    with open(os.path.join(ROOT, "tests", "golden", "helloworld.txt")) as f:
+        want = [ln.strip() for ln in f if ln.strip()]
+    assert [ln.strip() for ln in out] == want
