@@ -322,19 +322,27 @@ void b2World::MakeContact(b2Contact* c, const b2cuContact& rec)
 	c->m_nodeB.prev = c->m_nodeB.next = nullptr;
 }
 
-// Download the device contact set (key order) and materialise b2Contact objects + per-body edge lists.
+// Download the device contact set (key order) and materialise b2Contact objects + per-body edge lists.  While a
+// full upload is pending (after a destruction) the host records are the authoritative set.
 void b2World::RefreshContacts()
 {
 	if (!m_contactsStale) return;
 	m_contactsStale = false;
 	m_contacts.clear();
 	m_contactHeads.assign(m_bodies.size(), nullptr);
-	if (m_device == nullptr) return;
-	int32 n = 0;
-	b2cuGetContactCount(m_device, &n);
-	m_contactRecords.resize(n);
+	if (m_device != nullptr && !m_fullUpload)
+	{
+		int32 n = 0;
+		b2cuGetContactCount(m_device, &n);
+		m_contactRecords.resize(n);
+		if (n > 0) b2cuGetContacts(m_device, n, m_contactRecords.data(), &n);
+	}
+	else if (m_device == nullptr && !m_fullUpload)
+	{
+		m_contactRecords.clear();
+	}
+	const int32 n = (int32)m_contactRecords.size();
 	if (n == 0) return;
-	b2cuGetContacts(m_device, n, m_contactRecords.data(), &n);
 	m_contacts.resize(n);
 	for (int32 i = 0; i < n; ++i)
 	{
@@ -342,7 +350,6 @@ void b2World::RefreshContacts()
 		MakeContact(c, m_contactRecords[i]);
 		c->m_next = i + 1 < n ? &m_contacts[i + 1] : nullptr;
 	}
-	// edge lists: newest (highest key) first is as good as any; the reference's order is creation order
 	for (int32 i = 0; i < n; ++i)
 	{
 		b2Contact* c = &m_contacts[i];
@@ -445,7 +452,7 @@ void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vecto
 	m_contactCount = (int32)m_contactRecords.size();
 	m_contacts.clear();
 	m_contactHeads.clear();
-	m_contactsStale = false; // m_contactRecords is now authoritative until the next upload
+	m_contactsStale = true; // snapshots are rebuilt from m_contactRecords, which is authoritative until the upload
 	m_fullUpload = true;
 }
 
