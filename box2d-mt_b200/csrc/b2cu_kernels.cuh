@@ -77,8 +77,15 @@ __device__ __forceinline__ int LowerBound64(const uint64_t* __restrict__ keys, i
 // Collide: b2ContactManager::Collide (Box2D/Dynamics/b2ContactManager.cpp:177-230) fused with
 // b2Contact::UpdateImpl (Box2D/Dynamics/Contacts/b2Contact.cpp:173-298).  One thread per contact.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contactCount)
+__device__ __forceinline__ void AppendKey(const DeviceArrays& d, int counter, uint64_t* list, uint64_t key, int capacity)
 {
+	int slot = atomicAdd(&d.counters[counter], 1);
+	if (slot < capacity) list[slot] = key;
+}
+
+__global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contactCount, int capacity)
+{
+	int touchingCount = 0;
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		int2 pr = d.c.proxies[i];
@@ -113,6 +120,7 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 			{
 				d.c.flags[i] = flags | B2CU_CONTACT_INACTIVE;
 				d.cEvent[i] = 0;
+				if (flags & B2CU_CONTACT_TOUCHING) ++touchingCount;
 				continue;
 			}
 			flags &= ~B2CU_CONTACT_INACTIVE;
@@ -134,6 +142,7 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 			}
 			d.c.flags[i] = flags;
 			d.cEvent[i] = ev;
+			if (ev & B2CU_EV_DESTROY_TOUCHING) AppendKey(d, CNT_DESTROY_END, d.destroyEndKeys, d.c.key[i], capacity);
 			continue;
 		}
 
@@ -191,8 +200,19 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 			d.wake[bA] = 1;
 			ev = touching ? B2CU_EV_BEGIN : B2CU_EV_END;
 		}
-		if (touching) flags |= B2CU_CONTACT_TOUCHING;
-		else flags &= ~B2CU_CONTACT_TOUCHING;
+		if (touching)
+		{
+			flags |= B2CU_CONTACT_TOUCHING;
+			++touchingCount;
+		}
+		else
+		{
+			flags &= ~B2CU_CONTACT_TOUCHING;
+		}
+		// deferred Begin/End buffers (b2ContactManagerPerThreadData::m_beginContacts / m_endContacts); sorted by key
+		// afterwards, which is what b2ThreadDataSorter does for the reference (b2ContactManager.cpp:388-433)
+		if (ev == B2CU_EV_BEGIN) AppendKey(d, CNT_BEGIN, d.beginKeys, d.c.key[i], capacity);
+		else if (ev == B2CU_EV_END) AppendKey(d, CNT_END, d.endKeys, d.c.key[i], capacity);
 
 		d.c.flags[i] = flags;
 		d.c.m0[i] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
@@ -201,6 +221,8 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 		d.c.m3[i] = make_uint4(m.id[0], m.id[1], (uint32_t)m.type, (uint32_t)m.pointCount);
 		d.cEvent[i] = ev;
 	}
+	for (int dlt = 16; dlt > 0; dlt >>= 1) touchingCount += __shfl_down_sync(0xffffffffu, touchingCount, dlt);
+	if ((threadIdx.x & 31) == 0 && touchingCount) atomicAdd(&d.counters[CNT_TOUCHING], touchingCount);
 }
 
 // b2Body::SetAwake(true) for every body flagged by Collide / contact creation / contact destruction
@@ -368,8 +390,11 @@ __global__ void SelectConstraintsKernel(DeviceArrays d, int contactCount)
 // (Box2D/Dynamics/Contacts/b2ContactSolver.cpp:293-603) run one colour at a time in parallel.  Colours persist
 // across steps, so only new constraints are coloured.  Deterministic: ties are broken by contact index.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void ColourPrepareKernel(DeviceArrays d, const int* __restrict__ list, int* uncoloured)
+__global__ void __launch_bounds__(256) ColourPrepareKernel(DeviceArrays d, const int* __restrict__ list, int* uncoloured)
 {
+	__shared__ int hist[B2CU_MAX_COLOURS];
+	if (threadIdx.x < B2CU_MAX_COLOURS) hist[threadIdx.x] = 0;
+	__syncthreads();
 	int n = d.counters[CNT_CONSTRAINT];
 	B2CU_GRID_STRIDE(j, n)
 	{
@@ -381,6 +406,7 @@ __global__ void ColourPrepareKernel(DeviceArrays d, const int* __restrict__ list
 		{
 			if (IsDynamic(d.bflags[bA])) atomicOr(&d.colourMask[bA], 1u << c);
 			if (IsDynamic(d.bflags[bB])) atomicOr(&d.colourMask[bB], 1u << c);
+			atomicAdd(&hist[c], 1);
 		}
 		else
 		{
@@ -389,6 +415,8 @@ __global__ void ColourPrepareKernel(DeviceArrays d, const int* __restrict__ list
 			uncoloured[slot] = i;
 		}
 	}
+	__syncthreads();
+	if (threadIdx.x < B2CU_MAX_COLOURS && hist[threadIdx.x]) atomicAdd(&d.colourCount[threadIdx.x], hist[threadIdx.x]);
 }
 
 __device__ __forceinline__ uint32_t ColourFreeMask(const DeviceArrays& d, int bA, int bB, bool dynA, bool dynB)
@@ -412,6 +440,7 @@ __global__ void ColourProposeKernel(DeviceArrays d, const int* __restrict__ list
 		if (freeMask == 0u)
 		{
 			d.c.colour[i] = B2CU_COLOUR_OVERFLOW;
+			atomicAdd(&d.colourCount[B2CU_MAX_COLOURS], 1);
 			continue;
 		}
 		unsigned long long claim = ((unsigned long long)round << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
@@ -438,6 +467,7 @@ __global__ void ColourCommitKernel(DeviceArrays d, const int* __restrict__ list,
 			uint32_t freeMask = ColourFreeMask(d, bA, bB, dynA, dynB);
 			int c = __ffs((int)freeMask) - 1;
 			d.c.colour[i] = c;
+			atomicAdd(&d.colourCount[c], 1);
 			// this constraint is the only winner on each of its dynamic bodies this round
 			if (dynA) d.colourMask[bA] |= 1u << c;
 			if (dynB) d.colourMask[bB] |= 1u << c;
@@ -457,17 +487,6 @@ __global__ void ColourKeysKernel(DeviceArrays d, const int* __restrict__ list)
 	{
 		int i = list[j];
 		d.orderKeys[j] = ((uint64_t)(uint32_t)d.c.colour[i] << 32) | (uint32_t)i;
-	}
-}
-
-// colourCount[c] = first position of colour c in the sorted order (or -1)
-__global__ void ColourStartsKernel(DeviceArrays d)
-{
-	int n = d.counters[CNT_CONSTRAINT];
-	B2CU_GRID_STRIDE(j, n)
-	{
-		int c = (int)(d.orderKeys[j] >> 32);
-		if (j == 0 || (int)(d.orderKeys[j - 1] >> 32) != c) d.colourCount[c] = j;
 	}
 }
 
@@ -696,10 +715,10 @@ __global__ void __launch_bounds__(256) InitConstraintsKernel(DeviceArrays d, flo
 // b2ContactSolver::WarmStart (b2ContactSolver.cpp:253-291), constraints [begin, begin+count) of one colour
 __device__ __forceinline__ void WarmStartOne(const DeviceArrays& d, int k)
 {
-	int4 sb = d.sBody[k];
-	float4 ms = d.sMass[k];
-	float4 nf = d.sNormal[k];
-	float4 imp = d.sImp[k];
+	int4 sb = __ldcs(&d.sBody[k]);
+	float4 ms = __ldcs(&d.sMass[k]);
+	float4 nf = __ldcs(&d.sNormal[k]);
+	float4 imp = __ldcs(&d.sImp[k]);
 	int pointCount = sb.w & 0xFF;
 	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
 
@@ -711,7 +730,7 @@ __device__ __forceinline__ void WarmStartOne(const DeviceArrays& d, int k)
 
 	for (int j = 0; j < pointCount; ++j)
 	{
-		float4 r = j == 0 ? d.sP0a[k] : d.sP1a[k];
+		float4 r = j == 0 ? __ldcs(&d.sP0a[k]) : __ldcs(&d.sP1a[k]);
 		float ni = j == 0 ? imp.x : imp.z;
 		float ti = j == 0 ? imp.y : imp.w;
 		Vec2 rA = V(r.x, r.y), rB = V(r.z, r.w);
@@ -733,11 +752,11 @@ __global__ void __launch_bounds__(256) WarmStartKernel(DeviceArrays d, int begin
 // b2ContactSolver::SolveVelocityConstraints (b2ContactSolver.cpp:293-603) for one constraint
 __device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k)
 {
-	int4 sb = d.sBody[k];
-	float4 ms = d.sMass[k];
-	float4 nf = d.sNormal[k];
-	float4 imp = d.sImp[k];
-	float4 p0a = d.sP0a[k], p0b = d.sP0b[k];
+	int4 sb = __ldcs(&d.sBody[k]);
+	float4 ms = __ldcs(&d.sMass[k]);
+	float4 nf = __ldcs(&d.sNormal[k]);
+	float4 imp = __ldcs(&d.sImp[k]);
+	float4 p0a = __ldcs(&d.sP0a[k]), p0b = __ldcs(&d.sP0b[k]);
 	int pointCount = sb.w & 0xFF;
 	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
 
@@ -751,8 +770,8 @@ __device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k)
 	float4 p1a = make_float4(0.f, 0.f, 0.f, 0.f), p1b = make_float4(0.f, 0.f, 0.f, 0.f);
 	if (pointCount == 2)
 	{
-		p1a = d.sP1a[k];
-		p1b = d.sP1b[k];
+		p1a = __ldcs(&d.sP1a[k]);
+		p1b = __ldcs(&d.sP1b[k]);
 	}
 
 	// tangent constraints first
@@ -801,8 +820,8 @@ __device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k)
 	else
 	{
 		// block solver, total enumeration of the 2x2 LCP (b2ContactSolver.cpp:375-596)
-		float4 Kq = d.sK[k];
-		float4 NM = d.sNM[k];
+		float4 Kq = __ldcs(&d.sK[k]);
+		float4 NM = __ldcs(&d.sNM[k]);
 		Vec2 rA1 = V(p0a.x, p0a.y), rB1 = V(p0a.z, p0a.w);
 		Vec2 rA2 = V(p1a.x, p1a.y), rB2 = V(p1a.z, p1a.w);
 
@@ -869,7 +888,7 @@ __device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k)
 		// no solution: give up, as the reference does (:593-594)
 	}
 
-	d.sImp[k] = imp;
+	__stcs(&d.sImp[k], imp);
 	if (mA != 0.0f || iA != 0.0f) d.vel[sb.x] = make_float4(vA.x, vA.y, wA, vA4.w);
 	if (mB != 0.0f || iB != 0.0f) d.vel[sb.y] = make_float4(vB.x, vB.y, wB, vB4.w);
 }
@@ -942,12 +961,12 @@ __global__ void IntegratePositionsKernel(DeviceArrays d, int bodyCount, float h)
 // (b2Island.cpp:318-335), which is tracked per island root in islandMinSep[iteration][root].
 __device__ __forceinline__ float SolvePositionOne(const DeviceArrays& d, int k)
 {
-	int4 sb = d.sBody[k];
-	float4 ms = d.sMass[k];
-	float4 loc = d.sLocal[k];
-	float4 lps = d.sLocalP[k];
-	float4 cen = d.sCenters[k];
-	float4 rad = d.sRadius[k];
+	int4 sb = __ldcs(&d.sBody[k]);
+	float4 ms = __ldcs(&d.sMass[k]);
+	float4 loc = __ldcs(&d.sLocal[k]);
+	float4 lps = __ldcs(&d.sLocalP[k]);
+	float4 cen = __ldcs(&d.sCenters[k]);
+	float4 rad = __ldcs(&d.sRadius[k]);
 	int pointCount = sb.w >> 8;
 	int type = __float_as_int(rad.z);
 	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
@@ -1033,7 +1052,7 @@ __global__ void __launch_bounds__(256) SolvePositionKernel(DeviceArrays d, int b
 	B2CU_GRID_STRIDE(t, count)
 	{
 		int k = begin + t;
-		int root = __float_as_int(d.sRadius[k].w);
+		int root = __float_as_int(__ldcs(&d.sRadius[k]).w);
 		if (IslandDone(d, iteration, root, bodyCount)) continue;
 		float minSep = SolvePositionOne(d, k);
 		AtomicMinByRoot(d.islandMinSep + (size_t)iteration * bodyCount, root, FloatToOrdered(minSep));
@@ -1497,6 +1516,23 @@ __global__ void ToiFlagsKernel(DeviceArrays d, int contactCount, int* flagsOut)
 		}
 		flagsOut[i] = ok;
 	}
+}
+
+// is b2Contact::IsToiCandidate (b2Contact.cpp:300-324) satisfiable by any pair: a bullet body, or a non-dynamic
+// body carrying a fixture that is not thick-shape
+__global__ void ToiPossibleKernel(DeviceArrays d, int bodyCount, int proxyCount)
+{
+	bool any = false;
+	B2CU_GRID_STRIDE(i, bodyCount > proxyCount ? bodyCount : proxyCount)
+	{
+		if (i < bodyCount && (d.bflags[i] & B2CU_BODY_BULLET)) any = true;
+		if (i < proxyCount)
+		{
+			uint32_t pf = d.pgroup[i] >> 16;
+			if (!(pf & (B2CU_PROXY_THICK | B2CU_PROXY_SENSOR)) && !IsDynamic(d.bflags[d.pbody[i]])) any = true;
+		}
+	}
+	if (__any_sync(__activemask(), any) && any) d.counters[CNT_STICKY_TOI] = 1;
 }
 
 // end of step: clear island flags (b2World::ClearPostSolve, b2World.cpp:1433-1465), clear forces

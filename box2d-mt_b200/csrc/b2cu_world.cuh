@@ -27,8 +27,8 @@ enum Counter
 	CNT_DESTROY_END,      // of those, touching ones (EndContact from Destroy)
 	CNT_TOUCHING,         // touching contacts after Collide
 	CNT_CONSTRAINT,       // contacts handed to the solver
-	CNT_UNCOLOURED,       // constraints still without a colour (ping)
-	CNT_UNCOLOURED_NEXT,  // (pong)
+	CNT_UNCOLOURED,       // constraints still without a colour before colouring round r: CNT_UNCOLOURED + r
+	CNT_UNCOLOURED_LAST = CNT_UNCOLOURED + 7,
 	CNT_OVERFLOW,         // constraints with no free colour
 	CNT_MOVED,            // proxies in the move buffer
 	CNT_LARGE,            // proxies too large for the grid
@@ -40,6 +40,7 @@ enum Counter
 	CNT_TOI,
 	CNT_ERROR,            // != 0: a buffer overflowed
 	CNT_SCRATCH,
+	CNT_STICKY_TOI,       // not cleared per step: a TOI-candidate contact has existed
 	CNT_COUNT
 };
 
@@ -100,6 +101,7 @@ struct DeviceArrays
 	int* listB;
 	uint64_t* beginKeys;
 	uint64_t* endKeys;
+	uint64_t* destroyEndKeys; // EndContact of contacts destroyed while touching (reported after the sorted ends)
 	uint64_t* newKeys;      // new pair keys (unsorted, then sorted)
 	uint64_t* orderKeys;    // colour << 32 | contact index, sorted = solver order
 	uint64_t* solverKeys;   // contact key of the k-th constraint of the solver order (for b2cuGetSolverOrder)
@@ -157,7 +159,9 @@ struct b2cuWorld
 	int gridSize;        // hash table size (power of two)
 	float cellSize;
 	bool newProxies;     // e_newFixture: run FindNewContacts at the start of the next step
+	bool toiCheckDirty;  // bodies / proxies changed: re-evaluate whether TOI candidates are possible
 	int positionIterationsCapacity;
+	size_t l2WindowMax;  // 0: no persisting-L2 support
 
 	// last step
 	int beginCount, endCount, constraintCount, colourCount, overflowCount, toiCount;

@@ -135,6 +135,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->listB, CAP_CONTACT));
 	v.push_back(Desc(&d->beginKeys, CAP_CONTACT));
 	v.push_back(Desc(&d->endKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->destroyEndKeys, CAP_CONTACT));
 	v.push_back(Desc(&d->newKeys, CAP_CONTACT));
 	v.push_back(Desc(&d->orderKeys, CAP_CONTACT));
 	v.push_back(Desc(&d->solverKeys, CAP_CONTACT));
@@ -266,6 +267,32 @@ float ChooseCellSize(const std::vector<float>& extents)
 	return 2.0f * m;
 }
 
+// Pin one body array (16 B x bodies: vel during the velocity iterations, pos during the position iterations) in
+// L2 with an access-policy window: the constraint stream (hundreds of MB per iteration, loaded with evict-first
+// hints) then cannot evict the state every constraint gathers and scatters.
+void SetL2Window(b2cuWorld* w, const void* base, size_t bytes)
+{
+	if (w->l2WindowMax == 0) return;
+	cudaStreamAttrValue attr;
+	memset(&attr, 0, sizeof(attr));
+	attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+	attr.accessPolicyWindow.num_bytes = std::min(bytes, w->l2WindowMax);
+	attr.accessPolicyWindow.hitRatio = 1.0f;
+	attr.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+	attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+	cudaStreamSetAttribute(w->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+}
+
+// ascending sort of contact keys (min proxy << 32 | max proxy): LSD over the two id fields
+void SortKeys(b2cuWorld* w, uint64_t* keys, int n)
+{
+	if (n <= 1) return;
+	int bits = 1;
+	while ((1 << bits) < std::max(2, w->proxyCount)) ++bits;
+	RadixSort64(&w->prims, keys, n, 0, bits, w->stream);
+	RadixSort64(&w->prims, keys, n, 32, 32 + bits, w->stream);
+}
+
 // ---- broad-phase pair finding + contact set rebuild ------------------------------------------------------
 
 // Finds new pairs for the proxies flagged MOVED, then rebuilds the contact set (drop destroyed, merge new).
@@ -332,13 +359,7 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		return B2CU_OK; // contact set unchanged
 	}
 
-	if (newCount > 1)
-	{
-		int bits = 1;
-		while ((1 << bits) < std::max(2, np)) ++bits;
-		RadixSort64(&w->prims, d.newKeys, newCount, 0, bits, w->stream);
-		RadixSort64(&w->prims, d.newKeys, newCount, 32, 32 + bits, w->stream);
-	}
+	SortKeys(w, d.newKeys, newCount);
 	if (nc > 0)
 	{
 		LAUNCH(w, RebuildExistingKernel, GridFor(nc), kBlock, d, nc, d.listA, newCount);
@@ -408,7 +429,16 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 	new (&w->prims) PrimScratch();
 	w->device = def->device;
 	cudaDeviceProp prop;
-	if (cudaGetDeviceProperties(&prop, def->device) == cudaSuccess) g_smCount = prop.multiProcessorCount;
+	if (cudaGetDeviceProperties(&prop, def->device) == cudaSuccess)
+	{
+		g_smCount = prop.multiProcessorCount;
+		if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0)
+		{
+			size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)64 << 20);
+			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+				w->l2WindowMax = std::min(want, (size_t)prop.accessPolicyMaxWindowSize);
+		}
+	}
 	if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess)
 	{
 		delete w;
@@ -421,6 +451,7 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 	w->params.invDt0 = 0.0f;
 	w->positionIterationsCapacity = 4;
 	w->cellSize = 1.0f;
+	w->toiCheckDirty = true;
 	int rc = Reserve(w, std::max(def->bodyCapacity, 64), std::max(def->proxyCapacity, 64),
 	                 std::max(def->shapeCapacity, 16), std::max(def->contactCapacity, 256));
 	if (rc != B2CU_OK)
@@ -509,6 +540,7 @@ int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bo
 	    (rc = Upload(w, d.force, first, force)) || (rc = Upload(w, d.damp, first, damp)) ||
 	    (rc = Upload(w, d.bflags, first, flags)))
 		return rc;
+	w->toiCheckDirty = true;
 	return SyncCheck(w);
 }
 
@@ -599,6 +631,7 @@ int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* 
 	    (rc = Upload(w, d.pgroup, first, group)) || (rc = Upload(w, d.pmat, first, mat)))
 		return rc;
 	if (anyMoved) w->newProxies = true;
+	w->toiCheckDirty = true;
 	if (first == 0 && count > 0)
 	{
 		w->cellSize = ChooseCellSize(extents);
@@ -783,8 +816,17 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		CUDA_TRY(w, cudaMalloc(&d.islandMinSep, sizeof(int) * (size_t)positionIterations * (size_t)w->bodyCapacity));
 	}
 
-	CUDA_TRY(w, cudaMemsetAsync(d.counters, 0, sizeof(int) * CNT_COUNT, w->stream));
+	CUDA_TRY(w, cudaMemsetAsync(d.counters, 0, sizeof(int) * CNT_STICKY_TOI, w->stream));
 	cudaEventRecord(w->ev[0], w->stream);
+
+	if (w->toiCheckDirty)
+	{
+		// can any contact be a TOI candidate at all (b2Contact::IsToiCandidate)?  Worlds whose static geometry is
+		// all thick-shape and that have no bullets skip the TOI eligibility pass entirely.
+		CUDA_TRY(w, cudaMemsetAsync(d.counters + CNT_STICKY_TOI, 0, sizeof(int), w->stream));
+		LAUNCH(w, ToiPossibleKernel, GridFor(std::max(nb, np)), kBlock, d, nb, np);
+		w->toiCheckDirty = false;
+	}
 
 	int newContacts = 0, destroyed = 0, moved = 0;
 
@@ -804,22 +846,9 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	w->beginCount = w->endCount = 0;
 	if (nc > 0)
 	{
-		LAUNCH(w, CollideKernel, GridFor(nc), kBlock, d, nc);
+		// narrow phase; begin/end events are appended to the deferred buffers and sorted at the end of the step
+		LAUNCH(w, CollideKernel, GridFor(nc), kBlock, d, nc, w->contactCapacity);
 		LAUNCH(w, ApplyWakeKernel, GridFor(nb), kBlock, d, nb);
-		// deferred Begin/End buffers in key order (FinishCollide, b2ContactManager.cpp:388-439); EndContact calls
-		// made by Destroy come after the sorted ends
-		CompactMask(&w->prims, (const uint32_t*)d.cEvent, B2CU_EV_BEGIN, nc, d.listA, d.counters + CNT_BEGIN, w->stream);
-		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_BEGIN, (const int*)nullptr,
-		       d.beginKeys, w->contactCapacity);
-		CompactMask(&w->prims, (const uint32_t*)d.cEvent, B2CU_EV_END, nc, d.listA, d.counters + CNT_END, w->stream);
-		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_END, (const int*)nullptr,
-		       d.endKeys, w->contactCapacity);
-		CompactMask(&w->prims, (const uint32_t*)d.cEvent, B2CU_EV_DESTROY_TOUCHING, nc, d.listA,
-		            d.counters + CNT_DESTROY_END, w->stream);
-		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_DESTROY_END,
-		       d.counters + CNT_END, d.endKeys, w->contactCapacity);
-		LAUNCH(w, CountMaskKernel, GridFor(nc), kBlock, d.c.flags, (uint32_t)B2CU_CONTACT_TOUCHING, nc,
-		       d.counters + CNT_TOUCHING);
 	}
 	cudaEventRecord(w->ev[2], w->stream);
 
@@ -849,50 +878,58 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		{
 			LAUNCH(w, SelectConstraintsKernel, GridFor(nc), kBlock, d, nc);
 			CompactFlags(&w->prims, d.cSelect, nc, d.listA, d.counters + CNT_CONSTRAINT, w->stream);
+			CUDA_TRY(w, cudaMemsetAsync(d.colourCount, 0, sizeof(int) * (B2CU_MAX_COLOURS + 2), w->stream));
 			int* cur = d.listB;
 			int* next = d.listC;
 			LAUNCH(w, ColourPrepareKernel, GridFor(nc), kBlock, d, d.listA, cur);
+			// a fixed number of colouring rounds is queued without asking the device how many constraints are left
+			// (in steady state only the few new constraints are uncoloured and 2-3 rounds finish them); one
+			// read-back then gives the constraint count, the per-colour counts and what is left
+			const int kBlindRounds = 4;
+			uint32_t round = 1;
+			int counter = CNT_UNCOLOURED;
+			for (int r = 0; r < kBlindRounds; ++r)
+			{
+				int g = GridFor(std::max(1024, nc / 64));
+				LAUNCH(w, ColourProposeKernel, g, kBlock, d, cur, counter, round);
+				LAUNCH(w, ColourCommitKernel, g, kBlock, d, cur, counter, next, counter + 1, round);
+				std::swap(cur, next);
+				++counter;
+				++round;
+			}
 			if ((rc = ReadCounters(w))) return rc;
 			nConstraints = w->hostCounters[CNT_CONSTRAINT];
-			int remaining = w->hostCounters[CNT_UNCOLOURED];
-			int curCounter = CNT_UNCOLOURED, nextCounter = CNT_UNCOLOURED_NEXT;
-			uint32_t round = 1;
+			int remaining = w->hostCounters[counter];
 			while (remaining > 0)
 			{
-				LAUNCH(w, ColourProposeKernel, GridFor(remaining), kBlock, d, cur, curCounter, round);
-				LAUNCH(w, ColourCommitKernel, GridFor(remaining), kBlock, d, cur, curCounter, next, nextCounter, round);
-				if ((rc = ZeroCounter(w, curCounter))) return rc;
-				CUDA_TRY(w, cudaMemcpyAsync(w->hostCounters + nextCounter, d.counters + nextCounter, sizeof(int),
-				                            cudaMemcpyDeviceToHost, w->stream));
-				if ((rc = SyncCheck(w))) return rc;
+				// rare: more rounds, now one read-back per round; the two spare counters are ping-ponged
+				int nextCounter = counter == CNT_UNCOLOURED_LAST ? CNT_UNCOLOURED_LAST - 1 : counter + 1;
+				if ((rc = ZeroCounter(w, nextCounter))) return rc;
+				LAUNCH(w, ColourProposeKernel, GridFor(remaining), kBlock, d, cur, counter, round);
+				LAUNCH(w, ColourCommitKernel, GridFor(remaining), kBlock, d, cur, counter, next, nextCounter, round);
+				if ((rc = ReadCounters(w))) return rc;
 				remaining = w->hostCounters[nextCounter];
 				std::swap(cur, next);
-				std::swap(curCounter, nextCounter);
+				counter = nextCounter;
 				++round;
 				if (round > 100000u) return SetError(w, B2CU_ERR_CUDA, "colouring did not converge");
 			}
 			if (nConstraints > 0)
 			{
-				CUDA_TRY(w, cudaMemsetAsync(d.colourCount, 0xFF, sizeof(int) * (B2CU_MAX_COLOURS + 2), w->stream));
-				LAUNCH(w, ColourKeysKernel, GridFor(nConstraints), kBlock, d, d.listA);
-				RadixSort64(&w->prims, d.orderKeys, nConstraints, 32, 40, w->stream);
-				LAUNCH(w, ColourStartsKernel, GridFor(nConstraints), kBlock, d);
-				if ((rc = ReadCounters(w))) return rc;
-				for (int c = 0; c <= B2CU_MAX_COLOURS; ++c) colourStart[c] = w->hostCounters[CNT_COUNT + c];
-				colourStart[B2CU_MAX_COLOURS + 1] = nConstraints;
-				// fill the gaps of absent colours from the right
-				int nextStart = nConstraints;
-				for (int c = B2CU_MAX_COLOURS; c >= 0; --c)
-				{
-					if (colourStart[c] < 0) colourStart[c] = nextStart;
-					else nextStart = colourStart[c];
-				}
+				int at = 0;
 				for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
 				{
-					w->colourCounts[c] = colourStart[c + 1] - colourStart[c];
+					w->colourCounts[c] = w->hostCounters[CNT_COUNT + c];
+					colourStart[c] = at;
+					at += w->colourCounts[c];
 					if (c < B2CU_MAX_COLOURS && w->colourCounts[c] > 0) w->colourCount = c + 1;
 				}
+				colourStart[B2CU_MAX_COLOURS + 1] = at;
+				if (at != nConstraints)
+					return SetError(w, B2CU_ERR_CUDA, "internal: colour counts %d != constraints %d", at, nConstraints);
 				w->overflowCount = w->colourCounts[B2CU_MAX_COLOURS];
+				LAUNCH(w, ColourKeysKernel, GridFor(nConstraints), kBlock, d, d.listA);
+				RadixSort64(&w->prims, d.orderKeys, nConstraints, 32, 40, w->stream);
 			}
 		}
 		w->constraintCount = nConstraints;
@@ -917,6 +954,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		cudaEventRecord(w->ev[5], w->stream);
 		if (nConstraints > 0)
 		{
+			SetL2Window(w, d.vel, sizeof(float4) * (size_t)nb);
 			for (int it = 0; it < velocityIterations; ++it)
 			{
 				for (int c = 0; c < B2CU_MAX_COLOURS; ++c)
@@ -934,6 +972,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		LAUNCH(w, IntegratePositionsKernel, GridFor(nb), kBlock, d, nb, dt);
 		if (nConstraints > 0)
 		{
+			SetL2Window(w, d.pos, sizeof(float4) * (size_t)nb);
 			for (int it = 0; it < positionIterations; ++it)
 			{
 				for (int c = 0; c < B2CU_MAX_COLOURS; ++c)
@@ -946,12 +985,16 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 					LAUNCH(w, OverflowSolvePositionKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->overflowCount, it, nb);
 			}
 		}
+		if (nConstraints > 0) SetL2Window(w, nullptr, 0);
 		LAUNCH(w, FinalizeBodiesKernel, GridFor(nb), kBlock, d, nb, dt, allowSleep ? 1 : 0);
 		if (allowSleep) LAUNCH(w, SleepIslandsKernel, GridFor(nb), kBlock, d, nb, positionIterations);
 		cudaEventRecord(w->ev[7], w->stream);
 
 		// ---- SynchronizeFixtures + FindNewContacts (b2World.cpp:1410-1427) ----
 		if (np > 0) LAUNCH(w, SyncProxiesKernel, GridFor(np), kBlock, d, np);
+		// ClearPostSolve + ClearForces (b2World.cpp:1430, :1688-1691); done here so that the read-back of the
+		// broad-phase also carries the awake-body count
+		LAUNCH(w, EndStepBodiesKernel, GridFor(nb), kBlock, d, nb, (w->params.flags & B2CU_WORLD_CLEAR_FORCES) ? 1 : 0);
 		int n1 = 0, d1 = 0, m1 = 0;
 		if ((rc = FindNewContactsAndRebuild(w, &n1, &d1, &m1))) return rc;
 		newContacts += n1;
@@ -962,6 +1005,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	else
 	{
 		for (int k = 3; k < 8; ++k) cudaEventRecord(w->ev[k], w->stream);
+		LAUNCH(w, EndStepBodiesKernel, GridFor(nb), kBlock, d, nb, (w->params.flags & B2CU_WORLD_CLEAR_FORCES) ? 1 : 0);
 		int n1 = 0, d1 = 0, m1 = 0;
 		if ((rc = FindNewContactsAndRebuild(w, &n1, &d1, &m1))) return rc;
 		destroyed += d1;
@@ -969,26 +1013,48 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	cudaEvent_t evBroad = w->ev[8];
 	cudaEventRecord(evBroad, w->stream);
 
+	// ---- deferred event buffers in key order; EndContact calls made by Destroy come after the sorted ends
+	// (FinishCollide, b2ContactManager.cpp:388-439).  hostCounters is current: the rebuild has just read it.
+	{
+		int nBegin = std::min(w->hostCounters[CNT_BEGIN], w->contactCapacity);
+		int nEnd = std::min(w->hostCounters[CNT_END], w->contactCapacity);
+		int nDestroyEnd = std::min(w->hostCounters[CNT_DESTROY_END], w->contactCapacity - nEnd);
+		SortKeys(w, d.beginKeys, nBegin);
+		SortKeys(w, d.endKeys, nEnd);
+		SortKeys(w, d.destroyEndKeys, nDestroyEnd);
+		if (nDestroyEnd > 0)
+		{
+			CUDA_TRY(w, cudaMemcpyAsync(d.endKeys + nEnd, d.destroyEndKeys, sizeof(uint64_t) * nDestroyEnd,
+			                            cudaMemcpyDeviceToDevice, w->stream));
+		}
+		w->beginCount = nBegin;
+		w->endCount = nEnd + nDestroyEnd;
+	}
+
 	// ---- TOI eligibility compaction (b2World.cpp:283-352 filters; SolveTOI itself is host-driven) ----
 	w->toiCount = 0;
 	nc = w->contactCount;
-	if ((w->params.flags & B2CU_WORLD_CONTINUOUS) && dt > 0.0f && nc > 0)
+	const bool toiPass = (w->params.flags & B2CU_WORLD_CONTINUOUS) && dt > 0.0f && nc > 0 &&
+	                     w->hostCounters[CNT_STICKY_TOI] != 0;
+	if (toiPass)
 	{
 		LAUNCH(w, ToiFlagsKernel, GridFor(nc), kBlock, d, nc, d.cSelect);
 		CompactFlags(&w->prims, d.cSelect, nc, d.listA, d.counters + CNT_TOI, w->stream);
 		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_TOI, (const int*)nullptr,
 		       d.toiKeys, w->contactCapacity);
 	}
-
-	// ---- ClearPostSolve + ClearForces ----
-	LAUNCH(w, EndStepBodiesKernel, GridFor(nb), kBlock, d, nb, (w->params.flags & B2CU_WORLD_CLEAR_FORCES) ? 1 : 0);
 	cudaEvent_t evEnd = w->ev[9];
 	cudaEventRecord(evEnd, w->stream);
 
-	if ((rc = ReadCounters(w))) return rc;
-	w->beginCount = w->hostCounters[CNT_BEGIN];
-	w->endCount = w->hostCounters[CNT_END] + w->hostCounters[CNT_DESTROY_END];
-	w->toiCount = w->hostCounters[CNT_TOI];
+	if (toiPass)
+	{
+		if ((rc = ReadCounters(w))) return rc;
+		w->toiCount = w->hostCounters[CNT_TOI];
+	}
+	else
+	{
+		if ((rc = SyncCheck(w))) return rc;
+	}
 
 	float ms = 0.0f;
 	cudaEventElapsedTime(&ms, w->ev[0], evEnd); out.step = ms;
