@@ -36,6 +36,10 @@ DT, VEL_ITERS, POS_ITERS = 1.0 / 60.0, 8, 3
 SETTLE_STEPS = 300
 # algorithmic bytes per unit of work
 BYTES_VELOCITY_ITER = 220  # per touching contact per velocity iteration: 180 R + 40 W
+BYTES_WARM_START = 128
+BYTES_STORE = 32
+BYTES_POSITION_ITER = 136
+BYTES_INTEGRATE_POS = 48   # per body
 BYTES_PER_BODY = 212
 BYTES_PER_PROXY = 120
 BYTES_PER_CONTACT_NARROW = 208
@@ -232,10 +236,13 @@ def run_product_arm(args, rank, local_rank, world_size):
     last = infos[-1]
     n_constraints = float(np.mean([int(i["constraintCount"]) for i in infos]))
     n_contacts = float(np.mean([int(i["contactCount"]) for i in infos]))
-    vel_ms = float(np.mean([float(i["solveVelocity"]) for i in infos]))
+    # the solver kernel (one persistent cooperative launch per step: warm start, velocity iterations, impulse store,
+    # position integration, position iterations) is timed by the CUDA events around it (solveVelocity+solvePosition)
+    vel_ms = float(np.mean([float(i["solveVelocity"]) + float(i["solvePosition"]) for i in infos]))
     colours = float(np.mean([int(i["colourCount"]) for i in infos]))
     peak, peak_src = measured_peaks()
-    vel_bytes = n_constraints * BYTES_VELOCITY_ITER * VEL_ITERS
+    vel_bytes = (n_constraints * (BYTES_WARM_START + BYTES_VELOCITY_ITER * VEL_ITERS + BYTES_STORE +
+                                  BYTES_POSITION_ITER * POS_ITERS) + n_bodies * BYTES_INTEGRATE_POS)
     achieved = vel_bytes / (vel_ms * 1e-3) / 1e9 if vel_ms > 0 else 0.0
     step_bytes = (n_bodies * BYTES_PER_BODY + n_bodies * BYTES_PER_PROXY + n_contacts * BYTES_PER_CONTACT_NARROW +
                   n_constraints * BYTES_PER_CONSTRAINT_STEP)
@@ -285,10 +292,12 @@ def run_product_arm(args, rank, local_rank, world_size):
         "e2e": {"value": total_bodies * args.steps / e2e_elapsed, "unit": "body-steps/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_elapsed / args.steps},
         "gpu_launches": int(sum(int(i["kernelLaunches"]) for i in infos)),
-        "roofline": {"bound": "hbm", "kernel": "SolveVelocityKernel (all colour launches of a step)",
+        "roofline": {"bound": "hbm", "kernel": "SolverPersistentKernel (warm start + 8 velocity iterations + store + integrate + 3 position "
+                                                        "iterations, one cooperative launch per step)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None,
-                     "bytes_per_unit": "%d B per touching contact per velocity iteration" % BYTES_VELOCITY_ITER},
+                     "bytes_per_unit": "per touching contact: 128 warm start + 220 x 8 velocity + 32 store + 136 x 3 position "
+                                       "= 2328 B, + 48 B per body (SURVEY.md 8d)"},
         "cpu_baseline": cpu,
         "clocks": clocks,
         "build_s": build_s, "checksum": checksum, "last_step": {k: int(last[k]) for k in

@@ -2,6 +2,8 @@
 // Included only by world.cu.  Each kernel names the reference code it replaces.
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include "b2cu_collide.cuh"
 #include "b2cu_world.cuh"
 
@@ -1081,6 +1083,158 @@ __global__ void OverflowSolvePositionKernel(DeviceArrays d, int begin, int count
 			float minSep = SolvePositionOne(d, k);
 			atomicMin(&d.islandMinSep[iteration * bodyCount + root], FloatToOrdered(minSep));
 		}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The whole constraint solve of a step in ONE persistent cooperative kernel: warm start, velocity iterations,
+// impulse store, position integration and position iterations, one grid-wide barrier per colour phase instead
+// of one kernel launch per colour phase.  A pile is one island of ~12 colours, i.e. ~150 dependent phases of
+// ~200k constraints each: each phase moves only ~25 MB, so launch latency, not bandwidth, bounded the
+// multi-launch version.  Same per-constraint code (WarmStartOne / SolveVelocityOne / SolvePositionOne), same
+// order, same results.
+// ---------------------------------------------------------------------------------------------------------
+struct SolverPlan
+{
+	int colourStart[B2CU_MAX_COLOURS + 1];
+	int colourCount[B2CU_MAX_COLOURS + 1]; // [B2CU_MAX_COLOURS] = overflow list, solved by one thread
+	int constraintCount;
+	int bodyCount;
+	int velocityIterations;
+	int positionIterations;
+	int warmStarting;
+	float h;
+};
+
+__device__ __forceinline__ void IntegratePositionOne(const DeviceArrays& d, int b, float h)
+{
+	uint32_t bf = d.bflags[b];
+	if (IsStatic(bf) || !(bf & B2CU_BODY_ISLAND)) return;
+	float4 p = d.pos[b];
+	float4 v4 = d.vel[b];
+	Vec2 c = V(p.x, p.y);
+	float a = p.z;
+	Vec2 v = V(v4.x, v4.y);
+	float w = v4.z;
+
+	Vec2 translation = h * v;
+	if (Dot(translation, translation) > B2CU_MAX_TRANSLATION_SQUARED)
+	{
+		float ratio = B2CU_MAX_TRANSLATION / Length(translation);
+		v = V(v.x * ratio, v.y * ratio);
+	}
+	float rotation = h * w;
+	if (rotation * rotation > B2CU_MAX_ROTATION_SQUARED)
+	{
+		float ratio = B2CU_MAX_ROTATION / Abs(rotation);
+		w *= ratio;
+	}
+	c = c + h * v;
+	a += h * w;
+
+	d.pos[b] = make_float4(c.x, c.y, a, p.w);
+	d.vel[b] = make_float4(v.x, v.y, w, v4.w);
+}
+
+__device__ __forceinline__ void StoreImpulseOne(const DeviceArrays& d, int k)
+{
+	int4 sb = d.sBody[k];
+	float4 imp = d.sImp[k];
+	int i = sb.z;
+	int pointCount = sb.w & 0xFF;
+	float4 m1 = d.c.m1[i];
+	m1.z = imp.x;
+	m1.w = imp.y;
+	d.c.m1[i] = m1;
+	if (pointCount == 2)
+	{
+		float4 m2 = d.c.m2[i];
+		m2.z = imp.z;
+		m2.w = imp.w;
+		d.c.m2[i] = m2;
+	}
+}
+
+__global__ void __launch_bounds__(256) SolverPersistentKernel(DeviceArrays d, SolverPlan plan)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int stride = gridDim.x * blockDim.x;
+
+	if (plan.warmStarting)
+	{
+		for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
+		{
+			const int n = plan.colourCount[c];
+			if (n == 0) continue;
+			const int begin = plan.colourStart[c];
+			if (c < B2CU_MAX_COLOURS)
+			{
+				for (int t = tid; t < n; t += stride) WarmStartOne(d, begin + t);
+			}
+			else if (tid == 0)
+			{
+				for (int t = 0; t < n; ++t) WarmStartOne(d, begin + t);
+			}
+			grid.sync();
+		}
+	}
+
+	for (int it = 0; it < plan.velocityIterations; ++it)
+	{
+		for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
+		{
+			const int n = plan.colourCount[c];
+			if (n == 0) continue;
+			const int begin = plan.colourStart[c];
+			if (c < B2CU_MAX_COLOURS)
+			{
+				for (int t = tid; t < n; t += stride) SolveVelocityOne(d, begin + t);
+			}
+			else if (tid == 0)
+			{
+				for (int t = 0; t < n; ++t) SolveVelocityOne(d, begin + t);
+			}
+			grid.sync();
+		}
+	}
+
+	// b2ContactSolver::StoreImpulses, then b2Island::Solve position integration (independent of each other)
+	for (int k = tid; k < plan.constraintCount; k += stride) StoreImpulseOne(d, k);
+	for (int b = tid; b < plan.bodyCount; b += stride) IntegratePositionOne(d, b, plan.h);
+	grid.sync();
+
+	for (int it = 0; it < plan.positionIterations; ++it)
+	{
+		for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
+		{
+			const int n = plan.colourCount[c];
+			if (n == 0) continue;
+			const int begin = plan.colourStart[c];
+			if (c < B2CU_MAX_COLOURS)
+			{
+				for (int t = tid; t < n; t += stride)
+				{
+					int k = begin + t;
+					int root = __float_as_int(__ldcs(&d.sRadius[k]).w);
+					if (IslandDone(d, it, root, plan.bodyCount)) continue;
+					float minSep = SolvePositionOne(d, k);
+					AtomicMinByRoot(d.islandMinSep + (size_t)it * plan.bodyCount, root, FloatToOrdered(minSep));
+				}
+			}
+			else if (tid == 0)
+			{
+				for (int t = 0; t < n; ++t)
+				{
+					int k = begin + t;
+					int root = __float_as_int(d.sRadius[k].w);
+					if (IslandDone(d, it, root, plan.bodyCount)) continue;
+					float minSep = SolvePositionOne(d, k);
+					atomicMin(&d.islandMinSep[(size_t)it * plan.bodyCount + root], FloatToOrdered(minSep));
+				}
+			}
+			grid.sync();
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------

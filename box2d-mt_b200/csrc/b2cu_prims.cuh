@@ -23,6 +23,8 @@ struct PrimScratch
 
 // number of kernels launched by the primitives since the last reset (for b2cuStepInfo.kernelLaunches)
 extern int g_primLaunches;
+// optional hook called after every primitive kernel launch (tracing)
+extern void (*g_primTraceHook)(const char* name, cudaStream_t stream);
 
 cudaError_t PrimScratchAlloc(PrimScratch* s, int capacity);
 void PrimScratchFree(PrimScratch* s);
@@ -38,5 +40,9 @@ void CompactMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int n, in
 
 // stable ascending sort on bits [beginBit, endBit) of the keys; result ends up in `keys`
 void RadixSort64(PrimScratch* s, uint64_t* keys, int n, int beginBit, int endBit, cudaStream_t stream);
+
+// full 64-bit ascending sort of n <= 4096 keys in one CTA (bitonic network in shared memory)
+void SortSmall64(uint64_t* keys, int n, cudaStream_t stream);
+#define B2CU_SMALL_SORT_MAX 4096
 
 } // namespace b2cu

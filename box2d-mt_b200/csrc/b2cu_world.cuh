@@ -162,6 +162,8 @@ struct b2cuWorld
 	bool toiCheckDirty;  // bodies / proxies changed: re-evaluate whether TOI candidates are possible
 	int positionIterationsCapacity;
 	size_t l2WindowMax;  // 0: no persisting-L2 support
+	bool persistentSolver; // solve all colour phases in one cooperative kernel
+	int persistentGrid;
 
 	// last step
 	int beginCount, endCount, constraintCount, colourCount, overflowCount, toiCount;

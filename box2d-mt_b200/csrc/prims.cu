@@ -5,6 +5,13 @@ namespace b2cu
 {
 
 int g_primLaunches = 0;
+void (*g_primTraceHook)(const char* name, cudaStream_t stream) = nullptr;
+#define PRIM_MARK(name)                                  \
+	do                                                   \
+	{                                                    \
+		++g_primLaunches;                                \
+		if (g_primTraceHook) g_primTraceHook(name, stream); \
+	} while (0)
 
 static const int SCAN_BLOCK = 256;
 static const int SCAN_ITEMS = 4;
@@ -137,29 +144,30 @@ static void ScanImpl(PrimScratch* s, Loader load, int* out, int n, int* total, c
 		if (total)
 		{
 			SetIntKernel<<<1, 1, 0, stream>>>(total, 0);
-			++g_primLaunches;
+			PRIM_MARK("SetInt");
 		}
 		return;
 	}
 	int tiles1 = (n + SCAN_TILE - 1) / SCAN_TILE;
 	ScanTilesKernel<<<tiles1, SCAN_BLOCK, 0, stream>>>(load, out, s->scanLevel1, n, total);
-	++g_primLaunches;
+	PRIM_MARK("ScanTiles");
 	if (tiles1 > 1)
 	{
 		int tiles2 = (tiles1 + SCAN_TILE - 1) / SCAN_TILE;
 		IntLoader l1{s->scanLevel1};
 		ScanTilesKernel<<<tiles2, SCAN_BLOCK, 0, stream>>>(l1, s->scanLevel1, s->scanLevel2, tiles1, total);
-		++g_primLaunches;
+		PRIM_MARK("ScanTilesL1");
 		if (tiles2 > 1)
 		{
 			// third level: tiles2 <= 1024 for n < 2^30
 			IntLoader l2{s->scanLevel2};
 			ScanTilesKernel<<<1, SCAN_BLOCK, 0, stream>>>(l2, s->scanLevel2, (int*)nullptr, tiles2, total);
 			AddTileOffsetsKernel<<<(tiles1 + 255) / 256, 256, 0, stream>>>(s->scanLevel1, s->scanLevel2, tiles1);
-			g_primLaunches += 2;
+			PRIM_MARK("ScanL2");
+			PRIM_MARK("ScanL2Add");
 		}
 		AddTileOffsetsKernel<<<(n + 255) / 256, 256, 0, stream>>>(out, s->scanLevel1, n);
-		++g_primLaunches;
+		PRIM_MARK("AddTileOffsets");
 	}
 }
 
@@ -186,7 +194,7 @@ void CompactFlags(PrimScratch* s, const int* flags, int n, int* outIdx, int* out
 	if (n > 0)
 	{
 		CompactScatterKernel<<<(n + 255) / 256, 256, 0, stream>>>(l, s->compactPos, n, outIdx);
-		++g_primLaunches;
+		PRIM_MARK("CompactScatter");
 	}
 }
 
@@ -198,7 +206,7 @@ void CompactMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int n, in
 	if (n > 0)
 	{
 		CompactScatterKernel<<<(n + 255) / 256, 256, 0, stream>>>(l, s->compactPos, n, outIdx);
-		++g_primLaunches;
+		PRIM_MARK("CompactScatter");
 	}
 }
 
@@ -279,6 +287,46 @@ __global__ void __launch_bounds__(RADIX_BLOCK) RadixScatterKernel(const uint64_t
 	}
 }
 
+// one CTA, bitonic network in shared memory: full 64-bit ascending order (a superset of any [beginBit, endBit)
+// LSD request on keys whose other bits are equal or irrelevant)
+static const int SMALL_SORT_MAX = 4096;
+__global__ void __launch_bounds__(1024) SmallSort64Kernel(uint64_t* __restrict__ keys, int n)
+{
+	__shared__ uint64_t sh[SMALL_SORT_MAX];
+	int m = 1;
+	while (m < n) m <<= 1;
+	for (int i = threadIdx.x; i < m; i += blockDim.x) sh[i] = i < n ? keys[i] : 0xFFFFFFFFFFFFFFFFull;
+	__syncthreads();
+	for (int k = 2; k <= m; k <<= 1)
+	{
+		for (int j = k >> 1; j > 0; j >>= 1)
+		{
+			for (int i = threadIdx.x; i < m; i += blockDim.x)
+			{
+				int ixj = i ^ j;
+				if (ixj > i)
+				{
+					uint64_t a = sh[i], b = sh[ixj];
+					bool up = (i & k) == 0;
+					if ((a > b) == up)
+					{
+						sh[i] = b;
+						sh[ixj] = a;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	}
+	for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = sh[i];
+}
+
+void SortSmall64(uint64_t* keys, int n, cudaStream_t stream)
+{
+	SmallSort64Kernel<<<1, 1024, 0, stream>>>(keys, n);
+	PRIM_MARK("SmallSort64");
+}
+
 void RadixSort64(PrimScratch* s, uint64_t* keys, int n, int beginBit, int endBit, cudaStream_t stream)
 {
 	if (n <= 1)
@@ -291,10 +339,10 @@ void RadixSort64(PrimScratch* s, uint64_t* keys, int n, int beginBit, int endBit
 	for (int shift = beginBit; shift < endBit; shift += 8)
 	{
 		RadixHistogramKernel<<<numBlocks, RADIX_BLOCK, 0, stream>>>(src, n, shift, s->radixHist, numBlocks);
-		++g_primLaunches;
+		PRIM_MARK("RadixHistogram");
 		ExclusiveScan(s, s->radixHist, s->radixHist, 256 * numBlocks, nullptr, stream);
 		RadixScatterKernel<<<numBlocks, RADIX_BLOCK, 0, stream>>>(src, dst, n, shift, s->radixHist, numBlocks);
-		++g_primLaunches;
+		PRIM_MARK("RadixScatter");
 		uint64_t* t = src;
 		src = dst;
 		dst = t;

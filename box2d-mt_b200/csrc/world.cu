@@ -9,7 +9,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 using namespace b2cu;
@@ -50,11 +52,41 @@ int SetError(b2cuWorld* w, int code, const char* fmt, ...)
 			                __LINE__);                                                                      \
 	} while (0)
 
+// B2CU_TRACE=1: a CUDA event after every kernel launch; b2cuStep prints per-kernel device time (including the gap
+// before the kernel) for the step.  Developer aid only.
+struct TraceState
+{
+	bool enabled = false;
+	std::vector<cudaEvent_t> events;
+	std::vector<const char*> names;
+	size_t used = 0;
+};
+TraceState g_trace;
+
+b2cuWorld* g_traceWorld = nullptr;
+void TraceMark(b2cuWorld* w, const char* name);
+void PrimTraceHook(const char* name, cudaStream_t) { if (g_traceWorld) TraceMark(g_traceWorld, name); }
+
+void TraceMark(b2cuWorld* w, const char* name)
+{
+	if (!g_trace.enabled) return;
+	if (g_trace.used == g_trace.events.size())
+	{
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		g_trace.events.push_back(e);
+		g_trace.names.push_back(name);
+	}
+	g_trace.names[g_trace.used] = name;
+	cudaEventRecord(g_trace.events[g_trace.used++], w->stream);
+}
+
 #define LAUNCH(w, kernel, grid, block, ...)                 \
 	do                                                      \
 	{                                                       \
 		kernel<<<grid, block, 0, (w)->stream>>>(__VA_ARGS__); \
 		++(w)->launches;                                    \
+		TraceMark(w, #kernel);                              \
 	} while (0)
 
 enum CapKind
@@ -287,6 +319,11 @@ void SetL2Window(b2cuWorld* w, const void* base, size_t bytes)
 void SortKeys(b2cuWorld* w, uint64_t* keys, int n)
 {
 	if (n <= 1) return;
+	if (n <= B2CU_SMALL_SORT_MAX)
+	{
+		SortSmall64(keys, n, w->stream);
+		return;
+	}
 	int bits = 1;
 	while ((1 << bits) < std::max(2, w->proxyCount)) ++bits;
 	RadixSort64(&w->prims, keys, n, 0, bits, w->stream);
@@ -432,9 +469,10 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 	if (cudaGetDeviceProperties(&prop, def->device) == cudaSuccess)
 	{
 		g_smCount = prop.multiProcessorCount;
-		if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0)
+		const char* l2env = getenv("B2CU_L2_WINDOW");
+		if (l2env && atoi(l2env) > 0 && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0)
 		{
-			size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)64 << 20);
+			size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)atoi(l2env) << 20);
 			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
 				w->l2WindowMax = std::min(want, (size_t)prop.accessPolicyMaxWindowSize);
 		}
@@ -452,6 +490,19 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 	w->positionIterationsCapacity = 4;
 	w->cellSize = 1.0f;
 	w->toiCheckDirty = true;
+	{
+		// persistent cooperative solver: as many CTAs as can be co-resident
+		int coop = 0, perSm = 0;
+		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, def->device);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, SolverPersistentKernel, 256, 0);
+		const char* pe = getenv("B2CU_PERSISTENT");
+		w->persistentSolver = coop != 0 && perSm > 0 && !(pe && atoi(pe) == 0);
+		w->persistentGrid = g_smCount * perSm;
+	}
+	{
+		const char* t = getenv("B2CU_TRACE");
+		g_trace.enabled = t && atoi(t) > 0;
+	}
 	int rc = Reserve(w, std::max(def->bodyCapacity, 64), std::max(def->proxyCapacity, 64),
 	                 std::max(def->shapeCapacity, 16), std::max(def->contactCapacity, 256));
 	if (rc != B2CU_OK)
@@ -818,6 +869,10 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 
 	CUDA_TRY(w, cudaMemsetAsync(d.counters, 0, sizeof(int) * CNT_STICKY_TOI, w->stream));
 	cudaEventRecord(w->ev[0], w->stream);
+	g_trace.used = 0;
+	g_traceWorld = w;
+	g_primTraceHook = g_trace.enabled ? PrimTraceHook : nullptr;
+	TraceMark(w, "(start)");
 
 	if (w->toiCheckDirty)
 	{
@@ -940,7 +995,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		if (nConstraints > 0)
 		{
 			LAUNCH(w, InitConstraintsKernel, GridFor(nConstraints), kBlock, d, dtRatio, warmStarting ? 1 : 0);
-			if (warmStarting)
+			if (warmStarting && !w->persistentSolver)
 			{
 				for (int c = 0; c < B2CU_MAX_COLOURS; ++c)
 				{
@@ -952,6 +1007,30 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			}
 		}
 		cudaEventRecord(w->ev[5], w->stream);
+		if (nConstraints > 0 && w->persistentSolver)
+		{
+			// one persistent cooperative kernel for warm start + velocity + store + integrate + position
+			SolverPlan plan;
+			for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
+			{
+				plan.colourStart[c] = colourStart[c];
+				plan.colourCount[c] = w->colourCounts[c];
+			}
+			plan.constraintCount = nConstraints;
+			plan.bodyCount = nb;
+			plan.velocityIterations = velocityIterations;
+			plan.positionIterations = positionIterations;
+			plan.warmStarting = warmStarting ? 1 : 0;
+			plan.h = dt;
+			void* args[2] = {(void*)&d, (void*)&plan};
+			CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverPersistentKernel, dim3(w->persistentGrid), dim3(256),
+			                                        args, 0, w->stream));
+			++w->launches;
+			TraceMark(w, "SolverPersistentKernel");
+			cudaEventRecord(w->ev[6], w->stream);
+		}
+		else
+		{
 		if (nConstraints > 0)
 		{
 			SetL2Window(w, d.vel, sizeof(float4) * (size_t)nb);
@@ -984,6 +1063,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				if (w->overflowCount > 0)
 					LAUNCH(w, OverflowSolvePositionKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->overflowCount, it, nb);
 			}
+		}
 		}
 		if (nConstraints > 0) SetL2Window(w, nullptr, 0);
 		LAUNCH(w, FinalizeBodiesKernel, GridFor(nb), kBlock, d, nb, dt, allowSleep ? 1 : 0);
@@ -1054,6 +1134,30 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	else
 	{
 		if ((rc = SyncCheck(w))) return rc;
+	}
+
+	if (g_trace.enabled && g_trace.used > 1)
+	{
+		std::vector<std::pair<std::string, std::pair<float, int> > > rows;
+		for (size_t i = 1; i < g_trace.used; ++i)
+		{
+			float t = 0.0f;
+			cudaEventElapsedTime(&t, g_trace.events[i - 1], g_trace.events[i]);
+			size_t k = 0;
+			for (; k < rows.size(); ++k)
+				if (rows[k].first == g_trace.names[i]) break;
+			if (k == rows.size()) rows.push_back(std::make_pair(std::string(g_trace.names[i]), std::make_pair(0.0f, 0)));
+			rows[k].second.first += t;
+			rows[k].second.second += 1;
+		}
+		std::sort(rows.begin(), rows.end(), [](const std::pair<std::string, std::pair<float, int> >& a,
+		                                       const std::pair<std::string, std::pair<float, int> >& b) {
+			return a.second.first > b.second.first;
+		});
+		fprintf(stderr, "[b2cu trace] step: %zu marks\n", g_trace.used);
+		for (size_t k = 0; k < rows.size(); ++k)
+			fprintf(stderr, "[b2cu trace] %-32s n=%4d %9.3f ms\n", rows[k].first.c_str(), rows[k].second.second,
+			        rows[k].second.first);
 	}
 
 	float ms = 0.0f;
