@@ -1466,8 +1466,14 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 	int bodyA = d.pbody[a], bodyB = d.pbody[b];
 	if (bodyA == bodyB) return;
 	uint64_t key = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
-	int idx = LowerBound64(d.c.key, contactCount, key);
-	if (idx < contactCount && d.c.key[idx] == key && !(d.cEvent[idx] & B2CU_EV_DESTROY)) return;
+	// existing contact?  the keys whose low id is `a` are contiguous and start at lowStart[a]
+	for (int j = d.lowStart[a]; j >= 0 && j < contactCount; ++j)
+	{
+		uint64_t k = d.c.key[j];
+		if (k < key) continue;
+		if (k == key && !(d.cEvent[j] & B2CU_EV_DESTROY)) return;
+		break;
+	}
 	if (!IsDynamic(d.bflags[bodyA]) && !IsDynamic(d.bflags[bodyB])) return;
 	if (!DefaultFilter(d.pfilter[a], d.pgroup[a], d.pfilter[b], d.pgroup[b])) return;
 	if (d.shapes[d.pshape[a]].type == B2CU_SHAPE_EDGE && d.shapes[d.pshape[b]].type == B2CU_SHAPE_EDGE) return;
@@ -1562,6 +1568,16 @@ __global__ void __launch_bounds__(128) QueryPairsKernel(DeviceArrays d, int prox
 	}
 }
 
+// lowStart[p] = index of the first contact whose low proxy id is p (lowStart pre-set to -1)
+__global__ void BuildLowStartKernel(DeviceArrays d, int contactCount)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		int lo = (int)(d.c.key[i] >> 32);
+		if (i == 0 || (int)(d.c.key[i - 1] >> 32) != lo) d.lowStart[lo] = i;
+	}
+}
+
 __global__ void ClearMovedKernel(DeviceArrays d, int proxyCount)
 {
 	B2CU_GRID_STRIDE(p, proxyCount) { d.pgroup[p] &= ~((uint32_t)B2CU_PROXY_MOVED << 16); }
@@ -1572,11 +1588,6 @@ __global__ void ClearMovedKernel(DeviceArrays d, int proxyCount)
 // in key order.  Replaces FinishFindNewContacts / OnContactCreate / b2Contact::Create / Destroy bookkeeping
 // (b2ContactManager.cpp:120-172, 366-386, 507-564; b2Contact.cpp:72-157).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void KeepFlagsKernel(DeviceArrays d, int contactCount, int* keep)
-{
-	B2CU_GRID_STRIDE(i, contactCount) { keep[i] = (d.cEvent[i] & B2CU_EV_DESTROY) ? 0 : 1; }
-}
-
 __global__ void RebuildExistingKernel(DeviceArrays d, int contactCount, const int* __restrict__ keepRank, int newCount)
 {
 	B2CU_GRID_STRIDE(i, contactCount)

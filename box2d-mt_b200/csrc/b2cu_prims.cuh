@@ -32,6 +32,10 @@ void PrimScratchFree(PrimScratch* s);
 // out[i] = sum(in[0..i)), in and out may alias; *total (device) = sum of all, if total != nullptr
 void ExclusiveScan(PrimScratch* s, const int* in, int* out, int n, int* total, cudaStream_t stream);
 
+// out[i] = number of j < i with (flags[j] & mask) == 0
+void ExclusiveScanNotMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int* out, int n, int* total,
+                          cudaStream_t stream);
+
 // outIdx = ascending indices i with flags[i] != 0; *outCount (device) = how many
 void CompactFlags(PrimScratch* s, const int* flags, int n, int* outIdx, int* outCount, cudaStream_t stream);
 // same with a bit mask test: (flags[i] & mask) != 0
@@ -41,8 +45,8 @@ void CompactMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int n, in
 // stable ascending sort on bits [beginBit, endBit) of the keys; result ends up in `keys`
 void RadixSort64(PrimScratch* s, uint64_t* keys, int n, int beginBit, int endBit, cudaStream_t stream);
 
-// full 64-bit ascending sort of n <= 4096 keys in one CTA (bitonic network in shared memory)
-void SortSmall64(uint64_t* keys, int n, cudaStream_t stream);
-#define B2CU_SMALL_SORT_MAX 4096
+// full 64-bit ascending sort for small / medium lists: tile bitonic sort + merge rounds (few launches)
+void SortSmall64(PrimScratch* s, uint64_t* keys, int n, cudaStream_t stream);
+#define B2CU_SMALL_SORT_MAX (1 << 18)
 
 } // namespace b2cu

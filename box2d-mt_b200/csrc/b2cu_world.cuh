@@ -89,6 +89,7 @@ struct DeviceArrays
 	uint32_t* pgroup;   // (uint16)groupIndex | flags << 16
 	float2* pmat;       // friction, restitution
 	int* pfixture;      // caller's fixture id
+	int* lowStart;      // first contact whose key has this proxy as its low id (-1: none); rebuilt with the set
 
 	// ---- contacts ----
 	ContactSet c;       // live set

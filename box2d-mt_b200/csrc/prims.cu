@@ -31,6 +31,12 @@ struct NonZeroLoader
 	const int* p;
 	__device__ __forceinline__ int operator()(int i) const { return p[i] != 0 ? 1 : 0; }
 };
+struct NotMaskLoader
+{
+	const uint32_t* p;
+	uint32_t mask;
+	__device__ __forceinline__ int operator()(int i) const { return (p[i] & mask) == 0 ? 1 : 0; }
+};
 struct MaskLoader
 {
 	const uint32_t* p;
@@ -171,6 +177,13 @@ static void ScanImpl(PrimScratch* s, Loader load, int* out, int n, int* total, c
 	}
 }
 
+void ExclusiveScanNotMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int* out, int n, int* total,
+                          cudaStream_t stream)
+{
+	NotMaskLoader l{flags, mask};
+	ScanImpl(s, l, out, n, total, stream);
+}
+
 void ExclusiveScan(PrimScratch* s, const int* in, int* out, int n, int* total, cudaStream_t stream)
 {
 	IntLoader l{in};
@@ -287,15 +300,19 @@ __global__ void __launch_bounds__(RADIX_BLOCK) RadixScatterKernel(const uint64_t
 	}
 }
 
-// one CTA, bitonic network in shared memory: full 64-bit ascending order (a superset of any [beginBit, endBit)
-// LSD request on keys whose other bits are equal or irrelevant)
-static const int SMALL_SORT_MAX = 4096;
-__global__ void __launch_bounds__(1024) SmallSort64Kernel(uint64_t* __restrict__ keys, int n)
+// Sort of small / medium key lists (event buffers, new pairs: hundreds to ~10^5 keys) without the launch train
+// of the LSD radix sort: every CTA sorts one tile of 4096 keys with a bitonic network in shared memory, then
+// log2(tiles) merge rounds place each key by binary search in the sibling run.  Full 64-bit ascending order.
+static const int SORT_TILE = 4096;
+
+__global__ void __launch_bounds__(1024) TileSort64Kernel(uint64_t* __restrict__ keys, int n)
 {
-	__shared__ uint64_t sh[SMALL_SORT_MAX];
+	__shared__ uint64_t sh[SORT_TILE];
+	const int base = blockIdx.x * SORT_TILE;
+	const int count = min(SORT_TILE, n - base);
 	int m = 1;
-	while (m < n) m <<= 1;
-	for (int i = threadIdx.x; i < m; i += blockDim.x) sh[i] = i < n ? keys[i] : 0xFFFFFFFFFFFFFFFFull;
+	while (m < count) m <<= 1;
+	for (int i = threadIdx.x; i < m; i += blockDim.x) sh[i] = i < count ? keys[base + i] : 0xFFFFFFFFFFFFFFFFull;
 	__syncthreads();
 	for (int k = 2; k <= m; k <<= 1)
 	{
@@ -318,13 +335,50 @@ __global__ void __launch_bounds__(1024) SmallSort64Kernel(uint64_t* __restrict__
 			__syncthreads();
 		}
 	}
-	for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = sh[i];
+	for (int i = threadIdx.x; i < count; i += blockDim.x) keys[base + i] = sh[i];
 }
 
-void SortSmall64(uint64_t* keys, int n, cudaStream_t stream)
+// runs of length `run` are sorted; merge run pairs (2r, 2r+1) from src into dst
+__global__ void MergeRuns64Kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, int n, int run)
 {
-	SmallSort64Kernel<<<1, 1024, 0, stream>>>(keys, n);
-	PRIM_MARK("SmallSort64");
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int r = i / run;
+	int pairBase = (r & ~1) * run;
+	int sibBase = (r ^ 1) * run;
+	uint64_t key = src[i];
+	int sibCount = sibBase < n ? min(run, n - sibBase) : 0;
+	// left run: count sibling keys strictly smaller; right run: count sibling keys smaller or equal (stable)
+	int lo = 0, hi = sibCount;
+	const bool left = (r & 1) == 0;
+	while (lo < hi)
+	{
+		int mid = (lo + hi) >> 1;
+		uint64_t v = src[sibBase + mid];
+		bool goRight = left ? (v < key) : (v <= key);
+		if (goRight) lo = mid + 1;
+		else hi = mid;
+	}
+	dst[pairBase + (i - r * run) + lo] = key;
+}
+
+void SortSmall64(PrimScratch* s, uint64_t* keys, int n, cudaStream_t stream)
+{
+	if (n <= 1) return;
+	int tiles = (n + SORT_TILE - 1) / SORT_TILE;
+	TileSort64Kernel<<<tiles, 1024, 0, stream>>>(keys, n);
+	PRIM_MARK("TileSort64");
+	uint64_t* src = keys;
+	uint64_t* dst = s->radixAlt;
+	for (int run = SORT_TILE; run < n; run <<= 1)
+	{
+		MergeRuns64Kernel<<<(n + 255) / 256, 256, 0, stream>>>(src, dst, n, run);
+		PRIM_MARK("MergeRuns64");
+		uint64_t* t = src;
+		src = dst;
+		dst = t;
+	}
+	if (src != keys) cudaMemcpyAsync(keys, src, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, stream);
 }
 
 void RadixSort64(PrimScratch* s, uint64_t* keys, int n, int beginBit, int endBit, cudaStream_t stream)

@@ -159,6 +159,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->pgroup, CAP_PROXY));
 	v.push_back(Desc(&d->pmat, CAP_PROXY));
 	v.push_back(Desc(&d->pfixture, CAP_PROXY));
+	v.push_back(Desc(&d->lowStart, CAP_PROXY));
 	ContactSetDescs(&d->c, v);
 	ContactSetDescs(&d->cAlt, v);
 	v.push_back(Desc(&d->cEvent, CAP_CONTACT));
@@ -321,13 +322,21 @@ void SortKeys(b2cuWorld* w, uint64_t* keys, int n)
 	if (n <= 1) return;
 	if (n <= B2CU_SMALL_SORT_MAX)
 	{
-		SortSmall64(keys, n, w->stream);
+		SortSmall64(&w->prims, keys, n, w->stream);
 		return;
 	}
 	int bits = 1;
 	while ((1 << bits) < std::max(2, w->proxyCount)) ++bits;
 	RadixSort64(&w->prims, keys, n, 0, bits, w->stream);
 	RadixSort64(&w->prims, keys, n, 32, 32 + bits, w->stream);
+}
+
+// index of the sorted key array by low proxy id (existence checks of the broad-phase)
+int RebuildLowStart(b2cuWorld* w)
+{
+	CUDA_TRY(w, cudaMemsetAsync(w->d.lowStart, 0xFF, sizeof(int) * (size_t)w->proxyCapacity, w->stream));
+	if (w->contactCount > 0) LAUNCH(w, BuildLowStartKernel, GridFor(w->contactCount), kBlock, w->d, w->contactCount);
+	return B2CU_OK;
 }
 
 // ---- broad-phase pair finding + contact set rebuild ------------------------------------------------------
@@ -363,8 +372,8 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 	// destroyed contacts -> keep flags and ranks
 	if (nc > 0)
 	{
-		LAUNCH(w, KeepFlagsKernel, GridFor(nc), kBlock, d, nc, d.cSelect);
-		ExclusiveScan(&w->prims, d.cSelect, d.listA, nc, d.counters + CNT_KEEP, w->stream);
+		ExclusiveScanNotMask(&w->prims, (const uint32_t*)d.cEvent, B2CU_EV_DESTROY, d.listA, nc, d.counters + CNT_KEEP,
+		                     w->stream);
 	}
 
 	if ((rc = ReadCounters(w))) return rc;
@@ -409,7 +418,7 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 	std::swap(d.c, d.cAlt);
 	w->contactCount = keepCount + newCount;
 	CUDA_TRY(w, cudaMemsetAsync(d.cEvent, 0, sizeof(int) * (size_t)w->contactCapacity, w->stream));
-	return B2CU_OK;
+	return RebuildLowStart(w);
 }
 
 int CheckRange(b2cuWorld* w, int first, int count, int limit, const void* p)
@@ -563,7 +572,7 @@ int b2cuSetCounts(b2cuWorld* w, int32_t bodyCount, int32_t shapeCount, int32_t p
 	w->bodyCount = bodyCount;
 	w->shapeCount = shapeCount;
 	w->proxyCount = proxyCount;
-	return B2CU_OK;
+	return RebuildLowStart(w);
 }
 
 int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bodies)
@@ -778,6 +787,7 @@ int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
 		return rc;
 	CUDA_TRY(w, cudaMemsetAsync(d.cEvent, 0, sizeof(int) * (size_t)w->contactCapacity, w->stream));
 	w->contactCount = count;
+	if ((rc = RebuildLowStart(w))) return rc;
 	return SyncCheck(w);
 }
 
