@@ -1466,13 +1466,16 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 	int bodyA = d.pbody[a], bodyB = d.pbody[b];
 	if (bodyA == bodyB) return;
 	uint64_t key = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
-	// existing contact?  the keys whose low id is `a` are contiguous and start at lowStart[a]
-	for (int j = d.lowStart[a]; j >= 0 && j < contactCount; ++j)
+	// existing contact?  the keys whose low id is `a` are the contiguous range [lowStart[a], lowStart[a+1])
 	{
-		uint64_t k = d.c.key[j];
-		if (k < key) continue;
-		if (k == key && !(d.cEvent[j] & B2CU_EV_DESTROY)) return;
-		break;
+		int lo = d.lowStart[a], hi = d.lowStart[a + 1];
+		while (lo < hi)
+		{
+			int mid = (lo + hi) >> 1;
+			if (d.c.key[mid] < key) lo = mid + 1;
+			else hi = mid;
+		}
+		if (lo < d.lowStart[a + 1] && d.c.key[lo] == key && !(d.cEvent[lo] & B2CU_EV_DESTROY)) return;
 	}
 	if (!IsDynamic(d.bflags[bodyA]) && !IsDynamic(d.bflags[bodyB])) return;
 	if (!DefaultFilter(d.pfilter[a], d.pgroup[a], d.pfilter[b], d.pgroup[b])) return;
@@ -1568,14 +1571,10 @@ __global__ void __launch_bounds__(128) QueryPairsKernel(DeviceArrays d, int prox
 	}
 }
 
-// lowStart[p] = index of the first contact whose low proxy id is p (lowStart pre-set to -1)
-__global__ void BuildLowStartKernel(DeviceArrays d, int contactCount)
+// lowStart[p] = index of the first contact whose low proxy id is >= p, for p in [0, proxyCount]
+__global__ void BuildLowStartKernel(DeviceArrays d, int contactCount, int proxyCount)
 {
-	B2CU_GRID_STRIDE(i, contactCount)
-	{
-		int lo = (int)(d.c.key[i] >> 32);
-		if (i == 0 || (int)(d.c.key[i - 1] >> 32) != lo) d.lowStart[lo] = i;
-	}
+	B2CU_GRID_STRIDE(p, proxyCount + 1) { d.lowStart[p] = LowerBound64(d.c.key, contactCount, (uint64_t)(uint32_t)p << 32); }
 }
 
 __global__ void ClearMovedKernel(DeviceArrays d, int proxyCount)

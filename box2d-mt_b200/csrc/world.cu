@@ -96,6 +96,7 @@ enum CapKind
 	CAP_SHAPE,
 	CAP_CONTACT,
 	CAP_GRID,
+	CAP_PROXY1,
 	CAP_FIXED
 };
 
@@ -159,7 +160,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->pgroup, CAP_PROXY));
 	v.push_back(Desc(&d->pmat, CAP_PROXY));
 	v.push_back(Desc(&d->pfixture, CAP_PROXY));
-	v.push_back(Desc(&d->lowStart, CAP_PROXY));
+	v.push_back(Desc(&d->lowStart, CAP_PROXY1));
 	ContactSetDescs(&d->c, v);
 	ContactSetDescs(&d->cAlt, v);
 	v.push_back(Desc(&d->cEvent, CAP_CONTACT));
@@ -209,6 +210,7 @@ size_t CapOf(const b2cuWorld* w, const ArrayDesc& a)
 	case CAP_SHAPE: return (size_t)w->shapeCapacity;
 	case CAP_CONTACT: return (size_t)w->contactCapacity;
 	case CAP_GRID: return (size_t)w->gridSize + 1;
+	case CAP_PROXY1: return (size_t)w->proxyCapacity + 1;
 	default: return a.fixedCount;
 	}
 }
@@ -334,8 +336,7 @@ void SortKeys(b2cuWorld* w, uint64_t* keys, int n)
 // index of the sorted key array by low proxy id (existence checks of the broad-phase)
 int RebuildLowStart(b2cuWorld* w)
 {
-	CUDA_TRY(w, cudaMemsetAsync(w->d.lowStart, 0xFF, sizeof(int) * (size_t)w->proxyCapacity, w->stream));
-	if (w->contactCount > 0) LAUNCH(w, BuildLowStartKernel, GridFor(w->contactCount), kBlock, w->d, w->contactCount);
+	LAUNCH(w, BuildLowStartKernel, GridFor(w->proxyCount + 1), kBlock, w->d, w->contactCount, w->proxyCount);
 	return B2CU_OK;
 }
 
