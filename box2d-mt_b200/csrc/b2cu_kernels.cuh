@@ -20,6 +20,8 @@ namespace b2cu
 
 __device__ __forceinline__ bool IsStatic(uint32_t bf) { return (bf & B2CU_BODY_TYPE_MASK) == B2CU_STATIC_BODY; }
 __device__ __forceinline__ bool IsDynamic(uint32_t bf) { return (bf & B2CU_BODY_TYPE_MASK) == B2CU_DYNAMIC_BODY; }
+// dynamic and simulated by this shard (not a halo copy of a neighbour's body)
+__device__ __forceinline__ bool IsOwnedDynamic(uint32_t bf) { return IsDynamic(bf) && !(bf & B2CU_BODY_GHOST); }
 __device__ __forceinline__ bool IsAwakeNonStatic(uint32_t bf) { return (bf & B2CU_BODY_AWAKE) && !IsStatic(bf); }
 
 // ordered-int encoding of a float so that signed integer min == float min
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 
 		if (flags & B2CU_CONTACT_FILTER)
 		{
-			bool should = IsDynamic(fbA) || IsDynamic(fbB);
+			bool should = IsOwnedDynamic(fbA) || IsOwnedDynamic(fbB);
 			if (should)
 			{
 				should = DefaultFilter(d.pfilter[pr.x], gA, d.pfilter[pr.y], gB);
@@ -392,7 +394,18 @@ __global__ void SelectConstraintsKernel(DeviceArrays d, int contactCount)
 // (Box2D/Dynamics/Contacts/b2ContactSolver.cpp:293-603) run one colour at a time in parallel.  Colours persist
 // across steps, so only new constraints are coloured.  Deterministic: ties are broken by contact index.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ColourPrepareKernel(DeviceArrays d, const int* __restrict__ list, int* uncoloured)
+// Colour classes of a sharded world: constraints between own bodies take colours [0, crossBase), constraints that
+// touch a ghost body take colours [crossBase, 32); the two classes run in separate phases with a halo exchange
+// between them.  Unsharded worlds have crossBase = 32 (one class).  No free colour: overflow list of the class
+// (colour 32 / 33), solved serially.
+__device__ __forceinline__ uint32_t ColourClassMask(bool cross, int crossBase)
+{
+	uint32_t low = crossBase >= 32 ? 0xFFFFFFFFu : ((1u << crossBase) - 1u);
+	return cross ? ~low : low;
+}
+
+__global__ void __launch_bounds__(256) ColourPrepareKernel(DeviceArrays d, const int* __restrict__ list, int* uncoloured,
+                                                           int crossBase)
 {
 	__shared__ int hist[B2CU_MAX_COLOURS];
 	if (threadIdx.x < B2CU_MAX_COLOURS) hist[threadIdx.x] = 0;
@@ -404,10 +417,12 @@ __global__ void __launch_bounds__(256) ColourPrepareKernel(DeviceArrays d, const
 		int c = d.c.colour[i];
 		int2 pr = d.c.proxies[i];
 		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
-		if (c >= 0 && c < B2CU_MAX_COLOURS)
+		uint32_t fA = d.bflags[bA], fB = d.bflags[bB];
+		bool cross = ((fA | fB) & B2CU_BODY_GHOST) != 0;
+		if (c >= 0 && c < B2CU_MAX_COLOURS && ((ColourClassMask(cross, crossBase) >> c) & 1u))
 		{
-			if (IsDynamic(d.bflags[bA])) atomicOr(&d.colourMask[bA], 1u << c);
-			if (IsDynamic(d.bflags[bB])) atomicOr(&d.colourMask[bB], 1u << c);
+			if (IsDynamic(fA)) atomicOr(&d.colourMask[bA], 1u << c);
+			if (IsDynamic(fB)) atomicOr(&d.colourMask[bB], 1u << c);
 			atomicAdd(&hist[c], 1);
 		}
 		else
@@ -421,15 +436,18 @@ __global__ void __launch_bounds__(256) ColourPrepareKernel(DeviceArrays d, const
 	if (threadIdx.x < B2CU_MAX_COLOURS && hist[threadIdx.x]) atomicAdd(&d.colourCount[threadIdx.x], hist[threadIdx.x]);
 }
 
-__device__ __forceinline__ uint32_t ColourFreeMask(const DeviceArrays& d, int bA, int bB, bool dynA, bool dynB)
+__device__ __forceinline__ uint32_t ColourFreeMask(const DeviceArrays& d, int bA, int bB, uint32_t fA, uint32_t fB,
+                                                  int crossBase)
 {
 	uint32_t used = 0u;
-	if (dynA) used |= d.colourMask[bA];
-	if (dynB) used |= d.colourMask[bB];
-	return ~used;
+	if (IsDynamic(fA)) used |= d.colourMask[bA];
+	if (IsDynamic(fB)) used |= d.colourMask[bB];
+	bool cross = ((fA | fB) & B2CU_BODY_GHOST) != 0;
+	return ~used & ColourClassMask(cross, crossBase);
 }
 
-__global__ void ColourProposeKernel(DeviceArrays d, const int* __restrict__ list, int counterIndex, uint32_t round)
+__global__ void ColourProposeKernel(DeviceArrays d, const int* __restrict__ list, int counterIndex, uint32_t round,
+                                    int crossBase)
 {
 	int n = d.counters[counterIndex];
 	B2CU_GRID_STRIDE(j, n)
@@ -437,36 +455,38 @@ __global__ void ColourProposeKernel(DeviceArrays d, const int* __restrict__ list
 		int i = list[j];
 		int2 pr = d.c.proxies[i];
 		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
-		bool dynA = IsDynamic(d.bflags[bA]), dynB = IsDynamic(d.bflags[bB]);
-		uint32_t freeMask = ColourFreeMask(d, bA, bB, dynA, dynB);
+		uint32_t fA = d.bflags[bA], fB = d.bflags[bB];
+		uint32_t freeMask = ColourFreeMask(d, bA, bB, fA, fB, crossBase);
 		if (freeMask == 0u)
 		{
-			d.c.colour[i] = B2CU_COLOUR_OVERFLOW;
-			atomicAdd(&d.colourCount[B2CU_MAX_COLOURS], 1);
+			int overflow = ((fA | fB) & B2CU_BODY_GHOST) ? B2CU_COLOUR_OVERFLOW + 1 : B2CU_COLOUR_OVERFLOW;
+			d.c.colour[i] = overflow;
+			atomicAdd(&d.colourCount[overflow], 1);
 			continue;
 		}
 		unsigned long long claim = ((unsigned long long)round << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
-		if (dynA) atomicMax(&d.colourClaim[bA], claim);
-		if (dynB) atomicMax(&d.colourClaim[bB], claim);
+		if (IsDynamic(fA)) atomicMax(&d.colourClaim[bA], claim);
+		if (IsDynamic(fB)) atomicMax(&d.colourClaim[bB], claim);
 	}
 }
 
 __global__ void ColourCommitKernel(DeviceArrays d, const int* __restrict__ list, int counterIndex, int* next,
-                                   int nextCounterIndex, uint32_t round)
+                                   int nextCounterIndex, uint32_t round, int crossBase)
 {
 	int n = d.counters[counterIndex];
 	B2CU_GRID_STRIDE(j, n)
 	{
 		int i = list[j];
-		if (d.c.colour[i] == B2CU_COLOUR_OVERFLOW) continue;
+		if (d.c.colour[i] >= B2CU_COLOUR_OVERFLOW) continue;
 		int2 pr = d.c.proxies[i];
 		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
-		bool dynA = IsDynamic(d.bflags[bA]), dynB = IsDynamic(d.bflags[bB]);
+		uint32_t fA = d.bflags[bA], fB = d.bflags[bB];
+		bool dynA = IsDynamic(fA), dynB = IsDynamic(fB);
 		unsigned long long claim = ((unsigned long long)round << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
 		bool win = (!dynA || d.colourClaim[bA] == claim) && (!dynB || d.colourClaim[bB] == claim);
 		if (win)
 		{
-			uint32_t freeMask = ColourFreeMask(d, bA, bB, dynA, dynB);
+			uint32_t freeMask = ColourFreeMask(d, bA, bB, fA, fB, crossBase);
 			int c = __ffs((int)freeMask) - 1;
 			d.c.colour[i] = c;
 			atomicAdd(&d.colourCount[c], 1);
@@ -1093,16 +1113,49 @@ __global__ void OverflowSolvePositionKernel(DeviceArrays d, int begin, int count
 // multi-launch version.  Same per-constraint code (WarmStartOne / SolveVelocityOne / SolvePositionOne), same
 // order, same results.
 // ---------------------------------------------------------------------------------------------------------
+// Halo exchange state of a sharded world (b2cuShardConfigure / Connect).  Mailboxes are plain device buffers;
+// the ones of the neighbours are mapped peer memory (NVLink): a push is stores + __threadfence_system + a
+// sequence flag, a receive is a spin on the local flag.
+struct ShardState
+{
+	int rankCount;   // 1: unsharded, no exchange
+	int ghostCount, exportCount;
+	const int* ghostIds;   // bodies of this world that are copies of the upper neighbour's bodies
+	const int* exportIds;  // own bodies that are ghosts in the lower neighbour
+	float4* fromUpper;     // local mailbox written by the upper neighbour (owner -> ghost data)
+	float4* fromLower;     // local mailbox written by the lower neighbour (ghost -> owner data)
+	unsigned* flagFromUpper;
+	unsigned* flagFromLower;
+	float4* lowerFromUpper;   // lower neighbour's fromUpper mailbox (peer memory), nullptr on rank 0
+	unsigned* lowerFlagFromUpper;
+	float4* upperFromLower;   // upper neighbour's fromLower mailbox (peer memory), nullptr on the last rank
+	unsigned* upperFlagFromLower;
+	unsigned seq;             // sequence number of the next exchange
+};
+
+enum SolverOpType
+{
+	OP_PARALLEL = 0,   // one colour: constraints [start, start+count) in parallel
+	OP_SERIAL = 1,     // overflow list: one thread, in order
+	OP_PUSH_DOWN = 2,  // halo: owners -> ghost copies (to the lower neighbour), then receive from the upper one
+	OP_PUSH_UP = 3     // halo: ghost copies -> owners (to the upper neighbour), then receive from the lower one
+};
+
+#define B2CU_MAX_SOLVER_OPS (B2CU_MAX_COLOURS + 6)
+
 struct SolverPlan
 {
-	int colourStart[B2CU_MAX_COLOURS + 1];
-	int colourCount[B2CU_MAX_COLOURS + 1]; // [B2CU_MAX_COLOURS] = overflow list, solved by one thread
+	int opCount;
+	int opType[B2CU_MAX_SOLVER_OPS];
+	int opStart[B2CU_MAX_SOLVER_OPS];
+	int opSize[B2CU_MAX_SOLVER_OPS];
 	int constraintCount;
 	int bodyCount;
 	int velocityIterations;
 	int positionIterations;
 	int warmStarting;
 	float h;
+	ShardState shard;
 };
 
 __device__ __forceinline__ void IntegratePositionOne(const DeviceArrays& d, int b, float h)
@@ -1154,47 +1207,84 @@ __device__ __forceinline__ void StoreImpulseOne(const DeviceArrays& d, int k)
 	}
 }
 
+// field[ids[k]] -> peer mailbox, flag; then wait for the neighbour's push and scatter it into field
+__device__ __forceinline__ void HaloExchange(cooperative_groups::grid_group& grid, const ShardState& sh, float4* field,
+                                             bool down, unsigned seq, int tid, int stride)
+{
+	// send
+	const int* sendIds = down ? sh.exportIds : sh.ghostIds;
+	const int sendCount = down ? sh.exportCount : sh.ghostCount;
+	float4* sendBox = down ? sh.lowerFromUpper : sh.upperFromLower;
+	unsigned* sendFlag = down ? sh.lowerFlagFromUpper : sh.upperFlagFromLower;
+	if (sendBox != nullptr)
+	{
+		for (int k = tid; k < sendCount; k += stride) sendBox[k] = field[sendIds[k]];
+		__threadfence_system();
+	}
+	grid.sync();
+	if (sendBox != nullptr && tid == 0)
+	{
+		*reinterpret_cast<volatile unsigned*>(sendFlag) = seq;
+		__threadfence_system();
+	}
+	// receive
+	const int* recvIds = down ? sh.ghostIds : sh.exportIds;
+	const int recvCount = down ? sh.ghostCount : sh.exportCount;
+	const float4* recvBox = down ? sh.fromUpper : sh.fromLower;
+	const unsigned* recvFlag = down ? sh.flagFromUpper : sh.flagFromLower;
+	const bool hasPeer = down ? (sh.upperFromLower != nullptr) : (sh.lowerFromUpper != nullptr);
+	if (hasPeer && tid == 0)
+	{
+		while (*reinterpret_cast<const volatile unsigned*>(recvFlag) < seq)
+		{
+		}
+		__threadfence_system();
+	}
+	grid.sync();
+	if (hasPeer)
+	{
+		for (int k = tid; k < recvCount; k += stride) field[recvIds[k]] = __ldcv(&recvBox[k]);
+	}
+	grid.sync();
+}
+
 __global__ void __launch_bounds__(256) SolverPersistentKernel(DeviceArrays d, SolverPlan plan)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
+	unsigned seq = plan.shard.seq;
 
-	if (plan.warmStarting)
+	// pass 0 = warm start, passes 1..vIters = velocity iterations
+	for (int pass = plan.warmStarting ? 0 : 1; pass <= plan.velocityIterations; ++pass)
 	{
-		for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
+		for (int op = 0; op < plan.opCount; ++op)
 		{
-			const int n = plan.colourCount[c];
-			if (n == 0) continue;
-			const int begin = plan.colourStart[c];
-			if (c < B2CU_MAX_COLOURS)
+			const int type = plan.opType[op], begin = plan.opStart[op], n = plan.opSize[op];
+			if (type == OP_PARALLEL)
 			{
-				for (int t = tid; t < n; t += stride) WarmStartOne(d, begin + t);
+				if (pass == 0)
+					for (int t = tid; t < n; t += stride) WarmStartOne(d, begin + t);
+				else
+					for (int t = tid; t < n; t += stride) SolveVelocityOne(d, begin + t);
+				grid.sync();
 			}
-			else if (tid == 0)
+			else if (type == OP_SERIAL)
 			{
-				for (int t = 0; t < n; ++t) WarmStartOne(d, begin + t);
+				if (tid == 0)
+				{
+					for (int t = 0; t < n; ++t)
+					{
+						if (pass == 0) WarmStartOne(d, begin + t);
+						else SolveVelocityOne(d, begin + t);
+					}
+				}
+				grid.sync();
 			}
-			grid.sync();
-		}
-	}
-
-	for (int it = 0; it < plan.velocityIterations; ++it)
-	{
-		for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
-		{
-			const int n = plan.colourCount[c];
-			if (n == 0) continue;
-			const int begin = plan.colourStart[c];
-			if (c < B2CU_MAX_COLOURS)
+			else
 			{
-				for (int t = tid; t < n; t += stride) SolveVelocityOne(d, begin + t);
+				HaloExchange(grid, plan.shard, d.vel, type == OP_PUSH_DOWN, seq++, tid, stride);
 			}
-			else if (tid == 0)
-			{
-				for (int t = 0; t < n; ++t) SolveVelocityOne(d, begin + t);
-			}
-			grid.sync();
 		}
 	}
 
@@ -1205,12 +1295,10 @@ __global__ void __launch_bounds__(256) SolverPersistentKernel(DeviceArrays d, So
 
 	for (int it = 0; it < plan.positionIterations; ++it)
 	{
-		for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
+		for (int op = 0; op < plan.opCount; ++op)
 		{
-			const int n = plan.colourCount[c];
-			if (n == 0) continue;
-			const int begin = plan.colourStart[c];
-			if (c < B2CU_MAX_COLOURS)
+			const int type = plan.opType[op], begin = plan.opStart[op], n = plan.opSize[op];
+			if (type == OP_PARALLEL)
 			{
 				for (int t = tid; t < n; t += stride)
 				{
@@ -1220,20 +1308,70 @@ __global__ void __launch_bounds__(256) SolverPersistentKernel(DeviceArrays d, So
 					float minSep = SolvePositionOne(d, k);
 					AtomicMinByRoot(d.islandMinSep + (size_t)it * plan.bodyCount, root, FloatToOrdered(minSep));
 				}
+				grid.sync();
 			}
-			else if (tid == 0)
+			else if (type == OP_SERIAL)
 			{
-				for (int t = 0; t < n; ++t)
+				if (tid == 0)
 				{
-					int k = begin + t;
-					int root = __float_as_int(d.sRadius[k].w);
-					if (IslandDone(d, it, root, plan.bodyCount)) continue;
-					float minSep = SolvePositionOne(d, k);
-					atomicMin(&d.islandMinSep[(size_t)it * plan.bodyCount + root], FloatToOrdered(minSep));
+					for (int t = 0; t < n; ++t)
+					{
+						int k = begin + t;
+						int root = __float_as_int(d.sRadius[k].w);
+						if (IslandDone(d, it, root, plan.bodyCount)) continue;
+						float minSep = SolvePositionOne(d, k);
+						atomicMin(&d.islandMinSep[(size_t)it * plan.bodyCount + root], FloatToOrdered(minSep));
+					}
 				}
+				grid.sync();
 			}
-			grid.sync();
+			else
+			{
+				HaloExchange(grid, plan.shard, d.pos, type == OP_PUSH_DOWN, seq++, tid, stride);
+			}
 		}
+	}
+}
+
+// ---- step-start halo sync: the owner's full body state (5 float4 rows per body) to the ghost copies ----------
+#define B2CU_GHOST_ROWS 5
+__global__ void GhostSendKernel(DeviceArrays d, ShardState sh)
+{
+	B2CU_GRID_STRIDE(k, sh.exportCount)
+	{
+		int b = sh.exportIds[k];
+		float4* out = sh.lowerFromUpper + (size_t)k * B2CU_GHOST_ROWS;
+		out[0] = d.xf[b];
+		out[1] = d.pos[b];
+		out[2] = d.pos0[b];
+		out[3] = d.vel[b];
+		out[4] = d.force[b];
+	}
+	__threadfence_system();
+}
+__global__ void ShardSignalKernel(unsigned* flag, unsigned seq)
+{
+	*reinterpret_cast<volatile unsigned*>(flag) = seq;
+	__threadfence_system();
+}
+__global__ void ShardWaitKernel(const unsigned* flag, unsigned seq)
+{
+	while (*reinterpret_cast<const volatile unsigned*>(flag) < seq)
+	{
+	}
+	__threadfence_system();
+}
+__global__ void GhostApplyKernel(DeviceArrays d, ShardState sh)
+{
+	B2CU_GRID_STRIDE(k, sh.ghostCount)
+	{
+		int b = sh.ghostIds[k];
+		const float4* in = sh.fromUpper + (size_t)k * B2CU_GHOST_ROWS;
+		d.xf[b] = __ldcv(&in[0]);
+		d.pos[b] = __ldcv(&in[1]);
+		d.pos0[b] = __ldcv(&in[2]);
+		d.vel[b] = __ldcv(&in[3]);
+		d.force[b] = __ldcv(&in[4]);
 	}
 }
 
@@ -1477,7 +1615,8 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 		}
 		if (lo < d.lowStart[a + 1] && d.c.key[lo] == key && !(d.cEvent[lo] & B2CU_EV_DESTROY)) return;
 	}
-	if (!IsDynamic(d.bflags[bodyA]) && !IsDynamic(d.bflags[bodyB])) return;
+	// b2Body::ShouldCollide: at least one dynamic body; in a sharded world it must be one this shard owns
+	if (!IsOwnedDynamic(d.bflags[bodyA]) && !IsOwnedDynamic(d.bflags[bodyB])) return;
 	if (!DefaultFilter(d.pfilter[a], d.pgroup[a], d.pfilter[b], d.pgroup[b])) return;
 	if (d.shapes[d.pshape[a]].type == B2CU_SHAPE_EDGE && d.shapes[d.pshape[b]].type == B2CU_SHAPE_EDGE) return;
 	int slot = atomicAdd(&d.counters[CNT_NEW_PAIRS], 1);

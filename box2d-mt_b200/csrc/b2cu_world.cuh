@@ -165,10 +165,25 @@ struct b2cuWorld
 	size_t l2WindowMax;  // 0: no persisting-L2 support
 	bool persistentSolver; // solve all colour phases in one cooperative kernel
 	int persistentGrid;
+	int persistentGridMax;
+
+	// spatial sharding (b2cuShardConfigure / Connect)
+	int shardRank, shardCount;
+	int ghostCount, exportCount;
+	int* ghostIds;        // device
+	int* exportIds;       // device
+	unsigned char* mailbox; // device: flags + fromUpper + fromLower
+	size_t mailboxBytes;
+	unsigned char* peerLower; // mapped mailbox of rank-1 / rank+1 (nullptr if none)
+	unsigned char* peerUpper;
+	bool peerLowerIpc, peerUpperIpc;
+	int peerUpperGhostCountOfUpper; // the upper neighbour's own ghostCount (layout of its mailbox)
+	unsigned shardSeq;     // sequence number of the next halo exchange
 
 	// last step
 	int beginCount, endCount, constraintCount, colourCount, overflowCount, toiCount;
-	int colourCounts[B2CU_MAX_COLOURS + 1];
+	int colourCounts[B2CU_MAX_COLOURS + 2]; // [32] own-class overflow, [33] cross-class overflow
+	int colourStarts[B2CU_MAX_COLOURS + 3];
 
 	int* hostCounters;   // pinned, CNT_COUNT + colour counts
 	cudaEvent_t ev[10];

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <unistd.h>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -318,6 +319,59 @@ void SetL2Window(b2cuWorld* w, const void* base, size_t bytes)
 	cudaStreamSetAttribute(w->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
 }
 
+// ---- sharding -------------------------------------------------------------------------------------------
+const size_t kMailboxHeader = 256;
+size_t MailboxFromUpperBytes(int ghostCount) { return (((size_t)ghostCount * 8 * sizeof(float4)) + 255) & ~(size_t)255; }
+size_t MailboxFromLowerBytes(int exportCount) { return (((size_t)exportCount * 8 * sizeof(float4)) + 255) & ~(size_t)255; }
+
+ShardState MakeShardState(b2cuWorld* w)
+{
+	ShardState sh;
+	memset(&sh, 0, sizeof(sh));
+	sh.rankCount = w->shardCount > 0 ? w->shardCount : 1;
+	if (w->shardCount <= 1 || w->mailbox == nullptr) return sh;
+	sh.ghostCount = w->ghostCount;
+	sh.exportCount = w->exportCount;
+	sh.ghostIds = w->ghostIds;
+	sh.exportIds = w->exportIds;
+	sh.flagFromUpper = reinterpret_cast<unsigned*>(w->mailbox);
+	sh.flagFromLower = reinterpret_cast<unsigned*>(w->mailbox + 64);
+	sh.fromUpper = reinterpret_cast<float4*>(w->mailbox + kMailboxHeader);
+	sh.fromLower = reinterpret_cast<float4*>(w->mailbox + kMailboxHeader + MailboxFromUpperBytes(w->ghostCount));
+	if (w->peerLower)
+	{
+		sh.lowerFlagFromUpper = reinterpret_cast<unsigned*>(w->peerLower);
+		sh.lowerFromUpper = reinterpret_cast<float4*>(w->peerLower + kMailboxHeader);
+	}
+	if (w->peerUpper)
+	{
+		sh.upperFlagFromLower = reinterpret_cast<unsigned*>(w->peerUpper + 64);
+		sh.upperFromLower =
+			reinterpret_cast<float4*>(w->peerUpper + kMailboxHeader + MailboxFromUpperBytes(w->peerUpperGhostCountOfUpper));
+	}
+	sh.seq = w->shardSeq;
+	return sh;
+}
+
+// step-start halo sync: owners push the full state of their export bodies to the ghost copies below them
+int ShardSyncGhosts(b2cuWorld* w)
+{
+	if (w->shardCount <= 1) return B2CU_OK;
+	ShardState sh = MakeShardState(w);
+	const unsigned seq = w->shardSeq++;
+	if (sh.lowerFromUpper != nullptr)
+	{
+		if (w->exportCount > 0) LAUNCH(w, GhostSendKernel, GridFor(w->exportCount), kBlock, w->d, sh);
+		LAUNCH(w, ShardSignalKernel, 1, 1, sh.lowerFlagFromUpper, seq);
+	}
+	if (sh.upperFromLower != nullptr)
+	{
+		LAUNCH(w, ShardWaitKernel, 1, 1, sh.flagFromUpper, seq);
+		if (w->ghostCount > 0) LAUNCH(w, GhostApplyKernel, GridFor(w->ghostCount), kBlock, w->d, sh);
+	}
+	return B2CU_OK;
+}
+
 // ascending sort of contact keys (min proxy << 32 | max proxy): LSD over the two id fields
 void SortKeys(b2cuWorld* w, uint64_t* keys, int n)
 {
@@ -508,6 +562,9 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		const char* pe = getenv("B2CU_PERSISTENT");
 		w->persistentSolver = coop != 0 && perSm > 0 && !(pe && atoi(pe) == 0);
 		w->persistentGrid = g_smCount * perSm;
+		w->persistentGridMax = w->persistentGrid;
+		w->shardCount = 1;
+		w->shardSeq = 1;
 	}
 	{
 		const char* t = getenv("B2CU_TRACE");
@@ -533,6 +590,11 @@ void b2cuDestroyWorld(b2cuWorld* w)
 	std::vector<ArrayDesc> arrays = AllArrays(w);
 	for (size_t k = 0; k < arrays.size(); ++k) cudaFree(*arrays[k].ptr);
 	cudaFree(w->d.islandMinSep);
+	if (w->peerLower && w->peerLowerIpc) cudaIpcCloseMemHandle(w->peerLower);
+	if (w->peerUpper && w->peerUpperIpc) cudaIpcCloseMemHandle(w->peerUpper);
+	cudaFree(w->ghostIds);
+	cudaFree(w->exportIds);
+	cudaFree(w->mailbox);
 	PrimScratchFree(&w->prims);
 	cudaFreeHost(w->hostCounters);
 	for (int i = 0; i < 10; ++i) cudaEventDestroy(w->ev[i]);
@@ -894,6 +956,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		w->toiCheckDirty = false;
 	}
 
+	if (dt > 0.0f && (rc = ShardSyncGhosts(w))) return rc;
+
 	int newContacts = 0, destroyed = 0, moved = 0;
 
 	// ---- new fixtures: find their contacts first (b2World.cpp:1628-1639) ----
@@ -926,7 +990,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	w->constraintCount = 0;
 	w->colourCount = 0;
 	w->overflowCount = 0;
-	for (int c = 0; c <= B2CU_MAX_COLOURS; ++c) w->colourCounts[c] = 0;
+	for (int c = 0; c < B2CU_MAX_COLOURS + 2; ++c) w->colourCounts[c] = 0;
 
 	if (dt > 0.0f)
 	{
@@ -938,7 +1002,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		cudaEventRecord(w->ev[3], w->stream);
 
 		// ---- constraint selection + colouring ----
-		int colourStart[B2CU_MAX_COLOURS + 2];
+		int* colourStart = w->colourStarts;
+		const int crossBase = w->shardCount > 1 ? 16 : 32;
 		int nConstraints = 0;
 		if (nc > 0)
 		{
@@ -947,7 +1012,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			CUDA_TRY(w, cudaMemsetAsync(d.colourCount, 0, sizeof(int) * (B2CU_MAX_COLOURS + 2), w->stream));
 			int* cur = d.listB;
 			int* next = d.listC;
-			LAUNCH(w, ColourPrepareKernel, GridFor(nc), kBlock, d, d.listA, cur);
+			LAUNCH(w, ColourPrepareKernel, GridFor(nc), kBlock, d, d.listA, cur, crossBase);
 			// a fixed number of colouring rounds is queued without asking the device how many constraints are left
 			// (in steady state only the few new constraints are uncoloured and 2-3 rounds finish them); one
 			// read-back then gives the constraint count, the per-colour counts and what is left
@@ -957,8 +1022,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			for (int r = 0; r < kBlindRounds; ++r)
 			{
 				int g = GridFor(std::max(1024, nc / 64));
-				LAUNCH(w, ColourProposeKernel, g, kBlock, d, cur, counter, round);
-				LAUNCH(w, ColourCommitKernel, g, kBlock, d, cur, counter, next, counter + 1, round);
+				LAUNCH(w, ColourProposeKernel, g, kBlock, d, cur, counter, round, crossBase);
+				LAUNCH(w, ColourCommitKernel, g, kBlock, d, cur, counter, next, counter + 1, round, crossBase);
 				std::swap(cur, next);
 				++counter;
 				++round;
@@ -971,8 +1036,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				// rare: more rounds, now one read-back per round; the two spare counters are ping-ponged
 				int nextCounter = counter == CNT_UNCOLOURED_LAST ? CNT_UNCOLOURED_LAST - 1 : counter + 1;
 				if ((rc = ZeroCounter(w, nextCounter))) return rc;
-				LAUNCH(w, ColourProposeKernel, GridFor(remaining), kBlock, d, cur, counter, round);
-				LAUNCH(w, ColourCommitKernel, GridFor(remaining), kBlock, d, cur, counter, next, nextCounter, round);
+				LAUNCH(w, ColourProposeKernel, GridFor(remaining), kBlock, d, cur, counter, round, crossBase);
+				LAUNCH(w, ColourCommitKernel, GridFor(remaining), kBlock, d, cur, counter, next, nextCounter, round, crossBase);
 				if ((rc = ReadCounters(w))) return rc;
 				remaining = w->hostCounters[nextCounter];
 				std::swap(cur, next);
@@ -983,17 +1048,17 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			if (nConstraints > 0)
 			{
 				int at = 0;
-				for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
+				for (int c = 0; c < B2CU_MAX_COLOURS + 2; ++c)
 				{
 					w->colourCounts[c] = w->hostCounters[CNT_COUNT + c];
 					colourStart[c] = at;
 					at += w->colourCounts[c];
-					if (c < B2CU_MAX_COLOURS && w->colourCounts[c] > 0) w->colourCount = c + 1;
+					if (c < B2CU_MAX_COLOURS && w->colourCounts[c] > 0) ++w->colourCount;
 				}
-				colourStart[B2CU_MAX_COLOURS + 1] = at;
+				colourStart[B2CU_MAX_COLOURS + 2] = at;
 				if (at != nConstraints)
 					return SetError(w, B2CU_ERR_CUDA, "internal: colour counts %d != constraints %d", at, nConstraints);
-				w->overflowCount = w->colourCounts[B2CU_MAX_COLOURS];
+				w->overflowCount = w->colourCounts[B2CU_MAX_COLOURS] + w->colourCounts[B2CU_MAX_COLOURS + 1];
 				LAUNCH(w, ColourKeysKernel, GridFor(nConstraints), kBlock, d, d.listA);
 				RadixSort64(&w->prims, d.orderKeys, nConstraints, 32, 40, w->stream);
 			}
@@ -1013,26 +1078,53 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 					if (w->colourCounts[c] > 0)
 						LAUNCH(w, WarmStartKernel, GridFor(w->colourCounts[c]), kBlock, d, colourStart[c], w->colourCounts[c]);
 				}
-				if (w->overflowCount > 0)
-					LAUNCH(w, OverflowWarmStartKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->overflowCount);
+				if (w->colourCounts[B2CU_MAX_COLOURS] > 0)
+					LAUNCH(w, OverflowWarmStartKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->colourCounts[B2CU_MAX_COLOURS]);
 			}
 		}
 		cudaEventRecord(w->ev[5], w->stream);
-		if (nConstraints > 0 && w->persistentSolver)
+		if ((nConstraints > 0 || w->shardCount > 1) && w->persistentSolver)
 		{
-			// one persistent cooperative kernel for warm start + velocity + store + integrate + position
+			// one persistent cooperative kernel for warm start + velocity + store + integrate + position; in a
+			// sharded world it also carries the halo exchanges, so it runs even without constraints
 			SolverPlan plan;
-			for (int c = 0; c <= B2CU_MAX_COLOURS; ++c)
-			{
-				plan.colourStart[c] = colourStart[c];
-				plan.colourCount[c] = w->colourCounts[c];
-			}
+			memset(&plan, 0, sizeof(plan));
+			int nOps = 0;
+			auto addSegments = [&](int first, int last, int overflowColour) {
+				for (int c = first; c < last; ++c)
+				{
+					if (nConstraints > 0 && w->colourCounts[c] > 0)
+					{
+						plan.opType[nOps] = OP_PARALLEL;
+						plan.opStart[nOps] = colourStart[c];
+						plan.opSize[nOps] = w->colourCounts[c];
+						++nOps;
+					}
+				}
+				if (nConstraints > 0 && w->colourCounts[overflowColour] > 0)
+				{
+					plan.opType[nOps] = OP_SERIAL;
+					plan.opStart[nOps] = colourStart[overflowColour];
+					plan.opSize[nOps] = w->colourCounts[overflowColour];
+					++nOps;
+				}
+			};
+			addSegments(0, crossBase, B2CU_MAX_COLOURS);
+			if (w->shardCount > 1) plan.opType[nOps++] = OP_PUSH_DOWN;
+			addSegments(crossBase, B2CU_MAX_COLOURS, B2CU_MAX_COLOURS + 1);
+			if (w->shardCount > 1) plan.opType[nOps++] = OP_PUSH_UP;
+			plan.opCount = nOps;
 			plan.constraintCount = nConstraints;
 			plan.bodyCount = nb;
 			plan.velocityIterations = velocityIterations;
 			plan.positionIterations = positionIterations;
 			plan.warmStarting = warmStarting ? 1 : 0;
 			plan.h = dt;
+			plan.shard = MakeShardState(w);
+			if (w->shardCount > 1)
+			{
+				w->shardSeq += 2u * (unsigned)((warmStarting ? 1 : 0) + velocityIterations + positionIterations);
+			}
 			void* args[2] = {(void*)&d, (void*)&plan};
 			CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverPersistentKernel, dim3(w->persistentGrid), dim3(256),
 			                                        args, 0, w->stream));
@@ -1053,8 +1145,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 						LAUNCH(w, SolveVelocityKernel, GridFor(w->colourCounts[c]), kBlock, d, colourStart[c],
 						       w->colourCounts[c]);
 				}
-				if (w->overflowCount > 0)
-					LAUNCH(w, OverflowSolveVelocityKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->overflowCount);
+				if (w->colourCounts[B2CU_MAX_COLOURS] > 0)
+					LAUNCH(w, OverflowSolveVelocityKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->colourCounts[B2CU_MAX_COLOURS]);
 			}
 			LAUNCH(w, StoreImpulsesKernel, GridFor(nConstraints), kBlock, d);
 		}
@@ -1071,8 +1163,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 						LAUNCH(w, SolvePositionKernel, GridFor(w->colourCounts[c]), kBlock, d, colourStart[c],
 						       w->colourCounts[c], it, nb);
 				}
-				if (w->overflowCount > 0)
-					LAUNCH(w, OverflowSolvePositionKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->overflowCount, it, nb);
+				if (w->colourCounts[B2CU_MAX_COLOURS] > 0)
+					LAUNCH(w, OverflowSolvePositionKernel, 1, 32, d, colourStart[B2CU_MAX_COLOURS], w->colourCounts[B2CU_MAX_COLOURS], it, nb);
 			}
 		}
 		}
@@ -1255,17 +1347,29 @@ int b2cuGetSolverOrder(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int
 	if (count) *count = n;
 	int m = std::min(n, capacity);
 	if (m <= 0) return B2CU_OK;
-	if (keys)
-	{
-		CUDA_TRY(w, cudaMemcpyAsync(keys, w->d.solverKeys, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, w->stream));
-	}
-	std::vector<uint64_t> order(m);
-	CUDA_TRY(w, cudaMemcpyAsync(order.data(), w->d.orderKeys, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, w->stream));
+	// storage order is colour-sorted (0..31, 32, 33); the solver ran own colours, own overflow (32), cross colours,
+	// cross overflow (33): report that order
+	std::vector<uint64_t> stored(n), order(n);
+	CUDA_TRY(w, cudaMemcpyAsync(stored.data(), w->d.solverKeys, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, w->stream));
+	CUDA_TRY(w, cudaMemcpyAsync(order.data(), w->d.orderKeys, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, w->stream));
 	int rc = SyncCheck(w);
 	if (rc) return rc;
-	if (colour)
+	const int crossBase = w->shardCount > 1 ? 16 : 32;
+	std::vector<int> sequence;
+	for (int c = 0; c < crossBase; ++c) sequence.push_back(c);
+	sequence.push_back(B2CU_MAX_COLOURS);
+	for (int c = crossBase; c < B2CU_MAX_COLOURS; ++c) sequence.push_back(c);
+	sequence.push_back(B2CU_MAX_COLOURS + 1);
+	int at = 0;
+	for (size_t q = 0; q < sequence.size(); ++q)
 	{
-		for (int k = 0; k < m; ++k) colour[k] = (int32_t)(order[k] >> 32);
+		int c = sequence[q];
+		for (int k = w->colourStarts[c]; k < w->colourStarts[c] + w->colourCounts[c]; ++k, ++at)
+		{
+			if (at >= m) break;
+			if (keys) keys[at] = stored[k];
+			if (colour) colour[at] = (int32_t)(order[k] >> 32);
+		}
 	}
 	return B2CU_OK;
 }
@@ -1294,6 +1398,121 @@ int b2cuGetToiCandidates(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, i
 		CUDA_TRY(w, cudaMemcpyAsync(keys, w->d.toiKeys, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, w->stream));
 	}
 	return SyncCheck(w);
+}
+
+int b2cuShardConfigure(b2cuWorld* w, int32_t rank, int32_t rankCount, int32_t ghostCount, const int32_t* ghostBodies,
+                       int32_t exportCount, const int32_t* exportBodies, float gridFraction)
+{
+	if (!w || rankCount < 1 || rank < 0 || rank >= rankCount || ghostCount < 0 || exportCount < 0)
+		return B2CU_ERR_ARGUMENT;
+	if ((ghostCount > 0 && !ghostBodies) || (exportCount > 0 && !exportBodies)) return B2CU_ERR_ARGUMENT;
+	if (rankCount > 1 && !w->persistentSolver)
+		return SetError(w, B2CU_ERR_UNSUPPORTED, "sharding needs the persistent cooperative solver");
+	cudaSetDevice(w->device);
+	for (int i = 0; i < ghostCount; ++i)
+		if (ghostBodies[i] < 0 || ghostBodies[i] >= w->bodyCount)
+			return SetError(w, B2CU_ERR_ARGUMENT, "ghost body %d out of range", ghostBodies[i]);
+	for (int i = 0; i < exportCount; ++i)
+		if (exportBodies[i] < 0 || exportBodies[i] >= w->bodyCount)
+			return SetError(w, B2CU_ERR_ARGUMENT, "export body %d out of range", exportBodies[i]);
+	cudaFree(w->ghostIds);
+	cudaFree(w->exportIds);
+	cudaFree(w->mailbox);
+	w->ghostIds = w->exportIds = nullptr;
+	w->mailbox = nullptr;
+	w->shardRank = rank;
+	w->shardCount = rankCount;
+	w->ghostCount = ghostCount;
+	w->exportCount = exportCount;
+	w->shardSeq = 1;
+	CUDA_TRY(w, cudaMalloc(&w->ghostIds, sizeof(int) * std::max(1, ghostCount)));
+	CUDA_TRY(w, cudaMalloc(&w->exportIds, sizeof(int) * std::max(1, exportCount)));
+	if (ghostCount) CUDA_TRY(w, cudaMemcpy(w->ghostIds, ghostBodies, sizeof(int) * ghostCount, cudaMemcpyHostToDevice));
+	if (exportCount) CUDA_TRY(w, cudaMemcpy(w->exportIds, exportBodies, sizeof(int) * exportCount, cudaMemcpyHostToDevice));
+	w->mailboxBytes = kMailboxHeader + MailboxFromUpperBytes(ghostCount) + MailboxFromLowerBytes(exportCount);
+	CUDA_TRY(w, cudaMalloc(&w->mailbox, w->mailboxBytes));
+	CUDA_TRY(w, cudaMemset(w->mailbox, 0, w->mailboxBytes));
+	if (gridFraction > 0.0f && gridFraction < 1.0f)
+	{
+		// several shards on one device (tests): their cooperative kernels must be co-resident
+		int blocks = (int)(w->persistentGridMax * gridFraction);
+		w->persistentGrid = std::max(1, blocks);
+	}
+	else
+	{
+		w->persistentGrid = w->persistentGridMax;
+	}
+	return B2CU_OK;
+}
+
+int b2cuShardGetLink(b2cuWorld* w, b2cuShardLink* link)
+{
+	if (!w || !link || !w->mailbox) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	memset(link, 0, sizeof(*link));
+	cudaIpcMemHandle_t h;
+	CUDA_TRY(w, cudaIpcGetMemHandle(&h, w->mailbox));
+	static_assert(sizeof(h) <= sizeof(link->ipcHandle), "ipc handle size");
+	memcpy(link->ipcHandle, &h, sizeof(h));
+	link->localPointer = (uint64_t)(uintptr_t)w->mailbox;
+	link->processId = (int32_t)getpid();
+	link->device = w->device;
+	link->ghostCount = w->ghostCount;
+	link->exportCount = w->exportCount;
+	link->rank = w->shardRank;
+	link->rankCount = w->shardCount;
+	return B2CU_OK;
+}
+
+static int OpenPeer(b2cuWorld* w, const b2cuShardLink* link, unsigned char** out, bool* ipc)
+{
+	*out = nullptr;
+	*ipc = false;
+	if (link->processId == (int32_t)getpid())
+	{
+		if (link->device != w->device)
+		{
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, w->device, link->device);
+			if (!can) return SetError(w, B2CU_ERR_UNSUPPORTED, "device %d cannot access device %d", w->device, link->device);
+			cudaError_t e = cudaDeviceEnablePeerAccess(link->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+				return SetError(w, B2CU_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+			cudaGetLastError();
+		}
+		*out = reinterpret_cast<unsigned char*>((uintptr_t)link->localPointer);
+		return B2CU_OK;
+	}
+	cudaIpcMemHandle_t h;
+	memcpy(&h, link->ipcHandle, sizeof(h));
+	void* p = nullptr;
+	CUDA_TRY(w, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	*out = static_cast<unsigned char*>(p);
+	*ipc = true;
+	return B2CU_OK;
+}
+
+int b2cuShardConnect(b2cuWorld* w, const b2cuShardLink* lower, const b2cuShardLink* upper)
+{
+	if (!w || !w->mailbox) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	int rc;
+	if (lower)
+	{
+		if (lower->rank != w->shardRank - 1 || lower->ghostCount != w->exportCount)
+			return SetError(w, B2CU_ERR_ARGUMENT, "lower link: rank %d ghosts %d, expected rank %d ghosts %d", lower->rank,
+			                lower->ghostCount, w->shardRank - 1, w->exportCount);
+		if ((rc = OpenPeer(w, lower, &w->peerLower, &w->peerLowerIpc))) return rc;
+	}
+	if (upper)
+	{
+		if (upper->rank != w->shardRank + 1 || upper->exportCount != w->ghostCount)
+			return SetError(w, B2CU_ERR_ARGUMENT, "upper link: rank %d exports %d, expected rank %d exports %d",
+			                upper->rank, upper->exportCount, w->shardRank + 1, w->ghostCount);
+		if ((rc = OpenPeer(w, upper, &w->peerUpper, &w->peerUpperIpc))) return rc;
+		w->peerUpperGhostCountOfUpper = upper->ghostCount;
+	}
+	return B2CU_OK;
 }
 
 int b2cuCollidePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,

@@ -21,7 +21,7 @@ API = [
     "b2cuSetWorldParams", "b2cuSetInvDt0", "b2cuSetCounts", "b2cuSetBodies", "b2cuGetBodies", "b2cuSetShapes",
     "b2cuSetProxies", "b2cuGetProxies", "b2cuSetContacts", "b2cuGetContactCount", "b2cuGetContacts", "b2cuStep",
     "b2cuGetContactsByKey", "b2cuGetEvents", "b2cuGetSolverOrder", "b2cuGetIslandLabels", "b2cuGetToiCandidates", "b2cuCollidePairs",
-    "b2cuSinCos",
+    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect",
 ]
 
 
@@ -69,6 +69,9 @@ def load():
     lib.b2cuGetToiCandidates.argtypes = [vp, i32, vp, vp]
     lib.b2cuCollidePairs.argtypes = [i32, i32, vp, i32, vp, vp, vp, vp, vp]
     lib.b2cuSinCos.argtypes = [i32, i32, vp, vp, vp]
+    lib.b2cuShardConfigure.argtypes = [vp, i32, i32, i32, vp, i32, vp, f32]
+    lib.b2cuShardGetLink.argtypes = [vp, vp]
+    lib.b2cuShardConnect.argtypes = [vp, vp, vp]
     _lib = lib
     return lib
 
@@ -210,6 +213,23 @@ class World:
         if n.value:
             self._check(self.lib.b2cuGetSolverOrder(self.h, n.value, _ptr(keys), _ptr(colour), ctypes.byref(n)))
         return keys, colour
+
+    # ---- sharding ----
+    def shard_configure(self, rank, rank_count, ghost_bodies, export_bodies, grid_fraction=1.0):
+        g = np.ascontiguousarray(ghost_bodies, np.int32)
+        e = np.ascontiguousarray(export_bodies, np.int32)
+        self._check(self.lib.b2cuShardConfigure(self.h, rank, rank_count, len(g), _ptr(g), len(e), _ptr(e),
+                                                grid_fraction))
+
+    def shard_link(self):
+        link = np.zeros((), T.SHARD_LINK)
+        self._check(self.lib.b2cuShardGetLink(self.h, _ptr(link)))
+        return link
+
+    def shard_connect(self, lower=None, upper=None):
+        lo = None if lower is None else np.array(lower, dtype=T.SHARD_LINK, copy=True)
+        up = None if upper is None else np.array(upper, dtype=T.SHARD_LINK, copy=True)
+        self._check(self.lib.b2cuShardConnect(self.h, None if lo is None else _ptr(lo), None if up is None else _ptr(up)))
 
     def island_labels(self):
         out = np.zeros(self.body_count, np.int32)

@@ -50,6 +50,12 @@ WORLD_DEF = np.dtype([
     ("bodyCapacity", "i4"), ("proxyCapacity", "i4"), ("shapeCapacity", "i4"), ("contactCapacity", "i4"),
 ])
 
+SHARD_LINK = np.dtype([
+    ("ipcHandle", "u1", (64,)), ("localPointer", "u8"), ("processId", "i4"), ("device", "i4"),
+    ("ghostCount", "i4"), ("exportCount", "i4"), ("rank", "i4"), ("rankCount", "i4"),
+])
+assert SHARD_LINK.itemsize == 96
+
 STEP_INFO = np.dtype([
     ("step", "f4"), ("collide", "f4"), ("solve", "f4"), ("solveTraversal", "f4"), ("solveInit", "f4"),
     ("solveVelocity", "f4"), ("solvePosition", "f4"), ("solveTOI", "f4"), ("broadphase", "f4"),
@@ -65,6 +71,7 @@ STEP_INFO = np.dtype([
 STATIC_BODY, KINEMATIC_BODY, DYNAMIC_BODY = 0, 1, 2
 BODY_TYPE_MASK = 0x3
 BODY_ISLAND, BODY_AWAKE, BODY_AUTOSLEEP, BODY_BULLET, BODY_FIXED_ROTATION, BODY_ACTIVE = 0x4, 0x8, 0x10, 0x20, 0x40, 0x80
+BODY_GHOST = 0x100
 SHAPE_CIRCLE, SHAPE_EDGE, SHAPE_POLYGON = 0, 1, 2
 EDGE_HAS_VERTEX0, EDGE_HAS_VERTEX3 = 1, 2
 PROXY_SENSOR, PROXY_THICK, PROXY_MOVED = 1, 2, 4

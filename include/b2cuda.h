@@ -33,6 +33,8 @@
  *                                        used this step; feeds the permuted-order oracle
  *   b2cuGetToiCandidates                 TOI-eligible front partition of b2ContactManager::m_contacts
  *                                                                          Dynamics/b2ContactManager.cpp:659-713, b2World.cpp:317-341
+ *   b2cuShardConfigure / GetLink /       (new) spatial sharding of one large world over the GPUs of a box: halo
+ *   Connect                              bodies + per-iteration halo exchange over NVLink peer memory, SURVEY.md 8e
  *   b2cuCollidePairs                     b2CollidePolygons / b2CollideCircles / b2CollidePolygonAndCircle /
  *                                        b2CollideEdgeAndCircle / b2CollideEdgeAndPolygon, batched
  *                                                                          Collision/b2CollidePolygon.cpp, b2CollideCircle.cpp, b2CollideEdge.cpp
@@ -77,7 +79,8 @@ enum
 	B2CU_BODY_AUTOSLEEP = 0x0010,
 	B2CU_BODY_BULLET = 0x0020,
 	B2CU_BODY_FIXED_ROTATION = 0x0040,
-	B2CU_BODY_ACTIVE = 0x0080
+	B2CU_BODY_ACTIVE = 0x0080,
+	B2CU_BODY_GHOST = 0x0100   /* (new) halo copy of a body owned by the neighbouring shard, see b2cuShardConfigure */
 };
 
 typedef struct b2cuBody
@@ -280,6 +283,33 @@ B2CU_API int b2cuGetIslandLabels(b2cuWorld* w, int32_t first, int32_t count, int
 
 /* TOI-eligible contacts (candidate flag, active, enabled, toiCount <= b2_maxSubSteps), key order. */
 B2CU_API int b2cuGetToiCandidates(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* count);
+
+/* ---- spatial sharding (multi-GPU) ------------------------------------------------------------------------
+ * A large world is cut into strips along x, one b2cuWorld per GPU.  Shard s holds its own bodies, every static
+ * body, and GHOST copies (B2CU_BODY_GHOST) of the bodies of shard s+1 that lie within a margin of the common
+ * boundary.  A contact between an own body and a ghost is owned by shard s (the lower one); ghost-ghost and
+ * ghost-static pairs never become contacts.  Inside the solver every iteration runs
+ *     own constraints (all colours) -> halo push owner->ghost -> cross constraints -> halo push ghost->owner
+ * for velocities and then for positions, which is one sequential Gauss-Seidel order over the whole world.  The
+ * pushes are stores into the neighbour's mailbox through NVLink peer memory from inside the persistent solver
+ * kernel, followed by a system-scope fence and a sequence flag; there is no host round trip and no NCCL call on
+ * the data path.  ghostBodies[k] of shard s and exportBodies[k] of shard s+1 are the same body. */
+typedef struct b2cuShardLink
+{
+	unsigned char ipcHandle[64];   /* cudaIpcMemHandle_t of the mailbox allocation (other processes) */
+	uint64_t localPointer;         /* the same allocation as a device pointer (same process) */
+	int32_t processId;
+	int32_t device;
+	int32_t ghostCount, exportCount;
+	int32_t rank, rankCount;
+} b2cuShardLink;
+
+B2CU_API int b2cuShardConfigure(b2cuWorld* w, int32_t rank, int32_t rankCount, int32_t ghostCount,
+                                const int32_t* ghostBodies, int32_t exportCount, const int32_t* exportBodies,
+                                float gridFraction /* share of the SMs the persistent solver may occupy, (0,1] */);
+B2CU_API int b2cuShardGetLink(b2cuWorld* w, b2cuShardLink* link);
+/* lower / upper: the links of shards rank-1 / rank+1 (NULL at the ends) */
+B2CU_API int b2cuShardConnect(b2cuWorld* w, const b2cuShardLink* lower, const b2cuShardLink* upper);
 
 /* Batched stand-alone narrow phase: manifold i = collide(shapes[shapeA[i]], xfA[i], shapes[shapeB[i]], xfB[i]).
  * xf = (p.x, p.y, sin, cos).  Shape A must be the primary type (polygon/edge before circle, edge before polygon). */

@@ -1,0 +1,123 @@
+"""Spatial sharding: x-strips, ghost bodies, per-iteration halo exchange through peer mailboxes
+inside the persistent solver kernel.
+
+CPU: the partition logic.  GPU: a pile cut into two shards (two devices when the box has them, else two worlds
+sharing one device) must evolve exactly like the oracle stepping the WHOLE world with its island contacts in the
+merged shard order (own constraints of every shard, then cross constraints of every shard): body state, contact
+set and events bit-exact.  That proves the halo exchange implements one consistent sequential Gauss-Seidel."""
+import threading
+
+import numpy as np
+import pytest
+
+import b2cuda_types as T
+import b2shard
+import parity
+import ref
+import scenes
+
+
+def test_split_scene_partition():
+    scene = scenes.pile(40, 6)
+    arrays = scene.arrays()
+    plans, bounds = b2shard.split_scene(arrays, 3, margin=1.5)
+    bodies = arrays[0]
+    dynamic = np.where(bodies["type"] == T.DYNAMIC_BODY)[0]
+    owned = [set(p.body_ids[:len(p.body_ids) - len(p.ghost_local)]) for p in plans]
+    # every dynamic body is owned by exactly one shard, statics by all
+    for b in dynamic:
+        assert sum(b in o for o in owned) == 1
+    for b in np.where(bodies["type"] != T.DYNAMIC_BODY)[0]:
+        assert all(b in o for o in owned)
+    # ghosts of shard r are the exports of shard r+1, in the same order
+    for r in range(2):
+        g = plans[r].body_ids[plans[r].ghost_local]
+        e = plans[r + 1].body_ids[plans[r + 1].export_local]
+        assert len(g) > 0 and (g == e).all()
+        assert (bodies["px"][g] < bounds[r + 1] + 1.5).all()
+    assert len(plans[0].export_local) == 0 and len(plans[2].ghost_local) == 0
+    # fixtures follow their bodies and stay sorted by body
+    for p in plans:
+        f = p.arrays[2]
+        assert (np.diff(f["body"]) >= 0).all()
+        assert (p.arrays[0]["px"][f["body"]] == bodies["px"][arrays[2]["body"][p.fixture_ids]]).all()
+
+
+def _shard_worlds(gpu, scene, rank_count, margin):
+    arrays = scene.arrays()
+    plans, _ = b2shard.split_scene(arrays, rank_count, margin=margin)
+    ndev = gpu.device_count()
+    worlds, refs = [], []
+    for p in plans:
+        r = ref.RefWorld(arrays=p.arrays, gravity=scene.gravity, world_flags=scene.world_flags)
+        bodies, shapes, proxies, contacts = parity.ref_state(r)
+        bodies["flags"][p.ghost_local] |= T.BODY_GHOST
+        dev = p.rank % ndev
+        w = gpu.World(gravity=scene.gravity, flags=scene.world_flags, device=dev, body_capacity=len(bodies),
+                      proxy_capacity=len(proxies), shape_capacity=len(shapes), contact_capacity=16 * len(proxies))
+        w.load_state(bodies, shapes, proxies, contacts, inv_dt0=0.0)
+        worlds.append(w)
+        refs.append(r)
+    fraction = 1.0 if ndev >= rank_count else 0.9 / rank_count
+    b2shard.connect(worlds, plans, grid_fraction=fraction)
+    return worlds, plans
+
+
+def _step_all(worlds):
+    infos = [None] * len(worlds)
+    errors = []
+
+    def run(i):
+        try:
+            infos[i] = worlds[i].step()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(worlds))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    assert all(i is not None for i in infos), "a shard did not finish its step (halo exchange dead-locked?)"
+    return infos
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rank_count", [2, 3])
+def test_sharded_pile_matches_whole_world_oracle(gpu, rank_count):
+    scene = scenes.pile(36, 8)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    whole = ref.RefWorld(scene)
+    worlds, plans = _shard_worlds(gpu, scene, rank_count, margin=2.5)
+    cross_total = 0
+    for step in range(150):
+        _step_all(worlds)
+        own_keys, cross_keys = [], []
+        for w, p in zip(worlds, plans):
+            keys, colour = w.solver_order()
+            gk = b2shard.global_keys(p, keys)
+            is_cross = ((colour >= 16) & (colour < 32)) | (colour == 33)
+            own_keys.append(gk[~is_cross])
+            cross_keys.append(gk[is_cross])
+        order = np.concatenate(own_keys + cross_keys)
+        cross_total += sum(len(k) for k in cross_keys)
+        assert whole.step_ordered(order) == 0, step
+        wb = whole.bodies()
+        wc = T.contact_keys(whole.contacts())
+        seen = []
+        for w, p in zip(worlds, plans):
+            try:
+                parity.compare_bodies(w.get_bodies(), _with_ghost(wb[p.body_ids], p))
+            except AssertionError as e:
+                raise AssertionError("step %d shard %d: %s" % (step, p.rank, e))
+            seen.append(b2shard.global_keys(p, T.contact_keys(w.get_contacts())))
+        seen = np.sort(np.concatenate(seen))
+        assert len(seen) == len(wc) and (seen == wc).all(), "step %d: union of shard contact sets != whole world" % step
+    assert cross_total > 0, "the test never exercised a cross-shard contact"
+
+
+def _with_ghost(bodies, plan):
+    b = bodies.copy()
+    b["flags"][plan.ghost_local] |= T.BODY_GHOST
+    return b
