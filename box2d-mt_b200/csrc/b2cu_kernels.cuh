@@ -1340,7 +1340,9 @@ __global__ void GhostSendKernel(DeviceArrays d, ShardState sh)
 	B2CU_GRID_STRIDE(k, sh.exportCount)
 	{
 		int b = sh.exportIds[k];
-		float4* out = sh.lowerFromUpper + (size_t)k * B2CU_GHOST_ROWS;
+		// the sync rows live behind the per-iteration exchange rows of the mailbox: the first push of the solver may
+		// land before the receiver has read the sync rows
+		float4* out = sh.lowerFromUpper + (size_t)sh.exportCount + (size_t)k * B2CU_GHOST_ROWS;
 		out[0] = d.xf[b];
 		out[1] = d.pos[b];
 		out[2] = d.pos0[b];
@@ -1366,7 +1368,7 @@ __global__ void GhostApplyKernel(DeviceArrays d, ShardState sh)
 	B2CU_GRID_STRIDE(k, sh.ghostCount)
 	{
 		int b = sh.ghostIds[k];
-		const float4* in = sh.fromUpper + (size_t)k * B2CU_GHOST_ROWS;
+		const float4* in = sh.fromUpper + (size_t)sh.ghostCount + (size_t)k * B2CU_GHOST_ROWS;
 		d.xf[b] = __ldcv(&in[0]);
 		d.pos[b] = __ldcv(&in[1]);
 		d.pos0[b] = __ldcv(&in[2]);

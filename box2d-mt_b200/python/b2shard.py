@@ -43,7 +43,9 @@ def split_scene(arrays, rank_count, margin=2.0, bounds=None):
         else:
             ghosts = np.zeros(0, dtype=np.int64)
         exports = np.where(dynamic & (owner == r) & (xs < bounds[r] + margin))[0] if r > 0 else np.zeros(0, np.int64)
-        body_ids = np.concatenate([own, ghosts])
+        # local ids keep the global relative order, so that the fixture A / fixture B roles of a contact (lower proxy id
+        # first, b2ContactManager::AddPair) are the same in the shard and in the whole world
+        body_ids = np.sort(np.concatenate([own, ghosts]))
         local_of = np.full(len(bodies), -1)
         local_of[body_ids] = np.arange(len(body_ids))
         b = bodies[body_ids].copy()
