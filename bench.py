@@ -16,8 +16,9 @@ and stepped with b2World::Step(dt, 8, 3, b2CudaStepExecutor&).
 Reference arm (--impl reference): the reference's own CPU implementation alone, on a narrower pile of the same
 depth (a bounded sample of the workload), settled by the reference itself.
 
-N > 1 (torchrun): every rank steps its own strip of the pile in its own container (weak scaling, no data-path
-collective yet: cross-shard halo exchange is the next step); times are max-reduced over NCCL.
+N > 1 (torchrun): one pile of N x bodies cut into x-strips, one per rank, with ghost bodies and per-iteration halo
+exchange through NVLink peer mailboxes inside the persistent solver kernel (weak scaling; no NCCL on the data path;
+times are max-reduced over NCCL).
 """
 import argparse
 import json
@@ -165,22 +166,40 @@ def run_product_arm(args, rank, local_rank, world_size):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
 
     columns = max(16, args.bodies // ROWS)
-    scene = scenes.pile(columns, ROWS, seed=rank)
-    t0 = time.perf_counter()
-    world = b2host.HostWorld(scene, device=local_rank, download_bodies=False, events=False)
-    n_bodies = world.counts()[0]
-    build_s = time.perf_counter() - t0
-
-    # settle (setup, untimed)
-    for _ in range(args.settle):
-        world.step(DT, VEL_ITERS, POS_ITERS)
-
     dist = None
     if world_size > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
+
+    t0 = time.perf_counter()
+    if world_size == 1:
+        scene = scenes.pile(columns, ROWS, seed=0)
+        world = b2host.HostWorld(scene, device=local_rank, download_bodies=False, events=False)
+        n_bodies = world.counts()[0]
+    else:
+        # one pile of world_size x bodies, cut into x-strips: every rank holds its strip, the static container and
+        # ghost copies of the next strip's boundary bodies; the solver kernels exchange halo state through NVLink
+        # peer mailboxes (b2cuShard*)
+        import b2shard
+        scene = scenes.pile(columns * world_size, ROWS, seed=0)
+        plans, _ = b2shard.split_scene(scene.arrays(), world_size, margin=args.margin, only_rank=rank)
+        plan = plans[rank]
+        world = b2host.HostWorld(arrays=plan.arrays, gravity=scene.gravity, world_flags=scene.world_flags,
+                                 device=local_rank, download_bodies=False, events=False)
+        world.shard_configure(rank, world_size, plan.ghost_local, plan.export_local)
+        links = [None] * world_size
+        dist.all_gather_object(links, world.shard_link().tobytes())
+        links = [np.frombuffer(b, dtype=T.SHARD_LINK)[0] for b in links]
+        world.shard_connect(links[rank - 1] if rank > 0 else None, links[rank + 1] if rank + 1 < world_size else None)
+        n_bodies = world.counts()[0] - len(plan.ghost_local)
+        dist.barrier()
+    build_s = time.perf_counter() - t0
+
+    # settle (setup, untimed)
+    for _ in range(args.settle):
+        world.step(DT, VEL_ITERS, POS_ITERS)
 
     def barrier():
         if dist is not None:
@@ -192,6 +211,14 @@ def run_product_arm(args, rank, local_rank, world_size):
         import torch
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
     # ---- value: world resident on the device ----
@@ -227,10 +254,13 @@ def run_product_arm(args, rank, local_rank, world_size):
     e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
     barrier()
     h2d = block * T.BODY.itemsize
-    d2h = n_bodies * T.BODY.itemsize + 8 * int(infos[-1]["beginCount"] + infos[-1]["endCount"])
+    d2h = world.counts()[0] * T.BODY.itemsize + 8 * int(infos[-1]["beginCount"] + infos[-1]["endCount"])
     world.set_options(False, False)
+    total_bodies = int(sum_over_ranks(n_bodies))
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
         return
 
     last = infos[-1]
@@ -273,7 +303,6 @@ def run_product_arm(args, rank, local_rank, world_size):
         except Exception as e:  # the oracle is only the checker: its absence must not hide the product numbers
             cpu = {"value": None, "unit": "body-steps/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
 
-    total_bodies = n_bodies * world_size
     print(json.dumps({
         "metric": "body-steps/sec", "value": total_bodies * args.steps / elapsed, "unit": "body-steps/s",
         "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -284,8 +313,9 @@ def run_product_arm(args, rank, local_rank, world_size):
                    "contacts": n_contacts, "constraints": n_constraints, "colours": colours,
                    "l2": "working set per step (%.1f GB algorithmic) exceeds the 126 MB L2; no flush needed"
                          % (step_bytes / 1e9),
-                   "sharding": "one strip of the pile per GPU, own container, no halo exchange yet" if world_size > 1
-                   else "single GPU"},
+                   "sharding": ("x-strips of one %d-body pile, ghost bodies within %.1f m of the strip boundary, halo "
+                                "exchange through NVLink peer mailboxes inside the solver kernel (2 per iteration)"
+                                % (total_bodies, args.margin)) if world_size > 1 else "single GPU"},
         "device_ms_per_step": device_ms / args.steps,
         "phases_ms": phases,
         "step_roofline_frac": (step_bytes / (ms_per_step * 1e-3) / 1e9) / peak,
@@ -304,6 +334,8 @@ def run_product_arm(args, rank, local_rank, world_size):
                                                                ("contactCount", "constraintCount", "colourCount",
                                                                 "overflowCount", "moveCount", "kernelLaunches")},
     }))
+    if dist is not None:
+        dist.barrier()
 
 
 def main():
@@ -318,6 +350,7 @@ def main():
     ap.add_argument("--ref-bodies", type=int, default=50000, help="bodies of the --impl reference sample")
     ap.add_argument("--ref-settle", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--margin", type=float, default=3.0, help="ghost margin of a strip boundary (m)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -13,6 +13,8 @@
 
 struct b2cuWorld;
 struct b2cuStepInfo;
+struct b2cuShardLink;
+class b2Body;
 
 struct b2CudaStepOptions
 {
@@ -54,10 +56,21 @@ public:
 	/// the C-ABI handle of a world this executor has stepped (nullptr before its first step): for callers that
 	/// want the bulk / diagnostic entry points of include/b2cuda.h
 	b2cuWorld* GetDeviceWorld(b2World* world) const;
+	// ---- spatial sharding of one large scene over several GPUs (include/b2cuda.h, b2cuShard*) ----
+	/// This world is strip `rank` of `rankCount`.  `ghosts` are its bodies that are copies of bodies owned by strip
+	/// rank+1, `exports` its own bodies that strip rank-1 holds as ghosts (same order on both sides).  Uploads the
+	/// world to the device if it is not there yet.  Returns a b2cuStatus.
+	int32 ConfigureShard(b2World& world, int32 rank, int32 rankCount, b2Body* const* ghosts, int32 ghostCount,
+	                     b2Body* const* exports, int32 exportCount, float32 gridFraction = 1.0f);
+	int32 GetShardLink(b2World& world, b2cuShardLink* link);
+	int32 ConnectShard(b2World& world, const b2cuShardLink* lower, const b2cuShardLink* upper);
+
 	/// release the device copy of a world (called by ~b2World)
 	void DetachWorld(b2World* world);
 
 private:
+	b2cuWorld* EnsureDevice(b2World& world);
+
 	b2CudaStepOptions m_options;
 	b2TaskGroup m_group;
 	int32 m_status;

@@ -108,6 +108,26 @@ B2H_API void b2h_apply_force_range(void* p, int32 first, int32 count, float fx, 
 	}
 }
 
+B2H_API int b2h_shard_configure(void* p, int32 rank, int32 rankCount, const int32* ghosts, int32 ghostCount,
+                                const int32* exports, int32 exportCount, float gridFraction)
+{
+	Host* h = static_cast<Host*>(p);
+	std::vector<b2Body*> g(ghostCount), e(exportCount);
+	for (int32 i = 0; i < ghostCount; ++i) g[i] = h->bodies[ghosts[i]];
+	for (int32 i = 0; i < exportCount; ++i) e[i] = h->bodies[exports[i]];
+	return h->executor->ConfigureShard(*h->world, rank, rankCount, g.data(), ghostCount, e.data(), exportCount, gridFraction);
+}
+B2H_API int b2h_shard_link(void* p, b2cuShardLink* link)
+{
+	Host* h = static_cast<Host*>(p);
+	return h->executor->GetShardLink(*h->world, link);
+}
+B2H_API int b2h_shard_connect(void* p, const b2cuShardLink* lower, const b2cuShardLink* upper)
+{
+	Host* h = static_cast<Host*>(p);
+	return h->executor->ConnectShard(*h->world, lower, upper);
+}
+
 B2H_API void b2h_destroy(void* p)
 {
 	Host* h = static_cast<Host*>(p);

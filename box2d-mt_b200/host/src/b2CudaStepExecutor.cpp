@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <vector>
 
 namespace
 {
@@ -69,6 +70,72 @@ void b2CudaStepExecutor::SubmitTask(b2TaskGroup* taskGroup, b2Task* task)
 
 const b2cuStepInfo& b2CudaStepExecutor::GetLastStepInfo() const { return static_cast<Impl*>(m_impl)->info; }
 
+b2cuWorld* b2CudaStepExecutor::EnsureDevice(b2World& world)
+{
+	Impl* impl = static_cast<Impl*>(m_impl);
+	auto it = impl->worlds.find(&world);
+	if (it != impl->worlds.end()) return it->second;
+	b2cuWorld* device = nullptr;
+	b2cuWorldDef def;
+	memset(&def, 0, sizeof(def));
+	def.device = m_options.device;
+	def.gravity[0] = world.m_gravity.x;
+	def.gravity[1] = world.m_gravity.y;
+	def.bodyCapacity = (int32)world.m_states.size();
+	def.proxyCapacity = (int32)world.m_proxies.size();
+	def.shapeCapacity = (int32)world.m_shapes.size();
+	def.contactCapacity = 8 * (int32)world.m_proxies.size();
+	int rc = b2cuCreateWorld(&def, &device);
+	if (rc != B2CU_OK)
+	{
+		m_status = rc;
+		snprintf(m_error, sizeof(m_error), "b2cuCreateWorld failed with status %d (no CUDA device?)", rc);
+		world.m_lastStatus = rc;
+		return nullptr;
+	}
+	impl->worlds[&world] = device;
+	world.m_device = device;
+	world.m_owner = this;
+	if (world.m_bodiesUploaded > 0) world.m_fullUpload = true;
+	return device;
+}
+
+int32 b2CudaStepExecutor::ConfigureShard(b2World& world, int32 rank, int32 rankCount, b2Body* const* ghosts,
+                                         int32 ghostCount, b2Body* const* exports, int32 exportCount, float32 gridFraction)
+{
+	std::vector<int32> g(ghostCount), e(exportCount);
+	for (int32 i = 0; i < ghostCount; ++i)
+	{
+		g[i] = ghosts[i]->GetIndex();
+		world.m_states[g[i]].flags |= B2CU_BODY_GHOST;
+		world.MarkBodyDirty(g[i]);
+	}
+	for (int32 i = 0; i < exportCount; ++i) e[i] = exports[i]->GetIndex();
+	b2cuWorld* device = EnsureDevice(world);
+	if (device == nullptr) return m_status;
+	int rc = world.UploadDirty(device);
+	if (rc == B2CU_OK)
+		rc = b2cuShardConfigure(device, rank, rankCount, ghostCount, g.data(), exportCount, e.data(), gridFraction);
+	if (rc != B2CU_OK) snprintf(m_error, sizeof(m_error), "%s", b2cuGetLastError(device));
+	return m_status = rc;
+}
+
+int32 b2CudaStepExecutor::GetShardLink(b2World& world, b2cuShardLink* link)
+{
+	b2cuWorld* device = GetDeviceWorld(&world);
+	if (device == nullptr) return B2CU_ERR_ARGUMENT;
+	return b2cuShardGetLink(device, link);
+}
+
+int32 b2CudaStepExecutor::ConnectShard(b2World& world, const b2cuShardLink* lower, const b2cuShardLink* upper)
+{
+	b2cuWorld* device = GetDeviceWorld(&world);
+	if (device == nullptr) return B2CU_ERR_ARGUMENT;
+	int rc = b2cuShardConnect(device, lower, upper);
+	if (rc != B2CU_OK) snprintf(m_error, sizeof(m_error), "%s", b2cuGetLastError(device));
+	return rc;
+}
+
 bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 velocityIterations, int32 positionIterations)
 {
 	Impl* impl = static_cast<Impl*>(m_impl);
@@ -88,36 +155,8 @@ bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 veloc
 		world.m_fullUpload = true;
 	}
 
-	b2cuWorld* device = nullptr;
-	auto it = impl->worlds.find(&world);
-	if (it == impl->worlds.end())
-	{
-		b2cuWorldDef def;
-		memset(&def, 0, sizeof(def));
-		def.device = m_options.device;
-		def.gravity[0] = world.m_gravity.x;
-		def.gravity[1] = world.m_gravity.y;
-		def.bodyCapacity = (int32)world.m_states.size();
-		def.proxyCapacity = (int32)world.m_proxies.size();
-		def.shapeCapacity = (int32)world.m_shapes.size();
-		def.contactCapacity = 8 * (int32)world.m_proxies.size();
-		int rc = b2cuCreateWorld(&def, &device);
-		if (rc != B2CU_OK)
-		{
-			m_status = rc;
-			snprintf(m_error, sizeof(m_error), "b2cuCreateWorld failed with status %d (no CUDA device?)", rc);
-			world.m_lastStatus = rc;
-			return false;
-		}
-		impl->worlds[&world] = device;
-		world.m_device = device;
-		world.m_owner = this;
-		if (world.m_bodiesUploaded > 0) world.m_fullUpload = true;
-	}
-	else
-	{
-		device = it->second;
-	}
+	b2cuWorld* device = EnsureDevice(world);
+	if (device == nullptr) return false;
 
 	int rc = world.UploadDirty(device);
 	if (rc == B2CU_OK) rc = b2cuStep(device, timeStep, velocityIterations, positionIterations, &impl->info);

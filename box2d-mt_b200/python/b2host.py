@@ -34,6 +34,9 @@ def load():
     lib.b2h_create.restype = vp
     lib.b2h_create.argtypes = [f32, f32, u32, i32, i32, i32]
     lib.b2h_destroy.argtypes = [vp]
+    lib.b2h_shard_configure.argtypes = [vp, i32, i32, vp, i32, vp, i32, f32]
+    lib.b2h_shard_link.argtypes = [vp, vp]
+    lib.b2h_shard_connect.argtypes = [vp, vp, vp]
     lib.b2h_set_options.argtypes = [vp, i32, i32]
     lib.b2h_apply_force_range.argtypes = [vp, i32, i32, f32, f32]
     lib.b2h_build.argtypes = [vp, i32, vp, i32, vp, i32, vp]
@@ -172,6 +175,28 @@ class HostWorld:
 
     def apply_force_range(self, first, count, fx, fy):
         self.lib.b2h_apply_force_range(self.h, first, count, fx, fy)
+
+    # ---- sharding (b2CudaStepExecutor::ConfigureShard / GetShardLink / ConnectShard) ----
+    def shard_configure(self, rank, rank_count, ghost_bodies, export_bodies, grid_fraction=1.0):
+        g = np.ascontiguousarray(ghost_bodies, np.int32)
+        e = np.ascontiguousarray(export_bodies, np.int32)
+        rc = self.lib.b2h_shard_configure(self.h, rank, rank_count, _ptr(g), len(g), _ptr(e), len(e), grid_fraction)
+        if rc != 0:
+            raise RuntimeError("ConfigureShard failed (%d): %s" % (rc, self.lib.b2h_last_error(self.h).decode()))
+
+    def shard_link(self):
+        link = np.zeros((), T.SHARD_LINK)
+        rc = self.lib.b2h_shard_link(self.h, _ptr(link))
+        if rc != 0:
+            raise RuntimeError("GetShardLink failed (%d)" % rc)
+        return link
+
+    def shard_connect(self, lower=None, upper=None):
+        lo = None if lower is None else np.array(lower, dtype=T.SHARD_LINK, copy=True)
+        up = None if upper is None else np.array(upper, dtype=T.SHARD_LINK, copy=True)
+        rc = self.lib.b2h_shard_connect(self.h, None if lo is None else _ptr(lo), None if up is None else _ptr(up))
+        if rc != 0:
+            raise RuntimeError("ConnectShard failed (%d): %s" % (rc, self.lib.b2h_last_error(self.h).decode()))
 
     def destroy_body(self, body):
         self.lib.b2h_destroy_body(self.h, body)

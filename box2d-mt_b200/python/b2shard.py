@@ -26,7 +26,7 @@ def strip_bounds(xs, dynamic, rank_count):
     return np.array([-np.inf] + cuts + [np.inf])
 
 
-def split_scene(arrays, rank_count, margin=2.0, bounds=None):
+def split_scene(arrays, rank_count, margin=2.0, bounds=None, only_rank=None):
     bodies, shapes, fixtures = arrays
     dynamic = bodies["type"] == T.DYNAMIC_BODY
     xs = bodies["px"].astype(np.float64)
@@ -37,6 +37,9 @@ def split_scene(arrays, rank_count, margin=2.0, bounds=None):
     fixture_body = fixtures["body"]
     plans = []
     for r in range(rank_count):
+        if only_rank is not None and r != only_rank:
+            plans.append(None)
+            continue
         own = np.where(~dynamic | (owner == r))[0]
         if r + 1 < rank_count:
             ghosts = np.where(dynamic & (owner == r + 1) & (xs < bounds[r + 1] + margin))[0]
