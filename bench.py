@@ -261,6 +261,7 @@ def run_product_arm(args, rank, local_rank, world_size):
     if rank != 0:
         if dist is not None:
             dist.barrier()
+            dist.destroy_process_group()
         return
 
     last = infos[-1]
@@ -336,6 +337,7 @@ def run_product_arm(args, rank, local_rank, world_size):
     }))
     if dist is not None:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
