@@ -34,7 +34,8 @@ def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b2cuda.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", OUT]
+    extra = os.environ.get("B2CU_NVCC_FLAGS", "").split()
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", OUT]
     subprocess.run(cmd, check=True)
     return OUT
 

@@ -1248,7 +1248,15 @@ __device__ __forceinline__ void HaloExchange(cooperative_groups::grid_group& gri
 	grid.sync();
 }
 
-__global__ void __launch_bounds__(256) SolverPersistentKernel(DeviceArrays d, SolverPlan plan)
+// velocity half: warm start, velocity iterations, impulse store, position integration.  Compiled for 6 CTAs per
+// SM (<= 40 registers) so that one pass of the grid covers a whole colour of a million-body pile.
+#ifndef B2CU_VEL_BLOCKS
+#define B2CU_VEL_BLOCKS 6
+#endif
+#ifndef B2CU_POS_BLOCKS
+#define B2CU_POS_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, B2CU_VEL_BLOCKS) SolverVelocityPersistentKernel(DeviceArrays d, SolverPlan plan)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1291,7 +1299,15 @@ __global__ void __launch_bounds__(256) SolverPersistentKernel(DeviceArrays d, So
 	// b2ContactSolver::StoreImpulses, then b2Island::Solve position integration (independent of each other)
 	for (int k = tid; k < plan.constraintCount; k += stride) StoreImpulseOne(d, k);
 	for (int b = tid; b < plan.bodyCount; b += stride) IntegratePositionOne(d, b, plan.h);
-	grid.sync();
+}
+
+// position half: position iterations with the per-island early exit
+__global__ void __launch_bounds__(256, B2CU_POS_BLOCKS) SolverPositionPersistentKernel(DeviceArrays d, SolverPlan plan)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int stride = gridDim.x * blockDim.x;
+	unsigned seq = plan.shard.seq;
 
 	for (int it = 0; it < plan.positionIterations; ++it)
 	{

@@ -166,6 +166,7 @@ struct b2cuWorld
 	bool persistentSolver; // solve all colour phases in one cooperative kernel
 	int persistentGrid;
 	int persistentGridMax;
+	int persistentGridPosition, persistentGridPositionMax;
 
 	// spatial sharding (b2cuShardConfigure / Connect)
 	int shardRank, shardCount;

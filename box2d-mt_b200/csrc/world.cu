@@ -558,11 +558,15 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		// persistent cooperative solver: as many CTAs as can be co-resident
 		int coop = 0, perSm = 0;
 		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, def->device);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, SolverPersistentKernel, 256, 0);
+		int perSmPos = 0;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, SolverVelocityPersistentKernel, 256, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPos, SolverPositionPersistentKernel, 256, 0);
 		const char* pe = getenv("B2CU_PERSISTENT");
-		w->persistentSolver = coop != 0 && perSm > 0 && !(pe && atoi(pe) == 0);
+		w->persistentSolver = coop != 0 && perSm > 0 && perSmPos > 0 && !(pe && atoi(pe) == 0);
 		w->persistentGrid = g_smCount * perSm;
 		w->persistentGridMax = w->persistentGrid;
+		w->persistentGridPosition = g_smCount * perSmPos;
+		w->persistentGridPositionMax = w->persistentGridPosition;
 		w->shardCount = 1;
 		w->shardSeq = 1;
 	}
@@ -1121,15 +1125,21 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			plan.warmStarting = warmStarting ? 1 : 0;
 			plan.h = dt;
 			plan.shard = MakeShardState(w);
-			if (w->shardCount > 1)
-			{
-				w->shardSeq += 2u * (unsigned)((warmStarting ? 1 : 0) + velocityIterations + positionIterations);
-			}
 			void* args[2] = {(void*)&d, (void*)&plan};
-			CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverPersistentKernel, dim3(w->persistentGrid), dim3(256),
-			                                        args, 0, w->stream));
+			CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverVelocityPersistentKernel,
+			                                        dim3(w->persistentGrid), dim3(256), args, 0, w->stream));
 			++w->launches;
-			TraceMark(w, "SolverPersistentKernel");
+			TraceMark(w, "SolverVelocityPersistentKernel");
+			if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)((warmStarting ? 1 : 0) + velocityIterations);
+			plan.shard.seq = w->shardSeq;
+			if (positionIterations > 0)
+			{
+				CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverPositionPersistentKernel,
+				                                        dim3(w->persistentGridPosition), dim3(256), args, 0, w->stream));
+				++w->launches;
+				TraceMark(w, "SolverPositionPersistentKernel");
+				if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)positionIterations;
+			}
 			cudaEventRecord(w->ev[6], w->stream);
 		}
 		else
@@ -1435,12 +1445,13 @@ int b2cuShardConfigure(b2cuWorld* w, int32_t rank, int32_t rankCount, int32_t gh
 	if (gridFraction > 0.0f && gridFraction < 1.0f)
 	{
 		// several shards on one device (tests): their cooperative kernels must be co-resident
-		int blocks = (int)(w->persistentGridMax * gridFraction);
-		w->persistentGrid = std::max(1, blocks);
+		w->persistentGrid = std::max(1, (int)(w->persistentGridMax * gridFraction));
+		w->persistentGridPosition = std::max(1, (int)(w->persistentGridPositionMax * gridFraction));
 	}
 	else
 	{
 		w->persistentGrid = w->persistentGridMax;
+		w->persistentGridPosition = w->persistentGridPositionMax;
 	}
 	return B2CU_OK;
 }
