@@ -1251,7 +1251,7 @@ __device__ __forceinline__ void HaloExchange(cooperative_groups::grid_group& gri
 // velocity half: warm start, velocity iterations, impulse store, position integration.  Compiled for 6 CTAs per
 // SM (<= 40 registers) so that one pass of the grid covers a whole colour of a million-body pile.
 #ifndef B2CU_VEL_BLOCKS
-#define B2CU_VEL_BLOCKS 6
+#define B2CU_VEL_BLOCKS 4
 #endif
 #ifndef B2CU_POS_BLOCKS
 #define B2CU_POS_BLOCKS 3

@@ -563,6 +563,12 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPos, SolverPositionPersistentKernel, 256, 0);
 		const char* pe = getenv("B2CU_PERSISTENT");
 		w->persistentSolver = coop != 0 && perSm > 0 && perSmPos > 0 && !(pe && atoi(pe) == 0);
+		const char* pb = getenv("B2CU_PERSISTENT_BLOCKS");
+		if (pb && atoi(pb) > 0)
+		{
+			perSm = std::min(perSm, atoi(pb));
+			perSmPos = std::min(perSmPos, atoi(pb));
+		}
 		w->persistentGrid = g_smCount * perSm;
 		w->persistentGridMax = w->persistentGrid;
 		w->persistentGridPosition = g_smCount * perSmPos;
