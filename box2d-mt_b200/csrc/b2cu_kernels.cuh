@@ -1250,13 +1250,16 @@ __device__ __forceinline__ void HaloExchange(cooperative_groups::grid_group& gri
 
 // velocity half: warm start, velocity iterations, impulse store, position integration.  Compiled for 6 CTAs per
 // SM (<= 40 registers) so that one pass of the grid covers a whole colour of a million-body pile.
+#ifndef B2CU_SOLVER_THREADS
+#define B2CU_SOLVER_THREADS 256
+#endif
 #ifndef B2CU_VEL_BLOCKS
 #define B2CU_VEL_BLOCKS 4
 #endif
 #ifndef B2CU_POS_BLOCKS
 #define B2CU_POS_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(256, B2CU_VEL_BLOCKS) SolverVelocityPersistentKernel(DeviceArrays d, SolverPlan plan)
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVelocityPersistentKernel(DeviceArrays d, SolverPlan plan)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1302,7 +1305,7 @@ __global__ void __launch_bounds__(256, B2CU_VEL_BLOCKS) SolverVelocityPersistent
 }
 
 // position half: position iterations with the per-island early exit
-__global__ void __launch_bounds__(256, B2CU_POS_BLOCKS) SolverPositionPersistentKernel(DeviceArrays d, SolverPlan plan)
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPositionPersistentKernel(DeviceArrays d, SolverPlan plan)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;

@@ -559,8 +559,8 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		int coop = 0, perSm = 0;
 		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, def->device);
 		int perSmPos = 0;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, SolverVelocityPersistentKernel, 256, 0);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPos, SolverPositionPersistentKernel, 256, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, SolverVelocityPersistentKernel, B2CU_SOLVER_THREADS, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPos, SolverPositionPersistentKernel, B2CU_SOLVER_THREADS, 0);
 		const char* pe = getenv("B2CU_PERSISTENT");
 		w->persistentSolver = coop != 0 && perSm > 0 && perSmPos > 0 && !(pe && atoi(pe) == 0);
 		const char* pb = getenv("B2CU_PERSISTENT_BLOCKS");
@@ -1133,7 +1133,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			plan.shard = MakeShardState(w);
 			void* args[2] = {(void*)&d, (void*)&plan};
 			CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverVelocityPersistentKernel,
-			                                        dim3(w->persistentGrid), dim3(256), args, 0, w->stream));
+			                                        dim3(w->persistentGrid), dim3(B2CU_SOLVER_THREADS), args, 0, w->stream));
 			++w->launches;
 			TraceMark(w, "SolverVelocityPersistentKernel");
 			if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)((warmStarting ? 1 : 0) + velocityIterations);
@@ -1141,7 +1141,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			if (positionIterations > 0)
 			{
 				CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverPositionPersistentKernel,
-				                                        dim3(w->persistentGridPosition), dim3(256), args, 0, w->stream));
+				                                        dim3(w->persistentGridPosition), dim3(B2CU_SOLVER_THREADS), args, 0, w->stream));
 				++w->launches;
 				TraceMark(w, "SolverPositionPersistentKernel");
 				if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)positionIterations;
