@@ -735,12 +735,30 @@ __global__ void __launch_bounds__(256) InitConstraintsKernel(DeviceArrays d, flo
 }
 
 // b2ContactSolver::WarmStart (b2ContactSolver.cpp:253-291), constraints [begin, begin+count) of one colour
-__device__ __forceinline__ void WarmStartOne(const DeviceArrays& d, int k)
+// the per-constraint rows every velocity pass needs; loaded ahead of the colour barrier by the persistent solver
+struct VelPre
 {
-	int4 sb = __ldcs(&d.sBody[k]);
-	float4 ms = __ldcs(&d.sMass[k]);
-	float4 nf = __ldcs(&d.sNormal[k]);
-	float4 imp = __ldcs(&d.sImp[k]);
+	int4 sb;
+	float4 ms, nf, imp, p0a, p0b;
+};
+__device__ __forceinline__ VelPre LoadVelPre(const DeviceArrays& d, int k)
+{
+	VelPre p;
+	p.sb = __ldcs(&d.sBody[k]);
+	p.ms = __ldcs(&d.sMass[k]);
+	p.nf = __ldcs(&d.sNormal[k]);
+	p.imp = __ldcs(&d.sImp[k]);
+	p.p0a = __ldcs(&d.sP0a[k]);
+	p.p0b = __ldcs(&d.sP0b[k]);
+	return p;
+}
+
+__device__ __forceinline__ void WarmStartPre(const DeviceArrays& d, int k, const VelPre& pre)
+{
+	int4 sb = pre.sb;
+	float4 ms = pre.ms;
+	float4 nf = pre.nf;
+	float4 imp = pre.imp;
 	int pointCount = sb.w & 0xFF;
 	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
 
@@ -752,7 +770,7 @@ __device__ __forceinline__ void WarmStartOne(const DeviceArrays& d, int k)
 
 	for (int j = 0; j < pointCount; ++j)
 	{
-		float4 r = j == 0 ? __ldcs(&d.sP0a[k]) : __ldcs(&d.sP1a[k]);
+		float4 r = j == 0 ? pre.p0a : __ldcs(&d.sP1a[k]);
 		float ni = j == 0 ? imp.x : imp.z;
 		float ti = j == 0 ? imp.y : imp.w;
 		Vec2 rA = V(r.x, r.y), rB = V(r.z, r.w);
@@ -766,19 +784,21 @@ __device__ __forceinline__ void WarmStartOne(const DeviceArrays& d, int k)
 	if (mB != 0.0f || iB != 0.0f) d.vel[sb.y] = make_float4(vB.x, vB.y, wB, vB4.w);
 }
 
+__device__ __forceinline__ void WarmStartOne(const DeviceArrays& d, int k) { WarmStartPre(d, k, LoadVelPre(d, k)); }
+
 __global__ void __launch_bounds__(256) WarmStartKernel(DeviceArrays d, int begin, int count)
 {
 	B2CU_GRID_STRIDE(t, count) { WarmStartOne(d, begin + t); }
 }
 
 // b2ContactSolver::SolveVelocityConstraints (b2ContactSolver.cpp:293-603) for one constraint
-__device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k)
+__device__ __forceinline__ void SolveVelocityPre(const DeviceArrays& d, int k, const VelPre& pre)
 {
-	int4 sb = __ldcs(&d.sBody[k]);
-	float4 ms = __ldcs(&d.sMass[k]);
-	float4 nf = __ldcs(&d.sNormal[k]);
-	float4 imp = __ldcs(&d.sImp[k]);
-	float4 p0a = __ldcs(&d.sP0a[k]), p0b = __ldcs(&d.sP0b[k]);
+	int4 sb = pre.sb;
+	float4 ms = pre.ms;
+	float4 nf = pre.nf;
+	float4 imp = pre.imp;
+	float4 p0a = pre.p0a, p0b = pre.p0b;
 	int pointCount = sb.w & 0xFF;
 	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
 
@@ -915,6 +935,8 @@ __device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k)
 	if (mB != 0.0f || iB != 0.0f) d.vel[sb.y] = make_float4(vB.x, vB.y, wB, vB4.w);
 }
 
+__device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k) { SolveVelocityPre(d, k, LoadVelPre(d, k)); }
+
 __global__ void __launch_bounds__(256) SolveVelocityKernel(DeviceArrays d, int begin, int count)
 {
 	B2CU_GRID_STRIDE(t, count) { SolveVelocityOne(d, begin + t); }
@@ -981,14 +1003,31 @@ __global__ void IntegratePositionsKernel(DeviceArrays d, int bodyCount, float h)
 // b2ContactSolver::SolvePositionConstraints (b2ContactSolver.cpp:676-752) for one constraint.
 // Returns the smallest separation seen; islands stop iterating once theirs is >= -3*linearSlop
 // (b2Island.cpp:318-335), which is tracked per island root in islandMinSep[iteration][root].
-__device__ __forceinline__ float SolvePositionOne(const DeviceArrays& d, int k)
+struct PosPre
 {
-	int4 sb = __ldcs(&d.sBody[k]);
-	float4 ms = __ldcs(&d.sMass[k]);
-	float4 loc = __ldcs(&d.sLocal[k]);
-	float4 lps = __ldcs(&d.sLocalP[k]);
-	float4 cen = __ldcs(&d.sCenters[k]);
-	float4 rad = __ldcs(&d.sRadius[k]);
+	int4 sb;
+	float4 ms, loc, lps, cen, rad;
+};
+__device__ __forceinline__ PosPre LoadPosPre(const DeviceArrays& d, int k)
+{
+	PosPre p;
+	p.sb = __ldcs(&d.sBody[k]);
+	p.ms = __ldcs(&d.sMass[k]);
+	p.loc = __ldcs(&d.sLocal[k]);
+	p.lps = __ldcs(&d.sLocalP[k]);
+	p.cen = __ldcs(&d.sCenters[k]);
+	p.rad = __ldcs(&d.sRadius[k]);
+	return p;
+}
+
+__device__ __forceinline__ float SolvePositionPre(const DeviceArrays& d, const PosPre& pre)
+{
+	int4 sb = pre.sb;
+	float4 ms = pre.ms;
+	float4 loc = pre.loc;
+	float4 lps = pre.lps;
+	float4 cen = pre.cen;
+	float4 rad = pre.rad;
 	int pointCount = sb.w >> 8;
 	int type = __float_as_int(rad.z);
 	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
@@ -1060,6 +1099,8 @@ __device__ __forceinline__ float SolvePositionOne(const DeviceArrays& d, int k)
 	if (mB != 0.0f || iB != 0.0f) d.pos[sb.y] = make_float4(cB.x, cB.y, aB, pB4.w);
 	return minSeparation;
 }
+
+__device__ __forceinline__ float SolvePositionOne(const DeviceArrays& d, int k) { return SolvePositionPre(d, LoadPosPre(d, k)); }
 
 __device__ __forceinline__ bool IslandDone(const DeviceArrays& d, int iteration, int root, int bodyCount)
 {
@@ -1248,8 +1289,6 @@ __device__ __forceinline__ void HaloExchange(cooperative_groups::grid_group& gri
 	grid.sync();
 }
 
-// velocity half: warm start, velocity iterations, impulse store, position integration.  Compiled for 6 CTAs per
-// SM (<= 40 registers) so that one pass of the grid covers a whole colour of a million-body pile.
 #ifndef B2CU_SOLVER_THREADS
 #define B2CU_SOLVER_THREADS 256
 #endif
@@ -1259,25 +1298,77 @@ __device__ __forceinline__ void HaloExchange(cooperative_groups::grid_group& gri
 #ifndef B2CU_POS_BLOCKS
 #define B2CU_POS_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVelocityPersistentKernel(DeviceArrays d, SolverPlan plan)
+
+// first parallel op at or after (pass, op) in the flattened (pass, op) sequence; returns false at the end
+__device__ __forceinline__ bool NextParallelOp(const SolverPlan& plan, int passEnd, int& pass, int& op)
+{
+	while (pass <= passEnd)
+	{
+		for (; op < plan.opCount; ++op)
+			if (plan.opType[op] == OP_PARALLEL) return true;
+		op = 0;
+		++pass;
+	}
+	return false;
+}
+
+// velocity half: warm start, velocity iterations, impulse store, position integration.
+// Software-pipelined across the colour barriers: the rows of a thread's first constraint of the NEXT colour are
+// loaded before the grid barrier (they do not depend on other threads; only the body velocities do), so the
+// DRAM latency of every phase hides behind the barrier.
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVelocityPersistentKernel(DeviceArrays d,
+                                                                                                   SolverPlan plan)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	unsigned seq = plan.shard.seq;
+	const int firstPass = plan.warmStarting ? 0 : 1;
+	const int lastPass = plan.velocityIterations;
+
+	VelPre pre;
+	bool havePre = false;
+	{
+		int np = firstPass, no = 0;
+		if (NextParallelOp(plan, lastPass, np, no) && tid < plan.opSize[no])
+		{
+			pre = LoadVelPre(d, plan.opStart[no] + tid);
+			havePre = true;
+		}
+	}
 
 	// pass 0 = warm start, passes 1..vIters = velocity iterations
-	for (int pass = plan.warmStarting ? 0 : 1; pass <= plan.velocityIterations; ++pass)
+	for (int pass = firstPass; pass <= lastPass; ++pass)
 	{
 		for (int op = 0; op < plan.opCount; ++op)
 		{
 			const int type = plan.opType[op], begin = plan.opStart[op], n = plan.opSize[op];
 			if (type == OP_PARALLEL)
 			{
-				if (pass == 0)
-					for (int t = tid; t < n; t += stride) WarmStartOne(d, begin + t);
-				else
-					for (int t = tid; t < n; t += stride) SolveVelocityOne(d, begin + t);
+				if (tid < n)
+				{
+					if (!havePre) pre = LoadVelPre(d, begin + tid);
+					if (pass == 0) WarmStartPre(d, begin + tid, pre);
+					else SolveVelocityPre(d, begin + tid, pre);
+				}
+				havePre = false;
+				for (int t = tid + stride; t < n; t += stride)
+				{
+					if (pass == 0) WarmStartOne(d, begin + t);
+					else SolveVelocityOne(d, begin + t);
+				}
+				// prefetch for the next colour
+				int np = pass, no = op + 1;
+				if (NextParallelOp(plan, lastPass, np, no) && tid < plan.opSize[no])
+				{
+					// the impulses of that constraint were last written in an earlier phase, except when the next
+					// colour is this very one (a single colour): then they are loaded after the barrier
+					if (!(plan.opStart[no] == begin))
+					{
+						pre = LoadVelPre(d, plan.opStart[no] + tid);
+						havePre = true;
+					}
+				}
 				grid.sync();
 			}
 			else if (type == OP_SERIAL)
@@ -1304,15 +1395,28 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVe
 	for (int b = tid; b < plan.bodyCount; b += stride) IntegratePositionOne(d, b, plan.h);
 }
 
-// position half: position iterations with the per-island early exit
-__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPositionPersistentKernel(DeviceArrays d, SolverPlan plan)
+// position half: position iterations with the per-island early exit; same software pipelining
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPositionPersistentKernel(DeviceArrays d,
+                                                                                                   SolverPlan plan)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	unsigned seq = plan.shard.seq;
+	const int lastPass = plan.positionIterations - 1;
 
-	for (int it = 0; it < plan.positionIterations; ++it)
+	PosPre pre;
+	bool havePre = false;
+	{
+		int np = 0, no = 0;
+		if (NextParallelOp(plan, lastPass, np, no) && tid < plan.opSize[no])
+		{
+			pre = LoadPosPre(d, plan.opStart[no] + tid);
+			havePre = true;
+		}
+	}
+
+	for (int it = 0; it <= lastPass; ++it)
 	{
 		for (int op = 0; op < plan.opCount; ++op)
 		{
@@ -1321,11 +1425,19 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPo
 			{
 				for (int t = tid; t < n; t += stride)
 				{
-					int k = begin + t;
-					int root = __float_as_int(__ldcs(&d.sRadius[k]).w);
+					if (!(t == tid && havePre)) pre = LoadPosPre(d, begin + t);
+					int root = __float_as_int(pre.rad.w);
 					if (IslandDone(d, it, root, plan.bodyCount)) continue;
-					float minSep = SolvePositionOne(d, k);
+					float minSep = SolvePositionPre(d, pre);
 					AtomicMinByRoot(d.islandMinSep + (size_t)it * plan.bodyCount, root, FloatToOrdered(minSep));
+				}
+				havePre = false;
+				int np = it, no = op + 1;
+				if (NextParallelOp(plan, lastPass, np, no) && tid < plan.opSize[no])
+				{
+					// position rows are constants of the step: always safe to load ahead
+					pre = LoadPosPre(d, plan.opStart[no] + tid);
+					havePre = true;
 				}
 				grid.sync();
 			}
