@@ -1696,7 +1696,11 @@ __global__ void __launch_bounds__(256) GridCountKernel(DeviceArrays d, int proxy
 		bool moved = IsMovedProxy(d, p);
 		int level = ProxyLevel(fat, g.cell0);
 		atomicAdd(&sh[level], 1);
-		if (moved) atomicAdd(&sh[B2CU_GRID_LEVELS + 1 + level], 1);
+		if (moved)
+		{
+			atomicAdd(&sh[B2CU_GRID_LEVELS + 1 + level], 1);
+			d.movedList[atomicAdd(&d.counters[CNT_SCRATCH], 1)] = p;
+		}
 		if (level == B2CU_GRID_LEVELS)
 		{
 			d.cellOfProxy[p] = -1;
@@ -1757,13 +1761,81 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 	else d.counters[CNT_ERROR] = 1;
 }
 
-// One thread per proxy p.  p examines
+// Pair search of one proxy p:
 //   its own level       if p moved:  every overlapping r, except a moved r with a smaller id (r reports that pair)
 //   each coarser level  every overlapping r such that p or r moved (r never looks down at p's level)
 //   the huge list       like a coarser level
 // so each pair with a moved member is examined exactly once.
-__global__ void __launch_bounds__(128) QueryPairsKernel(DeviceArrays d, int proxyCount, GridParams g, int contactCount,
-                                                        int pairCapacity)
+__device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool movedP, const GridParams& g,
+                                           const int* shCount, const int* shMoved, int contactCount, int pairCapacity)
+{
+	float4 fp = d.fat[p];
+	int levelP = ProxyLevel(fp, g.cell0);
+	const int nHuge = shCount[B2CU_GRID_LEVELS];
+
+	for (int level = levelP; level < B2CU_GRID_LEVELS; ++level)
+	{
+		if (shCount[level] == 0) continue;
+		bool same = level == levelP;
+		if (!movedP && (same || shMoved[level] == 0)) continue;
+		float inv = LevelInvCell(g.invCell0, level);
+		int x0 = CellCoord(fp.x, inv) - 1, x1 = CellCoord(fp.z, inv);
+		int y0 = CellCoord(fp.y, inv) - 1, y1 = CellCoord(fp.w, inv);
+		for (int cy = y0; cy <= y1; ++cy)
+		{
+			for (int cx = x0; cx <= x1; ++cx)
+			{
+				uint32_t h = CellHash(level, cx, cy, g.mask);
+				int start = d.cellStart[h];
+				int end = start + d.cellCount[h];
+				for (int s = start; s < end; ++s)
+				{
+					int r = d.cellItems[s];
+					if (r == p) continue;
+					float4 fr = d.fat[r];
+					// a bucket can hold several cells and levels: take r only when it is registered in THIS cell
+					if (CellCoord(fr.x, inv) != cx || CellCoord(fr.y, inv) != cy) continue;
+					if (ProxyLevel(fr, g.cell0) != level) continue;
+					if (!AabbOverlap(fp, fr)) continue;
+					bool movedR = IsMovedProxy(d, r);
+					if (same)
+					{
+						if (movedR && r < p) continue;
+					}
+					else if (!movedP && !movedR)
+					{
+						continue;
+					}
+					TryAddPair(d, p, r, contactCount, pairCapacity);
+				}
+			}
+		}
+	}
+
+	if (nHuge > 0 && (movedP || shMoved[B2CU_GRID_LEVELS] > 0))
+	{
+		bool hugeP = levelP == B2CU_GRID_LEVELS;
+		for (int s = 0; s < nHuge; ++s)
+		{
+			int r = d.largeList[s];
+			if (r == p) continue;
+			if (!AabbOverlap(fp, d.fat[r])) continue;
+			bool movedR = IsMovedProxy(d, r);
+			if (hugeP)
+			{
+				if (!movedP || (movedR && r < p)) continue;
+			}
+			else if (!movedP && !movedR)
+			{
+				continue;
+			}
+			TryAddPair(d, p, r, contactCount, pairCapacity);
+		}
+	}
+}
+
+// dense pass over the compacted list of moved proxies (all lanes of a warp have work)
+__global__ void __launch_bounds__(128) QueryMovedKernel(DeviceArrays d, GridParams g, int contactCount, int pairCapacity)
 {
 	__shared__ int shCount[B2CU_GRID_LEVELS + 1];
 	__shared__ int shMoved[B2CU_GRID_LEVELS + 1];
@@ -1773,73 +1845,43 @@ __global__ void __launch_bounds__(128) QueryPairsKernel(DeviceArrays d, int prox
 		shMoved[threadIdx.x] = d.levelInfo[B2CU_GRID_LEVELS + 1 + threadIdx.x];
 	}
 	__syncthreads();
-	const int nHuge = shCount[B2CU_GRID_LEVELS];
+	const int n = d.counters[CNT_SCRATCH];
+	B2CU_GRID_STRIDE(t, n) { QueryProxy(d, d.movedList[t], true, g, shCount, shMoved, contactCount, pairCapacity); }
+}
 
+// proxies that did not move only have to look UP, at coarser levels that contain a moved proxy (a moved wall, a
+// bullet): usually there is none and the kernel returns at once
+__global__ void __launch_bounds__(128) QueryUnmovedKernel(DeviceArrays d, int proxyCount, GridParams g, int contactCount,
+                                                          int pairCapacity)
+{
+	__shared__ int shCount[B2CU_GRID_LEVELS + 1];
+	__shared__ int shMoved[B2CU_GRID_LEVELS + 1];
+	__shared__ int lowestMoved;
+	if (threadIdx.x <= B2CU_GRID_LEVELS)
+	{
+		shCount[threadIdx.x] = d.levelInfo[threadIdx.x];
+		shMoved[threadIdx.x] = d.levelInfo[B2CU_GRID_LEVELS + 1 + threadIdx.x];
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		int lm = B2CU_GRID_LEVELS + 1;
+		for (int l = B2CU_GRID_LEVELS; l >= 0; --l)
+			if (shMoved[l] > 0) lm = l;
+		lowestMoved = lm;
+	}
+	__syncthreads();
+	// a moved proxy on level L is only interesting to unmoved proxies on levels below L
+	if (lowestMoved == 0 || lowestMoved > B2CU_GRID_LEVELS)
+	{
+		bool anyAbove = false;
+		for (int l = 1; l <= B2CU_GRID_LEVELS; ++l) anyAbove |= shMoved[l] > 0;
+		if (!anyAbove) return;
+	}
 	B2CU_GRID_STRIDE(p, proxyCount)
 	{
-		float4 fp = d.fat[p];
-		bool movedP = IsMovedProxy(d, p);
-		int levelP = ProxyLevel(fp, g.cell0);
-
-		for (int level = levelP; level < B2CU_GRID_LEVELS; ++level)
-		{
-			if (shCount[level] == 0) continue;
-			bool same = level == levelP;
-			if (!movedP && (same || shMoved[level] == 0)) continue;
-			float inv = LevelInvCell(g.invCell0, level);
-			int x0 = CellCoord(fp.x, inv) - 1, x1 = CellCoord(fp.z, inv);
-			int y0 = CellCoord(fp.y, inv) - 1, y1 = CellCoord(fp.w, inv);
-			for (int cy = y0; cy <= y1; ++cy)
-			{
-				for (int cx = x0; cx <= x1; ++cx)
-				{
-					uint32_t h = CellHash(level, cx, cy, g.mask);
-					int start = d.cellStart[h];
-					int end = start + d.cellCount[h];
-					for (int s = start; s < end; ++s)
-					{
-						int r = d.cellItems[s];
-						if (r == p) continue;
-						float4 fr = d.fat[r];
-						// a bucket can hold several cells and levels: take r only when it is registered in THIS cell
-						if (CellCoord(fr.x, inv) != cx || CellCoord(fr.y, inv) != cy) continue;
-						if (ProxyLevel(fr, g.cell0) != level) continue;
-						if (!AabbOverlap(fp, fr)) continue;
-						bool movedR = IsMovedProxy(d, r);
-						if (same)
-						{
-							if (movedR && r < p) continue;
-						}
-						else if (!movedP && !movedR)
-						{
-							continue;
-						}
-						TryAddPair(d, p, r, contactCount, pairCapacity);
-					}
-				}
-			}
-		}
-
-		if (nHuge > 0 && (movedP || shMoved[B2CU_GRID_LEVELS] > 0))
-		{
-			bool hugeP = levelP == B2CU_GRID_LEVELS;
-			for (int s = 0; s < nHuge; ++s)
-			{
-				int r = d.largeList[s];
-				if (r == p) continue;
-				if (!AabbOverlap(fp, d.fat[r])) continue;
-				bool movedR = IsMovedProxy(d, r);
-				if (hugeP)
-				{
-					if (!movedP || (movedR && r < p)) continue;
-				}
-				else if (!movedP && !movedR)
-				{
-					continue;
-				}
-				TryAddPair(d, p, r, contactCount, pairCapacity);
-			}
-		}
+		if (IsMovedProxy(d, p)) continue;
+		QueryProxy(d, p, false, g, shCount, shMoved, contactCount, pairCapacity);
 	}
 }
 

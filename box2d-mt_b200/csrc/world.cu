@@ -405,6 +405,7 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 	int rc;
 
 	if ((rc = ZeroCounter(w, CNT_MOVED))) return rc;
+	if ((rc = ZeroCounter(w, CNT_SCRATCH))) return rc;
 	if ((rc = ZeroCounter(w, CNT_LARGE))) return rc;
 	if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
 	if ((rc = ZeroCounter(w, CNT_KEEP))) return rc;
@@ -421,7 +422,8 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		ExclusiveScan(&w->prims, d.cellCount, d.cellStart, w->gridSize, nullptr, w->stream);
 		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
 		LAUNCH(w, GridFillKernel, GridFor(np), kBlock, d, np);
-		LAUNCH(w, QueryPairsKernel, GridFor(np, 128), 128, d, np, grid, nc, w->contactCapacity);
+		LAUNCH(w, QueryMovedKernel, GridFor(np, 128), 128, d, grid, nc, w->contactCapacity);
+		LAUNCH(w, QueryUnmovedKernel, GridFor(np, 128), 128, d, np, grid, nc, w->contactCapacity);
 	}
 
 	// destroyed contacts -> keep flags and ranks
@@ -443,7 +445,8 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		DeviceArrays& dd = w->d;
 		if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
 		if ((rc = ZeroCounter(w, CNT_ERROR))) return rc;
-		LAUNCH(w, QueryPairsKernel, GridFor(np, 128), 128, dd, np, grid, nc, w->contactCapacity);
+		LAUNCH(w, QueryMovedKernel, GridFor(np, 128), 128, dd, grid, nc, w->contactCapacity);
+		LAUNCH(w, QueryUnmovedKernel, GridFor(np, 128), 128, dd, np, grid, nc, w->contactCapacity);
 		if ((rc = ReadCounters(w))) return rc;
 		if (w->hostCounters[CNT_ERROR])
 			return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
