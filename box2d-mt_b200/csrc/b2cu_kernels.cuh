@@ -17,6 +17,8 @@ namespace b2cu
 #define B2CU_EV_END 2
 #define B2CU_EV_DESTROY 4
 #define B2CU_EV_DESTROY_TOUCHING 8
+// internal contact flag: destroyed, slot not yet reclaimed (the contact set is compacted lazily)
+#define B2CU_CONTACT_DEAD 0x0100u
 
 __device__ __forceinline__ bool IsStatic(uint32_t bf) { return (bf & B2CU_BODY_TYPE_MASK) == B2CU_STATIC_BODY; }
 __device__ __forceinline__ bool IsDynamic(uint32_t bf) { return (bf & B2CU_BODY_TYPE_MASK) == B2CU_DYNAMIC_BODY; }
@@ -87,11 +89,12 @@ __device__ __forceinline__ void AppendKey(const DeviceArrays& d, int counter, ui
 	if (slot < capacity) list[slot] = key;
 }
 
-__global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contactCount, int capacity)
+__global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contactCount, int mainCount, int capacity)
 {
 	int touchingCount = 0;
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
+		if (d.c.flags[i] & B2CU_CONTACT_DEAD) continue;
 		int2 pr = d.c.proxies[i];
 		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
 		uint32_t fbA = d.bflags[bA], fbB = d.bflags[bB];
@@ -123,7 +126,6 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 			if (!active)
 			{
 				d.c.flags[i] = flags | B2CU_CONTACT_INACTIVE;
-				d.cEvent[i] = 0;
 				if (flags & B2CU_CONTACT_TOUCHING) ++touchingCount;
 				continue;
 			}
@@ -144,8 +146,8 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 				d.wake[bA] = 1;
 				d.wake[bB] = 1;
 			}
-			d.c.flags[i] = flags;
-			d.cEvent[i] = ev;
+			d.c.flags[i] = flags | B2CU_CONTACT_DEAD;
+			atomicAdd(&d.counters[i < mainCount ? CNT_DESTROY : CNT_DESTROY_B], 1);
 			if (ev & B2CU_EV_DESTROY_TOUCHING) AppendKey(d, CNT_DESTROY_END, d.destroyEndKeys, d.c.key[i], capacity);
 			continue;
 		}
@@ -223,7 +225,6 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 		d.c.m1[i] = make_float4(m.lp[0].x, m.lp[0].y, m.ni[0], m.ti[0]);
 		d.c.m2[i] = make_float4(m.lp[1].x, m.lp[1].y, m.ni[1], m.ti[1]);
 		d.c.m3[i] = make_uint4(m.id[0], m.id[1], (uint32_t)m.type, (uint32_t)m.pointCount);
-		d.cEvent[i] = ev;
 	}
 	for (int dlt = 16; dlt > 0; dlt >>= 1) touchingCount += __shfl_down_sync(0xffffffffu, touchingCount, dlt);
 	if ((threadIdx.x & 31) == 0 && touchingCount) atomicAdd(&d.counters[CNT_TOUCHING], touchingCount);
@@ -325,7 +326,7 @@ __device__ __forceinline__ bool IsSolidTouching(const DeviceArrays& d, int i)
 {
 	uint32_t f = d.c.flags[i];
 	if ((f & (B2CU_CONTACT_TOUCHING | B2CU_CONTACT_ENABLED)) != (B2CU_CONTACT_TOUCHING | B2CU_CONTACT_ENABLED)) return false;
-	if (d.cEvent[i] & B2CU_EV_DESTROY) return false;
+	if (f & B2CU_CONTACT_DEAD) return false;
 	return true;
 }
 
@@ -1293,7 +1294,7 @@ __device__ __forceinline__ void HaloExchange(cooperative_groups::grid_group& gri
 #define B2CU_SOLVER_THREADS 256
 #endif
 #ifndef B2CU_VEL_BLOCKS
-#define B2CU_VEL_BLOCKS 4
+#define B2CU_VEL_BLOCKS 3
 #endif
 #ifndef B2CU_POS_BLOCKS
 #define B2CU_POS_BLOCKS 3
@@ -1735,7 +1736,8 @@ __global__ void GridFillKernel(DeviceArrays d, int proxyCount)
 
 // b2ContactManager::AddPair: same body, existing contact, b2Body::ShouldCollide, default b2ContactFilter,
 // and the contact-class table (no edge-edge contact, b2Contact.cpp:44-50)
-__device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, int contactCount, int pairCapacity)
+__device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, int2 counts /* (all slots, main region) */,
+                                           int pairCapacity)
 {
 	int a = q < p ? q : p, b = q < p ? p : q;
 	int bodyA = d.pbody[a], bodyB = d.pbody[b];
@@ -1750,7 +1752,14 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 			if (d.c.key[mid] < key) lo = mid + 1;
 			else hi = mid;
 		}
-		if (lo < d.lowStart[a + 1] && d.c.key[lo] == key && !(d.cEvent[lo] & B2CU_EV_DESTROY)) return;
+		if (lo < d.lowStart[a + 1] && d.c.key[lo] == key && !(d.c.flags[lo] & B2CU_CONTACT_DEAD)) return;
+		// recent contacts sit in a small sorted tail behind the main region until the next compaction
+		const int nTail = counts.x - counts.y;
+		if (nTail > 0)
+		{
+			int j = counts.y + LowerBound64(d.c.key + counts.y, nTail, key);
+			if (j < counts.x && d.c.key[j] == key && !(d.c.flags[j] & B2CU_CONTACT_DEAD)) return;
+		}
 	}
 	// b2Body::ShouldCollide: at least one dynamic body; in a sharded world it must be one this shard owns
 	if (!IsOwnedDynamic(d.bflags[bodyA]) && !IsOwnedDynamic(d.bflags[bodyB])) return;
@@ -1767,7 +1776,7 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 //   the huge list       like a coarser level
 // so each pair with a moved member is examined exactly once.
 __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool movedP, const GridParams& g,
-                                           const int* shCount, const int* shMoved, int contactCount, int pairCapacity)
+                                           const int* shCount, const int* shMoved, int2 contactCount, int pairCapacity)
 {
 	float4 fp = d.fat[p];
 	int levelP = ProxyLevel(fp, g.cell0);
@@ -1835,7 +1844,7 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 }
 
 // dense pass over the compacted list of moved proxies (all lanes of a warp have work)
-__global__ void __launch_bounds__(128) QueryMovedKernel(DeviceArrays d, GridParams g, int contactCount, int pairCapacity)
+__global__ void __launch_bounds__(128) QueryMovedKernel(DeviceArrays d, GridParams g, int2 contactCount, int pairCapacity)
 {
 	__shared__ int shCount[B2CU_GRID_LEVELS + 1];
 	__shared__ int shMoved[B2CU_GRID_LEVELS + 1];
@@ -1851,7 +1860,7 @@ __global__ void __launch_bounds__(128) QueryMovedKernel(DeviceArrays d, GridPara
 
 // proxies that did not move only have to look UP, at coarser levels that contain a moved proxy (a moved wall, a
 // bullet): usually there is none and the kernel returns at once
-__global__ void __launch_bounds__(128) QueryUnmovedKernel(DeviceArrays d, int proxyCount, GridParams g, int contactCount,
+__global__ void __launch_bounds__(128) QueryUnmovedKernel(DeviceArrays d, int proxyCount, GridParams g, int2 contactCount,
                                                           int pairCapacity)
 {
 	__shared__ int shCount[B2CU_GRID_LEVELS + 1];
@@ -1891,6 +1900,11 @@ __global__ void BuildLowStartKernel(DeviceArrays d, int contactCount, int proxyC
 	B2CU_GRID_STRIDE(p, proxyCount + 1) { d.lowStart[p] = LowerBound64(d.c.key, contactCount, (uint64_t)(uint32_t)p << 32); }
 }
 
+__global__ void IotaKernel(int* out, int n)
+{
+	B2CU_GRID_STRIDE(i, n) { out[i] = i; }
+}
+
 __global__ void ClearMovedKernel(DeviceArrays d, int proxyCount)
 {
 	B2CU_GRID_STRIDE(p, proxyCount) { d.pgroup[p] &= ~((uint32_t)B2CU_PROXY_MOVED << 16); }
@@ -1901,13 +1915,21 @@ __global__ void ClearMovedKernel(DeviceArrays d, int proxyCount)
 // in key order.  Replaces FinishFindNewContacts / OnContactCreate / b2Contact::Create / Destroy bookkeeping
 // (b2ContactManager.cpp:120-172, 366-386, 507-564; b2Contact.cpp:72-157).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void RebuildExistingKernel(DeviceArrays d, int contactCount, const int* __restrict__ keepRank, int newCount)
+// Merge step of the lazily compacted contact set: the live contacts of c[srcBegin, srcBegin+srcCount) go to
+// cAlt[dstBegin + (rank among the live contacts of that range) + (number of live keys of the OTHER sorted run that
+// are smaller)].  otherRank == nullptr: the other run has no dead entries.
+__global__ void MergeMoveKernel(DeviceArrays d, int srcBegin, int srcCount, const int* __restrict__ srcRank,
+                                const uint64_t* __restrict__ otherKeys, int otherCount, const int* __restrict__ otherRank,
+                                int otherLive, int dstBegin)
 {
-	B2CU_GRID_STRIDE(i, contactCount)
+	B2CU_GRID_STRIDE(t, srcCount)
 	{
-		if (d.cEvent[i] & B2CU_EV_DESTROY) continue;
+		int i = srcBegin + t;
+		if (d.c.flags[i] & B2CU_CONTACT_DEAD) continue;
 		uint64_t key = d.c.key[i];
-		int dest = keepRank[i] + LowerBound64(d.newKeys, newCount, key);
+		int lb = LowerBound64(otherKeys, otherCount, key);
+		int less = otherRank ? (lb < otherCount ? otherRank[lb] : otherLive) : lb;
+		int dest = dstBegin + srcRank[t] + less;
 		d.cAlt.key[dest] = key;
 		d.cAlt.proxies[dest] = d.c.proxies[i];
 		d.cAlt.flags[dest] = d.c.flags[i];
@@ -1921,14 +1943,17 @@ __global__ void RebuildExistingKernel(DeviceArrays d, int contactCount, const in
 	}
 }
 
-__global__ void RebuildNewKernel(DeviceArrays d, int contactCount, const int* __restrict__ keepRank, int newCount)
+// new contacts (sorted keys) are created in cAlt, merged with the live contacts of the tail region
+// c[tailBegin, tailBegin+tailCount) (rank tailRank, tailLive of them)
+__global__ void RebuildNewKernel(DeviceArrays d, int tailBegin, int tailCount, const int* __restrict__ tailRank,
+                                 int tailLive, int newCount, int dstBegin)
 {
 	B2CU_GRID_STRIDE(j, newCount)
 	{
 		uint64_t key = d.newKeys[j];
-		int lb = LowerBound64(d.c.key, contactCount, key);
-		int keptBefore = lb < contactCount ? keepRank[lb] : d.counters[CNT_KEEP];
-		int dest = j + keptBefore;
+		int lb = LowerBound64(d.c.key + tailBegin, tailCount, key);
+		int keptBefore = lb < tailCount ? tailRank[lb] : tailLive;
+		int dest = dstBegin + j + keptBefore;
 
 		int a = (int)(key >> 32), b = (int)(key & 0xFFFFFFFFull);
 		int typeA = d.shapes[d.pshape[a]].type, typeB = d.shapes[d.pshape[b]].type;
@@ -1986,7 +2011,7 @@ __global__ void ToiFlagsKernel(DeviceArrays d, int contactCount, int* flagsOut)
 	{
 		uint32_t f = d.c.flags[i];
 		int ok = 0;
-		if ((f & B2CU_CONTACT_TOI_CANDIDATE) && (f & B2CU_CONTACT_ENABLED) && d.c.toiCount[i] <= B2CU_MAX_SUB_STEPS)
+		if (!(f & B2CU_CONTACT_DEAD) && (f & B2CU_CONTACT_TOI_CANDIDATE) && (f & B2CU_CONTACT_ENABLED) && d.c.toiCount[i] <= B2CU_MAX_SUB_STEPS)
 		{
 			int2 pr = d.c.proxies[i];
 			uint32_t fA = d.bflags[d.pbody[pr.x]], fB = d.bflags[d.pbody[pr.y]];
@@ -2072,15 +2097,21 @@ __global__ void CollidePairsKernel(const b2cuShape* __restrict__ shapes, int pai
 }
 
 // b2cuGetContactsByKey: one thread per requested key, AoS records out
-__global__ void GatherContactsByKeyKernel(DeviceArrays d, int contactCount, const uint64_t* __restrict__ keys, int n,
-                                          b2cuContact* __restrict__ out)
+__global__ void GatherContactsByKeyKernel(DeviceArrays d, int contactCount, int mainCount,
+                                          const uint64_t* __restrict__ keys, int n, b2cuContact* __restrict__ out)
 {
 	B2CU_GRID_STRIDE(j, n)
 	{
 		uint64_t key = keys[j];
-		int i = LowerBound64(d.c.key, contactCount, key);
+		int i = LowerBound64(d.c.key, mainCount, key);
+		bool found = i < mainCount && d.c.key[i] == key && !(d.c.flags[i] & B2CU_CONTACT_DEAD);
+		if (!found && contactCount > mainCount)
+		{
+			i = mainCount + LowerBound64(d.c.key + mainCount, contactCount - mainCount, key);
+			found = i < contactCount && d.c.key[i] == key && !(d.c.flags[i] & B2CU_CONTACT_DEAD);
+		}
 		b2cuContact o;
-		if (i < contactCount && d.c.key[i] == key)
+		if (found)
 		{
 			int2 pr = d.c.proxies[i];
 			float4 m0 = d.c.m0[i], m1 = d.c.m1[i], m2 = d.c.m2[i], mix = d.c.mix[i];

@@ -23,7 +23,8 @@ enum Counter
 {
 	CNT_BEGIN = 0,        // begin-touch events
 	CNT_END,              // end-touch events from Update
-	CNT_DESTROY,          // contacts destroyed in Collide
+	CNT_DESTROY,          // contacts destroyed in Collide (main region)
+	CNT_DESTROY_B,        // contacts destroyed in Collide (tail region)
 	CNT_DESTROY_END,      // of those, touching ones (EndContact from Destroy)
 	CNT_TOUCHING,         // touching contacts after Collide
 	CNT_CONSTRAINT,       // contacts handed to the solver
@@ -94,7 +95,6 @@ struct DeviceArrays
 	// ---- contacts ----
 	ContactSet c;       // live set
 	ContactSet cAlt;    // rebuild target
-	int* cEvent;        // per contact: bit0 begin, bit1 end, bit2 destroyed, bit3 destroyed while touching
 	int* cSelect;       // per contact: 1 = solver constraint this step
 
 	// ---- per-step lists ----
@@ -156,7 +156,11 @@ struct b2cuWorld
 	b2cu::PrimScratch prims;
 
 	int bodyCapacity, proxyCapacity, shapeCapacity, contactCapacity;
-	int bodyCount, proxyCount, shapeCount, contactCount;
+	int bodyCount, proxyCount, shapeCount;
+	int contactCount;    // contact slots in use: sorted main region [0, mainCount) + sorted tail [mainCount, contactCount)
+	int mainCount;
+	int deadMain;        // destroyed contacts still occupying slots of the main region
+	bool compactNow;     // force the compaction of the contact set at the end of the next step
 	int gridSize;        // hash table size (power of two)
 	float cellSize;
 	bool newProxies;     // e_newFixture: run FindNewContacts at the start of the next step

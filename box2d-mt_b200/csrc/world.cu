@@ -164,7 +164,6 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->lowStart, CAP_PROXY1));
 	ContactSetDescs(&d->c, v);
 	ContactSetDescs(&d->cAlt, v);
-	v.push_back(Desc(&d->cEvent, CAP_CONTACT));
 	v.push_back(Desc(&d->cSelect, CAP_CONTACT));
 	v.push_back(Desc(&d->listA, CAP_CONTACT));
 	v.push_back(Desc(&d->listB, CAP_CONTACT));
@@ -390,30 +389,61 @@ void SortKeys(b2cuWorld* w, uint64_t* keys, int n)
 // index of the sorted key array by low proxy id (existence checks of the broad-phase)
 int RebuildLowStart(b2cuWorld* w)
 {
-	LAUNCH(w, BuildLowStartKernel, GridFor(w->proxyCount + 1), kBlock, w->d, w->contactCount, w->proxyCount);
+	LAUNCH(w, BuildLowStartKernel, GridFor(w->proxyCount + 1), kBlock, w->d, w->mainCount, w->proxyCount);
 	return B2CU_OK;
 }
 
 // ---- broad-phase pair finding + contact set rebuild ------------------------------------------------------
 
 // Finds new pairs for the proxies flagged MOVED, then rebuilds the contact set (drop destroyed, merge new).
+// copy rows [begin, begin+count) of every contact array from one set to the other
+int CopyContactRange(b2cuWorld* w, ContactSet& dst, const ContactSet& src, int begin, int count)
+{
+	if (count <= 0) return B2CU_OK;
+#define COPY_ROWS(field)                                                                                         \
+	CUDA_TRY(w, cudaMemcpyAsync(dst.field + begin, src.field + begin, sizeof(*dst.field) * (size_t)count,          \
+	                            cudaMemcpyDeviceToDevice, w->stream))
+	COPY_ROWS(key);
+	COPY_ROWS(proxies);
+	COPY_ROWS(flags);
+	COPY_ROWS(m0);
+	COPY_ROWS(m1);
+	COPY_ROWS(m2);
+	COPY_ROWS(m3);
+	COPY_ROWS(mix);
+	COPY_ROWS(toiCount);
+	COPY_ROWS(colour);
+#undef COPY_ROWS
+	return B2CU_OK;
+}
+
+// Finds the new pairs of the proxies flagged MOVED and updates the contact set.
+//
+// The set is compacted lazily.  Slots [0, mainCount) are the big sorted main region, slots [mainCount, contactCount)
+// a small sorted tail.  Contacts destroyed by Collide only get the DEAD flag.  Every step the tail is rebuilt (its
+// live contacts merged with the new pairs: cost proportional to the churn, not to the set); the main region is
+// merged with the tail, and its dead slots reclaimed, only when the tail or the dead slots exceed a few percent of
+// it.  A settled million-body pile changes ~0.3% of its 5M contacts per step, so the full 1 GB merge runs every
+// ~15 steps instead of every step.
 int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut, int* movedOut)
 {
 	DeviceArrays& d = w->d;
 	const int np = w->proxyCount;
 	const int nc = w->contactCount;
+	const int nMain = w->mainCount;
+	const int nTail = nc - nMain;
 	int rc;
 
 	if ((rc = ZeroCounter(w, CNT_MOVED))) return rc;
 	if ((rc = ZeroCounter(w, CNT_SCRATCH))) return rc;
 	if ((rc = ZeroCounter(w, CNT_LARGE))) return rc;
 	if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
-	if ((rc = ZeroCounter(w, CNT_KEEP))) return rc;
 
 	GridParams grid;
 	grid.cell0 = w->cellSize;
 	grid.invCell0 = 1.0f / w->cellSize;
 	grid.mask = (uint32_t)w->gridSize - 1u;
+	const int2 counts = make_int2(nc, nMain);
 	if (np > 0)
 	{
 		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
@@ -422,61 +452,94 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		ExclusiveScan(&w->prims, d.cellCount, d.cellStart, w->gridSize, nullptr, w->stream);
 		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
 		LAUNCH(w, GridFillKernel, GridFor(np), kBlock, d, np);
-		LAUNCH(w, QueryMovedKernel, GridFor(np, 128), 128, d, grid, nc, w->contactCapacity);
-		LAUNCH(w, QueryUnmovedKernel, GridFor(np, 128), 128, d, np, grid, nc, w->contactCapacity);
-	}
-
-	// destroyed contacts -> keep flags and ranks
-	if (nc > 0)
-	{
-		ExclusiveScanNotMask(&w->prims, (const uint32_t*)d.cEvent, B2CU_EV_DESTROY, d.listA, nc, d.counters + CNT_KEEP,
-		                     w->stream);
+		LAUNCH(w, QueryMovedKernel, GridFor(np, 128), 128, d, grid, counts, w->contactCapacity);
+		LAUNCH(w, QueryUnmovedKernel, GridFor(np, 128), 128, d, np, grid, counts, w->contactCapacity);
 	}
 
 	if ((rc = ReadCounters(w))) return rc;
-	int keepCount = nc > 0 ? w->hostCounters[CNT_KEEP] : 0;
-	if (w->hostCounters[CNT_ERROR] || keepCount + w->hostCounters[CNT_NEW_PAIRS] > w->contactCapacity)
+	const int destroyedMain = w->hostCounters[CNT_DESTROY];
+	const int destroyedTail = w->hostCounters[CNT_DESTROY_B];
+	const int tailLive = nTail - destroyedTail;
+	if (w->hostCounters[CNT_ERROR] || nMain + tailLive + w->hostCounters[CNT_NEW_PAIRS] > w->contactCapacity)
 	{
-		// the pair buffer (or the rebuilt set) would overflow: grow geometrically and repeat the queries; the
-		// pair counter kept counting past the capacity, so the size needed is known
-		int needed = keepCount + w->hostCounters[CNT_NEW_PAIRS];
+		// the pair buffer (or the set) would overflow: grow geometrically and repeat the queries; the pair counter
+		// kept counting past the capacity, so the size needed is known
+		int needed = nMain + tailLive + w->hostCounters[CNT_NEW_PAIRS];
 		int grown = std::max(needed + needed / 4, 2 * w->contactCapacity);
 		if ((rc = Reserve(w, w->bodyCapacity, w->proxyCapacity, w->shapeCapacity, grown))) return rc;
 		DeviceArrays& dd = w->d;
 		if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
 		if ((rc = ZeroCounter(w, CNT_ERROR))) return rc;
-		LAUNCH(w, QueryMovedKernel, GridFor(np, 128), 128, dd, grid, nc, w->contactCapacity);
-		LAUNCH(w, QueryUnmovedKernel, GridFor(np, 128), 128, dd, np, grid, nc, w->contactCapacity);
+		LAUNCH(w, QueryMovedKernel, GridFor(np, 128), 128, dd, grid, counts, w->contactCapacity);
+		LAUNCH(w, QueryUnmovedKernel, GridFor(np, 128), 128, dd, np, grid, counts, w->contactCapacity);
 		if ((rc = ReadCounters(w))) return rc;
 		if (w->hostCounters[CNT_ERROR])
 			return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
 	}
 	if (np > 0) LAUNCH(w, ClearMovedKernel, GridFor(np), kBlock, w->d, np);
 	const int newCount = w->hostCounters[CNT_NEW_PAIRS];
-	const int moved = w->hostCounters[CNT_MOVED];
 	*newCountOut = newCount;
-	*destroyedOut = nc - keepCount;
-	*movedOut = moved;
+	*destroyedOut = destroyedMain + destroyedTail;
+	*movedOut = w->hostCounters[CNT_MOVED];
+	w->deadMain += destroyedMain;
 
-	if (newCount == 0 && keepCount == nc)
+	// ---- 1. tail' = live(tail) merged with the new pairs (built in cAlt, copied back) ----
+	int newTail = nTail;
+	if (newCount > 0 || destroyedTail > 0)
 	{
-		return B2CU_OK; // contact set unchanged
+		newTail = tailLive + newCount;
+		SortKeys(w, d.newKeys, newCount);
+		if (nTail > 0)
+		{
+			ExclusiveScanNotMask(&w->prims, d.c.flags + nMain, B2CU_CONTACT_DEAD, d.listA, nTail, nullptr, w->stream);
+			LAUNCH(w, MergeMoveKernel, GridFor(nTail), kBlock, d, nMain, nTail, d.listA, d.newKeys, newCount,
+			       (const int*)nullptr, newCount, nMain);
+		}
+		if (newCount > 0)
+		{
+			LAUNCH(w, RebuildNewKernel, GridFor(newCount), kBlock, d, nMain, nTail, d.listA, tailLive, newCount, nMain);
+			LAUNCH(w, ApplyWakeKernel, GridFor(w->bodyCount), kBlock, d, w->bodyCount);
+		}
+		if ((rc = CopyContactRange(w, d.c, d.cAlt, nMain, newTail))) return rc;
+		w->contactCount = nMain + newTail;
 	}
 
-	SortKeys(w, d.newKeys, newCount);
-	if (nc > 0)
+	// ---- 2. compaction of the main region when the tail or the dead slots have grown ----
+	const int tailLimit = std::max(8192, nMain / 16);
+	const int deadLimit = std::max(8192, nMain / 8);
+	if (newTail > 0 && (newTail > tailLimit || w->deadMain > deadLimit || w->compactNow))
 	{
-		LAUNCH(w, RebuildExistingKernel, GridFor(nc), kBlock, d, nc, d.listA, newCount);
+		const int mainLive = nMain - w->deadMain;
+		if (nMain > 0)
+		{
+			ExclusiveScanNotMask(&w->prims, d.c.flags, B2CU_CONTACT_DEAD, d.listA, nMain, nullptr, w->stream);
+			LAUNCH(w, MergeMoveKernel, GridFor(nMain), kBlock, d, 0, nMain, d.listA, d.c.key + nMain, newTail,
+			       (const int*)nullptr, newTail, 0);
+		}
+		// the tail has no dead entries (just rebuilt): its rank is the identity
+		LAUNCH(w, IotaKernel, GridFor(newTail), kBlock, d.listB, newTail);
+		LAUNCH(w, MergeMoveKernel, GridFor(newTail), kBlock, d, nMain, newTail, d.listB, d.c.key, nMain, d.listA, mainLive, 0);
+		std::swap(d.c, d.cAlt);
+		w->mainCount = mainLive + newTail;
+		w->contactCount = w->mainCount;
+		w->deadMain = 0;
+		w->compactNow = false;
+		if ((rc = RebuildLowStart(w))) return rc;
 	}
-	if (newCount > 0)
+	else if (newTail == 0 && (w->deadMain > deadLimit || (w->compactNow && w->deadMain > 0)))
 	{
-		LAUNCH(w, RebuildNewKernel, GridFor(newCount), kBlock, d, nc, d.listA, newCount);
-		LAUNCH(w, ApplyWakeKernel, GridFor(w->bodyCount), kBlock, d, w->bodyCount);
+		// nothing to merge, only dead slots to reclaim
+		const int mainLive = nMain - w->deadMain;
+		ExclusiveScanNotMask(&w->prims, d.c.flags, B2CU_CONTACT_DEAD, d.listA, nMain, nullptr, w->stream);
+		LAUNCH(w, MergeMoveKernel, GridFor(nMain), kBlock, d, 0, nMain, d.listA, d.newKeys, 0, (const int*)nullptr, 0, 0);
+		std::swap(d.c, d.cAlt);
+		w->mainCount = mainLive;
+		w->contactCount = mainLive;
+		w->deadMain = 0;
+		w->compactNow = false;
+		if ((rc = RebuildLowStart(w))) return rc;
 	}
-	std::swap(d.c, d.cAlt);
-	w->contactCount = keepCount + newCount;
-	CUDA_TRY(w, cudaMemsetAsync(d.cEvent, 0, sizeof(int) * (size_t)w->contactCapacity, w->stream));
-	return RebuildLowStart(w);
+	return B2CU_OK;
 }
 
 int CheckRange(b2cuWorld* w, int first, int count, int limit, const void* p)
@@ -861,8 +924,9 @@ int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
 	    (rc = Upload(w, d.c.m2, 0, m2)) || (rc = Upload(w, d.c.m3, 0, m3)) || (rc = Upload(w, d.c.mix, 0, mix)) ||
 	    (rc = Upload(w, d.c.toiCount, 0, toiCount)) || (rc = Upload(w, d.c.colour, 0, colour)))
 		return rc;
-	CUDA_TRY(w, cudaMemsetAsync(d.cEvent, 0, sizeof(int) * (size_t)w->contactCapacity, w->stream));
 	w->contactCount = count;
+	w->mainCount = count;
+	w->deadMain = 0;
 	if ((rc = RebuildLowStart(w))) return rc;
 	return SyncCheck(w);
 }
@@ -870,7 +934,7 @@ int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
 int b2cuGetContactCount(b2cuWorld* w, int32_t* count)
 {
 	if (!w || !count) return B2CU_ERR_ARGUMENT;
-	*count = w->contactCount;
+	*count = w->contactCount - w->deadMain;
 	return B2CU_OK;
 }
 
@@ -878,27 +942,41 @@ int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32
 {
 	if (!w || capacity < 0 || (capacity > 0 && !contacts)) return B2CU_ERR_ARGUMENT;
 	cudaSetDevice(w->device);
-	int count = std::min(capacity, w->contactCount);
-	if (countOut) *countOut = w->contactCount;
-	std::vector<int2> proxies(count);
-	std::vector<uint32_t> flags(count);
-	std::vector<float4> m0(count), m1(count), m2(count), mix(count);
-	std::vector<uint4> m3(count);
-	std::vector<int> toiCount(count);
-	std::vector<int> pbody(count > 0 ? w->proxyCount : 0);
-	std::vector<uint32_t> bflags(count > 0 ? w->bodyCount : 0);
+	const int slots = w->contactCount;
+	const int live = slots - w->deadMain;
+	if (countOut) *countOut = live;
+	if (capacity == 0 || slots == 0) return B2CU_OK;
+	std::vector<uint64_t> key(slots);
+	std::vector<int2> proxies(slots);
+	std::vector<uint32_t> flags(slots);
+	std::vector<float4> m0(slots), m1(slots), m2(slots), mix(slots);
+	std::vector<uint4> m3(slots);
+	std::vector<int> toiCount(slots);
+	std::vector<int> pbody(w->proxyCount);
+	std::vector<uint32_t> bflags(w->bodyCount);
 	DeviceArrays& d = w->d;
 	int rc;
 	if ((rc = Download(w, d.pbody, 0, pbody)) || (rc = Download(w, d.bflags, 0, bflags))) return rc;
-	if ((rc = Download(w, d.c.proxies, 0, proxies)) || (rc = Download(w, d.c.flags, 0, flags)) ||
-	    (rc = Download(w, d.c.m0, 0, m0)) || (rc = Download(w, d.c.m1, 0, m1)) || (rc = Download(w, d.c.m2, 0, m2)) ||
-	    (rc = Download(w, d.c.m3, 0, m3)) || (rc = Download(w, d.c.mix, 0, mix)) ||
+	if ((rc = Download(w, d.c.key, 0, key)) || (rc = Download(w, d.c.proxies, 0, proxies)) ||
+	    (rc = Download(w, d.c.flags, 0, flags)) || (rc = Download(w, d.c.m0, 0, m0)) || (rc = Download(w, d.c.m1, 0, m1)) ||
+	    (rc = Download(w, d.c.m2, 0, m2)) || (rc = Download(w, d.c.m3, 0, m3)) || (rc = Download(w, d.c.mix, 0, mix)) ||
 	    (rc = Download(w, d.c.toiCount, 0, toiCount)))
 		return rc;
 	if ((rc = SyncCheck(w))) return rc;
-	for (int j = 0; j < count; ++j)
+	// live slots in key order: the main region and the tail are each sorted; this read-out does not touch the
+	// device set (compacting here would change contact indices and with them the colouring of later steps)
+	std::vector<int> order;
+	order.reserve(live);
+	for (int i = 0; i < slots; ++i)
+		if (!(flags[i] & B2CU_CONTACT_DEAD)) order.push_back(i);
+	size_t mid = 0;
+	while (mid < order.size() && order[mid] < w->mainCount) ++mid;
+	std::inplace_merge(order.begin(), order.begin() + mid, order.end(), [&](int a, int b) { return key[a] < key[b]; });
+	const int count = std::min(capacity, (int)order.size());
+	for (int out = 0; out < count; ++out)
 	{
-		b2cuContact& c = contacts[j];
+		const int j = order[out];
+		b2cuContact& c = contacts[out];
 		c.proxyA = proxies[j].x;
 		c.proxyB = proxies[j].y;
 		// e_inactiveFlag is not stored on the device: it is a function of the bodies' awake state
@@ -907,7 +985,7 @@ int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32
 			uint32_t fA = bflags[pbody[proxies[j].x]], fB = bflags[pbody[proxies[j].y]];
 			bool activeA = (fA & B2CU_BODY_AWAKE) && (fA & B2CU_BODY_TYPE_MASK) != B2CU_STATIC_BODY;
 			bool activeB = (fB & B2CU_BODY_AWAKE) && (fB & B2CU_BODY_TYPE_MASK) != B2CU_STATIC_BODY;
-			uint32_t f = flags[j] & ~(uint32_t)B2CU_CONTACT_INACTIVE;
+			uint32_t f = flags[j] & ~(uint32_t)(B2CU_CONTACT_INACTIVE | B2CU_CONTACT_DEAD);
 			if (!activeA && !activeB) f |= B2CU_CONTACT_INACTIVE;
 			c.flags = f;
 		}
@@ -990,7 +1068,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	if (nc > 0)
 	{
 		// narrow phase; begin/end events are appended to the deferred buffers and sorted at the end of the step
-		LAUNCH(w, CollideKernel, GridFor(nc), kBlock, d, nc, w->contactCapacity);
+		LAUNCH(w, CollideKernel, GridFor(nc), kBlock, d, nc, w->mainCount, w->contactCapacity);
 		LAUNCH(w, ApplyWakeKernel, GridFor(nb), kBlock, d, nb);
 	}
 	cudaEventRecord(w->ev[2], w->stream);
@@ -1297,7 +1375,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 
 	out.bodyCount = nb;
 	out.proxyCount = np;
-	out.contactCount = w->contactCount;
+	out.contactCount = w->contactCount - w->deadMain;
 	out.touchingCount = w->hostCounters[CNT_TOUCHING];
 	out.constraintCount = w->constraintCount;
 	out.colourCount = w->colourCount;
@@ -1348,7 +1426,8 @@ int b2cuGetContactsByKey(b2cuWorld* w, int32_t count, const b2cuContactKey* keys
 	if (e == cudaSuccess) e = cudaMemcpyAsync(dKeys, keys, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, w->stream);
 	if (e == cudaSuccess)
 	{
-		GatherContactsByKeyKernel<<<GridFor(count), kBlock, 0, w->stream>>>(w->d, w->contactCount, dKeys, count, dOut);
+		GatherContactsByKeyKernel<<<GridFor(count), kBlock, 0, w->stream>>>(w->d, w->contactCount, w->mainCount, dKeys, count,
+		                                                                  dOut);
 		e = cudaMemcpyAsync(out, dOut, sizeof(b2cuContact) * count, cudaMemcpyDeviceToHost, w->stream);
 	}
 	if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
