@@ -160,6 +160,7 @@ struct b2cuWorld
 	int contactCount;    // contact slots in use: sorted main region [0, mainCount) + sorted tail [mainCount, contactCount)
 	int mainCount;
 	int deadMain;        // destroyed contacts still occupying slots of the main region
+	int compactMin;      // smallest tail / dead-slot count that triggers a compaction
 	bool compactNow;     // force the compaction of the contact set at the end of the next step
 	int gridSize;        // hash table size (power of two)
 	float cellSize;

@@ -505,8 +505,8 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 	}
 
 	// ---- 2. compaction of the main region when the tail or the dead slots have grown ----
-	const int tailLimit = std::max(8192, nMain / 16);
-	const int deadLimit = std::max(8192, nMain / 8);
+	const int tailLimit = std::max(w->compactMin, nMain / 16);
+	const int deadLimit = std::max(w->compactMin, nMain / 8);
 	if (newTail > 0 && (newTail > tailLimit || w->deadMain > deadLimit || w->compactNow))
 	{
 		const int mainLive = nMain - w->deadMain;
@@ -641,6 +641,11 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		w->persistentGridPositionMax = w->persistentGridPosition;
 		w->shardCount = 1;
 		w->shardSeq = 1;
+	}
+	{
+		// smallest tail / dead-slot count that triggers a compaction of the contact set (tests lower it)
+		const char* cm = getenv("B2CU_COMPACT_MIN");
+		w->compactMin = cm && atoi(cm) > 0 ? atoi(cm) : 8192;
 	}
 	{
 		const char* t = getenv("B2CU_TRACE");

@@ -135,6 +135,22 @@ def test_free_running_lockstep(gpu, name, steps):
         assert not (r.bodies()["flags"][1:] & T.BODY_AWAKE).any()
 
 
+@pytest.mark.parametrize("compact_min", [1, 24])
+def test_lockstep_with_frequent_compaction(gpu, compact_min, monkeypatch):
+    """The contact set is compacted lazily (dead flags + a small sorted tail, merged into the main region now and
+    then).  Force the merge to run (almost) every step and check that nothing observable changes."""
+    monkeypatch.setenv("B2CU_COMPACT_MIN", str(compact_min))
+    for name in ("pile", "tumbler"):
+        scene = _no_toi(SCENES[name]())
+        r = ref.RefWorld(scene)
+        g = parity.gpu_world_from_ref(gpu, r)
+        parity.lockstep(g, r, 200, tol=TOL)
+    scene = _no_toi(scenes.add_pair(300))
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    parity.lockstep(g, r, 60, tol=TOL)
+
+
 def test_add_pair_pair_set(gpu):
     """BASELINE config 2 (Add Pair, scaled down): broad-phase stress with a fast bullet box; pair set bit-exact
     every step.  Continuous physics is off on both sides (SolveTOI is host-driven and outside this test)."""
