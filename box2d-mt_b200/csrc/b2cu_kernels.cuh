@@ -89,7 +89,89 @@ __device__ __forceinline__ void AppendKey(const DeviceArrays& d, int counter, ui
 	if (slot < capacity) list[slot] = key;
 }
 
-__global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contactCount, int mainCount, int capacity)
+// b2Contact::Update (b2Contact.cpp:163-246) of live contact i: evaluate the manifold, carry the warm-start impulses
+// over by feature id, raise begin/end events and wake requests.  Returns 1 when the contact is touching afterwards.
+__device__ __forceinline__ int UpdateContact(const DeviceArrays& d, int i, int2 pr, int bA, int bB, uint32_t flags,
+                                             uint4 m3, const b2cuShape* sA, const b2cuShape* sB, int capacity)
+{
+	int touchingNow = 0;
+	// ---- b2Contact::Update ----
+	float4 o1 = d.c.m1[i], o2 = d.c.m2[i];
+	int oldCount = (int)m3.w;
+	flags |= B2CU_CONTACT_ENABLED;
+	bool wasTouching = (flags & B2CU_CONTACT_TOUCHING) != 0;
+
+	Manifold m;
+	float4 o0 = d.c.m0[i];
+	m.localNormal = V(o0.x, o0.y);
+	m.localPoint = V(o0.z, o0.w);
+	m.lp[0] = V(o1.x, o1.y);
+	m.lp[1] = V(o2.x, o2.y);
+	m.id[0] = m3.x;
+	m.id[1] = m3.y;
+	m.type = (int)m3.z;
+	m.pointCount = 0;
+
+	Xf xfA = MakeXf(d.xf[bA]);
+	Xf xfB = MakeXf(d.xf[bB]);
+	Evaluate(&m, sA, xfA, sB, xfB);
+	bool touching = m.pointCount > 0;
+
+	// warm-start transfer by feature id
+	for (int k = 0; k < m.pointCount; ++k)
+	{
+		float ni = 0.0f, ti = 0.0f;
+		uint32_t id2 = m.id[k];
+		if (oldCount > 0 && m3.x == id2)
+		{
+			ni = o1.z;
+			ti = o1.w;
+		}
+		else if (oldCount > 1 && m3.y == id2)
+		{
+			ni = o2.z;
+			ti = o2.w;
+		}
+		m.ni[k] = ni;
+		m.ti[k] = ti;
+	}
+	for (int k = m.pointCount; k < 2; ++k)
+	{
+		// points beyond pointCount keep their previous impulses, as the untouched b2ManifoldPoint would
+		m.ni[k] = k == 0 ? o1.z : o2.z;
+		m.ti[k] = k == 0 ? o1.w : o2.w;
+	}
+
+	int ev = 0;
+	if (touching != wasTouching)
+	{
+		// b2ContactManager::ConsumeAwakes wakes m_nodeB.other (= fixture A's body) only (:472-486)
+		d.wake[bA] = 1;
+		ev = touching ? B2CU_EV_BEGIN : B2CU_EV_END;
+	}
+	if (touching)
+	{
+		flags |= B2CU_CONTACT_TOUCHING;
+		touchingNow = 1;
+	}
+	else
+	{
+		flags &= ~B2CU_CONTACT_TOUCHING;
+	}
+	// deferred Begin/End buffers (b2ContactManagerPerThreadData::m_beginContacts / m_endContacts); sorted by key
+	// afterwards, which is what b2ThreadDataSorter does for the reference (b2ContactManager.cpp:388-433)
+	if (ev == B2CU_EV_BEGIN) AppendKey(d, CNT_BEGIN, d.beginKeys, d.c.key[i], capacity);
+	else if (ev == B2CU_EV_END) AppendKey(d, CNT_END, d.endKeys, d.c.key[i], capacity);
+
+	d.c.flags[i] = flags;
+	d.c.m0[i] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
+	d.c.m1[i] = make_float4(m.lp[0].x, m.lp[0].y, m.ni[0], m.ti[0]);
+	d.c.m2[i] = make_float4(m.lp[1].x, m.lp[1].y, m.ni[1], m.ti[1]);
+	d.c.m3[i] = make_uint4(m.id[0], m.id[1], (uint32_t)m.type, (uint32_t)m.pointCount);
+	return touchingNow;
+}
+
+__global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contactCount, int mainCount, int capacity, int* __restrict__ heavyList)
 {
 	int touchingCount = 0;
 	B2CU_GRID_STRIDE(i, contactCount)
@@ -99,7 +181,6 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
 		uint32_t fbA = d.bflags[bA], fbB = d.bflags[bB];
 		uint32_t flags = d.c.flags[i];
-		uint32_t gA = d.pgroup[pr.x], gB = d.pgroup[pr.y];
 		uint4 m3 = d.c.m3[i];
 		bool destroy = false;
 
@@ -108,7 +189,7 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 			bool should = IsOwnedDynamic(fbA) || IsOwnedDynamic(fbB);
 			if (should)
 			{
-				should = DefaultFilter(d.pfilter[pr.x], gA, d.pfilter[pr.y], gB);
+				should = DefaultFilter(d.pfilter[pr.x], d.pgroup[pr.x], d.pfilter[pr.y], d.pgroup[pr.y]);
 			}
 			if (!should)
 			{
@@ -152,79 +233,41 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 			continue;
 		}
 
-		// ---- b2Contact::Update ----
-		float4 o1 = d.c.m1[i], o2 = d.c.m2[i];
-		int oldCount = (int)m3.w;
-		flags |= B2CU_CONTACT_ENABLED;
-		bool wasTouching = (flags & B2CU_CONTACT_TOUCHING) != 0;
-
-		Manifold m;
-		float4 o0 = d.c.m0[i];
-		m.localNormal = V(o0.x, o0.y);
-		m.localPoint = V(o0.z, o0.w);
-		m.lp[0] = V(o1.x, o1.y);
-		m.lp[1] = V(o2.x, o2.y);
-		m.id[0] = m3.x;
-		m.id[1] = m3.y;
-		m.type = (int)m3.z;
-		m.pointCount = 0;
-
-		Xf xfA = MakeXf(d.xf[bA]);
-		Xf xfB = MakeXf(d.xf[bB]);
-		Evaluate(&m, d.shapes + d.pshape[pr.x], xfA, d.shapes + d.pshape[pr.y], xfB);
-		bool touching = m.pointCount > 0;
-
-		// warm-start transfer by feature id
-		for (int k = 0; k < m.pointCount; ++k)
+		const b2cuShape* sA = d.shapes + d.pshape[pr.x];
+		const b2cuShape* sB = d.shapes + d.pshape[pr.y];
+		// polygon-polygon and edge-polygon manifolds cost several times the others; running them in the same
+		// warps leaves most lanes idle, so they are queued for a second, dense pass (CollideHeavyKernel)
+		bool heavy = sB->type == B2CU_SHAPE_POLYGON && sA->type != B2CU_SHAPE_CIRCLE;
+		if (heavy)
 		{
-			float ni = 0.0f, ti = 0.0f;
-			uint32_t id2 = m.id[k];
-			if (oldCount > 0 && m3.x == id2)
-			{
-				ni = o1.z;
-				ti = o1.w;
-			}
-			else if (oldCount > 1 && m3.y == id2)
-			{
-				ni = o2.z;
-				ti = o2.w;
-			}
-			m.ni[k] = ni;
-			m.ti[k] = ti;
+			d.c.flags[i] = flags;
+			unsigned peers = __activemask();
+			int lane = threadIdx.x & 31;
+			int leader = __ffs(peers) - 1;
+			int base = 0;
+			if (lane == leader) base = atomicAdd(&d.counters[CNT_HEAVY], __popc(peers));
+			base = __shfl_sync(peers, base, leader);
+			heavyList[base + __popc(peers & ((1u << lane) - 1u))] = i;
+			continue;
 		}
-		for (int k = m.pointCount; k < 2; ++k)
-		{
-			// points beyond pointCount keep their previous impulses, as the untouched b2ManifoldPoint would
-			m.ni[k] = k == 0 ? o1.z : o2.z;
-			m.ti[k] = k == 0 ? o1.w : o2.w;
-		}
+		touchingCount += UpdateContact(d, i, pr, bA, bB, flags, m3, sA, sB, capacity);
+	}
+	for (int dlt = 16; dlt > 0; dlt >>= 1) touchingCount += __shfl_down_sync(0xffffffffu, touchingCount, dlt);
+	if ((threadIdx.x & 31) == 0 && touchingCount) atomicAdd(&d.counters[CNT_TOUCHING], touchingCount);
+}
 
-		int ev = 0;
-		if (touching != wasTouching)
-		{
-			// b2ContactManager::ConsumeAwakes wakes m_nodeB.other (= fixture A's body) only (:472-486)
-			d.wake[bA] = 1;
-			ev = touching ? B2CU_EV_BEGIN : B2CU_EV_END;
-		}
-		if (touching)
-		{
-			flags |= B2CU_CONTACT_TOUCHING;
-			++touchingCount;
-		}
-		else
-		{
-			flags &= ~B2CU_CONTACT_TOUCHING;
-		}
-		// deferred Begin/End buffers (b2ContactManagerPerThreadData::m_beginContacts / m_endContacts); sorted by key
-		// afterwards, which is what b2ThreadDataSorter does for the reference (b2ContactManager.cpp:388-433)
-		if (ev == B2CU_EV_BEGIN) AppendKey(d, CNT_BEGIN, d.beginKeys, d.c.key[i], capacity);
-		else if (ev == B2CU_EV_END) AppendKey(d, CNT_END, d.endKeys, d.c.key[i], capacity);
-
-		d.c.flags[i] = flags;
-		d.c.m0[i] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
-		d.c.m1[i] = make_float4(m.lp[0].x, m.lp[0].y, m.ni[0], m.ti[0]);
-		d.c.m2[i] = make_float4(m.lp[1].x, m.lp[1].y, m.ni[1], m.ti[1]);
-		d.c.m3[i] = make_uint4(m.id[0], m.id[1], (uint32_t)m.type, (uint32_t)m.pointCount);
+// second pass of Collide over the queued polygon-polygon / edge-polygon contacts
+__global__ void __launch_bounds__(256) CollideHeavyKernel(DeviceArrays d, const int* __restrict__ heavyList, int capacity)
+{
+	int touchingCount = 0;
+	int n = d.counters[CNT_HEAVY];
+	B2CU_GRID_STRIDE(k, n)
+	{
+		int i = heavyList[k];
+		int2 pr = d.c.proxies[i];
+		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		touchingCount += UpdateContact(d, i, pr, bA, bB, d.c.flags[i], d.c.m3[i], d.shapes + d.pshape[pr.x],
+		                               d.shapes + d.pshape[pr.y], capacity);
 	}
 	for (int dlt = 16; dlt > 0; dlt >>= 1) touchingCount += __shfl_down_sync(0xffffffffu, touchingCount, dlt);
 	if ((threadIdx.x & 31) == 0 && touchingCount) atomicAdd(&d.counters[CNT_TOUCHING], touchingCount);

@@ -41,6 +41,7 @@ enum Counter
 	CNT_TOI,
 	CNT_ERROR,            // != 0: a buffer overflowed
 	CNT_SCRATCH,
+	CNT_HEAVY,            // contacts queued for the dense polygon pass of Collide
 	CNT_STICKY_TOI,       // not cleared per step: a TOI-candidate contact has existed
 	CNT_COUNT
 };
@@ -187,6 +188,7 @@ struct b2cuWorld
 	unsigned shardSeq;     // sequence number of the next halo exchange
 
 	// last step
+	int endUpdateCount;  // EndContact events from Update (the rest of endCount come from Destroy)
 	int beginCount, endCount, constraintCount, colourCount, overflowCount, toiCount;
 	int colourCounts[B2CU_MAX_COLOURS + 2]; // [32] own-class overflow, [33] cross-class overflow
 	int colourStarts[B2CU_MAX_COLOURS + 3];

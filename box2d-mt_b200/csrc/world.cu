@@ -1073,7 +1073,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	if (nc > 0)
 	{
 		// narrow phase; begin/end events are appended to the deferred buffers and sorted at the end of the step
-		LAUNCH(w, CollideKernel, GridFor(nc), kBlock, d, nc, w->mainCount, w->contactCapacity);
+		LAUNCH(w, CollideKernel, GridFor(nc), kBlock, d, nc, w->mainCount, w->contactCapacity, d.listA);
+		LAUNCH(w, CollideHeavyKernel, GridFor(nc), kBlock, d, (const int*)d.listA, w->contactCapacity);
 		LAUNCH(w, ApplyWakeKernel, GridFor(nb), kBlock, d, nb);
 	}
 	cudaEventRecord(w->ev[2], w->stream);
@@ -1298,21 +1299,14 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	cudaEvent_t evBroad = w->ev[8];
 	cudaEventRecord(evBroad, w->stream);
 
-	// ---- deferred event buffers in key order; EndContact calls made by Destroy come after the sorted ends
-	// (FinishCollide, b2ContactManager.cpp:388-439).  hostCounters is current: the rebuild has just read it.
+	// ---- deferred event buffers: counts only; b2cuGetEvents puts them in callback order.  hostCounters is current:
+	// the broad-phase has just read it.
 	{
 		int nBegin = std::min(w->hostCounters[CNT_BEGIN], w->contactCapacity);
 		int nEnd = std::min(w->hostCounters[CNT_END], w->contactCapacity);
-		int nDestroyEnd = std::min(w->hostCounters[CNT_DESTROY_END], w->contactCapacity - nEnd);
-		SortKeys(w, d.beginKeys, nBegin);
-		SortKeys(w, d.endKeys, nEnd);
-		SortKeys(w, d.destroyEndKeys, nDestroyEnd);
-		if (nDestroyEnd > 0)
-		{
-			CUDA_TRY(w, cudaMemcpyAsync(d.endKeys + nEnd, d.destroyEndKeys, sizeof(uint64_t) * nDestroyEnd,
-			                            cudaMemcpyDeviceToDevice, w->stream));
-		}
+		int nDestroyEnd = std::min(w->hostCounters[CNT_DESTROY_END], w->contactCapacity);
 		w->beginCount = nBegin;
+		w->endUpdateCount = nEnd;
 		w->endCount = nEnd + nDestroyEnd;
 	}
 
@@ -1402,15 +1396,35 @@ int b2cuGetEvents(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* 
 {
 	if (!w || capacity < 0 || (capacity > 0 && !keys)) return B2CU_ERR_ARGUMENT;
 	cudaSetDevice(w->device);
-	int n = kind == B2CU_EVENT_BEGIN ? w->beginCount : w->endCount;
+	const int n = kind == B2CU_EVENT_BEGIN ? w->beginCount : w->endCount;
 	if (count) *count = n;
-	int m = std::min(n, capacity);
-	if (m > 0)
+	if (capacity == 0 || n == 0) return B2CU_OK;
+	// The device appends events in arrival order; the deferred-callback order (ascending key, EndContact calls made
+	// by Destroy after the sorted ends, b2ContactManager.cpp:388-439) is established here, when somebody asks: the
+	// lists are short and a step that nobody listens to pays nothing for the ordering.
+	std::vector<uint64_t> sorted(n);
+	if (kind == B2CU_EVENT_BEGIN)
 	{
-		CUDA_TRY(w, cudaMemcpyAsync(keys, kind == B2CU_EVENT_BEGIN ? w->d.beginKeys : w->d.endKeys, sizeof(uint64_t) * m,
-		                            cudaMemcpyDeviceToHost, w->stream));
+		CUDA_TRY(w, cudaMemcpyAsync(sorted.data(), w->d.beginKeys, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, w->stream));
+		int rc = SyncCheck(w);
+		if (rc) return rc;
+		std::sort(sorted.begin(), sorted.end());
 	}
-	return SyncCheck(w);
+	else
+	{
+		const int nEnd = w->endUpdateCount, nDestroy = n - nEnd;
+		if (nEnd > 0)
+			CUDA_TRY(w, cudaMemcpyAsync(sorted.data(), w->d.endKeys, sizeof(uint64_t) * nEnd, cudaMemcpyDeviceToHost, w->stream));
+		if (nDestroy > 0)
+			CUDA_TRY(w, cudaMemcpyAsync(sorted.data() + nEnd, w->d.destroyEndKeys, sizeof(uint64_t) * nDestroy,
+			                            cudaMemcpyDeviceToHost, w->stream));
+		int rc = SyncCheck(w);
+		if (rc) return rc;
+		std::sort(sorted.begin(), sorted.begin() + nEnd);
+		std::sort(sorted.begin() + nEnd, sorted.end());
+	}
+	memcpy(keys, sorted.data(), sizeof(uint64_t) * std::min(n, capacity));
+	return B2CU_OK;
 }
 
 int b2cuGetContactsByKey(b2cuWorld* w, int32_t count, const b2cuContactKey* keys, b2cuContact* out)
