@@ -1677,7 +1677,11 @@ __global__ void __launch_bounds__(256) SyncProxiesKernel(DeviceArrays d, int pro
 			if (dd.y < 0.0f) nb.y += dd.y;
 			else nb.w += dd.y;
 			d.fat[p] = nb;
-			d.pgroup[p] |= ((uint32_t)B2CU_PROXY_MOVED << 16);
+			// the box the proxy had when the step began, for the shortcut of QueryProxy
+			d.fatPrev[p] = fat;
+			uint32_t g = d.pgroup[p];
+			if (!(g & ((uint32_t)B2CU_PROXY_MOVED << 16))) g |= (uint32_t)B2CU_PROXY_MOVED_SYNC << 16;
+			d.pgroup[p] = g | ((uint32_t)B2CU_PROXY_MOVED << 16);
 		}
 	}
 }
@@ -1726,6 +1730,23 @@ __device__ __forceinline__ float LevelInvCell(float invCell0, int level) { retur
 __device__ __forceinline__ bool IsMovedProxy(const DeviceArrays& d, int p)
 {
 	return ((d.pgroup[p] >> 16) & B2CU_PROXY_MOVED) != 0;
+}
+
+// Broad-phase invariant (b2ContactManager::AddPair + b2ContactManager::Collide, b2ContactManager.cpp:117-262): when a
+// step begins, every pair of overlapping fat boxes that passes the filters has a contact, and Collide only destroys
+// the contacts whose fat boxes do not overlap.  So a pair whose boxes ALREADY overlapped at the beginning of the step
+// needs no lookup at all.  The box at the beginning of the step is fatPrev for a proxy SyncProxiesKernel moved
+// (MOVED_SYNC), fat for one that did not move; a proxy the caller touched (MOVED without MOVED_SYNC: new fixture,
+// SetTransform, Refilter, SetType) has no such history and always takes the full check.
+__device__ __forceinline__ bool StartBox(const DeviceArrays& d, int p, uint32_t proxyFlags, float4 fat, float4* box)
+{
+	if (proxyFlags & B2CU_PROXY_MOVED_SYNC)
+	{
+		*box = d.fatPrev[p];
+		return true;
+	}
+	*box = fat;
+	return !(proxyFlags & B2CU_PROXY_MOVED);
 }
 
 // levelInfo[l] = proxies on level l, levelInfo[LEVELS+1+l] = moved proxies on level l (l == LEVELS: huge)
@@ -1818,12 +1839,19 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 //   each coarser level  every overlapping r such that p or r moved (r never looks down at p's level)
 //   the huge list       like a coarser level
 // so each pair with a moved member is examined exactly once.
+// The cells a proxy must examine are dealt round-robin to the `lanes` threads that share the proxy (lane = 0..lanes-1):
+// one proxy is a chain of several hundred dependent loads, far too long for one thread when only the moved proxies
+// (a tenth of the world) are in flight.
 __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool movedP, const GridParams& g,
-                                           const int* shCount, const int* shMoved, int2 contactCount, int pairCapacity)
+                                           const int* shCount, const int* shMoved, int2 contactCount, int pairCapacity,
+                                           int lane, int lanes)
 {
 	float4 fp = d.fat[p];
 	int levelP = ProxyLevel(fp, g.cell0);
 	const int nHuge = shCount[B2CU_GRID_LEVELS];
+	int turn = 0;
+	float4 startP;
+	const bool knownP = StartBox(d, p, d.pgroup[p] >> 16, fp, &startP);
 
 	for (int level = levelP; level < B2CU_GRID_LEVELS; ++level)
 	{
@@ -1837,6 +1865,7 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 		{
 			for (int cx = x0; cx <= x1; ++cx)
 			{
+				if (turn++ % lanes != lane) continue;
 				uint32_t h = CellHash(level, cx, cy, g.mask);
 				int start = d.cellStart[h];
 				int end = start + d.cellCount[h];
@@ -1849,7 +1878,8 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 					if (CellCoord(fr.x, inv) != cx || CellCoord(fr.y, inv) != cy) continue;
 					if (ProxyLevel(fr, g.cell0) != level) continue;
 					if (!AabbOverlap(fp, fr)) continue;
-					bool movedR = IsMovedProxy(d, r);
+					uint32_t flagsR = d.pgroup[r] >> 16;
+					bool movedR = (flagsR & B2CU_PROXY_MOVED) != 0;
 					if (same)
 					{
 						if (movedR && r < p) continue;
@@ -1858,6 +1888,8 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 					{
 						continue;
 					}
+					float4 startR;
+					if (knownP && StartBox(d, r, flagsR, fr, &startR) && AabbOverlap(startP, startR)) continue;
 					TryAddPair(d, p, r, contactCount, pairCapacity);
 				}
 			}
@@ -1867,12 +1899,14 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 	if (nHuge > 0 && (movedP || shMoved[B2CU_GRID_LEVELS] > 0))
 	{
 		bool hugeP = levelP == B2CU_GRID_LEVELS;
-		for (int s = 0; s < nHuge; ++s)
+		for (int s = lane; s < nHuge; s += lanes)
 		{
 			int r = d.largeList[s];
 			if (r == p) continue;
-			if (!AabbOverlap(fp, d.fat[r])) continue;
-			bool movedR = IsMovedProxy(d, r);
+			float4 fr = d.fat[r];
+			if (!AabbOverlap(fp, fr)) continue;
+			uint32_t flagsR = d.pgroup[r] >> 16;
+			bool movedR = (flagsR & B2CU_PROXY_MOVED) != 0;
 			if (hugeP)
 			{
 				if (!movedP || (movedR && r < p)) continue;
@@ -1881,6 +1915,8 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 			{
 				continue;
 			}
+			float4 startR;
+			if (knownP && StartBox(d, r, flagsR, fr, &startR) && AabbOverlap(startP, startR)) continue;
 			TryAddPair(d, p, r, contactCount, pairCapacity);
 		}
 	}
@@ -1897,8 +1933,17 @@ __global__ void __launch_bounds__(128) QueryMovedKernel(DeviceArrays d, GridPara
 		shMoved[threadIdx.x] = d.levelInfo[B2CU_GRID_LEVELS + 1 + threadIdx.x];
 	}
 	__syncthreads();
-	const int n = d.counters[CNT_SCRATCH];
-	B2CU_GRID_STRIDE(t, n) { QueryProxy(d, d.movedList[t], true, g, shCount, shMoved, contactCount, pairCapacity); }
+	// threads per moved proxy: as many as the grid can give (a power of two up to a warp).  One proxy is a chain of
+	// a few hundred dependent loads; with few moved proxies the kernel time is that chain, so it is split.
+	const int moved = d.counters[CNT_SCRATCH];
+	const int threads = gridDim.x * blockDim.x;
+	int lanes = 1;
+	while (lanes < 32 && moved * lanes * 2 <= threads) lanes *= 2;
+	const int n = moved * lanes;
+	B2CU_GRID_STRIDE(t, n)
+	{
+		QueryProxy(d, d.movedList[t / lanes], true, g, shCount, shMoved, contactCount, pairCapacity, t % lanes, lanes);
+	}
 }
 
 // proxies that did not move only have to look UP, at coarser levels that contain a moved proxy (a moved wall, a
@@ -1933,7 +1978,7 @@ __global__ void __launch_bounds__(128) QueryUnmovedKernel(DeviceArrays d, int pr
 	B2CU_GRID_STRIDE(p, proxyCount)
 	{
 		if (IsMovedProxy(d, p)) continue;
-		QueryProxy(d, p, false, g, shCount, shMoved, contactCount, pairCapacity);
+		QueryProxy(d, p, false, g, shCount, shMoved, contactCount, pairCapacity, 0, 1);
 	}
 }
 
@@ -1950,7 +1995,7 @@ __global__ void IotaKernel(int* out, int n)
 
 __global__ void ClearMovedKernel(DeviceArrays d, int proxyCount)
 {
-	B2CU_GRID_STRIDE(p, proxyCount) { d.pgroup[p] &= ~((uint32_t)B2CU_PROXY_MOVED << 16); }
+	B2CU_GRID_STRIDE(p, proxyCount) { d.pgroup[p] &= ~((uint32_t)(B2CU_PROXY_MOVED | B2CU_PROXY_MOVED_SYNC) << 16); }
 }
 
 // ---------------------------------------------------------------------------------------------------------

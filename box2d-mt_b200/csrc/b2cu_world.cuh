@@ -60,6 +60,10 @@ struct ContactSet
 	int* colour;        // colour kept from the previous step (B2CU_COLOUR_NONE if it was not a constraint)
 };
 
+// device-only proxy flag (next to the public B2CU_PROXY_* bits): moved by SyncProxiesKernel in this step
+#define B2CU_PROXY_MOVED_SYNC 0x8
+#define B2CU_PROXY_PUBLIC_FLAGS 0x7
+
 struct DeviceArrays
 {
 	// ---- bodies (index = dense body id, creation order) ----
@@ -84,6 +88,7 @@ struct DeviceArrays
 
 	// ---- proxies (index = dense proxy id, fixture creation order) ----
 	float4* fat;
+	float4* fatPrev;    // fat box at the beginning of the step, valid for proxies flagged B2CU_PROXY_MOVED_SYNC
 	float4* aabb;
 	int* pbody;
 	int* pshape;

@@ -32,6 +32,13 @@ inline int GridFor(int n, int block = kBlock)
 	return blocks;
 }
 
+// QueryMovedKernel: 128-thread blocks, up to 16 resident blocks per SM; the kernel shares the threads out
+inline int QueryGrid(int proxyCount)
+{
+	(void)proxyCount;
+	return g_smCount * 16;
+}
+
 int SetError(b2cuWorld* w, int code, const char* fmt, ...)
 {
 	if (w)
@@ -154,6 +161,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->colourClaim, CAP_BODY));
 	v.push_back(Desc(&d->shapes, CAP_SHAPE));
 	v.push_back(Desc(&d->fat, CAP_PROXY));
+	v.push_back(Desc(&d->fatPrev, CAP_PROXY));
 	v.push_back(Desc(&d->aabb, CAP_PROXY));
 	v.push_back(Desc(&d->pbody, CAP_PROXY));
 	v.push_back(Desc(&d->pshape, CAP_PROXY));
@@ -293,6 +301,8 @@ int ZeroCounter(b2cuWorld* w, int index)
 
 float ChooseCellSize(const std::vector<float>& extents)
 {
+	// finest grid level = twice the median extent: the typical proxy stays on level 0 even when a fast step
+	// stretches its fat box, so QueryUnmovedKernel (needed when a coarser-level proxy moves) stays idle
 	if (extents.empty()) return 1.0f;
 	std::vector<float> e(extents);
 	size_t mid = e.size() / 2;
@@ -452,7 +462,7 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		ExclusiveScan(&w->prims, d.cellCount, d.cellStart, w->gridSize, nullptr, w->stream);
 		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
 		LAUNCH(w, GridFillKernel, GridFor(np), kBlock, d, np);
-		LAUNCH(w, QueryMovedKernel, GridFor(np, 128), 128, d, grid, counts, w->contactCapacity);
+		LAUNCH(w, QueryMovedKernel, QueryGrid(np), 128, d, grid, counts, w->contactCapacity);
 		LAUNCH(w, QueryUnmovedKernel, GridFor(np, 128), 128, d, np, grid, counts, w->contactCapacity);
 	}
 
@@ -470,7 +480,7 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		DeviceArrays& dd = w->d;
 		if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
 		if ((rc = ZeroCounter(w, CNT_ERROR))) return rc;
-		LAUNCH(w, QueryMovedKernel, GridFor(np, 128), 128, dd, grid, counts, w->contactCapacity);
+		LAUNCH(w, QueryMovedKernel, QueryGrid(np), 128, dd, grid, counts, w->contactCapacity);
 		LAUNCH(w, QueryUnmovedKernel, GridFor(np, 128), 128, dd, np, grid, counts, w->contactCapacity);
 		if ((rc = ReadCounters(w))) return rc;
 		if (w->hostCounters[CNT_ERROR])
@@ -599,6 +609,9 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 	if (cudaGetDeviceProperties(&prop, def->device) == cudaSuccess)
 	{
 		g_smCount = prop.multiProcessorCount;
+		// developer knob: DRAM->L2 fetch granularity (32/64/128 B); the step is dominated by 16-byte gathers
+		const char* fg = getenv("B2CU_L2_FETCH");
+		if (fg && atoi(fg) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
 		const char* l2env = getenv("B2CU_L2_WINDOW");
 		if (l2env && atoi(l2env) > 0 && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0)
 		{
@@ -823,7 +836,7 @@ int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* 
 		shape[i] = p.shape;
 		fixture[i] = p.fixture;
 		filter[i] = (uint32_t)p.categoryBits | ((uint32_t)p.maskBits << 16);
-		group[i] = (uint32_t)(uint16_t)p.groupIndex | ((uint32_t)p.flags << 16);
+		group[i] = (uint32_t)(uint16_t)p.groupIndex | ((uint32_t)(p.flags & B2CU_PROXY_PUBLIC_FLAGS) << 16);
 		mat[i] = make_float2(p.friction, p.restitution);
 		extents.push_back(std::max(p.fat[2] - p.fat[0], p.fat[3] - p.fat[1]));
 		if (p.flags & B2CU_PROXY_MOVED) anyMoved = true;
@@ -871,7 +884,7 @@ int b2cuGetProxies(b2cuWorld* w, int32_t first, int32_t count, b2cuProxy* proxie
 		p.categoryBits = (uint16_t)(filter[i] & 0xFFFFu);
 		p.maskBits = (uint16_t)(filter[i] >> 16);
 		p.groupIndex = (int16_t)(group[i] & 0xFFFFu);
-		p.flags = (uint16_t)(group[i] >> 16);
+		p.flags = (uint16_t)((group[i] >> 16) & B2CU_PROXY_PUBLIC_FLAGS);
 		p.fixture = fixture[i];
 		p.child = 0;
 	}
@@ -1038,6 +1051,10 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 
 	CUDA_TRY(w, cudaMemsetAsync(d.counters, 0, sizeof(int) * CNT_STICKY_TOI, w->stream));
 	cudaEventRecord(w->ev[0], w->stream);
+	{
+		const char* t = getenv("B2CU_TRACE");
+		g_trace.enabled = t && atoi(t) > 0;
+	}
 	g_trace.used = 0;
 	g_traceWorld = w;
 	g_primTraceHook = g_trace.enabled ? PrimTraceHook : nullptr;

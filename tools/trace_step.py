@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Developer tool: per-kernel device time of one steady-state step (B2CU_TRACE=1). usage: trace_step.py BODIES SETTLE"""
+"""Developer tool: per-kernel device time of one steady-state step (B2CU_TRACE=1). usage: trace_step.py BODIES SETTLE [STEPS] 2>&1 | python tools/trace_agg.py"""
 import os, sys
 os.environ["B2CU_TRACE"] = "0"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,3 +10,11 @@ w = b2host.HostWorld(scenes.pile(max(16, bodies // 100), 100), download_bodies=F
 for _ in range(settle):
     w.step()
 print("settled", flush=True)
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+os.environ["B2CU_TRACE"] = "1"
+for _ in range(steps):
+    w.step()
+    info = w.step_info()
+    print({k: int(info[k]) for k in ("contactCount", "constraintCount", "colourCount", "moveCount", "newContactCount",
+                                     "kernelLaunches")}, "step_ms %.3f" % float(info["step"]), flush=True)
+os.environ["B2CU_TRACE"] = "0"
