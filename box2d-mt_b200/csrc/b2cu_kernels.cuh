@@ -273,6 +273,72 @@ __global__ void __launch_bounds__(256) CollideHeavyKernel(DeviceArrays d, const 
 	if ((threadIdx.x & 31) == 0 && touchingCount) atomicAdd(&d.counters[CNT_TOUCHING], touchingCount);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Host transport of the body records: the caller's mirror is an array of b2cuBody (26 words, include/b2cuda.h),
+// the device keeps bodies as float4 columns.  The conversion runs here, through shared memory so that both the
+// column side and the record side are coalesced, and the PCIe copy is one contiguous transfer.
+// ---------------------------------------------------------------------------------------------------------
+#define B2CU_BODY_WORDS 26
+static_assert(sizeof(b2cuBody) == B2CU_BODY_WORDS * 4, "b2cuBody layout");
+
+__global__ void __launch_bounds__(256) PackBodiesKernel(DeviceArrays d, int first, int count, float* __restrict__ out)
+{
+	__shared__ float sh[256 * B2CU_BODY_WORDS];
+	for (int tile = blockIdx.x; tile * 256 < count; tile += gridDim.x)
+	{
+		int r = tile * 256 + threadIdx.x;
+		if (r < count)
+		{
+			int b = first + r;
+			float4 xf = d.xf[b], pos = d.pos[b], pos0 = d.pos0[b], vel = d.vel[b], mass = d.mass[b];
+			float4 force = d.force[b], damp = d.damp[b];
+			float* s = sh + threadIdx.x * B2CU_BODY_WORDS;
+			s[0] = xf.x; s[1] = xf.y; s[2] = xf.z; s[3] = xf.w;
+			s[4] = pos.x; s[5] = pos.y; s[6] = pos.z;
+			s[7] = pos0.x; s[8] = pos0.y; s[9] = pos0.z; s[10] = pos0.w;
+			s[11] = mass.z; s[12] = mass.w;
+			s[13] = vel.x; s[14] = vel.y; s[15] = vel.z;
+			s[16] = force.x; s[17] = force.y; s[18] = force.z;
+			s[19] = mass.x; s[20] = mass.y;
+			s[21] = damp.x; s[22] = damp.y; s[23] = damp.z;
+			s[24] = force.w;
+			s[25] = __uint_as_float(d.bflags[b]);
+		}
+		__syncthreads();
+		int n = min(256, count - tile * 256) * B2CU_BODY_WORDS;
+		float* o = out + (size_t)tile * 256 * B2CU_BODY_WORDS;
+		for (int i = threadIdx.x; i < n; i += 256) o[i] = sh[i];
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(256) UnpackBodiesKernel(DeviceArrays d, int first, int count, const float* __restrict__ in)
+{
+	__shared__ float sh[256 * B2CU_BODY_WORDS];
+	for (int tile = blockIdx.x; tile * 256 < count; tile += gridDim.x)
+	{
+		int n = min(256, count - tile * 256) * B2CU_BODY_WORDS;
+		const float* src = in + (size_t)tile * 256 * B2CU_BODY_WORDS;
+		for (int i = threadIdx.x; i < n; i += 256) sh[i] = src[i];
+		__syncthreads();
+		int r = tile * 256 + threadIdx.x;
+		if (r < count)
+		{
+			int b = first + r;
+			const float* s = sh + threadIdx.x * B2CU_BODY_WORDS;
+			d.xf[b] = make_float4(s[0], s[1], s[2], s[3]);
+			d.pos[b] = make_float4(s[4], s[5], s[6], 0.0f);
+			d.pos0[b] = make_float4(s[7], s[8], s[9], s[10]);
+			d.mass[b] = make_float4(s[19], s[20], s[11], s[12]);
+			d.vel[b] = make_float4(s[13], s[14], s[15], 0.0f);
+			d.force[b] = make_float4(s[16], s[17], s[18], s[24]);
+			d.damp[b] = make_float4(s[21], s[22], s[23], 0.0f);
+			d.bflags[b] = __float_as_uint(s[25]);
+		}
+		__syncthreads();
+	}
+}
+
 // b2Body::SetAwake(true) for every body flagged by Collide / contact creation / contact destruction
 // (Box2D/Dynamics/b2Body.h:690-718: sets e_awakeFlag and resets m_sleepTime).
 __global__ void ApplyWakeKernel(DeviceArrays d, int bodyCount)

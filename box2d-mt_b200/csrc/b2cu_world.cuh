@@ -199,6 +199,8 @@ struct b2cuWorld
 	int colourStarts[B2CU_MAX_COLOURS + 3];
 
 	int* hostCounters;   // pinned, CNT_COUNT + colour counts
+	float* bodyStage;    // device staging of b2cuBody records for b2cuGetBodies / b2cuSetBodies (lazy)
+	int bodyStageCapacity;
 	cudaEvent_t ev[10];
 	int launches;
 	char lastError[512];

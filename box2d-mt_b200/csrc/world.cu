@@ -14,6 +14,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <mutex>
+#include <unordered_set>
 
 using namespace b2cu;
 
@@ -684,6 +686,7 @@ void b2cuDestroyWorld(b2cuWorld* w)
 	std::vector<ArrayDesc> arrays = AllArrays(w);
 	for (size_t k = 0; k < arrays.size(); ++k) cudaFree(*arrays[k].ptr);
 	cudaFree(w->d.islandMinSep);
+	cudaFree(w->bodyStage);
 	if (w->peerLower && w->peerLowerIpc) cudaIpcCloseMemHandle(w->peerLower);
 	if (w->peerUpper && w->peerUpperIpc) cudaIpcCloseMemHandle(w->peerUpper);
 	cudaFree(w->ghostIds);
@@ -732,31 +735,31 @@ int b2cuSetCounts(b2cuWorld* w, int32_t bodyCount, int32_t shapeCount, int32_t p
 	return RebuildLowStart(w);
 }
 
+// device staging for the record <-> column conversion of the bodies
+static int EnsureBodyStage(b2cuWorld* w)
+{
+	if (w->bodyStage && w->bodyStageCapacity >= w->bodyCapacity) return B2CU_OK;
+	if (w->bodyStage)
+	{
+		CUDA_TRY(w, cudaStreamSynchronize(w->stream));
+		cudaFree(w->bodyStage);
+		w->bodyStage = nullptr;
+	}
+	CUDA_TRY(w, cudaMalloc(&w->bodyStage, sizeof(b2cuBody) * (size_t)w->bodyCapacity));
+	w->bodyStageCapacity = w->bodyCapacity;
+	return B2CU_OK;
+}
+
 int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bodies)
 {
 	int rc = CheckRange(w, first, count, w ? w->bodyCount : 0, bodies);
 	if (rc) return rc;
+	if (count == 0) return B2CU_OK;
 	cudaSetDevice(w->device);
-	std::vector<float4> xf(count), pos(count), pos0(count), vel(count), mass(count), force(count), damp(count);
-	std::vector<uint32_t> flags(count);
-	for (int i = 0; i < count; ++i)
-	{
-		const b2cuBody& b = bodies[i];
-		xf[i] = make_float4(b.px, b.py, b.qs, b.qc);
-		pos[i] = make_float4(b.cx, b.cy, b.a, 0.0f);
-		pos0[i] = make_float4(b.c0x, b.c0y, b.a0, b.alpha0);
-		vel[i] = make_float4(b.vx, b.vy, b.w, 0.0f);
-		mass[i] = make_float4(b.invMass, b.invI, b.lcx, b.lcy);
-		force[i] = make_float4(b.fx, b.fy, b.torque, b.sleepTime);
-		damp[i] = make_float4(b.linearDamping, b.angularDamping, b.gravityScale, 0.0f);
-		flags[i] = b.flags;
-	}
-	DeviceArrays& d = w->d;
-	if ((rc = Upload(w, d.xf, first, xf)) || (rc = Upload(w, d.pos, first, pos)) || (rc = Upload(w, d.pos0, first, pos0)) ||
-	    (rc = Upload(w, d.vel, first, vel)) || (rc = Upload(w, d.mass, first, mass)) ||
-	    (rc = Upload(w, d.force, first, force)) || (rc = Upload(w, d.damp, first, damp)) ||
-	    (rc = Upload(w, d.bflags, first, flags)))
-		return rc;
+	if ((rc = EnsureBodyStage(w))) return rc;
+	float* stage = w->bodyStage + (size_t)first * B2CU_BODY_WORDS;
+	CUDA_TRY(w, cudaMemcpyAsync(stage, bodies, sizeof(b2cuBody) * (size_t)count, cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(w, UnpackBodiesKernel, GridFor(count), kBlock, w->d, first, count, (const float*)stage);
 	w->toiCheckDirty = true;
 	return SyncCheck(w);
 }
@@ -765,31 +768,47 @@ int b2cuGetBodies(b2cuWorld* w, int32_t first, int32_t count, b2cuBody* bodies)
 {
 	int rc = CheckRange(w, first, count, w ? w->bodyCount : 0, bodies);
 	if (rc) return rc;
+	if (count == 0) return B2CU_OK;
 	cudaSetDevice(w->device);
-	std::vector<float4> xf(count), pos(count), pos0(count), vel(count), mass(count), force(count), damp(count);
-	std::vector<uint32_t> flags(count);
-	DeviceArrays& d = w->d;
-	if ((rc = Download(w, d.xf, first, xf)) || (rc = Download(w, d.pos, first, pos)) ||
-	    (rc = Download(w, d.pos0, first, pos0)) || (rc = Download(w, d.vel, first, vel)) ||
-	    (rc = Download(w, d.mass, first, mass)) || (rc = Download(w, d.force, first, force)) ||
-	    (rc = Download(w, d.damp, first, damp)) || (rc = Download(w, d.bflags, first, flags)))
-		return rc;
-	if ((rc = SyncCheck(w))) return rc;
-	for (int i = 0; i < count; ++i)
+	if ((rc = EnsureBodyStage(w))) return rc;
+	float* stage = w->bodyStage + (size_t)first * B2CU_BODY_WORDS;
+	LAUNCH(w, PackBodiesKernel, GridFor(count), kBlock, w->d, first, count, stage);
+	CUDA_TRY(w, cudaMemcpyAsync(bodies, stage, sizeof(b2cuBody) * (size_t)count, cudaMemcpyDeviceToHost, w->stream));
+	return SyncCheck(w);
+}
+
+// page-locked host memory for the caller's mirrors: transfers from ordinary (pageable) memory are staged by the
+// driver at a fraction of the PCIe rate
+namespace
+{
+std::mutex g_pinnedMutex;
+std::unordered_set<void*> g_pinned;
+}
+
+void* b2cuHostAlloc(size_t bytes)
+{
+	if (bytes == 0) bytes = 1;
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess && p)
 	{
-		b2cuBody& b = bodies[i];
-		b.px = xf[i].x; b.py = xf[i].y; b.qs = xf[i].z; b.qc = xf[i].w;
-		b.cx = pos[i].x; b.cy = pos[i].y; b.a = pos[i].z;
-		b.c0x = pos0[i].x; b.c0y = pos0[i].y; b.a0 = pos0[i].z; b.alpha0 = pos0[i].w;
-		b.lcx = mass[i].z; b.lcy = mass[i].w;
-		b.vx = vel[i].x; b.vy = vel[i].y; b.w = vel[i].z;
-		b.fx = force[i].x; b.fy = force[i].y; b.torque = force[i].z;
-		b.invMass = mass[i].x; b.invI = mass[i].y;
-		b.linearDamping = damp[i].x; b.angularDamping = damp[i].y; b.gravityScale = damp[i].z;
-		b.sleepTime = force[i].w;
-		b.flags = flags[i];
+		std::lock_guard<std::mutex> lock(g_pinnedMutex);
+		g_pinned.insert(p);
+		return p;
 	}
-	return B2CU_OK;
+	cudaGetLastError();
+	return malloc(bytes);
+}
+
+void b2cuHostFree(void* p)
+{
+	if (p == nullptr) return;
+	bool pinned = false;
+	{
+		std::lock_guard<std::mutex> lock(g_pinnedMutex);
+		pinned = g_pinned.erase(p) > 0;
+	}
+	if (pinned) cudaFreeHost(p);
+	else free(p);
 }
 
 int b2cuSetShapes(b2cuWorld* w, int32_t first, int32_t count, const b2cuShape* shapes)

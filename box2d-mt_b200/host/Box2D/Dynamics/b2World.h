@@ -17,6 +17,25 @@
 #include "Box2D/MT/b2TaskExecutor.h"
 #include "b2cuda.h"
 
+/// Allocator of the host mirrors: page-locked memory from the device library, so that the body records move
+/// between the mirror and the device in a single DMA transfer.
+template <typename T>
+struct b2MirrorAllocator
+{
+	typedef T value_type;
+	b2MirrorAllocator() {}
+	template <typename U>
+	b2MirrorAllocator(const b2MirrorAllocator<U>&) {}
+	T* allocate(size_t n) { return static_cast<T*>(b2cuHostAlloc(n * sizeof(T))); }
+	void deallocate(T* p, size_t) { b2cuHostFree(p); }
+	template <typename U>
+	bool operator==(const b2MirrorAllocator<U>&) const { return true; }
+	template <typename U>
+	bool operator!=(const b2MirrorAllocator<U>&) const { return false; }
+};
+typedef std::vector<b2cuBody, b2MirrorAllocator<b2cuBody> > b2BodyStateArray;
+typedef std::vector<b2cuProxy, b2MirrorAllocator<b2cuProxy> > b2ProxyStateArray;
+
 class b2CudaStepExecutor;
 
 class b2World
@@ -78,9 +97,9 @@ private:
 	friend class b2CudaStepExecutor;
 
 	// host mirror of the device state
-	std::vector<b2cuBody> m_states;
+	b2BodyStateArray m_states;
 	std::vector<b2Body*> m_bodies;
-	std::vector<b2cuProxy> m_proxies;
+	b2ProxyStateArray m_proxies;
 	std::vector<b2Fixture*> m_fixtures;
 	std::vector<b2cuShape> m_shapes;
 	std::unordered_map<std::string, int32> m_shapeLookup;

@@ -6,11 +6,6 @@
 
 namespace
 {
-inline b2cuBody& State(b2World* w, std::vector<b2cuBody>& v, int32 i)
-{
-	B2_NOT_USED(w);
-	return v[i];
-}
 inline const b2Vec2& AsVec2(const float& x) { return reinterpret_cast<const b2Vec2&>(x); }
 inline b2Vec2& AsVec2(float& x) { return reinterpret_cast<b2Vec2&>(x); }
 } // namespace

@@ -45,6 +45,7 @@
 #ifndef B2CUDA_H
 #define B2CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -250,6 +251,13 @@ B2CU_API int b2cuSetInvDt0(b2cuWorld* w, float invDt0);
 
 /* Resize the live element counts (new elements must then be filled with the Set calls). */
 B2CU_API int b2cuSetCounts(b2cuWorld* w, int32_t bodyCount, int32_t shapeCount, int32_t proxyCount);
+
+/* Page-locked host memory for the caller's record arrays (body / proxy / contact mirrors).  The reference keeps its
+ * bodies in host memory it allocates itself (b2BlockAllocator, Common/b2BlockAllocator.cpp:93-170); a mirror that
+ * lives in memory from b2cuHostAlloc moves over PCIe in one DMA transfer instead of being staged by the driver.
+ * Falls back to ordinary memory when no CUDA device is present.  Any pointer is accepted by the Set / Get calls. */
+B2CU_API void* b2cuHostAlloc(size_t bytes);
+B2CU_API void b2cuHostFree(void* p);
 
 B2CU_API int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bodies);
 B2CU_API int b2cuGetBodies(b2cuWorld* w, int32_t first, int32_t count, b2cuBody* bodies);
