@@ -91,7 +91,7 @@ __device__ __forceinline__ void AppendKey(const DeviceArrays& d, int counter, ui
 
 // b2Contact::Update (b2Contact.cpp:163-246) of live contact i: evaluate the manifold, carry the warm-start impulses
 // over by feature id, raise begin/end events and wake requests.  Returns 1 when the contact is touching afterwards.
-__device__ __forceinline__ int UpdateContact(const DeviceArrays& d, int i, int2 pr, int bA, int bB, uint32_t flags,
+__device__ __forceinline__ int UpdateContact(const DeviceArrays& d, int i, int4 pr, int bA, int bB, uint32_t flags,
                                              uint4 m3, const b2cuShape* sA, const b2cuShape* sB, int capacity)
 {
 	int touchingNow = 0;
@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		if (d.c.flags[i] & B2CU_CONTACT_DEAD) continue;
-		int2 pr = d.c.proxies[i];
-		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		int4 pr = d.c.proxies[i];
+		int bA = pr.z, bB = pr.w;
 		uint32_t fbA = d.bflags[bA], fbB = d.bflags[bB];
 		uint32_t flags = d.c.flags[i];
 		uint4 m3 = d.c.m3[i];
@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(256) CollideHeavyKernel(DeviceArrays d, const 
 	B2CU_GRID_STRIDE(k, n)
 	{
 		int i = heavyList[k];
-		int2 pr = d.c.proxies[i];
-		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		int4 pr = d.c.proxies[i];
+		int bA = pr.z, bB = pr.w;
 		touchingCount += UpdateContact(d, i, pr, bA, bB, d.c.flags[i], d.c.m3[i], d.shapes + d.pshape[pr.x],
 		                               d.shapes + d.pshape[pr.y], capacity);
 	}
@@ -336,6 +336,17 @@ __global__ void __launch_bounds__(256) UnpackBodiesKernel(DeviceArrays d, int fi
 			d.bflags[b] = __float_as_uint(s[25]);
 		}
 		__syncthreads();
+	}
+}
+
+// contacts carry the bodies of their two proxies next to the proxy ids (one gather level less in every contact
+// kernel); this fills them in after the caller has uploaded contacts or proxies
+__global__ void FillContactBodiesKernel(DeviceArrays d, int contactCount)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		int4 pr = d.c.proxies[i];
+		d.c.proxies[i] = make_int4(pr.x, pr.y, d.pbody[pr.x], d.pbody[pr.y]);
 	}
 }
 
@@ -444,8 +455,8 @@ __global__ void IslandUnionKernel(DeviceArrays d, int contactCount)
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		if (!IsSolidTouching(d, i)) continue;
-		int2 pr = d.c.proxies[i];
-		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		int4 pr = d.c.proxies[i];
+		int bA = pr.z, bB = pr.w;
 		if (IsStatic(d.bflags[bA]) || IsStatic(d.bflags[bB])) continue;
 		UfUnion(d.island, bA, bB);
 	}
@@ -489,8 +500,8 @@ __global__ void SelectConstraintsKernel(DeviceArrays d, int contactCount)
 		int sel = 0;
 		if (IsSolidTouching(d, i))
 		{
-			int2 pr = d.c.proxies[i];
-			uint32_t fA = d.bflags[d.pbody[pr.x]], fB = d.bflags[d.pbody[pr.y]];
+			int4 pr = d.c.proxies[i];
+			uint32_t fA = d.bflags[pr.z], fB = d.bflags[pr.w];
 			if ((!IsStatic(fA) && (fA & B2CU_BODY_ISLAND)) || (!IsStatic(fB) && (fB & B2CU_BODY_ISLAND))) sel = 1;
 		}
 		d.cSelect[i] = sel;
@@ -525,8 +536,8 @@ __global__ void __launch_bounds__(256) ColourPrepareKernel(DeviceArrays d, const
 	{
 		int i = list[j];
 		int c = d.c.colour[i];
-		int2 pr = d.c.proxies[i];
-		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		int4 pr = d.c.proxies[i];
+		int bA = pr.z, bB = pr.w;
 		uint32_t fA = d.bflags[bA], fB = d.bflags[bB];
 		bool cross = ((fA | fB) & B2CU_BODY_GHOST) != 0;
 		if (c >= 0 && c < B2CU_MAX_COLOURS && ((ColourClassMask(cross, crossBase) >> c) & 1u))
@@ -563,8 +574,8 @@ __global__ void ColourProposeKernel(DeviceArrays d, const int* __restrict__ list
 	B2CU_GRID_STRIDE(j, n)
 	{
 		int i = list[j];
-		int2 pr = d.c.proxies[i];
-		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		int4 pr = d.c.proxies[i];
+		int bA = pr.z, bB = pr.w;
 		uint32_t fA = d.bflags[bA], fB = d.bflags[bB];
 		uint32_t freeMask = ColourFreeMask(d, bA, bB, fA, fB, crossBase);
 		if (freeMask == 0u)
@@ -588,8 +599,8 @@ __global__ void ColourCommitKernel(DeviceArrays d, const int* __restrict__ list,
 	{
 		int i = list[j];
 		if (d.c.colour[i] >= B2CU_COLOUR_OVERFLOW) continue;
-		int2 pr = d.c.proxies[i];
-		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		int4 pr = d.c.proxies[i];
+		int bA = pr.z, bB = pr.w;
 		uint32_t fA = d.bflags[bA], fB = d.bflags[bB];
 		bool dynA = IsDynamic(fA), dynB = IsDynamic(fB);
 		unsigned long long claim = ((unsigned long long)round << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
@@ -665,14 +676,31 @@ __global__ void IntegrateVelocitiesKernel(DeviceArrays d, int bodyCount, float h
 // b2WorldManifold::Initialize (Box2D/Collision/b2Collision.cpp:22-86).  One thread per constraint, written
 // straight into the colour-sorted SoA.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) InitConstraintsKernel(DeviceArrays d, float dtRatio, int warmStarting)
+// cSelect[i] = 1 + position of contact i in the solver order (0: not a constraint)
+__global__ void __launch_bounds__(256) ConstraintSlotKernel(DeviceArrays d)
 {
 	int n = d.counters[CNT_CONSTRAINT];
-	B2CU_GRID_STRIDE(k, n)
+	B2CU_GRID_STRIDE(k, n) { d.cSelect[(int)(uint32_t)(d.orderKeys[k] & 0xFFFFFFFFull)] = k + 1; }
+}
+
+// Runs in CONTACT order (coalesced manifold reads, neighbouring contacts share their bodies) and writes row k of the
+// solver arrays: within one colour the solver order is the contact order, so the rows written by neighbouring
+// threads are neighbours too and the partial sectors merge in L2.
+#ifndef B2CU_INIT_XF
+#define B2CU_INIT_XF 0
+#endif
+#ifndef B2CU_INIT_BLOCKS
+#define B2CU_INIT_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(DeviceArrays d, int contactCount, float dtRatio,
+                                                                               int warmStarting)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
 	{
-		int i = (int)(uint32_t)(d.orderKeys[k] & 0xFFFFFFFFull);
-		int2 pr = d.c.proxies[i];
-		int bA = d.pbody[pr.x], bB = d.pbody[pr.y];
+		int k = d.cSelect[i] - 1;
+		if (k < 0) continue;
+		int4 pr = d.c.proxies[i];
+		int bA = pr.z, bB = pr.w;
 		float radiusA = d.shapes[d.pshape[pr.x]].radius;
 		float radiusB = d.shapes[d.pshape[pr.y]].radius;
 
@@ -693,8 +721,21 @@ __global__ void __launch_bounds__(256) InitConstraintsKernel(DeviceArrays d, flo
 		Vec2 localCenterA = V(msA.z, msA.w), localCenterB = V(msB.z, msB.w);
 
 		Xf xfA, xfB;
+#if B2CU_INIT_XF
+		// xf.q.Set(a) (b2ContactSolver.cpp:171-174): the body transform already holds sin/cos of this very angle
+		// (b2Body::SynchronizeTransform / SetTransform set m_xf.q from m_sweep.a); xf.p is recomputed as the
+		// reference does, it can differ from m_xf.p in the last bit after a SetTransform
+		float4 bxA = d.xf[bA], bxB = d.xf[bB];
+		xfA.q.s = bxA.z;
+		xfA.q.c = bxA.w;
+		xfB.q.s = bxB.z;
+		xfB.q.c = bxB.w;
+		(void)aA;
+		(void)aB;
+#else
 		xfA.q = SinCos(aA);
 		xfB.q = SinCos(aB);
+#endif
 		xfA.p = cA - Mul(xfA.q, localCenterA);
 		xfB.p = cB - Mul(xfB.q, localCenterB);
 
@@ -2146,7 +2187,7 @@ __global__ void RebuildNewKernel(DeviceArrays d, int tailBegin, int tailCount, c
 		float restitution = matA.y > matB.y ? matA.y : matB.y;      // b2MixRestitution, b2Contact.h:47-50
 
 		d.cAlt.key[dest] = key;
-		d.cAlt.proxies[dest] = make_int2(pA, pB);
+		d.cAlt.proxies[dest] = make_int4(pA, pB, bodyA, bodyB);
 		d.cAlt.flags[dest] = flags;
 		d.cAlt.m0[dest] = make_float4(0.f, 0.f, 0.f, 0.f);
 		d.cAlt.m1[dest] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -2167,8 +2208,8 @@ __global__ void ToiFlagsKernel(DeviceArrays d, int contactCount, int* flagsOut)
 		int ok = 0;
 		if (!(f & B2CU_CONTACT_DEAD) && (f & B2CU_CONTACT_TOI_CANDIDATE) && (f & B2CU_CONTACT_ENABLED) && d.c.toiCount[i] <= B2CU_MAX_SUB_STEPS)
 		{
-			int2 pr = d.c.proxies[i];
-			uint32_t fA = d.bflags[d.pbody[pr.x]], fB = d.bflags[d.pbody[pr.y]];
+			int4 pr = d.c.proxies[i];
+			uint32_t fA = d.bflags[pr.z], fB = d.bflags[pr.w];
 			if (IsAwakeNonStatic(fA) || IsAwakeNonStatic(fB)) ok = 1;
 		}
 		flagsOut[i] = ok;
@@ -2267,10 +2308,10 @@ __global__ void GatherContactsByKeyKernel(DeviceArrays d, int contactCount, int 
 		b2cuContact o;
 		if (found)
 		{
-			int2 pr = d.c.proxies[i];
+			int4 pr = d.c.proxies[i];
 			float4 m0 = d.c.m0[i], m1 = d.c.m1[i], m2 = d.c.m2[i], mix = d.c.mix[i];
 			uint4 m3 = d.c.m3[i];
-			uint32_t fA = d.bflags[d.pbody[pr.x]], fB = d.bflags[d.pbody[pr.y]];
+			uint32_t fA = d.bflags[pr.z], fB = d.bflags[pr.w];
 			uint32_t f = d.c.flags[i] & ~(uint32_t)B2CU_CONTACT_INACTIVE;
 			if (!IsAwakeNonStatic(fA) && !IsAwakeNonStatic(fB)) f |= B2CU_CONTACT_INACTIVE;
 			o.proxyA = pr.x;

@@ -49,7 +49,7 @@ enum Counter
 struct ContactSet
 {
 	uint64_t* key;      // (min proxy << 32) | max proxy, ascending
-	int2* proxies;      // (fixture A side, fixture B side) after the primary-type swap
+	int4* proxies;      // (proxy of fixture A, proxy of fixture B) after the primary-type swap, then their bodies
 	uint32_t* flags;    // B2CU_CONTACT_*
 	float4* m0;         // localNormal.xy, localPoint.xy
 	float4* m1;         // point0: localPoint.xy, normalImpulse, tangentImpulse
@@ -199,6 +199,7 @@ struct b2cuWorld
 	int colourStarts[B2CU_MAX_COLOURS + 3];
 
 	int* hostCounters;   // pinned, CNT_COUNT + colour counts
+	bool contactBodiesDirty; // contacts or proxies were uploaded: refresh the body half of ContactSet::proxies
 	float* bodyStage;    // device staging of b2cuBody records for b2cuGetBodies / b2cuSetBodies (lazy)
 	int bodyStageCapacity;
 	cudaEvent_t ev[10];

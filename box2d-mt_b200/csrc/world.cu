@@ -868,6 +868,7 @@ int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* 
 		return rc;
 	if (anyMoved) w->newProxies = true;
 	w->toiCheckDirty = true;
+	w->contactBodiesDirty = true;
 	if (first == 0 && count > 0)
 	{
 		w->cellSize = ChooseCellSize(extents);
@@ -932,7 +933,7 @@ int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
 	}
 	std::sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
 	std::vector<uint64_t> key(count);
-	std::vector<int2> proxies(count);
+	std::vector<int4> proxies(count);
 	std::vector<uint32_t> flags(count);
 	std::vector<float4> m0(count), m1(count), m2(count), mix(count);
 	std::vector<uint4> m3(count);
@@ -943,7 +944,7 @@ int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
 		const b2cuManifold& m = c.manifold;
 		key[j] = keys[order[j]];
 		if (j > 0 && key[j] == key[j - 1]) return SetError(w, B2CU_ERR_ARGUMENT, "duplicate contact key");
-		proxies[j] = make_int2(c.proxyA, c.proxyB);
+		proxies[j] = make_int4(c.proxyA, c.proxyB, 0, 0);
 		flags[j] = c.flags & ~(uint32_t)B2CU_CONTACT_ISLAND;
 		m0[j] = make_float4(m.localNormal[0], m.localNormal[1], m.localPoint[0], m.localPoint[1]);
 		m1[j] = make_float4(m.points[0].localPoint[0], m.points[0].localPoint[1], m.points[0].normalImpulse,
@@ -964,6 +965,7 @@ int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
 	w->contactCount = count;
 	w->mainCount = count;
 	w->deadMain = 0;
+	if (count > 0) LAUNCH(w, FillContactBodiesKernel, GridFor(count), kBlock, d, count);
 	if ((rc = RebuildLowStart(w))) return rc;
 	return SyncCheck(w);
 }
@@ -984,7 +986,7 @@ int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32
 	if (countOut) *countOut = live;
 	if (capacity == 0 || slots == 0) return B2CU_OK;
 	std::vector<uint64_t> key(slots);
-	std::vector<int2> proxies(slots);
+	std::vector<int4> proxies(slots);
 	std::vector<uint32_t> flags(slots);
 	std::vector<float4> m0(slots), m1(slots), m2(slots), mix(slots);
 	std::vector<uint4> m3(slots);
@@ -1086,6 +1088,12 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		CUDA_TRY(w, cudaMemsetAsync(d.counters + CNT_STICKY_TOI, 0, sizeof(int), w->stream));
 		LAUNCH(w, ToiPossibleKernel, GridFor(std::max(nb, np)), kBlock, d, nb, np);
 		w->toiCheckDirty = false;
+	}
+
+	if (w->contactBodiesDirty)
+	{
+		if (w->contactCount > 0) LAUNCH(w, FillContactBodiesKernel, GridFor(w->contactCount), kBlock, d, w->contactCount);
+		w->contactBodiesDirty = false;
 	}
 
 	if (dt > 0.0f && (rc = ShardSyncGhosts(w))) return rc;
@@ -1203,7 +1211,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		LAUNCH(w, IntegrateVelocitiesKernel, GridFor(nb), kBlock, d, nb, dt, w->params.gravity);
 		if (nConstraints > 0)
 		{
-			LAUNCH(w, InitConstraintsKernel, GridFor(nConstraints), kBlock, d, dtRatio, warmStarting ? 1 : 0);
+			LAUNCH(w, ConstraintSlotKernel, GridFor(nConstraints), kBlock, d);
+			LAUNCH(w, InitConstraintsKernel, GridFor(nc), kBlock, d, nc, dtRatio, warmStarting ? 1 : 0);
 			if (warmStarting && !w->persistentSolver)
 			{
 				for (int c = 0; c < B2CU_MAX_COLOURS; ++c)

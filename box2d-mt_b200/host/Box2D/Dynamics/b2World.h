@@ -117,7 +117,8 @@ private:
 
 	// driven by b2CudaStepExecutor::StepWorld
 	int32 UploadDirty(b2cuWorld* device);
-	int32 AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool downloadBodies, bool dispatchEvents);
+	int32 AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool downloadBodies, bool dispatchEvents,
+	                      float32* hostMs = nullptr);
 	void MakeContact(b2Contact* c, const b2cuContact& rec);
 
 	b2cuWorld* m_device;          // owned by the executor that last stepped this world

@@ -53,6 +53,9 @@ public:
 	const char* GetLastError() const { return m_error; }
 	/// counters and per-phase device timings of the last step
 	const b2cuStepInfo& GetLastStepInfo() const;
+	/// wall-clock milliseconds of the last StepWorld on the calling thread: [0] upload of the dirty records,
+	/// [1] b2cuStep, [2] download of the body mirror, [3] event download + listener dispatch
+	const float32* GetLastHostTimings() const { return m_hostMs; }
 	/// the C-ABI handle of a world this executor has stepped (nullptr before its first step): for callers that
 	/// want the bulk / diagnostic entry points of include/b2cuda.h
 	b2cuWorld* GetDeviceWorld(b2World* world) const;
@@ -72,6 +75,7 @@ private:
 	b2cuWorld* EnsureDevice(b2World& world);
 
 	b2CudaStepOptions m_options;
+	float32 m_hostMs[4];
 	b2TaskGroup m_group;
 	int32 m_status;
 	char m_error[512];

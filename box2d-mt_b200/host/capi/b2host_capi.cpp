@@ -324,6 +324,8 @@ B2H_API void b2h_profile(void* p, float* out13) { memcpy(out13, &static_cast<Hos
 
 B2H_API void b2h_step_info(void* p, b2cuStepInfo* out) { *out = static_cast<Host*>(p)->executor->GetLastStepInfo(); }
 
+B2H_API void b2h_host_timings(void* p, float* out4) { memcpy(out4, static_cast<Host*>(p)->executor->GetLastHostTimings(), 4 * sizeof(float)); }
+
 /// FNV-1a over (x, y, angle) of every body in GetBodyList() order: the trajectory hash of SURVEY.md 8c
 B2H_API uint32 b2h_hash(void* p)
 {

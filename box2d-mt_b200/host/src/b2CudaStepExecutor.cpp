@@ -1,5 +1,7 @@
 // b2CudaStepExecutor: runs b2World::Step on the device through the C ABI (include/b2cuda.h).
 #include "Box2D/MT/b2CudaStepExecutor.h"
+
+#include <chrono>
 #include "Box2D/Dynamics/b2World.h"
 
 #include <cstdio>
@@ -16,7 +18,7 @@ struct Impl
 };
 } // namespace
 
-b2CudaStepExecutor::b2CudaStepExecutor(const b2CudaStepOptions& options) : m_options(options), m_status(0)
+b2CudaStepExecutor::b2CudaStepExecutor(const b2CudaStepOptions& options) : m_options(options), m_hostMs(), m_status(0)
 {
 	m_error[0] = 0;
 	Impl* impl = new Impl;
@@ -158,8 +160,15 @@ bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 veloc
 	b2cuWorld* device = EnsureDevice(world);
 	if (device == nullptr) return false;
 
+	typedef std::chrono::steady_clock Clock;
+	Clock::time_point t0 = Clock::now();
 	int rc = world.UploadDirty(device);
+	Clock::time_point t1 = Clock::now();
 	if (rc == B2CU_OK) rc = b2cuStep(device, timeStep, velocityIterations, positionIterations, &impl->info);
+	Clock::time_point t2 = Clock::now();
+	m_hostMs[0] = std::chrono::duration<float, std::milli>(t1 - t0).count();
+	m_hostMs[1] = std::chrono::duration<float, std::milli>(t2 - t1).count();
+	m_hostMs[2] = m_hostMs[3] = 0.0f;
 	if (rc != B2CU_OK)
 	{
 		m_status = rc;
@@ -170,6 +179,6 @@ bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 veloc
 	}
 	if (timeStep > 0.0f) world.m_inv_dt0 = 1.0f / timeStep;
 	world.m_lastStatus = 0;
-	world.AfterDeviceStep(device, impl->info, m_options.downloadBodies, m_options.dispatchEvents);
+	world.AfterDeviceStep(device, impl->info, m_options.downloadBodies, m_options.dispatchEvents, m_hostMs + 2);
 	return true;
 }

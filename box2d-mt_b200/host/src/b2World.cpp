@@ -2,6 +2,8 @@
 // reference: Box2D/Dynamics/b2World.cpp (CreateBody :532-559, DestroyBody :561-640, Step :1613-1710) and
 // b2ContactManager.cpp (callback dispatch :388-439).
 #include "Box2D/Dynamics/b2World.h"
+
+#include <chrono>
 #include "Box2D/Collision/Shapes/b2CircleShape.h"
 #include "Box2D/Collision/Shapes/b2EdgeShape.h"
 #include "Box2D/Collision/Shapes/b2PolygonShape.h"
@@ -607,14 +609,19 @@ void b2World::DispatchEvents(b2cuWorld* device)
 		if (deferred[1][i]) m_contactListener->EndContact(&contacts[1][i]);
 }
 
-int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool downloadBodies, bool dispatchEvents)
+int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool downloadBodies, bool dispatchEvents,
+                               float32* hostMs)
 {
+	typedef std::chrono::steady_clock Clock;
+	Clock::time_point t0 = Clock::now();
 	m_contactCount = info.contactCount;
 	memcpy(&m_profile, &info, sizeof(b2Profile)); // the first 13 floats of b2cuStepInfo are the b2Profile fields
 	m_bodiesStale = true;
 	m_proxiesStale = true;
 	InvalidateSnapshots();
 	if (downloadBodies) RefreshBodies();
+	Clock::time_point t1 = Clock::now();
+	if (hostMs) hostMs[0] = std::chrono::duration<float, std::milli>(t1 - t0).count();
 	if (dispatchEvents && m_contactListener && (info.beginCount > 0 || info.endCount > 0))
 	{
 		// callbacks may read bodies: make sure the mirror is current
@@ -624,5 +631,6 @@ int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool
 		DispatchEvents(device);
 		m_locked = wasLocked;
 	}
+	if (hostMs) hostMs[1] = std::chrono::duration<float, std::milli>(Clock::now() - t1).count();
 	return 0;
 }

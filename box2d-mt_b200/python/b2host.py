@@ -53,6 +53,7 @@ def load():
     lib.b2h_solver_order.argtypes = [vp, i32, vp]
     lib.b2h_profile.argtypes = [vp, vp]
     lib.b2h_step_info.argtypes = [vp, vp]
+    lib.b2h_host_timings.argtypes = [vp, vp]
     lib.b2h_hash.argtypes = [vp]
     lib.b2h_hash.restype = u32
     lib.b2h_set_transform.argtypes = [vp, i32, f32, f32, f32]
@@ -153,6 +154,12 @@ class HostWorld:
     def step_info(self):
         out = np.zeros((), T.STEP_INFO)
         self.lib.b2h_step_info(self.h, _ptr(out))
+        return out
+
+    def host_timings(self):
+        """ms of the last step on the calling thread: upload, b2cuStep, body download, events"""
+        out = np.zeros(4, np.float32)
+        self.lib.b2h_host_timings(self.h, _ptr(out))
         return out
 
     def hash(self):
