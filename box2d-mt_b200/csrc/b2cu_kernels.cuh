@@ -339,6 +339,12 @@ __global__ void __launch_bounds__(256) UnpackBodiesKernel(DeviceArrays d, int fi
 	}
 }
 
+// pradius[p] = m_radius of the proxy's shape (b2Shape.h:93), read by the constraint initialisation
+__global__ void FillProxyRadiusKernel(DeviceArrays d, int proxyCount)
+{
+	B2CU_GRID_STRIDE(p, proxyCount) { d.pradius[p] = d.shapes[d.pshape[p]].radius; }
+}
+
 // contacts carry the bodies of their two proxies next to the proxy ids (one gather level less in every contact
 // kernel); this fills them in after the caller has uploaded contacts or proxies
 __global__ void FillContactBodiesKernel(DeviceArrays d, int contactCount)
@@ -690,19 +696,21 @@ __global__ void __launch_bounds__(256) ConstraintSlotKernel(DeviceArrays d)
 #define B2CU_INIT_XF 0
 #endif
 #ifndef B2CU_INIT_BLOCKS
-#define B2CU_INIT_BLOCKS 2
+#define B2CU_INIT_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(DeviceArrays d, int contactCount, float dtRatio,
-                                                                               int warmStarting)
+__global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(DeviceArrays d, const int* __restrict__ list,
+                                                                               float dtRatio, int warmStarting)
 {
-	B2CU_GRID_STRIDE(i, contactCount)
+	// list = the constraint contacts in ascending contact order (the compaction of cSelect)
+	int n = d.counters[CNT_CONSTRAINT];
+	B2CU_GRID_STRIDE(j, n)
 	{
+		int i = list[j];
 		int k = d.cSelect[i] - 1;
-		if (k < 0) continue;
 		int4 pr = d.c.proxies[i];
 		int bA = pr.z, bB = pr.w;
-		float radiusA = d.shapes[d.pshape[pr.x]].radius;
-		float radiusB = d.shapes[d.pshape[pr.y]].radius;
+		float radiusA = d.pradius[pr.x];
+		float radiusB = d.pradius[pr.y];
 
 		float4 m0 = d.c.m0[i], m1 = d.c.m1[i], m2 = d.c.m2[i];
 		uint4 m3 = d.c.m3[i];

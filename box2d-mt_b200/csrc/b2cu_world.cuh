@@ -96,6 +96,7 @@ struct DeviceArrays
 	uint32_t* pgroup;   // (uint16)groupIndex | flags << 16
 	float2* pmat;       // friction, restitution
 	int* pfixture;      // caller's fixture id
+	float* pradius;     // radius of the proxy's shape (copy of shapes[pshape].radius)
 	int* lowStart;      // first contact whose key has this proxy as its low id (-1: none); rebuilt with the set
 
 	// ---- contacts ----

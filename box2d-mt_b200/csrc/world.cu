@@ -171,6 +171,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->pgroup, CAP_PROXY));
 	v.push_back(Desc(&d->pmat, CAP_PROXY));
 	v.push_back(Desc(&d->pfixture, CAP_PROXY));
+	v.push_back(Desc(&d->pradius, CAP_PROXY));
 	v.push_back(Desc(&d->lowStart, CAP_PROXY1));
 	ContactSetDescs(&d->c, v);
 	ContactSetDescs(&d->cAlt, v);
@@ -826,6 +827,7 @@ int b2cuSetShapes(b2cuWorld* w, int32_t first, int32_t count, const b2cuShape* s
 	{
 		CUDA_TRY(w, cudaMemcpyAsync(w->d.shapes + first, shapes, sizeof(b2cuShape) * count, cudaMemcpyHostToDevice,
 		                            w->stream));
+		w->contactBodiesDirty = true; // pradius is derived from the shape table
 	}
 	return SyncCheck(w);
 }
@@ -1092,6 +1094,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 
 	if (w->contactBodiesDirty)
 	{
+		if (np > 0) LAUNCH(w, FillProxyRadiusKernel, GridFor(np), kBlock, d, np);
 		if (w->contactCount > 0) LAUNCH(w, FillContactBodiesKernel, GridFor(w->contactCount), kBlock, d, w->contactCount);
 		w->contactBodiesDirty = false;
 	}
@@ -1212,7 +1215,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		if (nConstraints > 0)
 		{
 			LAUNCH(w, ConstraintSlotKernel, GridFor(nConstraints), kBlock, d);
-			LAUNCH(w, InitConstraintsKernel, GridFor(nc), kBlock, d, nc, dtRatio, warmStarting ? 1 : 0);
+			LAUNCH(w, InitConstraintsKernel, GridFor(nConstraints), kBlock, d, (const int*)d.listA, dtRatio, warmStarting ? 1 : 0);
 			if (warmStarting && !w->persistentSolver)
 			{
 				for (int c = 0; c < B2CU_MAX_COLOURS; ++c)
