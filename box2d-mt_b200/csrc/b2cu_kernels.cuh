@@ -358,15 +358,21 @@ __global__ void FillContactBodiesKernel(DeviceArrays d, int contactCount)
 
 // b2Body::SetAwake(true) for every body flagged by Collide / contact creation / contact destruction
 // (Box2D/Dynamics/b2Body.h:690-718: sets e_awakeFlag and resets m_sleepTime).
-__global__ void ApplyWakeKernel(DeviceArrays d, int bodyCount)
+__global__ void ApplyWakeKernel(DeviceArrays d, int bodyCount, int* __restrict__ patch)
 {
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
 		if (d.wake[b])
 		{
 			d.wake[b] = 0;
-			d.bflags[b] |= B2CU_BODY_AWAKE;
-			d.force[b].w = 0.0f;
+			uint32_t bf = d.bflags[b];
+			float4 f = d.force[b];
+			// patch != nullptr: the body records are already on their way to the caller's mirror (b2cuSetBodyMirror);
+			// the bodies this changes are listed so that the mirror can be corrected afterwards
+			if (patch && (!(bf & B2CU_BODY_AWAKE) || f.w != 0.0f)) patch[atomicAdd(&d.counters[CNT_WAKE_PATCH], 1)] = b;
+			d.bflags[b] = bf | B2CU_BODY_AWAKE;
+			f.w = 0.0f;
+			d.force[b] = f;
 		}
 	}
 }

@@ -41,6 +41,7 @@ enum Counter
 	CNT_TOI,
 	CNT_ERROR,            // != 0: a buffer overflowed
 	CNT_SCRATCH,
+	CNT_WAKE_PATCH,       // bodies woken after the mirror copy of the step had started
 	CNT_HEAVY,            // contacts queued for the dense polygon pass of Collide
 	CNT_STICKY_TOI,       // not cleared per step: a TOI-candidate contact has existed
 	CNT_COUNT
@@ -76,6 +77,7 @@ struct DeviceArrays
 	float4* damp;    // linearDamping, angularDamping, gravityScale, -
 	uint32_t* bflags;
 	int* wake;            // wake request flags written by Collide / contact creation
+	int* wakePatch;       // see ApplyWakeKernel
 	int* island;          // union-find parent, then island label (root = smallest body id)
 	int* islandAwake;     // per root: any awake member
 	int* islandMinSleep;  // per root: min sleepTime (float bits, non-negative)
@@ -203,6 +205,18 @@ struct b2cuWorld
 	bool contactBodiesDirty; // contacts or proxies were uploaded: refresh the body half of ContactSet::proxies
 	float* bodyStage;    // device staging of b2cuBody records for b2cuGetBodies / b2cuSetBodies (lazy)
 	int bodyStageCapacity;
+	// body mirror (b2cuSetBodyMirror): every step copies the body records there, overlapping the broad-phase
+	b2cuBody* bodyMirror;
+	int bodyMirrorCount;
+	bool mirrorInFlight;
+	cudaStream_t copyStream;
+	cudaEvent_t evBodiesFinal, evPacked;
+	int* hostPatch;      // pinned, body capacity
+	int hostPatchCapacity;
+	void* queryScratch;  // device scratch of b2cuGetContactsByKey (grow-only)
+	size_t queryScratchBytes;
+	void* queryHost;     // page-locked host side of the same
+	size_t queryHostBytes;
 	cudaEvent_t ev[10];
 	int launches;
 	char lastError[512];

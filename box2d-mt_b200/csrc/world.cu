@@ -156,6 +156,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->damp, CAP_BODY));
 	v.push_back(Desc(&d->bflags, CAP_BODY));
 	v.push_back(Desc(&d->wake, CAP_BODY));
+	v.push_back(Desc(&d->wakePatch, CAP_BODY));
 	v.push_back(Desc(&d->island, CAP_BODY));
 	v.push_back(Desc(&d->islandAwake, CAP_BODY));
 	v.push_back(Desc(&d->islandMinSleep, CAP_BODY));
@@ -511,7 +512,10 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		if (newCount > 0)
 		{
 			LAUNCH(w, RebuildNewKernel, GridFor(newCount), kBlock, d, nMain, nTail, d.listA, tailLive, newCount, nMain);
-			LAUNCH(w, ApplyWakeKernel, GridFor(w->bodyCount), kBlock, d, w->bodyCount);
+			// the only body writer after the mirror copy has started: let the pack kernel finish reading first
+			if (w->mirrorInFlight) CUDA_TRY(w, cudaStreamWaitEvent(w->stream, w->evPacked, 0));
+			LAUNCH(w, ApplyWakeKernel, GridFor(w->bodyCount), kBlock, d, w->bodyCount,
+			       w->mirrorInFlight ? d.wakePatch : (int*)nullptr);
 		}
 		if ((rc = CopyContactRange(w, d.c, d.cAlt, nMain, newTail))) return rc;
 		w->contactCount = nMain + newTail;
@@ -629,6 +633,9 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		return B2CU_ERR_CUDA;
 	}
 	for (int i = 0; i < 10; ++i) cudaEventCreate(&w->ev[i]);
+	cudaStreamCreateWithFlags(&w->copyStream, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags(&w->evBodiesFinal, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&w->evPacked, cudaEventDisableTiming);
 	cudaMallocHost(&w->hostCounters, sizeof(int) * (CNT_COUNT + B2CU_MAX_COLOURS + 2));
 	w->params.gravity = make_float2(def->gravity[0], def->gravity[1]);
 	w->params.flags = def->flags;
@@ -688,6 +695,12 @@ void b2cuDestroyWorld(b2cuWorld* w)
 	for (size_t k = 0; k < arrays.size(); ++k) cudaFree(*arrays[k].ptr);
 	cudaFree(w->d.islandMinSep);
 	cudaFree(w->bodyStage);
+	cudaFree(w->queryScratch);
+	if (w->queryHost) cudaFreeHost(w->queryHost);
+	if (w->hostPatch) cudaFreeHost(w->hostPatch);
+	if (w->copyStream) cudaStreamDestroy(w->copyStream);
+	if (w->evBodiesFinal) cudaEventDestroy(w->evBodiesFinal);
+	if (w->evPacked) cudaEventDestroy(w->evPacked);
 	if (w->peerLower && w->peerLowerIpc) cudaIpcCloseMemHandle(w->peerLower);
 	if (w->peerUpper && w->peerUpperIpc) cudaIpcCloseMemHandle(w->peerUpper);
 	cudaFree(w->ghostIds);
@@ -1052,6 +1065,65 @@ int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32
 // ---------------------------------------------------------------------------------------------------------
 // the step
 // ---------------------------------------------------------------------------------------------------------
+// ---- body mirror: the step's own device -> host copy of the body records ----
+static int StartMirrorCopy(b2cuWorld* w)
+{
+	const int n = std::min(w->bodyMirrorCount, w->bodyCount);
+	if (w->bodyMirror == nullptr || n <= 0) return B2CU_OK;
+	int rc = EnsureBodyStage(w);
+	if (rc) return rc;
+	CUDA_TRY(w, cudaEventRecord(w->evBodiesFinal, w->stream));
+	CUDA_TRY(w, cudaStreamWaitEvent(w->copyStream, w->evBodiesFinal, 0));
+	PackBodiesKernel<<<GridFor(n), kBlock, 0, w->copyStream>>>(w->d, 0, n, w->bodyStage);
+	++w->launches;
+	CUDA_TRY(w, cudaEventRecord(w->evPacked, w->copyStream));
+	CUDA_TRY(w, cudaMemcpyAsync(w->bodyMirror, w->bodyStage, sizeof(b2cuBody) * (size_t)n, cudaMemcpyDeviceToHost,
+	                            w->copyStream));
+	w->mirrorInFlight = true;
+	return B2CU_OK;
+}
+
+static int FinishMirrorCopy(b2cuWorld* w)
+{
+	if (!w->mirrorInFlight) return B2CU_OK;
+	w->mirrorInFlight = false;
+	CUDA_TRY(w, cudaStreamSynchronize(w->copyStream));
+	// bodies woken by the contacts created after the copy had started (the new-contact path of b2ContactManager wakes both bodies,
+	// b2ContactManager.cpp:520-529): same change on the caller's side
+	const int patches = w->hostCounters[CNT_WAKE_PATCH];
+	if (patches > 0)
+	{
+		if (patches > w->hostPatchCapacity)
+		{
+			if (w->hostPatch) cudaFreeHost(w->hostPatch);
+			w->hostPatch = nullptr;
+			w->hostPatchCapacity = 0;
+			CUDA_TRY(w, cudaMallocHost(&w->hostPatch, sizeof(int) * (size_t)w->bodyCapacity));
+			w->hostPatchCapacity = w->bodyCapacity;
+		}
+		CUDA_TRY(w, cudaMemcpyAsync(w->hostPatch, w->d.wakePatch, sizeof(int) * (size_t)patches, cudaMemcpyDeviceToHost,
+		                            w->stream));
+		CUDA_TRY(w, cudaStreamSynchronize(w->stream));
+		const int n = std::min(w->bodyMirrorCount, w->bodyCount);
+		for (int k = 0; k < patches; ++k)
+		{
+			int b = w->hostPatch[k];
+			if (b < 0 || b >= n) continue;
+			w->bodyMirror[b].flags |= B2CU_BODY_AWAKE;
+			w->bodyMirror[b].sleepTime = 0.0f;
+		}
+	}
+	return B2CU_OK;
+}
+
+int b2cuSetBodyMirror(b2cuWorld* w, b2cuBody* mirror, int32_t count)
+{
+	if (!w || count < 0 || (count > 0 && !mirror)) return B2CU_ERR_ARGUMENT;
+	w->bodyMirror = count > 0 ? mirror : nullptr;
+	w->bodyMirrorCount = count;
+	return B2CU_OK;
+}
+
 int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positionIterations, b2cuStepInfo* info)
 {
 	if (!w || velocityIterations < 0 || positionIterations < 0) return B2CU_ERR_ARGUMENT;
@@ -1073,6 +1145,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	}
 
 	CUDA_TRY(w, cudaMemsetAsync(d.counters, 0, sizeof(int) * CNT_STICKY_TOI, w->stream));
+	w->mirrorInFlight = false;
 	cudaEventRecord(w->ev[0], w->stream);
 	{
 		const char* t = getenv("B2CU_TRACE");
@@ -1122,7 +1195,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		// narrow phase; begin/end events are appended to the deferred buffers and sorted at the end of the step
 		LAUNCH(w, CollideKernel, GridFor(nc), kBlock, d, nc, w->mainCount, w->contactCapacity, d.listA);
 		LAUNCH(w, CollideHeavyKernel, GridFor(nc), kBlock, d, (const int*)d.listA, w->contactCapacity);
-		LAUNCH(w, ApplyWakeKernel, GridFor(nb), kBlock, d, nb);
+		LAUNCH(w, ApplyWakeKernel, GridFor(nb), kBlock, d, nb, (int*)nullptr);
 	}
 	cudaEventRecord(w->ev[2], w->stream);
 
@@ -1329,6 +1402,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		// ClearPostSolve + ClearForces (b2World.cpp:1430, :1688-1691); done here so that the read-back of the
 		// broad-phase also carries the awake-body count
 		LAUNCH(w, EndStepBodiesKernel, GridFor(nb), kBlock, d, nb, (w->params.flags & B2CU_WORLD_CLEAR_FORCES) ? 1 : 0);
+		if ((rc = StartMirrorCopy(w))) return rc;
 		int n1 = 0, d1 = 0, m1 = 0;
 		if ((rc = FindNewContactsAndRebuild(w, &n1, &d1, &m1))) return rc;
 		newContacts += n1;
@@ -1340,6 +1414,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	{
 		for (int k = 3; k < 8; ++k) cudaEventRecord(w->ev[k], w->stream);
 		LAUNCH(w, EndStepBodiesKernel, GridFor(nb), kBlock, d, nb, (w->params.flags & B2CU_WORLD_CLEAR_FORCES) ? 1 : 0);
+		if ((rc = StartMirrorCopy(w))) return rc;
 		int n1 = 0, d1 = 0, m1 = 0;
 		if ((rc = FindNewContactsAndRebuild(w, &n1, &d1, &m1))) return rc;
 		destroyed += d1;
@@ -1373,15 +1448,16 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	cudaEvent_t evEnd = w->ev[9];
 	cudaEventRecord(evEnd, w->stream);
 
-	if (toiPass)
+	if (toiPass || w->mirrorInFlight)
 	{
 		if ((rc = ReadCounters(w))) return rc;
-		w->toiCount = w->hostCounters[CNT_TOI];
+		if (toiPass) w->toiCount = w->hostCounters[CNT_TOI];
 	}
 	else
 	{
 		if ((rc = SyncCheck(w))) return rc;
 	}
+	if ((rc = FinishMirrorCopy(w))) return rc;
 
 	if (g_trace.enabled && g_trace.used > 1)
 	{
@@ -1475,6 +1551,85 @@ int b2cuGetEvents(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* 
 	return B2CU_OK;
 }
 
+// grow-only scratch pair (device + page-locked host) used by the query entry points
+static int EnsureQueryScratch(b2cuWorld* w, size_t bytes)
+{
+	if (bytes > w->queryScratchBytes)
+	{
+		CUDA_TRY(w, cudaStreamSynchronize(w->stream));
+		cudaFree(w->queryScratch);
+		w->queryScratch = nullptr;
+		w->queryScratchBytes = 0;
+		size_t grown = std::max(bytes + bytes / 2, (size_t)1 << 20);
+		CUDA_TRY(w, cudaMalloc(&w->queryScratch, grown));
+		w->queryScratchBytes = grown;
+	}
+	return B2CU_OK;
+}
+
+static int EnsureQueryHost(b2cuWorld* w, size_t bytes)
+{
+	if (bytes > w->queryHostBytes)
+	{
+		if (w->queryHost) cudaFreeHost(w->queryHost);
+		w->queryHost = nullptr;
+		w->queryHostBytes = 0;
+		size_t grown = std::max(bytes + bytes / 2, (size_t)1 << 20);
+		CUDA_TRY(w, cudaMallocHost(&w->queryHost, grown));
+		w->queryHostBytes = grown;
+	}
+	return B2CU_OK;
+}
+
+int b2cuGetEventContacts(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* keys, b2cuContact* records,
+                         int32_t* count)
+{
+	if (!w || capacity < 0 || (capacity > 0 && (!keys || !records))) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	const int n = kind == B2CU_EVENT_BEGIN ? w->beginCount : w->endCount;
+	if (count) *count = n;
+	if (capacity == 0 || n == 0) return B2CU_OK;
+	// one round trip: the records are gathered on the device in arrival order, keys and records come back together,
+	// and the callback order of b2cuGetEvents is established on the host by sorting an index
+	const size_t keyBytes = (sizeof(uint64_t) * (size_t)n + 255) & ~(size_t)255;
+	const size_t total = keyBytes + sizeof(b2cuContact) * (size_t)n;
+	int rc;
+	if ((rc = EnsureQueryScratch(w, total)) || (rc = EnsureQueryHost(w, total))) return rc;
+	uint64_t* dKeys = reinterpret_cast<uint64_t*>(w->queryScratch);
+	b2cuContact* dOut = reinterpret_cast<b2cuContact*>(static_cast<char*>(w->queryScratch) + keyBytes);
+	int firstPart = n;
+	if (kind == B2CU_EVENT_BEGIN)
+	{
+		CUDA_TRY(w, cudaMemcpyAsync(dKeys, w->d.beginKeys, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, w->stream));
+	}
+	else
+	{
+		firstPart = w->endUpdateCount;
+		if (firstPart > 0)
+			CUDA_TRY(w, cudaMemcpyAsync(dKeys, w->d.endKeys, sizeof(uint64_t) * firstPart, cudaMemcpyDeviceToDevice, w->stream));
+		if (n - firstPart > 0)
+			CUDA_TRY(w, cudaMemcpyAsync(dKeys + firstPart, w->d.destroyEndKeys, sizeof(uint64_t) * (n - firstPart),
+			                            cudaMemcpyDeviceToDevice, w->stream));
+	}
+	LAUNCH(w, GatherContactsByKeyKernel, GridFor(n), kBlock, w->d, w->contactCount, w->mainCount, (const uint64_t*)dKeys, n, dOut);
+	CUDA_TRY(w, cudaMemcpyAsync(w->queryHost, w->queryScratch, total, cudaMemcpyDeviceToHost, w->stream));
+	if ((rc = SyncCheck(w))) return rc;
+	const uint64_t* hKeys = reinterpret_cast<const uint64_t*>(w->queryHost);
+	const b2cuContact* hOut = reinterpret_cast<const b2cuContact*>(static_cast<const char*>(w->queryHost) + keyBytes);
+	std::vector<int> order(n);
+	for (int i = 0; i < n; ++i) order[i] = i;
+	auto byKey = [hKeys](int a, int b) { return hKeys[a] < hKeys[b]; };
+	std::sort(order.begin(), order.begin() + firstPart, byKey);
+	std::sort(order.begin() + firstPart, order.end(), byKey);
+	const int m = std::min(n, capacity);
+	for (int j = 0; j < m; ++j)
+	{
+		keys[j] = hKeys[order[j]];
+		records[j] = hOut[order[j]];
+	}
+	return B2CU_OK;
+}
+
 int b2cuGetContactsByKey(b2cuWorld* w, int32_t count, const b2cuContactKey* keys, b2cuContact* out)
 {
 	if (!w || count < 0 || (count > 0 && (!keys || !out))) return B2CU_ERR_ARGUMENT;
@@ -1486,11 +1641,16 @@ int b2cuGetContactsByKey(b2cuWorld* w, int32_t count, const b2cuContactKey* keys
 		if (a < 0 || a >= w->proxyCount || b < 0 || b >= w->proxyCount)
 			return SetError(w, B2CU_ERR_ARGUMENT, "key %d: proxies %d,%d out of range", i, a, b);
 	}
-	uint64_t* dKeys = nullptr;
-	b2cuContact* dOut = nullptr;
-	CUDA_TRY(w, cudaMalloc(&dKeys, sizeof(uint64_t) * count));
-	cudaError_t e = cudaMalloc(&dOut, sizeof(b2cuContact) * count);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(dKeys, keys, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, w->stream);
+	// keys and records go through a grow-only device scratch (no allocation per call)
+	const size_t keyBytes = (sizeof(uint64_t) * (size_t)count + 255) & ~(size_t)255;
+	const size_t need = keyBytes + sizeof(b2cuContact) * (size_t)count;
+	{
+		int rcs = EnsureQueryScratch(w, need);
+		if (rcs) return rcs;
+	}
+	uint64_t* dKeys = reinterpret_cast<uint64_t*>(w->queryScratch);
+	b2cuContact* dOut = reinterpret_cast<b2cuContact*>(static_cast<char*>(w->queryScratch) + keyBytes);
+	cudaError_t e = cudaMemcpyAsync(dKeys, keys, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, w->stream);
 	if (e == cudaSuccess)
 	{
 		GatherContactsByKeyKernel<<<GridFor(count), kBlock, 0, w->stream>>>(w->d, w->contactCount, w->mainCount, dKeys, count,
@@ -1498,8 +1658,6 @@ int b2cuGetContactsByKey(b2cuWorld* w, int32_t count, const b2cuContactKey* keys
 		e = cudaMemcpyAsync(out, dOut, sizeof(b2cuContact) * count, cudaMemcpyDeviceToHost, w->stream);
 	}
 	if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
-	cudaFree(dKeys);
-	cudaFree(dOut);
 	if (e != cudaSuccess) return SetError(w, B2CU_ERR_CUDA, "b2cuGetContactsByKey: %s", cudaGetErrorString(e));
 	return B2CU_OK;
 }

@@ -268,6 +268,18 @@ B2H_API void b2h_get_transforms(void* p, float* xya, int32* awake)
 	}
 }
 
+/// sum of GetPosition().y over a body range, read through the per-body accessors (a cheap consumer of the mirror)
+B2H_API double b2h_sum_y(void* p, int32 first, int32 count)
+{
+	Host* h = static_cast<Host*>(p);
+	double sum = 0.0;
+	for (int32 i = first; i < first + count && i < (int32)h->bodies.size(); ++i)
+	{
+		if (h->bodies[i]) sum += h->bodies[i]->GetPosition().y;
+	}
+	return sum;
+}
+
 /// mass data computed on the host by CreateFixture / ResetMassData
 B2H_API void b2h_get_mass(void* p, float* massInertiaCenter)
 {

@@ -164,6 +164,15 @@ bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 veloc
 	Clock::time_point t0 = Clock::now();
 	int rc = world.UploadDirty(device);
 	Clock::time_point t1 = Clock::now();
+	// with downloadBodies the step itself copies the body records into the host mirror (overlapped with its
+	// broad-phase part); the mirror is current when b2cuStep returns
+	if (rc == B2CU_OK)
+	{
+		if (m_options.downloadBodies && !world.m_states.empty())
+			rc = b2cuSetBodyMirror(device, world.m_states.data(), (int32)world.m_states.size());
+		else
+			rc = b2cuSetBodyMirror(device, nullptr, 0);
+	}
 	if (rc == B2CU_OK) rc = b2cuStep(device, timeStep, velocityIterations, positionIterations, &impl->info);
 	Clock::time_point t2 = Clock::now();
 	m_hostMs[0] = std::chrono::duration<float, std::milli>(t1 - t0).count();

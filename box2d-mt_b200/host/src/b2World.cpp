@@ -577,28 +577,23 @@ int32 b2World::UploadDirty(b2cuWorld* device)
 void b2World::DispatchEvents(b2cuWorld* device)
 {
 	std::vector<b2cuContactKey> keys[2];
-	for (int32 kind = 0; kind < 2; ++kind)
-	{
-		int32 n = 0;
-		b2cuGetEvents(device, kind, 0, nullptr, &n);
-		keys[kind].resize(n);
-		if (n > 0) b2cuGetEvents(device, kind, n, keys[kind].data(), &n);
-	}
-	if (keys[0].empty() && keys[1].empty()) return;
-
 	std::vector<b2cuContact> recs[2];
 	std::vector<b2Contact> contacts[2];
 	std::vector<char> deferred[2];
 	for (int32 kind = 0; kind < 2; ++kind)
 	{
-		int32 n = (int32)keys[kind].size();
+		int32 n = 0;
+		b2cuGetEventContacts(device, kind, 0, nullptr, nullptr, &n);
+		keys[kind].resize(n);
 		recs[kind].resize(n);
 		contacts[kind].resize(n);
 		deferred[kind].assign(n, 0);
 		if (n == 0) continue;
-		b2cuGetContactsByKey(device, n, keys[kind].data(), recs[kind].data());
+		b2cuGetEventContacts(device, kind, n, keys[kind].data(), recs[kind].data(), &n);
 		for (int32 i = 0; i < n; ++i) MakeContact(&contacts[kind][i], recs[kind][i]);
 	}
+	if (keys[0].empty() && keys[1].empty()) return;
+
 	for (size_t i = 0; i < contacts[0].size(); ++i)
 		deferred[0][i] = m_contactListener->BeginContactImmediate(&contacts[0][i], 0) ? 1 : 0;
 	for (size_t i = 0; i < contacts[1].size(); ++i)
@@ -616,10 +611,10 @@ int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool
 	Clock::time_point t0 = Clock::now();
 	m_contactCount = info.contactCount;
 	memcpy(&m_profile, &info, sizeof(b2Profile)); // the first 13 floats of b2cuStepInfo are the b2Profile fields
-	m_bodiesStale = true;
+	// downloadBodies: b2cuStep has already written the records into m_states (b2cuSetBodyMirror)
+	m_bodiesStale = !downloadBodies;
 	m_proxiesStale = true;
 	InvalidateSnapshots();
-	if (downloadBodies) RefreshBodies();
 	Clock::time_point t1 = Clock::now();
 	if (hostMs) hostMs[0] = std::chrono::duration<float, std::milli>(t1 - t0).count();
 	if (dispatchEvents && m_contactListener && (info.beginCount > 0 || info.endCount > 0))

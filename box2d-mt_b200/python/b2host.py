@@ -54,6 +54,8 @@ def load():
     lib.b2h_profile.argtypes = [vp, vp]
     lib.b2h_step_info.argtypes = [vp, vp]
     lib.b2h_host_timings.argtypes = [vp, vp]
+    lib.b2h_sum_y.argtypes = [vp, ctypes.c_int32, ctypes.c_int32]
+    lib.b2h_sum_y.restype = ctypes.c_double
     lib.b2h_hash.argtypes = [vp]
     lib.b2h_hash.restype = u32
     lib.b2h_set_transform.argtypes = [vp, i32, f32, f32, f32]
@@ -161,6 +163,9 @@ class HostWorld:
         out = np.zeros(4, np.float32)
         self.lib.b2h_host_timings(self.h, _ptr(out))
         return out
+
+    def sum_y(self, first, count):
+        return float(self.lib.b2h_sum_y(self.h, first, count))
 
     def hash(self):
         return self.lib.b2h_hash(self.h)

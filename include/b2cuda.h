@@ -261,6 +261,12 @@ B2CU_API void b2cuHostFree(void* p);
 
 B2CU_API int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bodies);
 B2CU_API int b2cuGetBodies(b2cuWorld* w, int32_t first, int32_t count, b2cuBody* bodies);
+/* b2World::Step leaves the new transforms and velocities in the b2Body objects (b2Island::Solve, Dynamics/b2Island.cpp:
+ * 339-348).  With a mirror registered, every b2cuStep does the same for the caller's records of bodies
+ * [0, count): the copy starts as soon as the solver has finished with the bodies and overlaps the broad-phase part of
+ * the step; when b2cuStep returns the mirror is current (no b2cuGetBodies needed).  `mirror` should come from
+ * b2cuHostAlloc; NULL / 0 removes it.  The mirror must stay valid until it is replaced or the world destroyed. */
+B2CU_API int b2cuSetBodyMirror(b2cuWorld* w, b2cuBody* mirror, int32_t count);
 B2CU_API int b2cuSetShapes(b2cuWorld* w, int32_t first, int32_t count, const b2cuShape* shapes);
 B2CU_API int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* proxies);
 B2CU_API int b2cuGetProxies(b2cuWorld* w, int32_t first, int32_t count, b2cuProxy* proxies);
@@ -275,6 +281,11 @@ B2CU_API int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contac
  * (e.g. the contact of an EndContact event that was destroyed) yields a record with the proxies of the key in
  * primary-type order, flags 0 and an empty manifold. */
 B2CU_API int b2cuGetContactsByKey(b2cuWorld* w, int32_t count, const b2cuContactKey* keys, b2cuContact* out);
+/* b2cuGetEvents and b2cuGetContactsByKey in one round trip: the events of `kind` in callback order together with the
+ * record of each event's contact -- what b2ContactListener::BeginContact / EndContact receive as b2Contact*
+ * (Dynamics/b2WorldCallbacks.h:84-107). */
+B2CU_API int b2cuGetEventContacts(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* keys,
+                                  b2cuContact* records, int32_t* count);
 
 B2CU_API int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positionIterations,
                       b2cuStepInfo* info);
