@@ -10,7 +10,8 @@ and stepped with b2World::Step(dt, 8, 3, b2CudaStepExecutor&).
   e2e    the same through the same call with the host buffers in the loop: every step uploads that step's user
          input (forces on 1% of the bodies, edited through b2Body::ApplyForceToCenter) and downloads every body's
          state into the host mirror that b2Body::GetPosition() reads, plus the begin/end touch events
-  roofline      the dominant kernel (SolveVelocityKernel, all colour launches of a step) against measured HBM peak
+  roofline      the dominant kernel (SolverVelocityPersistentKernel, one cooperative launch per step) against the
+                measured HBM peak; traffic = its DRAM bytes from the committed ncu capture
   cpu_baseline  the compiled reference (oracle/_ref) with its own b2ThreadPoolTaskExecutor on the host cores, on a
                 bounded sample: a narrower pile of the same depth, started from the device-settled state
 Reference arm (--impl reference): the reference's own CPU implementation alone, on a narrower pile of the same
@@ -45,6 +46,19 @@ BYTES_PER_BODY = 212
 BYTES_PER_PROXY = 120
 BYTES_PER_CONTACT_NARROW = 208
 BYTES_PER_CONSTRAINT_STEP = 2794
+
+
+def ncu_traffic(n_constraints):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/r1_solver_traffic.json); scaled by the constraint count of
+    this run when the capture had a different one.  None when there is no capture."""
+    path = os.path.join(ROOT, "profiles", "r1_solver_traffic.json")
+    try:
+        with open(path) as f:
+            cap = json.load(f)
+        return float(cap["dram_bytes_per_launch"]) * float(n_constraints) / float(cap["constraints"])
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -275,11 +289,11 @@ def run_product_arm(args, rank, local_rank, world_size):
     n_contacts = float(np.mean([int(i["contactCount"]) for i in infos]))
     # the solver kernel (one persistent cooperative launch per step: warm start, velocity iterations, impulse store,
     # position integration, position iterations) is timed by the CUDA events around it (solveVelocity+solvePosition)
-    vel_ms = float(np.mean([float(i["solveVelocity"]) + float(i["solvePosition"]) for i in infos]))
+    vel_ms = float(np.mean([float(i["solveVelocity"]) for i in infos]))
     colours = float(np.mean([int(i["colourCount"]) for i in infos]))
     peak, peak_src = measured_peaks()
-    vel_bytes = (n_constraints * (BYTES_WARM_START + BYTES_VELOCITY_ITER * VEL_ITERS + BYTES_STORE +
-                                  BYTES_POSITION_ITER * POS_ITERS) + n_bodies * BYTES_INTEGRATE_POS)
+    vel_bytes = (n_constraints * (BYTES_WARM_START + BYTES_VELOCITY_ITER * VEL_ITERS + BYTES_STORE) +
+                 n_bodies * BYTES_INTEGRATE_POS)
     achieved = vel_bytes / (vel_ms * 1e-3) / 1e9 if vel_ms > 0 else 0.0
     step_bytes = (n_bodies * BYTES_PER_BODY + n_bodies * BYTES_PER_PROXY + n_contacts * BYTES_PER_CONTACT_NARROW +
                   n_constraints * BYTES_PER_CONSTRAINT_STEP)
@@ -331,12 +345,13 @@ def run_product_arm(args, rank, local_rank, world_size):
                 "host_ms": dict(zip(("apply_forces", "upload", "step", "download", "events"),
                                     [1e3 * apply_s / args.steps] + [float(x) / args.steps for x in host_ms]))},
         "gpu_launches": int(sum(int(i["kernelLaunches"]) for i in infos)),
-        "roofline": {"bound": "hbm", "kernel": "SolverPersistentKernel (warm start + 8 velocity iterations + store + integrate + 3 position "
-                                                        "iterations, one cooperative launch per step)",
+        "roofline": {"bound": "hbm", "kernel": "SolverVelocityPersistentKernel (warm start + 8 velocity iterations + impulse "
+                                                        "store + position integration, one cooperative launch per step)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
-                     "bytes_per_unit": "per touching contact: 128 warm start + 220 x 8 velocity + 32 store + 136 x 3 position "
-                                       "= 2328 B, + 48 B per body (SURVEY.md 8d)"},
+                     "frac": achieved / peak, "traffic": ncu_traffic(n_constraints),
+                     "ms_per_launch": vel_ms,
+                     "bytes_per_unit": "per touching contact: 128 warm start + 220 x 8 velocity + 32 store = 1920 B, "
+                                       "+ 48 B per body (SURVEY.md 8d)"},
         "cpu_baseline": cpu,
         "clocks": clocks,
         "build_s": build_s, "checksum": checksum, "last_step": {k: int(last[k]) for k in

@@ -1346,6 +1346,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			TraceMark(w, "SolverVelocityPersistentKernel");
 			if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)((warmStarting ? 1 : 0) + velocityIterations);
 			plan.shard.seq = w->shardSeq;
+			cudaEventRecord(w->ev[6], w->stream);
 			if (positionIterations > 0)
 			{
 				CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverPositionPersistentKernel,
@@ -1354,7 +1355,6 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				TraceMark(w, "SolverPositionPersistentKernel");
 				if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)positionIterations;
 			}
-			cudaEventRecord(w->ev[6], w->stream);
 		}
 		else
 		{
@@ -1477,6 +1477,10 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		                                       const std::pair<std::string, std::pair<float, int> >& b) {
 			return a.second.first > b.second.first;
 		});
+		fprintf(stderr, "[b2cu colours]");
+		for (int c = 0; c < B2CU_MAX_COLOURS + 2; ++c)
+			if (w->colourCounts[c] > 0) fprintf(stderr, " %d:%d", c, w->colourCounts[c]);
+		fprintf(stderr, "\n");
 		fprintf(stderr, "[b2cu trace] step: %zu marks\n", g_trace.used);
 		for (size_t k = 0; k < rows.size(); ++k)
 			fprintf(stderr, "[b2cu trace] %-32s n=%4d %9.3f ms\n", rows[k].first.c_str(), rows[k].second.second,

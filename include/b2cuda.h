@@ -29,6 +29,12 @@
  *                                        fetched for a list of keys only       Dynamics/Contacts/b2Contact.h:95-176
  *   b2cuGetEvents                        deferred BeginContact/EndContact buffers, sorted by proxy-id key
  *                                                                          Dynamics/b2ContactManager.cpp:388-439
+ *   b2cuGetEventContacts                 the two above in one round trip: what BeginContact / EndContact receive
+ *                                                                          Dynamics/b2WorldCallbacks.h:84-107
+ *   b2cuSetBodyMirror                    b2Island::Solve writing the new state into the b2Body objects
+ *                                                                          Dynamics/b2Island.cpp:339-348
+ *   b2cuHostAlloc / b2cuHostFree         the world's own allocation of its bodies (b2BlockAllocator)
+ *                                                                          Common/b2BlockAllocator.cpp:93-170
  *   b2cuGetSolverOrder                   (new) the colour-ordered constraint list the coloured Gauss-Seidel
  *                                        used this step; feeds the permuted-order oracle
  *   b2cuGetToiCandidates                 TOI-eligible front partition of b2ContactManager::m_contacts
