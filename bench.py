@@ -274,7 +274,7 @@ def run_product_arm(args, rank, local_rank, world_size):
     e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
     barrier()
     h2d = block * T.BODY.itemsize
-    d2h = world.counts()[0] * T.BODY.itemsize + 8 * int(infos[-1]["beginCount"] + infos[-1]["endCount"])
+    d2h = world.counts()[0] * T.BODY_STATE.itemsize + 8 * int(infos[-1]["beginCount"] + infos[-1]["endCount"])
     world.set_options(False, False)
     total_bodies = int(sum_over_ranks(n_bodies))
 

@@ -312,6 +312,36 @@ __global__ void __launch_bounds__(256) PackBodiesKernel(DeviceArrays d, int firs
 	}
 }
 
+#define B2CU_STATE_WORDS 16
+static_assert(sizeof(b2cuBodyState) == B2CU_STATE_WORDS * 4, "b2cuBodyState layout");
+
+// device -> host direction: only the fields a step changes (b2cuBodyState, 64 bytes)
+__global__ void __launch_bounds__(256) PackBodyStatesKernel(DeviceArrays d, int first, int count, float* __restrict__ out)
+{
+	__shared__ float sh[256 * (B2CU_STATE_WORDS + 1)]; // +1: the 16-word records would all hit the same banks
+	for (int tile = blockIdx.x; tile * 256 < count; tile += gridDim.x)
+	{
+		int r = tile * 256 + threadIdx.x;
+		if (r < count)
+		{
+			int b = first + r;
+			float4 xf = d.xf[b], pos = d.pos[b], pos0 = d.pos0[b], vel = d.vel[b];
+			float* s = sh + threadIdx.x * (B2CU_STATE_WORDS + 1);
+			s[0] = xf.x; s[1] = xf.y; s[2] = xf.z; s[3] = xf.w;
+			s[4] = pos.x; s[5] = pos.y; s[6] = pos.z;
+			s[7] = pos0.x; s[8] = pos0.y; s[9] = pos0.z; s[10] = pos0.w;
+			s[11] = vel.x; s[12] = vel.y; s[13] = vel.z;
+			s[14] = d.force[b].w;
+			s[15] = __uint_as_float(d.bflags[b]);
+		}
+		__syncthreads();
+		int n = min(256, count - tile * 256) * B2CU_STATE_WORDS;
+		float* o = out + (size_t)tile * 256 * B2CU_STATE_WORDS;
+		for (int i = threadIdx.x; i < n; i += 256) o[i] = sh[(i / B2CU_STATE_WORDS) * (B2CU_STATE_WORDS + 1) + (i % B2CU_STATE_WORDS)];
+		__syncthreads();
+	}
+}
+
 __global__ void __launch_bounds__(256) UnpackBodiesKernel(DeviceArrays d, int first, int count, const float* __restrict__ in)
 {
 	__shared__ float sh[256 * B2CU_BODY_WORDS];

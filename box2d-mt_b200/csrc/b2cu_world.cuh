@@ -206,7 +206,7 @@ struct b2cuWorld
 	float* bodyStage;    // device staging of b2cuBody records for b2cuGetBodies / b2cuSetBodies (lazy)
 	int bodyStageCapacity;
 	// body mirror (b2cuSetBodyMirror): every step copies the body records there, overlapping the broad-phase
-	b2cuBody* bodyMirror;
+	b2cuBodyState* bodyMirror;
 	int bodyMirrorCount;
 	bool mirrorInFlight;
 	cudaStream_t copyStream;
@@ -217,6 +217,8 @@ struct b2cuWorld
 	size_t queryScratchBytes;
 	void* queryHost;     // page-locked host side of the same
 	size_t queryHostBytes;
+	bool eventCacheValid;      // queryHost holds the keys + records of the last step's events
+	size_t eventCacheKeyBytes;
 	cudaEvent_t ev[10];
 	int launches;
 	char lastError[512];

@@ -1074,10 +1074,10 @@ static int StartMirrorCopy(b2cuWorld* w)
 	if (rc) return rc;
 	CUDA_TRY(w, cudaEventRecord(w->evBodiesFinal, w->stream));
 	CUDA_TRY(w, cudaStreamWaitEvent(w->copyStream, w->evBodiesFinal, 0));
-	PackBodiesKernel<<<GridFor(n), kBlock, 0, w->copyStream>>>(w->d, 0, n, w->bodyStage);
+	PackBodyStatesKernel<<<GridFor(n), kBlock, 0, w->copyStream>>>(w->d, 0, n, w->bodyStage);
 	++w->launches;
 	CUDA_TRY(w, cudaEventRecord(w->evPacked, w->copyStream));
-	CUDA_TRY(w, cudaMemcpyAsync(w->bodyMirror, w->bodyStage, sizeof(b2cuBody) * (size_t)n, cudaMemcpyDeviceToHost,
+	CUDA_TRY(w, cudaMemcpyAsync(w->bodyMirror, w->bodyStage, sizeof(b2cuBodyState) * (size_t)n, cudaMemcpyDeviceToHost,
 	                            w->copyStream));
 	w->mirrorInFlight = true;
 	return B2CU_OK;
@@ -1116,7 +1116,20 @@ static int FinishMirrorCopy(b2cuWorld* w)
 	return B2CU_OK;
 }
 
-int b2cuSetBodyMirror(b2cuWorld* w, b2cuBody* mirror, int32_t count)
+int b2cuGetBodyStates(b2cuWorld* w, int32_t first, int32_t count, b2cuBodyState* states)
+{
+	int rc = CheckRange(w, first, count, w ? w->bodyCount : 0, states);
+	if (rc) return rc;
+	if (count == 0) return B2CU_OK;
+	cudaSetDevice(w->device);
+	if ((rc = EnsureBodyStage(w))) return rc;
+	float* stage = w->bodyStage + (size_t)first * B2CU_STATE_WORDS;
+	LAUNCH(w, PackBodyStatesKernel, GridFor(count), kBlock, w->d, first, count, stage);
+	CUDA_TRY(w, cudaMemcpyAsync(states, stage, sizeof(b2cuBodyState) * (size_t)count, cudaMemcpyDeviceToHost, w->stream));
+	return SyncCheck(w);
+}
+
+int b2cuSetBodyMirror(b2cuWorld* w, b2cuBodyState* mirror, int32_t count)
 {
 	if (!w || count < 0 || (count > 0 && !mirror)) return B2CU_ERR_ARGUMENT;
 	w->bodyMirror = count > 0 ? mirror : nullptr;
@@ -1146,6 +1159,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 
 	CUDA_TRY(w, cudaMemsetAsync(d.counters, 0, sizeof(int) * CNT_STICKY_TOI, w->stream));
 	w->mirrorInFlight = false;
+	w->eventCacheValid = false;
 	cudaEventRecord(w->ev[0], w->stream);
 	{
 		const char* t = getenv("B2CU_TRACE");
@@ -1585,6 +1599,39 @@ static int EnsureQueryHost(b2cuWorld* w, size_t bytes)
 	return B2CU_OK;
 }
 
+// keys and contact records of ALL events of the last step, fetched in one round trip on the first request and
+// kept in the page-locked scratch: [begin | end (Update) | end (Destroy)] keys, then the records in the same order
+static int FetchEventRecords(b2cuWorld* w)
+{
+	if (w->eventCacheValid) return B2CU_OK;
+	const int nB = w->beginCount, nE = w->endUpdateCount, nD = w->endCount - w->endUpdateCount;
+	const int n = nB + nE + nD;
+	if (n == 0)
+	{
+		w->eventCacheValid = true;
+		return B2CU_OK;
+	}
+	const size_t keyBytes = (sizeof(uint64_t) * (size_t)n + 255) & ~(size_t)255;
+	const size_t total = keyBytes + sizeof(b2cuContact) * (size_t)n;
+	int rc;
+	if ((rc = EnsureQueryScratch(w, total)) || (rc = EnsureQueryHost(w, total))) return rc;
+	uint64_t* dKeys = reinterpret_cast<uint64_t*>(w->queryScratch);
+	b2cuContact* dOut = reinterpret_cast<b2cuContact*>(static_cast<char*>(w->queryScratch) + keyBytes);
+	if (nB > 0)
+		CUDA_TRY(w, cudaMemcpyAsync(dKeys, w->d.beginKeys, sizeof(uint64_t) * nB, cudaMemcpyDeviceToDevice, w->stream));
+	if (nE > 0)
+		CUDA_TRY(w, cudaMemcpyAsync(dKeys + nB, w->d.endKeys, sizeof(uint64_t) * nE, cudaMemcpyDeviceToDevice, w->stream));
+	if (nD > 0)
+		CUDA_TRY(w, cudaMemcpyAsync(dKeys + nB + nE, w->d.destroyEndKeys, sizeof(uint64_t) * nD, cudaMemcpyDeviceToDevice,
+		                            w->stream));
+	LAUNCH(w, GatherContactsByKeyKernel, GridFor(n), kBlock, w->d, w->contactCount, w->mainCount, (const uint64_t*)dKeys, n, dOut);
+	CUDA_TRY(w, cudaMemcpyAsync(w->queryHost, w->queryScratch, total, cudaMemcpyDeviceToHost, w->stream));
+	if ((rc = SyncCheck(w))) return rc;
+	w->eventCacheKeyBytes = keyBytes;
+	w->eventCacheValid = true;
+	return B2CU_OK;
+}
+
 int b2cuGetEventContacts(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* keys, b2cuContact* records,
                          int32_t* count)
 {
@@ -1593,33 +1640,15 @@ int b2cuGetEventContacts(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuConta
 	const int n = kind == B2CU_EVENT_BEGIN ? w->beginCount : w->endCount;
 	if (count) *count = n;
 	if (capacity == 0 || n == 0) return B2CU_OK;
-	// one round trip: the records are gathered on the device in arrival order, keys and records come back together,
-	// and the callback order of b2cuGetEvents is established on the host by sorting an index
-	const size_t keyBytes = (sizeof(uint64_t) * (size_t)n + 255) & ~(size_t)255;
-	const size_t total = keyBytes + sizeof(b2cuContact) * (size_t)n;
-	int rc;
-	if ((rc = EnsureQueryScratch(w, total)) || (rc = EnsureQueryHost(w, total))) return rc;
-	uint64_t* dKeys = reinterpret_cast<uint64_t*>(w->queryScratch);
-	b2cuContact* dOut = reinterpret_cast<b2cuContact*>(static_cast<char*>(w->queryScratch) + keyBytes);
-	int firstPart = n;
-	if (kind == B2CU_EVENT_BEGIN)
-	{
-		CUDA_TRY(w, cudaMemcpyAsync(dKeys, w->d.beginKeys, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, w->stream));
-	}
-	else
-	{
-		firstPart = w->endUpdateCount;
-		if (firstPart > 0)
-			CUDA_TRY(w, cudaMemcpyAsync(dKeys, w->d.endKeys, sizeof(uint64_t) * firstPart, cudaMemcpyDeviceToDevice, w->stream));
-		if (n - firstPart > 0)
-			CUDA_TRY(w, cudaMemcpyAsync(dKeys + firstPart, w->d.destroyEndKeys, sizeof(uint64_t) * (n - firstPart),
-			                            cudaMemcpyDeviceToDevice, w->stream));
-	}
-	LAUNCH(w, GatherContactsByKeyKernel, GridFor(n), kBlock, w->d, w->contactCount, w->mainCount, (const uint64_t*)dKeys, n, dOut);
-	CUDA_TRY(w, cudaMemcpyAsync(w->queryHost, w->queryScratch, total, cudaMemcpyDeviceToHost, w->stream));
-	if ((rc = SyncCheck(w))) return rc;
-	const uint64_t* hKeys = reinterpret_cast<const uint64_t*>(w->queryHost);
-	const b2cuContact* hOut = reinterpret_cast<const b2cuContact*>(static_cast<const char*>(w->queryHost) + keyBytes);
+	// the records are gathered on the device in arrival order, keys and records come back together, and the callback
+	// order of b2cuGetEvents is established on the host by sorting an index
+	int rc = FetchEventRecords(w);
+	if (rc) return rc;
+	const int offset = kind == B2CU_EVENT_BEGIN ? 0 : w->beginCount;
+	const int firstPart = kind == B2CU_EVENT_BEGIN ? n : w->endUpdateCount;
+	const uint64_t* hKeys = reinterpret_cast<const uint64_t*>(w->queryHost) + offset;
+	const b2cuContact* hOut =
+	    reinterpret_cast<const b2cuContact*>(static_cast<const char*>(w->queryHost) + w->eventCacheKeyBytes) + offset;
 	std::vector<int> order(n);
 	for (int i = 0; i < n; ++i) order[i] = i;
 	auto byKey = [hKeys](int a, int b) { return hKeys[a] < hKeys[b]; };

@@ -33,7 +33,46 @@ struct b2MirrorAllocator
 	template <typename U>
 	bool operator!=(const b2MirrorAllocator<U>&) const { return false; }
 };
-typedef std::vector<b2cuBody, b2MirrorAllocator<b2cuBody> > b2BodyStateArray;
+typedef std::vector<b2cuBodyState, b2MirrorAllocator<b2cuBodyState> > b2BodyStateArray;
+
+/// The fields of b2cuBody that only the host writes (the device clears the forces at the end of a step, as
+/// b2World::ClearForces does): they never travel device -> host, so they are kept apart from the b2cuBodyState
+/// records that every step copies back.
+struct b2BodyProps
+{
+	float lcx, lcy;
+	float fx, fy, torque;
+	float invMass, invI;
+	float linearDamping, angularDamping, gravityScale;
+};
+
+/// One body's record seen as a whole (the field names of b2cuBody) over the two arrays.
+struct b2BodyView
+{
+	float &px, &py, &qs, &qc, &cx, &cy, &a, &c0x, &c0y, &a0, &alpha0, &vx, &vy, &w, &sleepTime;
+	uint32_t& flags;
+	float &lcx, &lcy, &fx, &fy, &torque, &invMass, &invI, &linearDamping, &angularDamping, &gravityScale;
+	b2BodyView(b2cuBodyState& s, b2BodyProps& p)
+		: px(s.px), py(s.py), qs(s.qs), qc(s.qc), cx(s.cx), cy(s.cy), a(s.a), c0x(s.c0x), c0y(s.c0y), a0(s.a0),
+		  alpha0(s.alpha0), vx(s.vx), vy(s.vy), w(s.w), sleepTime(s.sleepTime), flags(s.flags), lcx(p.lcx), lcy(p.lcy),
+		  fx(p.fx), fy(p.fy), torque(p.torque), invMass(p.invMass), invI(p.invI), linearDamping(p.linearDamping),
+		  angularDamping(p.angularDamping), gravityScale(p.gravityScale)
+	{
+	}
+	void ToRecord(b2cuBody* out) const
+	{
+		out->px = px; out->py = py; out->qs = qs; out->qc = qc;
+		out->cx = cx; out->cy = cy; out->a = a;
+		out->c0x = c0x; out->c0y = c0y; out->a0 = a0; out->alpha0 = alpha0;
+		out->lcx = lcx; out->lcy = lcy;
+		out->vx = vx; out->vy = vy; out->w = w;
+		out->fx = fx; out->fy = fy; out->torque = torque;
+		out->invMass = invMass; out->invI = invI;
+		out->linearDamping = linearDamping; out->angularDamping = angularDamping; out->gravityScale = gravityScale;
+		out->sleepTime = sleepTime;
+		out->flags = flags;
+	}
+};
 typedef std::vector<b2cuProxy, b2MirrorAllocator<b2cuProxy> > b2ProxyStateArray;
 
 class b2CudaStepExecutor;
@@ -97,7 +136,12 @@ private:
 	friend class b2CudaStepExecutor;
 
 	// host mirror of the device state
-	b2BodyStateArray m_states;
+	b2BodyStateArray m_states;            // device-written part of the bodies (the step's body mirror)
+	std::vector<b2BodyProps> m_props;     // host-written part
+	std::vector<int32> m_forced;          // bodies with a non-zero force/torque on the host side
+	std::vector<b2cuBody, b2MirrorAllocator<b2cuBody> > m_uploadRows; // page-locked staging of the dirty rows
+	mutable std::vector<b2cuBody> m_records; // whole records, assembled on request (GetBodyStates)
+	b2BodyView BodyView(int32 i) { return b2BodyView(m_states[i], m_props[i]); }
 	std::vector<b2Body*> m_bodies;
 	b2ProxyStateArray m_proxies;
 	std::vector<b2Fixture*> m_fixtures;
@@ -106,6 +150,7 @@ private:
 
 	int32 InternShape(const b2Shape* shape);
 	void MarkBodyDirty(int32 index);
+	void MarkBodyForced(int32 index); // dirty + remembered: the step clears forces on the device, the host follows
 	void MarkProxyDirty(int32 index);
 	void RefreshBodies() const;    // device -> host mirror if stale
 	void RefreshProxies() const;

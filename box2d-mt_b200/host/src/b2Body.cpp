@@ -10,7 +10,7 @@ inline const b2Vec2& AsVec2(const float& x) { return reinterpret_cast<const b2Ve
 inline b2Vec2& AsVec2(float& x) { return reinterpret_cast<b2Vec2&>(x); }
 } // namespace
 
-#define B2_STATE() (m_world->m_states[m_index])
+#define B2_STATE() (m_world->BodyView(m_index))
 
 // ---- accessors -------------------------------------------------------------------------------------------
 
@@ -44,7 +44,7 @@ float32 b2Body::GetAngularVelocity() const
 }
 float32 b2Body::GetInertia() const
 {
-	const b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	return m_I + m_mass * b2Dot(AsVec2(s.lcx), AsVec2(s.lcx));
 }
 void b2Body::GetMassData(b2MassData* data) const
@@ -100,10 +100,10 @@ void b2Body::ApplyForce(const b2Vec2& force, const b2Vec2& point, bool wake)
 	if (GetType() != b2_dynamicBody) return;
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
-	b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	AsVec2(s.fx) += force;
 	s.torque += b2Cross(point - AsVec2(s.cx), force);
-	m_world->MarkBodyDirty(m_index);
+	m_world->MarkBodyForced(m_index);
 }
 
 void b2Body::ApplyForceToCenter(const b2Vec2& force, bool wake)
@@ -112,7 +112,7 @@ void b2Body::ApplyForceToCenter(const b2Vec2& force, bool wake)
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
 	AsVec2(B2_STATE().fx) += force;
-	m_world->MarkBodyDirty(m_index);
+	m_world->MarkBodyForced(m_index);
 }
 
 void b2Body::ApplyTorque(float32 torque, bool wake)
@@ -121,7 +121,7 @@ void b2Body::ApplyTorque(float32 torque, bool wake)
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
 	B2_STATE().torque += torque;
-	m_world->MarkBodyDirty(m_index);
+	m_world->MarkBodyForced(m_index);
 }
 
 void b2Body::ApplyLinearImpulse(const b2Vec2& impulse, const b2Vec2& point, bool wake)
@@ -129,7 +129,7 @@ void b2Body::ApplyLinearImpulse(const b2Vec2& impulse, const b2Vec2& point, bool
 	if (GetType() != b2_dynamicBody) return;
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
-	b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	AsVec2(s.vx) += s.invMass * impulse;
 	s.w += s.invI * b2Cross(point - AsVec2(s.cx), impulse);
 	m_world->MarkBodyDirty(m_index);
@@ -140,7 +140,7 @@ void b2Body::ApplyLinearImpulseToCenter(const b2Vec2& impulse, bool wake)
 	if (GetType() != b2_dynamicBody) return;
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
-	b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	AsVec2(s.vx) += s.invMass * impulse;
 	m_world->MarkBodyDirty(m_index);
 }
@@ -150,7 +150,7 @@ void b2Body::ApplyAngularImpulse(float32 impulse, bool wake)
 	if (GetType() != b2_dynamicBody) return;
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
-	b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	s.w += s.invI * impulse;
 	m_world->MarkBodyDirty(m_index);
 }
@@ -178,7 +178,7 @@ void b2Body::SetAwake(bool flag)
 {
 	if (m_world->IsLocked()) return;
 	m_world->RefreshBodies();
-	b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	if (flag)
 	{
 		s.flags |= B2CU_BODY_AWAKE;
@@ -240,7 +240,7 @@ void b2Body::SetType(b2BodyType type)
 	// body after the first step is outside this version of the GPU path
 	b2Assert(m_world->m_device == nullptr || type == GetType());
 	if (m_world->IsLocked() || type == GetType()) return;
-	b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	s.flags = (s.flags & ~(uint32)B2CU_BODY_TYPE_MASK) | (uint32)type;
 	ResetMassData();
 	if (type == b2_staticBody)
@@ -260,7 +260,7 @@ void b2Body::SetTransform(const b2Vec2& position, float32 angle)
 {
 	if (m_world->IsLocked()) return;
 	m_world->RefreshBodies();
-	b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	b2Transform xf;
 	xf.q.Set(angle);
 	xf.p = position;
@@ -322,7 +322,7 @@ void b2Body::SynchronizeProxies(const b2Transform& xf1, const b2Transform& xf2)
 void b2Body::ResetMassData()
 {
 	m_world->RefreshBodies();
-	b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	m_mass = 0.0f;
 	s.invMass = 0.0f;
 	m_I = 0.0f;
@@ -387,7 +387,7 @@ void b2Body::SetMassData(const b2MassData* massData)
 {
 	if (m_world->IsLocked() || GetType() != b2_dynamicBody) return;
 	m_world->RefreshBodies();
-	b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	s.invMass = 0.0f;
 	m_I = 0.0f;
 	s.invI = 0.0f;
@@ -431,7 +431,7 @@ b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def)
 	f->m_thickShape = def->thickShape;
 	f->m_userData = def->userData;
 
-	const b2cuBody& s = B2_STATE();
+	b2BodyView s = B2_STATE();
 	b2AABB aabb;
 	f->m_shape->ComputeAABB(&aabb, reinterpret_cast<const b2Transform&>(s.px), 0);
 

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 bool b2ContactFilter::ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB, uint32 threadId)
@@ -154,7 +155,22 @@ b2Body* b2World::CreateBody(const b2BodyDef* def)
 		b->m_mass = 0.0f;
 		s.invMass = 0.0f;
 	}
-	m_states.push_back(s);
+	{
+		b2cuBodyState st;
+		b2BodyProps pr;
+		st.px = s.px; st.py = s.py; st.qs = s.qs; st.qc = s.qc;
+		st.cx = s.cx; st.cy = s.cy; st.a = s.a;
+		st.c0x = s.c0x; st.c0y = s.c0y; st.a0 = s.a0; st.alpha0 = s.alpha0;
+		st.vx = s.vx; st.vy = s.vy; st.w = s.w;
+		st.sleepTime = s.sleepTime;
+		st.flags = s.flags;
+		pr.lcx = s.lcx; pr.lcy = s.lcy;
+		pr.fx = s.fx; pr.fy = s.fy; pr.torque = s.torque;
+		pr.invMass = s.invMass; pr.invI = s.invI;
+		pr.linearDamping = s.linearDamping; pr.angularDamping = s.angularDamping; pr.gravityScale = s.gravityScale;
+		m_states.push_back(st);
+		m_props.push_back(pr);
+	}
 	m_bodies.push_back(b);
 
 	// newest first, as the reference's body list
@@ -224,6 +240,12 @@ void b2World::MarkBodyDirty(int32 index)
 	m_bodyDirtyHi = std::max(m_bodyDirtyHi, index);
 }
 
+void b2World::MarkBodyForced(int32 index)
+{
+	MarkBodyDirty(index);
+	m_forced.push_back(index);
+}
+
 void b2World::MarkProxyDirty(int32 index)
 {
 	m_proxyDirtyLo = std::min(m_proxyDirtyLo, index);
@@ -243,10 +265,11 @@ void b2World::SetAllowSleeping(bool flag)
 void b2World::ClearForces()
 {
 	RefreshBodies();
-	for (size_t i = 0; i < m_states.size(); ++i)
+	for (size_t i = 0; i < m_props.size(); ++i)
 	{
-		m_states[i].fx = m_states[i].fy = m_states[i].torque = 0.0f;
+		m_props[i].fx = m_props[i].fy = m_props[i].torque = 0.0f;
 	}
+	m_forced.clear();
 	if (!m_states.empty())
 	{
 		MarkBodyDirty(0);
@@ -257,7 +280,10 @@ void b2World::ClearForces()
 const b2cuBody* b2World::GetBodyStates() const
 {
 	RefreshBodies();
-	return m_states.data();
+	b2World* self = const_cast<b2World*>(this);
+	m_records.resize(m_states.size());
+	for (size_t i = 0; i < m_states.size(); ++i) self->BodyView((int32)i).ToRecord(&m_records[i]);
+	return m_records.data();
 }
 
 const b2cuProxy* b2World::GetProxyStates() const
@@ -273,7 +299,7 @@ void b2World::RefreshBodies() const
 	if (!m_bodiesStale || m_device == nullptr) return;
 	b2World* self = const_cast<b2World*>(this);
 	int32 n = std::min(m_bodiesUploaded, (int32)m_states.size());
-	if (n > 0) b2cuGetBodies(m_device, 0, n, self->m_states.data());
+	if (n > 0) b2cuGetBodyStates(m_device, 0, n, self->m_states.data());
 	m_bodiesStale = false;
 }
 
@@ -432,13 +458,21 @@ void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vecto
 		if (!deadBody[i])
 		{
 			m_states[nb] = m_states[i];
+			m_props[nb] = m_props[i];
 			m_bodies[nb] = m_bodies[i];
 			m_bodies[nb]->m_index = nb;
 			++nb;
 		}
 	}
 	m_states.resize(nb);
+	m_props.resize(nb);
 	m_bodies.resize(nb);
+	{
+		size_t kept = 0;
+		for (size_t i = 0; i < m_forced.size(); ++i)
+			if (bodyMap[m_forced[i]] >= 0) m_forced[kept++] = bodyMap[m_forced[i]];
+		m_forced.resize(kept);
+	}
 
 	for (int32 i = 0; i < np; ++i)
 	{
@@ -546,7 +580,13 @@ int32 b2World::UploadDirty(b2cuWorld* device)
 	if (nb > m_bodiesUploaded || m_bodyDirtyHi >= 0)
 	{
 		if (nb == m_bodiesUploaded) hi = m_bodyDirtyHi;
-		if (lo <= hi && (rc = b2cuSetBodies(device, lo, hi - lo + 1, m_states.data() + lo))) return rc;
+		if (lo <= hi)
+		{
+			// whole records of the range, assembled from the two halves of the host mirror
+			if (m_uploadRows.size() < (size_t)(hi - lo + 1)) m_uploadRows.resize((size_t)(hi - lo + 1));
+			for (int32 i = lo; i <= hi; ++i) BodyView(i).ToRecord(&m_uploadRows[(size_t)(i - lo)]);
+			if ((rc = b2cuSetBodies(device, lo, hi - lo + 1, m_uploadRows.data()))) return rc;
+		}
 	}
 	lo = std::min(m_proxyDirtyLo, m_proxiesUploaded);
 	hi = std::max(m_proxyDirtyHi, np - 1);
@@ -576,6 +616,10 @@ int32 b2World::UploadDirty(b2cuWorld* device)
 // BeginContact calls in key order, then the deferred EndContact calls in key order.
 void b2World::DispatchEvents(b2cuWorld* device)
 {
+	static const bool timing = getenv("B2H_EVENT_TIMING") != nullptr;
+	typedef std::chrono::steady_clock Clock;
+	Clock::time_point t0 = Clock::now();
+	double queryMs = 0.0, makeMs = 0.0;
 	std::vector<b2cuContactKey> keys[2];
 	std::vector<b2cuContact> recs[2];
 	std::vector<b2Contact> contacts[2];
@@ -589,9 +633,27 @@ void b2World::DispatchEvents(b2cuWorld* device)
 		contacts[kind].resize(n);
 		deferred[kind].assign(n, 0);
 		if (n == 0) continue;
+		Clock::time_point ta = Clock::now();
 		b2cuGetEventContacts(device, kind, n, keys[kind].data(), recs[kind].data(), &n);
-		for (int32 i = 0; i < n; ++i) MakeContact(&contacts[kind][i], recs[kind][i]);
+		Clock::time_point tb = Clock::now();
+		for (int32 i = 0; i < n; ++i)
+		{
+			// the fixture table is far larger than the caches and the events hit it at random: ask ahead
+			if (i + 8 < n)
+			{
+				__builtin_prefetch(&m_fixtures[recs[kind][i + 8].proxyA]);
+				__builtin_prefetch(&m_fixtures[recs[kind][i + 8].proxyB]);
+			}
+			MakeContact(&contacts[kind][i], recs[kind][i]);
+		}
+		Clock::time_point tc = Clock::now();
+		queryMs += std::chrono::duration<double, std::milli>(tb - ta).count();
+		makeMs += std::chrono::duration<double, std::milli>(tc - tb).count();
 	}
+	if (timing)
+		fprintf(stderr, "[b2h events] begin %zu end %zu: query %.3f ms, make %.3f ms, alloc+rest %.3f ms\n", keys[0].size(),
+		        keys[1].size(), queryMs, makeMs,
+		        std::chrono::duration<double, std::milli>(Clock::now() - t0).count() - queryMs - makeMs);
 	if (keys[0].empty() && keys[1].empty()) return;
 
 	for (size_t i = 0; i < contacts[0].size(); ++i)
@@ -613,6 +675,22 @@ int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool
 	memcpy(&m_profile, &info, sizeof(b2Profile)); // the first 13 floats of b2cuStepInfo are the b2Profile fields
 	// downloadBodies: b2cuStep has already written the records into m_states (b2cuSetBodyMirror)
 	m_bodiesStale = !downloadBodies;
+	if (!m_forced.empty())
+	{
+		// the device cleared the forces (b2World::ClearForces at the end of Step, b2World.cpp:1688-1691) or, without
+		// auto-clear, zeroed those of the bodies it put to sleep (b2Body::SetAwake(false), b2Body.h:704-711)
+		if (!m_clearForces) RefreshBodies();
+		size_t kept = 0;
+		for (size_t i = 0; i < m_forced.size(); ++i)
+		{
+			int32 b = m_forced[i];
+			if (m_clearForces || !(m_states[b].flags & B2CU_BODY_AWAKE))
+				m_props[b].fx = m_props[b].fy = m_props[b].torque = 0.0f;
+			else
+				m_forced[kept++] = b;
+		}
+		m_forced.resize(kept);
+	}
 	m_proxiesStale = true;
 	InvalidateSnapshots();
 	Clock::time_point t1 = Clock::now();

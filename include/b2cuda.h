@@ -31,7 +31,8 @@
  *                                                                          Dynamics/b2ContactManager.cpp:388-439
  *   b2cuGetEventContacts                 the two above in one round trip: what BeginContact / EndContact receive
  *                                                                          Dynamics/b2WorldCallbacks.h:84-107
- *   b2cuSetBodyMirror                    b2Island::Solve writing the new state into the b2Body objects
+ *   b2cuGetBodyStates /                  b2Island::Solve writing the new state into the b2Body objects
+ *   b2cuSetBodyMirror
  *                                                                          Dynamics/b2Island.cpp:339-348
  *   b2cuHostAlloc / b2cuHostFree         the world's own allocation of its bodies (b2BlockAllocator)
  *                                                                          Common/b2BlockAllocator.cpp:93-170
@@ -103,6 +104,19 @@ typedef struct b2cuBody
 	float sleepTime;
 	uint32_t flags;
 } b2cuBody;
+
+/* The part of b2cuBody that a step changes (64 bytes): what b2Island::Solve writes back into the b2Body objects
+ * (Dynamics/b2Island.cpp:339-348) plus sleep time and flags.  The rest of b2cuBody (local centre, mass, damping,
+ * gravity scale, and the forces the caller applies) only ever travels host -> device. */
+typedef struct b2cuBodyState
+{
+	float px, py, qs, qc;          /* m_xf */
+	float cx, cy, a;               /* m_sweep.c, m_sweep.a */
+	float c0x, c0y, a0, alpha0;    /* m_sweep.c0, a0, alpha0 */
+	float vx, vy, w;               /* m_linearVelocity, m_angularVelocity */
+	float sleepTime;
+	uint32_t flags;
+} b2cuBodyState;
 
 /* ---- shape geometry ---------------------------------------------------------- */
 
@@ -267,12 +281,14 @@ B2CU_API void b2cuHostFree(void* p);
 
 B2CU_API int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bodies);
 B2CU_API int b2cuGetBodies(b2cuWorld* w, int32_t first, int32_t count, b2cuBody* bodies);
+/* The device -> host direction of the bodies: only the b2cuBodyState part (what a step changes). */
+B2CU_API int b2cuGetBodyStates(b2cuWorld* w, int32_t first, int32_t count, b2cuBodyState* states);
 /* b2World::Step leaves the new transforms and velocities in the b2Body objects (b2Island::Solve, Dynamics/b2Island.cpp:
- * 339-348).  With a mirror registered, every b2cuStep does the same for the caller's records of bodies
- * [0, count): the copy starts as soon as the solver has finished with the bodies and overlaps the broad-phase part of
- * the step; when b2cuStep returns the mirror is current (no b2cuGetBodies needed).  `mirror` should come from
+ * 339-348).  With a mirror registered, every b2cuStep does the same for the caller's records of bodies [0, count):
+ * the copy starts as soon as the solver has finished with the bodies and overlaps the broad-phase part of the step;
+ * when b2cuStep returns the mirror is current (no b2cuGetBodyStates needed).  `mirror` should come from
  * b2cuHostAlloc; NULL / 0 removes it.  The mirror must stay valid until it is replaced or the world destroyed. */
-B2CU_API int b2cuSetBodyMirror(b2cuWorld* w, b2cuBody* mirror, int32_t count);
+B2CU_API int b2cuSetBodyMirror(b2cuWorld* w, b2cuBodyState* mirror, int32_t count);
 B2CU_API int b2cuSetShapes(b2cuWorld* w, int32_t first, int32_t count, const b2cuShape* shapes);
 B2CU_API int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* proxies);
 B2CU_API int b2cuGetProxies(b2cuWorld* w, int32_t first, int32_t count, b2cuProxy* proxies);
