@@ -1945,7 +1945,9 @@ __global__ void GridFillKernel(DeviceArrays d, int proxyCount)
 		int h = d.cellOfProxy[p];
 		if (h < 0) continue;
 		int slot = d.cellStart[h] + atomicAdd(&d.cellCount[h], 1);
+		// the entry carries the fat box: a query reads its candidates as one contiguous run instead of one gather each
 		d.cellItems[slot] = p;
+		d.cellBoxes[slot] = d.fat[p];
 	}
 }
 
@@ -2024,7 +2026,7 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 				{
 					int r = d.cellItems[s];
 					if (r == p) continue;
-					float4 fr = d.fat[r];
+					float4 fr = d.cellBoxes[s];
 					// a bucket can hold several cells and levels: take r only when it is registered in THIS cell
 					if (CellCoord(fr.x, inv) != cx || CellCoord(fr.y, inv) != cy) continue;
 					if (ProxyLevel(fr, g.cell0) != level) continue;
@@ -2144,9 +2146,15 @@ __global__ void IotaKernel(int* out, int n)
 	B2CU_GRID_STRIDE(i, n) { out[i] = i; }
 }
 
-__global__ void ClearMovedKernel(DeviceArrays d, int proxyCount)
+// over the move buffer only (movedList holds every flagged proxy, GridCountKernel)
+__global__ void ClearMovedKernel(DeviceArrays d)
 {
-	B2CU_GRID_STRIDE(p, proxyCount) { d.pgroup[p] &= ~((uint32_t)(B2CU_PROXY_MOVED | B2CU_PROXY_MOVED_SYNC) << 16); }
+	const int n = d.counters[CNT_SCRATCH];
+	B2CU_GRID_STRIDE(t, n)
+	{
+		int p = d.movedList[t];
+		d.pgroup[p] &= ~((uint32_t)(B2CU_PROXY_MOVED | B2CU_PROXY_MOVED_SYNC) << 16);
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------

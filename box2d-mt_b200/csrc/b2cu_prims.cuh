@@ -12,8 +12,7 @@ namespace b2cu
 
 struct PrimScratch
 {
-	int* scanLevel1 = nullptr; // tile sums, capacity/1024 + 1
-	int* scanLevel2 = nullptr; // capacity/1M + 1
+	unsigned long long* scanState = nullptr; // ticket + one look-back word per tile
 	int* radixHist = nullptr;  // 256 * numBlocks
 	uint64_t* radixAlt = nullptr;
 	int* compactPos = nullptr; // capacity

@@ -126,6 +126,7 @@ struct DeviceArrays
 	int* cellCount;   // hash table, size gridSize (+1)
 	int* cellStart;
 	int* cellItems;   // proxy capacity
+	float4* cellBoxes; // fat box of each entry of cellItems
 	int* cellOfProxy; // proxy capacity (hash bucket or -1 for large)
 
 	// ---- solver constraints (index = position in solver order) ----

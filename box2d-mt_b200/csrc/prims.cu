@@ -104,12 +104,100 @@ __global__ void __launch_bounds__(SCAN_BLOCK) ScanTilesKernel(Loader load, int* 
 	}
 }
 
-__global__ void AddTileOffsetsKernel(int* __restrict__ out, const int* __restrict__ tileOffsets, int n)
+// Single-pass scan (decoupled look-back): a tile publishes its aggregate, then the inclusive prefix once it knows
+// its predecessors'.  Tile ids are handed out by an atomic ticket, so a tile only ever waits for tiles that are
+// already running.  state word = status << 32 | value, written with one 64-bit store.
+#define SCAN_STATE_AGGREGATE 1ull
+#define SCAN_STATE_INCLUSIVE 2ull
+
+template <typename Loader>
+__global__ void __launch_bounds__(SCAN_BLOCK) ScanLookbackKernel(Loader load, int* __restrict__ out,
+                                                                 unsigned long long* state, int* ticket, int n, int* total)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n)
+	__shared__ int warpSums[SCAN_BLOCK / 32];
+	__shared__ int shTile, shExclusive;
+	if (threadIdx.x == 0) shTile = atomicAdd(ticket, 1);
+	__syncthreads();
+	const int tile = shTile;
+	const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+
+	int v[SCAN_ITEMS];
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < n) ? load(base + k) : 0;
+	int tsum = 0;
+	int pre[SCAN_ITEMS];
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k)
 	{
-		out[i] += tileOffsets[i / SCAN_TILE];
+		pre[k] = tsum;
+		tsum += v[k];
+	}
+	int inc = tsum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		int t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d) inc += t;
+	}
+	if (lane == 31) warpSums[warp] = inc;
+	__syncthreads();
+	if (warp == 0)
+	{
+		int w = lane < SCAN_BLOCK / 32 ? warpSums[lane] : 0;
+		int winc = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			int t = __shfl_up_sync(0xffffffffu, winc, d);
+			if (lane >= d) winc += t;
+		}
+		if (lane < SCAN_BLOCK / 32) warpSums[lane] = winc - w; // exclusive warp offsets
+		// whole warp 0: publish the aggregate, then look back 32 predecessors at a time
+		const int aggregate = __shfl_sync(0xffffffffu, winc, SCAN_BLOCK / 32 - 1);
+		volatile unsigned long long* vs = state;
+		int exclusive = 0;
+		if (tile == 0)
+		{
+			if (lane == 0) vs[0] = (SCAN_STATE_INCLUSIVE << 32) | (unsigned)aggregate;
+		}
+		else
+		{
+			if (lane == 0) vs[tile] = (SCAN_STATE_AGGREGATE << 32) | (unsigned)aggregate;
+			for (int j0 = tile - 1;; j0 -= 32)
+			{
+				const int j = j0 - lane;
+				unsigned long long st = (SCAN_STATE_INCLUSIVE << 32); // before tile 0: prefix 0
+				if (j >= 0)
+				{
+					do
+					{
+						st = vs[j];
+					} while ((st >> 32) == 0ull);
+				}
+				const unsigned inclusiveLanes = __ballot_sync(0xffffffffu, (st >> 32) == SCAN_STATE_INCLUSIVE);
+				const int stop = inclusiveLanes ? __ffs((int)inclusiveLanes) - 1 : 31;
+				int val = lane <= stop ? (int)(unsigned)(st & 0xFFFFFFFFull) : 0;
+#pragma unroll
+				for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+				exclusive += val;
+				if (inclusiveLanes) break;
+			}
+			if (lane == 0) vs[tile] = (SCAN_STATE_INCLUSIVE << 32) | (unsigned)(exclusive + aggregate);
+		}
+		if (lane == 0)
+		{
+			shExclusive = exclusive;
+			if (total && tile == gridDim.x - 1) *total = exclusive + aggregate;
+		}
+	}
+	__syncthreads();
+	const int threadOffset = shExclusive + (inc - tsum) + warpSums[warp];
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k)
+	{
+		if (base + k < n) out[base + k] = threadOffset + pre[k];
 	}
 }
 
@@ -124,8 +212,7 @@ cudaError_t PrimScratchAlloc(PrimScratch* s, int capacity)
 	int histSize = 256 * s->radixBlocks;
 	int scanCap = capacity > histSize ? capacity : histSize;
 	cudaError_t e;
-	if ((e = cudaMalloc(&s->scanLevel1, sizeof(int) * (scanCap / SCAN_TILE + 2))) != cudaSuccess) return e;
-	if ((e = cudaMalloc(&s->scanLevel2, sizeof(int) * (scanCap / SCAN_TILE / SCAN_TILE + 2))) != cudaSuccess) return e;
+	if ((e = cudaMalloc(&s->scanState, sizeof(unsigned long long) * (scanCap / SCAN_TILE + 4))) != cudaSuccess) return e;
 	if ((e = cudaMalloc(&s->radixHist, sizeof(int) * histSize)) != cudaSuccess) return e;
 	if ((e = cudaMalloc(&s->radixAlt, sizeof(uint64_t) * capacity)) != cudaSuccess) return e;
 	if ((e = cudaMalloc(&s->compactPos, sizeof(int) * capacity)) != cudaSuccess) return e;
@@ -134,8 +221,7 @@ cudaError_t PrimScratchAlloc(PrimScratch* s, int capacity)
 
 void PrimScratchFree(PrimScratch* s)
 {
-	cudaFree(s->scanLevel1);
-	cudaFree(s->scanLevel2);
+	cudaFree(s->scanState);
 	cudaFree(s->radixHist);
 	cudaFree(s->radixAlt);
 	cudaFree(s->compactPos);
@@ -155,26 +241,17 @@ static void ScanImpl(PrimScratch* s, Loader load, int* out, int n, int* total, c
 		return;
 	}
 	int tiles1 = (n + SCAN_TILE - 1) / SCAN_TILE;
-	ScanTilesKernel<<<tiles1, SCAN_BLOCK, 0, stream>>>(load, out, s->scanLevel1, n, total);
-	PRIM_MARK("ScanTiles");
-	if (tiles1 > 1)
+	if (tiles1 == 1)
 	{
-		int tiles2 = (tiles1 + SCAN_TILE - 1) / SCAN_TILE;
-		IntLoader l1{s->scanLevel1};
-		ScanTilesKernel<<<tiles2, SCAN_BLOCK, 0, stream>>>(l1, s->scanLevel1, s->scanLevel2, tiles1, total);
-		PRIM_MARK("ScanTilesL1");
-		if (tiles2 > 1)
-		{
-			// third level: tiles2 <= 1024 for n < 2^30
-			IntLoader l2{s->scanLevel2};
-			ScanTilesKernel<<<1, SCAN_BLOCK, 0, stream>>>(l2, s->scanLevel2, (int*)nullptr, tiles2, total);
-			AddTileOffsetsKernel<<<(tiles1 + 255) / 256, 256, 0, stream>>>(s->scanLevel1, s->scanLevel2, tiles1);
-			PRIM_MARK("ScanL2");
-			PRIM_MARK("ScanL2Add");
-		}
-		AddTileOffsetsKernel<<<(n + 255) / 256, 256, 0, stream>>>(out, s->scanLevel1, n);
-		PRIM_MARK("AddTileOffsets");
+		ScanTilesKernel<<<1, SCAN_BLOCK, 0, stream>>>(load, out, (int*)nullptr, n, total);
+		PRIM_MARK("ScanTiles");
+		return;
 	}
+	// scanState: [ticket (8 bytes) | one state word per tile]
+	cudaMemsetAsync(s->scanState, 0, sizeof(unsigned long long) * (size_t)(tiles1 + 1), stream);
+	ScanLookbackKernel<<<tiles1, SCAN_BLOCK, 0, stream>>>(load, out, s->scanState + 1, reinterpret_cast<int*>(s->scanState), n,
+	                                                      total);
+	PRIM_MARK("ScanLookback");
 }
 
 void ExclusiveScanNotMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int* out, int n, int* total,

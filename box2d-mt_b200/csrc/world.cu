@@ -194,6 +194,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->cellCount, CAP_GRID));
 	v.push_back(Desc(&d->cellStart, CAP_GRID));
 	v.push_back(Desc(&d->cellItems, CAP_PROXY));
+	v.push_back(Desc(&d->cellBoxes, CAP_PROXY));
 	v.push_back(Desc(&d->cellOfProxy, CAP_PROXY));
 	v.push_back(Desc(&d->sBody, CAP_CONTACT));
 	v.push_back(Desc(&d->sMass, CAP_CONTACT));
@@ -490,7 +491,7 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		if (w->hostCounters[CNT_ERROR])
 			return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
 	}
-	if (np > 0) LAUNCH(w, ClearMovedKernel, GridFor(np), kBlock, w->d, np);
+	if (np > 0) LAUNCH(w, ClearMovedKernel, GridFor(np), kBlock, w->d);
 	const int newCount = w->hostCounters[CNT_NEW_PAIRS];
 	*newCountOut = newCount;
 	*destroyedOut = destroyedMain + destroyedTail;
