@@ -465,6 +465,20 @@ __device__ __forceinline__ int UfFind(int* parent, int x)
 	return x;
 }
 
+// root of x without touching the forest: for the pass that writes the final labels.  Path halving there would race
+// with those writes: a halving store of an ancestor, issued by a thread that read the pointers earlier, could land
+// AFTER the owner of that node has stored its root, leaving a non-root label behind (two labels for one island).
+__device__ __forceinline__ int UfFindReadOnly(const int* parent, int x)
+{
+	int p = parent[x];
+	while (p != x)
+	{
+		x = p;
+		p = parent[x];
+	}
+	return x;
+}
+
 __device__ __forceinline__ void UfUnion(int* parent, int a, int b)
 {
 	while (true)
@@ -520,7 +534,9 @@ __global__ void IslandMarkKernel(DeviceArrays d, int bodyCount)
 	int local = 0;
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
-		int r = UfFind(d.island, b);
+		// read-only find: the only stores of this kernel are final labels (a root), so a concurrent traversal through
+		// a node that has already been labelled simply jumps to the root
+		int r = UfFindReadOnly(d.island, b);
 		d.island[b] = r;
 		uint32_t bf = d.bflags[b];
 		if (!IsStatic(bf) && d.islandAwake[r])

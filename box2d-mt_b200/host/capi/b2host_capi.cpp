@@ -334,6 +334,13 @@ B2H_API int b2h_solver_order(void* p, int32 capacity, uint64* keys)
 
 B2H_API void b2h_profile(void* p, float* out13) { memcpy(out13, &static_cast<Host*>(p)->world->GetProfile(), 13 * sizeof(float)); }
 
+/// the C-ABI handle behind the world (nullptr before the first step), for the diagnostic entry points of b2cuda.h
+B2H_API void* b2h_device_handle(void* p)
+{
+	Host* h = static_cast<Host*>(p);
+	return h->executor->GetDeviceWorld(h->world);
+}
+
 B2H_API void b2h_step_info(void* p, b2cuStepInfo* out) { *out = static_cast<Host*>(p)->executor->GetLastStepInfo(); }
 
 B2H_API void b2h_host_timings(void* p, float* out4) { memcpy(out4, static_cast<Host*>(p)->executor->GetLastHostTimings(), 4 * sizeof(float)); }

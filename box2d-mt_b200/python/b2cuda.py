@@ -105,9 +105,20 @@ class World:
         self.h = h
         self.body_count = self.shape_count = self.proxy_count = 0
 
+    @classmethod
+    def attach(cls, handle, body_count, shape_count, proxy_count):
+        """Non-owning view of a b2cuWorld created elsewhere (b2CudaStepExecutor::GetDeviceWorld)."""
+        w = cls.__new__(cls)
+        w.lib = load()
+        w.h = ctypes.c_void_p(handle)
+        w.owned = False
+        w.body_count, w.shape_count, w.proxy_count = body_count, shape_count, proxy_count
+        return w
+
     def close(self):
         if getattr(self, "h", None):
-            self.lib.b2cuDestroyWorld(self.h)
+            if getattr(self, "owned", True):
+                self.lib.b2cuDestroyWorld(self.h)
             self.h = None
 
     def __del__(self):

@@ -54,6 +54,8 @@ def load():
     lib.b2h_profile.argtypes = [vp, vp]
     lib.b2h_step_info.argtypes = [vp, vp]
     lib.b2h_host_timings.argtypes = [vp, vp]
+    lib.b2h_device_handle.argtypes = [vp]
+    lib.b2h_device_handle.restype = ctypes.c_void_p
     lib.b2h_sum_y.argtypes = [vp, ctypes.c_int32, ctypes.c_int32]
     lib.b2h_sum_y.restype = ctypes.c_double
     lib.b2h_hash.argtypes = [vp]
@@ -163,6 +165,14 @@ class HostWorld:
         out = np.zeros(4, np.float32)
         self.lib.b2h_host_timings(self.h, _ptr(out))
         return out
+
+    def device_world(self):
+        """b2cuda.World view of the device copy (diagnostics: contacts, proxies, solver order)"""
+        import b2cuda
+        handle = self.lib.b2h_device_handle(self.h)
+        assert handle, "the world has not been stepped yet"
+        nb, np_, _ = self.counts()
+        return b2cuda.World.attach(handle, nb, 0, np_)
 
     def sum_y(self, first, count):
         return float(self.lib.b2h_sum_y(self.h, first, count))

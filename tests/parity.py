@@ -21,6 +21,8 @@ BODY_FLOAT_FIELDS = ["px", "py", "qs", "qc", "cx", "cy", "a", "c0x", "c0y", "a0"
 
 def dedupe_shapes(shapes, proxies):
     """Collapse identical geometry records (most scenes share one box) and remap proxies.shape."""
+    if len(shapes) == 0:
+        return shapes, proxies.copy()
     raw = shapes.view(np.uint8).reshape(len(shapes), -1)
     _, first, inverse = np.unique(raw, axis=0, return_index=True, return_inverse=True)
     order = np.argsort(first)

@@ -1,0 +1,148 @@
+"""Edge cases of the step, device vs oracle in lockstep (bit-exact), through the C ABI.
+
+Covers what the reference's own small tests and Testbed scenes exercise around the hot path besides stacks and
+piles: empty and contact-free worlds, dt = 0, every contact class against edge ground (ghost vertices included),
+restitution (the velocity-bias branch, b2ContactSolver.cpp:213-217), zero / high friction, damping, gravity scale,
+fixed rotation, kinematic bodies, collision filtering (category / mask / group, b2WorldCallbacks.cpp:24-38),
+several fixtures per body, warm starting off, sleeping off, a changing time step (dtRatio, b2ContactSolver.cpp:113).
+"""
+import numpy as np
+import pytest
+
+import b2cuda_types as T
+import b2scene
+import parity
+import ref
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(**kw):
+    s = scenes.Scene(**kw)
+    s.world_flags &= ~T.WORLD_CONTINUOUS  # SolveTOI is outside this version
+    return s
+
+
+def _run(gpu, scene, steps, **kw):
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    return parity.lockstep(g, r, steps, tol=0.0, **kw), g, r
+
+
+def test_empty_world(gpu):
+    infos, g, r = _run(gpu, _scene(), 3)
+    assert int(infos[-1]["bodyCount"]) == 0 and int(infos[-1]["contactCount"]) == 0
+
+
+def test_bodies_without_fixtures_and_no_contacts(gpu):
+    s = _scene()
+    s.body(T.STATIC_BODY, (0, 0))
+    s.body(T.DYNAMIC_BODY, (0, 5))                     # no fixture: unit mass, falls
+    b = s.body(T.DYNAMIC_BODY, (3, 5), vel=(1.0, 2.0), w=0.5, linear_damping=0.3, angular_damping=0.2, gravity_scale=0.5)
+    s.fixture(b, s.circle(0.5), density=1.0)
+    infos, g, r = _run(gpu, s, 60)
+    assert int(infos[-1]["contactCount"]) == 0
+    assert g.get_bodies()["py"][1] < 0.0  # it really fell
+
+
+def test_zero_time_step(gpu):
+    s = _scene()
+    ground = s.body(T.STATIC_BODY, (0, 0))
+    s.fixture(ground, s.box(10, 0.5, center=(0, -0.5)), thick=True)
+    b = s.body(T.DYNAMIC_BODY, (0, 0.4))
+    s.fixture(b, s.box(0.5, 0.5), density=1.0)
+    r = ref.RefWorld(s)
+    g = parity.gpu_world_from_ref(gpu, r)
+    parity.lockstep(g, r, 5, tol=0.0)
+    before = g.get_bodies().copy()
+    parity.lockstep(g, r, 2, dt=0.0, tol=0.0)          # b2World::Step with dt = 0: collide only
+    after = g.get_bodies()
+    assert (before["px"] == after["px"]).all() and (before["py"] == after["py"]).all()
+    parity.lockstep(g, r, 10, tol=0.0)                 # and the warm-start ratio after a zero step (inv_dt0 = 0)
+
+
+def _edge_ground(s):
+    """a chain of three edges with ghost vertices (the adjacency b2EPCollider uses), slightly V-shaped"""
+    g = s.body(T.STATIC_BODY, (0, 0))
+    pts = [(-12.0, 1.0), (-4.0, 0.0), (4.0, 0.0), (12.0, 1.5)]
+    s.fixture(g, s.edge(pts[0], pts[1], v3=pts[2]))
+    s.fixture(g, s.edge(pts[1], pts[2], v0=pts[0], v3=pts[3]))
+    s.fixture(g, s.edge(pts[2], pts[3], v0=pts[1]))
+    return g
+
+
+def test_every_shape_on_edge_ground(gpu):
+    s = _scene()
+    _edge_ground(s)
+    rng = np.random.default_rng(5)
+    shapes = [s.circle(0.3), s.box(0.4, 0.25)] + [s.polygon(scenes._regular_polygon(k, 0.35)) for k in range(3, 9)]
+    for i in range(40):
+        b = s.body(T.DYNAMIC_BODY, (-9.0 + 0.45 * i, 2.0 + 0.7 * (i % 3)), angle=float(rng.uniform(0, 6.28)))
+        s.fixture(b, shapes[i % len(shapes)], density=1.0, friction=0.3)
+    infos, g, r = _run(gpu, s, 300)
+    assert sum(int(i["beginCount"]) for i in infos) > 40
+
+
+def test_restitution_friction_and_fixed_rotation(gpu):
+    s = _scene()
+    ground = s.body(T.STATIC_BODY, (0, 0))
+    s.fixture(ground, s.box(20, 0.5, center=(0, -0.5), angle=0.05), thick=True, friction=0.6)
+    for i, (rest, fric) in enumerate([(0.0, 0.0), (0.3, 1.0), (0.8, 0.2), (1.0, 0.5)]):
+        b = s.body(T.DYNAMIC_BODY, (-6.0 + 4.0 * i, 4.0), vel=(1.0, -3.0))
+        s.fixture(b, s.circle(0.4), density=1.0, restitution=rest, friction=fric)
+        c = s.body(T.DYNAMIC_BODY, (-4.5 + 4.0 * i, 3.0), angle=0.3,
+                   flags=b2scene.BODYDEF_DEFAULT | (b2scene.BODYDEF_FIXED_ROTATION if i % 2 else 0))
+        s.fixture(c, s.box(0.4, 0.3), density=2.0, restitution=rest, friction=fric)
+    infos, g, r = _run(gpu, s, 240)
+    assert sum(int(i["endCount"]) for i in infos) > 0  # the bouncing ones leave the ground again
+
+
+def test_kinematic_platform_and_compound_bodies(gpu):
+    s = _scene()
+    ground = s.body(T.STATIC_BODY, (0, 0))
+    s.fixture(ground, s.box(30, 0.5, center=(0, -0.5)), thick=True)
+    lift = s.body(T.KINEMATIC_BODY, (0, 1.0), vel=(0.5, 0.2), w=0.1)
+    s.fixture(lift, s.box(3.0, 0.2))
+    for i in range(12):
+        b = s.body(T.DYNAMIC_BODY, (-2.5 + 0.45 * i, 2.0 + 0.5 * (i % 2)))
+        # two fixtures per body: an L of two boxes, and a box with a circle on top
+        s.fixture(b, s.box(0.2, 0.1), density=1.0)
+        if i % 2:
+            s.fixture(b, s.box(0.05, 0.2, center=(0.15, 0.25)), density=1.0)
+        else:
+            s.fixture(b, s.circle(0.12, p=(0.0, 0.2)), density=3.0)
+    infos, g, r = _run(gpu, s, 200)
+    assert max(int(i["constraintCount"]) for i in infos) > 10
+
+
+def test_collision_filtering(gpu):
+    s = _scene()
+    ground = s.body(T.STATIC_BODY, (0, 0))
+    s.fixture(ground, s.box(20, 0.5, center=(0, -0.5)), thick=True)
+    # same negative group never collide; same positive group always; otherwise category & mask both ways
+    specs = [dict(group=-1), dict(group=-1), dict(group=2, category=0x2, mask=0x1), dict(group=2, category=0x4, mask=0x1),
+             dict(category=0x2, mask=0xFFFD), dict(category=0x2, mask=0xFFFF), dict(category=0x8, mask=0x1)]
+    for i, f in enumerate(specs * 3):
+        b = s.body(T.DYNAMIC_BODY, (0.05 * (i % 7), 0.6 + 0.55 * i))
+        s.fixture(b, s.box(0.4, 0.25), density=1.0, **f)
+    infos, g, r = _run(gpu, s, 240)
+    assert int(infos[-1]["contactCount"]) > 0
+
+
+@pytest.mark.parametrize("flags", [T.WORLD_DEFAULT & ~T.WORLD_WARM_STARTING,
+                                   T.WORLD_DEFAULT & ~T.WORLD_ALLOW_SLEEP,
+                                   T.WORLD_DEFAULT & ~T.WORLD_CLEAR_FORCES])
+def test_world_switches(gpu, flags):
+    s = scenes.pile(6, 5, sleep=True)
+    s.world_flags = flags & ~T.WORLD_CONTINUOUS
+    infos, g, r = _run(gpu, s, 200)
+    assert max(int(i["constraintCount"]) for i in infos) > 0
+
+
+def test_varying_time_step_and_iterations(gpu):
+    s = scenes.pyramid(5, continuous=False)
+    r = ref.RefWorld(s)
+    g = parity.gpu_world_from_ref(gpu, r)
+    for dt, vi, pi in [(1 / 60.0, 8, 3), (1 / 30.0, 4, 1), (1 / 120.0, 10, 4), (1 / 60.0, 1, 0), (1 / 45.0, 6, 2)]:
+        parity.lockstep(g, r, 25, dt=dt, vel_iters=vi, pos_iters=pi, tol=0.0)
