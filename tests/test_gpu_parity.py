@@ -97,6 +97,7 @@ SCENES = {
     "pyramid6": lambda: scenes.pyramid(6, continuous=False),
     "pyramid20": lambda: scenes.pyramid(20, continuous=False),
     "pile": lambda: scenes.pile(12, 10),
+    "pile_5000": lambda: scenes.pile(100, 50),
     "pile_sleep": lambda: scenes.pile(8, 6, sleep=True),
     "tumbler": lambda: scenes.tumbler(100),
     "two_pyramids": lambda: scenes.pyramids(2, 6, thick_polygon_ground=True),
@@ -119,7 +120,8 @@ def test_single_step_teacher_forced(gpu, name):
     assert max(i["constraintCount"] for i in infos) > 0
 
 
-@pytest.mark.parametrize("name,steps", [("pyramid6", 300), ("pyramid20", 240), ("pile", 300), ("pile_sleep", 400),
+@pytest.mark.parametrize("name,steps", [("pyramid6", 300), ("pyramid20", 240), ("pile", 300), ("pile_5000", 200),
+                                        ("pile_sleep", 400),
                                         ("tumbler", 200), ("two_pyramids", 300)])
 def test_free_running_lockstep(gpu, name, steps):
     """Multi-step parity: the device world runs freely; the oracle follows in the GPU's solver order.  Pair set,
