@@ -198,15 +198,12 @@ def run_product_arm(args, rank, local_rank, world_size):
         # peer mailboxes (b2cuShard*)
         import b2shard
         scene = scenes.pile(columns * world_size, ROWS, seed=0)
-        plans, _ = b2shard.split_scene(scene.arrays(), world_size, margin=args.margin, only_rank=rank)
-        plan = plans[rank]
+        plan, _ = b2shard.rank_plan(scene.arrays(), rank, world_size, args.margin)
         world = b2host.HostWorld(arrays=plan.arrays, gravity=scene.gravity, world_flags=scene.world_flags,
                                  device=local_rank, download_bodies=False, events=False)
         world.shard_configure(rank, world_size, plan.ghost_local, plan.export_local)
-        links = [None] * world_size
-        dist.all_gather_object(links, world.shard_link().tobytes())
-        links = [np.frombuffer(b, dtype=T.SHARD_LINK)[0] for b in links]
-        world.shard_connect(links[rank - 1] if rank > 0 else None, links[rank + 1] if rank + 1 < world_size else None)
+        lower, upper = b2shard.exchange_links(dist, rank, world_size, world.shard_link())
+        world.shard_connect(lower, upper)
         n_bodies = world.counts()[0] - len(plan.ghost_local)
         dist.barrier()
     build_s = time.perf_counter() - t0
@@ -222,18 +219,14 @@ def run_product_arm(args, rank, local_rank, world_size):
     def max_over_ranks(x):
         if dist is None:
             return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        import b2shard
+        return b2shard.reduce_scalar(dist, x, "max", device="cuda")
 
     def sum_over_ranks(x):
         if dist is None:
             return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        import b2shard
+        return b2shard.reduce_scalar(dist, x, "sum", device="cuda")
 
     # ---- value: world resident on the device ----
     for _ in range(args.warmup):

@@ -86,6 +86,11 @@ __device__ __forceinline__ float FindMaxSeparation(int* edgeIndex, const b2cuSha
 	int count2 = poly2->count;
 	Xf xf = MulTXf(xf2, xf1);
 
+	// the vertices of poly2 are read once into registers: the n1 x n2 loop is then pure arithmetic
+	Vec2 v2s[B2CU_MAX_POLYGON_VERTICES];
+#pragma unroll
+	for (int j = 0; j < B2CU_MAX_POLYGON_VERTICES; ++j) v2s[j] = ShapeV(poly2, j);
+
 	int bestIndex = 0;
 	float maxSeparation = -B2CU_MAX_FLOAT;
 	for (int i = 0; i < count1; ++i)
@@ -94,12 +99,16 @@ __device__ __forceinline__ float FindMaxSeparation(int* edgeIndex, const b2cuSha
 		Vec2 v1 = Mul(xf, ShapeV(poly1, i));
 
 		float si = B2CU_MAX_FLOAT;
-		for (int j = 0; j < count2; ++j)
+#pragma unroll
+		for (int j = 0; j < B2CU_MAX_POLYGON_VERTICES; ++j)
 		{
-			float sij = Dot(n, ShapeV(poly2, j) - v1);
-			if (sij < si)
+			if (j < count2)
 			{
-				si = sij;
+				float sij = Dot(n, v2s[j] - v1);
+				if (sij < si)
+				{
+					si = sij;
+				}
 			}
 		}
 
@@ -267,19 +276,34 @@ __device__ __forceinline__ void CollidePolygonAndCircle(Manifold* m, const b2cuS
 	float radius = polygonA->radius + circleB->radius;
 	int vertexCount = polygonA->count;
 
-	for (int i = 0; i < vertexCount; ++i)
+	// all vertices and normals of the record are requested at once (unused slots are zero): the loop below would
+	// otherwise wait for two dependent L1 loads per vertex, and half of all contacts of a mixed pile come through here
+	Vec2 vs[B2CU_MAX_POLYGON_VERTICES], ns[B2CU_MAX_POLYGON_VERTICES];
+#pragma unroll
+	for (int i = 0; i < B2CU_MAX_POLYGON_VERTICES; ++i)
 	{
-		float s = Dot(ShapeN(polygonA, i), cLocal - ShapeV(polygonA, i));
-		if (s > radius)
+		vs[i] = ShapeV(polygonA, i);
+		ns[i] = ShapeN(polygonA, i);
+	}
+	bool outside = false;
+#pragma unroll
+	for (int i = 0; i < B2CU_MAX_POLYGON_VERTICES; ++i)
+	{
+		if (i < vertexCount && !outside)
 		{
-			return;
-		}
-		if (s > separation)
-		{
-			separation = s;
-			normalIndex = i;
+			float s = Dot(ns[i], cLocal - vs[i]);
+			if (s > radius)
+			{
+				outside = true;
+			}
+			else if (s > separation)
+			{
+				separation = s;
+				normalIndex = i;
+			}
 		}
 	}
+	if (outside) return;
 
 	int vertIndex1 = normalIndex;
 	int vertIndex2 = vertIndex1 + 1 < vertexCount ? vertIndex1 + 1 : 0;

@@ -79,3 +79,40 @@ def global_keys(plan, local_keys):
     a = plan.fixture_ids[(k >> np.uint64(32)).astype(np.int64)].astype(np.uint64)
     b = plan.fixture_ids[(k & np.uint64(0xFFFFFFFF)).astype(np.int64)].astype(np.uint64)
     return (np.minimum(a, b) << np.uint64(32)) | np.maximum(a, b)
+
+
+# ---- one process per shard (torchrun): the plumbing around the device calls ---------------------------------------
+# torch.distributed is used for rendezvous-time exchange and for reducing timings only; the per-step halo traffic
+# goes through the peer mailboxes inside the solver kernels (include/b2cuda.h, b2cuShardConnect).
+
+def rank_plan(arrays, rank, world_size, margin):
+    """The ShardPlan of this rank alone (every rank computes the same strip bounds from the same scene)."""
+    plans, bounds = split_scene(arrays, world_size, margin=margin, only_rank=rank)
+    return plans[rank], bounds
+
+
+def exchange_links(dist, rank, world_size, link):
+    """All-gather the b2cuShardLink records and return (lower neighbour's, upper neighbour's), None at the ends.
+    Checks that the halo lists of neighbouring ranks have matching lengths before any device memory is touched."""
+    blobs = [None] * world_size
+    dist.all_gather_object(blobs, np.asarray(link).tobytes())
+    links = [np.frombuffer(b, dtype=T.SHARD_LINK)[0] for b in blobs]
+    for r, l in enumerate(links):
+        if int(l["rank"]) != r or int(l["rankCount"]) != world_size:
+            raise RuntimeError("shard link of rank %d says rank %d of %d" % (r, int(l["rank"]), int(l["rankCount"])))
+    for r in range(world_size - 1):
+        if int(links[r]["ghostCount"]) != int(links[r + 1]["exportCount"]):
+            raise RuntimeError("rank %d holds %d ghosts but rank %d exports %d bodies" % (
+                r, int(links[r]["ghostCount"]), r + 1, int(links[r + 1]["exportCount"])))
+    lower = links[rank - 1] if rank > 0 else None
+    upper = links[rank + 1] if rank + 1 < world_size else None
+    return lower, upper
+
+
+def reduce_scalar(dist, x, op, device=None):
+    """max / sum of a python float over the ranks (the timings of bench.py: device time is the max over ranks)."""
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return float(t.item())
+
