@@ -744,9 +744,6 @@ __global__ void __launch_bounds__(256) ConstraintSlotKernel(DeviceArrays d)
 // Runs in CONTACT order (coalesced manifold reads, neighbouring contacts share their bodies) and writes row k of the
 // solver arrays: within one colour the solver order is the contact order, so the rows written by neighbouring
 // threads are neighbours too and the partial sectors merge in L2.
-#ifndef B2CU_INIT_XF
-#define B2CU_INIT_XF 0
-#endif
 #ifndef B2CU_INIT_BLOCKS
 #define B2CU_INIT_BLOCKS 3
 #endif
@@ -781,21 +778,8 @@ __global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(D
 		Vec2 localCenterA = V(msA.z, msA.w), localCenterB = V(msB.z, msB.w);
 
 		Xf xfA, xfB;
-#if B2CU_INIT_XF
-		// xf.q.Set(a) (b2ContactSolver.cpp:171-174): the body transform already holds sin/cos of this very angle
-		// (b2Body::SynchronizeTransform / SetTransform set m_xf.q from m_sweep.a); xf.p is recomputed as the
-		// reference does, it can differ from m_xf.p in the last bit after a SetTransform
-		float4 bxA = d.xf[bA], bxB = d.xf[bB];
-		xfA.q.s = bxA.z;
-		xfA.q.c = bxA.w;
-		xfB.q.s = bxB.z;
-		xfB.q.c = bxB.w;
-		(void)aA;
-		(void)aB;
-#else
 		xfA.q = SinCos(aA);
 		xfB.q = SinCos(aB);
-#endif
 		xfA.p = cA - Mul(xfA.q, localCenterA);
 		xfB.p = cB - Mul(xfB.q, localCenterB);
 
