@@ -375,6 +375,22 @@ __global__ void FillProxyRadiusKernel(DeviceArrays d, int proxyCount)
 	B2CU_GRID_STRIDE(p, proxyCount) { d.pradius[p] = d.shapes[d.pshape[p]].radius; }
 }
 
+// b2Fixture::Refilter (b2Fixture.cpp:197-210): the contacts of a refiltered proxy get e_filterFlag
+__global__ void FlagFilterContactsKernel(DeviceArrays d, int contactCount)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		uint32_t f = d.c.flags[i];
+		if (f & B2CU_CONTACT_DEAD) continue;
+		int4 pr = d.c.proxies[i];
+		if (((d.pgroup[pr.x] | d.pgroup[pr.y]) >> 16) & B2CU_PROXY_REFILTER) d.c.flags[i] = f | B2CU_CONTACT_FILTER;
+	}
+}
+__global__ void ClearProxyFlagKernel(DeviceArrays d, int proxyCount, uint32_t flag)
+{
+	B2CU_GRID_STRIDE(p, proxyCount) { d.pgroup[p] &= ~(flag << 16); }
+}
+
 // contacts carry the bodies of their two proxies next to the proxy ids (one gather level less in every contact
 // kernel); this fills them in after the caller has uploaded contacts or proxies
 __global__ void FillContactBodiesKernel(DeviceArrays d, int contactCount)
@@ -2153,7 +2169,7 @@ __global__ void ClearMovedKernel(DeviceArrays d)
 	B2CU_GRID_STRIDE(t, n)
 	{
 		int p = d.movedList[t];
-		d.pgroup[p] &= ~((uint32_t)(B2CU_PROXY_MOVED | B2CU_PROXY_MOVED_SYNC) << 16);
+		d.pgroup[p] &= ~((uint32_t)(B2CU_PROXY_MOVED | B2CU_PROXY_MOVED_SYNC | B2CU_PROXY_NEW) << 16);
 	}
 }
 

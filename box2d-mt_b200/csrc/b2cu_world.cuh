@@ -63,7 +63,7 @@ struct ContactSet
 
 // device-only proxy flag (next to the public B2CU_PROXY_* bits): moved by SyncProxiesKernel in this step
 #define B2CU_PROXY_MOVED_SYNC 0x8
-#define B2CU_PROXY_PUBLIC_FLAGS 0x7
+#define B2CU_PROXY_PUBLIC_FLAGS 0x37
 
 struct DeviceArrays
 {
@@ -203,6 +203,7 @@ struct b2cuWorld
 	int colourStarts[B2CU_MAX_COLOURS + 3];
 
 	int* hostCounters;   // pinned, CNT_COUNT + colour counts
+	bool refilterPending;    // a proxy was uploaded with B2CU_PROXY_REFILTER
 	bool contactBodiesDirty; // contacts or proxies were uploaded: refresh the body half of ContactSet::proxies
 	float* bodyStage;    // device staging of b2cuBody records for b2cuGetBodies / b2cuSetBodies (lazy)
 	int bodyStageCapacity;

@@ -874,7 +874,9 @@ int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* 
 		group[i] = (uint32_t)(uint16_t)p.groupIndex | ((uint32_t)(p.flags & B2CU_PROXY_PUBLIC_FLAGS) << 16);
 		mat[i] = make_float2(p.friction, p.restitution);
 		extents.push_back(std::max(p.fat[2] - p.fat[0], p.fat[3] - p.fat[1]));
-		if (p.flags & B2CU_PROXY_MOVED) anyMoved = true;
+		// the move buffer is only processed ahead of the step when a fixture is new (e_newFixture)
+		if ((p.flags & B2CU_PROXY_MOVED) && (p.flags & B2CU_PROXY_NEW)) anyMoved = true;
+		if (p.flags & B2CU_PROXY_REFILTER) w->refilterPending = true;
 	}
 	DeviceArrays& d = w->d;
 	if ((rc = Upload(w, d.fat, first, fat)) || (rc = Upload(w, d.aabb, first, aabb)) ||
@@ -1180,6 +1182,12 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		w->toiCheckDirty = false;
 	}
 
+	if (w->refilterPending)
+	{
+		if (w->contactCount > 0) LAUNCH(w, FlagFilterContactsKernel, GridFor(w->contactCount), kBlock, d, w->contactCount);
+		if (np > 0) LAUNCH(w, ClearProxyFlagKernel, GridFor(np), kBlock, d, np, (uint32_t)B2CU_PROXY_REFILTER);
+		w->refilterPending = false;
+	}
 	if (w->contactBodiesDirty)
 	{
 		if (np > 0) LAUNCH(w, FillProxyRadiusKernel, GridFor(np), kBlock, d, np);

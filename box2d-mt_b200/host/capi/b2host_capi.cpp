@@ -367,6 +367,14 @@ B2H_API void b2h_set_transform(void* p, int32 body, float x, float y, float angl
 {
 	static_cast<Host*>(p)->bodies[body]->SetTransform(b2Vec2(x, y), angle);
 }
+B2H_API void b2h_set_filter(void* p, int32 fixture, uint16 categoryBits, uint16 maskBits, int16 groupIndex)
+{
+	b2Filter f;
+	f.categoryBits = categoryBits;
+	f.maskBits = maskBits;
+	f.groupIndex = groupIndex;
+	static_cast<Host*>(p)->fixtures[fixture]->SetFilterData(f);
+}
 B2H_API void b2h_set_velocity(void* p, int32 body, float vx, float vy, float w)
 {
 	Host* h = static_cast<Host*>(p);

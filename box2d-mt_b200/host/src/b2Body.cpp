@@ -311,8 +311,7 @@ void b2Body::SynchronizeProxies(const b2Transform& xf1, const b2Transform& xf2)
 			p.fat[1] = b.lowerBound.y;
 			p.fat[2] = b.upperBound.x;
 			p.fat[3] = b.upperBound.y;
-			p.flags |= B2CU_PROXY_MOVED;
-			m_world->m_newFixture = true;
+			p.flags |= B2CU_PROXY_MOVED; // buffered move: its pairs are found at the end of the next step
 		}
 		m_world->MarkProxyDirty(f->m_proxyIndex);
 	}
@@ -452,7 +451,7 @@ b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def)
 	p.maskBits = f->m_filter.maskBits;
 	p.groupIndex = f->m_filter.groupIndex;
 	p.flags = (uint16)((f->m_isSensor ? B2CU_PROXY_SENSOR : 0) | (f->m_thickShape ? B2CU_PROXY_THICK : 0) |
-	                   B2CU_PROXY_MOVED);
+	                   B2CU_PROXY_MOVED | B2CU_PROXY_NEW);
 	p.fixture = (int32)m_world->m_proxies.size();
 	p.child = 0;
 	f->m_proxyIndex = p.fixture;
@@ -494,9 +493,8 @@ void b2Fixture::SetFilterData(const b2Filter& filter)
 	Refilter();
 }
 
-// reference b2Fixture.cpp:185-210 flags the attached contacts for re-filtering and touches the proxy.  Here the
-// proxy is touched, so the new filter applies to contacts created from now on; re-filtering EXISTING contacts
-// is outside this version
+// reference b2Fixture.cpp:187-220: the attached contacts are flagged for re-filtering (done on the device from the
+// REFILTER bit, before the next Collide) and the proxy is touched (buffered move)
 void b2Fixture::Refilter()
 {
 	if (m_body == nullptr || m_proxyIndex < 0) return;
@@ -506,8 +504,8 @@ void b2Fixture::Refilter()
 	p.categoryBits = m_filter.categoryBits;
 	p.maskBits = m_filter.maskBits;
 	p.groupIndex = m_filter.groupIndex;
-	p.flags |= B2CU_PROXY_MOVED;
-	w->m_newFixture = true;
+	// e_filterFlag on the fixture's contacts + TouchProxy (reference b2Fixture.cpp:187-220)
+	p.flags |= B2CU_PROXY_MOVED | B2CU_PROXY_REFILTER;
 	w->MarkProxyDirty(m_proxyIndex);
 }
 

@@ -595,7 +595,7 @@ int32 b2World::UploadDirty(b2cuWorld* device)
 		if (np == m_proxiesUploaded) hi = m_proxyDirtyHi;
 		if (lo <= hi && (rc = b2cuSetProxies(device, lo, hi - lo + 1, m_proxies.data() + lo))) return rc;
 		// the MOVED flag has been handed to the device's move buffer
-		for (int32 i = lo; i <= hi; ++i) m_proxies[i].flags &= ~(uint16)B2CU_PROXY_MOVED;
+		for (int32 i = lo; i <= hi; ++i) m_proxies[i].flags &= ~(uint16)(B2CU_PROXY_MOVED | B2CU_PROXY_NEW | B2CU_PROXY_REFILTER);
 	}
 	if (m_fullUpload)
 	{

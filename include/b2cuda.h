@@ -149,7 +149,12 @@ enum
 {
 	B2CU_PROXY_SENSOR = 0x0001,
 	B2CU_PROXY_THICK = 0x0002,
-	B2CU_PROXY_MOVED = 0x0004   /* in the broad-phase move buffer (b2BroadPhase::BufferMove) */
+	B2CU_PROXY_MOVED = 0x0004,  /* in the broad-phase move buffer (b2BroadPhase::BufferMove, TouchProxy): its new pairs are
+	                               found by the next FindNewContacts, i.e. at the END of the next step */
+	B2CU_PROXY_NEW = 0x0010,    /* with MOVED: the fixture is new (b2World::e_newFixture, set by b2Body::CreateFixture): the
+	                               next step finds the pairs of the whole move buffer FIRST (Dynamics/b2World.cpp:1628-1639) */
+	B2CU_PROXY_REFILTER = 0x0020 /* with MOVED: b2Fixture::Refilter (Dynamics/b2Fixture.cpp:187-220): the contacts of this
+	                               proxy are re-checked against the filters by the next Collide (e_filterFlag) */
 };
 
 typedef struct b2cuProxy

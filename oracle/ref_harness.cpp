@@ -597,6 +597,8 @@ void b2ref_export_proxies(b2refWorld* w, b2cuProxy* out, int32_t* treeProxyIds)
 			if (moved[p.proxyId])
 			{
 				o.flags |= B2CU_PROXY_MOVED;
+				// e_newFixture is a world flag: the whole move buffer is processed ahead of the next step
+				if (w->world->m_flags & b2World::e_newFixture) o.flags |= B2CU_PROXY_NEW;
 			}
 		}
 		if (treeProxyIds)
@@ -687,6 +689,15 @@ void b2ref_profile(b2refWorld* w, float* out13)
 void b2ref_set_transform(b2refWorld* w, int32_t body, float x, float y, float angle)
 {
 	w->bodies[body]->SetTransform(b2Vec2(x, y), angle);
+}
+
+void b2ref_set_filter(b2refWorld* w, int32_t fixture, uint16_t categoryBits, uint16_t maskBits, int16_t groupIndex)
+{
+	b2Filter f;
+	f.categoryBits = categoryBits;
+	f.maskBits = maskBits;
+	f.groupIndex = groupIndex;
+	w->fixtures[fixture]->SetFilterData(f); // calls Refilter()
 }
 
 void b2ref_set_velocity(b2refWorld* w, int32_t body, float vx, float vy, float angw)

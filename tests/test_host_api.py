@@ -158,6 +158,50 @@ def test_host_api_mutation_between_steps(gpu):
         parity.compare_bodies(h.bodies(), r.bodies())
 
 
+def _contact_sets_equal(h, r):
+    hk, ht, hp = h.contacts()
+    rc = r.contacts()
+    rk = T.contact_keys(rc)
+    assert (hk == rk).all() if len(hk) == len(rk) else False, (len(hk), len(rk))
+    rt = ((rc["flags"] & T.CONTACT_TOUCHING) != 0).astype(np.int32)
+    assert (ht == rt).all()
+    assert (hp == rc["manifold"]["pointCount"]).all()
+
+
+@pytest.mark.gpu
+def test_host_api_teleport_and_refilter_timing(gpu):
+    """SetTransform and Refilter buffer a proxy move: the reference finds the new pairs at the END of the next step (no
+    e_newFixture), and contacts of a refiltered fixture are re-checked by the next Collide (b2Fixture.cpp:187-220,
+    b2ContactManager.cpp:186-197).  Contact sets, touching flags and bodies must agree after every step."""
+    scene = scenes.pile(8, 6)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    for s in range(150):
+        if s == 40:
+            # teleport a body from the top of the pile right on top of another one
+            target = h.bodies()[20]
+            for w in (r, h):
+                w.set_transform(45, float(target["px"]) + 0.05, float(target["py"]) + 0.1, 0.2)
+        if s == 80:
+            # three neighbouring bodies of the bottom row (fixture i belongs to body i - 2: the container has three
+            # fixtures) join a negative group: the contacts among them are destroyed, all their others stay
+            for w in (r, h):
+                for fixture in (10, 11, 12):
+                    w.set_filter(fixture, 0x0001, 0xFFFF, -3)
+        if s == 110:
+            for w in (r, h):
+                for fixture in (10, 11, 12):
+                    w.set_filter(fixture, 0x0001, 0xFFFF, 0)
+        h.step()
+        assert r.step_ordered(h.solver_order()) == 0
+        try:
+            _contact_sets_equal(h, r)
+            parity.compare_bodies(h.bodies(), r.bodies())
+        except AssertionError as e:
+            raise AssertionError("step %d: %s" % (s, e))
+
+
 @pytest.mark.gpu
 def test_host_api_lazy_download(gpu):
     """downloadBodies=false: the mirror is refreshed on first access only; results are the same."""
