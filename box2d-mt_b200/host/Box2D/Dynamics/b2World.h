@@ -156,6 +156,7 @@ private:
 	void RefreshProxies() const;
 	void RefreshContacts();
 	void InvalidateSnapshots();
+	void DestroyContactsOfBody(int32 bodyIndex);
 	void DestroyFixtureInternal(b2Body* body, b2Fixture* fixture);
 	void RemoveProxies(const std::vector<int32>& proxyIds, const std::vector<int32>& bodyIds);
 	void DispatchEvents(b2cuWorld* device);

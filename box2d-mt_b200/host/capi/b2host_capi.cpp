@@ -367,6 +367,7 @@ B2H_API void b2h_set_transform(void* p, int32 body, float x, float y, float angl
 {
 	static_cast<Host*>(p)->bodies[body]->SetTransform(b2Vec2(x, y), angle);
 }
+B2H_API void b2h_set_type(void* p, int32 body, int32 type) { static_cast<Host*>(p)->bodies[body]->SetType((b2BodyType)type); }
 B2H_API void b2h_set_filter(void* p, int32 fixture, uint16 categoryBits, uint16 maskBits, int16 groupIndex)
 {
 	b2Filter f;

@@ -234,25 +234,45 @@ void b2Body::SetFixedRotation(bool flag)
 	ResetMassData();
 }
 
+// reference b2Body.cpp:118-188
 void b2Body::SetType(b2BodyType type)
 {
-	// reference b2Body.cpp:118-163 destroys the attached contacts and touches the proxies; changing the type of a
-	// body after the first step is outside this version of the GPU path
-	b2Assert(m_world->m_device == nullptr || type == GetType());
 	if (m_world->IsLocked() || type == GetType()) return;
-	b2BodyView s = B2_STATE();
-	s.flags = (s.flags & ~(uint32)B2CU_BODY_TYPE_MASK) | (uint32)type;
+	m_world->RefreshBodies();
+	{
+		b2BodyView s = B2_STATE();
+		s.flags = (s.flags & ~(uint32)B2CU_BODY_TYPE_MASK) | (uint32)type;
+	}
 	ResetMassData();
 	if (type == b2_staticBody)
 	{
+		b2BodyView s = B2_STATE();
 		s.vx = s.vy = s.w = 0.0f;
 		s.a0 = s.a;
 		s.c0x = s.cx;
 		s.c0y = s.cy;
+		// SynchronizeFixtures with xf1 from the (now equal) sweep start
+		b2Transform xf1;
+		xf1.q.Set(s.a0);
+		xf1.p = b2Vec2(s.c0x, s.c0y) - b2Mul(xf1.q, AsVec2(s.lcx));
+		SynchronizeProxies(xf1, GetTransform());
 	}
 	SetAwake(true);
-	s.fx = s.fy = s.torque = 0.0f;
+	{
+		b2BodyView s = B2_STATE();
+		s.fx = s.fy = s.torque = 0.0f;
+	}
 	m_world->MarkBodyDirty(m_index);
+
+	// delete the attached contacts, then touch the proxies so that new contacts are created when appropriate
+	m_world->DestroyContactsOfBody(m_index);
+	m_world->RefreshProxies();
+	for (b2Fixture* f = m_fixtureList; f; f = f->m_next)
+	{
+		if (f->m_proxyIndex < 0) continue;
+		m_world->m_proxies[f->m_proxyIndex].flags |= B2CU_PROXY_MOVED;
+		m_world->MarkProxyDirty(f->m_proxyIndex);
+	}
 }
 
 // reference b2Body.cpp:449-473

@@ -492,6 +492,45 @@ void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vecto
 	m_fullUpload = true;
 }
 
+// b2Body::SetType destroys every contact attached to the body (reference b2Body.cpp:168-176): EndContact for the
+// touching ones, both bodies woken if the manifold had points (b2ContactManager::Destroy).  The surviving records go
+// back to the device with the next step (full upload: rare operation, simplest exact path).
+void b2World::DestroyContactsOfBody(int32 bodyIndex)
+{
+	if (m_device == nullptr && !m_fullUpload) return; // never stepped: there are no contacts yet
+	RefreshBodies();
+	RefreshProxies();
+	m_contactsStale = true;
+	RefreshContacts();
+	std::vector<b2cuContact> kept;
+	kept.reserve(m_contactRecords.size());
+	for (size_t i = 0; i < m_contactRecords.size(); ++i)
+	{
+		const b2cuContact& rec = m_contactRecords[i];
+		if (m_proxies[rec.proxyA].body == bodyIndex || m_proxies[rec.proxyB].body == bodyIndex)
+		{
+			b2Contact* c = &m_contacts[i];
+			if (m_contactListener && c->IsTouching() && m_contactListener->EndContactImmediate(c, 0))
+			{
+				m_contactListener->EndContact(c);
+			}
+			if (rec.manifold.pointCount > 0)
+			{
+				c->m_fixtureA->GetBody()->SetAwake(true);
+				c->m_fixtureB->GetBody()->SetAwake(true);
+			}
+			continue;
+		}
+		kept.push_back(rec);
+	}
+	m_contactRecords.swap(kept);
+	m_contactCount = (int32)m_contactRecords.size();
+	m_contacts.clear();
+	m_contactHeads.clear();
+	m_contactsStale = true;
+	m_fullUpload = true;
+}
+
 void b2World::DestroyFixtureInternal(b2Body* body, b2Fixture* fixture)
 {
 	b2Fixture** link = &body->m_fixtureList;

@@ -62,6 +62,7 @@ def load():
     lib.b2h_hash.restype = u32
     lib.b2h_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_velocity.argtypes = [vp, i32, f32, f32, f32]
+    lib.b2h_set_type.argtypes = [vp, i32, i32]
     lib.b2h_set_filter.argtypes = [vp, i32, ctypes.c_uint16, ctypes.c_uint16, ctypes.c_int16]
     lib.b2h_apply_force.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_awake.argtypes = [vp, i32, i32]
@@ -183,6 +184,9 @@ class HostWorld:
 
     def set_transform(self, body, x, y, angle):
         self.lib.b2h_set_transform(self.h, body, x, y, angle)
+
+    def set_type(self, body, body_type):
+        self.lib.b2h_set_type(self.h, body, body_type)
 
     def set_filter(self, fixture, category, mask, group):
         self.lib.b2h_set_filter(self.h, fixture, category, mask, group)

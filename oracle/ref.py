@@ -50,6 +50,7 @@ def load(stock=False):
     lib.b2ref_toi_candidates.argtypes = [vp, i32, vp]
     lib.b2ref_profile.argtypes = [vp, vp]
     lib.b2ref_set_transform.argtypes = [vp, i32, f32, f32, f32]
+    lib.b2ref_set_type.argtypes = [vp, i32, i32]
     lib.b2ref_set_filter.argtypes = [vp, i32, ctypes.c_uint16, ctypes.c_uint16, ctypes.c_int16]
     lib.b2ref_set_velocity.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_apply_force.argtypes = [vp, i32, f32, f32, f32]
@@ -151,6 +152,9 @@ class RefWorld:
 
     def set_transform(self, body, x, y, angle):
         self.lib.b2ref_set_transform(self.h, body, x, y, angle)
+
+    def set_type(self, body, body_type):
+        self.lib.b2ref_set_type(self.h, body, body_type)
 
     def set_filter(self, fixture, category, mask, group):
         self.lib.b2ref_set_filter(self.h, fixture, category, mask, group)

@@ -700,6 +700,8 @@ void b2ref_set_filter(b2refWorld* w, int32_t fixture, uint16_t categoryBits, uin
 	w->fixtures[fixture]->SetFilterData(f); // calls Refilter()
 }
 
+void b2ref_set_type(b2refWorld* w, int32_t body, int32_t type) { w->bodies[body]->SetType((b2BodyType)type); }
+
 void b2ref_set_velocity(b2refWorld* w, int32_t body, float vx, float vy, float angw)
 {
 	w->bodies[body]->SetLinearVelocity(b2Vec2(vx, vy));

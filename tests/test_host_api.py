@@ -203,6 +203,30 @@ def test_host_api_teleport_and_refilter_timing(gpu):
 
 
 @pytest.mark.gpu
+def test_host_api_set_type_between_steps(gpu):
+    """b2Body::SetType after the world has been stepped: the body's contacts are destroyed at once, its proxies
+    touched, mass data reset (b2Body.cpp:118-188).  dynamic -> static -> dynamic -> kinematic."""
+    scene = scenes.pile(8, 6)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    changes = {50: (14, T.STATIC_BODY), 90: (14, T.DYNAMIC_BODY), 120: (30, T.KINEMATIC_BODY), 121: (31, T.STATIC_BODY)}
+    for s in range(170):
+        if s in changes:
+            body, kind = changes[s]
+            for w in (r, h):
+                w.set_type(body, kind)
+            assert h.counts()[2] == len(r.contacts()), "contacts of the body must be gone right away"
+        h.step()
+        assert r.step_ordered(h.solver_order()) == 0
+        try:
+            _contact_sets_equal(h, r)
+            parity.compare_bodies(h.bodies(), r.bodies())
+        except AssertionError as e:
+            raise AssertionError("step %d: %s" % (s, e))
+
+
+@pytest.mark.gpu
 def test_host_api_lazy_download(gpu):
     """downloadBodies=false: the mirror is refreshed on first access only; results are the same."""
     a = b2host.HostWorld(scenes.pile(8, 6), download_bodies=True)
