@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 			bool should = IsOwnedDynamic(fbA) || IsOwnedDynamic(fbB);
 			if (should)
 			{
-				should = DefaultFilter(d.pfilter[pr.x], d.pgroup[pr.x], d.pfilter[pr.y], d.pgroup[pr.y]);
+				// under a caller's pair filter an existing contact is kept: that filter is only consulted for new pairs
+				should = d.customFilter || DefaultFilter(d.pfilter[pr.x], d.pgroup[pr.x], d.pfilter[pr.y], d.pgroup[pr.y]);
 			}
 			if (!should)
 			{
@@ -1996,7 +1997,7 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 	}
 	// b2Body::ShouldCollide: at least one dynamic body; in a sharded world it must be one this shard owns
 	if (!IsOwnedDynamic(d.bflags[bodyA]) && !IsOwnedDynamic(d.bflags[bodyB])) return;
-	if (!DefaultFilter(d.pfilter[a], d.pgroup[a], d.pfilter[b], d.pgroup[b])) return;
+	if (!d.customFilter && !DefaultFilter(d.pfilter[a], d.pgroup[a], d.pfilter[b], d.pgroup[b])) return;
 	if (d.shapes[d.pshape[a]].type == B2CU_SHAPE_EDGE && d.shapes[d.pshape[b]].type == B2CU_SHAPE_EDGE) return;
 	int slot = atomicAdd(&d.counters[CNT_NEW_PAIRS], 1);
 	if (slot < pairCapacity) d.newKeys[slot] = key;

@@ -146,6 +146,7 @@ struct DeviceArrays
 	float4* sRadius;  // radiusA, radiusB, manifold type (int bits), island root of the constraint (int bits)
 
 	int* counters;    // CNT_COUNT ints
+	int customFilter; // != 0: a pair filter of the caller replaces the default filter rule (b2cuSetPairFilter)
 };
 
 struct WorldParams
@@ -203,6 +204,8 @@ struct b2cuWorld
 	int colourStarts[B2CU_MAX_COLOURS + 3];
 
 	int* hostCounters;   // pinned, CNT_COUNT + colour counts
+	b2cuPairFilterFn pairFilter;
+	void* pairFilterUser;
 	bool refilterPending;    // a proxy was uploaded with B2CU_PROXY_REFILTER
 	bool contactBodiesDirty; // contacts or proxies were uploaded: refresh the body half of ContactSet::proxies
 	float* bodyStage;    // device staging of b2cuBody records for b2cuGetBodies / b2cuSetBodies (lazy)

@@ -492,7 +492,29 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 			return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
 	}
 	if (np > 0) LAUNCH(w, ClearMovedKernel, GridFor(np), kBlock, w->d);
-	const int newCount = w->hostCounters[CNT_NEW_PAIRS];
+	int newCount = w->hostCounters[CNT_NEW_PAIRS];
+	if (w->pairFilter != nullptr && newCount > 0)
+	{
+		// the caller's b2ContactFilter decides about the candidate pairs before any contact exists (AddPair)
+		std::vector<uint64_t> cand((size_t)newCount);
+		std::vector<uint8_t> keep((size_t)newCount, 1);
+		CUDA_TRY(w, cudaMemcpyAsync(cand.data(), w->d.newKeys, sizeof(uint64_t) * (size_t)newCount, cudaMemcpyDeviceToHost,
+		                            w->stream));
+		if ((rc = SyncCheck(w))) return rc;
+		if (w->pairFilter(w->pairFilterUser, cand.data(), newCount, keep.data()) != 0)
+			return SetError(w, B2CU_ERR_ARGUMENT, "the pair filter callback failed");
+		int kept = 0;
+		for (int i = 0; i < newCount; ++i)
+			if (keep[i]) cand[kept++] = cand[i];
+		if (kept != newCount)
+		{
+			if (kept > 0)
+				CUDA_TRY(w, cudaMemcpyAsync(w->d.newKeys, cand.data(), sizeof(uint64_t) * (size_t)kept, cudaMemcpyHostToDevice,
+				                            w->stream));
+			if ((rc = SyncCheck(w))) return rc; // cand goes out of scope
+			newCount = kept;
+		}
+	}
 	*newCountOut = newCount;
 	*destroyedOut = destroyedMain + destroyedTail;
 	*movedOut = w->hostCounters[CNT_MOVED];
@@ -1116,6 +1138,15 @@ static int FinishMirrorCopy(b2cuWorld* w)
 			w->bodyMirror[b].sleepTime = 0.0f;
 		}
 	}
+	return B2CU_OK;
+}
+
+int b2cuSetPairFilter(b2cuWorld* w, b2cuPairFilterFn fn, void* user)
+{
+	if (!w) return B2CU_ERR_ARGUMENT;
+	w->pairFilter = fn;
+	w->pairFilterUser = user;
+	w->d.customFilter = fn != nullptr ? 1 : 0;
 	return B2CU_OK;
 }
 

@@ -3,6 +3,7 @@
 // b2World::Step(dt, vIters, pIters, b2CudaStepExecutor&), and read back through the public accessors.
 #include "Box2D/Box2D.h"
 
+#include <cstdint>
 #include <cstring>
 #include <vector>
 
@@ -52,6 +53,20 @@ public:
 	void EndContact(b2Contact* c) override { ends.push_back(c->GetKey()); }
 	std::vector<uint64> begins, ends;
 	int beginTouching = 0;
+};
+
+/// test filter: pairs whose fixture indices (creation order) sum to a multiple of `modulus` never collide
+class ModuloFilter : public b2ContactFilter
+{
+public:
+	explicit ModuloFilter(int32 m) : modulus(m) {}
+	bool ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB, uint32 threadId) override
+	{
+		B2_NOT_USED(threadId);
+		int32 a = (int32)(intptr_t)fixtureA->GetUserData(), b = (int32)(intptr_t)fixtureB->GetUserData();
+		return (a + b) % modulus != 0;
+	}
+	int32 modulus;
 };
 
 struct Host
@@ -215,6 +230,7 @@ B2H_API int b2h_build(void* p, int32 bodyCount, const BodyDefRec* bodies, int32 
 			def.filter.categoryBits = fd.categoryBits;
 			def.filter.maskBits = fd.maskBits;
 			def.filter.groupIndex = fd.groupIndex;
+			def.userData = (void*)(intptr_t)h->fixtures.size(); // fixture index in creation order
 			h->fixtures.push_back(body->CreateFixture(&def));
 			++f;
 		}
@@ -366,6 +382,11 @@ B2H_API uint32 b2h_hash(void* p)
 B2H_API void b2h_set_transform(void* p, int32 body, float x, float y, float angle)
 {
 	static_cast<Host*>(p)->bodies[body]->SetTransform(b2Vec2(x, y), angle);
+}
+B2H_API void b2h_set_modulo_filter(void* p, int32 modulus)
+{
+	Host* h = static_cast<Host*>(p);
+	h->world->SetContactFilter(modulus > 0 ? new ModuloFilter(modulus) : nullptr);
 }
 B2H_API void b2h_set_type(void* p, int32 body, int32 type) { static_cast<Host*>(p)->bodies[body]->SetType((b2BodyType)type); }
 B2H_API void b2h_set_filter(void* p, int32 fixture, uint16 categoryBits, uint16 maskBits, int16 groupIndex)

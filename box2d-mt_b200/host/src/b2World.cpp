@@ -570,14 +570,6 @@ void b2World::DestroyBody(b2Body* b)
 
 void b2World::Step(float32 timeStep, int32 velocityIterations, int32 positionIterations, b2TaskExecutor& executor)
 {
-	if (m_contactFilter != nullptr)
-	{
-		// only the default filter rule exists on the device (b2WorldCallbacks.h)
-		m_lastStatus = B2CU_ERR_UNSUPPORTED;
-		fprintf(stderr, "b2World::Step: custom b2ContactFilter is not supported by the GPU path\n");
-		b2Assert(false);
-		return;
-	}
 	m_locked = true;
 	bool ran = executor.StepWorld(*this, timeStep, velocityIterations, positionIterations);
 	m_locked = false;
@@ -648,6 +640,22 @@ int32 b2World::UploadDirty(b2cuWorld* device)
 	m_bodyDirtyLo = m_proxyDirtyLo = INT32_MAX;
 	m_bodyDirtyHi = m_proxyDirtyHi = -1;
 	m_newFixture = false;
+	return 0;
+}
+
+// b2cuPairFilterFn for a user b2ContactFilter: the same call b2ContactManager::AddPair makes (b2ContactManager.cpp:
+// 280-285), fixture A = the fixture with the lower proxy id
+int b2World::PairFilterThunk(void* user, const b2cuContactKey* keys, int32_t count, uint8_t* keep)
+{
+	b2World* self = static_cast<b2World*>(user);
+	if (self->m_contactFilter == nullptr) return 0;
+	const size_t n = self->m_fixtures.size();
+	for (int32_t i = 0; i < count; ++i)
+	{
+		size_t a = (size_t)(keys[i] >> 32), b = (size_t)(keys[i] & 0xFFFFFFFFull);
+		if (a >= n || b >= n) return 1;
+		keep[i] = self->m_contactFilter->ShouldCollide(self->m_fixtures[a], self->m_fixtures[b], 0) ? 1 : 0;
+	}
 	return 0;
 }
 

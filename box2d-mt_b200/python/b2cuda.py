@@ -21,7 +21,7 @@ API = [
     "b2cuSetWorldParams", "b2cuSetInvDt0", "b2cuSetCounts", "b2cuSetBodies", "b2cuGetBodies", "b2cuSetShapes",
     "b2cuSetProxies", "b2cuGetProxies", "b2cuSetContacts", "b2cuGetContactCount", "b2cuGetContacts", "b2cuStep",
     "b2cuGetContactsByKey", "b2cuGetEvents", "b2cuGetSolverOrder", "b2cuGetIslandLabels", "b2cuGetToiCandidates", "b2cuCollidePairs",
-    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuGetBodyStates", "b2cuGetEventContacts",
+    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuGetBodyStates", "b2cuGetEventContacts",
 ]
 
 
@@ -191,6 +191,27 @@ class World:
             self.set_inv_dt0(inv_dt0)
 
     # ---- stepping ----
+    def set_pair_filter(self, fn):
+        """fn(keys: uint64 array) -> bool array (True = the pair may collide), or None for the default rule"""
+        proto = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32,
+                                 ctypes.POINTER(ctypes.c_uint8))
+        if fn is None:
+            self._pair_filter = None
+            self._check(self.lib.b2cuSetPairFilter(self.h, None, None))
+            return
+
+        def thunk(user, keys, count, keep):
+            try:
+                k = np.ctypeslib.as_array(keys, shape=(count,))
+                out = np.asarray(fn(k.copy()), dtype=np.uint8)
+                np.ctypeslib.as_array(keep, shape=(count,))[:] = out
+                return 0
+            except Exception:  # never let an exception cross the C boundary
+                return 1
+
+        self._pair_filter = proto(thunk)  # keep the callback object alive
+        self._check(self.lib.b2cuSetPairFilter(self.h, self._pair_filter, None))
+
     def step(self, dt=1.0 / 60.0, vel_iters=8, pos_iters=3):
         info = np.zeros((), T.STEP_INFO)
         self._check(self.lib.b2cuStep(self.h, dt, vel_iters, pos_iters, _ptr(info)))

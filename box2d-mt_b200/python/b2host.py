@@ -63,6 +63,7 @@ def load():
     lib.b2h_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_velocity.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_type.argtypes = [vp, i32, i32]
+    lib.b2h_set_modulo_filter.argtypes = [vp, i32]
     lib.b2h_set_filter.argtypes = [vp, i32, ctypes.c_uint16, ctypes.c_uint16, ctypes.c_int16]
     lib.b2h_apply_force.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_awake.argtypes = [vp, i32, i32]
@@ -184,6 +185,9 @@ class HostWorld:
 
     def set_transform(self, body, x, y, angle):
         self.lib.b2h_set_transform(self.h, body, x, y, angle)
+
+    def set_modulo_filter(self, modulus):
+        self.lib.b2h_set_modulo_filter(self.h, modulus)
 
     def set_type(self, body, body_type):
         self.lib.b2h_set_type(self.h, body, body_type)

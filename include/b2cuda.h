@@ -36,6 +36,8 @@
  *                                                                          Dynamics/b2Island.cpp:339-348
  *   b2cuHostAlloc / b2cuHostFree         the world's own allocation of its bodies (b2BlockAllocator)
  *                                                                          Common/b2BlockAllocator.cpp:93-170
+ *   b2cuSetPairFilter                    b2ContactFilter::ShouldCollide of a user subclass, called from AddPair
+ *                                                                          Dynamics/b2WorldCallbacks.h:52-63, b2ContactManager.cpp:280-285
  *   b2cuGetSolverOrder                   (new) the colour-ordered constraint list the coloured Gauss-Seidel
  *                                        used this step; feeds the permuted-order oracle
  *   b2cuGetToiCandidates                 TOI-eligible front partition of b2ContactManager::m_contacts
@@ -313,6 +315,15 @@ B2CU_API int b2cuGetContactsByKey(b2cuWorld* w, int32_t count, const b2cuContact
  * (Dynamics/b2WorldCallbacks.h:84-107). */
 B2CU_API int b2cuGetEventContacts(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* keys,
                                   b2cuContact* records, int32_t* count);
+
+/* b2ContactFilter::ShouldCollide of a user subclass (Dynamics/b2WorldCallbacks.h:52-63), which the reference calls
+ * from b2ContactManager::AddPair when two fat boxes begin to overlap (Dynamics/b2ContactManager.cpp:280-285).  With a
+ * pair filter set, the device no longer applies the default category / mask / group rule: after every pair search of
+ * b2cuStep the candidate pairs (same-body, existing-contact and b2Body::ShouldCollide checks already done) are handed
+ * to `fn` on the calling thread, in one batch, before any contact is created or any body woken; fn sets keep[i] = 0 to
+ * reject pair i.  A non-zero return value of fn aborts the step with B2CU_ERR_ARGUMENT.  NULL restores the default. */
+typedef int (*b2cuPairFilterFn)(void* user, const b2cuContactKey* keys, int32_t count, uint8_t* keep);
+B2CU_API int b2cuSetPairFilter(b2cuWorld* w, b2cuPairFilterFn fn, void* user);
 
 B2CU_API int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positionIterations,
                       b2cuStepInfo* info);

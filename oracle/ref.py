@@ -51,6 +51,7 @@ def load(stock=False):
     lib.b2ref_profile.argtypes = [vp, vp]
     lib.b2ref_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_set_type.argtypes = [vp, i32, i32]
+    lib.b2ref_set_modulo_filter.argtypes = [vp, i32]
     lib.b2ref_set_filter.argtypes = [vp, i32, ctypes.c_uint16, ctypes.c_uint16, ctypes.c_int16]
     lib.b2ref_set_velocity.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_apply_force.argtypes = [vp, i32, f32, f32, f32]
@@ -152,6 +153,9 @@ class RefWorld:
 
     def set_transform(self, body, x, y, angle):
         self.lib.b2ref_set_transform(self.h, body, x, y, angle)
+
+    def set_modulo_filter(self, modulus):
+        self.lib.b2ref_set_modulo_filter(self.h, modulus)
 
     def set_type(self, body, body_type):
         self.lib.b2ref_set_type(self.h, body, body_type)

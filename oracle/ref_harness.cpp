@@ -700,6 +700,30 @@ void b2ref_set_filter(b2refWorld* w, int32_t fixture, uint16_t categoryBits, uin
 	w->fixtures[fixture]->SetFilterData(f); // calls Refilter()
 }
 
+// Test filter (parity of b2cuSetPairFilter): rejects the pairs whose fixture indices sum to a multiple of `modulus`,
+// everything else collides -- the category / mask / group rule is NOT applied, as with any user subclass.
+namespace
+{
+class ModuloFilter : public b2ContactFilter
+{
+public:
+	explicit ModuloFilter(int32 m) : modulus(m) {}
+	bool ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB, uint32 threadId) override
+	{
+		B2_NOT_USED(threadId);
+		int32 a = (int32)(intptr_t)fixtureA->GetUserData(), b = (int32)(intptr_t)fixtureB->GetUserData();
+		return (a + b) % modulus != 0;
+	}
+	int32 modulus;
+};
+} // namespace
+
+void b2ref_set_modulo_filter(b2refWorld* w, int32_t modulus)
+{
+	// owned by the process for the lifetime of the test (a handful of objects)
+	w->world->SetContactFilter(modulus > 0 ? new ModuloFilter(modulus) : nullptr);
+}
+
 void b2ref_set_type(b2refWorld* w, int32_t body, int32_t type) { w->bodies[body]->SetType((b2BodyType)type); }
 
 void b2ref_set_velocity(b2refWorld* w, int32_t body, float vx, float vy, float angw)

@@ -108,6 +108,8 @@ void b2ref_profile(b2refWorld* w, float* out13);
 /* mutators used by tests */
 void b2ref_set_transform(b2refWorld* w, int32_t body, float x, float y, float angle);
 void b2ref_set_type(b2refWorld* w, int32_t body, int32_t type); /* b2Body::SetType */
+/* installs a b2ContactFilter subclass: pairs whose fixture indices sum to a multiple of `modulus` never collide */
+void b2ref_set_modulo_filter(b2refWorld* w, int32_t modulus);
 /* b2Fixture::SetFilterData (which refilters) on fixture `fixture` (creation order) */
 void b2ref_set_filter(b2refWorld* w, int32_t fixture, uint16_t categoryBits, uint16_t maskBits, int16_t groupIndex);
 void b2ref_set_velocity(b2refWorld* w, int32_t body, float vx, float vy, float angw);

@@ -146,3 +146,29 @@ def test_varying_time_step_and_iterations(gpu):
     g = parity.gpu_world_from_ref(gpu, r)
     for dt, vi, pi in [(1 / 60.0, 8, 3), (1 / 30.0, 4, 1), (1 / 120.0, 10, 4), (1 / 60.0, 1, 0), (1 / 45.0, 6, 2)]:
         parity.lockstep(g, r, 25, dt=dt, vel_iters=vi, pos_iters=pi, tol=0.0)
+
+
+def test_custom_pair_filter(gpu):
+    """A user b2ContactFilter replaces the default rule for new pairs (b2ContactManager.cpp:280-285): the oracle gets
+    a b2ContactFilter subclass, the device the same rule through b2cuSetPairFilter."""
+    s = scenes.pile(10, 8)
+    s.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(s)
+    r.set_modulo_filter(5)
+    g = parity.gpu_world_from_ref(gpu, r)
+    calls = []
+
+    def rule(keys):
+        calls.append(len(keys))
+        a = (keys >> np.uint64(32)).astype(np.int64)
+        b = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        return (a + b) % 5 != 0
+
+    g.set_pair_filter(rule)
+    infos = parity.lockstep(g, r, 200, tol=0.0)
+    assert sum(calls) > 0
+    keys = T.contact_keys(g.get_contacts())
+    assert (((keys >> np.uint64(32)).astype(np.int64) + (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)) % 5 != 0).all()
+    # bodies really pass through each other where the rule says so: more overlap than the default world would allow
+    assert int(infos[-1]["contactCount"]) > 0
+

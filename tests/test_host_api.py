@@ -227,6 +227,27 @@ def test_host_api_set_type_between_steps(gpu):
 
 
 @pytest.mark.gpu
+def test_host_api_custom_contact_filter(gpu):
+    """b2World::SetContactFilter with a user subclass: evaluated on the host for the new pairs of every step."""
+    scene = scenes.pile(8, 6)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    for w in (r, h):
+        w.set_modulo_filter(4)
+    for s in range(150):
+        h.step()
+        assert r.step_ordered(h.solver_order()) == 0
+        try:
+            _contact_sets_equal(h, r)
+            parity.compare_bodies(h.bodies(), r.bodies())
+        except AssertionError as e:
+            raise AssertionError("step %d: %s" % (s, e))
+    hk, _, _ = h.contacts()
+    assert len(hk) > 0 and (((hk >> np.uint64(32)) + (hk & np.uint64(0xFFFFFFFF))) % np.uint64(4) != 0).all()
+
+
+@pytest.mark.gpu
 def test_host_api_lazy_download(gpu):
     """downloadBodies=false: the mirror is refreshed on first access only; results are the same."""
     a = b2host.HostWorld(scenes.pile(8, 6), download_bodies=True)
