@@ -161,11 +161,12 @@ private:
 	void DestroyFixtureInternal(b2Body* body, b2Fixture* fixture);
 	void RemoveProxies(const std::vector<int32>& proxyIds, const std::vector<int32>& bodyIds);
 	void DispatchEvents(b2cuWorld* device);
+	void DispatchPostSolve(b2cuWorld* device);
 
 	// driven by b2CudaStepExecutor::StepWorld
 	int32 UploadDirty(b2cuWorld* device);
 	int32 AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool downloadBodies, bool dispatchEvents,
-	                      float32* hostMs = nullptr);
+	                      float32* hostMs = nullptr, bool reportPostSolve = false);
 	void MakeContact(b2Contact* c, const b2cuContact& rec);
 
 	b2cuWorld* m_device;          // owned by the executor that last stepped this world

@@ -4,8 +4,11 @@
 //  * Begin/EndContactImmediate are invoked on the user thread with threadId 0, from the device's compacted
 //    event lists, right after the device step; returning true queues the deferred BeginContact/EndContact,
 //    which then run in ascending proxy-id key order, begins before ends (b2ContactManager.cpp:420-433).
-//  * PreSolve/PostSolve(Immediate) are never invoked by the GPU path in this version.
-//  * Only the default b2ContactFilter rule runs on the device; installing a custom filter makes Step fail.
+//  * PostSolveImmediate / PostSolve are invoked after the device step for every contact the solver handled when
+//    b2CudaStepOptions::reportPostSolve is set (Immediate first, deferred ones in key order); PreSolve is never
+//    invoked in this version.
+//  * The default b2ContactFilter rule runs on the device; a user subclass is called on the stepping thread for the
+//    candidate pairs of every pair search (include/b2cuda.h, b2cuSetPairFilter).
 #ifndef B2_WORLD_CALLBACKS_H
 #define B2_WORLD_CALLBACKS_H
 

@@ -18,7 +18,7 @@ class b2Body;
 
 struct b2CudaStepOptions
 {
-	b2CudaStepOptions() : device(0), downloadBodies(true), dispatchEvents(true) {}
+	b2CudaStepOptions() : device(0), downloadBodies(true), dispatchEvents(true), reportPostSolve(false) {}
 	/// CUDA device ordinal
 	int32 device;
 	/// refresh the host body mirror (transform, sweep, velocities, awake) after every step; when false the
@@ -26,6 +26,10 @@ struct b2CudaStepOptions
 	bool downloadBodies;
 	/// fetch begin/end touch events after every step and invoke the contact listener
 	bool dispatchEvents;
+	/// b2ContactListener::PostSolveImmediate / PostSolve for every contact the solver handled (b2Island::Report,
+	/// reference b2Island.cpp:533-570), after the device step, with the accumulated impulses of the step.  Off by
+	/// default: it brings the record of every solved contact to the host each step.
+	bool reportPostSolve;
 };
 
 class b2CudaStepExecutor : public b2TaskExecutor
@@ -47,6 +51,7 @@ public:
 	{
 		m_options.downloadBodies = options.downloadBodies;
 		m_options.dispatchEvents = options.dispatchEvents;
+		m_options.reportPostSolve = options.reportPostSolve;
 	}
 	/// status of the last StepWorld (0 = ok, else a b2cuStatus) and its message
 	int32 GetLastStatus() const { return m_status; }

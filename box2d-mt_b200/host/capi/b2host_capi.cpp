@@ -44,7 +44,24 @@ public:
 	bool BeginContactImmediate(b2Contact*, uint32) override { return true; }
 	bool EndContactImmediate(b2Contact*, uint32) override { return true; }
 	bool PreSolveImmediate(b2Contact*, const b2Manifold*, uint32) override { return false; }
-	bool PostSolveImmediate(b2Contact*, const b2ContactImpulse*, uint32) override { return false; }
+	bool PostSolveImmediate(b2Contact*, const b2ContactImpulse*, uint32) override { return recordPostSolve; }
+	void PostSolve(b2Contact* c, const b2ContactImpulse* impulse) override
+	{
+		// same digest as the oracle harness (oracle side: ref_harness.cpp RecordingListener::PostSolve)
+		uint64 d = c->GetKey() * 0x9E3779B97F4A7C15ull + (uint64)impulse->count;
+		for (int32 j = 0; j < impulse->count; ++j)
+		{
+			uint32 n, t;
+			memcpy(&n, &impulse->normalImpulses[j], 4);
+			memcpy(&t, &impulse->tangentImpulses[j], 4);
+			d += ((uint64)n << 32 | t) * (uint64)(2 * j + 3);
+		}
+		postSolveDigest += d;
+		++postSolveCount;
+	}
+	bool recordPostSolve = false;
+	uint64 postSolveDigest = 0;
+	long long postSolveCount = 0;
 	void BeginContact(b2Contact* c) override
 	{
 		begins.push_back(c->GetKey());
@@ -387,6 +404,20 @@ B2H_API void b2h_set_modulo_filter(void* p, int32 modulus)
 {
 	Host* h = static_cast<Host*>(p);
 	h->world->SetContactFilter(modulus > 0 ? new ModuloFilter(modulus) : nullptr);
+}
+B2H_API void b2h_record_post_solve(void* p, int32 on)
+{
+	Host* h = static_cast<Host*>(p);
+	h->recorder.recordPostSolve = on != 0;
+	b2CudaStepOptions opt = h->executor->GetOptions();
+	opt.reportPostSolve = on != 0;
+	h->executor->SetOptions(opt);
+}
+B2H_API void b2h_post_solve_digest(void* p, uint64* digest, long long* count)
+{
+	Host* h = static_cast<Host*>(p);
+	*digest = h->recorder.postSolveDigest;
+	*count = h->recorder.postSolveCount;
 }
 B2H_API void b2h_set_type(void* p, int32 body, int32 type) { static_cast<Host*>(p)->bodies[body]->SetType((b2BodyType)type); }
 B2H_API void b2h_set_filter(void* p, int32 fixture, uint16 categoryBits, uint16 maskBits, int16 groupIndex)

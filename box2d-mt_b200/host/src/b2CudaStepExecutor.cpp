@@ -191,6 +191,7 @@ bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 veloc
 	}
 	if (timeStep > 0.0f) world.m_inv_dt0 = 1.0f / timeStep;
 	world.m_lastStatus = 0;
-	world.AfterDeviceStep(device, impl->info, m_options.downloadBodies, m_options.dispatchEvents, m_hostMs + 2);
+	world.AfterDeviceStep(device, impl->info, m_options.downloadBodies, m_options.dispatchEvents, m_hostMs + 2,
+	                      m_options.reportPostSolve);
 	return true;
 }

@@ -713,8 +713,39 @@ void b2World::DispatchEvents(b2cuWorld* device)
 		if (deferred[1][i]) m_contactListener->EndContact(&contacts[1][i]);
 }
 
+// b2Island::Report (reference b2Island.cpp:533-570) after the fact: the accumulated impulses of the step are what
+// StoreImpulses left in the manifolds of the solved contacts
+void b2World::DispatchPostSolve(b2cuWorld* device)
+{
+	int32 n = 0;
+	if (b2cuGetSolverOrder(device, 0, nullptr, nullptr, &n) != B2CU_OK || n <= 0) return;
+	std::vector<b2cuContactKey> keys((size_t)n);
+	if (b2cuGetSolverOrder(device, n, keys.data(), nullptr, &n) != B2CU_OK) return;
+	// deferred PostSolve calls run in contact-key order (b2DeferredPostSolveLessThan, b2ContactManager.cpp:84-87)
+	std::sort(keys.begin(), keys.end());
+	std::vector<b2cuContact> recs((size_t)n);
+	if (b2cuGetContactsByKey(device, n, keys.data(), recs.data()) != B2CU_OK) return;
+	std::vector<b2Contact> contacts((size_t)n);
+	std::vector<b2ContactImpulse> impulses((size_t)n);
+	std::vector<char> deferred((size_t)n, 0);
+	for (int32 i = 0; i < n; ++i)
+	{
+		MakeContact(&contacts[i], recs[i]);
+		b2ContactImpulse& imp = impulses[i];
+		imp.count = recs[i].manifold.pointCount;
+		for (int32 j = 0; j < b2_maxManifoldPoints; ++j)
+		{
+			imp.normalImpulses[j] = j < imp.count ? recs[i].manifold.points[j].normalImpulse : 0.0f;
+			imp.tangentImpulses[j] = j < imp.count ? recs[i].manifold.points[j].tangentImpulse : 0.0f;
+		}
+		deferred[i] = m_contactListener->PostSolveImmediate(&contacts[i], &imp, 0) ? 1 : 0;
+	}
+	for (int32 i = 0; i < n; ++i)
+		if (deferred[i]) m_contactListener->PostSolve(&contacts[i], &impulses[i]);
+}
+
 int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool downloadBodies, bool dispatchEvents,
-                               float32* hostMs)
+                               float32* hostMs, bool reportPostSolve)
 {
 	typedef std::chrono::steady_clock Clock;
 	Clock::time_point t0 = Clock::now();
@@ -749,6 +780,14 @@ int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool
 		bool wasLocked = m_locked;
 		m_locked = true;
 		DispatchEvents(device);
+		m_locked = wasLocked;
+	}
+	if (reportPostSolve && m_contactListener && info.constraintCount > 0)
+	{
+		RefreshBodies();
+		bool wasLocked = m_locked;
+		m_locked = true;
+		DispatchPostSolve(device);
 		m_locked = wasLocked;
 	}
 	if (hostMs) hostMs[1] = std::chrono::duration<float, std::milli>(Clock::now() - t1).count();

@@ -76,11 +76,29 @@ public:
 	bool BeginContactImmediate(b2Contact*, uint32) override { return true; }
 	bool EndContactImmediate(b2Contact*, uint32) override { return true; }
 	bool PreSolveImmediate(b2Contact*, const b2Manifold*, uint32) override { return false; }
-	bool PostSolveImmediate(b2Contact*, const b2ContactImpulse*, uint32) override { return false; }
+	bool PostSolveImmediate(b2Contact*, const b2ContactImpulse*, uint32) override { return recordPostSolve; }
+	void PostSolve(b2Contact* c, const b2ContactImpulse* impulse) override
+	{
+		// order-independent digest of (key, count, impulses): the deferred calls of the reference and of the GPU path come in
+		// the same key order, but a sum of bit patterns does not care
+		uint64_t d = ContactKey(c) * 0x9E3779B97F4A7C15ull + (uint64_t)impulse->count;
+		for (int32 j = 0; j < impulse->count; ++j)
+		{
+			uint32_t n, t;
+			memcpy(&n, &impulse->normalImpulses[j], 4);
+			memcpy(&t, &impulse->tangentImpulses[j], 4);
+			d += ((uint64_t)n << 32 | t) * (uint64_t)(2 * j + 3);
+		}
+		postSolveDigest += d;
+		++postSolveCount;
+	}
 	void BeginContact(b2Contact* c) override { begins.push_back(ContactKey(c)); }
 	void EndContact(b2Contact* c) override { ends.push_back(ContactKey(c)); }
 
 	std::vector<uint64_t> begins, ends;
+	bool recordPostSolve = false;
+	uint64_t postSolveDigest = 0;
+	int64_t postSolveCount = 0;
 };
 
 } // namespace
@@ -722,6 +740,13 @@ void b2ref_set_modulo_filter(b2refWorld* w, int32_t modulus)
 {
 	// owned by the process for the lifetime of the test (a handful of objects)
 	w->world->SetContactFilter(modulus > 0 ? new ModuloFilter(modulus) : nullptr);
+}
+
+void b2ref_record_post_solve(b2refWorld* w, int32_t on) { w->listener.recordPostSolve = on != 0; }
+void b2ref_post_solve_digest(b2refWorld* w, uint64_t* digest, int64_t* count)
+{
+	*digest = w->listener.postSolveDigest;
+	*count = w->listener.postSolveCount;
 }
 
 void b2ref_set_type(b2refWorld* w, int32_t body, int32_t type) { w->bodies[body]->SetType((b2BodyType)type); }

@@ -248,6 +248,23 @@ def test_host_api_custom_contact_filter(gpu):
 
 
 @pytest.mark.gpu
+def test_host_api_post_solve_reports(gpu):
+    """b2CudaStepOptions::reportPostSolve: one PostSolve per solved contact and step, with the impulses the reference
+    reports (b2Island::Report): equal call counts and an equal digest over (key, count, impulses) of all calls."""
+    scene = scenes.pile(8, 6)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    r.record_post_solve()
+    h.record_post_solve()
+    for s in range(120):
+        h.step()
+        assert r.step_ordered(h.solver_order()) == 0
+        assert h.post_solve_digest() == r.post_solve_digest(), "step %d" % s
+    assert h.post_solve_digest()[1] > 1000
+
+
+@pytest.mark.gpu
 def test_host_api_lazy_download(gpu):
     """downloadBodies=false: the mirror is refreshed on first access only; results are the same."""
     a = b2host.HostWorld(scenes.pile(8, 6), download_bodies=True)
