@@ -376,6 +376,77 @@ __global__ void FillProxyRadiusKernel(DeviceArrays d, int proxyCount)
 	B2CU_GRID_STRIDE(p, proxyCount) { d.pradius[p] = d.shapes[d.pshape[p]].radius; }
 }
 
+// ---- PreSolve hook (b2cuSetPreSolveHook) ----
+// contacts the narrow phase has just updated and found touching: what b2Contact::Update reports to PreSolve
+__global__ void PreSolveSelectKernel(DeviceArrays d, int contactCount)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		uint32_t f = d.c.flags[i];
+		d.cSelect[i] = ((f & B2CU_CONTACT_TOUCHING) && !(f & (B2CU_CONTACT_DEAD | B2CU_CONTACT_INACTIVE))) ? 1 : 0;
+	}
+}
+// records of the selected contacts + their manifolds of the previous step (saved in cAlt before Collide)
+__global__ void PreSolveGatherKernel(DeviceArrays d, const int* __restrict__ list, int n, b2cuContact* __restrict__ out,
+                                     b2cuManifold* __restrict__ oldOut)
+{
+	B2CU_GRID_STRIDE(j, n)
+	{
+		int i = list[j];
+		int4 pr = d.c.proxies[i];
+		float4 m0 = d.c.m0[i], m1 = d.c.m1[i], m2 = d.c.m2[i], mix = d.c.mix[i];
+		uint4 m3 = d.c.m3[i];
+		b2cuContact o;
+		o.proxyA = pr.x;
+		o.proxyB = pr.y;
+		o.flags = d.c.flags[i];
+		o.friction = mix.x;
+		o.restitution = mix.y;
+		o.tangentSpeed = mix.z;
+		o.toiCount = d.c.toiCount[i];
+		o.toi = mix.w;
+		o.manifold.localNormal[0] = m0.x; o.manifold.localNormal[1] = m0.y;
+		o.manifold.localPoint[0] = m0.z; o.manifold.localPoint[1] = m0.w;
+		o.manifold.points[0].localPoint[0] = m1.x; o.manifold.points[0].localPoint[1] = m1.y;
+		o.manifold.points[0].normalImpulse = m1.z; o.manifold.points[0].tangentImpulse = m1.w;
+		o.manifold.points[1].localPoint[0] = m2.x; o.manifold.points[1].localPoint[1] = m2.y;
+		o.manifold.points[1].normalImpulse = m2.z; o.manifold.points[1].tangentImpulse = m2.w;
+		o.manifold.id[0] = m3.x; o.manifold.id[1] = m3.y;
+		o.manifold.type = (int32_t)m3.z;
+		o.manifold.pointCount = (int32_t)m3.w;
+		out[j] = o;
+		float4 p0 = d.cAlt.m0[i], p1 = d.cAlt.m1[i], p2 = d.cAlt.m2[i];
+		uint4 p3 = d.cAlt.m3[i];
+		b2cuManifold q;
+		q.localNormal[0] = p0.x; q.localNormal[1] = p0.y;
+		q.localPoint[0] = p0.z; q.localPoint[1] = p0.w;
+		q.points[0].localPoint[0] = p1.x; q.points[0].localPoint[1] = p1.y;
+		q.points[0].normalImpulse = p1.z; q.points[0].tangentImpulse = p1.w;
+		q.points[1].localPoint[0] = p2.x; q.points[1].localPoint[1] = p2.y;
+		q.points[1].normalImpulse = p2.z; q.points[1].tangentImpulse = p2.w;
+		q.id[0] = p3.x; q.id[1] = p3.y;
+		q.type = (int32_t)p3.z;
+		q.pointCount = (int32_t)p3.w;
+		oldOut[j] = q;
+	}
+}
+// b2Contact::SetEnabled(false) for a list of keys
+__global__ void DisableContactsKernel(DeviceArrays d, int contactCount, int mainCount, const uint64_t* __restrict__ keys, int n)
+{
+	B2CU_GRID_STRIDE(j, n)
+	{
+		uint64_t key = keys[j];
+		int i = LowerBound64(d.c.key, mainCount, key);
+		bool found = i < mainCount && d.c.key[i] == key && !(d.c.flags[i] & B2CU_CONTACT_DEAD);
+		if (!found && contactCount > mainCount)
+		{
+			i = mainCount + LowerBound64(d.c.key + mainCount, contactCount - mainCount, key);
+			found = i < contactCount && d.c.key[i] == key && !(d.c.flags[i] & B2CU_CONTACT_DEAD);
+		}
+		if (found) d.c.flags[i] &= ~(uint32_t)B2CU_CONTACT_ENABLED;
+	}
+}
+
 // b2Fixture::Refilter (b2Fixture.cpp:197-210): the contacts of a refiltered proxy get e_filterFlag
 __global__ void FlagFilterContactsKernel(DeviceArrays d, int contactCount)
 {

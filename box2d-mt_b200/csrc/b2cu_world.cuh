@@ -204,6 +204,10 @@ struct b2cuWorld
 	int colourStarts[B2CU_MAX_COLOURS + 3];
 
 	int* hostCounters;   // pinned, CNT_COUNT + colour counts
+	b2cuPreSolveFn preSolveHook;
+	void* preSolveUser;
+	bool inPreSolve;         // b2cuStep is inside the hook: the pre-solve entry points are valid
+	int preSolveCount;       // -1: the touching list has not been compacted yet in this hook
 	b2cuPairFilterFn pairFilter;
 	void* pairFilterUser;
 	bool refilterPending;    // a proxy was uploaded with B2CU_PROXY_REFILTER

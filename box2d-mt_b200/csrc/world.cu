@@ -1141,6 +1141,68 @@ static int FinishMirrorCopy(b2cuWorld* w)
 	return B2CU_OK;
 }
 
+static int EnsureQueryScratch(b2cuWorld* w, size_t bytes);
+
+int b2cuSetPreSolveHook(b2cuWorld* w, b2cuPreSolveFn fn, void* user)
+{
+	if (!w) return B2CU_ERR_ARGUMENT;
+	w->preSolveHook = fn;
+	w->preSolveUser = user;
+	return B2CU_OK;
+}
+
+int b2cuGetPreSolveContacts(b2cuWorld* w, int32_t capacity, b2cuContact* records, b2cuManifold* oldManifolds, int32_t* count)
+{
+	if (!w || capacity < 0 || (capacity > 0 && (!records || !oldManifolds))) return B2CU_ERR_ARGUMENT;
+	if (!w->inPreSolve) return SetError(w, B2CU_ERR_ARGUMENT, "b2cuGetPreSolveContacts is only valid inside the pre-solve hook");
+	cudaSetDevice(w->device);
+	DeviceArrays& d = w->d;
+	const int nc = w->contactCount;
+	int rc;
+	if (w->preSolveCount < 0)
+	{
+		int n = 0;
+		if (nc > 0)
+		{
+			LAUNCH(w, PreSolveSelectKernel, GridFor(nc), kBlock, d, nc);
+			CompactFlags(&w->prims, d.cSelect, nc, d.listA, d.counters + CNT_SCRATCH, w->stream);
+			CUDA_TRY(w, cudaMemcpyAsync(&w->hostCounters[CNT_SCRATCH], d.counters + CNT_SCRATCH, sizeof(int),
+			                            cudaMemcpyDeviceToHost, w->stream));
+			if ((rc = SyncCheck(w))) return rc;
+			n = w->hostCounters[CNT_SCRATCH];
+		}
+		w->preSolveCount = n;
+	}
+	const int n = w->preSolveCount;
+	if (count) *count = n;
+	const int m = std::min(n, capacity);
+	if (m <= 0) return B2CU_OK;
+	const size_t recBytes = (sizeof(b2cuContact) * (size_t)m + 255) & ~(size_t)255;
+	const size_t total = recBytes + sizeof(b2cuManifold) * (size_t)m;
+	if ((rc = EnsureQueryScratch(w, total))) return rc;
+	b2cuContact* dRec = reinterpret_cast<b2cuContact*>(w->queryScratch);
+	b2cuManifold* dOld = reinterpret_cast<b2cuManifold*>(static_cast<char*>(w->queryScratch) + recBytes);
+	LAUNCH(w, PreSolveGatherKernel, GridFor(m), kBlock, d, (const int*)d.listA, m, dRec, dOld);
+	CUDA_TRY(w, cudaMemcpyAsync(records, dRec, sizeof(b2cuContact) * (size_t)m, cudaMemcpyDeviceToHost, w->stream));
+	CUDA_TRY(w, cudaMemcpyAsync(oldManifolds, dOld, sizeof(b2cuManifold) * (size_t)m, cudaMemcpyDeviceToHost, w->stream));
+	return SyncCheck(w);
+}
+
+int b2cuDisableContacts(b2cuWorld* w, int32_t count, const b2cuContactKey* keys)
+{
+	if (!w || count < 0 || (count > 0 && !keys)) return B2CU_ERR_ARGUMENT;
+	if (!w->inPreSolve) return SetError(w, B2CU_ERR_ARGUMENT, "b2cuDisableContacts is only valid inside the pre-solve hook");
+	if (count == 0) return B2CU_OK;
+	cudaSetDevice(w->device);
+	int rc;
+	// the key list goes behind whatever the gather call left in the scratch (it has been copied out already)
+	if ((rc = EnsureQueryScratch(w, sizeof(uint64_t) * (size_t)count))) return rc;
+	uint64_t* dKeys = reinterpret_cast<uint64_t*>(w->queryScratch);
+	CUDA_TRY(w, cudaMemcpyAsync(dKeys, keys, sizeof(uint64_t) * (size_t)count, cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(w, DisableContactsKernel, GridFor(count), kBlock, w->d, w->contactCount, w->mainCount, (const uint64_t*)dKeys, count);
+	return SyncCheck(w);
+}
+
 int b2cuSetPairFilter(b2cuWorld* w, b2cuPairFilterFn fn, void* user)
 {
 	if (!w) return B2CU_ERR_ARGUMENT;
@@ -1247,9 +1309,27 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	if (nc > 0)
 	{
 		// narrow phase; begin/end events are appended to the deferred buffers and sorted at the end of the step
+		if (w->preSolveHook != nullptr)
+		{
+			// the manifolds of the previous step, for PreSolve (b2Contact::Update keeps `oldManifold` the same way)
+			CUDA_TRY(w, cudaMemcpyAsync(d.cAlt.m0, d.c.m0, sizeof(float4) * (size_t)nc, cudaMemcpyDeviceToDevice, w->stream));
+			CUDA_TRY(w, cudaMemcpyAsync(d.cAlt.m1, d.c.m1, sizeof(float4) * (size_t)nc, cudaMemcpyDeviceToDevice, w->stream));
+			CUDA_TRY(w, cudaMemcpyAsync(d.cAlt.m2, d.c.m2, sizeof(float4) * (size_t)nc, cudaMemcpyDeviceToDevice, w->stream));
+			CUDA_TRY(w, cudaMemcpyAsync(d.cAlt.m3, d.c.m3, sizeof(uint4) * (size_t)nc, cudaMemcpyDeviceToDevice, w->stream));
+		}
 		LAUNCH(w, CollideKernel, GridFor(nc), kBlock, d, nc, w->mainCount, w->contactCapacity, d.listA);
 		LAUNCH(w, CollideHeavyKernel, GridFor(nc), kBlock, d, (const int*)d.listA, w->contactCapacity);
 		LAUNCH(w, ApplyWakeKernel, GridFor(nb), kBlock, d, nb, (int*)nullptr);
+		if (w->preSolveHook != nullptr)
+		{
+			// FinishCollide's PreSolve calls: between the narrow phase and the solver, on the calling thread
+			if ((rc = SyncCheck(w))) return rc;
+			w->inPreSolve = true;
+			w->preSolveCount = -1;
+			int hookRc = w->preSolveHook(w->preSolveUser, w);
+			w->inPreSolve = false;
+			if (hookRc != 0) return SetError(w, B2CU_ERR_ARGUMENT, "the pre-solve hook failed (%d)", hookRc);
+		}
 	}
 	cudaEventRecord(w->ev[2], w->stream);
 

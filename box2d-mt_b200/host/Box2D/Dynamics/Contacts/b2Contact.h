@@ -26,6 +26,13 @@ public:
 	void GetWorldManifold(b2WorldManifold* worldManifold) const;
 	bool IsTouching() const { return (m_flags & e_touchingFlag) != 0; }
 	bool IsEnabled() const { return (m_flags & e_enabledFlag) != 0; }
+	/// Meaningful inside b2ContactListener::PreSolve: switches the contact off for the current step
+	/// (reference b2Contact.h:113, :299-309); needs b2CudaStepOptions::reportPreSolve
+	void SetEnabled(bool flag)
+	{
+		if (flag) m_flags |= e_enabledFlag;
+		else m_flags &= ~(uint32)e_enabledFlag;
+	}
 	b2Contact* GetNext() { return m_next; }
 	const b2Contact* GetNext() const { return m_next; }
 	b2Fixture* GetFixtureA() { return m_fixtureA; }

@@ -156,6 +156,7 @@ private:
 	void RefreshProxies() const;
 	void RefreshContacts();
 	void InvalidateSnapshots();
+	static int PreSolveThunk(void* user, b2cuWorld* device);
 	static int PairFilterThunk(void* user, const b2cuContactKey* keys, int32_t count, uint8_t* keep);
 	void DestroyContactsOfBody(int32 bodyIndex);
 	void DestroyFixtureInternal(b2Body* body, b2Fixture* fixture);

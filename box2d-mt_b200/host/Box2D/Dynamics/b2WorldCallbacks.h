@@ -5,8 +5,9 @@
 //    event lists, right after the device step; returning true queues the deferred BeginContact/EndContact,
 //    which then run in ascending proxy-id key order, begins before ends (b2ContactManager.cpp:420-433).
 //  * PostSolveImmediate / PostSolve are invoked after the device step for every contact the solver handled when
-//    b2CudaStepOptions::reportPostSolve is set (Immediate first, deferred ones in key order); PreSolve is never
-//    invoked in this version.
+//    b2CudaStepOptions::reportPostSolve is set (Immediate first, deferred ones in key order).
+//  * PreSolveImmediate / PreSolve are invoked between the narrow phase and the solver of the device step when
+//    b2CudaStepOptions::reportPreSolve is set; b2Contact::SetEnabled(false) there is honoured.
 //  * The default b2ContactFilter rule runs on the device; a user subclass is called on the stepping thread for the
 //    candidate pairs of every pair search (include/b2cuda.h, b2cuSetPairFilter).
 #ifndef B2_WORLD_CALLBACKS_H

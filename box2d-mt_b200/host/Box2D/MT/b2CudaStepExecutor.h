@@ -18,7 +18,7 @@ class b2Body;
 
 struct b2CudaStepOptions
 {
-	b2CudaStepOptions() : device(0), downloadBodies(true), dispatchEvents(true), reportPostSolve(false) {}
+	b2CudaStepOptions() : device(0), downloadBodies(true), dispatchEvents(true), reportPostSolve(false), reportPreSolve(false) {}
 	/// CUDA device ordinal
 	int32 device;
 	/// refresh the host body mirror (transform, sweep, velocities, awake) after every step; when false the
@@ -30,6 +30,11 @@ struct b2CudaStepOptions
 	/// reference b2Island.cpp:533-570), after the device step, with the accumulated impulses of the step.  Off by
 	/// default: it brings the record of every solved contact to the host each step.
 	bool reportPostSolve;
+	/// b2ContactListener::PreSolveImmediate / PreSolve for every touching contact, between the narrow phase and the
+	/// solver of the device step (reference b2Contact.cpp:283-297, b2ContactManager.cpp:430-433), with the manifold of
+	/// the previous step; b2Contact::SetEnabled(false) there keeps the contact out of this step's solve.  Off by
+	/// default: one device round trip and the records of all touching contacts per step.
+	bool reportPreSolve;
 };
 
 class b2CudaStepExecutor : public b2TaskExecutor
@@ -52,6 +57,7 @@ public:
 		m_options.downloadBodies = options.downloadBodies;
 		m_options.dispatchEvents = options.dispatchEvents;
 		m_options.reportPostSolve = options.reportPostSolve;
+		m_options.reportPreSolve = options.reportPreSolve;
 	}
 	/// status of the last StepWorld (0 = ok, else a b2cuStatus) and its message
 	int32 GetLastStatus() const { return m_status; }

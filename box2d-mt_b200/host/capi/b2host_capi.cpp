@@ -43,7 +43,19 @@ class Recorder : public b2ContactListener
 public:
 	bool BeginContactImmediate(b2Contact*, uint32) override { return true; }
 	bool EndContactImmediate(b2Contact*, uint32) override { return true; }
-	bool PreSolveImmediate(b2Contact*, const b2Manifold*, uint32) override { return false; }
+	bool PreSolveImmediate(b2Contact*, const b2Manifold*, uint32) override { return preSolveModulus > 0; }
+	void PreSolve(b2Contact* c, const b2Manifold* oldManifold) override
+	{
+		// the same test rule and digest as the oracle harness (ref_harness.cpp RecordingListener::PreSolve)
+		uint64 key = c->GetKey();
+		if (key % (uint64)preSolveModulus == 0) c->SetEnabled(false);
+		preSolveDigest += key * 0x9E3779B97F4A7C15ull + (uint64)oldManifold->pointCount * 7u +
+		                  (uint64)c->GetManifold()->pointCount;
+		++preSolveCount;
+	}
+	int preSolveModulus = 0;
+	uint64 preSolveDigest = 0;
+	long long preSolveCount = 0;
 	bool PostSolveImmediate(b2Contact*, const b2ContactImpulse*, uint32) override { return recordPostSolve; }
 	void PostSolve(b2Contact* c, const b2ContactImpulse* impulse) override
 	{
@@ -404,6 +416,20 @@ B2H_API void b2h_set_modulo_filter(void* p, int32 modulus)
 {
 	Host* h = static_cast<Host*>(p);
 	h->world->SetContactFilter(modulus > 0 ? new ModuloFilter(modulus) : nullptr);
+}
+B2H_API void b2h_set_pre_solve_rule(void* p, int32 modulus)
+{
+	Host* h = static_cast<Host*>(p);
+	h->recorder.preSolveModulus = modulus;
+	b2CudaStepOptions opt = h->executor->GetOptions();
+	opt.reportPreSolve = modulus > 0;
+	h->executor->SetOptions(opt);
+}
+B2H_API void b2h_pre_solve_digest(void* p, uint64* digest, long long* count)
+{
+	Host* h = static_cast<Host*>(p);
+	*digest = h->recorder.preSolveDigest;
+	*count = h->recorder.preSolveCount;
 }
 B2H_API void b2h_record_post_solve(void* p, int32 on)
 {

@@ -176,6 +176,9 @@ bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 veloc
 	// a user b2ContactFilter is consulted for the new pairs of the step, on this thread (b2cuSetPairFilter)
 	if (rc == B2CU_OK)
 		rc = b2cuSetPairFilter(device, world.m_contactFilter ? &b2World::PairFilterThunk : nullptr, &world);
+	if (rc == B2CU_OK)
+		rc = b2cuSetPreSolveHook(device, (m_options.reportPreSolve && world.m_contactListener) ? &b2World::PreSolveThunk : nullptr,
+		                         &world);
 	if (rc == B2CU_OK) rc = b2cuStep(device, timeStep, velocityIterations, positionIterations, &impl->info);
 	Clock::time_point t2 = Clock::now();
 	m_hostMs[0] = std::chrono::duration<float, std::milli>(t1 - t0).count();

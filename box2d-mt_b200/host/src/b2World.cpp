@@ -713,6 +713,49 @@ void b2World::DispatchEvents(b2cuWorld* device)
 		if (deferred[1][i]) m_contactListener->EndContact(&contacts[1][i]);
 }
 
+// b2cuPreSolveFn: the PreSolve calls of b2Contact::Update / b2ContactManager::FinishCollide, made from inside the
+// device step.  Immediate calls first, deferred ones in key order; contacts the callbacks disabled are switched off
+// on the device before the solver runs.
+int b2World::PreSolveThunk(void* user, b2cuWorld* device)
+{
+	b2World* self = static_cast<b2World*>(user);
+	if (self->m_contactListener == nullptr) return 0;
+	int32 n = 0;
+	if (b2cuGetPreSolveContacts(device, 0, nullptr, nullptr, &n) != B2CU_OK) return 1;
+	if (n <= 0) return 0;
+	std::vector<b2cuContact> recs((size_t)n);
+	std::vector<b2cuManifold> olds((size_t)n);
+	if (b2cuGetPreSolveContacts(device, n, recs.data(), olds.data(), &n) != B2CU_OK) return 1;
+	std::vector<b2Contact> contacts((size_t)n);
+	std::vector<b2Manifold> oldManifolds((size_t)n);
+	std::vector<char> deferred((size_t)n, 0);
+	for (int32 i = 0; i < n; ++i)
+	{
+		self->MakeContact(&contacts[i], recs[i]);
+		const b2cuManifold& m = olds[i];
+		b2Manifold& o = oldManifolds[i];
+		o.localNormal.Set(m.localNormal[0], m.localNormal[1]);
+		o.localPoint.Set(m.localPoint[0], m.localPoint[1]);
+		for (int32 j = 0; j < b2_maxManifoldPoints; ++j)
+		{
+			o.points[j].localPoint.Set(m.points[j].localPoint[0], m.points[j].localPoint[1]);
+			o.points[j].normalImpulse = m.points[j].normalImpulse;
+			o.points[j].tangentImpulse = m.points[j].tangentImpulse;
+			o.points[j].id.key = m.id[j];
+		}
+		o.type = (b2Manifold::Type)m.type;
+		o.pointCount = m.pointCount;
+		deferred[i] = self->m_contactListener->PreSolveImmediate(&contacts[i], &o, 0) ? 1 : 0;
+	}
+	for (int32 i = 0; i < n; ++i)
+		if (deferred[i]) self->m_contactListener->PreSolve(&contacts[i], &oldManifolds[i]);
+	std::vector<b2cuContactKey> off;
+	for (int32 i = 0; i < n; ++i)
+		if (!contacts[i].IsEnabled()) off.push_back(contacts[i].GetKey());
+	if (!off.empty() && b2cuDisableContacts(device, (int32)off.size(), off.data()) != B2CU_OK) return 1;
+	return 0;
+}
+
 // b2Island::Report (reference b2Island.cpp:533-570) after the fact: the accumulated impulses of the step are what
 // StoreImpulses left in the manifolds of the solved contacts
 void b2World::DispatchPostSolve(b2cuWorld* device)

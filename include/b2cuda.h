@@ -36,6 +36,9 @@
  *                                                                          Dynamics/b2Island.cpp:339-348
  *   b2cuHostAlloc / b2cuHostFree         the world's own allocation of its bodies (b2BlockAllocator)
  *                                                                          Common/b2BlockAllocator.cpp:93-170
+ *   b2cuSetPreSolveHook /                b2ContactListener::PreSolve between Collide and Solve, b2Contact::SetEnabled
+ *   b2cuGetPreSolveContacts /                                               Dynamics/Contacts/b2Contact.cpp:283-297,
+ *   b2cuDisableContacts                                                     Dynamics/b2ContactManager.cpp:430-433
  *   b2cuSetPairFilter                    b2ContactFilter::ShouldCollide of a user subclass, called from AddPair
  *                                                                          Dynamics/b2WorldCallbacks.h:52-63, b2ContactManager.cpp:280-285
  *   b2cuGetSolverOrder                   (new) the colour-ordered constraint list the coloured Gauss-Seidel
@@ -324,6 +327,20 @@ B2CU_API int b2cuGetEventContacts(b2cuWorld* w, int32_t kind, int32_t capacity, 
  * reject pair i.  A non-zero return value of fn aborts the step with B2CU_ERR_ARGUMENT.  NULL restores the default. */
 typedef int (*b2cuPairFilterFn)(void* user, const b2cuContactKey* keys, int32_t count, uint8_t* keep);
 B2CU_API int b2cuSetPairFilter(b2cuWorld* w, b2cuPairFilterFn fn, void* user);
+
+/* b2ContactListener::PreSolve (Dynamics/b2WorldCallbacks.h:109-121): the reference calls it from b2Contact::Update for
+ * every touching contact it has just updated, with the manifold of the previous step, and user code may switch the
+ * contact off for this step there (b2Contact::SetEnabled(false); Dynamics/Contacts/b2Contact.cpp:283-297, deferred
+ * calls in b2ContactManager::FinishCollide, b2ContactManager.cpp:430-433).  With a hook set, b2cuStep calls fn on the
+ * calling thread between its narrow phase and its solver; inside fn the caller may use b2cuGetPreSolveContacts (the
+ * touching contacts of this step in key order: new record + previous manifold) and b2cuDisableContacts (clears
+ * e_enabledFlag until the next update: the contact is left out of islands and solver).  A non-zero return value of fn
+ * aborts the step.  Costs a device round trip per step; NULL removes the hook. */
+typedef int (*b2cuPreSolveFn)(void* user, b2cuWorld* w);
+B2CU_API int b2cuSetPreSolveHook(b2cuWorld* w, b2cuPreSolveFn fn, void* user);
+B2CU_API int b2cuGetPreSolveContacts(b2cuWorld* w, int32_t capacity, b2cuContact* records, b2cuManifold* oldManifolds,
+                                     int32_t* count);
+B2CU_API int b2cuDisableContacts(b2cuWorld* w, int32_t count, const b2cuContactKey* keys);
 
 B2CU_API int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positionIterations,
                       b2cuStepInfo* info);

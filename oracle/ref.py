@@ -52,6 +52,8 @@ def load(stock=False):
     lib.b2ref_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_set_type.argtypes = [vp, i32, i32]
     lib.b2ref_record_post_solve.argtypes = [vp, i32]
+    lib.b2ref_set_pre_solve_rule.argtypes = [vp, i32]
+    lib.b2ref_pre_solve_digest.argtypes = [vp, vp, vp]
     lib.b2ref_post_solve_digest.argtypes = [vp, vp, vp]
     lib.b2ref_set_modulo_filter.argtypes = [vp, i32]
     lib.b2ref_set_filter.argtypes = [vp, i32, ctypes.c_uint16, ctypes.c_uint16, ctypes.c_int16]
@@ -158,6 +160,15 @@ class RefWorld:
 
     def set_modulo_filter(self, modulus):
         self.lib.b2ref_set_modulo_filter(self.h, modulus)
+
+    def set_pre_solve_rule(self, modulus):
+        self.lib.b2ref_set_pre_solve_rule(self.h, modulus)
+
+    def pre_solve_digest(self):
+        d = np.zeros(1, np.uint64)
+        c = np.zeros(1, np.int64)
+        self.lib.b2ref_pre_solve_digest(self.h, _ptr(d), _ptr(c))
+        return int(d[0]), int(c[0])
 
     def record_post_solve(self, on=True):
         self.lib.b2ref_record_post_solve(self.h, int(on))

@@ -75,7 +75,16 @@ class RecordingListener : public b2ContactListener
 public:
 	bool BeginContactImmediate(b2Contact*, uint32) override { return true; }
 	bool EndContactImmediate(b2Contact*, uint32) override { return true; }
-	bool PreSolveImmediate(b2Contact*, const b2Manifold*, uint32) override { return false; }
+	bool PreSolveImmediate(b2Contact*, const b2Manifold*, uint32) override { return preSolveModulus > 0; }
+	void PreSolve(b2Contact* c, const b2Manifold* oldManifold) override
+	{
+		// test rule: contacts whose key is a multiple of the modulus are switched off every step
+		uint64_t key = ContactKey(c);
+		if (key % (uint64_t)preSolveModulus == 0) c->SetEnabled(false);
+		preSolveDigest += key * 0x9E3779B97F4A7C15ull + (uint64_t)oldManifold->pointCount * 7u +
+		                  (uint64_t)c->GetManifold()->pointCount;
+		++preSolveCount;
+	}
 	bool PostSolveImmediate(b2Contact*, const b2ContactImpulse*, uint32) override { return recordPostSolve; }
 	void PostSolve(b2Contact* c, const b2ContactImpulse* impulse) override
 	{
@@ -96,6 +105,9 @@ public:
 	void EndContact(b2Contact* c) override { ends.push_back(ContactKey(c)); }
 
 	std::vector<uint64_t> begins, ends;
+	int preSolveModulus = 0;
+	uint64_t preSolveDigest = 0;
+	int64_t preSolveCount = 0;
 	bool recordPostSolve = false;
 	uint64_t postSolveDigest = 0;
 	int64_t postSolveCount = 0;
@@ -742,6 +754,12 @@ void b2ref_set_modulo_filter(b2refWorld* w, int32_t modulus)
 	w->world->SetContactFilter(modulus > 0 ? new ModuloFilter(modulus) : nullptr);
 }
 
+void b2ref_set_pre_solve_rule(b2refWorld* w, int32_t modulus) { w->listener.preSolveModulus = modulus; }
+void b2ref_pre_solve_digest(b2refWorld* w, uint64_t* digest, int64_t* count)
+{
+	*digest = w->listener.preSolveDigest;
+	*count = w->listener.preSolveCount;
+}
 void b2ref_record_post_solve(b2refWorld* w, int32_t on) { w->listener.recordPostSolve = on != 0; }
 void b2ref_post_solve_digest(b2refWorld* w, uint64_t* digest, int64_t* count)
 {

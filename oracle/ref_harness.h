@@ -109,6 +109,9 @@ void b2ref_profile(b2refWorld* w, float* out13);
 void b2ref_set_transform(b2refWorld* w, int32_t body, float x, float y, float angle);
 void b2ref_set_type(b2refWorld* w, int32_t body, int32_t type); /* b2Body::SetType */
 /* PostSolve recording: running digest over (contact key, impulse count, impulses) of every PostSolve call */
+/* PreSolve test rule: the listener disables every contact whose key is a multiple of `modulus` (0: off) */
+void b2ref_set_pre_solve_rule(b2refWorld* w, int32_t modulus);
+void b2ref_pre_solve_digest(b2refWorld* w, uint64_t* digest, int64_t* count);
 void b2ref_record_post_solve(b2refWorld* w, int32_t on);
 void b2ref_post_solve_digest(b2refWorld* w, uint64_t* digest, int64_t* count);
 /* installs a b2ContactFilter subclass: pairs whose fixture indices sum to a multiple of `modulus` never collide */

@@ -265,6 +265,31 @@ def test_host_api_post_solve_reports(gpu):
 
 
 @pytest.mark.gpu
+def test_host_api_pre_solve_can_disable_contacts(gpu):
+    """b2CudaStepOptions::reportPreSolve: PreSolve runs between the narrow phase and the solver of the device step
+    with the previous manifold, and SetEnabled(false) there keeps the contact out of the step's solve.  Both sides
+    disable every contact whose key is a multiple of 3: same calls (digest), same bodies, after every step."""
+    scene = scenes.pile(8, 6)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    r.set_pre_solve_rule(3)
+    h.set_pre_solve_rule(3)
+    for s in range(150):
+        h.step()
+        assert r.step_ordered(h.solver_order()) == 0
+        assert h.pre_solve_digest() == r.pre_solve_digest(), "step %d" % s
+        try:
+            parity.compare_bodies(h.bodies(), r.bodies())
+        except AssertionError as e:
+            raise AssertionError("step %d: %s" % (s, e))
+    assert h.pre_solve_digest()[1] > 1000
+    # bodies sink into each other where their contact is switched off: the rule really took effect
+    keys, touching, _ = h.contacts()
+    assert ((keys % np.uint64(3) == 0) & (touching != 0)).any()
+
+
+@pytest.mark.gpu
 def test_host_api_lazy_download(gpu):
     """downloadBodies=false: the mirror is refreshed on first access only; results are the same."""
     a = b2host.HostWorld(scenes.pile(8, 6), download_bodies=True)
