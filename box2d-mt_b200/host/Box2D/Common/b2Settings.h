@@ -22,42 +22,27 @@ typedef std::uint64_t uint64;
 typedef float float32;
 typedef double float64;
 
-#define b2_maxFloat FLT_MAX
-#define b2_epsilon FLT_EPSILON
-#define b2_pi 3.14159265359f
+// Tuning constants: typed constants instead of the reference's macros (same names, same values, usable in the same
+// expressions and as array bounds).
+constexpr float32 b2_maxFloat = FLT_MAX, b2_epsilon = FLT_EPSILON, b2_pi = 3.14159265359f;
 
-// collision
-#define b2_maxManifoldPoints 2
-#define b2_maxPolygonVertices 8
-#define b2_aabbExtension 0.1f
-#define b2_aabbMultiplier 2.0f
-#define b2_linearSlop 0.005f
-#define b2_angularSlop (2.0f / 180.0f * b2_pi)
-#define b2_polygonRadius (2.0f * b2_linearSlop)
-#define b2_maxSubSteps 8
+constexpr int32 b2_maxManifoldPoints = 2, b2_maxPolygonVertices = 8, b2_maxSubSteps = 8, b2_maxTOIContacts = 32;
+constexpr float32 b2_aabbExtension = 0.1f, b2_aabbMultiplier = 2.0f;                      // fat AABB rule
+constexpr float32 b2_linearSlop = 0.005f, b2_angularSlop = 2.0f / 180.0f * b2_pi;
+constexpr float32 b2_polygonRadius = 2.0f * b2_linearSlop;
 
-// dynamics
-#define b2_maxTOIContacts 32
-#define b2_velocityThreshold 1.0f
-#define b2_maxLinearCorrection 0.2f
-#define b2_maxAngularCorrection (8.0f / 180.0f * b2_pi)
-#define b2_maxTranslation 2.0f
-#define b2_maxTranslationSquared (b2_maxTranslation * b2_maxTranslation)
-#define b2_maxRotation (0.5f * b2_pi)
-#define b2_maxRotationSquared (b2_maxRotation * b2_maxRotation)
-#define b2_baumgarte 0.2f
-#define b2_toiBaugarte 0.75f
+constexpr float32 b2_velocityThreshold = 1.0f;                                            // restitution cut-off
+constexpr float32 b2_maxLinearCorrection = 0.2f, b2_maxAngularCorrection = 8.0f / 180.0f * b2_pi;
+constexpr float32 b2_maxTranslation = 2.0f, b2_maxTranslationSquared = b2_maxTranslation * b2_maxTranslation;
+constexpr float32 b2_maxRotation = 0.5f * b2_pi, b2_maxRotationSquared = b2_maxRotation * b2_maxRotation;
+constexpr float32 b2_baumgarte = 0.2f, b2_toiBaugarte = 0.75f;
 
-// sleep
-#define b2_timeToSleep 0.5f
-#define b2_linearSleepTolerance 0.01f
-#define b2_angularSleepTolerance (2.0f / 180.0f * b2_pi)
+constexpr float32 b2_timeToSleep = 0.5f;                                                  // island sleep rule
+constexpr float32 b2_linearSleepTolerance = 0.01f, b2_angularSleepTolerance = 2.0f / 180.0f * b2_pi;
 
-// multithreading limits kept for source compatibility with user tasks (reference :162-174)
-#define b2_cacheLineSize 64
-#define b2_maxThreads 8
-#define b2_maxRangeSubTasks b2_maxThreads
-#define b2_maxWorldStepTaskGroups 1
+// limits of the task layer, kept so that user task code compiles unchanged (reference :162-174)
+constexpr int32 b2_cacheLineSize = 64, b2_maxThreads = 8, b2_maxRangeSubTasks = b2_maxThreads;
+constexpr int32 b2_maxWorldStepTaskGroups = 1;
 
 struct b2Version
 {

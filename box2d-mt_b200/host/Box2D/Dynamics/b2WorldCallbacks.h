@@ -19,52 +19,47 @@ struct b2Manifold;
 class b2Contact;
 class b2Fixture;
 
-class b2DestructionListener
-{
-public:
-	virtual ~b2DestructionListener() {}
-	virtual void SayGoodbye(b2Fixture* fixture) = 0;
-};
-
-class b2ContactFilter
-{
-public:
-	virtual ~b2ContactFilter() {}
-	/// default rule: group index wins when equal and non-zero, else category/mask test (reference
-	/// b2WorldCallbacks.cpp:24-38).  The device evaluates exactly this rule.
-	virtual bool ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB, uint32 threadId);
-};
-
+/// What PostSolve reports: the impulses the solver accumulated on each manifold point during the step.
 struct b2ContactImpulse
 {
-	float32 normalImpulses[b2_maxManifoldPoints];
-	float32 tangentImpulses[b2_maxManifoldPoints];
+	float32 normalImpulses[b2_maxManifoldPoints], tangentImpulses[b2_maxManifoldPoints];
 	int32 count;
 };
 
+/// Contact events.  The four *Immediate methods are pure: each decides, per contact, whether the matching deferred
+/// method is called as well (return true).  On the GPU path all of them run on the stepping thread, threadId 0.
 class b2ContactListener
 {
 public:
-	virtual ~b2ContactListener() {}
-
-	virtual void BeginContact(b2Contact* contact) { B2_NOT_USED(contact); }
-	virtual void EndContact(b2Contact* contact) { B2_NOT_USED(contact); }
-	virtual void PreSolve(b2Contact* contact, const b2Manifold* oldManifold)
-	{
-		B2_NOT_USED(contact);
-		B2_NOT_USED(oldManifold);
-	}
-	virtual void PostSolve(b2Contact* contact, const b2ContactImpulse* impulse)
-	{
-		B2_NOT_USED(contact);
-		B2_NOT_USED(impulse);
-	}
-
-	/// return true to also receive the deferred callback
 	virtual bool BeginContactImmediate(b2Contact* contact, uint32 threadId) = 0;
 	virtual bool EndContactImmediate(b2Contact* contact, uint32 threadId) = 0;
 	virtual bool PreSolveImmediate(b2Contact* contact, const b2Manifold* oldManifold, uint32 threadId) = 0;
 	virtual bool PostSolveImmediate(b2Contact* contact, const b2ContactImpulse* impulse, uint32 threadId) = 0;
+
+	virtual void BeginContact(b2Contact*) {}
+	virtual void EndContact(b2Contact*) {}
+	virtual void PreSolve(b2Contact*, const b2Manifold* /*oldManifold*/) {}
+	virtual void PostSolve(b2Contact*, const b2ContactImpulse*) {}
+
+	virtual ~b2ContactListener() {}
+};
+
+/// Decides whether two fixtures whose fat boxes begin to overlap get a contact.  The base class is the default rule
+/// (group index wins when equal and non-zero, else the category / mask test; reference b2WorldCallbacks.cpp:24-38),
+/// which the device evaluates itself; a subclass is called on the stepping thread.
+class b2ContactFilter
+{
+public:
+	virtual bool ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB, uint32 threadId);
+	virtual ~b2ContactFilter() {}
+};
+
+/// Told about fixtures that disappear implicitly (their body is destroyed).
+class b2DestructionListener
+{
+public:
+	virtual void SayGoodbye(b2Fixture* fixture) = 0;
+	virtual ~b2DestructionListener() {}
 };
 
 #endif

@@ -13,49 +13,34 @@ class b2World;
 class b2TaskExecutor
 {
 public:
-	virtual ~b2TaskExecutor() {}
-
-	/// number of threads that can execute tasks; between 1 and b2_maxThreads
-	virtual uint32 GetThreadCount() const = 0;
-
-	virtual void SubmitTask(b2TaskGroup* taskGroup, b2Task* task)
+	/// THE ADDITION: run one whole world step.  An executor that cannot returns false (the default).
+	virtual bool StepWorld(b2World& /*world*/, float32 /*timeStep*/, int32 /*velocityIterations*/, int32 /*positionIterations*/)
 	{
-		B2_NOT_USED(taskGroup);
-		B2_NOT_USED(task);
-	}
-
-	virtual void Wait(b2TaskGroup* taskGroup, const b2ThreadContext& ctx)
-	{
-		B2_NOT_USED(taskGroup);
-		B2_NOT_USED(ctx);
-	}
-
-	virtual void SubmitTasks(b2TaskGroup* taskGroup, b2Task** tasks, uint32 count)
-	{
-		for (uint32 i = 0; i < count; ++i) SubmitTask(taskGroup, tasks[i]);
-	}
-
-	virtual b2TaskGroup* AcquireTaskGroup() { return nullptr; }
-
-	virtual void ReleaseTaskGroup(b2TaskGroup* taskGroup) { B2_NOT_USED(taskGroup); }
-
-	virtual void PartitionRange(b2Task::Type type, uint32 begin, uint32 end, b2PartitionedRange& output)
-	{
-		B2_NOT_USED(type);
-		output.ranges[0].begin = begin;
-		output.ranges[0].end = end;
-		output.count = 1;
-	}
-
-	/// Run one whole world step.  Return false if this executor cannot.
-	virtual bool StepWorld(b2World& world, float32 timeStep, int32 velocityIterations, int32 positionIterations)
-	{
-		B2_NOT_USED(world);
-		B2_NOT_USED(timeStep);
-		B2_NOT_USED(velocityIterations);
-		B2_NOT_USED(positionIterations);
 		return false;
 	}
+
+	/// how many threads execute tasks, 1 .. b2_maxThreads
+	virtual uint32 GetThreadCount() const = 0;
+
+	// ---- task submission, as in the reference; the defaults describe a single-threaded executor ----
+	virtual void SubmitTask(b2TaskGroup* /*taskGroup*/, b2Task* /*task*/) {}
+	virtual void SubmitTasks(b2TaskGroup* taskGroup, b2Task** tasks, uint32 count)
+	{
+		for (uint32 k = 0; k != count; ++k) SubmitTask(taskGroup, tasks[k]);
+	}
+	virtual void Wait(b2TaskGroup* /*taskGroup*/, const b2ThreadContext& /*ctx*/) {}
+	virtual b2TaskGroup* AcquireTaskGroup() { return nullptr; }
+	virtual void ReleaseTaskGroup(b2TaskGroup* /*taskGroup*/) {}
+
+	/// split [begin, end) into sub-ranges for range tasks; the default keeps it whole
+	virtual void PartitionRange(b2Task::Type /*type*/, uint32 begin, uint32 end, b2PartitionedRange& output)
+	{
+		output.count = 1;
+		output.ranges[0].begin = begin;
+		output.ranges[0].end = end;
+	}
+
+	virtual ~b2TaskExecutor() {}
 };
 
 #endif
