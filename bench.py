@@ -170,6 +170,25 @@ def run_reference_arm(args, rank, world_size):
     }))
 
 
+def bind_to_gpu_cpus(local_rank):
+    """Run this rank on the CPUs next to its GPU (NVML's affinity mask), so that the page-locked body mirror is
+    allocated and read on the GPU's own NUMA node.  Best effort: returns a description or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "cpus %d-%d (%d)" % (allowed[0], allowed[-1], len(allowed))
+    except Exception:
+        pass
+    return None
+
+
 def run_product_arm(args, rank, local_rank, world_size):
     import b2cuda
     import b2host
@@ -179,6 +198,7 @@ def run_product_arm(args, rank, local_rank, world_size):
     if b2cuda.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
 
+    numa = bind_to_gpu_cpus(local_rank)
     columns = max(16, args.bodies // ROWS)
     dist = None
     if world_size > 1:
@@ -347,7 +367,7 @@ def run_product_arm(args, rank, local_rank, world_size):
                                        "+ 48 B per body (SURVEY.md 8d)"},
         "cpu_baseline": cpu,
         "clocks": clocks,
-        "build_s": build_s, "checksum": checksum, "last_step": {k: int(last[k]) for k in
+        "build_s": build_s, "cpu_affinity": numa, "checksum": checksum, "last_step": {k: int(last[k]) for k in
                                                                ("contactCount", "constraintCount", "colourCount",
                                                                 "overflowCount", "moveCount", "kernelLaunches")},
     }))
