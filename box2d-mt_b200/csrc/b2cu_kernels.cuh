@@ -1868,6 +1868,7 @@ __device__ __forceinline__ float4 ComputeAABB(const b2cuShape* __restrict__ s, c
 		Vec2 v2 = Mul(xf, ShapeV(s, 1));
 		Vec2 lower = V(Min(v1.x, v2.x), Min(v1.y, v2.y));
 		Vec2 upper = V(Max(v1.x, v2.x), Max(v1.y, v2.y));
+		if (s->flags & B2CU_EDGE_CHAIN_CHILD) r = 0.0f; // b2ChainShape::ComputeAABB adds no margin
 		return make_float4(lower.x - r, lower.y - r, upper.x + r, upper.y + r);
 	}
 	Vec2 lower = Mul(xf, ShapeV(s, 0));

@@ -5,6 +5,7 @@
 #include "Box2D/Common/b2Settings.h"
 #include "Box2D/Common/b2Math.h"
 #include "Box2D/Collision/b2Collision.h"
+#include "Box2D/Collision/Shapes/b2ChainShape.h"
 #include "Box2D/Collision/Shapes/b2CircleShape.h"
 #include "Box2D/Collision/Shapes/b2EdgeShape.h"
 #include "Box2D/Collision/Shapes/b2PolygonShape.h"

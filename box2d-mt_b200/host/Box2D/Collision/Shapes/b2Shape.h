@@ -1,6 +1,6 @@
 // Shape base class (reference: Box2D/Collision/Shapes/b2Shape.h:26-104).  Shapes are host-side value objects:
 // user code builds them, b2Body::CreateFixture clones them, and their geometry is uploaded to the device
-// shape table.  Chain shapes are outside the GPU path.
+// shape table (a chain as one edge record per segment).
 #ifndef B2_SHAPE_H
 #define B2_SHAPE_H
 

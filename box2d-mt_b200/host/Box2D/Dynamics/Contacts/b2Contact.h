@@ -37,10 +37,10 @@ public:
 	const b2Contact* GetNext() const { return m_next; }
 	b2Fixture* GetFixtureA() { return m_fixtureA; }
 	const b2Fixture* GetFixtureA() const { return m_fixtureA; }
-	int32 GetChildIndexA() const { return 0; }
+	int32 GetChildIndexA() const { return m_indexA; }
 	b2Fixture* GetFixtureB() { return m_fixtureB; }
 	const b2Fixture* GetFixtureB() const { return m_fixtureB; }
-	int32 GetChildIndexB() const { return 0; }
+	int32 GetChildIndexB() const { return m_indexB; }
 	float32 GetFriction() const { return m_friction; }
 	float32 GetRestitution() const { return m_restitution; }
 	float32 GetTangentSpeed() const { return m_tangentSpeed; }
@@ -65,6 +65,7 @@ private:
 	uint64 m_key;
 	b2Fixture* m_fixtureA;
 	b2Fixture* m_fixtureB;
+	int32 m_indexA, m_indexB; // child (chain segment) of each fixture
 	b2Manifold m_manifold;
 	float32 m_friction, m_restitution, m_tangentSpeed;
 	b2Contact* m_next;

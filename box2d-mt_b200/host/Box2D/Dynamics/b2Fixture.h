@@ -65,6 +65,7 @@ public:
 	bool IsThickShape() const { return m_thickShape; }
 	/// dense proxy id on the device (-1 while the body is inactive)
 	int32 GetProxyIndex() const { return m_proxyIndex; }
+	int32 GetProxyCount() const { return m_proxyCount; }
 
 private:
 	friend class b2Body;
@@ -79,7 +80,8 @@ private:
 	b2Filter m_filter;
 	bool m_isSensor, m_thickShape;
 	void* m_userData;
-	int32 m_proxyIndex;
+	int32 m_proxyIndex; // first proxy of the fixture; a chain has one proxy per segment, consecutive
+	int32 m_proxyCount;
 };
 
 #endif

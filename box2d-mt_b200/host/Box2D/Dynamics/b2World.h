@@ -148,7 +148,7 @@ private:
 	std::vector<b2cuShape> m_shapes;
 	std::unordered_map<std::string, int32> m_shapeLookup;
 
-	int32 InternShape(const b2Shape* shape);
+	int32 InternShape(const b2Shape* shape, bool chainChild = false);
 	void MarkBodyDirty(int32 index);
 	void MarkBodyForced(int32 index); // dirty + remembered: the step clears forces on the device, the host follows
 	void MarkProxyDirty(int32 index);

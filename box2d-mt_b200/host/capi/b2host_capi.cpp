@@ -213,9 +213,19 @@ B2H_API int b2h_build(void* p, int32 bodyCount, const BodyDefRec* bodies, int32 
 			b2CircleShape circle;
 			b2EdgeShape edge;
 			b2PolygonShape poly;
+			b2ChainShape chain;
 			const b2Shape* shape = nullptr;
 			switch (sd.kind)
 			{
+			case 5: // chain of v[0..count): closed loop if flags & 1
+			{
+				b2Vec2 vs[b2_maxPolygonVertices];
+				for (int32 k = 0; k < sd.count; ++k) vs[k].Set(sd.v[k][0], sd.v[k][1]);
+				if (sd.flags & 1) chain.CreateLoop(vs, sd.count);
+				else chain.CreateChain(vs, sd.count);
+				shape = &chain;
+				break;
+			}
 			case 0:
 				circle.m_radius = sd.radius;
 				circle.m_p.Set(sd.v[0][0], sd.v[0][1]);

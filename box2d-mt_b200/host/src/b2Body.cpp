@@ -2,6 +2,8 @@
 // Semantics follow Box2D/Dynamics/b2Body.cpp and b2Fixture.cpp of the reference; storage does not (state lives
 // in b2World::m_states / m_proxies, the records that are mirrored to the device).
 #include "Box2D/Dynamics/b2Body.h"
+#include "Box2D/Collision/Shapes/b2ChainShape.h"
+#include "Box2D/Collision/Shapes/b2EdgeShape.h"
 #include "Box2D/Dynamics/b2World.h"
 
 namespace
@@ -270,8 +272,11 @@ void b2Body::SetType(b2BodyType type)
 	for (b2Fixture* f = m_fixtureList; f; f = f->m_next)
 	{
 		if (f->m_proxyIndex < 0) continue;
-		m_world->m_proxies[f->m_proxyIndex].flags |= B2CU_PROXY_MOVED;
-		m_world->MarkProxyDirty(f->m_proxyIndex);
+		for (int32 child = 0; child < f->m_proxyCount; ++child)
+		{
+			m_world->m_proxies[f->m_proxyIndex + child].flags |= B2CU_PROXY_MOVED;
+			m_world->MarkProxyDirty(f->m_proxyIndex + child);
+		}
 	}
 }
 
@@ -304,10 +309,12 @@ void b2Body::SynchronizeProxies(const b2Transform& xf1, const b2Transform& xf2)
 	for (b2Fixture* f = m_fixtureList; f; f = f->m_next)
 	{
 		if (f->m_proxyIndex < 0) continue;
-		b2cuProxy& p = m_world->m_proxies[f->m_proxyIndex];
+		for (int32 child = 0; child < f->m_proxyCount; ++child)
+		{
+		b2cuProxy& p = m_world->m_proxies[f->m_proxyIndex + child];
 		b2AABB a1, a2, ab;
-		f->m_shape->ComputeAABB(&a1, xf1, 0);
-		f->m_shape->ComputeAABB(&a2, xf2, 0);
+		f->m_shape->ComputeAABB(&a1, xf1, child);
+		f->m_shape->ComputeAABB(&a2, xf2, child);
 		ab.Combine(a1, a2);
 		p.aabb[0] = ab.lowerBound.x;
 		p.aabb[1] = ab.lowerBound.y;
@@ -333,7 +340,8 @@ void b2Body::SynchronizeProxies(const b2Transform& xf1, const b2Transform& xf2)
 			p.fat[3] = b.upperBound.y;
 			p.flags |= B2CU_PROXY_MOVED; // buffered move: its pairs are found at the end of the next step
 		}
-		m_world->MarkProxyDirty(f->m_proxyIndex);
+		m_world->MarkProxyDirty(f->m_proxyIndex + child);
+		}
 	}
 }
 
@@ -436,7 +444,6 @@ b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def)
 {
 	if (m_world->IsLocked()) return nullptr;
 	b2Assert(def->shape != nullptr);
-	b2Assert(def->shape->GetType() != b2Shape::e_chain); // chains are outside the GPU path
 	m_world->RefreshBodies();
 
 	b2Fixture* f = new b2Fixture;
@@ -450,33 +457,49 @@ b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def)
 	f->m_thickShape = def->thickShape;
 	f->m_userData = def->userData;
 
+	// one proxy per child (b2Fixture::CreateProxies, reference b2Fixture.cpp:122-137): a chain has one per segment, and
+	// its device geometry is that segment as an edge with ghost vertices
 	b2BodyView s = B2_STATE();
-	b2AABB aabb;
-	f->m_shape->ComputeAABB(&aabb, reinterpret_cast<const b2Transform&>(s.px), 0);
-
-	b2cuProxy p;
-	p.aabb[0] = aabb.lowerBound.x;
-	p.aabb[1] = aabb.lowerBound.y;
-	p.aabb[2] = aabb.upperBound.x;
-	p.aabb[3] = aabb.upperBound.y;
-	p.fat[0] = aabb.lowerBound.x - b2_aabbExtension;
-	p.fat[1] = aabb.lowerBound.y - b2_aabbExtension;
-	p.fat[2] = aabb.upperBound.x + b2_aabbExtension;
-	p.fat[3] = aabb.upperBound.y + b2_aabbExtension;
-	p.body = m_index;
-	p.shape = m_world->InternShape(f->m_shape);
-	p.friction = f->m_friction;
-	p.restitution = f->m_restitution;
-	p.categoryBits = f->m_filter.categoryBits;
-	p.maskBits = f->m_filter.maskBits;
-	p.groupIndex = f->m_filter.groupIndex;
-	p.flags = (uint16)((f->m_isSensor ? B2CU_PROXY_SENSOR : 0) | (f->m_thickShape ? B2CU_PROXY_THICK : 0) |
-	                   B2CU_PROXY_MOVED | B2CU_PROXY_NEW);
-	p.fixture = (int32)m_world->m_proxies.size();
-	p.child = 0;
-	f->m_proxyIndex = p.fixture;
-	m_world->m_proxies.push_back(p);
-	m_world->m_fixtures.push_back(f);
+	const b2Transform& xf = reinterpret_cast<const b2Transform&>(s.px);
+	const bool chain = f->m_shape->GetType() == b2Shape::e_chain;
+	f->m_proxyIndex = (int32)m_world->m_proxies.size();
+	f->m_proxyCount = f->m_shape->GetChildCount();
+	for (int32 child = 0; child < f->m_proxyCount; ++child)
+	{
+		b2AABB aabb;
+		f->m_shape->ComputeAABB(&aabb, xf, child);
+		b2cuProxy p;
+		p.aabb[0] = aabb.lowerBound.x;
+		p.aabb[1] = aabb.lowerBound.y;
+		p.aabb[2] = aabb.upperBound.x;
+		p.aabb[3] = aabb.upperBound.y;
+		p.fat[0] = aabb.lowerBound.x - b2_aabbExtension;
+		p.fat[1] = aabb.lowerBound.y - b2_aabbExtension;
+		p.fat[2] = aabb.upperBound.x + b2_aabbExtension;
+		p.fat[3] = aabb.upperBound.y + b2_aabbExtension;
+		p.body = m_index;
+		if (chain)
+		{
+			b2EdgeShape edge;
+			static_cast<const b2ChainShape*>(f->m_shape)->GetChildEdge(&edge, child);
+			p.shape = m_world->InternShape(&edge, true);
+		}
+		else
+		{
+			p.shape = m_world->InternShape(f->m_shape);
+		}
+		p.friction = f->m_friction;
+		p.restitution = f->m_restitution;
+		p.categoryBits = f->m_filter.categoryBits;
+		p.maskBits = f->m_filter.maskBits;
+		p.groupIndex = f->m_filter.groupIndex;
+		p.flags = (uint16)((f->m_isSensor ? B2CU_PROXY_SENSOR : 0) | (f->m_thickShape ? B2CU_PROXY_THICK : 0) |
+		                   B2CU_PROXY_MOVED | B2CU_PROXY_NEW);
+		p.fixture = f->m_proxyIndex;
+		p.child = child;
+		m_world->m_proxies.push_back(p);
+		m_world->m_fixtures.push_back(f);
+	}
 
 	f->m_next = m_fixtureList;
 	m_fixtureList = f;
@@ -520,13 +543,16 @@ void b2Fixture::Refilter()
 	if (m_body == nullptr || m_proxyIndex < 0) return;
 	b2World* w = m_body->m_world;
 	w->RefreshProxies();
-	b2cuProxy& p = w->m_proxies[m_proxyIndex];
-	p.categoryBits = m_filter.categoryBits;
-	p.maskBits = m_filter.maskBits;
-	p.groupIndex = m_filter.groupIndex;
-	// e_filterFlag on the fixture's contacts + TouchProxy (reference b2Fixture.cpp:187-220)
-	p.flags |= B2CU_PROXY_MOVED | B2CU_PROXY_REFILTER;
-	w->MarkProxyDirty(m_proxyIndex);
+	for (int32 child = 0; child < m_proxyCount; ++child)
+	{
+		b2cuProxy& p = w->m_proxies[m_proxyIndex + child];
+		p.categoryBits = m_filter.categoryBits;
+		p.maskBits = m_filter.maskBits;
+		p.groupIndex = m_filter.groupIndex;
+		// e_filterFlag on the fixture's contacts + TouchProxy (reference b2Fixture.cpp:187-220)
+		p.flags |= B2CU_PROXY_MOVED | B2CU_PROXY_REFILTER;
+		w->MarkProxyDirty(m_proxyIndex + child);
+	}
 }
 
 void b2Fixture::SetFriction(float32 friction)
@@ -535,8 +561,11 @@ void b2Fixture::SetFriction(float32 friction)
 	if (m_proxyIndex < 0) return;
 	b2World* w = m_body->m_world;
 	w->RefreshProxies();
-	w->m_proxies[m_proxyIndex].friction = friction;
-	w->MarkProxyDirty(m_proxyIndex);
+	for (int32 child = 0; child < m_proxyCount; ++child)
+	{
+		w->m_proxies[m_proxyIndex + child].friction = friction;
+		w->MarkProxyDirty(m_proxyIndex + child);
+	}
 }
 
 void b2Fixture::SetRestitution(float32 restitution)
@@ -545,8 +574,11 @@ void b2Fixture::SetRestitution(float32 restitution)
 	if (m_proxyIndex < 0) return;
 	b2World* w = m_body->m_world;
 	w->RefreshProxies();
-	w->m_proxies[m_proxyIndex].restitution = restitution;
-	w->MarkProxyDirty(m_proxyIndex);
+	for (int32 child = 0; child < m_proxyCount; ++child)
+	{
+		w->m_proxies[m_proxyIndex + child].restitution = restitution;
+		w->MarkProxyDirty(m_proxyIndex + child);
+	}
 }
 
 void b2Fixture::SetThickShape(bool flag)
@@ -555,18 +587,21 @@ void b2Fixture::SetThickShape(bool flag)
 	if (m_proxyIndex < 0) return;
 	b2World* w = m_body->m_world;
 	w->RefreshProxies();
-	b2cuProxy& p = w->m_proxies[m_proxyIndex];
-	if (flag) p.flags |= B2CU_PROXY_THICK;
-	else p.flags &= ~(uint16)B2CU_PROXY_THICK;
-	w->MarkProxyDirty(m_proxyIndex);
+	for (int32 child = 0; child < m_proxyCount; ++child)
+	{
+		b2cuProxy& p = w->m_proxies[m_proxyIndex + child];
+		if (flag) p.flags |= B2CU_PROXY_THICK;
+		else p.flags &= ~(uint16)B2CU_PROXY_THICK;
+		w->MarkProxyDirty(m_proxyIndex + child);
+	}
 }
 
 bool b2Fixture::TestPoint(const b2Vec2& p) const { return m_shape->TestPoint(m_body->GetTransform(), p); }
 
 const b2AABB& b2Fixture::GetAABB(int32 childIndex) const
 {
-	B2_NOT_USED(childIndex);
+	b2Assert(0 <= childIndex && childIndex < m_proxyCount);
 	b2World* w = m_body->m_world;
 	w->RefreshProxies();
-	return reinterpret_cast<const b2AABB&>(w->m_proxies[m_proxyIndex].aabb[0]);
+	return reinterpret_cast<const b2AABB&>(w->m_proxies[m_proxyIndex + childIndex].aabb[0]);
 }

@@ -5,6 +5,7 @@
 //   edge     Box2D/Collision/Shapes/b2EdgeShape.cpp:116-140
 //   polygon  Box2D/Collision/Shapes/b2PolygonShape.cpp:28-440
 #include "Box2D/Collision/Shapes/b2CircleShape.h"
+#include "Box2D/Collision/Shapes/b2ChainShape.h"
 #include "Box2D/Collision/Shapes/b2EdgeShape.h"
 #include "Box2D/Collision/Shapes/b2PolygonShape.h"
 
@@ -247,3 +248,58 @@ void b2PolygonShape::ComputeMass(b2MassData* massData, float32 density) const
 	// shift from the fan origin s to the centre of mass, then to the body origin
 	massData->I += massData->mass * (b2Dot(massData->center, massData->center) - b2Dot(center, center));
 }
+
+// ---- b2ChainShape (reference b2ChainShape.cpp) ------------------------------------------------------------
+
+void b2ChainShape::CreateLoop(const b2Vec2* vertices, int32 count)
+{
+	b2Assert(m_points.empty() && count >= 3);
+	m_points.assign(vertices, vertices + count);
+	m_points.push_back(vertices[0]); // closing vertex
+	// the loop's own neighbours are the ghost vertices of its first and last segment
+	m_prevVertex = m_points[m_points.size() - 2];
+	m_nextVertex = m_points[1];
+	m_hasPrevVertex = m_hasNextVertex = true;
+}
+
+void b2ChainShape::CreateChain(const b2Vec2* vertices, int32 count)
+{
+	b2Assert(m_points.empty() && count >= 2);
+	m_points.assign(vertices, vertices + count);
+	m_hasPrevVertex = m_hasNextVertex = false;
+	m_prevVertex.SetZero();
+	m_nextVertex.SetZero();
+}
+
+void b2ChainShape::GetChildEdge(b2EdgeShape* edge, int32 index) const
+{
+	const int32 last = (int32)m_points.size() - 2; // index of the last segment
+	b2Assert(0 <= index && index <= last);
+	edge->m_type = b2Shape::e_edge;
+	edge->m_radius = m_radius;
+	edge->m_vertex1 = m_points[index];
+	edge->m_vertex2 = m_points[index + 1];
+	edge->m_hasVertex0 = index > 0 ? true : m_hasPrevVertex;
+	edge->m_vertex0 = index > 0 ? m_points[index - 1] : m_prevVertex;
+	edge->m_hasVertex3 = index < last ? true : m_hasNextVertex;
+	edge->m_vertex3 = index < last ? m_points[index + 2] : m_nextVertex;
+}
+
+void b2ChainShape::ComputeAABB(b2AABB* aabb, const b2Transform& xf, int32 childIndex) const
+{
+	b2Assert(childIndex + 1 < (int32)m_points.size());
+	int32 i2 = childIndex + 1;
+	if (i2 == (int32)m_points.size()) i2 = 0;
+	b2Vec2 v1 = b2Mul(xf, m_points[childIndex]);
+	b2Vec2 v2 = b2Mul(xf, m_points[i2]);
+	aabb->lowerBound = b2Min(v1, v2);
+	aabb->upperBound = b2Max(v1, v2);
+}
+
+void b2ChainShape::ComputeMass(b2MassData* massData, float32) const
+{
+	massData->mass = 0.0f;
+	massData->center.SetZero();
+	massData->I = 0.0f;
+}
+

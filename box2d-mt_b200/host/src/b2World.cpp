@@ -102,7 +102,9 @@ b2World::b2World(const b2Vec2& gravity)
 b2World::~b2World()
 {
 	if (m_owner) m_owner->DetachWorld(this);
-	for (size_t i = 0; i < m_fixtures.size(); ++i) delete m_fixtures[i];
+	// m_fixtures has one entry per PROXY: a chain fixture appears once per segment
+	for (size_t i = 0; i < m_fixtures.size(); ++i)
+		if (m_proxies[i].child == 0) delete m_fixtures[i];
 	for (size_t i = 0; i < m_bodies.size(); ++i) delete m_bodies[i];
 }
 
@@ -182,7 +184,7 @@ b2Body* b2World::CreateBody(const b2BodyDef* def)
 	return b;
 }
 
-int32 b2World::InternShape(const b2Shape* shape)
+int32 b2World::InternShape(const b2Shape* shape, bool chainChild)
 {
 	b2cuShape r;
 	memset(&r, 0, sizeof(r));
@@ -202,12 +204,13 @@ int32 b2World::InternShape(const b2Shape* shape)
 	{
 		const b2EdgeShape* e = static_cast<const b2EdgeShape*>(shape);
 		r.type = B2CU_SHAPE_EDGE;
+		if (chainChild) r.flags |= B2CU_EDGE_CHAIN_CHILD;
 		r.count = 2;
 		r.v[0][0] = e->m_vertex1.x; r.v[0][1] = e->m_vertex1.y;
 		r.v[1][0] = e->m_vertex2.x; r.v[1][1] = e->m_vertex2.y;
 		r.v[2][0] = e->m_vertex0.x; r.v[2][1] = e->m_vertex0.y;
 		r.v[3][0] = e->m_vertex3.x; r.v[3][1] = e->m_vertex3.y;
-		r.flags = (e->m_hasVertex0 ? B2CU_EDGE_HAS_VERTEX0 : 0) | (e->m_hasVertex3 ? B2CU_EDGE_HAS_VERTEX3 : 0);
+		r.flags |= (e->m_hasVertex0 ? B2CU_EDGE_HAS_VERTEX0 : 0) | (e->m_hasVertex3 ? B2CU_EDGE_HAS_VERTEX3 : 0);
 		break;
 	}
 	default:
@@ -326,6 +329,8 @@ void b2World::MakeContact(b2Contact* c, const b2cuContact& rec)
 	c->m_key = ((uint64)lo << 32) | hi;
 	c->m_fixtureA = m_fixtures[rec.proxyA];
 	c->m_fixtureB = m_fixtures[rec.proxyB];
+	c->m_indexA = rec.proxyA - c->m_fixtureA->m_proxyIndex;
+	c->m_indexB = rec.proxyB - c->m_fixtureB->m_proxyIndex;
 	const b2cuManifold& m = rec.manifold;
 	c->m_manifold.localNormal.Set(m.localNormal[0], m.localNormal[1]);
 	c->m_manifold.localPoint.Set(m.localPoint[0], m.localPoint[1]);
@@ -444,7 +449,7 @@ void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vecto
 		{
 			m_proxies[np] = m_proxies[i];
 			m_fixtures[np] = m_fixtures[i];
-			m_fixtures[np]->m_proxyIndex = np;
+			if (m_proxies[np].child == 0) m_fixtures[np]->m_proxyIndex = np;
 			++np;
 		}
 	}
@@ -477,7 +482,7 @@ void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vecto
 	for (int32 i = 0; i < np; ++i)
 	{
 		m_proxies[i].body = bodyMap[m_proxies[i].body];
-		m_proxies[i].fixture = i;
+		m_proxies[i].fixture = m_fixtures[i]->m_proxyIndex;
 	}
 	for (size_t i = 0; i < kept.size(); ++i)
 	{
@@ -538,7 +543,8 @@ void b2World::DestroyFixtureInternal(b2Body* body, b2Fixture* fixture)
 	if (*link == nullptr) return;
 	*link = fixture->m_next;
 	--body->m_fixtureCount;
-	std::vector<int32> proxies(1, fixture->m_proxyIndex), bodies;
+	std::vector<int32> proxies, bodies;
+	for (int32 k = 0; k < fixture->m_proxyCount; ++k) proxies.push_back(fixture->m_proxyIndex + k);
 	RemoveProxies(proxies, bodies);
 	delete fixture;
 	body->ResetMassData();
@@ -552,7 +558,7 @@ void b2World::DestroyBody(b2Body* b)
 	for (b2Fixture* f = b->m_fixtureList; f; f = f->m_next)
 	{
 		if (m_destructionListener) m_destructionListener->SayGoodbye(f);
-		proxies.push_back(f->m_proxyIndex);
+		for (int32 k = 0; k < f->m_proxyCount; ++k) proxies.push_back(f->m_proxyIndex + k);
 	}
 	std::vector<b2Fixture*> doomed;
 	for (b2Fixture* f = b->m_fixtureList; f; f = f->m_next) doomed.push_back(f);

@@ -82,7 +82,7 @@ BODY_TYPE_MASK = 0x3
 BODY_ISLAND, BODY_AWAKE, BODY_AUTOSLEEP, BODY_BULLET, BODY_FIXED_ROTATION, BODY_ACTIVE = 0x4, 0x8, 0x10, 0x20, 0x40, 0x80
 BODY_GHOST = 0x100
 SHAPE_CIRCLE, SHAPE_EDGE, SHAPE_POLYGON = 0, 1, 2
-EDGE_HAS_VERTEX0, EDGE_HAS_VERTEX3 = 1, 2
+EDGE_HAS_VERTEX0, EDGE_HAS_VERTEX3, EDGE_CHAIN_CHILD = 1, 2, 4
 PROXY_SENSOR, PROXY_THICK, PROXY_MOVED = 1, 2, 4
 PROXY_NEW, PROXY_REFILTER = 0x10, 0x20
 CONTACT_ISLAND, CONTACT_TOUCHING, CONTACT_ENABLED, CONTACT_FILTER = 0x1, 0x2, 0x4, 0x8

@@ -22,7 +22,7 @@ FIXTURE_DEF = np.dtype([
 
 BODYDEF_ALLOW_SLEEP, BODYDEF_AWAKE, BODYDEF_FIXED_ROTATION, BODYDEF_BULLET, BODYDEF_ACTIVE = 1, 2, 4, 8, 16
 BODYDEF_DEFAULT = BODYDEF_ALLOW_SLEEP | BODYDEF_AWAKE | BODYDEF_ACTIVE
-KIND_CIRCLE, KIND_EDGE, KIND_POLYGON, KIND_BOX, KIND_RAW = 0, 1, 2, 3, 4
+KIND_CIRCLE, KIND_EDGE, KIND_POLYGON, KIND_BOX, KIND_RAW, KIND_CHAIN = 0, 1, 2, 3, 4, 5
 
 
 class Scene:
@@ -88,6 +88,16 @@ class Scene:
             s["v"][3] = v3
             fl |= T.EDGE_HAS_VERTEX3
         s["flags"] = fl
+        return self._add_shape(s)
+
+    def chain(self, verts, loop=False):
+        """b2ChainShape of up to 8 vertices: CreateLoop(verts) or CreateChain(verts); one proxy per segment"""
+        assert 2 <= len(verts) <= 8
+        s = np.zeros((), SHAPE_DEF)
+        s["kind"] = KIND_CHAIN
+        s["count"] = len(verts)
+        s["flags"] = 1 if loop else 0
+        s["v"][:len(verts)] = np.asarray(verts, dtype=np.float32)
         return self._add_shape(s)
 
     # -- bodies / fixtures -------------------------------------------------------

@@ -167,3 +167,21 @@ def pile(columns, rows, seed=0, pitch=0.56, radius=0.25, sleep=False, wall_heigh
     fixtures["maskBits"] = 0xFFFF
     s.add_bulk(bodies, fixtures)
     return s
+
+
+def chain_terrain(count=40, seed=3):
+    """Mixed bodies dropped on chain shapes: an open 8-vertex chain as a bumpy floor (continued on both sides by
+    plain edges with ghost vertices) and a closed loop as an obstacle -- every chain segment is its own proxy."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    floor = [(-14.0, 3.0), (-10.0, 0.5), (-6.0, 1.0), (-2.0, 0.0), (2.0, 0.4), (6.0, 0.0), (10.0, 1.2), (14.0, 3.5)]
+    s.fixture(g, s.chain(floor), friction=0.5)
+    s.fixture(g, s.chain([(-1.5, 2.0), (0.0, 1.4), (1.5, 2.0), (0.0, 2.8)], loop=True), friction=0.3)
+    s.fixture(g, s.edge((-18.0, 6.0), (-14.0, 3.0), v3=(-10.0, 0.5)))
+    rnd = _Rand(seed)
+    shapes = [s.circle(0.3), s.box(0.35, 0.25)] + [s.polygon(_regular_polygon(k, 0.33)) for k in (3, 5, 8)]
+    for i in range(count):
+        b = s.body(T.DYNAMIC_BODY, (-11.0 + 0.55 * i, 4.5 + 0.9 * (i % 4)), angle=float(rnd.uniform(0.0, 6.28, 1)[0]))
+        s.fixture(b, shapes[i % len(shapes)], density=1.0, friction=0.4, restitution=0.1 * (i % 3))
+    return s
+

@@ -128,13 +128,16 @@ typedef struct b2cuBodyState
 /* b2Shape::Type, Collision/Shapes/b2Shape.h:48-55 (chain is outside the GPU path) */
 enum { B2CU_SHAPE_CIRCLE = 0, B2CU_SHAPE_EDGE = 1, B2CU_SHAPE_POLYGON = 2 };
 
-enum { B2CU_EDGE_HAS_VERTEX0 = 1, B2CU_EDGE_HAS_VERTEX3 = 2 };
+/* edge records: ghost vertices present; CHAIN_CHILD: the edge is a segment of a b2ChainShape, whose child AABB has no
+ * radius margin (Collision/Shapes/b2ChainShape.cpp:173-189 against b2EdgeShape.cpp:116-129) */
+enum { B2CU_EDGE_HAS_VERTEX0 = 1, B2CU_EDGE_HAS_VERTEX3 = 2, B2CU_EDGE_CHAIN_CHILD = 4 };
 
 #define B2CU_MAX_POLYGON_VERTICES 8
 
 /* One geometry record, 160 bytes.
  *   circle : v[0] = m_p
- *   edge   : v[0] = m_vertex1, v[1] = m_vertex2, v[2] = m_vertex0, v[3] = m_vertex3, flags = hasVertex bits
+ *   edge   : v[0] = m_vertex1, v[1] = m_vertex2, v[2] = m_vertex0, v[3] = m_vertex3, flags = hasVertex bits;
+ *            a chain shape is one edge record per segment (flags |= B2CU_EDGE_CHAIN_CHILD), one proxy each
  *   polygon: v[i] = m_vertices[i], n[i] = m_normals[i], centroid = m_centroid, count = m_count          */
 typedef struct b2cuShape
 {

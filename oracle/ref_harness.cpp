@@ -59,6 +59,14 @@ inline int32 FixtureIndex(const b2Fixture* f)
 	return (int32)(intptr_t)f->GetUserData();
 }
 
+// Dense proxy ids: one per (fixture, child) in creation order -- a chain fixture has one per segment.  Filled by
+// b2ref_build; the contact keys, the exports and the event lists all use these ids.
+std::vector<int32>* g_proxyBaseOf(const b2World* world);
+inline int32 ProxyIndex(const b2Fixture* f, int32 child)
+{
+	return (*g_proxyBaseOf(f->GetBody()->GetWorld()))[FixtureIndex(f)] + child;
+}
+
 inline uint64_t MakeKey(int32 a, int32 b)
 {
 	uint32_t lo = (uint32_t)std::min(a, b), hi = (uint32_t)std::max(a, b);
@@ -67,7 +75,7 @@ inline uint64_t MakeKey(int32 a, int32 b)
 
 inline uint64_t ContactKey(const b2Contact* c)
 {
-	return MakeKey(FixtureIndex(c->GetFixtureA()), FixtureIndex(c->GetFixtureB()));
+	return MakeKey(ProxyIndex(c->GetFixtureA(), c->GetChildIndexA()), ProxyIndex(c->GetFixtureB(), c->GetChildIndexB()));
 }
 
 class RecordingListener : public b2ContactListener
@@ -122,7 +130,15 @@ struct b2refWorld
 	RecordingListener listener;
 	std::vector<b2Body*> bodies;
 	std::vector<b2Fixture*> fixtures;
+	std::vector<int32> proxyBase;                          // first proxy id of each fixture
+	std::vector<std::pair<b2Fixture*, int32> > proxies;    // (fixture, child) of each proxy id
 };
+
+namespace
+{
+std::unordered_map<const b2World*, b2refWorld*> g_worlds;
+std::vector<int32>* g_proxyBaseOf(const b2World* world) { return &g_worlds[world]->proxyBase; }
+} // namespace
 
 extern "C" {
 
@@ -136,6 +152,7 @@ b2refWorld* b2ref_create(float gx, float gy, uint32_t worldFlags, int32_t thread
 	w->world->SetSubStepping((worldFlags & B2CU_WORLD_SUB_STEPPING) != 0);
 	w->world->SetAutoClearForces((worldFlags & B2CU_WORLD_CLEAR_FORCES) != 0);
 	w->world->SetContactListener(&w->listener);
+	g_worlds[w->world] = w;
 	b2ThreadPoolOptions options;
 	options.totalThreadCount = threads;
 	w->executor = new b2ThreadPoolTaskExecutor(options);
@@ -148,16 +165,29 @@ void b2ref_destroy(b2refWorld* w)
 	{
 		return;
 	}
+	g_worlds.erase(w->world);
 	delete w->world;
 	delete w->executor;
 	delete w;
 }
 
 static void MakeShape(const b2refShapeDef& sd, b2CircleShape& circle, b2EdgeShape& edge, b2PolygonShape& poly,
-                      const b2Shape** out)
+                      b2ChainShape& chain, const b2Shape** out)
 {
 	switch (sd.kind)
 	{
+	case B2REF_SHAPE_CHAIN:
+	{
+		b2Vec2 vs[b2_maxPolygonVertices];
+		for (int32 i = 0; i < sd.count; ++i)
+		{
+			vs[i].Set(sd.v[i][0], sd.v[i][1]);
+		}
+		if (sd.flags & 1) chain.CreateLoop(vs, sd.count);
+		else chain.CreateChain(vs, sd.count);
+		*out = &chain;
+		break;
+	}
 	case B2REF_SHAPE_CIRCLE:
 		circle.m_radius = sd.radius;
 		circle.m_p.Set(sd.v[0][0], sd.v[0][1]);
@@ -248,8 +278,9 @@ int b2ref_build(b2refWorld* w, int32_t bodyCount, const b2refBodyDef* bodies, in
 			b2CircleShape circle;
 			b2EdgeShape edge;
 			b2PolygonShape poly;
+			b2ChainShape chain;
 			const b2Shape* shape = nullptr;
-			MakeShape(shapes[fd.shape], circle, edge, poly, &shape);
+			MakeShape(shapes[fd.shape], circle, edge, poly, chain, &shape);
 
 			b2FixtureDef def;
 			def.shape = shape;
@@ -264,6 +295,11 @@ int b2ref_build(b2refWorld* w, int32_t bodyCount, const b2refBodyDef* bodies, in
 			def.userData = (void*)(intptr_t)w->fixtures.size();
 			b2Fixture* fixture = body->CreateFixture(&def);
 			w->fixtures.push_back(fixture);
+			w->proxyBase.push_back((int32)w->proxies.size());
+			for (int32 child = 0; child < fixture->GetShape()->GetChildCount(); ++child)
+			{
+				w->proxies.push_back(std::make_pair(fixture, child));
+			}
 			++f;
 		}
 	}
@@ -476,7 +512,7 @@ int b2ref_step_ordered(b2refWorld* rw, float dt, int32_t velocityIterations, int
 void b2ref_counts(b2refWorld* w, int32_t* bodyCount, int32_t* fixtureCount, int32_t* contactCount)
 {
 	*bodyCount = (int32_t)w->bodies.size();
-	*fixtureCount = (int32_t)w->fixtures.size();
+	*fixtureCount = (int32_t)w->proxies.size(); /* proxies: one per (fixture, child) */
 	*contactCount = w->world->GetContactCount();
 }
 
@@ -575,9 +611,21 @@ static void ExportShape(const b2Shape* shape, b2cuShape* o)
 
 void b2ref_export_shapes(b2refWorld* w, b2cuShape* out)
 {
-	for (size_t i = 0; i < w->fixtures.size(); ++i)
+	for (size_t i = 0; i < w->proxies.size(); ++i)
 	{
-		ExportShape(w->fixtures[i]->GetShape(), out + i);
+		const b2Shape* shape = w->proxies[i].first->GetShape();
+		if (shape->GetType() == b2Shape::e_chain)
+		{
+			// the geometry of a chain proxy is its segment as an edge with ghost vertices (what b2ChainAnd*Contact collide)
+			b2EdgeShape edge;
+			((const b2ChainShape*)shape)->GetChildEdge(&edge, w->proxies[i].second);
+			ExportShape(&edge, out + i);
+			out[i].flags |= B2CU_EDGE_CHAIN_CHILD;
+		}
+		else
+		{
+			ExportShape(shape, out + i);
+		}
 	}
 }
 
@@ -595,9 +643,10 @@ void b2ref_export_proxies(b2refWorld* w, b2cuProxy* out, int32_t* treeProxyIds)
 		}
 	}
 
-	for (size_t i = 0; i < w->fixtures.size(); ++i)
+	for (size_t i = 0; i < w->proxies.size(); ++i)
 	{
-		const b2Fixture* f = w->fixtures[i];
+		const b2Fixture* f = w->proxies[i].first;
+		const int32 child = w->proxies[i].second;
 		b2cuProxy& o = out[i];
 		memset(&o, 0, sizeof(o));
 		o.body = (int32_t)(intptr_t)f->GetBody()->GetUserData();
@@ -608,12 +657,12 @@ void b2ref_export_proxies(b2refWorld* w, b2cuProxy* out, int32_t* treeProxyIds)
 		o.maskBits = f->m_filter.maskBits;
 		o.groupIndex = f->m_filter.groupIndex;
 		o.flags = (uint16_t)((f->m_isSensor ? B2CU_PROXY_SENSOR : 0) | (f->IsThickShape() ? B2CU_PROXY_THICK : 0));
-		o.fixture = (int32_t)i;
-		o.child = 0;
+		o.fixture = w->proxyBase[FixtureIndex(f)];
+		o.child = child;
 		int32 treeId = -1;
-		if (f->m_proxyCount > 0)
+		if (f->m_proxyCount > child)
 		{
-			const b2FixtureProxy& p = f->m_proxies[0];
+			const b2FixtureProxy& p = f->m_proxies[child];
 			treeId = p.proxyId;
 			o.aabb[0] = p.aabb.lowerBound.x;
 			o.aabb[1] = p.aabb.lowerBound.y;
@@ -670,8 +719,8 @@ int b2ref_export_contacts(b2refWorld* w, int32_t capacity, b2cuContact* out)
 		const b2Contact* c = sorted[i].second;
 		b2cuContact& o = out[i];
 		memset(&o, 0, sizeof(o));
-		o.proxyA = FixtureIndex(c->GetFixtureA());
-		o.proxyB = FixtureIndex(c->GetFixtureB());
+		o.proxyA = ProxyIndex(c->GetFixtureA(), c->GetChildIndexA());
+		o.proxyB = ProxyIndex(c->GetFixtureB(), c->GetChildIndexB());
 		o.flags = c->m_flags;
 		o.friction = c->m_friction;
 		o.restitution = c->m_restitution;

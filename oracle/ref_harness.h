@@ -44,7 +44,8 @@ enum
 	B2REF_SHAPE_EDGE = 1,    /* v1 = v[0], v2 = v[1], v0 = v[2], v3 = v[3], flags = hasVertex0 | hasVertex3<<1 */
 	B2REF_SHAPE_POLYGON = 2, /* b2PolygonShape::Set(v, count) */
 	B2REF_SHAPE_BOX = 3,     /* SetAsBox(v[0].x, v[0].y) or, if flags&1, SetAsBox(hx, hy, center = v[1], angle = v[2].x) */
-	B2REF_SHAPE_RAW = 4      /* polygon given with explicit vertices AND normals (n[]) and centroid, copied as is */
+	B2REF_SHAPE_RAW = 4,     /* polygon given with explicit vertices AND normals (n[]) and centroid, copied as is */
+	B2REF_SHAPE_CHAIN = 5    /* b2ChainShape of v[0..count): CreateLoop if flags&1 else CreateChain */
 };
 
 typedef struct b2refShapeDef
