@@ -5,6 +5,7 @@
 #include <cooperative_groups.h>
 
 #include "b2cu_collide.cuh"
+#include "b2cu_gjk.cuh"
 #include "b2cu_world.cuh"
 
 namespace b2cu
@@ -2395,6 +2396,30 @@ __global__ void EndStepBodiesKernel(DeviceArrays d, int bodyCount, int clearForc
 	}
 	for (int dlt = 16; dlt > 0; dlt >>= 1) local += __shfl_down_sync(0xffffffffu, local, dlt);
 	if ((threadIdx.x & 31) == 0 && local) atomicAdd(&d.counters[CNT_AWAKE_BODIES], local);
+}
+
+// stand-alone batched b2Distance (b2cuDistancePairs)
+__global__ void DistancePairsKernel(const b2cuShape* __restrict__ shapes, int pairCount, const int* __restrict__ shapeA,
+                                    const float4* __restrict__ xfA, const int* __restrict__ shapeB,
+                                    const float4* __restrict__ xfB, int useRadii, b2cuDistanceResult* __restrict__ out)
+{
+	B2CU_GRID_STRIDE(i, pairCount)
+	{
+		GjkCache cache;
+		cache.count = 0;
+		cache.metric = 0.0f;
+		GjkOutput g;
+		GjkDistance(&g, &cache, MakeGjkProxy(shapes + shapeA[i]), MakeXf(xfA[i]), MakeGjkProxy(shapes + shapeB[i]),
+		            MakeXf(xfB[i]), useRadii != 0);
+		b2cuDistanceResult o;
+		o.distance = g.distance;
+		o.pointA[0] = g.pointA.x;
+		o.pointA[1] = g.pointA.y;
+		o.pointB[0] = g.pointB.x;
+		o.pointB[1] = g.pointB.y;
+		o.iterations = g.iterations;
+		out[i] = o;
+	}
 }
 
 // stand-alone batched narrow phase (b2cuCollidePairs)

@@ -2033,6 +2033,47 @@ int b2cuCollidePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes
 	return e == cudaSuccess ? B2CU_OK : B2CU_ERR_CUDA;
 }
 
+int b2cuDistancePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
+                      const int32_t* shapeA, const float* xfA, const int32_t* shapeB, const float* xfB, int32_t useRadii,
+                      b2cuDistanceResult* results)
+{
+	if (shapeCount <= 0 || pairCount < 0 || !shapes || !shapeA || !shapeB || !xfA || !xfB || !results)
+		return B2CU_ERR_ARGUMENT;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return B2CU_ERR_NO_DEVICE;
+	if (cudaSetDevice(device) != cudaSuccess) return B2CU_ERR_CUDA;
+	if (pairCount == 0) return B2CU_OK;
+	b2cuShape* dShapes = nullptr;
+	int *dA = nullptr, *dB = nullptr;
+	float4 *dXa = nullptr, *dXb = nullptr;
+	b2cuDistanceResult* dOut = nullptr;
+	cudaError_t e = cudaSuccess;
+	if (e == cudaSuccess) e = cudaMalloc(&dShapes, sizeof(b2cuShape) * shapeCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dA, sizeof(int) * pairCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dB, sizeof(int) * pairCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dXa, sizeof(float4) * pairCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dXb, sizeof(float4) * pairCount);
+	if (e == cudaSuccess) e = cudaMalloc(&dOut, sizeof(b2cuDistanceResult) * pairCount);
+	if (e == cudaSuccess) e = cudaMemcpy(dShapes, shapes, sizeof(b2cuShape) * shapeCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dA, shapeA, sizeof(int) * pairCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dB, shapeB, sizeof(int) * pairCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dXa, xfA, sizeof(float4) * pairCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dXb, xfB, sizeof(float4) * pairCount, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+	{
+		DistancePairsKernel<<<GridFor(pairCount), kBlock>>>(dShapes, pairCount, dA, dXa, dB, dXb, useRadii, dOut);
+		e = cudaDeviceSynchronize();
+	}
+	if (e == cudaSuccess) e = cudaMemcpy(results, dOut, sizeof(b2cuDistanceResult) * pairCount, cudaMemcpyDeviceToHost);
+	cudaFree(dShapes);
+	cudaFree(dA);
+	cudaFree(dB);
+	cudaFree(dXa);
+	cudaFree(dXb);
+	cudaFree(dOut);
+	return e == cudaSuccess ? B2CU_OK : B2CU_ERR_CUDA;
+}
+
 int b2cuSinCos(int32_t device, int32_t count, const float* angles, float* sinOut, float* cosOut)
 {
 	if (count < 0 || !angles || !sinOut || !cosOut) return B2CU_ERR_ARGUMENT;

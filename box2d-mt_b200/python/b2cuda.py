@@ -21,7 +21,7 @@ API = [
     "b2cuSetWorldParams", "b2cuSetInvDt0", "b2cuSetCounts", "b2cuSetBodies", "b2cuGetBodies", "b2cuSetShapes",
     "b2cuSetProxies", "b2cuGetProxies", "b2cuSetContacts", "b2cuGetContactCount", "b2cuGetContacts", "b2cuStep",
     "b2cuGetContactsByKey", "b2cuGetEvents", "b2cuGetSolverOrder", "b2cuGetIslandLabels", "b2cuGetToiCandidates", "b2cuCollidePairs",
-    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts",
+    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuDistancePairs", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts",
 ]
 
 
@@ -281,6 +281,22 @@ def collide_pairs(shapes, shape_a, xf_a, shape_b, xf_b, device=0):
     rc = lib.b2cuCollidePairs(device, len(s), _ptr(s), len(ia), _ptr(ia), _ptr(xa), _ptr(ib), _ptr(xb), _ptr(out))
     if rc != 0:
         raise B2cuError(rc, "b2cuCollidePairs")
+    return out
+
+
+def distance_pairs(shapes, shape_a, xf_a, shape_b, xf_b, use_radii=True, device=0):
+    """Batched b2Distance with a cold cache; returns a DISTANCE_RESULT array."""
+    lib = load()
+    shapes = np.ascontiguousarray(shapes, T.SHAPE)
+    a = np.ascontiguousarray(shape_a, np.int32)
+    b = np.ascontiguousarray(shape_b, np.int32)
+    xa = np.ascontiguousarray(xf_a, np.float32)
+    xb = np.ascontiguousarray(xf_b, np.float32)
+    out = np.zeros(len(a), T.DISTANCE_RESULT)
+    rc = lib.b2cuDistancePairs(device, len(shapes), _ptr(shapes), len(a), _ptr(a), _ptr(xa), _ptr(b), _ptr(xb),
+                               1 if use_radii else 0, _ptr(out))
+    if rc != 0:
+        raise B2cuError(rc, "b2cuDistancePairs failed")
     return out
 
 

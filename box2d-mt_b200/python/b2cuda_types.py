@@ -54,6 +54,9 @@ CONTACT = np.dtype([
 ])
 assert CONTACT.itemsize == 96
 
+DISTANCE_RESULT = np.dtype([("distance", "f4"), ("pointA", "f4", (2,)), ("pointB", "f4", (2,)), ("iterations", "i4")])
+assert DISTANCE_RESULT.itemsize == 24
+
 WORLD_DEF = np.dtype([
     ("device", "i4"), ("gravity", "f4", (2,)), ("flags", "u4"),
     ("bodyCapacity", "i4"), ("proxyCapacity", "i4"), ("shapeCapacity", "i4"), ("contactCapacity", "i4"),

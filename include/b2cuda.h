@@ -47,6 +47,8 @@
  *                                                                          Dynamics/b2ContactManager.cpp:659-713, b2World.cpp:317-341
  *   b2cuShardConfigure / GetLink /       (new) spatial sharding of one large world over the GPUs of a box: halo
  *   Connect                              bodies + per-iteration halo exchange over NVLink peer memory, SURVEY.md 8e
+ *   b2cuDistancePairs                    b2Distance (GJK), batched; b2TestOverlap = its distance under 10 epsilon
+ *                                                                          Collision/b2Distance.cpp:452-603, b2Collision.cpp:233-252
  *   b2cuCollidePairs                     b2CollidePolygons / b2CollideCircles / b2CollidePolygonAndCircle /
  *                                        b2CollideEdgeAndCircle / b2CollideEdgeAndPolygon, batched
  *                                                                          Collision/b2CollidePolygon.cpp, b2CollideCircle.cpp, b2CollideEdge.cpp
@@ -393,6 +395,19 @@ B2CU_API int b2cuShardConnect(b2cuWorld* w, const b2cuShardLink* lower, const b2
 B2CU_API int b2cuCollidePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
                               const int32_t* shapeA, const float* xfA, const int32_t* shapeB, const float* xfB,
                               b2cuManifold* manifolds);
+
+/* Batched stand-alone b2Distance (Collision/b2Distance.cpp:452-603), cold simplex cache: closest points and distance
+ * of shapes[shapeA[i]] at xfA[i] and shapes[shapeB[i]] at xfB[i] (any two of circle / edge / polygon).  With useRadii
+ * the result is what b2TestOverlap thresholds (distance < 10 * b2_epsilon, Collision/b2Collision.cpp:233-252). */
+typedef struct b2cuDistanceResult
+{
+	float distance;
+	float pointA[2], pointB[2];
+	int32_t iterations;
+} b2cuDistanceResult;
+B2CU_API int b2cuDistancePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
+                               const int32_t* shapeA, const float* xfA, const int32_t* shapeB, const float* xfB,
+                               int32_t useRadii, b2cuDistanceResult* results);
 
 /* sin/cos used by every transform on the device (one correctly-rounded-in-practice fp32 sincos shared with the
  * oracle so that fat-AABB decisions are reproducible); evaluated on the device. */

@@ -207,6 +207,18 @@ def collide(shape_a, xf_a, shape_b, xf_b, stock_libm=False):
     return out
 
 
+def distance(shape_a, xf_a, shape_b, xf_b, use_radii=True):
+    """Reference b2Distance (cold cache) for two b2cuShape records and transforms (p.x, p.y, sin, cos)."""
+    lib = load(False)
+    sa = np.ascontiguousarray(shape_a, T.SHAPE)
+    sb = np.ascontiguousarray(shape_b, T.SHAPE)
+    xa = np.ascontiguousarray(xf_a, np.float32)
+    xb = np.ascontiguousarray(xf_b, np.float32)
+    out = np.zeros((), T.DISTANCE_RESULT)
+    lib.b2ref_distance(_ptr(sa), _ptr(xa), _ptr(sb), _ptr(xb), 1 if use_radii else 0, _ptr(out))
+    return out
+
+
 def sincos(x, stock_libm=False):
     lib = load(stock_libm)
     s, c = ctypes.c_float(), ctypes.c_float()

@@ -929,4 +929,38 @@ void b2ref_sincos(float x, float* s, float* c)
 	*c = r.c;
 }
 
+void b2ref_distance(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
+                    int32_t useRadii, b2cuDistanceResult* out)
+{
+	b2CircleShape circleA, circleB;
+	b2EdgeShape edgeA, edgeB;
+	b2PolygonShape polyA, polyB;
+	ImportShape(shapeA, circleA, edgeA, polyA);
+	ImportShape(shapeB, circleB, edgeB, polyB);
+	const b2Shape* sA = shapeA->type == B2CU_SHAPE_CIRCLE ? (const b2Shape*)&circleA
+	                    : (shapeA->type == B2CU_SHAPE_EDGE ? (const b2Shape*)&edgeA : (const b2Shape*)&polyA);
+	const b2Shape* sB = shapeB->type == B2CU_SHAPE_CIRCLE ? (const b2Shape*)&circleB
+	                    : (shapeB->type == B2CU_SHAPE_EDGE ? (const b2Shape*)&edgeB : (const b2Shape*)&polyB);
+	b2DistanceInput input;
+	input.proxyA.Set(sA, 0);
+	input.proxyB.Set(sB, 0);
+	input.transformA.p.Set(xfA[0], xfA[1]);
+	input.transformA.q.s = xfA[2];
+	input.transformA.q.c = xfA[3];
+	input.transformB.p.Set(xfB[0], xfB[1]);
+	input.transformB.q.s = xfB[2];
+	input.transformB.q.c = xfB[3];
+	input.useRadii = useRadii != 0;
+	b2SimplexCache cache;
+	cache.count = 0;
+	b2DistanceOutput output;
+	b2Distance(&output, &cache, &input);
+	out->distance = output.distance;
+	out->pointA[0] = output.pointA.x;
+	out->pointA[1] = output.pointA.y;
+	out->pointB[0] = output.pointB.x;
+	out->pointB[1] = output.pointB.y;
+	out->iterations = output.iterations;
+}
+
 } // extern "C"

@@ -129,6 +129,9 @@ uint32_t b2ref_hash(b2refWorld* w);
 /* Stand-alone manifold functions of the reference (b2Collide*.cpp) on b2cuShape records. */
 void b2ref_collide(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
                    b2cuManifold* out);
+/* the reference's b2Distance with a cold simplex cache, on geometry records (same conventions as b2ref_collide) */
+void b2ref_distance(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
+                    int32_t useRadii, b2cuDistanceResult* out);
 
 /* The interposed sin/cos the reference build actually calls (checks that interposition works). */
 void b2ref_sincos(float x, float* s, float* c);

@@ -93,6 +93,37 @@ def test_collide_pairs_bit_exact(gpu):
     assert touching > n // 10
 
 
+def test_distance_pairs_bit_exact(gpu):
+    """b2Distance (GJK) on the device against the reference's, on random pairs of every shape class, with and without
+    radii: distance, witness points and iteration count (b2Distance.cpp:452-603)."""
+    shapes = _shape_table()
+    rng = np.random.default_rng(11)
+    n = 4000
+    a = rng.integers(0, len(shapes), n)
+    b = rng.integers(0, len(shapes), n)
+    ang_a = rng.uniform(-np.pi, np.pi, n)
+    ang_b = rng.uniform(-np.pi, np.pi, n)
+    xa = np.zeros((n, 4), np.float32)
+    xb = np.zeros((n, 4), np.float32)
+    xa[:, :2] = rng.uniform(-0.5, 0.5, (n, 2))
+    xb[:, :2] = xa[:, :2] + rng.normal(0, 1.0, (n, 2))
+    xa[:, 2], xa[:, 3] = np.sin(ang_a), np.cos(ang_a)
+    xb[:, 2], xb[:, 3] = np.sin(ang_b), np.cos(ang_b)
+    xb[:300] = xa[:300]          # coincident frames: deep overlap, degenerate simplices
+    xb[300:600, :2] = xa[300:600, :2] + rng.normal(0, 0.05, (300, 2))
+    overlapping = 0
+    for use_radii in (True, False):
+        got = gpu.distance_pairs(shapes, a, xa, b, xb, use_radii)
+        for i in range(n):
+            want = ref.distance(shapes[a[i]], xa[i], shapes[b[i]], xb[i], use_radii)
+            assert got[i]["iterations"] == want["iterations"], (i, use_radii)
+            parity.assert_floats_equal("distance", got[i]["distance"], want["distance"], TOL)
+            parity.assert_floats_equal("pointA", got[i]["pointA"], want["pointA"], TOL)
+            parity.assert_floats_equal("pointB", got[i]["pointB"], want["pointB"], TOL)
+            overlapping += int(want["distance"] < 10 * np.finfo(np.float32).eps)
+    assert overlapping > n // 10
+
+
 SCENES = {
     "pyramid6": lambda: scenes.pyramid(6, continuous=False),
     "pyramid20": lambda: scenes.pyramid(20, continuous=False),
