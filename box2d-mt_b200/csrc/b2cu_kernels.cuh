@@ -20,6 +20,9 @@ namespace b2cu
 #define B2CU_EV_DESTROY_TOUCHING 8
 // internal contact flag: destroyed, slot not yet reclaimed (the contact set is compacted lazily)
 #define B2CU_CONTACT_DEAD 0x0100u
+// internal contact flag: one of the two fixtures is a sensor (b2Fixture::IsSensor): overlap test instead of a manifold,
+// never solid
+#define B2CU_CONTACT_SENSOR 0x0200u
 
 __device__ __forceinline__ bool IsStatic(uint32_t bf) { return (bf & B2CU_BODY_TYPE_MASK) == B2CU_STATIC_BODY; }
 __device__ __forceinline__ bool IsDynamic(uint32_t bf) { return (bf & B2CU_BODY_TYPE_MASK) == B2CU_DYNAMIC_BODY; }
@@ -115,8 +118,20 @@ __device__ __forceinline__ int UpdateContact(const DeviceArrays& d, int i, int4 
 
 	Xf xfA = MakeXf(d.xf[bA]);
 	Xf xfB = MakeXf(d.xf[bB]);
-	Evaluate(&m, sA, xfA, sB, xfB);
-	bool touching = m.pointCount > 0;
+	const bool sensor = (flags & B2CU_CONTACT_SENSOR) != 0;
+	bool touching;
+	if (sensor)
+	{
+		// sensors do not generate manifolds (b2Contact.cpp:193-202): overlap by distance, point count zeroed, the rest of
+		// the manifold left as it is
+		touching = TestOverlap(sA, xfA, sB, xfB);
+		m.pointCount = 0;
+	}
+	else
+	{
+		Evaluate(&m, sA, xfA, sB, xfB);
+		touching = m.pointCount > 0;
+	}
 
 	// warm-start transfer by feature id
 	for (int k = 0; k < m.pointCount; ++k)
@@ -146,8 +161,9 @@ __device__ __forceinline__ int UpdateContact(const DeviceArrays& d, int i, int4 
 	int ev = 0;
 	if (touching != wasTouching)
 	{
-		// b2ContactManager::ConsumeAwakes wakes m_nodeB.other (= fixture A's body) only (:472-486)
-		d.wake[bA] = 1;
+		// b2ContactManager::ConsumeAwakes wakes m_nodeB.other (= fixture A's body) only (:472-486); a sensor contact
+		// wakes nobody (the awake request sits in the non-sensor branch of Update, b2Contact.cpp:229-240)
+		if (!sensor) d.wake[bA] = 1;
 		ev = touching ? B2CU_EV_BEGIN : B2CU_EV_END;
 	}
 	if (touching)
@@ -165,6 +181,11 @@ __device__ __forceinline__ int UpdateContact(const DeviceArrays& d, int i, int4 
 	else if (ev == B2CU_EV_END) AppendKey(d, CNT_END, d.endKeys, d.c.key[i], capacity);
 
 	d.c.flags[i] = flags;
+	if (sensor)
+	{
+		d.c.m3[i] = make_uint4(m3.x, m3.y, m3.z, 0u);
+		return touchingNow;
+	}
 	d.c.m0[i] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
 	d.c.m1[i] = make_float4(m.lp[0].x, m.lp[0].y, m.ni[0], m.ti[0]);
 	d.c.m2[i] = make_float4(m.lp[1].x, m.lp[1].y, m.ni[1], m.ti[1]);
@@ -239,7 +260,7 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 		const b2cuShape* sB = d.shapes + d.pshape[pr.y];
 		// polygon-polygon and edge-polygon manifolds cost several times the others; running them in the same
 		// warps leaves most lanes idle, so they are queued for a second, dense pass (CollideHeavyKernel)
-		bool heavy = sB->type == B2CU_SHAPE_POLYGON && sA->type != B2CU_SHAPE_CIRCLE;
+		bool heavy = (sB->type == B2CU_SHAPE_POLYGON && sA->type != B2CU_SHAPE_CIRCLE) || (flags & B2CU_CONTACT_SENSOR);
 		if (heavy)
 		{
 			d.c.flags[i] = flags;
@@ -384,7 +405,7 @@ __global__ void PreSolveSelectKernel(DeviceArrays d, int contactCount)
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		uint32_t f = d.c.flags[i];
-		d.cSelect[i] = ((f & B2CU_CONTACT_TOUCHING) && !(f & (B2CU_CONTACT_DEAD | B2CU_CONTACT_INACTIVE))) ? 1 : 0;
+		d.cSelect[i] = ((f & B2CU_CONTACT_TOUCHING) && !(f & (B2CU_CONTACT_DEAD | B2CU_CONTACT_INACTIVE | B2CU_CONTACT_SENSOR))) ? 1 : 0;
 	}
 }
 // records of the selected contacts + their manifolds of the previous step (saved in cAlt before Collide)
@@ -400,7 +421,7 @@ __global__ void PreSolveGatherKernel(DeviceArrays d, const int* __restrict__ lis
 		b2cuContact o;
 		o.proxyA = pr.x;
 		o.proxyB = pr.y;
-		o.flags = d.c.flags[i];
+		o.flags = d.c.flags[i] & 0xFFu;
 		o.friction = mix.x;
 		o.restitution = mix.y;
 		o.tangentSpeed = mix.z;
@@ -472,6 +493,22 @@ __global__ void FillContactBodiesKernel(DeviceArrays d, int contactCount)
 	{
 		int4 pr = d.c.proxies[i];
 		d.c.proxies[i] = make_int4(pr.x, pr.y, d.pbody[pr.x], d.pbody[pr.y]);
+		// sensor-ness and TOI candidacy follow the fixtures (b2Fixture::SetSensor / SetThickShape recalculate them,
+		// b2Fixture.cpp:222-262): same rule as at creation (RebuildNewKernel)
+		uint32_t f = d.c.flags[i] & ~(B2CU_CONTACT_SENSOR | (uint32_t)B2CU_CONTACT_TOI_CANDIDATE);
+		uint32_t pf = (d.pgroup[pr.x] | d.pgroup[pr.y]) >> 16;
+		if (pf & B2CU_PROXY_SENSOR)
+		{
+			f |= B2CU_CONTACT_SENSOR;
+		}
+		else
+		{
+			uint32_t fbA = d.bflags[d.pbody[pr.x]], fbB = d.bflags[d.pbody[pr.y]];
+			bool includesNonDynamic = !IsDynamic(fbA) || !IsDynamic(fbB);
+			if (((fbA | fbB) & B2CU_BODY_BULLET) || (includesNonDynamic && !(pf & B2CU_PROXY_THICK)))
+				f |= B2CU_CONTACT_TOI_CANDIDATE;
+		}
+		d.c.flags[i] = f;
 	}
 }
 
@@ -591,7 +628,7 @@ __device__ __forceinline__ bool IsSolidTouching(const DeviceArrays& d, int i)
 {
 	uint32_t f = d.c.flags[i];
 	if ((f & (B2CU_CONTACT_TOUCHING | B2CU_CONTACT_ENABLED)) != (B2CU_CONTACT_TOUCHING | B2CU_CONTACT_ENABLED)) return false;
-	if (f & B2CU_CONTACT_DEAD) return false;
+	if (f & (B2CU_CONTACT_DEAD | B2CU_CONTACT_SENSOR)) return false;
 	return true;
 }
 
@@ -2305,7 +2342,7 @@ __global__ void RebuildNewKernel(DeviceArrays d, int tailBegin, int tailCount, c
 		uint32_t flA = d.pgroup[pA] >> 16, flB = d.pgroup[pB] >> 16;
 		bool sensor = ((flA | flB) & B2CU_PROXY_SENSOR) != 0;
 
-		uint32_t flags = B2CU_CONTACT_ENABLED;
+		uint32_t flags = B2CU_CONTACT_ENABLED | (sensor ? B2CU_CONTACT_SENSOR : 0u);
 		// b2Contact::IsToiCandidate, b2Contact.cpp:300-324
 		if (!sensor)
 		{
@@ -2478,7 +2515,7 @@ __global__ void GatherContactsByKeyKernel(DeviceArrays d, int contactCount, int 
 			float4 m0 = d.c.m0[i], m1 = d.c.m1[i], m2 = d.c.m2[i], mix = d.c.mix[i];
 			uint4 m3 = d.c.m3[i];
 			uint32_t fA = d.bflags[pr.z], fB = d.bflags[pr.w];
-			uint32_t f = d.c.flags[i] & ~(uint32_t)B2CU_CONTACT_INACTIVE;
+			uint32_t f = d.c.flags[i] & 0xFFu & ~(uint32_t)B2CU_CONTACT_INACTIVE;
 			if (!IsAwakeNonStatic(fA) && !IsAwakeNonStatic(fB)) f |= B2CU_CONTACT_INACTIVE;
 			o.proxyA = pr.x;
 			o.proxyB = pr.y;

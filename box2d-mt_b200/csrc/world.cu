@@ -883,8 +883,6 @@ int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* 
 	for (int i = 0; i < count; ++i)
 	{
 		const b2cuProxy& p = proxies[i];
-		if (p.flags & B2CU_PROXY_SENSOR)
-			return SetError(w, B2CU_ERR_UNSUPPORTED, "proxy %d: sensors are outside the GPU path", first + i);
 		if (p.body < 0 || p.body >= w->bodyCount || p.shape < 0 || p.shape >= w->shapeCount)
 			return SetError(w, B2CU_ERR_ARGUMENT, "proxy %d: body %d / shape %d out of range", first + i, p.body, p.shape);
 		fat[i] = make_float4(p.fat[0], p.fat[1], p.fat[2], p.fat[3]);
@@ -985,7 +983,7 @@ int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
 		key[j] = keys[order[j]];
 		if (j > 0 && key[j] == key[j - 1]) return SetError(w, B2CU_ERR_ARGUMENT, "duplicate contact key");
 		proxies[j] = make_int4(c.proxyA, c.proxyB, 0, 0);
-		flags[j] = c.flags & ~(uint32_t)B2CU_CONTACT_ISLAND;
+		flags[j] = c.flags & 0xFFu & ~(uint32_t)B2CU_CONTACT_ISLAND; // the bits above are the device's own
 		m0[j] = make_float4(m.localNormal[0], m.localNormal[1], m.localPoint[0], m.localPoint[1]);
 		m1[j] = make_float4(m.points[0].localPoint[0], m.points[0].localPoint[1], m.points[0].normalImpulse,
 		                    m.points[0].tangentImpulse);
@@ -1064,7 +1062,7 @@ int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32
 			uint32_t fA = bflags[pbody[proxies[j].x]], fB = bflags[pbody[proxies[j].y]];
 			bool activeA = (fA & B2CU_BODY_AWAKE) && (fA & B2CU_BODY_TYPE_MASK) != B2CU_STATIC_BODY;
 			bool activeB = (fB & B2CU_BODY_AWAKE) && (fB & B2CU_BODY_TYPE_MASK) != B2CU_STATIC_BODY;
-			uint32_t f = flags[j] & ~(uint32_t)(B2CU_CONTACT_INACTIVE | B2CU_CONTACT_DEAD);
+			uint32_t f = flags[j] & ~(uint32_t)(B2CU_CONTACT_INACTIVE | B2CU_CONTACT_DEAD | B2CU_CONTACT_SENSOR);
 			if (!activeA && !activeB) f |= B2CU_CONTACT_INACTIVE;
 			c.flags = f;
 		}

@@ -42,6 +42,8 @@ public:
 	b2Shape* GetShape() { return m_shape; }
 	const b2Shape* GetShape() const { return m_shape; }
 	bool IsSensor() const { return m_isSensor; }
+	/// a sensor reports overlaps (Begin/EndContact) but never collides (reference b2Fixture.cpp:222-239)
+	void SetSensor(bool sensor);
 	void SetFilterData(const b2Filter& filter);
 	const b2Filter& GetFilterData() const { return m_filter; }
 	void Refilter();

@@ -581,6 +581,23 @@ void b2Fixture::SetRestitution(float32 restitution)
 	}
 }
 
+void b2Fixture::SetSensor(bool sensor)
+{
+	if (sensor == m_isSensor) return;
+	m_body->SetAwake(true);
+	m_isSensor = sensor;
+	if (m_proxyIndex < 0) return;
+	b2World* w = m_body->m_world;
+	w->RefreshProxies();
+	for (int32 child = 0; child < m_proxyCount; ++child)
+	{
+		b2cuProxy& p = w->m_proxies[m_proxyIndex + child];
+		if (sensor) p.flags |= B2CU_PROXY_SENSOR;
+		else p.flags &= ~(uint16)B2CU_PROXY_SENSOR;
+		w->MarkProxyDirty(m_proxyIndex + child);
+	}
+}
+
 void b2Fixture::SetThickShape(bool flag)
 {
 	m_thickShape = flag;

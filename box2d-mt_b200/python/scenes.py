@@ -185,3 +185,23 @@ def chain_terrain(count=40, seed=3):
         s.fixture(b, shapes[i % len(shapes)], density=1.0, friction=0.4, restitution=0.1 * (i % 3))
     return s
 
+
+def sensors(count=30, seed=5):
+    """Sensor fixtures (b2Fixture::IsSensor): a static detection zone (box and circle sensors), dynamic bodies that
+    carry a sensor halo besides their solid fixture, all shape classes falling through the zones onto a floor."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.box(12.0, 0.5, center=(0.0, -0.5)), thick=True)
+    s.fixture(g, s.box(3.0, 0.6, center=(-3.0, 3.0), angle=0.2), sensor=True)
+    s.fixture(g, s.circle(1.2, p=(4.0, 2.5)), sensor=True)
+    s.fixture(g, s.edge((-8.0, 4.5), (-5.0, 4.0)), sensor=True)
+    rnd = _Rand(seed)
+    shapes = [s.circle(0.25), s.box(0.3, 0.2)] + [s.polygon(_regular_polygon(k, 0.28)) for k in (3, 6)]
+    halo = s.circle(0.6)
+    for i in range(count):
+        b = s.body(T.DYNAMIC_BODY, (-8.0 + 0.55 * i, 2.2 + 0.8 * (i % 3)), angle=float(rnd.uniform(0.0, 6.28, 1)[0]))
+        s.fixture(b, shapes[i % len(shapes)], density=1.0, friction=0.3)
+        if i % 3 == 0:
+            s.fixture(b, halo, sensor=True)
+    return s
+

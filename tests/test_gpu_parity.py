@@ -132,6 +132,7 @@ SCENES = {
     "pile_sleep": lambda: scenes.pile(8, 6, sleep=True),
     "tumbler": lambda: scenes.tumbler(100),
     "chains": lambda: scenes.chain_terrain(40),
+    "sensors": lambda: scenes.sensors(30),
     "two_pyramids": lambda: scenes.pyramids(2, 6, thick_polygon_ground=True),
 }
 
@@ -153,7 +154,7 @@ def test_single_step_teacher_forced(gpu, name):
 
 
 @pytest.mark.parametrize("name,steps", [("pyramid6", 300), ("pyramid20", 240), ("pile", 300), ("pile_5000", 200),
-                                        ("pile_sleep", 400), ("chains", 300),
+                                        ("pile_sleep", 400), ("chains", 300), ("sensors", 300),
                                         ("tumbler", 200), ("two_pyramids", 300)])
 def test_free_running_lockstep(gpu, name, steps):
     """Multi-step parity: the device world runs freely; the oracle follows in the GPU's solver order.  Pair set,

@@ -27,6 +27,7 @@ BUILD_SCENES = {
     "add_pair": lambda: scenes.add_pair(80),
     "stacks": lambda: scenes.pyramids(2, 5, thick_polygon_ground=True),
     "chains": lambda: scenes.chain_terrain(12),
+    "sensors": lambda: scenes.sensors(12),
 }
 
 
@@ -124,7 +125,7 @@ def _host_lockstep(scene, steps, check_events=True):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,steps", [("chains", 300), ("pyramid", 200), ("pile", 200), ("tumbler", 150), ("stacks", 200)])
+@pytest.mark.parametrize("name,steps", [("chains", 300), ("sensors", 250), ("pyramid", 200), ("pile", 200), ("tumbler", 150), ("stacks", 200)])
 def test_host_api_lockstep(gpu, name, steps):
     """TestMT.cpp:91-110 rule (position, angle, awake of every body after every step) between the reference and a
     world stepped through b2World::Step with a b2CudaStepExecutor; deferred Begin/End callbacks in the same order."""
