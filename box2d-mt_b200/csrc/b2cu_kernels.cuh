@@ -2435,6 +2435,37 @@ __global__ void EndStepBodiesKernel(DeviceArrays d, int bodyCount, int clearForc
 	if ((threadIdx.x & 31) == 0 && local) atomicAdd(&d.counters[CNT_AWAKE_BODIES], local);
 }
 
+// ---- world queries: one pass over the fat boxes (16 bytes per proxy: a million proxies are 16 MB, a few microseconds
+// of HBM time), then a stable compaction -- no tree to walk ----
+__global__ void QueryAabbSelectKernel(DeviceArrays d, int proxyCount, float4 box, int* __restrict__ flags)
+{
+	B2CU_GRID_STRIDE(p, proxyCount) { flags[p] = AabbOverlap(d.fat[p], box) ? 1 : 0; }
+}
+
+// b2DynamicTree::RayCast's node test (b2DynamicTree.h:203-287) applied to every proxy box: the box of the segment must
+// overlap, and the segment's line must not separate the box (|dot(v, p1 - c)| - dot(|v|, h) <= 0 with v normal to the ray)
+__global__ void RayCastSelectKernel(DeviceArrays d, int proxyCount, float2 p1, float2 p2, int* __restrict__ flags)
+{
+	Vec2 a = V(p1.x, p1.y), b = V(p2.x, p2.y);
+	Vec2 r = Normalized(b - a);
+	Vec2 v = CrossSV(1.0f, r);
+	Vec2 absV = V(fabsf(v.x), fabsf(v.y));
+	float4 seg = make_float4(Min(a.x, b.x), Min(a.y, b.y), Max(a.x, b.x), Max(a.y, b.y));
+	B2CU_GRID_STRIDE(p, proxyCount)
+	{
+		float4 f = d.fat[p];
+		int hit = 0;
+		if (AabbOverlap(f, seg))
+		{
+			Vec2 c = V(0.5f * (f.x + f.z), 0.5f * (f.y + f.w));
+			Vec2 h = V(0.5f * (f.z - f.x), 0.5f * (f.w - f.y));
+			float separation = fabsf(Dot(v, a - c)) - Dot(absV, h);
+			hit = separation > 0.0f ? 0 : 1;
+		}
+		flags[p] = hit;
+	}
+}
+
 // stand-alone batched b2Distance (b2cuDistancePairs)
 __global__ void DistancePairsKernel(const b2cuShape* __restrict__ shapes, int pairCount, const int* __restrict__ shapeA,
                                     const float4* __restrict__ xfA, const int* __restrict__ shapeB,

@@ -2031,6 +2031,50 @@ int b2cuCollidePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes
 	return e == cudaSuccess ? B2CU_OK : B2CU_ERR_CUDA;
 }
 
+// shared tail of the two query entry points: flags (cellOfProxy, free between steps) -> ascending id list (movedList)
+static int FinishProxyQuery(b2cuWorld* w, int32_t capacity, int32_t* proxyIds, int32_t* count)
+{
+	DeviceArrays& d = w->d;
+	const int np = w->proxyCount;
+	CompactFlags(&w->prims, d.cellOfProxy, np, d.movedList, d.counters + CNT_SCRATCH, w->stream);
+	CUDA_TRY(w, cudaMemcpyAsync(&w->hostCounters[CNT_SCRATCH], d.counters + CNT_SCRATCH, sizeof(int), cudaMemcpyDeviceToHost,
+	                            w->stream));
+	int rc = SyncCheck(w);
+	if (rc) return rc;
+	const int n = w->hostCounters[CNT_SCRATCH];
+	if (count) *count = n;
+	const int m = std::min(n, capacity);
+	if (m > 0)
+	{
+		CUDA_TRY(w, cudaMemcpyAsync(proxyIds, d.movedList, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, w->stream));
+		rc = SyncCheck(w);
+	}
+	return rc;
+}
+
+int b2cuQueryAABB(b2cuWorld* w, const float aabb[4], int32_t capacity, int32_t* proxyIds, int32_t* count)
+{
+	if (!w || !aabb || capacity < 0 || (capacity > 0 && !proxyIds)) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	if (count) *count = 0;
+	if (w->proxyCount == 0) return B2CU_OK;
+	LAUNCH(w, QueryAabbSelectKernel, GridFor(w->proxyCount), kBlock, w->d, w->proxyCount,
+	       make_float4(aabb[0], aabb[1], aabb[2], aabb[3]), w->d.cellOfProxy);
+	return FinishProxyQuery(w, capacity, proxyIds, count);
+}
+
+int b2cuRayCastCandidates(b2cuWorld* w, const float p1[2], const float p2[2], int32_t capacity, int32_t* proxyIds,
+                          int32_t* count)
+{
+	if (!w || !p1 || !p2 || capacity < 0 || (capacity > 0 && !proxyIds)) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	if (count) *count = 0;
+	if (w->proxyCount == 0) return B2CU_OK;
+	LAUNCH(w, RayCastSelectKernel, GridFor(w->proxyCount), kBlock, w->d, w->proxyCount, make_float2(p1[0], p1[1]),
+	       make_float2(p2[0], p2[1]), w->d.cellOfProxy);
+	return FinishProxyQuery(w, capacity, proxyIds, count);
+}
+
 int b2cuDistancePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
                       const int32_t* shapeA, const float* xfA, const int32_t* shapeB, const float* xfB, int32_t useRadii,
                       b2cuDistanceResult* results)

@@ -27,6 +27,7 @@ public:
 	b2Shape* Clone() const override { return new b2EdgeShape(*this); }
 	int32 GetChildCount() const override { return 1; }
 	bool TestPoint(const b2Transform&, const b2Vec2&) const override { return false; }
+	bool RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf, int32 childIndex) const override;
 	void ComputeAABB(b2AABB* aabb, const b2Transform& xf, int32 childIndex) const override;
 	void ComputeMass(b2MassData* massData, float32 density) const override;
 

@@ -23,6 +23,7 @@ public:
 	void SetAsBox(float32 hx, float32 hy, const b2Vec2& center, float32 angle);
 
 	bool TestPoint(const b2Transform& xf, const b2Vec2& p) const override;
+	bool RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf, int32 childIndex) const override;
 	void ComputeAABB(b2AABB* aabb, const b2Transform& xf, int32 childIndex) const override;
 	void ComputeMass(b2MassData* massData, float32 density) const override;
 

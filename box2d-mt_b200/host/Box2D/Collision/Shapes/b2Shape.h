@@ -28,6 +28,7 @@ public:
 	virtual void ComputeAABB(b2AABB* aabb, const b2Transform& xf, int32 childIndex) const = 0;
 	virtual void ComputeMass(b2MassData* massData, float32 density) const = 0;
 	virtual bool TestPoint(const b2Transform& xf, const b2Vec2& p) const = 0;
+	virtual bool RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf, int32 childIndex) const = 0;
 
 	/// heap copy owned by the caller (the reference clones into its block allocator)
 	virtual b2Shape* Clone() const = 0;

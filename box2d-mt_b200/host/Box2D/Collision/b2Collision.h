@@ -46,6 +46,18 @@ struct b2WorldManifold
 	float32 separations[b2_maxManifoldPoints];
 };
 
+/// segment p1 -> p1 + maxFraction * (p2 - p1), and where / with which surface normal it hits
+struct b2RayCastInput
+{
+	b2Vec2 p1, p2;
+	float32 maxFraction;
+};
+struct b2RayCastOutput
+{
+	b2Vec2 normal;
+	float32 fraction;
+};
+
 struct b2AABB
 {
 	bool IsValid() const

@@ -63,6 +63,7 @@ public:
 	void SetRestitution(float32 restitution);
 	/// swept tight AABB of the (single) child, as last synchronised by the device
 	const b2AABB& GetAABB(int32 childIndex) const;
+	bool RayCast(b2RayCastOutput* output, const b2RayCastInput& input, int32 childIndex) const;
 	void SetThickShape(bool flag);
 	bool IsThickShape() const { return m_thickShape; }
 	/// dense proxy id on the device (-1 while the body is inactive)

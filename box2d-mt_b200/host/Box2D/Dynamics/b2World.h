@@ -115,6 +115,12 @@ public:
 	int32 GetJointCount() const { return 0; }
 	int32 GetContactCount() const { return m_contactCount; }
 
+	/// every fixture whose fat box overlaps `aabb` (reference b2World.cpp:1752-1758); between steps only
+	void QueryAABB(b2QueryCallback* callback, const b2AABB& aabb);
+	/// every fixture hit by the segment, with the callback's clipping protocol (reference b2World.cpp:1760-1795)
+	void RayCast(b2RayCastCallback* callback, const b2Vec2& point1, const b2Vec2& point2);
+	/// move the origin of the world: every position has newOrigin subtracted (reference b2World.cpp:2084-2103)
+	void ShiftOrigin(const b2Vec2& newOrigin);
 	void SetGravity(const b2Vec2& gravity) { m_gravity = gravity; }
 	b2Vec2 GetGravity() const { return m_gravity; }
 	bool IsLocked() const { return m_locked; }
@@ -159,6 +165,7 @@ private:
 	static int PreSolveThunk(void* user, b2cuWorld* device);
 	static int PairFilterThunk(void* user, const b2cuContactKey* keys, int32_t count, uint8_t* keep);
 	void DestroyContactsOfBody(int32 bodyIndex);
+	void ProxyQuery(const b2AABB* box, const b2Vec2* p1, const b2Vec2* p2, std::vector<int32>& ids);
 	void DestroyFixtureInternal(b2Body* body, b2Fixture* fixture);
 	void RemoveProxies(const std::vector<int32>& proxyIds, const std::vector<int32>& bodyIds);
 	void DispatchEvents(b2cuWorld* device);

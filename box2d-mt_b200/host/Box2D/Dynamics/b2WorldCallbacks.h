@@ -16,6 +16,7 @@
 #include "Box2D/Common/b2Settings.h"
 
 struct b2Manifold;
+struct b2Vec2;
 class b2Contact;
 class b2Fixture;
 
@@ -52,6 +53,24 @@ class b2ContactFilter
 public:
 	virtual bool ShouldCollide(b2Fixture* fixtureA, b2Fixture* fixtureB, uint32 threadId);
 	virtual ~b2ContactFilter() {}
+};
+
+/// b2World::QueryAABB reports every fixture whose fat box overlaps the query box; return false to stop.
+class b2QueryCallback
+{
+public:
+	virtual bool ReportFixture(b2Fixture* fixture) = 0;
+	virtual ~b2QueryCallback() {}
+};
+
+/// b2World::RayCast reports every fixture the segment hits, in no particular order.  The return value steers the
+/// cast: -1 ignore this fixture, 0 stop, a fraction clips the segment there (closest hit: return `fraction`),
+/// 1 go on unclipped.
+class b2RayCastCallback
+{
+public:
+	virtual float32 ReportFixture(b2Fixture* fixture, const b2Vec2& point, const b2Vec2& normal, float32 fraction) = 0;
+	virtual ~b2RayCastCallback() {}
 };
 
 /// Told about fixtures that disappear implicitly (their body is destroyed).

@@ -3,6 +3,7 @@
 // b2World::Step(dt, vIters, pIters, b2CudaStepExecutor&), and read back through the public accessors.
 #include "Box2D/Box2D.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -455,6 +456,59 @@ B2H_API void b2h_post_solve_digest(void* p, uint64* digest, long long* count)
 	*digest = h->recorder.postSolveDigest;
 	*count = h->recorder.postSolveCount;
 }
+namespace
+{
+struct CollectQuery : public b2QueryCallback
+{
+	std::vector<int32> ids;
+	bool ReportFixture(b2Fixture* fixture) override
+	{
+		ids.push_back(fixture->GetProxyIndex());
+		return true;
+	}
+};
+struct ClosestRay : public b2RayCastCallback
+{
+	b2Fixture* fixture = nullptr;
+	b2Vec2 point, normal;
+	float32 fraction = 1.0f;
+	float32 ReportFixture(b2Fixture* f, const b2Vec2& p, const b2Vec2& n, float32 fr) override
+	{
+		fixture = f;
+		point = p;
+		normal = n;
+		fraction = fr;
+		return fr;
+	}
+};
+} // namespace
+
+B2H_API int32 b2h_query_aabb(void* p, const float* aabb, int32 capacity, int32* out)
+{
+	Host* h = static_cast<Host*>(p);
+	CollectQuery q;
+	b2AABB box;
+	box.lowerBound.Set(aabb[0], aabb[1]);
+	box.upperBound.Set(aabb[2], aabb[3]);
+	h->world->QueryAABB(&q, box);
+	std::sort(q.ids.begin(), q.ids.end());
+	for (int32 i = 0; i < (int32)q.ids.size() && i < capacity; ++i) out[i] = q.ids[i];
+	return (int32)q.ids.size();
+}
+B2H_API int32 b2h_ray_cast_closest(void* p, const float* p1, const float* p2, float* out)
+{
+	Host* h = static_cast<Host*>(p);
+	ClosestRay r;
+	h->world->RayCast(&r, b2Vec2(p1[0], p1[1]), b2Vec2(p2[0], p2[1]));
+	if (r.fixture == nullptr) return -1;
+	out[0] = r.point.x;
+	out[1] = r.point.y;
+	out[2] = r.normal.x;
+	out[3] = r.normal.y;
+	out[4] = r.fraction;
+	return r.fixture->GetProxyIndex();
+}
+B2H_API void b2h_shift_origin(void* p, float x, float y) { static_cast<Host*>(p)->world->ShiftOrigin(b2Vec2(x, y)); }
 B2H_API void b2h_set_type(void* p, int32 body, int32 type) { static_cast<Host*>(p)->bodies[body]->SetType((b2BodyType)type); }
 B2H_API void b2h_set_filter(void* p, int32 fixture, uint16 categoryBits, uint16 maskBits, int16 groupIndex)
 {

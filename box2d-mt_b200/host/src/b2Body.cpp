@@ -613,6 +613,11 @@ void b2Fixture::SetThickShape(bool flag)
 	}
 }
 
+bool b2Fixture::RayCast(b2RayCastOutput* output, const b2RayCastInput& input, int32 childIndex) const
+{
+	return m_shape->RayCast(output, input, m_body->GetTransform(), childIndex);
+}
+
 bool b2Fixture::TestPoint(const b2Vec2& p) const { return m_shape->TestPoint(m_body->GetTransform(), p); }
 
 const b2AABB& b2Fixture::GetAABB(int32 childIndex) const

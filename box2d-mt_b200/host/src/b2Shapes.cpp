@@ -303,3 +303,96 @@ void b2ChainShape::ComputeMass(b2MassData* massData, float32) const
 	massData->I = 0.0f;
 }
 
+// ---- ray casts (reference b2CircleShape.cpp:46-81, b2EdgeShape.cpp:54-114, b2PolygonShape.cpp:268-338) -------------
+
+bool b2CircleShape::RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf, int32) const
+{
+	// |s + a r|^2 = radius^2 with s from the centre to p1 and r = p2 - p1; smaller root
+	b2Vec2 centre = xf.p + b2Mul(xf.q, m_p);
+	b2Vec2 s = input.p1 - centre;
+	float32 b = b2Dot(s, s) - m_radius * m_radius;
+	b2Vec2 r = input.p2 - input.p1;
+	float32 c = b2Dot(s, r);
+	float32 rr = b2Dot(r, r);
+	float32 sigma = c * c - rr * b;
+	if (sigma < 0.0f || rr < b2_epsilon) return false;
+	float32 a = -(c + b2Sqrt(sigma));
+	if (0.0f <= a && a <= input.maxFraction * rr)
+	{
+		a /= rr;
+		output->fraction = a;
+		output->normal = s + a * r;
+		output->normal.Normalize();
+		return true;
+	}
+	return false;
+}
+
+bool b2EdgeShape::RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf, int32) const
+{
+	// in the edge's frame: hit the carrier line, then check that the hit lies between the end points
+	b2Vec2 p1 = b2MulT(xf.q, input.p1 - xf.p);
+	b2Vec2 p2 = b2MulT(xf.q, input.p2 - xf.p);
+	b2Vec2 d = p2 - p1;
+	b2Vec2 e = m_vertex2 - m_vertex1;
+	b2Vec2 normal(e.y, -e.x);
+	normal.Normalize();
+	float32 numerator = b2Dot(normal, m_vertex1 - p1);
+	float32 denominator = b2Dot(normal, d);
+	if (denominator == 0.0f) return false;
+	float32 t = numerator / denominator;
+	if (t < 0.0f || input.maxFraction < t) return false;
+	b2Vec2 q = p1 + t * d;
+	float32 rr = b2Dot(e, e);
+	if (rr == 0.0f) return false;
+	float32 along = b2Dot(q - m_vertex1, e) / rr;
+	if (along < 0.0f || 1.0f < along) return false;
+	output->fraction = t;
+	output->normal = numerator > 0.0f ? -b2Mul(xf.q, normal) : b2Mul(xf.q, normal);
+	return true;
+}
+
+bool b2PolygonShape::RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf, int32) const
+{
+	// clip the parameter interval [0, maxFraction] against every face half-plane, in the polygon's frame
+	b2Vec2 p1 = b2MulT(xf.q, input.p1 - xf.p);
+	b2Vec2 p2 = b2MulT(xf.q, input.p2 - xf.p);
+	b2Vec2 d = p2 - p1;
+	float32 lower = 0.0f, upper = input.maxFraction;
+	int32 entryFace = -1;
+	for (int32 i = 0; i < m_count; ++i)
+	{
+		float32 numerator = b2Dot(m_normals[i], m_vertices[i] - p1);
+		float32 denominator = b2Dot(m_normals[i], d);
+		if (denominator == 0.0f)
+		{
+			if (numerator < 0.0f) return false; // parallel and outside
+		}
+		else if (denominator < 0.0f && numerator < lower * denominator)
+		{
+			lower = numerator / denominator; // entering through this face
+			entryFace = i;
+		}
+		else if (denominator > 0.0f && numerator < upper * denominator)
+		{
+			upper = numerator / denominator; // leaving through this face
+		}
+		if (upper < lower) return false;
+	}
+	if (entryFace < 0) return false;
+	output->fraction = lower;
+	output->normal = b2Mul(xf.q, m_normals[entryFace]);
+	return true;
+}
+
+bool b2ChainShape::RayCast(b2RayCastOutput* output, const b2RayCastInput& input, const b2Transform& xf, int32 childIndex) const
+{
+	// the segment as a plain edge (reference b2ChainShape.cpp:153-171)
+	b2EdgeShape edge;
+	int32 i2 = childIndex + 1;
+	if (i2 == (int32)m_points.size()) i2 = 0;
+	edge.m_vertex1 = m_points[childIndex];
+	edge.m_vertex2 = m_points[i2];
+	return edge.RayCast(output, input, xf, 0);
+}
+

@@ -104,7 +104,7 @@ b2World::~b2World()
 	if (m_owner) m_owner->DetachWorld(this);
 	// m_fixtures has one entry per PROXY: a chain fixture appears once per segment
 	for (size_t i = 0; i < m_fixtures.size(); ++i)
-		if (m_proxies[i].child == 0) delete m_fixtures[i];
+		if (i == 0 || m_fixtures[i] != m_fixtures[i - 1]) delete m_fixtures[i];
 	for (size_t i = 0; i < m_bodies.size(); ++i) delete m_bodies[i];
 }
 
@@ -312,6 +312,12 @@ void b2World::RefreshProxies() const
 	b2World* self = const_cast<b2World*>(this);
 	int32 n = std::min(m_proxiesUploaded, (int32)m_proxies.size());
 	if (n > 0) b2cuGetProxies(m_device, 0, n, self->m_proxies.data());
+	// the device does not keep the child index: it follows from the fixture's first proxy
+	for (int32 i = 0; i < n; ++i)
+	{
+		self->m_proxies[i].child = i - m_fixtures[i]->m_proxyIndex;
+		self->m_proxies[i].fixture = m_fixtures[i]->m_proxyIndex;
+	}
 	m_proxiesStale = false;
 }
 
@@ -449,7 +455,7 @@ void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vecto
 		{
 			m_proxies[np] = m_proxies[i];
 			m_fixtures[np] = m_fixtures[i];
-			if (m_proxies[np].child == 0) m_fixtures[np]->m_proxyIndex = np;
+			if (np == 0 || m_fixtures[np] != m_fixtures[np - 1]) m_fixtures[np]->m_proxyIndex = np;
 			++np;
 		}
 	}
@@ -570,6 +576,110 @@ void b2World::DestroyBody(b2Body* b)
 	if (b == m_bodyList) m_bodyList = b->m_next;
 	--m_bodyCount;
 	delete b;
+}
+
+// ---- queries ---------------------------------------------------------------------------------------------
+
+// Candidate proxies of a box or segment query, ascending ids.  With a device copy the fat boxes are scanned there
+// (after the pending edits have been uploaded); a world that has never been stepped has no device copy yet and is
+// scanned here.
+void b2World::ProxyQuery(const b2AABB* box, const b2Vec2* p1, const b2Vec2* p2, std::vector<int32>& ids)
+{
+	ids.clear();
+	if (m_device != nullptr)
+	{
+		if (UploadDirty(m_device) != B2CU_OK) return;
+		int32 n = 0;
+		float a[4] = {0, 0, 0, 0}, q1[2] = {0, 0}, q2[2] = {0, 0};
+		if (box)
+		{
+			a[0] = box->lowerBound.x; a[1] = box->lowerBound.y; a[2] = box->upperBound.x; a[3] = box->upperBound.y;
+			if (b2cuQueryAABB(m_device, a, 0, nullptr, &n) != B2CU_OK || n == 0) return;
+			ids.resize((size_t)n);
+			b2cuQueryAABB(m_device, a, n, ids.data(), &n);
+		}
+		else
+		{
+			q1[0] = p1->x; q1[1] = p1->y; q2[0] = p2->x; q2[1] = p2->y;
+			if (b2cuRayCastCandidates(m_device, q1, q2, 0, nullptr, &n) != B2CU_OK || n == 0) return;
+			ids.resize((size_t)n);
+			b2cuRayCastCandidates(m_device, q1, q2, n, ids.data(), &n);
+		}
+		return;
+	}
+	b2AABB seg;
+	if (!box)
+	{
+		seg.lowerBound = b2Min(*p1, *p2);
+		seg.upperBound = b2Max(*p1, *p2);
+	}
+	for (size_t i = 0; i < m_proxies.size(); ++i)
+	{
+		const b2AABB& fat = reinterpret_cast<const b2AABB&>(m_proxies[i].fat[0]);
+		if (b2TestOverlap(fat, box ? *box : seg)) ids.push_back((int32)i);
+	}
+}
+
+void b2World::QueryAABB(b2QueryCallback* callback, const b2AABB& aabb)
+{
+	if (IsLocked() || callback == nullptr) return;
+	std::vector<int32> ids;
+	ProxyQuery(&aabb, nullptr, nullptr, ids);
+	for (size_t i = 0; i < ids.size(); ++i)
+		if (!callback->ReportFixture(m_fixtures[ids[i]])) break;
+}
+
+void b2World::RayCast(b2RayCastCallback* callback, const b2Vec2& point1, const b2Vec2& point2)
+{
+	if (IsLocked() || callback == nullptr) return;
+	std::vector<int32> ids;
+	ProxyQuery(nullptr, &point1, &point2, ids);
+	RefreshBodies();
+	b2RayCastInput input;
+	input.p1 = point1;
+	input.p2 = point2;
+	input.maxFraction = 1.0f;
+	for (size_t i = 0; i < ids.size(); ++i)
+	{
+		b2Fixture* fixture = m_fixtures[ids[i]];
+		b2RayCastOutput output;
+		if (!fixture->RayCast(&output, input, ids[i] - fixture->m_proxyIndex)) continue;
+		float32 fraction = output.fraction;
+		b2Vec2 point = (1.0f - fraction) * input.p1 + fraction * input.p2;
+		float32 value = callback->ReportFixture(fixture, point, output.normal, fraction);
+		if (value == 0.0f) return;           // the client has terminated the cast
+		if (value > 0.0f) input.maxFraction = value; // clip (value < 0: ignore this fixture and go on)
+	}
+}
+
+void b2World::ShiftOrigin(const b2Vec2& newOrigin)
+{
+	if (IsLocked()) return;
+	RefreshBodies();
+	RefreshProxies();
+	for (size_t i = 0; i < m_states.size(); ++i)
+	{
+		b2cuBodyState& s = m_states[i];
+		s.px -= newOrigin.x; s.py -= newOrigin.y;
+		s.cx -= newOrigin.x; s.cy -= newOrigin.y;
+		s.c0x -= newOrigin.x; s.c0y -= newOrigin.y;
+	}
+	for (size_t i = 0; i < m_proxies.size(); ++i)
+	{
+		b2cuProxy& p = m_proxies[i];
+		p.aabb[0] -= newOrigin.x; p.aabb[1] -= newOrigin.y; p.aabb[2] -= newOrigin.x; p.aabb[3] -= newOrigin.y;
+		p.fat[0] -= newOrigin.x; p.fat[1] -= newOrigin.y; p.fat[2] -= newOrigin.x; p.fat[3] -= newOrigin.y;
+	}
+	if (!m_states.empty())
+	{
+		MarkBodyDirty(0);
+		MarkBodyDirty((int32)m_states.size() - 1);
+	}
+	if (!m_proxies.empty())
+	{
+		MarkProxyDirty(0);
+		MarkProxyDirty((int32)m_proxies.size() - 1);
+	}
 }
 
 // ---- step ------------------------------------------------------------------------------------------------

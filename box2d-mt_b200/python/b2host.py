@@ -63,6 +63,11 @@ def load():
     lib.b2h_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_velocity.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_type.argtypes = [vp, i32, i32]
+    lib.b2h_query_aabb.argtypes = [vp, vp, i32, vp]
+    lib.b2h_query_aabb.restype = i32
+    lib.b2h_ray_cast_closest.argtypes = [vp, vp, vp, vp]
+    lib.b2h_ray_cast_closest.restype = i32
+    lib.b2h_shift_origin.argtypes = [vp, f32, f32]
     lib.b2h_record_post_solve.argtypes = [vp, i32]
     lib.b2h_set_pre_solve_rule.argtypes = [vp, i32]
     lib.b2h_pre_solve_digest.argtypes = [vp, vp, vp]
@@ -210,6 +215,21 @@ class HostWorld:
         c = np.zeros(1, np.int64)
         self.lib.b2h_post_solve_digest(self.h, _ptr(d), _ptr(c))
         return int(d[0]), int(c[0])
+
+    def query_aabb(self, box):
+        a = np.asarray(box, np.float32)
+        out = np.zeros(1 << 16, np.int32)
+        n = self.lib.b2h_query_aabb(self.h, _ptr(a), len(out), _ptr(out))
+        return out[:n]
+
+    def ray_cast_closest(self, p1, p2):
+        a, b = np.asarray(p1, np.float32), np.asarray(p2, np.float32)
+        out = np.zeros(5, np.float32)
+        proxy = self.lib.b2h_ray_cast_closest(self.h, _ptr(a), _ptr(b), _ptr(out))
+        return proxy, out
+
+    def shift_origin(self, x, y):
+        self.lib.b2h_shift_origin(self.h, x, y)
 
     def set_type(self, body, body_type):
         self.lib.b2h_set_type(self.h, body, body_type)

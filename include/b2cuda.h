@@ -47,6 +47,8 @@
  *                                                                          Dynamics/b2ContactManager.cpp:659-713, b2World.cpp:317-341
  *   b2cuShardConfigure / GetLink /       (new) spatial sharding of one large world over the GPUs of a box: halo
  *   Connect                              bodies + per-iteration halo exchange over NVLink peer memory, SURVEY.md 8e
+ *   b2cuQueryAABB / RayCastCandidates    b2World::QueryAABB / RayCast (tree queries on the fat boxes)
+ *                                                                          Dynamics/b2World.cpp:1752-1795
  *   b2cuDistancePairs                    b2Distance (GJK), batched; b2TestOverlap = its distance under 10 epsilon
  *                                                                          Collision/b2Distance.cpp:452-603, b2Collision.cpp:233-252
  *   b2cuCollidePairs                     b2CollidePolygons / b2CollideCircles / b2CollidePolygonAndCircle /
@@ -395,6 +397,16 @@ B2CU_API int b2cuShardConnect(b2cuWorld* w, const b2cuShardLink* lower, const b2
 B2CU_API int b2cuCollidePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
                               const int32_t* shapeA, const float* xfA, const int32_t* shapeB, const float* xfB,
                               b2cuManifold* manifolds);
+
+/* World queries between steps, on the fat boxes the broad-phase keeps (as the reference's tree queries do):
+ *   b2cuQueryAABB          b2World::QueryAABB  -> b2BroadPhase::Query    Dynamics/b2World.cpp:1752-1758
+ *   b2cuRayCastCandidates  b2World::RayCast    -> b2DynamicTree::RayCast Collision/b2DynamicTree.h:203-287: the proxies
+ *                          whose fat box the segment p1 -> p2 crosses (segment box overlap + the separating-axis test
+ *                          of the tree walk); the exact per-shape ray cast and the callback protocol are the caller's
+ * Both return ascending proxy ids; `count` receives the total even when it exceeds `capacity`. */
+B2CU_API int b2cuQueryAABB(b2cuWorld* w, const float aabb[4], int32_t capacity, int32_t* proxyIds, int32_t* count);
+B2CU_API int b2cuRayCastCandidates(b2cuWorld* w, const float p1[2], const float p2[2], int32_t capacity,
+                                   int32_t* proxyIds, int32_t* count);
 
 /* Batched stand-alone b2Distance (Collision/b2Distance.cpp:452-603), cold simplex cache: closest points and distance
  * of shapes[shapeA[i]] at xfA[i] and shapes[shapeB[i]] at xfB[i] (any two of circle / edge / polygon).  With useRadii

@@ -51,6 +51,10 @@ def load(stock=False):
     lib.b2ref_profile.argtypes = [vp, vp]
     lib.b2ref_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_set_type.argtypes = [vp, i32, i32]
+    lib.b2ref_query_aabb.argtypes = [vp, vp, i32, vp]
+    lib.b2ref_query_aabb.restype = i32
+    lib.b2ref_ray_cast_closest.argtypes = [vp, vp, vp, vp]
+    lib.b2ref_ray_cast_closest.restype = i32
     lib.b2ref_record_post_solve.argtypes = [vp, i32]
     lib.b2ref_set_pre_solve_rule.argtypes = [vp, i32]
     lib.b2ref_pre_solve_digest.argtypes = [vp, vp, vp]
@@ -178,6 +182,18 @@ class RefWorld:
         c = np.zeros(1, np.int64)
         self.lib.b2ref_post_solve_digest(self.h, _ptr(d), _ptr(c))
         return int(d[0]), int(c[0])
+
+    def query_aabb(self, box):
+        a = np.asarray(box, np.float32)
+        out = np.zeros(1 << 16, np.int32)
+        n = self.lib.b2ref_query_aabb(self.h, _ptr(a), len(out), _ptr(out))
+        return out[:n]
+
+    def ray_cast_closest(self, p1, p2):
+        a, b = np.asarray(p1, np.float32), np.asarray(p2, np.float32)
+        out = np.zeros(5, np.float32)
+        proxy = self.lib.b2ref_ray_cast_closest(self.h, _ptr(a), _ptr(b), _ptr(out))
+        return proxy, out
 
     def set_type(self, body, body_type):
         self.lib.b2ref_set_type(self.h, body, body_type)

@@ -929,6 +929,61 @@ void b2ref_sincos(float x, float* s, float* c)
 	*c = r.c;
 }
 
+namespace
+{
+struct CollectQuery : public b2QueryCallback
+{
+	std::vector<int32> ids;
+	bool ReportFixture(b2Fixture* fixture) override
+	{
+		// the reference reports a fixture once per overlapping child proxy; record fixtures (first proxy id)
+		ids.push_back(ProxyIndex(fixture, 0));
+		return true;
+	}
+};
+struct ClosestRay : public b2RayCastCallback
+{
+	b2Fixture* fixture = nullptr;
+	b2Vec2 point, normal;
+	float32 fraction = 1.0f;
+	float32 ReportFixture(b2Fixture* f, const b2Vec2& p, const b2Vec2& n, float32 fr) override
+	{
+		fixture = f;
+		point = p;
+		normal = n;
+		fraction = fr;
+		return fr; // clip to the closest hit so far
+	}
+};
+} // namespace
+
+/* b2World::QueryAABB: first proxy id of every reported fixture (with repeats for multi-child fixtures), sorted */
+int32_t b2ref_query_aabb(b2refWorld* w, const float aabb[4], int32_t capacity, int32_t* out)
+{
+	CollectQuery q;
+	b2AABB box;
+	box.lowerBound.Set(aabb[0], aabb[1]);
+	box.upperBound.Set(aabb[2], aabb[3]);
+	w->world->QueryAABB(&q, box);
+	std::sort(q.ids.begin(), q.ids.end());
+	for (int32_t i = 0; i < (int32_t)q.ids.size() && i < capacity; ++i) out[i] = q.ids[i];
+	return (int32_t)q.ids.size();
+}
+
+/* b2World::RayCast with a closest-hit callback: returns the first proxy id of the hit fixture or -1; out = point.xy, normal.xy, fraction */
+int32_t b2ref_ray_cast_closest(b2refWorld* w, const float p1[2], const float p2[2], float out[5])
+{
+	ClosestRay r;
+	w->world->RayCast(&r, b2Vec2(p1[0], p1[1]), b2Vec2(p2[0], p2[1]));
+	if (r.fixture == nullptr) return -1;
+	out[0] = r.point.x;
+	out[1] = r.point.y;
+	out[2] = r.normal.x;
+	out[3] = r.normal.y;
+	out[4] = r.fraction;
+	return ProxyIndex(r.fixture, 0);
+}
+
 void b2ref_distance(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
                     int32_t useRadii, b2cuDistanceResult* out)
 {

@@ -129,6 +129,9 @@ uint32_t b2ref_hash(b2refWorld* w);
 /* Stand-alone manifold functions of the reference (b2Collide*.cpp) on b2cuShape records. */
 void b2ref_collide(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
                    b2cuManifold* out);
+/* world queries of the reference (b2World::QueryAABB / RayCast), see ref_harness.cpp */
+int32_t b2ref_query_aabb(b2refWorld* w, const float aabb[4], int32_t capacity, int32_t* out);
+int32_t b2ref_ray_cast_closest(b2refWorld* w, const float p1[2], const float p2[2], float out[5]);
 /* the reference's b2Distance with a cold simplex cache, on geometry records (same conventions as b2ref_collide) */
 void b2ref_distance(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
                     int32_t useRadii, b2cuDistanceResult* out);

@@ -291,6 +291,54 @@ def test_host_api_pre_solve_can_disable_contacts(gpu):
     assert ((keys % np.uint64(3) == 0) & (touching != 0)).any()
 
 
+def _check_queries(h, r, rng, count=40):
+    for _ in range(count):
+        c = rng.uniform(-6.0, 6.0, 2)
+        e = rng.uniform(0.1, 2.5, 2)
+        box = [c[0] - e[0], c[1] - e[1] + 2.0, c[0] + e[0], c[1] + e[1] + 2.0]
+        assert (h.query_aabb(box) == r.query_aabb(box)).all()
+        p1 = rng.uniform(-8.0, 8.0, 2) + [0.0, 6.0]
+        p2 = rng.uniform(-8.0, 8.0, 2) + [0.0, -1.0]
+        hp, ho = h.ray_cast_closest(p1, p2)
+        rp, ro = r.ray_cast_closest(p1, p2)
+        # the closest hit does not depend on the order in which the candidates are visited
+        assert hp == rp, (p1, p2)
+        if hp >= 0:
+            assert (ho.view(np.uint32) == ro.view(np.uint32)).all()
+
+
+def test_world_queries_before_the_first_step():
+    scene = scenes.chain_terrain(12)
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    _check_queries(h, r, np.random.default_rng(2))
+
+
+@pytest.mark.gpu
+def test_world_queries_between_steps(gpu):
+    """b2World::QueryAABB / RayCast answered from the device's fat boxes, after steps and after host edits that have
+    not been stepped yet (SetTransform), and ShiftOrigin."""
+    scene = scenes.chain_terrain(24)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    rng = np.random.default_rng(4)
+    for s in range(90):
+        h.step()
+        assert r.step_ordered(h.solver_order()) == 0
+        if s % 30 == 29:
+            _check_queries(h, r, rng, 25)
+    for w in (r, h):
+        w.set_transform(5, 1.0, 6.0, 0.4)
+    _check_queries(h, r, rng, 25)
+    h.shift_origin(3.0, -1.0)
+    moved = h.bodies()
+    assert np.allclose(moved["px"] + 3.0, r.bodies()["px"], atol=1e-5) and np.allclose(moved["py"] - 1.0, r.bodies()["py"], atol=1e-5)
+    for _ in range(10):
+        h.step()
+    assert np.isfinite(h.bodies()["py"]).all()
+
+
 @pytest.mark.gpu
 def test_host_api_lazy_download(gpu):
     """downloadBodies=false: the mirror is refreshed on first access only; results are the same."""
