@@ -2036,6 +2036,12 @@ __global__ void __launch_bounds__(256) GridCountKernel(DeviceArrays d, int proxy
 	B2CU_GRID_STRIDE(p, proxyCount)
 	{
 		float4 fat = d.fat[p];
+		if ((d.pgroup[p] >> 16) & B2CU_PROXY_INACTIVE)
+		{
+			// proxy of an inactive body: in no cell and never queried (GridFillKernel skips negative cells)
+			d.cellOfProxy[p] = -2;
+			continue;
+		}
 		bool moved = IsMovedProxy(d, p);
 		int level = ProxyLevel(fat, g.cell0);
 		atomicAdd(&sh[level], 1);
@@ -2257,7 +2263,7 @@ __global__ void __launch_bounds__(128) QueryUnmovedKernel(DeviceArrays d, int pr
 	}
 	B2CU_GRID_STRIDE(p, proxyCount)
 	{
-		if (IsMovedProxy(d, p)) continue;
+		if ((d.pgroup[p] >> 16) & (B2CU_PROXY_MOVED | B2CU_PROXY_INACTIVE)) continue;
 		QueryProxy(d, p, false, g, shCount, shMoved, contactCount, pairCapacity, 0, 1);
 	}
 }
@@ -2439,7 +2445,10 @@ __global__ void EndStepBodiesKernel(DeviceArrays d, int bodyCount, int clearForc
 // of HBM time), then a stable compaction -- no tree to walk ----
 __global__ void QueryAabbSelectKernel(DeviceArrays d, int proxyCount, float4 box, int* __restrict__ flags)
 {
-	B2CU_GRID_STRIDE(p, proxyCount) { flags[p] = AabbOverlap(d.fat[p], box) ? 1 : 0; }
+	B2CU_GRID_STRIDE(p, proxyCount)
+	{
+		flags[p] = (AabbOverlap(d.fat[p], box) && !((d.pgroup[p] >> 16) & B2CU_PROXY_INACTIVE)) ? 1 : 0;
+	}
 }
 
 // b2DynamicTree::RayCast's node test (b2DynamicTree.h:203-287) applied to every proxy box: the box of the segment must
@@ -2455,7 +2464,7 @@ __global__ void RayCastSelectKernel(DeviceArrays d, int proxyCount, float2 p1, f
 	{
 		float4 f = d.fat[p];
 		int hit = 0;
-		if (AabbOverlap(f, seg))
+		if (AabbOverlap(f, seg) && !((d.pgroup[p] >> 16) & B2CU_PROXY_INACTIVE))
 		{
 			Vec2 c = V(0.5f * (f.x + f.z), 0.5f * (f.y + f.w));
 			Vec2 h = V(0.5f * (f.z - f.x), 0.5f * (f.w - f.y));

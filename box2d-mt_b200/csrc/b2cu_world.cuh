@@ -63,7 +63,7 @@ struct ContactSet
 
 // device-only proxy flag (next to the public B2CU_PROXY_* bits): moved by SyncProxiesKernel in this step
 #define B2CU_PROXY_MOVED_SYNC 0x8
-#define B2CU_PROXY_PUBLIC_FLAGS 0x37
+#define B2CU_PROXY_PUBLIC_FLAGS 0x77
 
 struct DeviceArrays
 {

@@ -509,6 +509,7 @@ B2H_API int32 b2h_ray_cast_closest(void* p, const float* p1, const float* p2, fl
 	return r.fixture->GetProxyIndex();
 }
 B2H_API void b2h_shift_origin(void* p, float x, float y) { static_cast<Host*>(p)->world->ShiftOrigin(b2Vec2(x, y)); }
+B2H_API void b2h_set_active(void* p, int32 body, int32 on) { static_cast<Host*>(p)->bodies[body]->SetActive(on != 0); }
 B2H_API void b2h_set_type(void* p, int32 body, int32 type) { static_cast<Host*>(p)->bodies[body]->SetType((b2BodyType)type); }
 B2H_API void b2h_set_filter(void* p, int32 fixture, uint16 categoryBits, uint16 maskBits, int16 groupIndex)
 {

@@ -219,11 +219,56 @@ void b2Body::SetBullet(bool flag)
 	m_world->MarkBodyDirty(m_index);
 }
 
+// reference b2Body.cpp:496-544.  The proxies keep their slots (ids) and are only flagged out of the broad-phase, so that
+// a body that comes back has the ids it had: the fixture A / fixture B roles of its future contacts follow the ids.
 void b2Body::SetActive(bool flag)
 {
-	// deactivation removes proxies (reference b2Body.cpp:492-542); outside this version of the GPU path
-	b2Assert(flag == IsActive());
-	B2_NOT_USED(flag);
+	if (m_world->IsLocked() || flag == IsActive()) return;
+	m_world->RefreshBodies();
+	m_world->RefreshProxies();
+	b2BodyView s = B2_STATE();
+	if (flag)
+	{
+		s.flags |= B2CU_BODY_ACTIVE;
+		// b2Fixture::CreateProxies at the current transform: tight box, fat box = tight box + margin, in the move buffer
+		// (no e_newFixture: the pairs are found by the pair search at the END of the next step)
+		const b2Transform& xf = reinterpret_cast<const b2Transform&>(s.px);
+		for (b2Fixture* f = m_fixtureList; f; f = f->m_next)
+		{
+			for (int32 child = 0; child < f->m_proxyCount; ++child)
+			{
+				b2cuProxy& p = m_world->m_proxies[f->m_proxyIndex + child];
+				b2AABB aabb;
+				f->m_shape->ComputeAABB(&aabb, xf, child);
+				p.aabb[0] = aabb.lowerBound.x;
+				p.aabb[1] = aabb.lowerBound.y;
+				p.aabb[2] = aabb.upperBound.x;
+				p.aabb[3] = aabb.upperBound.y;
+				p.fat[0] = aabb.lowerBound.x - b2_aabbExtension;
+				p.fat[1] = aabb.lowerBound.y - b2_aabbExtension;
+				p.fat[2] = aabb.upperBound.x + b2_aabbExtension;
+				p.fat[3] = aabb.upperBound.y + b2_aabbExtension;
+				p.flags = (uint16)((p.flags & ~(uint16)B2CU_PROXY_INACTIVE) | B2CU_PROXY_MOVED);
+				m_world->MarkProxyDirty(f->m_proxyIndex + child);
+			}
+		}
+	}
+	else
+	{
+		s.flags &= ~(uint32)B2CU_BODY_ACTIVE;
+		for (b2Fixture* f = m_fixtureList; f; f = f->m_next)
+		{
+			for (int32 child = 0; child < f->m_proxyCount; ++child)
+			{
+				b2cuProxy& p = m_world->m_proxies[f->m_proxyIndex + child];
+				p.flags = (uint16)((p.flags & ~(uint16)(B2CU_PROXY_MOVED | B2CU_PROXY_NEW)) | B2CU_PROXY_INACTIVE);
+				m_world->MarkProxyDirty(f->m_proxyIndex + child);
+			}
+		}
+		// destroy the attached contacts (EndContact for the touching ones)
+		m_world->DestroyContactsOfBody(m_index);
+	}
+	m_world->MarkBodyDirty(m_index);
 }
 
 void b2Body::SetFixedRotation(bool flag)
@@ -493,8 +538,9 @@ b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def)
 		p.categoryBits = f->m_filter.categoryBits;
 		p.maskBits = f->m_filter.maskBits;
 		p.groupIndex = f->m_filter.groupIndex;
+		// a fixture of an inactive body gets its proxy slots but stays out of the broad-phase (b2Body.cpp:216-220)
 		p.flags = (uint16)((f->m_isSensor ? B2CU_PROXY_SENSOR : 0) | (f->m_thickShape ? B2CU_PROXY_THICK : 0) |
-		                   B2CU_PROXY_MOVED | B2CU_PROXY_NEW);
+		                   (IsActive() ? (B2CU_PROXY_MOVED | B2CU_PROXY_NEW) : B2CU_PROXY_INACTIVE));
 		p.fixture = f->m_proxyIndex;
 		p.child = child;
 		m_world->m_proxies.push_back(p);

@@ -112,7 +112,6 @@ b2World::~b2World()
 b2Body* b2World::CreateBody(const b2BodyDef* def)
 {
 	if (IsLocked()) return nullptr;
-	b2Assert(def->active); // inactive bodies are outside this version of the GPU path
 	RefreshBodies();
 
 	b2Body* b = new b2Body;

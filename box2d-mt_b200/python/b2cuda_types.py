@@ -87,7 +87,7 @@ BODY_GHOST = 0x100
 SHAPE_CIRCLE, SHAPE_EDGE, SHAPE_POLYGON = 0, 1, 2
 EDGE_HAS_VERTEX0, EDGE_HAS_VERTEX3, EDGE_CHAIN_CHILD = 1, 2, 4
 PROXY_SENSOR, PROXY_THICK, PROXY_MOVED = 1, 2, 4
-PROXY_NEW, PROXY_REFILTER = 0x10, 0x20
+PROXY_NEW, PROXY_REFILTER, PROXY_INACTIVE = 0x10, 0x20, 0x40
 CONTACT_ISLAND, CONTACT_TOUCHING, CONTACT_ENABLED, CONTACT_FILTER = 0x1, 0x2, 0x4, 0x8
 CONTACT_BULLET_HIT, CONTACT_TOI, CONTACT_TOI_CANDIDATE, CONTACT_INACTIVE = 0x10, 0x20, 0x40, 0x80
 MANIFOLD_CIRCLES, MANIFOLD_FACE_A, MANIFOLD_FACE_B = 0, 1, 2

@@ -63,6 +63,7 @@ def load():
     lib.b2h_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_velocity.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_type.argtypes = [vp, i32, i32]
+    lib.b2h_set_active.argtypes = [vp, i32, i32]
     lib.b2h_query_aabb.argtypes = [vp, vp, i32, vp]
     lib.b2h_query_aabb.restype = i32
     lib.b2h_ray_cast_closest.argtypes = [vp, vp, vp, vp]
@@ -230,6 +231,9 @@ class HostWorld:
 
     def shift_origin(self, x, y):
         self.lib.b2h_shift_origin(self.h, x, y)
+
+    def set_active(self, body, on):
+        self.lib.b2h_set_active(self.h, body, int(on))
 
     def set_type(self, body, body_type):
         self.lib.b2h_set_type(self.h, body, body_type)

@@ -165,6 +165,8 @@ enum
 	                               found by the next FindNewContacts, i.e. at the END of the next step */
 	B2CU_PROXY_NEW = 0x0010,    /* with MOVED: the fixture is new (b2World::e_newFixture, set by b2Body::CreateFixture): the
 	                               next step finds the pairs of the whole move buffer FIRST (Dynamics/b2World.cpp:1628-1639) */
+	B2CU_PROXY_INACTIVE = 0x0040, /* the body is inactive (b2Body::SetActive(false) destroys its proxies, Dynamics/b2Body.cpp:
+	                                 496-544): the slot keeps its id but takes no part in the broad-phase or in queries */
 	B2CU_PROXY_REFILTER = 0x0020 /* with MOVED: b2Fixture::Refilter (Dynamics/b2Fixture.cpp:187-220): the contacts of this
 	                               proxy are re-checked against the filters by the next Collide (e_filterFlag) */
 };

@@ -51,6 +51,7 @@ def load(stock=False):
     lib.b2ref_profile.argtypes = [vp, vp]
     lib.b2ref_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_set_type.argtypes = [vp, i32, i32]
+    lib.b2ref_set_active.argtypes = [vp, i32, i32]
     lib.b2ref_query_aabb.argtypes = [vp, vp, i32, vp]
     lib.b2ref_query_aabb.restype = i32
     lib.b2ref_ray_cast_closest.argtypes = [vp, vp, vp, vp]
@@ -194,6 +195,9 @@ class RefWorld:
         out = np.zeros(5, np.float32)
         proxy = self.lib.b2ref_ray_cast_closest(self.h, _ptr(a), _ptr(b), _ptr(out))
         return proxy, out
+
+    def set_active(self, body, on):
+        self.lib.b2ref_set_active(self.h, body, int(on))
 
     def set_type(self, body, body_type):
         self.lib.b2ref_set_type(self.h, body, body_type)

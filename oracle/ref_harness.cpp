@@ -660,6 +660,7 @@ void b2ref_export_proxies(b2refWorld* w, b2cuProxy* out, int32_t* treeProxyIds)
 		o.fixture = w->proxyBase[FixtureIndex(f)];
 		o.child = child;
 		int32 treeId = -1;
+		if (f->m_proxyCount <= child) o.flags |= B2CU_PROXY_INACTIVE; /* body inactive: its proxies are gone */
 		if (f->m_proxyCount > child)
 		{
 			const b2FixtureProxy& p = f->m_proxies[child];
@@ -816,6 +817,7 @@ void b2ref_post_solve_digest(b2refWorld* w, uint64_t* digest, int64_t* count)
 	*count = w->listener.postSolveCount;
 }
 
+void b2ref_set_active(b2refWorld* w, int32_t body, int32_t on) { w->bodies[body]->SetActive(on != 0); }
 void b2ref_set_type(b2refWorld* w, int32_t body, int32_t type) { w->bodies[body]->SetType((b2BodyType)type); }
 
 void b2ref_set_velocity(b2refWorld* w, int32_t body, float vx, float vy, float angw)

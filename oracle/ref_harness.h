@@ -109,6 +109,7 @@ void b2ref_profile(b2refWorld* w, float* out13);
 /* mutators used by tests */
 void b2ref_set_transform(b2refWorld* w, int32_t body, float x, float y, float angle);
 void b2ref_set_type(b2refWorld* w, int32_t body, int32_t type); /* b2Body::SetType */
+void b2ref_set_active(b2refWorld* w, int32_t body, int32_t on); /* b2Body::SetActive */
 /* PostSolve recording: running digest over (contact key, impulse count, impulses) of every PostSolve call */
 /* PreSolve test rule: the listener disables every contact whose key is a multiple of `modulus` (0: off) */
 void b2ref_set_pre_solve_rule(b2refWorld* w, int32_t modulus);

@@ -205,6 +205,30 @@ def test_host_api_teleport_and_refilter_timing(gpu):
 
 
 @pytest.mark.gpu
+def test_host_api_set_active_between_steps(gpu):
+    """b2Body::SetActive(false / true) after the world has been stepped (b2Body.cpp:496-544): the body leaves the
+    simulation with its contacts, keeps its state, and comes back with new contacts one step later."""
+    scene = scenes.pile(8, 6)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    changes = {40: (12, False), 41: (13, False), 75: (12, True), 110: (13, True), 111: (30, False)}
+    for s in range(160):
+        if s in changes:
+            body, on = changes[s]
+            for w in (r, h):
+                w.set_active(body, on)
+            assert h.counts()[2] == len(r.contacts())
+        h.step()
+        assert r.step_ordered(h.solver_order()) == 0
+        try:
+            _contact_sets_equal(h, r)
+            parity.compare_bodies(h.bodies(), r.bodies())
+        except AssertionError as e:
+            raise AssertionError("step %d: %s" % (s, e))
+
+
+@pytest.mark.gpu
 def test_host_api_set_type_between_steps(gpu):
     """b2Body::SetType after the world has been stepped: the body's contacts are destroyed at once, its proxies
     touched, mass data reset (b2Body.cpp:118-188).  dynamic -> static -> dynamic -> kinematic."""
