@@ -172,3 +172,59 @@ def test_custom_pair_filter(gpu):
     # bodies really pass through each other where the rule says so: more overlap than the default world would allow
     assert int(infos[-1]["contactCount"]) > 0
 
+
+def test_more_than_32_contacts_on_one_body(gpu):
+    """A heavy disc buried in small ones has more touching contacts than there are colours (32): the surplus goes to
+    the serial overflow list of the solver, which must still reproduce the sequential Gauss-Seidel of the oracle."""
+    s = _scene()
+    ground = s.body(T.STATIC_BODY, (0, 0))
+    s.fixture(ground, s.box(12, 0.5, center=(0, -0.5)), thick=True)
+    s.fixture(ground, s.box(0.5, 6, center=(-5.5, 6)), thick=True)
+    s.fixture(ground, s.box(0.5, 6, center=(5.5, 6)), thick=True)
+    big = s.body(T.DYNAMIC_BODY, (0.0, 3.2))
+    s.fixture(big, s.circle(3.0), density=0.2, friction=0.3)
+    small = s.circle(0.12)
+    k = 0
+    for row in range(14):
+        for col in range(40):
+            x, y = -4.9 + 0.25 * col + 0.01 * (row % 2), 6.6 + 0.25 * row
+            b = s.body(T.DYNAMIC_BODY, (x, y))
+            s.fixture(b, small, density=1.0, friction=0.2)
+            k += 1
+    r = ref.RefWorld(s)
+    g = parity.gpu_world_from_ref(gpu, r)
+    infos = parity.lockstep(g, r, 220, tol=0.0, check_every=4)
+    assert max(int(i["overflowCount"]) for i in infos) > 0, "the scene must exhaust the colours"
+    assert max(int(i["colourCount"]) for i in infos) >= 30
+
+
+def test_proxy_larger_than_the_coarsest_grid_level(gpu):
+    """Tiny bodies make the finest grid cell tiny; a ground box a million times larger than them is beyond the coarsest
+    of the 24 grid levels and takes the `huge` list path of the broad-phase.  Pair set and state stay exact."""
+    s = _scene()
+    ground = s.body(T.STATIC_BODY, (0, 0))
+    s.fixture(ground, s.box(40000.0, 0.5, center=(0, -0.5)), thick=True)
+    tiny = s.circle(0.004)
+    box = s.box(0.004, 0.003)
+    for i in range(60):
+        b = s.body(T.DYNAMIC_BODY, (-0.3 + 0.01 * i, 0.02 + 0.011 * (i % 5)))
+        s.fixture(b, tiny if i % 2 else box, density=1.0)
+    mover = s.body(T.KINEMATIC_BODY, (0.0, 0.3), vel=(0.0, -0.05))
+    s.fixture(mover, s.box(30000.0, 0.05))          # a huge MOVING proxy as well
+    infos, g, r = _run(gpu, s, 200)
+    assert int(infos[-1]["contactCount"]) > 60
+
+
+def test_capacity_growth_from_nothing(gpu):
+    """Device buffers grow geometrically on their own: a world created with minimal capacities receives a scene, and the
+    contact set outgrows its buffer during the run (b2cuSetCounts, the contact capacity inside b2cuStep)."""
+    s = scenes.pile(20, 12)
+    s.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(s)
+    bodies, shapes, proxies, contacts = parity.ref_state(r)
+    g = gpu.World(gravity=r.gravity, flags=r.world_flags, body_capacity=1, proxy_capacity=1, shape_capacity=1,
+                  contact_capacity=1)
+    g.load_state(bodies, shapes, proxies, contacts, inv_dt0=r.inv_dt0())
+    infos = parity.lockstep(g, r, 150, tol=0.0, check_every=3)
+    assert int(infos[-1]["contactCount"]) > 1000
+
