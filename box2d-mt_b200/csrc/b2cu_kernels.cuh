@@ -6,6 +6,7 @@
 
 #include "b2cu_collide.cuh"
 #include "b2cu_gjk.cuh"
+#include "b2cu_toi.cuh"
 #include "b2cu_world.cuh"
 
 namespace b2cu
@@ -2495,6 +2496,36 @@ __global__ void DistancePairsKernel(const b2cuShape* __restrict__ shapes, int pa
 		o.pointB[0] = g.pointB.x;
 		o.pointB[1] = g.pointB.y;
 		o.iterations = g.iterations;
+		out[i] = o;
+	}
+}
+
+// stand-alone batched b2TimeOfImpact (b2cuTimeOfImpactPairs)
+__device__ __forceinline__ Sweep MakeSweep(const b2cuSweep& r)
+{
+	Sweep s;
+	s.localCenter = V(r.localCenter[0], r.localCenter[1]);
+	s.c0 = V(r.c0[0], r.c0[1]);
+	s.c = V(r.c[0], r.c[1]);
+	s.a0 = r.a0;
+	s.a = r.a;
+	s.alpha0 = r.alpha0;
+	return s;
+}
+
+__global__ void TimeOfImpactPairsKernel(const b2cuShape* __restrict__ shapes, int pairCount, const int* __restrict__ shapeA,
+                                        const b2cuSweep* __restrict__ sweepA, const int* __restrict__ shapeB,
+                                        const b2cuSweep* __restrict__ sweepB, const float* __restrict__ tMax,
+                                        b2cuToiResult* __restrict__ out)
+{
+	B2CU_GRID_STRIDE(i, pairCount)
+	{
+		float t;
+		int state = TimeOfImpact(&t, MakeGjkProxy(shapes + shapeA[i]), MakeSweep(sweepA[i]),
+		                         MakeGjkProxy(shapes + shapeB[i]), MakeSweep(sweepB[i]), tMax[i]);
+		b2cuToiResult o;
+		o.state = state;
+		o.t = t;
 		out[i] = o;
 	}
 }

@@ -2116,6 +2116,55 @@ int b2cuDistancePairs(int32_t device, int32_t shapeCount, const b2cuShape* shape
 	return e == cudaSuccess ? B2CU_OK : B2CU_ERR_CUDA;
 }
 
+// device copy of a host array for the stand-alone batched entries; freed by the caller
+static cudaError_t UploadArray(void* dstPointer, const void* src, size_t bytes, cudaError_t e)
+{
+	if (e != cudaSuccess) return e;
+	void** dst = (void**)dstPointer;
+	e = cudaMalloc(dst, bytes);
+	if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+	return e;
+}
+
+int b2cuTimeOfImpactPairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
+                          const int32_t* shapeA, const b2cuSweep* sweepA, const int32_t* shapeB, const b2cuSweep* sweepB,
+                          const float* tMax, b2cuToiResult* results)
+{
+	if (shapeCount <= 0 || pairCount < 0 || !shapes || !shapeA || !shapeB || !sweepA || !sweepB || !tMax || !results)
+		return B2CU_ERR_ARGUMENT;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return B2CU_ERR_NO_DEVICE;
+	if (cudaSetDevice(device) != cudaSuccess) return B2CU_ERR_CUDA;
+	if (pairCount == 0) return B2CU_OK;
+	b2cuShape* dShapes = nullptr;
+	int32_t *dA = nullptr, *dB = nullptr;
+	b2cuSweep *dSa = nullptr, *dSb = nullptr;
+	float* dT = nullptr;
+	b2cuToiResult* dOut = nullptr;
+	cudaError_t e = cudaSuccess;
+	e = UploadArray(&dShapes, shapes, sizeof(b2cuShape) * shapeCount, e);
+	e = UploadArray(&dA, shapeA, sizeof(int32_t) * pairCount, e);
+	e = UploadArray(&dB, shapeB, sizeof(int32_t) * pairCount, e);
+	e = UploadArray(&dSa, sweepA, sizeof(b2cuSweep) * pairCount, e);
+	e = UploadArray(&dSb, sweepB, sizeof(b2cuSweep) * pairCount, e);
+	e = UploadArray(&dT, tMax, sizeof(float) * pairCount, e);
+	if (e == cudaSuccess) e = cudaMalloc(&dOut, sizeof(b2cuToiResult) * pairCount);
+	if (e == cudaSuccess)
+	{
+		TimeOfImpactPairsKernel<<<GridFor(pairCount), kBlock>>>(dShapes, pairCount, dA, dSa, dB, dSb, dT, dOut);
+		e = cudaDeviceSynchronize();
+	}
+	if (e == cudaSuccess) e = cudaMemcpy(results, dOut, sizeof(b2cuToiResult) * pairCount, cudaMemcpyDeviceToHost);
+	cudaFree(dShapes);
+	cudaFree(dA);
+	cudaFree(dB);
+	cudaFree(dSa);
+	cudaFree(dSb);
+	cudaFree(dT);
+	cudaFree(dOut);
+	return e == cudaSuccess ? B2CU_OK : B2CU_ERR_CUDA;
+}
+
 int b2cuSinCos(int32_t device, int32_t count, const float* angles, float* sinOut, float* cosOut)
 {
 	if (count < 0 || !angles || !sinOut || !cosOut) return B2CU_ERR_ARGUMENT;

@@ -21,7 +21,7 @@ API = [
     "b2cuSetWorldParams", "b2cuSetInvDt0", "b2cuSetCounts", "b2cuSetBodies", "b2cuGetBodies", "b2cuSetShapes",
     "b2cuSetProxies", "b2cuGetProxies", "b2cuSetContacts", "b2cuGetContactCount", "b2cuGetContacts", "b2cuStep",
     "b2cuGetContactsByKey", "b2cuGetEvents", "b2cuGetSolverOrder", "b2cuGetIslandLabels", "b2cuGetToiCandidates", "b2cuCollidePairs",
-    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuDistancePairs", "b2cuQueryAABB", "b2cuRayCastCandidates", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts",
+    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuDistancePairs", "b2cuTimeOfImpactPairs", "b2cuQueryAABB", "b2cuRayCastCandidates", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts",
 ]
 
 
@@ -297,6 +297,23 @@ def distance_pairs(shapes, shape_a, xf_a, shape_b, xf_b, use_radii=True, device=
                                1 if use_radii else 0, _ptr(out))
     if rc != 0:
         raise B2cuError(rc, "b2cuDistancePairs failed")
+    return out
+
+
+def time_of_impact_pairs(shapes, shape_a, sweep_a, shape_b, sweep_b, t_max, device=0):
+    """Batched b2TimeOfImpact; returns a TOI_RESULT array."""
+    lib = load()
+    shapes = np.ascontiguousarray(shapes, T.SHAPE)
+    a = np.ascontiguousarray(shape_a, np.int32)
+    b = np.ascontiguousarray(shape_b, np.int32)
+    wa = np.ascontiguousarray(sweep_a, T.SWEEP)
+    wb = np.ascontiguousarray(sweep_b, T.SWEEP)
+    tm = np.ascontiguousarray(np.broadcast_to(np.asarray(t_max, np.float32), (len(a),)))
+    out = np.zeros(len(a), T.TOI_RESULT)
+    rc = lib.b2cuTimeOfImpactPairs(device, len(shapes), _ptr(shapes), len(a), _ptr(a), _ptr(wa), _ptr(b), _ptr(wb),
+                                   _ptr(tm), _ptr(out))
+    if rc != 0:
+        raise B2cuError(rc, "b2cuTimeOfImpactPairs failed")
     return out
 
 

@@ -56,6 +56,11 @@ assert CONTACT.itemsize == 96
 
 DISTANCE_RESULT = np.dtype([("distance", "f4"), ("pointA", "f4", (2,)), ("pointB", "f4", (2,)), ("iterations", "i4")])
 assert DISTANCE_RESULT.itemsize == 24
+SWEEP = np.dtype([("localCenter", "f4", (2,)), ("c0", "f4", (2,)), ("c", "f4", (2,)), ("a0", "f4"), ("a", "f4"), ("alpha0", "f4")])
+assert SWEEP.itemsize == 36
+TOI_RESULT = np.dtype([("state", "i4"), ("t", "f4")])
+assert TOI_RESULT.itemsize == 8
+TOI_UNKNOWN, TOI_FAILED, TOI_OVERLAPPED, TOI_TOUCHING, TOI_SEPARATED = range(5)
 
 WORLD_DEF = np.dtype([
     ("device", "i4"), ("gravity", "f4", (2,)), ("flags", "u4"),

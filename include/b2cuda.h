@@ -50,6 +50,7 @@
  *   b2cuQueryAABB / RayCastCandidates    b2World::QueryAABB / RayCast (tree queries on the fat boxes)
  *                                                                          Dynamics/b2World.cpp:1752-1795
  *   b2cuDistancePairs                    b2Distance (GJK), batched; b2TestOverlap = its distance under 10 epsilon
+ *   b2cuTimeOfImpactPairs                b2TimeOfImpact (conservative advancement), batched
  *                                                                          Collision/b2Distance.cpp:452-603, b2Collision.cpp:233-252
  *   b2cuCollidePairs                     b2CollidePolygons / b2CollideCircles / b2CollidePolygonAndCircle /
  *                                        b2CollideEdgeAndCircle / b2CollideEdgeAndPolygon, batched
@@ -422,6 +423,35 @@ typedef struct b2cuDistanceResult
 B2CU_API int b2cuDistancePairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
                                const int32_t* shapeA, const float* xfA, const int32_t* shapeB, const float* xfB,
                                int32_t useRadii, b2cuDistanceResult* results);
+
+/* Batched stand-alone b2TimeOfImpact (Collision/b2TimeOfImpact.cpp:256-497), the conservative-advancement root finder
+ * the continuous-collision pass (b2World::SolveTOI, Dynamics/b2World.cpp:1085-1390) is built on: first time in
+ * [0, tMax] at which shapes[shapeA[i]] moving along sweepA[i] and shapes[shapeB[i]] along sweepB[i] come within the
+ * target separation.  b2cuSweep restates b2Sweep (Common/b2Math.h:382-410), b2cuToiResult restates b2TOIOutput
+ * (Collision/b2TimeOfImpact.h:38-52) with the same state values. */
+typedef struct b2cuSweep
+{
+	float localCenter[2];
+	float c0[2], c[2];
+	float a0, a;
+	float alpha0;
+} b2cuSweep;
+enum
+{
+	B2CU_TOI_UNKNOWN = 0,
+	B2CU_TOI_FAILED = 1,
+	B2CU_TOI_OVERLAPPED = 2,
+	B2CU_TOI_TOUCHING = 3,
+	B2CU_TOI_SEPARATED = 4
+};
+typedef struct b2cuToiResult
+{
+	int32_t state;
+	float t;
+} b2cuToiResult;
+B2CU_API int b2cuTimeOfImpactPairs(int32_t device, int32_t shapeCount, const b2cuShape* shapes, int32_t pairCount,
+                                   const int32_t* shapeA, const b2cuSweep* sweepA, const int32_t* shapeB,
+                                   const b2cuSweep* sweepB, const float* tMax, b2cuToiResult* results);
 
 /* sin/cos used by every transform on the device (one correctly-rounded-in-practice fp32 sincos shared with the
  * oracle so that fat-AABB decisions are reproducible); evaluated on the device. */

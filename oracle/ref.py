@@ -239,6 +239,18 @@ def distance(shape_a, xf_a, shape_b, xf_b, use_radii=True):
     return out
 
 
+def time_of_impact(shape_a, sweep_a, shape_b, sweep_b, t_max=1.0):
+    """Reference b2TimeOfImpact for two b2cuShape records and SWEEP records; returns a TOI_RESULT scalar."""
+    lib = load(False)
+    sa = np.ascontiguousarray(shape_a, T.SHAPE)
+    sb = np.ascontiguousarray(shape_b, T.SHAPE)
+    wa = np.ascontiguousarray(sweep_a, T.SWEEP)
+    wb = np.ascontiguousarray(sweep_b, T.SWEEP)
+    out = np.zeros((), T.TOI_RESULT)
+    lib.b2ref_time_of_impact(_ptr(sa), _ptr(wa), _ptr(sb), _ptr(wb), ctypes.c_float(t_max), _ptr(out))
+    return out
+
+
 def sincos(x, stock_libm=False):
     lib = load(stock_libm)
     s, c = ctypes.c_float(), ctypes.c_float()

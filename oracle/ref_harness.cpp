@@ -1020,4 +1020,39 @@ void b2ref_distance(const b2cuShape* shapeA, const float xfA[4], const b2cuShape
 	out->iterations = output.iterations;
 }
 
+/* the reference's b2TimeOfImpact (Collision/b2TimeOfImpact.cpp:256-497) on geometry records and b2Sweep values */
+static void ImportSweep(const b2cuSweep* r, b2Sweep& s)
+{
+	s.localCenter.Set(r->localCenter[0], r->localCenter[1]);
+	s.c0.Set(r->c0[0], r->c0[1]);
+	s.c.Set(r->c[0], r->c[1]);
+	s.a0 = r->a0;
+	s.a = r->a;
+	s.alpha0 = r->alpha0;
+}
+
+void b2ref_time_of_impact(const b2cuShape* shapeA, const b2cuSweep* sweepA, const b2cuShape* shapeB,
+                          const b2cuSweep* sweepB, float tMax, b2cuToiResult* out)
+{
+	b2CircleShape circleA, circleB;
+	b2EdgeShape edgeA, edgeB;
+	b2PolygonShape polyA, polyB;
+	ImportShape(shapeA, circleA, edgeA, polyA);
+	ImportShape(shapeB, circleB, edgeB, polyB);
+	const b2Shape* sA = shapeA->type == B2CU_SHAPE_CIRCLE ? (const b2Shape*)&circleA
+	                    : (shapeA->type == B2CU_SHAPE_EDGE ? (const b2Shape*)&edgeA : (const b2Shape*)&polyA);
+	const b2Shape* sB = shapeB->type == B2CU_SHAPE_CIRCLE ? (const b2Shape*)&circleB
+	                    : (shapeB->type == B2CU_SHAPE_EDGE ? (const b2Shape*)&edgeB : (const b2Shape*)&polyB);
+	b2TOIInput input;
+	input.proxyA.Set(sA, 0);
+	input.proxyB.Set(sB, 0);
+	ImportSweep(sweepA, input.sweepA);
+	ImportSweep(sweepB, input.sweepB);
+	input.tMax = tMax;
+	b2TOIOutput output;
+	b2TimeOfImpact(&output, &input);
+	out->state = (int32_t)output.state;
+	out->t = output.t;
+}
+
 } // extern "C"

@@ -137,6 +137,10 @@ int32_t b2ref_ray_cast_closest(b2refWorld* w, const float p1[2], const float p2[
 void b2ref_distance(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
                     int32_t useRadii, b2cuDistanceResult* out);
 
+/* the reference's b2TimeOfImpact on geometry records and sweeps */
+void b2ref_time_of_impact(const b2cuShape* shapeA, const b2cuSweep* sweepA, const b2cuShape* shapeB,
+                          const b2cuSweep* sweepB, float tMax, b2cuToiResult* out);
+
 /* The interposed sin/cos the reference build actually calls (checks that interposition works). */
 void b2ref_sincos(float x, float* s, float* c);
 

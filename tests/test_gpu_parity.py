@@ -124,6 +124,46 @@ def test_distance_pairs_bit_exact(gpu):
     assert overlapping > n // 10
 
 
+def _random_sweeps(rng, n, start, spread, turn):
+    """n b2Sweep records: from around `start` towards a random point `spread` away, rotating up to `turn` radians."""
+    sw = np.zeros(n, T.SWEEP)
+    sw["localCenter"] = rng.uniform(-0.2, 0.2, (n, 2))
+    sw["c0"] = start + rng.uniform(-0.3, 0.3, (n, 2))
+    sw["c"] = sw["c0"] + rng.normal(0, spread, (n, 2))
+    sw["a0"] = rng.uniform(-8.0, 8.0, n)        # outside [0, 2 pi): exercises b2Sweep::Normalize
+    sw["a"] = sw["a0"] + rng.uniform(-turn, turn, n)
+    return sw
+
+
+def test_time_of_impact_bit_exact(gpu):
+    """b2TimeOfImpact on the device against the reference's (b2TimeOfImpact.cpp:256-497): state and time of random
+    sweeps of every shape class -- approaching, passing, spinning in place, starting in touch or overlap."""
+    shapes = _shape_table()
+    rng = np.random.default_rng(23)
+    n = 6000
+    a = rng.integers(0, len(shapes), n)
+    b = rng.integers(0, len(shapes), n)
+    sa = _random_sweeps(rng, n, np.zeros(2), 0.5, 1.0)
+    sb = _random_sweeps(rng, n, np.array([2.5, 0.0]), 0.5, 1.0)
+    # B heads for A: most of these hit
+    sb["c"][:4000] = sa["c"][:4000] + rng.normal(0, 0.4, (4000, 2))
+    # fast spinners (the root finder's hard case) and sweeps that start in overlap
+    sb["a"][1000:1500] = sb["a0"][1000:1500] + rng.uniform(-6.0, 6.0, 500)
+    sb["c0"][1500:1800] = sa["c0"][1500:1800] + rng.normal(0, 0.1, (300, 2))
+    # second halves of a step (alpha0 > 0 does not enter the routine, but travels with the record)
+    sa["alpha0"][2000:2500] = rng.uniform(0, 0.9, 500)
+    t_max = np.ones(n, np.float32)
+    t_max[2500:3000] = rng.uniform(0.1, 1.0, 500)
+    got = gpu.time_of_impact_pairs(shapes, a, sa, b, sb, t_max)
+    states = np.zeros(5, int)
+    for i in range(n):
+        want = ref.time_of_impact(shapes[a[i]], sa[i], shapes[b[i]], sb[i], float(t_max[i]))
+        assert got[i]["state"] == want["state"], (i, got[i], want)
+        parity.assert_floats_equal("t", got[i]["t"], want["t"], TOL)
+        states[int(want["state"])] += 1
+    assert states[T.TOI_TOUCHING] > n // 5 and states[T.TOI_SEPARATED] > n // 10 and states[T.TOI_OVERLAPPED] > 50, states
+
+
 SCENES = {
     "pyramid6": lambda: scenes.pyramid(6, continuous=False),
     "pyramid20": lambda: scenes.pyramid(20, continuous=False),
