@@ -2402,6 +2402,56 @@ __global__ void ToiFlagsKernel(DeviceArrays d, int contactCount, int* flagsOut)
 	}
 }
 
+// b2Body::m_sweep of a body, as the step left it: c0 / a0 = where the solver picked the body up, c / a = where it put it
+__device__ __forceinline__ Sweep LoadSweep(const DeviceArrays& d, int body)
+{
+	float4 p0 = d.pos0[body], p = d.pos[body], m = d.mass[body];
+	Sweep s;
+	s.localCenter = V(m.z, m.w);
+	s.c0 = V(p0.x, p0.y);
+	s.a0 = p0.z;
+	s.alpha0 = p0.w;
+	s.c = V(p.x, p.y);
+	s.a = p.z;
+	return s;
+}
+
+// First pass of b2World::SolveTOI over the eligible contacts (b2FindMinToiContactTask, b2World.cpp:298-351, and
+// b2World::ComputeToi :404-447): time of impact of every candidate from its bodies' sweeps.  After a complete step
+// every sweep starts at alpha0 = 0, so no sweep has to be advanced and the contacts are independent.
+__global__ void ToiFirstPassKernel(DeviceArrays d, const int* __restrict__ list, const int* __restrict__ countPtr,
+                                   float* __restrict__ alphaOut)
+{
+	const int count = *countPtr;
+	B2CU_GRID_STRIDE(k, count)
+	{
+		int i = list[k];
+		int4 pr = d.c.proxies[i];
+		Sweep sA = LoadSweep(d, pr.z), sB = LoadSweep(d, pr.w);
+		float alpha0 = sA.alpha0;
+		float t;
+		int state = TimeOfImpact(&t, MakeGjkProxy(d.shapes + d.pshape[pr.x]), sA, MakeGjkProxy(d.shapes + d.pshape[pr.y]),
+		                         sB, 1.0f);
+		float alpha = state == TOI_TOUCHING ? Min(alpha0 + (1.0f - alpha0) * t, 1.0f) : 1.0f;
+		alphaOut[k] = alpha;
+		// alpha is in [0, 1]: its bit pattern orders like the value
+		atomicMin(reinterpret_cast<unsigned int*>(d.counters + CNT_TOI_MIN_ALPHA), __float_as_uint(alpha));
+	}
+}
+
+// ... and the winner among equal alphas: the smallest contact key (b2Contact::ToiLessThan, b2Contact.cpp:326-334)
+__global__ void ToiMinKeyKernel(DeviceArrays d, const int* __restrict__ list, const int* __restrict__ countPtr,
+                                const float* __restrict__ alpha)
+{
+	const int count = *countPtr;
+	const unsigned int best = *reinterpret_cast<const unsigned int*>(d.counters + CNT_TOI_MIN_ALPHA);
+	B2CU_GRID_STRIDE(k, count)
+	{
+		if (__float_as_uint(alpha[k]) == best)
+			atomicMin(reinterpret_cast<unsigned long long*>(d.counters + CNT_TOI_MIN_KEY), (unsigned long long)d.c.key[list[k]]);
+	}
+}
+
 // is b2Contact::IsToiCandidate (b2Contact.cpp:300-324) satisfiable by any pair: a bullet body, or a non-dynamic
 // body carrying a fixture that is not thick-shape
 __global__ void ToiPossibleKernel(DeviceArrays d, int bodyCount, int proxyCount)

@@ -44,6 +44,9 @@ enum Counter
 	CNT_WAKE_PATCH,       // bodies woken after the mirror copy of the step had started
 	CNT_HEAVY,            // contacts queued for the dense polygon pass of Collide
 	CNT_STICKY_TOI,       // not cleared per step: a TOI-candidate contact has existed
+	CNT_TOI_MIN_ALPHA,    // first TOI pass: float bits of the smallest alpha (0xFFFFFFFF: no candidate)
+	CNT_TOI_MIN_KEY,      // 64 bits (two slots): smallest contact key among the candidates at that alpha
+	CNT_TOI_MIN_KEY_HI,
 	CNT_COUNT
 };
 
@@ -64,6 +67,8 @@ struct ContactSet
 // device-only proxy flag (next to the public B2CU_PROXY_* bits): moved by SyncProxiesKernel in this step
 #define B2CU_PROXY_MOVED_SYNC 0x8
 #define B2CU_PROXY_PUBLIC_FLAGS 0x77
+
+static_assert(CNT_TOI_MIN_KEY % 2 == 0, "64-bit atomics on the key slot need 8-byte alignment");
 
 struct DeviceArrays
 {
@@ -204,6 +209,9 @@ struct b2cuWorld
 	int colourStarts[B2CU_MAX_COLOURS + 3];
 
 	int* hostCounters;   // pinned, CNT_COUNT + colour counts
+	float toiMinAlpha;       // first TOI pass of the last step (b2cuStepInfo)
+	uint64_t toiMinKey;
+	int toiEventPending;
 	b2cuPreSolveFn preSolveHook;
 	void* preSolveUser;
 	bool inPreSolve;         // b2cuStep is inside the hook: the pre-solve entry points are valid

@@ -1566,7 +1566,11 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	}
 
 	// ---- TOI eligibility compaction (b2World.cpp:283-352 filters; SolveTOI itself is host-driven) ----
+	const int lastToiCount = w->toiCount;
 	w->toiCount = 0;
+	w->toiMinAlpha = 1.0f;
+	w->toiMinKey = ~0ull;
+	w->toiEventPending = 0;
 	nc = w->contactCount;
 	const bool toiPass = (w->params.flags & B2CU_WORLD_CONTINUOUS) && dt > 0.0f && nc > 0 &&
 	                     w->hostCounters[CNT_STICKY_TOI] != 0;
@@ -1576,6 +1580,14 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		CompactFlags(&w->prims, d.cSelect, nc, d.listA, d.counters + CNT_TOI, w->stream);
 		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_TOI, (const int*)nullptr,
 		       d.toiKeys, w->contactCapacity);
+		// first pass of SolveTOI: the earliest time of impact among the candidates.  The sub-steps it would trigger
+		// are not executed; the step reports whether the reference would have taken one.
+		float* toiAlpha = reinterpret_cast<float*>(d.listB);
+		CUDA_TRY(w, cudaMemsetAsync(d.counters + CNT_TOI_MIN_ALPHA, 0xFF, sizeof(int) * 3, w->stream));
+		const int toiGrid = GridFor(std::max(1024, std::min(nc, 2 * lastToiCount)));
+		LAUNCH(w, ToiFirstPassKernel, toiGrid, kBlock, d, (const int*)d.listA, (const int*)(d.counters + CNT_TOI), toiAlpha);
+		LAUNCH(w, ToiMinKeyKernel, toiGrid, kBlock, d, (const int*)d.listA, (const int*)(d.counters + CNT_TOI),
+		       (const float*)toiAlpha);
 	}
 	cudaEvent_t evEnd = w->ev[9];
 	cudaEventRecord(evEnd, w->stream);
@@ -1583,7 +1595,19 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	if (toiPass || w->mirrorInFlight)
 	{
 		if ((rc = ReadCounters(w))) return rc;
-		if (toiPass) w->toiCount = w->hostCounters[CNT_TOI];
+		if (toiPass)
+		{
+			w->toiCount = w->hostCounters[CNT_TOI];
+			uint32_t bits;
+			memcpy(&bits, &w->hostCounters[CNT_TOI_MIN_ALPHA], sizeof(bits));
+			if (w->toiCount > 0 && bits != 0xFFFFFFFFu)
+			{
+				memcpy(&w->toiMinAlpha, &bits, sizeof(float));
+				memcpy(&w->toiMinKey, &w->hostCounters[CNT_TOI_MIN_KEY], sizeof(uint64_t));
+				// b2World::SolveTOI (b2World.cpp:1069) stops at 1 - 10 epsilon < alpha
+				w->toiEventPending = !(1.0f - 10.0f * B2CU_EPSILON < w->toiMinAlpha);
+			}
+		}
 	}
 	else
 	{
@@ -1647,6 +1671,10 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	out.beginCount = w->beginCount;
 	out.endCount = w->endCount;
 	out.toiCandidateCount = w->toiCount;
+	out.toiEventPending = w->toiEventPending;
+	out.toiMinKey = w->toiMinKey;
+	out.toiMinAlpha = w->toiMinAlpha;
+	out.reserved2 = 0;
 	out.kernelLaunches = w->launches + g_primLaunches;
 	if (info) *info = out;
 	return B2CU_OK;

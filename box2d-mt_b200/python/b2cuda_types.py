@@ -82,7 +82,9 @@ STEP_INFO = np.dtype([
     ("islandBodyCount", "i4"), ("awakeBodyCount", "i4"), ("moveCount", "i4"),
     ("newContactCount", "i4"), ("destroyedContactCount", "i4"),
     ("beginCount", "i4"), ("endCount", "i4"), ("toiCandidateCount", "i4"), ("kernelLaunches", "i4"),
+    ("toiEventPending", "i4"), ("toiMinKey", "u8"), ("toiMinAlpha", "f4"), ("reserved2", "i4"),
 ])
+assert STEP_INFO.itemsize == 136 and STEP_INFO.fields["toiMinKey"][1] == 120
 
 # enums
 STATIC_BODY, KINEMATIC_BODY, DYNAMIC_BODY = 0, 1, 2

@@ -252,6 +252,10 @@ typedef struct b2cuWorldDef
 	int32_t contactCapacity;
 } b2cuWorldDef;
 
+/* contact key = (min(proxyA,proxyB) << 32) | max(proxyA,proxyB): the b2ContactProxyIds ordering key
+ * (Dynamics/Contacts/b2Contact.h:65-77) over dense proxy ids assigned in fixture creation order. */
+typedef uint64_t b2cuContactKey;
+
 /* Per-step report.  The first 13 floats mirror b2Profile (Dynamics/b2TimeStep.h:25-40), in ms,
  * measured with CUDA events on the step stream. */
 typedef struct b2cuStepInfo
@@ -270,13 +274,17 @@ typedef struct b2cuStepInfo
 	int32_t beginCount, endCount;
 	int32_t toiCandidateCount;
 	int32_t kernelLaunches;    /* kernels launched by this step */
+	/* First pass of b2World::SolveTOI (Dynamics/b2World.cpp:1026-1092, FindMinToiContact :1525-1580) on a continuous
+	 * world: the candidate with the earliest time of impact.  toiEventPending = 1 when the reference would go on to
+	 * sub-step this contact (alpha <= 1 - 10 epsilon); the sub-step itself is not executed by this version, so a
+	 * step that reports 1 has left the reference's trajectory. */
+	int32_t toiEventPending;
+	b2cuContactKey toiMinKey;  /* ~0 when there is no candidate */
+	float toiMinAlpha;         /* 1 when there is no candidate */
+	int32_t reserved2;
 } b2cuStepInfo;
 
 enum { B2CU_EVENT_BEGIN = 0, B2CU_EVENT_END = 1 };
-
-/* contact key = (min(proxyA,proxyB) << 32) | max(proxyA,proxyB): the b2ContactProxyIds ordering key
- * (Dynamics/Contacts/b2Contact.h:65-77) over dense proxy ids assigned in fixture creation order. */
-typedef uint64_t b2cuContactKey;
 
 B2CU_API int b2cuGetDeviceCount(void);
 B2CU_API const char* b2cuVersion(void);

@@ -48,6 +48,8 @@ def load(stock=False):
     lib.b2ref_export_contacts.argtypes = [vp, i32, vp]
     lib.b2ref_events.argtypes = [vp, i32, i32, vp]
     lib.b2ref_toi_candidates.argtypes = [vp, i32, vp]
+    lib.b2ref_first_toi.argtypes = [vp, vp, vp]
+    lib.b2ref_first_toi.restype = i32
     lib.b2ref_profile.argtypes = [vp, vp]
     lib.b2ref_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_set_type.argtypes = [vp, i32, i32]
@@ -145,6 +147,13 @@ class RefWorld:
             if n <= cap:
                 return out[:n]
             cap = n
+
+    def first_toi(self):
+        """(key, alpha) of the contact b2World::SolveTOI would pick first on the current state, or (None, 1.0)."""
+        key = ctypes.c_uint64()
+        alpha = ctypes.c_float()
+        found = self.lib.b2ref_first_toi(self.h, ctypes.byref(key), ctypes.byref(alpha))
+        return (int(key.value) if found else None), float(alpha.value)
 
     def toi_candidates(self):
         cap = max(16, self.counts()[2])

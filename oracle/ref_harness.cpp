@@ -760,6 +760,26 @@ int b2ref_toi_candidates(b2refWorld* w, int32_t capacity, uint64_t* keys)
 	return (int)v.size();
 }
 
+/* First pass of b2World::SolveTOI on the state the last Step left (valid when that step ran with continuous physics
+ * off, so that no sub-step has happened yet): the sequential b2World::FindMinToiContact (b2World.cpp:1582-1611), then
+ * the time-of-impact cache it filled is cleared again as ClearPostSolveTOI would.  Returns 1 and the winner's key /
+ * alpha when there is a candidate. */
+int32_t b2ref_first_toi(b2refWorld* w, uint64_t* key, float* alpha)
+{
+	b2Contact* minContact = nullptr;
+	float32 minAlpha = 1.0f;
+	w->world->FindMinToiContact(&minContact, &minAlpha);
+	b2ContactManager& cm = w->world->m_contactManager;
+	for (uint32 i = 0; i < cm.m_toiCount; ++i)
+	{
+		cm.m_contacts[i]->m_flags &= ~b2Contact::e_toiFlag;
+		cm.m_contacts[i]->m_toi = 1.0f;
+	}
+	*alpha = minAlpha;
+	*key = minContact ? ContactKey(minContact) : ~0ull;
+	return minContact != nullptr;
+}
+
 void b2ref_profile(b2refWorld* w, float* out13)
 {
 	const b2Profile& p = w->world->GetProfile();

@@ -137,6 +137,8 @@ int32_t b2ref_ray_cast_closest(b2refWorld* w, const float p1[2], const float p2[
 void b2ref_distance(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
                     int32_t useRadii, b2cuDistanceResult* out);
 
+/* first pass of b2World::SolveTOI on the current state (see ref_harness.cpp) */
+int32_t b2ref_first_toi(b2refWorld* w, uint64_t* key, float* alpha);
 /* the reference's b2TimeOfImpact on geometry records and sweeps */
 void b2ref_time_of_impact(const b2cuShape* shapeA, const b2cuSweep* sweepA, const b2cuShape* shapeB,
                           const b2cuSweep* sweepB, float tMax, b2cuToiResult* out);

@@ -226,6 +226,43 @@ def test_lockstep_with_frequent_compaction(gpu, compact_min, monkeypatch):
     parity.lockstep(g, r, 60, tol=TOL)
 
 
+@pytest.mark.parametrize("name,steps", [("add_pair", 90), ("pyramid6", 120), ("pile", 150), ("chains", 150),
+                                        ("pile_sleep", 400)])
+def test_first_toi_pass(gpu, name, steps):
+    """First pass of b2World::SolveTOI (b2World.cpp:1026-1092): on a continuous world the device evaluates the time of
+    impact of every eligible contact after the regular solve and reports the earliest (alpha, key) and whether the
+    reference would sub-step.  The oracle runs with continuous physics off -- so neither side sub-steps and they stay
+    in lockstep -- and its FindMinToiContact is called on the state each step leaves."""
+    make = (lambda: scenes.add_pair(300)) if name == "add_pair" else SCENES[name]
+    scene = _no_toi(make())
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    g.set_params(r.gravity, r.world_flags | T.WORLD_CONTINUOUS)
+    pending = candidates = 0
+    for s in range(steps):
+        info = g.step()
+        keys, _ = g.solver_order()
+        assert r.step_ordered(keys, 1.0 / 60.0, 8, 3) == 0
+        key, alpha = r.first_toi()
+        if key is None:
+            assert int(info["toiMinKey"]) == 0xFFFFFFFFFFFFFFFF and info["toiMinAlpha"] == 1.0 and not info["toiEventPending"], s
+            continue
+        candidates += 1
+        assert int(info["toiMinKey"]) == key, (s, hex(int(info["toiMinKey"])), hex(key), float(info["toiMinAlpha"]), alpha)
+        parity.assert_floats_equal("toiMinAlpha", info["toiMinAlpha"], np.float32(alpha), TOL)
+        want_pending = not (np.float32(1.0) - np.float32(10.0) * np.finfo(np.float32).eps < np.float32(alpha))
+        assert bool(info["toiEventPending"]) == want_pending, s
+        pending += int(want_pending)
+    # the oracle's query left no trace, and the device's pass changed nothing: still the same worlds
+    parity.compare_bodies(g.get_bodies(), r.bodies(), TOL)
+    parity.compare_contacts(g.get_contacts(), r.contacts(), TOL)
+    if name in ("pile", "pile_sleep"):
+        assert candidates == 0  # thick-shape container, no bullets: no contact is ever eligible
+    else:
+        assert candidates > steps // 4
+        assert pending > 0      # the bullet / the landing bodies do produce events the reference would sub-step
+
+
 def test_add_pair_pair_set(gpu):
     """BASELINE config 2 (Add Pair, scaled down): broad-phase stress with a fast bullet box; pair set bit-exact
     every step.  Continuous physics is off on both sides (SolveTOI is host-driven and outside this test)."""
