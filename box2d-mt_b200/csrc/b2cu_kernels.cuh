@@ -8,6 +8,7 @@
 #include "b2cu_gjk.cuh"
 #include "b2cu_toi.cuh"
 #include "b2cu_world.cuh"
+#include "b2cu_joints.cuh"
 
 namespace b2cu
 {
@@ -82,6 +83,16 @@ __device__ __forceinline__ int LowerBound64(const uint64_t* __restrict__ keys, i
 		else hi = mid;
 	}
 	return lo;
+}
+
+// b2Body::ShouldCollide, joint half (b2Body.cpp:437-446): bodies connected by a joint that does not allow it never collide
+__device__ __forceinline__ bool JointBlocks(const DeviceArrays& d, int bodyA, int bodyB)
+{
+	if (d.jointPairCount == 0) return false;
+	uint32_t lo = (uint32_t)(bodyA < bodyB ? bodyA : bodyB), hi = (uint32_t)(bodyA < bodyB ? bodyB : bodyA);
+	uint64_t key = ((uint64_t)lo << 32) | hi;
+	int k = LowerBound64(d.jointPairKeys, d.jointPairCount, key);
+	return k < d.jointPairCount && d.jointPairKeys[k] == key;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 
 		if (flags & B2CU_CONTACT_FILTER)
 		{
-			bool should = IsOwnedDynamic(fbA) || IsOwnedDynamic(fbB);
+			bool should = (IsOwnedDynamic(fbA) || IsOwnedDynamic(fbB)) && !JointBlocks(d, bA, bB);
 			if (should)
 			{
 				// under a caller's pair filter an existing contact is kept: that filter is only consulted for new pairs
@@ -481,6 +492,17 @@ __global__ void FlagFilterContactsKernel(DeviceArrays d, int contactCount)
 		if (((d.pgroup[pr.x] | d.pgroup[pr.y]) >> 16) & B2CU_PROXY_REFILTER) d.c.flags[i] = f | B2CU_CONTACT_FILTER;
 	}
 }
+// contacts between two bodies that a joint keeps from colliding get e_filterFlag; Collide then removes them
+__global__ void FlagJointContactsKernel(DeviceArrays d, int contactCount)
+{
+	B2CU_GRID_STRIDE(i, contactCount)
+	{
+		uint32_t f = d.c.flags[i];
+		if (f & B2CU_CONTACT_DEAD) continue;
+		int4 pr = d.c.proxies[i];
+		if (JointBlocks(d, pr.z, pr.w)) d.c.flags[i] = f | B2CU_CONTACT_FILTER;
+	}
+}
 __global__ void ClearProxyFlagKernel(DeviceArrays d, int proxyCount, uint32_t flag)
 {
 	B2CU_GRID_STRIDE(p, proxyCount) { d.pgroup[p] &= ~(flag << 16); }
@@ -641,6 +663,19 @@ __global__ void IslandUnionKernel(DeviceArrays d, int contactCount)
 		int4 pr = d.c.proxies[i];
 		int bA = pr.z, bB = pr.w;
 		if (IsStatic(d.bflags[bA]) || IsStatic(d.bflags[bB])) continue;
+		UfUnion(d.island, bA, bB);
+	}
+}
+
+// joints connect islands like touching contacts do (b2World.cpp:1286-1320): both bodies active, neither static
+__global__ void JointUnionKernel(DeviceArrays d, int jointCount)
+{
+	B2CU_GRID_STRIDE(j, jointCount)
+	{
+		int bA = d.joints[j].bodyA, bB = d.joints[j].bodyB;
+		uint32_t fA = d.bflags[bA], fB = d.bflags[bB];
+		if (IsStatic(fA) || IsStatic(fB)) continue;
+		if (!(fA & B2CU_BODY_ACTIVE) || !(fB & B2CU_BODY_ACTIVE)) continue;
 		UfUnion(d.island, bA, bB);
 	}
 }
@@ -1519,7 +1554,53 @@ struct SolverPlan
 	int warmStarting;
 	float h;
 	ShardState shard;
+	// joints: colour classes of DeviceArrays::jointOrder, solved before the contacts in a velocity iteration and after
+	// them in a position iteration (b2Island.cpp:259-273, :323-327, :363-380)
+	int jointOpCount;
+	int jointOpStart[B2CU_MAX_JOINT_OPS], jointOpSize[B2CU_MAX_JOINT_OPS], jointOpSerial[B2CU_MAX_JOINT_OPS];
+	float dtRatio;
 };
+
+enum { JOINT_INIT = 0, JOINT_VELOCITY = 1, JOINT_POSITION = 2 };
+
+__device__ __forceinline__ void JointRunOne(const DeviceArrays& d, const SolverPlan& plan, int mode, int iteration, int j)
+{
+	if (mode == JOINT_INIT)
+	{
+		JointInitOne(d, j, plan.dtRatio, plan.warmStarting);
+	}
+	else if (mode == JOINT_VELOCITY)
+	{
+		JointSolveVelocityOne(d, j, plan.h);
+	}
+	else
+	{
+		JointRow r = d.jointRows[j];
+		if (!r.solved || IslandDone(d, iteration, r.root, plan.bodyCount)) return;
+		// a joint out of tolerance keeps its island iterating, like a contact deeper than 3 slops
+		if (!JointSolvePositionOne(d, j, r))
+			atomicMin(&d.islandMinSep[(size_t)iteration * plan.bodyCount + r.root], FloatToOrdered(-B2CU_MAX_FLOAT));
+	}
+}
+
+// all joint classes of one iteration; every thread of the grid takes part in the barriers
+__device__ __forceinline__ void JointRunOps(cooperative_groups::grid_group& grid, const DeviceArrays& d, const SolverPlan& plan,
+                                            int mode, int iteration, int tid, int stride)
+{
+	for (int jo = 0; jo < plan.jointOpCount; ++jo)
+	{
+		const int begin = plan.jointOpStart[jo], n = plan.jointOpSize[jo];
+		if (!plan.jointOpSerial[jo])
+		{
+			for (int t = tid; t < n; t += stride) JointRunOne(d, plan, mode, iteration, d.jointOrder[begin + t]);
+		}
+		else if (tid == 0)
+		{
+			for (int t = 0; t < n; ++t) JointRunOne(d, plan, mode, iteration, d.jointOrder[begin + t]);
+		}
+		grid.sync();
+	}
+}
 
 __device__ __forceinline__ void IntegratePositionOne(const DeviceArrays& d, int b, float h)
 {
@@ -1638,14 +1719,17 @@ __device__ __forceinline__ bool NextParallelOp(const SolverPlan& plan, int passE
 // Software-pipelined across the colour barriers: the rows of a thread's first constraint of the NEXT colour are
 // loaded before the grid barrier (they do not depend on other threads; only the body velocities do), so the
 // DRAM latency of every phase hides behind the barrier.
-__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVelocityPersistentKernel(DeviceArrays d,
-                                                                                                   SolverPlan plan)
+// JOINTS: the world has joints (a separate instance, so that the joint code costs the contact-only instance nothing).
+template <bool JOINTS>
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_VEL_BLOCKS) SolverVelocityPersistentKernel(DeviceArrays d,
+                                                                                                                 SolverPlan plan)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	unsigned seq = plan.shard.seq;
-	const int firstPass = plan.warmStarting ? 0 : 1;
+	// joints are initialised in pass 0, after the contacts' warm start, whether or not warm starting is on
+	const int firstPass = (plan.warmStarting || (JOINTS && plan.jointOpCount > 0)) ? 0 : 1;
 	const int lastPass = plan.velocityIterations;
 
 	VelPre pre;
@@ -1662,7 +1746,9 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVe
 	// pass 0 = warm start, passes 1..vIters = velocity iterations
 	for (int pass = firstPass; pass <= lastPass; ++pass)
 	{
-		for (int op = 0; op < plan.opCount; ++op)
+		if (JOINTS && pass >= 1) JointRunOps(grid, d, plan, JOINT_VELOCITY, 0, tid, stride);
+		const int opCount = (JOINTS && pass == 0 && !plan.warmStarting) ? 0 : plan.opCount;
+		for (int op = 0; op < opCount; ++op)
 		{
 			const int type = plan.opType[op], begin = plan.opStart[op], n = plan.opSize[op];
 			if (type == OP_PARALLEL)
@@ -1710,6 +1796,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVe
 				HaloExchange(grid, plan.shard, d.vel, type == OP_PUSH_DOWN, seq++, tid, stride);
 			}
 		}
+		if (JOINTS && pass == 0) JointRunOps(grid, d, plan, JOINT_INIT, 0, tid, stride);
 	}
 
 	// b2ContactSolver::StoreImpulses, then b2Island::Solve position integration (independent of each other)
@@ -1718,8 +1805,9 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVe
 }
 
 // position half: position iterations with the per-island early exit; same software pipelining
-__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPositionPersistentKernel(DeviceArrays d,
-                                                                                                   SolverPlan plan)
+template <bool JOINTS>
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_POS_BLOCKS) SolverPositionPersistentKernel(DeviceArrays d,
+                                                                                                                 SolverPlan plan)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1783,6 +1871,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPo
 				HaloExchange(grid, plan.shard, d.pos, type == OP_PUSH_DOWN, seq++, tid, stride);
 			}
 		}
+		if (JOINTS) JointRunOps(grid, d, plan, JOINT_POSITION, it, tid, stride);
 	}
 }
 
@@ -2114,6 +2203,7 @@ __device__ __forceinline__ void TryAddPair(const DeviceArrays& d, int q, int p, 
 	}
 	// b2Body::ShouldCollide: at least one dynamic body; in a sharded world it must be one this shard owns
 	if (!IsOwnedDynamic(d.bflags[bodyA]) && !IsOwnedDynamic(d.bflags[bodyB])) return;
+	if (JointBlocks(d, bodyA, bodyB)) return;
 	if (!d.customFilter && !DefaultFilter(d.pfilter[a], d.pgroup[a], d.pfilter[b], d.pgroup[b])) return;
 	if (d.shapes[d.pshape[a]].type == B2CU_SHAPE_EDGE && d.shapes[d.pshape[b]].type == B2CU_SHAPE_EDGE) return;
 	int slot = atomicAdd(&d.counters[CNT_NEW_PAIRS], 1);

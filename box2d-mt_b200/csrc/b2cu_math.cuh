@@ -20,6 +20,7 @@
 #define B2CU_LINEAR_SLOP 0.005f
 #define B2CU_ANGULAR_SLOP (2.0f / 180.0f * B2CU_PI)
 #define B2CU_POLYGON_RADIUS (2.0f * B2CU_LINEAR_SLOP)
+#define B2CU_MAX_ANGULAR_CORRECTION (8.0f / 180.0f * B2CU_PI)
 #define B2CU_MAX_SUB_STEPS 8
 #define B2CU_VELOCITY_THRESHOLD 1.0f
 #define B2CU_MAX_LINEAR_CORRECTION 0.2f

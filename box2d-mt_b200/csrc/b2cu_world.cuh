@@ -70,6 +70,11 @@ struct ContactSet
 
 static_assert(CNT_TOI_MIN_KEY % 2 == 0, "64-bit atomics on the key slot need 8-byte alignment");
 
+#define B2CU_MAX_JOINT_COLOURS 8
+#define B2CU_MAX_JOINT_OPS (B2CU_MAX_JOINT_COLOURS + 1)
+
+struct JointRow;
+
 struct DeviceArrays
 {
 	// ---- bodies (index = dense body id, creation order) ----
@@ -152,6 +157,14 @@ struct DeviceArrays
 
 	int* counters;    // CNT_COUNT ints
 	int customFilter; // != 0: a pair filter of the caller replaces the default filter rule (b2cuSetPairFilter)
+
+	// ---- joints (index = joint id, the caller's table order) ----
+	b2cuJoint* joints;       // persistent records (impulses, limit state)
+	JointRow* jointRows;     // per-step rows
+	int* jointOrder;         // joint ids by (colour class, id): the order of the solve
+	const uint64_t* jointPairKeys; // sorted (min body << 32 | max body) of the joints that forbid collision
+	int jointCount;
+	int jointPairCount;
 };
 
 struct WorldParams
@@ -236,6 +249,13 @@ struct b2cuWorld
 	size_t queryHostBytes;
 	bool eventCacheValid;      // queryHost holds the keys + records of the last step's events
 	size_t eventCacheKeyBytes;
+	// joints (b2cuSetJoints)
+	int jointCapacity;
+	bool jointFilterPending; // the joint table changed: flag the contacts it forbids for filtering
+	bool jointColourDirty;   // bodies were uploaded since the joints were coloured (a body type may have changed)
+	int jointOpCount;        // colour classes of the joint order: parallel ones, then the serial overflow
+	int jointOpStart[B2CU_MAX_JOINT_OPS], jointOpSize[B2CU_MAX_JOINT_OPS], jointOpSerial[B2CU_MAX_JOINT_OPS];
+	int persistentGridJoints, persistentGridPositionJoints;
 	cudaEvent_t ev[10];
 	int launches;
 	char lastError[512];

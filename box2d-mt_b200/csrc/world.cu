@@ -13,6 +13,7 @@
 #include <unistd.h>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include <mutex>
 #include <unordered_set>
@@ -671,8 +672,13 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		int coop = 0, perSm = 0;
 		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, def->device);
 		int perSmPos = 0;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, SolverVelocityPersistentKernel, B2CU_SOLVER_THREADS, 0);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPos, SolverPositionPersistentKernel, B2CU_SOLVER_THREADS, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, SolverVelocityPersistentKernel<false>, B2CU_SOLVER_THREADS, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPos, SolverPositionPersistentKernel<false>, B2CU_SOLVER_THREADS, 0);
+		int perSmJ = 0, perSmPosJ = 0;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmJ, SolverVelocityPersistentKernel<true>, B2CU_SOLVER_THREADS, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPosJ, SolverPositionPersistentKernel<true>, B2CU_SOLVER_THREADS, 0);
+		w->persistentGridJoints = g_smCount * std::max(perSmJ, 0);
+		w->persistentGridPositionJoints = g_smCount * std::max(perSmPosJ, 0);
 		const char* pe = getenv("B2CU_PERSISTENT");
 		w->persistentSolver = coop != 0 && perSm > 0 && perSmPos > 0 && !(pe && atoi(pe) == 0);
 		const char* pb = getenv("B2CU_PERSISTENT_BLOCKS");
@@ -717,6 +723,10 @@ void b2cuDestroyWorld(b2cuWorld* w)
 	std::vector<ArrayDesc> arrays = AllArrays(w);
 	for (size_t k = 0; k < arrays.size(); ++k) cudaFree(*arrays[k].ptr);
 	cudaFree(w->d.islandMinSep);
+	cudaFree(w->d.joints);
+	cudaFree(w->d.jointRows);
+	cudaFree(w->d.jointOrder);
+	cudaFree((void*)w->d.jointPairKeys);
 	cudaFree(w->bodyStage);
 	cudaFree(w->queryScratch);
 	if (w->queryHost) cudaFreeHost(w->queryHost);
@@ -798,6 +808,7 @@ int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bo
 	CUDA_TRY(w, cudaMemcpyAsync(stage, bodies, sizeof(b2cuBody) * (size_t)count, cudaMemcpyHostToDevice, w->stream));
 	LAUNCH(w, UnpackBodiesKernel, GridFor(count), kBlock, w->d, first, count, (const float*)stage);
 	w->toiCheckDirty = true;
+	w->jointColourDirty = true;
 	return SyncCheck(w);
 }
 
@@ -947,6 +958,151 @@ int b2cuGetProxies(b2cuWorld* w, int32_t first, int32_t count, b2cuProxy* proxie
 		p.child = 0;
 	}
 	return B2CU_OK;
+}
+
+// ---- joints ------------------------------------------------------------------------------------------------------------
+
+// Colour classes of the joint table: joints in id order take the lowest class in which neither of their dynamic bodies
+// has a joint yet (non-dynamic bodies are not changed by an impulse, so they may be shared); what does not fit the
+// parallel classes is solved by one thread, in id order.  The solve order is (class, id).
+static int ColourJoints(b2cuWorld* w)
+{
+	const int nj = w->d.jointCount;
+	w->jointOpCount = 0;
+	w->jointColourDirty = false;
+	if (nj == 0) return B2CU_OK;
+	std::vector<b2cuJoint> joints((size_t)nj);
+	std::vector<uint32_t> bflags((size_t)w->bodyCount);
+	CUDA_TRY(w, cudaMemcpyAsync(joints.data(), w->d.joints, sizeof(b2cuJoint) * (size_t)nj, cudaMemcpyDeviceToHost, w->stream));
+	CUDA_TRY(w, cudaMemcpyAsync(bflags.data(), w->d.bflags, sizeof(uint32_t) * (size_t)w->bodyCount, cudaMemcpyDeviceToHost,
+	                            w->stream));
+	int rc = SyncCheck(w);
+	if (rc) return rc;
+	std::unordered_map<int, uint32_t> used; // dynamic body -> classes taken
+	std::vector<std::vector<int> > classes(B2CU_MAX_JOINT_COLOURS + 1);
+	for (int j = 0; j < nj; ++j)
+	{
+		uint32_t mask = 0;
+		const int bodies[2] = {joints[j].bodyA, joints[j].bodyB};
+		bool dynamic[2];
+		for (int k = 0; k < 2; ++k)
+		{
+			dynamic[k] = (bflags[bodies[k]] & B2CU_BODY_TYPE_MASK) == B2CU_DYNAMIC_BODY;
+			if (dynamic[k]) mask |= used[bodies[k]];
+		}
+		int colour = 0;
+		while (colour < B2CU_MAX_JOINT_COLOURS && (mask & (1u << colour))) ++colour;
+		classes[colour].push_back(j);
+		if (colour < B2CU_MAX_JOINT_COLOURS)
+			for (int k = 0; k < 2; ++k)
+				if (dynamic[k]) used[bodies[k]] |= 1u << colour;
+	}
+	std::vector<int> order;
+	order.reserve((size_t)nj);
+	for (int c = 0; c <= B2CU_MAX_JOINT_COLOURS; ++c)
+	{
+		if (classes[c].empty()) continue;
+		int op = w->jointOpCount++;
+		w->jointOpStart[op] = (int)order.size();
+		w->jointOpSize[op] = (int)classes[c].size();
+		w->jointOpSerial[op] = c == B2CU_MAX_JOINT_COLOURS ? 1 : 0;
+		order.insert(order.end(), classes[c].begin(), classes[c].end());
+	}
+	CUDA_TRY(w, cudaMemcpyAsync(w->d.jointOrder, order.data(), sizeof(int) * (size_t)nj, cudaMemcpyHostToDevice, w->stream));
+	return SyncCheck(w);
+}
+
+int b2cuSetJoints(b2cuWorld* w, int32_t count, const b2cuJoint* joints)
+{
+	if (!w || count < 0 || (count > 0 && !joints)) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	if (count > 0 && w->shardCount > 1) return SetError(w, B2CU_ERR_UNSUPPORTED, "joints in a sharded world");
+	std::vector<uint64_t> pairs;
+	for (int32_t j = 0; j < count; ++j)
+	{
+		const b2cuJoint& jt = joints[j];
+		if (jt.type != B2CU_JOINT_REVOLUTE)
+			return SetError(w, B2CU_ERR_UNSUPPORTED, "joint %d: type %d (only revolute joints are solved)", j, jt.type);
+		if (jt.bodyA < 0 || jt.bodyA >= w->bodyCount || jt.bodyB < 0 || jt.bodyB >= w->bodyCount || jt.bodyA == jt.bodyB)
+			return SetError(w, B2CU_ERR_ARGUMENT, "joint %d: bodies %d, %d", j, jt.bodyA, jt.bodyB);
+		if (!(jt.flags & B2CU_JOINT_COLLIDE_CONNECTED))
+		{
+			uint32_t lo = (uint32_t)std::min(jt.bodyA, jt.bodyB), hi = (uint32_t)std::max(jt.bodyA, jt.bodyB);
+			pairs.push_back(((uint64_t)lo << 32) | hi);
+		}
+	}
+	std::sort(pairs.begin(), pairs.end());
+	pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+	if (count > w->jointCapacity)
+	{
+		int cap = std::max(count, std::max(64, 2 * w->jointCapacity));
+		cudaFree(w->d.joints);
+		cudaFree(w->d.jointRows);
+		cudaFree(w->d.jointOrder);
+		cudaFree((void*)w->d.jointPairKeys);
+		w->d.joints = nullptr;
+		w->d.jointRows = nullptr;
+		w->d.jointOrder = nullptr;
+		w->d.jointPairKeys = nullptr;
+		w->jointCapacity = 0;
+		w->d.jointCount = 0;
+		w->d.jointPairCount = 0;
+		uint64_t* keys = nullptr;
+		CUDA_TRY(w, cudaMalloc(&w->d.joints, sizeof(b2cuJoint) * (size_t)cap));
+		CUDA_TRY(w, cudaMalloc(&w->d.jointRows, sizeof(JointRow) * (size_t)cap));
+		CUDA_TRY(w, cudaMalloc(&w->d.jointOrder, sizeof(int) * (size_t)cap));
+		CUDA_TRY(w, cudaMalloc(&keys, sizeof(uint64_t) * (size_t)cap));
+		w->d.jointPairKeys = keys;
+		w->jointCapacity = cap;
+	}
+	if (count > 0)
+	{
+		CUDA_TRY(w, cudaMemcpyAsync(w->d.joints, joints, sizeof(b2cuJoint) * (size_t)count, cudaMemcpyHostToDevice, w->stream));
+		CUDA_TRY(w, cudaMemsetAsync(w->d.jointRows, 0, sizeof(JointRow) * (size_t)count, w->stream));
+		if (!pairs.empty())
+			CUDA_TRY(w, cudaMemcpyAsync((void*)w->d.jointPairKeys, pairs.data(), sizeof(uint64_t) * pairs.size(),
+			                            cudaMemcpyHostToDevice, w->stream));
+	}
+	w->d.jointCount = count;
+	w->d.jointPairCount = (int)pairs.size();
+	w->jointFilterPending = true;
+	int rc = SyncCheck(w);
+	if (rc) return rc;
+	return ColourJoints(w);
+}
+
+int b2cuGetJointCount(b2cuWorld* w, int32_t* count)
+{
+	if (!w || !count) return B2CU_ERR_ARGUMENT;
+	*count = w->d.jointCount;
+	return B2CU_OK;
+}
+
+int b2cuGetJoints(b2cuWorld* w, int32_t first, int32_t count, b2cuJoint* joints)
+{
+	int rc = CheckRange(w, first, count, w ? w->d.jointCount : 0, joints);
+	if (rc) return rc;
+	if (count == 0) return B2CU_OK;
+	cudaSetDevice(w->device);
+	CUDA_TRY(w, cudaMemcpyAsync(joints, w->d.joints + first, sizeof(b2cuJoint) * (size_t)count, cudaMemcpyDeviceToHost,
+	                            w->stream));
+	return SyncCheck(w);
+}
+
+int b2cuGetJointOrder(b2cuWorld* w, int32_t capacity, int32_t* jointIds, int32_t* count)
+{
+	if (!w || capacity < 0 || (capacity > 0 && !jointIds)) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	if (w->d.jointCount > 0 && w->jointColourDirty)
+	{
+		int rc = ColourJoints(w);
+		if (rc) return rc;
+	}
+	if (count) *count = w->d.jointCount;
+	int m = std::min(capacity, w->d.jointCount);
+	if (m <= 0) return B2CU_OK;
+	CUDA_TRY(w, cudaMemcpyAsync(jointIds, w->d.jointOrder, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, w->stream));
+	return SyncCheck(w);
 }
 
 int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
@@ -1264,6 +1420,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	g_primTraceHook = g_trace.enabled ? PrimTraceHook : nullptr;
 	TraceMark(w, "(start)");
 
+	if (w->d.jointCount > 0 && w->jointColourDirty && (rc = ColourJoints(w))) return rc;
+
 	if (w->toiCheckDirty)
 	{
 		// can any contact be a TOI candidate at all (b2Contact::IsToiCandidate)?  Worlds whose static geometry is
@@ -1284,6 +1442,13 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		if (np > 0) LAUNCH(w, FillProxyRadiusKernel, GridFor(np), kBlock, d, np);
 		if (w->contactCount > 0) LAUNCH(w, FillContactBodiesKernel, GridFor(w->contactCount), kBlock, d, w->contactCount);
 		w->contactBodiesDirty = false;
+	}
+	if (w->jointFilterPending)
+	{
+		// b2World::CreateJoint (b2World.cpp:710-726): contacts between bodies the new joints keep apart are re-filtered
+		if (w->contactCount > 0 && d.jointPairCount > 0)
+			LAUNCH(w, FlagJointContactsKernel, GridFor(w->contactCount), kBlock, d, w->contactCount);
+		w->jointFilterPending = false;
 	}
 
 	if (dt > 0.0f && (rc = ShardSyncGhosts(w))) return rc;
@@ -1346,6 +1511,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		// ---- islands (serial DFS of b2World::Solve -> union-find) ----
 		LAUNCH(w, SolveInitBodiesKernel, GridFor(nb), kBlock, d, nb, positionIterations);
 		if (nc > 0) LAUNCH(w, IslandUnionKernel, GridFor(nc), kBlock, d, nc);
+		if (w->d.jointCount > 0) LAUNCH(w, JointUnionKernel, GridFor(w->d.jointCount), kBlock, d, w->d.jointCount);
 		LAUNCH(w, IslandFlattenKernel, GridFor(nb), kBlock, d, nb);
 		LAUNCH(w, IslandMarkKernel, GridFor(nb), kBlock, d, nb);
 		cudaEventRecord(w->ev[3], w->stream);
@@ -1433,7 +1599,10 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			}
 		}
 		cudaEventRecord(w->ev[5], w->stream);
-		if ((nConstraints > 0 || w->shardCount > 1) && w->persistentSolver)
+		const int nJoints = w->d.jointCount;
+		if (nJoints > 0 && (!w->persistentSolver || w->persistentGridJoints <= 0 || w->persistentGridPositionJoints <= 0))
+			return SetError(w, B2CU_ERR_UNSUPPORTED, "joints need the persistent cooperative solver");
+		if ((nConstraints > 0 || w->shardCount > 1 || nJoints > 0) && w->persistentSolver)
 		{
 			// one persistent cooperative kernel for warm start + velocity + store + integrate + position; in a
 			// sharded world it also carries the halo exchanges, so it runs even without constraints
@@ -1471,9 +1640,24 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			plan.warmStarting = warmStarting ? 1 : 0;
 			plan.h = dt;
 			plan.shard = MakeShardState(w);
+			plan.dtRatio = dtRatio;
+			plan.jointOpCount = nJoints > 0 ? w->jointOpCount : 0;
+			for (int jo = 0; jo < plan.jointOpCount; ++jo)
+			{
+				plan.jointOpStart[jo] = w->jointOpStart[jo];
+				plan.jointOpSize[jo] = w->jointOpSize[jo];
+				plan.jointOpSerial[jo] = w->jointOpSerial[jo];
+			}
 			void* args[2] = {(void*)&d, (void*)&plan};
-			CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverVelocityPersistentKernel,
-			                                        dim3(w->persistentGrid), dim3(B2CU_SOLVER_THREADS), args, 0, w->stream));
+			const void* velocityKernel = nJoints > 0 ? (const void*)SolverVelocityPersistentKernel<true>
+			                                         : (const void*)SolverVelocityPersistentKernel<false>;
+			const void* positionKernel = nJoints > 0 ? (const void*)SolverPositionPersistentKernel<true>
+			                                         : (const void*)SolverPositionPersistentKernel<false>;
+			const int velocityGrid = nJoints > 0 ? std::min(w->persistentGrid, w->persistentGridJoints) : w->persistentGrid;
+			const int positionGrid =
+			    nJoints > 0 ? std::min(w->persistentGridPosition, w->persistentGridPositionJoints) : w->persistentGridPosition;
+			CUDA_TRY(w, cudaLaunchCooperativeKernel(velocityKernel, dim3(velocityGrid), dim3(B2CU_SOLVER_THREADS), args, 0,
+			                                        w->stream));
 			++w->launches;
 			TraceMark(w, "SolverVelocityPersistentKernel");
 			if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)((warmStarting ? 1 : 0) + velocityIterations);
@@ -1481,8 +1665,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			cudaEventRecord(w->ev[6], w->stream);
 			if (positionIterations > 0)
 			{
-				CUDA_TRY(w, cudaLaunchCooperativeKernel((const void*)SolverPositionPersistentKernel,
-				                                        dim3(w->persistentGridPosition), dim3(B2CU_SOLVER_THREADS), args, 0, w->stream));
+				CUDA_TRY(w, cudaLaunchCooperativeKernel(positionKernel, dim3(positionGrid), dim3(B2CU_SOLVER_THREADS), args, 0,
+				                                        w->stream));
 				++w->launches;
 				TraceMark(w, "SolverPositionPersistentKernel");
 				if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)positionIterations;

@@ -21,7 +21,7 @@ API = [
     "b2cuSetWorldParams", "b2cuSetInvDt0", "b2cuSetCounts", "b2cuSetBodies", "b2cuGetBodies", "b2cuSetShapes",
     "b2cuSetProxies", "b2cuGetProxies", "b2cuSetContacts", "b2cuGetContactCount", "b2cuGetContacts", "b2cuStep",
     "b2cuGetContactsByKey", "b2cuGetEvents", "b2cuGetSolverOrder", "b2cuGetIslandLabels", "b2cuGetToiCandidates", "b2cuCollidePairs",
-    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuDistancePairs", "b2cuTimeOfImpactPairs", "b2cuQueryAABB", "b2cuRayCastCandidates", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts",
+    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuDistancePairs", "b2cuTimeOfImpactPairs", "b2cuQueryAABB", "b2cuRayCastCandidates", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts", "b2cuSetJoints", "b2cuGetJointCount", "b2cuGetJoints", "b2cuGetJointOrder",
 ]
 
 
@@ -69,6 +69,10 @@ def load():
     lib.b2cuGetToiCandidates.argtypes = [vp, i32, vp, vp]
     lib.b2cuCollidePairs.argtypes = [i32, i32, vp, i32, vp, vp, vp, vp, vp]
     lib.b2cuSinCos.argtypes = [i32, i32, vp, vp, vp]
+    lib.b2cuSetJoints.argtypes = [vp, i32, vp]
+    lib.b2cuGetJointCount.argtypes = [vp, vp]
+    lib.b2cuGetJoints.argtypes = [vp, i32, i32, vp]
+    lib.b2cuGetJointOrder.argtypes = [vp, i32, vp, vp]
     lib.b2cuShardConfigure.argtypes = [vp, i32, i32, i32, vp, i32, vp, f32]
     lib.b2cuShardGetLink.argtypes = [vp, vp]
     lib.b2cuShardConnect.argtypes = [vp, vp, vp]
@@ -211,6 +215,26 @@ class World:
 
         self._pair_filter = proto(thunk)  # keep the callback object alive
         self._check(self.lib.b2cuSetPairFilter(self.h, self._pair_filter, None))
+
+    def set_joints(self, joints):
+        j = np.ascontiguousarray(joints, T.JOINT)
+        self._check(self.lib.b2cuSetJoints(self.h, len(j), _ptr(j) if len(j) else None))
+
+    def get_joints(self):
+        n = ctypes.c_int32()
+        self._check(self.lib.b2cuGetJointCount(self.h, ctypes.byref(n)))
+        out = np.zeros(n.value, T.JOINT)
+        if n.value:
+            self._check(self.lib.b2cuGetJoints(self.h, 0, n.value, _ptr(out)))
+        return out
+
+    def joint_order(self):
+        n = ctypes.c_int32()
+        self._check(self.lib.b2cuGetJointCount(self.h, ctypes.byref(n)))
+        out = np.zeros(n.value, np.int32)
+        if n.value:
+            self._check(self.lib.b2cuGetJointOrder(self.h, n.value, _ptr(out), ctypes.byref(n)))
+        return out
 
     def step(self, dt=1.0 / 60.0, vel_iters=8, pos_iters=3):
         info = np.zeros((), T.STEP_INFO)

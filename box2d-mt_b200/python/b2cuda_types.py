@@ -86,6 +86,16 @@ STEP_INFO = np.dtype([
 ])
 assert STEP_INFO.itemsize == 136 and STEP_INFO.fields["toiMinKey"][1] == 120
 
+JOINT = np.dtype([
+    ("type", "i4"), ("bodyA", "i4"), ("bodyB", "i4"), ("flags", "u4"),
+    ("localAnchorA", "f4", (2,)), ("localAnchorB", "f4", (2,)),
+    ("referenceAngle", "f4"), ("lowerAngle", "f4"), ("upperAngle", "f4"), ("maxMotorTorque", "f4"), ("motorSpeed", "f4"),
+    ("impulse", "f4", (3,)), ("motorImpulse", "f4"), ("limitState", "i4"), ("reserved", "i4", (2,)),
+])
+assert JOINT.itemsize == 80
+JOINT_REVOLUTE = 1
+JOINT_COLLIDE_CONNECTED, JOINT_ENABLE_LIMIT, JOINT_ENABLE_MOTOR = 1, 2, 4
+
 # enums
 STATIC_BODY, KINEMATIC_BODY, DYNAMIC_BODY = 0, 1, 2
 BODY_TYPE_MASK = 0x3

@@ -40,6 +40,7 @@ class Scene:
         self.body_count = 0
         self.fixture_count = 0
         self._last_fixture_body = -1
+        self.joints = []
 
     # -- shapes ------------------------------------------------------------------
     def _add_shape(self, rec):
@@ -134,6 +135,30 @@ class Scene:
         self._pending_fixtures.append(f)
         self.fixture_count += 1
         return self.fixture_count - 1
+
+    def revolute_joint(self, body_a, body_b, local_anchor_a, local_anchor_b, reference_angle=0.0, collide_connected=False,
+                       limits=None, motor=None):
+        """b2RevoluteJointDef with explicit local anchors (b2RevoluteJoint.h:36-86); limits = (lower, upper) enables the
+        limit, motor = (speed, max torque) enables the motor.  Returns the joint id."""
+        j = np.zeros((), T.JOINT)
+        j["type"] = T.JOINT_REVOLUTE
+        j["bodyA"], j["bodyB"] = body_a, body_b
+        j["localAnchorA"] = local_anchor_a
+        j["localAnchorB"] = local_anchor_b
+        j["referenceAngle"] = reference_angle
+        flags = T.JOINT_COLLIDE_CONNECTED if collide_connected else 0
+        if limits is not None:
+            flags |= T.JOINT_ENABLE_LIMIT
+            j["lowerAngle"], j["upperAngle"] = limits
+        if motor is not None:
+            flags |= T.JOINT_ENABLE_MOTOR
+            j["motorSpeed"], j["maxMotorTorque"] = motor
+        j["flags"] = flags
+        self.joints.append(j)
+        return len(self.joints) - 1
+
+    def joint_array(self):
+        return np.array(self.joints, dtype=T.JOINT) if self.joints else np.zeros(0, T.JOINT)
 
     def _flush(self):
         if self._pending_bodies:

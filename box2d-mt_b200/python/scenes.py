@@ -7,7 +7,7 @@ does in float32 is done in np.float32 here so that body placement is bit-identic
 import numpy as np
 
 import b2cuda_types as T
-from b2scene import Scene, BODY_DEF, FIXTURE_DEF, BODYDEF_DEFAULT, BODYDEF_BULLET, BODYDEF_ALLOW_SLEEP
+from b2scene import Scene, BODY_DEF, FIXTURE_DEF, BODYDEF_DEFAULT, BODYDEF_BULLET, BODYDEF_ALLOW_SLEEP, BODYDEF_FIXED_ROTATION
 
 F = np.float32
 
@@ -97,7 +97,7 @@ def add_pair(count=400, seed=0):
     return s
 
 
-def tumbler(count=800, seed=0, scale=None):
+def tumbler(count=800, seed=0, scale=None, motor_joint=False):
     """Testbed/Tests/Tumbler.h:47-54 walls on a KINEMATIC body at (0,10) spinning at 0.05*pi rad/s
     (the revolute-joint motor is replaced by a kinematic container), scaled so that `count`
     boxes of half-extent 0.125 pre-placed on a jittered grid fit inside."""
@@ -105,7 +105,13 @@ def tumbler(count=800, seed=0, scale=None):
     if scale is None:
         scale = max(1.0, float(np.sqrt(count / 800.0)))
     k = scale
-    c = s.body(T.KINEMATIC_BODY, (0.0, 10.0 * k), w=0.05 * np.pi, flags=BODYDEF_DEFAULT & ~BODYDEF_ALLOW_SLEEP)
+    if motor_joint:
+        # the Testbed's own arrangement (Tumbler.h:33-68): a dynamic container on a revolute joint with a motor
+        g = s.body(T.STATIC_BODY, (0.0, 0.0))
+        c = s.body(T.DYNAMIC_BODY, (0.0, 10.0 * k), flags=BODYDEF_DEFAULT & ~BODYDEF_ALLOW_SLEEP)
+        s.revolute_joint(g, c, (0.0, 10.0 * k), (0.0, 0.0), motor=(0.05 * np.pi, 1e8))
+    else:
+        c = s.body(T.KINEMATIC_BODY, (0.0, 10.0 * k), w=0.05 * np.pi, flags=BODYDEF_DEFAULT & ~BODYDEF_ALLOW_SLEEP)
     s.fixture(c, s.box(0.5 * k, 10.0 * k, center=(10.0 * k, 0.0), angle=0.0), density=5.0, thick=True)
     s.fixture(c, s.box(0.5 * k, 10.0 * k, center=(-10.0 * k, 0.0), angle=0.0), density=5.0, thick=True)
     s.fixture(c, s.box(10.0 * k, 0.5 * k, center=(0.0, 10.0 * k), angle=0.0), density=5.0, thick=True)
@@ -205,3 +211,68 @@ def sensors(count=30, seed=5):
             s.fixture(b, halo, sensor=True)
     return s
 
+
+
+def hanging_chains(chains=6, links=20, seed=0):
+    """Testbed/Tests/Chain.h:26-60, several times over: chains of box links (0.6 x 0.125 half-extents, density 20) hinged
+    end to end by revolute joints that do not let neighbours collide, the first link hinged to the static ground; the
+    chains hang side by side over a thick floor and swing into each other.  A few hinges carry angle limits."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.box(40.0, 1.0, center=(0.0, -1.0), angle=0.0), thick=True)
+    link = s.box(0.6, 0.125)
+    y = 25.0
+    for c in range(chains):
+        x0 = -12.0 + 5.0 * c
+        prev = g
+        for i in range(links):
+            b = s.body(T.DYNAMIC_BODY, (x0 + 0.5 + i, y))
+            s.fixture(b, link, density=20.0, friction=0.2)
+            anchor = (float(F(x0 + i)), y)
+            la = anchor if prev == g else (0.5, 0.0)
+            limits = (-0.25 * np.pi, 0.5 * np.pi) if (i % 5 == 2 and c % 2 == 0) else None
+            s.revolute_joint(prev, b, la, (-0.5, 0.0), limits=limits)
+            prev = b
+    return s
+
+
+def joint_zoo(seed=0):
+    """Every branch of the revolute joint: free hinges, angle limits (lower / upper / equal), motors weak and strong, a
+    hub with more joints than there are parallel colour classes, a joint between two dynamic bodies that may collide,
+    a body with fixed rotation, a joint to a kinematic body, sleeping allowed."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.edge((-40.0, 0.0), (40.0, 0.0)))
+    bar = s.box(1.0, 0.1)
+    small = s.box(0.25, 0.25)
+    # pendulums on the ground body
+    for i in range(8):
+        x = -20.0 + 4.0 * i
+        b = s.body(T.DYNAMIC_BODY, (x + 1.0, 6.0), w=float(i) - 3.0)
+        s.fixture(b, bar, density=1.0)
+        limits = [None, (-0.5, 0.5), (0.0, 0.0), (-2.0, 0.2), None, (-0.1, 1.5), None, (0.3, 0.3)][i]
+        motor = [None, None, None, None, (1.0, 5.0), (-2.0, 1000.0), (0.5, 0.0), None][i]
+        s.revolute_joint(g, b, (x, 6.0), (-1.0, 0.0), limits=limits, motor=motor)
+    # a hub with 12 spokes: more joints on one dynamic body than parallel classes
+    hub = s.body(T.DYNAMIC_BODY, (0.0, 14.0))
+    s.fixture(hub, s.circle(0.5), density=2.0)
+    s.revolute_joint(g, hub, (0.0, 14.0), (0.0, 0.0), motor=(1.0, 200.0))
+    for k in range(12):
+        a = 2.0 * np.pi * k / 12
+        ca, sa = float(F(np.cos(a))), float(F(np.sin(a)))
+        b = s.body(T.DYNAMIC_BODY, (float(F(1.5 * ca)), float(F(14.0 + 1.5 * sa))), angle=float(F(a)))
+        s.fixture(b, bar, density=0.5)
+        s.revolute_joint(hub, b, (float(F(0.5 * ca)), float(F(0.5 * sa))), (-1.0, 0.0), collide_connected=(k % 3 == 0))
+    # two free bodies hinged together, falling on the ground; one cannot rotate
+    a = s.body(T.DYNAMIC_BODY, (10.0, 3.0))
+    s.fixture(a, small, density=1.0)
+    b = s.body(T.DYNAMIC_BODY, (10.6, 3.0), flags=BODYDEF_DEFAULT | BODYDEF_FIXED_ROTATION)
+    s.fixture(b, small, density=1.0)
+    s.revolute_joint(a, b, (0.3, 0.0), (-0.3, 0.0), collide_connected=True)
+    # a crank on a kinematic body
+    k = s.body(T.KINEMATIC_BODY, (-10.0, 12.0), w=1.0)
+    s.fixture(k, small)
+    b = s.body(T.DYNAMIC_BODY, (-8.5, 12.0))
+    s.fixture(b, bar, density=1.0)
+    s.revolute_joint(k, b, (0.5, 0.0), (-1.0, 0.0))
+    return s

@@ -22,6 +22,7 @@
  *   b2cuSetProxies / b2cuGetProxies      b2Fixture + b2FixtureProxy + tree-leaf fat AABB
  *                                                                          Dynamics/b2Fixture.h:100-106, Collision/b2DynamicTree.h:36
  *   b2cuSetContacts / b2cuGetContacts    b2Contact persistent state (m_flags, m_manifold, mixes, TOI)
+ *   b2cuSetJoints / b2cuGetJoints        b2Joint table (revolute joints), persistent impulses
  *                                                                          Dynamics/Contacts/b2Contact.h:231-259
  *   b2cuStep                             b2World::Step(dt, velocityIterations, positionIterations, executor)
  *                                                                          Dynamics/b2World.cpp:1613-1710
@@ -324,6 +325,44 @@ B2CU_API int b2cuGetProxies(b2cuWorld* w, int32_t first, int32_t count, b2cuProx
 /* Replace the whole contact set (teacher forcing, checkpoint restore).  Any order; sorted on device. */
 B2CU_API int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts);
 B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
+
+/* Joints (Dynamics/Joints/b2Joint.h:28-226).  This version solves revolute joints (b2RevoluteJoint.cpp:64-400: point
+ * constraint, angular limit, motor, warm starting) as rows of the coloured solver: inside every velocity iteration the
+ * joints run before the contacts, inside every position iteration after them, as b2Island::Solve orders them
+ * (Dynamics/b2Island.cpp:259-273, :323-327, :363-380).  A joint links the islands of its two bodies
+ * (b2World.cpp:1286-1320) and, unless COLLIDE_CONNECTED, keeps them from colliding (b2Body::ShouldCollide,
+ * b2Body.cpp:428-449).  `type` uses b2JointType's values; other types are refused with B2CU_ERR_UNSUPPORTED.
+ * impulse / motorImpulse / limitState are the joint's persistent solver state (m_impulse, m_motorImpulse,
+ * m_limitState) and round-trip through Get / Set. */
+enum { B2CU_JOINT_REVOLUTE = 1 };
+enum
+{
+	B2CU_JOINT_COLLIDE_CONNECTED = 1,
+	B2CU_JOINT_ENABLE_LIMIT = 2,
+	B2CU_JOINT_ENABLE_MOTOR = 4
+};
+enum { B2CU_LIMIT_INACTIVE = 0, B2CU_LIMIT_AT_LOWER = 1, B2CU_LIMIT_AT_UPPER = 2, B2CU_LIMIT_EQUAL = 3 };
+typedef struct b2cuJoint
+{
+	int32_t type;
+	int32_t bodyA, bodyB;
+	uint32_t flags;
+	float localAnchorA[2], localAnchorB[2];
+	float referenceAngle, lowerAngle, upperAngle;
+	float maxMotorTorque, motorSpeed;
+	float impulse[3];
+	float motorImpulse;
+	int32_t limitState;
+	int32_t reserved[2];
+} b2cuJoint;
+/* Replace the world's joint table (b2World::CreateJoint / DestroyJoint, b2World.cpp:659-841, applied as a whole: the
+ * caller keeps the list).  Joint ids are indices into this table. */
+B2CU_API int b2cuSetJoints(b2cuWorld* w, int32_t count, const b2cuJoint* joints);
+B2CU_API int b2cuGetJointCount(b2cuWorld* w, int32_t* count);
+B2CU_API int b2cuGetJoints(b2cuWorld* w, int32_t first, int32_t count, b2cuJoint* joints);
+/* The order in which the joints are solved inside an iteration (colour classes of joints that share no dynamic body,
+ * ascending id inside a class): what a sequential Gauss-Seidel must follow to reproduce the step bit for bit. */
+B2CU_API int b2cuGetJointOrder(b2cuWorld* w, int32_t capacity, int32_t* jointIds, int32_t* count);
 /* Contacts in key order. */
 B2CU_API int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32_t* count);
 

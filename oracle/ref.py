@@ -50,6 +50,10 @@ def load(stock=False):
     lib.b2ref_toi_candidates.argtypes = [vp, i32, vp]
     lib.b2ref_first_toi.argtypes = [vp, vp, vp]
     lib.b2ref_first_toi.restype = i32
+    lib.b2ref_set_joints.argtypes = [vp, i32, vp]
+    lib.b2ref_set_joints.restype = i32
+    lib.b2ref_set_joint_order.argtypes = [vp, i32, vp]
+    lib.b2ref_export_joints.argtypes = [vp, vp]
     lib.b2ref_profile.argtypes = [vp, vp]
     lib.b2ref_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_set_type.argtypes = [vp, i32, i32]
@@ -94,6 +98,26 @@ class RefWorld:
             raise RuntimeError("b2ref_build failed: %d" % rc)
         self.gravity = gravity
         self.world_flags = world_flags
+        self.joint_count = 0
+        if scene is not None and getattr(scene, "joints", None):
+            self.set_joints(scene.joint_array())
+
+    def set_joints(self, joints):
+        j = np.ascontiguousarray(joints, T.JOINT)
+        if self.lib.b2ref_set_joints(self.h, len(j), _ptr(j)) != 0:
+            raise RuntimeError("b2ref_set_joints failed")
+        self.joint_count = len(j)
+
+    def set_joint_order(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        assert len(ids) == self.joint_count
+        self.lib.b2ref_set_joint_order(self.h, len(ids), _ptr(ids))
+
+    def joints(self):
+        out = np.zeros(self.joint_count, T.JOINT)
+        if self.joint_count:
+            self.lib.b2ref_export_joints(self.h, _ptr(out))
+        return out
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -132,6 +132,8 @@ struct b2refWorld
 	std::vector<b2Fixture*> fixtures;
 	std::vector<int32> proxyBase;                          // first proxy id of each fixture
 	std::vector<std::pair<b2Fixture*, int32> > proxies;    // (fixture, child) of each proxy id
+	std::vector<b2Joint*> joints;                          // b2ref_set_joints, table order
+	std::unordered_map<const b2Joint*, int32> jointRank;   // position in the caller's solve order
 };
 
 namespace
@@ -327,6 +329,7 @@ static int SolveOrdered(b2refWorld* rw, const b2TimeStep& step, const std::unord
 
 	std::vector<b2Body*> islandBodies;
 	std::vector<b2Contact*> islandContacts;
+	std::vector<b2Joint*> islandJoints;
 	std::vector<b2Body*> pending;
 	std::vector<b2Velocity> velocities;
 	std::vector<b2Position> positions;
@@ -341,6 +344,7 @@ static int SolveOrdered(b2refWorld* rw, const b2TimeStep& step, const std::unord
 
 		islandBodies.clear();
 		islandContacts.clear();
+		islandJoints.clear();
 		pending.clear();
 		pending.push_back(seed);
 		seed->m_flags |= b2Body::e_islandFlag;
@@ -385,7 +389,27 @@ static int SolveOrdered(b2refWorld* rw, const b2TimeStep& step, const std::unord
 				pending.push_back(other);
 				other->m_flags |= b2Body::e_islandFlag;
 			}
-			/* joints: worlds with joints are outside the GPU path and are not built by this harness */
+			/* joints (b2World.cpp:1291-1318) */
+			for (b2JointEdge* je = b->m_jointList; je; je = je->next)
+			{
+				if (je->joint->m_islandFlag)
+				{
+					continue;
+				}
+				b2Body* other = je->other;
+				if (!other->IsActive())
+				{
+					continue;
+				}
+				islandJoints.push_back(je->joint);
+				je->joint->m_islandFlag = true;
+				if (other->m_flags & b2Body::e_islandFlag)
+				{
+					continue;
+				}
+				pending.push_back(other);
+				other->m_flags |= b2Body::e_islandFlag;
+			}
 		}
 
 		for (size_t j = 0; j < islandBodies.size(); ++j)
@@ -430,8 +454,15 @@ static int SolveOrdered(b2refWorld* rw, const b2TimeStep& step, const std::unord
 
 		velocities.resize(islandBodies.size());
 		positions.resize(islandBodies.size());
-		b2Island island((int32)islandBodies.size(), (int32)islandContacts.size(), 0, islandBodies.data(),
-		                islandContacts.data(), nullptr, velocities.data(), positions.data());
+		/* ... and the caller's joint order (joints it did not rank keep their discovery order, behind the ranked ones) */
+		std::stable_sort(islandJoints.begin(), islandJoints.end(), [rw](const b2Joint* a, const b2Joint* b) {
+			auto ia = rw->jointRank.find(a), ib = rw->jointRank.find(b);
+			int32 ra = ia == rw->jointRank.end() ? INT32_MAX : ia->second;
+			int32 rb = ib == rw->jointRank.end() ? INT32_MAX : ib->second;
+			return ra < rb;
+		});
+		b2Island island((int32)islandBodies.size(), (int32)islandContacts.size(), (int32)islandJoints.size(),
+		                islandBodies.data(), islandContacts.data(), islandJoints.data(), velocities.data(), positions.data());
 		island.Solve(&td.m_profile, step, world->m_gravity, &world->m_stackAllocator, cm.m_contactListener, 0,
 		             world->m_allowSleep, td.m_postSolves);
 	}
@@ -778,6 +809,87 @@ int32_t b2ref_first_toi(b2refWorld* w, uint64_t* key, float* alpha)
 	*alpha = minAlpha;
 	*key = minContact ? ContactKey(minContact) : ~0ull;
 	return minContact != nullptr;
+}
+
+/* Joints from b2cuJoint records (revolute only), created in table order; replaces the joints made by an earlier call. */
+int32_t b2ref_set_joints(b2refWorld* w, int32_t count, const b2cuJoint* joints)
+{
+	for (size_t i = 0; i < w->joints.size(); ++i)
+	{
+		w->world->DestroyJoint(w->joints[i]);
+	}
+	w->joints.clear();
+	w->jointRank.clear();
+	for (int32_t i = 0; i < count; ++i)
+	{
+		const b2cuJoint& j = joints[i];
+		if (j.type != B2CU_JOINT_REVOLUTE)
+		{
+			return -1;
+		}
+		b2RevoluteJointDef def;
+		def.bodyA = w->bodies[j.bodyA];
+		def.bodyB = w->bodies[j.bodyB];
+		def.collideConnected = (j.flags & B2CU_JOINT_COLLIDE_CONNECTED) != 0;
+		def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
+		def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+		def.referenceAngle = j.referenceAngle;
+		def.enableLimit = (j.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
+		def.lowerAngle = j.lowerAngle;
+		def.upperAngle = j.upperAngle;
+		def.enableMotor = (j.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
+		def.motorSpeed = j.motorSpeed;
+		def.maxMotorTorque = j.maxMotorTorque;
+		b2RevoluteJoint* joint = (b2RevoluteJoint*)w->world->CreateJoint(&def);
+		joint->m_impulse.Set(j.impulse[0], j.impulse[1], j.impulse[2]);
+		joint->m_motorImpulse = j.motorImpulse;
+		joint->m_limitState = (b2LimitState)j.limitState;
+		w->joints.push_back(joint);
+		w->jointRank[joint] = i;
+	}
+	return 0;
+}
+
+/* the order in which b2ref_step_ordered solves the joints of an island: ids[k] is solved k-th */
+void b2ref_set_joint_order(b2refWorld* w, int32_t count, const int32_t* ids)
+{
+	w->jointRank.clear();
+	for (int32_t k = 0; k < count; ++k)
+	{
+		w->jointRank[w->joints[ids[k]]] = k;
+	}
+}
+
+void b2ref_export_joints(b2refWorld* w, b2cuJoint* out)
+{
+	for (size_t i = 0; i < w->joints.size(); ++i)
+	{
+		const b2RevoluteJoint* j = (const b2RevoluteJoint*)w->joints[i];
+		b2cuJoint& o = out[i];
+		memset(&o, 0, sizeof(o));
+		o.type = B2CU_JOINT_REVOLUTE;
+		for (size_t b = 0; b < w->bodies.size(); ++b)
+		{
+			if (w->bodies[b] == j->m_bodyA) o.bodyA = (int32_t)b;
+			if (w->bodies[b] == j->m_bodyB) o.bodyB = (int32_t)b;
+		}
+		o.flags = (j->m_collideConnected ? B2CU_JOINT_COLLIDE_CONNECTED : 0) | (j->m_enableLimit ? B2CU_JOINT_ENABLE_LIMIT : 0) |
+		          (j->m_enableMotor ? B2CU_JOINT_ENABLE_MOTOR : 0);
+		o.localAnchorA[0] = j->m_localAnchorA.x;
+		o.localAnchorA[1] = j->m_localAnchorA.y;
+		o.localAnchorB[0] = j->m_localAnchorB.x;
+		o.localAnchorB[1] = j->m_localAnchorB.y;
+		o.referenceAngle = j->m_referenceAngle;
+		o.lowerAngle = j->m_lowerAngle;
+		o.upperAngle = j->m_upperAngle;
+		o.maxMotorTorque = j->m_maxMotorTorque;
+		o.motorSpeed = j->m_motorSpeed;
+		o.impulse[0] = j->m_impulse.x;
+		o.impulse[1] = j->m_impulse.y;
+		o.impulse[2] = j->m_impulse.z;
+		o.motorImpulse = j->m_motorImpulse;
+		o.limitState = (int32_t)j->m_limitState;
+	}
 }
 
 void b2ref_profile(b2refWorld* w, float* out13)

@@ -137,6 +137,10 @@ int32_t b2ref_ray_cast_closest(b2refWorld* w, const float p1[2], const float p2[
 void b2ref_distance(const b2cuShape* shapeA, const float xfA[4], const b2cuShape* shapeB, const float xfB[4],
                     int32_t useRadii, b2cuDistanceResult* out);
 
+/* joints (revolute) from b2cuJoint records; the solve order of b2ref_step_ordered; state export */
+int32_t b2ref_set_joints(b2refWorld* w, int32_t count, const b2cuJoint* joints);
+void b2ref_set_joint_order(b2refWorld* w, int32_t count, const int32_t* ids);
+void b2ref_export_joints(b2refWorld* w, b2cuJoint* out);
 /* first pass of b2World::SolveTOI on the current state (see ref_harness.cpp) */
 int32_t b2ref_first_toi(b2refWorld* w, uint64_t* key, float* alpha);
 /* the reference's b2TimeOfImpact on geometry records and sweeps */

@@ -48,6 +48,8 @@ def gpu_world_from_ref(b2cuda, ref, **caps):
                      body_capacity=len(bodies), proxy_capacity=len(proxies), shape_capacity=len(shapes),
                      contact_capacity=max(1024, 16 * len(proxies)), **caps)
     w.load_state(bodies, shapes, proxies, contacts, inv_dt0=ref.inv_dt0())
+    if ref.joint_count:
+        w.set_joints(ref.joints())
     return w
 
 
@@ -138,6 +140,16 @@ def compare_contacts(gc, rc, tol=0.0, impulses=True):
         assert_floats_equal("contact." + f, gc[f], rc[f])
 
 
+def compare_joints(gj, rj, tol=0.0):
+    """persistent joint state: accumulated impulses, motor impulse, limit state"""
+    assert len(gj) == len(rj), "joint count %d != %d" % (len(gj), len(rj))
+    if not (gj["limitState"] == rj["limitState"]).all():
+        i = int(np.nonzero(gj["limitState"] != rj["limitState"])[0][0])
+        raise AssertionError("joint %d limit state: got %d want %d" % (i, gj["limitState"][i], rj["limitState"][i]))
+    assert_floats_equal("joint impulse", gj["impulse"], rj["impulse"], tol)
+    assert_floats_equal("joint motorImpulse", gj["motorImpulse"], rj["motorImpulse"], tol)
+
+
 def compare_events(gpu, ref):
     for kind, name in ((T.EVENT_BEGIN, "begin"), (T.EVENT_END, "end")):
         g = gpu.events(kind)
@@ -155,6 +167,10 @@ def lockstep(gpu, ref, steps, dt=1.0 / 60.0, vel_iters=8, pos_iters=3, teacher=F
     for s in range(steps):
         if teacher and s > 0:
             force_state(gpu, ref)
+        if ref.joint_count:
+            if teacher and s > 0:
+                gpu.set_joints(ref.joints())
+            ref.set_joint_order(gpu.joint_order())
         info = gpu.step(dt, vel_iters, pos_iters)
         keys, _ = gpu.solver_order()
         unranked = ref.step_ordered(keys, dt, vel_iters, pos_iters)
@@ -167,6 +183,8 @@ def lockstep(gpu, ref, steps, dt=1.0 / 60.0, vel_iters=8, pos_iters=3, teacher=F
                 compare_bodies(gpu.get_bodies(), ref.bodies(), tol)
                 compare_proxies(gpu.get_proxies(), ref.proxies())
                 compare_events(gpu, ref)
+                if ref.joint_count:
+                    compare_joints(gpu.get_joints(), ref.joints(), tol)
             except AssertionError as e:
                 raise AssertionError("step %d: %s" % (s, e))
         infos.append(info)
