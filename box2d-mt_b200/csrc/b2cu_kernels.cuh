@@ -492,6 +492,18 @@ __global__ void FlagFilterContactsKernel(DeviceArrays d, int contactCount)
 		if (((d.pgroup[pr.x] | d.pgroup[pr.y]) >> 16) & B2CU_PROXY_REFILTER) d.c.flags[i] = f | B2CU_CONTACT_FILTER;
 	}
 }
+// The start-box shortcut of the pair search assumes that a pair whose boxes overlapped before has been judged before and
+// would be judged the same again.  A pair of bodies that a joint kept apart until it was destroyed is the exception:
+// the reference finds that pair at the next move of either proxy (b2BroadPhase::UpdatePairs -> AddPair), so it must
+// go through the full test.
+__device__ __forceinline__ bool JointFreed(const DeviceArrays& d, int bodyA, int bodyB)
+{
+	uint32_t lo = (uint32_t)(bodyA < bodyB ? bodyA : bodyB), hi = (uint32_t)(bodyA < bodyB ? bodyB : bodyA);
+	uint64_t key = ((uint64_t)lo << 32) | hi;
+	int k = LowerBound64(d.jointFreedKeys, d.jointFreedCount, key);
+	return k < d.jointFreedCount && d.jointFreedKeys[k] == key;
+}
+
 // contacts between two bodies that a joint keeps from colliding get e_filterFlag; Collide then removes them
 __global__ void FlagJointContactsKernel(DeviceArrays d, int contactCount)
 {
@@ -2266,7 +2278,9 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 						continue;
 					}
 					float4 startR;
-					if (knownP && StartBox(d, r, flagsR, fr, &startR) && AabbOverlap(startP, startR)) continue;
+					if (knownP && StartBox(d, r, flagsR, fr, &startR) && AabbOverlap(startP, startR) &&
+					    !(d.jointFreedCount != 0 && JointFreed(d, d.pbody[p], d.pbody[r])))
+						continue;
 					TryAddPair(d, p, r, contactCount, pairCapacity);
 				}
 			}
@@ -2293,7 +2307,9 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 				continue;
 			}
 			float4 startR;
-			if (knownP && StartBox(d, r, flagsR, fr, &startR) && AabbOverlap(startP, startR)) continue;
+			if (knownP && StartBox(d, r, flagsR, fr, &startR) && AabbOverlap(startP, startR) &&
+					    !(d.jointFreedCount != 0 && JointFreed(d, d.pbody[p], d.pbody[r])))
+						continue;
 			TryAddPair(d, p, r, contactCount, pairCapacity);
 		}
 	}

@@ -163,8 +163,10 @@ struct DeviceArrays
 	JointRow* jointRows;     // per-step rows
 	int* jointOrder;         // joint ids by (colour class, id): the order of the solve
 	const uint64_t* jointPairKeys; // sorted (min body << 32 | max body) of the joints that forbid collision
+	const uint64_t* jointFreedKeys; // sorted body pairs that a joint used to keep apart (see JointFreed)
 	int jointCount;
 	int jointPairCount;
+	int jointFreedCount;
 };
 
 struct WorldParams
@@ -251,6 +253,10 @@ struct b2cuWorld
 	size_t eventCacheKeyBytes;
 	// joints (b2cuSetJoints)
 	int jointCapacity;
+	uint64_t* jointPairsHost;  // host copies of the two pair lists (malloc)
+	int jointPairsHostCount;
+	uint64_t* jointFreedHost;
+	int jointFreedHostCount, jointFreedCapacity;
 	bool jointFilterPending; // the joint table changed: flag the contacts it forbids for filtering
 	bool jointColourDirty;   // bodies were uploaded since the joints were coloured (a body type may have changed)
 	int jointOpCount;        // colour classes of the joint order: parallel ones, then the serial overflow

@@ -727,6 +727,9 @@ void b2cuDestroyWorld(b2cuWorld* w)
 	cudaFree(w->d.jointRows);
 	cudaFree(w->d.jointOrder);
 	cudaFree((void*)w->d.jointPairKeys);
+	cudaFree((void*)w->d.jointFreedKeys);
+	free(w->jointPairsHost);
+	free(w->jointFreedHost);
 	cudaFree(w->bodyStage);
 	cudaFree(w->queryScratch);
 	if (w->queryHost) cudaFreeHost(w->queryHost);
@@ -1033,6 +1036,45 @@ int b2cuSetJoints(b2cuWorld* w, int32_t count, const b2cuJoint* joints)
 	}
 	std::sort(pairs.begin(), pairs.end());
 	pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+	// body pairs that stop being kept apart: the pair search must look at them afresh (JointFreed)
+	{
+		std::vector<uint64_t> freed(w->jointFreedHost, w->jointFreedHost + w->jointFreedHostCount);
+		for (int k = 0; k < w->jointPairsHostCount; ++k)
+			if (!std::binary_search(pairs.begin(), pairs.end(), w->jointPairsHost[k])) freed.push_back(w->jointPairsHost[k]);
+		std::sort(freed.begin(), freed.end());
+		freed.erase(std::unique(freed.begin(), freed.end()), freed.end());
+		std::vector<uint64_t> kept;
+		for (size_t k = 0; k < freed.size(); ++k)
+			if (!std::binary_search(pairs.begin(), pairs.end(), freed[k])) kept.push_back(freed[k]);
+		if ((int)kept.size() > w->jointFreedCapacity)
+		{
+			int cap = std::max((int)kept.size(), std::max(64, 2 * w->jointFreedCapacity));
+			cudaFree((void*)w->d.jointFreedKeys);
+			w->d.jointFreedKeys = nullptr;
+			w->d.jointFreedCount = 0;
+			free(w->jointFreedHost);
+			w->jointFreedHost = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)cap);
+			w->jointFreedHostCount = 0;
+			w->jointFreedCapacity = 0;
+			uint64_t* keys = nullptr;
+			CUDA_TRY(w, cudaMalloc(&keys, sizeof(uint64_t) * (size_t)cap));
+			w->d.jointFreedKeys = keys;
+			w->jointFreedCapacity = cap;
+		}
+		if (!kept.empty())
+		{
+			memcpy(w->jointFreedHost, kept.data(), sizeof(uint64_t) * kept.size());
+			CUDA_TRY(w, cudaMemcpyAsync((void*)w->d.jointFreedKeys, kept.data(), sizeof(uint64_t) * kept.size(),
+			                            cudaMemcpyHostToDevice, w->stream));
+			CUDA_TRY(w, cudaStreamSynchronize(w->stream));
+		}
+		w->jointFreedHostCount = (int)kept.size();
+		w->d.jointFreedCount = (int)kept.size();
+		free(w->jointPairsHost);
+		w->jointPairsHost = pairs.empty() ? nullptr : (uint64_t*)malloc(sizeof(uint64_t) * pairs.size());
+		if (!pairs.empty()) memcpy(w->jointPairsHost, pairs.data(), sizeof(uint64_t) * pairs.size());
+		w->jointPairsHostCount = (int)pairs.size();
+	}
 	if (count > w->jointCapacity)
 	{
 		int cap = std::max(count, std::max(64, 2 * w->jointCapacity));

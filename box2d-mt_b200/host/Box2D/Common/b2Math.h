@@ -44,6 +44,15 @@ struct b2Vec2
 	float32 x, y;
 };
 
+struct b2Vec3
+{
+	b2Vec3() {}
+	b2Vec3(float32 xIn, float32 yIn, float32 zIn) : x(xIn), y(yIn), z(zIn) {}
+	void SetZero() { x = y = z = 0.0f; }
+	void Set(float32 x_, float32 y_, float32 z_) { x = x_; y = y_; z = z_; }
+	float32 x, y, z;
+};
+
 struct b2Mat22
 {
 	b2Mat22() {}

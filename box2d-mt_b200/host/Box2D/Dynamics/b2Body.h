@@ -37,6 +37,8 @@ struct b2BodyDef
 
 /// adjacency record of the contact graph (reference: Box2D/Dynamics/Contacts/b2Contact.h:79-90); valid until
 /// the next Step
+struct b2JointEdge;
+
 struct b2ContactEdge
 {
 	b2Body* other;
@@ -101,6 +103,9 @@ public:
 	const b2Fixture* GetFixtureList() const { return m_fixtureList; }
 	/// contacts attached to this body (built from the device contact set on first use after a step)
 	b2ContactEdge* GetContactList();
+	/// joints attached to this body (reference b2Body.h:369-373)
+	b2JointEdge* GetJointList() { return m_jointList; }
+	const b2JointEdge* GetJointList() const { return m_jointList; }
 	b2Body* GetNext() { return m_next; }
 	const b2Body* GetNext() const { return m_next; }
 	void* GetUserData() const { return m_userData; }
@@ -114,6 +119,7 @@ private:
 	friend class b2World;
 	friend class b2Fixture;
 	friend class b2Contact;
+	friend class b2Joint;
 	b2Body() {}
 	~b2Body() {}
 	void SynchronizeProxies(const b2Transform& xf1, const b2Transform& xf2);
@@ -123,6 +129,7 @@ private:
 	float32 m_mass, m_I;
 	b2Fixture* m_fixtureList;
 	int32 m_fixtureCount;
+	b2JointEdge* m_jointList;
 	b2Body* m_prev;
 	b2Body* m_next;
 	void* m_userData;

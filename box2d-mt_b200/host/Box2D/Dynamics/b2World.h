@@ -1,8 +1,7 @@
 // b2World (reference: Box2D/Dynamics/b2World.h:43-469, b2World.cpp).  Owns bodies and fixtures as host handles
 // over struct-of-arrays state (the records of include/b2cuda.h) that is mirrored to the device; Step delegates
-// to the executor (b2CudaStepExecutor).  Joints, chain shapes, sensors, world queries and debug draw are outside
-// this version of the GPU path and are not declared, so that their use fails at compile time
-// instead of being silently ignored.
+// to the executor (b2CudaStepExecutor).  Joint types other than the revolute joint and debug draw are outside this
+// version of the GPU path: the former are refused by CreateJoint, the latter is not declared.
 #ifndef B2_WORLD_H
 #define B2_WORLD_H
 
@@ -14,6 +13,7 @@
 #include "Box2D/Dynamics/b2TimeStep.h"
 #include "Box2D/Dynamics/b2WorldCallbacks.h"
 #include "Box2D/Dynamics/Contacts/b2Contact.h"
+#include "Box2D/Dynamics/Joints/b2Joint.h"
 #include "Box2D/MT/b2TaskExecutor.h"
 #include "b2cuda.h"
 
@@ -90,6 +90,13 @@ public:
 	b2Body* CreateBody(const b2BodyDef* def);
 	void DestroyBody(b2Body* body);
 
+	/// reference: b2World.h:87-95.  Revolute joints only in this version: any other type returns nullptr and sets
+	/// GetLastStepStatus() to B2CU_ERR_UNSUPPORTED.  Not while the world is locked.
+	b2Joint* CreateJoint(const b2JointDef* def);
+	void DestroyJoint(b2Joint* joint);
+	b2Joint* GetJointList() { return m_jointList; }
+	const b2Joint* GetJointList() const { return m_jointList; }
+
 	/// reference: b2World.h:105-108.  Fails loudly (assert + GetLastStepStatus() != 0) if the executor cannot run
 	/// the step on a GPU.
 	void Step(float32 timeStep, int32 velocityIterations, int32 positionIterations, b2TaskExecutor& executor);
@@ -112,7 +119,7 @@ public:
 
 	int32 GetProxyCount() const { return (int32)m_proxies.size(); }
 	int32 GetBodyCount() const { return m_bodyCount; }
-	int32 GetJointCount() const { return 0; }
+	int32 GetJointCount() const { return (int32)m_joints.size(); }
 	int32 GetContactCount() const { return m_contactCount; }
 
 	/// every fixture whose fat box overlaps `aabb` (reference b2World.cpp:1752-1758); between steps only
@@ -139,6 +146,7 @@ private:
 	friend class b2Body;
 	friend class b2Fixture;
 	friend class b2Contact;
+	friend class b2Joint;
 	friend class b2CudaStepExecutor;
 
 	// host mirror of the device state
@@ -161,6 +169,7 @@ private:
 	void RefreshBodies() const;    // device -> host mirror if stale
 	void RefreshProxies() const;
 	void RefreshContacts();
+	void RefreshJoints() const;    // device -> joint objects (accumulated impulses) if stale
 	void InvalidateSnapshots();
 	static int PreSolveThunk(void* user, b2cuWorld* device);
 	static int PairFilterThunk(void* user, const b2cuContactKey* keys, int32_t count, uint8_t* keep);
@@ -188,6 +197,10 @@ private:
 	std::vector<b2Contact> m_contacts;
 	std::vector<b2ContactEdge*> m_contactHeads;
 
+	std::vector<b2Joint*> m_joints;   // creation order = rows of the device joint table
+	b2Joint* m_jointList;
+	bool m_jointsDirty;               // the table must be sent again before the next step
+	mutable bool m_jointsStale;       // the device holds newer impulses than the joint objects
 	b2Body* m_bodyList;
 	int32 m_bodyCount;
 	int32 m_contactCount;

@@ -74,9 +74,13 @@ public:
 };
 
 /// Told about fixtures that disappear implicitly (their body is destroyed).
+class b2Joint;
+
 class b2DestructionListener
 {
 public:
+	/// a joint is about to be destroyed because one of its bodies is (reference b2WorldCallbacks.h:46-48)
+	virtual void SayGoodbye(b2Joint* joint) { (void)joint; }
 	virtual void SayGoodbye(b2Fixture* fixture) = 0;
 	virtual ~b2DestructionListener() {}
 };

@@ -106,6 +106,7 @@ struct Host
 	Recorder recorder;
 	std::vector<b2Body*> bodies;
 	std::vector<b2Fixture*> fixtures;
+	std::vector<b2RevoluteJoint*> joints;
 };
 
 } // namespace
@@ -385,6 +386,87 @@ B2H_API int b2h_solver_order(void* p, int32 capacity, uint64* keys)
 	if (!dev) return 0;
 	int32 n = 0;
 	b2cuGetSolverOrder(dev, capacity, keys, nullptr, &n);
+	return n;
+}
+
+// ---- joints: b2World::CreateJoint / DestroyJoint and the b2RevoluteJoint accessors, from / to b2cuJoint rows ----
+B2H_API int b2h_create_joints(void* p, int32 count, const b2cuJoint* rows)
+{
+	Host* h = static_cast<Host*>(p);
+	for (int32 i = 0; i < count; ++i)
+	{
+		const b2cuJoint& r = rows[i];
+		if (r.type != B2CU_JOINT_REVOLUTE) return -1;
+		b2RevoluteJointDef def;
+		def.bodyA = h->bodies[r.bodyA];
+		def.bodyB = h->bodies[r.bodyB];
+		def.collideConnected = (r.flags & B2CU_JOINT_COLLIDE_CONNECTED) != 0;
+		def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
+		def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
+		def.referenceAngle = r.referenceAngle;
+		def.enableLimit = (r.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
+		def.lowerAngle = r.lowerAngle;
+		def.upperAngle = r.upperAngle;
+		def.enableMotor = (r.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
+		def.motorSpeed = r.motorSpeed;
+		def.maxMotorTorque = r.maxMotorTorque;
+		b2Joint* j = h->world->CreateJoint(&def);
+		if (j == nullptr) return -2;
+		h->joints.push_back(static_cast<b2RevoluteJoint*>(j));
+	}
+	return 0;
+}
+
+B2H_API void b2h_destroy_joint(void* p, int32 joint)
+{
+	Host* h = static_cast<Host*>(p);
+	h->world->DestroyJoint(h->joints[joint]);
+	h->joints.erase(h->joints.begin() + joint);
+}
+
+/// per joint: reaction force x, y, reaction torque, motor torque (all at inv_dt), joint angle, joint speed
+B2H_API void b2h_joint_readings(void* p, float inv_dt, float* out6)
+{
+	Host* h = static_cast<Host*>(p);
+	for (size_t i = 0; i < h->joints.size(); ++i)
+	{
+		const b2RevoluteJoint* j = h->joints[i];
+		b2Vec2 f = j->GetReactionForce(inv_dt);
+		float* o = out6 + 6 * i;
+		o[0] = f.x;
+		o[1] = f.y;
+		o[2] = j->GetReactionTorque(inv_dt);
+		o[3] = j->GetMotorTorque(inv_dt);
+		o[4] = j->GetJointAngle();
+		o[5] = j->GetJointSpeed();
+	}
+}
+
+B2H_API void b2h_joint_set_motor(void* p, int32 joint, int32 enable, float speed, float maxTorque)
+{
+	b2RevoluteJoint* j = static_cast<Host*>(p)->joints[joint];
+	j->EnableMotor(enable != 0);
+	j->SetMotorSpeed(speed);
+	j->SetMaxMotorTorque(maxTorque);
+}
+
+B2H_API void b2h_joint_set_limits(void* p, int32 joint, int32 enable, float lower, float upper)
+{
+	b2RevoluteJoint* j = static_cast<Host*>(p)->joints[joint];
+	j->EnableLimit(enable != 0);
+	j->SetLimits(lower, upper);
+}
+
+B2H_API int b2h_joint_count(void* p) { return static_cast<Host*>(p)->world->GetJointCount(); }
+
+/// the order in which the device solves the joints (valid after a step)
+B2H_API int b2h_joint_order(void* p, int32 capacity, int32* ids)
+{
+	Host* h = static_cast<Host*>(p);
+	b2cuWorld* dev = h->executor->GetDeviceWorld(h->world);
+	if (!dev) return 0;
+	int32 n = 0;
+	b2cuGetJointOrder(dev, capacity, ids, &n);
 	return n;
 }
 

@@ -1,0 +1,151 @@
+// Host side of the joints (reference: Box2D/Dynamics/Joints/b2Joint.cpp, b2RevoluteJoint.cpp:36-62, :379-512; the
+// world's part is b2World::CreateJoint / DestroyJoint, b2World.cpp:659-841).  Nothing is solved here: the joint objects
+// hold parameters and the persistent impulses, and exchange them with the device's joint table.
+#include "Box2D/Dynamics/Joints/b2RevoluteJoint.h"
+#include "Box2D/Dynamics/b2Body.h"
+#include "Box2D/Dynamics/b2World.h"
+
+b2Joint::b2Joint(const b2JointDef* def)
+	: m_type(def->type), m_prev(nullptr), m_next(nullptr), m_bodyA(def->bodyA), m_bodyB(def->bodyB), m_world(nullptr),
+	  m_index(-1), m_collideConnected(def->collideConnected), m_userData(def->userData)
+{
+	b2Assert(def->bodyA != def->bodyB);
+	m_edgeA.joint = m_edgeB.joint = nullptr;
+	m_edgeA.other = m_edgeB.other = nullptr;
+	m_edgeA.prev = m_edgeA.next = m_edgeB.prev = m_edgeB.next = nullptr;
+}
+
+bool b2Joint::IsActive() const { return m_bodyA->IsActive() && m_bodyB->IsActive(); }
+
+void b2Joint::Refresh() const { m_world->RefreshJoints(); }
+
+void b2Joint::Touch()
+{
+	m_world->RefreshJoints();
+	m_world->m_jointsDirty = true;
+}
+
+// ---- revolute ----------------------------------------------------------------------------------------------------------
+
+void b2RevoluteJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor)
+{
+	bodyA = bA;
+	bodyB = bB;
+	localAnchorA = bA->GetLocalPoint(anchor);
+	localAnchorB = bB->GetLocalPoint(anchor);
+	referenceAngle = bB->GetAngle() - bA->GetAngle();
+}
+
+b2RevoluteJoint::b2RevoluteJoint(const b2RevoluteJointDef* def)
+	: b2Joint(def), m_localAnchorA(def->localAnchorA), m_localAnchorB(def->localAnchorB),
+	  m_referenceAngle(def->referenceAngle), m_enableLimit(def->enableLimit), m_enableMotor(def->enableMotor),
+	  m_lowerAngle(def->lowerAngle), m_upperAngle(def->upperAngle), m_motorSpeed(def->motorSpeed),
+	  m_maxMotorTorque(def->maxMotorTorque), m_impulse(0.0f, 0.0f, 0.0f), m_motorImpulse(0.0f), m_limitState(e_inactiveLimit)
+{
+}
+
+void b2RevoluteJoint::WriteRecord(b2cuJoint* out) const
+{
+	b2cuJoint r = b2cuJoint();
+	r.type = B2CU_JOINT_REVOLUTE;
+	r.bodyA = m_bodyA->GetIndex();
+	r.bodyB = m_bodyB->GetIndex();
+	r.flags = (m_collideConnected ? B2CU_JOINT_COLLIDE_CONNECTED : 0u) | (m_enableLimit ? B2CU_JOINT_ENABLE_LIMIT : 0u) |
+	          (m_enableMotor ? B2CU_JOINT_ENABLE_MOTOR : 0u);
+	r.localAnchorA[0] = m_localAnchorA.x;
+	r.localAnchorA[1] = m_localAnchorA.y;
+	r.localAnchorB[0] = m_localAnchorB.x;
+	r.localAnchorB[1] = m_localAnchorB.y;
+	r.referenceAngle = m_referenceAngle;
+	r.lowerAngle = m_lowerAngle;
+	r.upperAngle = m_upperAngle;
+	r.maxMotorTorque = m_maxMotorTorque;
+	r.motorSpeed = m_motorSpeed;
+	r.impulse[0] = m_impulse.x;
+	r.impulse[1] = m_impulse.y;
+	r.impulse[2] = m_impulse.z;
+	r.motorImpulse = m_motorImpulse;
+	r.limitState = (int32_t)m_limitState;
+	*out = r;
+}
+
+void b2RevoluteJoint::ReadRecord(const b2cuJoint& in)
+{
+	m_impulse.Set(in.impulse[0], in.impulse[1], in.impulse[2]);
+	m_motorImpulse = in.motorImpulse;
+	m_limitState = (b2LimitState)in.limitState;
+}
+
+b2Vec2 b2RevoluteJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2RevoluteJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+float32 b2RevoluteJoint::GetJointAngle() const { return m_bodyB->GetAngle() - m_bodyA->GetAngle() - m_referenceAngle; }
+float32 b2RevoluteJoint::GetJointSpeed() const { return m_bodyB->GetAngularVelocity() - m_bodyA->GetAngularVelocity(); }
+
+b2Vec2 b2RevoluteJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	return b2Vec2(inv_dt * m_impulse.x, inv_dt * m_impulse.y);
+}
+
+float32 b2RevoluteJoint::GetReactionTorque(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_impulse.z;
+}
+
+float32 b2RevoluteJoint::GetMotorTorque(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_motorImpulse;
+}
+
+void b2RevoluteJoint::WakeBodies()
+{
+	m_bodyA->SetAwake(true);
+	m_bodyB->SetAwake(true);
+}
+
+void b2RevoluteJoint::EnableMotor(bool flag)
+{
+	if (flag == m_enableMotor) return;
+	Touch();
+	WakeBodies();
+	m_enableMotor = flag;
+}
+
+void b2RevoluteJoint::SetMotorSpeed(float32 speed)
+{
+	if (speed == m_motorSpeed) return;
+	Touch();
+	WakeBodies();
+	m_motorSpeed = speed;
+}
+
+void b2RevoluteJoint::SetMaxMotorTorque(float32 torque)
+{
+	if (torque == m_maxMotorTorque) return;
+	Touch();
+	WakeBodies();
+	m_maxMotorTorque = torque;
+}
+
+void b2RevoluteJoint::EnableLimit(bool flag)
+{
+	if (flag == m_enableLimit) return;
+	Touch();
+	WakeBodies();
+	m_enableLimit = flag;
+	m_impulse.z = 0.0f;
+}
+
+void b2RevoluteJoint::SetLimits(float32 lower, float32 upper)
+{
+	b2Assert(lower <= upper);
+	if (lower == m_lowerAngle && upper == m_upperAngle) return;
+	Touch();
+	WakeBodies();
+	m_impulse.z = 0.0f;
+	m_lowerAngle = lower;
+	m_upperAngle = upper;
+}

@@ -2,6 +2,7 @@
 // reference: Box2D/Dynamics/b2World.cpp (CreateBody :532-559, DestroyBody :561-640, Step :1613-1710) and
 // b2ContactManager.cpp (callback dispatch :388-439).
 #include "Box2D/Dynamics/b2World.h"
+#include "Box2D/Dynamics/Joints/b2RevoluteJoint.h"
 
 #include <chrono>
 #include "Box2D/Collision/Shapes/b2CircleShape.h"
@@ -91,7 +92,8 @@ void b2Contact::GetWorldManifold(b2WorldManifold* worldManifold) const
 b2World::b2World(const b2Vec2& gravity)
 	: m_device(nullptr), m_owner(nullptr), m_fullUpload(false), m_bodiesUploaded(0), m_proxiesUploaded(0),
 	  m_shapesUploaded(0), m_bodyDirtyLo(INT32_MAX), m_bodyDirtyHi(-1), m_proxyDirtyLo(INT32_MAX), m_proxyDirtyHi(-1),
-	  m_bodiesStale(false), m_proxiesStale(false), m_contactsStale(true), m_bodyList(nullptr), m_bodyCount(0),
+	  m_bodiesStale(false), m_proxiesStale(false), m_contactsStale(true), m_jointList(nullptr), m_jointsDirty(false),
+	  m_jointsStale(false), m_bodyList(nullptr), m_bodyCount(0),
 	  m_contactCount(0), m_gravity(gravity), m_allowSleep(true), m_warmStarting(true), m_continuousPhysics(true),
 	  m_subStepping(false), m_clearForces(true), m_locked(false), m_newFixture(false), m_inv_dt0(0.0f),
 	  m_destructionListener(nullptr), m_contactFilter(nullptr), m_contactListener(nullptr), m_lastStatus(0)
@@ -105,6 +107,7 @@ b2World::~b2World()
 	// m_fixtures has one entry per PROXY: a chain fixture appears once per segment
 	for (size_t i = 0; i < m_fixtures.size(); ++i)
 		if (i == 0 || m_fixtures[i] != m_fixtures[i - 1]) delete m_fixtures[i];
+	for (size_t i = 0; i < m_joints.size(); ++i) delete m_joints[i];
 	for (size_t i = 0; i < m_bodies.size(); ++i) delete m_bodies[i];
 }
 
@@ -119,6 +122,7 @@ b2Body* b2World::CreateBody(const b2BodyDef* def)
 	b->m_index = (int32)m_states.size();
 	b->m_fixtureList = nullptr;
 	b->m_fixtureCount = 0;
+	b->m_jointList = nullptr;
 	b->m_userData = def->userData;
 	b->m_I = 0.0f;
 
@@ -303,6 +307,78 @@ void b2World::RefreshBodies() const
 	int32 n = std::min(m_bodiesUploaded, (int32)m_states.size());
 	if (n > 0) b2cuGetBodyStates(m_device, 0, n, self->m_states.data());
 	m_bodiesStale = false;
+}
+
+void b2World::RefreshJoints() const
+{
+	if (!m_jointsStale || m_device == nullptr) return;
+	m_jointsStale = false;
+	int32 n = 0;
+	if (b2cuGetJointCount(m_device, &n) != B2CU_OK || n != (int32)m_joints.size() || n == 0) return;
+	std::vector<b2cuJoint> rows((size_t)n);
+	if (b2cuGetJoints(m_device, 0, n, rows.data()) != B2CU_OK) return;
+	for (int32 i = 0; i < n; ++i) m_joints[i]->ReadRecord(rows[i]);
+}
+
+// reference b2World.cpp:659-733
+b2Joint* b2World::CreateJoint(const b2JointDef* def)
+{
+	if (IsLocked()) return nullptr;
+	if (def->type != e_revoluteJoint)
+	{
+		m_lastStatus = B2CU_ERR_UNSUPPORTED;
+		return nullptr;
+	}
+	RefreshJoints();
+	b2Joint* j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
+	j->m_world = this;
+	j->m_index = (int32)m_joints.size();
+	m_joints.push_back(j);
+
+	j->m_prev = nullptr;
+	j->m_next = m_jointList;
+	if (m_jointList) m_jointList->m_prev = j;
+	m_jointList = j;
+
+	b2JointEdge* edges[2] = {&j->m_edgeA, &j->m_edgeB};
+	b2Body* ends[2] = {j->m_bodyA, j->m_bodyB};
+	for (int32 k = 0; k < 2; ++k)
+	{
+		edges[k]->joint = j;
+		edges[k]->other = ends[1 - k];
+		edges[k]->prev = nullptr;
+		edges[k]->next = ends[k]->m_jointList;
+		if (ends[k]->m_jointList) ends[k]->m_jointList->prev = edges[k];
+		ends[k]->m_jointList = edges[k];
+	}
+	// contacts the joint forbids are re-filtered by the device when the table arrives (b2cuSetJoints)
+	m_jointsDirty = true;
+	return j;
+}
+
+// reference b2World.cpp:735-841
+void b2World::DestroyJoint(b2Joint* j)
+{
+	if (IsLocked() || j == nullptr) return;
+	RefreshJoints();
+	if (j->m_prev) j->m_prev->m_next = j->m_next;
+	if (j->m_next) j->m_next->m_prev = j->m_prev;
+	if (j == m_jointList) m_jointList = j->m_next;
+
+	b2JointEdge* edges[2] = {&j->m_edgeA, &j->m_edgeB};
+	b2Body* ends[2] = {j->m_bodyA, j->m_bodyB};
+	for (int32 k = 0; k < 2; ++k)
+	{
+		// wake the bodies: whatever the joint held up may now fall
+		ends[k]->SetAwake(true);
+		if (edges[k]->prev) edges[k]->prev->next = edges[k]->next;
+		if (edges[k]->next) edges[k]->next->prev = edges[k]->prev;
+		if (edges[k] == ends[k]->m_jointList) ends[k]->m_jointList = edges[k]->next;
+	}
+	m_joints.erase(m_joints.begin() + j->m_index);
+	for (size_t i = 0; i < m_joints.size(); ++i) m_joints[i]->m_index = (int32)i;
+	delete j;
+	m_jointsDirty = true;
 }
 
 void b2World::RefreshProxies() const
@@ -559,6 +635,19 @@ void b2World::DestroyFixtureInternal(b2Body* body, b2Fixture* fixture)
 void b2World::DestroyBody(b2Body* b)
 {
 	if (IsLocked() || b == nullptr) return;
+	// the joints attached to the body go first (reference b2World.cpp:594-610)
+	while (b->m_jointList)
+	{
+		b2Joint* doomedJoint = b->m_jointList->joint;
+		if (m_destructionListener) m_destructionListener->SayGoodbye(doomedJoint);
+		DestroyJoint(doomedJoint);
+	}
+	if (!m_joints.empty())
+	{
+		// body rows are renumbered below: the joint table is rebuilt from the objects
+		RefreshJoints();
+		m_jointsDirty = true;
+	}
 	std::vector<int32> proxies, bodies(1, b->m_index);
 	for (b2Fixture* f = b->m_fixtureList; f; f = f->m_next)
 	{
@@ -742,6 +831,15 @@ int32 b2World::UploadDirty(b2cuWorld* device)
 		if (lo <= hi && (rc = b2cuSetProxies(device, lo, hi - lo + 1, m_proxies.data() + lo))) return rc;
 		// the MOVED flag has been handed to the device's move buffer
 		for (int32 i = lo; i <= hi; ++i) m_proxies[i].flags &= ~(uint16)(B2CU_PROXY_MOVED | B2CU_PROXY_NEW | B2CU_PROXY_REFILTER);
+	}
+	if (m_jointsDirty || (m_fullUpload && !m_joints.empty()))
+	{
+		// the joint table as a whole; the objects hold the current impulses (every edit refreshed them first)
+		std::vector<b2cuJoint> rows(m_joints.size());
+		for (size_t i = 0; i < m_joints.size(); ++i) m_joints[i]->WriteRecord(&rows[i]);
+		if ((rc = b2cuSetJoints(device, (int32)rows.size(), rows.empty() ? nullptr : rows.data()))) return rc;
+		m_jointsDirty = false;
+		m_jointsStale = false;
 	}
 	if (m_fullUpload)
 	{
@@ -928,6 +1026,7 @@ int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool
 		m_forced.resize(kept);
 	}
 	m_proxiesStale = true;
+	if (!m_joints.empty()) m_jointsStale = true;
 	InvalidateSnapshots();
 	Clock::time_point t1 = Clock::now();
 	if (hostMs) hostMs[0] = std::chrono::duration<float, std::milli>(t1 - t0).count();

@@ -51,6 +51,13 @@ def load():
     lib.b2h_get_contacts.argtypes = [vp, i32, vp, vp, vp]
     lib.b2h_events.argtypes = [vp, i32, i32, vp]
     lib.b2h_solver_order.argtypes = [vp, i32, vp]
+    lib.b2h_create_joints.argtypes = [vp, i32, vp]
+    lib.b2h_destroy_joint.argtypes = [vp, i32]
+    lib.b2h_joint_readings.argtypes = [vp, f32, vp]
+    lib.b2h_joint_set_motor.argtypes = [vp, i32, i32, f32, f32]
+    lib.b2h_joint_set_limits.argtypes = [vp, i32, i32, f32, f32]
+    lib.b2h_joint_count.argtypes = [vp]
+    lib.b2h_joint_order.argtypes = [vp, i32, vp]
     lib.b2h_profile.argtypes = [vp, vp]
     lib.b2h_step_info.argtypes = [vp, vp]
     lib.b2h_host_timings.argtypes = [vp, vp]
@@ -102,6 +109,39 @@ class HostWorld:
         rc = self.lib.b2h_build(self.h, len(b), _ptr(b), len(s), _ptr(s), len(f), _ptr(f))
         if rc != 0:
             raise RuntimeError("b2h_build failed: %d" % rc)
+        if scene is not None and getattr(scene, "joints", None):
+            self.create_joints(scene.joint_array())
+
+    # ---- joints (b2World::CreateJoint / b2RevoluteJoint) ----
+    def create_joints(self, joints):
+        j = np.ascontiguousarray(joints, T.JOINT)
+        rc = self.lib.b2h_create_joints(self.h, len(j), _ptr(j))
+        if rc != 0:
+            raise RuntimeError("b2World::CreateJoint failed: %d" % rc)
+
+    def destroy_joint(self, joint):
+        self.lib.b2h_destroy_joint(self.h, joint)
+
+    def joint_count(self):
+        return self.lib.b2h_joint_count(self.h)
+
+    def joint_order(self):
+        out = np.zeros(self.joint_count(), np.int32)
+        n = self.lib.b2h_joint_order(self.h, len(out), _ptr(out))
+        return out[:n]
+
+    def joint_readings(self, inv_dt=60.0):
+        """per joint: reaction force x, y, reaction torque, motor torque, joint angle, joint speed"""
+        out = np.zeros((self.joint_count(), 6), np.float32)
+        if len(out):
+            self.lib.b2h_joint_readings(self.h, ctypes.c_float(inv_dt), _ptr(out))
+        return out
+
+    def joint_set_motor(self, joint, enable, speed, max_torque):
+        self.lib.b2h_joint_set_motor(self.h, joint, int(enable), ctypes.c_float(speed), ctypes.c_float(max_torque))
+
+    def joint_set_limits(self, joint, enable, lower, upper):
+        self.lib.b2h_joint_set_limits(self.h, joint, int(enable), ctypes.c_float(lower), ctypes.c_float(upper))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -54,6 +54,10 @@ def load(stock=False):
     lib.b2ref_set_joints.restype = i32
     lib.b2ref_set_joint_order.argtypes = [vp, i32, vp]
     lib.b2ref_export_joints.argtypes = [vp, vp]
+    lib.b2ref_joint_set_motor.argtypes = [vp, i32, i32, f32, f32]
+    lib.b2ref_joint_set_limits.argtypes = [vp, i32, i32, f32, f32]
+    lib.b2ref_destroy_joint.argtypes = [vp, i32]
+    lib.b2ref_joint_readings.argtypes = [vp, f32, vp]
     lib.b2ref_profile.argtypes = [vp, vp]
     lib.b2ref_set_transform.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_set_type.argtypes = [vp, i32, i32]
@@ -112,6 +116,22 @@ class RefWorld:
         ids = np.ascontiguousarray(ids, np.int32)
         assert len(ids) == self.joint_count
         self.lib.b2ref_set_joint_order(self.h, len(ids), _ptr(ids))
+
+    def joint_set_motor(self, joint, enable, speed, max_torque):
+        self.lib.b2ref_joint_set_motor(self.h, joint, int(enable), ctypes.c_float(speed), ctypes.c_float(max_torque))
+
+    def joint_set_limits(self, joint, enable, lower, upper):
+        self.lib.b2ref_joint_set_limits(self.h, joint, int(enable), ctypes.c_float(lower), ctypes.c_float(upper))
+
+    def destroy_joint(self, joint):
+        self.lib.b2ref_destroy_joint(self.h, joint)
+        self.joint_count -= 1
+
+    def joint_readings(self, inv_dt=60.0):
+        out = np.zeros((self.joint_count, 6), np.float32)
+        if self.joint_count:
+            self.lib.b2ref_joint_readings(self.h, ctypes.c_float(inv_dt), _ptr(out))
+        return out
 
     def joints(self):
         out = np.zeros(self.joint_count, T.JOINT)

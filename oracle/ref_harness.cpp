@@ -860,6 +860,45 @@ void b2ref_set_joint_order(b2refWorld* w, int32_t count, const int32_t* ids)
 	}
 }
 
+void b2ref_joint_set_motor(b2refWorld* w, int32_t joint, int32_t enable, float speed, float maxTorque)
+{
+	b2RevoluteJoint* j = (b2RevoluteJoint*)w->joints[joint];
+	j->EnableMotor(enable != 0);
+	j->SetMotorSpeed(speed);
+	j->SetMaxMotorTorque(maxTorque);
+}
+
+void b2ref_joint_set_limits(b2refWorld* w, int32_t joint, int32_t enable, float lower, float upper)
+{
+	b2RevoluteJoint* j = (b2RevoluteJoint*)w->joints[joint];
+	j->EnableLimit(enable != 0);
+	j->SetLimits(lower, upper);
+}
+
+void b2ref_destroy_joint(b2refWorld* w, int32_t joint)
+{
+	w->jointRank.erase(w->joints[joint]);
+	w->world->DestroyJoint(w->joints[joint]);
+	w->joints.erase(w->joints.begin() + joint);
+}
+
+/* per joint: reaction force x, y, reaction torque, motor torque (at inv_dt), joint angle, joint speed */
+void b2ref_joint_readings(b2refWorld* w, float inv_dt, float* out6)
+{
+	for (size_t i = 0; i < w->joints.size(); ++i)
+	{
+		const b2RevoluteJoint* j = (const b2RevoluteJoint*)w->joints[i];
+		b2Vec2 f = j->GetReactionForce(inv_dt);
+		float* o = out6 + 6 * i;
+		o[0] = f.x;
+		o[1] = f.y;
+		o[2] = j->GetReactionTorque(inv_dt);
+		o[3] = j->GetMotorTorque(inv_dt);
+		o[4] = j->GetJointAngle();
+		o[5] = j->GetJointSpeed();
+	}
+}
+
 void b2ref_export_joints(b2refWorld* w, b2cuJoint* out)
 {
 	for (size_t i = 0; i < w->joints.size(); ++i)

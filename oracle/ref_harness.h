@@ -141,6 +141,10 @@ void b2ref_distance(const b2cuShape* shapeA, const float xfA[4], const b2cuShape
 int32_t b2ref_set_joints(b2refWorld* w, int32_t count, const b2cuJoint* joints);
 void b2ref_set_joint_order(b2refWorld* w, int32_t count, const int32_t* ids);
 void b2ref_export_joints(b2refWorld* w, b2cuJoint* out);
+void b2ref_joint_set_motor(b2refWorld* w, int32_t joint, int32_t enable, float speed, float maxTorque);
+void b2ref_joint_set_limits(b2refWorld* w, int32_t joint, int32_t enable, float lower, float upper);
+void b2ref_destroy_joint(b2refWorld* w, int32_t joint);
+void b2ref_joint_readings(b2refWorld* w, float inv_dt, float* out6);
 /* first pass of b2World::SolveTOI on the current state (see ref_harness.cpp) */
 int32_t b2ref_first_toi(b2refWorld* w, uint64_t* key, float* alpha);
 /* the reference's b2TimeOfImpact on geometry records and sweeps */

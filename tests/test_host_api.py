@@ -106,9 +106,14 @@ def _host_lockstep(scene, steps, check_events=True):
     begins = 0
     for s in range(steps):
         h.step()
+        if r.joint_count:
+            r.set_joint_order(h.joint_order())
         assert r.step_ordered(h.solver_order()) == 0, s
         try:
             parity.compare_bodies(h.bodies(), r.bodies())
+            if r.joint_count:
+                # b2RevoluteJoint::GetReactionForce / GetReactionTorque / GetMotorTorque / GetJointAngle / GetJointSpeed
+                parity.assert_floats_equal("joint readings", h.joint_readings(), r.joint_readings())
             xya, awake = h.transforms()
             rb = r.bodies()
             assert (xya[:, 0] == rb["px"]).all() and (xya[:, 1] == rb["py"]).all() and (xya[:, 2] == rb["a"]).all()
@@ -139,6 +144,53 @@ def test_host_api_lockstep(gpu, name, steps):
     assert (points == rc["manifold"]["pointCount"]).all()
     prof = h.profile()
     assert prof[0] > 0 and prof[2] > 0  # step and solve times come from device events
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,steps", [("tumbler_joint", 150), ("hanging_chains", 300), ("joint_zoo", 300)])
+def test_host_api_joints_lockstep(gpu, name, steps):
+    """Worlds with revolute joints built through b2World::CreateJoint (the Testbed's Tumbler with its motor joint,
+    hanging chains, every branch of the joint) and stepped through b2World::Step stay bit-identical to the reference:
+    bodies, events and what the b2RevoluteJoint accessors report."""
+    make = {"tumbler_joint": lambda: scenes.tumbler(60, motor_joint=True), "hanging_chains": lambda: scenes.hanging_chains(3, 10),
+            "joint_zoo": scenes.joint_zoo}[name]
+    h, r, begins = _host_lockstep(make(), steps)
+    assert h.joint_count() == r.joint_count > 0
+    assert h.hash() == r.hash()
+
+
+@pytest.mark.gpu
+def test_host_api_joint_edits_between_steps(gpu):
+    """SetMotorSpeed / EnableMotor / SetLimits / EnableLimit between steps (they wake the bodies and reset the limit
+    impulse), DestroyJoint, and DestroyBody taking its joints along: the worlds stay in lockstep."""
+    scene = scenes.joint_zoo()
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+
+    def run(n):
+        for s in range(n):
+            h.step()
+            r.set_joint_order(h.joint_order())
+            assert r.step_ordered(h.solver_order()) == 0
+            parity.compare_bodies(h.bodies(), r.bodies())
+            parity.assert_floats_equal("joint readings", h.joint_readings(), r.joint_readings())
+
+    run(40)
+    for w in (h, r):
+        w.joint_set_motor(0, True, 2.0, 50.0)       # a free pendulum gets a motor
+        w.joint_set_motor(4, False, 1.0, 5.0)       # a motor is switched off
+        w.joint_set_limits(6, True, -0.3, 0.4)      # limits appear
+        w.joint_set_limits(1, False, -0.5, 0.5)     # limits go away
+    run(60)
+    for w in (h, r):
+        w.joint_set_limits(3, True, -1.0, 1.0)      # limits move while the joint is at one of them
+        w.destroy_joint(8)                          # the hub's motor joint: the hub falls with its spokes
+    run(80)
+    for w in (h, r):
+        w.destroy_joint(w.joint_count() - 1 if w is h else w.joint_count - 1)
+    run(40)
+    assert h.joint_count() == r.joint_count
 
 
 @pytest.mark.gpu
