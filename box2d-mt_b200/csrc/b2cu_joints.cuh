@@ -1,7 +1,8 @@
-// b2cu_joints.cuh -- joints as rows of the coloured solver.  Restates b2RevoluteJoint::InitVelocityConstraints /
-// SolveVelocityConstraints / SolvePositionConstraints (Box2D/Dynamics/Joints/b2RevoluteJoint.cpp:64-400) and the small
-// linear solves they use (b2Mat33::Solve33 / Solve22, Box2D/Common/b2Math.cpp:25-53; b2Mat22::Solve, b2Math.h:221-233)
-// with the same fp32 arithmetic in the same order.  One thread solves one joint; joints of one colour class share no
+// b2cu_joints.cuh -- joints as rows of the coloured solver.  Restates InitVelocityConstraints / SolveVelocityConstraints
+// / SolvePositionConstraints of b2RevoluteJoint (Box2D/Dynamics/Joints/b2RevoluteJoint.cpp:64-400), b2DistanceJoint
+// (b2DistanceJoint.cpp:63-222) and b2WeldJoint (b2WeldJoint.cpp:59-308), and the small linear solves they use
+// (b2Mat33::Solve33 / Solve22 / GetInverse22 / GetSymInverse33, Box2D/Common/b2Math.cpp:25-94; b2Mat22::Solve,
+// b2Math.h:221-233) with the same fp32 arithmetic in the same order.  One thread solves one joint; joints of one colour class share no
 // dynamic body, so a class is solved in parallel and the classes one after the other.
 #pragma once
 
@@ -35,8 +36,10 @@ struct JointRow
 	Vec2 rA, rB;
 	Vec2 localCenterA, localCenterB;
 	float invMassA, invMassB, invIA, invIB;
-	Vec3 ex, ey, ez; // m_mass
-	float motorMass;
+	Vec3 ex, ey, ez; // m_mass (revolute: K; weld: its inverse)
+	float motorMass; // revolute: motor mass; distance: m_mass
+	Vec2 u;          // distance: unit vector from anchor A to anchor B
+	float gamma, bias; // soft constraint terms (distance, weld)
 	int root;   // island of the joint (position early exit)
 	int solved; // in an awake island this step
 };
@@ -69,23 +72,17 @@ __device__ __forceinline__ void StoreVelocity(const DeviceArrays& d, int body, f
 	if (invMass != 0.0f || invI != 0.0f) d.vel[body] = make_float4(v.x, v.y, w, keep);
 }
 
-// b2RevoluteJoint::InitVelocityConstraints (:64-183)
-__device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float dtRatio, int warmStarting)
+// Is the joint part of this step's solve, and in which island?  The island search adds a joint from an island body when
+// the body across is active (b2World.cpp:1286-1320).  Also loads the body constants every joint type starts from.
+__device__ __forceinline__ bool JointPrepare(const DeviceArrays& d, const b2cuJoint& jt, JointRow& r)
 {
-	b2cuJoint jt = d.joints[j];
-	JointRow r;
 	const int bA = jt.bodyA, bB = jt.bodyB;
 	const uint32_t fA = d.bflags[bA], fB = d.bflags[bB];
-	// the island search adds a joint from an island body when the body across is active (b2World.cpp:1286-1320)
 	const bool staticA = (fA & B2CU_BODY_TYPE_MASK) == B2CU_STATIC_BODY, staticB = (fB & B2CU_BODY_TYPE_MASK) == B2CU_STATIC_BODY;
 	const bool islandA = !staticA && (fA & B2CU_BODY_ISLAND), islandB = !staticB && (fB & B2CU_BODY_ISLAND);
 	r.solved = (islandA || islandB) && (fA & B2CU_BODY_ACTIVE) && (fB & B2CU_BODY_ACTIVE) ? 1 : 0;
 	r.root = islandA ? d.island[bA] : (islandB ? d.island[bB] : 0);
-	if (!r.solved)
-	{
-		d.jointRows[j].solved = 0;
-		return;
-	}
+	if (!r.solved) return false;
 	float4 massA = d.mass[bA], massB = d.mass[bB];
 	r.localCenterA = V(massA.z, massA.w);
 	r.localCenterB = V(massB.z, massB.w);
@@ -93,7 +90,31 @@ __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float
 	r.invMassB = massB.x;
 	r.invIA = massA.y;
 	r.invIB = massB.y;
+	r.u = V(0.0f, 0.0f);
+	r.gamma = r.bias = r.motorMass = 0.0f;
+	r.ex = r.ey = r.ez = V3(0.0f, 0.0f, 0.0f);
+	return true;
+}
 
+// K of the point + angle constraint shared by the revolute and the weld joint
+__device__ __forceinline__ void PointAngleK(JointRow& r, Vec2 rA, Vec2 rB)
+{
+	float mA = r.invMassA, mB = r.invMassB, iA = r.invIA, iB = r.invIB;
+	r.ex.x = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
+	r.ey.x = -rA.y * rA.x * iA - rB.y * rB.x * iB;
+	r.ez.x = -rA.y * iA - rB.y * iB;
+	r.ex.y = r.ey.x;
+	r.ey.y = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
+	r.ez.y = rA.x * iA + rB.x * iB;
+	r.ex.z = r.ez.x;
+	r.ey.z = r.ez.y;
+	r.ez.z = iA + iB;
+}
+
+// b2RevoluteJoint::InitVelocityConstraints (:64-183)
+__device__ __forceinline__ void RevoluteInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio, int warmStarting)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
 	float4 pA = d.pos[bA], pB = d.pos[bB];
 	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
 	float aA = pA.z, aB = pB.z;
@@ -108,15 +129,7 @@ __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float
 	float iA = r.invIA, iB = r.invIB;
 	bool fixedRotation = (iA + iB == 0.0f);
 
-	r.ex.x = mA + mB + r.rA.y * r.rA.y * iA + r.rB.y * r.rB.y * iB;
-	r.ey.x = -r.rA.y * r.rA.x * iA - r.rB.y * r.rB.x * iB;
-	r.ez.x = -r.rA.y * iA - r.rB.y * iB;
-	r.ex.y = r.ey.x;
-	r.ey.y = mA + mB + r.rA.x * r.rA.x * iA + r.rB.x * r.rB.x * iB;
-	r.ez.y = r.rA.x * iA + r.rB.x * iB;
-	r.ex.z = r.ez.x;
-	r.ey.z = r.ez.y;
-	r.ez.z = iA + iB;
+	PointAngleK(r, r.rA, r.rB);
 
 	r.motorMass = iA + iB;
 	if (r.motorMass > 0.0f) r.motorMass = 1.0f / r.motorMass;
@@ -179,11 +192,8 @@ __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float
 }
 
 // b2RevoluteJoint::SolveVelocityConstraints (:185-294); h = the step's dt
-__device__ __forceinline__ void JointSolveVelocityOne(const DeviceArrays& d, int j, float h)
+__device__ __forceinline__ void RevoluteSolveVelocity(const DeviceArrays& d, int j, const JointRow& r, b2cuJoint jt, float h)
 {
-	JointRow r = d.jointRows[j];
-	if (!r.solved) return;
-	b2cuJoint jt = d.joints[j];
 	const int bA = jt.bodyA, bB = jt.bodyB;
 	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
 	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
@@ -273,9 +283,8 @@ __device__ __forceinline__ void JointSolveVelocityOne(const DeviceArrays& d, int
 }
 
 // b2RevoluteJoint::SolvePositionConstraints (:296-377); returns "within tolerance"
-__device__ __forceinline__ bool JointSolvePositionOne(const DeviceArrays& d, int j, const JointRow& r)
+__device__ __forceinline__ bool RevoluteSolvePosition(const DeviceArrays& d, const JointRow& r, const b2cuJoint& jt)
 {
-	b2cuJoint jt = d.joints[j];
 	const int bA = jt.bodyA, bB = jt.bodyB;
 	float4 pA = d.pos[bA], pB = d.pos[bB];
 	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
@@ -341,6 +350,394 @@ __device__ __forceinline__ bool JointSolvePositionOne(const DeviceArrays& d, int
 	if (r.invMassA != 0.0f || r.invIA != 0.0f) d.pos[bA] = make_float4(cA.x, cA.y, aA, pA.w);
 	if (r.invMassB != 0.0f || r.invIB != 0.0f) d.pos[bB] = make_float4(cB.x, cB.y, aB, pB.w);
 	return positionError <= B2CU_LINEAR_SLOP && angularError <= B2CU_ANGULAR_SLOP;
+}
+
+// ---- distance joint (b2DistanceJoint.cpp:63-222) ------------------------------------------------------------------------
+
+__device__ __forceinline__ void DistanceInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio, int warmStarting,
+                                             float h)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+
+	Rot qA = SinCos(pA.z), qB = SinCos(pB.z);
+	r.rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	r.rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	r.u = cB + r.rB - cA - r.rA;
+
+	// anchors on top of each other: no direction
+	float length = Length(r.u);
+	if (length > B2CU_LINEAR_SLOP) r.u = (1.0f / length) * r.u;
+	else r.u = V(0.0f, 0.0f);
+
+	float crAu = Cross(r.rA, r.u);
+	float crBu = Cross(r.rB, r.u);
+	float invMass = r.invMassA + r.invIA * crAu * crAu + r.invMassB + r.invIB * crBu * crBu;
+	float mass = invMass != 0.0f ? 1.0f / invMass : 0.0f;
+
+	if (jt.frequencyHz > 0.0f)
+	{
+		// spring and damper folded into the constraint
+		float C = length - jt.length;
+		float omega = 2.0f * B2CU_PI * jt.frequencyHz;
+		float dd = 2.0f * mass * jt.dampingRatio * omega;
+		float k = mass * omega * omega;
+		r.gamma = h * (dd + h * k);
+		r.gamma = r.gamma != 0.0f ? 1.0f / r.gamma : 0.0f;
+		r.bias = C * h * k * r.gamma;
+		invMass += r.gamma;
+		mass = invMass != 0.0f ? 1.0f / invMass : 0.0f;
+	}
+	else
+	{
+		r.gamma = 0.0f;
+		r.bias = 0.0f;
+	}
+	r.motorMass = mass;
+
+	if (warmStarting)
+	{
+		jt.impulse[0] *= dtRatio;
+		Vec2 P = jt.impulse[0] * r.u;
+		vA = vA - r.invMassA * P;
+		wA -= r.invIA * Cross(r.rA, P);
+		vB = vB + r.invMassB * P;
+		wB += r.invIB * Cross(r.rB, P);
+	}
+	else
+	{
+		jt.impulse[0] = 0.0f;
+	}
+
+	StoreVelocity(d, bA, r.invMassA, r.invIA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, r.invMassB, r.invIB, vB, wB, vB4.w);
+	jt.axis[0] = r.u.x; // b2DistanceJoint::GetReactionForce reads m_u
+	jt.axis[1] = r.u.y;
+	d.jointRows[j] = r;
+	d.joints[j] = jt;
+}
+
+__device__ __forceinline__ void DistanceSolveVelocity(const DeviceArrays& d, int j, const JointRow& r, const b2cuJoint& jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+
+	Vec2 vpA = vA + CrossSV(wA, r.rA);
+	Vec2 vpB = vB + CrossSV(wB, r.rB);
+	float Cdot = Dot(r.u, vpB - vpA);
+
+	float impulse = -r.motorMass * (Cdot + r.bias + r.gamma * jt.impulse[0]);
+	float total = jt.impulse[0] + impulse;
+
+	Vec2 P = impulse * r.u;
+	vA = vA - r.invMassA * P;
+	wA -= r.invIA * Cross(r.rA, P);
+	vB = vB + r.invMassB * P;
+	wB += r.invIB * Cross(r.rB, P);
+
+	StoreVelocity(d, bA, r.invMassA, r.invIA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, r.invMassB, r.invIB, vB, wB, vB4.w);
+	d.joints[j].impulse[0] = total;
+}
+
+__device__ __forceinline__ bool DistanceSolvePosition(const DeviceArrays& d, const JointRow& r, const b2cuJoint& jt)
+{
+	// a soft distance constraint is not corrected in position
+	if (jt.frequencyHz > 0.0f) return true;
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	float aA = pA.z, aB = pB.z;
+
+	Rot qA = SinCos(aA), qB = SinCos(aB);
+	Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	Vec2 u = cB + rB - cA - rA;
+
+	// b2Vec2::Normalize
+	float length = Length(u);
+	if (length < B2CU_EPSILON)
+	{
+		length = 0.0f;
+	}
+	else
+	{
+		float inv = 1.0f / length;
+		u = V(u.x * inv, u.y * inv);
+	}
+	float C = length - jt.length;
+	C = Clamp(C, -B2CU_MAX_LINEAR_CORRECTION, B2CU_MAX_LINEAR_CORRECTION);
+
+	float impulse = -r.motorMass * C;
+	Vec2 P = impulse * u;
+
+	cA = cA - r.invMassA * P;
+	aA -= r.invIA * Cross(rA, P);
+	cB = cB + r.invMassB * P;
+	aB += r.invIB * Cross(rB, P);
+
+	if (r.invMassA != 0.0f || r.invIA != 0.0f) d.pos[bA] = make_float4(cA.x, cA.y, aA, pA.w);
+	if (r.invMassB != 0.0f || r.invIB != 0.0f) d.pos[bB] = make_float4(cB.x, cB.y, aB, pB.w);
+	return Abs(C) < B2CU_LINEAR_SLOP;
+}
+
+// ---- weld joint (b2WeldJoint.cpp:59-308) --------------------------------------------------------------------------------
+
+// b2Mat33::GetInverse22 / GetSymInverse33 of the K in r.ex/ey/ez, in place
+__device__ __forceinline__ void InvertK22(JointRow& r)
+{
+	float a = r.ex.x, b = r.ey.x, c = r.ex.y, dd = r.ey.y;
+	float det = a * dd - b * c;
+	if (det != 0.0f) det = 1.0f / det;
+	r.ex = V3(det * dd, -det * c, 0.0f);
+	r.ey = V3(-det * b, det * a, 0.0f);
+	r.ez = V3(0.0f, 0.0f, 0.0f);
+}
+
+__device__ __forceinline__ void InvertKSym33(JointRow& r)
+{
+	float det = Dot3(r.ex, Cross3(r.ey, r.ez));
+	if (det != 0.0f) det = 1.0f / det;
+	float a11 = r.ex.x, a12 = r.ey.x, a13 = r.ez.x;
+	float a22 = r.ey.y, a23 = r.ez.y;
+	float a33 = r.ez.z;
+	Vec3 ex, ey, ez;
+	ex.x = det * (a22 * a33 - a23 * a23);
+	ex.y = det * (a13 * a23 - a12 * a33);
+	ex.z = det * (a12 * a23 - a13 * a22);
+	ey.x = ex.y;
+	ey.y = det * (a11 * a33 - a13 * a13);
+	ey.z = det * (a13 * a12 - a11 * a23);
+	ez.x = ex.z;
+	ez.y = ey.z;
+	ez.z = det * (a11 * a22 - a12 * a12);
+	r.ex = ex;
+	r.ey = ey;
+	r.ez = ez;
+}
+
+__device__ __forceinline__ void WeldInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio, int warmStarting,
+                                         float h)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	float aA = pA.z, aB = pB.z;
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+
+	Rot qA = SinCos(aA), qB = SinCos(aB);
+	r.rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	r.rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+	PointAngleK(r, r.rA, r.rB);
+
+	if (jt.frequencyHz > 0.0f)
+	{
+		InvertK22(r);
+		float invM = iA + iB;
+		float m = invM > 0.0f ? 1.0f / invM : 0.0f;
+		float C = aB - aA - jt.referenceAngle;
+		float omega = 2.0f * B2CU_PI * jt.frequencyHz;
+		float dd = 2.0f * m * jt.dampingRatio * omega;
+		float k = m * omega * omega;
+		r.gamma = h * (dd + h * k);
+		r.gamma = r.gamma != 0.0f ? 1.0f / r.gamma : 0.0f;
+		r.bias = C * h * k * r.gamma;
+		invM += r.gamma;
+		r.ez.z = invM != 0.0f ? 1.0f / invM : 0.0f;
+	}
+	else if (r.ez.z == 0.0f)
+	{
+		InvertK22(r);
+		r.gamma = 0.0f;
+		r.bias = 0.0f;
+	}
+	else
+	{
+		InvertKSym33(r);
+		r.gamma = 0.0f;
+		r.bias = 0.0f;
+	}
+
+	if (warmStarting)
+	{
+		jt.impulse[0] *= dtRatio;
+		jt.impulse[1] *= dtRatio;
+		jt.impulse[2] *= dtRatio;
+		Vec2 P = V(jt.impulse[0], jt.impulse[1]);
+		vA = vA - mA * P;
+		wA -= iA * (Cross(r.rA, P) + jt.impulse[2]);
+		vB = vB + mB * P;
+		wB += iB * (Cross(r.rB, P) + jt.impulse[2]);
+	}
+	else
+	{
+		jt.impulse[0] = jt.impulse[1] = jt.impulse[2] = 0.0f;
+	}
+
+	StoreVelocity(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, mB, iB, vB, wB, vB4.w);
+	d.jointRows[j] = r;
+	d.joints[j] = jt;
+}
+
+__device__ __forceinline__ void WeldSolveVelocity(const DeviceArrays& d, int j, const JointRow& r, b2cuJoint jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+
+	if (jt.frequencyHz > 0.0f)
+	{
+		// soft angle first, then the point
+		float Cdot2 = wB - wA;
+		float impulse2 = -r.ez.z * (Cdot2 + r.bias + r.gamma * jt.impulse[2]);
+		jt.impulse[2] += impulse2;
+		wA -= iA * impulse2;
+		wB += iB * impulse2;
+
+		Vec2 Cdot1 = vB + CrossSV(wB, r.rB) - vA - CrossSV(wA, r.rA);
+		Vec2 m22 = V(r.ex.x * Cdot1.x + r.ey.x * Cdot1.y, r.ex.y * Cdot1.x + r.ey.y * Cdot1.y);
+		Vec2 impulse1 = -m22;
+		jt.impulse[0] += impulse1.x;
+		jt.impulse[1] += impulse1.y;
+
+		Vec2 P = impulse1;
+		vA = vA - mA * P;
+		wA -= iA * Cross(r.rA, P);
+		vB = vB + mB * P;
+		wB += iB * Cross(r.rB, P);
+	}
+	else
+	{
+		Vec2 Cdot1 = vB + CrossSV(wB, r.rB) - vA - CrossSV(wA, r.rA);
+		float Cdot2 = wB - wA;
+		// b2Mul(m_mass, Cdot) = Cdot.x * ex + Cdot.y * ey + Cdot.z * ez
+		Vec3 mv;
+		mv.x = Cdot1.x * r.ex.x + Cdot1.y * r.ey.x + Cdot2 * r.ez.x;
+		mv.y = Cdot1.x * r.ex.y + Cdot1.y * r.ey.y + Cdot2 * r.ez.y;
+		mv.z = Cdot1.x * r.ex.z + Cdot1.y * r.ey.z + Cdot2 * r.ez.z;
+		Vec3 impulse = V3(-mv.x, -mv.y, -mv.z);
+		jt.impulse[0] += impulse.x;
+		jt.impulse[1] += impulse.y;
+		jt.impulse[2] += impulse.z;
+
+		Vec2 P = V(impulse.x, impulse.y);
+		vA = vA - mA * P;
+		wA -= iA * (Cross(r.rA, P) + impulse.z);
+		vB = vB + mB * P;
+		wB += iB * (Cross(r.rB, P) + impulse.z);
+	}
+
+	StoreVelocity(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, mB, iB, vB, wB, vB4.w);
+	d.joints[j].impulse[0] = jt.impulse[0];
+	d.joints[j].impulse[1] = jt.impulse[1];
+	d.joints[j].impulse[2] = jt.impulse[2];
+}
+
+__device__ __forceinline__ bool WeldSolvePosition(const DeviceArrays& d, const JointRow& r, const b2cuJoint& jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	float aA = pA.z, aB = pB.z;
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+
+	Rot qA = SinCos(aA), qB = SinCos(aB);
+	Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+
+	float positionError, angularError;
+	JointRow K = r;
+	PointAngleK(K, rA, rB);
+
+	if (jt.frequencyHz > 0.0f)
+	{
+		Vec2 C1 = cB + rB - cA - rA;
+		positionError = Length(C1);
+		angularError = 0.0f;
+		Vec2 P = -Solve22(K.ex.x, K.ey.x, K.ex.y, K.ey.y, C1);
+		cA = cA - mA * P;
+		aA -= iA * Cross(rA, P);
+		cB = cB + mB * P;
+		aB += iB * Cross(rB, P);
+	}
+	else
+	{
+		Vec2 C1 = cB + rB - cA - rA;
+		float C2 = aB - aA - jt.referenceAngle;
+		positionError = Length(C1);
+		angularError = Abs(C2);
+
+		Vec3 impulse;
+		if (K.ez.z > 0.0f)
+		{
+			Vec3 s = Solve33(K, V3(C1.x, C1.y, C2));
+			impulse = V3(-s.x, -s.y, -s.z);
+		}
+		else
+		{
+			Vec2 s = -Solve22(K.ex.x, K.ey.x, K.ex.y, K.ey.y, C1);
+			impulse = V3(s.x, s.y, 0.0f);
+		}
+		Vec2 P = V(impulse.x, impulse.y);
+		cA = cA - mA * P;
+		aA -= iA * (Cross(rA, P) + impulse.z);
+		cB = cB + mB * P;
+		aB += iB * (Cross(rB, P) + impulse.z);
+	}
+
+	if (mA != 0.0f || iA != 0.0f) d.pos[bA] = make_float4(cA.x, cA.y, aA, pA.w);
+	if (mB != 0.0f || iB != 0.0f) d.pos[bB] = make_float4(cB.x, cB.y, aB, pB.w);
+	return positionError <= B2CU_LINEAR_SLOP && angularError <= B2CU_ANGULAR_SLOP;
+}
+
+// ---- dispatch by joint type -------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float dtRatio, int warmStarting, float h)
+{
+	b2cuJoint jt = d.joints[j];
+	JointRow r;
+	if (!JointPrepare(d, jt, r))
+	{
+		d.jointRows[j].solved = 0;
+		return;
+	}
+	if (jt.type == B2CU_JOINT_REVOLUTE) RevoluteInit(d, j, jt, r, dtRatio, warmStarting);
+	else if (jt.type == B2CU_JOINT_DISTANCE) DistanceInit(d, j, jt, r, dtRatio, warmStarting, h);
+	else WeldInit(d, j, jt, r, dtRatio, warmStarting, h);
+}
+
+__device__ __forceinline__ void JointSolveVelocityOne(const DeviceArrays& d, int j, float h)
+{
+	JointRow r = d.jointRows[j];
+	if (!r.solved) return;
+	b2cuJoint jt = d.joints[j];
+	if (jt.type == B2CU_JOINT_REVOLUTE) RevoluteSolveVelocity(d, j, r, jt, h);
+	else if (jt.type == B2CU_JOINT_DISTANCE) DistanceSolveVelocity(d, j, r, jt);
+	else WeldSolveVelocity(d, j, r, jt);
+}
+
+__device__ __forceinline__ bool JointSolvePositionOne(const DeviceArrays& d, int j, const JointRow& r)
+{
+	b2cuJoint jt = d.joints[j];
+	if (jt.type == B2CU_JOINT_REVOLUTE) return RevoluteSolvePosition(d, r, jt);
+	if (jt.type == B2CU_JOINT_DISTANCE) return DistanceSolvePosition(d, r, jt);
+	return WeldSolvePosition(d, r, jt);
 }
 
 } // namespace b2cu

@@ -1579,7 +1579,7 @@ __device__ __forceinline__ void JointRunOne(const DeviceArrays& d, const SolverP
 {
 	if (mode == JOINT_INIT)
 	{
-		JointInitOne(d, j, plan.dtRatio, plan.warmStarting);
+		JointInitOne(d, j, plan.dtRatio, plan.warmStarting, plan.h);
 	}
 	else if (mode == JOINT_VELOCITY)
 	{

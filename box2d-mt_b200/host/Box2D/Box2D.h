@@ -17,6 +17,8 @@
 #include "Box2D/Dynamics/Contacts/b2Contact.h"
 #include "Box2D/Dynamics/Joints/b2Joint.h"
 #include "Box2D/Dynamics/Joints/b2RevoluteJoint.h"
+#include "Box2D/Dynamics/Joints/b2DistanceJoint.h"
+#include "Box2D/Dynamics/Joints/b2WeldJoint.h"
 #include "Box2D/MT/b2Task.h"
 #include "Box2D/MT/b2TaskExecutor.h"
 #include "Box2D/MT/b2CudaStepExecutor.h"

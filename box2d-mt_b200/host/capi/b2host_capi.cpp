@@ -106,7 +106,7 @@ struct Host
 	Recorder recorder;
 	std::vector<b2Body*> bodies;
 	std::vector<b2Fixture*> fixtures;
-	std::vector<b2RevoluteJoint*> joints;
+	std::vector<b2Joint*> joints;
 };
 
 } // namespace
@@ -396,23 +396,57 @@ B2H_API int b2h_create_joints(void* p, int32 count, const b2cuJoint* rows)
 	for (int32 i = 0; i < count; ++i)
 	{
 		const b2cuJoint& r = rows[i];
-		if (r.type != B2CU_JOINT_REVOLUTE) return -1;
-		b2RevoluteJointDef def;
-		def.bodyA = h->bodies[r.bodyA];
-		def.bodyB = h->bodies[r.bodyB];
-		def.collideConnected = (r.flags & B2CU_JOINT_COLLIDE_CONNECTED) != 0;
-		def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
-		def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
-		def.referenceAngle = r.referenceAngle;
-		def.enableLimit = (r.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
-		def.lowerAngle = r.lowerAngle;
-		def.upperAngle = r.upperAngle;
-		def.enableMotor = (r.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
-		def.motorSpeed = r.motorSpeed;
-		def.maxMotorTorque = r.maxMotorTorque;
-		b2Joint* j = h->world->CreateJoint(&def);
+		b2Joint* j = nullptr;
+		const bool collideConnected = (r.flags & B2CU_JOINT_COLLIDE_CONNECTED) != 0;
+		if (r.type == B2CU_JOINT_REVOLUTE)
+		{
+			b2RevoluteJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
+			def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
+			def.referenceAngle = r.referenceAngle;
+			def.enableLimit = (r.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
+			def.lowerAngle = r.lowerAngle;
+			def.upperAngle = r.upperAngle;
+			def.enableMotor = (r.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
+			def.motorSpeed = r.motorSpeed;
+			def.maxMotorTorque = r.maxMotorTorque;
+			j = h->world->CreateJoint(&def);
+		}
+		else if (r.type == B2CU_JOINT_DISTANCE)
+		{
+			b2DistanceJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
+			def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
+			def.length = r.length;
+			def.frequencyHz = r.frequencyHz;
+			def.dampingRatio = r.dampingRatio;
+			j = h->world->CreateJoint(&def);
+		}
+		else if (r.type == B2CU_JOINT_WELD)
+		{
+			b2WeldJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
+			def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
+			def.referenceAngle = r.referenceAngle;
+			def.frequencyHz = r.frequencyHz;
+			def.dampingRatio = r.dampingRatio;
+			j = h->world->CreateJoint(&def);
+		}
+		else
+		{
+			return -1;
+		}
 		if (j == nullptr) return -2;
-		h->joints.push_back(static_cast<b2RevoluteJoint*>(j));
+		h->joints.push_back(j);
 	}
 	return 0;
 }
@@ -430,21 +464,26 @@ B2H_API void b2h_joint_readings(void* p, float inv_dt, float* out6)
 	Host* h = static_cast<Host*>(p);
 	for (size_t i = 0; i < h->joints.size(); ++i)
 	{
-		const b2RevoluteJoint* j = h->joints[i];
-		b2Vec2 f = j->GetReactionForce(inv_dt);
+		const b2Joint* base = h->joints[i];
+		b2Vec2 f = base->GetReactionForce(inv_dt);
 		float* o = out6 + 6 * i;
 		o[0] = f.x;
 		o[1] = f.y;
-		o[2] = j->GetReactionTorque(inv_dt);
-		o[3] = j->GetMotorTorque(inv_dt);
-		o[4] = j->GetJointAngle();
-		o[5] = j->GetJointSpeed();
+		o[2] = base->GetReactionTorque(inv_dt);
+		o[3] = o[4] = o[5] = 0.0f;
+		if (base->GetType() == e_revoluteJoint)
+		{
+			const b2RevoluteJoint* j = static_cast<const b2RevoluteJoint*>(base);
+			o[3] = j->GetMotorTorque(inv_dt);
+			o[4] = j->GetJointAngle();
+			o[5] = j->GetJointSpeed();
+		}
 	}
 }
 
 B2H_API void b2h_joint_set_motor(void* p, int32 joint, int32 enable, float speed, float maxTorque)
 {
-	b2RevoluteJoint* j = static_cast<Host*>(p)->joints[joint];
+	b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(static_cast<Host*>(p)->joints[joint]);
 	j->EnableMotor(enable != 0);
 	j->SetMotorSpeed(speed);
 	j->SetMaxMotorTorque(maxTorque);
@@ -452,9 +491,28 @@ B2H_API void b2h_joint_set_motor(void* p, int32 joint, int32 enable, float speed
 
 B2H_API void b2h_joint_set_limits(void* p, int32 joint, int32 enable, float lower, float upper)
 {
-	b2RevoluteJoint* j = static_cast<Host*>(p)->joints[joint];
+	b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(static_cast<Host*>(p)->joints[joint]);
 	j->EnableLimit(enable != 0);
 	j->SetLimits(lower, upper);
+}
+
+/// b2DistanceJoint::SetLength / SetFrequency / SetDampingRatio, b2WeldJoint::SetFrequency / SetDampingRatio
+B2H_API void b2h_joint_set_spring(void* p, int32 joint, float length, float frequencyHz, float dampingRatio)
+{
+	b2Joint* base = static_cast<Host*>(p)->joints[joint];
+	if (base->GetType() == e_distanceJoint)
+	{
+		b2DistanceJoint* j = static_cast<b2DistanceJoint*>(base);
+		j->SetLength(length);
+		j->SetFrequency(frequencyHz);
+		j->SetDampingRatio(dampingRatio);
+	}
+	else if (base->GetType() == e_weldJoint)
+	{
+		b2WeldJoint* j = static_cast<b2WeldJoint*>(base);
+		j->SetFrequency(frequencyHz);
+		j->SetDampingRatio(dampingRatio);
+	}
 }
 
 B2H_API int b2h_joint_count(void* p) { return static_cast<Host*>(p)->world->GetJointCount(); }

@@ -1,7 +1,10 @@
-// Host side of the joints (reference: Box2D/Dynamics/Joints/b2Joint.cpp, b2RevoluteJoint.cpp:36-62, :379-512; the
+// Host side of the joints (reference: Box2D/Dynamics/Joints/b2Joint.cpp, b2RevoluteJoint.cpp:36-62, :379-512, b2DistanceJoint.cpp,
+// b2WeldJoint.cpp; the
 // world's part is b2World::CreateJoint / DestroyJoint, b2World.cpp:659-841).  Nothing is solved here: the joint objects
 // hold parameters and the persistent impulses, and exchange them with the device's joint table.
 #include "Box2D/Dynamics/Joints/b2RevoluteJoint.h"
+#include "Box2D/Dynamics/Joints/b2DistanceJoint.h"
+#include "Box2D/Dynamics/Joints/b2WeldJoint.h"
 #include "Box2D/Dynamics/b2Body.h"
 #include "Box2D/Dynamics/b2World.h"
 
@@ -148,4 +151,149 @@ void b2RevoluteJoint::SetLimits(float32 lower, float32 upper)
 	m_impulse.z = 0.0f;
 	m_lowerAngle = lower;
 	m_upperAngle = upper;
+}
+
+// ---- distance (reference b2DistanceJoint.cpp:40-61, :224-260) -----------------------------------------------------------
+
+void b2DistanceJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchorA, const b2Vec2& anchorB)
+{
+	bodyA = bA;
+	bodyB = bB;
+	localAnchorA = bA->GetLocalPoint(anchorA);
+	localAnchorB = bB->GetLocalPoint(anchorB);
+	length = (anchorB - anchorA).Length();
+}
+
+b2DistanceJoint::b2DistanceJoint(const b2DistanceJointDef* def)
+	: b2Joint(def), m_localAnchorA(def->localAnchorA), m_localAnchorB(def->localAnchorB), m_length(def->length),
+	  m_frequencyHz(def->frequencyHz), m_dampingRatio(def->dampingRatio), m_impulse(0.0f), m_u(0.0f, 0.0f)
+{
+}
+
+static void WriteCommon(b2cuJoint* r, int32 type, const b2Body* bodyA, const b2Body* bodyB, bool collideConnected,
+                        const b2Vec2& anchorA, const b2Vec2& anchorB)
+{
+	*r = b2cuJoint();
+	r->type = type;
+	r->bodyA = bodyA->GetIndex();
+	r->bodyB = bodyB->GetIndex();
+	r->flags = collideConnected ? B2CU_JOINT_COLLIDE_CONNECTED : 0u;
+	r->localAnchorA[0] = anchorA.x;
+	r->localAnchorA[1] = anchorA.y;
+	r->localAnchorB[0] = anchorB.x;
+	r->localAnchorB[1] = anchorB.y;
+}
+
+void b2DistanceJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_DISTANCE, m_bodyA, m_bodyB, m_collideConnected, m_localAnchorA, m_localAnchorB);
+	out->length = m_length;
+	out->frequencyHz = m_frequencyHz;
+	out->dampingRatio = m_dampingRatio;
+	out->impulse[0] = m_impulse;
+	out->axis[0] = m_u.x;
+	out->axis[1] = m_u.y;
+}
+
+void b2DistanceJoint::ReadRecord(const b2cuJoint& in)
+{
+	m_impulse = in.impulse[0];
+	m_u.Set(in.axis[0], in.axis[1]);
+}
+
+b2Vec2 b2DistanceJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2DistanceJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+b2Vec2 b2DistanceJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	float32 scale = inv_dt * m_impulse;
+	return b2Vec2(scale * m_u.x, scale * m_u.y);
+}
+
+float32 b2DistanceJoint::GetReactionTorque(float32 inv_dt) const
+{
+	B2_NOT_USED(inv_dt);
+	return 0.0f;
+}
+
+void b2DistanceJoint::SetLength(float32 length)
+{
+	if (length == m_length) return;
+	Touch();
+	m_length = length;
+}
+
+void b2DistanceJoint::SetFrequency(float32 hz)
+{
+	if (hz == m_frequencyHz) return;
+	Touch();
+	m_frequencyHz = hz;
+}
+
+void b2DistanceJoint::SetDampingRatio(float32 ratio)
+{
+	if (ratio == m_dampingRatio) return;
+	Touch();
+	m_dampingRatio = ratio;
+}
+
+// ---- weld (reference b2WeldJoint.cpp:37-57, :310-332) -------------------------------------------------------------------
+
+void b2WeldJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor)
+{
+	bodyA = bA;
+	bodyB = bB;
+	localAnchorA = bA->GetLocalPoint(anchor);
+	localAnchorB = bB->GetLocalPoint(anchor);
+	referenceAngle = bB->GetAngle() - bA->GetAngle();
+}
+
+b2WeldJoint::b2WeldJoint(const b2WeldJointDef* def)
+	: b2Joint(def), m_localAnchorA(def->localAnchorA), m_localAnchorB(def->localAnchorB),
+	  m_referenceAngle(def->referenceAngle), m_frequencyHz(def->frequencyHz), m_dampingRatio(def->dampingRatio),
+	  m_impulse(0.0f, 0.0f, 0.0f)
+{
+}
+
+void b2WeldJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_WELD, m_bodyA, m_bodyB, m_collideConnected, m_localAnchorA, m_localAnchorB);
+	out->referenceAngle = m_referenceAngle;
+	out->frequencyHz = m_frequencyHz;
+	out->dampingRatio = m_dampingRatio;
+	out->impulse[0] = m_impulse.x;
+	out->impulse[1] = m_impulse.y;
+	out->impulse[2] = m_impulse.z;
+}
+
+void b2WeldJoint::ReadRecord(const b2cuJoint& in) { m_impulse.Set(in.impulse[0], in.impulse[1], in.impulse[2]); }
+
+b2Vec2 b2WeldJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2WeldJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+b2Vec2 b2WeldJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	return b2Vec2(inv_dt * m_impulse.x, inv_dt * m_impulse.y);
+}
+
+float32 b2WeldJoint::GetReactionTorque(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_impulse.z;
+}
+
+void b2WeldJoint::SetFrequency(float32 hz)
+{
+	if (hz == m_frequencyHz) return;
+	Touch();
+	m_frequencyHz = hz;
+}
+
+void b2WeldJoint::SetDampingRatio(float32 ratio)
+{
+	if (ratio == m_dampingRatio) return;
+	Touch();
+	m_dampingRatio = ratio;
 }

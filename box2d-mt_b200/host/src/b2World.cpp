@@ -3,6 +3,8 @@
 // b2ContactManager.cpp (callback dispatch :388-439).
 #include "Box2D/Dynamics/b2World.h"
 #include "Box2D/Dynamics/Joints/b2RevoluteJoint.h"
+#include "Box2D/Dynamics/Joints/b2DistanceJoint.h"
+#include "Box2D/Dynamics/Joints/b2WeldJoint.h"
 
 #include <chrono>
 #include "Box2D/Collision/Shapes/b2CircleShape.h"
@@ -324,13 +326,16 @@ void b2World::RefreshJoints() const
 b2Joint* b2World::CreateJoint(const b2JointDef* def)
 {
 	if (IsLocked()) return nullptr;
-	if (def->type != e_revoluteJoint)
+	if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint)
 	{
 		m_lastStatus = B2CU_ERR_UNSUPPORTED;
 		return nullptr;
 	}
 	RefreshJoints();
-	b2Joint* j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
+	b2Joint* j;
+	if (def->type == e_revoluteJoint) j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
+	else if (def->type == e_distanceJoint) j = new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def));
+	else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
 	j->m_world = this;
 	j->m_index = (int32)m_joints.size();
 	m_joints.push_back(j);

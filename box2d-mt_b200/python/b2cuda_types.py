@@ -90,10 +90,11 @@ JOINT = np.dtype([
     ("type", "i4"), ("bodyA", "i4"), ("bodyB", "i4"), ("flags", "u4"),
     ("localAnchorA", "f4", (2,)), ("localAnchorB", "f4", (2,)),
     ("referenceAngle", "f4"), ("lowerAngle", "f4"), ("upperAngle", "f4"), ("maxMotorTorque", "f4"), ("motorSpeed", "f4"),
-    ("impulse", "f4", (3,)), ("motorImpulse", "f4"), ("limitState", "i4"), ("reserved", "i4", (2,)),
+    ("length", "f4"), ("frequencyHz", "f4"), ("dampingRatio", "f4"), ("axis", "f4", (2,)),
+    ("impulse", "f4", (3,)), ("motorImpulse", "f4"), ("limitState", "i4"), ("reserved", "i4"),
 ])
-assert JOINT.itemsize == 80
-JOINT_REVOLUTE = 1
+assert JOINT.itemsize == 96
+JOINT_REVOLUTE, JOINT_DISTANCE, JOINT_WELD = 1, 3, 8
 JOINT_COLLIDE_CONNECTED, JOINT_ENABLE_LIMIT, JOINT_ENABLE_MOTOR = 1, 2, 4
 
 # enums

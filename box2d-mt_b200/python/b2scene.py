@@ -157,6 +157,35 @@ class Scene:
         self.joints.append(j)
         return len(self.joints) - 1
 
+    def _joint(self, jtype, body_a, body_b, local_anchor_a, local_anchor_b, collide_connected):
+        j = np.zeros((), T.JOINT)
+        j["type"] = jtype
+        j["bodyA"], j["bodyB"] = body_a, body_b
+        j["localAnchorA"] = local_anchor_a
+        j["localAnchorB"] = local_anchor_b
+        j["flags"] = T.JOINT_COLLIDE_CONNECTED if collide_connected else 0
+        return j
+
+    def distance_joint(self, body_a, body_b, local_anchor_a, local_anchor_b, length, frequency_hz=0.0, damping_ratio=0.0,
+                       collide_connected=False):
+        """b2DistanceJointDef (b2DistanceJoint.h:32-64): a rod of the given length, a spring-damper when frequency_hz > 0"""
+        j = self._joint(T.JOINT_DISTANCE, body_a, body_b, local_anchor_a, local_anchor_b, collide_connected)
+        j["length"] = length
+        j["frequencyHz"] = frequency_hz
+        j["dampingRatio"] = damping_ratio
+        self.joints.append(j)
+        return len(self.joints) - 1
+
+    def weld_joint(self, body_a, body_b, local_anchor_a, local_anchor_b, reference_angle=0.0, frequency_hz=0.0,
+                   damping_ratio=0.0, collide_connected=False):
+        """b2WeldJointDef (b2WeldJoint.h:28-58): the two bodies glued at the anchor, the angle soft when frequency_hz > 0"""
+        j = self._joint(T.JOINT_WELD, body_a, body_b, local_anchor_a, local_anchor_b, collide_connected)
+        j["referenceAngle"] = reference_angle
+        j["frequencyHz"] = frequency_hz
+        j["dampingRatio"] = damping_ratio
+        self.joints.append(j)
+        return len(self.joints) - 1
+
     def joint_array(self):
         return np.array(self.joints, dtype=T.JOINT) if self.joints else np.zeros(0, T.JOINT)
 

@@ -276,3 +276,63 @@ def joint_zoo(seed=0):
     s.fixture(b, bar, density=1.0)
     s.revolute_joint(k, b, (0.5, 0.0), (-1.0, 0.0))
     return s
+
+
+def rods_and_welds(seed=0):
+    """Distance and weld joints in every variant: the Testbed's Web (Web.h:27-110: four boxes held by eight soft rods), a
+    rigid-rod pendulum chain, a cantilever of boxes welded rigidly (Cantilever.h:41-70) and one welded with a soft angle,
+    a weld between bodies that cannot rotate, rods whose anchors coincide.  Everything falls on / hangs over a ground."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.edge((-40.0, 0.0), (40.0, 0.0)))
+    small = s.box(0.5, 0.5)
+    # web
+    corners = [(-5.0, 5.0), (5.0, 5.0), (5.0, 15.0), (-5.0, 15.0)]
+    web = []
+    for c in corners:
+        b = s.body(T.DYNAMIC_BODY, c)
+        s.fixture(b, small, density=5.0)
+        web.append(b)
+    outer = [(-10.0, 0.0), (10.0, 0.0), (10.0, 20.0), (-10.0, 20.0)]
+    inner = [(-0.5, -0.5), (0.5, -0.5), (0.5, 0.5), (-0.5, 0.5)]
+    for k in range(4):
+        p1 = np.array(outer[k], np.float32)
+        p2 = np.array(corners[k], np.float32) + np.array(inner[k], np.float32)
+        s.distance_joint(g, web[k], outer[k], inner[k], float(F(np.hypot(*(p2 - p1)))), frequency_hz=2.0, damping_ratio=0.0)
+    sides = [((0.5, 0.0), (-0.5, 0.0)), ((0.0, 0.5), (0.0, -0.5)), ((-0.5, 0.0), (0.5, 0.0)), ((0.0, -0.5), (0.0, 0.5))]
+    for k in range(4):
+        a, b = web[k], web[(k + 1) % 4]
+        la, lb = sides[k]
+        p1 = np.array(corners[k], np.float32) + np.array(la, np.float32)
+        p2 = np.array(corners[(k + 1) % 4], np.float32) + np.array(lb, np.float32)
+        s.distance_joint(a, b, la, lb, float(F(np.hypot(*(p2 - p1)))), frequency_hz=2.0, damping_ratio=0.3)
+    # rigid-rod pendulum chain hanging from the ground body
+    prev, anchor = g, (20.0, 18.0)
+    for i in range(6):
+        b = s.body(T.DYNAMIC_BODY, (20.0 + 1.5 * (i + 1), 18.0))
+        s.fixture(b, s.circle(0.3), density=2.0)
+        s.distance_joint(prev, b, anchor, (0.0, 0.0), 1.5, collide_connected=(i % 2 == 0))
+        prev, anchor = b, (0.0, 0.0)
+    # cantilevers: rigid welds, and welds with a soft angle
+    plank = s.box(0.5, 0.125)
+    for row, (hz, ratio) in enumerate([(0.0, 0.0), (5.0, 0.7)]):
+        prev = g
+        y = 8.0 + 4.0 * row
+        for i in range(6):
+            b = s.body(T.DYNAMIC_BODY, (-30.0 + 0.5 + i, y))
+            s.fixture(b, plank, density=20.0)
+            la = (-30.0 + i, y) if prev == g else (0.5, 0.0)
+            s.weld_joint(prev, b, la, (-0.5, 0.0), frequency_hz=hz, damping_ratio=ratio)
+            prev = b
+    # two bodies without rotation welded together; two bodies whose rod has zero length
+    a = s.body(T.DYNAMIC_BODY, (-18.0, 4.0), flags=BODYDEF_DEFAULT | BODYDEF_FIXED_ROTATION)
+    s.fixture(a, small, density=1.0)
+    b = s.body(T.DYNAMIC_BODY, (-16.8, 4.0), flags=BODYDEF_DEFAULT | BODYDEF_FIXED_ROTATION)
+    s.fixture(b, small, density=1.0)
+    s.weld_joint(a, b, (0.6, 0.0), (-0.6, 0.0))
+    a = s.body(T.DYNAMIC_BODY, (-14.0, 6.0))
+    s.fixture(a, small, density=1.0)
+    b = s.body(T.DYNAMIC_BODY, (-14.0, 6.0), vel=(1.0, 0.0))
+    s.fixture(b, s.circle(0.4), density=1.0)
+    s.distance_joint(a, b, (0.0, 0.0), (0.0, 0.0), 0.0)
+    return s

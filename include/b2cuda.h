@@ -326,15 +326,22 @@ B2CU_API int b2cuGetProxies(b2cuWorld* w, int32_t first, int32_t count, b2cuProx
 B2CU_API int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts);
 B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
 
-/* Joints (Dynamics/Joints/b2Joint.h:28-226).  This version solves revolute joints (b2RevoluteJoint.cpp:64-400: point
- * constraint, angular limit, motor, warm starting) as rows of the coloured solver: inside every velocity iteration the
- * joints run before the contacts, inside every position iteration after them, as b2Island::Solve orders them
- * (Dynamics/b2Island.cpp:259-273, :323-327, :363-380).  A joint links the islands of its two bodies
- * (b2World.cpp:1286-1320) and, unless COLLIDE_CONNECTED, keeps them from colliding (b2Body::ShouldCollide,
- * b2Body.cpp:428-449).  `type` uses b2JointType's values; other types are refused with B2CU_ERR_UNSUPPORTED.
- * impulse / motorImpulse / limitState are the joint's persistent solver state (m_impulse, m_motorImpulse,
- * m_limitState) and round-trip through Get / Set. */
-enum { B2CU_JOINT_REVOLUTE = 1 };
+/* Joints (Dynamics/Joints/b2Joint.h:28-226).  This version solves
+ *   revolute joints   b2RevoluteJoint.cpp:64-400   point constraint, angular limit, motor
+ *   distance joints   b2DistanceJoint.cpp:63-222   rigid or spring-damper rod between two anchors
+ *   weld joints       b2WeldJoint.cpp:59-308       point + angle, rigid or with a soft angle
+ * as rows of the coloured solver: inside every velocity iteration the joints run before the contacts, inside every
+ * position iteration after them, as b2Island::Solve orders them (Dynamics/b2Island.cpp:259-273, :323-327, :363-380),
+ * with warm starting.  A joint links the islands of its two bodies (b2World.cpp:1286-1320) and, unless
+ * COLLIDE_CONNECTED, keeps them from colliding (b2Body::ShouldCollide, b2Body.cpp:428-449).  `type` uses b2JointType's
+ * values; other types are refused with B2CU_ERR_UNSUPPORTED.
+ * Fields by type: revolute  referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, flags LIMIT / MOTOR
+ *                 distance  length, frequencyHz, dampingRatio
+ *                 weld      referenceAngle, frequencyHz, dampingRatio
+ * impulse / motorImpulse / limitState are the joint's persistent solver state (m_impulse -- a scalar in impulse[0] for
+ * the distance joint --, m_motorImpulse, m_limitState) and round-trip through Get / Set; axis is written by the step:
+ * the distance joint's unit vector m_u, which b2DistanceJoint::GetReactionForce needs. */
+enum { B2CU_JOINT_REVOLUTE = 1, B2CU_JOINT_DISTANCE = 3, B2CU_JOINT_WELD = 8 };
 enum
 {
 	B2CU_JOINT_COLLIDE_CONNECTED = 1,
@@ -350,10 +357,12 @@ typedef struct b2cuJoint
 	float localAnchorA[2], localAnchorB[2];
 	float referenceAngle, lowerAngle, upperAngle;
 	float maxMotorTorque, motorSpeed;
+	float length, frequencyHz, dampingRatio;
+	float axis[2];
 	float impulse[3];
 	float motorImpulse;
 	int32_t limitState;
-	int32_t reserved[2];
+	int32_t reserved;
 } b2cuJoint;
 /* Replace the world's joint table (b2World::CreateJoint / DestroyJoint, b2World.cpp:659-841, applied as a whole: the
  * caller keeps the list).  Joint ids are indices into this table. */

@@ -823,27 +823,66 @@ int32_t b2ref_set_joints(b2refWorld* w, int32_t count, const b2cuJoint* joints)
 	for (int32_t i = 0; i < count; ++i)
 	{
 		const b2cuJoint& j = joints[i];
-		if (j.type != B2CU_JOINT_REVOLUTE)
+		b2Joint* joint = nullptr;
+		b2Body* bodyA = w->bodies[j.bodyA];
+		b2Body* bodyB = w->bodies[j.bodyB];
+		const bool collideConnected = (j.flags & B2CU_JOINT_COLLIDE_CONNECTED) != 0;
+		if (j.type == B2CU_JOINT_REVOLUTE)
+		{
+			b2RevoluteJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
+			def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+			def.referenceAngle = j.referenceAngle;
+			def.enableLimit = (j.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
+			def.lowerAngle = j.lowerAngle;
+			def.upperAngle = j.upperAngle;
+			def.enableMotor = (j.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
+			def.motorSpeed = j.motorSpeed;
+			def.maxMotorTorque = j.maxMotorTorque;
+			b2RevoluteJoint* rj = (b2RevoluteJoint*)w->world->CreateJoint(&def);
+			rj->m_impulse.Set(j.impulse[0], j.impulse[1], j.impulse[2]);
+			rj->m_motorImpulse = j.motorImpulse;
+			rj->m_limitState = (b2LimitState)j.limitState;
+			joint = rj;
+		}
+		else if (j.type == B2CU_JOINT_DISTANCE)
+		{
+			b2DistanceJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
+			def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+			def.length = j.length;
+			def.frequencyHz = j.frequencyHz;
+			def.dampingRatio = j.dampingRatio;
+			b2DistanceJoint* dj = (b2DistanceJoint*)w->world->CreateJoint(&def);
+			dj->m_impulse = j.impulse[0];
+			dj->m_u.Set(j.axis[0], j.axis[1]);
+			joint = dj;
+		}
+		else if (j.type == B2CU_JOINT_WELD)
+		{
+			b2WeldJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
+			def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+			def.referenceAngle = j.referenceAngle;
+			def.frequencyHz = j.frequencyHz;
+			def.dampingRatio = j.dampingRatio;
+			b2WeldJoint* wj = (b2WeldJoint*)w->world->CreateJoint(&def);
+			wj->m_impulse.Set(j.impulse[0], j.impulse[1], j.impulse[2]);
+			joint = wj;
+		}
+		else
 		{
 			return -1;
 		}
-		b2RevoluteJointDef def;
-		def.bodyA = w->bodies[j.bodyA];
-		def.bodyB = w->bodies[j.bodyB];
-		def.collideConnected = (j.flags & B2CU_JOINT_COLLIDE_CONNECTED) != 0;
-		def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
-		def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
-		def.referenceAngle = j.referenceAngle;
-		def.enableLimit = (j.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
-		def.lowerAngle = j.lowerAngle;
-		def.upperAngle = j.upperAngle;
-		def.enableMotor = (j.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
-		def.motorSpeed = j.motorSpeed;
-		def.maxMotorTorque = j.maxMotorTorque;
-		b2RevoluteJoint* joint = (b2RevoluteJoint*)w->world->CreateJoint(&def);
-		joint->m_impulse.Set(j.impulse[0], j.impulse[1], j.impulse[2]);
-		joint->m_motorImpulse = j.motorImpulse;
-		joint->m_limitState = (b2LimitState)j.limitState;
 		w->joints.push_back(joint);
 		w->jointRank[joint] = i;
 	}
@@ -875,6 +914,24 @@ void b2ref_joint_set_limits(b2refWorld* w, int32_t joint, int32_t enable, float 
 	j->SetLimits(lower, upper);
 }
 
+void b2ref_joint_set_spring(b2refWorld* w, int32_t joint, float length, float frequencyHz, float dampingRatio)
+{
+	b2Joint* base = w->joints[joint];
+	if (base->GetType() == e_distanceJoint)
+	{
+		b2DistanceJoint* j = (b2DistanceJoint*)base;
+		j->SetLength(length);
+		j->SetFrequency(frequencyHz);
+		j->SetDampingRatio(dampingRatio);
+	}
+	else if (base->GetType() == e_weldJoint)
+	{
+		b2WeldJoint* j = (b2WeldJoint*)base;
+		j->SetFrequency(frequencyHz);
+		j->SetDampingRatio(dampingRatio);
+	}
+}
+
 void b2ref_destroy_joint(b2refWorld* w, int32_t joint)
 {
 	w->jointRank.erase(w->joints[joint]);
@@ -887,15 +944,20 @@ void b2ref_joint_readings(b2refWorld* w, float inv_dt, float* out6)
 {
 	for (size_t i = 0; i < w->joints.size(); ++i)
 	{
-		const b2RevoluteJoint* j = (const b2RevoluteJoint*)w->joints[i];
-		b2Vec2 f = j->GetReactionForce(inv_dt);
+		const b2Joint* base = w->joints[i];
+		b2Vec2 f = base->GetReactionForce(inv_dt);
 		float* o = out6 + 6 * i;
 		o[0] = f.x;
 		o[1] = f.y;
-		o[2] = j->GetReactionTorque(inv_dt);
-		o[3] = j->GetMotorTorque(inv_dt);
-		o[4] = j->GetJointAngle();
-		o[5] = j->GetJointSpeed();
+		o[2] = base->GetReactionTorque(inv_dt);
+		o[3] = o[4] = o[5] = 0.0f;
+		if (base->GetType() == e_revoluteJoint)
+		{
+			const b2RevoluteJoint* j = (const b2RevoluteJoint*)base;
+			o[3] = j->GetMotorTorque(inv_dt);
+			o[4] = j->GetJointAngle();
+			o[5] = j->GetJointSpeed();
+		}
 	}
 }
 
@@ -903,31 +965,65 @@ void b2ref_export_joints(b2refWorld* w, b2cuJoint* out)
 {
 	for (size_t i = 0; i < w->joints.size(); ++i)
 	{
-		const b2RevoluteJoint* j = (const b2RevoluteJoint*)w->joints[i];
+		const b2Joint* base = w->joints[i];
 		b2cuJoint& o = out[i];
 		memset(&o, 0, sizeof(o));
-		o.type = B2CU_JOINT_REVOLUTE;
 		for (size_t b = 0; b < w->bodies.size(); ++b)
 		{
-			if (w->bodies[b] == j->m_bodyA) o.bodyA = (int32_t)b;
-			if (w->bodies[b] == j->m_bodyB) o.bodyB = (int32_t)b;
+			if (w->bodies[b] == base->m_bodyA) o.bodyA = (int32_t)b;
+			if (w->bodies[b] == base->m_bodyB) o.bodyB = (int32_t)b;
 		}
-		o.flags = (j->m_collideConnected ? B2CU_JOINT_COLLIDE_CONNECTED : 0) | (j->m_enableLimit ? B2CU_JOINT_ENABLE_LIMIT : 0) |
-		          (j->m_enableMotor ? B2CU_JOINT_ENABLE_MOTOR : 0);
-		o.localAnchorA[0] = j->m_localAnchorA.x;
-		o.localAnchorA[1] = j->m_localAnchorA.y;
-		o.localAnchorB[0] = j->m_localAnchorB.x;
-		o.localAnchorB[1] = j->m_localAnchorB.y;
-		o.referenceAngle = j->m_referenceAngle;
-		o.lowerAngle = j->m_lowerAngle;
-		o.upperAngle = j->m_upperAngle;
-		o.maxMotorTorque = j->m_maxMotorTorque;
-		o.motorSpeed = j->m_motorSpeed;
-		o.impulse[0] = j->m_impulse.x;
-		o.impulse[1] = j->m_impulse.y;
-		o.impulse[2] = j->m_impulse.z;
-		o.motorImpulse = j->m_motorImpulse;
-		o.limitState = (int32_t)j->m_limitState;
+		o.flags = base->m_collideConnected ? B2CU_JOINT_COLLIDE_CONNECTED : 0;
+		if (base->GetType() == e_revoluteJoint)
+		{
+			const b2RevoluteJoint* j = (const b2RevoluteJoint*)base;
+			o.type = B2CU_JOINT_REVOLUTE;
+			o.flags |= (j->m_enableLimit ? B2CU_JOINT_ENABLE_LIMIT : 0) | (j->m_enableMotor ? B2CU_JOINT_ENABLE_MOTOR : 0);
+			o.localAnchorA[0] = j->m_localAnchorA.x;
+			o.localAnchorA[1] = j->m_localAnchorA.y;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			o.referenceAngle = j->m_referenceAngle;
+			o.lowerAngle = j->m_lowerAngle;
+			o.upperAngle = j->m_upperAngle;
+			o.maxMotorTorque = j->m_maxMotorTorque;
+			o.motorSpeed = j->m_motorSpeed;
+			o.impulse[0] = j->m_impulse.x;
+			o.impulse[1] = j->m_impulse.y;
+			o.impulse[2] = j->m_impulse.z;
+			o.motorImpulse = j->m_motorImpulse;
+			o.limitState = (int32_t)j->m_limitState;
+		}
+		else if (base->GetType() == e_distanceJoint)
+		{
+			const b2DistanceJoint* j = (const b2DistanceJoint*)base;
+			o.type = B2CU_JOINT_DISTANCE;
+			o.localAnchorA[0] = j->m_localAnchorA.x;
+			o.localAnchorA[1] = j->m_localAnchorA.y;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			o.length = j->m_length;
+			o.frequencyHz = j->m_frequencyHz;
+			o.dampingRatio = j->m_dampingRatio;
+			o.impulse[0] = j->m_impulse;
+			o.axis[0] = j->m_u.x;
+			o.axis[1] = j->m_u.y;
+		}
+		else
+		{
+			const b2WeldJoint* j = (const b2WeldJoint*)base;
+			o.type = B2CU_JOINT_WELD;
+			o.localAnchorA[0] = j->m_localAnchorA.x;
+			o.localAnchorA[1] = j->m_localAnchorA.y;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			o.referenceAngle = j->m_referenceAngle;
+			o.frequencyHz = j->m_frequencyHz;
+			o.dampingRatio = j->m_dampingRatio;
+			o.impulse[0] = j->m_impulse.x;
+			o.impulse[1] = j->m_impulse.y;
+			o.impulse[2] = j->m_impulse.z;
+		}
 	}
 }
 

@@ -147,13 +147,14 @@ def test_host_api_lockstep(gpu, name, steps):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,steps", [("tumbler_joint", 150), ("hanging_chains", 300), ("joint_zoo", 300)])
+@pytest.mark.parametrize("name,steps", [("tumbler_joint", 150), ("hanging_chains", 300), ("joint_zoo", 300),
+                                        ("rods_and_welds", 300)])
 def test_host_api_joints_lockstep(gpu, name, steps):
-    """Worlds with revolute joints built through b2World::CreateJoint (the Testbed's Tumbler with its motor joint,
-    hanging chains, every branch of the joint) and stepped through b2World::Step stay bit-identical to the reference:
-    bodies, events and what the b2RevoluteJoint accessors report."""
+    """Worlds with revolute, distance and weld joints built through b2World::CreateJoint (the Testbed's Tumbler with its
+    motor joint, hanging chains, every branch of the revolute joint, the Web and the Cantilever) and stepped through
+    b2World::Step stay bit-identical to the reference: bodies, events and what the joints' accessors report."""
     make = {"tumbler_joint": lambda: scenes.tumbler(60, motor_joint=True), "hanging_chains": lambda: scenes.hanging_chains(3, 10),
-            "joint_zoo": scenes.joint_zoo}[name]
+            "joint_zoo": scenes.joint_zoo, "rods_and_welds": scenes.rods_and_welds}[name]
     h, r, begins = _host_lockstep(make(), steps)
     assert h.joint_count() == r.joint_count > 0
     assert h.hash() == r.hash()
@@ -191,6 +192,36 @@ def test_host_api_joint_edits_between_steps(gpu):
         w.destroy_joint(w.joint_count() - 1 if w is h else w.joint_count - 1)
     run(40)
     assert h.joint_count() == r.joint_count
+
+
+@pytest.mark.gpu
+def test_host_api_spring_edits_between_steps(gpu):
+    """b2DistanceJoint::SetLength / SetFrequency / SetDampingRatio and b2WeldJoint::SetFrequency / SetDampingRatio
+    between steps (they do not wake anything), and rods cut with DestroyJoint."""
+    scene = scenes.rods_and_welds()
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+
+    def run(n):
+        for s in range(n):
+            h.step()
+            r.set_joint_order(h.joint_order())
+            assert r.step_ordered(h.solver_order()) == 0
+            parity.compare_bodies(h.bodies(), r.bodies())
+            parity.assert_floats_equal("joint readings", h.joint_readings(), r.joint_readings())
+
+    run(50)
+    for w in (h, r):
+        w.joint_set_spring(0, 9.0, 4.0, 0.5)     # a web rod gets shorter and stiffer
+        w.joint_set_spring(5, 12.0, 0.0, 0.0)    # another one turns rigid
+        w.joint_set_spring(14, 0.0, 3.0, 0.2)    # a rigid weld gets a soft angle
+        w.joint_set_spring(22, 0.0, 0.0, 0.0)    # a soft weld turns rigid
+    run(80)
+    for w in (h, r):
+        w.destroy_joint(1)                       # cut a web rod
+        w.destroy_joint(7)                       # and the pendulum chain's top rod (index shifted by one)
+    run(80)
 
 
 @pytest.mark.gpu
@@ -465,3 +496,28 @@ def test_hello_world_program_runs(gpu, tmp_path):
         gx, gy, ga = (float(v) for v in g.split())
         wx, wy, wa = (float(v) for v in w.split())
         assert abs(gx - wx) < 0.005 and abs(gy - wy) <= 0.011 and abs(ga - wa) < 0.005
+
+
+def _compile_cpp(tmp_path, name):
+    exe = tmp_path / name
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", HOST, "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-L", os.path.join(ROOT, "box2d-mt_b200"),
+                    "-lbox2d_b200", "-lb2cuda", "-Wl,-rpath," + os.path.join(ROOT, "box2d-mt_b200"), "-o", str(exe)],
+                   check=True)
+    return exe
+
+
+def test_tumbler_program_compiles_against_host_api(tmp_path):
+    assert _compile_cpp(tmp_path, "tumbler").exists()
+
+
+@pytest.mark.gpu
+def test_tumbler_program_runs(gpu, tmp_path):
+    """The Testbed's Tumbler as user code: the motor joint turns the drum at its set speed, every box stays inside."""
+    exe = _compile_cpp(tmp_path, "tumbler")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    angle, speed, torque, x0, y0, x1, y1 = (float(v) for v in out)
+    assert abs(speed - 0.05 * np.pi) < 1e-4
+    assert abs(angle - 0.05 * np.pi * 400 / 60) < 1e-2
+    assert torque != 0.0
+    assert -10.0 < x0 and x1 < 10.0 and 0.0 < y0 and y1 < 20.0
