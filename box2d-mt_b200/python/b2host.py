@@ -113,6 +113,14 @@ class HostWorld:
         if scene is not None and getattr(scene, "joints", None):
             self.create_joints(scene.joint_array())
 
+    def add(self, scene):
+        """CreateBody / CreateFixture for every body of another Scene (appended; between steps)"""
+        b, s, f = scene.arrays()
+        rc = self.lib.b2h_build(self.h, len(b), _ptr(np.ascontiguousarray(b, BODY_DEF)), len(s),
+                                _ptr(np.ascontiguousarray(s, SHAPE_DEF)), len(f), _ptr(np.ascontiguousarray(f, FIXTURE_DEF)))
+        if rc != 0:
+            raise RuntimeError("b2h_build failed: %d" % rc)
+
     # ---- joints (b2World::CreateJoint / b2RevoluteJoint) ----
     def create_joints(self, joints):
         j = np.ascontiguousarray(joints, T.JOINT)

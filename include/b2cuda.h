@@ -80,7 +80,7 @@ typedef enum b2cuStatus
 	B2CU_ERR_CUDA = -1,        /* a CUDA runtime call failed */
 	B2CU_ERR_CAPACITY = -2,    /* a device buffer overflowed its capacity (grow and retry) */
 	B2CU_ERR_ARGUMENT = -3,    /* bad argument */
-	B2CU_ERR_UNSUPPORTED = -4, /* feature outside the GPU path (joints, chains, sensors, custom filters) */
+	B2CU_ERR_UNSUPPORTED = -4, /* feature outside the GPU path (a joint type that is not solved, joints in a sharded world) */
 	B2CU_ERR_NO_DEVICE = -5    /* no CUDA device: there is no CPU fallback */
 } b2cuStatus;
 

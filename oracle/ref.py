@@ -107,6 +107,14 @@ class RefWorld:
         if scene is not None and getattr(scene, "joints", None):
             self.set_joints(scene.joint_array())
 
+    def add(self, scene):
+        """CreateBody / CreateFixture for every body of another Scene (appended; between steps)"""
+        b, s, f = scene.arrays()
+        rc = self.lib.b2ref_build(self.h, len(b), _ptr(np.ascontiguousarray(b, BODY_DEF)), len(s),
+                                  _ptr(np.ascontiguousarray(s, SHAPE_DEF)), len(f), _ptr(np.ascontiguousarray(f, FIXTURE_DEF)))
+        if rc != 0:
+            raise RuntimeError("b2ref_build failed: %d" % rc)
+
     def set_joints(self, joints):
         j = np.ascontiguousarray(joints, T.JOINT)
         if self.lib.b2ref_set_joints(self.h, len(j), _ptr(j)) != 0:

@@ -1,6 +1,6 @@
 // The Testbed's Tumbler (Testbed/Tests/Tumbler.h:24-98) as a user program against this library's host API: a dynamic
 // container turned by the motor of a revolute joint, one small box dropped in per step.  Exercises b2World::CreateJoint,
-// b2RevoluteJointDef and CreateBody between steps.  Prints the joint's readings and where the boxes are.
+// b2RevoluteJointDef and CreateBody between steps.  Prints the joint's readings and where the boxes are in the drum's frame.
 #include <cstdio>
 
 #include "Box2D/Box2D.h"
@@ -64,7 +64,7 @@ int main()
 	float32 lo[2] = {1e9f, 1e9f}, hi[2] = {-1e9f, -1e9f};
 	for (int32 k = 0; k < made; ++k)
 	{
-		b2Vec2 p = boxes[k]->GetPosition();
+		b2Vec2 p = drum->GetLocalPoint(boxes[k]->GetPosition()); // in the drum's frame
 		lo[0] = b2Min(lo[0], p.x);
 		lo[1] = b2Min(lo[1], p.y);
 		hi[0] = b2Max(hi[0], p.x);

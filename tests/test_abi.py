@@ -40,18 +40,20 @@ def test_record_layouts_match_header(tmp_path):
     prog = tmp_path / "sizes.c"
     prog.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "b2cuda.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b2cuBody), sizeof(b2cuShape),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b2cuBody), sizeof(b2cuShape),'
         ' sizeof(b2cuProxy), sizeof(b2cuManifold), sizeof(b2cuContact), sizeof(b2cuWorldDef), sizeof(b2cuStepInfo),'
         ' offsetof(b2cuBody, flags), offsetof(b2cuProxy, fixture), offsetof(b2cuContact, manifold),'
         ' sizeof(b2cuBodyState), offsetof(b2cuBodyState, vx), sizeof(b2cuShardLink),'
-        ' sizeof(b2cuDistanceResult), sizeof(b2cuSweep), offsetof(b2cuSweep, a0), sizeof(b2cuToiResult));return 0;}\n')
+        ' sizeof(b2cuDistanceResult), sizeof(b2cuSweep), offsetof(b2cuSweep, a0), sizeof(b2cuToiResult),'
+        ' sizeof(b2cuJoint), offsetof(b2cuJoint, impulse), offsetof(b2cuStepInfo, toiMinKey));return 0;}\n')
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [T.BODY.itemsize, T.SHAPE.itemsize, T.PROXY.itemsize, T.MANIFOLD.itemsize, T.CONTACT.itemsize,
             T.WORLD_DEF.itemsize, T.STEP_INFO.itemsize, T.BODY.fields["flags"][1], T.PROXY.fields["fixture"][1],
             T.CONTACT.fields["manifold"][1], T.BODY_STATE.itemsize, T.BODY_STATE.fields["vx"][1], T.SHARD_LINK.itemsize,
-            T.DISTANCE_RESULT.itemsize, T.SWEEP.itemsize, T.SWEEP.fields["a0"][1], T.TOI_RESULT.itemsize]
+            T.DISTANCE_RESULT.itemsize, T.SWEEP.itemsize, T.SWEEP.fields["a0"][1], T.TOI_RESULT.itemsize,
+            T.JOINT.itemsize, T.JOINT.fields["impulse"][1], T.STEP_INFO.fields["toiMinKey"][1]]
     assert got == want
 
 
