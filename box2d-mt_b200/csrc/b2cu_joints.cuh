@@ -1,6 +1,7 @@
 // b2cu_joints.cuh -- joints as rows of the coloured solver.  Restates InitVelocityConstraints / SolveVelocityConstraints
 // / SolvePositionConstraints of b2RevoluteJoint (Box2D/Dynamics/Joints/b2RevoluteJoint.cpp:64-400), b2DistanceJoint
-// (b2DistanceJoint.cpp:63-222) and b2WeldJoint (b2WeldJoint.cpp:59-308), and the small linear solves they use
+// (b2DistanceJoint.cpp:63-222), b2WeldJoint (b2WeldJoint.cpp:59-308) and b2PrismaticJoint
+// (b2PrismaticJoint.cpp:100-478), and the small linear solves they use
 // (b2Mat33::Solve33 / Solve22 / GetInverse22 / GetSymInverse33, Box2D/Common/b2Math.cpp:25-94; b2Mat22::Solve,
 // b2Math.h:221-233) with the same fp32 arithmetic in the same order.  One thread solves one joint; joints of one colour class share no
 // dynamic body, so a class is solved in parallel and the classes one after the other.
@@ -38,7 +39,9 @@ struct JointRow
 	float invMassA, invMassB, invIA, invIB;
 	Vec3 ex, ey, ez; // m_mass (revolute: K; weld: its inverse)
 	float motorMass; // revolute: motor mass; distance: m_mass
-	Vec2 u;          // distance: unit vector from anchor A to anchor B
+	Vec2 u;          // distance: unit vector from anchor A to anchor B; prismatic: m_localXAxisA (normalised)
+	Vec2 axis, perp; // prismatic: m_axis, m_perp
+	float a1, a2, s1, s2; // prismatic Jacobian terms
 	float gamma, bias; // soft constraint terms (distance, weld)
 	int root;   // island of the joint (position early exit)
 	int solved; // in an awake island this step
@@ -90,7 +93,8 @@ __device__ __forceinline__ bool JointPrepare(const DeviceArrays& d, const b2cuJo
 	r.invMassB = massB.x;
 	r.invIA = massA.y;
 	r.invIB = massB.y;
-	r.u = V(0.0f, 0.0f);
+	r.u = r.axis = r.perp = V(0.0f, 0.0f);
+	r.a1 = r.a2 = r.s1 = r.s2 = 0.0f;
 	r.gamma = r.bias = r.motorMass = 0.0f;
 	r.ex = r.ey = r.ez = V3(0.0f, 0.0f, 0.0f);
 	return true;
@@ -415,8 +419,8 @@ __device__ __forceinline__ void DistanceInit(const DeviceArrays& d, int j, b2cuJ
 
 	StoreVelocity(d, bA, r.invMassA, r.invIA, vA, wA, vA4.w);
 	StoreVelocity(d, bB, r.invMassB, r.invIB, vB, wB, vB4.w);
-	jt.axis[0] = r.u.x; // b2DistanceJoint::GetReactionForce reads m_u
-	jt.axis[1] = r.u.y;
+	jt.lastSolve[0] = r.u.x; // b2DistanceJoint::GetReactionForce reads m_u
+	jt.lastSolve[1] = r.u.y;
 	d.jointRows[j] = r;
 	d.joints[j] = jt;
 }
@@ -706,6 +710,310 @@ __device__ __forceinline__ bool WeldSolvePosition(const DeviceArrays& d, const J
 	return positionError <= B2CU_LINEAR_SLOP && angularError <= B2CU_ANGULAR_SLOP;
 }
 
+// ---- prismatic joint (b2PrismaticJoint.cpp:100-478) ---------------------------------------------------------------------
+
+// b2PrismaticJoint::b2PrismaticJoint (:100-125): the local axis of the definition, normalised (b2Vec2::Normalize)
+__device__ __forceinline__ Vec2 PrismaticLocalAxis(const b2cuJoint& jt)
+{
+	Vec2 a = V(jt.axis[0], jt.axis[1]);
+	float length = Length(a);
+	if (length < B2CU_EPSILON) return a;
+	float inv = 1.0f / length;
+	return V(a.x * inv, a.y * inv);
+}
+
+__device__ __forceinline__ void PrismaticInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio, int warmStarting)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+
+	Rot qA = SinCos(pA.z), qB = SinCos(pB.z);
+	Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	Vec2 dd = (cB - cA) + rB - rA;
+
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+
+	r.u = PrismaticLocalAxis(jt);
+	Vec2 localY = CrossSV(1.0f, r.u);
+
+	// motor Jacobian and effective mass
+	r.axis = Mul(qA, r.u);
+	r.a1 = Cross(dd + rA, r.axis);
+	r.a2 = Cross(rB, r.axis);
+	r.motorMass = mA + mB + iA * r.a1 * r.a1 + iB * r.a2 * r.a2;
+	if (r.motorMass > 0.0f) r.motorMass = 1.0f / r.motorMass;
+
+	// the prismatic constraint: no motion along perp, no relative rotation
+	r.perp = Mul(qA, localY);
+	r.s1 = Cross(dd + rA, r.perp);
+	r.s2 = Cross(rB, r.perp);
+	{
+		float k11 = mA + mB + iA * r.s1 * r.s1 + iB * r.s2 * r.s2;
+		float k12 = iA * r.s1 + iB * r.s2;
+		float k13 = iA * r.s1 * r.a1 + iB * r.s2 * r.a2;
+		float k22 = iA + iB;
+		if (k22 == 0.0f) k22 = 1.0f; // bodies with fixed rotation
+		float k23 = iA * r.a1 + iB * r.a2;
+		float k33 = mA + mB + iA * r.a1 * r.a1 + iB * r.a2 * r.a2;
+		r.ex = V3(k11, k12, k13);
+		r.ey = V3(k12, k22, k23);
+		r.ez = V3(k13, k23, k33);
+	}
+
+	const bool enableMotor = (jt.flags & B2CU_JOINT_ENABLE_MOTOR) != 0, enableLimit = (jt.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
+	if (enableLimit)
+	{
+		float jointTranslation = Dot(r.axis, dd);
+		if (Abs(jt.upperAngle - jt.lowerAngle) < 2.0f * B2CU_LINEAR_SLOP)
+		{
+			jt.limitState = B2CU_LIMIT_EQUAL;
+		}
+		else if (jointTranslation <= jt.lowerAngle)
+		{
+			if (jt.limitState != B2CU_LIMIT_AT_LOWER)
+			{
+				jt.limitState = B2CU_LIMIT_AT_LOWER;
+				jt.impulse[2] = 0.0f;
+			}
+		}
+		else if (jointTranslation >= jt.upperAngle)
+		{
+			if (jt.limitState != B2CU_LIMIT_AT_UPPER)
+			{
+				jt.limitState = B2CU_LIMIT_AT_UPPER;
+				jt.impulse[2] = 0.0f;
+			}
+		}
+		else
+		{
+			jt.limitState = B2CU_LIMIT_INACTIVE;
+			jt.impulse[2] = 0.0f;
+		}
+	}
+	else
+	{
+		jt.limitState = B2CU_LIMIT_INACTIVE;
+		jt.impulse[2] = 0.0f;
+	}
+
+	if (!enableMotor) jt.motorImpulse = 0.0f;
+
+	if (warmStarting)
+	{
+		jt.impulse[0] *= dtRatio;
+		jt.impulse[1] *= dtRatio;
+		jt.impulse[2] *= dtRatio;
+		jt.motorImpulse *= dtRatio;
+
+		Vec2 P = jt.impulse[0] * r.perp + (jt.motorImpulse + jt.impulse[2]) * r.axis;
+		float LA = jt.impulse[0] * r.s1 + jt.impulse[1] + (jt.motorImpulse + jt.impulse[2]) * r.a1;
+		float LB = jt.impulse[0] * r.s2 + jt.impulse[1] + (jt.motorImpulse + jt.impulse[2]) * r.a2;
+		vA = vA - mA * P;
+		wA -= iA * LA;
+		vB = vB + mB * P;
+		wB += iB * LB;
+	}
+	else
+	{
+		jt.impulse[0] = jt.impulse[1] = jt.impulse[2] = 0.0f;
+		jt.motorImpulse = 0.0f;
+	}
+
+	StoreVelocity(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, mB, iB, vB, wB, vB4.w);
+	jt.lastSolve[0] = r.axis.x; // b2PrismaticJoint::GetReactionForce reads m_axis and m_perp
+	jt.lastSolve[1] = r.axis.y;
+	jt.lastSolve[2] = r.perp.x;
+	jt.lastSolve[3] = r.perp.y;
+	d.jointRows[j] = r;
+	d.joints[j] = jt;
+}
+
+__device__ __forceinline__ void PrismaticSolveVelocity(const DeviceArrays& d, int j, const JointRow& r, b2cuJoint jt, float h)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+	const bool enableMotor = (jt.flags & B2CU_JOINT_ENABLE_MOTOR) != 0, enableLimit = (jt.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
+
+	// linear motor
+	if (enableMotor && jt.limitState != B2CU_LIMIT_EQUAL)
+	{
+		float Cdot = Dot(r.axis, vB - vA) + r.a2 * wB - r.a1 * wA;
+		float impulse = r.motorMass * (jt.motorSpeed - Cdot);
+		float oldImpulse = jt.motorImpulse;
+		float maxImpulse = h * jt.maxMotorTorque;
+		jt.motorImpulse = Clamp(jt.motorImpulse + impulse, -maxImpulse, maxImpulse);
+		impulse = jt.motorImpulse - oldImpulse;
+
+		Vec2 P = impulse * r.axis;
+		float LA = impulse * r.a1;
+		float LB = impulse * r.a2;
+		vA = vA - mA * P;
+		wA -= iA * LA;
+		vB = vB + mB * P;
+		wB += iB * LB;
+	}
+
+	Vec2 Cdot1;
+	Cdot1.x = Dot(r.perp, vB - vA) + r.s2 * wB - r.s1 * wA;
+	Cdot1.y = wB - wA;
+
+	if (enableLimit && jt.limitState != B2CU_LIMIT_INACTIVE)
+	{
+		// prismatic constraint and limit together, 3x3
+		float Cdot2 = Dot(r.axis, vB - vA) + r.a2 * wB - r.a1 * wA;
+		Vec3 f1 = V3(jt.impulse[0], jt.impulse[1], jt.impulse[2]);
+		Vec3 df = Solve33(r, V3(-Cdot1.x, -Cdot1.y, -Cdot2));
+		Vec3 imp = V3(f1.x + df.x, f1.y + df.y, f1.z + df.z);
+
+		if (jt.limitState == B2CU_LIMIT_AT_LOWER) imp.z = Max(imp.z, 0.0f);
+		else if (jt.limitState == B2CU_LIMIT_AT_UPPER) imp.z = Min(imp.z, 0.0f);
+
+		// with the limit impulse clamped, re-solve the other two rows
+		Vec2 b = -Cdot1 - (imp.z - f1.z) * V(r.ez.x, r.ez.y);
+		Vec2 f2r = Solve22(r.ex.x, r.ey.x, r.ex.y, r.ey.y, b) + V(f1.x, f1.y);
+		imp.x = f2r.x;
+		imp.y = f2r.y;
+
+		df = V3(imp.x - f1.x, imp.y - f1.y, imp.z - f1.z);
+		jt.impulse[0] = imp.x;
+		jt.impulse[1] = imp.y;
+		jt.impulse[2] = imp.z;
+
+		Vec2 P = df.x * r.perp + df.z * r.axis;
+		float LA = df.x * r.s1 + df.y + df.z * r.a1;
+		float LB = df.x * r.s2 + df.y + df.z * r.a2;
+		vA = vA - mA * P;
+		wA -= iA * LA;
+		vB = vB + mB * P;
+		wB += iB * LB;
+	}
+	else
+	{
+		Vec2 df = Solve22(r.ex.x, r.ey.x, r.ex.y, r.ey.y, -Cdot1);
+		jt.impulse[0] += df.x;
+		jt.impulse[1] += df.y;
+
+		Vec2 P = df.x * r.perp;
+		float LA = df.x * r.s1 + df.y;
+		float LB = df.x * r.s2 + df.y;
+		vA = vA - mA * P;
+		wA -= iA * LA;
+		vB = vB + mB * P;
+		wB += iB * LB;
+	}
+
+	StoreVelocity(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, mB, iB, vB, wB, vB4.w);
+	d.joints[j].impulse[0] = jt.impulse[0];
+	d.joints[j].impulse[1] = jt.impulse[1];
+	d.joints[j].impulse[2] = jt.impulse[2];
+	d.joints[j].motorImpulse = jt.motorImpulse;
+}
+
+__device__ __forceinline__ bool PrismaticSolvePosition(const DeviceArrays& d, const JointRow& r, const b2cuJoint& jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	float aA = pA.z, aB = pB.z;
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+
+	Rot qA = SinCos(aA), qB = SinCos(aB);
+	Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	Vec2 dd = cB + rB - cA - rA;
+
+	Vec2 axis = Mul(qA, r.u);
+	float a1 = Cross(dd + rA, axis);
+	float a2 = Cross(rB, axis);
+	Vec2 perp = Mul(qA, CrossSV(1.0f, r.u));
+	float s1 = Cross(dd + rA, perp);
+	float s2 = Cross(rB, perp);
+
+	Vec3 impulse;
+	Vec2 C1;
+	C1.x = Dot(perp, dd);
+	C1.y = aB - aA - jt.referenceAngle;
+
+	float linearError = Abs(C1.x);
+	float angularError = Abs(C1.y);
+
+	bool active = false;
+	float C2 = 0.0f;
+	if (jt.flags & B2CU_JOINT_ENABLE_LIMIT)
+	{
+		float translation = Dot(axis, dd);
+		if (Abs(jt.upperAngle - jt.lowerAngle) < 2.0f * B2CU_LINEAR_SLOP)
+		{
+			C2 = Clamp(translation, -B2CU_MAX_LINEAR_CORRECTION, B2CU_MAX_LINEAR_CORRECTION);
+			linearError = Max(linearError, Abs(translation));
+			active = true;
+		}
+		else if (translation <= jt.lowerAngle)
+		{
+			C2 = Clamp(translation - jt.lowerAngle + B2CU_LINEAR_SLOP, -B2CU_MAX_LINEAR_CORRECTION, 0.0f);
+			linearError = Max(linearError, jt.lowerAngle - translation);
+			active = true;
+		}
+		else if (translation >= jt.upperAngle)
+		{
+			C2 = Clamp(translation - jt.upperAngle - B2CU_LINEAR_SLOP, 0.0f, B2CU_MAX_LINEAR_CORRECTION);
+			linearError = Max(linearError, translation - jt.upperAngle);
+			active = true;
+		}
+	}
+
+	if (active)
+	{
+		float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+		float k12 = iA * s1 + iB * s2;
+		float k13 = iA * s1 * a1 + iB * s2 * a2;
+		float k22 = iA + iB;
+		if (k22 == 0.0f) k22 = 1.0f;
+		float k23 = iA * a1 + iB * a2;
+		float k33 = mA + mB + iA * a1 * a1 + iB * a2 * a2;
+		JointRow K = r;
+		K.ex = V3(k11, k12, k13);
+		K.ey = V3(k12, k22, k23);
+		K.ez = V3(k13, k23, k33);
+		impulse = Solve33(K, V3(-C1.x, -C1.y, -C2));
+	}
+	else
+	{
+		float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+		float k12 = iA * s1 + iB * s2;
+		float k22 = iA + iB;
+		if (k22 == 0.0f) k22 = 1.0f;
+		Vec2 impulse1 = Solve22(k11, k12, k12, k22, -C1);
+		impulse = V3(impulse1.x, impulse1.y, 0.0f);
+	}
+
+	Vec2 P = impulse.x * perp + impulse.z * axis;
+	float LA = impulse.x * s1 + impulse.y + impulse.z * a1;
+	float LB = impulse.x * s2 + impulse.y + impulse.z * a2;
+
+	cA = cA - mA * P;
+	aA -= iA * LA;
+	cB = cB + mB * P;
+	aB += iB * LB;
+
+	if (mA != 0.0f || iA != 0.0f) d.pos[bA] = make_float4(cA.x, cA.y, aA, pA.w);
+	if (mB != 0.0f || iB != 0.0f) d.pos[bB] = make_float4(cB.x, cB.y, aB, pB.w);
+	return linearError <= B2CU_LINEAR_SLOP && angularError <= B2CU_ANGULAR_SLOP;
+}
+
 // ---- dispatch by joint type -------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float dtRatio, int warmStarting, float h)
@@ -718,6 +1026,7 @@ __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float
 		return;
 	}
 	if (jt.type == B2CU_JOINT_REVOLUTE) RevoluteInit(d, j, jt, r, dtRatio, warmStarting);
+	else if (jt.type == B2CU_JOINT_PRISMATIC) PrismaticInit(d, j, jt, r, dtRatio, warmStarting);
 	else if (jt.type == B2CU_JOINT_DISTANCE) DistanceInit(d, j, jt, r, dtRatio, warmStarting, h);
 	else WeldInit(d, j, jt, r, dtRatio, warmStarting, h);
 }
@@ -728,6 +1037,7 @@ __device__ __forceinline__ void JointSolveVelocityOne(const DeviceArrays& d, int
 	if (!r.solved) return;
 	b2cuJoint jt = d.joints[j];
 	if (jt.type == B2CU_JOINT_REVOLUTE) RevoluteSolveVelocity(d, j, r, jt, h);
+	else if (jt.type == B2CU_JOINT_PRISMATIC) PrismaticSolveVelocity(d, j, r, jt, h);
 	else if (jt.type == B2CU_JOINT_DISTANCE) DistanceSolveVelocity(d, j, r, jt);
 	else WeldSolveVelocity(d, j, r, jt);
 }
@@ -736,6 +1046,7 @@ __device__ __forceinline__ bool JointSolvePositionOne(const DeviceArrays& d, int
 {
 	b2cuJoint jt = d.joints[j];
 	if (jt.type == B2CU_JOINT_REVOLUTE) return RevoluteSolvePosition(d, r, jt);
+	if (jt.type == B2CU_JOINT_PRISMATIC) return PrismaticSolvePosition(d, r, jt);
 	if (jt.type == B2CU_JOINT_DISTANCE) return DistanceSolvePosition(d, r, jt);
 	return WeldSolvePosition(d, r, jt);
 }

@@ -415,6 +415,24 @@ B2H_API int b2h_create_joints(void* p, int32 count, const b2cuJoint* rows)
 			def.maxMotorTorque = r.maxMotorTorque;
 			j = h->world->CreateJoint(&def);
 		}
+		else if (r.type == B2CU_JOINT_PRISMATIC)
+		{
+			b2PrismaticJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
+			def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
+			def.localAxisA.Set(r.axis[0], r.axis[1]);
+			def.referenceAngle = r.referenceAngle;
+			def.enableLimit = (r.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
+			def.lowerTranslation = r.lowerAngle;
+			def.upperTranslation = r.upperAngle;
+			def.enableMotor = (r.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
+			def.motorSpeed = r.motorSpeed;
+			def.maxMotorForce = r.maxMotorTorque;
+			j = h->world->CreateJoint(&def);
+		}
 		else if (r.type == B2CU_JOINT_DISTANCE)
 		{
 			b2DistanceJointDef def;
@@ -478,11 +496,26 @@ B2H_API void b2h_joint_readings(void* p, float inv_dt, float* out6)
 			o[4] = j->GetJointAngle();
 			o[5] = j->GetJointSpeed();
 		}
+		else if (base->GetType() == e_prismaticJoint)
+		{
+			const b2PrismaticJoint* j = static_cast<const b2PrismaticJoint*>(base);
+			o[3] = j->GetMotorForce(inv_dt);
+			o[4] = j->GetJointTranslation();
+			o[5] = j->GetJointSpeed();
+		}
 	}
 }
 
 B2H_API void b2h_joint_set_motor(void* p, int32 joint, int32 enable, float speed, float maxTorque)
 {
+	if (static_cast<Host*>(p)->joints[joint]->GetType() == e_prismaticJoint)
+	{
+		b2PrismaticJoint* pj = static_cast<b2PrismaticJoint*>(static_cast<Host*>(p)->joints[joint]);
+		pj->EnableMotor(enable != 0);
+		pj->SetMotorSpeed(speed);
+		pj->SetMaxMotorForce(maxTorque);
+		return;
+	}
 	b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(static_cast<Host*>(p)->joints[joint]);
 	j->EnableMotor(enable != 0);
 	j->SetMotorSpeed(speed);
@@ -491,6 +524,13 @@ B2H_API void b2h_joint_set_motor(void* p, int32 joint, int32 enable, float speed
 
 B2H_API void b2h_joint_set_limits(void* p, int32 joint, int32 enable, float lower, float upper)
 {
+	if (static_cast<Host*>(p)->joints[joint]->GetType() == e_prismaticJoint)
+	{
+		b2PrismaticJoint* pj = static_cast<b2PrismaticJoint*>(static_cast<Host*>(p)->joints[joint]);
+		pj->EnableLimit(enable != 0);
+		pj->SetLimits(lower, upper);
+		return;
+	}
 	b2RevoluteJoint* j = static_cast<b2RevoluteJoint*>(static_cast<Host*>(p)->joints[joint]);
 	j->EnableLimit(enable != 0);
 	j->SetLimits(lower, upper);

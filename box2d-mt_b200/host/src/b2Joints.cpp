@@ -5,6 +5,7 @@
 #include "Box2D/Dynamics/Joints/b2RevoluteJoint.h"
 #include "Box2D/Dynamics/Joints/b2DistanceJoint.h"
 #include "Box2D/Dynamics/Joints/b2WeldJoint.h"
+#include "Box2D/Dynamics/Joints/b2PrismaticJoint.h"
 #include "Box2D/Dynamics/b2Body.h"
 #include "Box2D/Dynamics/b2World.h"
 
@@ -191,14 +192,14 @@ void b2DistanceJoint::WriteRecord(b2cuJoint* out) const
 	out->frequencyHz = m_frequencyHz;
 	out->dampingRatio = m_dampingRatio;
 	out->impulse[0] = m_impulse;
-	out->axis[0] = m_u.x;
-	out->axis[1] = m_u.y;
+	out->lastSolve[0] = m_u.x;
+	out->lastSolve[1] = m_u.y;
 }
 
 void b2DistanceJoint::ReadRecord(const b2cuJoint& in)
 {
 	m_impulse = in.impulse[0];
-	m_u.Set(in.axis[0], in.axis[1]);
+	m_u.Set(in.lastSolve[0], in.lastSolve[1]);
 }
 
 b2Vec2 b2DistanceJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
@@ -296,4 +297,150 @@ void b2WeldJoint::SetDampingRatio(float32 ratio)
 	if (ratio == m_dampingRatio) return;
 	Touch();
 	m_dampingRatio = ratio;
+}
+
+// ---- prismatic (reference b2PrismaticJoint.cpp:91-125, :490-635) ---------------------------------------------------------
+
+void b2PrismaticJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor, const b2Vec2& axis)
+{
+	bodyA = bA;
+	bodyB = bB;
+	localAnchorA = bA->GetLocalPoint(anchor);
+	localAnchorB = bB->GetLocalPoint(anchor);
+	localAxisA = bA->GetLocalVector(axis);
+	referenceAngle = bB->GetAngle() - bA->GetAngle();
+}
+
+b2PrismaticJoint::b2PrismaticJoint(const b2PrismaticJointDef* def)
+	: b2Joint(def), m_localAnchorA(def->localAnchorA), m_localAnchorB(def->localAnchorB), m_localAxisGiven(def->localAxisA),
+	  m_localXAxisA(def->localAxisA), m_referenceAngle(def->referenceAngle), m_enableLimit(def->enableLimit),
+	  m_enableMotor(def->enableMotor), m_lowerTranslation(def->lowerTranslation), m_upperTranslation(def->upperTranslation),
+	  m_maxMotorForce(def->maxMotorForce), m_motorSpeed(def->motorSpeed), m_impulse(0.0f, 0.0f, 0.0f), m_motorImpulse(0.0f),
+	  m_limitState(e_inactiveLimit), m_axis(0.0f, 0.0f), m_perp(0.0f, 0.0f)
+{
+	m_localXAxisA.Normalize();
+}
+
+void b2PrismaticJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_PRISMATIC, m_bodyA, m_bodyB, m_collideConnected, m_localAnchorA, m_localAnchorB);
+	out->flags |= (m_enableLimit ? B2CU_JOINT_ENABLE_LIMIT : 0u) | (m_enableMotor ? B2CU_JOINT_ENABLE_MOTOR : 0u);
+	out->axis[0] = m_localAxisGiven.x;
+	out->axis[1] = m_localAxisGiven.y;
+	out->referenceAngle = m_referenceAngle;
+	out->lowerAngle = m_lowerTranslation;
+	out->upperAngle = m_upperTranslation;
+	out->maxMotorTorque = m_maxMotorForce;
+	out->motorSpeed = m_motorSpeed;
+	out->impulse[0] = m_impulse.x;
+	out->impulse[1] = m_impulse.y;
+	out->impulse[2] = m_impulse.z;
+	out->motorImpulse = m_motorImpulse;
+	out->limitState = (int32_t)m_limitState;
+	out->lastSolve[0] = m_axis.x;
+	out->lastSolve[1] = m_axis.y;
+	out->lastSolve[2] = m_perp.x;
+	out->lastSolve[3] = m_perp.y;
+}
+
+void b2PrismaticJoint::ReadRecord(const b2cuJoint& in)
+{
+	m_impulse.Set(in.impulse[0], in.impulse[1], in.impulse[2]);
+	m_motorImpulse = in.motorImpulse;
+	m_limitState = (b2LimitState)in.limitState;
+	m_axis.Set(in.lastSolve[0], in.lastSolve[1]);
+	m_perp.Set(in.lastSolve[2], in.lastSolve[3]);
+}
+
+b2Vec2 b2PrismaticJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2PrismaticJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+b2Vec2 b2PrismaticJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * (m_impulse.x * m_perp + (m_motorImpulse + m_impulse.z) * m_axis);
+}
+
+float32 b2PrismaticJoint::GetReactionTorque(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_impulse.y;
+}
+
+float32 b2PrismaticJoint::GetMotorForce(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_motorImpulse;
+}
+
+float32 b2PrismaticJoint::GetJointTranslation() const
+{
+	b2Vec2 d = m_bodyB->GetWorldPoint(m_localAnchorB) - m_bodyA->GetWorldPoint(m_localAnchorA);
+	b2Vec2 axis = m_bodyA->GetWorldVector(m_localXAxisA);
+	return b2Dot(d, axis);
+}
+
+float32 b2PrismaticJoint::GetJointSpeed() const
+{
+	const b2Rot& qA = m_bodyA->GetTransform().q;
+	const b2Rot& qB = m_bodyB->GetTransform().q;
+	b2Vec2 rA = b2Mul(qA, m_localAnchorA - m_bodyA->GetLocalCenter());
+	b2Vec2 rB = b2Mul(qB, m_localAnchorB - m_bodyB->GetLocalCenter());
+	b2Vec2 p1 = m_bodyA->GetWorldCenter() + rA;
+	b2Vec2 p2 = m_bodyB->GetWorldCenter() + rB;
+	b2Vec2 d = p2 - p1;
+	b2Vec2 axis = b2Mul(qA, m_localXAxisA);
+	b2Vec2 vA = m_bodyA->GetLinearVelocity(), vB = m_bodyB->GetLinearVelocity();
+	float32 wA = m_bodyA->GetAngularVelocity(), wB = m_bodyB->GetAngularVelocity();
+	return b2Dot(d, b2Cross(wA, axis)) + b2Dot(axis, vB + b2Cross(wB, rB) - vA - b2Cross(wA, rA));
+}
+
+void b2PrismaticJoint::WakeBodies()
+{
+	m_bodyA->SetAwake(true);
+	m_bodyB->SetAwake(true);
+}
+
+void b2PrismaticJoint::EnableLimit(bool flag)
+{
+	if (flag == m_enableLimit) return;
+	Touch();
+	WakeBodies();
+	m_enableLimit = flag;
+	m_impulse.z = 0.0f;
+}
+
+void b2PrismaticJoint::SetLimits(float32 lower, float32 upper)
+{
+	b2Assert(lower <= upper);
+	if (lower == m_lowerTranslation && upper == m_upperTranslation) return;
+	Touch();
+	WakeBodies();
+	m_lowerTranslation = lower;
+	m_upperTranslation = upper;
+	m_impulse.z = 0.0f;
+}
+
+void b2PrismaticJoint::EnableMotor(bool flag)
+{
+	if (flag == m_enableMotor) return;
+	Touch();
+	WakeBodies();
+	m_enableMotor = flag;
+}
+
+void b2PrismaticJoint::SetMotorSpeed(float32 speed)
+{
+	if (speed == m_motorSpeed) return;
+	Touch();
+	WakeBodies();
+	m_motorSpeed = speed;
+}
+
+void b2PrismaticJoint::SetMaxMotorForce(float32 force)
+{
+	if (force == m_maxMotorForce) return;
+	Touch();
+	WakeBodies();
+	m_maxMotorForce = force;
 }

@@ -5,6 +5,7 @@
 #include "Box2D/Dynamics/Joints/b2RevoluteJoint.h"
 #include "Box2D/Dynamics/Joints/b2DistanceJoint.h"
 #include "Box2D/Dynamics/Joints/b2WeldJoint.h"
+#include "Box2D/Dynamics/Joints/b2PrismaticJoint.h"
 
 #include <chrono>
 #include "Box2D/Collision/Shapes/b2CircleShape.h"
@@ -326,7 +327,7 @@ void b2World::RefreshJoints() const
 b2Joint* b2World::CreateJoint(const b2JointDef* def)
 {
 	if (IsLocked()) return nullptr;
-	if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint)
+	if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint && def->type != e_prismaticJoint)
 	{
 		m_lastStatus = B2CU_ERR_UNSUPPORTED;
 		return nullptr;
@@ -335,6 +336,7 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def)
 	b2Joint* j;
 	if (def->type == e_revoluteJoint) j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
 	else if (def->type == e_distanceJoint) j = new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def));
+	else if (def->type == e_prismaticJoint) j = new b2PrismaticJoint(static_cast<const b2PrismaticJointDef*>(def));
 	else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
 	j->m_world = this;
 	j->m_index = (int32)m_joints.size();

@@ -186,6 +186,24 @@ class Scene:
         self.joints.append(j)
         return len(self.joints) - 1
 
+    def prismatic_joint(self, body_a, body_b, local_anchor_a, local_anchor_b, local_axis_a, reference_angle=0.0,
+                        collide_connected=False, limits=None, motor=None):
+        """b2PrismaticJointDef (b2PrismaticJoint.h:30-83): body B slides along an axis fixed in body A; limits = (lower,
+        upper) translation, motor = (speed, max force).  The axis need not be a unit vector."""
+        j = self._joint(T.JOINT_PRISMATIC, body_a, body_b, local_anchor_a, local_anchor_b, collide_connected)
+        j["axis"] = local_axis_a
+        j["referenceAngle"] = reference_angle
+        flags = int(j["flags"])
+        if limits is not None:
+            flags |= T.JOINT_ENABLE_LIMIT
+            j["lowerAngle"], j["upperAngle"] = limits
+        if motor is not None:
+            flags |= T.JOINT_ENABLE_MOTOR
+            j["motorSpeed"], j["maxMotorTorque"] = motor
+        j["flags"] = flags
+        self.joints.append(j)
+        return len(self.joints) - 1
+
     def joint_array(self):
         return np.array(self.joints, dtype=T.JOINT) if self.joints else np.zeros(0, T.JOINT)
 

@@ -336,3 +336,49 @@ def rods_and_welds(seed=0):
     s.fixture(b, s.circle(0.4), density=1.0)
     s.distance_joint(a, b, (0.0, 0.0), (0.0, 0.0), 0.0)
     return s
+
+
+def sliders(seed=0):
+    """Prismatic joints in every branch (Testbed/Tests/Prismatic.h:26-70 and more): sliders on the ground body along
+    slanted, non-unit axes with limits (lower / upper / equal / none) and motors (strong, weak, none), a piston between
+    two dynamic bodies (SliderCrank.h:27-110: crank and rod on revolute joints, piston on a prismatic one), bodies that
+    cannot rotate, a slider on a kinematic carrier; over a ground edge that the free bodies fall on."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.edge((-40.0, 0.0), (40.0, 0.0)))
+    box = s.box(1.0, 0.5)
+    axes = [(2.0, 1.0), (1.0, 0.0), (0.0, 1.0), (-1.0, 3.0), (1.0, 1.0), (0.6, 0.8), (5.0, 0.0), (1.0, -0.2)]
+    limits = [(0.0, 4.0), (-2.0, 2.0), (1.0, 1.0), None, (-0.5, 3.0), (-3.0, 0.0), None, (0.0, 0.0)]
+    motors = [(10.0, 10000.0), None, None, (1.0, 50.0), (-2.0, 20.0), None, (0.5, 0.0), (3.0, 1000.0)]
+    for i in range(8):
+        x = -28.0 + 8.0 * i
+        b = s.body(T.DYNAMIC_BODY, (x, 10.0), angle=0.1 * i, w=0.5 * (i - 3),
+                   flags=BODYDEF_DEFAULT | (BODYDEF_FIXED_ROTATION if i == 5 else 0))
+        s.fixture(b, box, density=5.0)
+        s.prismatic_joint(g, b, (x, 10.0), (0.0, 0.0), axes[i], reference_angle=float(F(0.1 * i)), limits=limits[i],
+                          motor=motors[i], collide_connected=(i % 2 == 1))
+    # slider crank
+    crank = s.body(T.DYNAMIC_BODY, (0.0, 22.0))
+    s.fixture(crank, s.box(0.5, 2.0), density=2.0)
+    s.revolute_joint(g, crank, (0.0, 20.0), (0.0, -2.0), motor=(1.0 * np.pi, 10000.0))
+    rod = s.body(T.DYNAMIC_BODY, (0.0, 28.0))
+    s.fixture(rod, s.box(0.5, 4.0), density=2.0)
+    s.revolute_joint(crank, rod, (0.0, 2.0), (0.0, -4.0))
+    piston = s.body(T.DYNAMIC_BODY, (0.0, 32.0), flags=BODYDEF_DEFAULT | BODYDEF_FIXED_ROTATION)
+    s.fixture(piston, s.box(1.5, 1.5), density=2.0)
+    s.revolute_joint(rod, piston, (0.0, 4.0), (0.0, 0.0))
+    s.prismatic_joint(g, piston, (0.0, 32.0), (0.0, 0.0), (0.0, 1.0), motor=(0.0, 1000.0))
+    payload = s.body(T.DYNAMIC_BODY, (0.0, 38.0))
+    s.fixture(payload, s.box(1.5, 1.5), density=2.0)
+    # a telescope of two dynamic bodies, and a slider carried by a kinematic body
+    a = s.body(T.DYNAMIC_BODY, (20.0, 3.0))
+    s.fixture(a, box, density=1.0)
+    b = s.body(T.DYNAMIC_BODY, (22.5, 3.0))
+    s.fixture(b, box, density=1.0)
+    s.prismatic_joint(a, b, (1.0, 0.0), (-1.5, 0.0), (1.0, 0.0), limits=(-0.5, 1.0), collide_connected=True)
+    k = s.body(T.KINEMATIC_BODY, (-20.0, 25.0), vel=(0.5, 0.0), w=0.2)
+    s.fixture(k, s.box(0.5, 0.5))
+    b = s.body(T.DYNAMIC_BODY, (-20.0, 23.0))
+    s.fixture(b, box, density=1.0)
+    s.prismatic_joint(k, b, (0.0, -0.5), (0.0, 1.5), (0.0, -2.0), limits=(-1.0, 3.0))
+    return s

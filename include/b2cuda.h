@@ -330,18 +330,23 @@ B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
  *   revolute joints   b2RevoluteJoint.cpp:64-400   point constraint, angular limit, motor
  *   distance joints   b2DistanceJoint.cpp:63-222   rigid or spring-damper rod between two anchors
  *   weld joints       b2WeldJoint.cpp:59-308       point + angle, rigid or with a soft angle
+ *   prismatic joints  b2PrismaticJoint.cpp:127-478 slider along an axis of body A, translation limit, motor
  * as rows of the coloured solver: inside every velocity iteration the joints run before the contacts, inside every
  * position iteration after them, as b2Island::Solve orders them (Dynamics/b2Island.cpp:259-273, :323-327, :363-380),
  * with warm starting.  A joint links the islands of its two bodies (b2World.cpp:1286-1320) and, unless
  * COLLIDE_CONNECTED, keeps them from colliding (b2Body::ShouldCollide, b2Body.cpp:428-449).  `type` uses b2JointType's
  * values; other types are refused with B2CU_ERR_UNSUPPORTED.
- * Fields by type: revolute  referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, flags LIMIT / MOTOR
- *                 distance  length, frequencyHz, dampingRatio
- *                 weld      referenceAngle, frequencyHz, dampingRatio
+ * Fields by type: revolute   referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, flags LIMIT / MOTOR
+ *                 prismatic  axis (b2PrismaticJointDef::localAxisA as given; normalised as the constructor does),
+ *                            referenceAngle, lowerAngle / upperAngle (= lower / upper translation), maxMotorTorque
+ *                            (= maxMotorForce), motorSpeed, flags LIMIT / MOTOR
+ *                 distance   length, frequencyHz, dampingRatio
+ *                 weld       referenceAngle, frequencyHz, dampingRatio
  * impulse / motorImpulse / limitState are the joint's persistent solver state (m_impulse -- a scalar in impulse[0] for
- * the distance joint --, m_motorImpulse, m_limitState) and round-trip through Get / Set; axis is written by the step:
- * the distance joint's unit vector m_u, which b2DistanceJoint::GetReactionForce needs. */
-enum { B2CU_JOINT_REVOLUTE = 1, B2CU_JOINT_DISTANCE = 3, B2CU_JOINT_WELD = 8 };
+ * the distance joint --, m_motorImpulse, m_limitState) and round-trip through Get / Set.  lastSolve is written by the
+ * step with the world-space directions of its solve, which GetReactionForce needs: the distance joint's m_u in
+ * [0..1], the prismatic joint's m_axis in [0..1] and m_perp in [2..3]. */
+enum { B2CU_JOINT_REVOLUTE = 1, B2CU_JOINT_PRISMATIC = 2, B2CU_JOINT_DISTANCE = 3, B2CU_JOINT_WELD = 8 };
 enum
 {
 	B2CU_JOINT_COLLIDE_CONNECTED = 1,
@@ -359,6 +364,7 @@ typedef struct b2cuJoint
 	float maxMotorTorque, motorSpeed;
 	float length, frequencyHz, dampingRatio;
 	float axis[2];
+	float lastSolve[4];
 	float impulse[3];
 	float motorImpulse;
 	int32_t limitState;

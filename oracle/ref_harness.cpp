@@ -134,6 +134,7 @@ struct b2refWorld
 	std::vector<std::pair<b2Fixture*, int32> > proxies;    // (fixture, child) of each proxy id
 	std::vector<b2Joint*> joints;                          // b2ref_set_joints, table order
 	std::unordered_map<const b2Joint*, int32> jointRank;   // position in the caller's solve order
+	std::unordered_map<const b2Joint*, b2Vec2> rawAxis;    // b2PrismaticJointDef::localAxisA as given (the joint keeps it normalised)
 };
 
 namespace
@@ -848,6 +849,31 @@ int32_t b2ref_set_joints(b2refWorld* w, int32_t count, const b2cuJoint* joints)
 			rj->m_limitState = (b2LimitState)j.limitState;
 			joint = rj;
 		}
+		else if (j.type == B2CU_JOINT_PRISMATIC)
+		{
+			b2PrismaticJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
+			def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+			def.localAxisA.Set(j.axis[0], j.axis[1]);
+			def.referenceAngle = j.referenceAngle;
+			def.enableLimit = (j.flags & B2CU_JOINT_ENABLE_LIMIT) != 0;
+			def.lowerTranslation = j.lowerAngle;
+			def.upperTranslation = j.upperAngle;
+			def.enableMotor = (j.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
+			def.motorSpeed = j.motorSpeed;
+			def.maxMotorForce = j.maxMotorTorque;
+			b2PrismaticJoint* pj = (b2PrismaticJoint*)w->world->CreateJoint(&def);
+			pj->m_impulse.Set(j.impulse[0], j.impulse[1], j.impulse[2]);
+			pj->m_motorImpulse = j.motorImpulse;
+			pj->m_limitState = (b2LimitState)j.limitState;
+			pj->m_axis.Set(j.lastSolve[0], j.lastSolve[1]);
+			pj->m_perp.Set(j.lastSolve[2], j.lastSolve[3]);
+			w->rawAxis[pj] = def.localAxisA;
+			joint = pj;
+		}
 		else if (j.type == B2CU_JOINT_DISTANCE)
 		{
 			b2DistanceJointDef def;
@@ -861,7 +887,7 @@ int32_t b2ref_set_joints(b2refWorld* w, int32_t count, const b2cuJoint* joints)
 			def.dampingRatio = j.dampingRatio;
 			b2DistanceJoint* dj = (b2DistanceJoint*)w->world->CreateJoint(&def);
 			dj->m_impulse = j.impulse[0];
-			dj->m_u.Set(j.axis[0], j.axis[1]);
+			dj->m_u.Set(j.lastSolve[0], j.lastSolve[1]);
 			joint = dj;
 		}
 		else if (j.type == B2CU_JOINT_WELD)
@@ -901,6 +927,14 @@ void b2ref_set_joint_order(b2refWorld* w, int32_t count, const int32_t* ids)
 
 void b2ref_joint_set_motor(b2refWorld* w, int32_t joint, int32_t enable, float speed, float maxTorque)
 {
+	if (w->joints[joint]->GetType() == e_prismaticJoint)
+	{
+		b2PrismaticJoint* pj = (b2PrismaticJoint*)w->joints[joint];
+		pj->EnableMotor(enable != 0);
+		pj->SetMotorSpeed(speed);
+		pj->SetMaxMotorForce(maxTorque);
+		return;
+	}
 	b2RevoluteJoint* j = (b2RevoluteJoint*)w->joints[joint];
 	j->EnableMotor(enable != 0);
 	j->SetMotorSpeed(speed);
@@ -909,6 +943,13 @@ void b2ref_joint_set_motor(b2refWorld* w, int32_t joint, int32_t enable, float s
 
 void b2ref_joint_set_limits(b2refWorld* w, int32_t joint, int32_t enable, float lower, float upper)
 {
+	if (w->joints[joint]->GetType() == e_prismaticJoint)
+	{
+		b2PrismaticJoint* pj = (b2PrismaticJoint*)w->joints[joint];
+		pj->EnableLimit(enable != 0);
+		pj->SetLimits(lower, upper);
+		return;
+	}
 	b2RevoluteJoint* j = (b2RevoluteJoint*)w->joints[joint];
 	j->EnableLimit(enable != 0);
 	j->SetLimits(lower, upper);
@@ -935,6 +976,7 @@ void b2ref_joint_set_spring(b2refWorld* w, int32_t joint, float length, float fr
 void b2ref_destroy_joint(b2refWorld* w, int32_t joint)
 {
 	w->jointRank.erase(w->joints[joint]);
+	w->rawAxis.erase(w->joints[joint]);
 	w->world->DestroyJoint(w->joints[joint]);
 	w->joints.erase(w->joints.begin() + joint);
 }
@@ -956,6 +998,13 @@ void b2ref_joint_readings(b2refWorld* w, float inv_dt, float* out6)
 			const b2RevoluteJoint* j = (const b2RevoluteJoint*)base;
 			o[3] = j->GetMotorTorque(inv_dt);
 			o[4] = j->GetJointAngle();
+			o[5] = j->GetJointSpeed();
+		}
+		else if (base->GetType() == e_prismaticJoint)
+		{
+			const b2PrismaticJoint* j = (const b2PrismaticJoint*)base;
+			o[3] = j->GetMotorForce(inv_dt);
+			o[4] = j->GetJointTranslation();
 			o[5] = j->GetJointSpeed();
 		}
 	}
@@ -994,6 +1043,33 @@ void b2ref_export_joints(b2refWorld* w, b2cuJoint* out)
 			o.motorImpulse = j->m_motorImpulse;
 			o.limitState = (int32_t)j->m_limitState;
 		}
+		else if (base->GetType() == e_prismaticJoint)
+		{
+			const b2PrismaticJoint* j = (const b2PrismaticJoint*)base;
+			o.type = B2CU_JOINT_PRISMATIC;
+			o.flags |= (j->m_enableLimit ? B2CU_JOINT_ENABLE_LIMIT : 0) | (j->m_enableMotor ? B2CU_JOINT_ENABLE_MOTOR : 0);
+			o.localAnchorA[0] = j->m_localAnchorA.x;
+			o.localAnchorA[1] = j->m_localAnchorA.y;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			b2Vec2 raw = w->rawAxis[j];
+			o.axis[0] = raw.x;
+			o.axis[1] = raw.y;
+			o.referenceAngle = j->m_referenceAngle;
+			o.lowerAngle = j->m_lowerTranslation;
+			o.upperAngle = j->m_upperTranslation;
+			o.maxMotorTorque = j->m_maxMotorForce;
+			o.motorSpeed = j->m_motorSpeed;
+			o.impulse[0] = j->m_impulse.x;
+			o.impulse[1] = j->m_impulse.y;
+			o.impulse[2] = j->m_impulse.z;
+			o.motorImpulse = j->m_motorImpulse;
+			o.limitState = (int32_t)j->m_limitState;
+			o.lastSolve[0] = j->m_axis.x;
+			o.lastSolve[1] = j->m_axis.y;
+			o.lastSolve[2] = j->m_perp.x;
+			o.lastSolve[3] = j->m_perp.y;
+		}
 		else if (base->GetType() == e_distanceJoint)
 		{
 			const b2DistanceJoint* j = (const b2DistanceJoint*)base;
@@ -1006,8 +1082,8 @@ void b2ref_export_joints(b2refWorld* w, b2cuJoint* out)
 			o.frequencyHz = j->m_frequencyHz;
 			o.dampingRatio = j->m_dampingRatio;
 			o.impulse[0] = j->m_impulse;
-			o.axis[0] = j->m_u.x;
-			o.axis[1] = j->m_u.y;
+			o.lastSolve[0] = j->m_u.x;
+			o.lastSolve[1] = j->m_u.y;
 		}
 		else
 		{

@@ -148,13 +148,13 @@ def test_host_api_lockstep(gpu, name, steps):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,steps", [("tumbler_joint", 150), ("hanging_chains", 300), ("joint_zoo", 300),
-                                        ("rods_and_welds", 300)])
+                                        ("rods_and_welds", 300), ("sliders", 300)])
 def test_host_api_joints_lockstep(gpu, name, steps):
     """Worlds with revolute, distance and weld joints built through b2World::CreateJoint (the Testbed's Tumbler with its
     motor joint, hanging chains, every branch of the revolute joint, the Web and the Cantilever) and stepped through
     b2World::Step stay bit-identical to the reference: bodies, events and what the joints' accessors report."""
     make = {"tumbler_joint": lambda: scenes.tumbler(60, motor_joint=True), "hanging_chains": lambda: scenes.hanging_chains(3, 10),
-            "joint_zoo": scenes.joint_zoo, "rods_and_welds": scenes.rods_and_welds}[name]
+            "joint_zoo": scenes.joint_zoo, "rods_and_welds": scenes.rods_and_welds, "sliders": scenes.sliders}[name]
     h, r, begins = _host_lockstep(make(), steps)
     assert h.joint_count() == r.joint_count > 0
     assert h.hash() == r.hash()
@@ -218,6 +218,32 @@ def test_host_api_tumbler_with_bodies_created_between_steps(gpu):
             raise AssertionError("step %d: %s" % (s, e))
     assert h.counts()[2] == r.counts()[2]
     parity.assert_floats_equal("joint readings", h.joint_readings(), r.joint_readings())
+
+
+@pytest.mark.gpu
+def test_host_api_slider_edits_between_steps(gpu):
+    """b2PrismaticJoint::EnableMotor / SetMotorSpeed / SetMaxMotorForce / EnableLimit / SetLimits between steps."""
+    scene = scenes.sliders()
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+
+    def run(n):
+        for s in range(n):
+            h.step()
+            r.set_joint_order(h.joint_order())
+            assert r.step_ordered(h.solver_order()) == 0
+            parity.compare_bodies(h.bodies(), r.bodies())
+            parity.assert_floats_equal("joint readings", h.joint_readings(), r.joint_readings())
+
+    run(60)
+    for w in (h, r):
+        w.joint_set_motor(0, True, -5.0, 2000.0)   # the strong motor reverses
+        w.joint_set_motor(1, True, 1.0, 100.0)     # a passive slider gets a motor
+        w.joint_set_limits(3, True, -1.0, 1.0)     # an unlimited one gets limits
+        w.joint_set_limits(4, False, -0.5, 3.0)    # limits removed
+        w.joint_set_limits(2, True, 0.5, 2.5)      # equal limits open up
+    run(120)
 
 
 @pytest.mark.gpu
