@@ -1,7 +1,8 @@
 // b2cu_joints.cuh -- joints as rows of the coloured solver.  Restates InitVelocityConstraints / SolveVelocityConstraints
 // / SolvePositionConstraints of b2RevoluteJoint (Box2D/Dynamics/Joints/b2RevoluteJoint.cpp:64-400), b2DistanceJoint
 // (b2DistanceJoint.cpp:63-222), b2WeldJoint (b2WeldJoint.cpp:59-308) and b2PrismaticJoint
-// (b2PrismaticJoint.cpp:100-478), and the small linear solves they use
+// (b2PrismaticJoint.cpp:100-478), b2WheelJoint (b2WheelJoint.cpp:78-318), b2RopeJoint (b2RopeJoint.cpp:47-195),
+// b2FrictionJoint (b2FrictionJoint.cpp:58-190) and b2MotorJoint (b2MotorJoint.cpp:66-200), and the small linear solves they use
 // (b2Mat33::Solve33 / Solve22 / GetInverse22 / GetSymInverse33, Box2D/Common/b2Math.cpp:25-94; b2Mat22::Solve,
 // b2Math.h:221-233) with the same fp32 arithmetic in the same order.  One thread solves one joint; joints of one colour class share no
 // dynamic body, so a class is solved in parallel and the classes one after the other.
@@ -1014,6 +1015,466 @@ __device__ __forceinline__ bool PrismaticSolvePosition(const DeviceArrays& d, co
 	return linearError <= B2CU_LINEAR_SLOP && angularError <= B2CU_ANGULAR_SLOP;
 }
 
+// ---- wheel joint (b2WheelJoint.cpp:78-318) ------------------------------------------------------------------------------
+// Row use: axis = m_ax, perp = m_ay, a1 = m_sAx, a2 = m_sBx, s1 = m_sAy, s2 = m_sBy, motorMass = m_motorMass, gamma / bias,
+// ex.x = m_mass, ex.y = m_springMass.  With the spring off the reference leaves m_ax, m_sAx and m_sBx at whatever they were
+// and still runs the spring row with them (its mass is 0, so only signs of zero are at stake): they persist in
+// lastSolve[0..1] and work[0..1].
+
+__device__ __forceinline__ void WheelInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio, int warmStarting,
+                                          float h)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+
+	Rot qA = SinCos(pA.z), qB = SinCos(pB.z);
+	Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	Vec2 dd = cB + rB - cA - rA;
+	Vec2 localX = V(jt.axis[0], jt.axis[1]); // not normalised by the reference either
+	Vec2 localY = CrossSV(1.0f, localX);
+
+	// point on line
+	r.perp = Mul(qA, localY);
+	r.s1 = Cross(dd + rA, r.perp);
+	r.s2 = Cross(rB, r.perp);
+	float mass = mA + mB + iA * r.s1 * r.s1 + iB * r.s2 * r.s2;
+	if (mass > 0.0f) mass = 1.0f / mass;
+
+	// spring
+	float springMass = 0.0f;
+	r.bias = 0.0f;
+	r.gamma = 0.0f;
+	r.axis = V(jt.lastSolve[0], jt.lastSolve[1]);
+	r.a1 = jt.work[0];
+	r.a2 = jt.work[1];
+	if (jt.frequencyHz > 0.0f)
+	{
+		r.axis = Mul(qA, localX);
+		r.a1 = Cross(dd + rA, r.axis);
+		r.a2 = Cross(rB, r.axis);
+		float invMass = mA + mB + iA * r.a1 * r.a1 + iB * r.a2 * r.a2;
+		if (invMass > 0.0f)
+		{
+			springMass = 1.0f / invMass;
+			float C = Dot(dd, r.axis);
+			float omega = 2.0f * B2CU_PI * jt.frequencyHz;
+			float damp = 2.0f * springMass * jt.dampingRatio * omega;
+			float k = springMass * omega * omega;
+			r.gamma = h * (damp + h * k);
+			if (r.gamma > 0.0f) r.gamma = 1.0f / r.gamma;
+			r.bias = C * h * k * r.gamma;
+			springMass = invMass + r.gamma;
+			if (springMass > 0.0f) springMass = 1.0f / springMass;
+		}
+	}
+	else
+	{
+		jt.impulse[1] = 0.0f;
+	}
+
+	// motor
+	if (jt.flags & B2CU_JOINT_ENABLE_MOTOR)
+	{
+		r.motorMass = iA + iB;
+		if (r.motorMass > 0.0f) r.motorMass = 1.0f / r.motorMass;
+	}
+	else
+	{
+		r.motorMass = 0.0f;
+		jt.motorImpulse = 0.0f;
+	}
+	r.ex = V3(mass, springMass, 0.0f);
+
+	if (warmStarting)
+	{
+		jt.impulse[0] *= dtRatio;
+		jt.impulse[1] *= dtRatio;
+		jt.motorImpulse *= dtRatio;
+		Vec2 P = jt.impulse[0] * r.perp + jt.impulse[1] * r.axis;
+		float LA = jt.impulse[0] * r.s1 + jt.impulse[1] * r.a1 + jt.motorImpulse;
+		float LB = jt.impulse[0] * r.s2 + jt.impulse[1] * r.a2 + jt.motorImpulse;
+		vA = vA - mA * P;
+		wA -= iA * LA;
+		vB = vB + mB * P;
+		wB += iB * LB;
+	}
+	else
+	{
+		jt.impulse[0] = 0.0f;
+		jt.impulse[1] = 0.0f;
+		jt.motorImpulse = 0.0f;
+	}
+
+	StoreVelocity(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, mB, iB, vB, wB, vB4.w);
+	jt.lastSolve[0] = r.axis.x;
+	jt.lastSolve[1] = r.axis.y;
+	jt.lastSolve[2] = r.perp.x;
+	jt.lastSolve[3] = r.perp.y;
+	jt.work[0] = r.a1;
+	jt.work[1] = r.a2;
+	d.jointRows[j] = r;
+	d.joints[j] = jt;
+}
+
+__device__ __forceinline__ void WheelSolveVelocity(const DeviceArrays& d, int j, const JointRow& r, b2cuJoint jt, float h)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+
+	// spring
+	{
+		float Cdot = Dot(r.axis, vB - vA) + r.a2 * wB - r.a1 * wA;
+		float impulse = -r.ex.y * (Cdot + r.bias + r.gamma * jt.impulse[1]);
+		jt.impulse[1] += impulse;
+		Vec2 P = impulse * r.axis;
+		float LA = impulse * r.a1;
+		float LB = impulse * r.a2;
+		vA = vA - mA * P;
+		wA -= iA * LA;
+		vB = vB + mB * P;
+		wB += iB * LB;
+	}
+	// motor
+	{
+		float Cdot = wB - wA - jt.motorSpeed;
+		float impulse = -r.motorMass * Cdot;
+		float oldImpulse = jt.motorImpulse;
+		float maxImpulse = h * jt.maxMotorTorque;
+		jt.motorImpulse = Clamp(jt.motorImpulse + impulse, -maxImpulse, maxImpulse);
+		impulse = jt.motorImpulse - oldImpulse;
+		wA -= iA * impulse;
+		wB += iB * impulse;
+	}
+	// point on line
+	{
+		float Cdot = Dot(r.perp, vB - vA) + r.s2 * wB - r.s1 * wA;
+		float impulse = -r.ex.x * Cdot;
+		jt.impulse[0] += impulse;
+		Vec2 P = impulse * r.perp;
+		float LA = impulse * r.s1;
+		float LB = impulse * r.s2;
+		vA = vA - mA * P;
+		wA -= iA * LA;
+		vB = vB + mB * P;
+		wB += iB * LB;
+	}
+
+	StoreVelocity(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, mB, iB, vB, wB, vB4.w);
+	d.joints[j].impulse[0] = jt.impulse[0];
+	d.joints[j].impulse[1] = jt.impulse[1];
+	d.joints[j].motorImpulse = jt.motorImpulse;
+}
+
+__device__ __forceinline__ bool WheelSolvePosition(const DeviceArrays& d, const JointRow& r, const b2cuJoint& jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	float aA = pA.z, aB = pB.z;
+
+	Rot qA = SinCos(aA), qB = SinCos(aB);
+	Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	Vec2 dd = (cB - cA) + rB - rA;
+	Vec2 ay = Mul(qA, CrossSV(1.0f, V(jt.axis[0], jt.axis[1])));
+
+	float sAy = Cross(dd + rA, ay);
+	float sBy = Cross(rB, ay);
+	float C = Dot(dd, ay);
+
+	// the reference uses the Jacobian terms of the velocity solve here (m_sAy, m_sBy), not the fresh ones
+	float k = r.invMassA + r.invMassB + r.invIA * r.s1 * r.s1 + r.invIB * r.s2 * r.s2;
+	float impulse = k != 0.0f ? -C / k : 0.0f;
+
+	Vec2 P = impulse * ay;
+	float LA = impulse * sAy;
+	float LB = impulse * sBy;
+	cA = cA - r.invMassA * P;
+	aA -= r.invIA * LA;
+	cB = cB + r.invMassB * P;
+	aB += r.invIB * LB;
+
+	if (r.invMassA != 0.0f || r.invIA != 0.0f) d.pos[bA] = make_float4(cA.x, cA.y, aA, pA.w);
+	if (r.invMassB != 0.0f || r.invIB != 0.0f) d.pos[bB] = make_float4(cB.x, cB.y, aB, pB.w);
+	return Abs(C) <= B2CU_LINEAR_SLOP;
+}
+
+// ---- rope joint (b2RopeJoint.cpp:47-195) --------------------------------------------------------------------------------
+// Row use: u = m_u, motorMass = m_mass, bias = m_length.  limitState = m_state.
+
+__device__ __forceinline__ void RopeInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio, int warmStarting)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+
+	Rot qA = SinCos(pA.z), qB = SinCos(pB.z);
+	r.rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	r.rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	r.u = cB + r.rB - cA - r.rA;
+	r.bias = Length(r.u);
+
+	float C = r.bias - jt.length;
+	jt.limitState = C > 0.0f ? B2CU_LIMIT_AT_UPPER : B2CU_LIMIT_INACTIVE;
+
+	if (r.bias > B2CU_LINEAR_SLOP)
+	{
+		r.u = (1.0f / r.bias) * r.u;
+	}
+	else
+	{
+		// slack and degenerate: nothing to apply, the velocities stay as they are
+		r.u = V(0.0f, 0.0f);
+		r.motorMass = 0.0f;
+		jt.impulse[0] = 0.0f;
+		jt.lastSolve[0] = jt.lastSolve[1] = 0.0f;
+		d.jointRows[j] = r;
+		d.joints[j] = jt;
+		return;
+	}
+
+	float crA = Cross(r.rA, r.u);
+	float crB = Cross(r.rB, r.u);
+	float invMass = r.invMassA + r.invIA * crA * crA + r.invMassB + r.invIB * crB * crB;
+	r.motorMass = invMass != 0.0f ? 1.0f / invMass : 0.0f;
+
+	if (warmStarting)
+	{
+		jt.impulse[0] *= dtRatio;
+		Vec2 P = jt.impulse[0] * r.u;
+		vA = vA - r.invMassA * P;
+		wA -= r.invIA * Cross(r.rA, P);
+		vB = vB + r.invMassB * P;
+		wB += r.invIB * Cross(r.rB, P);
+	}
+	else
+	{
+		jt.impulse[0] = 0.0f;
+	}
+
+	StoreVelocity(d, bA, r.invMassA, r.invIA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, r.invMassB, r.invIB, vB, wB, vB4.w);
+	jt.lastSolve[0] = r.u.x;
+	jt.lastSolve[1] = r.u.y;
+	d.jointRows[j] = r;
+	d.joints[j] = jt;
+}
+
+__device__ __forceinline__ void RopeSolveVelocity(const DeviceArrays& d, int j, const JointRow& r, const b2cuJoint& jt, float h)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+
+	Vec2 vpA = vA + CrossSV(wA, r.rA);
+	Vec2 vpB = vB + CrossSV(wB, r.rB);
+	float C = r.bias - jt.length;
+	float Cdot = Dot(r.u, vpB - vpA);
+	// the rope is still slack: let it run out exactly this step
+	if (C < 0.0f) Cdot += (1.0f / h) * C;
+
+	float impulse = -r.motorMass * Cdot;
+	float oldImpulse = jt.impulse[0];
+	float total = Min(0.0f, oldImpulse + impulse);
+	impulse = total - oldImpulse;
+
+	Vec2 P = impulse * r.u;
+	vA = vA - r.invMassA * P;
+	wA -= r.invIA * Cross(r.rA, P);
+	vB = vB + r.invMassB * P;
+	wB += r.invIB * Cross(r.rB, P);
+
+	StoreVelocity(d, bA, r.invMassA, r.invIA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, r.invMassB, r.invIB, vB, wB, vB4.w);
+	d.joints[j].impulse[0] = total;
+}
+
+__device__ __forceinline__ bool RopeSolvePosition(const DeviceArrays& d, const JointRow& r, const b2cuJoint& jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	float aA = pA.z, aB = pB.z;
+
+	Rot qA = SinCos(aA), qB = SinCos(aB);
+	Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	Vec2 u = cB + rB - cA - rA;
+
+	float length = Length(u);
+	if (length < B2CU_EPSILON)
+	{
+		length = 0.0f;
+	}
+	else
+	{
+		float inv = 1.0f / length;
+		u = V(u.x * inv, u.y * inv);
+	}
+	float C = length - jt.length;
+	C = Clamp(C, 0.0f, B2CU_MAX_LINEAR_CORRECTION);
+
+	float impulse = -r.motorMass * C;
+	Vec2 P = impulse * u;
+	cA = cA - r.invMassA * P;
+	aA -= r.invIA * Cross(rA, P);
+	cB = cB + r.invMassB * P;
+	aB += r.invIB * Cross(rB, P);
+
+	if (r.invMassA != 0.0f || r.invIA != 0.0f) d.pos[bA] = make_float4(cA.x, cA.y, aA, pA.w);
+	if (r.invMassB != 0.0f || r.invIB != 0.0f) d.pos[bB] = make_float4(cB.x, cB.y, aB, pB.w);
+	return length - jt.length < B2CU_LINEAR_SLOP;
+}
+
+// ---- friction joint (b2FrictionJoint.cpp:58-190) and motor joint (b2MotorJoint.cpp:66-200) -------------------------------
+// Both apply a bounded linear and a bounded angular impulse; the motor joint drives towards an offset instead of rest.
+// Row use: ex.x, ex.y, ey.x, ey.y = m_linearMass (ex, ey columns), motorMass = m_angularMass, u = m_linearError,
+// bias = m_angularError.  Record: length = maxForce, maxMotorTorque = maxTorque; motor joint: axis = linearOffset,
+// referenceAngle = angularOffset, dampingRatio = correctionFactor.  impulse[0..1] = m_linearImpulse, impulse[2] = m_angularImpulse.
+
+__device__ __forceinline__ void FrictionMotorInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio,
+                                                  int warmStarting, bool motor)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	float aA = pA.z, aB = pB.z;
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+
+	Rot qA = SinCos(aA), qB = SinCos(aB);
+	if (motor)
+	{
+		r.rA = Mul(qA, V(jt.axis[0], jt.axis[1]) - r.localCenterA);
+		r.rB = Mul(qB, -r.localCenterB);
+	}
+	else
+	{
+		r.rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+		r.rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	}
+
+	float kxx = mA + mB + iA * r.rA.y * r.rA.y + iB * r.rB.y * r.rB.y;
+	float kxy = -iA * r.rA.x * r.rA.y - iB * r.rB.x * r.rB.y;
+	float kyy = mA + mB + iA * r.rA.x * r.rA.x + iB * r.rB.x * r.rB.x;
+	{
+		// b2Mat22::GetInverse of ex = (kxx, kxy), ey = (kxy, kyy)
+		float a = kxx, b = kxy, c = kxy, dd = kyy;
+		float det = a * dd - b * c;
+		if (det != 0.0f) det = 1.0f / det;
+		r.ex = V3(det * dd, -det * c, 0.0f);
+		r.ey = V3(-det * b, det * a, 0.0f);
+	}
+	r.motorMass = iA + iB;
+	if (r.motorMass > 0.0f) r.motorMass = 1.0f / r.motorMass;
+
+	if (motor)
+	{
+		r.u = cB + r.rB - cA - r.rA;
+		r.bias = aB - aA - jt.referenceAngle;
+	}
+
+	if (warmStarting)
+	{
+		jt.impulse[0] *= dtRatio;
+		jt.impulse[1] *= dtRatio;
+		jt.impulse[2] *= dtRatio;
+		Vec2 P = V(jt.impulse[0], jt.impulse[1]);
+		vA = vA - mA * P;
+		wA -= iA * (Cross(r.rA, P) + jt.impulse[2]);
+		vB = vB + mB * P;
+		wB += iB * (Cross(r.rB, P) + jt.impulse[2]);
+	}
+	else
+	{
+		jt.impulse[0] = jt.impulse[1] = jt.impulse[2] = 0.0f;
+	}
+
+	StoreVelocity(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, mB, iB, vB, wB, vB4.w);
+	d.jointRows[j] = r;
+	d.joints[j] = jt;
+}
+
+__device__ __forceinline__ void FrictionMotorSolveVelocity(const DeviceArrays& d, int j, const JointRow& r, b2cuJoint jt, float h,
+                                                           bool motor)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	float mA = r.invMassA, mB = r.invMassB;
+	float iA = r.invIA, iB = r.invIB;
+	const float inv_h = 1.0f / h;
+
+	// angular part
+	{
+		float Cdot = wB - wA;
+		if (motor) Cdot = wB - wA + inv_h * jt.dampingRatio * r.bias;
+		float impulse = -r.motorMass * Cdot;
+		float oldImpulse = jt.impulse[2];
+		float maxImpulse = h * jt.maxMotorTorque;
+		jt.impulse[2] = Clamp(oldImpulse + impulse, -maxImpulse, maxImpulse);
+		impulse = jt.impulse[2] - oldImpulse;
+		wA -= iA * impulse;
+		wB += iB * impulse;
+	}
+	// linear part
+	{
+		Vec2 Cdot = vB + CrossSV(wB, r.rB) - vA - CrossSV(wA, r.rA);
+		if (motor) Cdot = Cdot + (inv_h * jt.dampingRatio) * r.u;
+		Vec2 mv = V(r.ex.x * Cdot.x + r.ey.x * Cdot.y, r.ex.y * Cdot.x + r.ey.y * Cdot.y);
+		Vec2 impulse = -mv;
+		Vec2 oldImpulse = V(jt.impulse[0], jt.impulse[1]);
+		Vec2 total = oldImpulse + impulse;
+		float maxImpulse = h * jt.length;
+		if (Dot(total, total) > maxImpulse * maxImpulse)
+		{
+			// b2Vec2::Normalize, then scale
+			float length = Length(total);
+			if (!(length < B2CU_EPSILON))
+			{
+				float inv = 1.0f / length;
+				total = V(total.x * inv, total.y * inv);
+			}
+			total = V(total.x * maxImpulse, total.y * maxImpulse);
+		}
+		impulse = total - oldImpulse;
+		jt.impulse[0] = total.x;
+		jt.impulse[1] = total.y;
+		vA = vA - mA * impulse;
+		wA -= iA * Cross(r.rA, impulse);
+		vB = vB + mB * impulse;
+		wB += iB * Cross(r.rB, impulse);
+	}
+
+	StoreVelocity(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, mB, iB, vB, wB, vB4.w);
+	d.joints[j].impulse[0] = jt.impulse[0];
+	d.joints[j].impulse[1] = jt.impulse[1];
+	d.joints[j].impulse[2] = jt.impulse[2];
+}
+
 // ---- dispatch by joint type -------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float dtRatio, int warmStarting, float h)
@@ -1028,6 +1489,10 @@ __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float
 	if (jt.type == B2CU_JOINT_REVOLUTE) RevoluteInit(d, j, jt, r, dtRatio, warmStarting);
 	else if (jt.type == B2CU_JOINT_PRISMATIC) PrismaticInit(d, j, jt, r, dtRatio, warmStarting);
 	else if (jt.type == B2CU_JOINT_DISTANCE) DistanceInit(d, j, jt, r, dtRatio, warmStarting, h);
+	else if (jt.type == B2CU_JOINT_WHEEL) WheelInit(d, j, jt, r, dtRatio, warmStarting, h);
+	else if (jt.type == B2CU_JOINT_ROPE) RopeInit(d, j, jt, r, dtRatio, warmStarting);
+	else if (jt.type == B2CU_JOINT_FRICTION) FrictionMotorInit(d, j, jt, r, dtRatio, warmStarting, false);
+	else if (jt.type == B2CU_JOINT_MOTOR) FrictionMotorInit(d, j, jt, r, dtRatio, warmStarting, true);
 	else WeldInit(d, j, jt, r, dtRatio, warmStarting, h);
 }
 
@@ -1039,6 +1504,10 @@ __device__ __forceinline__ void JointSolveVelocityOne(const DeviceArrays& d, int
 	if (jt.type == B2CU_JOINT_REVOLUTE) RevoluteSolveVelocity(d, j, r, jt, h);
 	else if (jt.type == B2CU_JOINT_PRISMATIC) PrismaticSolveVelocity(d, j, r, jt, h);
 	else if (jt.type == B2CU_JOINT_DISTANCE) DistanceSolveVelocity(d, j, r, jt);
+	else if (jt.type == B2CU_JOINT_WHEEL) WheelSolveVelocity(d, j, r, jt, h);
+	else if (jt.type == B2CU_JOINT_ROPE) RopeSolveVelocity(d, j, r, jt, h);
+	else if (jt.type == B2CU_JOINT_FRICTION) FrictionMotorSolveVelocity(d, j, r, jt, h, false);
+	else if (jt.type == B2CU_JOINT_MOTOR) FrictionMotorSolveVelocity(d, j, r, jt, h, true);
 	else WeldSolveVelocity(d, j, r, jt);
 }
 
@@ -1048,6 +1517,9 @@ __device__ __forceinline__ bool JointSolvePositionOne(const DeviceArrays& d, int
 	if (jt.type == B2CU_JOINT_REVOLUTE) return RevoluteSolvePosition(d, r, jt);
 	if (jt.type == B2CU_JOINT_PRISMATIC) return PrismaticSolvePosition(d, r, jt);
 	if (jt.type == B2CU_JOINT_DISTANCE) return DistanceSolvePosition(d, r, jt);
+	if (jt.type == B2CU_JOINT_WHEEL) return WheelSolvePosition(d, r, jt);
+	if (jt.type == B2CU_JOINT_ROPE) return RopeSolvePosition(d, r, jt);
+	if (jt.type == B2CU_JOINT_FRICTION || jt.type == B2CU_JOINT_MOTOR) return true;
 	return WeldSolvePosition(d, r, jt);
 }
 

@@ -1025,9 +1025,9 @@ int b2cuSetJoints(b2cuWorld* w, int32_t count, const b2cuJoint* joints)
 	{
 		const b2cuJoint& jt = joints[j];
 		if (jt.type != B2CU_JOINT_REVOLUTE && jt.type != B2CU_JOINT_PRISMATIC && jt.type != B2CU_JOINT_DISTANCE &&
-		    jt.type != B2CU_JOINT_WELD)
-			return SetError(w, B2CU_ERR_UNSUPPORTED, "joint %d: type %d (revolute, prismatic, distance and weld joints are solved)",
-			                j, jt.type);
+		    jt.type != B2CU_JOINT_WELD && jt.type != B2CU_JOINT_WHEEL && jt.type != B2CU_JOINT_ROPE &&
+		    jt.type != B2CU_JOINT_FRICTION && jt.type != B2CU_JOINT_MOTOR)
+			return SetError(w, B2CU_ERR_UNSUPPORTED, "joint %d: type %d (pulley, gear and mouse joints are not solved)", j, jt.type);
 		if (jt.bodyA < 0 || jt.bodyA >= w->bodyCount || jt.bodyB < 0 || jt.bodyB >= w->bodyCount || jt.bodyA == jt.bodyB)
 			return SetError(w, B2CU_ERR_ARGUMENT, "joint %d: bodies %d, %d", j, jt.bodyA, jt.bodyB);
 		if (!(jt.flags & B2CU_JOINT_COLLIDE_CONNECTED))

@@ -433,6 +433,58 @@ B2H_API int b2h_create_joints(void* p, int32 count, const b2cuJoint* rows)
 			def.maxMotorForce = r.maxMotorTorque;
 			j = h->world->CreateJoint(&def);
 		}
+		else if (r.type == B2CU_JOINT_WHEEL)
+		{
+			b2WheelJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
+			def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
+			def.localAxisA.Set(r.axis[0], r.axis[1]);
+			def.enableMotor = (r.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
+			def.maxMotorTorque = r.maxMotorTorque;
+			def.motorSpeed = r.motorSpeed;
+			def.frequencyHz = r.frequencyHz;
+			def.dampingRatio = r.dampingRatio;
+			j = h->world->CreateJoint(&def);
+		}
+		else if (r.type == B2CU_JOINT_ROPE)
+		{
+			b2RopeJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
+			def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
+			def.maxLength = r.length;
+			j = h->world->CreateJoint(&def);
+		}
+		else if (r.type == B2CU_JOINT_FRICTION)
+		{
+			b2FrictionJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
+			def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
+			def.maxForce = r.length;
+			def.maxTorque = r.maxMotorTorque;
+			j = h->world->CreateJoint(&def);
+		}
+		else if (r.type == B2CU_JOINT_MOTOR)
+		{
+			b2MotorJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.linearOffset.Set(r.axis[0], r.axis[1]);
+			def.angularOffset = r.referenceAngle;
+			def.maxForce = r.length;
+			def.maxTorque = r.maxMotorTorque;
+			def.correctionFactor = r.dampingRatio;
+			j = h->world->CreateJoint(&def);
+		}
 		else if (r.type == B2CU_JOINT_DISTANCE)
 		{
 			b2DistanceJointDef def;
@@ -502,6 +554,13 @@ B2H_API void b2h_joint_readings(void* p, float inv_dt, float* out6)
 			o[3] = j->GetMotorForce(inv_dt);
 			o[4] = j->GetJointTranslation();
 			o[5] = j->GetJointSpeed();
+		}
+		else if (base->GetType() == e_wheelJoint)
+		{
+			const b2WheelJoint* j = static_cast<const b2WheelJoint*>(base);
+			o[3] = j->GetMotorTorque(inv_dt);
+			o[4] = j->GetJointTranslation();
+			o[5] = j->GetJointLinearSpeed();
 		}
 	}
 }

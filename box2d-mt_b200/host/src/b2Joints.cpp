@@ -6,6 +6,10 @@
 #include "Box2D/Dynamics/Joints/b2DistanceJoint.h"
 #include "Box2D/Dynamics/Joints/b2WeldJoint.h"
 #include "Box2D/Dynamics/Joints/b2PrismaticJoint.h"
+#include "Box2D/Dynamics/Joints/b2WheelJoint.h"
+#include "Box2D/Dynamics/Joints/b2RopeJoint.h"
+#include "Box2D/Dynamics/Joints/b2FrictionJoint.h"
+#include "Box2D/Dynamics/Joints/b2MotorJoint.h"
 #include "Box2D/Dynamics/b2Body.h"
 #include "Box2D/Dynamics/b2World.h"
 
@@ -443,4 +447,351 @@ void b2PrismaticJoint::SetMaxMotorForce(float32 force)
 	Touch();
 	WakeBodies();
 	m_maxMotorForce = force;
+}
+
+// ---- wheel (reference b2WheelJoint.cpp:40-76, :320-470) ------------------------------------------------------------------
+
+void b2WheelJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor, const b2Vec2& axis)
+{
+	bodyA = bA;
+	bodyB = bB;
+	localAnchorA = bA->GetLocalPoint(anchor);
+	localAnchorB = bB->GetLocalPoint(anchor);
+	localAxisA = bA->GetLocalVector(axis);
+}
+
+b2WheelJoint::b2WheelJoint(const b2WheelJointDef* def)
+	: b2Joint(def), m_localAnchorA(def->localAnchorA), m_localAnchorB(def->localAnchorB), m_localXAxisA(def->localAxisA),
+	  m_enableMotor(def->enableMotor), m_maxMotorTorque(def->maxMotorTorque), m_motorSpeed(def->motorSpeed),
+	  m_frequencyHz(def->frequencyHz), m_dampingRatio(def->dampingRatio), m_impulse(0.0f), m_springImpulse(0.0f),
+	  m_motorImpulse(0.0f), m_ax(0.0f, 0.0f), m_ay(0.0f, 0.0f), m_sAx(0.0f), m_sBx(0.0f)
+{
+}
+
+void b2WheelJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_WHEEL, m_bodyA, m_bodyB, m_collideConnected, m_localAnchorA, m_localAnchorB);
+	out->flags |= m_enableMotor ? B2CU_JOINT_ENABLE_MOTOR : 0u;
+	out->axis[0] = m_localXAxisA.x;
+	out->axis[1] = m_localXAxisA.y;
+	out->maxMotorTorque = m_maxMotorTorque;
+	out->motorSpeed = m_motorSpeed;
+	out->frequencyHz = m_frequencyHz;
+	out->dampingRatio = m_dampingRatio;
+	out->impulse[0] = m_impulse;
+	out->impulse[1] = m_springImpulse;
+	out->motorImpulse = m_motorImpulse;
+	out->lastSolve[0] = m_ax.x;
+	out->lastSolve[1] = m_ax.y;
+	out->lastSolve[2] = m_ay.x;
+	out->lastSolve[3] = m_ay.y;
+	out->work[0] = m_sAx;
+	out->work[1] = m_sBx;
+}
+
+void b2WheelJoint::ReadRecord(const b2cuJoint& in)
+{
+	m_impulse = in.impulse[0];
+	m_springImpulse = in.impulse[1];
+	m_motorImpulse = in.motorImpulse;
+	m_ax.Set(in.lastSolve[0], in.lastSolve[1]);
+	m_ay.Set(in.lastSolve[2], in.lastSolve[3]);
+	m_sAx = in.work[0];
+	m_sBx = in.work[1];
+}
+
+b2Vec2 b2WheelJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2WheelJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+b2Vec2 b2WheelJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * (m_impulse * m_ay + m_springImpulse * m_ax);
+}
+
+float32 b2WheelJoint::GetReactionTorque(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_motorImpulse;
+}
+
+float32 b2WheelJoint::GetMotorTorque(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_motorImpulse;
+}
+
+float32 b2WheelJoint::GetJointTranslation() const
+{
+	b2Vec2 d = m_bodyB->GetWorldPoint(m_localAnchorB) - m_bodyA->GetWorldPoint(m_localAnchorA);
+	return b2Dot(d, m_bodyA->GetWorldVector(m_localXAxisA));
+}
+
+float32 b2WheelJoint::GetJointLinearSpeed() const
+{
+	const b2Rot& qA = m_bodyA->GetTransform().q;
+	const b2Rot& qB = m_bodyB->GetTransform().q;
+	b2Vec2 rA = b2Mul(qA, m_localAnchorA - m_bodyA->GetLocalCenter());
+	b2Vec2 rB = b2Mul(qB, m_localAnchorB - m_bodyB->GetLocalCenter());
+	b2Vec2 p1 = m_bodyA->GetWorldCenter() + rA;
+	b2Vec2 p2 = m_bodyB->GetWorldCenter() + rB;
+	b2Vec2 d = p2 - p1;
+	b2Vec2 axis = b2Mul(qA, m_localXAxisA);
+	b2Vec2 vA = m_bodyA->GetLinearVelocity(), vB = m_bodyB->GetLinearVelocity();
+	float32 wA = m_bodyA->GetAngularVelocity(), wB = m_bodyB->GetAngularVelocity();
+	return b2Dot(d, b2Cross(wA, axis)) + b2Dot(axis, vB + b2Cross(wB, rB) - vA - b2Cross(wA, rA));
+}
+
+float32 b2WheelJoint::GetJointAngle() const { return m_bodyB->GetAngle() - m_bodyA->GetAngle(); }
+float32 b2WheelJoint::GetJointAngularSpeed() const { return m_bodyB->GetAngularVelocity() - m_bodyA->GetAngularVelocity(); }
+
+void b2WheelJoint::EnableMotor(bool flag)
+{
+	if (flag == m_enableMotor) return;
+	Touch();
+	m_bodyA->SetAwake(true);
+	m_bodyB->SetAwake(true);
+	m_enableMotor = flag;
+}
+
+void b2WheelJoint::SetMotorSpeed(float32 speed)
+{
+	if (speed == m_motorSpeed) return;
+	Touch();
+	m_bodyA->SetAwake(true);
+	m_bodyB->SetAwake(true);
+	m_motorSpeed = speed;
+}
+
+void b2WheelJoint::SetMaxMotorTorque(float32 torque)
+{
+	if (torque == m_maxMotorTorque) return;
+	Touch();
+	m_bodyA->SetAwake(true);
+	m_bodyB->SetAwake(true);
+	m_maxMotorTorque = torque;
+}
+
+void b2WheelJoint::SetSpringFrequencyHz(float32 hz)
+{
+	if (hz == m_frequencyHz) return;
+	Touch();
+	m_frequencyHz = hz;
+}
+
+void b2WheelJoint::SetSpringDampingRatio(float32 ratio)
+{
+	if (ratio == m_dampingRatio) return;
+	Touch();
+	m_dampingRatio = ratio;
+}
+
+// ---- rope (reference b2RopeJoint.cpp:34-45, :197-228) --------------------------------------------------------------------
+
+b2RopeJoint::b2RopeJoint(const b2RopeJointDef* def)
+	: b2Joint(def), m_localAnchorA(def->localAnchorA), m_localAnchorB(def->localAnchorB), m_maxLength(def->maxLength),
+	  m_impulse(0.0f), m_state(e_inactiveLimit), m_u(0.0f, 0.0f)
+{
+}
+
+void b2RopeJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_ROPE, m_bodyA, m_bodyB, m_collideConnected, m_localAnchorA, m_localAnchorB);
+	out->length = m_maxLength;
+	out->impulse[0] = m_impulse;
+	out->limitState = (int32_t)m_state;
+	out->lastSolve[0] = m_u.x;
+	out->lastSolve[1] = m_u.y;
+}
+
+void b2RopeJoint::ReadRecord(const b2cuJoint& in)
+{
+	m_impulse = in.impulse[0];
+	m_state = (b2LimitState)in.limitState;
+	m_u.Set(in.lastSolve[0], in.lastSolve[1]);
+}
+
+b2Vec2 b2RopeJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2RopeJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+b2Vec2 b2RopeJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	float32 scale = inv_dt * m_impulse;
+	return b2Vec2(scale * m_u.x, scale * m_u.y);
+}
+
+float32 b2RopeJoint::GetReactionTorque(float32 inv_dt) const
+{
+	B2_NOT_USED(inv_dt);
+	return 0.0f;
+}
+
+b2LimitState b2RopeJoint::GetLimitState() const
+{
+	Refresh();
+	return m_state;
+}
+
+void b2RopeJoint::SetMaxLength(float32 length)
+{
+	if (length == m_maxLength) return;
+	Touch();
+	m_maxLength = length;
+}
+
+// ---- friction (reference b2FrictionJoint.cpp:36-56, :192-236) ------------------------------------------------------------
+
+void b2FrictionJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& anchor)
+{
+	bodyA = bA;
+	bodyB = bB;
+	localAnchorA = bA->GetLocalPoint(anchor);
+	localAnchorB = bB->GetLocalPoint(anchor);
+}
+
+b2FrictionJoint::b2FrictionJoint(const b2FrictionJointDef* def)
+	: b2Joint(def), m_localAnchorA(def->localAnchorA), m_localAnchorB(def->localAnchorB), m_maxForce(def->maxForce),
+	  m_maxTorque(def->maxTorque), m_linearImpulse(0.0f, 0.0f), m_angularImpulse(0.0f)
+{
+}
+
+void b2FrictionJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_FRICTION, m_bodyA, m_bodyB, m_collideConnected, m_localAnchorA, m_localAnchorB);
+	out->length = m_maxForce;
+	out->maxMotorTorque = m_maxTorque;
+	out->impulse[0] = m_linearImpulse.x;
+	out->impulse[1] = m_linearImpulse.y;
+	out->impulse[2] = m_angularImpulse;
+}
+
+void b2FrictionJoint::ReadRecord(const b2cuJoint& in)
+{
+	m_linearImpulse.Set(in.impulse[0], in.impulse[1]);
+	m_angularImpulse = in.impulse[2];
+}
+
+b2Vec2 b2FrictionJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2FrictionJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+b2Vec2 b2FrictionJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_linearImpulse;
+}
+
+float32 b2FrictionJoint::GetReactionTorque(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_angularImpulse;
+}
+
+void b2FrictionJoint::SetMaxForce(float32 force)
+{
+	b2Assert(b2IsValid(force) && force >= 0.0f);
+	if (force == m_maxForce) return;
+	Touch();
+	m_maxForce = force;
+}
+
+void b2FrictionJoint::SetMaxTorque(float32 torque)
+{
+	b2Assert(b2IsValid(torque) && torque >= 0.0f);
+	if (torque == m_maxTorque) return;
+	Touch();
+	m_maxTorque = torque;
+}
+
+// ---- motor (reference b2MotorJoint.cpp:39-64, :202-300) ------------------------------------------------------------------
+
+void b2MotorJointDef::Initialize(b2Body* bA, b2Body* bB)
+{
+	bodyA = bA;
+	bodyB = bB;
+	linearOffset = bA->GetLocalPoint(bB->GetPosition());
+	angularOffset = bB->GetAngle() - bA->GetAngle();
+}
+
+b2MotorJoint::b2MotorJoint(const b2MotorJointDef* def)
+	: b2Joint(def), m_linearOffset(def->linearOffset), m_angularOffset(def->angularOffset), m_maxForce(def->maxForce),
+	  m_maxTorque(def->maxTorque), m_correctionFactor(def->correctionFactor), m_linearImpulse(0.0f, 0.0f), m_angularImpulse(0.0f)
+{
+}
+
+void b2MotorJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_MOTOR, m_bodyA, m_bodyB, m_collideConnected, b2Vec2(0.0f, 0.0f), b2Vec2(0.0f, 0.0f));
+	out->axis[0] = m_linearOffset.x;
+	out->axis[1] = m_linearOffset.y;
+	out->referenceAngle = m_angularOffset;
+	out->length = m_maxForce;
+	out->maxMotorTorque = m_maxTorque;
+	out->dampingRatio = m_correctionFactor;
+	out->impulse[0] = m_linearImpulse.x;
+	out->impulse[1] = m_linearImpulse.y;
+	out->impulse[2] = m_angularImpulse;
+}
+
+void b2MotorJoint::ReadRecord(const b2cuJoint& in)
+{
+	m_linearImpulse.Set(in.impulse[0], in.impulse[1]);
+	m_angularImpulse = in.impulse[2];
+}
+
+b2Vec2 b2MotorJoint::GetAnchorA() const { return m_bodyA->GetPosition(); }
+b2Vec2 b2MotorJoint::GetAnchorB() const { return m_bodyB->GetPosition(); }
+
+b2Vec2 b2MotorJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_linearImpulse;
+}
+
+float32 b2MotorJoint::GetReactionTorque(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_angularImpulse;
+}
+
+void b2MotorJoint::SetLinearOffset(const b2Vec2& linearOffset)
+{
+	if (linearOffset.x == m_linearOffset.x && linearOffset.y == m_linearOffset.y) return;
+	Touch();
+	m_bodyA->SetAwake(true);
+	m_bodyB->SetAwake(true);
+	m_linearOffset = linearOffset;
+}
+
+void b2MotorJoint::SetAngularOffset(float32 angularOffset)
+{
+	if (angularOffset == m_angularOffset) return;
+	Touch();
+	m_bodyA->SetAwake(true);
+	m_bodyB->SetAwake(true);
+	m_angularOffset = angularOffset;
+}
+
+void b2MotorJoint::SetMaxForce(float32 force)
+{
+	b2Assert(b2IsValid(force) && force >= 0.0f);
+	if (force == m_maxForce) return;
+	Touch();
+	m_maxForce = force;
+}
+
+void b2MotorJoint::SetMaxTorque(float32 torque)
+{
+	b2Assert(b2IsValid(torque) && torque >= 0.0f);
+	if (torque == m_maxTorque) return;
+	Touch();
+	m_maxTorque = torque;
+}
+
+void b2MotorJoint::SetCorrectionFactor(float32 factor)
+{
+	b2Assert(b2IsValid(factor) && 0.0f <= factor && factor <= 1.0f);
+	if (factor == m_correctionFactor) return;
+	Touch();
+	m_correctionFactor = factor;
 }

@@ -6,6 +6,10 @@
 #include "Box2D/Dynamics/Joints/b2DistanceJoint.h"
 #include "Box2D/Dynamics/Joints/b2WeldJoint.h"
 #include "Box2D/Dynamics/Joints/b2PrismaticJoint.h"
+#include "Box2D/Dynamics/Joints/b2WheelJoint.h"
+#include "Box2D/Dynamics/Joints/b2RopeJoint.h"
+#include "Box2D/Dynamics/Joints/b2FrictionJoint.h"
+#include "Box2D/Dynamics/Joints/b2MotorJoint.h"
 
 #include <chrono>
 #include "Box2D/Collision/Shapes/b2CircleShape.h"
@@ -327,7 +331,7 @@ void b2World::RefreshJoints() const
 b2Joint* b2World::CreateJoint(const b2JointDef* def)
 {
 	if (IsLocked()) return nullptr;
-	if (def->type != e_revoluteJoint && def->type != e_distanceJoint && def->type != e_weldJoint && def->type != e_prismaticJoint)
+	if (def->type == e_unknownJoint || def->type == e_pulleyJoint || def->type == e_mouseJoint || def->type == e_gearJoint)
 	{
 		m_lastStatus = B2CU_ERR_UNSUPPORTED;
 		return nullptr;
@@ -337,6 +341,10 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def)
 	if (def->type == e_revoluteJoint) j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
 	else if (def->type == e_distanceJoint) j = new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def));
 	else if (def->type == e_prismaticJoint) j = new b2PrismaticJoint(static_cast<const b2PrismaticJointDef*>(def));
+	else if (def->type == e_wheelJoint) j = new b2WheelJoint(static_cast<const b2WheelJointDef*>(def));
+	else if (def->type == e_ropeJoint) j = new b2RopeJoint(static_cast<const b2RopeJointDef*>(def));
+	else if (def->type == e_frictionJoint) j = new b2FrictionJoint(static_cast<const b2FrictionJointDef*>(def));
+	else if (def->type == e_motorJoint) j = new b2MotorJoint(static_cast<const b2MotorJointDef*>(def));
 	else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
 	j->m_world = this;
 	j->m_index = (int32)m_joints.size();

@@ -91,10 +91,12 @@ JOINT = np.dtype([
     ("localAnchorA", "f4", (2,)), ("localAnchorB", "f4", (2,)),
     ("referenceAngle", "f4"), ("lowerAngle", "f4"), ("upperAngle", "f4"), ("maxMotorTorque", "f4"), ("motorSpeed", "f4"),
     ("length", "f4"), ("frequencyHz", "f4"), ("dampingRatio", "f4"), ("axis", "f4", (2,)),
-    ("lastSolve", "f4", (4,)), ("impulse", "f4", (3,)), ("motorImpulse", "f4"), ("limitState", "i4"), ("reserved", "i4"),
+    ("lastSolve", "f4", (4,)), ("work", "f4", (4,)), ("impulse", "f4", (3,)), ("motorImpulse", "f4"), ("limitState", "i4"),
+    ("reserved", "i4"),
 ])
-assert JOINT.itemsize == 112
+assert JOINT.itemsize == 128
 JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_WELD = 1, 2, 3, 8
+JOINT_WHEEL, JOINT_FRICTION, JOINT_ROPE, JOINT_MOTOR = 7, 9, 10, 11
 JOINT_COLLIDE_CONNECTED, JOINT_ENABLE_LIMIT, JOINT_ENABLE_MOTOR = 1, 2, 4
 
 # enums

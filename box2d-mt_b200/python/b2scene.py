@@ -204,6 +204,47 @@ class Scene:
         self.joints.append(j)
         return len(self.joints) - 1
 
+    def wheel_joint(self, body_a, body_b, local_anchor_a, local_anchor_b, local_axis_a, frequency_hz=2.0, damping_ratio=0.7,
+                    motor=None, collide_connected=False):
+        """b2WheelJointDef (b2WheelJoint.h:30-72): B's anchor stays on a line of A, held by a spring; motor = (speed,
+        max torque) drives B's rotation"""
+        j = self._joint(T.JOINT_WHEEL, body_a, body_b, local_anchor_a, local_anchor_b, collide_connected)
+        j["axis"] = local_axis_a
+        j["frequencyHz"] = frequency_hz
+        j["dampingRatio"] = damping_ratio
+        if motor is not None:
+            j["flags"] = int(j["flags"]) | T.JOINT_ENABLE_MOTOR
+            j["motorSpeed"], j["maxMotorTorque"] = motor
+        self.joints.append(j)
+        return len(self.joints) - 1
+
+    def rope_joint(self, body_a, body_b, local_anchor_a, local_anchor_b, max_length, collide_connected=False):
+        """b2RopeJointDef (b2RopeJoint.h:28-48)"""
+        j = self._joint(T.JOINT_ROPE, body_a, body_b, local_anchor_a, local_anchor_b, collide_connected)
+        j["length"] = max_length
+        self.joints.append(j)
+        return len(self.joints) - 1
+
+    def friction_joint(self, body_a, body_b, local_anchor_a, local_anchor_b, max_force, max_torque, collide_connected=False):
+        """b2FrictionJointDef (b2FrictionJoint.h:25-51)"""
+        j = self._joint(T.JOINT_FRICTION, body_a, body_b, local_anchor_a, local_anchor_b, collide_connected)
+        j["length"] = max_force
+        j["maxMotorTorque"] = max_torque
+        self.joints.append(j)
+        return len(self.joints) - 1
+
+    def motor_joint(self, body_a, body_b, linear_offset, angular_offset, max_force=1.0, max_torque=1.0, correction_factor=0.3,
+                    collide_connected=False):
+        """b2MotorJointDef (b2MotorJoint.h:25-54)"""
+        j = self._joint(T.JOINT_MOTOR, body_a, body_b, (0.0, 0.0), (0.0, 0.0), collide_connected)
+        j["axis"] = linear_offset
+        j["referenceAngle"] = angular_offset
+        j["length"] = max_force
+        j["maxMotorTorque"] = max_torque
+        j["dampingRatio"] = correction_factor
+        self.joints.append(j)
+        return len(self.joints) - 1
+
     def joint_array(self):
         return np.array(self.joints, dtype=T.JOINT) if self.joints else np.zeros(0, T.JOINT)
 

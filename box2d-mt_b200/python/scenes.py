@@ -382,3 +382,55 @@ def sliders(seed=0):
     s.fixture(b, box, density=1.0)
     s.prismatic_joint(k, b, (0.0, -0.5), (0.0, 1.5), (0.0, -2.0), limits=(-1.0, 3.0))
     return s
+
+
+def machines(seed=0):
+    """Wheel, rope, friction and motor joints: the Testbed's Car (Car.h:36-230: chassis on two sprung wheels, one driven)
+    on bumpy ground, a second car whose suspension is rigid (frequency 0) and undriven, a weight on a rope hung from a
+    swinging arm (RopeJoint.h), boxes dragged over the ground by friction joints to it (ApplyForce.h:80-110) and a body
+    steered by a motor joint (MotorJoint.h:30-80), strong and saturated."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.edge((-60.0, 0.0), (60.0, 0.0)), friction=0.6)
+    for i in range(8):
+        s.fixture(g, s.box(0.6, 0.15, center=(6.0 + 4.0 * i, 0.1), angle=0.2 * (i % 3 - 1)), friction=0.6)
+    wheel = s.circle(0.4)
+    for n, (x, hz, motor) in enumerate([(-20.0, 4.0, (-12.0, 20.0)), (-40.0, 0.0, None)]):
+        chassis = s.body(T.DYNAMIC_BODY, (x, 1.0))
+        s.fixture(chassis, s.polygon([(-1.5, -0.5), (1.5, -0.5), (1.5, 0.0), (0.0, 0.9), (-1.15, 0.9), (-1.5, 0.2)]), density=1.0)
+        w1 = s.body(T.DYNAMIC_BODY, (x - 1.0, 0.35))
+        s.fixture(w1, wheel, density=1.0, friction=0.9)
+        w2 = s.body(T.DYNAMIC_BODY, (x + 1.0, 0.4))
+        s.fixture(w2, wheel, density=1.0, friction=0.9)
+        s.wheel_joint(chassis, w1, (-1.0, -0.65), (0.0, 0.0), (0.0, 1.0), frequency_hz=hz, damping_ratio=0.7, motor=motor)
+        s.wheel_joint(chassis, w2, (1.0, -0.6), (0.0, 0.0), (0.0, 1.0), frequency_hz=hz, damping_ratio=0.7,
+                      motor=(0.0, 10.0) if n == 0 else None)
+    # rope: an arm on a hinge, a weight on a rope from its tip (slack at first), a second rope with coinciding anchors
+    arm = s.body(T.DYNAMIC_BODY, (2.0, 14.0), w=2.0)
+    s.fixture(arm, s.box(2.0, 0.125), density=20.0)
+    s.revolute_joint(g, arm, (0.0, 14.0), (-2.0, 0.0))
+    weight = s.body(T.DYNAMIC_BODY, (4.0, 12.5))
+    s.fixture(weight, s.box(0.75, 0.75), density=10.0)
+    s.rope_joint(arm, weight, (2.0, 0.0), (0.0, 0.75), 3.0)
+    bead = s.body(T.DYNAMIC_BODY, (4.0, 14.0))
+    s.fixture(bead, s.circle(0.2), density=1.0)
+    s.rope_joint(arm, bead, (2.0, 0.0), (0.0, 0.0), 1.0, collide_connected=True)
+    # friction joints to the ground: top-down style drag (gravity scale 0 would be the Testbed's; here they also rest)
+    for i in range(4):
+        b = s.body(T.DYNAMIC_BODY, (-8.0 + 2.5 * i, 0.5), vel=(6.0, 0.0), w=3.0 * (i - 1.5), gravity_scale=0.0)
+        s.fixture(b, s.box(0.5, 0.5), density=1.0, friction=0.3)
+        s.friction_joint(g, b, (-8.0 + 2.5 * i, 0.5), (0.0, 0.0), [0.0, 2.0, 10.0, 500.0][i], [0.5, 0.0, 1.0, 100.0][i],
+                         collide_connected=(i % 2 == 0))
+    # motor joints: one strong enough to hold its body in the air at an offset, one saturated, one between two dynamic bodies
+    b = s.body(T.DYNAMIC_BODY, (30.0, 8.0))
+    s.fixture(b, s.box(2.0, 0.5), density=2.0, friction=0.6)
+    s.motor_joint(g, b, (33.0, 10.0), 0.5, max_force=1000.0, max_torque=1000.0, collide_connected=True)
+    b = s.body(T.DYNAMIC_BODY, (40.0, 8.0))
+    s.fixture(b, s.box(1.0, 0.5), density=2.0, friction=0.6)
+    s.motor_joint(g, b, (40.0, 12.0), -1.0, max_force=10.0, max_torque=2.0, correction_factor=0.8, collide_connected=True)
+    a = s.body(T.DYNAMIC_BODY, (50.0, 3.0))
+    s.fixture(a, s.box(1.0, 1.0), density=1.0)
+    b = s.body(T.DYNAMIC_BODY, (50.0, 6.0))
+    s.fixture(b, s.box(0.5, 0.5), density=1.0)
+    s.motor_joint(a, b, (0.0, 2.5), 0.3, max_force=200.0, max_torque=50.0, collide_connected=True)
+    return s

@@ -331,6 +331,10 @@ B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
  *   distance joints   b2DistanceJoint.cpp:63-222   rigid or spring-damper rod between two anchors
  *   weld joints       b2WeldJoint.cpp:59-308       point + angle, rigid or with a soft angle
  *   prismatic joints  b2PrismaticJoint.cpp:127-478 slider along an axis of body A, translation limit, motor
+ *   wheel joints      b2WheelJoint.cpp:78-318      point on a line of body A with a suspension spring, rotational motor
+ *   rope joints       b2RopeJoint.cpp:47-195       maximum distance between two anchors
+ *   friction joints   b2FrictionJoint.cpp:58-190   bounded linear and angular friction between two bodies
+ *   motor joints      b2MotorJoint.cpp:66-200      drives body B to an offset from body A with bounded force / torque
  * as rows of the coloured solver: inside every velocity iteration the joints run before the contacts, inside every
  * position iteration after them, as b2Island::Solve orders them (Dynamics/b2Island.cpp:259-273, :323-327, :363-380),
  * with warm starting.  A joint links the islands of its two bodies (b2World.cpp:1286-1320) and, unless
@@ -342,11 +346,28 @@ B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
  *                            (= maxMotorForce), motorSpeed, flags LIMIT / MOTOR
  *                 distance   length, frequencyHz, dampingRatio
  *                 weld       referenceAngle, frequencyHz, dampingRatio
+ *                 wheel      axis (localAxisA, used as given), maxMotorTorque, motorSpeed, frequencyHz, dampingRatio,
+ *                            flag MOTOR; impulse[0] = m_impulse, impulse[1] = m_springImpulse
+ *                 rope       length (= maxLength); limitState = m_state
+ *                 friction   length (= maxForce), maxMotorTorque (= maxTorque); impulse[0..1] linear, impulse[2] angular
+ *                 motor      axis (= linearOffset), referenceAngle (= angularOffset), length (= maxForce),
+ *                            maxMotorTorque (= maxTorque), dampingRatio (= correctionFactor); impulses as friction
  * impulse / motorImpulse / limitState are the joint's persistent solver state (m_impulse -- a scalar in impulse[0] for
  * the distance joint --, m_motorImpulse, m_limitState) and round-trip through Get / Set.  lastSolve is written by the
- * step with the world-space directions of its solve, which GetReactionForce needs: the distance joint's m_u in
- * [0..1], the prismatic joint's m_axis in [0..1] and m_perp in [2..3]. */
-enum { B2CU_JOINT_REVOLUTE = 1, B2CU_JOINT_PRISMATIC = 2, B2CU_JOINT_DISTANCE = 3, B2CU_JOINT_WELD = 8 };
+ * step with the world-space directions of its solve, which GetReactionForce needs: the distance and rope joints' m_u
+ * in [0..1], the prismatic joint's m_axis in [0..1] and m_perp in [2..3], the wheel joint's m_ax and m_ay likewise.
+ * work is solver scratch that the reference carries from step to step (wheel: m_sAx, m_sBx). */
+enum
+{
+	B2CU_JOINT_REVOLUTE = 1,
+	B2CU_JOINT_PRISMATIC = 2,
+	B2CU_JOINT_DISTANCE = 3,
+	B2CU_JOINT_WHEEL = 7,
+	B2CU_JOINT_WELD = 8,
+	B2CU_JOINT_FRICTION = 9,
+	B2CU_JOINT_ROPE = 10,
+	B2CU_JOINT_MOTOR = 11
+};
 enum
 {
 	B2CU_JOINT_COLLIDE_CONNECTED = 1,
@@ -365,6 +386,7 @@ typedef struct b2cuJoint
 	float length, frequencyHz, dampingRatio;
 	float axis[2];
 	float lastSolve[4];
+	float work[4];
 	float impulse[3];
 	float motorImpulse;
 	int32_t limitState;

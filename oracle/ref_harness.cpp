@@ -874,6 +874,76 @@ int32_t b2ref_set_joints(b2refWorld* w, int32_t count, const b2cuJoint* joints)
 			w->rawAxis[pj] = def.localAxisA;
 			joint = pj;
 		}
+		else if (j.type == B2CU_JOINT_WHEEL)
+		{
+			b2WheelJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
+			def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+			def.localAxisA.Set(j.axis[0], j.axis[1]);
+			def.enableMotor = (j.flags & B2CU_JOINT_ENABLE_MOTOR) != 0;
+			def.maxMotorTorque = j.maxMotorTorque;
+			def.motorSpeed = j.motorSpeed;
+			def.frequencyHz = j.frequencyHz;
+			def.dampingRatio = j.dampingRatio;
+			b2WheelJoint* wj = (b2WheelJoint*)w->world->CreateJoint(&def);
+			wj->m_impulse = j.impulse[0];
+			wj->m_springImpulse = j.impulse[1];
+			wj->m_motorImpulse = j.motorImpulse;
+			wj->m_ax.Set(j.lastSolve[0], j.lastSolve[1]);
+			wj->m_ay.Set(j.lastSolve[2], j.lastSolve[3]);
+			wj->m_sAx = j.work[0];
+			wj->m_sBx = j.work[1];
+			joint = wj;
+		}
+		else if (j.type == B2CU_JOINT_ROPE)
+		{
+			b2RopeJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
+			def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+			def.maxLength = j.length;
+			b2RopeJoint* rj = (b2RopeJoint*)w->world->CreateJoint(&def);
+			rj->m_impulse = j.impulse[0];
+			rj->m_state = (b2LimitState)j.limitState;
+			rj->m_u.Set(j.lastSolve[0], j.lastSolve[1]);
+			joint = rj;
+		}
+		else if (j.type == B2CU_JOINT_FRICTION)
+		{
+			b2FrictionJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
+			def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+			def.maxForce = j.length;
+			def.maxTorque = j.maxMotorTorque;
+			b2FrictionJoint* fj = (b2FrictionJoint*)w->world->CreateJoint(&def);
+			fj->m_linearImpulse.Set(j.impulse[0], j.impulse[1]);
+			fj->m_angularImpulse = j.impulse[2];
+			joint = fj;
+		}
+		else if (j.type == B2CU_JOINT_MOTOR)
+		{
+			b2MotorJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.linearOffset.Set(j.axis[0], j.axis[1]);
+			def.angularOffset = j.referenceAngle;
+			def.maxForce = j.length;
+			def.maxTorque = j.maxMotorTorque;
+			def.correctionFactor = j.dampingRatio;
+			b2MotorJoint* mj = (b2MotorJoint*)w->world->CreateJoint(&def);
+			mj->m_linearImpulse.Set(j.impulse[0], j.impulse[1]);
+			mj->m_angularImpulse = j.impulse[2];
+			joint = mj;
+		}
 		else if (j.type == B2CU_JOINT_DISTANCE)
 		{
 			b2DistanceJointDef def;
@@ -1007,6 +1077,13 @@ void b2ref_joint_readings(b2refWorld* w, float inv_dt, float* out6)
 			o[4] = j->GetJointTranslation();
 			o[5] = j->GetJointSpeed();
 		}
+		else if (base->GetType() == e_wheelJoint)
+		{
+			const b2WheelJoint* j = (const b2WheelJoint*)base;
+			o[3] = j->GetMotorTorque(inv_dt);
+			o[4] = j->GetJointTranslation();
+			o[5] = j->GetJointLinearSpeed();
+		}
 	}
 }
 
@@ -1069,6 +1146,73 @@ void b2ref_export_joints(b2refWorld* w, b2cuJoint* out)
 			o.lastSolve[1] = j->m_axis.y;
 			o.lastSolve[2] = j->m_perp.x;
 			o.lastSolve[3] = j->m_perp.y;
+		}
+		else if (base->GetType() == e_wheelJoint)
+		{
+			const b2WheelJoint* j = (const b2WheelJoint*)base;
+			o.type = B2CU_JOINT_WHEEL;
+			o.flags |= j->m_enableMotor ? B2CU_JOINT_ENABLE_MOTOR : 0;
+			o.localAnchorA[0] = j->m_localAnchorA.x;
+			o.localAnchorA[1] = j->m_localAnchorA.y;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			o.axis[0] = j->m_localXAxisA.x;
+			o.axis[1] = j->m_localXAxisA.y;
+			o.maxMotorTorque = j->m_maxMotorTorque;
+			o.motorSpeed = j->m_motorSpeed;
+			o.frequencyHz = j->m_frequencyHz;
+			o.dampingRatio = j->m_dampingRatio;
+			o.impulse[0] = j->m_impulse;
+			o.impulse[1] = j->m_springImpulse;
+			o.motorImpulse = j->m_motorImpulse;
+			o.lastSolve[0] = j->m_ax.x;
+			o.lastSolve[1] = j->m_ax.y;
+			o.lastSolve[2] = j->m_ay.x;
+			o.lastSolve[3] = j->m_ay.y;
+			o.work[0] = j->m_sAx;
+			o.work[1] = j->m_sBx;
+		}
+		else if (base->GetType() == e_ropeJoint)
+		{
+			const b2RopeJoint* j = (const b2RopeJoint*)base;
+			o.type = B2CU_JOINT_ROPE;
+			o.localAnchorA[0] = j->m_localAnchorA.x;
+			o.localAnchorA[1] = j->m_localAnchorA.y;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			o.length = j->m_maxLength;
+			o.impulse[0] = j->m_impulse;
+			o.limitState = (int32_t)j->m_state;
+			o.lastSolve[0] = j->m_u.x;
+			o.lastSolve[1] = j->m_u.y;
+		}
+		else if (base->GetType() == e_frictionJoint)
+		{
+			const b2FrictionJoint* j = (const b2FrictionJoint*)base;
+			o.type = B2CU_JOINT_FRICTION;
+			o.localAnchorA[0] = j->m_localAnchorA.x;
+			o.localAnchorA[1] = j->m_localAnchorA.y;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			o.length = j->m_maxForce;
+			o.maxMotorTorque = j->m_maxTorque;
+			o.impulse[0] = j->m_linearImpulse.x;
+			o.impulse[1] = j->m_linearImpulse.y;
+			o.impulse[2] = j->m_angularImpulse;
+		}
+		else if (base->GetType() == e_motorJoint)
+		{
+			const b2MotorJoint* j = (const b2MotorJoint*)base;
+			o.type = B2CU_JOINT_MOTOR;
+			o.axis[0] = j->m_linearOffset.x;
+			o.axis[1] = j->m_linearOffset.y;
+			o.referenceAngle = j->m_angularOffset;
+			o.length = j->m_maxForce;
+			o.maxMotorTorque = j->m_maxTorque;
+			o.dampingRatio = j->m_correctionFactor;
+			o.impulse[0] = j->m_linearImpulse.x;
+			o.impulse[1] = j->m_linearImpulse.y;
+			o.impulse[2] = j->m_angularImpulse;
 		}
 		else if (base->GetType() == e_distanceJoint)
 		{
