@@ -2,7 +2,8 @@
 // / SolvePositionConstraints of b2RevoluteJoint (Box2D/Dynamics/Joints/b2RevoluteJoint.cpp:64-400), b2DistanceJoint
 // (b2DistanceJoint.cpp:63-222), b2WeldJoint (b2WeldJoint.cpp:59-308) and b2PrismaticJoint
 // (b2PrismaticJoint.cpp:100-478), b2WheelJoint (b2WheelJoint.cpp:78-318), b2RopeJoint (b2RopeJoint.cpp:47-195),
-// b2FrictionJoint (b2FrictionJoint.cpp:58-190) and b2MotorJoint (b2MotorJoint.cpp:66-200), and the small linear solves they use
+// b2FrictionJoint (b2FrictionJoint.cpp:58-190), b2MotorJoint (b2MotorJoint.cpp:66-200), b2PulleyJoint
+// (b2PulleyJoint.cpp:74-264) and b2MouseJoint (b2MouseJoint.cpp:96-190), and the small linear solves they use
 // (b2Mat33::Solve33 / Solve22 / GetInverse22 / GetSymInverse33, Box2D/Common/b2Math.cpp:25-94; b2Mat22::Solve,
 // b2Math.h:221-233) with the same fp32 arithmetic in the same order.  One thread solves one joint; joints of one colour class share no
 // dynamic body, so a class is solved in parallel and the classes one after the other.
@@ -1475,6 +1476,219 @@ __device__ __forceinline__ void FrictionMotorSolveVelocity(const DeviceArrays& d
 	d.joints[j].impulse[2] = jt.impulse[2];
 }
 
+// ---- pulley joint (b2PulleyJoint.cpp:74-264) ----------------------------------------------------------------------------
+// Record: axis = groundAnchorA, (lowerAngle, upperAngle) = groundAnchorB, length = lengthA, referenceAngle = lengthB,
+// motorSpeed = ratio.  Row use: u = m_uA, axis = m_uB, motorMass = m_mass.
+
+__device__ __forceinline__ Vec2 PulleyDirection(Vec2 u)
+{
+	float length = Length(u);
+	if (length > 10.0f * B2CU_LINEAR_SLOP) return (1.0f / length) * u;
+	return V(0.0f, 0.0f);
+}
+
+__device__ __forceinline__ void PulleyInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio, int warmStarting)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	const float ratio = jt.motorSpeed;
+
+	Rot qA = SinCos(pA.z), qB = SinCos(pB.z);
+	r.rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	r.rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	r.u = PulleyDirection(cA + r.rA - V(jt.axis[0], jt.axis[1]));
+	r.axis = PulleyDirection(cB + r.rB - V(jt.lowerAngle, jt.upperAngle));
+
+	float ruA = Cross(r.rA, r.u);
+	float ruB = Cross(r.rB, r.axis);
+	float mA = r.invMassA + r.invIA * ruA * ruA;
+	float mB = r.invMassB + r.invIB * ruB * ruB;
+	r.motorMass = mA + ratio * ratio * mB;
+	if (r.motorMass > 0.0f) r.motorMass = 1.0f / r.motorMass;
+
+	if (warmStarting)
+	{
+		jt.impulse[0] *= dtRatio;
+		Vec2 PA = -(jt.impulse[0]) * r.u;
+		Vec2 PB = (-ratio * jt.impulse[0]) * r.axis;
+		vA = vA + r.invMassA * PA;
+		wA += r.invIA * Cross(r.rA, PA);
+		vB = vB + r.invMassB * PB;
+		wB += r.invIB * Cross(r.rB, PB);
+	}
+	else
+	{
+		jt.impulse[0] = 0.0f;
+	}
+
+	StoreVelocity(d, bA, r.invMassA, r.invIA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, r.invMassB, r.invIB, vB, wB, vB4.w);
+	jt.lastSolve[0] = r.axis.x; // b2PulleyJoint::GetReactionForce reads m_uB
+	jt.lastSolve[1] = r.axis.y;
+	d.jointRows[j] = r;
+	d.joints[j] = jt;
+}
+
+__device__ __forceinline__ void PulleySolveVelocity(const DeviceArrays& d, int j, const JointRow& r, const b2cuJoint& jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
+	float wA = vA4.z, wB = vB4.z;
+	const float ratio = jt.motorSpeed;
+
+	Vec2 vpA = vA + CrossSV(wA, r.rA);
+	Vec2 vpB = vB + CrossSV(wB, r.rB);
+	float Cdot = -Dot(r.u, vpA) - ratio * Dot(r.axis, vpB);
+	float impulse = -r.motorMass * Cdot;
+	float total = jt.impulse[0] + impulse;
+
+	Vec2 PA = -impulse * r.u;
+	Vec2 PB = -ratio * impulse * r.axis;
+	vA = vA + r.invMassA * PA;
+	wA += r.invIA * Cross(r.rA, PA);
+	vB = vB + r.invMassB * PB;
+	wB += r.invIB * Cross(r.rB, PB);
+
+	StoreVelocity(d, bA, r.invMassA, r.invIA, vA, wA, vA4.w);
+	StoreVelocity(d, bB, r.invMassB, r.invIB, vB, wB, vB4.w);
+	d.joints[j].impulse[0] = total;
+}
+
+__device__ __forceinline__ bool PulleySolvePosition(const DeviceArrays& d, const JointRow& r, const b2cuJoint& jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB;
+	float4 pA = d.pos[bA], pB = d.pos[bB];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y);
+	float aA = pA.z, aB = pB.z;
+	const float ratio = jt.motorSpeed;
+
+	Rot qA = SinCos(aA), qB = SinCos(aB);
+	Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+	Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	Vec2 uA = cA + rA - V(jt.axis[0], jt.axis[1]);
+	Vec2 uB = cB + rB - V(jt.lowerAngle, jt.upperAngle);
+	float lengthA = Length(uA);
+	float lengthB = Length(uB);
+	uA = lengthA > 10.0f * B2CU_LINEAR_SLOP ? (1.0f / lengthA) * uA : V(0.0f, 0.0f);
+	uB = lengthB > 10.0f * B2CU_LINEAR_SLOP ? (1.0f / lengthB) * uB : V(0.0f, 0.0f);
+
+	float ruA = Cross(rA, uA);
+	float ruB = Cross(rB, uB);
+	float mA = r.invMassA + r.invIA * ruA * ruA;
+	float mB = r.invMassB + r.invIB * ruB * ruB;
+	float mass = mA + ratio * ratio * mB;
+	if (mass > 0.0f) mass = 1.0f / mass;
+
+	// m_constant = lengthA + ratio * lengthB of the definition
+	float constant = jt.length + ratio * jt.referenceAngle;
+	float C = constant - lengthA - ratio * lengthB;
+	float linearError = Abs(C);
+	float impulse = -mass * C;
+
+	Vec2 PA = -impulse * uA;
+	Vec2 PB = -ratio * impulse * uB;
+	cA = cA + r.invMassA * PA;
+	aA += r.invIA * Cross(rA, PA);
+	cB = cB + r.invMassB * PB;
+	aB += r.invIB * Cross(rB, PB);
+
+	if (r.invMassA != 0.0f || r.invIA != 0.0f) d.pos[bA] = make_float4(cA.x, cA.y, aA, pA.w);
+	if (r.invMassB != 0.0f || r.invIB != 0.0f) d.pos[bB] = make_float4(cB.x, cB.y, aB, pB.w);
+	return linearError < B2CU_LINEAR_SLOP;
+}
+
+// ---- mouse joint (b2MouseJoint.cpp:96-190) --------------------------------------------------------------------------------
+// Only body B is constrained (towards a world target).  Record: axis = target, length = maxForce, frequencyHz,
+// dampingRatio, maxMotorTorque = b2Body::GetMass() of body B (the reference uses the mass, not its stored inverse).
+// Row use: ex / ey = m_mass (inverse of K), u = m_C, gamma.
+
+__device__ __forceinline__ void MouseInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio, int warmStarting,
+                                          float h)
+{
+	const int bB = jt.bodyB;
+	float4 pB = d.pos[bB];
+	float4 vB4 = d.vel[bB];
+	Vec2 cB = V(pB.x, pB.y);
+	Vec2 vB = V(vB4.x, vB4.y);
+	float wB = vB4.z;
+	Rot qB = SinCos(pB.z);
+
+	float mass = jt.maxMotorTorque;
+	float omega = 2.0f * B2CU_PI * jt.frequencyHz;
+	float dd = 2.0f * mass * jt.dampingRatio * omega;
+	float k = mass * (omega * omega);
+	r.gamma = h * (dd + h * k);
+	if (r.gamma != 0.0f) r.gamma = 1.0f / r.gamma;
+	float beta = h * k * r.gamma;
+
+	r.rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+	{
+		float kxx = r.invMassB + r.invIB * r.rB.y * r.rB.y + r.gamma;
+		float kxy = -r.invIB * r.rB.x * r.rB.y;
+		float kyy = r.invMassB + r.invIB * r.rB.x * r.rB.x + r.gamma;
+		float a = kxx, b = kxy, c = kxy, e = kyy;
+		float det = a * e - b * c;
+		if (det != 0.0f) det = 1.0f / det;
+		r.ex = V3(det * e, -det * c, 0.0f);
+		r.ey = V3(-det * b, det * a, 0.0f);
+	}
+	r.u = cB + r.rB - V(jt.axis[0], jt.axis[1]);
+	r.u = V(r.u.x * beta, r.u.y * beta);
+
+	wB *= 0.98f; // the reference's own damping fudge
+
+	if (warmStarting)
+	{
+		jt.impulse[0] *= dtRatio;
+		jt.impulse[1] *= dtRatio;
+		Vec2 P = V(jt.impulse[0], jt.impulse[1]);
+		vB = vB + r.invMassB * P;
+		wB += r.invIB * Cross(r.rB, P);
+	}
+	else
+	{
+		jt.impulse[0] = jt.impulse[1] = 0.0f;
+	}
+
+	// body B's velocity is stored unconditionally (the 0.98 factor applies even to a body without mass)
+	d.vel[bB] = make_float4(vB.x, vB.y, wB, vB4.w);
+	d.jointRows[j] = r;
+	d.joints[j] = jt;
+}
+
+__device__ __forceinline__ void MouseSolveVelocity(const DeviceArrays& d, int j, const JointRow& r, const b2cuJoint& jt, float h)
+{
+	const int bB = jt.bodyB;
+	float4 vB4 = d.vel[bB];
+	Vec2 vB = V(vB4.x, vB4.y);
+	float wB = vB4.z;
+
+	Vec2 Cdot = vB + CrossSV(wB, r.rB);
+	Vec2 old = V(jt.impulse[0], jt.impulse[1]);
+	Vec2 rhs = -(Cdot + r.u + r.gamma * old);
+	Vec2 impulse = V(r.ex.x * rhs.x + r.ey.x * rhs.y, r.ex.y * rhs.x + r.ey.y * rhs.y);
+	Vec2 total = old + impulse;
+	float maxImpulse = h * jt.length;
+	if (Dot(total, total) > maxImpulse * maxImpulse)
+	{
+		float scale = maxImpulse / Length(total);
+		total = V(total.x * scale, total.y * scale);
+	}
+	impulse = total - old;
+
+	vB = vB + r.invMassB * impulse;
+	wB += r.invIB * Cross(r.rB, impulse);
+
+	d.vel[bB] = make_float4(vB.x, vB.y, wB, vB4.w);
+	d.joints[j].impulse[0] = total.x;
+	d.joints[j].impulse[1] = total.y;
+}
+
 // ---- dispatch by joint type -------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float dtRatio, int warmStarting, float h)
@@ -1493,6 +1707,8 @@ __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float
 	else if (jt.type == B2CU_JOINT_ROPE) RopeInit(d, j, jt, r, dtRatio, warmStarting);
 	else if (jt.type == B2CU_JOINT_FRICTION) FrictionMotorInit(d, j, jt, r, dtRatio, warmStarting, false);
 	else if (jt.type == B2CU_JOINT_MOTOR) FrictionMotorInit(d, j, jt, r, dtRatio, warmStarting, true);
+	else if (jt.type == B2CU_JOINT_PULLEY) PulleyInit(d, j, jt, r, dtRatio, warmStarting);
+	else if (jt.type == B2CU_JOINT_MOUSE) MouseInit(d, j, jt, r, dtRatio, warmStarting, h);
 	else WeldInit(d, j, jt, r, dtRatio, warmStarting, h);
 }
 
@@ -1508,6 +1724,8 @@ __device__ __forceinline__ void JointSolveVelocityOne(const DeviceArrays& d, int
 	else if (jt.type == B2CU_JOINT_ROPE) RopeSolveVelocity(d, j, r, jt, h);
 	else if (jt.type == B2CU_JOINT_FRICTION) FrictionMotorSolveVelocity(d, j, r, jt, h, false);
 	else if (jt.type == B2CU_JOINT_MOTOR) FrictionMotorSolveVelocity(d, j, r, jt, h, true);
+	else if (jt.type == B2CU_JOINT_PULLEY) PulleySolveVelocity(d, j, r, jt);
+	else if (jt.type == B2CU_JOINT_MOUSE) MouseSolveVelocity(d, j, r, jt, h);
 	else WeldSolveVelocity(d, j, r, jt);
 }
 
@@ -1519,7 +1737,8 @@ __device__ __forceinline__ bool JointSolvePositionOne(const DeviceArrays& d, int
 	if (jt.type == B2CU_JOINT_DISTANCE) return DistanceSolvePosition(d, r, jt);
 	if (jt.type == B2CU_JOINT_WHEEL) return WheelSolvePosition(d, r, jt);
 	if (jt.type == B2CU_JOINT_ROPE) return RopeSolvePosition(d, r, jt);
-	if (jt.type == B2CU_JOINT_FRICTION || jt.type == B2CU_JOINT_MOTOR) return true;
+	if (jt.type == B2CU_JOINT_FRICTION || jt.type == B2CU_JOINT_MOTOR || jt.type == B2CU_JOINT_MOUSE) return true;
+	if (jt.type == B2CU_JOINT_PULLEY) return PulleySolvePosition(d, r, jt);
 	return WeldSolvePosition(d, r, jt);
 }
 

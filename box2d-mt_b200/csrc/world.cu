@@ -991,6 +991,7 @@ static int ColourJoints(b2cuWorld* w)
 		for (int k = 0; k < 2; ++k)
 		{
 			dynamic[k] = (bflags[bodies[k]] & B2CU_BODY_TYPE_MASK) == B2CU_DYNAMIC_BODY;
+			if (k == 0 && joints[j].type == B2CU_JOINT_MOUSE) dynamic[k] = false; // a mouse joint writes body B only
 			if (dynamic[k]) mask |= used[bodies[k]];
 		}
 		int colour = 0;
@@ -1024,10 +1025,8 @@ int b2cuSetJoints(b2cuWorld* w, int32_t count, const b2cuJoint* joints)
 	for (int32_t j = 0; j < count; ++j)
 	{
 		const b2cuJoint& jt = joints[j];
-		if (jt.type != B2CU_JOINT_REVOLUTE && jt.type != B2CU_JOINT_PRISMATIC && jt.type != B2CU_JOINT_DISTANCE &&
-		    jt.type != B2CU_JOINT_WELD && jt.type != B2CU_JOINT_WHEEL && jt.type != B2CU_JOINT_ROPE &&
-		    jt.type != B2CU_JOINT_FRICTION && jt.type != B2CU_JOINT_MOTOR)
-			return SetError(w, B2CU_ERR_UNSUPPORTED, "joint %d: type %d (pulley, gear and mouse joints are not solved)", j, jt.type);
+		if (jt.type < B2CU_JOINT_REVOLUTE || jt.type > B2CU_JOINT_MOTOR || jt.type == 6 /* e_gearJoint */)
+			return SetError(w, B2CU_ERR_UNSUPPORTED, "joint %d: type %d (the gear joint is not solved)", j, jt.type);
 		if (jt.bodyA < 0 || jt.bodyA >= w->bodyCount || jt.bodyB < 0 || jt.bodyB >= w->bodyCount || jt.bodyA == jt.bodyB)
 			return SetError(w, B2CU_ERR_ARGUMENT, "joint %d: bodies %d, %d", j, jt.bodyA, jt.bodyB);
 		if (!(jt.flags & B2CU_JOINT_COLLIDE_CONNECTED))

@@ -485,6 +485,33 @@ B2H_API int b2h_create_joints(void* p, int32 count, const b2cuJoint* rows)
 			def.correctionFactor = r.dampingRatio;
 			j = h->world->CreateJoint(&def);
 		}
+		else if (r.type == B2CU_JOINT_PULLEY)
+		{
+			b2PulleyJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(r.localAnchorA[0], r.localAnchorA[1]);
+			def.localAnchorB.Set(r.localAnchorB[0], r.localAnchorB[1]);
+			def.groundAnchorA.Set(r.axis[0], r.axis[1]);
+			def.groundAnchorB.Set(r.lowerAngle, r.upperAngle);
+			def.lengthA = r.length;
+			def.lengthB = r.referenceAngle;
+			def.ratio = r.motorSpeed;
+			j = h->world->CreateJoint(&def);
+		}
+		else if (r.type == B2CU_JOINT_MOUSE)
+		{
+			b2MouseJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.target.Set(r.axis[0], r.axis[1]);
+			def.maxForce = r.length;
+			def.frequencyHz = r.frequencyHz;
+			def.dampingRatio = r.dampingRatio;
+			j = h->world->CreateJoint(&def);
+		}
 		else if (r.type == B2CU_JOINT_DISTANCE)
 		{
 			b2DistanceJointDef def;
@@ -612,6 +639,14 @@ B2H_API void b2h_joint_set_spring(void* p, int32 joint, float length, float freq
 		j->SetFrequency(frequencyHz);
 		j->SetDampingRatio(dampingRatio);
 	}
+}
+
+/// b2MouseJoint::SetTarget / b2MotorJoint::SetLinearOffset
+B2H_API void b2h_joint_set_target(void* p, int32 joint, float x, float y)
+{
+	b2Joint* base = static_cast<Host*>(p)->joints[joint];
+	if (base->GetType() == e_mouseJoint) static_cast<b2MouseJoint*>(base)->SetTarget(b2Vec2(x, y));
+	else if (base->GetType() == e_motorJoint) static_cast<b2MotorJoint*>(base)->SetLinearOffset(b2Vec2(x, y));
 }
 
 B2H_API int b2h_joint_count(void* p) { return static_cast<Host*>(p)->world->GetJointCount(); }

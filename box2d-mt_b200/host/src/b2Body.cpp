@@ -394,6 +394,12 @@ void b2Body::SynchronizeProxies(const b2Transform& xf1, const b2Transform& xf2)
 void b2Body::ResetMassData()
 {
 	m_world->RefreshBodies();
+	if (m_jointList)
+	{
+		// a mouse joint's row carries this body's mass
+		m_world->RefreshJoints();
+		m_world->m_jointsDirty = true;
+	}
 	b2BodyView s = B2_STATE();
 	m_mass = 0.0f;
 	s.invMass = 0.0f;

@@ -10,6 +10,8 @@
 #include "Box2D/Dynamics/Joints/b2RopeJoint.h"
 #include "Box2D/Dynamics/Joints/b2FrictionJoint.h"
 #include "Box2D/Dynamics/Joints/b2MotorJoint.h"
+#include "Box2D/Dynamics/Joints/b2PulleyJoint.h"
+#include "Box2D/Dynamics/Joints/b2MouseJoint.h"
 #include "Box2D/Dynamics/b2Body.h"
 #include "Box2D/Dynamics/b2World.h"
 
@@ -794,4 +796,147 @@ void b2MotorJoint::SetCorrectionFactor(float32 factor)
 	if (factor == m_correctionFactor) return;
 	Touch();
 	m_correctionFactor = factor;
+}
+
+// ---- pulley (reference b2PulleyJoint.cpp:36-72, :266-340) ----------------------------------------------------------------
+
+void b2PulleyJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec2& groundA, const b2Vec2& groundB, const b2Vec2& anchorA,
+                                  const b2Vec2& anchorB, float32 r)
+{
+	bodyA = bA;
+	bodyB = bB;
+	groundAnchorA = groundA;
+	groundAnchorB = groundB;
+	localAnchorA = bA->GetLocalPoint(anchorA);
+	localAnchorB = bB->GetLocalPoint(anchorB);
+	lengthA = (anchorA - groundA).Length();
+	lengthB = (anchorB - groundB).Length();
+	ratio = r;
+	b2Assert(ratio > b2_epsilon);
+}
+
+b2PulleyJoint::b2PulleyJoint(const b2PulleyJointDef* def)
+	: b2Joint(def), m_groundAnchorA(def->groundAnchorA), m_groundAnchorB(def->groundAnchorB), m_localAnchorA(def->localAnchorA),
+	  m_localAnchorB(def->localAnchorB), m_lengthA(def->lengthA), m_lengthB(def->lengthB), m_ratio(def->ratio), m_impulse(0.0f),
+	  m_uB(0.0f, 0.0f)
+{
+	b2Assert(def->ratio != 0.0f);
+}
+
+void b2PulleyJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_PULLEY, m_bodyA, m_bodyB, m_collideConnected, m_localAnchorA, m_localAnchorB);
+	out->axis[0] = m_groundAnchorA.x;
+	out->axis[1] = m_groundAnchorA.y;
+	out->lowerAngle = m_groundAnchorB.x;
+	out->upperAngle = m_groundAnchorB.y;
+	out->length = m_lengthA;
+	out->referenceAngle = m_lengthB;
+	out->motorSpeed = m_ratio;
+	out->impulse[0] = m_impulse;
+	out->lastSolve[0] = m_uB.x;
+	out->lastSolve[1] = m_uB.y;
+}
+
+void b2PulleyJoint::ReadRecord(const b2cuJoint& in)
+{
+	m_impulse = in.impulse[0];
+	m_uB.Set(in.lastSolve[0], in.lastSolve[1]);
+}
+
+b2Vec2 b2PulleyJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2PulleyJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+b2Vec2 b2PulleyJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	b2Vec2 P = m_impulse * m_uB;
+	return inv_dt * P;
+}
+
+float32 b2PulleyJoint::GetReactionTorque(float32 inv_dt) const
+{
+	B2_NOT_USED(inv_dt);
+	return 0.0f;
+}
+
+float32 b2PulleyJoint::GetCurrentLengthA() const { return (m_bodyA->GetWorldPoint(m_localAnchorA) - m_groundAnchorA).Length(); }
+float32 b2PulleyJoint::GetCurrentLengthB() const { return (m_bodyB->GetWorldPoint(m_localAnchorB) - m_groundAnchorB).Length(); }
+
+void b2PulleyJoint::ShiftOrigin(const b2Vec2& newOrigin)
+{
+	Touch();
+	m_groundAnchorA -= newOrigin;
+	m_groundAnchorB -= newOrigin;
+}
+
+// ---- mouse (reference b2MouseJoint.cpp:32-94, :192-215) ------------------------------------------------------------------
+
+b2MouseJoint::b2MouseJoint(const b2MouseJointDef* def)
+	: b2Joint(def), m_targetA(def->target), m_maxForce(def->maxForce), m_frequencyHz(def->frequencyHz),
+	  m_dampingRatio(def->dampingRatio), m_impulse(0.0f, 0.0f)
+{
+	b2Assert(def->target.IsValid());
+	m_localAnchorB = b2MulT(m_bodyB->GetTransform(), m_targetA);
+}
+
+void b2MouseJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_MOUSE, m_bodyA, m_bodyB, m_collideConnected, b2Vec2(0.0f, 0.0f), m_localAnchorB);
+	out->axis[0] = m_targetA.x;
+	out->axis[1] = m_targetA.y;
+	out->length = m_maxForce;
+	out->frequencyHz = m_frequencyHz;
+	out->dampingRatio = m_dampingRatio;
+	out->maxMotorTorque = m_bodyB->GetMass(); // the solve uses the mass itself, not the stored inverse
+	out->impulse[0] = m_impulse.x;
+	out->impulse[1] = m_impulse.y;
+}
+
+void b2MouseJoint::ReadRecord(const b2cuJoint& in) { m_impulse.Set(in.impulse[0], in.impulse[1]); }
+
+b2Vec2 b2MouseJoint::GetAnchorA() const { return m_targetA; }
+b2Vec2 b2MouseJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+b2Vec2 b2MouseJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	return inv_dt * m_impulse;
+}
+
+float32 b2MouseJoint::GetReactionTorque(float32 inv_dt) const { return inv_dt * 0.0f; }
+
+void b2MouseJoint::SetTarget(const b2Vec2& target)
+{
+	if (target.x == m_targetA.x && target.y == m_targetA.y) return;
+	Touch();
+	m_bodyB->SetAwake(true);
+	m_targetA = target;
+}
+
+void b2MouseJoint::SetMaxForce(float32 force)
+{
+	if (force == m_maxForce) return;
+	Touch();
+	m_maxForce = force;
+}
+
+void b2MouseJoint::SetFrequency(float32 hz)
+{
+	if (hz == m_frequencyHz) return;
+	Touch();
+	m_frequencyHz = hz;
+}
+
+void b2MouseJoint::SetDampingRatio(float32 ratio)
+{
+	if (ratio == m_dampingRatio) return;
+	Touch();
+	m_dampingRatio = ratio;
+}
+
+void b2MouseJoint::ShiftOrigin(const b2Vec2& newOrigin)
+{
+	Touch();
+	m_targetA -= newOrigin;
 }

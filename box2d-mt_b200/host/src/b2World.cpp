@@ -10,6 +10,8 @@
 #include "Box2D/Dynamics/Joints/b2RopeJoint.h"
 #include "Box2D/Dynamics/Joints/b2FrictionJoint.h"
 #include "Box2D/Dynamics/Joints/b2MotorJoint.h"
+#include "Box2D/Dynamics/Joints/b2PulleyJoint.h"
+#include "Box2D/Dynamics/Joints/b2MouseJoint.h"
 
 #include <chrono>
 #include "Box2D/Collision/Shapes/b2CircleShape.h"
@@ -331,7 +333,7 @@ void b2World::RefreshJoints() const
 b2Joint* b2World::CreateJoint(const b2JointDef* def)
 {
 	if (IsLocked()) return nullptr;
-	if (def->type == e_unknownJoint || def->type == e_pulleyJoint || def->type == e_mouseJoint || def->type == e_gearJoint)
+	if (def->type == e_unknownJoint || def->type == e_gearJoint)
 	{
 		m_lastStatus = B2CU_ERR_UNSUPPORTED;
 		return nullptr;
@@ -345,6 +347,8 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def)
 	else if (def->type == e_ropeJoint) j = new b2RopeJoint(static_cast<const b2RopeJointDef*>(def));
 	else if (def->type == e_frictionJoint) j = new b2FrictionJoint(static_cast<const b2FrictionJointDef*>(def));
 	else if (def->type == e_motorJoint) j = new b2MotorJoint(static_cast<const b2MotorJointDef*>(def));
+	else if (def->type == e_pulleyJoint) j = new b2PulleyJoint(static_cast<const b2PulleyJointDef*>(def));
+	else if (def->type == e_mouseJoint) j = new b2MouseJoint(static_cast<const b2MouseJointDef*>(def));
 	else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
 	j->m_world = this;
 	j->m_index = (int32)m_joints.size();
@@ -783,6 +787,8 @@ void b2World::ShiftOrigin(const b2Vec2& newOrigin)
 		MarkProxyDirty(0);
 		MarkProxyDirty((int32)m_proxies.size() - 1);
 	}
+	// joints that hold world points (reference b2World.cpp:2096-2099)
+	for (size_t i = 0; i < m_joints.size(); ++i) m_joints[i]->ShiftOrigin(newOrigin);
 }
 
 // ---- step ------------------------------------------------------------------------------------------------

@@ -57,6 +57,7 @@ def load():
     lib.b2h_joint_set_motor.argtypes = [vp, i32, i32, f32, f32]
     lib.b2h_joint_set_limits.argtypes = [vp, i32, i32, f32, f32]
     lib.b2h_joint_count.argtypes = [vp]
+    lib.b2h_joint_set_target.argtypes = [vp, i32, f32, f32]
     lib.b2h_joint_set_spring.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_joint_order.argtypes = [vp, i32, vp]
     lib.b2h_profile.argtypes = [vp, vp]
@@ -152,6 +153,9 @@ class HostWorld:
     def joint_set_spring(self, joint, length, frequency_hz, damping_ratio):
         self.lib.b2h_joint_set_spring(self.h, joint, ctypes.c_float(length), ctypes.c_float(frequency_hz),
                                       ctypes.c_float(damping_ratio))
+
+    def joint_set_target(self, joint, x, y):
+        self.lib.b2h_joint_set_target(self.h, joint, ctypes.c_float(x), ctypes.c_float(y))
 
     def joint_set_limits(self, joint, enable, lower, upper):
         self.lib.b2h_joint_set_limits(self.h, joint, int(enable), ctypes.c_float(lower), ctypes.c_float(upper))

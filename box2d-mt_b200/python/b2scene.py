@@ -245,6 +245,29 @@ class Scene:
         self.joints.append(j)
         return len(self.joints) - 1
 
+    def pulley_joint(self, body_a, body_b, ground_anchor_a, ground_anchor_b, local_anchor_a, local_anchor_b, length_a,
+                     length_b, ratio=1.0, collide_connected=True):
+        """b2PulleyJointDef (b2PulleyJoint.h:29-74)"""
+        j = self._joint(T.JOINT_PULLEY, body_a, body_b, local_anchor_a, local_anchor_b, collide_connected)
+        j["axis"] = ground_anchor_a
+        j["lowerAngle"], j["upperAngle"] = ground_anchor_b
+        j["length"] = length_a
+        j["referenceAngle"] = length_b
+        j["motorSpeed"] = ratio
+        self.joints.append(j)
+        return len(self.joints) - 1
+
+    def mouse_joint(self, body_a, body_b, local_anchor_b, target, max_force, frequency_hz=5.0, damping_ratio=0.7):
+        """b2MouseJointDef (b2MouseJoint.h:28-60).  local_anchor_b must be the target in body B's frame at creation
+        (which is what the reference's constructor computes from the target)."""
+        j = self._joint(T.JOINT_MOUSE, body_a, body_b, (0.0, 0.0), local_anchor_b, False)
+        j["axis"] = target
+        j["length"] = max_force
+        j["frequencyHz"] = frequency_hz
+        j["dampingRatio"] = damping_ratio
+        self.joints.append(j)
+        return len(self.joints) - 1
+
     def joint_array(self):
         return np.array(self.joints, dtype=T.JOINT) if self.joints else np.zeros(0, T.JOINT)
 

@@ -7,7 +7,8 @@ does in float32 is done in np.float32 here so that body placement is bit-identic
 import numpy as np
 
 import b2cuda_types as T
-from b2scene import Scene, BODY_DEF, FIXTURE_DEF, BODYDEF_DEFAULT, BODYDEF_BULLET, BODYDEF_ALLOW_SLEEP, BODYDEF_FIXED_ROTATION
+from b2scene import (Scene, BODY_DEF, FIXTURE_DEF, BODYDEF_DEFAULT, BODYDEF_BULLET, BODYDEF_ALLOW_SLEEP,
+                     BODYDEF_FIXED_ROTATION, BODYDEF_AWAKE)
 
 F = np.float32
 
@@ -433,4 +434,34 @@ def machines(seed=0):
     b = s.body(T.DYNAMIC_BODY, (50.0, 6.0))
     s.fixture(b, s.box(0.5, 0.5), density=1.0)
     s.motor_joint(a, b, (0.0, 2.5), 0.3, max_force=200.0, max_torque=50.0, collide_connected=True)
+    return s
+
+
+def pulleys_and_mice(seed=0):
+    """Pulley joints (Testbed/Tests/Pulleys.h:27-72: two boxes over two ground anchors; here also a block and tackle with
+    ratio 2 and an unbalanced pair that runs one rope out) and mouse joints (the Testbed's drag: a box pulled towards a
+    target that the test moves, one pull saturating its force limit, one on a body that is asleep at first)."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.edge((-40.0, 0.0), (40.0, 0.0)))
+    s.fixture(g, s.circle(2.0, p=(-10.0, 18.0)))
+    s.fixture(g, s.circle(2.0, p=(10.0, 18.0)))
+    box = s.box(1.0, 2.0)
+    for n, (x0, ratio, d1, d2) in enumerate([(-10.0, 1.5, 5.0, 5.0), (12.0, 1.0, 5.0, 20.0), (26.0, 2.0, 5.0, 5.0)]):
+        a = s.body(T.DYNAMIC_BODY, (x0 - 4.0, 12.0))
+        s.fixture(a, box, density=d1)
+        b = s.body(T.DYNAMIC_BODY, (x0 + 4.0, 12.0))
+        s.fixture(b, box, density=d2)
+        s.pulley_joint(a, b, (x0 - 4.0, 22.0), (x0 + 4.0, 22.0), (0.0, 2.0), (0.0, 2.0), 8.0, 8.0, ratio=ratio,
+                       collide_connected=(n != 1))
+    small = s.box(0.5, 0.5)
+    b = s.body(T.DYNAMIC_BODY, (-30.0, 5.0))
+    s.fixture(b, small, density=1.0)
+    s.mouse_joint(g, b, (0.25, 0.25), (-29.75, 5.25), 1000.0)
+    b = s.body(T.DYNAMIC_BODY, (-25.0, 0.5))
+    s.fixture(b, small, density=5.0)
+    s.mouse_joint(g, b, (0.0, 0.5), (-25.0, 1.0), 10.0, frequency_hz=2.0, damping_ratio=0.1)
+    b = s.body(T.DYNAMIC_BODY, (-20.0, 0.5), flags=BODYDEF_DEFAULT & ~BODYDEF_AWAKE)
+    s.fixture(b, small, density=1.0)
+    s.mouse_joint(g, b, (0.0, 0.0), (-20.0, 0.5), 500.0)
     return s

@@ -335,11 +335,13 @@ B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
  *   rope joints       b2RopeJoint.cpp:47-195       maximum distance between two anchors
  *   friction joints   b2FrictionJoint.cpp:58-190   bounded linear and angular friction between two bodies
  *   motor joints      b2MotorJoint.cpp:66-200      drives body B to an offset from body A with bounded force / torque
+ *   pulley joints     b2PulleyJoint.cpp:74-264     lengthA + ratio * lengthB constant over two ground anchors
+ *   mouse joints      b2MouseJoint.cpp:96-190      soft bounded pull of a point of body B towards a world target
  * as rows of the coloured solver: inside every velocity iteration the joints run before the contacts, inside every
  * position iteration after them, as b2Island::Solve orders them (Dynamics/b2Island.cpp:259-273, :323-327, :363-380),
  * with warm starting.  A joint links the islands of its two bodies (b2World.cpp:1286-1320) and, unless
  * COLLIDE_CONNECTED, keeps them from colliding (b2Body::ShouldCollide, b2Body.cpp:428-449).  `type` uses b2JointType's
- * values; other types are refused with B2CU_ERR_UNSUPPORTED.
+ * values; the gear joint is refused with B2CU_ERR_UNSUPPORTED.
  * Fields by type: revolute   referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, flags LIMIT / MOTOR
  *                 prismatic  axis (b2PrismaticJointDef::localAxisA as given; normalised as the constructor does),
  *                            referenceAngle, lowerAngle / upperAngle (= lower / upper translation), maxMotorTorque
@@ -352,16 +354,24 @@ B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
  *                 friction   length (= maxForce), maxMotorTorque (= maxTorque); impulse[0..1] linear, impulse[2] angular
  *                 motor      axis (= linearOffset), referenceAngle (= angularOffset), length (= maxForce),
  *                            maxMotorTorque (= maxTorque), dampingRatio (= correctionFactor); impulses as friction
+ *                 pulley     axis (= groundAnchorA), lowerAngle / upperAngle (= groundAnchorB.x / .y), length (= lengthA),
+ *                            referenceAngle (= lengthB), motorSpeed (= ratio)
+ *                 mouse      axis (= target), length (= maxForce), frequencyHz, dampingRatio, maxMotorTorque (= the mass of
+ *                            body B, b2Body::GetMass(): the reference reads the mass, not its inverse); localAnchorB is
+ *                            the grabbed point; body A takes no part in the solve
  * impulse / motorImpulse / limitState are the joint's persistent solver state (m_impulse -- a scalar in impulse[0] for
  * the distance joint --, m_motorImpulse, m_limitState) and round-trip through Get / Set.  lastSolve is written by the
  * step with the world-space directions of its solve, which GetReactionForce needs: the distance and rope joints' m_u
- * in [0..1], the prismatic joint's m_axis in [0..1] and m_perp in [2..3], the wheel joint's m_ax and m_ay likewise.
+ * in [0..1], the pulley joint's m_uB in [0..1], the prismatic joint's m_axis in [0..1] and m_perp in [2..3], the wheel
+ * joint's m_ax and m_ay likewise.
  * work is solver scratch that the reference carries from step to step (wheel: m_sAx, m_sBx). */
 enum
 {
 	B2CU_JOINT_REVOLUTE = 1,
 	B2CU_JOINT_PRISMATIC = 2,
 	B2CU_JOINT_DISTANCE = 3,
+	B2CU_JOINT_PULLEY = 4,
+	B2CU_JOINT_MOUSE = 5,
 	B2CU_JOINT_WHEEL = 7,
 	B2CU_JOINT_WELD = 8,
 	B2CU_JOINT_FRICTION = 9,

@@ -57,6 +57,7 @@ def load(stock=False):
     lib.b2ref_joint_set_motor.argtypes = [vp, i32, i32, f32, f32]
     lib.b2ref_joint_set_limits.argtypes = [vp, i32, i32, f32, f32]
     lib.b2ref_destroy_joint.argtypes = [vp, i32]
+    lib.b2ref_joint_set_target.argtypes = [vp, i32, f32, f32]
     lib.b2ref_joint_set_spring.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_joint_readings.argtypes = [vp, f32, vp]
     lib.b2ref_profile.argtypes = [vp, vp]
@@ -135,6 +136,9 @@ class RefWorld:
     def joint_set_spring(self, joint, length, frequency_hz, damping_ratio):
         self.lib.b2ref_joint_set_spring(self.h, joint, ctypes.c_float(length), ctypes.c_float(frequency_hz),
                                         ctypes.c_float(damping_ratio))
+
+    def joint_set_target(self, joint, x, y):
+        self.lib.b2ref_joint_set_target(self.h, joint, ctypes.c_float(x), ctypes.c_float(y))
 
     def destroy_joint(self, joint):
         self.lib.b2ref_destroy_joint(self.h, joint)

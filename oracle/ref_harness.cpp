@@ -944,6 +944,40 @@ int32_t b2ref_set_joints(b2refWorld* w, int32_t count, const b2cuJoint* joints)
 			mj->m_angularImpulse = j.impulse[2];
 			joint = mj;
 		}
+		else if (j.type == B2CU_JOINT_PULLEY)
+		{
+			b2PulleyJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.localAnchorA.Set(j.localAnchorA[0], j.localAnchorA[1]);
+			def.localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+			def.groundAnchorA.Set(j.axis[0], j.axis[1]);
+			def.groundAnchorB.Set(j.lowerAngle, j.upperAngle);
+			def.lengthA = j.length;
+			def.lengthB = j.referenceAngle;
+			def.ratio = j.motorSpeed;
+			b2PulleyJoint* pj = (b2PulleyJoint*)w->world->CreateJoint(&def);
+			pj->m_impulse = j.impulse[0];
+			pj->m_uB.Set(j.lastSolve[0], j.lastSolve[1]);
+			joint = pj;
+		}
+		else if (j.type == B2CU_JOINT_MOUSE)
+		{
+			b2MouseJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.target.Set(j.axis[0], j.axis[1]);
+			def.maxForce = j.length;
+			def.frequencyHz = j.frequencyHz;
+			def.dampingRatio = j.dampingRatio;
+			b2MouseJoint* mj = (b2MouseJoint*)w->world->CreateJoint(&def);
+			/* the constructor derives the grabbed point from the target; the record states it */
+			mj->m_localAnchorB.Set(j.localAnchorB[0], j.localAnchorB[1]);
+			mj->m_impulse.Set(j.impulse[0], j.impulse[1]);
+			joint = mj;
+		}
 		else if (j.type == B2CU_JOINT_DISTANCE)
 		{
 			b2DistanceJointDef def;
@@ -1041,6 +1075,14 @@ void b2ref_joint_set_spring(b2refWorld* w, int32_t joint, float length, float fr
 		j->SetFrequency(frequencyHz);
 		j->SetDampingRatio(dampingRatio);
 	}
+}
+
+/* b2MouseJoint::SetTarget / b2MotorJoint::SetLinearOffset */
+void b2ref_joint_set_target(b2refWorld* w, int32_t joint, float x, float y)
+{
+	b2Joint* base = w->joints[joint];
+	if (base->GetType() == e_mouseJoint) ((b2MouseJoint*)base)->SetTarget(b2Vec2(x, y));
+	else if (base->GetType() == e_motorJoint) ((b2MotorJoint*)base)->SetLinearOffset(b2Vec2(x, y));
 }
 
 void b2ref_destroy_joint(b2refWorld* w, int32_t joint)
@@ -1213,6 +1255,40 @@ void b2ref_export_joints(b2refWorld* w, b2cuJoint* out)
 			o.impulse[0] = j->m_linearImpulse.x;
 			o.impulse[1] = j->m_linearImpulse.y;
 			o.impulse[2] = j->m_angularImpulse;
+		}
+		else if (base->GetType() == e_pulleyJoint)
+		{
+			const b2PulleyJoint* j = (const b2PulleyJoint*)base;
+			o.type = B2CU_JOINT_PULLEY;
+			o.localAnchorA[0] = j->m_localAnchorA.x;
+			o.localAnchorA[1] = j->m_localAnchorA.y;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			o.axis[0] = j->m_groundAnchorA.x;
+			o.axis[1] = j->m_groundAnchorA.y;
+			o.lowerAngle = j->m_groundAnchorB.x;
+			o.upperAngle = j->m_groundAnchorB.y;
+			o.length = j->m_lengthA;
+			o.referenceAngle = j->m_lengthB;
+			o.motorSpeed = j->m_ratio;
+			o.impulse[0] = j->m_impulse;
+			o.lastSolve[0] = j->m_uB.x;
+			o.lastSolve[1] = j->m_uB.y;
+		}
+		else if (base->GetType() == e_mouseJoint)
+		{
+			const b2MouseJoint* j = (const b2MouseJoint*)base;
+			o.type = B2CU_JOINT_MOUSE;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			o.axis[0] = j->m_targetA.x;
+			o.axis[1] = j->m_targetA.y;
+			o.length = j->m_maxForce;
+			o.frequencyHz = j->m_frequencyHz;
+			o.dampingRatio = j->m_dampingRatio;
+			o.maxMotorTorque = j->m_bodyB->GetMass();
+			o.impulse[0] = j->m_impulse.x;
+			o.impulse[1] = j->m_impulse.y;
 		}
 		else if (base->GetType() == e_distanceJoint)
 		{

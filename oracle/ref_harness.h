@@ -144,6 +144,7 @@ void b2ref_export_joints(b2refWorld* w, b2cuJoint* out);
 void b2ref_joint_set_motor(b2refWorld* w, int32_t joint, int32_t enable, float speed, float maxTorque);
 void b2ref_joint_set_limits(b2refWorld* w, int32_t joint, int32_t enable, float lower, float upper);
 void b2ref_joint_set_spring(b2refWorld* w, int32_t joint, float length, float frequencyHz, float dampingRatio);
+void b2ref_joint_set_target(b2refWorld* w, int32_t joint, float x, float y);
 void b2ref_destroy_joint(b2refWorld* w, int32_t joint);
 void b2ref_joint_readings(b2refWorld* w, float inv_dt, float* out6);
 /* first pass of b2World::SolveTOI on the current state (see ref_harness.cpp) */

@@ -148,13 +148,13 @@ def test_host_api_lockstep(gpu, name, steps):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,steps", [("tumbler_joint", 150), ("hanging_chains", 300), ("joint_zoo", 300),
-                                        ("rods_and_welds", 300), ("sliders", 300), ("machines", 300)])
+                                        ("rods_and_welds", 300), ("sliders", 300), ("machines", 300), ("pulleys_and_mice", 300)])
 def test_host_api_joints_lockstep(gpu, name, steps):
     """Worlds with revolute, distance and weld joints built through b2World::CreateJoint (the Testbed's Tumbler with its
     motor joint, hanging chains, every branch of the revolute joint, the Web and the Cantilever) and stepped through
     b2World::Step stay bit-identical to the reference: bodies, events and what the joints' accessors report."""
     make = {"tumbler_joint": lambda: scenes.tumbler(60, motor_joint=True), "hanging_chains": lambda: scenes.hanging_chains(3, 10),
-            "joint_zoo": scenes.joint_zoo, "rods_and_welds": scenes.rods_and_welds, "sliders": scenes.sliders, "machines": scenes.machines}[name]
+            "joint_zoo": scenes.joint_zoo, "rods_and_welds": scenes.rods_and_welds, "sliders": scenes.sliders, "machines": scenes.machines, "pulleys_and_mice": scenes.pulleys_and_mice}[name]
     h, r, begins = _host_lockstep(make(), steps)
     assert h.joint_count() == r.joint_count > 0
     assert h.hash() == r.hash()
@@ -244,6 +244,32 @@ def test_host_api_slider_edits_between_steps(gpu):
         w.joint_set_limits(4, False, -0.5, 3.0)    # limits removed
         w.joint_set_limits(2, True, 0.5, 2.5)      # equal limits open up
     run(120)
+
+
+@pytest.mark.gpu
+def test_host_api_mouse_drag(gpu):
+    """b2MouseJoint::SetTarget every few steps (a drag), b2MotorJoint::SetLinearOffset, and the mouse joint released
+    (DestroyJoint), as an interactive program does."""
+    scene = scenes.pulleys_and_mice()
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+    for s in range(200):
+        if s % 5 == 0:
+            for w in (h, r):
+                w.joint_set_target(3, -29.75 + 0.1 * s, 5.25 + 2.0 * np.sin(0.1 * s))
+                w.joint_set_target(5, -20.0 - 0.05 * s, 0.5 + 0.02 * s)   # wakes the sleeping body
+        if s == 120:
+            for w in (h, r):
+                w.destroy_joint(4)
+        h.step()
+        r.set_joint_order(h.joint_order())
+        assert r.step_ordered(h.solver_order()) == 0, s
+        try:
+            parity.compare_bodies(h.bodies(), r.bodies())
+            parity.assert_floats_equal("joint readings", h.joint_readings(), r.joint_readings())
+        except AssertionError as e:
+            raise AssertionError("step %d: %s" % (s, e))
 
 
 @pytest.mark.gpu
