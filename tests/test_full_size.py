@@ -112,3 +112,42 @@ def test_window_of_the_pile_follows_the_broadphase_rule(pile_worlds):
     # a new overlap gets its contact in the same step; a contact outlives the overlap of its boxes by at most one step
     assert want <= got, (len(want), len(got), len(want - got))
     assert len(got - want) <= max(8, len(got) // 20), (len(want), len(got))
+
+
+def test_joint_chains_at_scale():
+    """40,000 revolute joints (1000 hanging chains of 40 links that swing into each other and onto the floor): two
+    device worlds agree bit for bit, the joint order is a proper colouring (no two joints of one class share a dynamic
+    body), and the hinges hold (the reference itself leaves up to 0.045 of anchor error on a swinging 40-link chain with
+    3 position iterations; here chains also hit each other)."""
+    scene = scenes.hanging_chains(1000, 40)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    a = b2host.HostWorld(scene, download_bodies=False, events=False)
+    b = b2host.HostWorld(scene, download_bodies=False, events=False)
+    for _ in range(120):
+        a.step()
+        b.step()
+    ba, bb = a.bodies(), b.bodies()
+    assert ba.tobytes() == bb.tobytes()
+    ja, jb = a.device_world().get_joints(), b.device_world().get_joints()
+    assert len(ja) == 40000 and ja.tobytes() == jb.tobytes()
+
+    # colouring: walk the order, a class ends where a dynamic body would repeat
+    order = a.device_world().joint_order()
+    assert sorted(order.tolist()) == list(range(len(ja)))
+    dynamic = (ba["flags"] & T.BODY_TYPE_MASK) == T.DYNAMIC_BODY
+    seen, classes = set(), 1
+    for j in order:
+        ends = [int(x) for x in (ja["bodyA"][j], ja["bodyB"][j]) if dynamic[x]]
+        if any(e in seen for e in ends):
+            seen, classes = set(), classes + 1
+        seen.update(ends)
+    assert classes <= 3   # a chain needs two classes; ids inside a class ascend, so at most one extra break
+
+    # hinges hold: world anchors of both sides coincide
+    def world(anchor, body):
+        s, c = ba["qs"][body], ba["qc"][body]
+        return np.stack([ba["px"][body] + c * anchor[:, 0] - s * anchor[:, 1], ba["py"][body] + s * anchor[:, 0] + c * anchor[:, 1]], 1)
+
+    gap = np.linalg.norm(world(ja["localAnchorA"], ja["bodyA"]) - world(ja["localAnchorB"], ja["bodyB"]), axis=1)
+    assert gap.max() < 0.15, gap.max()   # well inside a link's half-thickness
+    assert np.abs(ja["impulse"][:, :2]).max() > 1.0   # the joints do carry load
