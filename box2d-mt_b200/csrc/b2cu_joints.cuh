@@ -3,7 +3,8 @@
 // (b2DistanceJoint.cpp:63-222), b2WeldJoint (b2WeldJoint.cpp:59-308) and b2PrismaticJoint
 // (b2PrismaticJoint.cpp:100-478), b2WheelJoint (b2WheelJoint.cpp:78-318), b2RopeJoint (b2RopeJoint.cpp:47-195),
 // b2FrictionJoint (b2FrictionJoint.cpp:58-190), b2MotorJoint (b2MotorJoint.cpp:66-200), b2PulleyJoint
-// (b2PulleyJoint.cpp:74-264) and b2MouseJoint (b2MouseJoint.cpp:96-190), and the small linear solves they use
+// (b2PulleyJoint.cpp:74-264), b2MouseJoint (b2MouseJoint.cpp:96-190) and b2GearJoint (b2GearJoint.cpp:131-390), and the
+// small linear solves they use
 // (b2Mat33::Solve33 / Solve22 / GetInverse22 / GetSymInverse33, Box2D/Common/b2Math.cpp:25-94; b2Mat22::Solve,
 // b2Math.h:221-233) with the same fp32 arithmetic in the same order.  One thread solves one joint; joints of one colour class share no
 // dynamic body, so a class is solved in parallel and the classes one after the other.
@@ -1689,6 +1690,216 @@ __device__ __forceinline__ void MouseSolveVelocity(const DeviceArrays& d, int j,
 	d.joints[j].impulse[1] = total.y;
 }
 
+// ---- gear joint (b2GearJoint.cpp:131-390) ---------------------------------------------------------------------------------
+// Couples the coordinates of two other joints (each revolute or prismatic): coordinateA + ratio * coordinateB = constant.
+// Four bodies take part: A and B are the second bodies of joint 1 and 2, C and D their first bodies.
+// Record: limitState = body C, reserved = body D, flags GEAR_PRISMATIC_1 / _2, axis = localAnchorC, (lowerAngle,
+// upperAngle) = localAnchorD, work[0..1] = localAxisC, work[2..3] = localAxisD, referenceAngle = referenceAngleA,
+// maxMotorTorque = referenceAngleB, motorSpeed = ratio, length = constant.
+// Row use: ex = (lcC, mC), ey = (lcD, mD), ez = (iC, iD, -), axis = JvAC, perp = JvBD, a1 = JwA, a2 = JwB, s1 = JwC, s2 = JwD,
+// motorMass = m_mass.
+
+__device__ __forceinline__ void StoreVelocity4(const DeviceArrays& d, int body, float invMass, float invI, Vec2 v, float w, float keep)
+{
+	if (invMass != 0.0f || invI != 0.0f) d.vel[body] = make_float4(v.x, v.y, w, keep);
+}
+
+__device__ __forceinline__ void GearInit(const DeviceArrays& d, int j, b2cuJoint jt, JointRow r, float dtRatio, int warmStarting)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB, bC = jt.limitState, bD = jt.reserved;
+	float4 massC = d.mass[bC], massD = d.mass[bD];
+	Vec2 lcC = V(massC.z, massC.w), lcD = V(massD.z, massD.w);
+	float mA = r.invMassA, mB = r.invMassB, mC = massC.x, mD = massD.x;
+	float iA = r.invIA, iB = r.invIB, iC = massC.y, iD = massD.y;
+	r.ex = V3(lcC.x, lcC.y, mC);
+	r.ey = V3(lcD.x, lcD.y, mD);
+	r.ez = V3(iC, iD, 0.0f);
+	const float ratio = jt.motorSpeed;
+
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB], vC4 = d.vel[bC], vD4 = d.vel[bD];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y), vC = V(vC4.x, vC4.y), vD = V(vD4.x, vD4.y);
+	float wA = vA4.z, wB = vB4.z, wC = vC4.z, wD = vD4.z;
+	Rot qA = SinCos(d.pos[bA].z), qB = SinCos(d.pos[bB].z), qC = SinCos(d.pos[bC].z), qD = SinCos(d.pos[bD].z);
+
+	float mass = 0.0f;
+	if (!(jt.flags & B2CU_JOINT_GEAR_PRISMATIC_1))
+	{
+		r.axis = V(0.0f, 0.0f);
+		r.a1 = 1.0f;
+		r.s1 = 1.0f;
+		mass += iA + iC;
+	}
+	else
+	{
+		Vec2 u = Mul(qC, V(jt.work[0], jt.work[1]));
+		Vec2 rC = Mul(qC, V(jt.axis[0], jt.axis[1]) - lcC);
+		Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+		r.axis = u;
+		r.s1 = Cross(rC, u);
+		r.a1 = Cross(rA, u);
+		mass += mC + mA + iC * r.s1 * r.s1 + iA * r.a1 * r.a1;
+	}
+	if (!(jt.flags & B2CU_JOINT_GEAR_PRISMATIC_2))
+	{
+		r.perp = V(0.0f, 0.0f);
+		r.a2 = ratio;
+		r.s2 = ratio;
+		mass += ratio * ratio * (iB + iD);
+	}
+	else
+	{
+		Vec2 u = Mul(qD, V(jt.work[2], jt.work[3]));
+		Vec2 rD = Mul(qD, V(jt.lowerAngle, jt.upperAngle) - lcD);
+		Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+		r.perp = ratio * u;
+		r.s2 = ratio * Cross(rD, u);
+		r.a2 = ratio * Cross(rB, u);
+		mass += ratio * ratio * (mD + mB) + iD * r.s2 * r.s2 + iB * r.a2 * r.a2;
+	}
+	r.motorMass = mass > 0.0f ? 1.0f / mass : 0.0f;
+
+	if (warmStarting)
+	{
+		// note: the reference does not scale the gear impulse by dtRatio
+		float imp = jt.impulse[0];
+		vA = vA + (mA * imp) * r.axis;
+		wA += iA * imp * r.a1;
+		vB = vB + (mB * imp) * r.perp;
+		wB += iB * imp * r.a2;
+		vC = vC - (mC * imp) * r.axis;
+		wC -= iC * imp * r.s1;
+		vD = vD - (mD * imp) * r.perp;
+		wD -= iD * imp * r.s2;
+	}
+	else
+	{
+		jt.impulse[0] = 0.0f;
+	}
+
+	StoreVelocity4(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity4(d, bB, mB, iB, vB, wB, vB4.w);
+	StoreVelocity4(d, bC, mC, iC, vC, wC, vC4.w);
+	StoreVelocity4(d, bD, mD, iD, vD, wD, vD4.w);
+	jt.lastSolve[0] = r.axis.x; // GetReactionForce / GetReactionTorque read m_JvAC and m_JwA
+	jt.lastSolve[1] = r.axis.y;
+	jt.lastSolve[2] = r.a1;
+	d.jointRows[j] = r;
+	d.joints[j] = jt;
+}
+
+__device__ __forceinline__ void GearSolveVelocity(const DeviceArrays& d, int j, const JointRow& r, const b2cuJoint& jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB, bC = jt.limitState, bD = jt.reserved;
+	float mA = r.invMassA, mB = r.invMassB, mC = r.ex.z, mD = r.ey.z;
+	float iA = r.invIA, iB = r.invIB, iC = r.ez.x, iD = r.ez.y;
+	float4 vA4 = d.vel[bA], vB4 = d.vel[bB], vC4 = d.vel[bC], vD4 = d.vel[bD];
+	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y), vC = V(vC4.x, vC4.y), vD = V(vD4.x, vD4.y);
+	float wA = vA4.z, wB = vB4.z, wC = vC4.z, wD = vD4.z;
+
+	float Cdot = Dot(r.axis, vA - vC) + Dot(r.perp, vB - vD);
+	Cdot += (r.a1 * wA - r.s1 * wC) + (r.a2 * wB - r.s2 * wD);
+	float impulse = -r.motorMass * Cdot;
+	float total = jt.impulse[0] + impulse;
+
+	vA = vA + (mA * impulse) * r.axis;
+	wA += iA * impulse * r.a1;
+	vB = vB + (mB * impulse) * r.perp;
+	wB += iB * impulse * r.a2;
+	vC = vC - (mC * impulse) * r.axis;
+	wC -= iC * impulse * r.s1;
+	vD = vD - (mD * impulse) * r.perp;
+	wD -= iD * impulse * r.s2;
+
+	StoreVelocity4(d, bA, mA, iA, vA, wA, vA4.w);
+	StoreVelocity4(d, bB, mB, iB, vB, wB, vB4.w);
+	StoreVelocity4(d, bC, mC, iC, vC, wC, vC4.w);
+	StoreVelocity4(d, bD, mD, iD, vD, wD, vD4.w);
+	d.joints[j].impulse[0] = total;
+}
+
+__device__ __forceinline__ bool GearSolvePosition(const DeviceArrays& d, const JointRow& r, const b2cuJoint& jt)
+{
+	const int bA = jt.bodyA, bB = jt.bodyB, bC = jt.limitState, bD = jt.reserved;
+	float mA = r.invMassA, mB = r.invMassB, mC = r.ex.z, mD = r.ey.z;
+	float iA = r.invIA, iB = r.invIB, iC = r.ez.x, iD = r.ez.y;
+	Vec2 lcC = V(r.ex.x, r.ex.y), lcD = V(r.ey.x, r.ey.y);
+	const float ratio = jt.motorSpeed;
+	float4 pA = d.pos[bA], pB = d.pos[bB], pC = d.pos[bC], pD = d.pos[bD];
+	Vec2 cA = V(pA.x, pA.y), cB = V(pB.x, pB.y), cC = V(pC.x, pC.y), cD = V(pD.x, pD.y);
+	float aA = pA.z, aB = pB.z, aC = pC.z, aD = pD.z;
+	Rot qA = SinCos(aA), qB = SinCos(aB), qC = SinCos(aC), qD = SinCos(aD);
+
+	float coordinateA, coordinateB;
+	Vec2 JvAC, JvBD;
+	float JwA, JwB, JwC, JwD;
+	float mass = 0.0f;
+
+	if (!(jt.flags & B2CU_JOINT_GEAR_PRISMATIC_1))
+	{
+		JvAC = V(0.0f, 0.0f);
+		JwA = 1.0f;
+		JwC = 1.0f;
+		mass += iA + iC;
+		coordinateA = aA - aC - jt.referenceAngle;
+	}
+	else
+	{
+		Vec2 localAxisC = V(jt.work[0], jt.work[1]);
+		Vec2 u = Mul(qC, localAxisC);
+		Vec2 rC = Mul(qC, V(jt.axis[0], jt.axis[1]) - lcC);
+		Vec2 rA = Mul(qA, V(jt.localAnchorA[0], jt.localAnchorA[1]) - r.localCenterA);
+		JvAC = u;
+		JwC = Cross(rC, u);
+		JwA = Cross(rA, u);
+		mass += mC + mA + iC * JwC * JwC + iA * JwA * JwA;
+		Vec2 pc = V(jt.axis[0], jt.axis[1]) - lcC;
+		Vec2 pa = MulT(qC, rA + (cA - cC));
+		coordinateA = Dot(pa - pc, localAxisC);
+	}
+	if (!(jt.flags & B2CU_JOINT_GEAR_PRISMATIC_2))
+	{
+		JvBD = V(0.0f, 0.0f);
+		JwB = ratio;
+		JwD = ratio;
+		mass += ratio * ratio * (iB + iD);
+		coordinateB = aB - aD - jt.maxMotorTorque;
+	}
+	else
+	{
+		Vec2 localAxisD = V(jt.work[2], jt.work[3]);
+		Vec2 u = Mul(qD, localAxisD);
+		Vec2 rD = Mul(qD, V(jt.lowerAngle, jt.upperAngle) - lcD);
+		Vec2 rB = Mul(qB, V(jt.localAnchorB[0], jt.localAnchorB[1]) - r.localCenterB);
+		JvBD = ratio * u;
+		JwD = ratio * Cross(rD, u);
+		JwB = ratio * Cross(rB, u);
+		mass += ratio * ratio * (mD + mB) + iD * JwD * JwD + iB * JwB * JwB;
+		Vec2 pd = V(jt.lowerAngle, jt.upperAngle) - lcD;
+		Vec2 pb = MulT(qD, rB + (cB - cD));
+		coordinateB = Dot(pb - pd, localAxisD);
+	}
+
+	float C = (coordinateA + ratio * coordinateB) - jt.length;
+	float impulse = 0.0f;
+	if (mass > 0.0f) impulse = -C / mass;
+
+	cA = cA + mA * impulse * JvAC;
+	aA += iA * impulse * JwA;
+	cB = cB + mB * impulse * JvBD;
+	aB += iB * impulse * JwB;
+	cC = cC - mC * impulse * JvAC;
+	aC -= iC * impulse * JwC;
+	cD = cD - mD * impulse * JvBD;
+	aD -= iD * impulse * JwD;
+
+	if (mA != 0.0f || iA != 0.0f) d.pos[bA] = make_float4(cA.x, cA.y, aA, pA.w);
+	if (mB != 0.0f || iB != 0.0f) d.pos[bB] = make_float4(cB.x, cB.y, aB, pB.w);
+	if (mC != 0.0f || iC != 0.0f) d.pos[bC] = make_float4(cC.x, cC.y, aC, pC.w);
+	if (mD != 0.0f || iD != 0.0f) d.pos[bD] = make_float4(cD.x, cD.y, aD, pD.w);
+	// the reference never measures the gear's error: it always reports "solved"
+	return true;
+}
+
 // ---- dispatch by joint type -------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float dtRatio, int warmStarting, float h)
@@ -1709,6 +1920,7 @@ __device__ __forceinline__ void JointInitOne(const DeviceArrays& d, int j, float
 	else if (jt.type == B2CU_JOINT_MOTOR) FrictionMotorInit(d, j, jt, r, dtRatio, warmStarting, true);
 	else if (jt.type == B2CU_JOINT_PULLEY) PulleyInit(d, j, jt, r, dtRatio, warmStarting);
 	else if (jt.type == B2CU_JOINT_MOUSE) MouseInit(d, j, jt, r, dtRatio, warmStarting, h);
+	else if (jt.type == B2CU_JOINT_GEAR) GearInit(d, j, jt, r, dtRatio, warmStarting);
 	else WeldInit(d, j, jt, r, dtRatio, warmStarting, h);
 }
 
@@ -1726,6 +1938,7 @@ __device__ __forceinline__ void JointSolveVelocityOne(const DeviceArrays& d, int
 	else if (jt.type == B2CU_JOINT_MOTOR) FrictionMotorSolveVelocity(d, j, r, jt, h, true);
 	else if (jt.type == B2CU_JOINT_PULLEY) PulleySolveVelocity(d, j, r, jt);
 	else if (jt.type == B2CU_JOINT_MOUSE) MouseSolveVelocity(d, j, r, jt, h);
+	else if (jt.type == B2CU_JOINT_GEAR) GearSolveVelocity(d, j, r, jt);
 	else WeldSolveVelocity(d, j, r, jt);
 }
 
@@ -1739,6 +1952,7 @@ __device__ __forceinline__ bool JointSolvePositionOne(const DeviceArrays& d, int
 	if (jt.type == B2CU_JOINT_ROPE) return RopeSolvePosition(d, r, jt);
 	if (jt.type == B2CU_JOINT_FRICTION || jt.type == B2CU_JOINT_MOTOR || jt.type == B2CU_JOINT_MOUSE) return true;
 	if (jt.type == B2CU_JOINT_PULLEY) return PulleySolvePosition(d, r, jt);
+	if (jt.type == B2CU_JOINT_GEAR) return GearSolvePosition(d, r, jt);
 	return WeldSolvePosition(d, r, jt);
 }
 

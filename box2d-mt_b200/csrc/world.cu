@@ -986,9 +986,11 @@ static int ColourJoints(b2cuWorld* w)
 	for (int j = 0; j < nj; ++j)
 	{
 		uint32_t mask = 0;
-		const int bodies[2] = {joints[j].bodyA, joints[j].bodyB};
-		bool dynamic[2];
-		for (int k = 0; k < 2; ++k)
+		// a gear joint also writes the first bodies of its two joints
+		const int nBodies = joints[j].type == B2CU_JOINT_GEAR ? 4 : 2;
+		const int bodies[4] = {joints[j].bodyA, joints[j].bodyB, joints[j].limitState, joints[j].reserved};
+		bool dynamic[4];
+		for (int k = 0; k < nBodies; ++k)
 		{
 			dynamic[k] = (bflags[bodies[k]] & B2CU_BODY_TYPE_MASK) == B2CU_DYNAMIC_BODY;
 			if (k == 0 && joints[j].type == B2CU_JOINT_MOUSE) dynamic[k] = false; // a mouse joint writes body B only
@@ -998,7 +1000,7 @@ static int ColourJoints(b2cuWorld* w)
 		while (colour < B2CU_MAX_JOINT_COLOURS && (mask & (1u << colour))) ++colour;
 		classes[colour].push_back(j);
 		if (colour < B2CU_MAX_JOINT_COLOURS)
-			for (int k = 0; k < 2; ++k)
+			for (int k = 0; k < nBodies; ++k)
 				if (dynamic[k]) used[bodies[k]] |= 1u << colour;
 	}
 	std::vector<int> order;
@@ -1025,8 +1027,11 @@ int b2cuSetJoints(b2cuWorld* w, int32_t count, const b2cuJoint* joints)
 	for (int32_t j = 0; j < count; ++j)
 	{
 		const b2cuJoint& jt = joints[j];
-		if (jt.type < B2CU_JOINT_REVOLUTE || jt.type > B2CU_JOINT_MOTOR || jt.type == 6 /* e_gearJoint */)
-			return SetError(w, B2CU_ERR_UNSUPPORTED, "joint %d: type %d (the gear joint is not solved)", j, jt.type);
+		if (jt.type < B2CU_JOINT_REVOLUTE || jt.type > B2CU_JOINT_MOTOR)
+			return SetError(w, B2CU_ERR_UNSUPPORTED, "joint %d: unknown type %d", j, jt.type);
+		if (jt.type == B2CU_JOINT_GEAR &&
+		    (jt.limitState < 0 || jt.limitState >= w->bodyCount || jt.reserved < 0 || jt.reserved >= w->bodyCount))
+			return SetError(w, B2CU_ERR_ARGUMENT, "gear joint %d: bodies C, D = %d, %d", j, jt.limitState, jt.reserved);
 		if (jt.bodyA < 0 || jt.bodyA >= w->bodyCount || jt.bodyB < 0 || jt.bodyB >= w->bodyCount || jt.bodyA == jt.bodyB)
 			return SetError(w, B2CU_ERR_ARGUMENT, "joint %d: bodies %d, %d", j, jt.bodyA, jt.bodyB);
 		if (!(jt.flags & B2CU_JOINT_COLLIDE_CONNECTED))

@@ -1,8 +1,7 @@
 // Joint base class (reference: Box2D/Dynamics/Joints/b2Joint.h:28-226).  A joint is a host handle: its parameters and
 // its persistent solver state (accumulated impulses) live in the object, travel to the device as one b2cuJoint row of
 // the world's joint table, and come back after a step when somebody asks for them.  The solve itself is the device's
-// (csrc/b2cu_joints.cuh).  This version of the GPU path solves every joint type except the gear joint,
-// which b2World::CreateJoint refuses.
+// (csrc/b2cu_joints.cuh).  This version of the GPU path solves all eleven joint types.
 #ifndef B2_JOINT_H
 #define B2_JOINT_H
 

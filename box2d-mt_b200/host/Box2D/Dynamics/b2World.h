@@ -1,7 +1,7 @@
 // b2World (reference: Box2D/Dynamics/b2World.h:43-469, b2World.cpp).  Owns bodies and fixtures as host handles
 // over struct-of-arrays state (the records of include/b2cuda.h) that is mirrored to the device; Step delegates
-// to the executor (b2CudaStepExecutor).  The gear joint and debug draw are
-// outside this version of the GPU path: the former are refused by CreateJoint, the latter is not declared.
+// to the executor (b2CudaStepExecutor).  Debug draw is outside this version of the
+// GPU path and is not declared.
 #ifndef B2_WORLD_H
 #define B2_WORLD_H
 
@@ -90,7 +90,7 @@ public:
 	b2Body* CreateBody(const b2BodyDef* def);
 	void DestroyBody(b2Body* body);
 
-	/// reference: b2World.h:87-95.  Every joint type but the gear joint in this version: that one returns nullptr and sets
+	/// reference: b2World.h:87-95.  All eleven joint types; an unknown type returns nullptr and sets
 	/// GetLastStepStatus() to B2CU_ERR_UNSUPPORTED.  Not while the world is locked.
 	b2Joint* CreateJoint(const b2JointDef* def);
 	void DestroyJoint(b2Joint* joint);

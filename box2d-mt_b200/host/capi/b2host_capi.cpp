@@ -512,6 +512,19 @@ B2H_API int b2h_create_joints(void* p, int32 count, const b2cuJoint* rows)
 			def.dampingRatio = r.dampingRatio;
 			j = h->world->CreateJoint(&def);
 		}
+		else if (r.type == B2CU_JOINT_GEAR)
+		{
+			int32 i1 = (int32)r.frequencyHz, i2 = (int32)r.dampingRatio; // rows of the joints it couples
+			if (i1 < 0 || i2 < 0 || i1 >= (int32)h->joints.size() || i2 >= (int32)h->joints.size()) return -3;
+			b2GearJointDef def;
+			def.bodyA = h->bodies[r.bodyA];
+			def.bodyB = h->bodies[r.bodyB];
+			def.collideConnected = collideConnected;
+			def.joint1 = h->joints[i1];
+			def.joint2 = h->joints[i2];
+			def.ratio = r.motorSpeed;
+			j = h->world->CreateJoint(&def);
+		}
 		else if (r.type == B2CU_JOINT_DISTANCE)
 		{
 			b2DistanceJointDef def;

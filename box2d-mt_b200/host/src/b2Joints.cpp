@@ -12,6 +12,7 @@
 #include "Box2D/Dynamics/Joints/b2MotorJoint.h"
 #include "Box2D/Dynamics/Joints/b2PulleyJoint.h"
 #include "Box2D/Dynamics/Joints/b2MouseJoint.h"
+#include "Box2D/Dynamics/Joints/b2GearJoint.h"
 #include "Box2D/Dynamics/b2Body.h"
 #include "Box2D/Dynamics/b2World.h"
 
@@ -939,4 +940,104 @@ void b2MouseJoint::ShiftOrigin(const b2Vec2& newOrigin)
 {
 	Touch();
 	m_targetA -= newOrigin;
+}
+
+// ---- gear (reference b2GearJoint.cpp:45-129, :392-420) -------------------------------------------------------------------
+
+// one side of the gear: anchors, axis and reference angle of a revolute / prismatic joint, and its current coordinate
+static float32 GearSide(b2Joint* joint, b2JointType type, b2Body* bodyFirst, b2Body* bodySecond, b2Vec2* anchorFirst,
+                        b2Vec2* anchorSecond, b2Vec2* axisFirst, float32* referenceAngle)
+{
+	const b2Transform& xfSecond = bodySecond->GetTransform();
+	const b2Transform& xfFirst = bodyFirst->GetTransform();
+	if (type == e_revoluteJoint)
+	{
+		b2RevoluteJoint* revolute = static_cast<b2RevoluteJoint*>(joint);
+		*anchorFirst = revolute->GetLocalAnchorA();
+		*anchorSecond = revolute->GetLocalAnchorB();
+		*referenceAngle = revolute->GetReferenceAngle();
+		axisFirst->SetZero();
+		return bodySecond->GetAngle() - bodyFirst->GetAngle() - *referenceAngle;
+	}
+	b2PrismaticJoint* prismatic = static_cast<b2PrismaticJoint*>(joint);
+	*anchorFirst = prismatic->GetLocalAnchorA();
+	*anchorSecond = prismatic->GetLocalAnchorB();
+	*referenceAngle = prismatic->GetReferenceAngle();
+	*axisFirst = prismatic->GetLocalAxisA();
+	b2Vec2 pFirst = *anchorFirst;
+	b2Vec2 pSecond = b2MulT(xfFirst.q, b2Mul(xfSecond.q, *anchorSecond) + (xfSecond.p - xfFirst.p));
+	return b2Dot(pSecond - pFirst, *axisFirst);
+}
+
+b2GearJoint::b2GearJoint(const b2GearJointDef* def)
+	: b2Joint(def), m_joint1(def->joint1), m_joint2(def->joint2), m_typeA(def->joint1->GetType()), m_typeB(def->joint2->GetType()),
+	  m_ratio(def->ratio), m_impulse(0.0f), m_JvAC(0.0f, 0.0f), m_JwA(0.0f)
+{
+	b2Assert(m_typeA == e_revoluteJoint || m_typeA == e_prismaticJoint);
+	b2Assert(m_typeB == e_revoluteJoint || m_typeB == e_prismaticJoint);
+	m_bodyC = m_joint1->GetBodyA();
+	m_bodyA = m_joint1->GetBodyB();
+	float32 coordinateA = GearSide(m_joint1, m_typeA, m_bodyC, m_bodyA, &m_localAnchorC, &m_localAnchorA, &m_localAxisC, &m_referenceAngleA);
+	m_bodyD = m_joint2->GetBodyA();
+	m_bodyB = m_joint2->GetBodyB();
+	float32 coordinateB = GearSide(m_joint2, m_typeB, m_bodyD, m_bodyB, &m_localAnchorD, &m_localAnchorB, &m_localAxisD, &m_referenceAngleB);
+	m_constant = coordinateA + m_ratio * coordinateB;
+}
+
+void b2GearJoint::WriteRecord(b2cuJoint* out) const
+{
+	WriteCommon(out, B2CU_JOINT_GEAR, m_bodyA, m_bodyB, m_collideConnected, m_localAnchorA, m_localAnchorB);
+	out->flags |= (m_typeA == e_prismaticJoint ? B2CU_JOINT_GEAR_PRISMATIC_1 : 0u) | (m_typeB == e_prismaticJoint ? B2CU_JOINT_GEAR_PRISMATIC_2 : 0u);
+	out->limitState = m_bodyC->GetIndex();
+	out->reserved = m_bodyD->GetIndex();
+	out->axis[0] = m_localAnchorC.x;
+	out->axis[1] = m_localAnchorC.y;
+	out->lowerAngle = m_localAnchorD.x;
+	out->upperAngle = m_localAnchorD.y;
+	out->work[0] = m_localAxisC.x;
+	out->work[1] = m_localAxisC.y;
+	out->work[2] = m_localAxisD.x;
+	out->work[3] = m_localAxisD.y;
+	out->referenceAngle = m_referenceAngleA;
+	out->maxMotorTorque = m_referenceAngleB;
+	out->motorSpeed = m_ratio;
+	out->length = m_constant;
+	out->frequencyHz = (float32)m_joint1->GetIndex();
+	out->dampingRatio = (float32)m_joint2->GetIndex();
+	out->impulse[0] = m_impulse;
+	out->lastSolve[0] = m_JvAC.x;
+	out->lastSolve[1] = m_JvAC.y;
+	out->lastSolve[2] = m_JwA;
+}
+
+void b2GearJoint::ReadRecord(const b2cuJoint& in)
+{
+	m_impulse = in.impulse[0];
+	m_JvAC.Set(in.lastSolve[0], in.lastSolve[1]);
+	m_JwA = in.lastSolve[2];
+}
+
+b2Vec2 b2GearJoint::GetAnchorA() const { return m_bodyA->GetWorldPoint(m_localAnchorA); }
+b2Vec2 b2GearJoint::GetAnchorB() const { return m_bodyB->GetWorldPoint(m_localAnchorB); }
+
+b2Vec2 b2GearJoint::GetReactionForce(float32 inv_dt) const
+{
+	Refresh();
+	b2Vec2 P = m_impulse * m_JvAC;
+	return inv_dt * P;
+}
+
+float32 b2GearJoint::GetReactionTorque(float32 inv_dt) const
+{
+	Refresh();
+	float32 L = m_impulse * m_JwA;
+	return inv_dt * L;
+}
+
+void b2GearJoint::SetRatio(float32 ratio)
+{
+	b2Assert(b2IsValid(ratio));
+	if (ratio == m_ratio) return;
+	Touch();
+	m_ratio = ratio;
 }

@@ -12,6 +12,7 @@
 #include "Box2D/Dynamics/Joints/b2MotorJoint.h"
 #include "Box2D/Dynamics/Joints/b2PulleyJoint.h"
 #include "Box2D/Dynamics/Joints/b2MouseJoint.h"
+#include "Box2D/Dynamics/Joints/b2GearJoint.h"
 
 #include <chrono>
 #include "Box2D/Collision/Shapes/b2CircleShape.h"
@@ -333,12 +334,13 @@ void b2World::RefreshJoints() const
 b2Joint* b2World::CreateJoint(const b2JointDef* def)
 {
 	if (IsLocked()) return nullptr;
-	if (def->type == e_unknownJoint || def->type == e_gearJoint)
+	if (def->type <= e_unknownJoint || def->type > e_motorJoint)
 	{
 		m_lastStatus = B2CU_ERR_UNSUPPORTED;
 		return nullptr;
 	}
 	RefreshJoints();
+	RefreshBodies(); // constructors that read the bodies' transforms (gear, mouse) need the current ones
 	b2Joint* j;
 	if (def->type == e_revoluteJoint) j = new b2RevoluteJoint(static_cast<const b2RevoluteJointDef*>(def));
 	else if (def->type == e_distanceJoint) j = new b2DistanceJoint(static_cast<const b2DistanceJointDef*>(def));
@@ -349,6 +351,7 @@ b2Joint* b2World::CreateJoint(const b2JointDef* def)
 	else if (def->type == e_motorJoint) j = new b2MotorJoint(static_cast<const b2MotorJointDef*>(def));
 	else if (def->type == e_pulleyJoint) j = new b2PulleyJoint(static_cast<const b2PulleyJointDef*>(def));
 	else if (def->type == e_mouseJoint) j = new b2MouseJoint(static_cast<const b2MouseJointDef*>(def));
+	else if (def->type == e_gearJoint) j = new b2GearJoint(static_cast<const b2GearJointDef*>(def));
 	else j = new b2WeldJoint(static_cast<const b2WeldJointDef*>(def));
 	j->m_world = this;
 	j->m_index = (int32)m_joints.size();

@@ -97,7 +97,8 @@ JOINT = np.dtype([
 assert JOINT.itemsize == 128
 JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_WELD = 1, 2, 3, 8
 JOINT_WHEEL, JOINT_FRICTION, JOINT_ROPE, JOINT_MOTOR = 7, 9, 10, 11
-JOINT_PULLEY, JOINT_MOUSE = 4, 5
+JOINT_PULLEY, JOINT_MOUSE, JOINT_GEAR = 4, 5, 6
+JOINT_GEAR_PRISMATIC_1, JOINT_GEAR_PRISMATIC_2 = 0x100, 0x200
 JOINT_COLLIDE_CONNECTED, JOINT_ENABLE_LIMIT, JOINT_ENABLE_MOTOR = 1, 2, 4
 
 # enums

@@ -268,6 +268,17 @@ class Scene:
         self.joints.append(j)
         return len(self.joints) - 1
 
+    def gear_joint(self, joint1, joint2, ratio, collide_connected=False):
+        """b2GearJointDef (b2GearJoint.h:28-53) over two earlier revolute / prismatic joints of this scene; everything
+        else the reference's constructor derives from them."""
+        j1, j2 = self.joints[joint1], self.joints[joint2]
+        j = self._joint(T.JOINT_GEAR, int(j1["bodyB"]), int(j2["bodyB"]), (0.0, 0.0), (0.0, 0.0), collide_connected)
+        j["frequencyHz"], j["dampingRatio"] = joint1, joint2
+        j["motorSpeed"] = ratio
+        j["limitState"], j["reserved"] = int(j1["bodyA"]), int(j2["bodyA"])
+        self.joints.append(j)
+        return len(self.joints) - 1
+
     def joint_array(self):
         return np.array(self.joints, dtype=T.JOINT) if self.joints else np.zeros(0, T.JOINT)
 

@@ -465,3 +465,43 @@ def pulleys_and_mice(seed=0):
     s.fixture(b, small, density=1.0)
     s.mouse_joint(g, b, (0.0, 0.0), (-20.0, 0.5), 500.0)
     return s
+
+
+def gears(seed=0):
+    """Gear joints (Testbed/Tests/Gears.h:27-185): two wheels on revolute joints to the ground geared r2 : r1, the larger
+    one geared to a rack on a prismatic joint; a second train whose wheels ride on a dynamic frame (so that the gear
+    moves four dynamic bodies), driven by a motor; a prismatic-prismatic gear (two sliders moving in opposition)."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.edge((-50.0, 0.0), (50.0, 0.0)))
+    r1, r2 = 1.0, 2.0
+    b1 = s.body(T.DYNAMIC_BODY, (-3.0, 12.0), w=2.0)
+    s.fixture(b1, s.circle(r1), density=5.0)
+    j1 = s.revolute_joint(g, b1, (-3.0, 12.0), (0.0, 0.0))
+    b2 = s.body(T.DYNAMIC_BODY, (0.0, 12.0))
+    s.fixture(b2, s.circle(r2), density=5.0)
+    j2 = s.revolute_joint(g, b2, (0.0, 12.0), (0.0, 0.0))
+    b3 = s.body(T.DYNAMIC_BODY, (2.5, 12.0))
+    s.fixture(b3, s.box(0.5, 5.0), density=5.0)
+    j3 = s.prismatic_joint(g, b3, (2.5, 12.0), (0.0, 0.0), (0.0, 1.0), limits=(-5.0, 5.0))
+    s.gear_joint(j1, j2, r2 / r1)
+    s.gear_joint(j2, j3, -1.0 / r2)
+    # a gear train on a dynamic frame that stands on the ground
+    frame = s.body(T.DYNAMIC_BODY, (20.0, 1.0))
+    s.fixture(frame, s.box(4.0, 1.0), density=1.0, friction=0.8)
+    wa = s.body(T.DYNAMIC_BODY, (18.0, 4.0))
+    s.fixture(wa, s.circle(1.0), density=2.0)
+    ja = s.revolute_joint(frame, wa, (-2.0, 3.0), (0.0, 0.0), motor=(3.0, 50.0))
+    wb = s.body(T.DYNAMIC_BODY, (21.0, 4.0))
+    s.fixture(wb, s.circle(2.0), density=2.0)
+    jb = s.revolute_joint(frame, wb, (1.0, 3.0), (0.0, 0.0))
+    s.gear_joint(ja, jb, 2.0, collide_connected=True)
+    # two sliders in opposition
+    sa = s.body(T.DYNAMIC_BODY, (-20.0, 6.0), vel=(2.0, 0.0))
+    s.fixture(sa, s.box(1.0, 0.5), density=1.0)
+    pa = s.prismatic_joint(g, sa, (-20.0, 6.0), (0.0, 0.0), (1.0, 0.0), limits=(-4.0, 4.0))
+    sb = s.body(T.DYNAMIC_BODY, (-20.0, 9.0))
+    s.fixture(sb, s.box(1.0, 0.5), density=3.0)
+    pb = s.prismatic_joint(g, sb, (-20.0, 9.0), (0.0, 0.0), (3.0, 0.0))
+    s.gear_joint(pa, pb, 1.0)
+    return s

@@ -337,11 +337,12 @@ B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
  *   motor joints      b2MotorJoint.cpp:66-200      drives body B to an offset from body A with bounded force / torque
  *   pulley joints     b2PulleyJoint.cpp:74-264     lengthA + ratio * lengthB constant over two ground anchors
  *   mouse joints      b2MouseJoint.cpp:96-190      soft bounded pull of a point of body B towards a world target
+ *   gear joints       b2GearJoint.cpp:131-390      couples the coordinates of two revolute / prismatic joints (four bodies)
  * as rows of the coloured solver: inside every velocity iteration the joints run before the contacts, inside every
  * position iteration after them, as b2Island::Solve orders them (Dynamics/b2Island.cpp:259-273, :323-327, :363-380),
  * with warm starting.  A joint links the islands of its two bodies (b2World.cpp:1286-1320) and, unless
  * COLLIDE_CONNECTED, keeps them from colliding (b2Body::ShouldCollide, b2Body.cpp:428-449).  `type` uses b2JointType's
- * values; the gear joint is refused with B2CU_ERR_UNSUPPORTED.
+ * values: all eleven types are solved.
  * Fields by type: revolute   referenceAngle, lowerAngle, upperAngle, maxMotorTorque, motorSpeed, flags LIMIT / MOTOR
  *                 prismatic  axis (b2PrismaticJointDef::localAxisA as given; normalised as the constructor does),
  *                            referenceAngle, lowerAngle / upperAngle (= lower / upper translation), maxMotorTorque
@@ -359,6 +360,13 @@ B2CU_API int b2cuGetContactCount(b2cuWorld* w, int32_t* count);
  *                 mouse      axis (= target), length (= maxForce), frequencyHz, dampingRatio, maxMotorTorque (= the mass of
  *                            body B, b2Body::GetMass(): the reference reads the mass, not its inverse); localAnchorB is
  *                            the grabbed point; body A takes no part in the solve
+ *                 gear       bodyA / bodyB = second bodies of joint 1 / 2, limitState / reserved = their first bodies (C /
+ *                            D, body ids), flags GEAR_PRISMATIC_1 / _2 (else revolute), localAnchorA / B as in joint 1 / 2,
+ *                            axis (= localAnchorC), lowerAngle / upperAngle (= localAnchorD), work[0..1] (= localAxisC),
+ *                            work[2..3] (= localAxisD), referenceAngle (= referenceAngleA), maxMotorTorque (= referenceAngleB),
+ *                            motorSpeed (= ratio), length (= the constant coordinateA + ratio * coordinateB the
+ *                            constructor computes), frequencyHz / dampingRatio (= table ids of joint 1 / 2, for the
+ *                            host side only); lastSolve = m_JvAC, m_JwA
  * impulse / motorImpulse / limitState are the joint's persistent solver state (m_impulse -- a scalar in impulse[0] for
  * the distance joint --, m_motorImpulse, m_limitState) and round-trip through Get / Set.  lastSolve is written by the
  * step with the world-space directions of its solve, which GetReactionForce needs: the distance and rope joints' m_u
@@ -372,6 +380,7 @@ enum
 	B2CU_JOINT_DISTANCE = 3,
 	B2CU_JOINT_PULLEY = 4,
 	B2CU_JOINT_MOUSE = 5,
+	B2CU_JOINT_GEAR = 6,
 	B2CU_JOINT_WHEEL = 7,
 	B2CU_JOINT_WELD = 8,
 	B2CU_JOINT_FRICTION = 9,
@@ -382,7 +391,9 @@ enum
 {
 	B2CU_JOINT_COLLIDE_CONNECTED = 1,
 	B2CU_JOINT_ENABLE_LIMIT = 2,
-	B2CU_JOINT_ENABLE_MOTOR = 4
+	B2CU_JOINT_ENABLE_MOTOR = 4,
+	B2CU_JOINT_GEAR_PRISMATIC_1 = 0x100, /* gear: joint 1 / joint 2 is a prismatic joint (else revolute) */
+	B2CU_JOINT_GEAR_PRISMATIC_2 = 0x200
 };
 enum { B2CU_LIMIT_INACTIVE = 0, B2CU_LIMIT_AT_LOWER = 1, B2CU_LIMIT_AT_UPPER = 2, B2CU_LIMIT_EQUAL = 3 };
 typedef struct b2cuJoint

@@ -978,6 +978,32 @@ int32_t b2ref_set_joints(b2refWorld* w, int32_t count, const b2cuJoint* joints)
 			mj->m_impulse.Set(j.impulse[0], j.impulse[1]);
 			joint = mj;
 		}
+		else if (j.type == B2CU_JOINT_GEAR)
+		{
+			/* the two joints it couples are earlier rows of the table */
+			int32_t i1 = (int32_t)j.frequencyHz, i2 = (int32_t)j.dampingRatio;
+			if (i1 < 0 || i2 < 0 || i1 >= i || i2 >= i)
+			{
+				return -3;
+			}
+			b2GearJointDef def;
+			def.bodyA = bodyA;
+			def.bodyB = bodyB;
+			def.collideConnected = collideConnected;
+			def.joint1 = w->joints[i1];
+			def.joint2 = w->joints[i2];
+			def.ratio = j.motorSpeed;
+			b2GearJoint* gj = (b2GearJoint*)w->world->CreateJoint(&def);
+			/* the constructor measures the constant on the current transforms; a row that already has one states it */
+			if (j.length != 0.0f || j.impulse[0] != 0.0f)
+			{
+				gj->m_constant = j.length;
+			}
+			gj->m_impulse = j.impulse[0];
+			gj->m_JvAC.Set(j.lastSolve[0], j.lastSolve[1]);
+			gj->m_JwA = j.lastSolve[2];
+			joint = gj;
+		}
 		else if (j.type == B2CU_JOINT_DISTANCE)
 		{
 			b2DistanceJointDef def;
@@ -1289,6 +1315,43 @@ void b2ref_export_joints(b2refWorld* w, b2cuJoint* out)
 			o.maxMotorTorque = j->m_bodyB->GetMass();
 			o.impulse[0] = j->m_impulse.x;
 			o.impulse[1] = j->m_impulse.y;
+		}
+		else if (base->GetType() == e_gearJoint)
+		{
+			const b2GearJoint* j = (const b2GearJoint*)base;
+			o.type = B2CU_JOINT_GEAR;
+			o.flags |= (j->m_typeA == e_prismaticJoint ? B2CU_JOINT_GEAR_PRISMATIC_1 : 0) |
+			           (j->m_typeB == e_prismaticJoint ? B2CU_JOINT_GEAR_PRISMATIC_2 : 0);
+			for (size_t b = 0; b < w->bodies.size(); ++b)
+			{
+				if (w->bodies[b] == j->m_bodyC) o.limitState = (int32_t)b;
+				if (w->bodies[b] == j->m_bodyD) o.reserved = (int32_t)b;
+			}
+			for (size_t k = 0; k < w->joints.size(); ++k)
+			{
+				if (w->joints[k] == j->m_joint1) o.frequencyHz = (float)k;
+				if (w->joints[k] == j->m_joint2) o.dampingRatio = (float)k;
+			}
+			o.localAnchorA[0] = j->m_localAnchorA.x;
+			o.localAnchorA[1] = j->m_localAnchorA.y;
+			o.localAnchorB[0] = j->m_localAnchorB.x;
+			o.localAnchorB[1] = j->m_localAnchorB.y;
+			o.axis[0] = j->m_localAnchorC.x;
+			o.axis[1] = j->m_localAnchorC.y;
+			o.lowerAngle = j->m_localAnchorD.x;
+			o.upperAngle = j->m_localAnchorD.y;
+			o.work[0] = j->m_localAxisC.x;
+			o.work[1] = j->m_localAxisC.y;
+			o.work[2] = j->m_localAxisD.x;
+			o.work[3] = j->m_localAxisD.y;
+			o.referenceAngle = j->m_referenceAngleA;
+			o.maxMotorTorque = j->m_referenceAngleB;
+			o.motorSpeed = j->m_ratio;
+			o.length = j->m_constant;
+			o.impulse[0] = j->m_impulse;
+			o.lastSolve[0] = j->m_JvAC.x;
+			o.lastSolve[1] = j->m_JvAC.y;
+			o.lastSolve[2] = j->m_JwA;
 		}
 		else if (base->GetType() == e_distanceJoint)
 		{

@@ -181,6 +181,7 @@ SCENES = {
     "sliders": lambda: scenes.sliders(),
     "machines": lambda: scenes.machines(),
     "pulleys_and_mice": lambda: scenes.pulleys_and_mice(),
+    "gears": lambda: scenes.gears(),
 }
 
 
@@ -203,7 +204,7 @@ def test_single_step_teacher_forced(gpu, name):
 @pytest.mark.parametrize("name,steps", [("pyramid6", 300), ("pyramid20", 240), ("pile", 300), ("pile_5000", 200),
                                         ("pile_sleep", 400), ("chains", 300), ("sensors", 300),
                                         ("tumbler", 200), ("two_pyramids", 300), ("tumbler_joint", 200),
-                                        ("hanging_chains", 400), ("joint_zoo", 400), ("rods_and_welds", 400), ("sliders", 400), ("machines", 400), ("pulleys_and_mice", 400)])
+                                        ("hanging_chains", 400), ("joint_zoo", 400), ("rods_and_welds", 400), ("sliders", 400), ("machines", 400), ("pulleys_and_mice", 400), ("gears", 400)])
 def test_free_running_lockstep(gpu, name, steps):
     """Multi-step parity: the device world runs freely; the oracle follows in the GPU's solver order.  Pair set,
     events, manifolds, fat AABBs, body state and awake flags are compared after every step."""

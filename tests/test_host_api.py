@@ -148,13 +148,13 @@ def test_host_api_lockstep(gpu, name, steps):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,steps", [("tumbler_joint", 150), ("hanging_chains", 300), ("joint_zoo", 300),
-                                        ("rods_and_welds", 300), ("sliders", 300), ("machines", 300), ("pulleys_and_mice", 300)])
+                                        ("rods_and_welds", 300), ("sliders", 300), ("machines", 300), ("pulleys_and_mice", 300), ("gears", 300)])
 def test_host_api_joints_lockstep(gpu, name, steps):
     """Worlds with revolute, distance and weld joints built through b2World::CreateJoint (the Testbed's Tumbler with its
     motor joint, hanging chains, every branch of the revolute joint, the Web and the Cantilever) and stepped through
     b2World::Step stay bit-identical to the reference: bodies, events and what the joints' accessors report."""
     make = {"tumbler_joint": lambda: scenes.tumbler(60, motor_joint=True), "hanging_chains": lambda: scenes.hanging_chains(3, 10),
-            "joint_zoo": scenes.joint_zoo, "rods_and_welds": scenes.rods_and_welds, "sliders": scenes.sliders, "machines": scenes.machines, "pulleys_and_mice": scenes.pulleys_and_mice}[name]
+            "joint_zoo": scenes.joint_zoo, "rods_and_welds": scenes.rods_and_welds, "sliders": scenes.sliders, "machines": scenes.machines, "pulleys_and_mice": scenes.pulleys_and_mice, "gears": scenes.gears}[name]
     h, r, begins = _host_lockstep(make(), steps)
     assert h.joint_count() == r.joint_count > 0
     assert h.hash() == r.hash()
