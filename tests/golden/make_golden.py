@@ -35,6 +35,15 @@ def main():
         "pile_12x10_240": ("pile", [12, 10], 240),
         "add_pair_200_120": ("add_pair", [200], 120),
         "tumbler_100_240": ("tumbler", [100], 240),
+        # joints, every type (the scenes of the joint parity tests)
+        "tumbler_joint_100_240": ("tumbler", [100, 0, None, True], 240),
+        "hanging_chains_4x12_300": ("hanging_chains", [4, 12], 300),
+        "joint_zoo_300": ("joint_zoo", [], 300),
+        "rods_and_welds_300": ("rods_and_welds", [], 300),
+        "sliders_300": ("sliders", [], 300),
+        "machines_300": ("machines", [], 300),
+        "pulleys_and_mice_300": ("pulleys_and_mice", [], 300),
+        "gears_300": ("gears", [], 300),
     }
     out = {}
     for name, (scene, args, steps) in cases.items():
