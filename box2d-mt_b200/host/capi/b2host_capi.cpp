@@ -825,6 +825,9 @@ B2H_API void b2h_destroy_body(void* p, int32 body)
 	if (h->bodies[body] == nullptr) return;
 	h->world->DestroyBody(h->bodies[body]);
 	h->bodies[body] = nullptr;
+	// DestroyBody took the body's joints along: the handle table follows the world's joint list (rows = GetIndex())
+	h->joints.assign((size_t)h->world->GetJointCount(), nullptr);
+	for (b2Joint* j = h->world->GetJointList(); j; j = j->GetNext()) h->joints[(size_t)j->GetIndex()] = j;
 }
 
 } // extern "C"

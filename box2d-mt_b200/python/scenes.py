@@ -505,3 +505,28 @@ def gears(seed=0):
     pb = s.prismatic_joint(g, sb, (-20.0, 9.0), (0.0, 0.0), (3.0, 0.0))
     s.gear_joint(pa, pb, 1.0)
     return s
+
+
+def resting_linkage(seed=0):
+    """Jointed bodies that come to rest and fall asleep: a hinged two-bar linkage, a welded pair and a pair on a distance
+    rod lying on the ground, each in its own island.  Sleeping is on."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.box(40.0, 1.0, center=(0.0, -1.0), angle=0.0), thick=True)
+    bar = s.box(1.0, 0.25)
+    a = s.body(T.DYNAMIC_BODY, (-10.0, 0.5))
+    s.fixture(a, bar, density=1.0, friction=0.6)
+    b = s.body(T.DYNAMIC_BODY, (-8.0, 0.5))
+    s.fixture(b, bar, density=1.0, friction=0.6)
+    s.revolute_joint(a, b, (1.0, 0.0), (-1.0, 0.0), limits=(-0.5, 0.5))
+    a = s.body(T.DYNAMIC_BODY, (0.0, 0.6))
+    s.fixture(a, bar, density=1.0, friction=0.6)
+    b = s.body(T.DYNAMIC_BODY, (2.0, 0.6))
+    s.fixture(b, bar, density=1.0, friction=0.6)
+    s.weld_joint(a, b, (1.0, 0.0), (-1.0, 0.0))
+    a = s.body(T.DYNAMIC_BODY, (10.0, 0.5))
+    s.fixture(a, s.circle(0.5), density=1.0, friction=0.6)
+    b = s.body(T.DYNAMIC_BODY, (13.0, 0.5))
+    s.fixture(b, bar, density=1.0, friction=0.6)
+    s.distance_joint(a, b, (0.0, 0.0), (-1.0, 0.0), 2.0)
+    return s

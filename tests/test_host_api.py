@@ -273,6 +273,55 @@ def test_host_api_mouse_drag(gpu):
 
 
 @pytest.mark.gpu
+def test_host_api_jointed_islands_sleep_and_wake(gpu):
+    """Islands held together by joints fall asleep as a whole (the joints' position error has to be within tolerance
+    for that, b2Island.cpp:363-395) and wake as a whole when a joint is edited."""
+    scene = scenes.resting_linkage()
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+
+    def run(n):
+        for s in range(n):
+            h.step()
+            r.set_joint_order(h.joint_order())
+            assert r.step_ordered(h.solver_order()) == 0
+            parity.compare_bodies(h.bodies(), r.bodies())
+            parity.assert_floats_equal("joint readings", h.joint_readings(), r.joint_readings())
+
+    run(200)
+    awake = (r.bodies()["flags"][1:] & T.BODY_AWAKE) != 0
+    assert not awake.any(), "everything should have come to rest and gone to sleep"
+    assert int(h.step_info()["awakeBodyCount"]) == 0
+    for w in (h, r):
+        w.joint_set_motor(0, True, 1.0, 20.0)     # wakes the two bars of the linkage, and only them
+    run(3)
+    awake = (r.bodies()["flags"][1:] & T.BODY_AWAKE) != 0
+    assert awake[:2].all() and not awake[2:].any()
+    run(100)
+
+
+@pytest.mark.gpu
+def test_host_api_destroy_body_takes_its_joints(gpu):
+    """b2World::DestroyBody destroys the joints attached to the body first (b2World.cpp:594-610): the hub of the joint
+    zoo goes, its motor joint and twelve spoke joints go with it, the spokes fall."""
+    scene = scenes.joint_zoo()
+    h = b2host.HostWorld(scene)
+    for _ in range(30):
+        h.step()
+    n = h.joint_count()
+    h.destroy_body(9)      # the hub: bodies 1..8 are the pendulums
+    assert h.joint_count() == n - 13
+    for _ in range(120):
+        h.step()
+    b = h.bodies()
+    assert np.isfinite(b["px"]).all() and np.isfinite(b["py"]).all()
+    spokes = b[9:21]       # rows shift down by one after the hub's row is removed
+    assert (spokes["py"] < 8.0).all(), "the spokes (12.5 .. 15.5 up) are no longer held: they lie on the pendulums or the ground"
+    assert len(h.device_world().get_joints()) == n - 13
+
+
+@pytest.mark.gpu
 def test_host_api_spring_edits_between_steps(gpu):
     """b2DistanceJoint::SetLength / SetFrequency / SetDampingRatio and b2WeldJoint::SetFrequency / SetDampingRatio
     between steps (they do not wake anything), and rods cut with DestroyJoint."""
