@@ -928,6 +928,12 @@ void b2World::DispatchEvents(b2cuWorld* device)
 				__builtin_prefetch(&m_fixtures[recs[kind][i + 8].proxyA]);
 				__builtin_prefetch(&m_fixtures[recs[kind][i + 8].proxyB]);
 			}
+			// ... and, once those table entries have arrived, for the fixture objects they point to
+			if (i + 4 < n)
+			{
+				__builtin_prefetch(m_fixtures[recs[kind][i + 4].proxyA]);
+				__builtin_prefetch(m_fixtures[recs[kind][i + 4].proxyB]);
+			}
 			MakeContact(&contacts[kind][i], recs[kind][i]);
 		}
 		Clock::time_point tc = Clock::now();
