@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
 
 HOST = os.path.join(HERE, "host")
 HOST_OUT = os.path.join(HERE, "libbox2d_b200.so")
-HOST_SOURCES = ["src/b2Common.cpp", "src/b2Shapes.cpp", "src/b2Body.cpp", "src/b2World.cpp", "src/b2Joints.cpp",
+HOST_SOURCES = ["src/b2Common.cpp", "src/b2Shapes.cpp", "src/b2Body.cpp", "src/b2World.cpp", "src/b2Joints.cpp", "src/b2Dump.cpp",
                 "src/b2CudaStepExecutor.cpp", "capi/b2host_capi.cpp"]
 
 

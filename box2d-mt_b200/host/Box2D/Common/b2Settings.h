@@ -54,4 +54,8 @@ extern b2Version b2_mtVersion;    // Box2D-MT layer version (0.1.0)
 
 void b2Log(const char* string, ...);
 
+/// user-overridable allocation of the reference (b2Settings.h:176-183); the code b2World::Dump writes uses them
+void* b2Alloc(int32 size);
+void b2Free(void* mem);
+
 #endif

@@ -128,6 +128,8 @@ public:
 	void RayCast(b2RayCastCallback* callback, const b2Vec2& point1, const b2Vec2& point2);
 	/// move the origin of the world: every position has newOrigin subtracted (reference b2World.cpp:2084-2103)
 	void ShiftOrigin(const b2Vec2& newOrigin);
+	/// C++ code that rebuilds this world, through b2Log (reference b2World.cpp:2107-2164)
+	void Dump();
 	void SetGravity(const b2Vec2& gravity) { m_gravity = gravity; }
 	b2Vec2 GetGravity() const { return m_gravity; }
 	bool IsLocked() const { return m_locked; }

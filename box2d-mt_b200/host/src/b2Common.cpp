@@ -4,11 +4,15 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 b2Version b2_version = {2, 3, 2};
 b2Version b2_mtVersion = {0, 1, 0};
 const b2Vec2 b2Vec2_zero(0.0f, 0.0f);
+
+void* b2Alloc(int32 size) { return malloc((size_t)size); }
+void b2Free(void* mem) { free(mem); }
 
 void b2Log(const char* string, ...)
 {
