@@ -151,3 +151,41 @@ def test_joint_chains_at_scale():
     gap = np.linalg.norm(world(ja["localAnchorA"], ja["bodyA"]) - world(ja["localAnchorB"], ja["bodyB"]), axis=1)
     assert gap.max() < 0.15, gap.max()   # well inside a link's half-thickness
     assert np.abs(ja["impulse"][:, :2]).max() > 1.0   # the joints do carry load
+
+
+# ---- the other BASELINE.json configurations at their stated sizes, in lockstep with the oracle ---------------------------
+# (the oracle manages these sizes at 0.05 - 0.5 s per step, so a few dozen steps are affordable)
+
+import parity  # noqa: E402
+import ref  # noqa: E402
+
+
+def _lockstep(scene, steps, check_every):
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    import b2cuda
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(b2cuda, r)
+    return parity.lockstep(g, r, steps, check_every=check_every), g, r
+
+
+def test_add_pair_10k_pair_set_bit_exact():
+    """BASELINE configs[1]: 10,000 small circles and one fast bullet box.  The broad-phase pair set, the manifolds, the
+    events and the bodies are compared with the oracle while the box ploughs through the cloud."""
+    # 14 steps: the box reaches the cloud at step 5; later the compressed cloud has millions of contacts and the oracle
+    # needs seconds per step
+    infos, g, r = _lockstep(scenes.add_pair(10000), 14, check_every=2)
+    assert max(int(i["contactCount"]) for i in infos) > 200000
+    assert (np.sort(T.contact_keys(g.get_contacts())) == np.sort(T.contact_keys(r.contacts()))).all()
+
+
+def test_tumbler_20k_lockstep():
+    """BASELINE configs[2]: 20,000 small boxes in the rotating kinematic drum."""
+    infos, g, r = _lockstep(scenes.tumbler(20000), 24, check_every=4)
+    assert int(infos[-1]["contactCount"]) > 50000
+
+
+def test_stacks_100k_lockstep():
+    """BASELINE configs[3]: 476 pyramids of 20 rows (99,960 boxes) on thick static ground, sleeping enabled."""
+    # the boxes start a quarter of a metre above their rests: first contacts after 14 steps
+    infos, g, r = _lockstep(scenes.pyramids(476, 20, thick_polygon_ground=True), 30, check_every=5)
+    assert int(infos[-1]["constraintCount"]) > 50000
