@@ -22,8 +22,9 @@
  *   b2cuSetProxies / b2cuGetProxies      b2Fixture + b2FixtureProxy + tree-leaf fat AABB
  *                                                                          Dynamics/b2Fixture.h:100-106, Collision/b2DynamicTree.h:36
  *   b2cuSetContacts / b2cuGetContacts    b2Contact persistent state (m_flags, m_manifold, mixes, TOI)
- *   b2cuSetJoints / b2cuGetJoints        b2Joint table (revolute joints), persistent impulses
  *                                                                          Dynamics/Contacts/b2Contact.h:231-259
+ *   b2cuSetJoints / b2cuGetJoints /      b2World::CreateJoint / DestroyJoint and the eleven b2Joint classes: parameters,
+ *   b2cuGetJointCount / GetJointOrder    accumulated impulses, limit states   Dynamics/b2World.cpp:659-841, Dynamics/Joints/*.h
  *   b2cuStep                             b2World::Step(dt, velocityIterations, positionIterations, executor)
  *                                                                          Dynamics/b2World.cpp:1613-1710
  *   b2cuGetContactsByKey                 b2Contact objects handed to listener callbacks (manifold, flags, mixes),
@@ -51,8 +52,9 @@
  *   b2cuQueryAABB / RayCastCandidates    b2World::QueryAABB / RayCast (tree queries on the fat boxes)
  *                                                                          Dynamics/b2World.cpp:1752-1795
  *   b2cuDistancePairs                    b2Distance (GJK), batched; b2TestOverlap = its distance under 10 epsilon
- *   b2cuTimeOfImpactPairs                b2TimeOfImpact (conservative advancement), batched
  *                                                                          Collision/b2Distance.cpp:452-603, b2Collision.cpp:233-252
+ *   b2cuTimeOfImpactPairs                b2TimeOfImpact (conservative advancement), batched
+ *                                                                          Collision/b2TimeOfImpact.cpp:256-497
  *   b2cuCollidePairs                     b2CollidePolygons / b2CollideCircles / b2CollidePolygonAndCircle /
  *                                        b2CollideEdgeAndCircle / b2CollideEdgeAndPolygon, batched
  *                                                                          Collision/b2CollidePolygon.cpp, b2CollideCircle.cpp, b2CollideEdge.cpp
