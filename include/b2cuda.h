@@ -24,7 +24,7 @@
  *   b2cuSetContacts / b2cuGetContacts    b2Contact persistent state (m_flags, m_manifold, mixes, TOI)
  *                                                                          Dynamics/Contacts/b2Contact.h:231-259
  *   b2cuSetJoints / b2cuGetJoints /      b2World::CreateJoint / DestroyJoint and the eleven b2Joint classes: parameters,
- *   b2cuGetJointCount / GetJointOrder    accumulated impulses, limit states   Dynamics/b2World.cpp:659-841, Dynamics/Joints/*.h
+ *   b2cuGetJointCount / GetJointOrder    accumulated impulses, limit states   Dynamics/b2World.cpp:659-841, Dynamics/Joints/
  *   b2cuStep                             b2World::Step(dt, velocityIterations, positionIterations, executor)
  *                                                                          Dynamics/b2World.cpp:1613-1710
  *   b2cuGetContactsByKey                 b2Contact objects handed to listener callbacks (manifold, flags, mixes),
