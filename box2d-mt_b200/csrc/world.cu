@@ -1816,9 +1816,12 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		// are not executed; the step reports whether the reference would have taken one.
 		float* toiAlpha = reinterpret_cast<float*>(d.listB);
 		CUDA_TRY(w, cudaMemsetAsync(d.counters + CNT_TOI_MIN_ALPHA, 0xFF, sizeof(int) * 3, w->stream));
-		const int toiGrid = GridFor(std::max(1024, std::min(nc, 2 * lastToiCount)));
-		LAUNCH(w, ToiFirstPassKernel, toiGrid, kBlock, d, (const int*)d.listA, (const int*)(d.counters + CNT_TOI), toiAlpha);
-		LAUNCH(w, ToiMinKeyKernel, toiGrid, kBlock, d, (const int*)d.listA, (const int*)(d.counters + CNT_TOI),
+		// one candidate is a long, divergent root search: small blocks, so that a thousand candidates already spread
+		// over most SMs (the count of the last step sizes the grid; the kernels stride over whatever there is)
+		const int toiBlock = 64;
+		const int toiGrid = std::max(16, std::min(8 * g_smCount, (2 * std::max(lastToiCount, 512) + toiBlock - 1) / toiBlock));
+		LAUNCH(w, ToiFirstPassKernel, toiGrid, toiBlock, d, (const int*)d.listA, (const int*)(d.counters + CNT_TOI), toiAlpha);
+		LAUNCH(w, ToiMinKeyKernel, toiGrid, toiBlock, d, (const int*)d.listA, (const int*)(d.counters + CNT_TOI),
 		       (const float*)toiAlpha);
 	}
 	cudaEvent_t evEnd = w->ev[9];
