@@ -667,10 +667,20 @@ __device__ __forceinline__ bool IsSolidTouching(const DeviceArrays& d, int i)
 	return true;
 }
 
-__global__ void IslandUnionKernel(DeviceArrays d, int contactCount)
+// Two sweeps (the idea of sampling-based connected components): the first unites over every `sample`-th contact only,
+// which already connects almost everything a pile connects; IslandCompressKernel then points every body at its root,
+// and the second sweep finds for most of the remaining contacts, after one hop each, that both bodies share a root.
+// phase 0: contacts with i % sample == 0; phase 1: the others; sample == 1 with phase 0: everything in one sweep.
+__global__ void IslandUnionKernel(DeviceArrays d, int contactCount, int sample, int phase)
 {
-	B2CU_GRID_STRIDE(i, contactCount)
+	const int chunk = (contactCount + 31) / 32;
+	B2CU_GRID_STRIDE(g, (sample < 0 ? chunk * 32 : contactCount))
 	{
+		// sample < 0 (experiment): the lanes of a warp take contacts from 32 distant parts of the (key-sorted) set, so
+		// that they do not all unite into the same body
+		const int i = sample < 0 ? (g & 31) * chunk + (g >> 5) : g;
+		if (i >= contactCount) continue;
+		if (sample > 1 && ((i % sample == 0) != (phase == 0))) continue;
 		if (!IsSolidTouching(d, i)) continue;
 		int4 pr = d.c.proxies[i];
 		int bA = pr.z, bB = pr.w;
@@ -690,6 +700,13 @@ __global__ void JointUnionKernel(DeviceArrays d, int jointCount)
 		if (!(fA & B2CU_BODY_ACTIVE) || !(fB & B2CU_BODY_ACTIVE)) continue;
 		UfUnion(d.island, bA, bB);
 	}
+}
+
+// between the two sweeps: every body straight under its current root (no unions run meanwhile, so roots are fixed;
+// a concurrent reader sees either the old ancestor or the root, both on its path)
+__global__ void IslandCompressKernel(DeviceArrays d, int bodyCount)
+{
+	B2CU_GRID_STRIDE(b, bodyCount) { d.island[b] = UfFindReadOnly(d.island, b); }
 }
 
 __global__ void IslandFlattenKernel(DeviceArrays d, int bodyCount)

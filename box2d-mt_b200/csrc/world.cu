@@ -1558,7 +1558,23 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	{
 		// ---- islands (serial DFS of b2World::Solve -> union-find) ----
 		LAUNCH(w, SolveInitBodiesKernel, GridFor(nb), kBlock, d, nb, positionIterations);
-		if (nc > 0) LAUNCH(w, IslandUnionKernel, GridFor(nc), kBlock, d, nc);
+		if (nc > 0)
+		{
+			static const int sample = []() {
+				const char* e = getenv("B2CU_UNION_SAMPLE");
+				return e && atoi(e) != 0 ? atoi(e) : 2;
+			}();
+			if (sample > 1 && nc >= 4096)
+			{
+				LAUNCH(w, IslandUnionKernel, GridFor(nc), kBlock, d, nc, sample, 0);
+				LAUNCH(w, IslandCompressKernel, GridFor(nb), kBlock, d, nb);
+				LAUNCH(w, IslandUnionKernel, GridFor(nc), kBlock, d, nc, sample, 1);
+			}
+			else
+			{
+				LAUNCH(w, IslandUnionKernel, GridFor(nc), kBlock, d, nc, sample < 0 ? -1 : 1, 0);
+			}
+		}
 		if (w->d.jointCount > 0) LAUNCH(w, JointUnionKernel, GridFor(w->d.jointCount), kBlock, d, w->d.jointCount);
 		LAUNCH(w, IslandFlattenKernel, GridFor(nb), kBlock, d, nb);
 		LAUNCH(w, IslandMarkKernel, GridFor(nb), kBlock, d, nb);
@@ -1701,9 +1717,25 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			                                         : (const void*)SolverVelocityPersistentKernel<false>;
 			const void* positionKernel = nJoints > 0 ? (const void*)SolverPositionPersistentKernel<true>
 			                                         : (const void*)SolverPositionPersistentKernel<false>;
-			const int velocityGrid = nJoints > 0 ? std::min(w->persistentGrid, w->persistentGridJoints) : w->persistentGrid;
-			const int positionGrid =
+			int velocityGrid = nJoints > 0 ? std::min(w->persistentGrid, w->persistentGridJoints) : w->persistentGrid;
+			int positionGrid =
 			    nJoints > 0 ? std::min(w->persistentGridPosition, w->persistentGridPositionJoints) : w->persistentGridPosition;
+			if (w->shardCount == 1)
+			{
+				// a world whose largest colour class does not fill the co-resident grid is bound by the grid barrier, and
+				// the barrier is cheaper with fewer CTAs: launch only as many as that class can occupy
+				int largest = 0;
+				for (int op = 0; op < nOps; ++op) largest = std::max(largest, plan.opSize[op]);
+				for (int jo = 0; jo < plan.jointOpCount; ++jo) largest = std::max(largest, plan.jointOpSize[jo]);
+				static const int minGrid = []() {
+					const char* e = getenv("B2CU_MIN_SOLVER_GRID");
+					return e && atoi(e) > 0 ? atoi(e) : 0;
+				}();
+				const int floorGrid = minGrid > 0 ? minGrid : std::max(1, g_smCount); // below one CTA per SM nothing more is gained
+				const int want = std::max(floorGrid, (largest + B2CU_SOLVER_THREADS - 1) / B2CU_SOLVER_THREADS);
+				velocityGrid = std::min(velocityGrid, want);
+				positionGrid = std::min(positionGrid, want);
+			}
 			CUDA_TRY(w, cudaLaunchCooperativeKernel(velocityKernel, dim3(velocityGrid), dim3(B2CU_SOLVER_THREADS), args, 0,
 			                                        w->stream));
 			++w->launches;
