@@ -302,6 +302,37 @@ def test_host_api_jointed_islands_sleep_and_wake(gpu):
 
 
 @pytest.mark.gpu
+def test_host_api_joints_of_inactive_bodies_rest(gpu):
+    """A joint with an inactive body is not simulated (b2World.cpp:1300-1304) and does not link islands; it comes back
+    with the body (b2Body::SetActive)."""
+    scene = scenes.joint_zoo()
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+
+    def run(n):
+        for s in range(n):
+            h.step()
+            r.set_joint_order(h.joint_order())
+            assert r.step_ordered(h.solver_order()) == 0
+            parity.compare_bodies(h.bodies(), r.bodies())
+            parity.assert_floats_equal("joint readings", h.joint_readings(), r.joint_readings())
+
+    run(30)
+    for w in (h, r):
+        w.set_active(2, False)      # a pendulum with limits: its joint to the ground goes quiet
+        w.set_active(9, False)      # the hub: thirteen joints go quiet, the spokes fall free
+    run(60)
+    before = h.joint_readings()[1].copy()
+    run(5)
+    assert (h.joint_readings()[1][:4] == before[:4]).all()   # impulses of the resting joint do not change
+    for w in (h, r):
+        w.set_active(9, True)
+        w.set_active(2, True)
+    run(90)
+
+
+@pytest.mark.gpu
 def test_host_api_destroy_body_takes_its_joints(gpu):
     """b2World::DestroyBody destroys the joints attached to the body first (b2World.cpp:594-610): the hub of the joint
     zoo goes, its motor joint and twelve spoke joints go with it, the spokes fall."""
