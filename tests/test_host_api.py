@@ -333,6 +333,34 @@ def test_host_api_joints_of_inactive_bodies_rest(gpu):
 
 
 @pytest.mark.gpu
+def test_host_api_jointed_body_changes_type_and_teleports(gpu):
+    """b2Body::SetType on a link in the middle of a chain (the joint colouring depends on which bodies are dynamic: a
+    static link may be shared by both of its joints' classes; islands stop at it) and b2Body::SetTransform of a link far
+    away from its hinges (the position solver pulls it back under its correction clamps)."""
+    scene = scenes.hanging_chains(2, 10)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    h = b2host.HostWorld(scene)
+
+    def run(n):
+        for s in range(n):
+            h.step()
+            r.set_joint_order(h.joint_order())
+            assert r.step_ordered(h.solver_order()) == 0
+            parity.compare_bodies(h.bodies(), r.bodies())
+            parity.assert_floats_equal("joint readings", h.joint_readings(), r.joint_readings())
+
+    run(40)
+    for w in (h, r):
+        w.set_type(5, T.STATIC_BODY)          # link 5 of the first chain freezes where it is
+    run(60)
+    for w in (h, r):
+        w.set_type(5, T.DYNAMIC_BODY)
+        w.set_transform(14, 0.0, 30.0, 1.0)   # a link of the second chain is moved two metres off
+    run(80)
+
+
+@pytest.mark.gpu
 def test_host_api_destroy_body_takes_its_joints(gpu):
     """b2World::DestroyBody destroys the joints attached to the body first (b2World.cpp:594-610): the hub of the joint
     zoo goes, its motor joint and twelve spoke joints go with it, the spokes fall."""
