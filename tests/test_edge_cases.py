@@ -228,3 +228,54 @@ def test_capacity_growth_from_nothing(gpu):
     infos = parity.lockstep(g, r, 150, tol=0.0, check_every=3)
     assert int(infos[-1]["contactCount"]) > 1000
 
+
+
+def test_joint_table_edge_cases(gpu):
+    """b2cuSetJoints: bad rows are refused with a message and leave the table as it was; an empty table removes every
+    joint; a joint between two static bodies is accepted and never solved; replacing the table keeps stepping exact."""
+    s = _scene()
+    g0 = s.body(T.STATIC_BODY, (0, 0))
+    s.fixture(g0, s.box(20, 0.5, center=(0, -0.5)), thick=True)
+    g1 = s.body(T.STATIC_BODY, (0, 10))
+    a = s.body(T.DYNAMIC_BODY, (0.0, 5.0))
+    s.fixture(a, s.box(0.5, 0.5), density=1.0)
+    b = s.body(T.DYNAMIC_BODY, (2.0, 5.0))
+    s.fixture(b, s.circle(0.5), density=1.0)
+    s.revolute_joint(g1, a, (0.0, 0.0), (0.0, 5.0))
+    s.distance_joint(a, b, (0.0, 0.0), (0.0, 0.0), 2.0)
+    s.weld_joint(g0, g1, (0.0, 10.0), (0.0, 0.0))           # static - static: in no island, never solved
+    r = ref.RefWorld(s)
+    g = parity.gpu_world_from_ref(gpu, r)
+    parity.lockstep(g, r, 40, tol=0.0)
+    assert (g.get_joints()["impulse"][2] == 0.0).all()
+
+    good = g.get_joints()
+    for field, value, code in (("bodyA", 99, -3), ("bodyB", -1, -3), ("type", 12, -4), ("type", 0, -4)):
+        bad = good.copy()
+        bad[field][1] = value
+        with pytest.raises(gpu.B2cuError) as err:
+            g.set_joints(bad)
+        assert err.value.code == code, (field, value)
+    same = good.copy()
+    same["bodyB"][1] = same["bodyA"][1]                       # a joint from a body to itself
+    with pytest.raises(gpu.B2cuError):
+        g.set_joints(same)
+    gear = good[:1].copy()
+    gear["type"] = T.JOINT_GEAR
+    gear["limitState"] = 77                                   # body C out of range
+    with pytest.raises(gpu.B2cuError):
+        g.set_joints(gear)
+    # the refused tables changed nothing
+    assert g.get_joints().tobytes() == good.tobytes()
+    parity.lockstep(g, r, 20, tol=0.0)
+
+    # cut the rod on both sides, then remove everything
+    keep = g.get_joints()[[0, 2]]
+    g.set_joints(keep)
+    r.destroy_joint(1)
+    parity.lockstep(g, r, 40, tol=0.0)
+    g.set_joints(keep[:0])
+    r.destroy_joint(1)
+    r.destroy_joint(0)
+    assert len(g.get_joints()) == 0 and len(g.joint_order()) == 0
+    parity.lockstep(g, r, 40, tol=0.0)
