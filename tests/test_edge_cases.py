@@ -279,3 +279,22 @@ def test_joint_table_edge_cases(gpu):
     r.destroy_joint(0)
     assert len(g.get_joints()) == 0 and len(g.joint_order()) == 0
     parity.lockstep(g, r, 40, tol=0.0)
+
+
+@pytest.mark.parametrize("name", ["joint_zoo", "machines", "gears", "rods_and_welds", "sliders", "pulleys_and_mice"])
+def test_joints_with_varying_dt_and_without_warm_starting(gpu, name):
+    """The joints' warm start scales the stored impulses by dt / dt0 (the gear joint, alone, does not), soft constraints
+    and motors use dt and 1 / dt directly: step with a changing dt, then with warm starting switched off."""
+    scene = getattr(scenes, name)()
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    for dt in (1.0 / 60.0, 1.0 / 30.0, 1.0 / 120.0, 1.0 / 45.0, 1.0 / 60.0):
+        parity.lockstep(g, r, 12, dt=dt, tol=0.0)
+    parity.lockstep(g, r, 3, dt=0.0, tol=0.0)           # dt = 0: collide only, joints untouched
+    scene = getattr(scenes, name)()
+    scene.world_flags &= ~(T.WORLD_CONTINUOUS | T.WORLD_WARM_STARTING)
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    parity.lockstep(g, r, 60, tol=0.0, vel_iters=5, pos_iters=2)
+    assert (g.get_joints()["impulse"] != 0.0).any()
