@@ -398,7 +398,9 @@ __global__ void __launch_bounds__(256) UnpackBodiesKernel(DeviceArrays d, int fi
 			d.vel[b] = make_float4(s[13], s[14], s[15], 0.0f);
 			d.force[b] = make_float4(s[16], s[17], s[18], s[24]);
 			d.damp[b] = make_float4(s[21], s[22], s[23], 0.0f);
-			d.bflags[b] = __float_as_uint(s[25]);
+			const uint32_t flags = __float_as_uint(s[25]);
+			if (d.jointCount > 0 && ((flags ^ d.bflags[b]) & B2CU_BODY_TYPE_MASK)) d.counters[CNT_BODY_TYPE_CHANGED] = 1;
+			d.bflags[b] = flags;
 		}
 		__syncthreads();
 	}

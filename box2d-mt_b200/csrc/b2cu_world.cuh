@@ -47,6 +47,7 @@ enum Counter
 	CNT_TOI_MIN_ALPHA,    // first TOI pass: float bits of the smallest alpha (0xFFFFFFFF: no candidate)
 	CNT_TOI_MIN_KEY,      // 64 bits (two slots): smallest contact key among the candidates at that alpha
 	CNT_TOI_MIN_KEY_HI,
+	CNT_BODY_TYPE_CHANGED, // sticky: an uploaded body row changed the body's type (the joint colouring depends on it)
 	CNT_COUNT
 };
 

@@ -811,8 +811,18 @@ int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bo
 	CUDA_TRY(w, cudaMemcpyAsync(stage, bodies, sizeof(b2cuBody) * (size_t)count, cudaMemcpyHostToDevice, w->stream));
 	LAUNCH(w, UnpackBodiesKernel, GridFor(count), kBlock, w->d, first, count, (const float*)stage);
 	w->toiCheckDirty = true;
-	w->jointColourDirty = true;
-	return SyncCheck(w);
+	if (w->d.jointCount == 0) return SyncCheck(w);
+	// the joint colouring depends on which bodies are dynamic: recolour only if a type really changed
+	CUDA_TRY(w, cudaMemcpyAsync(&w->hostCounters[CNT_BODY_TYPE_CHANGED], w->d.counters + CNT_BODY_TYPE_CHANGED, sizeof(int),
+	                            cudaMemcpyDeviceToHost, w->stream));
+	if ((rc = SyncCheck(w))) return rc;
+	if (w->hostCounters[CNT_BODY_TYPE_CHANGED])
+	{
+		w->jointColourDirty = true;
+		w->hostCounters[CNT_BODY_TYPE_CHANGED] = 0;
+		return ZeroCounter(w, CNT_BODY_TYPE_CHANGED);
+	}
+	return B2CU_OK;
 }
 
 int b2cuGetBodies(b2cuWorld* w, int32_t first, int32_t count, b2cuBody* bodies)
@@ -1116,6 +1126,7 @@ int b2cuSetJoints(b2cuWorld* w, int32_t count, const b2cuJoint* joints)
 	w->jointFilterPending = true;
 	int rc = SyncCheck(w);
 	if (rc) return rc;
+	if ((rc = ZeroCounter(w, CNT_BODY_TYPE_CHANGED))) return rc;
 	return ColourJoints(w);
 }
 
