@@ -450,6 +450,8 @@ __global__ void PreSolveGatherKernel(DeviceArrays d, const int* __restrict__ lis
 		o.manifold.id[0] = m3.x; o.manifold.id[1] = m3.y;
 		o.manifold.type = (int32_t)m3.z;
 		o.manifold.pointCount = (int32_t)m3.w;
+		o.stamp = d.c.stamp[i];
+		o.reserved = 0u;
 		out[j] = o;
 		float4 p0 = d.cAlt.m0[i], p1 = d.cAlt.m1[i], p2 = d.cAlt.m2[i];
 		uint4 p3 = d.cAlt.m3[i];
@@ -2446,13 +2448,14 @@ __global__ void MergeMoveKernel(DeviceArrays d, int srcBegin, int srcCount, cons
 		d.cAlt.mix[dest] = d.c.mix[i];
 		d.cAlt.toiCount[dest] = d.c.toiCount[i];
 		d.cAlt.colour[dest] = d.c.colour[i];
+		d.cAlt.stamp[dest] = d.c.stamp[i];
 	}
 }
 
 // new contacts (sorted keys) are created in cAlt, merged with the live contacts of the tail region
 // c[tailBegin, tailBegin+tailCount) (rank tailRank, tailLive of them)
 __global__ void RebuildNewKernel(DeviceArrays d, int tailBegin, int tailCount, const int* __restrict__ tailRank,
-                                 int tailLive, int newCount, int dstBegin)
+                                 int tailLive, int newCount, int dstBegin, uint32_t stamp)
 {
 	B2CU_GRID_STRIDE(j, newCount)
 	{
@@ -2507,6 +2510,7 @@ __global__ void RebuildNewKernel(DeviceArrays d, int tailBegin, int tailCount, c
 		d.cAlt.mix[dest] = make_float4(friction, restitution, 0.0f, 1.0f);
 		d.cAlt.toiCount[dest] = 0;
 		d.cAlt.colour[dest] = B2CU_COLOUR_NONE;
+		d.cAlt.stamp[dest] = stamp;
 	}
 }
 
@@ -2780,9 +2784,13 @@ __global__ void GatherContactsByKeyKernel(DeviceArrays d, int contactCount, int 
 			o.manifold.id[0] = m3.x; o.manifold.id[1] = m3.y;
 			o.manifold.type = (int32_t)m3.z;
 			o.manifold.pointCount = (int32_t)m3.w;
+			o.stamp = d.c.stamp[i];
+			o.reserved = 0u;
 		}
 		else
 		{
+			o.stamp = 0u;
+			o.reserved = 0u;
 			int a = (int)(key >> 32), b = (int)(key & 0xFFFFFFFFull);
 			bool swap = NeedsSwap(d.shapes[d.pshape[a]].type, d.shapes[d.pshape[b]].type);
 			o.proxyA = swap ? b : a;
@@ -2820,3 +2828,5 @@ __global__ void SinCosKernel(int n, const float* __restrict__ x, float* __restri
 }
 
 } // namespace b2cu
+
+#include "b2cu_toi_step.cuh"

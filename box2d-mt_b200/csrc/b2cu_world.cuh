@@ -43,6 +43,10 @@ enum Counter
 	CNT_SCRATCH,
 	CNT_WAKE_PATCH,       // bodies woken after the mirror copy of the step had started
 	CNT_HEAVY,            // contacts queued for the dense polygon pass of Collide
+	CNT_TOI_WORK,         // FindMinToiContact pass: contacts whose time of impact has to be (re)computed
+	CNT_TOI_LIST,         // time-of-impact event: entries of the two bodies' contact lists
+	CNT_TOI_EVENTS,       // begin / end touch events raised inside the sub-steps of this step
+	CNT_TOI_PAD,          // keeps the 64-bit slot below 8-byte aligned
 	CNT_STICKY_TOI,       // not cleared per step: a TOI-candidate contact has existed
 	CNT_TOI_MIN_ALPHA,    // first TOI pass: float bits of the smallest alpha (0xFFFFFFFF: no candidate)
 	CNT_TOI_MIN_KEY,      // 64 bits (two slots): smallest contact key among the candidates at that alpha
@@ -63,6 +67,7 @@ struct ContactSet
 	float4* mix;        // friction, restitution, tangentSpeed, toi
 	int* toiCount;
 	int* colour;        // colour kept from the previous step (B2CU_COLOUR_NONE if it was not a constraint)
+	uint32_t* stamp;    // creation batch (b2cuContact::stamp): orders the bodies' contact lists for the TOI islands
 };
 
 // device-only proxy flag (next to the public B2CU_PROXY_* bits): moved by SyncProxiesKernel in this step
@@ -70,6 +75,12 @@ struct ContactSet
 #define B2CU_PROXY_PUBLIC_FLAGS 0x77
 
 static_assert(CNT_TOI_MIN_KEY % 2 == 0, "64-bit atomics on the key slot need 8-byte alignment");
+
+// DeviceArrays::toiScratch layout (ints)
+#define B2CU_TOI_SCR_SOLID 0       // 1: the event's contact was solid and an island was solved
+#define B2CU_TOI_SCR_BODY_COUNT 1  // bodies of the island, then their ids
+#define B2CU_TOI_SCR_BODIES 2
+#define B2CU_TOI_SCRATCH_INTS 80
 
 #define B2CU_MAX_JOINT_COLOURS 8
 #define B2CU_MAX_JOINT_OPS (B2CU_MAX_JOINT_COLOURS + 1)
@@ -132,6 +143,12 @@ struct DeviceArrays
 	int* levelInfo;         // per grid level: proxy count, then moved count
 	int* colourCount;       // [B2CU_MAX_COLOURS + 1]
 	uint64_t* toiKeys;
+	// time-of-impact sub-steps (b2cu_toi_step.cuh)
+	uint64_t* toiListKeys;   // contact capacity: (side, ~stamp, ~index) of the contacts on the two event bodies' lists
+	uint64_t* toiListSorted; // the same in list order
+	uint64_t* toiEventKeys;  // contact capacity: keys of the begin / end events of the sub-steps, in call order
+	int* toiEventKinds;
+	int* toiScratch;         // B2CU_TOI_SCRATCH_INTS: state handed from one kernel of an event to the next
 
 	// ---- broad-phase grid ----
 	int* cellCount;   // hash table, size gridSize (+1)
@@ -228,6 +245,9 @@ struct b2cuWorld
 	float toiMinAlpha;       // first TOI pass of the last step (b2cuStepInfo)
 	uint64_t toiMinKey;
 	int toiEventPending;
+	int toiSubSteps, toiEventCount, toiNewContacts; // sub-steps of the last step
+	bool stepComplete;       // b2World::m_stepComplete: false while a sub-stepping world is between two events
+	uint32_t contactBatch;   // stamp of the next batch of new contacts
 	b2cuPreSolveFn preSolveHook;
 	void* preSolveUser;
 	bool inPreSolve;         // b2cuStep is inside the hook: the pre-solve entry points are valid

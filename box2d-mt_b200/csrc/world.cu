@@ -142,6 +142,7 @@ void ContactSetDescs(ContactSet* c, std::vector<ArrayDesc>& v)
 	v.push_back(Desc(&c->mix, CAP_CONTACT));
 	v.push_back(Desc(&c->toiCount, CAP_CONTACT));
 	v.push_back(Desc(&c->colour, CAP_CONTACT));
+	v.push_back(Desc(&c->stamp, CAP_CONTACT));
 }
 
 std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
@@ -188,6 +189,11 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->solverKeys, CAP_CONTACT));
 	v.push_back(Desc(&d->listC, CAP_CONTACT));
 	v.push_back(Desc(&d->toiKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->toiListKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->toiListSorted, CAP_CONTACT));
+	v.push_back(Desc(&d->toiEventKeys, CAP_CONTACT));
+	v.push_back(Desc(&d->toiEventKinds, CAP_CONTACT));
+	v.push_back(Desc(&d->toiScratch, CAP_FIXED, B2CU_TOI_SCRATCH_INTS));
 	v.push_back(Desc(&d->movedList, CAP_PROXY));
 	v.push_back(Desc(&d->largeList, CAP_PROXY));
 	v.push_back(Desc(&d->levelInfo, CAP_FIXED, 64));
@@ -429,9 +435,12 @@ int CopyContactRange(b2cuWorld* w, ContactSet& dst, const ContactSet& src, int b
 	COPY_ROWS(mix);
 	COPY_ROWS(toiCount);
 	COPY_ROWS(colour);
+	COPY_ROWS(stamp);
 #undef COPY_ROWS
 	return B2CU_OK;
 }
+
+int RebuildContactSet(b2cuWorld* w, int newCount, int destroyedMain, int destroyedTail, int* newCountOut, int* destroyedOut);
 
 // Finds the new pairs of the proxies flagged MOVED and updates the contact set.
 //
@@ -493,7 +502,20 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 			return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
 	}
 	if (np > 0) LAUNCH(w, ClearMovedKernel, GridFor(np), kBlock, w->d);
-	int newCount = w->hostCounters[CNT_NEW_PAIRS];
+	*movedOut = w->hostCounters[CNT_MOVED];
+	return RebuildContactSet(w, w->hostCounters[CNT_NEW_PAIRS], destroyedMain, destroyedTail, newCountOut, destroyedOut);
+}
+
+// Second half of FindNewContacts: the new pairs (unsorted keys in newKeys, `newCount` of them) become contacts and the
+// destroyed ones leave the set.  Also used after every time-of-impact event (no destroyed contacts there).
+int RebuildContactSet(b2cuWorld* w, int newCount, int destroyedMain, int destroyedTail, int* newCountOut, int* destroyedOut)
+{
+	DeviceArrays& d = w->d;
+	const int nc = w->contactCount;
+	const int nMain = w->mainCount;
+	const int nTail = nc - nMain;
+	const int tailLive = nTail - destroyedTail;
+	int rc;
 	if (w->pairFilter != nullptr && newCount > 0)
 	{
 		// the caller's b2ContactFilter decides about the candidate pairs before any contact exists (AddPair)
@@ -518,8 +540,10 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 	}
 	*newCountOut = newCount;
 	*destroyedOut = destroyedMain + destroyedTail;
-	*movedOut = w->hostCounters[CNT_MOVED];
 	w->deadMain += destroyedMain;
+	// every batch of new contacts gets the next creation stamp (b2cuContact::stamp)
+	const uint32_t stamp = w->contactBatch;
+	if (newCount > 0) ++w->contactBatch;
 
 	// ---- 1. tail' = live(tail) merged with the new pairs (built in cAlt, copied back) ----
 	int newTail = nTail;
@@ -535,7 +559,7 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		}
 		if (newCount > 0)
 		{
-			LAUNCH(w, RebuildNewKernel, GridFor(newCount), kBlock, d, nMain, nTail, d.listA, tailLive, newCount, nMain);
+			LAUNCH(w, RebuildNewKernel, GridFor(newCount), kBlock, d, nMain, nTail, d.listA, tailLive, newCount, nMain, stamp);
 			// the only body writer after the mirror copy has started: let the pack kernel finish reading first
 			if (w->mirrorInFlight) CUDA_TRY(w, cudaStreamWaitEvent(w->stream, w->evPacked, 0));
 			LAUNCH(w, ApplyWakeKernel, GridFor(w->bodyCount), kBlock, d, w->bodyCount,
@@ -580,6 +604,128 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 		w->compactNow = false;
 		if ((rc = RebuildLowStart(w))) return rc;
 	}
+	return B2CU_OK;
+}
+
+
+// ---- continuous collision: b2World::SolveTOI (b2World.cpp:1026-1093) --------------------------------------------
+// One FindMinToiContact pass: the earliest (alpha, key) among the eligible candidates lands in the counters.
+int ToiFindMin(b2cuWorld* w)
+{
+	DeviceArrays& d = w->d;
+	const int nc = w->contactCount;
+	int rc;
+	if ((rc = ZeroCounter(w, CNT_TOI))) return rc;
+	if ((rc = ZeroCounter(w, CNT_TOI_WORK))) return rc;
+	CUDA_TRY(w, cudaMemsetAsync(d.counters + CNT_TOI_MIN_ALPHA, 0xFF, sizeof(int) * 3, w->stream));
+	LAUNCH(w, ToiSelectKernel, GridFor(nc), kBlock, d, nc, d.listA);
+	// one candidate is a long, divergent root search: small blocks, so that a thousand candidates already spread over
+	// most SMs (the count of the last pass sizes the grid; the kernel strides over whatever there is)
+	const int toiBlock = 64;
+	const int toiGrid = std::max(16, std::min(8 * g_smCount, (2 * std::max(w->toiCount, 512) + toiBlock - 1) / toiBlock));
+	LAUNCH(w, ToiComputeKernel, toiGrid, toiBlock, d, (const int*)d.listA);
+	LAUNCH(w, ToiMinKeyAllKernel, GridFor(nc), kBlock, d, nc);
+	return ReadCounters(w);
+}
+
+// The sub-step loop.  Host-driven, one event at a time in the reference's order; all arithmetic and
+// all state stay on the device, the host only reads the winner of each pass and the number of new pairs of each event.
+int SolveTOI(b2cuWorld* w, float dt, int velocityIterations)
+{
+	DeviceArrays& d = w->d;
+	int rc;
+	w->toiCount = 0;
+	w->toiMinAlpha = 1.0f;
+	w->toiMinKey = ~0ull;
+	w->toiEventPending = 0;
+	w->toiSubSteps = 0;
+	w->toiEventCount = 0;
+	w->toiNewContacts = 0;
+	if (w->contactCount == 0 || w->hostCounters[CNT_STICKY_TOI] == 0)
+	{
+		w->stepComplete = true;
+		return B2CU_OK;
+	}
+	const bool subStepping = (w->params.flags & B2CU_WORLD_SUB_STEPPING) != 0;
+	// flags are cleared at the end only if some contact was evaluated (or a previous call left them behind)
+	bool clearPostSolve = !w->stepComplete;
+	bool first = true;
+	for (;;)
+	{
+		if ((rc = ToiFindMin(w))) return rc;
+		uint32_t bits;
+		memcpy(&bits, &w->hostCounters[CNT_TOI_MIN_ALPHA], sizeof(bits));
+		const bool have = bits != 0xFFFFFFFFu;
+		float minAlpha = 1.0f;
+		uint64_t minKey = ~0ull;
+		if (have)
+		{
+			memcpy(&minAlpha, &bits, sizeof(float));
+			memcpy(&minKey, &w->hostCounters[CNT_TOI_MIN_KEY], sizeof(uint64_t));
+			clearPostSolve = true;
+		}
+		if (first)
+		{
+			w->toiCount = w->hostCounters[CNT_TOI];
+			w->toiMinAlpha = minAlpha;
+			w->toiMinKey = minKey;
+			first = false;
+		}
+		if (!have || 1.0f - 10.0f * B2CU_EPSILON < minAlpha)
+		{
+			// no more events (b2World.cpp:1069-1078)
+			w->stepComplete = true;
+			if (clearPostSolve) LAUNCH(w, ToiClearKernel, GridFor(std::max(w->contactCount, w->bodyCount)), kBlock, d, w->contactCount, w->bodyCount);
+			break;
+		}
+		if (w->shardCount > 1)
+			return SetError(w, B2CU_ERR_UNSUPPORTED, "time-of-impact sub-steps are not supported in a sharded world "
+			                                         "(switch continuous physics off or keep the world on one GPU)");
+
+		// ---- StepSolveTOI (b2World.cpp:851-1024) ----
+		const int nc = w->contactCount;
+		const int np = w->proxyCount;
+		if ((rc = ZeroCounter(w, CNT_TOI_LIST))) return rc;
+		if ((rc = ZeroCounter(w, CNT_SCRATCH))) return rc;
+		if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
+		LAUNCH(w, ToiEventPrepareKernel, GridFor(nc), kBlock, d, nc, w->mainCount, minKey, w->contactCapacity);
+		LAUNCH(w, ToiEventKernel, 1, B2CU_TOI_THREADS, d, nc, w->mainCount, minKey, minAlpha, dt, velocityIterations,
+		       w->contactCapacity);
+		LAUNCH(w, ToiAfterEventKernel, GridFor(std::max(np, nc)), kBlock, d, np, nc);
+		const int2 counts = make_int2(nc, w->mainCount);
+		LAUNCH(w, ToiFindPairsKernel, GridFor(np), kBlock, d, np, counts, w->contactCapacity);
+		if ((rc = ReadCounters(w))) return rc;
+		if (w->hostCounters[CNT_ERROR] || nc + w->hostCounters[CNT_NEW_PAIRS] > w->contactCapacity)
+		{
+			if (w->hostCounters[CNT_TOI_LIST] > w->contactCapacity || w->hostCounters[CNT_TOI_EVENTS] > w->contactCapacity)
+				return SetError(w, B2CU_ERR_CAPACITY, "time-of-impact event: list %d / events %d exceed the contact capacity %d",
+				                w->hostCounters[CNT_TOI_LIST], w->hostCounters[CNT_TOI_EVENTS], w->contactCapacity);
+			// the pair buffer would overflow: grow and repeat the pair search (the moved flags are still set)
+			int needed = nc + w->hostCounters[CNT_NEW_PAIRS];
+			int grown = std::max(needed + needed / 4, 2 * w->contactCapacity);
+			if ((rc = Reserve(w, w->bodyCapacity, w->proxyCapacity, w->shapeCapacity, grown))) return rc;
+			if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
+			if ((rc = ZeroCounter(w, CNT_ERROR))) return rc;
+			LAUNCH(w, ToiFindPairsKernel, GridFor(np), kBlock, w->d, np, counts, w->contactCapacity);
+			if ((rc = ReadCounters(w))) return rc;
+			if (w->hostCounters[CNT_ERROR])
+				return SetError(w, B2CU_ERR_CAPACITY, "new-pair buffer overflow (contact capacity %d)", w->contactCapacity);
+		}
+		if (w->hostCounters[CNT_SCRATCH] > 0) LAUNCH(w, ClearMovedKernel, GridFor(w->hostCounters[CNT_SCRATCH]), kBlock, w->d);
+		int created = 0, destroyed = 0;
+		if (w->hostCounters[CNT_NEW_PAIRS] > 0 &&
+		    (rc = RebuildContactSet(w, w->hostCounters[CNT_NEW_PAIRS], 0, 0, &created, &destroyed)))
+			return rc;
+		w->toiNewContacts += created;
+		++w->toiSubSteps;
+		if (subStepping)
+		{
+			w->stepComplete = false;
+			w->toiEventPending = 1;
+			break;
+		}
+	}
+	w->toiEventCount = std::min(w->hostCounters[CNT_TOI_EVENTS], w->contactCapacity);
 	return B2CU_OK;
 }
 
@@ -667,6 +813,8 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 	w->positionIterationsCapacity = 4;
 	w->cellSize = 1.0f;
 	w->toiCheckDirty = true;
+	w->stepComplete = true;
+	w->contactBatch = 1;
 	{
 		// persistent cooperative solver: as many CTAs as can be co-resident
 		int coop = 0, perSm = 0;
@@ -1191,9 +1339,13 @@ int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
 	std::vector<float4> m0(count), m1(count), m2(count), mix(count);
 	std::vector<uint4> m3(count);
 	std::vector<int> toiCount(count), colour(count, B2CU_COLOUR_NONE);
+	std::vector<uint32_t> stamp(count);
+	uint32_t maxStamp = 0;
 	for (int j = 0; j < count; ++j)
 	{
 		const b2cuContact& c = contacts[order[j]];
+		stamp[j] = c.stamp;
+		maxStamp = std::max(maxStamp, c.stamp);
 		const b2cuManifold& m = c.manifold;
 		key[j] = keys[order[j]];
 		if (j > 0 && key[j] == key[j - 1]) return SetError(w, B2CU_ERR_ARGUMENT, "duplicate contact key");
@@ -1213,8 +1365,11 @@ int b2cuSetContacts(b2cuWorld* w, int32_t count, const b2cuContact* contacts)
 	if ((rc = Upload(w, d.c.key, 0, key)) || (rc = Upload(w, d.c.proxies, 0, proxies)) ||
 	    (rc = Upload(w, d.c.flags, 0, flags)) || (rc = Upload(w, d.c.m0, 0, m0)) || (rc = Upload(w, d.c.m1, 0, m1)) ||
 	    (rc = Upload(w, d.c.m2, 0, m2)) || (rc = Upload(w, d.c.m3, 0, m3)) || (rc = Upload(w, d.c.mix, 0, mix)) ||
-	    (rc = Upload(w, d.c.toiCount, 0, toiCount)) || (rc = Upload(w, d.c.colour, 0, colour)))
+	    (rc = Upload(w, d.c.toiCount, 0, toiCount)) || (rc = Upload(w, d.c.colour, 0, colour)) ||
+	    (rc = Upload(w, d.c.stamp, 0, stamp)))
 		return rc;
+	// contacts created from now on are younger than all of these
+	w->contactBatch = maxStamp + 1u;
 	w->contactCount = count;
 	w->mainCount = count;
 	w->deadMain = 0;
@@ -1244,6 +1399,7 @@ int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32
 	std::vector<float4> m0(slots), m1(slots), m2(slots), mix(slots);
 	std::vector<uint4> m3(slots);
 	std::vector<int> toiCount(slots);
+	std::vector<uint32_t> stamp(slots);
 	std::vector<int> pbody(w->proxyCount);
 	std::vector<uint32_t> bflags(w->bodyCount);
 	DeviceArrays& d = w->d;
@@ -1252,7 +1408,7 @@ int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32
 	if ((rc = Download(w, d.c.key, 0, key)) || (rc = Download(w, d.c.proxies, 0, proxies)) ||
 	    (rc = Download(w, d.c.flags, 0, flags)) || (rc = Download(w, d.c.m0, 0, m0)) || (rc = Download(w, d.c.m1, 0, m1)) ||
 	    (rc = Download(w, d.c.m2, 0, m2)) || (rc = Download(w, d.c.m3, 0, m3)) || (rc = Download(w, d.c.mix, 0, mix)) ||
-	    (rc = Download(w, d.c.toiCount, 0, toiCount)))
+	    (rc = Download(w, d.c.toiCount, 0, toiCount)) || (rc = Download(w, d.c.stamp, 0, stamp)))
 		return rc;
 	if ((rc = SyncCheck(w))) return rc;
 	// live slots in key order: the main region and the tail are each sorted; this read-out does not touch the
@@ -1286,6 +1442,8 @@ int b2cuGetContacts(b2cuWorld* w, int32_t capacity, b2cuContact* contacts, int32
 		c.tangentSpeed = mix[j].z;
 		c.toi = mix[j].w;
 		c.toiCount = toiCount[j];
+		c.stamp = stamp[j];
+		c.reserved = 0u;
 		b2cuManifold& m = c.manifold;
 		m.localNormal[0] = m0[j].x; m.localNormal[1] = m0[j].y;
 		m.localPoint[0] = m0[j].z; m.localPoint[1] = m0[j].w;
@@ -1565,7 +1723,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	w->overflowCount = 0;
 	for (int c = 0; c < B2CU_MAX_COLOURS + 2; ++c) w->colourCounts[c] = 0;
 
-	if (dt > 0.0f)
+	// b2World.cpp:1670: a sub-stepping world that stopped between two time-of-impact events does not solve again
+	if (dt > 0.0f && w->stepComplete)
 	{
 		// ---- islands (serial DFS of b2World::Solve -> union-find) ----
 		LAUNCH(w, SolveInitBodiesKernel, GridFor(nb), kBlock, d, nb, positionIterations);
@@ -1815,7 +1974,6 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		newContacts += n1;
 		destroyed += d1;
 		moved += m1;
-		w->params.invDt0 = invDt;
 	}
 	else
 	{
@@ -1826,6 +1984,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		if ((rc = FindNewContactsAndRebuild(w, &n1, &d1, &m1))) return rc;
 		destroyed += d1;
 	}
+	if (dt > 0.0f) w->params.invDt0 = invDt;
 	cudaEvent_t evBroad = w->ev[8];
 	cudaEventRecord(evBroad, w->stream);
 
@@ -1840,58 +1999,36 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		w->endCount = nEnd + nDestroyEnd;
 	}
 
-	// ---- TOI eligibility compaction (b2World.cpp:283-352 filters; SolveTOI itself is host-driven) ----
-	const int lastToiCount = w->toiCount;
-	w->toiCount = 0;
-	w->toiMinAlpha = 1.0f;
-	w->toiMinKey = ~0ull;
-	w->toiEventPending = 0;
-	nc = w->contactCount;
-	const bool toiPass = (w->params.flags & B2CU_WORLD_CONTINUOUS) && dt > 0.0f && nc > 0 &&
-	                     w->hostCounters[CNT_STICKY_TOI] != 0;
-	if (toiPass)
+	// ---- continuous collision: b2World::SolveTOI (b2World.cpp:1677-1682) ----
+	if ((w->params.flags & B2CU_WORLD_CONTINUOUS) && dt > 0.0f)
 	{
-		LAUNCH(w, ToiFlagsKernel, GridFor(nc), kBlock, d, nc, d.cSelect);
-		CompactFlags(&w->prims, d.cSelect, nc, d.listA, d.counters + CNT_TOI, w->stream);
-		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_TOI, (const int*)nullptr,
-		       d.toiKeys, w->contactCapacity);
-		// first pass of SolveTOI: the earliest time of impact among the candidates.  The sub-steps it would trigger
-		// are not executed; the step reports whether the reference would have taken one.
-		float* toiAlpha = reinterpret_cast<float*>(d.listB);
-		CUDA_TRY(w, cudaMemsetAsync(d.counters + CNT_TOI_MIN_ALPHA, 0xFF, sizeof(int) * 3, w->stream));
-		// one candidate is a long, divergent root search: small blocks, so that a thousand candidates already spread
-		// over most SMs (the count of the last step sizes the grid; the kernels stride over whatever there is)
-		const int toiBlock = 64;
-		const int toiGrid = std::max(16, std::min(8 * g_smCount, (2 * std::max(lastToiCount, 512) + toiBlock - 1) / toiBlock));
-		LAUNCH(w, ToiFirstPassKernel, toiGrid, toiBlock, d, (const int*)d.listA, (const int*)(d.counters + CNT_TOI), toiAlpha);
-		LAUNCH(w, ToiMinKeyKernel, toiGrid, toiBlock, d, (const int*)d.listA, (const int*)(d.counters + CNT_TOI),
-		       (const float*)toiAlpha);
+		if ((rc = SolveTOI(w, dt, velocityIterations))) return rc;
+	}
+	else
+	{
+		w->toiCount = 0;
+		w->toiMinAlpha = 1.0f;
+		w->toiMinKey = ~0ull;
+		w->toiEventPending = 0;
+		w->toiSubSteps = w->toiEventCount = w->toiNewContacts = 0;
 	}
 	cudaEvent_t evEnd = w->ev[9];
 	cudaEventRecord(evEnd, w->stream);
 
-	if (toiPass || w->mirrorInFlight)
+	if (w->mirrorInFlight)
 	{
 		if ((rc = ReadCounters(w))) return rc;
-		if (toiPass)
-		{
-			w->toiCount = w->hostCounters[CNT_TOI];
-			uint32_t bits;
-			memcpy(&bits, &w->hostCounters[CNT_TOI_MIN_ALPHA], sizeof(bits));
-			if (w->toiCount > 0 && bits != 0xFFFFFFFFu)
-			{
-				memcpy(&w->toiMinAlpha, &bits, sizeof(float));
-				memcpy(&w->toiMinKey, &w->hostCounters[CNT_TOI_MIN_KEY], sizeof(uint64_t));
-				// b2World::SolveTOI (b2World.cpp:1069) stops at 1 - 10 epsilon < alpha
-				w->toiEventPending = !(1.0f - 10.0f * B2CU_EPSILON < w->toiMinAlpha);
-			}
-		}
 	}
 	else
 	{
 		if ((rc = SyncCheck(w))) return rc;
 	}
 	if ((rc = FinishMirrorCopy(w))) return rc;
+	if (w->toiSubSteps > 0 && w->bodyMirror != nullptr && std::min(w->bodyMirrorCount, w->bodyCount) > 0)
+	{
+		// the sub-steps moved bodies after the mirror copy of the step had been taken: take it again
+		if ((rc = b2cuGetBodyStates(w, 0, std::min(w->bodyMirrorCount, w->bodyCount), w->bodyMirror))) return rc;
+	}
 
 	if (g_trace.enabled && g_trace.used > 1)
 	{
@@ -1952,7 +2089,9 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	out.toiEventPending = w->toiEventPending;
 	out.toiMinKey = w->toiMinKey;
 	out.toiMinAlpha = w->toiMinAlpha;
-	out.reserved2 = 0;
+	out.toiSubSteps = w->toiSubSteps;
+	out.toiEventCount = w->toiEventCount;
+	out.toiNewContactCount = w->toiNewContacts;
 	out.kernelLaunches = w->launches + g_primLaunches;
 	if (info) *info = out;
 	return B2CU_OK;
@@ -1991,6 +2130,23 @@ int b2cuGetEvents(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* 
 	}
 	memcpy(keys, sorted.data(), sizeof(uint64_t) * std::min(n, capacity));
 	return B2CU_OK;
+}
+
+int b2cuGetToiEvents(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* kinds, b2cuContact* records,
+                     int32_t* count)
+{
+	if (!w || capacity < 0 || (capacity > 0 && (!keys || !kinds))) return B2CU_ERR_ARGUMENT;
+	cudaSetDevice(w->device);
+	const int n = w->toiEventCount;
+	if (count) *count = n;
+	const int m = std::min(n, capacity);
+	if (m <= 0) return B2CU_OK;
+	// already in call order: the sub-steps run one after the other and one thread appends
+	CUDA_TRY(w, cudaMemcpyAsync(keys, w->d.toiEventKeys, sizeof(uint64_t) * (size_t)m, cudaMemcpyDeviceToHost, w->stream));
+	CUDA_TRY(w, cudaMemcpyAsync(kinds, w->d.toiEventKinds, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, w->stream));
+	int rc = SyncCheck(w);
+	if (rc || records == nullptr) return rc;
+	return b2cuGetContactsByKey(w, m, keys, records);
 }
 
 // grow-only scratch pair (device + page-locked host) used by the query entry points
@@ -2170,14 +2326,34 @@ int b2cuGetToiCandidates(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, i
 {
 	if (!w || capacity < 0 || (capacity > 0 && !keys)) return B2CU_ERR_ARGUMENT;
 	cudaSetDevice(w->device);
-	int n = w->toiCount;
+	// evaluated when asked for (the step itself never needs the list in key order)
+	DeviceArrays& d = w->d;
+	const int nc = w->contactCount;
+	int n = 0;
+	int rc;
+	if (nc > 0)
+	{
+		LAUNCH(w, ToiFlagsKernel, GridFor(nc), kBlock, d, nc, d.cSelect);
+		CompactFlags(&w->prims, d.cSelect, nc, d.listA, d.counters + CNT_SCRATCH, w->stream);
+		LAUNCH(w, GatherKeysKernel, GridFor(nc), kBlock, d.c.key, d.listA, d.counters + CNT_SCRATCH, (const int*)nullptr,
+		       d.toiKeys, w->contactCapacity);
+		CUDA_TRY(w, cudaMemcpyAsync(&w->hostCounters[CNT_SCRATCH], d.counters + CNT_SCRATCH, sizeof(int),
+		                            cudaMemcpyDeviceToHost, w->stream));
+		if ((rc = SyncCheck(w))) return rc;
+		n = w->hostCounters[CNT_SCRATCH];
+	}
 	if (count) *count = n;
 	int m = std::min(n, capacity);
 	if (m > 0)
 	{
-		CUDA_TRY(w, cudaMemcpyAsync(keys, w->d.toiKeys, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, w->stream));
+		// main region and tail are each in key order
+		std::vector<uint64_t> all((size_t)n);
+		CUDA_TRY(w, cudaMemcpyAsync(all.data(), d.toiKeys, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, w->stream));
+		if ((rc = SyncCheck(w))) return rc;
+		std::sort(all.begin(), all.end());
+		memcpy(keys, all.data(), sizeof(uint64_t) * (size_t)m);
 	}
-	return SyncCheck(w);
+	return B2CU_OK;
 }
 
 int b2cuShardConfigure(b2cuWorld* w, int32_t rank, int32_t rankCount, int32_t ghostCount, const int32_t* ghostBodies,

@@ -944,8 +944,6 @@ void b2World::DispatchEvents(b2cuWorld* device)
 		fprintf(stderr, "[b2h events] begin %zu end %zu: query %.3f ms, make %.3f ms, alloc+rest %.3f ms\n", keys[0].size(),
 		        keys[1].size(), queryMs, makeMs,
 		        std::chrono::duration<double, std::milli>(Clock::now() - t0).count() - queryMs - makeMs);
-	if (keys[0].empty() && keys[1].empty()) return;
-
 	for (size_t i = 0; i < contacts[0].size(); ++i)
 		deferred[0][i] = m_contactListener->BeginContactImmediate(&contacts[0][i], 0) ? 1 : 0;
 	for (size_t i = 0; i < contacts[1].size(); ++i)
@@ -954,6 +952,32 @@ void b2World::DispatchEvents(b2cuWorld* device)
 		if (deferred[0][i]) m_contactListener->BeginContact(&contacts[0][i]);
 	for (size_t i = 0; i < contacts[1].size(); ++i)
 		if (deferred[1][i]) m_contactListener->EndContact(&contacts[1][i]);
+
+	// Calls made from inside the time-of-impact sub-steps (b2Contact::Update from b2World::StepSolveTOI, reference
+	// b2World.cpp:866 and :936): single-threaded there, so the Immediate call and the deferred call come back to back,
+	// event by event, after all callbacks of the discrete part of the step.
+	int32 nToi = 0;
+	b2cuGetToiEvents(device, 0, nullptr, nullptr, nullptr, &nToi);
+	if (nToi > 0)
+	{
+		std::vector<b2cuContactKey> toiKeys((size_t)nToi);
+		std::vector<int32_t> toiKinds((size_t)nToi);
+		std::vector<b2cuContact> toiRecs((size_t)nToi);
+		if (b2cuGetToiEvents(device, nToi, toiKeys.data(), toiKinds.data(), toiRecs.data(), &nToi) != B2CU_OK) return;
+		for (int32 i = 0; i < nToi; ++i)
+		{
+			b2Contact c;
+			MakeContact(&c, toiRecs[(size_t)i]);
+			if (toiKinds[(size_t)i] == B2CU_EVENT_BEGIN)
+			{
+				if (m_contactListener->BeginContactImmediate(&c, 0)) m_contactListener->BeginContact(&c);
+			}
+			else
+			{
+				if (m_contactListener->EndContactImmediate(&c, 0)) m_contactListener->EndContact(&c);
+			}
+		}
+	}
 }
 
 // b2cuPreSolveFn: the PreSolve calls of b2Contact::Update / b2ContactManager::FinishCollide, made from inside the
@@ -1060,7 +1084,7 @@ int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool
 	InvalidateSnapshots();
 	Clock::time_point t1 = Clock::now();
 	if (hostMs) hostMs[0] = std::chrono::duration<float, std::milli>(t1 - t0).count();
-	if (dispatchEvents && m_contactListener && (info.beginCount > 0 || info.endCount > 0))
+	if (dispatchEvents && m_contactListener && (info.beginCount > 0 || info.endCount > 0 || info.toiEventCount > 0))
 	{
 		// callbacks may read bodies: make sure the mirror is current
 		RefreshBodies();

@@ -21,7 +21,7 @@ API = [
     "b2cuSetWorldParams", "b2cuSetInvDt0", "b2cuSetCounts", "b2cuSetBodies", "b2cuGetBodies", "b2cuSetShapes",
     "b2cuSetProxies", "b2cuGetProxies", "b2cuSetContacts", "b2cuGetContactCount", "b2cuGetContacts", "b2cuStep",
     "b2cuGetContactsByKey", "b2cuGetEvents", "b2cuGetSolverOrder", "b2cuGetIslandLabels", "b2cuGetToiCandidates", "b2cuCollidePairs",
-    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuDistancePairs", "b2cuTimeOfImpactPairs", "b2cuQueryAABB", "b2cuRayCastCandidates", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts", "b2cuSetJoints", "b2cuGetJointCount", "b2cuGetJoints", "b2cuGetJointOrder",
+    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuDistancePairs", "b2cuTimeOfImpactPairs", "b2cuQueryAABB", "b2cuRayCastCandidates", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts", "b2cuGetToiEvents", "b2cuSetJoints", "b2cuGetJointCount", "b2cuGetJoints", "b2cuGetJointOrder",
 ]
 
 
@@ -67,6 +67,7 @@ def load():
     lib.b2cuGetContactsByKey.argtypes = [vp, i32, vp, vp]
     lib.b2cuGetSolverOrder.argtypes = [vp, i32, vp, vp, vp]
     lib.b2cuGetToiCandidates.argtypes = [vp, i32, vp, vp]
+    lib.b2cuGetToiEvents.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.b2cuCollidePairs.argtypes = [i32, i32, vp, i32, vp, vp, vp, vp, vp]
     lib.b2cuSinCos.argtypes = [i32, i32, vp, vp, vp]
     lib.b2cuSetJoints.argtypes = [vp, i32, vp]
@@ -249,8 +250,25 @@ class World:
             self._check(fn(self.h, *args, n.value, _ptr(out), ctypes.byref(n)))
         return out
 
+    def toi_events(self, records=False):
+        """(keys, kinds[, contact records]) of the begin / end events raised inside the time-of-impact sub-steps of the
+        last step, in call order."""
+        n = ctypes.c_int32()
+        self._check(self.lib.b2cuGetToiEvents(self.h, 0, None, None, None, ctypes.byref(n)))
+        keys = np.zeros(n.value, np.uint64)
+        kinds = np.zeros(n.value, np.int32)
+        recs = np.zeros(n.value, T.CONTACT)
+        if n.value:
+            self._check(self.lib.b2cuGetToiEvents(self.h, n.value, _ptr(keys), _ptr(kinds),
+                                                  _ptr(recs) if records else None, ctypes.byref(n)))
+        return (keys, kinds, recs) if records else (keys, kinds)
+
     def events(self, kind):
-        return self._keys(self.lib.b2cuGetEvents, kind)
+        """Callback order of the reference for one kind of event: the deferred calls of the discrete step in key order,
+        then the calls made from inside the time-of-impact sub-steps as they happened."""
+        discrete = self._keys(self.lib.b2cuGetEvents, kind)
+        keys, kinds = self.toi_events()
+        return np.concatenate([discrete, keys[kinds == kind]])
 
     def contacts_by_key(self, keys):
         k = np.ascontiguousarray(keys, np.uint64)

@@ -51,8 +51,9 @@ CONTACT = np.dtype([
     ("friction", "f4"), ("restitution", "f4"), ("tangentSpeed", "f4"),
     ("toiCount", "i4"), ("toi", "f4"),
     ("manifold", MANIFOLD),
+    ("stamp", "u4"), ("reserved", "u4"),
 ])
-assert CONTACT.itemsize == 96
+assert CONTACT.itemsize == 104
 
 DISTANCE_RESULT = np.dtype([("distance", "f4"), ("pointA", "f4", (2,)), ("pointB", "f4", (2,)), ("iterations", "i4")])
 assert DISTANCE_RESULT.itemsize == 24
@@ -82,9 +83,10 @@ STEP_INFO = np.dtype([
     ("islandBodyCount", "i4"), ("awakeBodyCount", "i4"), ("moveCount", "i4"),
     ("newContactCount", "i4"), ("destroyedContactCount", "i4"),
     ("beginCount", "i4"), ("endCount", "i4"), ("toiCandidateCount", "i4"), ("kernelLaunches", "i4"),
-    ("toiEventPending", "i4"), ("toiMinKey", "u8"), ("toiMinAlpha", "f4"), ("reserved2", "i4"),
+    ("toiEventPending", "i4"), ("toiMinKey", "u8"), ("toiMinAlpha", "f4"), ("toiSubSteps", "i4"),
+    ("toiEventCount", "i4"), ("toiNewContactCount", "i4"),
 ])
-assert STEP_INFO.itemsize == 136 and STEP_INFO.fields["toiMinKey"][1] == 120
+assert STEP_INFO.itemsize == 144 and STEP_INFO.fields["toiMinKey"][1] == 120
 
 JOINT = np.dtype([
     ("type", "i4"), ("bodyA", "i4"), ("bodyB", "i4"), ("flags", "u4"),

@@ -530,3 +530,35 @@ def resting_linkage(seed=0):
     s.fixture(b, bar, density=1.0, friction=0.6)
     s.distance_joint(a, b, (0.0, 0.0), (-1.0, 0.0), 2.0)
     return s
+
+
+def bullets(count=12, seed=7):
+    """Continuous-collision scene: bullets and fast ordinary bodies against thin static geometry (an edge floor, a thin
+    box wall, an edge ceiling) and against each other -- the situations of Testbed/Tests/BulletTest.h, ContinuousTest.h
+    and TunnelingTest.h in one world.  Every contact with the static geometry is a time-of-impact candidate (no
+    thick-shape fixtures), bullets are candidates against everything; at 60 Hz the fast bodies cross the wall's
+    thickness in one step, so the reference only keeps them out through b2World::SolveTOI."""
+    s = Scene()
+    g = s.body(T.STATIC_BODY, (0.0, 0.0))
+    s.fixture(g, s.edge((-30.0, 0.0), (30.0, 0.0)), density=0.0)
+    s.fixture(g, s.box(0.05, 6.0, center=(10.0, 6.0), angle=0.0), density=0.0)
+    s.fixture(g, s.edge((-30.0, 14.0), (30.0, 14.0)), density=0.0)
+    s.fixture(g, s.box(0.05, 6.0, center=(-12.0, 6.0), angle=0.0), density=0.0)
+    rnd = _Rand(seed)
+    ys = rnd.uniform(1.0, 11.0, count)
+    vs = rnd.uniform(60.0, 240.0, count)
+    box = s.box(0.25, 0.25)
+    ball = s.circle(0.2)
+    tri = s.polygon(_regular_polygon(3, 0.3))
+    for i in range(count):
+        bullet = i % 3 != 2
+        flags = BODYDEF_DEFAULT | (BODYDEF_BULLET if bullet else 0)
+        direction = 1.0 if i % 2 == 0 else -1.0
+        b = s.body(T.DYNAMIC_BODY, (-2.0 + 0.7 * i * direction * 0.1, float(ys[i])), angle=0.3 * i,
+                   vel=(direction * float(vs[i]), -20.0 + 5.0 * (i % 5)), w=3.0 * (i % 4), flags=flags)
+        s.fixture(b, (box, ball, tri)[i % 3], density=1.0 + (i % 2), restitution=0.2 * (i % 3))
+    # a small heap of ordinary boxes in front of the wall that the bullets plough through
+    for i in range(12):
+        b = s.body(T.DYNAMIC_BODY, (6.0 + 0.55 * (i % 4), 0.3 + 0.55 * (i // 4)))
+        s.fixture(b, box, density=0.5)
+    return s

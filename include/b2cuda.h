@@ -47,6 +47,8 @@
  *                                        used this step; feeds the permuted-order oracle
  *   b2cuGetToiCandidates                 TOI-eligible front partition of b2ContactManager::m_contacts
  *                                                                          Dynamics/b2ContactManager.cpp:659-713, b2World.cpp:317-341
+ *   b2cuGetToiEvents                     BeginContact / EndContact calls made from inside b2World::SolveTOI
+ *                                                                          Dynamics/b2World.cpp:851-1024, Contacts/b2Contact.cpp:247-281
  *   b2cuShardConfigure / GetLink /       (new) spatial sharding of one large world over the GPUs of a box: halo
  *   Connect                              bodies + per-iteration halo exchange over NVLink peer memory, SURVEY.md 8e
  *   b2cuQueryAABB / RayCastCandidates    b2World::QueryAABB / RayCast (tree queries on the fat boxes)
@@ -231,6 +233,14 @@ typedef struct b2cuContact
 	int32_t toiCount;
 	float toi;
 	b2cuManifold manifold;
+	/* creation order: the reference links a new contact at the HEAD of both bodies' contact lists (b2ContactManager::
+	 * OnContactCreate, Dynamics/b2ContactManager.cpp:530-556) and b2World::StepSolveTOI walks those lists (b2World.cpp:
+	 * 899-970), so which 32 contacts join a time-of-impact island, and in which order they are solved, follows the order
+	 * of creation.  A body's list is its contacts by (stamp descending, key descending): every batch of new contacts
+	 * (one b2ContactManager::FindNewContacts call, created in key order) gets the next stamp.  Round-trips through
+	 * b2cuGetContacts / b2cuSetContacts; any values with that meaning do (e.g. the rank in b2World::GetContactList). */
+	uint32_t stamp;
+	uint32_t reserved;
 } b2cuContact;
 
 /* ---- world -------------------------------------------------------------------- */
@@ -277,14 +287,17 @@ typedef struct b2cuStepInfo
 	int32_t beginCount, endCount;
 	int32_t toiCandidateCount;
 	int32_t kernelLaunches;    /* kernels launched by this step */
-	/* First pass of b2World::SolveTOI (Dynamics/b2World.cpp:1026-1092, FindMinToiContact :1525-1580) on a continuous
-	 * world: the candidate with the earliest time of impact.  toiEventPending = 1 when the reference would go on to
-	 * sub-step this contact (alpha <= 1 - 10 epsilon); the sub-step itself is not executed by this version, so a
-	 * step that reports 1 has left the reference's trajectory. */
+	/* b2World::SolveTOI (Dynamics/b2World.cpp:1026-1092) on a continuous world.  toiMinKey / toiMinAlpha: the result of
+	 * its FIRST FindMinToiContact pass (:1525-1580), the candidate with the earliest time of impact.  toiSubSteps: how
+	 * many time-of-impact events (b2World::StepSolveTOI, :851-1024) the step then executed.  toiEventPending = 1 only
+	 * on a sub-stepping world (b2World::SetSubStepping) whose step stopped after one event with more to come
+	 * (m_stepComplete == false): the next b2cuStep continues with the events and skips the solve. */
 	int32_t toiEventPending;
 	b2cuContactKey toiMinKey;  /* ~0 when there is no candidate */
 	float toiMinAlpha;         /* 1 when there is no candidate */
-	int32_t reserved2;
+	int32_t toiSubSteps;
+	int32_t toiEventCount;     /* BeginContact / EndContact events raised inside the sub-steps (b2cuGetToiEvents) */
+	int32_t toiNewContactCount; /* contacts created by the sub-steps' FindNewContacts */
 } b2cuStepInfo;
 
 enum { B2CU_EVENT_BEGIN = 0, B2CU_EVENT_END = 1 };
@@ -465,6 +478,14 @@ B2CU_API int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_
 /* Begin/End touch events of the last step as contact keys, sorted ascending (deferred-callback order). */
 B2CU_API int b2cuGetEvents(b2cuWorld* w, int32_t kind, int32_t capacity, b2cuContactKey* keys, int32_t* count);
 
+/* Begin / End touch events raised INSIDE the time-of-impact sub-steps of the last step, in the order in which the
+ * reference makes those calls (b2Contact::Update called from b2World::StepSolveTOI, single-threaded: Immediate callback
+ * and deferred callback back to back, Dynamics/Contacts/b2Contact.cpp:247-281), i.e. after every callback of the
+ * discrete part of the step.  kinds[i] is B2CU_EVENT_BEGIN or B2CU_EVENT_END; records[i] (optional) is the contact as it
+ * is at the end of the step.  b2cuGetEvents / b2cuGetEventContacts list only the events of the discrete part. */
+B2CU_API int b2cuGetToiEvents(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* kinds,
+                              b2cuContact* records, int32_t* count);
+
 /* Solver order of the last step: keys[i] is the i-th constraint, colour[i] its colour (overflow = colourCount). */
 B2CU_API int b2cuGetSolverOrder(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* colour,
                                 int32_t* count);
@@ -472,7 +493,7 @@ B2CU_API int b2cuGetSolverOrder(b2cuWorld* w, int32_t capacity, b2cuContactKey* 
 /* Island label (smallest body index of the island) per body after the last step; -1 = not in an island. */
 B2CU_API int b2cuGetIslandLabels(b2cuWorld* w, int32_t first, int32_t count, int32_t* labels);
 
-/* TOI-eligible contacts (candidate flag, active, enabled, toiCount <= b2_maxSubSteps), key order. */
+/* TOI-eligible contacts of the current state (candidate flag, active, enabled, toiCount <= b2_maxSubSteps), key order. */
 B2CU_API int b2cuGetToiCandidates(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int32_t* count);
 
 /* ---- spatial sharding (multi-GPU) ------------------------------------------------------------------------

@@ -741,8 +741,13 @@ static void ExportManifold(const b2Manifold& m, b2cuManifold* o)
 int b2ref_export_contacts(b2refWorld* w, int32_t capacity, b2cuContact* out)
 {
 	std::vector<std::pair<uint64_t, const b2Contact*>> sorted;
+	// b2ContactManager::AddToContactList links a new contact at the head of the world list, exactly as OnContactCreate
+	// does with the two bodies' lists (b2ContactManager.cpp:530-556, :715-725): the position counted from the TAIL is a
+	// creation rank that orders every body's contact list (newest first) -- the b2cuContact::stamp
+	std::unordered_map<const b2Contact*, uint32_t> rankFromHead;
 	for (const b2Contact* c = w->world->GetContactList(); c; c = c->GetNext())
 	{
+		rankFromHead[c] = (uint32_t)sorted.size();
 		sorted.push_back(std::make_pair(ContactKey(c), c));
 	}
 	std::sort(sorted.begin(), sorted.end());
@@ -761,6 +766,7 @@ int b2ref_export_contacts(b2refWorld* w, int32_t capacity, b2cuContact* out)
 		o.toiCount = c->m_toiCount;
 		o.toi = c->m_toi;
 		ExportManifold(c->m_manifold, &o.manifold);
+		o.stamp = (uint32_t)n - 1u - rankFromHead[c];
 	}
 	return n;
 }
