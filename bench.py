@@ -2,6 +2,7 @@
 """bench.py -- body-steps/s of b2World::Step on the BASELINE.json pile workload.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--bodies B] [--impl reference]
+                    [--workload pile|add_pair|tumbler|stacks_awake|stacks_asleep] [--scaling weak|strong]
 
 Product arm (default): the 1M-body mixed polygon/circle pile (BASELINE.json configs[4]) is built
 through the reference-facing host API (b2World::CreateBody / b2Body::CreateFixture in libbox2d_b200.so), settled,
@@ -46,6 +47,42 @@ BYTES_PER_BODY = 212
 BYTES_PER_PROXY = 120
 BYTES_PER_CONTACT_NARROW = 208
 BYTES_PER_CONSTRAINT_STEP = 2794
+
+
+def make_workload(name, bodies, scenes):
+    """(scene, settle steps, description) of a BASELINE.json configuration."""
+    if name == "pile":
+        columns = max(16, bodies // ROWS)
+        return (scenes.pile(columns, ROWS, seed=0), None,
+                "pile_%s (BASELINE.json configs[4]: mixed polygon/circle pile in a wide static container, 60 Hz, 8 velocity "
+                "/ 3 position iterations, no sleeping" % ("1m" if bodies >= 1000000 else "%dk" % (bodies // 1000)))
+    if name == "add_pair":
+        return (scenes.add_pair(10000), 0,
+                "add_pair_10k (BASELINE.json configs[1]: 10 000 circles + one bullet box at 150 m/s, zero gravity, continuous "
+                "physics on; timed from the first step, through the impact")
+    if name == "tumbler":
+        return (scenes.tumbler(20000), 600,
+                "tumbler_20k (BASELINE.json configs[2]: 20 000 boxes in a rotating kinematic drum, no sleeping")
+    if name in ("stacks_awake", "stacks_asleep"):
+        scene = scenes.pyramids(476, 20, thick_polygon_ground=True)
+        if name == "stacks_awake":
+            return (scene, 0, "stacks_100k awake window (BASELINE.json configs[3]: 476 pyramids of 20 rows = 99 960 boxes on a "
+                              "thick static ground, sleeping on; the first steps, everything awake")
+        return (scene, 700, "stacks_100k asleep window (BASELINE.json configs[3]: 476 pyramids of 20 rows = 99 960 boxes, "
+                            "sleeping on; after every island has gone to sleep")
+    raise SystemExit("unknown workload %r" % name)
+
+
+def kernel_traffic():
+    """Per-kernel DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the committed `ncu --set full`
+    capture of the 1M-body pile (profiles/r2_kernel_traffic.json, made by tools/ncu_traffic.py), with the counts of that
+    capture so that a run with other counts can scale them.  {} when there is no capture."""
+    path = os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def ncu_traffic(n_constraints):
@@ -141,32 +178,58 @@ def reference_world_from_states(scene_arrays, states, gravity, flags, threads):
     return ref.RefWorld(arrays=(b, s, f), gravity=gravity, world_flags=flags, threads=threads)
 
 
+def pow2_threads(cores, cap):
+    t = 1
+    while 2 * t <= min(cores, cap):
+        t *= 2
+    return t
+
+
 def run_reference_arm(args, rank, world_size):
-    """The reference's own CPU implementation (oracle/_ref built from /root/reference) on the host cores."""
+    """The reference's own CPU implementation (oracle/_ref built from /root/reference) on the host cores: its own
+    b2World::Step with its own b2ThreadPoolTaskExecutor on the workload of the product arm -- for the pile a narrower
+    strip of the same depth (throughput is per body; 1M bodies would take ~3 s per step), settled by the reference
+    itself.  Two rows: the reference as shipped (b2_maxThreads = 8, b2Settings.h:165) is the headline of this arm;
+    `cpu_rows` adds the copy compiled with the cap raised to 32 on all the host's cores (largest power of two)."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref
     import scenes
     cores = os.cpu_count() or 1
-    threads = min(8, cores)  # b2_maxThreads = 8 is a compile-time cap of the reference (b2Settings.h:165)
-    columns = max(16, args.ref_bodies // ROWS)
-    scene = scenes.pile(columns, ROWS)
-    w = ref.RefWorld(scene, threads=threads)
-    n = w.counts()[0]
-    settle_reference(w, args.ref_settle)
-    elapsed = time_reference(w, args.warmup, args.steps)
-    value = n * args.steps / elapsed
-    sample = ("pile %d columns x %d rows (%d bodies, a narrower strip of the 1M-body pile), settled %d steps by the "
-              "reference, then %d timed steps" % (columns, ROWS, n, args.ref_settle, args.steps))
+    rows = []
+    for variant, cap in ((True, 8), ("mt", 32)):
+        threads = pow2_threads(cores, cap)
+        if variant == "mt" and threads <= 8:
+            continue
+        try:
+            if args.workload == "pile":
+                columns = max(16, args.ref_bodies // ROWS)
+                scene, settle = scenes.pile(columns, ROWS), args.ref_settle
+                what = "pile %d columns x %d rows (a narrower strip of the %d-body pile)" % (columns, ROWS, args.bodies)
+            else:
+                scene, settle, what = make_workload(args.workload, args.bodies, scenes)
+            w = ref.RefWorld(scene, threads=threads, stock_libm=variant)
+            n = w.counts()[0]
+            settle_reference(w, settle or 0)
+            elapsed = time_reference(w, args.warmup, args.steps)
+            rows.append({"value": n * args.steps / elapsed, "unit": "body-steps/s", "cores": threads, "kind": "reference",
+                         "ms_per_step": 1e3 * elapsed / args.steps, "bodies": n,
+                         "sample": "%s, %d bodies, settled %d steps by the reference, then %d warm-up + %d timed steps; "
+                                   "b2ThreadPoolTaskExecutor with %d threads (host has %d cores; b2_maxThreads = %d%s)"
+                                   % (what, n, settle or 0, args.warmup, args.steps, threads, cores, cap,
+                                      "" if cap == 8 else ", patched copy, oracle/build_ref.py build_mt")})
+        except Exception as e:
+            rows.append({"value": None, "unit": "body-steps/s", "cores": threads, "kind": "reference",
+                         "sample": "unavailable: %r" % (e,)})
+    head = rows[0]
     print(json.dumps({
-        "impl": "reference", "metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pile_1m (1M-body mixed polygon/circle pile, 60 Hz, 8/3 iterations)",
-                   "bodies_per_gpu": args.bodies, "sample_bodies": n},
-        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference", "sample": sample},
-        "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "body-steps/sec", "value": head["value"], "unit": "body-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head.get("ms_per_step"),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "bodies_per_gpu": args.bodies, "sample_bodies": head.get("bodies")},
+        "cpu_baseline": head, "cpu_rows": rows,
+        "e2e": {"value": head["value"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
@@ -199,7 +262,6 @@ def run_product_arm(args, rank, local_rank, world_size):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
 
     numa = bind_to_gpu_cpus(local_rank)
-    columns = max(16, args.bodies // ROWS)
     dist = None
     if world_size > 1:
         import torch
@@ -208,16 +270,29 @@ def run_product_arm(args, rank, local_rank, world_size):
         dist.init_process_group("nccl")
 
     t0 = time.perf_counter()
+    strong = args.scaling == "strong"
     if world_size == 1:
-        scene = scenes.pile(columns, ROWS, seed=0)
+        scene, settle, workload = make_workload(args.workload, args.bodies, scenes)
+        if settle is None:
+            settle = args.settle
+        workload += ", settled %d steps)" % settle
         world = b2host.HostWorld(scene, device=local_rank, download_bodies=False, events=False)
         n_bodies = world.counts()[0]
+        columns = max(16, args.bodies // ROWS)
     else:
-        # one pile of world_size x bodies, cut into x-strips: every rank holds its strip, the static container and
-        # ghost copies of the next strip's boundary bodies; the solver kernels exchange halo state through NVLink
-        # peer mailboxes (b2cuShard*)
+        # ONE pile cut into x-strips: every rank holds its strip, the static container and ghost copies of the next
+        # strip's boundary bodies; the solver kernels exchange halo state through NVLink peer mailboxes (b2cuShard*,
+        # DESIGN.md 8).  weak: world_size x bodies in total (bodies per GPU fixed); strong: `bodies` in total.
+        if args.workload != "pile":
+            raise SystemExit("bench.py: only the pile workload is sharded")
         import b2shard
+        settle = args.settle
+        columns = max(16, args.bodies // ROWS) if not strong else max(16 * world_size, args.bodies // ROWS) // world_size
         scene = scenes.pile(columns * world_size, ROWS, seed=0)
+        scene.world_flags &= ~T.WORLD_CONTINUOUS  # the container is thick-shape and nothing is a bullet: no TOI candidates
+        workload = ("pile_%dk x %d GPUs (BASELINE.json configs[4]: one mixed polygon/circle pile in a wide static container, "
+                    "60 Hz, 8 velocity / 3 position iterations, no sleeping, settled %d steps)"
+                    % (columns * ROWS // 1000, world_size, settle))
         plan, _ = b2shard.rank_plan(scene.arrays(), rank, world_size, args.margin)
         world = b2host.HostWorld(arrays=plan.arrays, gravity=scene.gravity, world_flags=scene.world_flags,
                                  device=local_rank, download_bodies=False, events=False)
@@ -229,7 +304,7 @@ def run_product_arm(args, rank, local_rank, world_size):
     build_s = time.perf_counter() - t0
 
     # settle (setup, untimed)
-    for _ in range(args.settle):
+    for _ in range(settle):
         world.step(DT, VEL_ITERS, POS_ITERS)
 
     def barrier():
@@ -314,44 +389,107 @@ def run_product_arm(args, rank, local_rank, world_size):
     phases = {k: float(np.mean([float(i[k]) for i in infos])) for k in
               ("collide", "solveTraversal", "solveInit", "solveVelocity", "solvePosition", "broadphase", "solveTOI")}
 
-    # ---- cpu_baseline: the compiled reference on a narrower strip, started from a device-settled state ----
-    cpu = None
-    if not args.no_cpu_baseline:
+    # ---- per-phase rooflines: algorithmic bytes of SURVEY.md 8d with this run's counts over the CUDA-event time of the
+    # phase; traffic = the phase's kernels' dram bytes from the committed ncu capture, scaled to this run's counts ----
+    n_proxies = float(last["proxyCount"])
+    n_new = float(np.mean([int(i["newContactCount"]) for i in infos]))
+    phase_bytes = {
+        "collide": n_contacts * BYTES_PER_CONTACT_NARROW,
+        "solveTraversal": n_constraints * 50.0,
+        "solveInit": n_constraints * 416.0 + n_bodies * 84.0,
+        "solveVelocity": vel_bytes,
+        "solvePosition": n_constraints * BYTES_POSITION_ITER * POS_ITERS + n_bodies * 80.0,
+        "broadphase": n_proxies * (BYTES_PER_PROXY + 20.0) + 8.0 * n_new + 8.0 * n_contacts,
+    }
+    phase_units = {"collide": ("contacts", n_contacts), "solveTraversal": ("constraints", n_constraints),
+                   "solveInit": ("constraints", n_constraints), "solveVelocity": ("constraints", n_constraints),
+                   "solvePosition": ("constraints", n_constraints), "broadphase": ("proxies", n_proxies)}
+    cap = kernel_traffic()
+    phase_rooflines = []
+    for name in ("collide", "solveTraversal", "solveInit", "solveVelocity", "solvePosition", "broadphase"):
+        ms = phases[name]
+        ach = phase_bytes[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        traffic = None
         try:
-            cols_s = max(16, args.cpu_bodies // ROWS)
-            scene_s = scenes.pile(cols_s, ROWS, seed=1234)
-            gw = b2host.HostWorld(scene_s, device=local_rank, download_bodies=False, events=False)
-            for _ in range(args.settle):
-                gw.step(DT, VEL_ITERS, POS_ITERS)
-            states = gw.bodies()
+            unit, count = phase_units[name]
+            traffic = float(cap["phases"][name]["dram_bytes"]) * count / float(cap["counts"][unit])
+        except Exception:
+            pass
+        phase_rooflines.append({"phase": name, "ms": ms, "bound": "hbm", "algorithmic_bytes": phase_bytes[name],
+                                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                                "kernels": (cap.get("phases", {}).get(name, {}) or {}).get("kernels")})
+
+    # ---- cpu_baseline: the compiled reference on a bounded sample of the same workload.  For the pile: a narrower
+    # strip of the same depth started from a device-settled state (settling is setup, not the thing measured) ----
+    cpu = None
+    cpu_rows = []
+    if not args.no_cpu_baseline and world_size == 1:
+        try:
             cores = os.cpu_count() or 1
-            threads = min(8, cores)
-            rw = reference_world_from_states(scene_s.arrays(), states, scene_s.gravity, scene_s.world_flags, threads)
-            ns = rw.counts()[0]
-            cpu_steps = 4
-            cpu_elapsed = time_reference(rw, 2, cpu_steps)
-            cpu = {"value": ns * cpu_steps / cpu_elapsed, "unit": "body-steps/s", "cores": threads, "kind": "reference",
-                   "sample": "pile %d columns x %d rows (%d bodies) from the device-settled state, 2 warm-up + %d timed "
-                             "steps of the compiled reference with b2ThreadPoolTaskExecutor(%d threads; host has %d "
-                             "cores; b2_maxThreads caps it at 8)" % (cols_s, ROWS, ns, cpu_steps, threads, cores)}
+            if args.workload == "pile":
+                cols_s = max(16, args.cpu_bodies // ROWS)
+                scene_s = scenes.pile(cols_s, ROWS, seed=1234)
+                gw = b2host.HostWorld(scene_s, device=local_rank, download_bodies=False, events=False)
+                for _ in range(settle):
+                    gw.step(DT, VEL_ITERS, POS_ITERS)
+                states = gw.bodies()
+                del gw
+                what = "pile %d columns x %d rows from the device-settled state" % (cols_s, ROWS)
+                cpu_steps, cpu_warm = 4, 2
+            else:
+                scene_s, _, what = make_workload(args.workload, args.bodies, scenes)
+                states = None
+                cpu_steps, cpu_warm = max(4, min(args.steps, 30)), 0
+            for variant, capn in ((True, 8), ("mt", 32)):
+                threads = pow2_threads(cores, capn)
+                if variant == "mt" and threads <= 8:
+                    continue
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import ref
+                if states is not None:
+                    b_, s_, f_ = scene_s.arrays()
+                    b_ = b_.copy()
+                    b_["px"], b_["py"], b_["angle"] = states["px"], states["py"], states["a"]
+                    b_["vx"], b_["vy"], b_["w"] = states["vx"], states["vy"], states["w"]
+                    rw = ref.RefWorld(arrays=(b_, s_, f_), gravity=scene_s.gravity, world_flags=scene_s.world_flags,
+                                      threads=threads, stock_libm=variant)
+                else:
+                    rw = ref.RefWorld(scene_s, threads=threads, stock_libm=variant)
+                    for _ in range(settle):
+                        rw.step(DT, VEL_ITERS, POS_ITERS)
+                ns = rw.counts()[0]
+                cpu_elapsed = time_reference(rw, cpu_warm, cpu_steps)
+                cpu_rows.append({"value": ns * cpu_steps / cpu_elapsed, "unit": "body-steps/s", "cores": threads,
+                                 "kind": "reference", "ms_per_step": 1e3 * cpu_elapsed / cpu_steps, "bodies": ns,
+                                 "sample": "%s (%d bodies), %d warm-up + %d timed steps of the compiled reference with "
+                                           "b2ThreadPoolTaskExecutor(%d threads; host has %d cores; b2_maxThreads = %d%s)"
+                                           % (what, ns, cpu_warm, cpu_steps, threads, cores, capn,
+                                              "" if capn == 8 else ", patched copy")})
+                del rw
+            cpu = cpu_rows[0]
         except Exception as e:  # the oracle is only the checker: its absence must not hide the product numbers
             cpu = {"value": None, "unit": "body-steps/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
 
     print(json.dumps({
         "metric": "body-steps/sec", "value": total_bodies * args.steps / elapsed, "unit": "body-steps/s",
         "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pile_1m (BASELINE.json configs[4]: mixed polygon/circle pile in a wide static container, "
-                               "60 Hz, 8 velocity / 3 position iterations, no sleeping, settled %d steps)" % args.settle,
-                   "bodies_per_gpu": n_bodies, "columns": columns, "rows": ROWS,
+        "higher_is_better": True, "scaling": args.scaling if world_size > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload,
+                   "bodies_per_gpu": n_bodies, "bodies_total": total_bodies, "columns": columns, "rows": ROWS,
                    "contacts": n_contacts, "constraints": n_constraints, "colours": colours,
-                   "l2": "working set per step (%.1f GB algorithmic) exceeds the 126 MB L2; no flush needed"
-                         % (step_bytes / 1e9),
+                   "continuous_physics": bool(scene.world_flags & T.WORLD_CONTINUOUS),
+                   "toi_sub_steps_per_step": float(np.mean([int(i["toiSubSteps"]) for i in infos])),
+                   "l2": ("working set per step (%.2f GB algorithmic) exceeds the 126 MB L2; no flush needed" % (step_bytes / 1e9))
+                         if step_bytes > 2.0e8 else
+                         ("working set per step %.3f GB algorithmic: the step's kernels stream more than L2 between two uses "
+                          "of a row only partly; no explicit flush (every step rewrites all rows)" % (step_bytes / 1e9)),
                    "sharding": ("x-strips of one %d-body pile, ghost bodies within %.1f m of the strip boundary, halo "
                                 "exchange through NVLink peer mailboxes inside the solver kernel (2 per iteration)"
                                 % (total_bodies, args.margin)) if world_size > 1 else "single GPU"},
         "device_ms_per_step": device_ms / args.steps,
         "phases_ms": phases,
+        "phase_rooflines": phase_rooflines,
         "step_roofline_frac": (step_bytes / (ms_per_step * 1e-3) / 1e9) / peak,
         "e2e": {"value": total_bodies * args.steps / e2e_elapsed, "unit": "body-steps/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_elapsed / args.steps,
@@ -361,15 +499,16 @@ def run_product_arm(args, rank, local_rank, world_size):
         "roofline": {"bound": "hbm", "kernel": "SolverVelocityPersistentKernel (warm start + 8 velocity iterations + impulse "
                                                         "store + position integration, one cooperative launch per step)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(n_constraints),
+                     "frac": achieved / peak, "traffic": phase_rooflines[3]["traffic"] or ncu_traffic(n_constraints),
                      "ms_per_launch": vel_ms,
                      "bytes_per_unit": "per touching contact: 128 warm start + 220 x 8 velocity + 32 store = 1920 B, "
                                        "+ 48 B per body (SURVEY.md 8d)"},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "cpu_rows": cpu_rows,
         "clocks": clocks,
         "build_s": build_s, "cpu_affinity": numa, "checksum": checksum, "last_step": {k: int(last[k]) for k in
                                                                ("contactCount", "constraintCount", "colourCount",
-                                                                "overflowCount", "moveCount", "kernelLaunches")},
+                                                                "overflowCount", "moveCount", "kernelLaunches",
+                                                                "toiCandidateCount", "toiSubSteps")},
     }))
     if dist is not None:
         dist.barrier()
@@ -384,9 +523,12 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--bodies", type=int, default=1000000, help="bodies per GPU")
     ap.add_argument("--settle", type=int, default=SETTLE_STEPS)
-    ap.add_argument("--cpu-bodies", type=int, default=25000, help="bodies of the cpu_baseline sample")
-    ap.add_argument("--ref-bodies", type=int, default=50000, help="bodies of the --impl reference sample")
-    ap.add_argument("--ref-settle", type=int, default=150)
+    ap.add_argument("--cpu-bodies", type=int, default=200000, help="bodies of the cpu_baseline sample (pile)")
+    ap.add_argument("--ref-bodies", type=int, default=100000, help="bodies of the --impl reference sample (pile)")
+    ap.add_argument("--ref-settle", type=int, default=120)
+    ap.add_argument("--workload", default="pile", choices=["pile", "add_pair", "tumbler", "stacks_awake", "stacks_asleep"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = `bodies` per GPU, strong = `bodies` in total (the 1M-body pile cut N ways)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--margin", type=float, default=3.0, help="ghost margin of a strip boundary (m)")
     args = ap.parse_args()

@@ -399,7 +399,11 @@ __global__ void __launch_bounds__(256) UnpackBodiesKernel(DeviceArrays d, int fi
 			d.force[b] = make_float4(s[16], s[17], s[18], s[24]);
 			d.damp[b] = make_float4(s[21], s[22], s[23], 0.0f);
 			const uint32_t flags = __float_as_uint(s[25]);
-			if (d.jointCount > 0 && ((flags ^ d.bflags[b]) & B2CU_BODY_TYPE_MASK)) d.counters[CNT_BODY_TYPE_CHANGED] = 1;
+			// bit 0: a body type changed (the joint colouring depends on it); bit 1: type or bullet flag changed (the
+			// time-of-impact candidacy of the body's contacts depends on them, b2Contact::IsToiCandidate)
+			const uint32_t diff = flags ^ d.bflags[b];
+			if (diff & (B2CU_BODY_TYPE_MASK | B2CU_BODY_BULLET))
+				atomicOr(&d.counters[CNT_BODY_TYPE_CHANGED], ((diff & B2CU_BODY_TYPE_MASK) ? 1 : 0) | 2);
 			d.bflags[b] = flags;
 		}
 		__syncthreads();

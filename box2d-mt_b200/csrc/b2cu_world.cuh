@@ -213,6 +213,7 @@ struct b2cuWorld
 	bool compactNow;     // force the compaction of the contact set at the end of the next step
 	int gridSize;        // hash table size (power of two)
 	float cellSize;
+	int cellChosenCount; // proxies in the world when cellSize was chosen
 	bool newProxies;     // e_newFixture: run FindNewContacts at the start of the next step
 	bool toiCheckDirty;  // bodies / proxies changed: re-evaluate whether TOI candidates are possible
 	int positionIterationsCapacity;

@@ -959,14 +959,16 @@ int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2cuBody* bo
 	CUDA_TRY(w, cudaMemcpyAsync(stage, bodies, sizeof(b2cuBody) * (size_t)count, cudaMemcpyHostToDevice, w->stream));
 	LAUNCH(w, UnpackBodiesKernel, GridFor(count), kBlock, w->d, first, count, (const float*)stage);
 	w->toiCheckDirty = true;
-	if (w->d.jointCount == 0) return SyncCheck(w);
-	// the joint colouring depends on which bodies are dynamic: recolour only if a type really changed
+	// what depends on the bodies' types and bullet flags is redone only if one of them really changed
 	CUDA_TRY(w, cudaMemcpyAsync(&w->hostCounters[CNT_BODY_TYPE_CHANGED], w->d.counters + CNT_BODY_TYPE_CHANGED, sizeof(int),
 	                            cudaMemcpyDeviceToHost, w->stream));
 	if ((rc = SyncCheck(w))) return rc;
-	if (w->hostCounters[CNT_BODY_TYPE_CHANGED])
+	const int changed = w->hostCounters[CNT_BODY_TYPE_CHANGED];
+	if (changed)
 	{
-		w->jointColourDirty = true;
+		if ((changed & 1) && w->d.jointCount > 0) w->jointColourDirty = true;
+		// b2Body::SetBullet / SetType -> b2ContactManager::RecalculateToiCandidacy (b2ContactManager.cpp:566-640)
+		if (changed & 2) w->contactBodiesDirty = true;
 		w->hostCounters[CNT_BODY_TYPE_CHANGED] = 0;
 		return ZeroCounter(w, CNT_BODY_TYPE_CHANGED);
 	}
@@ -1079,9 +1081,22 @@ int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* 
 	if (anyMoved) w->newProxies = true;
 	w->toiCheckDirty = true;
 	w->contactBodiesDirty = true;
-	if (first == 0 && count > 0)
+	if (first == 0 && count == w->proxyCount && count > 0)
 	{
+		// the whole table: the finest grid level follows the typical proxy
 		w->cellSize = ChooseCellSize(extents);
+		w->cellChosenCount = count;
+	}
+	else if (w->proxyCount >= 2 * std::max(1, w->cellChosenCount))
+	{
+		// the world has doubled since the cell size was chosen (a program that creates bodies as it runs): choose again
+		// from all the boxes.  An upload of a few rows (a ground fixture whose friction changed) never moves the cell size.
+		std::vector<float4> all((size_t)w->proxyCount);
+		if ((rc = Download(w, d.fat, 0, all)) || (rc = SyncCheck(w))) return rc;
+		std::vector<float> ext(all.size());
+		for (size_t i = 0; i < all.size(); ++i) ext[i] = std::max(all[i].z - all[i].x, all[i].w - all[i].y);
+		w->cellSize = ChooseCellSize(ext);
+		w->cellChosenCount = w->proxyCount;
 	}
 	return SyncCheck(w);
 }

@@ -819,6 +819,29 @@ B2H_API void b2h_apply_force(void* p, int32 body, float fx, float fy, float torq
 	h->bodies[body]->ApplyTorque(torque, true);
 }
 B2H_API void b2h_set_awake(void* p, int32 body, int32 awake) { static_cast<Host*>(p)->bodies[body]->SetAwake(awake != 0); }
+/// b2Body::SetLinearDamping (0) / SetAngularDamping (1) / SetGravityScale (2) / SetBullet (3) / SetSleepingAllowed (4)
+B2H_API void b2h_set_body_param(void* p, int32 body, int32 which, float value)
+{
+	b2Body* b = static_cast<Host*>(p)->bodies[body];
+	switch (which)
+	{
+	case 0: b->SetLinearDamping(value); break;
+	case 1: b->SetAngularDamping(value); break;
+	case 2: b->SetGravityScale(value); break;
+	case 3: b->SetBullet(value != 0.0f); break;
+	case 4: b->SetSleepingAllowed(value != 0.0f); break;
+	default: break;
+	}
+}
+/// b2Body::DestroyFixture of fixture `fixture` (creation order)
+B2H_API void b2h_destroy_fixture(void* p, int32 fixture)
+{
+	Host* h = static_cast<Host*>(p);
+	b2Fixture* f = h->fixtures[fixture];
+	if (f == nullptr) return;
+	f->GetBody()->DestroyFixture(f);
+	h->fixtures[fixture] = nullptr;
+}
 B2H_API void b2h_destroy_body(void* p, int32 body)
 {
 	Host* h = static_cast<Host*>(p);

@@ -99,6 +99,7 @@ void b2Body::SetAngularVelocity(float32 omega)
 
 void b2Body::ApplyForce(const b2Vec2& force, const b2Vec2& point, bool wake)
 {
+	m_world->RefreshBodies();
 	if (GetType() != b2_dynamicBody) return;
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
@@ -128,6 +129,7 @@ void b2Body::ApplyTorque(float32 torque, bool wake)
 
 void b2Body::ApplyLinearImpulse(const b2Vec2& impulse, const b2Vec2& point, bool wake)
 {
+	m_world->RefreshBodies();
 	if (GetType() != b2_dynamicBody) return;
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
@@ -139,6 +141,8 @@ void b2Body::ApplyLinearImpulse(const b2Vec2& impulse, const b2Vec2& point, bool
 
 void b2Body::ApplyLinearImpulseToCenter(const b2Vec2& impulse, bool wake)
 {
+	// the device owns position, velocity, sleep time and flags between steps: edit the current row, not a stale one
+	m_world->RefreshBodies();
 	if (GetType() != b2_dynamicBody) return;
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
@@ -149,6 +153,8 @@ void b2Body::ApplyLinearImpulseToCenter(const b2Vec2& impulse, bool wake)
 
 void b2Body::ApplyAngularImpulse(float32 impulse, bool wake)
 {
+	// the device owns position, velocity, sleep time and flags between steps: edit the current row, not a stale one
+	m_world->RefreshBodies();
 	if (GetType() != b2_dynamicBody) return;
 	if (wake && !IsAwake()) SetAwake(true);
 	if (!IsAwake()) return;
@@ -159,16 +165,22 @@ void b2Body::ApplyAngularImpulse(float32 impulse, bool wake)
 
 void b2Body::SetLinearDamping(float32 d)
 {
+	// the device owns position, velocity, sleep time and flags between steps: edit the current row, not a stale one
+	m_world->RefreshBodies();
 	B2_STATE().linearDamping = d;
 	m_world->MarkBodyDirty(m_index);
 }
 void b2Body::SetAngularDamping(float32 d)
 {
+	// the device owns position, velocity, sleep time and flags between steps: edit the current row, not a stale one
+	m_world->RefreshBodies();
 	B2_STATE().angularDamping = d;
 	m_world->MarkBodyDirty(m_index);
 }
 void b2Body::SetGravityScale(float32 scale)
 {
+	// the device owns position, velocity, sleep time and flags between steps: edit the current row, not a stale one
+	m_world->RefreshBodies();
 	B2_STATE().gravityScale = scale;
 	m_world->MarkBodyDirty(m_index);
 }
@@ -198,6 +210,8 @@ void b2Body::SetAwake(bool flag)
 
 void b2Body::SetSleepingAllowed(bool flag)
 {
+	// the device owns position, velocity, sleep time and flags between steps: edit the current row, not a stale one
+	m_world->RefreshBodies();
 	if (flag)
 	{
 		B2_STATE().flags |= B2CU_BODY_AUTOSLEEP;
@@ -212,8 +226,9 @@ void b2Body::SetSleepingAllowed(bool flag)
 
 void b2Body::SetBullet(bool flag)
 {
-	// the TOI-candidate flag of existing contacts is fixed at contact creation on the device; changing the
-	// bullet flag of a body that already has contacts is outside this version
+	// the device re-evaluates the time-of-impact candidacy of the body's contacts when the uploaded row changes the
+	// flag (b2ContactManager::RecalculateToiCandidacy, reference b2Body.h / b2ContactManager.cpp:566-640)
+	m_world->RefreshBodies();
 	if (flag) B2_STATE().flags |= B2CU_BODY_BULLET;
 	else B2_STATE().flags &= ~(uint32)B2CU_BODY_BULLET;
 	m_world->MarkBodyDirty(m_index);

@@ -34,6 +34,7 @@ b2CudaStepExecutor::~b2CudaStepExecutor()
 		// the world keeps its host mirror; a later step with another executor re-uploads everything
 		it->first->RefreshBodies();
 		it->first->RefreshProxies();
+		it->first->RefreshJoints();
 		it->first->m_contactsStale = true;
 		it->first->RefreshContacts();
 		it->first->m_contactsStale = false;
@@ -149,6 +150,7 @@ bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 veloc
 		// last stepped by another executor: take the world over (its state comes back through the host mirror)
 		world.RefreshBodies();
 		world.RefreshProxies();
+		world.RefreshJoints();
 		world.m_contactsStale = true;
 		world.RefreshContacts();
 		world.m_contactsStale = false;

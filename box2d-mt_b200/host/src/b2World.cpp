@@ -858,7 +858,9 @@ int32 b2World::UploadDirty(b2cuWorld* device)
 	}
 	if (m_jointsDirty || (m_fullUpload && !m_joints.empty()))
 	{
-		// the joint table as a whole; the objects hold the current impulses (every edit refreshed them first)
+		// the joint table as a whole.  The objects must hold the CURRENT accumulated impulses and limit states: a full
+		// upload can be requested by code that never looked at the joints (DestroyFixture, SetType on another body)
+		if (device == m_device) RefreshJoints();
 		std::vector<b2cuJoint> rows(m_joints.size());
 		for (size_t i = 0; i < m_joints.size(); ++i) m_joints[i]->WriteRecord(&rows[i]);
 		if ((rc = b2cuSetJoints(device, (int32)rows.size(), rows.empty() ? nullptr : rows.data()))) return rc;

@@ -87,6 +87,8 @@ def load():
     lib.b2h_apply_force.argtypes = [vp, i32, f32, f32, f32]
     lib.b2h_set_awake.argtypes = [vp, i32, i32]
     lib.b2h_destroy_body.argtypes = [vp, i32]
+    lib.b2h_set_body_param.argtypes = [vp, i32, i32, f32]
+    lib.b2h_destroy_fixture.argtypes = [vp, i32]
     _lib = lib
     return lib
 
@@ -337,3 +339,11 @@ class HostWorld:
 
     def destroy_body(self, body):
         self.lib.b2h_destroy_body(self.h, body)
+
+    def destroy_fixture(self, fixture):
+        self.lib.b2h_destroy_fixture(self.h, fixture)
+
+    LINEAR_DAMPING, ANGULAR_DAMPING, GRAVITY_SCALE, BULLET, SLEEPING_ALLOWED = range(5)
+
+    def set_body_param(self, body, which, value):
+        self.lib.b2h_set_body_param(self.h, body, which, float(value))

@@ -31,7 +31,14 @@ def load(stock=False):
     sys.path.insert(0, _HERE)
     import build_ref
     build_ref.build()
-    lib = ctypes.CDLL(build_ref.lib_path(stock))
+    if stock == "mt":
+        # the reference with b2_maxThreads raised to 32 (build_ref.build_mt): timing rows of bench.py only
+        path = build_ref.build_mt()
+        if path is None:
+            raise RuntimeError("oracle/_ref/libb2ref_mt32.so was not prebuilt")
+        lib = ctypes.CDLL(path)
+    else:
+        lib = ctypes.CDLL(build_ref.lib_path(stock))
     vp, i32, f32, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float, ctypes.c_uint32
     lib.b2ref_create.restype = vp
     lib.b2ref_create.argtypes = [f32, f32, u32, i32]
@@ -77,6 +84,8 @@ def load(stock=False):
     lib.b2ref_set_velocity.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_apply_force.argtypes = [vp, i32, f32, f32, f32]
     lib.b2ref_set_awake.argtypes = [vp, i32, i32]
+    lib.b2ref_set_body_param.argtypes = [vp, i32, i32, f32]
+    lib.b2ref_destroy_last_fixture.argtypes = [vp]
     lib.b2ref_hash.restype = u32
     lib.b2ref_hash.argtypes = [vp]
     lib.b2ref_collide.argtypes = [vp, vp, vp, vp, vp]
@@ -283,6 +292,12 @@ class RefWorld:
 
     def set_awake(self, body, awake):
         self.lib.b2ref_set_awake(self.h, body, int(awake))
+
+    def set_body_param(self, body, which, value):
+        self.lib.b2ref_set_body_param(self.h, body, which, float(value))
+
+    def destroy_last_fixture(self):
+        self.lib.b2ref_destroy_last_fixture(self.h)
 
 
 def collide(shape_a, xf_a, shape_b, xf_b, stock_libm=False):

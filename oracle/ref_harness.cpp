@@ -1469,6 +1469,30 @@ void b2ref_set_awake(b2refWorld* w, int32_t body, int32_t awake)
 	w->bodies[body]->SetAwake(awake != 0);
 }
 
+void b2ref_set_body_param(b2refWorld* w, int32_t body, int32_t which, float value)
+{
+	b2Body* b = w->bodies[body];
+	switch (which)
+	{
+	case 0: b->SetLinearDamping(value); break;
+	case 1: b->SetAngularDamping(value); break;
+	case 2: b->SetGravityScale(value); break;
+	case 3: b->SetBullet(value != 0.0f); break;
+	case 4: b->SetSleepingAllowed(value != 0.0f); break;
+	default: break;
+	}
+}
+
+/* b2Body::DestroyFixture of the LAST fixture created (so that no proxy id of the harness changes) */
+void b2ref_destroy_last_fixture(b2refWorld* w)
+{
+	b2Fixture* f = w->fixtures.back();
+	f->GetBody()->DestroyFixture(f);
+	w->fixtures.pop_back();
+	w->proxyBase.pop_back();
+	while (!w->proxies.empty() && w->proxies.back().first == f) w->proxies.pop_back();
+}
+
 uint32_t b2ref_hash(b2refWorld* w)
 {
 	uint32_t h = 2166136261u;

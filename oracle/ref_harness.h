@@ -123,6 +123,9 @@ void b2ref_set_filter(b2refWorld* w, int32_t fixture, uint16_t categoryBits, uin
 void b2ref_set_velocity(b2refWorld* w, int32_t body, float vx, float vy, float angw);
 void b2ref_apply_force(b2refWorld* w, int32_t body, float fx, float fy, float torque);
 void b2ref_set_awake(b2refWorld* w, int32_t body, int32_t awake);
+/* b2Body::SetLinearDamping (0) / SetAngularDamping (1) / SetGravityScale (2) / SetBullet (3) / SetSleepingAllowed (4) */
+void b2ref_set_body_param(b2refWorld* w, int32_t body, int32_t which, float value);
+void b2ref_destroy_last_fixture(b2refWorld* w);
 
 /* FNV-1a 32 over raw bytes of (pos.x, pos.y, angle) for all bodies in GetBodyList() order */
 uint32_t b2ref_hash(b2refWorld* w);

@@ -20,7 +20,6 @@ pytestmark = pytest.mark.gpu
 
 def _scene(**kw):
     s = scenes.Scene(**kw)
-    s.world_flags &= ~T.WORLD_CONTINUOUS  # SolveTOI is outside this version
     return s
 
 
@@ -135,13 +134,13 @@ def test_collision_filtering(gpu):
                                    T.WORLD_DEFAULT & ~T.WORLD_CLEAR_FORCES])
 def test_world_switches(gpu, flags):
     s = scenes.pile(6, 5, sleep=True)
-    s.world_flags = flags & ~T.WORLD_CONTINUOUS
+    s.world_flags = flags
     infos, g, r = _run(gpu, s, 200)
     assert max(int(i["constraintCount"]) for i in infos) > 0
 
 
 def test_varying_time_step_and_iterations(gpu):
-    s = scenes.pyramid(5, continuous=False)
+    s = scenes.pyramid(5)
     r = ref.RefWorld(s)
     g = parity.gpu_world_from_ref(gpu, r)
     for dt, vi, pi in [(1 / 60.0, 8, 3), (1 / 30.0, 4, 1), (1 / 120.0, 10, 4), (1 / 60.0, 1, 0), (1 / 45.0, 6, 2)]:
@@ -152,7 +151,6 @@ def test_custom_pair_filter(gpu):
     """A user b2ContactFilter replaces the default rule for new pairs (b2ContactManager.cpp:280-285): the oracle gets
     a b2ContactFilter subclass, the device the same rule through b2cuSetPairFilter."""
     s = scenes.pile(10, 8)
-    s.world_flags &= ~T.WORLD_CONTINUOUS
     r = ref.RefWorld(s)
     r.set_modulo_filter(5)
     g = parity.gpu_world_from_ref(gpu, r)
@@ -219,7 +217,6 @@ def test_capacity_growth_from_nothing(gpu):
     """Device buffers grow geometrically on their own: a world created with minimal capacities receives a scene, and the
     contact set outgrows its buffer during the run (b2cuSetCounts, the contact capacity inside b2cuStep)."""
     s = scenes.pile(20, 12)
-    s.world_flags &= ~T.WORLD_CONTINUOUS
     r = ref.RefWorld(s)
     bodies, shapes, proxies, contacts = parity.ref_state(r)
     g = gpu.World(gravity=r.gravity, flags=r.world_flags, body_capacity=1, proxy_capacity=1, shape_capacity=1,
@@ -286,14 +283,13 @@ def test_joints_with_varying_dt_and_without_warm_starting(gpu, name):
     """The joints' warm start scales the stored impulses by dt / dt0 (the gear joint, alone, does not), soft constraints
     and motors use dt and 1 / dt directly: step with a changing dt, then with warm starting switched off."""
     scene = getattr(scenes, name)()
-    scene.world_flags &= ~T.WORLD_CONTINUOUS
     r = ref.RefWorld(scene)
     g = parity.gpu_world_from_ref(gpu, r)
     for dt in (1.0 / 60.0, 1.0 / 30.0, 1.0 / 120.0, 1.0 / 45.0, 1.0 / 60.0):
         parity.lockstep(g, r, 12, dt=dt, tol=0.0)
     parity.lockstep(g, r, 3, dt=0.0, tol=0.0)           # dt = 0: collide only, joints untouched
     scene = getattr(scenes, name)()
-    scene.world_flags &= ~(T.WORLD_CONTINUOUS | T.WORLD_WARM_STARTING)
+    scene.world_flags &= ~T.WORLD_WARM_STARTING
     r = ref.RefWorld(scene)
     g = parity.gpu_world_from_ref(gpu, r)
     parity.lockstep(g, r, 60, tol=0.0, vel_iters=5, pos_iters=2)

@@ -120,7 +120,6 @@ def test_joint_chains_at_scale():
     body), and the hinges hold (the reference itself leaves up to 0.045 of anchor error on a swinging 40-link chain with
     3 position iterations; here chains also hit each other)."""
     scene = scenes.hanging_chains(1000, 40)
-    scene.world_flags &= ~T.WORLD_CONTINUOUS
     a = b2host.HostWorld(scene, download_bodies=False, events=False)
     b = b2host.HostWorld(scene, download_bodies=False, events=False)
     for _ in range(120):
@@ -161,7 +160,6 @@ import ref  # noqa: E402
 
 
 def _lockstep(scene, steps, check_every):
-    scene.world_flags &= ~T.WORLD_CONTINUOUS
     import b2cuda
     r = ref.RefWorld(scene)
     g = parity.gpu_world_from_ref(b2cuda, r)

@@ -165,8 +165,8 @@ def test_time_of_impact_bit_exact(gpu):
 
 
 SCENES = {
-    "pyramid6": lambda: scenes.pyramid(6, continuous=False),
-    "pyramid20": lambda: scenes.pyramid(20, continuous=False),
+    "pyramid6": lambda: scenes.pyramid(6),
+    "pyramid20": lambda: scenes.pyramid(20),
     "pile": lambda: scenes.pile(12, 10),
     "pile_5000": lambda: scenes.pile(100, 50),
     "pile_sleep": lambda: scenes.pile(8, 6, sleep=True),
@@ -185,16 +185,11 @@ SCENES = {
 }
 
 
-def _no_toi(scene):
-    scene.world_flags &= ~T.WORLD_CONTINUOUS
-    return scene
-
-
 @pytest.mark.parametrize("name", sorted(SCENES))
 def test_single_step_teacher_forced(gpu, name):
     """Single-step parity from identical state: before every step the oracle's bodies, fat AABBs
     and contacts (manifolds, impulses) are injected into the device; after the step everything must be equal."""
-    scene = _no_toi(SCENES[name]())
+    scene = SCENES[name]()
     r = ref.RefWorld(scene)
     g = parity.gpu_world_from_ref(gpu, r)
     infos = parity.lockstep(g, r, 60, teacher=True, tol=TOL)
@@ -208,7 +203,7 @@ def test_single_step_teacher_forced(gpu, name):
 def test_free_running_lockstep(gpu, name, steps):
     """Multi-step parity: the device world runs freely; the oracle follows in the GPU's solver order.  Pair set,
     events, manifolds, fat AABBs, body state and awake flags are compared after every step."""
-    scene = _no_toi(SCENES[name]())
+    scene = SCENES[name]()
     r = ref.RefWorld(scene)
     g = parity.gpu_world_from_ref(gpu, r)
     infos = parity.lockstep(g, r, steps, tol=TOL)
@@ -225,57 +220,80 @@ def test_lockstep_with_frequent_compaction(gpu, compact_min, monkeypatch):
     then).  Force the merge to run (almost) every step and check that nothing observable changes."""
     monkeypatch.setenv("B2CU_COMPACT_MIN", str(compact_min))
     for name in ("pile", "tumbler"):
-        scene = _no_toi(SCENES[name]())
+        scene = SCENES[name]()
         r = ref.RefWorld(scene)
         g = parity.gpu_world_from_ref(gpu, r)
         parity.lockstep(g, r, 200, tol=TOL)
-    scene = _no_toi(scenes.add_pair(300))
+    scene = scenes.add_pair(300)
     r = ref.RefWorld(scene)
     g = parity.gpu_world_from_ref(gpu, r)
     parity.lockstep(g, r, 60, tol=TOL)
 
 
-@pytest.mark.parametrize("name,steps", [("add_pair", 90), ("pyramid6", 120), ("pile", 150), ("chains", 150),
-                                        ("pile_sleep", 400)])
-def test_first_toi_pass(gpu, name, steps):
-    """First pass of b2World::SolveTOI (b2World.cpp:1026-1092): on a continuous world the device evaluates the time of
-    impact of every eligible contact after the regular solve and reports the earliest (alpha, key) and whether the
-    reference would sub-step.  The oracle runs with continuous physics off -- so neither side sub-steps and they stay
-    in lockstep -- and its FindMinToiContact is called on the state each step leaves."""
-    make = (lambda: scenes.add_pair(300)) if name == "add_pair" else SCENES[name]
-    scene = _no_toi(make())
+TOI_SCENES = {
+    "hello": (scenes.hello_world, 90),              # one landing: one event
+    "pyramid20": (lambda: scenes.pyramid(20), 150),  # the Testbed's Pyramid on its edge ground, reference defaults
+    "bullets": (scenes.bullets, 240),                # bullets and fast bodies against thin walls and each other
+    "add_pair": (lambda: scenes.add_pair(300), 90),  # the bullet box through a cloud of circles
+    "chains": (lambda: scenes.chain_terrain(40), 200),
+}
+
+
+@pytest.mark.parametrize("name", sorted(TOI_SCENES))
+def test_time_of_impact_sub_steps(gpu, name):
+    """b2World::SolveTOI (b2World.cpp:1026-1093) with continuous physics ON on both sides: every FindMinToiContact pass,
+    every time-of-impact event (StepSolveTOI :851-1024: the two bodies advanced, the 32-contact island taken from the
+    bodies' contact lists in creation order, b2Island::SolveTOI, SynchronizeFixtures, FindNewContacts) and the final
+    ClearPostSolveTOI.  The oracle runs the reference's own SolveTOI; bodies, contacts (manifolds, impulses, flags),
+    fat boxes and the begin / end callbacks -- those of the sub-steps in call order -- are compared after every step."""
+    make, steps = TOI_SCENES[name]
+    scene = make()
+    assert scene.world_flags & T.WORLD_CONTINUOUS
     r = ref.RefWorld(scene)
     g = parity.gpu_world_from_ref(gpu, r)
-    g.set_params(r.gravity, r.world_flags | T.WORLD_CONTINUOUS)
-    pending = candidates = 0
-    for s in range(steps):
-        info = g.step()
-        keys, _ = g.solver_order()
-        assert r.step_ordered(keys, 1.0 / 60.0, 8, 3) == 0
-        key, alpha = r.first_toi()
-        if key is None:
-            assert int(info["toiMinKey"]) == 0xFFFFFFFFFFFFFFFF and info["toiMinAlpha"] == 1.0 and not info["toiEventPending"], s
-            continue
-        candidates += 1
-        assert int(info["toiMinKey"]) == key, (s, hex(int(info["toiMinKey"])), hex(key), float(info["toiMinAlpha"]), alpha)
-        parity.assert_floats_equal("toiMinAlpha", info["toiMinAlpha"], np.float32(alpha), TOL)
-        want_pending = not (np.float32(1.0) - np.float32(10.0) * np.finfo(np.float32).eps < np.float32(alpha))
-        assert bool(info["toiEventPending"]) == want_pending, s
-        pending += int(want_pending)
-    # the oracle's query left no trace, and the device's pass changed nothing: still the same worlds
-    parity.compare_bodies(g.get_bodies(), r.bodies(), TOL)
-    parity.compare_contacts(g.get_contacts(), r.contacts(), TOL)
-    if name in ("pile", "pile_sleep"):
-        assert candidates == 0  # thick-shape container, no bullets: no contact is ever eligible
-    else:
-        assert candidates > steps // 4
-        assert pending > 0      # the bullet / the landing bodies do produce events the reference would sub-step
+    infos = parity.lockstep(g, r, steps, tol=TOL)
+    sub = sum(int(i["toiSubSteps"]) for i in infos)
+    assert sub > 0, "the scene was meant to produce time-of-impact events"
+    assert max(int(i["toiCandidateCount"]) for i in infos) > 0
+    if name in ("bullets", "add_pair"):
+        # events that create contacts (the per-event FindNewContacts) and raise callbacks inside the sub-steps
+        assert sum(int(i["toiNewContactCount"]) for i in infos) > 0
+        assert sum(int(i["toiEventCount"]) for i in infos) > 0
+        # a contact can be the earliest more than once per step; the reference stops at b2_maxSubSteps (b2Contact.h:412-416)
+        assert max(int(i["toiSubSteps"]) for i in infos) > 8
+    # after the step the time-of-impact bookkeeping is reset (ClearPostSolveTOI): alpha0 = 0, toi = 1, toiCount = 0
+    assert (g.get_bodies()["alpha0"] == 0).all()
+    c = g.get_contacts()
+    assert (c["toi"] == 1).all() and (c["toiCount"] == 0).all() and not (c["flags"] & (T.CONTACT_TOI | T.CONTACT_ISLAND)).any()
+
+
+@pytest.mark.parametrize("name", ["bullets", "pyramid6", "add_pair"])
+def test_time_of_impact_teacher_forced(gpu, name):
+    """Single-step parity with continuous physics on: the oracle's state (bodies, proxies, contacts WITH their creation
+    stamps, which fix the order of the bodies' contact lists) is injected before every step."""
+    make = {"bullets": scenes.bullets, "pyramid6": lambda: scenes.pyramid(6), "add_pair": lambda: scenes.add_pair(200)}[name]
+    r = ref.RefWorld(make())
+    g = parity.gpu_world_from_ref(gpu, r)
+    infos = parity.lockstep(g, r, 120, teacher=True, tol=TOL)
+    assert sum(int(i["toiSubSteps"]) for i in infos) > 0
+
+
+def test_sub_stepping_world(gpu):
+    """b2World::SetSubStepping(true): one time-of-impact event per Step; while events remain the next Step skips the
+    solve (m_stepComplete, b2World.cpp:1670, :1084-1088)."""
+    scene = scenes.bullets()
+    scene.world_flags |= T.WORLD_SUB_STEPPING
+    r = ref.RefWorld(scene)
+    g = parity.gpu_world_from_ref(gpu, r)
+    infos = parity.lockstep(g, r, 300, tol=TOL)
+    assert max(int(i["toiSubSteps"]) for i in infos) == 1
+    assert sum(int(i["toiEventPending"]) for i in infos) > 10
 
 
 def test_add_pair_pair_set(gpu):
     """BASELINE config 2 (Add Pair, scaled down): broad-phase stress with a fast bullet box; pair set bit-exact
-    every step.  Continuous physics is off on both sides (SolveTOI is host-driven and outside this test)."""
-    scene = _no_toi(scenes.add_pair(400))
+    every step, through the bullet's impact, with continuous physics on."""
+    scene = scenes.add_pair(400)
     r = ref.RefWorld(scene)
     g = parity.gpu_world_from_ref(gpu, r)
     infos = parity.lockstep(g, r, 90, tol=TOL)
@@ -285,7 +303,7 @@ def test_add_pair_pair_set(gpu):
 def test_deterministic_repeat(gpu):
     """Two device worlds built from the same scene stay bit-identical (the reference's reproducibility claim,
     README.md:161-173, restated for the GPU path)."""
-    scene = _no_toi(scenes.pile(16, 12))
+    scene = scenes.pile(16, 12)
     r = ref.RefWorld(scene)
     a = parity.gpu_world_from_ref(gpu, r)
     b = parity.gpu_world_from_ref(gpu, r)
@@ -300,7 +318,7 @@ def test_deterministic_repeat(gpu):
 def test_invariants_long_run(gpu):
     """1000-step invariants on a resting stack (Testbed/Tests/SleepCollideTest.h:104-110 rule: no body below the
     ground; bounded penetration; the pyramid stays standing)."""
-    scene = _no_toi(scenes.pyramid(10, continuous=False))
+    scene = scenes.pyramid(10)
     r = ref.RefWorld(scene)
     g = parity.gpu_world_from_ref(gpu, r)
     for _ in range(1000):

@@ -14,7 +14,6 @@ import scenes  # noqa: E402
 
 
 def run(name, scene, steps, warm=60):
-    scene.world_flags &= ~T.WORLD_CONTINUOUS
     h = b2host.HostWorld(scene, download_bodies=False, events=False)
     for _ in range(warm):
         h.step()
