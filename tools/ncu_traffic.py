@@ -38,7 +38,7 @@ def main():
     order = []
     for r in reader:
         key = r["ID"]
-        name = re.sub(r"\(.*$", "", r["Kernel Name"]).split("::")[-1].split("<")[0].strip()
+        name = re.sub(r"^void\s+", "", re.sub(r"\(.*$", "", r["Kernel Name"])).split("::")[-1].split("<")[0].strip()
         if key not in per_launch:
             per_launch[key] = {"name": name, "bytes": 0.0, "ns": 0.0}
             order.append(key)
