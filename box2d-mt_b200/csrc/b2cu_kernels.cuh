@@ -923,7 +923,8 @@ __global__ void IntegrateVelocitiesKernel(DeviceArrays d, int bodyCount, float h
 			float ad = 1.0f / (1.0f + h * dm.y);
 			lin = V(lin.x * ld, lin.y * ld);
 			w = w * ad;
-			d.vel[b] = make_float4(lin.x, lin.y, w, v.w);
+			// .w = 0: the update counter of the dataflow solver (b2cu_solver_flow.cuh) starts here
+			d.vel[b] = make_float4(lin.x, lin.y, w, 0.0f);
 		}
 	}
 }
@@ -1147,7 +1148,8 @@ __device__ __forceinline__ VelPre LoadVelPre(const DeviceArrays& d, int k)
 	return p;
 }
 
-__device__ __forceinline__ void WarmStartPre(const DeviceArrays& d, int k, const VelPre& pre)
+// the arithmetic of one constraint's warm start on the two bodies' velocity rows (x, y = v, z = w; .w is not touched)
+__device__ __forceinline__ void WarmStartCore(const DeviceArrays& d, int k, const VelPre& pre, float4& vA4, float4& vB4)
 {
 	int4 sb = pre.sb;
 	float4 ms = pre.ms;
@@ -1156,7 +1158,6 @@ __device__ __forceinline__ void WarmStartPre(const DeviceArrays& d, int k, const
 	int pointCount = sb.w & 0xFF;
 	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
 
-	float4 vA4 = d.vel[sb.x], vB4 = d.vel[sb.y];
 	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
 	float wA = vA4.z, wB = vB4.z;
 	Vec2 normal = V(nf.x, nf.y);
@@ -1174,8 +1175,18 @@ __device__ __forceinline__ void WarmStartPre(const DeviceArrays& d, int k, const
 		wB += iB * Cross(rB, P);
 		vB = vB + mB * P;
 	}
-	if (mA != 0.0f || iA != 0.0f) d.vel[sb.x] = make_float4(vA.x, vA.y, wA, vA4.w);
-	if (mB != 0.0f || iB != 0.0f) d.vel[sb.y] = make_float4(vB.x, vB.y, wB, vB4.w);
+	vA4.x = vA.x; vA4.y = vA.y; vA4.z = wA;
+	vB4.x = vB.x; vB4.y = vB.y; vB4.z = wB;
+}
+
+__device__ __forceinline__ void WarmStartPre(const DeviceArrays& d, int k, const VelPre& pre)
+{
+	const int4 sb = pre.sb;
+	const float4 ms = pre.ms;
+	float4 vA4 = d.vel[sb.x], vB4 = d.vel[sb.y];
+	WarmStartCore(d, k, pre, vA4, vB4);
+	if (ms.x != 0.0f || ms.y != 0.0f) d.vel[sb.x] = vA4;
+	if (ms.z != 0.0f || ms.w != 0.0f) d.vel[sb.y] = vB4;
 }
 
 __device__ __forceinline__ void WarmStartOne(const DeviceArrays& d, int k) { WarmStartPre(d, k, LoadVelPre(d, k)); }
@@ -1186,7 +1197,7 @@ __global__ void __launch_bounds__(256) WarmStartKernel(DeviceArrays d, int begin
 }
 
 // b2ContactSolver::SolveVelocityConstraints (b2ContactSolver.cpp:293-603) for one constraint
-__device__ __forceinline__ void SolveVelocityPre(const DeviceArrays& d, int k, const VelPre& pre)
+__device__ __forceinline__ void SolveVelocityCore(const DeviceArrays& d, int k, const VelPre& pre, float4& vA4, float4& vB4)
 {
 	int4 sb = pre.sb;
 	float4 ms = pre.ms;
@@ -1196,7 +1207,6 @@ __device__ __forceinline__ void SolveVelocityPre(const DeviceArrays& d, int k, c
 	int pointCount = sb.w & 0xFF;
 	float mA = ms.x, iA = ms.y, mB = ms.z, iB = ms.w;
 
-	float4 vA4 = d.vel[sb.x], vB4 = d.vel[sb.y];
 	Vec2 vA = V(vA4.x, vA4.y), vB = V(vB4.x, vB4.y);
 	float wA = vA4.z, wB = vB4.z;
 	Vec2 normal = V(nf.x, nf.y);
@@ -1325,8 +1335,19 @@ __device__ __forceinline__ void SolveVelocityPre(const DeviceArrays& d, int k, c
 	}
 
 	__stcs(&d.sImp[k], imp);
-	if (mA != 0.0f || iA != 0.0f) d.vel[sb.x] = make_float4(vA.x, vA.y, wA, vA4.w);
-	if (mB != 0.0f || iB != 0.0f) d.vel[sb.y] = make_float4(vB.x, vB.y, wB, vB4.w);
+	vA4.x = vA.x; vA4.y = vA.y; vA4.z = wA;
+	vB4.x = vB.x; vB4.y = vB.y; vB4.z = wB;
+}
+
+
+__device__ __forceinline__ void SolveVelocityPre(const DeviceArrays& d, int k, const VelPre& pre)
+{
+	const int4 sb = pre.sb;
+	const float4 ms = pre.ms;
+	float4 vA4 = d.vel[sb.x], vB4 = d.vel[sb.y];
+	SolveVelocityCore(d, k, pre, vA4, vB4);
+	if (ms.x != 0.0f || ms.y != 0.0f) d.vel[sb.x] = vA4;
+	if (ms.z != 0.0f || ms.w != 0.0f) d.vel[sb.y] = vB4;
 }
 
 __device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k) { SolveVelocityPre(d, k, LoadVelPre(d, k)); }
@@ -1414,7 +1435,8 @@ __device__ __forceinline__ PosPre LoadPosPre(const DeviceArrays& d, int k)
 	return p;
 }
 
-__device__ __forceinline__ float SolvePositionPre(const DeviceArrays& d, const PosPre& pre)
+// the arithmetic of one constraint's position correction on the two bodies' position rows (x, y = c, z = a)
+__device__ __forceinline__ float SolvePositionCore(const PosPre& pre, float4& pA4, float4& pB4)
 {
 	int4 sb = pre.sb;
 	float4 ms = pre.ms;
@@ -1428,7 +1450,6 @@ __device__ __forceinline__ float SolvePositionPre(const DeviceArrays& d, const P
 	Vec2 localCenterA = V(cen.x, cen.y), localCenterB = V(cen.z, cen.w);
 	Vec2 localNormal = V(loc.x, loc.y), localPoint = V(loc.z, loc.w);
 
-	float4 pA4 = d.pos[sb.x], pB4 = d.pos[sb.y];
 	Vec2 cA = V(pA4.x, pA4.y), cB = V(pB4.x, pB4.y);
 	float aA = pA4.z, aB = pB4.z;
 	float minSeparation = B2CU_MAX_FLOAT;
@@ -1489,8 +1510,20 @@ __device__ __forceinline__ float SolvePositionPre(const DeviceArrays& d, const P
 		aB += iB * Cross(rB, P);
 	}
 
-	if (mA != 0.0f || iA != 0.0f) d.pos[sb.x] = make_float4(cA.x, cA.y, aA, pA4.w);
-	if (mB != 0.0f || iB != 0.0f) d.pos[sb.y] = make_float4(cB.x, cB.y, aB, pB4.w);
+	pA4.x = cA.x; pA4.y = cA.y; pA4.z = aA;
+	pB4.x = cB.x; pB4.y = cB.y; pB4.z = aB;
+	return minSeparation;
+}
+
+
+__device__ __forceinline__ float SolvePositionPre(const DeviceArrays& d, const PosPre& pre)
+{
+	const int4 sb = pre.sb;
+	const float4 ms = pre.ms;
+	float4 pA4 = d.pos[sb.x], pB4 = d.pos[sb.y];
+	float minSeparation = SolvePositionCore(pre, pA4, pB4);
+	if (ms.x != 0.0f || ms.y != 0.0f) d.pos[sb.x] = pA4;
+	if (ms.z != 0.0f || ms.w != 0.0f) d.pos[sb.y] = pB4;
 	return minSeparation;
 }
 
@@ -1584,6 +1617,7 @@ struct SolverPlan
 	int opType[B2CU_MAX_SOLVER_OPS];
 	int opStart[B2CU_MAX_SOLVER_OPS];
 	int opSize[B2CU_MAX_SOLVER_OPS];
+	int opColour[B2CU_MAX_SOLVER_OPS]; // colour of a parallel op (the dataflow kernels derive the bodies' update ranks from it)
 	int constraintCount;
 	int bodyCount;
 	int velocityIterations;
@@ -1665,7 +1699,7 @@ __device__ __forceinline__ void IntegratePositionOne(const DeviceArrays& d, int 
 	c = c + h * v;
 	a += h * w;
 
-	d.pos[b] = make_float4(c.x, c.y, a, p.w);
+	d.pos[b] = make_float4(c.x, c.y, a, 0.0f); // .w = 0: update counter of the dataflow position solver
 	d.vel[b] = make_float4(v.x, v.y, w, v4.w);
 }
 
@@ -2833,4 +2867,5 @@ __global__ void SinCosKernel(int n, const float* __restrict__ x, float* __restri
 
 } // namespace b2cu
 
+#include "b2cu_solver_flow.cuh"
 #include "b2cu_toi_step.cuh"

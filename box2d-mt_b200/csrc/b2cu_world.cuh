@@ -46,7 +46,7 @@ enum Counter
 	CNT_TOI_WORK,         // FindMinToiContact pass: contacts whose time of impact has to be (re)computed
 	CNT_TOI_LIST,         // time-of-impact event: entries of the two bodies' contact lists
 	CNT_TOI_EVENTS,       // begin / end touch events raised inside the sub-steps of this step
-	CNT_TOI_PAD,          // keeps the 64-bit slot below 8-byte aligned
+	CNT_FLOW_STUCK,       // != 0: a dependency wait of the dataflow solver timed out (the step fails)
 	CNT_STICKY_TOI,       // not cleared per step: a TOI-candidate contact has existed
 	CNT_TOI_MIN_ALPHA,    // first TOI pass: float bits of the smallest alpha (0xFFFFFFFF: no candidate)
 	CNT_TOI_MIN_KEY,      // 64 bits (two slots): smallest contact key among the candidates at that alpha
@@ -222,6 +222,7 @@ struct b2cuWorld
 	int persistentGrid;
 	int persistentGridMax;
 	int persistentGridPosition, persistentGridPositionMax;
+	int flowGrid, flowGridPosition; // co-resident grids of the dataflow solver kernels (0: unavailable)
 
 	// spatial sharding (b2cuShardConfigure / Connect)
 	int shardRank, shardCount;

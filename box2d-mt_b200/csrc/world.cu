@@ -837,6 +837,13 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		}
 		w->persistentGrid = g_smCount * perSm;
 		w->persistentGridMax = w->persistentGrid;
+		{
+			int perSmFlow = 0, perSmFlowPos = 0;
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlow, SolverVelocityFlowKernel, B2CU_SOLVER_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowPos, SolverPositionFlowKernel, B2CU_SOLVER_THREADS, 0);
+			w->flowGrid = coop != 0 ? g_smCount * perSmFlow : 0;
+			w->flowGridPosition = coop != 0 ? g_smCount * perSmFlowPos : 0;
+		}
 		w->persistentGridPosition = g_smCount * perSmPos;
 		w->persistentGridPositionMax = w->persistentGridPosition;
 		w->shardCount = 1;
@@ -1866,6 +1873,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 						plan.opType[nOps] = OP_PARALLEL;
 						plan.opStart[nOps] = colourStart[c];
 						plan.opSize[nOps] = w->colourCounts[c];
+						plan.opColour[nOps] = c;
 						++nOps;
 					}
 				}
@@ -1898,14 +1906,30 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				plan.jointOpSerial[jo] = w->jointOpSerial[jo];
 			}
 			void* args[2] = {(void*)&d, (void*)&plan};
-			const void* velocityKernel = nJoints > 0 ? (const void*)SolverVelocityPersistentKernel<true>
-			                                         : (const void*)SolverVelocityPersistentKernel<false>;
-			const void* positionKernel = nJoints > 0 ? (const void*)SolverPositionPersistentKernel<true>
-			                                         : (const void*)SolverPositionPersistentKernel<false>;
+			// dataflow instance (b2cu_solver_flow.cuh): no colour barriers.  Needs every constraint coloured (no serial
+			// list), no joints, no halo exchange
+			static const bool flowEnabled = []() {
+				const char* e = getenv("B2CU_FLOW");
+				return !(e && atoi(e) == 0);
+			}();
+			const bool flow = flowEnabled && nJoints == 0 && w->shardCount == 1 && w->overflowCount == 0 && nConstraints > 0 &&
+			                  w->flowGrid > 0 && w->flowGridPosition > 0;
+			const void* velocityKernel = flow ? (const void*)SolverVelocityFlowKernel
+			                                  : nJoints > 0 ? (const void*)SolverVelocityPersistentKernel<true>
+			                                                : (const void*)SolverVelocityPersistentKernel<false>;
+			const void* positionKernel = flow ? (const void*)SolverPositionFlowKernel
+			                                  : nJoints > 0 ? (const void*)SolverPositionPersistentKernel<true>
+			                                                : (const void*)SolverPositionPersistentKernel<false>;
 			int velocityGrid = nJoints > 0 ? std::min(w->persistentGrid, w->persistentGridJoints) : w->persistentGrid;
 			int positionGrid =
 			    nJoints > 0 ? std::min(w->persistentGridPosition, w->persistentGridPositionJoints) : w->persistentGridPosition;
-			if (w->shardCount == 1)
+			if (flow)
+			{
+				// no barriers to keep cheap: the more threads, the fewer constraints each takes in sequence
+				velocityGrid = w->flowGrid;
+				positionGrid = w->flowGridPosition;
+			}
+			else if (w->shardCount == 1)
 			{
 				// a world whose largest colour class does not fill the co-resident grid is bound by the grid barrier, and
 				// the barrier is cheaper with fewer CTAs: launch only as many as that class can occupy
@@ -1989,6 +2013,9 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		newContacts += n1;
 		destroyed += d1;
 		moved += m1;
+		if (w->hostCounters[CNT_FLOW_STUCK])
+			return SetError(w, B2CU_ERR_CUDA, "internal: a dependency wait of the dataflow solver timed out; the step is invalid "
+			                                  "(B2CU_FLOW=0 selects the barrier solver)");
 	}
 	else
 	{
