@@ -880,13 +880,21 @@ __global__ void ColourCommitKernel(DeviceArrays d, const int* __restrict__ list,
 	}
 }
 
+// Solver order = (colour, class, contact index).  The order inside a colour is free (its constraints share no dynamic
+// body); putting like constraints next to each other makes the warps of the solver kernels uniform: the one-point and
+// the two-point (block solver) paths of SolveVelocityConstraints, and the three manifold types of the position solver,
+// no longer run in the same warp, and a constraint's index tells whether it has a second point to load.
+// class: 0 circles manifold, 1 one-point face manifold, 2 two-point face A, 3 two-point face B.
+#define B2CU_ORDER_COLOUR_SHIFT 34
 __global__ void ColourKeysKernel(DeviceArrays d, const int* __restrict__ list)
 {
 	int n = d.counters[CNT_CONSTRAINT];
 	B2CU_GRID_STRIDE(j, n)
 	{
 		int i = list[j];
-		d.orderKeys[j] = ((uint64_t)(uint32_t)d.c.colour[i] << 32) | (uint32_t)i;
+		uint4 m3 = d.c.m3[i];
+		uint32_t cls = m3.z == B2CU_MANIFOLD_CIRCLES ? 0u : m3.w < 2u ? 1u : m3.z == B2CU_MANIFOLD_FACE_A ? 2u : 3u;
+		d.orderKeys[j] = ((uint64_t)(((uint32_t)d.c.colour[i] << 2) | cls) << 32) | (uint32_t)i;
 	}
 }
 
@@ -1116,12 +1124,22 @@ __global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(D
 		d.sMass[k] = make_float4(mA, iA, mB, iB);
 		d.sNormal[k] = make_float4(normal.x, normal.y, friction, tangentSpeed);
 		d.sP0a[k] = pa[0];
-		d.sP0b[k] = pb[0];
-		d.sP1a[k] = pa[1];
-		d.sP1b[k] = pb[1];
+		// second point: only rA / rB and the velocity bias are kept; its masses and the block solver's K and inverse are
+		// recomputed by the solver from rA, rB, the normal and the body masses (the same expressions on the same values:
+		// the same bits), which takes 48 bytes per iteration off every two-point constraint
+		d.sP0b[k] = make_float4(pb[0].x, pb[0].y, pb[0].z, pb[1].z);
 		d.sImp[k] = make_float4(imp[0], imp[1], imp[2], imp[3]);
-		d.sK[k] = K;
-		d.sNM[k] = NM;
+		if (pointCount == 2)
+		{
+			d.sP1a[k] = pa[1];
+			// first two-point row of the colour (rows are ordered one-point first inside a colour, ColourKeysKernel)
+			const int colour = d.c.colour[i];
+			const unsigned peers = __match_any_sync(__activemask(), colour);
+			const int first = __reduce_min_sync(peers, k);
+			if ((int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicMin(&d.colourTwoStart[colour], first);
+		}
+		(void)K;
+		(void)NM;
 		d.sLocal[k] = m0;
 		d.sLocalP[k] = make_float4(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
 		d.sCenters[k] = make_float4(localCenterA.x, localCenterA.y, localCenterB.x, localCenterB.y);
@@ -1134,9 +1152,11 @@ __global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(D
 struct VelPre
 {
 	int4 sb;
-	float4 ms, nf, imp, p0a, p0b;
+	float4 ms, nf, imp, p0a, p0b, p1a;
 };
-__device__ __forceinline__ VelPre LoadVelPre(const DeviceArrays& d, int k)
+// two: the row is in the two-point part of its colour (k >= colourTwoStart[colour]): its second point is loaded in the
+// same breath as the rest instead of after the point count has arrived
+__device__ __forceinline__ VelPre LoadVelPre(const DeviceArrays& d, int k, bool two)
 {
 	VelPre p;
 	p.sb = __ldcs(&d.sBody[k]);
@@ -1145,6 +1165,14 @@ __device__ __forceinline__ VelPre LoadVelPre(const DeviceArrays& d, int k)
 	p.imp = __ldcs(&d.sImp[k]);
 	p.p0a = __ldcs(&d.sP0a[k]);
 	p.p0b = __ldcs(&d.sP0b[k]);
+	p.p1a = two ? __ldcs(&d.sP1a[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+	return p;
+}
+// without the hint: decided by the row itself (one dependent load more for two-point rows)
+__device__ __forceinline__ VelPre LoadVelPre(const DeviceArrays& d, int k)
+{
+	VelPre p = LoadVelPre(d, k, false);
+	if ((p.sb.w >> 8) == 2) p.p1a = __ldcs(&d.sP1a[k]);
 	return p;
 }
 
@@ -1165,7 +1193,7 @@ __device__ __forceinline__ void WarmStartCore(const DeviceArrays& d, int k, cons
 
 	for (int j = 0; j < pointCount; ++j)
 	{
-		float4 r = j == 0 ? pre.p0a : __ldcs(&d.sP1a[k]);
+		float4 r = j == 0 ? pre.p0a : pre.p1a;
 		float ni = j == 0 ? imp.x : imp.z;
 		float ti = j == 0 ? imp.y : imp.w;
 		Vec2 rA = V(r.x, r.y), rB = V(r.z, r.w);
@@ -1213,11 +1241,21 @@ __device__ __forceinline__ void SolveVelocityCore(const DeviceArrays& d, int k, 
 	Vec2 tangent = CrossVS(normal, 1.0f);
 	float friction = nf.z, tangentSpeed = nf.w;
 
-	float4 p1a = make_float4(0.f, 0.f, 0.f, 0.f), p1b = make_float4(0.f, 0.f, 0.f, 0.f);
+	// second point: rA / rB from the row, bias from p0b.w, the two masses recomputed as InitializeVelocityConstraints
+	// computes them (b2ContactSolver.cpp:194-210)
+	const float4 p1a = pre.p1a;
+	float4 p1b = make_float4(0.f, 0.f, p0b.w, 0.f);
 	if (pointCount == 2)
 	{
-		p1a = __ldcs(&d.sP1a[k]);
-		p1b = __ldcs(&d.sP1b[k]);
+		Vec2 rA = V(p1a.x, p1a.y), rB = V(p1a.z, p1a.w);
+		float rnA = Cross(rA, normal);
+		float rnB = Cross(rB, normal);
+		float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+		p1b.x = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+		float rtA = Cross(rA, tangent);
+		float rtB = Cross(rB, tangent);
+		float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+		p1b.y = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
 	}
 
 	// tangent constraints first
@@ -1266,10 +1304,27 @@ __device__ __forceinline__ void SolveVelocityCore(const DeviceArrays& d, int k, 
 	else
 	{
 		// block solver, total enumeration of the 2x2 LCP (b2ContactSolver.cpp:375-596)
-		float4 Kq = __ldcs(&d.sK[k]);
-		float4 NM = __ldcs(&d.sNM[k]);
 		Vec2 rA1 = V(p0a.x, p0a.y), rB1 = V(p0a.z, p0a.w);
 		Vec2 rA2 = V(p1a.x, p1a.y), rB2 = V(p1a.z, p1a.w);
+		// K and its inverse as InitializeVelocityConstraints prepares them (b2ContactSolver.cpp:214-244)
+		float4 Kq, NM;
+		{
+			float rn1A = Cross(rA1, normal);
+			float rn1B = Cross(rB1, normal);
+			float rn2A = Cross(rA2, normal);
+			float rn2B = Cross(rB2, normal);
+			float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+			float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+			float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+			Kq = make_float4(k11, k12, k22, 0.0f);
+			float a = k11, b = k12, c = k12, dd = k22;
+			float det = a * dd - b * c;
+			if (det != 0.0f)
+			{
+				det = 1.0f / det;
+			}
+			NM = make_float4(det * dd, -det * b, -det * c, det * a);
+		}
 
 		Vec2 a = V(imp.x, imp.z);
 
@@ -1630,6 +1685,8 @@ struct SolverPlan
 	int jointOpCount;
 	int jointOpStart[B2CU_MAX_JOINT_OPS], jointOpSize[B2CU_MAX_JOINT_OPS], jointOpSerial[B2CU_MAX_JOINT_OPS];
 	float dtRatio;
+	int flowPrefetch;   // dataflow kernels: L2 prefetch of the next round's rows (B2CU_FLOW_PREFETCH)
+	int debugSkipStore; // timing experiments only (B2CU_DEBUG_SKIP_STORE): leave the impulse store out
 };
 
 enum { JOINT_INIT = 0, JOINT_VELOCITY = 1, JOINT_POSITION = 2 };

@@ -66,6 +66,26 @@ __device__ __forceinline__ void IntegratePositionRow(const DeviceArrays& d, int 
 	d.vel[b] = make_float4(v.x, v.y, w, 0.0f);
 }
 
+__device__ __forceinline__ void PrefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// row index this thread handles in the round after (op, base), or -1: the next slice of the same colour, else the first
+// slice of the next colour (of the next pass after the last colour)
+__device__ __forceinline__ int FlowNextRow(const SolverPlan& plan, int op, int base, int tid, int stride, bool lastPass)
+{
+	if (base + stride < plan.opSize[op])
+	{
+		const int t = base + stride + tid;
+		return t < plan.opSize[op] ? plan.opStart[op] + t : -1;
+	}
+	int next = op + 1;
+	if (next == plan.opCount)
+	{
+		if (lastPass) return -1;
+		next = 0;
+	}
+	return tid < plan.opSize[next] ? plan.opStart[next] + tid : -1;
+}
+
 // polls before a wait is declared stuck (seconds of wall time): the step then fails loudly instead of hanging the GPU
 #define B2CU_FLOW_SPIN_LIMIT (1 << 22)
 // true when this wait must be given up: it has polled too long, or some other wait already has (checked now and then)
@@ -87,7 +107,10 @@ __device__ __forceinline__ int FlowExpected(uint32_t mask, int colour, int passI
 }
 
 // warm start + velocity iterations + impulse store + position integration
-__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVelocityFlowKernel(DeviceArrays d, SolverPlan plan)
+#ifndef B2CU_FLOW_VEL_BLOCKS
+#define B2CU_FLOW_VEL_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_FLOW_VEL_BLOCKS) SolverVelocityFlowKernel(DeviceArrays d, SolverPlan plan)
 {
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
@@ -99,6 +122,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVe
 		for (int op = 0; op < plan.opCount; ++op)
 		{
 			const int begin = plan.opStart[op], n = plan.opSize[op], colour = plan.opColour[op];
+			const int twoStart = d.colourTwoStart[colour];
 			for (int base = 0; base < n; base += stride) // warp-uniform trip count
 			{
 				const int t = base + tid;
@@ -108,11 +132,25 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVe
 				bool dynA = false, dynB = false;
 				if (!done)
 				{
-					pre = LoadVelPre(d, begin + t);
+					pre = LoadVelPre(d, begin + t, begin + t >= twoStart);
 					dynA = pre.ms.x != 0.0f || pre.ms.y != 0.0f;
 					dynB = pre.ms.z != 0.0f || pre.ms.w != 0.0f;
 					if (dynA) expA = FlowExpected(d.colourMask[pre.sb.x], colour, passIndex);
 					if (dynB) expB = FlowExpected(d.colourMask[pre.sb.y], colour, passIndex);
+				}
+				if (plan.flowPrefetch)
+				{
+					// the rows of this thread's next constraint on their way into L2 while this one is solved
+					const int kn = FlowNextRow(plan, op, base, tid, stride, pass == lastPass);
+					if (kn >= 0)
+					{
+						PrefetchL2(&d.sBody[kn]);
+						PrefetchL2(&d.sMass[kn]);
+						PrefetchL2(&d.sNormal[kn]);
+						PrefetchL2(&d.sImp[kn]);
+						PrefetchL2(&d.sP0a[kn]);
+						PrefetchL2(&d.sP0b[kn]);
+					}
 				}
 				int spins = 0;
 				for (;;)
@@ -146,7 +184,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_VEL_BLOCKS) SolverVe
 		}
 	}
 	// b2ContactSolver::StoreImpulses: every thread for the rows it solved (nobody else knows that they are final)
-	for (int op = 0; op < plan.opCount; ++op)
+	for (int op = 0; op < plan.opCount && !plan.debugSkipStore; ++op)
 	{
 		const int begin = plan.opStart[op], n = plan.opSize[op];
 		for (int t = tid; t < n; t += stride) StoreImpulseOne(d, begin + t);
@@ -216,6 +254,19 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPo
 					dynB = pre.ms.z != 0.0f || pre.ms.w != 0.0f;
 					if (dynA) expA = FlowExpected(d.colourMask[pre.sb.x], colour, it);
 					if (dynB) expB = FlowExpected(d.colourMask[pre.sb.y], colour, it);
+				}
+				if (plan.flowPrefetch)
+				{
+					const int kn = FlowNextRow(plan, op, base, tid, stride, it + 1 == plan.positionIterations);
+					if (kn >= 0)
+					{
+						PrefetchL2(&d.sBody[kn]);
+						PrefetchL2(&d.sMass[kn]);
+						PrefetchL2(&d.sLocal[kn]);
+						PrefetchL2(&d.sLocalP[kn]);
+						PrefetchL2(&d.sCenters[kn]);
+						PrefetchL2(&d.sRadius[kn]);
+					}
 				}
 				int spins = 0;
 				float minSep = 0.0f;

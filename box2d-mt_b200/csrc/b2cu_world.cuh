@@ -142,6 +142,7 @@ struct DeviceArrays
 	int* largeList;         // proxies larger than the coarsest grid cell
 	int* levelInfo;         // per grid level: proxy count, then moved count
 	int* colourCount;       // [B2CU_MAX_COLOURS + 1]
+	int* colourTwoStart;    // [B2CU_MAX_COLOURS + 2]: first row of a colour whose manifold has two points (rows are ordered one-point first)
 	uint64_t* toiKeys;
 	// time-of-impact sub-steps (b2cu_toi_step.cuh)
 	uint64_t* toiListKeys;   // contact capacity: (side, ~stamp, ~index) of the contacts on the two event bodies' lists
@@ -162,12 +163,9 @@ struct DeviceArrays
 	float4* sMass;    // mA, iA, mB, iB
 	float4* sNormal;  // normal.xy, friction, tangentSpeed
 	float4* sP0a;     // rA.xy, rB.xy
-	float4* sP0b;     // normalMass, tangentMass, velocityBias, -
-	float4* sP1a;
-	float4* sP1b;
+	float4* sP0b;     // normalMass, tangentMass, velocityBias of point 0, velocityBias of point 1
+	float4* sP1a;     // second point: rA.xy, rB.xy (two-point rows only)
 	float4* sImp;     // normalImpulse0, tangentImpulse0, normalImpulse1, tangentImpulse1
-	float4* sK;       // k11, k12, k22, -
-	float4* sNM;      // normalMass matrix: ex.x, ey.x, ex.y, ey.y
 	float4* sLocal;   // localNormal.xy, localPoint.xy
 	float4* sLocalP;  // localPoints[0].xy, localPoints[1].xy
 	float4* sCenters; // localCenterA.xy, localCenterB.xy

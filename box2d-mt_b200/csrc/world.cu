@@ -198,6 +198,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->largeList, CAP_PROXY));
 	v.push_back(Desc(&d->levelInfo, CAP_FIXED, 64));
 	v.push_back(Desc(&d->colourCount, CAP_FIXED, B2CU_MAX_COLOURS + 2));
+	v.push_back(Desc(&d->colourTwoStart, CAP_FIXED, B2CU_MAX_COLOURS + 2));
 	v.push_back(Desc(&d->cellCount, CAP_GRID));
 	v.push_back(Desc(&d->cellStart, CAP_GRID));
 	v.push_back(Desc(&d->cellItems, CAP_PROXY));
@@ -209,10 +210,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->sP0a, CAP_CONTACT));
 	v.push_back(Desc(&d->sP0b, CAP_CONTACT));
 	v.push_back(Desc(&d->sP1a, CAP_CONTACT));
-	v.push_back(Desc(&d->sP1b, CAP_CONTACT));
 	v.push_back(Desc(&d->sImp, CAP_CONTACT));
-	v.push_back(Desc(&d->sK, CAP_CONTACT));
-	v.push_back(Desc(&d->sNM, CAP_CONTACT));
 	v.push_back(Desc(&d->sLocal, CAP_CONTACT));
 	v.push_back(Desc(&d->sLocalP, CAP_CONTACT));
 	v.push_back(Desc(&d->sCenters, CAP_CONTACT));
@@ -1831,7 +1829,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 					return SetError(w, B2CU_ERR_CUDA, "internal: colour counts %d != constraints %d", at, nConstraints);
 				w->overflowCount = w->colourCounts[B2CU_MAX_COLOURS] + w->colourCounts[B2CU_MAX_COLOURS + 1];
 				LAUNCH(w, ColourKeysKernel, GridFor(nConstraints), kBlock, d, d.listA);
-				RadixSort64(&w->prims, d.orderKeys, nConstraints, 32, 40, w->stream);
+				RadixSort64(&w->prims, d.orderKeys, nConstraints, 32, 40, w->stream); // (colour << 2 | class) < 256
+				CUDA_TRY(w, cudaMemsetAsync(d.colourTwoStart, 0x7F, sizeof(int) * (B2CU_MAX_COLOURS + 2), w->stream));
 			}
 		}
 		w->constraintCount = nConstraints;
@@ -1898,6 +1897,12 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			plan.h = dt;
 			plan.shard = MakeShardState(w);
 			plan.dtRatio = dtRatio;
+			{
+				static const int skip = []() { const char* e = getenv("B2CU_DEBUG_SKIP_STORE"); return e ? atoi(e) : 0; }();
+				plan.debugSkipStore = skip;
+				static const int prefetch = []() { const char* e = getenv("B2CU_FLOW_PREFETCH"); return e ? atoi(e) : 0; }();
+				plan.flowPrefetch = prefetch;
+			}
 			plan.jointOpCount = nJoints > 0 ? w->jointOpCount : 0;
 			for (int jo = 0; jo < plan.jointOpCount; ++jo)
 			{
@@ -1948,7 +1953,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			CUDA_TRY(w, cudaLaunchCooperativeKernel(velocityKernel, dim3(velocityGrid), dim3(B2CU_SOLVER_THREADS), args, 0,
 			                                        w->stream));
 			++w->launches;
-			TraceMark(w, "SolverVelocityPersistentKernel");
+			TraceMark(w, flow ? "SolverVelocityFlowKernel" : "SolverVelocityPersistentKernel");
+			if (plan.debugSkipStore == 2 && flow) LAUNCH(w, StoreImpulsesKernel, GridFor(nConstraints), kBlock, d);
 			if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)((warmStarting ? 1 : 0) + velocityIterations);
 			plan.shard.seq = w->shardSeq;
 			cudaEventRecord(w->ev[6], w->stream);
@@ -1957,7 +1963,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				CUDA_TRY(w, cudaLaunchCooperativeKernel(positionKernel, dim3(positionGrid), dim3(B2CU_SOLVER_THREADS), args, 0,
 				                                        w->stream));
 				++w->launches;
-				TraceMark(w, "SolverPositionPersistentKernel");
+				TraceMark(w, flow ? "SolverPositionFlowKernel" : "SolverPositionPersistentKernel");
 				if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)positionIterations;
 			}
 		}
@@ -2346,7 +2352,7 @@ int b2cuGetSolverOrder(b2cuWorld* w, int32_t capacity, b2cuContactKey* keys, int
 		{
 			if (at >= m) break;
 			if (keys) keys[at] = stored[k];
-			if (colour) colour[at] = (int32_t)(order[k] >> 32);
+			if (colour) colour[at] = (int32_t)(order[k] >> B2CU_ORDER_COLOUR_SHIFT);
 		}
 	}
 	return B2CU_OK;
