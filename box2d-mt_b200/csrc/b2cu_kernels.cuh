@@ -1654,6 +1654,7 @@ struct ShardState
 	float4* upperFromLower;   // upper neighbour's fromLower mailbox (peer memory), nullptr on the last rank
 	unsigned* upperFlagFromLower;
 	unsigned seq;             // sequence number of the next exchange
+	int* stuck;               // set when a wait for a neighbour gave up (the step then fails instead of hanging the GPU)
 };
 
 enum SolverOpType
@@ -1685,8 +1686,50 @@ struct SolverPlan
 	int jointOpCount;
 	int jointOpStart[B2CU_MAX_JOINT_OPS], jointOpSize[B2CU_MAX_JOINT_OPS], jointOpSerial[B2CU_MAX_JOINT_OPS];
 	float dtRatio;
+	unsigned* softBarrier; // counter of GridSync (zeroed before the launch); nullptr: cooperative launch
 	int flowPrefetch;   // dataflow kernels: L2 prefetch of the next round's rows (B2CU_FLOW_PREFETCH)
 	int debugSkipStore; // timing experiments only (B2CU_DEBUG_SKIP_STORE): leave the impulse store out
+};
+
+// Grid-wide barrier of the persistent solver kernels.  Normally cooperative_groups' (the kernel is a cooperative
+// launch).  A sharded world whose neighbours share its device cannot use cooperative launches -- the driver runs
+// cooperative grids of one device one after the other, and shards wait for each other INSIDE their kernels -- so there
+// the kernels are ordinary launches sized to stay co-resident (b2cuShardConfigure's gridFraction) and synchronise on a
+// counter of their own: every CTA adds one, thread 0 of each spins until the count reaches the round's target.
+struct GridSync
+{
+	unsigned* counter; // nullptr: cooperative launch
+	unsigned blocks;
+	unsigned round;
+	int* stuck;
+	__device__ __forceinline__ void sync()
+	{
+		if (counter == nullptr)
+		{
+			cooperative_groups::this_grid().sync();
+			return;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			__threadfence();
+			const unsigned target = (round + 1u) * blocks;
+			atomicAdd(counter, 1u);
+			long long spins = 0;
+			while (*reinterpret_cast<volatile unsigned*>(counter) < target)
+			{
+				if (*reinterpret_cast<volatile int*>(stuck) != 0) break;
+				if (++spins > (1ll << 25))
+				{
+					*reinterpret_cast<volatile int*>(stuck) = 3;
+					break;
+				}
+			}
+			__threadfence();
+		}
+		++round;
+		__syncthreads();
+	}
 };
 
 enum { JOINT_INIT = 0, JOINT_VELOCITY = 1, JOINT_POSITION = 2 };
@@ -1712,7 +1755,7 @@ __device__ __forceinline__ void JointRunOne(const DeviceArrays& d, const SolverP
 }
 
 // all joint classes of one iteration; every thread of the grid takes part in the barriers
-__device__ __forceinline__ void JointRunOps(cooperative_groups::grid_group& grid, const DeviceArrays& d, const SolverPlan& plan,
+__device__ __forceinline__ void JointRunOps(GridSync& grid, const DeviceArrays& d, const SolverPlan& plan,
                                             int mode, int iteration, int tid, int stride)
 {
 	for (int jo = 0; jo < plan.jointOpCount; ++jo)
@@ -1780,7 +1823,7 @@ __device__ __forceinline__ void StoreImpulseOne(const DeviceArrays& d, int k)
 }
 
 // field[ids[k]] -> peer mailbox, flag; then wait for the neighbour's push and scatter it into field
-__device__ __forceinline__ void HaloExchange(cooperative_groups::grid_group& grid, const ShardState& sh, float4* field,
+__device__ __forceinline__ void HaloExchange(GridSync& grid, const ShardState& sh, float4* field,
                                              bool down, unsigned seq, int tid, int stride)
 {
 	// send
@@ -1799,20 +1842,32 @@ __device__ __forceinline__ void HaloExchange(cooperative_groups::grid_group& gri
 		*reinterpret_cast<volatile unsigned*>(sendFlag) = seq;
 		__threadfence_system();
 	}
-	// receive
+	// receive: every CTA watches the local flag itself (one thread each, an L2-resident word), so no barrier is needed
+	// between "the neighbour's push has arrived" and the scatter
 	const int* recvIds = down ? sh.ghostIds : sh.exportIds;
 	const int recvCount = down ? sh.ghostCount : sh.exportCount;
 	const float4* recvBox = down ? sh.fromUpper : sh.fromLower;
 	const unsigned* recvFlag = down ? sh.flagFromUpper : sh.flagFromLower;
 	const bool hasPeer = down ? (sh.upperFromLower != nullptr) : (sh.lowerFromUpper != nullptr);
-	if (hasPeer && tid == 0)
+	if (hasPeer)
 	{
-		while (*reinterpret_cast<const volatile unsigned*>(recvFlag) < seq)
+		if (threadIdx.x == 0)
 		{
+			// bounded: a neighbour that never arrives (its kernel not co-resident, its process gone) must not hang the GPU
+			long long spins = 0;
+			while (*reinterpret_cast<const volatile unsigned*>(recvFlag) < seq)
+			{
+				if (*reinterpret_cast<volatile int*>(sh.stuck) != 0) break;
+				if (++spins > (1ll << 25))
+				{
+					*reinterpret_cast<volatile int*>(sh.stuck) = 2;
+					break;
+				}
+			}
+			__threadfence_system();
 		}
-		__threadfence_system();
+		__syncthreads();
 	}
-	grid.sync();
 	if (hasPeer)
 	{
 		for (int k = tid; k < recvCount; k += stride) field[recvIds[k]] = __ldcv(&recvBox[k]);
@@ -1852,7 +1907,7 @@ template <bool JOINTS>
 __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_VEL_BLOCKS) SolverVelocityPersistentKernel(DeviceArrays d,
                                                                                                                  SolverPlan plan)
 {
-	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	GridSync grid = {plan.softBarrier, gridDim.x, 0u, plan.shard.stuck};
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	unsigned seq = plan.shard.seq;
@@ -1937,7 +1992,7 @@ template <bool JOINTS>
 __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_POS_BLOCKS) SolverPositionPersistentKernel(DeviceArrays d,
                                                                                                                  SolverPlan plan)
 {
-	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	GridSync grid = {plan.softBarrier, gridDim.x, 0u, plan.shard.stuck};
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	unsigned seq = plan.shard.seq;
@@ -2026,10 +2081,16 @@ __global__ void ShardSignalKernel(unsigned* flag, unsigned seq)
 	*reinterpret_cast<volatile unsigned*>(flag) = seq;
 	__threadfence_system();
 }
-__global__ void ShardWaitKernel(const unsigned* flag, unsigned seq)
+__global__ void ShardWaitKernel(const unsigned* flag, unsigned seq, int* stuck)
 {
+	long long spins = 0;
 	while (*reinterpret_cast<const volatile unsigned*>(flag) < seq)
 	{
+		if (++spins > (1ll << 25))
+		{
+			*stuck = 2;
+			break;
+		}
 	}
 	__threadfence_system();
 }

@@ -234,6 +234,8 @@ struct b2cuWorld
 	bool peerLowerIpc, peerUpperIpc;
 	int peerUpperGhostCountOfUpper; // the upper neighbour's own ghostCount (layout of its mailbox)
 	unsigned shardSeq;     // sequence number of the next halo exchange
+	bool shardSoftBarrier; // a neighbouring shard lives on this device: see GridSync
+	unsigned* softBarrierCounter;
 
 	// last step
 	int endUpdateCount;  // EndContact events from Update (the rest of endCount come from Destroy)

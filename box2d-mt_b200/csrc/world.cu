@@ -348,6 +348,7 @@ ShardState MakeShardState(b2cuWorld* w)
 	ShardState sh;
 	memset(&sh, 0, sizeof(sh));
 	sh.rankCount = w->shardCount > 0 ? w->shardCount : 1;
+	sh.stuck = w->d.counters + CNT_FLOW_STUCK;
 	if (w->shardCount <= 1 || w->mailbox == nullptr) return sh;
 	sh.ghostCount = w->ghostCount;
 	sh.exportCount = w->exportCount;
@@ -385,7 +386,7 @@ int ShardSyncGhosts(b2cuWorld* w)
 	}
 	if (sh.upperFromLower != nullptr)
 	{
-		LAUNCH(w, ShardWaitKernel, 1, 1, sh.flagFromUpper, seq);
+		LAUNCH(w, ShardWaitKernel, 1, 1, sh.flagFromUpper, seq, w->d.counters + CNT_FLOW_STUCK);
 		if (w->ghostCount > 0) LAUNCH(w, GhostApplyKernel, GridFor(w->ghostCount), kBlock, w->d, sh);
 	}
 	return B2CU_OK;
@@ -870,6 +871,7 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 
 void b2cuDestroyWorld(b2cuWorld* w)
 {
+	if (w && w->softBarrierCounter) cudaFree(w->softBarrierCounter);
 	if (!w) return;
 	cudaSetDevice(w->device);
 	cudaStreamSynchronize(w->stream);
@@ -1950,8 +1952,16 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				velocityGrid = std::min(velocityGrid, want);
 				positionGrid = std::min(positionGrid, want);
 			}
-			CUDA_TRY(w, cudaLaunchCooperativeKernel(velocityKernel, dim3(velocityGrid), dim3(B2CU_SOLVER_THREADS), args, 0,
-			                                        w->stream));
+			// shards that share their device with a neighbour: ordinary launches + the kernels' own grid barrier (GridSync)
+			const bool soft = w->shardSoftBarrier && w->shardCount > 1 && !flow;
+			auto launchSolver = [&](const void* kernel, int grid) -> cudaError_t {
+				if (!soft) return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(B2CU_SOLVER_THREADS), args, 0, w->stream);
+				cudaError_t e = cudaMemsetAsync(w->softBarrierCounter, 0, sizeof(unsigned), w->stream);
+				if (e != cudaSuccess) return e;
+				return cudaLaunchKernel(kernel, dim3(grid), dim3(B2CU_SOLVER_THREADS), args, 0, w->stream);
+			};
+			plan.softBarrier = soft ? w->softBarrierCounter : nullptr;
+			CUDA_TRY(w, launchSolver(velocityKernel, velocityGrid));
 			++w->launches;
 			TraceMark(w, flow ? "SolverVelocityFlowKernel" : "SolverVelocityPersistentKernel");
 			if (plan.debugSkipStore == 2 && flow) LAUNCH(w, StoreImpulsesKernel, GridFor(nConstraints), kBlock, d);
@@ -1960,8 +1970,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			cudaEventRecord(w->ev[6], w->stream);
 			if (positionIterations > 0)
 			{
-				CUDA_TRY(w, cudaLaunchCooperativeKernel(positionKernel, dim3(positionGrid), dim3(B2CU_SOLVER_THREADS), args, 0,
-				                                        w->stream));
+				CUDA_TRY(w, launchSolver(positionKernel, positionGrid));
 				++w->launches;
 				TraceMark(w, flow ? "SolverPositionFlowKernel" : "SolverPositionPersistentKernel");
 				if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)positionIterations;
@@ -2020,8 +2029,10 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		destroyed += d1;
 		moved += m1;
 		if (w->hostCounters[CNT_FLOW_STUCK])
-			return SetError(w, B2CU_ERR_CUDA, "internal: a dependency wait of the dataflow solver timed out; the step is invalid "
-			                                  "(B2CU_FLOW=0 selects the barrier solver)");
+			return SetError(w, B2CU_ERR_CUDA,
+			                "a bounded wait inside a solver kernel gave up (code %d: 1 = dependency wait of the dataflow solver, 2 = halo "
+			                "push of the neighbouring shard, 3 = grid barrier of a co-resident shard); the step is invalid",
+			                w->hostCounters[CNT_FLOW_STUCK]);
 	}
 	else
 	{
@@ -2517,6 +2528,15 @@ int b2cuShardConnect(b2cuWorld* w, const b2cuShardLink* lower, const b2cuShardLi
 		if ((rc = OpenPeer(w, upper, &w->peerUpper, &w->peerUpperIpc))) return rc;
 		w->peerUpperGhostCountOfUpper = upper->ghostCount;
 	}
+	// a neighbour on this very device: cooperative launches of one device run one after the other, but the shards wait
+	// for each other inside their solver kernels, so these kernels become ordinary launches with their own grid barrier
+	w->shardSoftBarrier = (lower && lower->device == w->device) || (upper && upper->device == w->device);
+	{
+		const char* e = getenv("B2CU_SOFT_BARRIER");
+		if (e) w->shardSoftBarrier = atoi(e) != 0;
+	}
+	if (w->shardSoftBarrier && w->softBarrierCounter == nullptr)
+		CUDA_TRY(w, cudaMalloc(&w->softBarrierCounter, sizeof(unsigned)));
 	return B2CU_OK;
 }
 

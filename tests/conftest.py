@@ -3,6 +3,12 @@ import sys
 
 import pytest
 
+# Shards that share ONE device (tests/test_sharding.py on a one-GPU box) wait for each other inside their solver kernels.
+# With CUDA's default lazy module loading the first launch of any not-yet-loaded kernel synchronises the whole context --
+# behind the neighbour's spinning kernel: a dead-lock until the bounded waits give up.  Eager loading (set before CUDA
+# initialises) loads every kernel up front.  One GPU per shard, the deployment case, does not need this.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "box2d-mt_b200", "python"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"),
           ROOT):
