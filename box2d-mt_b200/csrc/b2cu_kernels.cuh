@@ -902,7 +902,7 @@ __global__ void ColourKeysKernel(DeviceArrays d, const int* __restrict__ list)
 // b2Island::Solve, body part 1 (Box2D/Dynamics/b2Island.cpp:192-230): integrate velocities, damping, store
 // c0/a0.  Streaming kernel over bodies.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void IntegrateVelocitiesKernel(DeviceArrays d, int bodyCount, float h, float2 gravity)
+__global__ void IntegrateVelocitiesKernel(DeviceArrays d, int bodyCount, float h, float2 gravity, int flowBase)
 {
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
@@ -932,7 +932,7 @@ __global__ void IntegrateVelocitiesKernel(DeviceArrays d, int bodyCount, float h
 			lin = V(lin.x * ld, lin.y * ld);
 			w = w * ad;
 			// .w = 0: the update counter of the dataflow solver (b2cu_solver_flow.cuh) starts here
-			d.vel[b] = make_float4(lin.x, lin.y, w, 0.0f);
+			d.vel[b] = make_float4(lin.x, lin.y, w, __int_as_float(flowBase));
 		}
 	}
 }
@@ -1686,6 +1686,7 @@ struct SolverPlan
 	int jointOpCount;
 	int jointOpStart[B2CU_MAX_JOINT_OPS], jointOpSize[B2CU_MAX_JOINT_OPS], jointOpSerial[B2CU_MAX_JOINT_OPS];
 	float dtRatio;
+	int flowBase;          // dataflow kernels: the versions of this step start at this value
 	unsigned* softBarrier; // counter of GridSync (zeroed before the launch); nullptr: cooperative launch
 	int flowPrefetch;   // dataflow kernels: L2 prefetch of the next round's rows (B2CU_FLOW_PREFETCH)
 	int debugSkipStore; // timing experiments only (B2CU_DEBUG_SKIP_STORE): leave the impulse store out
@@ -1921,7 +1922,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_VEL_BLO
 		int np = firstPass, no = 0;
 		if (NextParallelOp(plan, lastPass, np, no) && tid < plan.opSize[no])
 		{
-			pre = LoadVelPre(d, plan.opStart[no] + tid);
+			pre = LoadVelPre(d, plan.opStart[no] + tid, plan.opStart[no] + tid >= d.colourTwoStart[plan.opColour[no]]);
 			havePre = true;
 		}
 	}
@@ -1936,17 +1937,20 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_VEL_BLO
 			const int type = plan.opType[op], begin = plan.opStart[op], n = plan.opSize[op];
 			if (type == OP_PARALLEL)
 			{
+				// rows at or behind twoStart have a second point (ColourKeysKernel's order): loaded with the rest of the row
+				const int twoStart = d.colourTwoStart[plan.opColour[op]];
 				if (tid < n)
 				{
-					if (!havePre) pre = LoadVelPre(d, begin + tid);
+					if (!havePre) pre = LoadVelPre(d, begin + tid, begin + tid >= twoStart);
 					if (pass == 0) WarmStartPre(d, begin + tid, pre);
 					else SolveVelocityPre(d, begin + tid, pre);
 				}
 				havePre = false;
 				for (int t = tid + stride; t < n; t += stride)
 				{
-					if (pass == 0) WarmStartOne(d, begin + t);
-					else SolveVelocityOne(d, begin + t);
+					const VelPre more = LoadVelPre(d, begin + t, begin + t >= twoStart);
+					if (pass == 0) WarmStartPre(d, begin + t, more);
+					else SolveVelocityPre(d, begin + t, more);
 				}
 				// prefetch for the next colour
 				int np = pass, no = op + 1;
@@ -1956,7 +1960,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_VEL_BLO
 					// colour is this very one (a single colour): then they are loaded after the barrier
 					if (!(plan.opStart[no] == begin))
 					{
-						pre = LoadVelPre(d, plan.opStart[no] + tid);
+						pre = LoadVelPre(d, plan.opStart[no] + tid, plan.opStart[no] + tid >= d.colourTwoStart[plan.opColour[no]]);
 						havePre = true;
 					}
 				}

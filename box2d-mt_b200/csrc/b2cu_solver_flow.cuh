@@ -41,7 +41,7 @@ __device__ __forceinline__ void StoreRow128(float4* p, float4 v)
 
 // b2Island::Solve position integration (b2Island.cpp:283-313) of body b from the velocity row just read; the rows are
 // written back with version 0 for the position iterations
-__device__ __forceinline__ void IntegratePositionRow(const DeviceArrays& d, int b, float h, float4 v4)
+__device__ __forceinline__ void IntegratePositionRow(const DeviceArrays& d, int b, float h, float4 v4, int base)
 {
 	float4 p = d.pos[b];
 	Vec2 c = V(p.x, p.y);
@@ -62,7 +62,7 @@ __device__ __forceinline__ void IntegratePositionRow(const DeviceArrays& d, int 
 	}
 	c = c + h * v;
 	a += h * w;
-	d.pos[b] = make_float4(c.x, c.y, a, 0.0f);
+	d.pos[b] = make_float4(c.x, c.y, a, __int_as_float(base));
 	d.vel[b] = make_float4(v.x, v.y, w, 0.0f);
 }
 
@@ -84,6 +84,76 @@ __device__ __forceinline__ int FlowNextRow(const SolverPlan& plan, int op, int b
 		next = 0;
 	}
 	return tid < plan.opSize[next] ? plan.opStart[next] + tid : -1;
+}
+
+// ---- sharded worlds: the halo bodies' rows travel between the shards inside the same dataflow -----------------------
+// A halo body (a GHOST here = an EXPORT of the upper neighbour) is updated first by its owner's constraints (colours
+// 0-15 there), then by the lower shard's cross constraints (colours 16-31 there); its colour mask is the union of the
+// two sides' masks (exchanged once per step, HaloMaskKernels), so both sides number its updates alike.  Whoever applies
+// the LAST update of its side in a pass also stores the row -- state and version, one 16-byte system-scope store over
+// NVLink -- into the neighbour's mailbox; a constraint that waits for a halo body accepts the expected version from the
+// local row or from the mailbox, whichever shows it.  No flags, no fences, no barriers: the transfer of a boundary
+// body overlaps everything that does not depend on it.
+#define B2CU_HALO_EXPORT 0x40000000
+__device__ __forceinline__ float4 LoadRowSys(const float4* p)
+{
+	float4 v;
+	asm volatile("{\n\t.reg .b128 r;\n\tld.relaxed.sys.global.b128 r, [%4];\n\tmov.b128 {%0,%1,%2,%3}, r;\n\t}"
+	             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+	             : "l"(p)
+	             : "memory");
+	return v;
+}
+__device__ __forceinline__ void StoreRowSys(float4* p, float4 v)
+{
+	asm volatile("{\n\t.reg .b128 r;\n\tmov.b128 r, {%1,%2,%3,%4};\n\tst.relaxed.sys.global.b128 [%0], r;\n\t}" ::"l"(p), "f"(v.x),
+	             "f"(v.y), "f"(v.z), "f"(v.w)
+	             : "memory");
+}
+// mailbox rows of the dataflow: [6n, 7n) velocity rows, [7n, 8n) position rows of a box that holds n halo bodies
+__device__ __forceinline__ const float4* HaloIn(const ShardState& sh, int slot, int region)
+{
+	const int k = slot & ~B2CU_HALO_EXPORT;
+	return (slot & B2CU_HALO_EXPORT) ? sh.fromLower + (size_t)(6 + region) * sh.exportCount + k
+	                                 : sh.fromUpper + (size_t)(6 + region) * sh.ghostCount + k;
+}
+__device__ __forceinline__ float4* HaloOut(const ShardState& sh, int slot, int region)
+{
+	const int k = slot & ~B2CU_HALO_EXPORT;
+	return (slot & B2CU_HALO_EXPORT) ? sh.lowerFromUpper + (size_t)(6 + region) * sh.exportCount + k
+	                                 : sh.upperFromLower + (size_t)(6 + region) * sh.ghostCount + k;
+}
+// is the update of colour `colour` the last one this shard applies to the halo body in a pass?
+__device__ __forceinline__ bool HaloLastOfSide(uint32_t mask, int colour, int slot)
+{
+	const uint32_t side = (slot & B2CU_HALO_EXPORT) ? (mask & 0xFFFFu) : mask; // an export's own colours are the low half
+	return (side >> (colour + 1)) == 0u;
+}
+// the row of body b at version `expected`, from the local array or (halo bodies) from the neighbour's last push
+__device__ __forceinline__ bool FlowAcquire(const ShardState& sh, const float4* rows, int b, int slot, int region, int expected,
+                                            float4* out)
+{
+	float4 v = LoadRow128(&rows[b]);
+	if (__float_as_int(v.w) == expected)
+	{
+		*out = v;
+		return true;
+	}
+	if (slot >= 0)
+	{
+		const float4* in = HaloIn(sh, slot, region);
+		if (in != nullptr)
+		{
+			v = LoadRowSys(in);
+			if (__float_as_int(v.w) == expected)
+			{
+				*out = v;
+				return true;
+			}
+		}
+	}
+	*out = v;
+	return false;
 }
 
 // polls before a wait is declared stuck (seconds of wall time): the step then fails loudly instead of hanging the GPU
@@ -110,17 +180,20 @@ __device__ __forceinline__ int FlowExpected(uint32_t mask, int colour, int passI
 #ifndef B2CU_FLOW_VEL_BLOCKS
 #define B2CU_FLOW_VEL_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_FLOW_VEL_BLOCKS) SolverVelocityFlowKernel(DeviceArrays d, SolverPlan plan)
+template <bool SHARD>
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, SHARD ? 3 : B2CU_FLOW_VEL_BLOCKS) SolverVelocityFlowKernel(DeviceArrays d, SolverPlan plan)
 {
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	const int firstPass = plan.warmStarting ? 0 : 1;
 	const int lastPass = plan.velocityIterations;
+	const int base0 = plan.flowBase; // versions of this step start here (stale mailbox rows of earlier steps never match)
 	int passIndex = 0;
 	for (int pass = firstPass; pass <= lastPass; ++pass, ++passIndex)
 	{
 		for (int op = 0; op < plan.opCount; ++op)
 		{
+			if (plan.opType[op] != OP_PARALLEL) continue; // (sharded plans carry the barrier kernels' halo ops too)
 			const int begin = plan.opStart[op], n = plan.opSize[op], colour = plan.opColour[op];
 			const int twoStart = d.colourTwoStart[colour];
 			for (int base = 0; base < n; base += stride) // warp-uniform trip count
@@ -128,15 +201,26 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_FLOW_VEL_BLOCKS) Sol
 				const int t = base + tid;
 				bool done = t >= n;
 				VelPre pre;
-				int expA = 0, expB = 0;
+				int expA = 0, expB = 0, slotA = -1, slotB = -1;
+				uint32_t maskA = 0u, maskB = 0u;
 				bool dynA = false, dynB = false;
 				if (!done)
 				{
 					pre = LoadVelPre(d, begin + t, begin + t >= twoStart);
 					dynA = pre.ms.x != 0.0f || pre.ms.y != 0.0f;
 					dynB = pre.ms.z != 0.0f || pre.ms.w != 0.0f;
-					if (dynA) expA = FlowExpected(d.colourMask[pre.sb.x], colour, passIndex);
-					if (dynB) expB = FlowExpected(d.colourMask[pre.sb.y], colour, passIndex);
+					if (dynA)
+					{
+						maskA = d.colourMask[pre.sb.x];
+						expA = base0 + FlowExpected(maskA, colour, passIndex);
+						if (SHARD) slotA = d.haloSlot[pre.sb.x];
+					}
+					if (dynB)
+					{
+						maskB = d.colourMask[pre.sb.y];
+						expB = base0 + FlowExpected(maskB, colour, passIndex);
+						if (SHARD) slotB = d.haloSlot[pre.sb.y];
+					}
 				}
 				if (plan.flowPrefetch)
 				{
@@ -157,9 +241,21 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_FLOW_VEL_BLOCKS) Sol
 				{
 					if (!done)
 					{
-						float4 vA = LoadRow128(&d.vel[pre.sb.x]);
-						float4 vB = LoadRow128(&d.vel[pre.sb.y]);
-						bool ready = (!dynA || __float_as_int(vA.w) == expA) && (!dynB || __float_as_int(vB.w) == expB);
+						float4 vA, vB;
+						bool readyA, readyB;
+						if (dynA) readyA = FlowAcquire(plan.shard, d.vel, pre.sb.x, slotA, 0, expA, &vA);
+						else
+						{
+							vA = LoadRow128(&d.vel[pre.sb.x]);
+							readyA = true;
+						}
+						if (dynB) readyB = FlowAcquire(plan.shard, d.vel, pre.sb.y, slotB, 0, expB, &vB);
+						else
+						{
+							vB = LoadRow128(&d.vel[pre.sb.y]);
+							readyB = true;
+						}
+						bool ready = readyA && readyB;
 						if (!ready && FlowStuck(d, ++spins)) ready = true;
 						if (ready)
 						{
@@ -169,11 +265,13 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_FLOW_VEL_BLOCKS) Sol
 							{
 								vA.w = __int_as_float(expA + 1);
 								StoreRow128(&d.vel[pre.sb.x], vA);
+								if (SHARD && slotA >= 0 && HaloLastOfSide(maskA, colour, slotA)) StoreRowSys(HaloOut(plan.shard, slotA, 0), vA);
 							}
 							if (dynB)
 							{
 								vB.w = __int_as_float(expB + 1);
 								StoreRow128(&d.vel[pre.sb.y], vB);
+								if (SHARD && slotB >= 0 && HaloLastOfSide(maskB, colour, slotB)) StoreRowSys(HaloOut(plan.shard, slotB, 0), vB);
 							}
 							done = true;
 						}
@@ -186,6 +284,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_FLOW_VEL_BLOCKS) Sol
 	// b2ContactSolver::StoreImpulses: every thread for the rows it solved (nobody else knows that they are final)
 	for (int op = 0; op < plan.opCount && !plan.debugSkipStore; ++op)
 	{
+		if (plan.opType[op] != OP_PARALLEL) continue;
 		const int begin = plan.opStart[op], n = plan.opSize[op];
 		for (int t = tid; t < n; t += stride) StoreImpulseOne(d, begin + t);
 	}
@@ -194,24 +293,32 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_FLOW_VEL_BLOCKS) Sol
 	{
 		const int b = base + tid;
 		bool done = b >= plan.bodyCount;
-		int expected = 0;
+		int expected = 0, slot = -1;
+		bool dynamic = false;
 		if (!done)
 		{
 			const uint32_t bf = d.bflags[b];
 			if (IsStatic(bf) || !(bf & B2CU_BODY_ISLAND)) done = true;
-			else expected = IsDynamic(bf) ? passIndex * __popc(d.colourMask[b]) : 0;
+			else
+			{
+				dynamic = IsDynamic(bf);
+				expected = base0 + (dynamic ? passIndex * __popc(d.colourMask[b]) : 0);
+				if (SHARD && dynamic) slot = d.haloSlot[b];
+			}
 		}
 		int spins = 0;
 		for (;;)
 		{
 			if (!done)
 			{
-				float4 v = LoadRow128(&d.vel[b]);
-				bool ready = !IsDynamic(d.bflags[b]) || __float_as_int(v.w) == expected;
+				float4 v;
+				bool ready = true;
+				if (dynamic) ready = FlowAcquire(plan.shard, d.vel, b, slot, 0, expected, &v);
+				else v = LoadRow128(&d.vel[b]);
 				if (!ready && FlowStuck(d, ++spins)) ready = true;
 				if (ready)
 				{
-					IntegratePositionRow(d, b, plan.h, v);
+					IntegratePositionRow(d, b, plan.h, v, plan.flowBase);
 					done = true;
 				}
 			}
@@ -223,37 +330,63 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_FLOW_VEL_BLOCKS) Sol
 // position iterations.  An island stops iterating once the smallest separation of its previous iteration is within
 // tolerance (b2Island.cpp:318-335): that is a property of the whole island, so iterations stay separated by a grid
 // barrier (3 per step); inside an iteration the colours flow.
+template <bool SHARD>
 __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPositionFlowKernel(DeviceArrays d, SolverPlan plan)
 {
-	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	GridSync grid = {plan.softBarrier, gridDim.x, 0u, plan.shard.stuck};
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
+	const int base0 = plan.flowBase;
 	for (int it = 0; it < plan.positionIterations; ++it)
 	{
 		for (int op = 0; op < plan.opCount; ++op)
 		{
+			if (plan.opType[op] != OP_PARALLEL) continue;
 			const int begin = plan.opStart[op], n = plan.opSize[op], colour = plan.opColour[op];
 			for (int base = 0; base < n; base += stride)
 			{
 				const int t = base + tid;
 				bool done = t >= n;
+				bool skip = false; // island done: no correction, but the halo bodies' versions still advance (see below)
 				PosPre pre;
-				int expA = 0, expB = 0, root = 0;
+				int expA = 0, expB = 0, root = 0, slotA = -1, slotB = -1;
+				uint32_t maskA = 0u, maskB = 0u;
 				bool dynA = false, dynB = false;
 				if (!done)
 				{
 					pre = LoadPosPre(d, begin + t);
 					root = __float_as_int(pre.rad.w);
-					// an island that is done was done in every later iteration too: its bodies' versions stand still and
-					// nobody waits for them (all constraints of a dynamic body belong to its island)
-					if (IslandDone(d, it, root, plan.bodyCount)) done = true;
+					dynA = pre.ms.x != 0.0f || pre.ms.y != 0.0f;
+					dynB = pre.ms.z != 0.0f || pre.ms.w != 0.0f;
+					if (SHARD)
+					{
+						if (dynA) slotA = d.haloSlot[pre.sb.x];
+						if (dynB) slotB = d.haloSlot[pre.sb.y];
+					}
+					// An island that is done was done in every later iteration too: its bodies' versions stand still and
+					// nobody of this shard waits for them (all constraints of a dynamic body belong to its island).  The
+					// NEIGHBOUR does wait for a halo body (its island is another one and may still iterate): a skipped
+					// constraint passes a halo body's row on unchanged, with the version it would have written.
+					if (IslandDone(d, it, root, plan.bodyCount))
+					{
+						skip = true;
+						dynA = dynA && slotA >= 0;
+						dynB = dynB && slotB >= 0;
+						if (!dynA && !dynB) done = true;
+					}
 				}
 				if (!done)
 				{
-					dynA = pre.ms.x != 0.0f || pre.ms.y != 0.0f;
-					dynB = pre.ms.z != 0.0f || pre.ms.w != 0.0f;
-					if (dynA) expA = FlowExpected(d.colourMask[pre.sb.x], colour, it);
-					if (dynB) expB = FlowExpected(d.colourMask[pre.sb.y], colour, it);
+					if (dynA)
+					{
+						maskA = d.colourMask[pre.sb.x];
+						expA = base0 + FlowExpected(maskA, colour, it);
+					}
+					if (dynB)
+					{
+						maskB = d.colourMask[pre.sb.y];
+						expB = base0 + FlowExpected(maskB, colour, it);
+					}
 				}
 				if (plan.flowPrefetch)
 				{
@@ -275,25 +408,34 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPo
 				{
 					if (!done)
 					{
-						float4 pA = LoadRow128(&d.pos[pre.sb.x]);
-						float4 pB = LoadRow128(&d.pos[pre.sb.y]);
-						bool ready = (!dynA || __float_as_int(pA.w) == expA) && (!dynB || __float_as_int(pB.w) == expB);
+						float4 pA, pB;
+						bool readyA = true, readyB = true;
+						if (dynA) readyA = FlowAcquire(plan.shard, d.pos, pre.sb.x, slotA, 1, expA, &pA);
+						else pA = LoadRow128(&d.pos[pre.sb.x]);
+						if (dynB) readyB = FlowAcquire(plan.shard, d.pos, pre.sb.y, slotB, 1, expB, &pB);
+						else pB = LoadRow128(&d.pos[pre.sb.y]);
+						bool ready = readyA && readyB;
 						if (!ready && FlowStuck(d, ++spins)) ready = true;
 						if (ready)
 						{
-							minSep = SolvePositionCore(pre, pA, pB);
+							if (!skip)
+							{
+								minSep = SolvePositionCore(pre, pA, pB);
+								solved = true;
+							}
 							if (dynA)
 							{
 								pA.w = __int_as_float(expA + 1);
 								StoreRow128(&d.pos[pre.sb.x], pA);
+								if (SHARD && slotA >= 0 && HaloLastOfSide(maskA, colour, slotA)) StoreRowSys(HaloOut(plan.shard, slotA, 1), pA);
 							}
 							if (dynB)
 							{
 								pB.w = __int_as_float(expB + 1);
 								StoreRow128(&d.pos[pre.sb.y], pB);
+								if (SHARD && slotB >= 0 && HaloLastOfSide(maskB, colour, slotB)) StoreRowSys(HaloOut(plan.shard, slotB, 1), pB);
 							}
 							done = true;
-							solved = true;
 						}
 					}
 					if (__all_sync(0xffffffffu, done)) break;
@@ -302,6 +444,65 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPo
 			}
 		}
 		if (it + 1 < plan.positionIterations) grid.sync();
+	}
+	if (SHARD)
+	{
+		// the halo bodies end the step with the row of whoever updated them last: the local one or the neighbour's push
+		const int nHalo = plan.shard.ghostCount + plan.shard.exportCount;
+		for (int base = 0; base < nHalo; base += stride)
+		{
+			const int k = base + tid;
+			bool done = k >= nHalo;
+			int b = 0, slot = -1, expected = 0;
+			if (!done)
+			{
+				b = k < plan.shard.ghostCount ? plan.shard.ghostIds[k] : plan.shard.exportIds[k - plan.shard.ghostCount];
+				slot = d.haloSlot[b];
+				const uint32_t bf = d.bflags[b];
+				if (!IsDynamic(bf) || !(bf & B2CU_BODY_ISLAND)) done = true;
+				else expected = base0 + plan.positionIterations * __popc(d.colourMask[b]);
+			}
+			int spins = 0;
+			for (;;)
+			{
+				if (!done)
+				{
+					float4 p;
+					bool ready = FlowAcquire(plan.shard, d.pos, b, slot, 1, expected, &p);
+					if (!ready && FlowStuck(d, ++spins)) ready = true;
+					if (ready)
+					{
+						StoreRow128(&d.pos[b], p);
+						done = true;
+					}
+				}
+				if (__all_sync(0xffffffffu, done)) break;
+			}
+		}
+	}
+}
+
+// Once per step, after the colouring: the halo bodies' colour masks of the two sides are united (own colours 0-15 on
+// the owner's side, cross colours 16-31 on the lower shard's side), so that both sides count a body's updates alike.
+__global__ void HaloMaskSendKernel(DeviceArrays d, ShardState sh)
+{
+	const int n = sh.ghostCount > sh.exportCount ? sh.ghostCount : sh.exportCount;
+	B2CU_GRID_STRIDE(k, n)
+	{
+		if (k < sh.exportCount && sh.lowerFromUpper != nullptr)
+			sh.lowerFromUpper[k] = make_float4(__uint_as_float(d.colourMask[sh.exportIds[k]] & 0xFFFFu), 0.f, 0.f, 0.f);
+		if (k < sh.ghostCount && sh.upperFromLower != nullptr)
+			sh.upperFromLower[k] = make_float4(__uint_as_float(d.colourMask[sh.ghostIds[k]] & 0xFFFF0000u), 0.f, 0.f, 0.f);
+	}
+	__threadfence_system();
+}
+__global__ void HaloMaskApplyKernel(DeviceArrays d, ShardState sh)
+{
+	const int n = sh.ghostCount > sh.exportCount ? sh.ghostCount : sh.exportCount;
+	B2CU_GRID_STRIDE(k, n)
+	{
+		if (k < sh.ghostCount) d.colourMask[sh.ghostIds[k]] |= __float_as_uint(__ldcv(&sh.fromUpper[k]).x) & 0xFFFFu;
+		if (k < sh.exportCount) d.colourMask[sh.exportIds[k]] |= __float_as_uint(__ldcv(&sh.fromLower[k]).x) & 0xFFFF0000u;
 	}
 }
 

@@ -105,6 +105,7 @@ struct DeviceArrays
 	int* islandMinSleep;  // per root: min sleepTime (float bits, non-negative)
 	int* islandMinSep;    // [positionIterations][root]: min separation of the iteration (ordered-int float)
 	uint32_t* colourMask; // per body: colours used by its constraints
+	int* haloSlot;        // per body: -1, or its slot in the halo lists (| B2CU_HALO_EXPORT for an export), sharded worlds
 	unsigned long long* colourClaim; // per body: (round << 32) | (~contact index), max wins
 
 	// ---- shape geometry table ----
@@ -234,6 +235,11 @@ struct b2cuWorld
 	bool peerLowerIpc, peerUpperIpc;
 	int peerUpperGhostCountOfUpper; // the upper neighbour's own ghostCount (layout of its mailbox)
 	unsigned shardSeq;     // sequence number of the next halo exchange
+	bool shardFlow;        // the shards use the dataflow solver (halo rows travel inside it) instead of the barrier kernels
+	uint32_t flowEpoch;    // steps taken: the dataflow versions of a step start at (flowEpoch & 0xFFF) << 19
+	int flowGridMax, flowGridPositionMax;
+	int shardFlowGrid, shardFlowGridPosition;
+	int flowBase;
 	bool shardSoftBarrier; // a neighbouring shard lives on this device: see GridSync
 	unsigned* softBarrierCounter;
 

@@ -163,6 +163,7 @@ std::vector<ArrayDesc> AllArrays(b2cuWorld* w)
 	v.push_back(Desc(&d->islandAwake, CAP_BODY));
 	v.push_back(Desc(&d->islandMinSleep, CAP_BODY));
 	v.push_back(Desc(&d->colourMask, CAP_BODY));
+	v.push_back(Desc(&d->haloSlot, CAP_BODY));
 	v.push_back(Desc(&d->colourClaim, CAP_BODY));
 	v.push_back(Desc(&d->shapes, CAP_SHAPE));
 	v.push_back(Desc(&d->fat, CAP_PROXY));
@@ -388,6 +389,13 @@ int ShardSyncGhosts(b2cuWorld* w)
 	{
 		LAUNCH(w, ShardWaitKernel, 1, 1, sh.flagFromUpper, seq, w->d.counters + CNT_FLOW_STUCK);
 		if (w->ghostCount > 0) LAUNCH(w, GhostApplyKernel, GridFor(w->ghostCount), kBlock, w->d, sh);
+	}
+	if (w->shardFlow)
+	{
+		// and the other way round: the upper neighbour may not begin its step (and push rows of it into this shard's
+		// mailbox) before this shard has finished with the rows of the last one
+		if (sh.upperFromLower != nullptr) LAUNCH(w, ShardSignalKernel, 1, 1, sh.upperFlagFromLower, seq);
+		if (sh.lowerFromUpper != nullptr) LAUNCH(w, ShardWaitKernel, 1, 1, sh.flagFromLower, seq, w->d.counters + CNT_FLOW_STUCK);
 	}
 	return B2CU_OK;
 }
@@ -838,10 +846,15 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		w->persistentGridMax = w->persistentGrid;
 		{
 			int perSmFlow = 0, perSmFlowPos = 0;
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlow, SolverVelocityFlowKernel, B2CU_SOLVER_THREADS, 0);
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowPos, SolverPositionFlowKernel, B2CU_SOLVER_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlow, SolverVelocityFlowKernel<false>, B2CU_SOLVER_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowPos, SolverPositionFlowKernel<false>, B2CU_SOLVER_THREADS, 0);
+			int perSmFlowS = 0, perSmFlowPosS = 0;
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowS, SolverVelocityFlowKernel<true>, B2CU_SOLVER_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowPosS, SolverPositionFlowKernel<true>, B2CU_SOLVER_THREADS, 0);
 			w->flowGrid = coop != 0 ? g_smCount * perSmFlow : 0;
 			w->flowGridPosition = coop != 0 ? g_smCount * perSmFlowPos : 0;
+			w->flowGridMax = coop != 0 ? g_smCount * perSmFlowS : 0;          // sharded instances
+			w->flowGridPositionMax = coop != 0 ? g_smCount * perSmFlowPosS : 0;
 		}
 		w->persistentGridPosition = g_smCount * perSmPos;
 		w->persistentGridPositionMax = w->persistentGridPosition;
@@ -1839,7 +1852,8 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 		cudaEventRecord(w->ev[4], w->stream);
 
 		// ---- b2Island::Solve ----
-		LAUNCH(w, IntegrateVelocitiesKernel, GridFor(nb), kBlock, d, nb, dt, w->params.gravity);
+		w->flowBase = (int)((w->flowEpoch++ & 0xFFFu) << 19);
+		LAUNCH(w, IntegrateVelocitiesKernel, GridFor(nb), kBlock, d, nb, dt, w->params.gravity, w->flowBase);
 		if (nConstraints > 0)
 		{
 			LAUNCH(w, ConstraintSlotKernel, GridFor(nConstraints), kBlock, d);
@@ -1919,22 +1933,43 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				const char* e = getenv("B2CU_FLOW");
 				return !(e && atoi(e) == 0);
 			}();
-			const bool flow = flowEnabled && nJoints == 0 && w->shardCount == 1 && w->overflowCount == 0 && nConstraints > 0 &&
-			                  w->flowGrid > 0 && w->flowGridPosition > 0;
-			const void* velocityKernel = flow ? (const void*)SolverVelocityFlowKernel
+			const bool sharded = w->shardCount > 1;
+			if (sharded && w->shardFlow && (nJoints > 0 || w->overflowCount > 0))
+				return SetError(w, B2CU_ERR_UNSUPPORTED, "a sharded world on the dataflow solver cannot have joints or a body with more "
+				                                         "constraints than colours (%d overflow constraints); B2CU_SHARD_FLOW=0 on every "
+				                                         "shard selects the barrier kernels", w->overflowCount);
+			const bool flow = sharded ? (w->shardFlow && w->flowGridMax > 0 && w->flowGridPositionMax > 0)
+			                          : (flowEnabled && nJoints == 0 && w->overflowCount == 0 && nConstraints > 0 && w->flowGrid > 0 &&
+			                             w->flowGridPosition > 0);
+			const void* velocityKernel = flow ? (sharded ? (const void*)SolverVelocityFlowKernel<true> : (const void*)SolverVelocityFlowKernel<false>)
 			                                  : nJoints > 0 ? (const void*)SolverVelocityPersistentKernel<true>
 			                                                : (const void*)SolverVelocityPersistentKernel<false>;
-			const void* positionKernel = flow ? (const void*)SolverPositionFlowKernel
+			const void* positionKernel = flow ? (sharded ? (const void*)SolverPositionFlowKernel<true> : (const void*)SolverPositionFlowKernel<false>)
 			                                  : nJoints > 0 ? (const void*)SolverPositionPersistentKernel<true>
 			                                                : (const void*)SolverPositionPersistentKernel<false>;
+			plan.flowBase = w->flowBase;
+			if (flow && sharded)
+			{
+				// unite the halo bodies' colour masks of the two sides (b2cu_solver_flow.cuh); rows [0, n) of the mailboxes
+				ShardState sh = plan.shard;
+				const unsigned seq = w->shardSeq++;
+				const int nHalo = std::max(w->ghostCount, w->exportCount);
+				if (nHalo > 0) LAUNCH(w, HaloMaskSendKernel, GridFor(nHalo), kBlock, d, sh);
+				if (sh.lowerFromUpper != nullptr) LAUNCH(w, ShardSignalKernel, 1, 1, sh.lowerFlagFromUpper, seq);
+				if (sh.upperFromLower != nullptr) LAUNCH(w, ShardSignalKernel, 1, 1, sh.upperFlagFromLower, seq);
+				if (sh.upperFromLower != nullptr) LAUNCH(w, ShardWaitKernel, 1, 1, sh.flagFromUpper, seq, w->d.counters + CNT_FLOW_STUCK);
+				if (sh.lowerFromUpper != nullptr) LAUNCH(w, ShardWaitKernel, 1, 1, sh.flagFromLower, seq, w->d.counters + CNT_FLOW_STUCK);
+				if (nHalo > 0) LAUNCH(w, HaloMaskApplyKernel, GridFor(nHalo), kBlock, d, sh);
+				plan.shard.seq = w->shardSeq;
+			}
 			int velocityGrid = nJoints > 0 ? std::min(w->persistentGrid, w->persistentGridJoints) : w->persistentGrid;
 			int positionGrid =
 			    nJoints > 0 ? std::min(w->persistentGridPosition, w->persistentGridPositionJoints) : w->persistentGridPosition;
 			if (flow)
 			{
 				// no barriers to keep cheap: the more threads, the fewer constraints each takes in sequence
-				velocityGrid = w->flowGrid;
-				positionGrid = w->flowGridPosition;
+				velocityGrid = sharded ? w->shardFlowGrid : w->flowGrid;
+				positionGrid = sharded ? w->shardFlowGridPosition : w->flowGridPosition;
 			}
 			else if (w->shardCount == 1)
 			{
@@ -1953,7 +1988,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				positionGrid = std::min(positionGrid, want);
 			}
 			// shards that share their device with a neighbour: ordinary launches + the kernels' own grid barrier (GridSync)
-			const bool soft = w->shardSoftBarrier && w->shardCount > 1 && !flow;
+			const bool soft = w->shardSoftBarrier && w->shardCount > 1;
 			auto launchSolver = [&](const void* kernel, int grid) -> cudaError_t {
 				if (!soft) return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(B2CU_SOLVER_THREADS), args, 0, w->stream);
 				cudaError_t e = cudaMemsetAsync(w->softBarrierCounter, 0, sizeof(unsigned), w->stream);
@@ -1965,7 +2000,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			++w->launches;
 			TraceMark(w, flow ? "SolverVelocityFlowKernel" : "SolverVelocityPersistentKernel");
 			if (plan.debugSkipStore == 2 && flow) LAUNCH(w, StoreImpulsesKernel, GridFor(nConstraints), kBlock, d);
-			if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)((warmStarting ? 1 : 0) + velocityIterations);
+			if (w->shardCount > 1 && !flow) w->shardSeq += 2u * (unsigned)((warmStarting ? 1 : 0) + velocityIterations);
 			plan.shard.seq = w->shardSeq;
 			cudaEventRecord(w->ev[6], w->stream);
 			if (positionIterations > 0)
@@ -1973,7 +2008,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				CUDA_TRY(w, launchSolver(positionKernel, positionGrid));
 				++w->launches;
 				TraceMark(w, flow ? "SolverPositionFlowKernel" : "SolverPositionPersistentKernel");
-				if (w->shardCount > 1) w->shardSeq += 2u * (unsigned)positionIterations;
+				if (w->shardCount > 1 && !flow) w->shardSeq += 2u * (unsigned)positionIterations;
 			}
 		}
 		else
@@ -2447,16 +2482,22 @@ int b2cuShardConfigure(b2cuWorld* w, int32_t rank, int32_t rankCount, int32_t gh
 	w->mailboxBytes = kMailboxHeader + MailboxFromUpperBytes(ghostCount) + MailboxFromLowerBytes(exportCount);
 	CUDA_TRY(w, cudaMalloc(&w->mailbox, w->mailboxBytes));
 	CUDA_TRY(w, cudaMemset(w->mailbox, 0, w->mailboxBytes));
-	if (gridFraction > 0.0f && gridFraction < 1.0f)
+	const float fraction = (gridFraction > 0.0f && gridFraction < 1.0f) ? gridFraction : 1.0f;
+	// several shards on one device (tests): their persistent kernels must be co-resident
+	w->persistentGrid = std::max(1, (int)(w->persistentGridMax * fraction));
+	w->persistentGridPosition = std::max(1, (int)(w->persistentGridPositionMax * fraction));
+	w->shardFlowGrid = std::max(1, (int)(w->flowGridMax * fraction));
+	w->shardFlowGridPosition = std::max(1, (int)(w->flowGridPositionMax * fraction));
 	{
-		// several shards on one device (tests): their cooperative kernels must be co-resident
-		w->persistentGrid = std::max(1, (int)(w->persistentGridMax * gridFraction));
-		w->persistentGridPosition = std::max(1, (int)(w->persistentGridPositionMax * gridFraction));
+		const char* e = getenv("B2CU_SHARD_FLOW");
+		w->shardFlow = rankCount > 1 && !(e && atoi(e) == 0);
 	}
-	else
+	// slot of every halo body in the mailboxes of the dataflow solver
 	{
-		w->persistentGrid = w->persistentGridMax;
-		w->persistentGridPosition = w->persistentGridPositionMax;
+		std::vector<int> slots((size_t)std::max(1, w->bodyCapacity), -1);
+		for (int i = 0; i < ghostCount; ++i) slots[(size_t)ghostBodies[i]] = i;
+		for (int i = 0; i < exportCount; ++i) slots[(size_t)exportBodies[i]] = i | 0x40000000;
+		CUDA_TRY(w, cudaMemcpy(w->d.haloSlot, slots.data(), sizeof(int) * (size_t)w->bodyCapacity, cudaMemcpyHostToDevice));
 	}
 	return B2CU_OK;
 }

@@ -66,9 +66,10 @@ def _shard_worlds(gpu, scene, rank_count, margin):
         w.load_state(bodies, shapes, proxies, contacts, inv_dt0=0.0)
         worlds.append(w)
         refs.append(r)
-    fraction = 1.0 if ndev >= rank_count else 0.9 / rank_count / ((rank_count + ndev - 1) // ndev) * rank_count / rank_count
-    if ndev < rank_count:
-        fraction = 0.9 / ((rank_count + ndev - 1) // ndev)
+    # share of the SMs per world when several shards sit on one device: two thirds of the device in all (the occupancy
+    # query promises three solver CTAs per SM, but side by side with another world's kernels only two fit reliably)
+    per_device = (rank_count + ndev - 1) // ndev
+    fraction = 1.0 if per_device == 1 else 0.6 / per_device
     b2shard.connect(worlds, plans, grid_fraction=fraction)
     return worlds, plans
 
