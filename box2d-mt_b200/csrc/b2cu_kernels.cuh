@@ -347,27 +347,26 @@ __global__ void __launch_bounds__(256) PackBodiesKernel(DeviceArrays d, int firs
 	}
 }
 
-#define B2CU_STATE_WORDS 16
+#define B2CU_STATE_WORDS 12
 static_assert(sizeof(b2cuBodyState) == B2CU_STATE_WORDS * 4, "b2cuBodyState layout");
 
-// device -> host direction: only the fields a step changes (b2cuBodyState, 64 bytes)
+// device -> host direction: only the fields a step changes and callers read (b2cuBodyState, 48 bytes)
 __global__ void __launch_bounds__(256) PackBodyStatesKernel(DeviceArrays d, int first, int count, float* __restrict__ out)
 {
-	__shared__ float sh[256 * (B2CU_STATE_WORDS + 1)]; // +1: the 16-word records would all hit the same banks
+	__shared__ float sh[256 * (B2CU_STATE_WORDS + 1)]; // +1: rows of a multiple of four words would collide in the banks
 	for (int tile = blockIdx.x; tile * 256 < count; tile += gridDim.x)
 	{
 		int r = tile * 256 + threadIdx.x;
 		if (r < count)
 		{
 			int b = first + r;
-			float4 xf = d.xf[b], pos = d.pos[b], pos0 = d.pos0[b], vel = d.vel[b];
+			float4 xf = d.xf[b], pos = d.pos[b], vel = d.vel[b];
 			float* s = sh + threadIdx.x * (B2CU_STATE_WORDS + 1);
 			s[0] = xf.x; s[1] = xf.y; s[2] = xf.z; s[3] = xf.w;
 			s[4] = pos.x; s[5] = pos.y; s[6] = pos.z;
-			s[7] = pos0.x; s[8] = pos0.y; s[9] = pos0.z; s[10] = pos0.w;
-			s[11] = vel.x; s[12] = vel.y; s[13] = vel.z;
-			s[14] = d.force[b].w;
-			s[15] = __uint_as_float(d.bflags[b]);
+			s[7] = vel.x; s[8] = vel.y; s[9] = vel.z;
+			s[10] = d.force[b].w;
+			s[11] = __uint_as_float(d.bflags[b]);
 		}
 		__syncthreads();
 		int n = min(256, count - tile * 256) * B2CU_STATE_WORDS;
@@ -407,6 +406,19 @@ __global__ void __launch_bounds__(256) UnpackBodiesKernel(DeviceArrays d, int fi
 			d.bflags[b] = flags;
 		}
 		__syncthreads();
+	}
+}
+
+// b2cuSetBodyForces: (fx, fy, torque) rows into the force column; the sleep timer in its fourth lane stays
+__global__ void SetBodyForcesKernel(DeviceArrays d, int first, int count, const float* __restrict__ in)
+{
+	B2CU_GRID_STRIDE(r, count)
+	{
+		float4 f = d.force[first + r];
+		f.x = in[3 * r];
+		f.y = in[3 * r + 1];
+		f.z = in[3 * r + 2];
+		d.force[first + r] = f;
 	}
 }
 
@@ -1686,6 +1698,9 @@ struct SolverPlan
 	int jointOpCount;
 	int jointOpStart[B2CU_MAX_JOINT_OPS], jointOpSize[B2CU_MAX_JOINT_OPS], jointOpSerial[B2CU_MAX_JOINT_OPS];
 	float dtRatio;
+	int ovStart, ovCount;  // dataflow kernels: rows of the serial overflow list (unsharded worlds)
+	const int* ovRank;     // [2 * ovCount]: overflow rows before row j on its body A / body B
+	const int* ovDeg;      // per body: its overflow rows
 	int flowBase;          // dataflow kernels: the versions of this step start at this value
 	unsigned* softBarrier; // counter of GridSync (zeroed before the launch); nullptr: cooperative launch
 	int flowPrefetch;   // dataflow kernels: L2 prefetch of the next round's rows (B2CU_FLOW_PREFETCH)

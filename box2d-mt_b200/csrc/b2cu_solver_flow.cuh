@@ -171,17 +171,49 @@ __device__ __forceinline__ bool FlowStuck(const DeviceArrays& d, int spins)
 }
 
 // version a constraint of colour `colour` must find on a body in its `passIndex`-th pass
-__device__ __forceinline__ int FlowExpected(uint32_t mask, int colour, int passIndex)
+__device__ __forceinline__ int FlowExpected(uint32_t mask, int colour, int passIndex, int extraDeg = 0)
 {
-	return passIndex * __popc(mask) + __popc(mask & ((1u << colour) - 1u));
+	return passIndex * (__popc(mask) + extraDeg) + __popc(mask & ((1u << colour) - 1u));
 }
 
+// Constraints that found no free colour (a body with more contacts than colours: the bullet box of Add Pair ploughing
+// through a thousand circles) come after the colours in every pass, in list order.  For the dataflow they are simply
+// further updates of their bodies: overflow row j is update number popcount(mask) + (overflow rows before j on that
+// body) of the pass, and a body's degree grows by its overflow rows.  FlowOverflowPrepKernel counts both.
+// keys[2j + side] = body << 32 | (2j + side) for the dynamic bodies of overflow row j (others: ~0, sorted to the end)
+__global__ void FlowOverflowKeysKernel(DeviceArrays d, int ovStart, int ovCount, uint64_t* __restrict__ keys)
+{
+	B2CU_GRID_STRIDE(j, ovCount)
+	{
+		const int4 sb = d.sBody[ovStart + j];
+		const float4 ms = d.sMass[ovStart + j];
+		const bool dynA = ms.x != 0.0f || ms.y != 0.0f, dynB = ms.z != 0.0f || ms.w != 0.0f;
+		keys[2 * j] = dynA ? (((uint64_t)(uint32_t)sb.x << 32) | (uint32_t)(2 * j)) : ~0ull;
+		keys[2 * j + 1] = dynB ? (((uint64_t)(uint32_t)sb.y << 32) | (uint32_t)(2 * j + 1)) : ~0ull;
+	}
+}
+// after the sort: the position of a key inside its body's run is the rank of that row on that body; the run length is
+// the body's extra degree
+__global__ void FlowOverflowRanksKernel(const uint64_t* __restrict__ keys, int n, int* __restrict__ ovRank, int* __restrict__ ovDeg)
+{
+	B2CU_GRID_STRIDE(p, n)
+	{
+		const uint64_t key = keys[p];
+		if (key == ~0ull) continue;
+		const uint64_t body = key >> 32;
+		const int first = LowerBound64(keys, n, body << 32);
+		ovRank[(int)(uint32_t)(key & 0xFFFFFFFFull)] = p - first;
+		if (p == first) ovDeg[(int)body] = LowerBound64(keys, n, (body + 1) << 32) - first;
+	}
+}
+
+// the serial overflow list of one velocity pass (kept out of line: its registers must not cost the main loop anything)
 // warm start + velocity iterations + impulse store + position integration
 #ifndef B2CU_FLOW_VEL_BLOCKS
 #define B2CU_FLOW_VEL_BLOCKS 4
 #endif
-template <bool SHARD>
-__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, SHARD ? 3 : B2CU_FLOW_VEL_BLOCKS) SolverVelocityFlowKernel(DeviceArrays d, SolverPlan plan)
+template <bool SHARD, bool OVERFLOW>
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, (SHARD || OVERFLOW) ? 3 : B2CU_FLOW_VEL_BLOCKS) SolverVelocityFlowKernel(const __grid_constant__ DeviceArrays d, const __grid_constant__ SolverPlan plan)
 {
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
@@ -193,9 +225,12 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, SHARD ? 3 : B2CU_FLOW_VEL
 	{
 		for (int op = 0; op < plan.opCount; ++op)
 		{
-			if (plan.opType[op] != OP_PARALLEL) continue; // (sharded plans carry the barrier kernels' halo ops too)
-			const int begin = plan.opStart[op], n = plan.opSize[op], colour = plan.opColour[op];
-			const int twoStart = d.colourTwoStart[colour];
+			// the overflow list (constraints that found no free colour) is one more op: its rows carry explicit ranks,
+			// and the rows of one body form a chain through the same versions (sharded plans also carry halo ops: skipped)
+			const bool overflowOp = OVERFLOW && plan.opType[op] == OP_SERIAL;
+			if (plan.opType[op] != OP_PARALLEL && !overflowOp) continue;
+			const int begin = plan.opStart[op], n = plan.opSize[op], colour = overflowOp ? 0 : plan.opColour[op];
+			const int twoStart = overflowOp ? 0x7FFFFFFF : d.colourTwoStart[colour];
 			for (int base = 0; base < n; base += stride) // warp-uniform trip count
 			{
 				const int t = base + tid;
@@ -206,19 +241,21 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, SHARD ? 3 : B2CU_FLOW_VEL
 				bool dynA = false, dynB = false;
 				if (!done)
 				{
-					pre = LoadVelPre(d, begin + t, begin + t >= twoStart);
+					pre = overflowOp ? LoadVelPre(d, begin + t) : LoadVelPre(d, begin + t, begin + t >= twoStart);
 					dynA = pre.ms.x != 0.0f || pre.ms.y != 0.0f;
 					dynB = pre.ms.z != 0.0f || pre.ms.w != 0.0f;
 					if (dynA)
 					{
 						maskA = d.colourMask[pre.sb.x];
-						expA = base0 + FlowExpected(maskA, colour, passIndex);
+						expA = base0 + (overflowOp ? passIndex * (__popc(maskA) + plan.ovDeg[pre.sb.x]) + __popc(maskA) + plan.ovRank[2 * t]
+						                           : FlowExpected(maskA, colour, passIndex, OVERFLOW ? plan.ovDeg[pre.sb.x] : 0));
 						if (SHARD) slotA = d.haloSlot[pre.sb.x];
 					}
 					if (dynB)
 					{
 						maskB = d.colourMask[pre.sb.y];
-						expB = base0 + FlowExpected(maskB, colour, passIndex);
+						expB = base0 + (overflowOp ? passIndex * (__popc(maskB) + plan.ovDeg[pre.sb.y]) + __popc(maskB) + plan.ovRank[2 * t + 1]
+						                           : FlowExpected(maskB, colour, passIndex, OVERFLOW ? plan.ovDeg[pre.sb.y] : 0));
 						if (SHARD) slotB = d.haloSlot[pre.sb.y];
 					}
 				}
@@ -284,7 +321,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, SHARD ? 3 : B2CU_FLOW_VEL
 	// b2ContactSolver::StoreImpulses: every thread for the rows it solved (nobody else knows that they are final)
 	for (int op = 0; op < plan.opCount && !plan.debugSkipStore; ++op)
 	{
-		if (plan.opType[op] != OP_PARALLEL) continue;
+		if (plan.opType[op] != OP_PARALLEL && !(OVERFLOW && plan.opType[op] == OP_SERIAL)) continue;
 		const int begin = plan.opStart[op], n = plan.opSize[op];
 		for (int t = tid; t < n; t += stride) StoreImpulseOne(d, begin + t);
 	}
@@ -302,7 +339,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, SHARD ? 3 : B2CU_FLOW_VEL
 			else
 			{
 				dynamic = IsDynamic(bf);
-				expected = base0 + (dynamic ? passIndex * __popc(d.colourMask[b]) : 0);
+				expected = base0 + (dynamic ? passIndex * (__popc(d.colourMask[b]) + (OVERFLOW ? plan.ovDeg[b] : 0)) : 0);
 				if (SHARD && dynamic) slot = d.haloSlot[b];
 			}
 		}
@@ -330,8 +367,8 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, SHARD ? 3 : B2CU_FLOW_VEL
 // position iterations.  An island stops iterating once the smallest separation of its previous iteration is within
 // tolerance (b2Island.cpp:318-335): that is a property of the whole island, so iterations stay separated by a grid
 // barrier (3 per step); inside an iteration the colours flow.
-template <bool SHARD>
-__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPositionFlowKernel(DeviceArrays d, SolverPlan plan)
+template <bool SHARD, bool OVERFLOW>
+__global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPositionFlowKernel(const __grid_constant__ DeviceArrays d, const __grid_constant__ SolverPlan plan)
 {
 	GridSync grid = {plan.softBarrier, gridDim.x, 0u, plan.shard.stuck};
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,8 +378,9 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPo
 	{
 		for (int op = 0; op < plan.opCount; ++op)
 		{
-			if (plan.opType[op] != OP_PARALLEL) continue;
-			const int begin = plan.opStart[op], n = plan.opSize[op], colour = plan.opColour[op];
+			const bool overflowOp = OVERFLOW && plan.opType[op] == OP_SERIAL;
+			if (plan.opType[op] != OP_PARALLEL && !overflowOp) continue;
+			const int begin = plan.opStart[op], n = plan.opSize[op], colour = overflowOp ? 0 : plan.opColour[op];
 			for (int base = 0; base < n; base += stride)
 			{
 				const int t = base + tid;
@@ -380,12 +418,14 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPo
 					if (dynA)
 					{
 						maskA = d.colourMask[pre.sb.x];
-						expA = base0 + FlowExpected(maskA, colour, it);
+						expA = base0 + (overflowOp ? it * (__popc(maskA) + plan.ovDeg[pre.sb.x]) + __popc(maskA) + plan.ovRank[2 * t]
+						                           : FlowExpected(maskA, colour, it, OVERFLOW ? plan.ovDeg[pre.sb.x] : 0));
 					}
 					if (dynB)
 					{
 						maskB = d.colourMask[pre.sb.y];
-						expB = base0 + FlowExpected(maskB, colour, it);
+						expB = base0 + (overflowOp ? it * (__popc(maskB) + plan.ovDeg[pre.sb.y]) + __popc(maskB) + plan.ovRank[2 * t + 1]
+						                           : FlowExpected(maskB, colour, it, OVERFLOW ? plan.ovDeg[pre.sb.y] : 0));
 					}
 				}
 				if (plan.flowPrefetch)

@@ -278,6 +278,8 @@ struct b2cuWorld
 	size_t queryScratchBytes;
 	void* queryHost;     // page-locked host side of the same
 	size_t queryHostBytes;
+	bool eventPrefetch;        // b2cuSetEventPrefetch
+	bool eventCachePending;    // the copy of the event records into queryHost was started by the step itself
 	bool eventCacheValid;      // queryHost holds the keys + records of the last step's events
 	size_t eventCacheKeyBytes;
 	// joints (b2cuSetJoints)

@@ -846,11 +846,11 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		w->persistentGridMax = w->persistentGrid;
 		{
 			int perSmFlow = 0, perSmFlowPos = 0;
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlow, SolverVelocityFlowKernel<false>, B2CU_SOLVER_THREADS, 0);
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowPos, SolverPositionFlowKernel<false>, B2CU_SOLVER_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlow, SolverVelocityFlowKernel<false, false>, B2CU_SOLVER_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowPos, SolverPositionFlowKernel<false, false>, B2CU_SOLVER_THREADS, 0);
 			int perSmFlowS = 0, perSmFlowPosS = 0;
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowS, SolverVelocityFlowKernel<true>, B2CU_SOLVER_THREADS, 0);
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowPosS, SolverPositionFlowKernel<true>, B2CU_SOLVER_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowS, SolverVelocityFlowKernel<true, false>, B2CU_SOLVER_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFlowPosS, SolverPositionFlowKernel<true, false>, B2CU_SOLVER_THREADS, 0);
 			w->flowGrid = coop != 0 ? g_smCount * perSmFlow : 0;
 			w->flowGridPosition = coop != 0 ? g_smCount * perSmFlowPos : 0;
 			w->flowGridMax = coop != 0 ? g_smCount * perSmFlowS : 0;          // sharded instances
@@ -1548,6 +1548,7 @@ static int FinishMirrorCopy(b2cuWorld* w)
 }
 
 static int EnsureQueryScratch(b2cuWorld* w, size_t bytes);
+static int IssueEventRecords(b2cuWorld* w, bool* issued);
 
 int b2cuSetPreSolveHook(b2cuWorld* w, b2cuPreSolveFn fn, void* user)
 {
@@ -1628,6 +1629,38 @@ int b2cuGetBodyStates(b2cuWorld* w, int32_t first, int32_t count, b2cuBodyState*
 	float* stage = w->bodyStage + (size_t)first * B2CU_STATE_WORDS;
 	LAUNCH(w, PackBodyStatesKernel, GridFor(count), kBlock, w->d, first, count, stage);
 	CUDA_TRY(w, cudaMemcpyAsync(states, stage, sizeof(b2cuBodyState) * (size_t)count, cudaMemcpyDeviceToHost, w->stream));
+	return SyncCheck(w);
+}
+
+int b2cuGetBodySweepStarts(b2cuWorld* w, int32_t first, int32_t count, b2cuSweepStart* starts)
+{
+	int rc = CheckRange(w, first, count, w ? w->bodyCount : 0, starts);
+	if (rc) return rc;
+	if (count == 0) return B2CU_OK;
+	cudaSetDevice(w->device);
+	// the column is stored as (c0.x, c0.y, a0, alpha0) rows already
+	static_assert(sizeof(b2cuSweepStart) == sizeof(float4), "b2cuSweepStart layout");
+	CUDA_TRY(w, cudaMemcpyAsync(starts, w->d.pos0 + first, sizeof(float4) * (size_t)count, cudaMemcpyDeviceToHost, w->stream));
+	return SyncCheck(w);
+}
+
+int b2cuSetEventPrefetch(b2cuWorld* w, int32_t on)
+{
+	if (!w) return B2CU_ERR_ARGUMENT;
+	w->eventPrefetch = on != 0;
+	return B2CU_OK;
+}
+
+int b2cuSetBodyForces(b2cuWorld* w, int32_t first, int32_t count, const float* forces)
+{
+	int rc = CheckRange(w, first, count, w ? w->bodyCount : 0, forces);
+	if (rc) return rc;
+	if (count == 0) return B2CU_OK;
+	cudaSetDevice(w->device);
+	if ((rc = EnsureBodyStage(w))) return rc;
+	float* stage = w->bodyStage + (size_t)first * 3;
+	CUDA_TRY(w, cudaMemcpyAsync(stage, forces, sizeof(float) * 3 * (size_t)count, cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(w, SetBodyForcesKernel, GridFor(count), kBlock, w->d, first, count, (const float*)stage);
 	return SyncCheck(w);
 }
 
@@ -1939,12 +1972,42 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 				                                         "constraints than colours (%d overflow constraints); B2CU_SHARD_FLOW=0 on every "
 				                                         "shard selects the barrier kernels", w->overflowCount);
 			const bool flow = sharded ? (w->shardFlow && w->flowGridMax > 0 && w->flowGridPositionMax > 0)
-			                          : (flowEnabled && nJoints == 0 && w->overflowCount == 0 && nConstraints > 0 && w->flowGrid > 0 &&
-			                             w->flowGridPosition > 0);
-			const void* velocityKernel = flow ? (sharded ? (const void*)SolverVelocityFlowKernel<true> : (const void*)SolverVelocityFlowKernel<false>)
+			                          : (flowEnabled && nJoints == 0 && nConstraints > 0 && w->flowGrid > 0 && w->flowGridPosition > 0);
+			plan.ovStart = plan.ovCount = 0;
+			plan.ovRank = nullptr;
+			plan.ovDeg = nullptr;
+			if (flow && !sharded && w->overflowCount > 0)
+			{
+				// the overflow list inside the dataflow: rank of every row on its two bodies (its place in the body's chain)
+				// and the bodies' extra degree, by sorting (body, row) keys
+				plan.ovStart = colourStart[B2CU_MAX_COLOURS];
+				plan.ovCount = w->colourCounts[B2CU_MAX_COLOURS];
+				plan.ovRank = d.listC;
+				plan.ovDeg = d.islandAwake; // free once the islands are marked
+				const int nKeys = 2 * plan.ovCount;
+				if (nKeys > w->contactCapacity)
+					return SetError(w, B2CU_ERR_CAPACITY, "overflow list of %d constraints exceeds the scratch (contact capacity %d)",
+					                plan.ovCount, w->contactCapacity);
+				CUDA_TRY(w, cudaMemsetAsync(d.islandAwake, 0, sizeof(int) * (size_t)nb, w->stream));
+				LAUNCH(w, FlowOverflowKeysKernel, GridFor(plan.ovCount), kBlock, d, plan.ovStart, plan.ovCount, d.toiListKeys);
+				{
+					int bitsRow = 1, bitsBody = 1;
+					while ((1 << bitsRow) < std::max(2, nKeys)) ++bitsRow;
+					while ((1 << bitsBody) < std::max(2, nb)) ++bitsBody;
+					RadixSort64(&w->prims, d.toiListKeys, nKeys, 0, bitsRow, w->stream);
+					RadixSort64(&w->prims, d.toiListKeys, nKeys, 32, 32 + bitsBody + 1, w->stream); // +1: the ~0 keys sort last
+				}
+				LAUNCH(w, FlowOverflowRanksKernel, GridFor(nKeys), kBlock, (const uint64_t*)d.toiListKeys, nKeys, d.listC, d.islandAwake);
+			}
+			const bool ov = flow && !sharded && w->overflowCount > 0;
+			const void* velocityKernel = flow ? (sharded ? (const void*)SolverVelocityFlowKernel<true, false>
+			                                             : ov ? (const void*)SolverVelocityFlowKernel<false, true>
+			                                                  : (const void*)SolverVelocityFlowKernel<false, false>)
 			                                  : nJoints > 0 ? (const void*)SolverVelocityPersistentKernel<true>
 			                                                : (const void*)SolverVelocityPersistentKernel<false>;
-			const void* positionKernel = flow ? (sharded ? (const void*)SolverPositionFlowKernel<true> : (const void*)SolverPositionFlowKernel<false>)
+			const void* positionKernel = flow ? (sharded ? (const void*)SolverPositionFlowKernel<true, false>
+			                                             : ov ? (const void*)SolverPositionFlowKernel<false, true>
+			                                                  : (const void*)SolverPositionFlowKernel<false, false>)
 			                                  : nJoints > 0 ? (const void*)SolverPositionPersistentKernel<true>
 			                                                : (const void*)SolverPositionPersistentKernel<false>;
 			plan.flowBase = w->flowBase;
@@ -1968,7 +2031,7 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 			if (flow)
 			{
 				// no barriers to keep cheap: the more threads, the fewer constraints each takes in sequence
-				velocityGrid = sharded ? w->shardFlowGrid : w->flowGrid;
+				velocityGrid = sharded ? w->shardFlowGrid : ov ? std::min(w->flowGrid, w->flowGridMax) : w->flowGrid;
 				positionGrid = sharded ? w->shardFlowGridPosition : w->flowGridPosition;
 			}
 			else if (w->shardCount == 1)
@@ -2109,6 +2172,15 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	cudaEvent_t evEnd = w->ev[9];
 	cudaEventRecord(evEnd, w->stream);
 
+	// a listener will want the contacts of the step's events: gather them and start their way to the host now, behind
+	// the step's own work, instead of in a round trip of its own afterwards (events of time-of-impact sub-steps refer
+	// to contacts as they are at the very end and are fetched on request)
+	w->eventCachePending = false;
+	if (w->eventPrefetch && (w->beginCount > 0 || w->endCount > 0))
+	{
+		if ((rc = IssueEventRecords(w, &w->eventCachePending))) return rc;
+	}
+
 	if (w->mirrorInFlight)
 	{
 		if ((rc = ReadCounters(w))) return rc;
@@ -2116,6 +2188,12 @@ int b2cuStep(b2cuWorld* w, float dt, int32_t velocityIterations, int32_t positio
 	else
 	{
 		if ((rc = SyncCheck(w))) return rc;
+	}
+	if (w->eventCachePending)
+	{
+		// the step stream has been synchronised above: the records are on the host
+		w->eventCacheValid = true;
+		w->eventCachePending = false;
 	}
 	if ((rc = FinishMirrorCopy(w))) return rc;
 	if (w->toiSubSteps > 0 && w->bodyMirror != nullptr && std::min(w->bodyMirrorCount, w->bodyCount) > 0)
@@ -2275,16 +2353,13 @@ static int EnsureQueryHost(b2cuWorld* w, size_t bytes)
 
 // keys and contact records of ALL events of the last step, fetched in one round trip on the first request and
 // kept in the page-locked scratch: [begin | end (Update) | end (Destroy)] keys, then the records in the same order
-static int FetchEventRecords(b2cuWorld* w)
+// device half: gather + copy started on the step stream, no synchronisation
+static int IssueEventRecords(b2cuWorld* w, bool* issued)
 {
-	if (w->eventCacheValid) return B2CU_OK;
+	*issued = false;
 	const int nB = w->beginCount, nE = w->endUpdateCount, nD = w->endCount - w->endUpdateCount;
 	const int n = nB + nE + nD;
-	if (n == 0)
-	{
-		w->eventCacheValid = true;
-		return B2CU_OK;
-	}
+	if (n == 0) return B2CU_OK;
 	const size_t keyBytes = (sizeof(uint64_t) * (size_t)n + 255) & ~(size_t)255;
 	const size_t total = keyBytes + sizeof(b2cuContact) * (size_t)n;
 	int rc;
@@ -2300,8 +2375,18 @@ static int FetchEventRecords(b2cuWorld* w)
 		                            w->stream));
 	LAUNCH(w, GatherContactsByKeyKernel, GridFor(n), kBlock, w->d, w->contactCount, w->mainCount, (const uint64_t*)dKeys, n, dOut);
 	CUDA_TRY(w, cudaMemcpyAsync(w->queryHost, w->queryScratch, total, cudaMemcpyDeviceToHost, w->stream));
-	if ((rc = SyncCheck(w))) return rc;
 	w->eventCacheKeyBytes = keyBytes;
+	*issued = true;
+	return B2CU_OK;
+}
+
+static int FetchEventRecords(b2cuWorld* w)
+{
+	if (w->eventCacheValid) return B2CU_OK;
+	bool issued = false;
+	int rc = IssueEventRecords(w, &issued);
+	if (rc) return rc;
+	if (issued && (rc = SyncCheck(w))) return rc;
 	w->eventCacheValid = true;
 	return B2CU_OK;
 }

@@ -52,9 +52,9 @@ struct b2BodyView
 	float &px, &py, &qs, &qc, &cx, &cy, &a, &c0x, &c0y, &a0, &alpha0, &vx, &vy, &w, &sleepTime;
 	uint32_t& flags;
 	float &lcx, &lcy, &fx, &fy, &torque, &invMass, &invI, &linearDamping, &angularDamping, &gravityScale;
-	b2BodyView(b2cuBodyState& s, b2BodyProps& p)
-		: px(s.px), py(s.py), qs(s.qs), qc(s.qc), cx(s.cx), cy(s.cy), a(s.a), c0x(s.c0x), c0y(s.c0y), a0(s.a0),
-		  alpha0(s.alpha0), vx(s.vx), vy(s.vy), w(s.w), sleepTime(s.sleepTime), flags(s.flags), lcx(p.lcx), lcy(p.lcy),
+	b2BodyView(b2cuBodyState& s, b2cuSweepStart& z, b2BodyProps& p)
+		: px(s.px), py(s.py), qs(s.qs), qc(s.qc), cx(s.cx), cy(s.cy), a(s.a), c0x(z.c0x), c0y(z.c0y), a0(z.a0),
+		  alpha0(z.alpha0), vx(s.vx), vy(s.vy), w(s.w), sleepTime(s.sleepTime), flags(s.flags), lcx(p.lcx), lcy(p.lcy),
 		  fx(p.fx), fy(p.fy), torque(p.torque), invMass(p.invMass), invI(p.invI), linearDamping(p.linearDamping),
 		  angularDamping(p.angularDamping), gravityScale(p.gravityScale)
 	{
@@ -153,11 +153,16 @@ private:
 
 	// host mirror of the device state
 	b2BodyStateArray m_states;            // device-written part of the bodies (the step's body mirror)
+	std::vector<b2cuSweepStart> m_sweepStarts; // sweep starts of the bodies (see RefreshSweepStarts)
+	mutable bool m_sweepStartsStale;
 	std::vector<b2BodyProps> m_props;     // host-written part
 	std::vector<int32> m_forced;          // bodies with a non-zero force/torque on the host side
 	std::vector<b2cuBody, b2MirrorAllocator<b2cuBody> > m_uploadRows; // page-locked staging of the dirty rows
 	mutable std::vector<b2cuBody> m_records; // whole records, assembled on request (GetBodyStates)
-	b2BodyView BodyView(int32 i) { return b2BodyView(m_states[i], m_props[i]); }
+	b2BodyView BodyView(int32 i) { return b2BodyView(m_states[i], m_sweepStarts[i], m_props[i]); }
+	/// m_sweep.c0 / a0 / alpha0 of the bodies: device-owned, not part of the step's mirror; current only after this call.
+	/// Every host code path that reads or writes them (SetTransform, SetType, mass data, ShiftOrigin, row uploads) makes it.
+	void RefreshSweepStarts() const;
 	std::vector<b2Body*> m_bodies;
 	b2ProxyStateArray m_proxies;
 	std::vector<b2Fixture*> m_fixtures;
@@ -193,6 +198,13 @@ private:
 	bool m_fullUpload;            // everything (including the contact set) must be re-sent
 	int32 m_bodiesUploaded, m_proxiesUploaded, m_shapesUploaded;
 	int32 m_bodyDirtyLo, m_bodyDirtyHi, m_proxyDirtyLo, m_proxyDirtyHi;
+	int32 m_forceDirtyLo, m_forceDirtyHi; // rows whose force / torque alone changed (b2Body::ApplyForce on awake bodies)
+	std::vector<float> m_forceRows;       // staging of b2cuSetBodyForces
+	// event dispatch scratch, kept between steps (growing only: no allocation, no construction per step)
+	std::vector<b2cuContactKey> m_eventKeys[2];
+	std::vector<b2cuContact> m_eventRecs[2];
+	std::vector<b2Contact> m_eventContacts[2];
+	std::vector<char> m_eventDeferred[2];
 	mutable bool m_bodiesStale, m_proxiesStale;
 	bool m_contactsStale;
 	std::vector<b2cuContact> m_contactRecords;

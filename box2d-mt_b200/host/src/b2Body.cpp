@@ -301,6 +301,7 @@ void b2Body::SetType(b2BodyType type)
 {
 	if (m_world->IsLocked() || type == GetType()) return;
 	m_world->RefreshBodies();
+	m_world->RefreshSweepStarts();
 	{
 		b2BodyView s = B2_STATE();
 		s.flags = (s.flags & ~(uint32)B2CU_BODY_TYPE_MASK) | (uint32)type;
@@ -345,6 +346,7 @@ void b2Body::SetTransform(const b2Vec2& position, float32 angle)
 {
 	if (m_world->IsLocked()) return;
 	m_world->RefreshBodies();
+	m_world->RefreshSweepStarts();
 	b2BodyView s = B2_STATE();
 	b2Transform xf;
 	xf.q.Set(angle);
@@ -409,6 +411,7 @@ void b2Body::SynchronizeProxies(const b2Transform& xf1, const b2Transform& xf2)
 void b2Body::ResetMassData()
 {
 	m_world->RefreshBodies();
+	m_world->RefreshSweepStarts();
 	if (m_jointList)
 	{
 		// a mouse joint's row carries this body's mass
@@ -480,6 +483,7 @@ void b2Body::SetMassData(const b2MassData* massData)
 {
 	if (m_world->IsLocked() || GetType() != b2_dynamicBody) return;
 	m_world->RefreshBodies();
+	m_world->RefreshSweepStarts();
 	b2BodyView s = B2_STATE();
 	s.invMass = 0.0f;
 	m_I = 0.0f;

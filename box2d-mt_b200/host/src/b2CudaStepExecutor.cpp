@@ -33,6 +33,7 @@ b2CudaStepExecutor::~b2CudaStepExecutor()
 	{
 		// the world keeps its host mirror; a later step with another executor re-uploads everything
 		it->first->RefreshBodies();
+		it->first->RefreshSweepStarts();
 		it->first->RefreshProxies();
 		it->first->RefreshJoints();
 		it->first->m_contactsStale = true;
@@ -149,6 +150,7 @@ bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 veloc
 	{
 		// last stepped by another executor: take the world over (its state comes back through the host mirror)
 		world.RefreshBodies();
+		world.RefreshSweepStarts();
 		world.RefreshProxies();
 		world.RefreshJoints();
 		world.m_contactsStale = true;
@@ -181,6 +183,8 @@ bool b2CudaStepExecutor::StepWorld(b2World& world, float32 timeStep, int32 veloc
 	if (rc == B2CU_OK)
 		rc = b2cuSetPreSolveHook(device, (m_options.reportPreSolve && world.m_contactListener) ? &b2World::PreSolveThunk : nullptr,
 		                         &world);
+	// a listener will be handed the contacts of the step's events: let the step bring their records along
+	if (rc == B2CU_OK) rc = b2cuSetEventPrefetch(device, (m_options.dispatchEvents && world.m_contactListener) ? 1 : 0);
 	if (rc == B2CU_OK) rc = b2cuStep(device, timeStep, velocityIterations, positionIterations, &impl->info);
 	Clock::time_point t2 = Clock::now();
 	m_hostMs[0] = std::chrono::duration<float, std::milli>(t1 - t0).count();

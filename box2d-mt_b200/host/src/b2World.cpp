@@ -100,9 +100,9 @@ void b2Contact::GetWorldManifold(b2WorldManifold* worldManifold) const
 // ---- construction ---------------------------------------------------------------------------------------
 
 b2World::b2World(const b2Vec2& gravity)
-	: m_device(nullptr), m_owner(nullptr), m_fullUpload(false), m_bodiesUploaded(0), m_proxiesUploaded(0),
+	: m_sweepStartsStale(false), m_device(nullptr), m_owner(nullptr), m_fullUpload(false), m_bodiesUploaded(0), m_proxiesUploaded(0),
 	  m_shapesUploaded(0), m_bodyDirtyLo(INT32_MAX), m_bodyDirtyHi(-1), m_proxyDirtyLo(INT32_MAX), m_proxyDirtyHi(-1),
-	  m_bodiesStale(false), m_proxiesStale(false), m_contactsStale(true), m_jointList(nullptr), m_jointsDirty(false),
+	  m_forceDirtyLo(INT32_MAX), m_forceDirtyHi(-1), m_bodiesStale(false), m_proxiesStale(false), m_contactsStale(true), m_jointList(nullptr), m_jointsDirty(false),
 	  m_jointsStale(false), m_bodyList(nullptr), m_bodyCount(0),
 	  m_contactCount(0), m_gravity(gravity), m_allowSleep(true), m_warmStarting(true), m_continuousPhysics(true),
 	  m_subStepping(false), m_clearForces(true), m_locked(false), m_newFixture(false), m_inv_dt0(0.0f),
@@ -172,10 +172,11 @@ b2Body* b2World::CreateBody(const b2BodyDef* def)
 	}
 	{
 		b2cuBodyState st;
+		b2cuSweepStart z;
 		b2BodyProps pr;
 		st.px = s.px; st.py = s.py; st.qs = s.qs; st.qc = s.qc;
 		st.cx = s.cx; st.cy = s.cy; st.a = s.a;
-		st.c0x = s.c0x; st.c0y = s.c0y; st.a0 = s.a0; st.alpha0 = s.alpha0;
+		z.c0x = s.c0x; z.c0y = s.c0y; z.a0 = s.a0; z.alpha0 = s.alpha0;
 		st.vx = s.vx; st.vy = s.vy; st.w = s.w;
 		st.sleepTime = s.sleepTime;
 		st.flags = s.flags;
@@ -184,6 +185,7 @@ b2Body* b2World::CreateBody(const b2BodyDef* def)
 		pr.invMass = s.invMass; pr.invI = s.invI;
 		pr.linearDamping = s.linearDamping; pr.angularDamping = s.angularDamping; pr.gravityScale = s.gravityScale;
 		m_states.push_back(st);
+		m_sweepStarts.push_back(z);
 		m_props.push_back(pr);
 	}
 	m_bodies.push_back(b);
@@ -258,7 +260,9 @@ void b2World::MarkBodyDirty(int32 index)
 
 void b2World::MarkBodyForced(int32 index)
 {
-	MarkBodyDirty(index);
+	// only m_force / m_torque of the row changed: it travels as 12 bytes (b2cuSetBodyForces), not as a whole record
+	m_forceDirtyLo = std::min(m_forceDirtyLo, index);
+	m_forceDirtyHi = std::max(m_forceDirtyHi, index);
 	m_forced.push_back(index);
 }
 
@@ -296,6 +300,7 @@ void b2World::ClearForces()
 const b2cuBody* b2World::GetBodyStates() const
 {
 	RefreshBodies();
+	RefreshSweepStarts();
 	b2World* self = const_cast<b2World*>(this);
 	m_records.resize(m_states.size());
 	for (size_t i = 0; i < m_states.size(); ++i) self->BodyView((int32)i).ToRecord(&m_records[i]);
@@ -317,6 +322,15 @@ void b2World::RefreshBodies() const
 	int32 n = std::min(m_bodiesUploaded, (int32)m_states.size());
 	if (n > 0) b2cuGetBodyStates(m_device, 0, n, self->m_states.data());
 	m_bodiesStale = false;
+}
+
+void b2World::RefreshSweepStarts() const
+{
+	if (!m_sweepStartsStale || m_device == nullptr) return;
+	b2World* self = const_cast<b2World*>(this);
+	int32 n = std::min(m_bodiesUploaded, (int32)m_sweepStarts.size());
+	if (n > 0) b2cuGetBodySweepStarts(m_device, 0, n, self->m_sweepStarts.data());
+	m_sweepStartsStale = false;
 }
 
 void b2World::RefreshJoints() const
@@ -510,6 +524,7 @@ b2Contact* b2World::GetContactList()
 void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vector<int32>& bodyIds)
 {
 	RefreshBodies();
+	RefreshSweepStarts();
 	RefreshProxies();
 	// contact records as they are on the device
 	m_contactsStale = true;
@@ -566,6 +581,7 @@ void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vecto
 		if (!deadBody[i])
 		{
 			m_states[nb] = m_states[i];
+			m_sweepStarts[nb] = m_sweepStarts[i];
 			m_props[nb] = m_props[i];
 			m_bodies[nb] = m_bodies[i];
 			m_bodies[nb]->m_index = nb;
@@ -573,6 +589,7 @@ void b2World::RemoveProxies(const std::vector<int32>& proxyIds, const std::vecto
 		}
 	}
 	m_states.resize(nb);
+	m_sweepStarts.resize(nb);
 	m_props.resize(nb);
 	m_bodies.resize(nb);
 	{
@@ -766,13 +783,14 @@ void b2World::ShiftOrigin(const b2Vec2& newOrigin)
 {
 	if (IsLocked()) return;
 	RefreshBodies();
+	RefreshSweepStarts();
 	RefreshProxies();
 	for (size_t i = 0; i < m_states.size(); ++i)
 	{
 		b2cuBodyState& s = m_states[i];
 		s.px -= newOrigin.x; s.py -= newOrigin.y;
 		s.cx -= newOrigin.x; s.cy -= newOrigin.y;
-		s.c0x -= newOrigin.x; s.c0y -= newOrigin.y;
+		m_sweepStarts[i].c0x -= newOrigin.x; m_sweepStarts[i].c0y -= newOrigin.y;
 	}
 	for (size_t i = 0; i < m_proxies.size(); ++i)
 	{
@@ -841,10 +859,29 @@ int32 b2World::UploadDirty(b2cuWorld* device)
 		if (nb == m_bodiesUploaded) hi = m_bodyDirtyHi;
 		if (lo <= hi)
 		{
-			// whole records of the range, assembled from the two halves of the host mirror
+			// whole records of the range, assembled from the parts of the host mirror; the sweep starts are the device's
+			RefreshSweepStarts();
 			if (m_uploadRows.size() < (size_t)(hi - lo + 1)) m_uploadRows.resize((size_t)(hi - lo + 1));
 			for (int32 i = lo; i <= hi; ++i) BodyView(i).ToRecord(&m_uploadRows[(size_t)(i - lo)]);
 			if ((rc = b2cuSetBodies(device, lo, hi - lo + 1, m_uploadRows.data()))) return rc;
+		}
+	}
+	if (m_forceDirtyHi >= 0)
+	{
+		// applied forces of rows that were not uploaded as a whole above
+		const int32 flo = m_forceDirtyLo, fhi = std::min(m_forceDirtyHi, nb - 1);
+		if (flo <= fhi)
+		{
+			const size_t n = (size_t)(fhi - flo + 1);
+			if (m_forceRows.size() < 3 * n) m_forceRows.resize(3 * n);
+			for (size_t i = 0; i < n; ++i)
+			{
+				const b2BodyProps& pr = m_props[(size_t)flo + i];
+				m_forceRows[3 * i] = pr.fx;
+				m_forceRows[3 * i + 1] = pr.fy;
+				m_forceRows[3 * i + 2] = pr.torque;
+			}
+			if ((rc = b2cuSetBodyForces(device, flo, (int32)n, m_forceRows.data()))) return rc;
 		}
 	}
 	lo = std::min(m_proxyDirtyLo, m_proxiesUploaded);
@@ -876,8 +913,8 @@ int32 b2World::UploadDirty(b2cuWorld* device)
 	m_bodiesUploaded = nb;
 	m_proxiesUploaded = np;
 	m_shapesUploaded = ns;
-	m_bodyDirtyLo = m_proxyDirtyLo = INT32_MAX;
-	m_bodyDirtyHi = m_proxyDirtyHi = -1;
+	m_bodyDirtyLo = m_proxyDirtyLo = m_forceDirtyLo = INT32_MAX;
+	m_bodyDirtyHi = m_proxyDirtyHi = m_forceDirtyHi = -1;
 	m_newFixture = false;
 	return 0;
 }
@@ -906,18 +943,23 @@ void b2World::DispatchEvents(b2cuWorld* device)
 	typedef std::chrono::steady_clock Clock;
 	Clock::time_point t0 = Clock::now();
 	double queryMs = 0.0, makeMs = 0.0;
-	std::vector<b2cuContactKey> keys[2];
-	std::vector<b2cuContact> recs[2];
-	std::vector<b2Contact> contacts[2];
-	std::vector<char> deferred[2];
+	std::vector<b2cuContactKey>* keys = m_eventKeys;
+	std::vector<b2cuContact>* recs = m_eventRecs;
+	std::vector<b2Contact>* contacts = m_eventContacts;
+	std::vector<char>* deferred = m_eventDeferred;
+	int32 counts[2] = {0, 0};
 	for (int32 kind = 0; kind < 2; ++kind)
 	{
 		int32 n = 0;
 		b2cuGetEventContacts(device, kind, 0, nullptr, nullptr, &n);
-		keys[kind].resize(n);
-		recs[kind].resize(n);
-		contacts[kind].resize(n);
-		deferred[kind].assign(n, 0);
+		counts[kind] = n;
+		if ((int32)keys[kind].size() < n)
+		{
+			keys[kind].resize(n);
+			recs[kind].resize(n);
+			contacts[kind].resize(n);
+			deferred[kind].resize(n);
+		}
 		if (n == 0) continue;
 		Clock::time_point ta = Clock::now();
 		b2cuGetEventContacts(device, kind, n, keys[kind].data(), recs[kind].data(), &n);
@@ -943,16 +985,16 @@ void b2World::DispatchEvents(b2cuWorld* device)
 		makeMs += std::chrono::duration<double, std::milli>(tc - tb).count();
 	}
 	if (timing)
-		fprintf(stderr, "[b2h events] begin %zu end %zu: query %.3f ms, make %.3f ms, alloc+rest %.3f ms\n", keys[0].size(),
-		        keys[1].size(), queryMs, makeMs,
+		fprintf(stderr, "[b2h events] begin %d end %d: query %.3f ms, make %.3f ms, alloc+rest %.3f ms\n", counts[0],
+		        counts[1], queryMs, makeMs,
 		        std::chrono::duration<double, std::milli>(Clock::now() - t0).count() - queryMs - makeMs);
-	for (size_t i = 0; i < contacts[0].size(); ++i)
+	for (int32 i = 0; i < counts[0]; ++i)
 		deferred[0][i] = m_contactListener->BeginContactImmediate(&contacts[0][i], 0) ? 1 : 0;
-	for (size_t i = 0; i < contacts[1].size(); ++i)
+	for (int32 i = 0; i < counts[1]; ++i)
 		deferred[1][i] = m_contactListener->EndContactImmediate(&contacts[1][i], 0) ? 1 : 0;
-	for (size_t i = 0; i < contacts[0].size(); ++i)
+	for (int32 i = 0; i < counts[0]; ++i)
 		if (deferred[0][i]) m_contactListener->BeginContact(&contacts[0][i]);
-	for (size_t i = 0; i < contacts[1].size(); ++i)
+	for (int32 i = 0; i < counts[1]; ++i)
 		if (deferred[1][i]) m_contactListener->EndContact(&contacts[1][i]);
 
 	// Calls made from inside the time-of-impact sub-steps (b2Contact::Update from b2World::StepSolveTOI, reference
@@ -1065,6 +1107,7 @@ int32 b2World::AfterDeviceStep(b2cuWorld* device, const b2cuStepInfo& info, bool
 	memcpy(&m_profile, &info, sizeof(b2Profile)); // the first 13 floats of b2cuStepInfo are the b2Profile fields
 	// downloadBodies: b2cuStep has already written the records into m_states (b2cuSetBodyMirror)
 	m_bodiesStale = !downloadBodies;
+	m_sweepStartsStale = true;
 	if (!m_forced.empty())
 	{
 		// the device cleared the forces (b2World::ClearForces at the end of Step, b2World.cpp:1688-1691) or, without

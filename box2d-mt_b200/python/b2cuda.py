@@ -21,7 +21,7 @@ API = [
     "b2cuSetWorldParams", "b2cuSetInvDt0", "b2cuSetCounts", "b2cuSetBodies", "b2cuGetBodies", "b2cuSetShapes",
     "b2cuSetProxies", "b2cuGetProxies", "b2cuSetContacts", "b2cuGetContactCount", "b2cuGetContacts", "b2cuStep",
     "b2cuGetContactsByKey", "b2cuGetEvents", "b2cuGetSolverOrder", "b2cuGetIslandLabels", "b2cuGetToiCandidates", "b2cuCollidePairs",
-    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuDistancePairs", "b2cuTimeOfImpactPairs", "b2cuQueryAABB", "b2cuRayCastCandidates", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts", "b2cuGetToiEvents", "b2cuSetJoints", "b2cuGetJointCount", "b2cuGetJoints", "b2cuGetJointOrder",
+    "b2cuSinCos", "b2cuShardConfigure", "b2cuShardGetLink", "b2cuShardConnect", "b2cuHostAlloc", "b2cuHostFree", "b2cuSetBodyMirror", "b2cuSetPairFilter", "b2cuDistancePairs", "b2cuTimeOfImpactPairs", "b2cuQueryAABB", "b2cuRayCastCandidates", "b2cuSetPreSolveHook", "b2cuGetPreSolveContacts", "b2cuDisableContacts", "b2cuGetBodyStates", "b2cuGetEventContacts", "b2cuGetToiEvents", "b2cuSetBodyForces", "b2cuSetEventPrefetch", "b2cuGetBodySweepStarts", "b2cuSetJoints", "b2cuGetJointCount", "b2cuGetJoints", "b2cuGetJointOrder",
 ]
 
 

@@ -18,11 +18,10 @@ assert BODY.itemsize == 104
 BODY_STATE = np.dtype([
     ("px", "f4"), ("py", "f4"), ("qs", "f4"), ("qc", "f4"),
     ("cx", "f4"), ("cy", "f4"), ("a", "f4"),
-    ("c0x", "f4"), ("c0y", "f4"), ("a0", "f4"), ("alpha0", "f4"),
     ("vx", "f4"), ("vy", "f4"), ("w", "f4"),
     ("sleepTime", "f4"), ("flags", "u4"),
 ])
-assert BODY_STATE.itemsize == 64
+assert BODY_STATE.itemsize == 48
 
 SHAPE = np.dtype([
     ("type", "i4"), ("count", "i4"), ("radius", "f4"), ("flags", "u4"),

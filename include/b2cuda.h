@@ -36,6 +36,7 @@
  *   b2cuGetBodyStates /                  b2Island::Solve writing the new state into the b2Body objects
  *   b2cuSetBodyMirror
  *                                                                          Dynamics/b2Island.cpp:339-348
+ *   b2cuSetBodyForces                    b2Body::ApplyForce / ApplyTorque on awake bodies                    Dynamics/b2Body.h:740-790
  *   b2cuHostAlloc / b2cuHostFree         the world's own allocation of its bodies (b2BlockAllocator)
  *                                                                          Common/b2BlockAllocator.cpp:93-170
  *   b2cuSetPreSolveHook /                b2ContactListener::PreSolve between Collide and Solve, b2Contact::SetEnabled
@@ -120,18 +121,26 @@ typedef struct b2cuBody
 	uint32_t flags;
 } b2cuBody;
 
-/* The part of b2cuBody that a step changes (64 bytes): what b2Island::Solve writes back into the b2Body objects
- * (Dynamics/b2Island.cpp:339-348) plus sleep time and flags.  The rest of b2cuBody (local centre, mass, damping,
- * gravity scale, and the forces the caller applies) only ever travels host -> device. */
+/* The part of b2cuBody that a step changes and callers read back (48 bytes): what b2Island::Solve writes into the
+ * b2Body objects (Dynamics/b2Island.cpp:339-348: m_xf, m_sweep.c / a, velocities) plus sleep time and flags.  This is the
+ * record of the per-step body mirror (b2cuSetBodyMirror).  The rest of b2cuBody only ever travels host -> device (local
+ * centre, mass, damping, gravity scale, applied forces) or is internal to the step: */
 typedef struct b2cuBodyState
 {
-	float px, py, qs, qc;          /* m_xf */
+	float px, py, qs, qc;          /* m_xf: origin position, sin, cos */
 	float cx, cy, a;               /* m_sweep.c, m_sweep.a */
-	float c0x, c0y, a0, alpha0;    /* m_sweep.c0, a0, alpha0 */
 	float vx, vy, w;               /* m_linearVelocity, m_angularVelocity */
 	float sleepTime;
 	uint32_t flags;
 } b2cuBodyState;
+
+/* ... the start of the body's sweep, m_sweep.c0 / a0 / alpha0 (Common/b2Math.h:382-410): where the last solve picked
+ * the body up.  The step needs it (SynchronizeFixtures, time of impact); no accessor of b2Body returns it, so it stays
+ * on the device and is fetched only when the caller is about to re-upload whole b2cuBody rows. */
+typedef struct b2cuSweepStart
+{
+	float c0x, c0y, a0, alpha0;
+} b2cuSweepStart;
 
 /* ---- shape geometry ---------------------------------------------------------- */
 
@@ -327,12 +336,21 @@ B2CU_API int b2cuSetBodies(b2cuWorld* w, int32_t first, int32_t count, const b2c
 B2CU_API int b2cuGetBodies(b2cuWorld* w, int32_t first, int32_t count, b2cuBody* bodies);
 /* The device -> host direction of the bodies: only the b2cuBodyState part (what a step changes). */
 B2CU_API int b2cuGetBodyStates(b2cuWorld* w, int32_t first, int32_t count, b2cuBodyState* states);
+B2CU_API int b2cuGetBodySweepStarts(b2cuWorld* w, int32_t first, int32_t count, b2cuSweepStart* starts);
 /* b2World::Step leaves the new transforms and velocities in the b2Body objects (b2Island::Solve, Dynamics/b2Island.cpp:
  * 339-348).  With a mirror registered, every b2cuStep does the same for the caller's records of bodies [0, count):
  * the copy starts as soon as the solver has finished with the bodies and overlaps the broad-phase part of the step;
  * when b2cuStep returns the mirror is current (no b2cuGetBodyStates needed).  `mirror` should come from
  * b2cuHostAlloc; NULL / 0 removes it.  The mirror must stay valid until it is replaced or the world destroyed. */
 B2CU_API int b2cuSetBodyMirror(b2cuWorld* w, b2cuBodyState* mirror, int32_t count);
+/* b2Body::ApplyForce / ApplyForceToCenter / ApplyTorque on bodies that are awake only add to m_force / m_torque
+ * (Dynamics/b2Body.h:740-790): the per-step user input of a running simulation.  forces = (fx, fy, torque) per body,
+ * 12 bytes instead of the 104 of a whole b2cuBody row; nothing else of the bodies is touched. */
+B2CU_API int b2cuSetBodyForces(b2cuWorld* w, int32_t first, int32_t count, const float* forces);
+/* With prefetch on, b2cuStep itself gathers the contact records of the step's begin / end events and starts their
+ * copy to the host before it returns, so that b2cuGetEventContacts finds them there (a listener is installed:
+ * the callbacks will ask for them anyway).  Off by default. */
+B2CU_API int b2cuSetEventPrefetch(b2cuWorld* w, int32_t on);
 B2CU_API int b2cuSetShapes(b2cuWorld* w, int32_t first, int32_t count, const b2cuShape* shapes);
 B2CU_API int b2cuSetProxies(b2cuWorld* w, int32_t first, int32_t count, const b2cuProxy* proxies);
 B2CU_API int b2cuGetProxies(b2cuWorld* w, int32_t first, int32_t count, b2cuProxy* proxies);
