@@ -226,7 +226,8 @@ def run_reference_arm(args, rank, world_size):
     print(json.dumps({
         "impl": "reference", "metric": "body-steps/sec", "value": head["value"], "unit": "body-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": head.get("ms_per_step"),
-        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling or ("strong" if world_size > 1 else "weak"), "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "bodies_per_gpu": args.bodies, "sample_bodies": head.get("bodies")},
         "cpu_baseline": head, "cpu_rows": rows,
         "e2e": {"value": head["value"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -270,7 +271,25 @@ def run_product_arm(args, rank, local_rank, world_size):
         dist.init_process_group("nccl")
 
     t0 = time.perf_counter()
-    strong = args.scaling == "strong"
+    scaling = args.scaling or ("strong" if world_size > 1 else "weak")
+
+    def sharded_pile(mode):
+        """ONE pile cut into x-strips: every rank holds its strip, the static container and ghost copies of the next
+        strip's boundary bodies; the halo bodies' rows cross NVLink inside the solver kernels (b2cuShard*).
+        weak: world_size x bodies in total (bodies per GPU fixed); strong: `bodies` in total (the 1M-body pile cut N ways)."""
+        import b2shard
+        cols = max(16, args.bodies // ROWS) if mode == "weak" else max(16 * world_size, args.bodies // ROWS) // world_size
+        sc = scenes.pile(cols * world_size, ROWS, seed=0)
+        sc.world_flags &= ~T.WORLD_CONTINUOUS  # the container is thick-shape and nothing is a bullet: no TOI candidates
+        plan, _ = b2shard.rank_plan(sc.arrays(), rank, world_size, args.margin)
+        wd = b2host.HostWorld(arrays=plan.arrays, gravity=sc.gravity, world_flags=sc.world_flags,
+                              device=local_rank, download_bodies=False, events=False)
+        wd.shard_configure(rank, world_size, plan.ghost_local, plan.export_local)
+        lower, upper = b2shard.exchange_links(dist, rank, world_size, wd.shard_link())
+        wd.shard_connect(lower, upper)
+        dist.barrier()
+        return wd, wd.counts()[0] - len(plan.ghost_local), cols, sc
+
     if world_size == 1:
         scene, settle, workload = make_workload(args.workload, args.bodies, scenes)
         if settle is None:
@@ -280,27 +299,13 @@ def run_product_arm(args, rank, local_rank, world_size):
         n_bodies = world.counts()[0]
         columns = max(16, args.bodies // ROWS)
     else:
-        # ONE pile cut into x-strips: every rank holds its strip, the static container and ghost copies of the next
-        # strip's boundary bodies; the solver kernels exchange halo state through NVLink peer mailboxes (b2cuShard*,
-        # DESIGN.md 8).  weak: world_size x bodies in total (bodies per GPU fixed); strong: `bodies` in total.
         if args.workload != "pile":
             raise SystemExit("bench.py: only the pile workload is sharded")
-        import b2shard
         settle = args.settle
-        columns = max(16, args.bodies // ROWS) if not strong else max(16 * world_size, args.bodies // ROWS) // world_size
-        scene = scenes.pile(columns * world_size, ROWS, seed=0)
-        scene.world_flags &= ~T.WORLD_CONTINUOUS  # the container is thick-shape and nothing is a bullet: no TOI candidates
-        workload = ("pile_%dk x %d GPUs (BASELINE.json configs[4]: one mixed polygon/circle pile in a wide static container, "
-                    "60 Hz, 8 velocity / 3 position iterations, no sleeping, settled %d steps)"
-                    % (columns * ROWS // 1000, world_size, settle))
-        plan, _ = b2shard.rank_plan(scene.arrays(), rank, world_size, args.margin)
-        world = b2host.HostWorld(arrays=plan.arrays, gravity=scene.gravity, world_flags=scene.world_flags,
-                                 device=local_rank, download_bodies=False, events=False)
-        world.shard_configure(rank, world_size, plan.ghost_local, plan.export_local)
-        lower, upper = b2shard.exchange_links(dist, rank, world_size, world.shard_link())
-        world.shard_connect(lower, upper)
-        n_bodies = world.counts()[0] - len(plan.ghost_local)
-        dist.barrier()
+        world, n_bodies, columns, scene = sharded_pile(scaling)
+        workload = ("pile_%dk x %d GPUs, %s scaling (BASELINE.json configs[4]: one mixed polygon/circle pile in a wide static "
+                    "container, 60 Hz, 8 velocity / 3 position iterations, no sleeping, settled %d steps)"
+                    % (columns * ROWS // 1000, world_size, scaling, settle))
     build_s = time.perf_counter() - t0
 
     # settle (setup, untimed)
@@ -365,6 +370,27 @@ def run_product_arm(args, rank, local_rank, world_size):
     d2h = world.counts()[0] * T.BODY_STATE.itemsize + 8 * int(infos[-1]["beginCount"] + infos[-1]["endCount"])
     world.set_options(False, False)
     total_bodies = int(sum_over_ranks(n_bodies))
+
+    # ---- N > 1: the other scaling mode as a side measurement (same code path, device-resident value only) ----
+    other = None
+    if world_size > 1 and not args.no_other_scaling:
+        other_mode = "weak" if scaling == "strong" else "strong"
+        del world
+        w2, n2, cols2, _ = sharded_pile(other_mode)
+        for _ in range(settle):
+            w2.step(DT, VEL_ITERS, POS_ITERS)
+        for _ in range(args.warmup):
+            w2.step(DT, VEL_ITERS, POS_ITERS)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            w2.step(DT, VEL_ITERS, POS_ITERS)
+        el2 = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        total2 = int(sum_over_ranks(n2))
+        other = {"scaling": other_mode, "bodies_total": total2, "bodies_per_gpu": n2, "ms_per_step": 1e3 * el2 / args.steps,
+                 "value": total2 * args.steps / el2, "unit": "body-steps/s", "steps": args.steps}
+        del w2
 
     if rank != 0:
         if dist is not None:
@@ -473,7 +499,7 @@ def run_product_arm(args, rank, local_rank, world_size):
     print(json.dumps({
         "metric": "body-steps/sec", "value": total_bodies * args.steps / elapsed, "unit": "body-steps/s",
         "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": args.scaling if world_size > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "other_scaling": other,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload,
                    "bodies_per_gpu": n_bodies, "bodies_total": total_bodies, "columns": columns, "rows": ROWS,
@@ -527,8 +553,10 @@ def main():
     ap.add_argument("--ref-bodies", type=int, default=100000, help="bodies of the --impl reference sample (pile)")
     ap.add_argument("--ref-settle", type=int, default=120)
     ap.add_argument("--workload", default="pile", choices=["pile", "add_pair", "tumbler", "stacks_awake", "stacks_asleep"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = `bodies` per GPU, strong = `bodies` in total (the 1M-body pile cut N ways)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: strong (default) = `bodies` in total, the 1M-body pile of BASELINE.json cut N ways; weak = "
+                         "`bodies` per GPU.  The other mode is measured too and reported under other_scaling")
+    ap.add_argument("--no-other-scaling", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--margin", type=float, default=3.0, help="ghost margin of a strip boundary (m)")
     args = ap.parse_args()

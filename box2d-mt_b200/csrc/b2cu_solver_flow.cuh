@@ -156,6 +156,15 @@ __device__ __forceinline__ bool FlowAcquire(const ShardState& sh, const float4* 
 	return false;
 }
 
+// the neighbour's last push of a halo body, if it is the expected version
+__device__ __forceinline__ bool FlowAcquireMail(const ShardState& sh, int slot, int region, int expected, float4* out)
+{
+	const float4 v = LoadRowSys(HaloIn(sh, slot, region));
+	if (__float_as_int(v.w) != expected) return false;
+	*out = v;
+	return true;
+}
+
 // polls before a wait is declared stuck (seconds of wall time): the step then fails loudly instead of hanging the GPU
 #define B2CU_FLOW_SPIN_LIMIT (1 << 22)
 // true when this wait must be given up: it has polled too long, or some other wait already has (checked now and then)
@@ -278,19 +287,15 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, (SHARD || OVERFLOW) ? 3 :
 				{
 					if (!done)
 					{
-						float4 vA, vB;
-						bool readyA, readyB;
-						if (dynA) readyA = FlowAcquire(plan.shard, d.vel, pre.sb.x, slotA, 0, expA, &vA);
-						else
+						// both rows in flight before either is looked at
+						float4 vA = LoadRow128(&d.vel[pre.sb.x]);
+						float4 vB = LoadRow128(&d.vel[pre.sb.y]);
+						bool readyA = !dynA || __float_as_int(vA.w) == expA;
+						bool readyB = !dynB || __float_as_int(vB.w) == expB;
+						if (SHARD)
 						{
-							vA = LoadRow128(&d.vel[pre.sb.x]);
-							readyA = true;
-						}
-						if (dynB) readyB = FlowAcquire(plan.shard, d.vel, pre.sb.y, slotB, 0, expB, &vB);
-						else
-						{
-							vB = LoadRow128(&d.vel[pre.sb.y]);
-							readyB = true;
+							if (!readyA && slotA >= 0) readyA = FlowAcquireMail(plan.shard, slotA, 0, expA, &vA);
+							if (!readyB && slotB >= 0) readyB = FlowAcquireMail(plan.shard, slotB, 0, expB, &vB);
 						}
 						bool ready = readyA && readyB;
 						if (!ready && FlowStuck(d, ++spins)) ready = true;
@@ -448,12 +453,15 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPo
 				{
 					if (!done)
 					{
-						float4 pA, pB;
-						bool readyA = true, readyB = true;
-						if (dynA) readyA = FlowAcquire(plan.shard, d.pos, pre.sb.x, slotA, 1, expA, &pA);
-						else pA = LoadRow128(&d.pos[pre.sb.x]);
-						if (dynB) readyB = FlowAcquire(plan.shard, d.pos, pre.sb.y, slotB, 1, expB, &pB);
-						else pB = LoadRow128(&d.pos[pre.sb.y]);
+						float4 pA = LoadRow128(&d.pos[pre.sb.x]);
+						float4 pB = LoadRow128(&d.pos[pre.sb.y]);
+						bool readyA = !dynA || __float_as_int(pA.w) == expA;
+						bool readyB = !dynB || __float_as_int(pB.w) == expB;
+						if (SHARD)
+						{
+							if (!readyA && slotA >= 0) readyA = FlowAcquireMail(plan.shard, slotA, 1, expA, &pA);
+							if (!readyB && slotB >= 0) readyB = FlowAcquireMail(plan.shard, slotB, 1, expB, &pB);
+						}
 						bool ready = readyA && readyB;
 						if (!ready && FlowStuck(d, ++spins)) ready = true;
 						if (ready)

@@ -17,6 +17,8 @@ import scenes
 
 CASES = {
     "pile": (lambda: scenes.pile(int(os.environ.get("SAN_COLUMNS", "1000")), 100), 6),
+    # a small pile that has settled: full colour set, warm starting, position iterations with early exits, sleeping
+    "pile_settled": (lambda: scenes.pile(60, 20, sleep=True), 150),
     "joints": (scenes.machines, 30),
     "bullets": (scenes.bullets, 60),
     "add_pair": (lambda: scenes.add_pair(600), 30),
