@@ -11,16 +11,17 @@ and stepped with b2World::Step(dt, 8, 3, b2CudaStepExecutor&).
   e2e    the same through the same call with the host buffers in the loop: every step uploads that step's user
          input (forces on 1% of the bodies, edited through b2Body::ApplyForceToCenter) and downloads every body's
          state into the host mirror that b2Body::GetPosition() reads, plus the begin/end touch events
-  roofline      the dominant kernel (SolverVelocityPersistentKernel, one cooperative launch per step) against the
+  roofline      the dominant kernel (SolverVelocityFlowKernel, one launch per step) against the
                 measured HBM peak; traffic = its DRAM bytes from the committed ncu capture
   cpu_baseline  the compiled reference (oracle/_ref) with its own b2ThreadPoolTaskExecutor on the host cores, on a
                 bounded sample: a narrower pile of the same depth, started from the device-settled state
 Reference arm (--impl reference): the reference's own CPU implementation alone, on a narrower pile of the same
 depth (a bounded sample of the workload), settled by the reference itself.
 
-N > 1 (torchrun): one pile of N x bodies cut into x-strips, one per rank, with ghost bodies and per-iteration halo
-exchange through NVLink peer mailboxes inside the persistent solver kernel (weak scaling; no NCCL on the data path;
-times are max-reduced over NCCL).
+N > 1 (torchrun): one pile cut into x-strips, one per rank, with ghost bodies; the boundary bodies' rows travel as
+versioned 16-byte stores into NVLink peer mailboxes from inside the solver kernels (no NCCL on the data path; times
+are max-reduced over NCCL).  Default: strong scaling of the 1M-body pile, with the weak-scaling run (1M bodies per GPU)
+measured alongside under other_scaling.
 """
 import argparse
 import json
@@ -510,8 +511,8 @@ def run_product_arm(args, rank, local_rank, world_size):
                          if step_bytes > 2.0e8 else
                          ("working set per step %.3f GB algorithmic: the step's kernels stream more than L2 between two uses "
                           "of a row only partly; no explicit flush (every step rewrites all rows)" % (step_bytes / 1e9)),
-                   "sharding": ("x-strips of one %d-body pile, ghost bodies within %.1f m of the strip boundary, halo "
-                                "exchange through NVLink peer mailboxes inside the solver kernel (2 per iteration)"
+                   "sharding": ("x-strips of one %d-body pile, ghost bodies within %.1f m of the strip boundary; boundary "
+                                "rows pushed as versioned 16-byte stores into NVLink peer mailboxes by the solver kernels"
                                 % (total_bodies, args.margin)) if world_size > 1 else "single GPU"},
         "device_ms_per_step": device_ms / args.steps,
         "phases_ms": phases,
@@ -522,8 +523,8 @@ def run_product_arm(args, rank, local_rank, world_size):
                 "host_ms": dict(zip(("apply_forces", "upload", "step", "download", "events"),
                                     [1e3 * apply_s / args.steps] + [float(x) / args.steps for x in host_ms]))},
         "gpu_launches": int(sum(int(i["kernelLaunches"]) for i in infos)),
-        "roofline": {"bound": "hbm", "kernel": "SolverVelocityPersistentKernel (warm start + 8 velocity iterations + impulse "
-                                                        "store + position integration, one cooperative launch per step)",
+        "roofline": {"bound": "hbm", "kernel": "SolverVelocityFlowKernel (warm start + 8 velocity iterations + impulse store + "
+                                                        "position integration; one launch per step, ordered by per-body row versions)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": phase_rooflines[3]["traffic"] or ncu_traffic(n_constraints),
                      "ms_per_launch": vel_ms,

@@ -18,8 +18,8 @@ PHASE_OF = [
     (r"^Collide|^ApplyWake", "collide"),
     (r"^SolveInitBodies|^Island|^JointUnion|^SelectConstraints|^Colour", "solveTraversal"),
     (r"^IntegrateVelocities|^ConstraintSlot|^InitConstraints", "solveInit"),
-    (r"^SolverVelocityPersistent|^WarmStart|^SolveVelocity|^StoreImpulses", "solveVelocity"),
-    (r"^SolverPositionPersistent|^SolvePosition|^IntegratePositions|^FinalizeBodies|^SleepIslands", "solvePosition"),
+    (r"^SolverVelocity|^HaloMask|^WarmStart|^SolveVelocity|^StoreImpulses", "solveVelocity"),
+    (r"^SolverPosition|^FlowOverflow|^SolvePosition|^IntegratePositions|^FinalizeBodies|^SleepIslands", "solvePosition"),
     (r"^SyncProxies|^EndStepBodies|^Grid|^Query|^ClearMoved|^MergeMove|^RebuildNew|^BuildLowStart|^Iota|^PackBodyStates",
      "broadphase"),
     (r"^Toi", "solveTOI"),
