@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
 HOST = os.path.join(HERE, "host")
 HOST_OUT = os.path.join(HERE, "libbox2d_b200.so")
 HOST_SOURCES = ["src/b2Common.cpp", "src/b2Shapes.cpp", "src/b2Body.cpp", "src/b2World.cpp", "src/b2Joints.cpp", "src/b2Dump.cpp",
-                "src/b2CudaStepExecutor.cpp", "capi/b2host_capi.cpp"]
+                "src/b2CudaStepExecutor.cpp", "src/b2CudaShardedWorld.cpp", "capi/b2host_capi.cpp"]
 
 
 def host_lib_path():
@@ -59,7 +59,7 @@ def build_host(force=False):
         deps += [os.path.join(d, f) for f in files]
     if not force and os.path.exists(HOST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_OUT) for d in deps):
         return HOST_OUT
-    cmd = ["g++", "-std=c++11", "-O2", "-DNDEBUG", "-fPIC", "-shared", "-ffp-contract=off",
+    cmd = ["g++", "-std=c++11", "-O2", "-DNDEBUG", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
            "-Wall", "-I" + HOST, "-I" + os.path.join(HERE, "..", "include")] + srcs + \
           ["-L" + HERE, "-lb2cuda", "-Wl,-rpath,$ORIGIN", "-o", HOST_OUT]
     subprocess.run(cmd, check=True)

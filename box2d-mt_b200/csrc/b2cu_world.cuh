@@ -280,6 +280,8 @@ struct b2cuWorld
 	size_t queryHostBytes;
 	bool eventPrefetch;        // b2cuSetEventPrefetch
 	bool eventCachePending;    // the copy of the event records into queryHost was started by the step itself
+	void* eventOrder;         // host scratch of b2cuGetEventContacts: 2 x eventOrderCapacity (key, index) pairs
+	size_t eventOrderCapacity;
 	bool eventCacheValid;      // queryHost holds the keys + records of the last step's events
 	size_t eventCacheKeyBytes;
 	// joints (b2cuSetJoints)

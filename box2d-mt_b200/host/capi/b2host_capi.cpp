@@ -853,4 +853,67 @@ B2H_API void b2h_destroy_body(void* p, int32 body)
 	for (b2Joint* j = h->world->GetJointList(); j; j = j->GetNext()) h->joints[(size_t)j->GetIndex()] = j;
 }
 
+// ---- b2CudaShardedWorld (Box2D/MT/b2CudaShardedWorld.h) ----
+
+/// planner only, no device: the strip `rank` of `shardCount` of this host's scene.  bodyIds[capacity] receives the scene
+/// body index of every strip body, ghostLocal / exportLocal the strip-local indices of the halo lists, counts =
+/// {bodies, ghosts, exports, fixtures}, bounds[shardCount + 1] the strip boundaries.  Returns 0, or -1 if capacity is short.
+B2H_API int b2h_plan_strip(void* p, int32 shardCount, int32 rank, float margin, int32 capacity, int32* bodyIds,
+                           int32* ghostLocal, int32* exportLocal, int32* counts, double* bounds)
+{
+	Host* h = static_cast<Host*>(p);
+	std::vector<float64> b;
+	b2CudaShardedWorld::ComputeBounds(*h->world, shardCount, b);
+	for (size_t i = 0; i < b.size(); ++i) bounds[i] = b[i];
+	b2World* strip = b2CudaShardedWorld::MakeStripWorld(*h->world);
+	b2ShardStrip info;
+	b2CudaShardedWorld::BuildStrip(*h->world, b, rank, margin, *strip, info);
+	counts[0] = (int32)info.bodies.size();
+	counts[1] = (int32)info.ghosts.size();
+	counts[2] = (int32)info.exports.size();
+	counts[3] = strip->GetProxyCount();
+	int rc = 0;
+	if (counts[0] > capacity) rc = -1;
+	else
+	{
+		for (size_t i = 0; i < info.sources.size(); ++i) bodyIds[i] = info.sources[i]->GetIndex();
+		for (size_t i = 0; i < info.ghosts.size(); ++i) ghostLocal[i] = info.ghosts[i]->GetIndex();
+		for (size_t i = 0; i < info.exports.size(); ++i) exportLocal[i] = info.exports[i]->GetIndex();
+	}
+	delete strip;
+	return rc;
+}
+
+B2H_API void* b2h_sharded_create(void* p, int32 shardCount, float margin, const int32* devices, float gridFraction)
+{
+	Host* h = static_cast<Host*>(p);
+	return new b2CudaShardedWorld(*h->world, shardCount, margin, devices, gridFraction);
+}
+B2H_API int b2h_sharded_status(void* s) { return static_cast<b2CudaShardedWorld*>(s)->GetLastStatus(); }
+B2H_API const char* b2h_sharded_error(void* s) { return static_cast<b2CudaShardedWorld*>(s)->GetLastError(); }
+B2H_API int b2h_sharded_step(void* s, float dt, int32 velocityIterations, int32 positionIterations)
+{
+	b2CudaShardedWorld* w = static_cast<b2CudaShardedWorld*>(s);
+	w->Step(dt, velocityIterations, positionIterations);
+	return w->GetLastStatus();
+}
+/// copies the stepped state back into the scene the sharded world was made from
+B2H_API void b2h_sharded_gather(void* s, void* p) { static_cast<b2CudaShardedWorld*>(s)->Gather(*static_cast<Host*>(p)->world); }
+/// (x, y, angle) of the bodies of strip `rank` in strip order; returns their number
+B2H_API int b2h_sharded_strip_transforms(void* s, int32 rank, int32 capacity, float* xya)
+{
+	b2CudaShardedWorld* w = static_cast<b2CudaShardedWorld*>(s);
+	const b2ShardStrip& info = w->GetStripInfo(rank);
+	int32 n = (int32)info.bodies.size();
+	for (int32 i = 0; i < n && i < capacity; ++i)
+	{
+		const b2Body* b = info.bodies[(size_t)i];
+		xya[3 * i + 0] = b->GetPosition().x;
+		xya[3 * i + 1] = b->GetPosition().y;
+		xya[3 * i + 2] = b->GetAngle();
+	}
+	return n;
+}
+B2H_API void b2h_sharded_destroy(void* s) { delete static_cast<b2CudaShardedWorld*>(s); }
+
 } // extern "C"

@@ -89,6 +89,16 @@ def load():
     lib.b2h_destroy_body.argtypes = [vp, i32]
     lib.b2h_set_body_param.argtypes = [vp, i32, i32, f32]
     lib.b2h_destroy_fixture.argtypes = [vp, i32]
+    lib.b2h_plan_strip.argtypes = [vp, i32, i32, f32, i32, vp, vp, vp, vp, vp]
+    lib.b2h_sharded_create.argtypes = [vp, i32, f32, vp, f32]
+    lib.b2h_sharded_create.restype = vp
+    lib.b2h_sharded_status.argtypes = [vp]
+    lib.b2h_sharded_error.argtypes = [vp]
+    lib.b2h_sharded_error.restype = ctypes.c_char_p
+    lib.b2h_sharded_step.argtypes = [vp, f32, i32, i32]
+    lib.b2h_sharded_gather.argtypes = [vp, vp]
+    lib.b2h_sharded_strip_transforms.argtypes = [vp, i32, i32, vp]
+    lib.b2h_sharded_destroy.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -166,6 +176,25 @@ class HostWorld:
         if getattr(self, "h", None):
             self.lib.b2h_destroy(self.h)
             self.h = None
+
+    # ---- b2CudaShardedWorld (Box2D/MT/b2CudaShardedWorld.h) ----
+    def plan_strip(self, shard_count, rank, margin=2.0):
+        """The C++ planner alone (no device): (scene body ids, ghost local ids, export local ids, fixtures, bounds) of a strip."""
+        n = self.counts()[0]
+        ids = np.zeros(n, np.int32)
+        ghosts = np.zeros(n, np.int32)
+        exports = np.zeros(n, np.int32)
+        counts = np.zeros(4, np.int32)
+        bounds = np.zeros(shard_count + 1, np.float64)
+        rc = self.lib.b2h_plan_strip(self.h, shard_count, rank, ctypes.c_float(margin), n, _ptr(ids), _ptr(ghosts),
+                                     _ptr(exports), _ptr(counts), _ptr(bounds))
+        if rc != 0:
+            raise RuntimeError("b2h_plan_strip failed: %d" % rc)
+        return ids[:counts[0]], ghosts[:counts[1]], exports[:counts[2]], int(counts[3]), bounds
+
+    def shard(self, shard_count, margin=2.0, devices=None, grid_fraction=1.0):
+        """b2CudaShardedWorld over this (unstepped) world"""
+        return ShardedWorld(self, shard_count, margin, devices, grid_fraction)
 
     def counts(self):
         a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
@@ -347,3 +376,37 @@ class HostWorld:
 
     def set_body_param(self, body, which, value):
         self.lib.b2h_set_body_param(self.h, body, which, float(value))
+
+
+class ShardedWorld:
+    """b2CudaShardedWorld: one scene cut into x-strips, one strip per GPU, stepped concurrently."""
+
+    def __init__(self, host, shard_count, margin=2.0, devices=None, grid_fraction=1.0):
+        self.lib = load()
+        self.host = host
+        self.count = shard_count
+        dev = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        self.s = self.lib.b2h_sharded_create(host.h, shard_count, ctypes.c_float(margin),
+                                             None if dev is None else _ptr(dev), ctypes.c_float(grid_fraction))
+        if self.lib.b2h_sharded_status(self.s) != 0:
+            raise RuntimeError("b2CudaShardedWorld: %s" % self.lib.b2h_sharded_error(self.s).decode())
+
+    def step(self, dt=1.0 / 60.0, vel_iters=8, pos_iters=3):
+        rc = self.lib.b2h_sharded_step(self.s, ctypes.c_float(dt), vel_iters, pos_iters)
+        if rc != 0:
+            raise RuntimeError("b2CudaShardedWorld::Step: %d %s" % (rc, self.lib.b2h_sharded_error(self.s).decode()))
+
+    def gather(self):
+        """copy the stepped state back into the host world this was made from"""
+        self.lib.b2h_sharded_gather(self.s, self.host.h)
+
+    def strip_transforms(self, rank):
+        n = self.lib.b2h_sharded_strip_transforms(self.s, rank, 0, None)
+        out = np.zeros((n, 3), np.float32)
+        self.lib.b2h_sharded_strip_transforms(self.s, rank, n, _ptr(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "s", None):
+            self.lib.b2h_sharded_destroy(self.s)
+            self.s = None

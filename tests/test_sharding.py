@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import b2cuda_types as T
+import b2host
 import b2shard
 import parity
 import ref
@@ -42,6 +43,22 @@ def test_split_scene_partition():
         f = p.arrays[2]
         assert (np.diff(f["body"]) >= 0).all()
         assert (p.arrays[0]["px"][f["body"]] == bodies["px"][arrays[2]["body"][p.fixture_ids]]).all()
+
+
+@pytest.mark.parametrize("rank_count,margin", [(2, 2.5), (3, 1.5), (5, 0.75)])
+def test_cpp_planner_cuts_the_same_strips(rank_count, margin):
+    """b2CudaShardedWorld's planner (C++, from a live b2World) against b2shard.split_scene (from the scene arrays)."""
+    scene = scenes.pile(40, 6)
+    arrays = scene.arrays()
+    plans, bounds = b2shard.split_scene(arrays, rank_count, margin=margin)
+    host = b2host.HostWorld(scene, events=False)
+    for p in plans:
+        ids, ghosts, exports, fixtures, b = host.plan_strip(rank_count, p.rank, margin)
+        assert (b == bounds).all()
+        assert len(ids) == len(p.body_ids) and (ids == p.body_ids).all()
+        assert len(ghosts) == len(p.ghost_local) and (ghosts == p.ghost_local).all()
+        assert len(exports) == len(p.export_local) and (exports == p.export_local).all()
+        assert fixtures == len(p.fixture_ids)
 
 
 def _shard_worlds(gpu, scene, rank_count, margin):
@@ -166,3 +183,37 @@ def test_sharded_pile_full_iterations_stays_close_to_single_gpu(gpu):
             e = up[plans[p.rank + 1].export_local]
             for f in ("px", "py", "a", "vx", "vy", "w"):
                 assert (g[f] == e[f]).all(), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rank_count", [2, 3])
+def test_cpp_sharded_world_steps_like_the_planned_device_worlds(gpu, rank_count):
+    """b2CudaShardedWorld (C++: planner, one b2World + b2CudaStepExecutor per strip, one host thread per strip) against
+    the strips planned in Python and loaded through the C ABI, which the tests above tie to the whole-world oracle."""
+    scene = scenes.pile(36, 8)
+    scene.world_flags &= ~T.WORLD_CONTINUOUS
+    worlds, plans = _shard_worlds(gpu, scene, rank_count, margin=2.5)
+    ndev = gpu.device_count()
+    per_device = (rank_count + ndev - 1) // ndev
+    host = b2host.HostWorld(scene, events=False)
+    sharded = host.shard(rank_count, margin=2.5, devices=[r % ndev for r in range(rank_count)],
+                         grid_fraction=1.0 if per_device == 1 else 0.6 / per_device)
+    for step in range(60):
+        _step_all(worlds)
+        sharded.step()
+        for r, (w, p) in enumerate(zip(worlds, plans)):
+            b = w.get_bodies()
+            got = sharded.strip_transforms(r)
+            want = np.stack([b["px"], b["py"], b["a"]], axis=1)
+            assert got.shape == want.shape
+            assert (got.view(np.uint32) == want.view(np.uint32)).all(), "step %d strip %d" % (step, r)
+    # Gather brings the owners' state back into the scene the strips were cut from
+    sharded.gather()
+    xya, _ = host.transforms()
+    for r, p in enumerate(plans):
+        own = np.ones(len(p.body_ids), bool)
+        own[p.ghost_local] = False
+        dyn = scene.arrays()[0]["type"][p.body_ids] == T.DYNAMIC_BODY
+        got = sharded.strip_transforms(r)
+        sel = own & dyn
+        assert (xya[p.body_ids[sel]].view(np.uint32) == got[sel].view(np.uint32)).all()
