@@ -120,6 +120,7 @@ private:
 	friend class b2Fixture;
 	friend class b2Contact;
 	friend class b2Joint;
+	friend class b2CudaShardedWorld;
 	b2Body() {}
 	~b2Body() {}
 	void SynchronizeProxies(const b2Transform& xf1, const b2Transform& xf2);

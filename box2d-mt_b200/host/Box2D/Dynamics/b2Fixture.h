@@ -73,6 +73,7 @@ public:
 private:
 	friend class b2Body;
 	friend class b2World;
+	friend class b2CudaShardedWorld;
 	b2Fixture() {}
 	~b2Fixture() { delete m_shape; }
 

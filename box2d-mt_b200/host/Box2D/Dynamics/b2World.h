@@ -76,6 +76,7 @@ struct b2BodyView
 typedef std::vector<b2cuProxy, b2MirrorAllocator<b2cuProxy> > b2ProxyStateArray;
 
 class b2CudaStepExecutor;
+class b2CudaShardedWorld;
 
 class b2World
 {
@@ -150,6 +151,7 @@ private:
 	friend class b2Contact;
 	friend class b2Joint;
 	friend class b2CudaStepExecutor;
+	friend class b2CudaShardedWorld;
 
 	// host mirror of the device state
 	b2BodyStateArray m_states;            // device-written part of the bodies (the step's body mirror)

@@ -16,8 +16,13 @@
 // bounds from the same scene, builds its own strip with BuildStrip and links it with ConfigureShard / GetShardLink /
 // ConnectShard of b2CudaStepExecutor, exchanging the b2cuShardLink records over its own transport.
 //
-// Limits (the device layer's, include/b2cuda.h): strips are fixed at construction (a body that drifts further than
-// `margin` past its strip's boundary is no longer seen by the neighbour), no joints, time-of-impact events are refused.
+// Bodies migrate between strips by re-planning: Rebalance() reads the whole state back (bodies with sweeps and sleep
+// timers, fat boxes, the contact set with its manifolds and accumulated impulses), cuts new strips of equal
+// population at the bodies' current positions and uploads them, so the simulation goes on exactly where it was.  Call
+// it every few hundred steps, or when bodies have travelled a good part of `margin` (a body that drifts further than
+// `margin` past its strip's boundary between two calls is no longer seen by the neighbour).
+//
+// Limits (the device layer's, include/b2cuda.h): no joints, time-of-impact events are refused.
 #ifndef B2_CUDA_SHARDED_WORLD_H
 #define B2_CUDA_SHARDED_WORLD_H
 
@@ -30,7 +35,8 @@
 struct b2ShardStrip
 {
 	std::vector<b2Body*> bodies;        ///< the strip's bodies in creation order
-	std::vector<const b2Body*> sources; ///< the scene body each one is a copy of
+	std::vector<int32> globalIds;       ///< index of each one in the scene (creation order there)
+	std::vector<int32> proxyGlobal;     ///< scene proxy id of each of the strip's proxies
 	std::vector<b2Body*> ghosts;        ///< strip bodies owned by strip rank+1
 	std::vector<b2Body*> exports;       ///< strip bodies that strip rank-1 holds as ghosts
 };
@@ -49,6 +55,15 @@ public:
 	/// copies transform, velocities and the awake flag of every dynamic body from the strip that owns it into `scene`
 	/// (the world given to the constructor, or any world with the same bodies in the same creation order)
 	void Gather(b2World& scene) const;
+	/// Re-plans the strips at the bodies' current positions (equal population again; or the given shardCount + 1
+	/// boundaries) and carries the whole state over: migration of bodies and contacts between GPUs.  Between steps only.
+	bool Rebalance(const float64* bounds = nullptr);
+	/// Rebalance() by itself every `steps` calls of Step (0, the default: never)
+	void SetRebalanceInterval(int32 steps) { m_rebalanceEvery = steps; }
+	/// the executors' per-step host transport (b2CudaStepOptions::downloadBodies / dispatchEvents), all strips alike
+	void SetTransport(bool downloadBodies, bool dispatchEvents);
+	/// contacts Rebalance could not place because one of their bodies had left the halo of its neighbour (0 in a healthy run)
+	int32 GetLostContacts() const { return m_lostContacts; }
 
 	int32 GetShardCount() const { return (int32)m_strips.size(); }
 	b2World& GetStrip(int32 rank) { return *m_worlds[rank]; }
@@ -76,6 +91,7 @@ private:
 	b2CudaShardedWorld& operator=(const b2CudaShardedWorld&);
 	struct Workers;
 	void Fail(int32 status, const char* what);
+	int32 Link(std::vector<b2World*>& worlds, std::vector<b2CudaStepExecutor*>& executors, std::vector<b2ShardStrip>& strips);
 
 	std::vector<b2World*> m_worlds;
 	std::vector<b2CudaStepExecutor*> m_executors;
@@ -83,6 +99,11 @@ private:
 	std::vector<float64> m_bounds;
 	std::vector<int32> m_owner;
 	std::vector<int32> m_localIndex; // of a scene body in its owning strip's `bodies`
+	std::vector<int32> m_devices;
+	float32 m_margin, m_gridFraction;
+	int32 m_lostContacts;
+	int32 m_rebalanceEvery, m_stepsSinceRebalance;
+	bool m_downloadBodies, m_dispatchEvents;
 	Workers* m_workers;
 	int32 m_status;
 	char m_error[512];

@@ -876,7 +876,7 @@ B2H_API int b2h_plan_strip(void* p, int32 shardCount, int32 rank, float margin, 
 	if (counts[0] > capacity) rc = -1;
 	else
 	{
-		for (size_t i = 0; i < info.sources.size(); ++i) bodyIds[i] = info.sources[i]->GetIndex();
+		for (size_t i = 0; i < info.globalIds.size(); ++i) bodyIds[i] = info.globalIds[i];
 		for (size_t i = 0; i < info.ghosts.size(); ++i) ghostLocal[i] = info.ghosts[i]->GetIndex();
 		for (size_t i = 0; i < info.exports.size(); ++i) exportLocal[i] = info.exports[i]->GetIndex();
 	}
@@ -912,6 +912,77 @@ B2H_API int b2h_sharded_strip_transforms(void* s, int32 rank, int32 capacity, fl
 		xya[3 * i + 1] = b->GetPosition().y;
 		xya[3 * i + 2] = b->GetAngle();
 	}
+	return n;
+}
+/// Rebalance(): bounds = NULL (equal population at the current positions) or shardCount + 1 values.  Returns the status.
+B2H_API int b2h_sharded_rebalance(void* s, const double* bounds)
+{
+	b2CudaShardedWorld* w = static_cast<b2CudaShardedWorld*>(s);
+	w->Rebalance(bounds);
+	return w->GetLastStatus();
+}
+B2H_API void b2h_sharded_set_transport(void* s, int32 downloadBodies, int32 events)
+{
+	static_cast<b2CudaShardedWorld*>(s)->SetTransport(downloadBodies != 0, events != 0);
+}
+B2H_API void b2h_sharded_set_rebalance_interval(void* s, int32 steps) { static_cast<b2CudaShardedWorld*>(s)->SetRebalanceInterval(steps); }
+B2H_API int b2h_sharded_lost_contacts(void* s) { return static_cast<b2CudaShardedWorld*>(s)->GetLostContacts(); }
+B2H_API void b2h_sharded_bounds(void* s, double* out)
+{
+	const std::vector<float64>& b = static_cast<b2CudaShardedWorld*>(s)->GetBounds();
+	for (size_t i = 0; i < b.size(); ++i) out[i] = b[i];
+}
+/// counts = {bodies, ghosts, exports, proxies}; ids / ghostLocal / exportLocal may be NULL (counts only)
+B2H_API void b2h_sharded_strip_plan(void* s, int32 rank, int32* counts, int32* ids, int32* ghostLocal, int32* exportLocal)
+{
+	const b2ShardStrip& info = static_cast<b2CudaShardedWorld*>(s)->GetStripInfo(rank);
+	counts[0] = (int32)info.bodies.size();
+	counts[1] = (int32)info.ghosts.size();
+	counts[2] = (int32)info.exports.size();
+	counts[3] = (int32)info.proxyGlobal.size();
+	if (ids) for (size_t i = 0; i < info.globalIds.size(); ++i) ids[i] = info.globalIds[i];
+	if (ghostLocal) for (size_t i = 0; i < info.ghosts.size(); ++i) ghostLocal[i] = info.ghosts[i]->GetIndex();
+	if (exportLocal) for (size_t i = 0; i < info.exports.size(); ++i) exportLocal[i] = info.exports[i]->GetIndex();
+}
+/// whole body records of a strip, in strip order
+B2H_API void b2h_sharded_strip_bodies(void* s, int32 rank, b2cuBody* out)
+{
+	b2World& w = static_cast<b2CudaShardedWorld*>(s)->GetStrip(rank);
+	memcpy(out, w.GetBodyStates(), sizeof(b2cuBody) * (size_t)w.GetBodyCount());
+}
+namespace
+{
+uint64 GlobalKey(const b2ShardStrip& info, uint64 key)
+{
+	uint64 a = (uint64)info.proxyGlobal[(size_t)(key >> 32)], b = (uint64)info.proxyGlobal[(size_t)(key & 0xFFFFFFFFull)];
+	return (std::min(a, b) << 32) | std::max(a, b);
+}
+}
+/// the strip's constraints of the last step in solve order, keys over SCENE proxy ids, with their colours
+B2H_API int b2h_sharded_solver_order(void* s, int32 rank, int32 capacity, uint64* keys, int32* colour)
+{
+	b2CudaShardedWorld* w = static_cast<b2CudaShardedWorld*>(s);
+	b2cuWorld* device = w->GetExecutor(rank).GetDeviceWorld(&w->GetStrip(rank));
+	int32 n = 0;
+	if (device == nullptr || b2cuGetSolverOrder(device, capacity, keys, colour, &n) != B2CU_OK) return -1;
+	const b2ShardStrip& info = w->GetStripInfo(rank);
+	for (int32 i = 0; i < n && i < capacity; ++i) keys[i] = GlobalKey(info, keys[i]);
+	return n;
+}
+/// the strip's contact set as keys over SCENE proxy ids (unsorted)
+B2H_API int b2h_sharded_contact_keys(void* s, int32 rank, int32 capacity, uint64* keys)
+{
+	b2CudaShardedWorld* w = static_cast<b2CudaShardedWorld*>(s);
+	b2cuWorld* device = w->GetExecutor(rank).GetDeviceWorld(&w->GetStrip(rank));
+	int32 n = 0;
+	if (device == nullptr || b2cuGetContactCount(device, &n) != B2CU_OK) return -1;
+	if (n > capacity) return n;
+	std::vector<b2cuContact> recs((size_t)n);
+	if (n > 0 && b2cuGetContacts(device, n, recs.data(), &n) != B2CU_OK) return -1;
+	const b2ShardStrip& info = w->GetStripInfo(rank);
+	for (int32 i = 0; i < n; ++i)
+		keys[i] = GlobalKey(info, ((uint64)(uint32)std::min(recs[(size_t)i].proxyA, recs[(size_t)i].proxyB) << 32) |
+		                              (uint64)(uint32)std::max(recs[(size_t)i].proxyA, recs[(size_t)i].proxyB));
 	return n;
 }
 B2H_API void b2h_sharded_destroy(void* s) { delete static_cast<b2CudaShardedWorld*>(s); }

@@ -99,6 +99,15 @@ def load():
     lib.b2h_sharded_gather.argtypes = [vp, vp]
     lib.b2h_sharded_strip_transforms.argtypes = [vp, i32, i32, vp]
     lib.b2h_sharded_destroy.argtypes = [vp]
+    lib.b2h_sharded_rebalance.argtypes = [vp, vp]
+    lib.b2h_sharded_lost_contacts.argtypes = [vp]
+    lib.b2h_sharded_set_transport.argtypes = [vp, i32, i32]
+    lib.b2h_sharded_set_rebalance_interval.argtypes = [vp, i32]
+    lib.b2h_sharded_bounds.argtypes = [vp, vp]
+    lib.b2h_sharded_strip_plan.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.b2h_sharded_strip_bodies.argtypes = [vp, i32, vp]
+    lib.b2h_sharded_solver_order.argtypes = [vp, i32, i32, vp, vp]
+    lib.b2h_sharded_contact_keys.argtypes = [vp, i32, i32, vp]
     _lib = lib
     return lib
 
@@ -399,6 +408,58 @@ class ShardedWorld:
     def gather(self):
         """copy the stepped state back into the host world this was made from"""
         self.lib.b2h_sharded_gather(self.s, self.host.h)
+
+    def rebalance(self, bounds=None):
+        """b2CudaShardedWorld::Rebalance: new strips at the current positions (or at the given boundaries), state carried over"""
+        b = None if bounds is None else np.ascontiguousarray(bounds, np.float64)
+        rc = self.lib.b2h_sharded_rebalance(self.s, None if b is None else _ptr(b))
+        if rc != 0:
+            raise RuntimeError("b2CudaShardedWorld::Rebalance: %d %s" % (rc, self.lib.b2h_sharded_error(self.s).decode()))
+
+    def set_transport(self, download_bodies, events):
+        self.lib.b2h_sharded_set_transport(self.s, int(download_bodies), int(events))
+
+    def set_rebalance_interval(self, steps):
+        self.lib.b2h_sharded_set_rebalance_interval(self.s, steps)
+
+    def lost_contacts(self):
+        return self.lib.b2h_sharded_lost_contacts(self.s)
+
+    def bounds(self):
+        out = np.zeros(self.count + 1, np.float64)
+        self.lib.b2h_sharded_bounds(self.s, _ptr(out))
+        return out
+
+    def strip_plan(self, rank):
+        """(scene body ids, ghost local ids, export local ids, proxy count) of a strip as it is now"""
+        counts = np.zeros(4, np.int32)
+        self.lib.b2h_sharded_strip_plan(self.s, rank, _ptr(counts), None, None, None)
+        ids = np.zeros(counts[0], np.int32)
+        ghosts = np.zeros(counts[1], np.int32)
+        exports = np.zeros(counts[2], np.int32)
+        self.lib.b2h_sharded_strip_plan(self.s, rank, _ptr(counts), _ptr(ids), _ptr(ghosts), _ptr(exports))
+        return ids, ghosts, exports, int(counts[3])
+
+    def strip_bodies(self, rank):
+        out = np.zeros(len(self.strip_plan(rank)[0]), T.BODY)
+        self.lib.b2h_sharded_strip_bodies(self.s, rank, _ptr(out))
+        return out
+
+    def strip_solver_order(self, rank, capacity=1 << 20):
+        """(keys over scene proxy ids, colours) of the strip's constraints of the last step, in solve order"""
+        keys = np.zeros(capacity, np.uint64)
+        colour = np.zeros(capacity, np.int32)
+        n = self.lib.b2h_sharded_solver_order(self.s, rank, capacity, _ptr(keys), _ptr(colour))
+        if n < 0 or n > capacity:
+            raise RuntimeError("b2h_sharded_solver_order: %d" % n)
+        return keys[:n], colour[:n]
+
+    def strip_contact_keys(self, rank, capacity=1 << 20):
+        keys = np.zeros(capacity, np.uint64)
+        n = self.lib.b2h_sharded_contact_keys(self.s, rank, capacity, _ptr(keys))
+        if n < 0 or n > capacity:
+            raise RuntimeError("b2h_sharded_contact_keys: %d" % n)
+        return keys[:n]
 
     def strip_transforms(self, rank):
         n = self.lib.b2h_sharded_strip_transforms(self.s, rank, 0, None)
