@@ -174,6 +174,13 @@ __device__ __forceinline__ int FindContactSlot(const DeviceArrays& d, int contac
 }
 
 #define B2CU_TOI_LIST_SIDE (1ull << 63)
+// state of one entry of the two contact lists during the island search of ToiEventKernel
+#define B2CU_TOI_SORT_KEYS 4096
+#define B2CU_TOI_WALK_TOUCHING 1 // its manifold at the time of impact has points
+#define B2CU_TOI_WALK_SKIP 2     // already in the island (the event's own contact)
+#define B2CU_TOI_WALK_VISITED 4  // the walk reaches it before the island is full
+#define B2CU_TOI_WALK_BEGIN 8    // its update raises BeginContact
+#define B2CU_TOI_WALK_END 16     // ... EndContact
 __device__ __forceinline__ uint64_t ToiListKey(int side, uint32_t stamp, int slot)
 {
 	return ((uint64_t)side << 63) | ((uint64_t)(0xFFFFFFFFu - stamp) << 31) | (uint64_t)(0x7FFFFFFF - slot);
@@ -237,6 +244,15 @@ __device__ __forceinline__ void ToiSetAwake(const DeviceArrays& d, int b)
 		f.w = 0.0f;
 		d.force[b] = f;
 	}
+}
+
+// the same from several threads at once (the parallel part of the island search): flag bits by atomic OR, the timer by a
+// store of the one value every writer agrees on
+__device__ __forceinline__ void ToiSetAwakeShared(const DeviceArrays& d, int b)
+{
+	atomicOr(&d.bflags[b], (uint32_t)B2CU_BODY_AWAKE);
+	float* timer = reinterpret_cast<float*>(&d.force[b]) + 3;
+	if (*timer != 0.0f) *timer = 0.0f;
 }
 
 // b2Body::SynchronizeTransform (b2Body.h:958-962)
@@ -306,7 +322,10 @@ __device__ __forceinline__ void ToiLoadManifold(const DeviceArrays& d, int i, Ma
 // The rest of b2Contact::Update (single-threaded flavour, b2Contact.cpp:205-281) once the new manifold geometry is known:
 // impulses carried over by feature id, touching flag, both bodies woken when touching changed, begin / end events in
 // call order.  Returns whether the contact touches now.
-__device__ __forceinline__ bool ToiCommitUpdate(const DeviceArrays& d, int i, int bA, int bB, Manifold& m, int capacity)
+// kind of the event the update raises: -1 none, else B2CU_EVENT_BEGIN / B2CU_EVENT_END.  `shared`: other threads may be
+// updating other contacts of the same bodies at the same time; `joins`: the contact enters the island being built.
+__device__ __forceinline__ bool ToiCommitUpdateCore(const DeviceArrays& d, int i, int bA, int bB, Manifold& m, bool shared,
+                                                    bool joins, int* eventKind)
 {
 	uint32_t flags = d.c.flags[i] | B2CU_CONTACT_ENABLED;
 	const bool wasTouching = (flags & B2CU_CONTACT_TOUCHING) != 0;
@@ -338,18 +357,34 @@ __device__ __forceinline__ bool ToiCommitUpdate(const DeviceArrays& d, int i, in
 	}
 	if (touching != wasTouching)
 	{
-		ToiSetAwake(d, bA);
-		ToiSetAwake(d, bB);
+		if (shared)
+		{
+			ToiSetAwakeShared(d, bA);
+			ToiSetAwakeShared(d, bB);
+		}
+		else
+		{
+			ToiSetAwake(d, bA);
+			ToiSetAwake(d, bB);
+		}
 	}
 	if (touching) flags |= B2CU_CONTACT_TOUCHING;
 	else flags &= ~(uint32_t)B2CU_CONTACT_TOUCHING;
-	if (touching && !wasTouching) ToiAppendEvent(d, B2CU_EVENT_BEGIN, d.c.key[i], capacity);
-	if (!touching && wasTouching) ToiAppendEvent(d, B2CU_EVENT_END, d.c.key[i], capacity);
+	if (joins && touching) flags |= B2CU_CONTACT_ISLAND;
+	*eventKind = touching == wasTouching ? -1 : touching ? B2CU_EVENT_BEGIN : B2CU_EVENT_END;
 	d.c.flags[i] = flags;
 	d.c.m0[i] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
 	d.c.m1[i] = make_float4(m.lp[0].x, m.lp[0].y, m.ni[0], m.ti[0]);
 	d.c.m2[i] = make_float4(m.lp[1].x, m.lp[1].y, m.ni[1], m.ti[1]);
 	d.c.m3[i] = make_uint4(m.id[0], m.id[1], (uint32_t)m.type, (uint32_t)m.pointCount);
+	return touching;
+}
+
+__device__ __forceinline__ bool ToiCommitUpdate(const DeviceArrays& d, int i, int bA, int bB, Manifold& m, int capacity)
+{
+	int kind;
+	const bool touching = ToiCommitUpdateCore(d, i, bA, bB, m, false, false, &kind);
+	if (kind >= 0) ToiAppendEvent(d, kind, d.c.key[i], capacity);
 	return touching;
 }
 
@@ -382,6 +417,7 @@ struct ToiIsland
 	int contacts[B2CU_TOI_MAX_CONTACTS];
 	float cx[B2CU_TOI_MAX_BODIES], cy[B2CU_TOI_MAX_BODIES], a[B2CU_TOI_MAX_BODIES];
 	float vx[B2CU_TOI_MAX_BODIES], vy[B2CU_TOI_MAX_BODIES], w[B2CU_TOI_MAX_BODIES];
+	float qs[B2CU_TOI_MAX_BODIES], qc[B2CU_TOI_MAX_BODIES]; // sin / cos of a[]: of the bodies the position solver cannot move
 	ToiConstraint rows[B2CU_TOI_MAX_CONTACTS];
 };
 
@@ -447,11 +483,23 @@ __device__ __forceinline__ bool ToiSolvePositions(ToiIsland& is, int toiIndexA, 
 		float aA = is.a[indexA];
 		Vec2 cB = V(is.cx[indexB], is.cy[indexB]);
 		float aB = is.a[indexB];
+		const bool movesA = indexA == toiIndexA || indexA == toiIndexB, movesB = indexB == toiIndexA || indexB == toiIndexB;
 		for (int j = 0; j < pc.pointCount; ++j)
 		{
 			Xf xfA, xfB;
-			xfA.q = SinCos(aA);
-			xfB.q = SinCos(aB);
+			// a body without mass here keeps its angle through all iterations: its rotation was evaluated once
+			if (movesA) xfA.q = SinCos(aA);
+			else
+			{
+				xfA.q.s = is.qs[indexA];
+				xfA.q.c = is.qc[indexA];
+			}
+			if (movesB) xfB.q = SinCos(aB);
+			else
+			{
+				xfB.q.s = is.qs[indexB];
+				xfB.q.c = is.qc[indexB];
+			}
 			xfA.p = cA - Mul(xfA.q, pc.localCenterA);
 			xfB.p = cB - Mul(xfB.q, pc.localCenterB);
 			Vec2 normal, point;
@@ -760,10 +808,22 @@ __global__ void __launch_bounds__(B2CU_TOI_THREADS) ToiEventKernel(DeviceArrays 
 	__shared__ int shI0, shSolid, shBodyA, shBodyB;
 	const int tid = threadIdx.x;
 	const int listCount = min(d.counters[CNT_TOI_LIST], capacity);
+#ifdef B2CU_TOI_PROFILE
+	long long stamps[6];
+#define B2CU_TOI_STAMP(k) stamps[k] = clock64()
+#else
+#define B2CU_TOI_STAMP(k)
+#endif
+	// sorted list keys and, per list entry, B2CU_TOI_WALK_* (long lists: in global memory; the candidate list of the
+	// pass, listA, is spent by now)
+	__shared__ uint64_t shKeys[B2CU_TOI_SORT_KEYS];
+	__shared__ __align__(8) uint8_t shWalk[B2CU_TOI_SORT_KEYS];
+	__shared__ int shSideStart, shWalkEnd[2];
 
 	if (tid == 0)
 	{
 		shSolid = 0;
+		shSideStart = 0x7FFFFFFF;
 		d.toiScratch[B2CU_TOI_SCR_SOLID] = 0;
 		d.toiScratch[B2CU_TOI_SCR_BODY_COUNT] = 0;
 		const int i0 = FindContactSlot(d, contactCount, mainCount, minKey);
@@ -815,23 +875,58 @@ __global__ void __launch_bounds__(B2CU_TOI_THREADS) ToiEventKernel(DeviceArrays 
 	__syncthreads();
 	if (shI0 < 0 || !shSolid) return;
 	const int bodyA = shBodyA, bodyB = shBodyB;
+	B2CU_TOI_STAMP(0);
 
-	// ---- the two contact lists in list order: rank sort of the (unique) keys ----
-	for (int e = tid; e < listCount; e += B2CU_TOI_THREADS)
+	// ---- the two contact lists in list order: sort of the (unique) keys.  Up to B2CU_TOI_SORT_KEYS entries in shared
+	// memory (bitonic network); longer lists by counting ranks in global memory ----
+	const bool inShared = listCount <= B2CU_TOI_SORT_KEYS;
+	if (inShared)
 	{
-		const uint64_t key = d.toiListKeys[e];
-		int rank = 0;
-		for (int k = 0; k < listCount; ++k) rank += d.toiListKeys[k] < key ? 1 : 0;
-		d.toiListSorted[rank] = key;
+		int padded = 2;
+		while (padded < listCount) padded <<= 1;
+		for (int e = tid; e < padded; e += B2CU_TOI_THREADS) shKeys[e] = e < listCount ? d.toiListKeys[e] : ~0ull;
+		__syncthreads();
+		for (int k = 2; k <= padded; k <<= 1)
+		{
+			for (int j = k >> 1; j > 0; j >>= 1)
+			{
+				for (int t = tid; t < (padded >> 1); t += B2CU_TOI_THREADS)
+				{
+					const int lo = 2 * t - (t & (j - 1)); // the element of the pair with bit j clear
+					const int hi = lo + j;
+					const uint64_t a = shKeys[lo], b = shKeys[hi];
+					const bool ascending = (lo & k) == 0;
+					if ((a > b) == ascending)
+					{
+						shKeys[lo] = b;
+						shKeys[hi] = a;
+					}
+				}
+				__syncthreads();
+			}
+		}
 	}
-	__syncthreads();
+	else
+	{
+		for (int e = tid; e < listCount; e += B2CU_TOI_THREADS)
+		{
+			const uint64_t key = d.toiListKeys[e];
+			int rank = 0;
+			for (int k = 0; k < listCount; ++k) rank += d.toiListKeys[k] < key ? 1 : 0;
+			d.toiListSorted[rank] = key;
+		}
+		__syncthreads();
+	}
+	const uint64_t* sorted = inShared ? shKeys : d.toiListSorted;
+	uint8_t* walk = inShared ? shWalk : reinterpret_cast<uint8_t*>(d.listA);
+	B2CU_TOI_STAMP(1);
 
 	// ---- manifolds of the listed contacts with the other body advanced to the time of impact (b2World.cpp:933-941).
 	// Independent of the order of the walk: a body that is already in the island sits at that time already, and
 	// advancing a sweep to the time it is at changes nothing.  Results wait in cAlt rows until the walk commits them. ----
 	for (int e = tid; e < listCount; e += B2CU_TOI_THREADS)
 	{
-		const uint64_t key = d.toiListSorted[e];
+		const uint64_t key = sorted[e];
 		const int i = ToiListSlot(key);
 		const int body = (key & B2CU_TOI_LIST_SIDE) ? bodyB : bodyA;
 		int4 pr = d.c.proxies[i];
@@ -846,79 +941,133 @@ __global__ void __launch_bounds__(B2CU_TOI_THREADS) ToiEventKernel(DeviceArrays 
 		d.cAlt.m1[e] = make_float4(m.lp[0].x, m.lp[0].y, 0.0f, 0.0f);
 		d.cAlt.m2[e] = make_float4(m.lp[1].x, m.lp[1].y, 0.0f, 0.0f);
 		d.cAlt.m3[e] = make_uint4(m.id[0], m.id[1], (uint32_t)m.type, (uint32_t)m.pointCount);
+		walk[e] = (uint8_t)((m.pointCount > 0 ? B2CU_TOI_WALK_TOUCHING : 0) |
+		                    ((d.c.flags[i] & B2CU_CONTACT_ISLAND) ? B2CU_TOI_WALK_SKIP : 0));
+		// where the second body's list begins
+		if ((key & B2CU_TOI_LIST_SIDE) && (e == 0 || !(sorted[e - 1] & B2CU_TOI_LIST_SIDE))) shSideStart = e;
 	}
 	__syncthreads();
+	B2CU_TOI_STAMP(2);
 
+	// ---- the walk (b2World.cpp:897-970), in three parts.  Which contacts the walk looks at, which of them join the
+	// island and which bodies come with them depends on the list order (the island stops growing at 32 contacts / 64
+	// bodies), but only through the touching states that are already known: one thread settles that on the flags ... ----
 	if (tid == 0)
 	{
-		// ---- the walk (b2World.cpp:897-970) ----
-		int e = 0;
+		const int sideStart = min(shSideStart, listCount);
 		for (int side = 0; side < 2; ++side)
 		{
-			bool open = true; // false once a capacity check has ended this body's loop
-			for (; e < listCount; ++e)
+			int e = side ? sideStart : 0;
+			const int end = side ? listCount : sideStart;
+			for (; e < end; ++e)
 			{
-				const uint64_t key = d.toiListSorted[e];
-				if (((key & B2CU_TOI_LIST_SIDE) != 0) != (side == 1)) break;
-				if (!open) continue;
-				if (is.bodyCount == B2CU_TOI_MAX_BODIES || is.contactCount == B2CU_TOI_MAX_CONTACTS)
+				// a full island ends this body's loop (:905-909, :916-919)
+				if (is.bodyCount == B2CU_TOI_MAX_BODIES || is.contactCount == B2CU_TOI_MAX_CONTACTS) break;
+				if (inShared && (e & 7) == 0 && e + 8 <= end)
 				{
-					open = false;
-					continue;
+					// eight entries at once while none of them touches or is to be skipped: they are visited, nothing else
+					uint64_t* group = reinterpret_cast<uint64_t*>(shWalk + e);
+					const uint64_t g = *group;
+					if ((g & 0x0303030303030303ull) == 0)
+					{
+						*group = g | 0x0404040404040404ull;
+						e += 7;
+						continue;
+					}
 				}
-				const int i = ToiListSlot(key);
-				if (d.c.flags[i] & B2CU_CONTACT_ISLAND) continue;
+				int info = walk[e];
+				if (info & B2CU_TOI_WALK_SKIP) continue;
+				info |= B2CU_TOI_WALK_VISITED;
+				walk[e] = (uint8_t)info;
+				if (!(info & B2CU_TOI_WALK_TOUCHING)) continue;
+				const int i = ToiListSlot(sorted[e]);
+				is.contacts[is.contactCount++] = i;
 				const int body = side ? bodyB : bodyA;
 				int4 pr = d.c.proxies[i];
 				const int other = pr.z == body ? pr.w : pr.z;
-				const float4 backupPos0 = d.pos0[other], backupPos = d.pos[other];
-				const bool inIsland = (d.bflags[other] & B2CU_BODY_ISLAND) != 0;
-				if (!inIsland) ToiAdvanceBody(d, other, minAlpha);
-				Manifold m;
-				{
-					float4 g0 = d.cAlt.m0[e], g1 = d.cAlt.m1[e], g2 = d.cAlt.m2[e];
-					uint4 g3 = d.cAlt.m3[e];
-					m.localNormal = V(g0.x, g0.y);
-					m.localPoint = V(g0.z, g0.w);
-					m.lp[0] = V(g1.x, g1.y);
-					m.lp[1] = V(g2.x, g2.y);
-					m.id[0] = g3.x;
-					m.id[1] = g3.y;
-					m.type = (int)g3.z;
-					m.pointCount = (int)g3.w;
-					m.ni[0] = m.ni[1] = m.ti[0] = m.ti[1] = 0.0f;
-				}
-				const bool touching = ToiCommitUpdate(d, i, pr.z, pr.w, m, capacity);
-				if (!touching)
-				{
-					d.pos0[other] = backupPos0;
-					d.pos[other] = backupPos;
-					ToiSyncTransform(d, other);
-					continue;
-				}
-				d.c.flags[i] |= B2CU_CONTACT_ISLAND;
-				is.contacts[is.contactCount++] = i;
-				if (inIsland) continue;
-				const uint32_t fo = d.bflags[other];
-				d.bflags[other] = fo | B2CU_BODY_ISLAND;
-				if (!IsStatic(fo)) ToiSetAwake(d, other);
-				is.bodies[is.bodyCount++] = other;
+				bool inIsland = false;
+				for (int k = 0; k < is.bodyCount; ++k) inIsland |= is.bodies[k] == other;
+				if (!inIsland) is.bodies[is.bodyCount++] = other;
 			}
+			shWalkEnd[side] = e;
 		}
-
-		// ---- b2Island::SolveTOI (b2Island.cpp:398-530) ----
-		for (int k = 0; k < is.bodyCount; ++k)
+	}
+	__syncthreads();
+	B2CU_TOI_STAMP(3);
+	// ... then every visited contact is updated (b2Contact::Update with the other body advanced; a contact that does not
+	// touch leaves that body where it was), and every body that joined is advanced, flagged and woken (:933-968) ...
+	for (int side = 0; side < 2; ++side)
+	{
+		const int begin = side ? min(shSideStart, listCount) : 0;
+		for (int e = begin + tid; e < shWalkEnd[side]; e += B2CU_TOI_THREADS)
 		{
-			const int b = is.bodies[k];
-			float4 p = d.pos[b], v = d.vel[b];
-			is.cx[k] = p.x;
-			is.cy[k] = p.y;
-			is.a[k] = p.z;
-			is.vx[k] = v.x;
-			is.vy[k] = v.y;
-			is.w[k] = v.z;
+			int info = walk[e];
+			if (!(info & B2CU_TOI_WALK_VISITED)) continue;
+			const int i = ToiListSlot(sorted[e]);
+			int4 pr = d.c.proxies[i];
+			Manifold m;
+			{
+				float4 g0 = d.cAlt.m0[e], g1 = d.cAlt.m1[e], g2 = d.cAlt.m2[e];
+				uint4 g3 = d.cAlt.m3[e];
+				m.localNormal = V(g0.x, g0.y);
+				m.localPoint = V(g0.z, g0.w);
+				m.lp[0] = V(g1.x, g1.y);
+				m.lp[1] = V(g2.x, g2.y);
+				m.id[0] = g3.x;
+				m.id[1] = g3.y;
+				m.type = (int)g3.z;
+				m.pointCount = (int)g3.w;
+				m.ni[0] = m.ni[1] = m.ti[0] = m.ti[1] = 0.0f;
+			}
+			int kind;
+			ToiCommitUpdateCore(d, i, pr.z, pr.w, m, true, true, &kind);
+			if (kind >= 0) walk[e] = (uint8_t)(info | (kind == B2CU_EVENT_BEGIN ? B2CU_TOI_WALK_BEGIN : B2CU_TOI_WALK_END));
 		}
-		for (int k = 0; k < is.contactCount; ++k) ToiMakeRow(d, is, is.contacts[k], is.rows[k]);
+	}
+	for (int k = 2 + tid; k < is.bodyCount; k += B2CU_TOI_THREADS)
+	{
+		const int other = is.bodies[k];
+		ToiAdvanceBody(d, other, minAlpha);
+		const uint32_t fo = atomicOr(&d.bflags[other], (uint32_t)B2CU_BODY_ISLAND);
+		if (!IsStatic(fo)) ToiSetAwakeShared(d, other);
+	}
+	__syncthreads();
+	B2CU_TOI_STAMP(4);
+
+	// ... and the begin / end events are raised in the order of the walk
+	if (tid == 0)
+	{
+		for (int side = 0; side < 2; ++side)
+			for (int e = side ? min(shSideStart, listCount) : 0; e < shWalkEnd[side]; ++e)
+			{
+				const int info = walk[e];
+				if (info & (B2CU_TOI_WALK_BEGIN | B2CU_TOI_WALK_END))
+					ToiAppendEvent(d, (info & B2CU_TOI_WALK_BEGIN) ? B2CU_EVENT_BEGIN : B2CU_EVENT_END,
+					               d.c.key[ToiListSlot(sorted[e])], capacity);
+			}
+	}
+
+	// ---- b2Island::SolveTOI (b2Island.cpp:398-530): bodies and rows are set up by all threads, the sequential
+	// impulses are one thread's ----
+	for (int k = tid; k < is.bodyCount; k += B2CU_TOI_THREADS)
+	{
+		const int b = is.bodies[k];
+		float4 p = d.pos[b], v = d.vel[b];
+		is.cx[k] = p.x;
+		is.cy[k] = p.y;
+		is.a[k] = p.z;
+		is.vx[k] = v.x;
+		is.vy[k] = v.y;
+		is.w[k] = v.z;
+		Rot q = SinCos(p.z);
+		is.qs[k] = q.s;
+		is.qc[k] = q.c;
+	}
+	__syncthreads();
+	for (int k = tid; k < is.contactCount; k += B2CU_TOI_THREADS) ToiMakeRow(d, is, is.contacts[k], is.rows[k]);
+	__syncthreads();
+	if (tid == 0)
+	{
 		const int toiIndexA = 0, toiIndexB = 1;
 		for (int it = 0; it < 20; ++it)
 		{
@@ -931,42 +1080,56 @@ __global__ void __launch_bounds__(B2CU_TOI_THREADS) ToiEventKernel(DeviceArrays 
 			p0 = d.pos0[bodyB];
 			d.pos0[bodyB] = make_float4(is.cx[toiIndexB], is.cy[toiIndexB], is.a[toiIndexB], p0.w);
 		}
-		for (int k = 0; k < is.contactCount; ++k) ToiInitVelocityRow(is, is.rows[k]);
+	}
+	__syncthreads();
+	for (int k = tid; k < is.contactCount; k += B2CU_TOI_THREADS) ToiInitVelocityRow(is, is.rows[k]);
+	__syncthreads();
+	if (tid == 0)
+	{
 		for (int it = 0; it < velocityIterations; ++it)
 		{
 			for (int k = 0; k < is.contactCount; ++k) ToiSolveVelocityRow(is, is.rows[k]);
 		}
-		// the impulses of a time-of-impact solve are not stored for warm starting (:488-489)
-		const float h = (1.0f - minAlpha) * dt;
-		for (int k = 0; k < is.bodyCount; ++k)
+	}
+	__syncthreads();
+	// the impulses of a time-of-impact solve are not stored for warm starting (:488-489)
+	const float h = (1.0f - minAlpha) * dt;
+	for (int k = tid; k < is.bodyCount; k += B2CU_TOI_THREADS)
+	{
+		Vec2 c = V(is.cx[k], is.cy[k]);
+		float a = is.a[k];
+		Vec2 v = V(is.vx[k], is.vy[k]);
+		float w = is.w[k];
+		Vec2 translation = h * v;
+		if (Dot(translation, translation) > B2CU_MAX_TRANSLATION_SQUARED)
 		{
-			Vec2 c = V(is.cx[k], is.cy[k]);
-			float a = is.a[k];
-			Vec2 v = V(is.vx[k], is.vy[k]);
-			float w = is.w[k];
-			Vec2 translation = h * v;
-			if (Dot(translation, translation) > B2CU_MAX_TRANSLATION_SQUARED)
-			{
-				float ratio = B2CU_MAX_TRANSLATION / Length(translation);
-				v = V(v.x * ratio, v.y * ratio);
-			}
-			float rotation = h * w;
-			if (rotation * rotation > B2CU_MAX_ROTATION_SQUARED)
-			{
-				float ratio = B2CU_MAX_ROTATION / Abs(rotation);
-				w *= ratio;
-			}
-			c = c + h * v;
-			a += h * w;
-			const int b = is.bodies[k];
-			float4 p = d.pos[b], v4 = d.vel[b];
-			d.pos[b] = make_float4(c.x, c.y, a, p.w);
-			d.vel[b] = make_float4(v.x, v.y, w, v4.w);
-			ToiSyncTransform(d, b);
-			d.toiScratch[B2CU_TOI_SCR_BODIES + k] = b;
+			float ratio = B2CU_MAX_TRANSLATION / Length(translation);
+			v = V(v.x * ratio, v.y * ratio);
 		}
+		float rotation = h * w;
+		if (rotation * rotation > B2CU_MAX_ROTATION_SQUARED)
+		{
+			float ratio = B2CU_MAX_ROTATION / Abs(rotation);
+			w *= ratio;
+		}
+		c = c + h * v;
+		a += h * w;
+		const int b = is.bodies[k];
+		float4 p = d.pos[b], v4 = d.vel[b];
+		d.pos[b] = make_float4(c.x, c.y, a, p.w);
+		d.vel[b] = make_float4(v.x, v.y, w, v4.w);
+		ToiSyncTransform(d, b);
+		d.toiScratch[B2CU_TOI_SCR_BODIES + k] = b;
+	}
+	if (tid == 0)
+	{
 		d.toiScratch[B2CU_TOI_SCR_BODY_COUNT] = is.bodyCount;
 		d.toiScratch[B2CU_TOI_SCR_SOLID] = 1;
+#ifdef B2CU_TOI_PROFILE
+		stamps[5] = clock64();
+		printf("toi event: list %d island %d/%d  sort %lld spec %lld scan %lld commit %lld solve %lld cycles\n", listCount, is.contactCount,
+		       is.bodyCount, stamps[1] - stamps[0], stamps[2] - stamps[1], stamps[3] - stamps[2], stamps[4] - stamps[3], stamps[5] - stamps[4]);
+#endif
 	}
 }
 

@@ -3,6 +3,7 @@
 // b2cuStep replaces b2World::Step (Box2D/Dynamics/b2World.cpp:1613-1710) and keeps its phase order:
 //   [FindNewContacts if new fixtures] -> Collide -> Solve (islands, solver, SynchronizeFixtures,
 //   FindNewContacts) -> TOI candidate compaction -> ClearForces.
+#include <cstdio>
 #include "b2cu_kernels.cuh"
 
 #include <algorithm>
