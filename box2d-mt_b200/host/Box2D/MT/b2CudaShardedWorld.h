@@ -22,6 +22,11 @@
 // it every few hundred steps, or when bodies have travelled a good part of `margin` (a body that drifts further than
 // `margin` past its strip's boundary between two calls is no longer seen by the neighbour).
 //
+// Listeners and filters are per strip (GetStrip(r).SetContactListener(...)); a strip's callbacks are made on the host
+// thread that steps it (strip 0: the caller's thread), concurrently with the other strips'.  Bodies are created and
+// destroyed in the scene before it is sharded, not in the strips.  Rebalance() makes new strip worlds: pointers to strip
+// bodies and per-strip listeners do not survive it.
+//
 // Limits (the device layer's, include/b2cuda.h): no joints, time-of-impact events are refused.
 #ifndef B2_CUDA_SHARDED_WORLD_H
 #define B2_CUDA_SHARDED_WORLD_H
