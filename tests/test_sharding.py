@@ -6,6 +6,7 @@ sharing one device) must evolve exactly like the oracle stepping the WHOLE world
 merged shard order (own constraints of every shard, then cross constraints of every shard): body state, contact
 set and events bit-exact.  That proves the halo exchange implements one consistent sequential Gauss-Seidel."""
 import os
+import subprocess
 import threading
 
 import numpy as np
@@ -274,3 +275,37 @@ def test_cpp_sharded_world_rebalance_migrates_bodies_bit_exactly(gpu):
         wc = T.contact_keys(whole.contacts())
         assert len(seen) == len(wc) and (seen == wc).all(), "step %d: union of strip contact sets != whole world" % step
     assert moved_bodies > 20, "the boundary shifts did not move bodies between strips"
+
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _compile_sharded_pile(tmp_path):
+    exe = tmp_path / "sharded_pile"
+    lib = os.path.join(ROOT, "box2d-mt_b200")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-pthread", "-I", os.path.join(lib, "host"), "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "sharded_pile.cpp"), "-L", lib, "-lbox2d_b200", "-lb2cuda",
+                    "-Wl,-rpath," + lib, "-o", str(exe)], check=True)
+    return exe
+
+
+def test_sharded_pile_program_compiles_against_host_api(tmp_path):
+    """tests/cpp/sharded_pile.cpp: b2CudaShardedWorld as a C++ user sees it (construct, Step, Rebalance, Gather)"""
+    assert _compile_sharded_pile(tmp_path).exists()
+
+
+@pytest.mark.gpu
+def test_sharded_pile_program_runs(gpu, tmp_path):
+    """The same program on two GPUs: the pile settles, nothing falls through the container, no contact is lost when the
+    strips are re-planned, and two runs give the same bits."""
+    if gpu.device_count() < 2:
+        pytest.skip("sharding tests need at least 2 GPUs (run with gpurun --gpus 2); see profiles/ for the recorded run")
+    exe = _compile_sharded_pile(tmp_path)
+    runs = [subprocess.run([str(exe), "2", "60", "10", "240"], capture_output=True, text=True, check=True).stdout.split()
+            for _ in range(2)]
+    bodies, strips, held, lost, lowest, fastest, digest = runs[0]
+    assert int(bodies) == 600 and int(strips) == 2
+    assert int(held) > 600 + 2          # every strip holds the container, the lower one ghosts on top
+    assert int(lost) == 0
+    assert float(lowest) > 0.15 and float(fastest) < 0.5
+    assert runs[1] == runs[0]
