@@ -207,6 +207,7 @@ __device__ __forceinline__ int UpdateContact(const DeviceArrays& d, int i, int4 
 
 __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contactCount, int mainCount, int capacity, int* __restrict__ heavyList)
 {
+	GridDependencyWait();
 	int touchingCount = 0;
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(256) CollideKernel(DeviceArrays d, int contact
 // second pass of Collide over the queued polygon-polygon / edge-polygon contacts
 __global__ void __launch_bounds__(256) CollideHeavyKernel(DeviceArrays d, const int* __restrict__ heavyList, int capacity)
 {
+	GridDependencyWait();
 	int touchingCount = 0;
 	int n = d.counters[CNT_HEAVY];
 	B2CU_GRID_STRIDE(k, n)
@@ -318,6 +320,7 @@ static_assert(sizeof(b2cuBody) == B2CU_BODY_WORDS * 4, "b2cuBody layout");
 
 __global__ void __launch_bounds__(256) PackBodiesKernel(DeviceArrays d, int first, int count, float* __restrict__ out)
 {
+	GridDependencyWait();
 	__shared__ float sh[256 * B2CU_BODY_WORDS];
 	for (int tile = blockIdx.x; tile * 256 < count; tile += gridDim.x)
 	{
@@ -353,6 +356,7 @@ static_assert(sizeof(b2cuBodyState) == B2CU_STATE_WORDS * 4, "b2cuBodyState layo
 // device -> host direction: only the fields a step changes and callers read (b2cuBodyState, 48 bytes)
 __global__ void __launch_bounds__(256) PackBodyStatesKernel(DeviceArrays d, int first, int count, float* __restrict__ out)
 {
+	GridDependencyWait();
 	__shared__ float sh[256 * (B2CU_STATE_WORDS + 1)]; // +1: rows of a multiple of four words would collide in the banks
 	for (int tile = blockIdx.x; tile * 256 < count; tile += gridDim.x)
 	{
@@ -378,6 +382,7 @@ __global__ void __launch_bounds__(256) PackBodyStatesKernel(DeviceArrays d, int 
 
 __global__ void __launch_bounds__(256) UnpackBodiesKernel(DeviceArrays d, int first, int count, const float* __restrict__ in)
 {
+	GridDependencyWait();
 	__shared__ float sh[256 * B2CU_BODY_WORDS];
 	for (int tile = blockIdx.x; tile * 256 < count; tile += gridDim.x)
 	{
@@ -412,6 +417,7 @@ __global__ void __launch_bounds__(256) UnpackBodiesKernel(DeviceArrays d, int fi
 // b2cuSetBodyForces: (fx, fy, torque) rows into the force column; the sleep timer in its fourth lane stays
 __global__ void SetBodyForcesKernel(DeviceArrays d, int first, int count, const float* __restrict__ in)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(r, count)
 	{
 		float4 f = d.force[first + r];
@@ -425,6 +431,7 @@ __global__ void SetBodyForcesKernel(DeviceArrays d, int first, int count, const 
 // pradius[p] = m_radius of the proxy's shape (b2Shape.h:93), read by the constraint initialisation
 __global__ void FillProxyRadiusKernel(DeviceArrays d, int proxyCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(p, proxyCount) { d.pradius[p] = d.shapes[d.pshape[p]].radius; }
 }
 
@@ -432,6 +439,7 @@ __global__ void FillProxyRadiusKernel(DeviceArrays d, int proxyCount)
 // contacts the narrow phase has just updated and found touching: what b2Contact::Update reports to PreSolve
 __global__ void PreSolveSelectKernel(DeviceArrays d, int contactCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		uint32_t f = d.c.flags[i];
@@ -442,6 +450,7 @@ __global__ void PreSolveSelectKernel(DeviceArrays d, int contactCount)
 __global__ void PreSolveGatherKernel(DeviceArrays d, const int* __restrict__ list, int n, b2cuContact* __restrict__ out,
                                      b2cuManifold* __restrict__ oldOut)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(j, n)
 	{
 		int i = list[j];
@@ -487,6 +496,7 @@ __global__ void PreSolveGatherKernel(DeviceArrays d, const int* __restrict__ lis
 // b2Contact::SetEnabled(false) for a list of keys
 __global__ void DisableContactsKernel(DeviceArrays d, int contactCount, int mainCount, const uint64_t* __restrict__ keys, int n)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(j, n)
 	{
 		uint64_t key = keys[j];
@@ -504,6 +514,7 @@ __global__ void DisableContactsKernel(DeviceArrays d, int contactCount, int main
 // b2Fixture::Refilter (b2Fixture.cpp:197-210): the contacts of a refiltered proxy get e_filterFlag
 __global__ void FlagFilterContactsKernel(DeviceArrays d, int contactCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		uint32_t f = d.c.flags[i];
@@ -527,6 +538,7 @@ __device__ __forceinline__ bool JointFreed(const DeviceArrays& d, int bodyA, int
 // contacts between two bodies that a joint keeps from colliding get e_filterFlag; Collide then removes them
 __global__ void FlagJointContactsKernel(DeviceArrays d, int contactCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		uint32_t f = d.c.flags[i];
@@ -537,6 +549,7 @@ __global__ void FlagJointContactsKernel(DeviceArrays d, int contactCount)
 }
 __global__ void ClearProxyFlagKernel(DeviceArrays d, int proxyCount, uint32_t flag)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(p, proxyCount) { d.pgroup[p] &= ~(flag << 16); }
 }
 
@@ -544,6 +557,7 @@ __global__ void ClearProxyFlagKernel(DeviceArrays d, int proxyCount, uint32_t fl
 // kernel); this fills them in after the caller has uploaded contacts or proxies
 __global__ void FillContactBodiesKernel(DeviceArrays d, int contactCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		int4 pr = d.c.proxies[i];
@@ -571,6 +585,7 @@ __global__ void FillContactBodiesKernel(DeviceArrays d, int contactCount)
 // (Box2D/Dynamics/b2Body.h:690-718: sets e_awakeFlag and resets m_sleepTime).
 __global__ void ApplyWakeKernel(DeviceArrays d, int bodyCount, int* __restrict__ patch)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
 		if (d.wake[b])
@@ -593,6 +608,7 @@ __global__ void GatherKeysKernel(const uint64_t* __restrict__ key, const int* __
                                  const int* __restrict__ count, const int* __restrict__ offset,
                                  uint64_t* __restrict__ out, int capacity)
 {
+	GridDependencyWait();
 	int n = *count;
 	int off = offset ? *offset : 0;
 	B2CU_GRID_STRIDE(j, n)
@@ -603,6 +619,7 @@ __global__ void GatherKeysKernel(const uint64_t* __restrict__ key, const int* __
 
 __global__ void CountMaskKernel(const uint32_t* __restrict__ flags, uint32_t mask, int n, int* counter)
 {
+	GridDependencyWait();
 	int local = 0;
 	B2CU_GRID_STRIDE(i, n)
 	{
@@ -619,6 +636,7 @@ __global__ void CountMaskKernel(const uint32_t* __restrict__ flags, uint32_t mas
 // ---------------------------------------------------------------------------------------------------------
 __global__ void SolveInitBodiesKernel(DeviceArrays d, int bodyCount, int positionIterations)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
 		d.island[b] = b;
@@ -693,6 +711,7 @@ __device__ __forceinline__ bool IsSolidTouching(const DeviceArrays& d, int i)
 // phase 0: contacts with i % sample == 0; phase 1: the others; sample == 1 with phase 0: everything in one sweep.
 __global__ void IslandUnionKernel(DeviceArrays d, int contactCount, int sample, int phase)
 {
+	GridDependencyWait();
 	const int chunk = (contactCount + 31) / 32;
 	B2CU_GRID_STRIDE(g, (sample < 0 ? chunk * 32 : contactCount))
 	{
@@ -712,6 +731,7 @@ __global__ void IslandUnionKernel(DeviceArrays d, int contactCount, int sample, 
 // joints connect islands like touching contacts do (b2World.cpp:1286-1320): both bodies active, neither static
 __global__ void JointUnionKernel(DeviceArrays d, int jointCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(j, jointCount)
 	{
 		int bA = d.joints[j].bodyA, bB = d.joints[j].bodyB;
@@ -726,11 +746,13 @@ __global__ void JointUnionKernel(DeviceArrays d, int jointCount)
 // a concurrent reader sees either the old ancestor or the root, both on its path)
 __global__ void IslandCompressKernel(DeviceArrays d, int bodyCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(b, bodyCount) { d.island[b] = UfFindReadOnly(d.island, b); }
 }
 
 __global__ void IslandFlattenKernel(DeviceArrays d, int bodyCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
 		int r = UfFind(d.island, b);
@@ -742,6 +764,7 @@ __global__ void IslandFlattenKernel(DeviceArrays d, int bodyCount)
 
 __global__ void IslandMarkKernel(DeviceArrays d, int bodyCount)
 {
+	GridDependencyWait();
 	int local = 0;
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
@@ -764,6 +787,7 @@ __global__ void IslandMarkKernel(DeviceArrays d, int bodyCount)
 // which contacts go to the solver: touching, enabled, solid, attached to a body of an awake island
 __global__ void SelectConstraintsKernel(DeviceArrays d, int contactCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		int sel = 0;
@@ -797,6 +821,7 @@ __device__ __forceinline__ uint32_t ColourClassMask(bool cross, int crossBase)
 __global__ void __launch_bounds__(256) ColourPrepareKernel(DeviceArrays d, const int* __restrict__ list, int* uncoloured,
                                                            int crossBase)
 {
+	GridDependencyWait();
 	__shared__ int hist[B2CU_MAX_COLOURS];
 	if (threadIdx.x < B2CU_MAX_COLOURS) hist[threadIdx.x] = 0;
 	__syncthreads();
@@ -839,6 +864,7 @@ __device__ __forceinline__ uint32_t ColourFreeMask(const DeviceArrays& d, int bA
 __global__ void ColourProposeKernel(DeviceArrays d, const int* __restrict__ list, int counterIndex, uint32_t round,
                                     int crossBase)
 {
+	GridDependencyWait();
 	int n = d.counters[counterIndex];
 	B2CU_GRID_STRIDE(j, n)
 	{
@@ -863,6 +889,7 @@ __global__ void ColourProposeKernel(DeviceArrays d, const int* __restrict__ list
 __global__ void ColourCommitKernel(DeviceArrays d, const int* __restrict__ list, int counterIndex, int* next,
                                    int nextCounterIndex, uint32_t round, int crossBase)
 {
+	GridDependencyWait();
 	int n = d.counters[counterIndex];
 	B2CU_GRID_STRIDE(j, n)
 	{
@@ -900,6 +927,7 @@ __global__ void ColourCommitKernel(DeviceArrays d, const int* __restrict__ list,
 #define B2CU_ORDER_COLOUR_SHIFT 34
 __global__ void ColourKeysKernel(DeviceArrays d, const int* __restrict__ list)
 {
+	GridDependencyWait();
 	int n = d.counters[CNT_CONSTRAINT];
 	B2CU_GRID_STRIDE(j, n)
 	{
@@ -916,6 +944,7 @@ __global__ void ColourKeysKernel(DeviceArrays d, const int* __restrict__ list)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void IntegrateVelocitiesKernel(DeviceArrays d, int bodyCount, float h, float2 gravity, int flowBase)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
 		uint32_t bf = d.bflags[b];
@@ -957,6 +986,7 @@ __global__ void IntegrateVelocitiesKernel(DeviceArrays d, int bodyCount, float h
 // cSelect[i] = 1 + position of contact i in the solver order (0: not a constraint)
 __global__ void __launch_bounds__(256) ConstraintSlotKernel(DeviceArrays d)
 {
+	GridDependencyWait();
 	int n = d.counters[CNT_CONSTRAINT];
 	B2CU_GRID_STRIDE(k, n) { d.cSelect[(int)(uint32_t)(d.orderKeys[k] & 0xFFFFFFFFull)] = k + 1; }
 }
@@ -970,6 +1000,7 @@ __global__ void __launch_bounds__(256) ConstraintSlotKernel(DeviceArrays d)
 __global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(DeviceArrays d, const int* __restrict__ list,
                                                                                float dtRatio, int warmStarting)
 {
+	GridDependencyWait();
 	// list = the constraint contacts in ascending contact order (the compaction of cSelect)
 	int n = d.counters[CNT_CONSTRAINT];
 	B2CU_GRID_STRIDE(j, n)
@@ -1233,6 +1264,7 @@ __device__ __forceinline__ void WarmStartOne(const DeviceArrays& d, int k) { War
 
 __global__ void __launch_bounds__(256) WarmStartKernel(DeviceArrays d, int begin, int count)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(t, count) { WarmStartOne(d, begin + t); }
 }
 
@@ -1421,12 +1453,14 @@ __device__ __forceinline__ void SolveVelocityOne(const DeviceArrays& d, int k) {
 
 __global__ void __launch_bounds__(256) SolveVelocityKernel(DeviceArrays d, int begin, int count)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(t, count) { SolveVelocityOne(d, begin + t); }
 }
 
 // b2ContactSolver::StoreImpulses (b2ContactSolver.cpp:605-618)
 __global__ void StoreImpulsesKernel(DeviceArrays d)
 {
+	GridDependencyWait();
 	int n = d.counters[CNT_CONSTRAINT];
 	B2CU_GRID_STRIDE(k, n)
 	{
@@ -1451,6 +1485,7 @@ __global__ void StoreImpulsesKernel(DeviceArrays d)
 // b2Island::Solve, body part 2 (b2Island.cpp:283-313): clamp and integrate positions
 __global__ void IntegratePositionsKernel(DeviceArrays d, int bodyCount, float h)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
 		uint32_t bf = d.bflags[b];
@@ -1606,6 +1641,7 @@ __device__ __forceinline__ bool IslandDone(const DeviceArrays& d, int iteration,
 __global__ void __launch_bounds__(256) SolvePositionKernel(DeviceArrays d, int begin, int count, int iteration,
                                                            int bodyCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(t, count)
 	{
 		int k = begin + t;
@@ -1619,16 +1655,19 @@ __global__ void __launch_bounds__(256) SolvePositionKernel(DeviceArrays d, int b
 // overflow constraints (no free colour): solved one after the other by a single thread, in key order
 __global__ void OverflowWarmStartKernel(DeviceArrays d, int begin, int count)
 {
+	GridDependencyWait();
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 		for (int t = 0; t < count; ++t) WarmStartOne(d, begin + t);
 }
 __global__ void OverflowSolveVelocityKernel(DeviceArrays d, int begin, int count)
 {
+	GridDependencyWait();
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 		for (int t = 0; t < count; ++t) SolveVelocityOne(d, begin + t);
 }
 __global__ void OverflowSolvePositionKernel(DeviceArrays d, int begin, int count, int iteration, int bodyCount)
 {
+	GridDependencyWait();
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 		for (int t = 0; t < count; ++t)
 		{
@@ -1923,6 +1962,7 @@ template <bool JOINTS>
 __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_VEL_BLOCKS) SolverVelocityPersistentKernel(DeviceArrays d,
                                                                                                                  SolverPlan plan)
 {
+	GridDependencyWait();
 	GridSync grid = {plan.softBarrier, gridDim.x, 0u, plan.shard.stuck};
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
@@ -2011,6 +2051,7 @@ template <bool JOINTS>
 __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_POS_BLOCKS) SolverPositionPersistentKernel(DeviceArrays d,
                                                                                                                  SolverPlan plan)
 {
+	GridDependencyWait();
 	GridSync grid = {plan.softBarrier, gridDim.x, 0u, plan.shard.stuck};
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
@@ -2081,6 +2122,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, JOINTS ? 2 : B2CU_POS_BLO
 #define B2CU_GHOST_ROWS 5
 __global__ void GhostSendKernel(DeviceArrays d, ShardState sh)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(k, sh.exportCount)
 	{
 		int b = sh.exportIds[k];
@@ -2097,11 +2139,13 @@ __global__ void GhostSendKernel(DeviceArrays d, ShardState sh)
 }
 __global__ void ShardSignalKernel(unsigned* flag, unsigned seq)
 {
+	GridDependencyWait();
 	*reinterpret_cast<volatile unsigned*>(flag) = seq;
 	__threadfence_system();
 }
 __global__ void ShardWaitKernel(const unsigned* flag, unsigned seq, int* stuck)
 {
+	GridDependencyWait();
 	long long spins = 0;
 	while (*reinterpret_cast<const volatile unsigned*>(flag) < seq)
 	{
@@ -2115,6 +2159,7 @@ __global__ void ShardWaitKernel(const unsigned* flag, unsigned seq, int* stuck)
 }
 __global__ void GhostApplyKernel(DeviceArrays d, ShardState sh)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(k, sh.ghostCount)
 	{
 		int b = sh.ghostIds[k];
@@ -2132,6 +2177,7 @@ __global__ void GhostApplyKernel(DeviceArrays d, ShardState sh)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void FinalizeBodiesKernel(DeviceArrays d, int bodyCount, float h, int allowSleep)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
 		uint32_t bf = d.bflags[b];
@@ -2166,6 +2212,7 @@ __global__ void FinalizeBodiesKernel(DeviceArrays d, int bodyCount, float h, int
 
 __global__ void SleepIslandsKernel(DeviceArrays d, int bodyCount, int positionIterations)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
 		uint32_t bf = d.bflags[b];
@@ -2221,6 +2268,7 @@ __device__ __forceinline__ float4 ComputeAABB(const b2cuShape* __restrict__ s, c
 
 __global__ void __launch_bounds__(256) SyncProxiesKernel(DeviceArrays d, int proxyCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(p, proxyCount)
 	{
 		int b = d.pbody[p];
@@ -2328,6 +2376,7 @@ __device__ __forceinline__ bool StartBox(const DeviceArrays& d, int p, uint32_t 
 // levelInfo[l] = proxies on level l, levelInfo[LEVELS+1+l] = moved proxies on level l (l == LEVELS: huge)
 __global__ void __launch_bounds__(256) GridCountKernel(DeviceArrays d, int proxyCount, GridParams g)
 {
+	GridDependencyWait();
 	__shared__ int sh[2 * (B2CU_GRID_LEVELS + 1)];
 	if (threadIdx.x < 2 * (B2CU_GRID_LEVELS + 1)) sh[threadIdx.x] = 0;
 	__syncthreads();
@@ -2371,6 +2420,7 @@ __global__ void __launch_bounds__(256) GridCountKernel(DeviceArrays d, int proxy
 
 __global__ void GridFillKernel(DeviceArrays d, int proxyCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(p, proxyCount)
 	{
 		int h = d.cellOfProxy[p];
@@ -2514,6 +2564,7 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 // dense pass over the compacted list of moved proxies (all lanes of a warp have work)
 __global__ void __launch_bounds__(128) QueryMovedKernel(DeviceArrays d, GridParams g, int2 contactCount, int pairCapacity)
 {
+	GridDependencyWait();
 	__shared__ int shCount[B2CU_GRID_LEVELS + 1];
 	__shared__ int shMoved[B2CU_GRID_LEVELS + 1];
 	if (threadIdx.x <= B2CU_GRID_LEVELS)
@@ -2540,6 +2591,7 @@ __global__ void __launch_bounds__(128) QueryMovedKernel(DeviceArrays d, GridPara
 __global__ void __launch_bounds__(128) QueryUnmovedKernel(DeviceArrays d, int proxyCount, GridParams g, int2 contactCount,
                                                           int pairCapacity)
 {
+	GridDependencyWait();
 	__shared__ int shCount[B2CU_GRID_LEVELS + 1];
 	__shared__ int shMoved[B2CU_GRID_LEVELS + 1];
 	__shared__ int lowestMoved;
@@ -2574,17 +2626,20 @@ __global__ void __launch_bounds__(128) QueryUnmovedKernel(DeviceArrays d, int pr
 // lowStart[p] = index of the first contact whose low proxy id is >= p, for p in [0, proxyCount]
 __global__ void BuildLowStartKernel(DeviceArrays d, int contactCount, int proxyCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(p, proxyCount + 1) { d.lowStart[p] = LowerBound64(d.c.key, contactCount, (uint64_t)(uint32_t)p << 32); }
 }
 
 __global__ void IotaKernel(int* out, int n)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, n) { out[i] = i; }
 }
 
 // over the move buffer only (movedList holds every flagged proxy, GridCountKernel)
 __global__ void ClearMovedKernel(DeviceArrays d)
 {
+	GridDependencyWait();
 	const int n = d.counters[CNT_SCRATCH];
 	B2CU_GRID_STRIDE(t, n)
 	{
@@ -2605,6 +2660,7 @@ __global__ void MergeMoveKernel(DeviceArrays d, int srcBegin, int srcCount, cons
                                 const uint64_t* __restrict__ otherKeys, int otherCount, const int* __restrict__ otherRank,
                                 int otherLive, int dstBegin)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(t, srcCount)
 	{
 		int i = srcBegin + t;
@@ -2632,6 +2688,7 @@ __global__ void MergeMoveKernel(DeviceArrays d, int srcBegin, int srcCount, cons
 __global__ void RebuildNewKernel(DeviceArrays d, int tailBegin, int tailCount, const int* __restrict__ tailRank,
                                  int tailLive, int newCount, int dstBegin, uint32_t stamp)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(j, newCount)
 	{
 		uint64_t key = d.newKeys[j];
@@ -2692,6 +2749,7 @@ __global__ void RebuildNewKernel(DeviceArrays d, int tailBegin, int tailCount, c
 // TOI eligibility (b2World.cpp:317-341 filters + b2Contact::IsMinToiCandidate, b2Contact.h:404-419)
 __global__ void ToiFlagsKernel(DeviceArrays d, int contactCount, int* flagsOut)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
 		uint32_t f = d.c.flags[i];
@@ -2726,6 +2784,7 @@ __device__ __forceinline__ Sweep LoadSweep(const DeviceArrays& d, int body)
 __global__ void ToiFirstPassKernel(DeviceArrays d, const int* __restrict__ list, const int* __restrict__ countPtr,
                                    float* __restrict__ alphaOut)
 {
+	GridDependencyWait();
 	const int count = *countPtr;
 	B2CU_GRID_STRIDE(k, count)
 	{
@@ -2747,6 +2806,7 @@ __global__ void ToiFirstPassKernel(DeviceArrays d, const int* __restrict__ list,
 __global__ void ToiMinKeyKernel(DeviceArrays d, const int* __restrict__ list, const int* __restrict__ countPtr,
                                 const float* __restrict__ alpha)
 {
+	GridDependencyWait();
 	const int count = *countPtr;
 	const unsigned int best = *reinterpret_cast<const unsigned int*>(d.counters + CNT_TOI_MIN_ALPHA);
 	B2CU_GRID_STRIDE(k, count)
@@ -2760,6 +2820,7 @@ __global__ void ToiMinKeyKernel(DeviceArrays d, const int* __restrict__ list, co
 // body carrying a fixture that is not thick-shape
 __global__ void ToiPossibleKernel(DeviceArrays d, int bodyCount, int proxyCount)
 {
+	GridDependencyWait();
 	bool any = false;
 	B2CU_GRID_STRIDE(i, bodyCount > proxyCount ? bodyCount : proxyCount)
 	{
@@ -2777,6 +2838,7 @@ __global__ void ToiPossibleKernel(DeviceArrays d, int bodyCount, int proxyCount)
 // (b2World::ClearForces :1506-1523), count awake bodies
 __global__ void EndStepBodiesKernel(DeviceArrays d, int bodyCount, int clearForces)
 {
+	GridDependencyWait();
 	int local = 0;
 	B2CU_GRID_STRIDE(b, bodyCount)
 	{
@@ -2800,6 +2862,7 @@ __global__ void EndStepBodiesKernel(DeviceArrays d, int bodyCount, int clearForc
 // of HBM time), then a stable compaction -- no tree to walk ----
 __global__ void QueryAabbSelectKernel(DeviceArrays d, int proxyCount, float4 box, int* __restrict__ flags)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(p, proxyCount)
 	{
 		flags[p] = (AabbOverlap(d.fat[p], box) && !((d.pgroup[p] >> 16) & B2CU_PROXY_INACTIVE)) ? 1 : 0;
@@ -2810,6 +2873,7 @@ __global__ void QueryAabbSelectKernel(DeviceArrays d, int proxyCount, float4 box
 // overlap, and the segment's line must not separate the box (|dot(v, p1 - c)| - dot(|v|, h) <= 0 with v normal to the ray)
 __global__ void RayCastSelectKernel(DeviceArrays d, int proxyCount, float2 p1, float2 p2, int* __restrict__ flags)
 {
+	GridDependencyWait();
 	Vec2 a = V(p1.x, p1.y), b = V(p2.x, p2.y);
 	Vec2 r = Normalized(b - a);
 	Vec2 v = CrossSV(1.0f, r);
@@ -2835,6 +2899,7 @@ __global__ void DistancePairsKernel(const b2cuShape* __restrict__ shapes, int pa
                                     const float4* __restrict__ xfA, const int* __restrict__ shapeB,
                                     const float4* __restrict__ xfB, int useRadii, b2cuDistanceResult* __restrict__ out)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, pairCount)
 	{
 		GjkCache cache;
@@ -2872,6 +2937,7 @@ __global__ void TimeOfImpactPairsKernel(const b2cuShape* __restrict__ shapes, in
                                         const b2cuSweep* __restrict__ sweepB, const float* __restrict__ tMax,
                                         b2cuToiResult* __restrict__ out)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, pairCount)
 	{
 		float t;
@@ -2889,6 +2955,7 @@ __global__ void CollidePairsKernel(const b2cuShape* __restrict__ shapes, int pai
                                    const float4* __restrict__ xfA, const int* __restrict__ shapeB,
                                    const float4* __restrict__ xfB, b2cuManifold* __restrict__ out)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, pairCount)
 	{
 		Manifold m;
@@ -2923,6 +2990,7 @@ __global__ void CollidePairsKernel(const b2cuShape* __restrict__ shapes, int pai
 __global__ void GatherContactsByKeyKernel(DeviceArrays d, int contactCount, int mainCount,
                                           const uint64_t* __restrict__ keys, int n, b2cuContact* __restrict__ out)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(j, n)
 	{
 		uint64_t key = keys[j];
@@ -2994,6 +3062,7 @@ __global__ void GatherContactsByKeyKernel(DeviceArrays d, int contactCount, int 
 
 __global__ void SinCosKernel(int n, const float* __restrict__ x, float* __restrict__ s, float* __restrict__ c)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, n)
 	{
 		Rot q = SinCos(x[i]);

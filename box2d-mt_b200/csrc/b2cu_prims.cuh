@@ -10,6 +10,33 @@
 namespace b2cu
 {
 
+// Programmatic dependent launch: the step is ~50 short kernels in a row on one stream, and between two of them the GPU
+// idles for ~3 us (drain, launch, ramp).  Kernels launched with the programmatic-serialization attribute (LaunchPdl) are
+// scheduled while their predecessor is still running and wait HERE, first thing, for it to complete with its memory
+// operations visible (measured on B200: 6.2 -> 3.3 us per dependent launch of a short kernel).  In a kernel launched the
+// ordinary way the instruction does nothing.  Every kernel executes it unconditionally: a kernel that returned without
+// it could complete before its predecessor and let ITS successor start too early.
+#ifdef __CUDACC__
+__device__ __forceinline__ void GridDependencyWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern bool g_pdl; // B2CU_PDL=0 turns the attribute off (ordinary stream order)
+template <typename... Params, typename... Args>
+inline cudaError_t LaunchPdl(void (*kernel)(Params...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = stream;
+	cudaLaunchAttribute attribute[1];
+	attribute[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attribute[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+	cfg.attrs = attribute;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+#endif
+
 struct PrimScratch
 {
 	unsigned long long* scanState = nullptr; // ticket + one look-back word per tile

@@ -192,6 +192,7 @@ __device__ __forceinline__ int FlowExpected(uint32_t mask, int colour, int passI
 // keys[2j + side] = body << 32 | (2j + side) for the dynamic bodies of overflow row j (others: ~0, sorted to the end)
 __global__ void FlowOverflowKeysKernel(DeviceArrays d, int ovStart, int ovCount, uint64_t* __restrict__ keys)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(j, ovCount)
 	{
 		const int4 sb = d.sBody[ovStart + j];
@@ -205,6 +206,7 @@ __global__ void FlowOverflowKeysKernel(DeviceArrays d, int ovStart, int ovCount,
 // the body's extra degree
 __global__ void FlowOverflowRanksKernel(const uint64_t* __restrict__ keys, int n, int* __restrict__ ovRank, int* __restrict__ ovDeg)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(p, n)
 	{
 		const uint64_t key = keys[p];
@@ -224,6 +226,7 @@ __global__ void FlowOverflowRanksKernel(const uint64_t* __restrict__ keys, int n
 template <bool SHARD, bool OVERFLOW>
 __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, (SHARD || OVERFLOW) ? 3 : B2CU_FLOW_VEL_BLOCKS) SolverVelocityFlowKernel(const __grid_constant__ DeviceArrays d, const __grid_constant__ SolverPlan plan)
 {
+	GridDependencyWait();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	const int firstPass = plan.warmStarting ? 0 : 1;
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, (SHARD || OVERFLOW) ? 3 :
 template <bool SHARD, bool OVERFLOW>
 __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPositionFlowKernel(const __grid_constant__ DeviceArrays d, const __grid_constant__ SolverPlan plan)
 {
+	GridDependencyWait();
 	GridSync grid = {plan.softBarrier, gridDim.x, 0u, plan.shard.stuck};
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
@@ -534,6 +538,7 @@ __global__ void __launch_bounds__(B2CU_SOLVER_THREADS, B2CU_POS_BLOCKS) SolverPo
 // the owner's side, cross colours 16-31 on the lower shard's side), so that both sides count a body's updates alike.
 __global__ void HaloMaskSendKernel(DeviceArrays d, ShardState sh)
 {
+	GridDependencyWait();
 	const int n = sh.ghostCount > sh.exportCount ? sh.ghostCount : sh.exportCount;
 	B2CU_GRID_STRIDE(k, n)
 	{
@@ -546,6 +551,7 @@ __global__ void HaloMaskSendKernel(DeviceArrays d, ShardState sh)
 }
 __global__ void HaloMaskApplyKernel(DeviceArrays d, ShardState sh)
 {
+	GridDependencyWait();
 	const int n = sh.ghostCount > sh.exportCount ? sh.ghostCount : sh.exportCount;
 	B2CU_GRID_STRIDE(k, n)
 	{

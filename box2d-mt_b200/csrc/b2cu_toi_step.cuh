@@ -49,6 +49,7 @@ __device__ __forceinline__ bool ToiEligible(const DeviceArrays& d, int i, uint32
 // directly, the others are listed for ToiComputeKernel.
 __global__ void __launch_bounds__(256) ToiSelectKernel(DeviceArrays d, int contactCount, int* __restrict__ work)
 {
+	GridDependencyWait();
 	int eligible = 0;
 	B2CU_GRID_STRIDE(i, contactCount)
 	{
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) ToiSelectKernel(DeviceArrays d, int conta
 // all sit at the event's alpha, so whichever thread advances a neighbour writes the same 16 bytes.
 __global__ void __launch_bounds__(64) ToiComputeKernel(DeviceArrays d, const int* __restrict__ work)
 {
+	GridDependencyWait();
 	const int count = d.counters[CNT_TOI_WORK];
 	B2CU_GRID_STRIDE(k, count)
 	{
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(64) ToiComputeKernel(DeviceArrays d, const int
 // the winner among equal alphas: the smallest contact key (b2Contact::ToiLessThan, b2Contact.cpp:326-334)
 __global__ void __launch_bounds__(256) ToiMinKeyAllKernel(DeviceArrays d, int contactCount)
 {
+	GridDependencyWait();
 	const unsigned int best = *reinterpret_cast<const unsigned int*>(d.counters + CNT_TOI_MIN_ALPHA);
 	if (best == 0xFFFFFFFFu) return;
 	B2CU_GRID_STRIDE(i, contactCount)
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(256) ToiMinKeyAllKernel(DeviceArrays d, int co
 // every body (static ones too) goes back to alpha0 = 0
 __global__ void __launch_bounds__(256) ToiClearKernel(DeviceArrays d, int contactCount, int bodyCount)
 {
+	GridDependencyWait();
 	B2CU_GRID_STRIDE(i, (contactCount > bodyCount ? contactCount : bodyCount))
 	{
 		if (i < contactCount)
@@ -195,6 +199,7 @@ __device__ __forceinline__ int ToiListSlot(uint64_t k) { return 0x7FFFFFFF - (in
 __global__ void __launch_bounds__(256) ToiEventPrepareKernel(DeviceArrays d, int contactCount, int mainCount, uint64_t minKey,
                                                              int capacity)
 {
+	GridDependencyWait();
 	__shared__ int sh[3];
 	if (threadIdx.x == 0)
 	{
@@ -804,6 +809,7 @@ __global__ void __launch_bounds__(B2CU_TOI_THREADS) ToiEventKernel(DeviceArrays 
                                                                    uint64_t minKey, float minAlpha, float dt,
                                                                    int velocityIterations, int capacity)
 {
+	GridDependencyWait();
 	__shared__ ToiIsland is;
 	__shared__ int shI0, shSolid, shBodyA, shBodyB;
 	const int tid = threadIdx.x;
@@ -1138,6 +1144,7 @@ __global__ void __launch_bounds__(B2CU_TOI_THREADS) ToiEventKernel(DeviceArrays 
 // e_islandFlag and e_toiFlag, so that the next FindMinToiContact recomputes them.
 __global__ void __launch_bounds__(256) ToiAfterEventKernel(DeviceArrays d, int proxyCount, int contactCount)
 {
+	GridDependencyWait();
 	if (!d.toiScratch[B2CU_TOI_SCR_SOLID]) return;
 	B2CU_GRID_STRIDE(t, (proxyCount > contactCount ? proxyCount : contactCount))
 	{
@@ -1199,6 +1206,7 @@ __global__ void __launch_bounds__(256) ToiAfterEventKernel(DeviceArrays d, int p
 #define B2CU_TOI_MOVED_TILE 128
 __global__ void __launch_bounds__(256) ToiFindPairsKernel(DeviceArrays d, int proxyCount, int2 contactCounts, int pairCapacity)
 {
+	GridDependencyWait();
 	__shared__ float4 shBox[B2CU_TOI_MOVED_TILE];
 	__shared__ int shId[B2CU_TOI_MOVED_TILE];
 	if (blockIdx.x == 0)

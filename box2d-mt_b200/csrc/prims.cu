@@ -5,6 +5,7 @@ namespace b2cu
 {
 
 int g_primLaunches = 0;
+bool g_pdl = true;
 void (*g_primTraceHook)(const char* name, cudaStream_t stream) = nullptr;
 #define PRIM_MARK(name)                                  \
 	do                                                   \
@@ -48,6 +49,7 @@ template <typename Loader>
 __global__ void __launch_bounds__(SCAN_BLOCK) ScanTilesKernel(Loader load, int* __restrict__ out,
                                                               int* __restrict__ tileSums, int n, int* total)
 {
+	GridDependencyWait();
 	__shared__ int warpSums[SCAN_BLOCK / 32];
 	const int tile = blockIdx.x;
 	const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
@@ -114,6 +116,7 @@ template <typename Loader>
 __global__ void __launch_bounds__(SCAN_BLOCK) ScanLookbackKernel(Loader load, int* __restrict__ out,
                                                                  unsigned long long* state, int* ticket, int n, int* total)
 {
+	GridDependencyWait();
 	__shared__ int warpSums[SCAN_BLOCK / 32];
 	__shared__ int shTile, shExclusive;
 	if (threadIdx.x == 0) shTile = atomicAdd(ticket, 1);
@@ -201,7 +204,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) ScanLookbackKernel(Loader load, in
 	}
 }
 
-__global__ void SetIntKernel(int* p, int v) { *p = v; }
+__global__ void SetIntKernel(int* p, int v) {
+	GridDependencyWait(); *p = v; }
 
 cudaError_t PrimScratchAlloc(PrimScratch* s, int capacity)
 {
@@ -235,7 +239,7 @@ static void ScanImpl(PrimScratch* s, Loader load, int* out, int n, int* total, c
 	{
 		if (total)
 		{
-			SetIntKernel<<<1, 1, 0, stream>>>(total, 0);
+			LaunchPdl(SetIntKernel, dim3(1), dim3(1), stream, total, 0);
 			PRIM_MARK("SetInt");
 		}
 		return;
@@ -243,13 +247,13 @@ static void ScanImpl(PrimScratch* s, Loader load, int* out, int n, int* total, c
 	int tiles1 = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (tiles1 == 1)
 	{
-		ScanTilesKernel<<<1, SCAN_BLOCK, 0, stream>>>(load, out, (int*)nullptr, n, total);
+		LaunchPdl(ScanTilesKernel<Loader>, dim3(1), dim3(SCAN_BLOCK), stream, load, out, (int*)nullptr, n, total);
 		PRIM_MARK("ScanTiles");
 		return;
 	}
 	// scanState: [ticket (8 bytes) | one state word per tile]
 	cudaMemsetAsync(s->scanState, 0, sizeof(unsigned long long) * (size_t)(tiles1 + 1), stream);
-	ScanLookbackKernel<<<tiles1, SCAN_BLOCK, 0, stream>>>(load, out, s->scanState + 1, reinterpret_cast<int*>(s->scanState), n,
+	LaunchPdl(ScanLookbackKernel<Loader>, dim3(tiles1), dim3(SCAN_BLOCK), stream, load, out, s->scanState + 1, reinterpret_cast<int*>(s->scanState), n,
 	                                                      total);
 	PRIM_MARK("ScanLookback");
 }
@@ -270,6 +274,7 @@ void ExclusiveScan(PrimScratch* s, const int* in, int* out, int n, int* total, c
 template <typename Loader>
 __global__ void CompactScatterKernel(Loader load, const int* __restrict__ pos, int n, int* __restrict__ outIdx)
 {
+	GridDependencyWait();
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n && load(i))
 	{
@@ -283,7 +288,7 @@ void CompactFlags(PrimScratch* s, const int* flags, int n, int* outIdx, int* out
 	ScanImpl(s, l, s->compactPos, n, outCount, stream);
 	if (n > 0)
 	{
-		CompactScatterKernel<<<(n + 255) / 256, 256, 0, stream>>>(l, s->compactPos, n, outIdx);
+		LaunchPdl(CompactScatterKernel<NonZeroLoader>, dim3((n + 255) / 256), dim3(256), stream, l, s->compactPos, n, outIdx);
 		PRIM_MARK("CompactScatter");
 	}
 }
@@ -295,7 +300,7 @@ void CompactMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int n, in
 	ScanImpl(s, l, s->compactPos, n, outCount, stream);
 	if (n > 0)
 	{
-		CompactScatterKernel<<<(n + 255) / 256, 256, 0, stream>>>(l, s->compactPos, n, outIdx);
+		LaunchPdl(CompactScatterKernel<MaskLoader>, dim3((n + 255) / 256), dim3(256), stream, l, s->compactPos, n, outIdx);
 		PRIM_MARK("CompactScatter");
 	}
 }
@@ -305,6 +310,7 @@ void CompactMask(PrimScratch* s, const uint32_t* flags, uint32_t mask, int n, in
 __global__ void __launch_bounds__(RADIX_BLOCK) RadixHistogramKernel(const uint64_t* __restrict__ keys, int n, int shift,
                                                                     int* __restrict__ hist, int numBlocks)
 {
+	GridDependencyWait();
 	__shared__ int sh[256];
 	sh[threadIdx.x] = 0;
 	__syncthreads();
@@ -327,6 +333,7 @@ __global__ void __launch_bounds__(RADIX_BLOCK) RadixScatterKernel(const uint64_t
                                                                   uint64_t* __restrict__ out, int n, int shift,
                                                                   const int* __restrict__ offsets, int numBlocks)
 {
+	GridDependencyWait();
 	__shared__ int warpCount[RADIX_BLOCK / 32][256];
 	__shared__ int running[256];
 	const int lane = threadIdx.x & 31;
@@ -384,6 +391,7 @@ static const int SORT_TILE = 4096;
 
 __global__ void __launch_bounds__(1024) TileSort64Kernel(uint64_t* __restrict__ keys, int n)
 {
+	GridDependencyWait();
 	__shared__ uint64_t sh[SORT_TILE];
 	const int base = blockIdx.x * SORT_TILE;
 	const int count = min(SORT_TILE, n - base);
@@ -418,6 +426,7 @@ __global__ void __launch_bounds__(1024) TileSort64Kernel(uint64_t* __restrict__ 
 // runs of length `run` are sorted; merge run pairs (2r, 2r+1) from src into dst
 __global__ void MergeRuns64Kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, int n, int run)
 {
+	GridDependencyWait();
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	int r = i / run;
@@ -443,13 +452,13 @@ void SortSmall64(PrimScratch* s, uint64_t* keys, int n, cudaStream_t stream)
 {
 	if (n <= 1) return;
 	int tiles = (n + SORT_TILE - 1) / SORT_TILE;
-	TileSort64Kernel<<<tiles, 1024, 0, stream>>>(keys, n);
+	LaunchPdl(TileSort64Kernel, dim3(tiles), dim3(1024), stream, keys, n);
 	PRIM_MARK("TileSort64");
 	uint64_t* src = keys;
 	uint64_t* dst = s->radixAlt;
 	for (int run = SORT_TILE; run < n; run <<= 1)
 	{
-		MergeRuns64Kernel<<<(n + 255) / 256, 256, 0, stream>>>(src, dst, n, run);
+		LaunchPdl(MergeRuns64Kernel, dim3((n + 255) / 256), dim3(256), stream, src, dst, n, run);
 		PRIM_MARK("MergeRuns64");
 		uint64_t* t = src;
 		src = dst;
@@ -469,10 +478,10 @@ void RadixSort64(PrimScratch* s, uint64_t* keys, int n, int beginBit, int endBit
 	uint64_t* dst = s->radixAlt;
 	for (int shift = beginBit; shift < endBit; shift += 8)
 	{
-		RadixHistogramKernel<<<numBlocks, RADIX_BLOCK, 0, stream>>>(src, n, shift, s->radixHist, numBlocks);
+		LaunchPdl(RadixHistogramKernel, dim3(numBlocks), dim3(RADIX_BLOCK), stream, src, n, shift, s->radixHist, numBlocks);
 		PRIM_MARK("RadixHistogram");
 		ExclusiveScan(s, s->radixHist, s->radixHist, 256 * numBlocks, nullptr, stream);
-		RadixScatterKernel<<<numBlocks, RADIX_BLOCK, 0, stream>>>(src, dst, n, shift, s->radixHist, numBlocks);
+		LaunchPdl(RadixScatterKernel, dim3(numBlocks), dim3(RADIX_BLOCK), stream, src, dst, n, shift, s->radixHist, numBlocks);
 		PRIM_MARK("RadixScatter");
 		uint64_t* t = src;
 		src = dst;

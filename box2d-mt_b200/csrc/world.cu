@@ -97,7 +97,7 @@ void TraceMark(b2cuWorld* w, const char* name)
 #define LAUNCH(w, kernel, grid, block, ...)                 \
 	do                                                      \
 	{                                                       \
-		kernel<<<grid, block, 0, (w)->stream>>>(__VA_ARGS__); \
+		LaunchPdl(kernel, dim3(grid), dim3(block), (w)->stream, __VA_ARGS__); \
 		++(w)->launches;                                    \
 		TraceMark(w, #kernel);                              \
 	} while (0)
@@ -836,6 +836,10 @@ int b2cuCreateWorld(const b2cuWorldDef* def, b2cuWorld** out)
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPosJ, SolverPositionPersistentKernel<true>, B2CU_SOLVER_THREADS, 0);
 		w->persistentGridJoints = g_smCount * std::max(perSmJ, 0);
 		w->persistentGridPositionJoints = g_smCount * std::max(perSmPosJ, 0);
+		{
+			const char* pdl = getenv("B2CU_PDL");
+			g_pdl = !(pdl && atoi(pdl) == 0);
+		}
 		const char* pe = getenv("B2CU_PERSISTENT");
 		w->persistentSolver = coop != 0 && perSm > 0 && perSmPos > 0 && !(pe && atoi(pe) == 0);
 		const char* pb = getenv("B2CU_PERSISTENT_BLOCKS");
