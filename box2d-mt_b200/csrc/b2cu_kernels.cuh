@@ -2373,6 +2373,18 @@ __device__ __forceinline__ bool StartBox(const DeviceArrays& d, int p, uint32_t 
 	return !(proxyFlags & B2CU_PROXY_MOVED);
 }
 
+// the counters and level statistics of one pair search, zeroed by one launch instead of five memset nodes
+__global__ void BroadphaseResetKernel(DeviceArrays d)
+{
+	GridDependencyWait();
+	const int t = threadIdx.x;
+	if (t < 64) d.levelInfo[t] = 0;
+	if (t == 64) d.counters[CNT_MOVED] = 0;
+	if (t == 65) d.counters[CNT_SCRATCH] = 0;
+	if (t == 66) d.counters[CNT_LARGE] = 0;
+	if (t == 67) d.counters[CNT_NEW_PAIRS] = 0;
+}
+
 // levelInfo[l] = proxies on level l, levelInfo[LEVELS+1+l] = moved proxies on level l (l == LEVELS: huge)
 __global__ void __launch_bounds__(256) GridCountKernel(DeviceArrays d, int proxyCount, GridParams g)
 {
@@ -2425,7 +2437,10 @@ __global__ void GridFillKernel(DeviceArrays d, int proxyCount)
 	{
 		int h = d.cellOfProxy[p];
 		if (h < 0) continue;
-		int slot = d.cellStart[h] + atomicAdd(&d.cellCount[h], 1);
+		// the counts of GridCountKernel are used up as cursors (a cell is filled from its end; the order inside a cell
+		// is immaterial, the pair search produces a set), so nothing has to be zeroed between the two kernels and the
+		// array is clean for the next step's count
+		int slot = d.cellStart[h] + atomicSub(&d.cellCount[h], 1) - 1;
 		// the entry carries the fat box: a query reads its candidates as one contiguous run instead of one gather each
 		d.cellItems[slot] = p;
 		d.cellBoxes[slot] = d.fat[p];
@@ -2503,7 +2518,7 @@ __device__ __forceinline__ void QueryProxy(const DeviceArrays& d, int p, bool mo
 				if (turn++ % lanes != lane) continue;
 				uint32_t h = CellHash(level, cx, cy, g.mask);
 				int start = d.cellStart[h];
-				int end = start + d.cellCount[h];
+				int end = d.cellStart[h + 1];
 				for (int s = start; s < end; ++s)
 				{
 					int r = d.cellItems[s];

@@ -279,6 +279,7 @@ struct b2cuWorld
 	void* queryHost;     // page-locked host side of the same
 	size_t queryHostBytes;
 	bool eventPrefetch;        // b2cuSetEventPrefetch
+	bool gridDirty;            // cellCount may hold counts of an interrupted grid build
 	bool eventCachePending;    // the copy of the event records into queryHost was started by the step itself
 	void* eventOrder;         // host scratch of b2cuGetEventContacts: 2 x eventOrderCapacity (key, index) pairs
 	size_t eventOrderCapacity;

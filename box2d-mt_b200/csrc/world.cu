@@ -468,10 +468,7 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 	const int nTail = nc - nMain;
 	int rc;
 
-	if ((rc = ZeroCounter(w, CNT_MOVED))) return rc;
-	if ((rc = ZeroCounter(w, CNT_SCRATCH))) return rc;
-	if ((rc = ZeroCounter(w, CNT_LARGE))) return rc;
-	if ((rc = ZeroCounter(w, CNT_NEW_PAIRS))) return rc;
+	LAUNCH(w, BroadphaseResetKernel, 1, 128, d);
 
 	GridParams grid;
 	grid.cell0 = w->cellSize;
@@ -480,12 +477,14 @@ int FindNewContactsAndRebuild(b2cuWorld* w, int* newCountOut, int* destroyedOut,
 	const int2 counts = make_int2(nc, nMain);
 	if (np > 0)
 	{
-		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
-		CUDA_TRY(w, cudaMemsetAsync(d.levelInfo, 0, sizeof(int) * 64, w->stream));
+		// cellCount is all zero here: Reserve clears it and GridFillKernel leaves it so (w->gridDirty: after a failed step)
+		if (w->gridDirty) CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
+		w->gridDirty = true;
 		LAUNCH(w, GridCountKernel, GridFor(np), kBlock, d, np, grid);
-		ExclusiveScan(&w->prims, d.cellCount, d.cellStart, w->gridSize, nullptr, w->stream);
-		CUDA_TRY(w, cudaMemsetAsync(d.cellCount, 0, sizeof(int) * (w->gridSize + 1), w->stream));
+		// one entry more than there are cells: cellStart[h + 1] closes the last cell's run
+		ExclusiveScan(&w->prims, d.cellCount, d.cellStart, w->gridSize + 1, nullptr, w->stream);
 		LAUNCH(w, GridFillKernel, GridFor(np), kBlock, d, np);
+		w->gridDirty = false;
 		LAUNCH(w, QueryMovedKernel, QueryGrid(np), 128, d, grid, counts, w->contactCapacity);
 		LAUNCH(w, QueryUnmovedKernel, GridFor(np, 128), 128, d, np, grid, counts, w->contactCapacity);
 	}
