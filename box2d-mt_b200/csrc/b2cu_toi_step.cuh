@@ -10,10 +10,12 @@
 //                       (b2TimeOfImpact of the others, one thread each), ToiMinKeyKernel (ToiLessThan tie-break)
 //   StepSolveTOI        ToiEventPrepareKernel  the contact lists of the two bodies: a scan of the contact set, ordered
 //                                              afterwards by creation stamp (newest first, as OnContactCreate links them)
-//                       ToiEventKernel         ONE CTA: advance the two bodies, update the contact, evaluate the listed
-//                                              contacts' manifolds in parallel, walk the list in order (one thread: the
-//                                              32-contact / 64-body caps make it sequential), solve the island, write
-//                                              the bodies back
+//                       ToiEventKernel         ONE CTA: advance the two bodies, update the contact, sort the lists
+//                                              (shared memory), evaluate the listed contacts' manifolds in parallel,
+//                                              settle on one byte per entry what the walk visits before the 32-contact /
+//                                              64-body caps end it (one thread, flags only), commit the visited contacts
+//                                              and the joined bodies in parallel, solve the island (rows and bodies set
+//                                              up by all threads, the sequential impulses by one), write the bodies back
 //                       ToiAfterEventKernel    SynchronizeFixtures of the displaced bodies + the flag reset of their
 //                                              contacts (b2World.cpp:995-1013)
 //                       ToiFindPairsKernel     FindNewContacts for the handful of moved proxies: every proxy of the
