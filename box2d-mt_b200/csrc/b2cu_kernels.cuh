@@ -997,6 +997,13 @@ __global__ void __launch_bounds__(256) ConstraintSlotKernel(DeviceArrays d)
 #ifndef B2CU_INIT_BLOCKS
 #define B2CU_INIT_BLOCKS 3
 #endif
+// the rows are written once here and read next by the solver kernels, 400 MB later: streaming stores keep them from
+// pushing the body rows this kernel gathers out of L2
+#ifndef B2CU_ROW_STORE_PLAIN
+#define B2CU_ROW_STORE(p, v) __stcs(p, v)
+#else
+#define B2CU_ROW_STORE(p, v) (*(p) = (v))
+#endif
 __global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(DeviceArrays d, const int* __restrict__ list,
                                                                                float dtRatio, int warmStarting)
 {
@@ -1162,19 +1169,19 @@ __global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(D
 		uint32_t bfA = d.bflags[bA];
 		int root = d.island[IsStatic(bfA) ? bB : bA];
 
-		d.solverKeys[k] = d.c.key[i];
-		d.sBody[k] = make_int4(bA, bB, i, solvePoints | (pointCount << 8));
-		d.sMass[k] = make_float4(mA, iA, mB, iB);
-		d.sNormal[k] = make_float4(normal.x, normal.y, friction, tangentSpeed);
-		d.sP0a[k] = pa[0];
+		B2CU_ROW_STORE(&d.solverKeys[k], d.c.key[i]);
+		B2CU_ROW_STORE(&d.sBody[k], make_int4(bA, bB, i, solvePoints | (pointCount << 8)));
+		B2CU_ROW_STORE(&d.sMass[k], make_float4(mA, iA, mB, iB));
+		B2CU_ROW_STORE(&d.sNormal[k], make_float4(normal.x, normal.y, friction, tangentSpeed));
+		B2CU_ROW_STORE(&d.sP0a[k], pa[0]);
 		// second point: only rA / rB and the velocity bias are kept; its masses and the block solver's K and inverse are
 		// recomputed by the solver from rA, rB, the normal and the body masses (the same expressions on the same values:
 		// the same bits), which takes 48 bytes per iteration off every two-point constraint
-		d.sP0b[k] = make_float4(pb[0].x, pb[0].y, pb[0].z, pb[1].z);
-		d.sImp[k] = make_float4(imp[0], imp[1], imp[2], imp[3]);
+		B2CU_ROW_STORE(&d.sP0b[k], make_float4(pb[0].x, pb[0].y, pb[0].z, pb[1].z));
+		B2CU_ROW_STORE(&d.sImp[k], make_float4(imp[0], imp[1], imp[2], imp[3]));
 		if (pointCount == 2)
 		{
-			d.sP1a[k] = pa[1];
+			B2CU_ROW_STORE(&d.sP1a[k], pa[1]);
 			// first two-point row of the colour (rows are ordered one-point first inside a colour, ColourKeysKernel)
 			const int colour = d.c.colour[i];
 			const unsigned peers = __match_any_sync(__activemask(), colour);
@@ -1183,10 +1190,10 @@ __global__ void __launch_bounds__(256, B2CU_INIT_BLOCKS) InitConstraintsKernel(D
 		}
 		(void)K;
 		(void)NM;
-		d.sLocal[k] = m0;
-		d.sLocalP[k] = make_float4(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
-		d.sCenters[k] = make_float4(localCenterA.x, localCenterA.y, localCenterB.x, localCenterB.y);
-		d.sRadius[k] = make_float4(radiusA, radiusB, __int_as_float(type), __int_as_float(root));
+		B2CU_ROW_STORE(&d.sLocal[k], m0);
+		B2CU_ROW_STORE(&d.sLocalP[k], make_float4(lp[0].x, lp[0].y, lp[1].x, lp[1].y));
+		B2CU_ROW_STORE(&d.sCenters[k], make_float4(localCenterA.x, localCenterA.y, localCenterB.x, localCenterB.y));
+		B2CU_ROW_STORE(&d.sRadius[k], make_float4(radiusA, radiusB, __int_as_float(type), __int_as_float(root)));
 	}
 }
 
